@@ -1,0 +1,256 @@
+"""Shared helpers for the test-suite: ctypes views of the oracle (oracle/liboracle.so), of the
+unmodified reference (oracle/_ref/libmecatref.so, only when it has been built) and small
+numpy utilities for packed volumes.  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+class Volume(C.Structure):
+    """orc_volume / mecat_volume: same layout (oracle.h, include/mecat_b200.h)."""
+    _fields_ = [("num_reads", C.c_int32), ("num_bases", C.c_int32), ("start_read_id", C.c_int32),
+                ("offset_size", C.POINTER(C.c_int32)), ("pac", C.POINTER(C.c_uint8))]
+
+
+class PwParams(C.Structure):
+    _fields_ = [("task", C.c_int32), ("num_candidates", C.c_int32), ("min_align_size", C.c_int32),
+                ("min_kmer_match", C.c_int32), ("tech", C.c_int32)]
+
+
+def pw_params(task=1, n=100, a=2000, k=4, x=0):
+    return PwParams(task, n, a, k, x)
+
+
+EC_DTYPE = np.dtype([(n, "<i4") for n in
+                     ("qdir", "qid", "qext", "qsize", "qoff", "qend", "sdir", "sid", "sext", "ssize", "soff",
+                      "send", "score")])
+M4_DTYPE = np.dtype([("qid", "<i8"), ("sid", "<i8"), ("ident", "<f8"), ("vscore", "<i4"), ("qdir", "<i4"),
+                     ("qoff", "<i8"), ("qend", "<i8"), ("qsize", "<i8"), ("sdir", "<i4"), ("pad", "<i4"),
+                     ("soff", "<i8"), ("send", "<i8"), ("ssize", "<i8"), ("qext", "<i8"), ("sext", "<i8")])
+assert EC_DTYPE.itemsize == 52 and M4_DTYPE.itemsize == 104
+
+
+class PackedVolume:
+    """A 2-bit packed volume held in numpy arrays, in the on-disk layout of `wrk/volN`
+    (reference split_database.cpp:136-153)."""
+
+    def __init__(self, offset_size, pac, num_bases, start_read_id=0):
+        self.offset_size = np.ascontiguousarray(offset_size, dtype=np.int32).reshape(-1, 2)
+        self.pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        self.num_reads = self.offset_size.shape[0]
+        self.num_bases = int(num_bases)
+        self.start_read_id = int(start_read_id)
+
+    def c(self):
+        return Volume(self.num_reads, self.num_bases, self.start_read_id,
+                      self.offset_size.ctypes.data_as(C.POINTER(C.c_int32)),
+                      self.pac.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+    @staticmethod
+    def from_seqs(seqs, start_read_id=0):
+        """seqs: list of ASCII strings/bytes of pure ACGT.  One pad base after every read."""
+        lut = np.zeros(256, dtype=np.uint8)
+        for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+            lut[ch] = v
+        total = sum(len(s) + 1 for s in seqs)
+        codes = np.zeros(((total + 3) // 4) * 4, dtype=np.uint8)
+        os_ = np.zeros((len(seqs), 2), dtype=np.int32)
+        cur = 0
+        for i, s in enumerate(seqs):
+            b = s.encode() if isinstance(s, str) else bytes(s)
+            a = np.frombuffer(b, dtype=np.uint8)
+            codes[cur:cur + len(a)] = lut[a]
+            os_[i] = (cur, len(a))
+            cur += len(a) + 1
+        q = codes.reshape(-1, 4)
+        pac = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+        return PackedVolume(os_, pac.astype(np.uint8), total, start_read_id)
+
+    @staticmethod
+    def load(path):
+        """Read a reference `volN` file."""
+        with open(path, "rb") as f:
+            hdr = np.frombuffer(f.read(12), dtype="<i4")
+            n, nb, sid = int(hdr[0]), int(hdr[1]), int(hdr[2])
+            os_ = np.frombuffer(f.read(8 * n), dtype="<i4").reshape(-1, 2).copy()
+            pac = np.frombuffer(f.read((nb + 3) // 4), dtype=np.uint8).copy()
+        return PackedVolume(os_, pac, nb, sid)
+
+    def codes(self, rid, strand=0):
+        """Unpacked base codes (0..3) of one read; strand 1 = reverse complement."""
+        off, sz = self.offset_size[rid]
+        idx = np.arange(off, off + sz, dtype=np.int64)
+        c = (self.pac[idx >> 2] >> (((~idx) & 3) << 1)) & 3
+        if strand:
+            c = (3 - c)[::-1]
+        return np.ascontiguousarray(c, dtype=np.int8)
+
+
+def read_fasta(path):
+    seqs, cur = [], []
+    with open(path, "rb") as f:
+        for line in f:
+            if line.startswith(b">"):
+                if cur:
+                    seqs.append(b"".join(cur))
+                    cur = []
+            else:
+                cur.append(line.strip())
+    if cur:
+        seqs.append(b"".join(cur))
+    return seqs
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+
+
+def gen_reads(path, n, genome_len, seed, mean=15000, sd=1500, err=0.15, genome_out=None):
+    build_oracle()
+    cmd = [os.path.join(ORACLE_DIR, "gen_reads"), path, str(n), str(genome_len), str(seed), str(mean), str(sd),
+           str(err)]
+    if genome_out:
+        cmd.append(genome_out)
+    subprocess.check_call(cmd)
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    build_oracle()
+    L = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+    VP, PP = C.POINTER(Volume), C.POINTER(PwParams)
+    i32p, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
+    L.orc_index_build.restype = C.c_void_p
+    L.orc_index_build.argtypes = [VP]
+    L.orc_index_free.argtypes = [C.c_void_p]
+    L.orc_index_lookup.restype = C.c_int
+    L.orc_index_lookup.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(i32p)]
+    L.orc_index_num_kmers.restype = C.c_int64
+    L.orc_index_num_kmers.argtypes = [C.c_void_p]
+    L.orc_seeding.restype = C.c_int
+    L.orc_seeding.argtypes = [C.c_void_p, VP, VP, C.c_int, C.c_int, i32p, i16p, i16p, C.c_int]
+    L.orc_insert_loc.argtypes = [i16p, i16p, i16p, C.c_int, C.c_int]
+    L.orc_find_location.restype = C.c_int
+    L.orc_find_location.argtypes = [i32p, i32p, i32p, i32p, C.c_int, i32p, C.c_int]
+    L.orc_pw_candidates.restype = C.c_int
+    L.orc_pw_candidates.argtypes = [C.c_void_p, VP, VP, C.c_int, PP, i32p]
+    L.orc_diff_go.restype = C.c_int
+    L.orc_diff_go.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, i32p,
+                              C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_int]
+    L.orc_diff_align_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, i32p]
+    L.orc_pw_tile.restype = C.c_int
+    L.orc_pw_tile.argtypes = [VP, VP, PP, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.orc_free.argtypes = [C.c_void_p]
+    L.orc_cns_get_alignment.restype = C.c_int
+    L.orc_cns_get_alignment.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double,
+                                        C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_int]
+    L.orc_normalize_gaps.restype = C.c_int
+    L.orc_normalize_gaps.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    _oracle = L
+    return L
+
+
+def oracle_pw_tile(ref, reads, params, threads=8):
+    L = oracle()
+    out, n = C.c_void_p(), C.c_size_t()
+    rv, qv = ref.c(), reads.c()
+    rc = L.orc_pw_tile(C.byref(rv), C.byref(qv), C.byref(params), threads, C.byref(out), C.byref(n))
+    assert rc == 0
+    dt = EC_DTYPE if params.task == 0 else M4_DTYPE
+    arr = np.frombuffer(C.string_at(out.value, n.value * dt.itemsize), dtype=dt).copy()
+    L.orc_free(out)
+    return arr
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "libmecatref.so"))
+
+
+_ref = None
+
+
+def ref():
+    """ctypes handle on the unmodified reference (function-level shim)."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    L = C.CDLL(os.path.join(REF_DIR, "libmecatref.so"))
+    i32p, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
+    L.ref_volume_new.restype = C.c_void_p
+    L.ref_volume_new.argtypes = [C.c_int]
+    L.ref_volume_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.ref_volume_set_start_id.argtypes = [C.c_void_p, C.c_int]
+    L.ref_volume_load.restype = C.c_void_p
+    L.ref_volume_load.argtypes = [C.c_char_p]
+    L.ref_volume_dump.argtypes = [C.c_void_p, C.c_char_p]
+    L.ref_volume_free.argtypes = [C.c_void_p]
+    for f in ("ref_volume_num_reads", "ref_volume_num_bases", "ref_volume_start_id"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.ref_volume_pac.restype = C.POINTER(C.c_uint8)
+    L.ref_volume_pac.argtypes = [C.c_void_p]
+    L.ref_volume_offsets.restype = i32p
+    L.ref_volume_offsets.argtypes = [C.c_void_p]
+    L.ref_read_id_from_offset.argtypes = [C.c_void_p, C.c_int]
+    L.ref_index_create.restype = C.c_void_p
+    L.ref_index_create.argtypes = [C.c_void_p, C.c_int]
+    L.ref_index_free.argtypes = [C.c_void_p]
+    L.ref_index_count.argtypes = [C.c_void_p, C.c_uint32]
+    L.ref_index_list.restype = i32p
+    L.ref_index_list.argtypes = [C.c_void_p, C.c_uint32]
+    L.ref_pw_set_options.argtypes = [C.c_int] * 4
+    L.ref_insert_loc.argtypes = [i16p, C.c_int, C.c_int]
+    L.ref_find_location.argtypes = [i32p, i32p, i32p, i32p, C.c_int, i32p, C.c_int]
+    L.ref_pw_ctx_new.restype = C.c_void_p
+    L.ref_pw_ctx_new.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_pw_ctx_free.argtypes = [C.c_void_p]
+    L.ref_pw_seeding_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, i16p, i16p, C.c_int]
+    L.ref_pw_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p]
+    L.ref_diff_new.restype = C.c_void_p
+    L.ref_diff_free.argtypes = [C.c_void_p]
+    L.ref_diff_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, i32p,
+                              C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    L.ref_diff_align_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, i32p]
+    L.ref_cns_drd_new.restype = C.c_void_p
+    L.ref_cns_drd_free.argtypes = [C.c_void_p]
+    L.ref_cns_get_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_double, C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_int]
+    L.ref_normalize_gaps.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    _ref = L
+    return L
+
+
+def ec_lines(ec):
+    """ExtensionCandidate records -> sorted `.can` lines (alignment.cpp:18-32)."""
+    out = ["%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d" % (e["qid"], e["sid"], e["qdir"], e["sdir"], e["qext"], e["sext"],
+                                                   e["score"], e["qsize"], e["ssize"]) for e in ec]
+    return sorted(out)
+
+
+def fmt_g6(x):
+    """default ostream << double : %g with 6 significant digits."""
+    return "%g" % x
+
+
+def m4_lines(m4, gapped=False):
+    """M4 records -> sorted `.m4` lines (pw_impl.cpp:509-531)."""
+    out = []
+    for m in m4:
+        s = "%d\t%d\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d" % (
+            m["qid"], m["sid"], fmt_g6(m["ident"]), m["vscore"], m["qdir"], m["qoff"], m["qend"], m["qsize"],
+            m["sdir"], m["soff"], m["send"], m["ssize"])
+        if gapped:
+            s += "\t%d\t%d" % (m["qext"], m["sext"])
+        out.append(s)
+    return sorted(out)
