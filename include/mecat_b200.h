@@ -1,0 +1,146 @@
+/* include/mecat_b200.h -- C ABI of the B200-native MECAT overlap hot path.
+ *
+ * The reference (xiaochuanle/MECAT) has no plugin/FFI layer; its seams are ordinary C++
+ * functions called once per read.  A per-read call is too fine for a GPU, so the boundary
+ * sits at the batch seams its drivers already have.  Each entry
+ * point names the reference interface it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions: one context per device, used from one host thread; 0 = success, any other
+ * value = failure with text in mecat_b200_last_error(); inputs are borrowed for the call;
+ * outputs are library-owned host buffers released with mecat_b200_free().  The library
+ * never aborts and has no CPU fallback: without a CUDA device mecat_b200_init fails.
+ */
+#ifndef MECAT_B200_H
+#define MECAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MECAT_B200_ABI_VERSION 1
+
+typedef struct mecat_b200_ctx mecat_b200_ctx;
+
+/* A 2-bit packed read volume exactly as the reference keeps it in `wrk/volN`
+ * (volume_t, src/common/split_database.h:18-24; file layout split_database.cpp:136-153):
+ * offset_size = num_reads x {offset,size}; pac holds (num_bases+3)/4 bytes, base i in byte
+ * i>>2 at shift ((~i)&3)<<1 (packed_db.h:98-107); one zero pad base follows every read. */
+typedef struct {
+	int32_t num_reads, num_bases, start_read_id;
+	const int32_t* offset_size;
+	const uint8_t* pac;
+} mecat_volume;
+
+/* Mirrors options_t (src/mecat2pw/pw_options.h:9-21): -j, -n, -a, -k, -x. */
+typedef struct {
+	int32_t task;            /* 0 = candidates (.can), 1 = overlaps (.m4)            */
+	int32_t num_candidates;  /* -n, default 100                                      */
+	int32_t min_align_size;  /* -a, default 2000 (pacbio)                            */
+	int32_t min_kmer_match;  /* -k, default 4 (pacbio)                               */
+	int32_t tech;            /* -x, 0 = pacbio (the only technology of this path)    */
+} mecat_pw_params;
+
+/* ExtensionCandidate, src/common/alignment.h:8-13 (13 x int32 = 52 bytes). */
+typedef struct {
+	int32_t qdir, qid, qext, qsize, qoff, qend;
+	int32_t sdir, sid, sext, ssize, soff, send;
+	int32_t score;
+} mecat_candidate;
+
+/* M4Record, src/common/alignment.h:21-37 (104 bytes; idx_t = int64). */
+typedef struct {
+	int64_t qid, sid;
+	double ident;
+	int32_t vscore, qdir;
+	int64_t qoff, qend, qsize;
+	int32_t sdir, pad_;
+	int64_t soff, send, ssize, qext, sext;
+} mecat_m4;
+
+/* One gapped-extension request: GapAligner::go(query, qstart, qsize, target, tstart,
+ * tsize, min_aln) (src/common/gapalign.h:14-16) with both sequences named by read index
+ * inside an uploaded volume.  qstrand 1 = the query is the reverse complement of the
+ * read and qstart is in that orientation (pw_impl.cpp:676-688). */
+typedef struct {
+	int32_t qread, qstrand, qstart;
+	int32_t sread, sstart;
+} mecat_extend_task;
+
+/* Results of DiffAligner::go + accessors (src/common/diff_gapalign.cpp:295-349,
+ * diff_gapalign.h:159-181): ok = aligned columns >= min_aln; ident = 100*matches/columns. */
+typedef struct {
+	int32_t ok, qstart, qend, sstart, send, columns, matches, pad_;
+	double ident;
+} mecat_extend_result;
+
+/* Per-call device timing (milliseconds, CUDA events on the context's stream). */
+typedef struct {
+	float h2d_ms, index_ms, seed_ms, walk_ms, extend_ms, d2h_ms, total_ms;
+	int64_t kernel_launches;
+	int64_t num_hits, num_candidates, num_extend_blocks;
+	/* dominant-kernel figures for the roofline */
+	float index_sort_ms;
+	int64_t index_kmers;
+} mecat_b200_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int mecat_b200_abi_version(void);
+int mecat_b200_device_count(void);
+/* nccl_comm_or_null: reserved for the multi-GPU block rotation; unused at N=1. */
+int mecat_b200_init(mecat_b200_ctx** ctx, int device, void* nccl_comm_or_null);
+void mecat_b200_destroy(mecat_b200_ctx* ctx);
+const char* mecat_b200_last_error(mecat_b200_ctx* ctx);
+void mecat_b200_free(mecat_b200_ctx* ctx, void* p);
+int mecat_b200_get_stats(mecat_b200_ctx* ctx, mecat_b200_stats* out);
+
+/* ---- volumes resident in HBM --------------------------------------------------------
+ * replaces load_volume (split_database.cpp:156-181) + extract_one_seq/reverse_complement
+ * (split_database.cpp:122-133, pw_impl.cpp:69-81): the packed bases are copied to the
+ * device once and re-laid out in both walking directions. */
+int mecat_b200_volume_upload(mecat_b200_ctx* ctx, const mecat_volume* v, void** dvol);
+int mecat_b200_volume_release(mecat_b200_ctx* ctx, void* dvol);
+
+/* ---- A1: k-mer index of an index volume ----------------------------------------------
+ * replaces create_ref_index (src/common/lookup_table.cpp:64-160). */
+int mecat_b200_index_build(mecat_b200_ctx* ctx, void* dvol_ref, void** index);
+int mecat_b200_index_release(mecat_b200_ctx* ctx, void* index);
+/* test hook: number of kept k-mer starts and (optionally) the CSR arrays copied to the host:
+ * begin = 2^26+1 uint32, positions = *num_kmers int32; either pointer may be NULL. */
+int mecat_b200_index_export(mecat_b200_ctx* ctx, void* index, int64_t* num_kmers, uint32_t* begin,
+                            int32_t* positions);
+
+/* ---- A2-A12: one (index volume, query volume) tile -----------------------------------
+ * replaces the body of process_one_volume for one query volume (pw_impl.cpp:859-879):
+ * candidate_detect (task 0, pw_impl.cpp:720-818) or pairwise_mapping (task 1, :623-718).
+ * Device-resident inputs; records come back read by read, inside a read in the
+ * reference's own order.  *records = mecat_candidate[] or mecat_m4[]. */
+int mecat_b200_pw_tile(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads,
+                       const mecat_pw_params* p, void** records, size_t* n);
+
+/* Same, with host buffers in and out (upload + index build + tile + download): the
+ * end-to-end call a host driver makes per tile when nothing is cached. */
+int mecat_b200_pw_candidates(mecat_b200_ctx* ctx, const mecat_volume* ref, const mecat_volume* reads,
+                             const mecat_pw_params* p, mecat_candidate** ec, size_t* n);
+int mecat_b200_pw_overlaps(mecat_b200_ctx* ctx, const mecat_volume* ref, const mecat_volume* reads,
+                           const mecat_pw_params* p, mecat_m4** m4, size_t* n);
+
+/* test hook: raw candidate_save lists of get_candidates (pw_impl.cpp:288-465), 12 ints per
+ * candidate (loc1 loc2 left1 left2 right1 right2 score num1 num2 readno readstart chain),
+ * counts[r] candidates for read r, rows concatenated in read order. */
+int mecat_b200_pw_raw_candidates(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads,
+                                 const mecat_pw_params* p, int32_t** rows, int32_t** counts, size_t* n);
+
+/* ---- A8-A11: batched gapped extension --------------------------------------------------
+ * replaces GapAligner::go per candidate (pw_impl.cpp:688, mecat2ref_aux.cpp:152).
+ * policy 0 = pw/ref flavour (common/diff_gapalign.cpp). */
+int mecat_b200_extend_batch(mecat_b200_ctx* ctx, int policy, void* dvol_query, void* dvol_subject,
+                            const mecat_extend_task* tasks, size_t ntasks, int min_align_size,
+                            mecat_extend_result** results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MECAT_B200_H */

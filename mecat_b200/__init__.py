@@ -1,0 +1,12 @@
+"""mecat_b200 -- B200-native (sm_100a) implementation of MECAT's all-vs-all overlap hot path.
+
+Layout:
+  csrc/        hand-written CUDA kernels + the C ABI (include/mecat_b200.h) + C++ host driver
+  api.py       ctypes binding of the C ABI (the only route from Python to the product)
+  build.py     in-tree build of libmecat_b200.so / bin/mecat2pw
+"""
+from .api import (Context, HostVolume, MecatB200Error, PwParams, pw_params, load_library, LIB_PATH, EXPORTS,
+                  EC_DTYPE, M4_DTYPE, TASK_DTYPE, RESULT_DTYPE)
+
+__all__ = ["Context", "HostVolume", "MecatB200Error", "PwParams", "pw_params", "load_library", "LIB_PATH", "EXPORTS",
+           "EC_DTYPE", "M4_DTYPE", "TASK_DTYPE", "RESULT_DTYPE"]

@@ -1,0 +1,222 @@
+"""ctypes binding of the C ABI in include/mecat_b200.h.
+
+This is the only way Python reaches the product: every call goes through
+mecat_b200/libmecat_b200.so (hand-written sm_100a kernels).  There is no CPU fallback --
+a missing library or a machine without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmecat_b200.so")
+
+
+class MecatB200Error(RuntimeError):
+    pass
+
+
+class Volume(C.Structure):
+    _fields_ = [("num_reads", C.c_int32), ("num_bases", C.c_int32), ("start_read_id", C.c_int32),
+                ("offset_size", C.POINTER(C.c_int32)), ("pac", C.POINTER(C.c_uint8))]
+
+
+class PwParams(C.Structure):
+    _fields_ = [("task", C.c_int32), ("num_candidates", C.c_int32), ("min_align_size", C.c_int32),
+                ("min_kmer_match", C.c_int32), ("tech", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("index_ms", C.c_float), ("seed_ms", C.c_float), ("walk_ms", C.c_float),
+                ("extend_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
+                ("kernel_launches", C.c_int64), ("num_hits", C.c_int64), ("num_candidates", C.c_int64),
+                ("num_extend_blocks", C.c_int64), ("index_sort_ms", C.c_float), ("index_kmers", C.c_int64)]
+
+
+EC_DTYPE = np.dtype([(n, "<i4") for n in
+                     ("qdir", "qid", "qext", "qsize", "qoff", "qend", "sdir", "sid", "sext", "ssize", "soff",
+                      "send", "score")])
+M4_DTYPE = np.dtype([("qid", "<i8"), ("sid", "<i8"), ("ident", "<f8"), ("vscore", "<i4"), ("qdir", "<i4"),
+                     ("qoff", "<i8"), ("qend", "<i8"), ("qsize", "<i8"), ("sdir", "<i4"), ("pad", "<i4"),
+                     ("soff", "<i8"), ("send", "<i8"), ("ssize", "<i8"), ("qext", "<i8"), ("sext", "<i8")])
+TASK_DTYPE = np.dtype([(n, "<i4") for n in ("qread", "qstrand", "qstart", "sread", "sstart")])
+RESULT_DTYPE = np.dtype([("ok", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("sstart", "<i4"), ("send", "<i4"),
+                         ("columns", "<i4"), ("matches", "<i4"), ("pad", "<i4"), ("ident", "<f8")])
+
+EXPORTS = [
+    "mecat_b200_abi_version", "mecat_b200_device_count", "mecat_b200_init", "mecat_b200_destroy",
+    "mecat_b200_last_error", "mecat_b200_free", "mecat_b200_get_stats", "mecat_b200_volume_upload",
+    "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_release", "mecat_b200_index_export",
+    "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
+    "mecat_b200_extend_batch",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the product library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MecatB200Error("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    VP, PP, vp = C.POINTER(Volume), C.POINTER(PwParams), C.c_void_p
+    L.mecat_b200_init.argtypes = [C.POINTER(vp), C.c_int, vp]
+    L.mecat_b200_destroy.argtypes = [vp]
+    L.mecat_b200_last_error.restype = C.c_char_p
+    L.mecat_b200_last_error.argtypes = [vp]
+    L.mecat_b200_free.argtypes = [vp, vp]
+    L.mecat_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.mecat_b200_volume_upload.argtypes = [vp, VP, C.POINTER(vp)]
+    L.mecat_b200_volume_release.argtypes = [vp, vp]
+    L.mecat_b200_index_build.argtypes = [vp, vp, C.POINTER(vp)]
+    L.mecat_b200_index_release.argtypes = [vp, vp]
+    L.mecat_b200_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
+    L.mecat_b200_pw_tile.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_pw_candidates.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_pw_overlaps.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_pw_raw_candidates.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_extend_batch.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    _lib = L
+    return L
+
+
+class HostVolume:
+    """A packed volume in host memory in the reference's `volN` layout."""
+
+    def __init__(self, offset_size, pac, num_bases, start_read_id=0):
+        self.offset_size = np.ascontiguousarray(offset_size, dtype=np.int32).reshape(-1, 2)
+        self.pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        self.num_reads = int(self.offset_size.shape[0])
+        self.num_bases = int(num_bases)
+        self.start_read_id = int(start_read_id)
+
+    def c(self):
+        return Volume(self.num_reads, self.num_bases, self.start_read_id,
+                      self.offset_size.ctypes.data_as(C.POINTER(C.c_int32)),
+                      self.pac.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+    @staticmethod
+    def load(path):
+        with open(path, "rb") as f:
+            hdr = np.frombuffer(f.read(12), dtype="<i4")
+            n, nb, sid = int(hdr[0]), int(hdr[1]), int(hdr[2])
+            os_ = np.frombuffer(f.read(8 * n), dtype="<i4").reshape(-1, 2).copy()
+            pac = np.frombuffer(f.read((nb + 3) // 4), dtype=np.uint8).copy()
+        return HostVolume(os_, pac, nb, sid)
+
+
+def pw_params(task=1, num_candidates=100, min_align_size=2000, min_kmer_match=4, tech=0):
+    """Defaults of mecat2pw for PacBio (pw_options.cpp:8-13,30-50)."""
+    return PwParams(task, num_candidates, min_align_size, min_kmer_match, tech)
+
+
+class Context:
+    """One context per device (mecat_b200_init)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.mecat_b200_init(C.byref(self.h), device, None)
+        if rc != 0:
+            raise MecatB200Error("mecat_b200_init(device=%d) failed with code %d (no CUDA device? there is no CPU fallback)"
+                                 % (device, rc))
+
+    def close(self):
+        if self.h:
+            self.L.mecat_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MecatB200Error("%s: %s" % (what, self.L.mecat_b200_last_error(self.h).decode()))
+
+    def _take(self, ptr, n, dtype):
+        if not ptr.value or n == 0:
+            if ptr.value:
+                self.L.mecat_b200_free(self.h, ptr)
+            return np.zeros(0, dtype=dtype)
+        arr = np.frombuffer(C.string_at(ptr.value, n * dtype.itemsize), dtype=dtype).copy()
+        self.L.mecat_b200_free(self.h, ptr)
+        return arr
+
+    def stats(self):
+        s = Stats()
+        self._check(self.L.mecat_b200_get_stats(self.h, C.byref(s)), "get_stats")
+        return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
+
+    # ---- device-resident objects
+    def upload(self, vol):
+        d = C.c_void_p()
+        cv = vol.c()
+        self._check(self.L.mecat_b200_volume_upload(self.h, C.byref(cv), C.byref(d)), "volume_upload")
+        return d
+
+    def release_volume(self, d):
+        self.L.mecat_b200_volume_release(self.h, d)
+
+    def index_build(self, dvol):
+        i = C.c_void_p()
+        self._check(self.L.mecat_b200_index_build(self.h, dvol, C.byref(i)), "index_build")
+        return i
+
+    def release_index(self, i):
+        self.L.mecat_b200_index_release(self.h, i)
+
+    def index_export(self, index):
+        n = C.c_int64()
+        self._check(self.L.mecat_b200_index_export(self.h, index, C.byref(n), None, None), "index_export")
+        begin = np.zeros((1 << 26) + 1, dtype=np.uint32)
+        pos = np.zeros(max(1, n.value), dtype=np.int32)
+        self._check(self.L.mecat_b200_index_export(self.h, index, C.byref(n), begin.ctypes.data_as(C.c_void_p),
+                                                   pos.ctypes.data_as(C.c_void_p)), "index_export")
+        return begin, pos[:n.value]
+
+    def pw_tile(self, index, dref, dreads, params):
+        out, n = C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_pw_tile(self.h, index, dref, dreads, C.byref(params), C.byref(out), C.byref(n)),
+                    "pw_tile")
+        return self._take(out, n.value, EC_DTYPE if params.task == 0 else M4_DTYPE)
+
+    def pw_raw_candidates(self, index, dref, dreads, params, num_reads):
+        """Test hook: (rows[n,12], counts[num_reads]) = the candidate_save lists of every read."""
+        rows, counts, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_pw_raw_candidates(self.h, index, dref, dreads, C.byref(params), C.byref(rows),
+                                                        C.byref(counts), C.byref(n)), "pw_raw_candidates")
+        i4 = np.dtype("<i4")
+        cnt = self._take(counts, num_reads, i4)
+        r = self._take(rows, max(1, n.value) * 12, i4).reshape(-1, 12)[:n.value]
+        return r, cnt
+
+    # ---- host-buffer entry points (the end-to-end calls)
+    def pw_candidates(self, ref, reads, params=None):
+        p = params or pw_params(task=0)
+        out, n = C.c_void_p(), C.c_size_t()
+        rv, qv = ref.c(), reads.c()
+        self._check(self.L.mecat_b200_pw_candidates(self.h, C.byref(rv), C.byref(qv), C.byref(p), C.byref(out),
+                                                    C.byref(n)), "pw_candidates")
+        return self._take(out, n.value, EC_DTYPE)
+
+    def pw_overlaps(self, ref, reads, params=None):
+        p = params or pw_params(task=1)
+        out, n = C.c_void_p(), C.c_size_t()
+        rv, qv = ref.c(), reads.c()
+        self._check(self.L.mecat_b200_pw_overlaps(self.h, C.byref(rv), C.byref(qv), C.byref(p), C.byref(out),
+                                                  C.byref(n)), "pw_overlaps")
+        return self._take(out, n.value, M4_DTYPE)
+
+    def extend_batch(self, dquery, dsubject, tasks, min_align_size=2000, policy=0):
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        out = C.c_void_p()
+        self._check(self.L.mecat_b200_extend_batch(self.h, policy, dquery, dsubject, tasks.ctypes.data_as(C.c_void_p),
+                                                   len(tasks), min_align_size, C.byref(out)), "extend_batch")
+        return self._take(out, len(tasks), RESULT_DTYPE)

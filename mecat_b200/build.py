@@ -1,0 +1,74 @@
+"""Builds the in-tree native artefacts:
+
+  mecat_b200/libmecat_b200.so   CUDA kernels + C ABI (include/mecat_b200.h), sm_100a only
+  mecat_b200/bin/mecat2pw       C++ host driver with the reference's CLI (links the library)
+
+nvcc cross-compiles without a GPU.  Nothing here touches oracle/.
+"""
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(ROOT, "build", "obj")
+LIB = os.path.join(HERE, "libmecat_b200.so")
+BIN = os.path.join(HERE, "bin")
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+HOSTCXX = "/usr/bin/g++"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+              "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2,-pthread", "-Xptxas", "-v"]
+
+CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "capi.cu"]
+
+
+def _newer(src_list, out):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in src_list)
+
+
+def _compile(cu):
+    src = os.path.join(CSRC, cu)
+    obj = os.path.join(OBJ, cu.replace(".cu", ".o"))
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "mecat_b200.h")]
+    if not _newer(deps, obj):
+        return obj, ""
+    p = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (cu, p.stdout, p.stderr))
+    return obj, p.stderr
+
+
+def build(verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(BIN, exist_ok=True)
+    with cf.ThreadPoolExecutor(max_workers=len(CU)) as ex:
+        res = list(ex.map(_compile, CU))
+    objs = [r[0] for r in res]
+    log = "\n".join(r[1] for r in res if r[1])
+    if log:
+        with open(os.path.join(ROOT, "build", "ptxas.log"), "w") as f:
+            f.write(log)
+        if verbose:
+            print(log)
+    if _newer(objs, LIB):
+        subprocess.check_call([NVCC, "-shared", "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-o", LIB] + objs)
+    host = os.path.join(CSRC, "host")
+    exe = os.path.join(BIN, "mecat2pw")
+    srcs = [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith(".cpp")] if os.path.isdir(host) else []
+    if srcs and _newer(srcs + [LIB] + [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")], exe):
+        subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe]
+                              + srcs + ["-L", HERE, "-lmecat_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return LIB
+
+
+if __name__ == "__main__":
+    build(verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,450 @@
+// mecat_b200/csrc/capi.cu -- the C ABI of include/mecat_b200.h.
+//
+// Host-side glue only: argument checks, device buffers, launches, and the per-read record
+// assembly that the reference does on the CPU after its hot loops
+// (candidate_detect pw_impl.cpp:767-793, fill_m4record :467-506, append_m4v :576-610).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+using namespace mb;
+
+struct mecat_b200_ctx : public mb::Ctx {};
+
+namespace {
+
+struct EvTimer
+{
+	Ctx* c;
+	int slot;
+	EvTimer(Ctx* c_, int slot_) : c(c_), slot(slot_) { cudaEventRecord(c->ev[2 * slot], c->stream); }
+	float stop()
+	{
+		cudaEventRecord(c->ev[2 * slot + 1], c->stream);
+		cudaEventSynchronize(c->ev[2 * slot + 1]);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, c->ev[2 * slot], c->ev[2 * slot + 1]);
+		return ms;
+	}
+};
+
+__global__ void k_extend_finalize(const ExtendTask* __restrict__ tasks, const ExtendHalf* __restrict__ halves, size_t n,
+                                  int min_aln, mecat_extend_result* __restrict__ out)
+{
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const ExtendTask t = tasks[i];
+	const ExtendHalf L = halves[2 * i], R = halves[2 * i + 1];
+	mecat_extend_result r;
+	r.columns = L.cols + R.cols;
+	r.matches = L.matches + R.matches;
+	r.qstart = t.qstart - L.qadv; r.qend = t.qstart + R.qadv;
+	r.sstart = t.sstart - L.tadv; r.send = t.sstart + R.tadv;
+	r.ok = r.columns >= min_aln;
+	r.pad_ = 0;
+	// OutputStore::calc_ident, diff_gapalign.h:90-97: 100.0 * n / size in IEEE double
+	r.ident = r.columns ? __ddiv_rn(__dmul_rn(100.0, (double)r.matches), (double)r.columns) : 0.0;
+	out[i] = r;
+}
+
+// ExtensionCandidate assembly: candidate_detect, pw_impl.cpp:767-793
+__global__ void k_make_ec(const RawCand* __restrict__ cands, const int32_t* __restrict__ counts,
+                          const int64_t* __restrict__ outpos, int maxc, int nreads, const int2* __restrict__ qoffsz,
+                          int qstart_id, const int2* __restrict__ soffsz, int sstart_id, mecat_candidate* __restrict__ ec,
+                          ExtendTask* __restrict__ tasks)
+{
+	int r = blockIdx.x;
+	if (r >= nreads) return;
+	const int n = counts[r];
+	const int64_t base = outpos[r];
+	const int qsize = qoffsz[r].y;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		const RawCand c = cands[(size_t)r * maxc + i];
+		int qstart = c.loc2, sstart = c.loc1;
+		if (qstart && sstart) { qstart += KMER / 2; sstart += KMER / 2; }
+		const int sidx = c.readno - sstart_id;
+		if (ec) {
+			mecat_candidate e;
+			e.qdir = c.chain; e.qid = r + qstart_id; e.qext = qstart; e.qsize = qsize; e.qoff = 0; e.qend = 0;
+			e.sdir = 0; e.sid = c.readno; e.sext = sstart; e.ssize = soffsz[sidx].y; e.soff = 0; e.send = 0;
+			e.score = c.score;
+			if (e.qdir == 1) e.qext = e.qsize - 1 - e.qext;
+			ec[base + i] = e;
+		}
+		if (tasks) {
+			ExtendTask t;
+			t.qread = r; t.qstrand = c.chain; t.qstart = qstart; t.sread = sidx; t.sstart = sstart;
+			tasks[base + i] = t;
+		}
+	}
+}
+
+struct M4Less   // CmpM4RecordByQidAndOvlpSize, pw_impl.cpp:539-548
+{
+	bool operator()(const mecat_m4& a, const mecat_m4& b) const
+	{
+		if (a.qid != b.qid) return a.qid < b.qid;
+		const int64_t oa = std::min(a.qend - a.qoff, a.send - a.soff), ob = std::min(b.qend - b.qoff, b.send - b.soff);
+		return oa > ob;
+	}
+};
+
+int check(mecat_b200_ctx* c) { return c ? 0 : 1; }
+
+}  // namespace
+
+extern "C" {
+
+int mecat_b200_abi_version(void) { return MECAT_B200_ABI_VERSION; }
+
+int mecat_b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int mecat_b200_init(mecat_b200_ctx** out, int device, void* /*nccl_comm_or_null*/)
+{
+	if (!out) return 1;
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return 2;   // no CPU fallback
+	if (cudaSetDevice(device) != cudaSuccess) return 3;
+	mecat_b200_ctx* c = new mecat_b200_ctx;
+	c->device = device;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+	memset(&c->stats, 0, sizeof c->stats);
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 4; }
+	for (auto& e : c->ev) cudaEventCreate(&e);
+	if (cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return 5; }
+	cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
+	*out = c;
+	return 0;
+}
+
+void mecat_b200_destroy(mecat_b200_ctx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto& e : c->ev) cudaEventDestroy(e);
+	cudaFree(c->d_counters);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char* mecat_b200_last_error(mecat_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void mecat_b200_free(mecat_b200_ctx*, void* p) { free(p); }
+
+int mecat_b200_get_stats(mecat_b200_ctx* c, mecat_b200_stats* out)
+{
+	if (check(c) || !out) return 1;
+	*out = c->stats;
+	return 0;
+}
+
+int mecat_b200_volume_upload(mecat_b200_ctx* c, const mecat_volume* v, void** dvol)
+{
+	if (check(c) || !dvol) return 1;
+	cudaSetDevice(c->device);
+	DVolume* d = nullptr;
+	EvTimer t(c, 0);
+	int rc = volume_upload(c, v, &d);
+	c->stats.h2d_ms += t.stop();
+	if (rc) return rc;
+	*dvol = d;
+	return 0;
+}
+
+int mecat_b200_volume_release(mecat_b200_ctx* c, void* dvol)
+{
+	if (check(c)) return 1;
+	cudaSetDevice(c->device);
+	volume_release((DVolume*)dvol);
+	return 0;
+}
+
+int mecat_b200_index_build(mecat_b200_ctx* c, void* dvol_ref, void** index)
+{
+	if (check(c) || !dvol_ref || !index) return 1;
+	cudaSetDevice(c->device);
+	DIndex* idx = nullptr;
+	EvTimer t(c, 1);
+	int rc = index_build(c, (DVolume*)dvol_ref, &idx);
+	c->stats.index_ms += t.stop();
+	if (rc) return rc;
+	*index = idx;
+	return 0;
+}
+
+int mecat_b200_index_release(mecat_b200_ctx* c, void* index)
+{
+	if (check(c)) return 1;
+	cudaSetDevice(c->device);
+	index_release((DIndex*)index);
+	return 0;
+}
+
+int mecat_b200_index_export(mecat_b200_ctx* c, void* index, int64_t* num_kmers, uint32_t* begin, int32_t* positions)
+{
+	if (check(c) || !index) return 1;
+	cudaSetDevice(c->device);
+	DIndex* I = (DIndex*)index;
+	if (num_kmers) *num_kmers = I->num_kmers;
+	if (begin) MB_CUDA(c, cudaMemcpy(begin, I->begin, sizeof(uint32_t) * ((size_t)NCODES + 1), cudaMemcpyDeviceToHost));
+	if (positions && I->num_kmers) MB_CUDA(c, cudaMemcpy(positions, I->pos, sizeof(int32_t) * (size_t)I->num_kmers, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, const mecat_extend_task* tasks,
+                            size_t ntasks, int min_align_size, mecat_extend_result** results)
+{
+	if (check(c) || !dq || !ds || !results) return 1;
+	if (policy != 0) MB_FAIL(c, "extend_batch: policy %d not available (0 = pw/ref flavour)", policy);
+	cudaSetDevice(c->device);
+	*results = nullptr;
+	if (!ntasks) return 0;
+	const DVolume* Q = (const DVolume*)dq;
+	const DVolume* S = (const DVolume*)ds;
+	for (size_t i = 0; i < ntasks; ++i) {
+		const mecat_extend_task& t = tasks[i];
+		if (t.qread < 0 || t.qread >= Q->num_reads || t.sread < 0 || t.sread >= S->num_reads)
+			MB_FAIL(c, "extend_batch: task %zu names a read outside its volume", i);
+		if (t.qstart < 0 || t.qstart > Q->h_offsz[2 * t.qread + 1] || t.sstart < 0 || t.sstart > S->h_offsz[2 * t.sread + 1])
+			MB_FAIL(c, "extend_batch: task %zu start point outside its read", i);
+	}
+	static_assert(sizeof(ExtendTask) == sizeof(mecat_extend_task), "task layout");
+	ExtendTask* d_tasks = nullptr;
+	ExtendHalf* d_halves = nullptr;
+	mecat_extend_result* d_res = nullptr;
+	int rc = 0;
+	auto body = [&]() -> int {
+		MB_CUDA(c, cudaMalloc(&d_tasks, sizeof(ExtendTask) * ntasks));
+		MB_CUDA(c, cudaMalloc(&d_halves, sizeof(ExtendHalf) * 2 * ntasks));
+		MB_CUDA(c, cudaMalloc(&d_res, sizeof(mecat_extend_result) * ntasks));
+		MB_CUDA(c, cudaMemcpyAsync(d_tasks, tasks, sizeof(ExtendTask) * ntasks, cudaMemcpyHostToDevice, c->stream));
+		EvTimer t(c, 2);
+		if (extend_launch(c, Q, S, d_tasks, ntasks, d_halves)) return 1;
+		k_extend_finalize<<<(unsigned)((ntasks + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, ntasks, min_align_size, d_res);
+		MB_CUDA(c, cudaGetLastError());
+		c->stats.kernel_launches += 1;
+		c->stats.extend_ms += t.stop();
+		mecat_extend_result* h = (mecat_extend_result*)malloc(sizeof(mecat_extend_result) * ntasks);
+		if (!h) MB_FAIL(c, "extend_batch: out of host memory");
+		cudaError_t e = cudaMemcpyAsync(h, d_res, sizeof(mecat_extend_result) * ntasks, cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		if (e != cudaSuccess) { free(h); MB_FAIL(c, "extend_batch: D2H: %s", cudaGetErrorString(e)); }
+		*results = h;
+		return 0;
+	};
+	rc = body();
+	cudaFree(d_tasks); cudaFree(d_halves); cudaFree(d_res);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// One (index volume, query volume) tile.
+static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* reads, const mecat_pw_params* p,
+                        void** records, size_t* n, int32_t** raw_rows, int32_t** raw_counts)
+{
+	if (p->num_candidates < 1) MB_FAIL(c, "pw_tile: number of candidates must be > 0");
+	if (p->tech != 0) MB_FAIL(c, "pw_tile: only -x 0 (pacbio, diff aligner) is on this path");
+	if (p->task != 0 && p->task != 1) MB_FAIL(c, "pw_tile: task (-j) must be 0 or 1, not %d", p->task);
+	const int N = reads->num_reads, maxc = p->num_candidates;
+	*n = 0;
+	if (records) *records = nullptr;
+	if (N == 0) return 0;
+	RawCand* d_cands = nullptr;
+	int32_t* d_counts = nullptr;
+	int64_t* d_outpos = nullptr;
+	mecat_candidate* d_ec = nullptr;
+	ExtendTask* d_tasks = nullptr;
+	ExtendHalf* d_halves = nullptr;
+	mecat_extend_result* d_res = nullptr;
+	std::vector<int32_t> h_counts(N);
+	std::vector<int64_t> h_outpos(N + 1);
+	auto body = [&]() -> int {
+		MB_CUDA(c, cudaMalloc(&d_cands, sizeof(RawCand) * (size_t)N * maxc));
+		MB_CUDA(c, cudaMalloc(&d_counts, sizeof(int32_t) * (size_t)N));
+		{
+			EvTimer t(c, 3);
+			if (seed_candidates(c, idx, ref, reads, p, d_cands, d_counts)) return 1;
+			c->stats.seed_ms += t.stop();
+		}
+		MB_CUDA(c, cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		size_t total = 0;
+		for (int i = 0; i < N; ++i) { h_outpos[i] = (int64_t)total; total += (size_t)h_counts[i]; }
+		h_outpos[N] = (int64_t)total;
+		c->stats.num_candidates += (int64_t)total;
+		if (raw_rows) {
+			// test hook: the raw candidate_save lists
+			std::vector<RawCand> all((size_t)N * maxc);
+			MB_CUDA(c, cudaMemcpy(all.data(), d_cands, sizeof(RawCand) * all.size(), cudaMemcpyDeviceToHost));
+			int32_t* rows = (int32_t*)malloc(sizeof(RawCand) * (total ? total : 1));
+			int32_t* cnts = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+			if (!rows || !cnts) { free(rows); free(cnts); MB_FAIL(c, "pw_tile: out of host memory"); }
+			size_t k = 0;
+			for (int r = 0; r < N; ++r) {
+				memcpy(rows + 12 * k, all.data() + (size_t)r * maxc, sizeof(RawCand) * (size_t)h_counts[r]);
+				k += (size_t)h_counts[r];
+				cnts[r] = h_counts[r];
+			}
+			*raw_rows = rows; *raw_counts = cnts; *n = total;
+			return 0;
+		}
+		if (total == 0) return 0;
+		MB_CUDA(c, cudaMalloc(&d_outpos, sizeof(int64_t) * (size_t)(N + 1)));
+		MB_CUDA(c, cudaMemcpyAsync(d_outpos, h_outpos.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->stream));
+		if (p->task == 0) {
+			MB_CUDA(c, cudaMalloc(&d_ec, sizeof(mecat_candidate) * total));
+			k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
+			                                   ref->offsz, ref->start_read_id, d_ec, nullptr);
+			MB_CUDA(c, cudaGetLastError());
+			c->stats.kernel_launches += 1;
+			mecat_candidate* h = (mecat_candidate*)malloc(sizeof(mecat_candidate) * total);
+			if (!h) MB_FAIL(c, "pw_tile: out of host memory");
+			EvTimer t(c, 4);
+			cudaError_t e = cudaMemcpyAsync(h, d_ec, sizeof(mecat_candidate) * total, cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+			c->stats.d2h_ms += t.stop();
+			if (e != cudaSuccess) { free(h); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
+			*records = h; *n = total;
+			return 0;
+		}
+		// task 1: extend every candidate, then assemble M4 records per read
+		MB_CUDA(c, cudaMalloc(&d_tasks, sizeof(ExtendTask) * total));
+		MB_CUDA(c, cudaMalloc(&d_halves, sizeof(ExtendHalf) * 2 * total));
+		MB_CUDA(c, cudaMalloc(&d_res, sizeof(mecat_extend_result) * total));
+		k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
+		                                   ref->offsz, ref->start_read_id, nullptr, d_tasks);
+		MB_CUDA(c, cudaGetLastError());
+		c->stats.kernel_launches += 1;
+		{
+			EvTimer t(c, 2);
+			if (extend_launch(c, reads, ref, d_tasks, total, d_halves)) return 1;
+			k_extend_finalize<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, total, p->min_align_size, d_res);
+			MB_CUDA(c, cudaGetLastError());
+			c->stats.kernel_launches += 1;
+			c->stats.extend_ms += t.stop();
+		}
+		std::vector<ExtendTask> h_tasks(total);
+		std::vector<mecat_extend_result> h_res(total);
+		std::vector<int32_t> h_score(total);
+		{
+			EvTimer t(c, 4);
+			MB_CUDA(c, cudaMemcpyAsync(h_tasks.data(), d_tasks, sizeof(ExtendTask) * total, cudaMemcpyDeviceToHost, c->stream));
+			MB_CUDA(c, cudaMemcpyAsync(h_res.data(), d_res, sizeof(mecat_extend_result) * total, cudaMemcpyDeviceToHost, c->stream));
+			// vscore = candidate score: strided gather of RawCand.score
+			std::vector<RawCand> all((size_t)N * maxc);
+			MB_CUDA(c, cudaMemcpyAsync(all.data(), d_cands, sizeof(RawCand) * all.size(), cudaMemcpyDeviceToHost, c->stream));
+			MB_CUDA(c, cudaStreamSynchronize(c->stream));
+			for (int r = 0; r < N; ++r)
+				for (int i = 0; i < h_counts[r]; ++i) h_score[(size_t)h_outpos[r] + i] = all[(size_t)r * maxc + i].score;
+			c->stats.d2h_ms += t.stop();
+		}
+		// fill_m4record + append_m4v (sort, containment filter) per read, on the host like the reference
+		mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * total);
+		if (!out) MB_FAIL(c, "pw_tile: out of host memory");
+		size_t nout = 0;
+		std::vector<mecat_m4> loc;
+		std::vector<char> valid;
+		for (int r = 0; r < N; ++r) {
+			loc.clear();
+			const int64_t qsize = reads->h_offsz[2 * r + 1];
+			const int64_t qid = r + reads->start_read_id;
+			for (int64_t k = h_outpos[r]; k < h_outpos[r + 1]; ++k) {
+				const mecat_extend_result& R = h_res[k];
+				if (!R.ok) continue;
+				const ExtendTask& t = h_tasks[k];
+				mecat_m4 m;
+				memset(&m, 0, sizeof m);
+				m.qid = t.sread + ref->start_read_id; m.sid = qid; m.ident = R.ident; m.vscore = h_score[k]; m.qdir = 0;
+				m.qoff = R.sstart; m.qend = R.send; m.qsize = ref->h_offsz[2 * t.sread + 1]; m.ssize = qsize; m.qext = t.sstart;
+				if (!t.qstrand) { m.sdir = 0; m.soff = R.qstart; m.send = R.qend; m.sext = t.qstart; }
+				else { m.sdir = 1; m.soff = qsize - R.qend; m.send = qsize - R.qstart; m.sext = qsize - 1 - t.qstart; }
+				loc.push_back(m);
+			}
+			if (loc.empty()) continue;
+			std::sort(loc.begin(), loc.end(), M4Less());
+			valid.assign(loc.size(), 1);
+			for (size_t i = 0; i < loc.size();) {
+				size_t j = i + 1;
+				while (j < loc.size() && loc[j].qid == loc[i].qid) ++j;
+				for (size_t a = i; a < j; ++a) {
+					if (!valid[a]) continue;
+					for (size_t b = a + 1; b < j; ++b) {
+						if (!valid[b] || loc[a].sdir != loc[b].sdir) continue;
+						if (loc[b].qoff + 100 >= loc[a].qoff && loc[b].qend - 100 <= loc[a].qend &&
+						    loc[b].soff + 100 >= loc[a].soff && loc[b].send - 100 <= loc[a].send) valid[b] = 0;
+					}
+				}
+				i = j;
+			}
+			for (size_t i = 0; i < loc.size(); ++i) if (valid[i]) out[nout++] = loc[i];
+		}
+		*records = out; *n = nout;
+		return 0;
+	};
+	int rc = body();
+	cudaFree(d_cands); cudaFree(d_counts); cudaFree(d_outpos); cudaFree(d_ec);
+	cudaFree(d_tasks); cudaFree(d_halves); cudaFree(d_res);
+	return rc;
+}
+
+int mecat_b200_pw_tile(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvol_reads, const mecat_pw_params* p,
+                       void** records, size_t* n)
+{
+	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !records || !n) return 1;
+	cudaSetDevice(c->device);
+	EvTimer t(c, 5);
+	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, records, n, nullptr, nullptr);
+	c->stats.total_ms += t.stop();
+	return rc;
+}
+
+int mecat_b200_pw_raw_candidates(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvol_reads,
+                                 const mecat_pw_params* p, int32_t** rows, int32_t** counts, size_t* n)
+{
+	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !rows || !counts || !n) return 1;
+	cudaSetDevice(c->device);
+	return pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, nullptr, n, rows, counts);
+}
+
+static int pw_host(mecat_b200_ctx* c, const mecat_volume* ref, const mecat_volume* reads, const mecat_pw_params* p, int task,
+                   void** records, size_t* n)
+{
+	if (check(c) || !ref || !reads || !p || !records || !n) return 1;
+	cudaSetDevice(c->device);
+	mecat_pw_params q = *p;
+	q.task = task;
+	void *dref = nullptr, *dreads = nullptr, *idx = nullptr;
+	const bool same = (ref == reads) || (ref->pac == reads->pac && ref->num_bases == reads->num_bases &&
+	                                     ref->start_read_id == reads->start_read_id);
+	int rc = mecat_b200_volume_upload(c, ref, &dref);
+	if (!rc) { if (same) dreads = dref; else rc = mecat_b200_volume_upload(c, reads, &dreads); }
+	if (!rc) rc = mecat_b200_index_build(c, dref, &idx);
+	if (!rc) rc = mecat_b200_pw_tile(c, idx, dref, dreads, &q, records, n);
+	if (idx) mecat_b200_index_release(c, idx);
+	if (dreads && dreads != dref) mecat_b200_volume_release(c, dreads);
+	if (dref) mecat_b200_volume_release(c, dref);
+	return rc;
+}
+
+int mecat_b200_pw_candidates(mecat_b200_ctx* c, const mecat_volume* ref, const mecat_volume* reads,
+                             const mecat_pw_params* p, mecat_candidate** ec, size_t* n)
+{
+	return pw_host(c, ref, reads, p, 0, (void**)ec, n);
+}
+
+int mecat_b200_pw_overlaps(mecat_b200_ctx* c, const mecat_volume* ref, const mecat_volume* reads,
+                           const mecat_pw_params* p, mecat_m4** m4, size_t* n)
+{
+	return pw_host(c, ref, reads, p, 1, (void**)m4, n);
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// mecat_b200/csrc/common.cuh -- shared declarations of the device library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mecat_b200.h"
+
+namespace mb {
+
+// ---- algorithm constants of the path (reference src/mecat2pw/pw_impl.h:10-19, pw_impl.cpp:20)
+constexpr int KMER = 13;            // kmer_size
+constexpr int STRIDE = 10;          // BC: every 10th k-mer of the query is looked up
+constexpr int SLOTS = 40;           // SM: seeds kept per bucket
+constexpr int SEGW = 2000;          // ZV: bucket width in index-volume bases
+constexpr int MAX_OCC = 128;        // lookup_table.cpp:97
+constexpr uint32_t NCODES = 1u << (2 * KMER);
+
+struct Ctx;
+
+// Device-resident volume.  `fwd` holds base i at bits 2*(i%16) of word i/16 (LSB first, so a
+// walk over increasing positions is a funnel shift away); `rev` holds the same bases in
+// reverse order (rev base i = base N-1-i), which turns the left extension and the reverse
+// strand into forward walks too.  Both arrays carry 8 zero words of slack at the end.
+struct DVolume
+{
+	int32_t num_reads = 0, num_bases = 0, start_read_id = 0;
+	int2* offsz = nullptr;          // {offset,size} per read
+	uint32_t* fwd = nullptr;
+	uint32_t* rev = nullptr;
+	size_t words = 0;
+	int32_t max_read = 0;
+	std::vector<int32_t> h_offsz;   // host copy (record assembly)
+};
+
+struct DIndex
+{
+	uint32_t* begin = nullptr;      // NCODES + 1 (CSR over kept k-mers)
+	int32_t* pos = nullptr;         // kept k-mer start positions, ascending inside a list
+	int64_t num_kmers = 0;
+};
+
+struct Ctx
+{
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	mecat_b200_stats stats;
+	unsigned long long* d_counters = nullptr;   // 16 device counters (statistics, arena cursors)
+	cudaEvent_t ev[16] = {};
+};
+
+#define MB_CUDA(ctx, call)                                                                      \
+	do {                                                                                        \
+		cudaError_t e__ = (call);                                                               \
+		if (e__ != cudaSuccess) {                                                               \
+			char b__[512];                                                                      \
+			snprintf(b__, sizeof b__, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+			(ctx)->err = b__;                                                                   \
+			return 1;                                                                           \
+		}                                                                                       \
+	} while (0)
+
+#define MB_FAIL(ctx, ...)                                  \
+	do {                                                   \
+		char b__[512];                                     \
+		snprintf(b__, sizeof b__, __VA_ARGS__);            \
+		(ctx)->err = b__;                                  \
+		return 1;                                          \
+	} while (0)
+
+// ---- internal entry points (one per translation unit)
+int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out);
+void volume_release(DVolume* v);
+int index_build(Ctx* c, const DVolume* v, DIndex** out);
+void index_release(DIndex* i);
+
+struct ExtendTask          // device-side extension request (global array)
+{
+	int32_t qread, qstrand, qstart, sread, sstart;
+};
+struct ExtendHalf          // result of one direction of one task
+{
+	int32_t cols, matches, qadv, tadv;
+};
+int extend_launch(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* d_tasks, size_t ntasks,
+                  ExtendHalf* d_halves /* 2*ntasks: left then right */);
+
+struct RawCand             // candidate_save, pw_impl.h:21-25
+{
+	int32_t loc1, loc2, left1, left2, right1, right2, score, num1, num2, readno, readstart, chain;
+};
+// Seeding + scoring + candidate selection for every read of `reads`; fills d_cands
+// (num_reads x maxc RawCand, the per-read list in reference order) and d_counts.
+int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume* reads,
+                    const mecat_pw_params* p, RawCand* d_cands, int32_t* d_counts);
+
+// ---- device helpers
+__device__ __forceinline__ uint32_t ld_bases32(const uint32_t* __restrict__ a, uint32_t base)
+{
+	// 16 bases starting at `base`, LSB first
+	uint32_t w = base >> 4, sh = (base & 15u) << 1;
+	uint32_t lo = __ldg(a + w), hi = __ldg(a + w + 1);
+	return __funnelshift_r(lo, hi, sh);
+}
+
+__device__ __forceinline__ uint32_t rev_groups2(uint32_t x)
+{
+	// reverse the order of the sixteen 2-bit groups of x
+	x = __brev(x);
+	return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
+
+// DDF consistency |dloc/(dseed*10) - 1| < 0.25 in exact integer form.  The reference
+// evaluates it in float32 (pw_impl.cpp:135,165) or float64 (:412,429); for the operand
+// ranges of this path the rounded quotient can never cross 0.75 / 1.25,
+// so 15*b < 2*a < 25*b (b > 0), 25*b < 2*a < 15*b (b < 0), false for b == 0 is identical.
+__host__ __device__ __forceinline__ bool ddf_close(int a, int b)
+{
+	int a2 = 2 * a;
+	if (b > 0) return 15 * b < a2 && a2 < 25 * b;
+	if (b < 0) return 25 * b < a2 && a2 < 15 * b;
+	return false;
+}
+
+}  // namespace mb

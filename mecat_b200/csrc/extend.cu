@@ -1,0 +1,257 @@
+// mecat_b200/csrc/extend.cu -- batched O(nd) gapped extension (pw / ref flavour).
+//
+// Replaces, for a whole batch of candidates at once, the reference's per-candidate
+//   DiffAligner::go            src/common/diff_gapalign.cpp:295-349
+//   dw_in_one_direction        src/common/diff_gapalign.cpp:221-292
+//   retrieve_next_aln_block    src/common/gapalign.cpp:10-45
+//   Align                      src/common/diff_gapalign.cpp:107-219
+//   GetAlignString + trim_mismatch_end   diff_gapalign.cpp:40-104, gapalign.cpp:48-67
+//
+// Mapping: one warp owns one (candidate, direction) chain of <= 720 x 720 blocks.  The two
+// block operands are staged 2 bit/base in shared memory in walking order, so a snake
+// compares 16 bases per XOR + FFS.  One row of the furthest-reaching recurrence is one warp
+// step: lane j owns diagonal min_k + 2j (32 diagonals per pass); the neighbours k-1 / k+1 of
+// the previous row are read from a per-warp shared array that is updated in place (a row
+// only reads cells of the other parity, exactly like the reference's V array).
+//
+// No traceback is stored.  What the reference needs from the alignment string of a block is
+// (a) its length and (b) where the last run of >= 4 matching columns ends
+// (trim_mismatch_end).  A diff alignment has no mismatch columns -- it is snakes separated by
+// single indels -- so that run is the tail of the last snake of length >= 4 on the path.
+// Every cell therefore carries, next to its furthest x, the packed (x, y, d) of the last
+// long snake on its own path ("anchor"); the end cell's anchor gives, in closed form,
+//   columns up to the run end = (x + y + d) / 2,   matches = (x + y - d) / 2.
+#include "common.cuh"
+
+namespace mb {
+
+namespace {
+
+constexpr int EXT_WARPS = 4;
+constexpr int KOFF = 404;                 // > max_d for the largest block (0.3 * (599 + 718) = 395)
+constexpr int VL_N = (2 * KOFF + 8) / 2;  // entries per parity
+constexpr int SEQ_WORDS = 48;             // 719 bases = 45 words (+1 funnel, +2 slack)
+constexpr uint32_t NO_ANCHOR = 0xFFFFFFFFu;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct WarpSmem
+{
+	uint32_t sq[SEQ_WORDS];
+	uint32_t st[SEQ_WORDS];
+	uint2 vl[2][VL_N];        // .x = furthest x on the diagonal, .y = packed anchor
+};
+
+struct Walk                   // one sequence seen as a forward walk
+{
+	const uint32_t* arr;
+	uint32_t g0;              // array index of walk position 0
+	uint32_t comp;            // 0 or 0xFFFFFFFF
+	int len;
+};
+
+__device__ __forceinline__ uint32_t pack_anchor(int x, int y, int d) { return (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)d << 20); }
+
+__device__ __forceinline__ uint32_t seq16(const uint32_t* s, int i)
+{
+	int w = i >> 4;
+	return __funnelshift_r(s[w], s[w + 1], (i & 15) << 1);
+}
+
+__device__ __forceinline__ int dtrunc_mul(double a, int b) { return (int)__dmul_rn(a, (double)b); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(EXT_WARPS * 32)
+k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, const int2* __restrict__ qoffsz, int qN,
+         const uint32_t* __restrict__ sfwd, const uint32_t* __restrict__ srev, const int2* __restrict__ soffsz, int sN,
+         const ExtendTask* __restrict__ tasks, size_t ntasks, ExtendHalf* __restrict__ halves,
+         unsigned long long* __restrict__ block_counter)
+{
+	__shared__ WarpSmem smem[EXT_WARPS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const size_t item = (size_t)blockIdx.x * EXT_WARPS + warp;
+	if (item >= 2 * ntasks) return;
+	WarpSmem& S = smem[warp];
+	const ExtendTask t = tasks[item >> 1];
+	const int right = (int)(item & 1);
+
+	const int2 qo = qoffsz[t.qread], so = soffsz[t.sread];
+	Walk Q, T;
+	if (right) {
+		if (!t.qstrand) { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + t.qstart); Q.comp = 0; }
+		else { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - qo.y + t.qstart); Q.comp = FULL; }
+		Q.len = qo.y - t.qstart;
+		T.arr = sfwd; T.g0 = (uint32_t)(so.x + t.sstart); T.comp = 0; T.len = so.y - t.sstart;
+	} else {
+		if (!t.qstrand) { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - t.qstart); Q.comp = 0; }
+		else { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + qo.y - t.qstart); Q.comp = FULL; }
+		Q.len = t.qstart;
+		T.arr = srev; T.g0 = (uint32_t)(sN - so.x - t.sstart); T.comp = 0; T.len = t.sstart;
+	}
+
+	int qi = 0, ti = 0;
+	int cols = 0, mats = 0, qadv = 0, tadv = 0;
+	unsigned nblocks = 0;
+
+	for (;;) {
+		// ---- retrieve_next_aln_block
+		const int qleft = Q.len - qi, tleft = T.len - ti;
+		int qblk, tblk;
+		bool last;
+		if (qleft < 600 || tleft < 600) {
+			int a = (int)__dadd_rn((double)tleft, __dmul_rn((double)tleft, 0.2));
+			int b = (int)__dadd_rn((double)qleft, __dmul_rn((double)qleft, 0.2));
+			qblk = min(qleft, a);
+			tblk = min(tleft, b);
+			last = true;
+		} else { qblk = tblk = 500; last = false; }
+		const int tol = dtrunc_mul(0.3, max(qblk, tblk));
+		const int max_d = dtrunc_mul(.3, qblk + tblk);
+		++nblocks;
+
+		// ---- stage operands, clear the diagonal arrays (fill(U,0), fill(V,0))
+		{
+			const int qw = (qblk + 15) / 16 + 1, tw = (tblk + 15) / 16 + 1;
+			for (int i = lane; i < qw; i += 32) S.sq[i] = ld_bases32(Q.arr, Q.g0 + (uint32_t)qi + 16u * i) ^ Q.comp;
+			for (int i = lane; i < tw; i += 32) S.st[i] = ld_bases32(T.arr, T.g0 + (uint32_t)ti + 16u * i) ^ T.comp;
+			const uint2 z = make_uint2(0u, NO_ANCHOR);
+			for (int i = lane; i < 2 * VL_N; i += 32) (&S.vl[0][0])[i] = z;
+		}
+		__syncwarp();
+
+		// ---- Align
+		int min_k = 0, max_k = 0, best_m = -1;
+		int last_min = 0, last_max = 0, rows = 0;
+		bool aligned = false;
+		int ex = 0, ey = 0, ed = 0;
+		uint32_t ea = NO_ANCHOR;
+		for (int d = 0; d < max_d; ++d) {
+			if (max_k - min_k > 2 * tol) break;
+			const int n = ((max_k - min_k) >> 1) + 1;
+			int rowmax = -1;
+			for (int base = 0; base < n; base += 32) {
+				const int j = base + lane;
+				const bool act = j < n;
+				const int k = min_k + 2 * j;
+				int x = 0, y = 0;
+				uint32_t anc = NO_ANCHOR;
+				bool hit = false;
+				if (act) {
+					const int kk = k + KOFF, p = kk & 1;
+					const uint2 lf = S.vl[p ^ 1][(kk - 1) >> 1], rt = S.vl[p ^ 1][(kk + 1) >> 1];
+					if (k == min_k || (k != max_k && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
+					else { x = (int)lf.x + 1; anc = lf.y; }
+					y = x - k;
+					const int x1 = x;
+					while (x < qblk && y < tblk) {
+						const uint32_t diff = seq16(S.sq, x) ^ seq16(S.st, y);
+						int m = diff ? ((__ffs(diff) - 1) >> 1) : 16;
+						m = min(m, min(qblk - x, tblk - y));
+						x += m; y += m;
+						if (m < 16) break;
+					}
+					if (x - x1 >= 4) anc = pack_anchor(x, y, d);
+					S.vl[p][kk >> 1] = make_uint2((uint32_t)x, anc);
+					hit = (x >= qblk) || (y >= tblk);
+				}
+				const unsigned hm = __ballot_sync(FULL, hit);
+				rowmax = max(rowmax, __reduce_max_sync(FULL, act ? x + y : -1));
+				if (hm) {
+					const int src = __ffs(hm) - 1;
+					ex = __shfl_sync(FULL, x, src);
+					ey = __shfl_sync(FULL, y, src);
+					ea = __shfl_sync(FULL, anc, src);
+					ed = d;
+					aligned = true;
+					break;
+				}
+			}
+			__syncwarp();
+			if (aligned) break;
+			best_m = max(best_m, rowmax);
+			// re-band to the diagonals within `tol` of the best, widened by one
+			int lo = 0x7fffffff, hi = -0x7fffffff;
+			for (int base = 0; base < n; base += 32) {
+				const int j = base + lane;
+				const int k = min_k + 2 * j;
+				bool keep = false;
+				if (j < n) {
+					const int kk = k + KOFF;
+					keep = 2 * (int)S.vl[kk & 1][kk >> 1].x - k >= best_m - tol;
+				}
+				const unsigned km = __ballot_sync(FULL, keep);
+				if (km) {
+					lo = min(lo, min_k + 2 * (base + __ffs(km) - 1));
+					hi = max(hi, min_k + 2 * (base + 31 - __clz(km)));
+				}
+			}
+			last_min = min_k; last_max = max_k; ++rows;
+			min_k = lo - 1; max_k = hi + 1;
+		}
+		if (!aligned && rows > 0) {
+			// best (x+y) cell: first k of the last completed row that reaches best_m
+			const int n = ((last_max - last_min) >> 1) + 1;
+			for (int base = 0; base < n; base += 32) {
+				const int j = base + lane;
+				const int k = last_min + 2 * j;
+				uint2 c = make_uint2(0u, NO_ANCHOR);
+				bool is = false;
+				if (j < n) {
+					const int kk = k + KOFF;
+					c = S.vl[kk & 1][kk >> 1];
+					is = 2 * (int)c.x - k == best_m;
+				}
+				const unsigned bm = __ballot_sync(FULL, is);
+				if (bm) {
+					const int src = __ffs(bm) - 1;
+					const int bx = __shfl_sync(FULL, (int)c.x, src);
+					const int bk = __shfl_sync(FULL, k, src);
+					const uint32_t ba = __shfl_sync(FULL, c.y, src);
+					if (bx > 0) { ex = bx; ey = bx - bk; ed = rows - 1; ea = ba; }
+					break;
+				}
+			}
+		}
+		__syncwarp();
+
+		// ---- trim_mismatch_end + chain bookkeeping (dw_in_one_direction)
+		if (ea == NO_ANCHOR) break;
+		const int ax = (int)(ea & 1023u), ay = (int)((ea >> 10) & 1023u), ad = (int)(ea >> 20);
+		const int acols = (ax + ay + ad) >> 1, amat = (ax + ay - ad) >> 1;
+		if (acols < 6) break;
+		const bool full_map = (qblk - ex <= 20) || (tblk - ey <= 20);
+		if (last || !full_map) {
+			cols += acols; mats += amat; qadv += ax; tadv += ay;
+			break;
+		}
+		cols += acols - 4; mats += amat - 4; qadv += ax - 4; tadv += ay - 4;
+		qi += ax - 4; ti += ay - 4;
+	}
+	if (lane == 0) {
+		ExtendHalf h;
+		h.cols = cols; h.matches = mats; h.qadv = qadv; h.tadv = tadv;
+		halves[item] = h;
+		if (block_counter) atomicAdd(block_counter, (unsigned long long)nblocks);
+	}
+}
+
+int extend_launch(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* d_tasks, size_t ntasks,
+                  ExtendHalf* d_halves)
+{
+	if (!ntasks) return 0;
+	unsigned long long* d_counter = c->d_counters;
+	MB_CUDA(c, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), c->stream));
+	const size_t items = 2 * ntasks;
+	const unsigned grid = (unsigned)((items + EXT_WARPS - 1) / EXT_WARPS);
+	k_extend<<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
+	                                                 s->num_bases, d_tasks, ntasks, d_halves, d_counter);
+	MB_CUDA(c, cudaGetLastError());
+	c->stats.kernel_launches += 1;
+	unsigned long long nb = 0;
+	MB_CUDA(c, cudaMemcpyAsync(&nb, d_counter, sizeof nb, cudaMemcpyDeviceToHost, c->stream));
+	MB_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->stats.num_extend_blocks += (int64_t)nb;
+	return 0;
+}
+
+}  // namespace mb

@@ -1,0 +1,241 @@
+// mecat_b200/csrc/index.cu -- k = 13 direct-address index of an index volume (A1).
+//
+// Replaces create_ref_index + fill_ref_index_offsets_func (src/common/lookup_table.cpp:64-160,
+// 26-61).  Same content: for every read, every 13-mer start; k-mers that occur more than 128
+// times in the volume are dropped (:97); the start positions of a k-mer are stored in
+// ascending order (every reference fill thread scans the reads in order, :36-58).
+//
+// Layout in HBM: CSR.  begin[2^26 + 1] (uint32) and pos[num_kmers] (int32), i.e. the
+// reference's kmer_counts / kmer_starts / kmer_offsets triple without the pointer table.
+//
+// Kernels (all HBM bound): count (atomic histogram over the 2^26 codes), cutoff + exclusive
+// scan, fill (atomic cursor per code), and a per-list register bitonic sort that restores the
+// ascending order the atomics lost.
+#include "common.cuh"
+
+namespace mb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t kmer_code_at(const uint32_t* __restrict__ fwd, uint32_t p)
+{
+	// 13 bases starting at p, first base most significant (lookup_table.cpp:79-90)
+	return rev_groups2(ld_bases32(fwd, p)) >> 6;
+}
+
+__global__ void k_kmer_count(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
+                             uint32_t* __restrict__ counts)
+{
+	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
+		const int2 o = offsz[r];
+		const int nk = o.y - (KMER - 1);
+		for (int i = threadIdx.x; i < nk; i += blockDim.x) atomicAdd(&counts[kmer_code_at(fwd, (uint32_t)(o.x + i))], 1u);
+	}
+}
+
+__global__ void k_kmer_fill(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
+                            const uint32_t* __restrict__ begin, uint32_t* __restrict__ cursor, int32_t* __restrict__ pos)
+{
+	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
+		const int2 o = offsz[r];
+		const int nk = o.y - (KMER - 1);
+		for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+			const uint32_t p = (uint32_t)(o.x + i);
+			const uint32_t code = kmer_code_at(fwd, p);
+			const uint32_t b = begin[code];
+			if (begin[code + 1] != b) pos[b + atomicAdd(&cursor[code], 1u)] = (int32_t)p;
+		}
+	}
+}
+
+// ---- exclusive scan of min(count, cutoff -> 0) over 2^26 codes: reduce / top / down-sweep
+constexpr int SCAN_T = 256, SCAN_E = 16, SCAN_TILE = SCAN_T * SCAN_E;   // 4096 codes per block
+
+__device__ __forceinline__ uint32_t kept(uint32_t c) { return c > (uint32_t)MAX_OCC ? 0u : c; }
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const uint32_t* __restrict__ counts, uint32_t* __restrict__ tile_sum)
+{
+	__shared__ uint32_t red[SCAN_T / 32];
+	const size_t base = (size_t)blockIdx.x * SCAN_TILE;
+	uint32_t s = 0;
+	for (int e = 0; e < SCAN_E; ++e) s += kept(counts[base + (size_t)e * SCAN_T + threadIdx.x]);
+	s = __reduce_add_sync(0xFFFFFFFFu, s);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int i = 0; i < SCAN_T / 32; ++i) t += red[i];
+		tile_sum[blockIdx.x] = t;
+	}
+}
+
+// single block: exclusive scan of ntiles (= 16384) tile sums in place; writes the grand total
+__global__ void __launch_bounds__(1024) k_scan_top(uint32_t* __restrict__ tile_sum, int ntiles, uint32_t* __restrict__ total)
+{
+	__shared__ uint32_t part[1024];
+	const int per = (ntiles + 1023) / 1024;
+	const int lo = threadIdx.x * per, hi = min(ntiles, lo + per);
+	uint32_t s = 0;
+	for (int i = lo; i < hi; ++i) s += tile_sum[i];
+	part[threadIdx.x] = s;
+	__syncthreads();
+	for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele inclusive
+		uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+		__syncthreads();
+		part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	uint32_t run = part[threadIdx.x] - s;
+	for (int i = lo; i < hi; ++i) { uint32_t v = tile_sum[i]; tile_sum[i] = run; run += v; }
+	if (threadIdx.x == 1023) *total = part[1023];
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_down(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ tile_sum,
+                                                       uint32_t* __restrict__ begin)
+{
+	// thread t owns SCAN_E consecutive codes so that the running sum stays in registers
+	__shared__ uint32_t wsum[SCAN_T / 32];
+	const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_E;
+	uint32_t v[SCAN_E];
+	const uint4* src = reinterpret_cast<const uint4*>(counts + base);
+#pragma unroll
+	for (int e = 0; e < SCAN_E / 4; ++e) {
+		uint4 q = src[e];
+		v[4 * e] = kept(q.x); v[4 * e + 1] = kept(q.y); v[4 * e + 2] = kept(q.z); v[4 * e + 3] = kept(q.w);
+	}
+	uint32_t s = 0;
+#pragma unroll
+	for (int e = 0; e < SCAN_E; ++e) s += v[e];
+	// exclusive scan of s across the block
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = s;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+		if (lane >= off) inc += n;
+	}
+	if (lane == 31) wsum[warp] = inc;
+	__syncthreads();
+	uint32_t woff = 0;
+	for (int w = 0; w < warp; ++w) woff += wsum[w];
+	uint32_t run = tile_sum[blockIdx.x] + woff + inc - s;
+	uint32_t o[SCAN_E];
+#pragma unroll
+	for (int e = 0; e < SCAN_E; ++e) { o[e] = run; run += v[e]; }
+	uint4* dst = reinterpret_cast<uint4*>(begin + base);
+#pragma unroll
+	for (int e = 0; e < SCAN_E / 4; ++e) dst[e] = make_uint4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+}
+
+// ---- per-list ascending sort: one warp per k-mer list, R registers per lane (list <= 32*R)
+template <int R>
+__device__ __forceinline__ void warp_sort_list(int32_t* __restrict__ p, int n, int lane)
+{
+	int32_t v[R];
+#pragma unroll
+	for (int j = 0; j < R; ++j) { int i = j * 32 + lane; v[j] = i < n ? p[i] : 0x7fffffff; }
+#pragma unroll
+	for (int size = 2; size <= 32 * R; size <<= 1) {
+#pragma unroll
+		for (int stride = size >> 1; stride > 0; stride >>= 1) {
+			if (stride >= 32) {
+				const int rs = stride >> 5;
+#pragma unroll
+				for (int j = 0; j < R; ++j) {
+					const int pj = j ^ rs;
+					if (pj > j) {
+						const int i = j * 32 + lane;
+						const bool up = ((i & size) == 0) || size == 32 * R;
+						int32_t a = v[j], b = v[pj];
+						if ((a > b) == up) { v[j] = b; v[pj] = a; }
+					}
+				}
+			} else {
+#pragma unroll
+				for (int j = 0; j < R; ++j) {
+					const int i = j * 32 + lane;
+					const bool up = ((i & size) == 0) || size == 32 * R;
+					const int32_t o = __shfl_xor_sync(0xFFFFFFFFu, v[j], stride);
+					const bool lower = (lane & stride) == 0;
+					v[j] = (lower == up) ? min(v[j], o) : max(v[j], o);
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < R; ++j) { int i = j * 32 + lane; if (i < n) p[i] = v[j]; }
+}
+
+constexpr int SORT_WARPS = 8, SORT_CODES_PER_WARP = 32;
+
+__global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_lists(const uint32_t* __restrict__ begin, int32_t* __restrict__ pos)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t c0 = ((uint32_t)blockIdx.x * SORT_WARPS + (threadIdx.x >> 5)) * SORT_CODES_PER_WARP;
+	const uint32_t b_lane = begin[c0 + lane];
+	const uint32_t b_next = begin[c0 + lane + 1];
+	for (int i = 0; i < SORT_CODES_PER_WARP; ++i) {
+		const uint32_t b = __shfl_sync(0xFFFFFFFFu, b_lane, i);
+		const int n = (int)(__shfl_sync(0xFFFFFFFFu, b_next, i) - b);
+		if (n < 2) continue;
+		if (n <= 32) warp_sort_list<1>(pos + b, n, lane);
+		else if (n <= 64) warp_sort_list<2>(pos + b, n, lane);
+		else warp_sort_list<4>(pos + b, n, lane);
+	}
+}
+
+}  // namespace
+
+int index_build(Ctx* c, const DVolume* v, DIndex** out)
+{
+	DIndex* I = new DIndex;
+	uint32_t* d_counts = nullptr;
+	uint32_t* d_tiles = nullptr;
+	uint32_t* d_total = nullptr;
+	const int ntiles = (int)(NCODES / SCAN_TILE);
+	auto body = [&]() -> int {
+		MB_CUDA(c, cudaMalloc(&d_counts, sizeof(uint32_t) * (size_t)NCODES));
+		MB_CUDA(c, cudaMalloc(&I->begin, sizeof(uint32_t) * ((size_t)NCODES + 4)));
+		MB_CUDA(c, cudaMalloc(&d_tiles, sizeof(uint32_t) * (size_t)ntiles));
+		MB_CUDA(c, cudaMalloc(&d_total, sizeof(uint32_t)));
+		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
+		const int grid_reads = v->num_reads < 1 ? 1 : (v->num_reads > 65535 * 8 ? 65535 * 8 : v->num_reads);
+		if (v->num_reads > 0) k_kmer_count<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, d_counts);
+		k_scan_reduce<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles);
+		k_scan_top<<<1, 1024, 0, c->stream>>>(d_tiles, ntiles, d_total);
+		k_scan_down<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles, I->begin);
+		MB_CUDA(c, cudaGetLastError());
+		c->stats.kernel_launches += 4;
+		uint32_t total = 0;
+		MB_CUDA(c, cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		MB_CUDA(c, cudaMemcpyAsync(I->begin + NCODES, &total, sizeof total, cudaMemcpyHostToDevice, c->stream));
+		I->num_kmers = total;
+		MB_CUDA(c, cudaMalloc(&I->pos, sizeof(int32_t) * ((size_t)total + 1)));
+		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
+		if (total) {
+			k_kmer_fill<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->begin, d_counts, I->pos);
+			k_sort_lists<<<NCODES / (SORT_WARPS * SORT_CODES_PER_WARP), SORT_WARPS * 32, 0, c->stream>>>(I->begin, I->pos);
+			MB_CUDA(c, cudaGetLastError());
+			c->stats.kernel_launches += 2;
+		}
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->stats.index_kmers = total;
+		return 0;
+	};
+	int rc = body();
+	cudaFree(d_counts); cudaFree(d_tiles); cudaFree(d_total);
+	if (rc) { index_release(I); return rc; }
+	*out = I;
+	return 0;
+}
+
+void index_release(DIndex* i)
+{
+	if (!i) return;
+	cudaFree(i->begin);
+	cudaFree(i->pos);
+	delete i;
+}
+
+}  // namespace mb

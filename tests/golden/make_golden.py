@@ -1,0 +1,71 @@
+"""Regenerates tests/golden/* from the UNMODIFIED reference binaries (oracle/_ref, built by
+`make -C oracle ref` in the build container where /root/reference exists).
+
+  python tests/golden/make_golden.py
+
+Cases (reads come from oracle/gen_reads, a seeded deterministic generator):
+  small : 250 reads, mean 6 kb, genome 100 kb, seed 3   -> FASTA committed (gzip)
+  cfg0  : 1000 reads, mean 15 kb, genome 1 Mb, seed 7   -> BASELINE.json configs[0]; FASTA
+          regenerated on demand, its sha256 is committed
+For each: vol0 sha256 (split_raw_dataset), sorted `mecat2pw -j 0` lines, sorted
+`mecat2pw -j 1 -g 1` lines.
+"""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from util import gen_reads, REF_DIR  # noqa: E402
+
+CASES = {
+    "small": dict(n=250, genome=100000, seed=3, mean=6000, sd=1500),
+    "cfg0": dict(n=1000, genome=1000000, seed=7, mean=15000, sd=1500),
+}
+
+
+def sha(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for b in iter(lambda: f.read(1 << 20), b""):
+            h.update(b)
+    return h.hexdigest()
+
+
+def main():
+    meta = {}
+    for name, c in CASES.items():
+        tmp = tempfile.mkdtemp(prefix="golden_")
+        fa = os.path.join(tmp, "reads.fa")
+        gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+        m = dict(c)
+        m["fasta_sha256"] = sha(fa)
+        for job, ext, extra in ((0, "can", []), (1, "m4", ["-g", "1"])):
+            wrk = os.path.join(tmp, "wrk%d" % job)
+            out = os.path.join(tmp, "out." + ext)
+            subprocess.check_call([os.path.join(REF_DIR, "mecat2pw"), "-j", str(job), "-d", fa, "-o", out, "-w", wrk,
+                                   "-t", "8"] + extra, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            lines = sorted(open(out).read().splitlines())
+            with gzip.open(os.path.join(HERE, "%s.%s.gz" % (name, ext)), "wt") as f:
+                f.write("\n".join(lines) + "\n")
+            m["num_" + ext] = len(lines)
+            if job == 0:
+                m["vol0_sha256"] = sha(os.path.join(wrk, "vol0"))
+        if name == "small":
+            with open(fa, "rb") as f, gzip.open(os.path.join(HERE, "small.fa.gz"), "wb") as g:
+                shutil.copyfileobj(f, g)
+        meta[name] = m
+        shutil.rmtree(tmp)
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    print(json.dumps(meta, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,250 @@
+"""GPU parity tests (-m gpu): every result of the CUDA path, obtained through the C ABI, is
+compared bit for bit with the CPU oracle and with golden outputs of the unmodified reference."""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+from util import PackedVolume
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))
+
+
+def gold_lines(name, ext):
+    with gzip.open(os.path.join(util.GOLDEN, "%s.%s.gz" % (name, ext)), "rt") as f:
+        return f.read().splitlines()
+
+
+def host_volume(v):
+    import mecat_b200
+    return mecat_b200.HostVolume(v.offset_size, v.pac, v.num_bases, v.start_read_id)
+
+
+@pytest.fixture(scope="module")
+def small_vol():
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f:
+        seqs = [l for l in f.read().split(b"\n") if l and not l.startswith(b">")]
+    return PackedVolume.from_seqs(seqs)
+
+
+@pytest.fixture(scope="module")
+def cfg0_vol(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cfg0")
+    fa = str(d / "cfg0.fa")
+    c = GOLD["cfg0"]
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == c["fasta_sha256"]
+    return PackedVolume.from_seqs(util.read_fasta(fa))
+
+
+def report(tag, mine, want, limit=8):
+    if mine == want:
+        return
+    sm, sw = set(mine), set(want)
+    msg = ["%s: %d lines vs %d expected; %d only-mine, %d only-expected" % (tag, len(mine), len(want), len(sm - sw), len(sw - sm))]
+    msg += ["  mine: " + x for x in sorted(sm - sw)[:limit]]
+    msg += ["  want: " + x for x in sorted(sw - sm)[:limit]]
+    os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(util.ROOT, "gpurun_out", "mismatch_%s.txt" % tag), "w") as f:
+        f.write("\n".join(msg) + "\n")
+        f.write("\n".join("M " + x for x in sorted(sm - sw)) + "\n")
+        f.write("\n".join("W " + x for x in sorted(sw - sm)) + "\n")
+    pytest.fail("\n".join(msg))
+
+
+# ---------------------------------------------------------------- A1
+def test_index_matches_oracle(gpu_ctx, small_vol):
+    O = util.oracle()
+    cv = small_vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    d = gpu_ctx.upload(host_volume(small_vol))
+    idx = gpu_ctx.index_build(d)
+    begin, pos = gpu_ctx.index_export(idx)
+    assert len(pos) == O.orc_index_num_kmers(oidx)
+    lst = C.POINTER(C.c_int32)()
+    lens = np.diff(begin.astype(np.int64))
+    assert lens.max() <= 128
+    nz = np.nonzero(lens)[0]
+    rng = np.random.default_rng(2)
+    for code in list(rng.choice(nz, size=3000, replace=False)) + list(rng.integers(0, 1 << 26, size=500)):
+        n = O.orc_index_lookup(oidx, int(code), C.byref(lst))
+        assert n == lens[code]
+        assert [lst[i] for i in range(n)] == list(pos[begin[code]:begin[code] + n])
+    # whole-array property: every list ascending, every position a valid 13-mer start of the right code
+    starts = pos.astype(np.int64)
+    same = np.repeat(np.arange(len(lens)), lens)
+    asc = (np.diff(starts) > 0) | (np.diff(same) != 0)
+    assert asc.all()
+    gpu_ctx.release_index(idx)
+    gpu_ctx.release_volume(d)
+    O.orc_index_free(oidx)
+
+
+# ---------------------------------------------------------------- A8-A11
+def oracle_extend(vq, vs, tasks, min_aln):
+    O = util.oracle()
+    out = (C.c_int32 * 8)()
+    ident = C.c_double()
+    res = []
+    cache = {}
+    for t in tasks:
+        kq = (int(t["qread"]), int(t["qstrand"]))
+        if kq not in cache:
+            cache[kq] = np.concatenate([[0], vq.codes(kq[0], kq[1]), [0]]).astype(np.int8)
+        ks = ("s", int(t["sread"]))
+        if ks not in cache:
+            cache[ks] = np.concatenate([[0], vs.codes(ks[1], 0), [0]]).astype(np.int8)
+        q, s = cache[kq], cache[ks]
+        O.orc_diff_go(C.cast(q.ctypes.data + 1, C.c_char_p), int(t["qstart"]), len(q) - 2,
+                      C.cast(s.ctypes.data + 1, C.c_char_p), int(t["sstart"]), len(s) - 2, min_aln, out, C.byref(ident), None, None, 0)
+        res.append((out[0], out[1], out[2], out[3], out[4], out[5], out[6], ident.value))
+    return res
+
+
+def test_extend_matches_oracle(gpu_ctx, small_vol):
+    import mecat_b200
+    O = util.oracle()
+    cv = small_vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    p = util.pw_params(task=0)
+    out = (C.c_int32 * (12 * 101))()
+    tasks = []
+    for rid in range(small_vol.num_reads):
+        n = O.orc_pw_candidates(oidx, C.byref(cv), C.byref(cv), rid, C.byref(p), out)
+        for i in range(n):
+            c = out[12 * i:12 * i + 12]
+            qstart, sstart = c[1], c[0]
+            if qstart and sstart:
+                qstart += 6; sstart += 6
+            tasks.append((rid, c[11], qstart, c[9], sstart))
+    O.orc_index_free(oidx)
+    rng = np.random.default_rng(4)
+    n = small_vol.num_reads
+    # edge cases: start points at the very ends, unrelated pairs, random interior points
+    for it in range(300):
+        a, b = int(rng.integers(0, n)), int(rng.integers(0, n))
+        la, lb = int(small_vol.offset_size[a][1]), int(small_vol.offset_size[b][1])
+        mode = it % 4
+        if mode == 0: qs, ss = 0, 0
+        elif mode == 1: qs, ss = la, lb
+        elif mode == 2: qs, ss = int(rng.integers(0, la + 1)), int(rng.integers(0, lb + 1))
+        else: qs, ss = la // 2, 0
+        tasks.append((a, it & 1, qs, b, ss))
+    tasks = np.array(tasks, dtype=mecat_b200.TASK_DTYPE)
+    d = gpu_ctx.upload(host_volume(small_vol))
+    got = gpu_ctx.extend_batch(d, d, tasks, 2000)
+    gpu_ctx.release_volume(d)
+    want = oracle_extend(small_vol, small_vol, tasks, 2000)
+    bad = []
+    for i, (g, w) in enumerate(zip(got, want)):
+        gg = (int(g["ok"]), int(g["qstart"]), int(g["qend"]), int(g["sstart"]), int(g["send"]), int(g["columns"]), int(g["matches"]), float(g["ident"]))
+        if gg != tuple(w):
+            bad.append((i, tuple(int(x) for x in tasks[i]), gg, tuple(w)))
+    if bad:
+        os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(util.ROOT, "gpurun_out", "mismatch_extend.txt"), "w") as f:
+            for b in bad:
+                f.write(repr(b) + "\n")
+    assert not bad, "%d of %d extension results differ; first: %r" % (len(bad), len(tasks), bad[0])
+
+
+# ---------------------------------------------------------------- A2-A6
+def test_raw_candidates_match_oracle(gpu_ctx, small_vol):
+    O = util.oracle()
+    cv = small_vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    p = util.pw_params(task=0)
+    d = gpu_ctx.upload(host_volume(small_vol))
+    idx = gpu_ctx.index_build(d)
+    import mecat_b200
+    rows, counts = gpu_ctx.pw_raw_candidates(idx, d, d, mecat_b200.pw_params(task=0), small_vol.num_reads)
+    gpu_ctx.release_index(idx)
+    gpu_ctx.release_volume(d)
+    out = (C.c_int32 * (12 * 101))()
+    k = 0
+    bad = []
+    for rid in range(small_vol.num_reads):
+        n = O.orc_pw_candidates(oidx, C.byref(cv), C.byref(cv), rid, C.byref(p), out)
+        want = [tuple(out[12 * i:12 * i + 12]) for i in range(n)]
+        got = [tuple(int(x) for x in rows[k + i]) for i in range(int(counts[rid]))]
+        k += int(counts[rid])
+        if got != want:
+            bad.append((rid, got, want))
+    O.orc_index_free(oidx)
+    if bad:
+        os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(util.ROOT, "gpurun_out", "mismatch_rawcand.txt"), "w") as f:
+            for rid, got, want in bad:
+                f.write("read %d\n" % rid)
+                for g in got: f.write("  G %r\n" % (g,))
+                for w in want: f.write("  W %r\n" % (w,))
+    assert not bad, "%d reads differ; first read %d" % (len(bad), bad[0][0])
+
+
+# ---------------------------------------------------------------- whole tiles vs the reference binaries
+def test_small_can_matches_reference(gpu_ctx, small_vol):
+    hv = host_volume(small_vol)
+    ec = gpu_ctx.pw_candidates(hv, hv)
+    report("small_can", util.ec_lines(ec), gold_lines("small", "can"))
+
+
+def test_small_m4_matches_reference(gpu_ctx, small_vol):
+    hv = host_volume(small_vol)
+    m4 = gpu_ctx.pw_overlaps(hv, hv)
+    report("small_m4", util.m4_lines(m4, gapped=True), gold_lines("small", "m4"))
+
+
+def test_cfg0_can_matches_reference(gpu_ctx, cfg0_vol):
+    hv = host_volume(cfg0_vol)
+    ec = gpu_ctx.pw_candidates(hv, hv)
+    report("cfg0_can", util.ec_lines(ec), gold_lines("cfg0", "can"))
+
+
+def test_cfg0_m4_matches_reference(gpu_ctx, cfg0_vol):
+    hv = host_volume(cfg0_vol)
+    m4 = gpu_ctx.pw_overlaps(hv, hv)
+    report("cfg0_m4", util.m4_lines(m4, gapped=True), gold_lines("cfg0", "m4"))
+
+
+def test_off_diagonal_tile_matches_oracle(gpu_ctx, small_vol):
+    n = small_vol.num_reads // 2
+    seqs = [bytes(b"ACGT"[c] for c in small_vol.codes(i)) for i in range(small_vol.num_reads)]
+    a = PackedVolume.from_seqs(seqs[:n], 0)
+    b = PackedVolume.from_seqs(seqs[n:], n)
+    for task in (0, 1):
+        want = util.oracle_pw_tile(a, b, util.pw_params(task=task), threads=4)
+        import mecat_b200
+        if task == 0:
+            got = gpu_ctx.pw_candidates(host_volume(a), host_volume(b), mecat_b200.pw_params(task=0))
+            report("offdiag_can", util.ec_lines(got), util.ec_lines(want))
+        else:
+            got = gpu_ctx.pw_overlaps(host_volume(a), host_volume(b), mecat_b200.pw_params(task=1))
+            report("offdiag_m4", util.m4_lines(got, True), util.m4_lines(want, True))
+
+
+def test_candidate_cap_and_order(gpu_ctx, small_vol):
+    """-n 3: per read the first 3 candidates of the -n 100 list, in the same order."""
+    import mecat_b200
+    hv = host_volume(small_vol)
+    full = gpu_ctx.pw_candidates(hv, hv, mecat_b200.pw_params(task=0))
+    cut = gpu_ctx.pw_candidates(hv, hv, mecat_b200.pw_params(task=0, num_candidates=3))
+    want = util.oracle_pw_tile(small_vol, small_vol, util.pw_params(task=0, n=3), threads=4)
+    assert [tuple(x) for x in cut.tolist()] == [tuple(x) for x in want.tolist()]   # same order, not only same set
+    assert len(full) >= len(cut)
+
+
+def test_empty_and_tiny_inputs(gpu_ctx):
+    import mecat_b200
+    tiny = PackedVolume.from_seqs([b"ACGTACGTAC", b"A", b"ACGTTGCATGCATGCATGCAAGCTTAGC" * 3])
+    hv = host_volume(tiny)
+    assert len(gpu_ctx.pw_candidates(hv, hv)) == 0
+    assert len(gpu_ctx.pw_overlaps(hv, hv)) == 0
+    with pytest.raises(mecat_b200.MecatB200Error):
+        gpu_ctx.pw_candidates(hv, hv, mecat_b200.pw_params(task=0, num_candidates=0))
