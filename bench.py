@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native mecat2pw hot path.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): overlapped read-pairs / second of `mecat2pw` (default job -j 1: block
+k-mer seeding -> DDF candidate scoring -> O(nd) diff extension), i.e. M4 records produced per
+second of wall time, whole job, on synthetic PacBio-CLR reads (15 kb, 15 % error).
+
+A "step" is one pass of the hot path over the whole workload:
+  N = 1   BASELINE configs[1]: all-vs-all on 100 000 x 15 kb reads (one 1.59 Gbase volume):
+          k-mer index build + seeding/scoring of every read + extension of every candidate.
+  N > 1   N such volumes (N x 100 000 reads, genome N x 100 Mb, same 15x coverage), all
+          N(N+1)/2 (index volume, query volume) tiles; packed query volumes rotate round the
+          ring of ranks over NCCL/NVLink, rank g serves indices g and N-1-g (mecat_b200/multi.py).
+`value`  = records / step time with the packed volume(s) already resident in HBM.
+`e2e`    = the same through the host-buffer C-ABI call (mecat_b200_pw_overlaps): pinned host
+           volume -> H2D -> index -> tile -> D2H records, all inside the timed region.
+`--impl reference` times the UNMODIFIED reference binary (oracle/_ref/mecat2pw -j 1, all host
+threads) on a bounded sample of the same read model (see cpu_sample()).
+Inputs (>= 400 MB packed + 6 GB index) are far larger than the 126 MB L2: no flush needed.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READS_PER_VOLUME = 100000
+GENOME_PER_VOLUME = 100000000
+SEED = 11
+METRIC = "overlapped read-pairs/sec (mecat2pw)"
+UNIT = "pairs/s"
+SAMPLE_READS = 6000           # bounded CPU sample: 6 000 reads from a 6 Mb genome (same 15x coverage)
+SAMPLE_GENOME = 6000000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def tmp_root():
+    d = os.environ.get("MECAT_BENCH_TMP") or os.path.join(tempfile.gettempdir(), "mecat_b200_bench")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def gen_exe():
+    exe = os.path.join(ROOT, "mecat_b200", "bin", "gen_reads")
+    if not os.path.exists(exe):
+        from mecat_b200 import build
+        build.build()
+    return exe
+
+
+def make_reads(path, n, genome, seed):
+    if os.path.exists(path) and os.path.getsize(path) > n * 2000:
+        return
+    t = time.time()
+    subprocess.check_call([gen_exe(), path + ".tmp", str(n), str(genome), str(seed)])
+    os.replace(path + ".tmp", path)
+    log("[bench] generated %d reads (genome %d, seed %d) in %.1f s" % (n, genome, seed, time.time() - t))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for i, nme in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference
+def cpu_sample(threads=None, keep=None):
+    """Runs the unmodified reference binary (oracle/_ref/mecat2pw -j 1 -t <all cores>) on the
+    bounded sample and returns (pairs, seconds, cores, description)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "mecat2pw")
+    cores = threads or os.cpu_count() or 1
+    desc = ("mecat2pw -j 1 -t %d on %d synthetic CLR reads (15 kb, 15%% err, genome %d, seed %d): same read model "
+            "and coverage as the workload, ~1/17 of its reads, so the index volume is 17x smaller and the CPU sees "
+            "~17x fewer random 13-mer hits per read than at full size (optimistic for the CPU)"
+            % (cores, SAMPLE_READS, SAMPLE_GENOME, SEED))
+    if not os.path.exists(exe):
+        return None, None, cores, "oracle/_ref/mecat2pw not built", "unavailable"
+    d = tmp_root()
+    fa = os.path.join(d, "sample_%d_%d.fa" % (SAMPLE_READS, SEED))
+    make_reads(fa, SAMPLE_READS, SAMPLE_GENOME, SEED)
+    wrk = tempfile.mkdtemp(prefix="refwrk_", dir=d)
+    out = os.path.join(wrk, "out.m4")
+    t = time.perf_counter()
+    subprocess.check_call([exe, "-j", "1", "-d", fa, "-o", out, "-w", os.path.join(wrk, "w"), "-t", str(cores)],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t
+    with open(out, "rb") as f:
+        pairs = sum(1 for _ in f)
+    if keep:
+        shutil.copy(out, keep)
+    shutil.rmtree(wrk, ignore_errors=True)
+    return pairs, dt, cores, desc, "reference"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, pairs = [], 0
+    for i in range(args.warmup + args.steps):
+        pairs, dt, cores, desc, kind = cpu_sample()
+        if pairs is None:
+            print(json.dumps({"impl": "reference", "unavailable": desc}))
+            return
+        if i >= args.warmup:
+            times.append(dt)
+        log("[bench] reference step %d: %d pairs in %.2f s" % (i, pairs, dt))
+    total = sum(times)
+    value = pairs * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "mecat2pw -j 1 all-vs-all, %d x %d synthetic PacBio-CLR reads (15 kb mean, 15%% error, 15x), "
+                        "%d volume(s), %d tile(s)" % (n, READS_PER_VOLUME, n, n * (n + 1) // 2),
+            "reads": n * READS_PER_VOLUME, "genome": n * GENOME_PER_VOLUME, "seed": SEED,
+            "params": "-n 100 -a 2000 -k 4 -x 0", "l2": "inputs larger than L2 (no flush)",
+            "parallelism": "1 gpu" if n == 1 else "%d gpus: query-volume ring over NCCL, mirror-paired indices" % n}
+
+
+# ------------------------------------------------------------------------------------------ ours
+def pinned_volume(vol):
+    """Copy the packed volume into pinned host memory (torch) so the H2D inside e2e is a DMA."""
+    import numpy as np
+    import torch
+    import mecat_b200
+    pac = torch.empty(len(vol.pac), dtype=torch.uint8, pin_memory=True)
+    pac.numpy()[:] = vol.pac
+    osz = torch.empty(vol.offset_size.size, dtype=torch.int32, pin_memory=True)
+    osz.numpy()[:] = vol.offset_size.reshape(-1)
+    hv = mecat_b200.HostVolume(osz.numpy().reshape(-1, 2), pac.numpy(), vol.num_bases, vol.start_read_id)
+    hv._keep = (pac, osz)
+    assert hv.pac.ctypes.data == pac.data_ptr()
+    return hv
+
+
+def roofline_for(stats, peaks):
+    """Roofline entry for the dominant kernel of the timed steps."""
+    km = stats["kernel_ms"]
+    launches = stats["kernel_launches"]
+    name = max(km, key=lambda k: km[k])
+    B = stats["index_bases"]        # summed over steps
+    K = stats["index_kmers"]
+    H = stats["num_hits"]
+    C = stats["num_candidates"]
+    ncodes = 1 << 26
+    steps = max(1, launches["index_count"])
+    alg = {
+        # bytes the algorithm must move per launch
+        "index_count": B / 4 + 4.0 * K + 4.0 * ncodes * steps,            # packed bases in, one counter update per k-mer
+        "index_fill": B / 4 + 4.0 * K + 8.0 * ncodes * steps,             # packed bases in, begin[] in, one position out per kept k-mer
+        "index_sort": 8.0 * K + 4.0 * ncodes * steps,                     # positions in and out, begin[] in
+        "index_scan": 12.0 * ncodes * steps,
+        "seed": 3 * 4.0 * H + 0.0,                                        # three streaming passes over the hit positions
+        "extend": C * (2 * 15000 / 4 + 52 + 32),                          # two packed reads in, one record out per candidate
+    }.get(name, 0.0)
+    ms = km[name]
+    achieved = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak if peak else None, "traffic": None,
+            "ms_per_launch": ms / max(1, launches[name]), "launches": launches[name],
+            "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
+            "kernel_ms_share": {k: round(v / max(1e-9, sum(km.values())), 4) for k, v in km.items() if v > 0}}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import mecat_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from mecat_b200 import multi
+        return multi.run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample,
+                               roofline_for)
+    torch.cuda.set_device(local)
+    d = tmp_root()
+    nreads = args.reads or READS_PER_VOLUME
+    genome = int(GENOME_PER_VOLUME * (nreads / READS_PER_VOLUME))
+    fa = os.path.join(d, "reads_%d_%d.fa" % (nreads, SEED))
+    make_reads(fa, nreads, genome, SEED)
+    wrk = os.path.join(d, "wrk_%d" % nreads)
+    t = time.time()
+    names = mecat_b200.split_dataset(fa, wrk)
+    assert len(names) == 1, "workload must fit one volume"
+    vol = mecat_b200.HostVolume.load(names[0])
+    hv = pinned_volume(vol)
+    log("[bench] split + load: %.1f s; %d reads, %d bases" % (time.time() - t, vol.num_reads, vol.num_bases))
+    params = mecat_b200.pw_params(task=1)
+    ctx = mecat_b200.Context(local)
+    dvol = ctx.upload(hv)
+
+    def step_resident():
+        idx = ctx.index_build(dvol)
+        rec = ctx.pw_tile(idx, dvol, dvol, params)
+        ctx.release_index(idx)
+        return len(rec)
+
+    def step_e2e():
+        return len(ctx.pw_overlaps(hv, hv, params))
+
+    for i in range(args.warmup):
+        t = time.perf_counter()
+        n = step_resident()
+        log("[bench] warmup %d: %d pairs in %.2f s" % (i, n, time.perf_counter() - t))
+    ctx.reset_stats()
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pairs = 0
+    for i in range(args.steps):
+        pairs += step_resident()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    stats = ctx.stats()
+    clocks = sampler.stop()
+    log("[bench] resident: %d pairs in %.2f s; kernel ms %s" % (pairs, dt, json.dumps(stats["kernel_ms"])))
+    # end to end through the host-buffer C-ABI call
+    step_e2e()
+    ctx.reset_stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    epairs = 0
+    esteps = max(1, min(args.steps, 3))
+    for i in range(esteps):
+        epairs += step_e2e()
+    torch.cuda.synchronize()
+    edt = time.perf_counter() - t0
+    estats = ctx.stats()
+    ctx.release_volume(dvol)
+    ctx.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = roofline_for(stats, peaks)
+    cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "skipped (--no-cpu)"}
+    if not args.no_cpu:
+        cp, cdt, cores, desc, kind = cpu_sample()
+        if cp is not None:
+            cb = {"value": cp / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "seconds": cdt, "pairs": cp}
+        else:
+            cb = {"value": None, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    line = {
+        "metric": METRIC, "value": pairs / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": workload_config(1) if not args.reads else
+        dict(workload_config(1), reads=nreads, genome=genome, workload="REDUCED debug workload (%d reads)" % nreads),
+        "clocks": clocks,
+        "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": estats["h2d_bytes"] // esteps,
+                "d2h_bytes_per_step": estats["d2h_bytes"] // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
+        "gpu_launches": stats["gpu_launches"],
+        "roofline": roof, "cpu_baseline": cb,
+        "pairs_per_step": pairs // args.steps,
+        "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
+        "host_ms_per_step": round(stats["host_ms"] / args.steps, 3), "d2h_ms_per_step": round(stats["d2h_ms"] / args.steps, 3),
+        "hits_per_step": stats["num_hits"] // args.steps, "candidates_per_step": stats["num_candidates"] // args.steps,
+        "extend_blocks_per_step": stats["num_extend_blocks"] // args.steps,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=0, help="debug only: reduced workload (result is not the headline)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,14 +76,27 @@ typedef struct {
 	double ident;
 } mecat_extend_result;
 
-/* Per-call device timing (milliseconds, CUDA events on the context's stream). */
+/* Device time per kernel (milliseconds, CUDA events on the context's own stream, summed over
+ * launches since the last reset) and traffic counters.  Indices into kernel_ms / kernel_launches: */
+enum {
+	MECAT_K_ORIENT = 0,  /* volume re-layout (fwd / reversed 2-bit words)            */
+	MECAT_K_COUNT = 1,   /* index: k-mer histogram                                   */
+	MECAT_K_SCAN = 2,    /* index: cutoff + exclusive scan                           */
+	MECAT_K_FILL = 3,    /* index: position scatter                                  */
+	MECAT_K_SORT = 4,    /* index: per-list ordering                                 */
+	MECAT_K_SEED = 5,    /* seeding: hit streaming, bucket records                   */
+	MECAT_K_WALK = 6,    /* DDF scoring + candidate walk                             */
+	MECAT_K_MERGE = 7,   /* per-read candidate merge + record assembly               */
+	MECAT_K_EXTEND = 8,  /* O(nd) diff extension                                     */
+	MECAT_K_FINAL = 9,   /* extension result assembly                                */
+	MECAT_K_NUM = 16
+};
 typedef struct {
-	float h2d_ms, index_ms, seed_ms, walk_ms, extend_ms, d2h_ms, total_ms;
-	int64_t kernel_launches;
-	int64_t num_hits, num_candidates, num_extend_blocks;
-	/* dominant-kernel figures for the roofline */
-	float index_sort_ms;
-	int64_t index_kmers;
+	float kernel_ms[MECAT_K_NUM];
+	int64_t kernel_launches[MECAT_K_NUM];
+	float h2d_ms, d2h_ms, host_ms, total_ms;
+	int64_t h2d_bytes, d2h_bytes;
+	int64_t num_hits, num_candidates, num_extend_blocks, index_kmers, index_bases, num_records;
 } mecat_b200_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
@@ -95,6 +108,17 @@ void mecat_b200_destroy(mecat_b200_ctx* ctx);
 const char* mecat_b200_last_error(mecat_b200_ctx* ctx);
 void mecat_b200_free(mecat_b200_ctx* ctx, void* p);
 int mecat_b200_get_stats(mecat_b200_ctx* ctx, mecat_b200_stats* out);
+int mecat_b200_reset_stats(mecat_b200_ctx* ctx);
+
+/* ---- on-disk volumes (host only, byte-compatible with the reference) -----------------------
+ * replaces split_raw_dataset / dump_volume (src/common/split_database.cpp:222-266,136-153):
+ * FASTA/FASTQ -> wrk_dir/vol0..N-1 + wrk_dir/fileindex.txt.  max_volume_bases <= 0 selects the
+ * reference's 2 140 000 000-base cap (MCS, split_database.h:6). */
+int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_t max_volume_bases,
+                             int* num_volumes, char* err, int err_cap);
+/* replaces load_volume / delete_volume_t (split_database.cpp:156-181,95-101). */
+int mecat_b200_volume_load(const char* path, mecat_volume* out);
+void mecat_b200_volume_unload(mecat_volume* v);
 
 /* ---- volumes resident in HBM --------------------------------------------------------
  * replaces load_volume (split_database.cpp:156-181) + extract_one_seq/reverse_complement

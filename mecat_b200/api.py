@@ -27,11 +27,16 @@ class PwParams(C.Structure):
                 ("min_kmer_match", C.c_int32), ("tech", C.c_int32)]
 
 
+KERNEL_NAMES = ["orient", "index_count", "index_scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
+                "finalize"]
+
+
 class Stats(C.Structure):
-    _fields_ = [("h2d_ms", C.c_float), ("index_ms", C.c_float), ("seed_ms", C.c_float), ("walk_ms", C.c_float),
-                ("extend_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_int64), ("num_hits", C.c_int64), ("num_candidates", C.c_int64),
-                ("num_extend_blocks", C.c_int64), ("index_sort_ms", C.c_float), ("index_kmers", C.c_int64)]
+    _fields_ = [("kernel_ms", C.c_float * 16), ("kernel_launches", C.c_int64 * 16),
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("host_ms", C.c_float), ("total_ms", C.c_float),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("num_hits", C.c_int64), ("num_candidates", C.c_int64), ("num_extend_blocks", C.c_int64),
+                ("index_kmers", C.c_int64), ("index_bases", C.c_int64), ("num_records", C.c_int64)]
 
 
 EC_DTYPE = np.dtype([(n, "<i4") for n in
@@ -46,10 +51,11 @@ RESULT_DTYPE = np.dtype([("ok", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("ss
 
 EXPORTS = [
     "mecat_b200_abi_version", "mecat_b200_device_count", "mecat_b200_init", "mecat_b200_destroy",
-    "mecat_b200_last_error", "mecat_b200_free", "mecat_b200_get_stats", "mecat_b200_volume_upload",
+    "mecat_b200_last_error", "mecat_b200_free", "mecat_b200_get_stats", "mecat_b200_reset_stats",
+    "mecat_b200_volume_upload",
     "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
-    "mecat_b200_extend_batch",
+    "mecat_b200_extend_batch", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
 ]
 
 _lib = None
@@ -70,6 +76,7 @@ def load_library():
     L.mecat_b200_last_error.argtypes = [vp]
     L.mecat_b200_free.argtypes = [vp, vp]
     L.mecat_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.mecat_b200_reset_stats.argtypes = [vp]
     L.mecat_b200_volume_upload.argtypes = [vp, VP, C.POINTER(vp)]
     L.mecat_b200_volume_release.argtypes = [vp, vp]
     L.mecat_b200_index_build.argtypes = [vp, vp, C.POINTER(vp)]
@@ -80,6 +87,9 @@ def load_library():
     L.mecat_b200_pw_overlaps.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_raw_candidates.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_extend_batch.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.mecat_b200_split_dataset.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.mecat_b200_volume_load.argtypes = [C.c_char_p, VP]
+    L.mecat_b200_volume_unload.argtypes = [VP]
     _lib = L
     return L
 
@@ -107,6 +117,20 @@ class HostVolume:
             os_ = np.frombuffer(f.read(8 * n), dtype="<i4").reshape(-1, 2).copy()
             pac = np.frombuffer(f.read((nb + 3) // 4), dtype=np.uint8).copy()
         return HostVolume(os_, pac, nb, sid)
+
+
+def split_dataset(reads_path, wrk_dir, max_volume_bases=0):
+    """FASTA/FASTQ -> wrk_dir/volN + fileindex.txt (the reference's split_raw_dataset). Returns the volume paths."""
+    L = load_library()
+    os.makedirs(wrk_dir, exist_ok=True)
+    n = C.c_int()
+    err = C.create_string_buffer(512)
+    if L.mecat_b200_split_dataset(reads_path.encode(), wrk_dir.encode(), max_volume_bases, C.byref(n), err, 512) != 0:
+        raise MecatB200Error(err.value.decode())
+    with open(os.path.join(wrk_dir, "fileindex.txt")) as f:
+        names = [l.strip() for l in f if l.strip()]
+    assert len(names) == n.value
+    return names
 
 
 def pw_params(task=1, num_candidates=100, min_align_size=2000, min_kmer_match=4, tech=0):
@@ -152,7 +176,14 @@ class Context:
     def stats(self):
         s = Stats()
         self._check(self.L.mecat_b200_get_stats(self.h, C.byref(s)), "get_stats")
-        return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
+        d = {f[0]: getattr(s, f[0]) for f in Stats._fields_[2:]}
+        d["kernel_ms"] = {n: float(s.kernel_ms[i]) for i, n in enumerate(KERNEL_NAMES)}
+        d["kernel_launches"] = {n: int(s.kernel_launches[i]) for i, n in enumerate(KERNEL_NAMES)}
+        d["gpu_launches"] = int(sum(s.kernel_launches))
+        return d
+
+    def reset_stats(self):
+        self.L.mecat_b200_reset_stats(self.h)
 
     # ---- device-resident objects
     def upload(self, vol):

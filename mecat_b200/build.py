@@ -2,6 +2,7 @@
 
   mecat_b200/libmecat_b200.so   CUDA kernels + C ABI (include/mecat_b200.h), sm_100a only
   mecat_b200/bin/mecat2pw       C++ host driver with the reference's CLI (links the library)
+  mecat_b200/bin/gen_reads      seeded synthetic CLR read generator (tools/gen_reads.cpp; test/bench tooling)
 
 nvcc cross-compiles without a GPU.  Nothing here touches oracle/.
 """
@@ -51,6 +52,10 @@ def build(verbose=False):
     with cf.ThreadPoolExecutor(max_workers=len(CU)) as ex:
         res = list(ex.map(_compile, CU))
     objs = [r[0] for r in res]
+    hio_src, hio_obj = os.path.join(CSRC, "host_io.cpp"), os.path.join(OBJ, "host_io.o")
+    if _newer([hio_src, os.path.join(ROOT, "include", "mecat_b200.h")], hio_obj):
+        subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-fPIC", "-c", hio_src, "-o", hio_obj])
+    objs.append(hio_obj)
     log = "\n".join(r[1] for r in res if r[1])
     if log:
         with open(os.path.join(ROOT, "build", "ptxas.log"), "w") as f:
@@ -66,6 +71,9 @@ def build(verbose=False):
     if srcs and _newer(srcs + [LIB] + [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")], exe):
         subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe]
                               + srcs + ["-L", HERE, "-lmecat_b200", "-Wl,-rpath,$ORIGIN/.."])
+    gen_src, gen_exe = os.path.join(ROOT, "tools", "gen_reads.cpp"), os.path.join(BIN, "gen_reads")
+    if _newer([gen_src], gen_exe):
+        subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-o", gen_exe, gen_src])
     return LIB
 
 

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -15,19 +16,10 @@ struct mecat_b200_ctx : public mb::Ctx {};
 
 namespace {
 
-struct EvTimer
+struct WallTimer   // host clock, for the copies and the host-side record assembly
 {
-	Ctx* c;
-	int slot;
-	EvTimer(Ctx* c_, int slot_) : c(c_), slot(slot_) { cudaEventRecord(c->ev[2 * slot], c->stream); }
-	float stop()
-	{
-		cudaEventRecord(c->ev[2 * slot + 1], c->stream);
-		cudaEventSynchronize(c->ev[2 * slot + 1]);
-		float ms = 0;
-		cudaEventElapsedTime(&ms, c->ev[2 * slot], c->ev[2 * slot + 1]);
-		return ms;
-	}
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	float stop() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 __global__ void k_extend_finalize(const ExtendTask* __restrict__ tasks, const ExtendHalf* __restrict__ halves, size_t n,
@@ -53,7 +45,7 @@ __global__ void k_extend_finalize(const ExtendTask* __restrict__ tasks, const Ex
 __global__ void k_make_ec(const RawCand* __restrict__ cands, const int32_t* __restrict__ counts,
                           const int64_t* __restrict__ outpos, int maxc, int nreads, const int2* __restrict__ qoffsz,
                           int qstart_id, const int2* __restrict__ soffsz, int sstart_id, mecat_candidate* __restrict__ ec,
-                          ExtendTask* __restrict__ tasks)
+                          ExtendTask* __restrict__ tasks, int32_t* __restrict__ scores)
 {
 	int r = blockIdx.x;
 	if (r >= nreads) return;
@@ -77,6 +69,7 @@ __global__ void k_make_ec(const RawCand* __restrict__ cands, const int32_t* __re
 			ExtendTask t;
 			t.qread = r; t.qstrand = c.chain; t.qstart = qstart; t.sread = sidx; t.sstart = sstart;
 			tasks[base + i] = t;
+			scores[base + i] = c.score;
 		}
 	}
 }
@@ -119,7 +112,6 @@ int mecat_b200_init(mecat_b200_ctx** out, int device, void* /*nccl_comm_or_null*
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
 	memset(&c->stats, 0, sizeof c->stats);
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 4; }
-	for (auto& e : c->ev) cudaEventCreate(&e);
 	if (cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return 5; }
 	cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
 	*out = c;
@@ -131,7 +123,8 @@ void mecat_b200_destroy(mecat_b200_ctx* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	for (auto& e : c->ev) cudaEventDestroy(e);
+	c->resolve_timers();
+	for (auto& e : c->pool) cudaEventDestroy(e);
 	cudaFree(c->d_counters);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -147,12 +140,19 @@ int mecat_b200_get_stats(mecat_b200_ctx* c, mecat_b200_stats* out)
 	return 0;
 }
 
+int mecat_b200_reset_stats(mecat_b200_ctx* c)
+{
+	if (check(c)) return 1;
+	memset(&c->stats, 0, sizeof c->stats);
+	return 0;
+}
+
 int mecat_b200_volume_upload(mecat_b200_ctx* c, const mecat_volume* v, void** dvol)
 {
 	if (check(c) || !dvol) return 1;
 	cudaSetDevice(c->device);
 	DVolume* d = nullptr;
-	EvTimer t(c, 0);
+	WallTimer t;
 	int rc = volume_upload(c, v, &d);
 	c->stats.h2d_ms += t.stop();
 	if (rc) return rc;
@@ -173,9 +173,7 @@ int mecat_b200_index_build(mecat_b200_ctx* c, void* dvol_ref, void** index)
 	if (check(c) || !dvol_ref || !index) return 1;
 	cudaSetDevice(c->device);
 	DIndex* idx = nullptr;
-	EvTimer t(c, 1);
 	int rc = index_build(c, (DVolume*)dvol_ref, &idx);
-	c->stats.index_ms += t.stop();
 	if (rc) return rc;
 	*index = idx;
 	return 0;
@@ -227,17 +225,20 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
 		MB_CUDA(c, cudaMalloc(&d_halves, sizeof(ExtendHalf) * 2 * ntasks));
 		MB_CUDA(c, cudaMalloc(&d_res, sizeof(mecat_extend_result) * ntasks));
 		MB_CUDA(c, cudaMemcpyAsync(d_tasks, tasks, sizeof(ExtendTask) * ntasks, cudaMemcpyHostToDevice, c->stream));
-		EvTimer t(c, 2);
 		if (extend_launch(c, Q, S, d_tasks, ntasks, d_halves)) return 1;
-		k_extend_finalize<<<(unsigned)((ntasks + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, ntasks, min_align_size, d_res);
+		{
+			KScope ks(c, MECAT_K_FINAL);
+			k_extend_finalize<<<(unsigned)((ntasks + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, ntasks, min_align_size, d_res);
+		}
 		MB_CUDA(c, cudaGetLastError());
-		c->stats.kernel_launches += 1;
-		c->stats.extend_ms += t.stop();
 		mecat_extend_result* h = (mecat_extend_result*)malloc(sizeof(mecat_extend_result) * ntasks);
 		if (!h) MB_FAIL(c, "extend_batch: out of host memory");
 		cudaError_t e = cudaMemcpyAsync(h, d_res, sizeof(mecat_extend_result) * ntasks, cudaMemcpyDeviceToHost, c->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		if (e != cudaSuccess) { free(h); MB_FAIL(c, "extend_batch: D2H: %s", cudaGetErrorString(e)); }
+		c->resolve_timers();
+		c->stats.h2d_bytes += (int64_t)(sizeof(ExtendTask) * ntasks);
+		c->stats.d2h_bytes += (int64_t)(sizeof(mecat_extend_result) * ntasks);
 		*results = h;
 		return 0;
 	};
@@ -265,22 +266,20 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 	ExtendTask* d_tasks = nullptr;
 	ExtendHalf* d_halves = nullptr;
 	mecat_extend_result* d_res = nullptr;
+	int32_t* d_scores = nullptr;
 	std::vector<int32_t> h_counts(N);
 	std::vector<int64_t> h_outpos(N + 1);
 	auto body = [&]() -> int {
 		MB_CUDA(c, cudaMalloc(&d_cands, sizeof(RawCand) * (size_t)N * maxc));
 		MB_CUDA(c, cudaMalloc(&d_counts, sizeof(int32_t) * (size_t)N));
-		{
-			EvTimer t(c, 3);
-			if (seed_candidates(c, idx, ref, reads, p, d_cands, d_counts)) return 1;
-			c->stats.seed_ms += t.stop();
-		}
+		if (seed_candidates(c, idx, ref, reads, p, d_cands, d_counts)) return 1;
 		MB_CUDA(c, cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
 		size_t total = 0;
 		for (int i = 0; i < N; ++i) { h_outpos[i] = (int64_t)total; total += (size_t)h_counts[i]; }
 		h_outpos[N] = (int64_t)total;
 		c->stats.num_candidates += (int64_t)total;
+		c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * N;
 		if (raw_rows) {
 			// test hook: the raw candidate_save lists
 			std::vector<RawCand> all((size_t)N * maxc);
@@ -302,17 +301,23 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		MB_CUDA(c, cudaMemcpyAsync(d_outpos, h_outpos.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->stream));
 		if (p->task == 0) {
 			MB_CUDA(c, cudaMalloc(&d_ec, sizeof(mecat_candidate) * total));
-			k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
-			                                   ref->offsz, ref->start_read_id, d_ec, nullptr);
+			{
+				KScope ks(c, MECAT_K_MERGE);
+				k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
+				                                   ref->offsz, ref->start_read_id, d_ec, nullptr, nullptr);
+			}
 			MB_CUDA(c, cudaGetLastError());
-			c->stats.kernel_launches += 1;
 			mecat_candidate* h = (mecat_candidate*)malloc(sizeof(mecat_candidate) * total);
 			if (!h) MB_FAIL(c, "pw_tile: out of host memory");
-			EvTimer t(c, 4);
+			WallTimer t;
 			cudaError_t e = cudaMemcpyAsync(h, d_ec, sizeof(mecat_candidate) * total, cudaMemcpyDeviceToHost, c->stream);
 			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 			c->stats.d2h_ms += t.stop();
 			if (e != cudaSuccess) { free(h); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
+			c->resolve_timers();
+			c->stats.d2h_bytes += (int64_t)(sizeof(mecat_candidate) * total);
+			c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1);
+			c->stats.num_records += (int64_t)total;
 			*records = h; *n = total;
 			return 0;
 		}
@@ -320,33 +325,34 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		MB_CUDA(c, cudaMalloc(&d_tasks, sizeof(ExtendTask) * total));
 		MB_CUDA(c, cudaMalloc(&d_halves, sizeof(ExtendHalf) * 2 * total));
 		MB_CUDA(c, cudaMalloc(&d_res, sizeof(mecat_extend_result) * total));
-		k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
-		                                   ref->offsz, ref->start_read_id, nullptr, d_tasks);
-		MB_CUDA(c, cudaGetLastError());
-		c->stats.kernel_launches += 1;
+		MB_CUDA(c, cudaMalloc(&d_scores, sizeof(int32_t) * total));
 		{
-			EvTimer t(c, 2);
-			if (extend_launch(c, reads, ref, d_tasks, total, d_halves)) return 1;
-			k_extend_finalize<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, total, p->min_align_size, d_res);
-			MB_CUDA(c, cudaGetLastError());
-			c->stats.kernel_launches += 1;
-			c->stats.extend_ms += t.stop();
+			KScope ks(c, MECAT_K_MERGE);
+			k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
+			                                   ref->offsz, ref->start_read_id, nullptr, d_tasks, d_scores);
 		}
+		MB_CUDA(c, cudaGetLastError());
+		if (extend_launch(c, reads, ref, d_tasks, total, d_halves)) return 1;
+		{
+			KScope ks(c, MECAT_K_FINAL);
+			k_extend_finalize<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, total, p->min_align_size, d_res);
+		}
+		MB_CUDA(c, cudaGetLastError());
 		std::vector<ExtendTask> h_tasks(total);
 		std::vector<mecat_extend_result> h_res(total);
 		std::vector<int32_t> h_score(total);
 		{
-			EvTimer t(c, 4);
+			WallTimer t;
 			MB_CUDA(c, cudaMemcpyAsync(h_tasks.data(), d_tasks, sizeof(ExtendTask) * total, cudaMemcpyDeviceToHost, c->stream));
 			MB_CUDA(c, cudaMemcpyAsync(h_res.data(), d_res, sizeof(mecat_extend_result) * total, cudaMemcpyDeviceToHost, c->stream));
-			// vscore = candidate score: strided gather of RawCand.score
-			std::vector<RawCand> all((size_t)N * maxc);
-			MB_CUDA(c, cudaMemcpyAsync(all.data(), d_cands, sizeof(RawCand) * all.size(), cudaMemcpyDeviceToHost, c->stream));
+			MB_CUDA(c, cudaMemcpyAsync(h_score.data(), d_scores, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, c->stream));
 			MB_CUDA(c, cudaStreamSynchronize(c->stream));
-			for (int r = 0; r < N; ++r)
-				for (int i = 0; i < h_counts[r]; ++i) h_score[(size_t)h_outpos[r] + i] = all[(size_t)r * maxc + i].score;
 			c->stats.d2h_ms += t.stop();
+			c->resolve_timers();
+			c->stats.d2h_bytes += (int64_t)((sizeof(ExtendTask) + sizeof(mecat_extend_result) + 4) * total);
+			c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1);
 		}
+		WallTimer host_timer;
 		// fill_m4record + append_m4v (sort, containment filter) per read, on the host like the reference
 		mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * total);
 		if (!out) MB_FAIL(c, "pw_tile: out of host memory");
@@ -387,12 +393,14 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			}
 			for (size_t i = 0; i < loc.size(); ++i) if (valid[i]) out[nout++] = loc[i];
 		}
+		c->stats.host_ms += host_timer.stop();
+		c->stats.num_records += (int64_t)nout;
 		*records = out; *n = nout;
 		return 0;
 	};
 	int rc = body();
 	cudaFree(d_cands); cudaFree(d_counts); cudaFree(d_outpos); cudaFree(d_ec);
-	cudaFree(d_tasks); cudaFree(d_halves); cudaFree(d_res);
+	cudaFree(d_tasks); cudaFree(d_halves); cudaFree(d_res); cudaFree(d_scores);
 	return rc;
 }
 
@@ -401,7 +409,7 @@ int mecat_b200_pw_tile(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvo
 {
 	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !records || !n) return 1;
 	cudaSetDevice(c->device);
-	EvTimer t(c, 5);
+	WallTimer t;
 	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, records, n, nullptr, nullptr);
 	c->stats.total_ms += t.stop();
 	return rc;

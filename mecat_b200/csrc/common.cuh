@@ -52,7 +52,41 @@ struct Ctx
 	std::string err;
 	mecat_b200_stats stats;
 	unsigned long long* d_counters = nullptr;   // 16 device counters (statistics, arena cursors)
-	cudaEvent_t ev[16] = {};
+	// per-kernel CUDA-event timing on `stream`
+	struct Pending { int slot; cudaEvent_t a, b; };
+	std::vector<Pending> pending;
+	std::vector<cudaEvent_t> pool;
+	cudaEvent_t get_event()
+	{
+		if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		return e;
+	}
+	// call after the stream has been synchronised
+	void resolve_timers()
+	{
+		for (auto& p : pending) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) stats.kernel_ms[p.slot] += ms;
+			pool.push_back(p.a); pool.push_back(p.b);
+		}
+		pending.clear();
+	}
+};
+
+// times everything enqueued on the context stream during its lifetime into stats.kernel_ms[slot]
+struct KScope
+{
+	Ctx* c; int slot; cudaEvent_t a; int launches;
+	KScope(Ctx* c_, int slot_, int launches_ = 1) : c(c_), slot(slot_), launches(launches_) { a = c->get_event(); cudaEventRecord(a, c->stream); }
+	~KScope()
+	{
+		cudaEvent_t b = c->get_event();
+		cudaEventRecord(b, c->stream);
+		c->pending.push_back({slot, a, b});
+		c->stats.kernel_launches[slot] += launches;
+	}
 };
 
 #define MB_CUDA(ctx, call)                                                                      \

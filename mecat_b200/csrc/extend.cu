@@ -243,13 +243,16 @@ int extend_launch(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* 
 	MB_CUDA(c, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), c->stream));
 	const size_t items = 2 * ntasks;
 	const unsigned grid = (unsigned)((items + EXT_WARPS - 1) / EXT_WARPS);
-	k_extend<<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
-	                                                 s->num_bases, d_tasks, ntasks, d_halves, d_counter);
+	{
+		KScope ks(c, MECAT_K_EXTEND);
+		k_extend<<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
+		                                                 s->num_bases, d_tasks, ntasks, d_halves, d_counter);
+	}
 	MB_CUDA(c, cudaGetLastError());
-	c->stats.kernel_launches += 1;
 	unsigned long long nb = 0;
 	MB_CUDA(c, cudaMemcpyAsync(&nb, d_counter, sizeof nb, cudaMemcpyDeviceToHost, c->stream));
 	MB_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->resolve_timers();
 	c->stats.num_extend_blocks += (int64_t)nb;
 	return 0;
 }

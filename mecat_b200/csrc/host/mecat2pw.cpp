@@ -1,0 +1,271 @@
+// mecat_b200/csrc/host/mecat2pw.cpp -- host driver with the reference's mecat2pw command line.
+//
+// Same flags, same work-directory protocol and same output text as the reference
+//   main / merge_results           src/mecat2pw/pw.cpp:34-85
+//   parse_arguments                src/mecat2pw/pw_options.cpp:73-211
+//   process_one_volume             src/mecat2pw/pw_impl.cpp:835-882
+//   operator<<(ExtensionCandidate) src/common/alignment.cpp:18-32
+//   output_m4record                src/mecat2pw/pw_impl.cpp:509-531
+// but every hot loop runs on the GPU through the C ABI (include/mecat_b200.h).  `-t` is
+// accepted and ignored (there are no CPU worker threads).  GPUs: MECAT_GPUS=n (default 1)
+// round-robins index volumes over the first n devices, one host thread per device; each
+// device writes the same wrk/r_N files the reference does, so resume works unchanged.
+#include <dirent.h>
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mecat_b200.h"
+
+namespace {
+
+struct Options
+{
+	int task = 1;
+	const char* reads = NULL;
+	const char* output = NULL;
+	const char* wrk_dir = NULL;
+	int num_threads = 1;
+	int num_candidates = 100;
+	int min_align_size = 2000;
+	int min_kmer_match = 4;
+	int output_gapped_start_point = 0;
+	int tech = 0;
+};
+
+void print_usage(const char* prog)
+{
+	fprintf(stderr, "\n\nusage:\n%s [-j task] [-d dataset] [-o output] [-w working dir] [-t threads] [-n candidates] [-g 0/1]\n\n", prog);
+	fprintf(stderr, "options:\n");
+	fprintf(stderr, "-j <integer>\tjob: 0 = seeding, 1 = align\n\t\tdefault: 1\n");
+	fprintf(stderr, "-d <string>\treads file name\n");
+	fprintf(stderr, "-o <string>\toutput file name\n");
+	fprintf(stderr, "-w <string>\tworking folder name, will be created if not exist\n");
+	fprintf(stderr, "-t <integer>\tnumber of cput threads (accepted, unused: the hot path runs on the GPU)\n\t\tdefault: 1\n");
+	fprintf(stderr, "-n <integer>\tnumber of candidates for gapped extension\n\t\tDefault: 100\n");
+	fprintf(stderr, "-a <integer>\tminimum size of overlaps\n\t\tDefault: 2000 if x = 0, 500 if x = 1\n");
+	fprintf(stderr, "-k <integer>\tminimum number of kmer match a matched block has\n\t\tDefault: 4 if x = 0, 2 if x = 1\n");
+	fprintf(stderr, "-g <0/1>\twhether print gapped extension start point, 0 = no, 1 = yes\n\t\tDefault: 0\n");
+	fprintf(stderr, "-x <0/x>\tsequencing technology: 0 = pacbio, 1 = nanopore\n\t\tDefault: 0\n");
+}
+
+int parse_arguments(int argc, char* argv[], Options* o)
+{
+	int task = -1, num_threads = -1, num_candidates = -1, min_align_size = -1, min_kmer_match = -1, gapped = -1, tech = 0;
+	int c;
+	opterr = 0;
+	while ((c = getopt(argc, argv, "j:d:o:w:t:n:g:x:a:k:")) != -1) {
+		switch (c) {
+		case 'j': task = atoi(optarg); break;
+		case 'd': o->reads = optarg; break;
+		case 'o': o->output = optarg; break;
+		case 'w': o->wrk_dir = optarg; break;
+		case 't': num_threads = atoi(optarg); break;
+		case 'n': num_candidates = atoi(optarg); break;
+		case 'a': min_align_size = atoi(optarg); break;
+		case 'k': min_kmer_match = atoi(optarg); break;
+		case 'g':
+			if (optarg[0] == '0') gapped = 0;
+			else if (optarg[0] == '1') gapped = 1;
+			else { fprintf(stderr, "argument to option '-g' must be either '0' or '1'\n"); return 1; }
+			break;
+		case 'x':
+			if (optarg[0] == '0') tech = 0;
+			else if (optarg[0] == '1') tech = 1;
+			else { fprintf(stderr, "invalid argument to option 'x': %s\n", optarg); abort(); }
+			break;
+		case '?': fprintf(stderr, "unrecognised option '%c'\n", (char)optopt); return 1;
+		case ':': fprintf(stderr, "argument to option '%c' is not provided!\n", (char)optopt); return 1;
+		}
+	}
+	o->tech = tech;
+	if (tech == 1) { o->min_align_size = 500; o->min_kmer_match = 2; }
+	if (task != -1) o->task = task;
+	if (num_threads != -1) o->num_threads = num_threads;
+	if (num_candidates != -1) o->num_candidates = num_candidates;
+	if (min_align_size != -1) o->min_align_size = min_align_size;
+	if (min_kmer_match != -1) o->min_kmer_match = min_kmer_match;
+	if (gapped != -1) o->output_gapped_start_point = gapped;
+	int ret = 0;
+	if (o->task != 0 && o->task != 1) { fprintf(stderr, "task (-j) must be 0 or 1, not %d.\n", o->task); ret = 1; }
+	if (!o->reads) { fprintf(stderr, "dataset must be specified.\n"); ret = 1; }
+	else if (!o->output) { fprintf(stderr, "output must be specified.\n"); ret = 1; }
+	else if (!o->wrk_dir) { fprintf(stderr, "working directory must be specified.\n"); ret = 1; }
+	else if (o->num_threads < 1) { fprintf(stderr, "number of cpu threads must be > 0.\n"); ret = 1; }
+	else if (o->num_candidates < 1) { fprintf(stderr, "number of candidates must be > 0.\n"); ret = 1; }
+	if (ret) return ret;
+	if (o->tech != 0) {
+		fprintf(stderr, "-x 1 (nanopore, X-drop aligner) is not part of the GPU path; use the reference binary for it.\n");
+		return 1;
+	}
+	DIR* dir = opendir(o->wrk_dir);
+	if (!dir) {
+		if (mkdir(o->wrk_dir, S_IRWXU) == -1) { fprintf(stderr, "fail to create folder '%s'!\n", o->wrk_dir); exit(1); }
+	} else closedir(dir);
+	return 0;
+}
+
+struct StderrTimer   // DynamicTimer, src/common/defs.h:175-191
+{
+	std::string name;
+	timeval t0;
+	explicit StderrTimer(const std::string& n) : name(n) { fprintf(stderr, "[%s] begins.\n", name.c_str()); gettimeofday(&t0, NULL); }
+	~StderrTimer()
+	{
+		timeval t1;
+		gettimeofday(&t1, NULL);
+		fprintf(stderr, "[%s] takes %.2f secs.\n", name.c_str(), t1.tv_sec - t0.tv_sec + 1.0 * (t1.tv_usec - t0.tv_usec) / 1000000);
+	}
+};
+
+std::string results_name(const char* wrk, int vid, bool working)
+{
+	std::string n(wrk);
+	if (n[n.size() - 1] != '/') n += '/';
+	std::ostringstream os;
+	os << "r_" << vid;
+	if (working) os << ".working";
+	return n + os.str();
+}
+
+void write_candidates(std::ostream& out, const mecat_candidate* ec, size_t n)
+{
+	for (size_t i = 0; i < n; ++i) {
+		const mecat_candidate& e = ec[i];
+		out << e.qid << '\t' << e.sid << '\t' << e.qdir << '\t' << e.sdir << '\t' << e.qext << '\t' << e.sext << '\t'
+		    << e.score << '\t' << e.qsize << '\t' << e.ssize << '\n';
+	}
+}
+
+void write_m4(std::ostream& out, const mecat_m4* m, size_t n, bool gapped)
+{
+	for (size_t i = 0; i < n; ++i) {
+		const mecat_m4& r = m[i];
+		out << r.qid << '\t' << r.sid << '\t' << r.ident << '\t' << r.vscore << '\t' << r.qdir << '\t' << r.qoff << '\t'
+		    << r.qend << '\t' << r.qsize << '\t' << r.sdir << '\t' << r.soff << '\t' << r.send << '\t' << r.ssize;
+		if (gapped) out << '\t' << r.qext << '\t' << r.sext;
+		out << "\n";
+	}
+}
+
+bool process_one_volume(mecat_b200_ctx* ctx, const Options& opt, int svid, const std::vector<std::string>& vols, std::ostream& out)
+{
+	mecat_pw_params p = {opt.task, opt.num_candidates, opt.min_align_size, opt.min_kmer_match, opt.tech};
+	mecat_volume ref;
+	if (mecat_b200_volume_load(vols[svid].c_str(), &ref)) { fprintf(stderr, "failed to open file '%s'.\n", vols[svid].c_str()); return false; }
+	void *dref = NULL, *index = NULL;
+	bool ok = true;
+	{
+		StderrTimer t("create_ref_index");
+		ok = mecat_b200_volume_upload(ctx, &ref, &dref) == 0 && mecat_b200_index_build(ctx, dref, &index) == 0;
+	}
+	for (int vid = svid; ok && vid < (int)vols.size(); ++vid) {
+		char info[64];
+		snprintf(info, sizeof info, "process volume %d", vid);
+		StderrTimer t(info);
+		fprintf(stderr, "processing %s\n", vols[vid].c_str());
+		void* dreads = dref;
+		mecat_volume reads;
+		memset(&reads, 0, sizeof reads);
+		if (vid != svid) {
+			if (mecat_b200_volume_load(vols[vid].c_str(), &reads)) { fprintf(stderr, "failed to open file '%s'.\n", vols[vid].c_str()); ok = false; break; }
+			ok = mecat_b200_volume_upload(ctx, &reads, &dreads) == 0;
+		}
+		void* rec = NULL;
+		size_t n = 0;
+		if (ok) ok = mecat_b200_pw_tile(ctx, index, dref, dreads, &p, &rec, &n) == 0;
+		if (ok) {
+			if (opt.task == 0) write_candidates(out, (const mecat_candidate*)rec, n);
+			else write_m4(out, (const mecat_m4*)rec, n, opt.output_gapped_start_point != 0);
+		}
+		mecat_b200_free(ctx, rec);
+		if (vid != svid) { if (dreads) mecat_b200_volume_release(ctx, dreads); mecat_b200_volume_unload(&reads); }
+	}
+	if (!ok) fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(ctx));
+	if (index) mecat_b200_index_release(ctx, index);
+	if (dref) mecat_b200_volume_release(ctx, dref);
+	mecat_b200_volume_unload(&ref);
+	return ok;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+	Options opt;
+	if (parse_arguments(argc, argv, &opt)) { print_usage(argv[0]); return 1; }
+	int num_vols = 0;
+	{
+		StderrTimer t("split_raw_dataset");
+		char err[512];
+		const char* cap = getenv("MECAT_VOLUME_BASES");   // test hook: smaller volumes (reference: MCS, split_database.h:6-7)
+		if (mecat_b200_split_dataset(opt.reads, opt.wrk_dir, cap ? atoll(cap) : 0, &num_vols, err, sizeof err)) {
+			fprintf(stderr, "%s\n", err);
+			return 1;
+		}
+	}
+	std::vector<std::string> vols;
+	{
+		std::string idx(opt.wrk_dir);
+		if (idx[idx.size() - 1] != '/') idx += '/';
+		idx += "fileindex.txt";
+		std::cout << idx << "\n";
+		std::ifstream in(idx.c_str());
+		std::string l;
+		while (std::getline(in, l)) { if (!l.empty() && l[l.size() - 1] == '\r') l.erase(l.size() - 1); if (!l.empty()) vols.push_back(l); }
+	}
+	if ((int)vols.size() != num_vols) { fprintf(stderr, "volume index is inconsistent\n"); return 1; }
+
+	int ngpus = 1;
+	if (const char* g = getenv("MECAT_GPUS")) ngpus = atoi(g);
+	const int have = mecat_b200_device_count();
+	if (have < 1) { fprintf(stderr, "mecat2pw: no CUDA device found (this build has no CPU path)\n"); return 1; }
+	if (ngpus < 1) ngpus = 1;
+	if (ngpus > have) ngpus = have;
+	if (ngpus > num_vols) ngpus = num_vols > 0 ? num_vols : 1;
+
+	std::atomic<int> next(0), failed(0);
+	auto worker = [&](int dev) {
+		mecat_b200_ctx* ctx = NULL;
+		if (mecat_b200_init(&ctx, dev, NULL)) { fprintf(stderr, "mecat2pw: cannot initialise GPU %d\n", dev); failed = 1; return; }
+		for (;;) {
+			const int i = next.fetch_add(1);
+			if (i >= num_vols || failed) break;
+			const std::string done = results_name(opt.wrk_dir, i, false);
+			if (access(done.c_str(), F_OK) == 0) { fprintf(stderr, "volume %d has been finished\n", i); continue; }
+			const std::string working = results_name(opt.wrk_dir, i, true);
+			std::ofstream out(working.c_str());
+			if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", working.c_str()); failed = 1; break; }
+			if (!process_one_volume(ctx, opt, i, vols, out)) { failed = 1; break; }
+			out.close();
+			if (rename(working.c_str(), done.c_str()) != 0) { failed = 1; break; }
+		}
+		mecat_b200_destroy(ctx);
+	};
+	std::vector<std::thread> th;
+	for (int d = 1; d < ngpus; ++d) th.emplace_back(worker, d);
+	worker(0);
+	for (auto& t : th) t.join();
+	if (failed) return 1;
+
+	// merge_results: r_0 .. r_{n-1} concatenated in volume order (pw.cpp:34-46)
+	std::ofstream merged(opt.output, std::ios::binary);
+	if (!merged) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
+	for (int i = 0; i < num_vols; ++i) {
+		std::ifstream in(results_name(opt.wrk_dir, i, false).c_str(), std::ios::binary);
+		if (in.peek() != std::ifstream::traits_type::eof()) merged << in.rdbuf();
+	}
+	return 0;
+}

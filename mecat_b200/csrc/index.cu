@@ -200,12 +200,17 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 		MB_CUDA(c, cudaMalloc(&d_total, sizeof(uint32_t)));
 		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
 		const int grid_reads = v->num_reads < 1 ? 1 : (v->num_reads > 65535 * 8 ? 65535 * 8 : v->num_reads);
-		if (v->num_reads > 0) k_kmer_count<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, d_counts);
-		k_scan_reduce<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles);
-		k_scan_top<<<1, 1024, 0, c->stream>>>(d_tiles, ntiles, d_total);
-		k_scan_down<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles, I->begin);
+		if (v->num_reads > 0) {
+			KScope ks(c, MECAT_K_COUNT);
+			k_kmer_count<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, d_counts);
+		}
+		{
+			KScope ks(c, MECAT_K_SCAN, 3);
+			k_scan_reduce<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles);
+			k_scan_top<<<1, 1024, 0, c->stream>>>(d_tiles, ntiles, d_total);
+			k_scan_down<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles, I->begin);
+		}
 		MB_CUDA(c, cudaGetLastError());
-		c->stats.kernel_launches += 4;
 		uint32_t total = 0;
 		MB_CUDA(c, cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -214,13 +219,20 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 		MB_CUDA(c, cudaMalloc(&I->pos, sizeof(int32_t) * ((size_t)total + 1)));
 		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
 		if (total) {
-			k_kmer_fill<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->begin, d_counts, I->pos);
-			k_sort_lists<<<NCODES / (SORT_WARPS * SORT_CODES_PER_WARP), SORT_WARPS * 32, 0, c->stream>>>(I->begin, I->pos);
+			{
+				KScope ks(c, MECAT_K_FILL);
+				k_kmer_fill<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->begin, d_counts, I->pos);
+			}
+			{
+				KScope ks(c, MECAT_K_SORT);
+				k_sort_lists<<<NCODES / (SORT_WARPS * SORT_CODES_PER_WARP), SORT_WARPS * 32, 0, c->stream>>>(I->begin, I->pos);
+			}
 			MB_CUDA(c, cudaGetLastError());
-			c->stats.kernel_launches += 2;
 		}
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
-		c->stats.index_kmers = total;
+		c->resolve_timers();
+		c->stats.index_kmers += total;
+		c->stats.index_bases += v->num_bases;
 		return 0;
 	};
 	int rc = body();

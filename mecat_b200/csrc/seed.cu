@@ -865,9 +865,11 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 			S.read0 = r0; S.nreads = nb; S.gate = 2 * p->min_kmer_match;
 			S.arena = d_arena; S.arena_bytes = arena_bytes; S.arena_cursor = d_cursor; S.work_counter = d_work;
 			S.desc = d_desc; S.scratch = d_scratch; S.kcap = kcap; S.hcap = hcap; S.hit_counter = d_hits;
-			k_seed<<<nctas, SEED_THREADS, smem, c->stream>>>(S);
+			{
+				KScope ks(c, MECAT_K_SEED);
+				k_seed<<<nctas, SEED_THREADS, smem, c->stream>>>(S);
+			}
 			MB_CUDA(c, cudaGetLastError());
-			c->stats.kernel_launches += 1;
 			// status check (arena overflow -> retry the batch with fewer reads)
 			MB_CUDA(c, cudaMemcpyAsync(h_desc.data(), d_desc, sizeof(StrandDesc) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, c->stream));
 			MB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -888,15 +890,21 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 			Wp.roffsz = ref->offsz; Wp.r_nreads = ref->num_reads; Wp.r_start_id = ref->start_read_id;
 			Wp.gate = 2 * p->min_kmer_match; Wp.min_span = 1800; Wp.maxc = maxc;
 			Wp.lists = d_lists; Wp.nlist = d_nlist;
-			k_walk<<<(2 * nb + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, c->stream>>>(Wp);
-			k_merge<<<(nb * 32 + 127) / 128, 128, 0, c->stream>>>(d_lists, d_nlist, r0, nb, maxc, d_cands, d_counts);
+			{
+				KScope ks(c, MECAT_K_WALK);
+				k_walk<<<(2 * nb + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, c->stream>>>(Wp);
+			}
+			{
+				KScope ks(c, MECAT_K_MERGE);
+				k_merge<<<(nb * 32 + 127) / 128, 128, 0, c->stream>>>(d_lists, d_nlist, r0, nb, maxc, d_cands, d_counts);
+			}
 			MB_CUDA(c, cudaGetLastError());
-			c->stats.kernel_launches += 2;
 			r0 += nb;
 		}
 		unsigned long long hits = 0;
 		MB_CUDA(c, cudaMemcpyAsync(&hits, d_hits, 8, cudaMemcpyDeviceToHost, c->stream));
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->resolve_timers();
 		c->stats.num_hits += (int64_t)hits;
 		return 0;
 	};

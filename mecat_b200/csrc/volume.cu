@@ -72,10 +72,14 @@ int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out)
 	if (v->num_reads && (e = cudaMemcpyAsync(d->offsz, v->offset_size, sizeof(int2) * (size_t)v->num_reads, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "H2D offsets");
 	const int T = 256;
 	const unsigned G = (unsigned)((d->words + T - 1) / T);
-	k_orient_fwd<<<G, T, 0, c->stream>>>(d_pac, d->fwd, src_words, d->words);
-	k_orient_rev<<<G, T, 0, c->stream>>>(d->fwd, d->rev, v->num_bases, d->words);
-	c->stats.kernel_launches += 2;
+	{
+		KScope ks(c, MECAT_K_ORIENT, 2);
+		k_orient_fwd<<<G, T, 0, c->stream>>>(d_pac, d->fwd, src_words, d->words);
+		k_orient_rev<<<G, T, 0, c->stream>>>(d->fwd, d->rev, v->num_bases, d->words);
+	}
 	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e, "orient kernels");
+	c->resolve_timers();
+	c->stats.h2d_bytes += (int64_t)pac_bytes + (int64_t)sizeof(int2) * v->num_reads;
 	cudaFree(d_pac);
 	*out = d;
 	return 0;

@@ -4,6 +4,7 @@ numpy utilities for packed volumes.  Test infrastructure only."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -113,8 +114,12 @@ def build_oracle():
 
 
 def gen_reads(path, n, genome_len, seed, mean=15000, sd=1500, err=0.15, genome_out=None):
-    build_oracle()
-    cmd = [os.path.join(ORACLE_DIR, "gen_reads"), path, str(n), str(genome_len), str(seed), str(mean), str(sd),
+    exe = os.path.join(ROOT, "mecat_b200", "bin", "gen_reads")
+    if not os.path.exists(exe):
+        sys.path.insert(0, ROOT)
+        from mecat_b200 import build as _b
+        _b.build()
+    cmd = [exe, path, str(n), str(genome_len), str(seed), str(mean), str(sd),
            str(err)]
     if genome_out:
         cmd.append(genome_out)

@@ -1,4 +1,4 @@
-// oracle/gen_reads.cpp -- TEST/BENCH TOOLING (synthetic PacBio-CLR-like reads).
+// tools/gen_reads.cpp -- TEST/BENCH TOOLING (synthetic PacBio-CLR-like reads).
 //
 //   gen_reads <out.fasta> <num_reads> <genome_len> <seed> [mean_len=15000] [sd_len=1500]
 //             [err=0.15] [genome_out.fasta]
