@@ -250,18 +250,30 @@ def run_ours(args):
     ctx = mecat_b200.Context(local)
     dvol = ctx.upload(hv)
 
-    def step_resident():
+    digests = set()
+
+    def digest(rec):
+        # order-sensitive fingerprint of the records of one step (determinism check across steps)
+        w = np.frombuffer(rec.tobytes(), dtype=np.uint64)
+        return (len(rec), int(np.bitwise_xor.reduce(w * np.arange(1, len(w) + 1, dtype=np.uint64))) if len(w) else 0)
+
+    def step_resident(check=False):
         idx = ctx.index_build(dvol)
         rec = ctx.pw_tile(idx, dvol, dvol, params)
         ctx.release_index(idx)
+        if check:
+            digests.add(digest(rec))
         return len(rec)
 
-    def step_e2e():
-        return len(ctx.pw_overlaps(hv, hv, params))
+    def step_e2e(check=False):
+        rec = ctx.pw_overlaps(hv, hv, params)
+        if check:
+            digests.add(digest(rec))
+        return len(rec)
 
     for i in range(args.warmup):
         t = time.perf_counter()
-        n = step_resident()
+        n = step_resident(check=True)
         log("[bench] warmup %d: %d pairs in %.2f s" % (i, n, time.perf_counter() - t))
     ctx.reset_stats()
     sampler = ClockSampler(local)
@@ -276,7 +288,7 @@ def run_ours(args):
     clocks = sampler.stop()
     log("[bench] resident: %d pairs in %.2f s; kernel ms %s" % (pairs, dt, json.dumps(stats["kernel_ms"])))
     # end to end through the host-buffer C-ABI call
-    step_e2e()
+    step_e2e(check=True)
     ctx.reset_stats()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -313,6 +325,7 @@ def run_ours(args):
         "gpu_launches": stats["gpu_launches"],
         "roofline": roof, "cpu_baseline": cb,
         "pairs_per_step": pairs // args.steps,
+        "deterministic": len(digests) == 1,   # warm-up steps and the e2e call produced identical record arrays
         "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
         "host_ms_per_step": round(stats["host_ms"] / args.steps, 3), "d2h_ms_per_step": round(stats["d2h_ms"] / args.steps, 3),
         "hits_per_step": stats["num_hits"] // args.steps, "candidates_per_step": stats["num_candidates"] // args.steps,

@@ -31,7 +31,7 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int SEED_THREADS = 1024;
 constexpr int CNT_SLOTS = 65536;            // hashed 16-bit hit counters (128 KB)
-constexpr int BIT_WORDS = 2048;             // hashed bitmaps, 65536 bits each
+constexpr int BIT_WORDS = 2048;             // hashed interest bitmap (65536 bits) / anchor claim slots
 constexpr uint32_t CNT_SAT = 0x8000u;       // counters stop growing here (no wrap with <= 1024 racing adds)
 constexpr int MAX_KM = 32766;               // seed ordinals are `short` in the reference (pw_impl.h:31)
 
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 {
 	extern __shared__ uint32_t smem_u32[];
 	uint32_t* cnt = smem_u32;                         // CNT_SLOTS / 2 words
-	uint32_t* anchor_bits = cnt + CNT_SLOTS / 2;      // BIT_WORDS
-	uint32_t* want_bits = anchor_bits + BIT_WORDS;    // BIT_WORDS
+	uint32_t* anchor_tab = cnt + CNT_SLOTS / 2;       // BIT_WORDS claim slots (bucket ids)
+	uint32_t* want_bits = anchor_tab + BIT_WORDS;     // BIT_WORDS words = 65536 hashed bits
 	int* misc = (int*)(want_bits + BIT_WORDS);        // 64 ints: scan scratch [0..33), counters
 	int* wslots = misc + 64;                          // per warp: 3 x 41 ints for the overflow replay
 	__shared__ unsigned int s_item;
@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		const int W = (L + SEGW - 1) / SEGW;          // reach of a candidate's neighbour vote, in buckets
 
 		// ---- clear
-		for (int i = tid; i < CNT_SLOTS / 2 + 2 * BIT_WORDS; i += blockDim.x) cnt[i] = 0u;
+		for (int i = tid; i < CNT_SLOTS / 2; i += blockDim.x) cnt[i] = 0u;
+		for (int i = tid; i < BIT_WORDS; i += blockDim.x) { anchor_tab[i] = 0xFFFFFFFFu; want_bits[i] = 0u; }
 		if (tid < 64) misc[tid] = 0;
 		// ---- k-mer lookup
 		for (int km = tid; km < nk; km += blockDim.x) {
@@ -285,10 +286,16 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 				uint32_t c = (cnt[hh >> 1] >> ((hh & 1u) << 4)) & 0xFFFFu;
 				if (seg > 0) { const uint32_t hp = seg_hash(seg - 1); c += (cnt[hp >> 1] >> ((hp & 1u) << 4)) & 0xFFFFu; }
 				if ((int)c >= P.gate) {
-					const uint32_t old = atomicOr(&anchor_bits[hh >> 5], 1u << (hh & 31u));
-					if (!(old & (1u << (hh & 31u)))) {
+					// One thread per possible anchor marks its window.  The claim table is keyed by the
+					// exact bucket id: a slot held by a different bucket only costs a redundant marking,
+					// it can never suppress one (a hashed "already done" bit could, and did).
+					uint32_t* slot = &anchor_tab[hh & (BIT_WORDS - 1)];
+					if (*(volatile uint32_t*)slot != seg && atomicCAS(slot, 0xFFFFFFFFu, seg) != seg) {
 						const int lo = max(0, (int)seg - W), hi = (int)seg + W;
-						for (int s2 = lo; s2 <= hi; ++s2) { const uint32_t h2 = seg_hash((uint32_t)s2); atomicOr(&want_bits[h2 >> 5], 1u << (h2 & 31u)); }
+						for (int s2 = lo; s2 <= hi; ++s2) {
+							const uint32_t h2 = seg_hash((uint32_t)s2), bit = 1u << (h2 & 31u);
+							if (!(want_bits[h2 >> 5] & bit)) atomicOr(&want_bits[h2 >> 5], bit);
+						}
 					}
 				}
 			}

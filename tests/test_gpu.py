@@ -188,6 +188,91 @@ def test_raw_candidates_match_oracle(gpu_ctx, small_vol):
     assert not bad, "%d reads differ; first read %d" % (len(bad), bad[0][0])
 
 
+# ---------------------------------------------------------------- repeat-rich stress (long lists, overflow buckets)
+@pytest.fixture(scope="module", params=[10, 18])
+def repeat_vol(request):
+    return PackedVolume.from_seqs(util.repeat_reads(copies=request.param))
+
+
+def test_repeat_index_every_list(gpu_ctx, repeat_vol):
+    O = util.oracle()
+    cv = repeat_vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    d = gpu_ctx.upload(host_volume(repeat_vol))
+    idx = gpu_ctx.index_build(d)
+    begin, pos = gpu_ctx.index_export(idx)
+    gpu_ctx.release_index(idx)
+    gpu_ctx.release_volume(d)
+    assert len(pos) == O.orc_index_num_kmers(oidx)
+    lens = np.diff(begin.astype(np.int64))
+    lst = C.POINTER(C.c_int32)()
+    nz = np.nonzero(lens)[0]
+    assert lens.max() > 64, "fixture no longer exercises the 4-register sort"
+    want = np.empty(len(pos), dtype=np.int32)
+    k = 0
+    for code in nz:
+        n = O.orc_index_lookup(oidx, int(code), C.byref(lst))
+        assert n == lens[code]
+        want[k:k + n] = np.ctypeslib.as_array(lst, shape=(n,))
+        k += n
+    O.orc_index_free(oidx)
+    assert k == len(pos)
+    assert (want == pos).all()
+
+
+def test_repeat_raw_candidates(gpu_ctx, repeat_vol):
+    import mecat_b200
+    O = util.oracle()
+    cv = repeat_vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    p = util.pw_params(task=0)
+    d = gpu_ctx.upload(host_volume(repeat_vol))
+    idx = gpu_ctx.index_build(d)
+    rows, counts = gpu_ctx.pw_raw_candidates(idx, d, d, mecat_b200.pw_params(task=0), repeat_vol.num_reads)
+    gpu_ctx.release_index(idx)
+    gpu_ctx.release_volume(d)
+    out = (C.c_int32 * (12 * 101))()
+    k, bad = 0, []
+    for rid in range(repeat_vol.num_reads):
+        n = O.orc_pw_candidates(oidx, C.byref(cv), C.byref(cv), rid, C.byref(p), out)
+        want = [tuple(out[12 * i:12 * i + 12]) for i in range(n)]
+        got = [tuple(int(x) for x in rows[k + i]) for i in range(int(counts[rid]))]
+        k += int(counts[rid])
+        if got != want:
+            bad.append((rid, got, want))
+    O.orc_index_free(oidx)
+    if bad:
+        os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(util.ROOT, "gpurun_out", "mismatch_repeat_rawcand.txt"), "w") as f:
+            for rid, got, want in bad:
+                f.write("read %d  got %d want %d\n" % (rid, len(got), len(want)))
+                for i in range(max(len(got), len(want))):
+                    g = got[i] if i < len(got) else None
+                    w = want[i] if i < len(want) else None
+                    if g != w:
+                        f.write("  [%d] G %r\n      W %r\n" % (i, g, w))
+    assert not bad, "%d reads differ; first read %d" % (len(bad), bad[0][0])
+
+
+def test_repeat_tiles(gpu_ctx, repeat_vol):
+    import mecat_b200
+    hv = host_volume(repeat_vol)
+    want = util.oracle_pw_tile(repeat_vol, repeat_vol, util.pw_params(task=0), threads=8)
+    got = gpu_ctx.pw_candidates(hv, hv)
+    report("repeat_can", util.ec_lines(got), util.ec_lines(want))
+    assert [tuple(x) for x in got.tolist()] == [tuple(x) for x in want.tolist()]
+    want = util.oracle_pw_tile(repeat_vol, repeat_vol, util.pw_params(task=1), threads=8)
+    got = gpu_ctx.pw_overlaps(hv, hv)
+    report("repeat_m4", util.m4_lines(got, True), util.m4_lines(want, True))
+
+
+def test_deterministic_across_runs(gpu_ctx, cfg0_vol):
+    hv = host_volume(cfg0_vol)
+    a = gpu_ctx.pw_overlaps(hv, hv)
+    b = gpu_ctx.pw_overlaps(hv, hv)
+    assert a.tobytes() == b.tobytes()
+
+
 # ---------------------------------------------------------------- whole tiles vs the reference binaries
 def test_small_can_matches_reference(gpu_ctx, small_vol):
     hv = host_volume(small_vol)

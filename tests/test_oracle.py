@@ -190,6 +190,34 @@ def test_oracle_functions_against_reference(small_vol):
     R.ref_volume_free(rv)
 
 
+@needs_ref
+@pytest.mark.parametrize("copies", [10, 18])
+def test_oracle_on_repeat_rich_reads_against_reference(copies):
+    """Long k-mer lists, the >128 cutoff, insert_loc far from self hits, full candidate lists."""
+    R, O = util.ref(), util.oracle()
+    reads = util.repeat_reads(copies=copies, n_reads=120)
+    vol = PackedVolume.from_seqs(reads)
+    rv = ref_volume(reads)
+    ridx = R.ref_index_create(rv, 1)
+    cv = vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    R.ref_pw_set_options(100, 2000, 4, 0)
+    ctx = R.ref_pw_ctx_new(rv, ridx)
+    out_r = (C.c_int32 * (12 * 101))(); out_o = (C.c_int32 * (12 * 101))()
+    p = pw_params(task=0)
+    full = 0
+    for rid in range(vol.num_reads):
+        nr = R.ref_pw_candidates(ctx, rv, rid, 0, out_r)
+        no = O.orc_pw_candidates(oidx, C.byref(cv), C.byref(cv), rid, C.byref(p), out_o)
+        assert nr == no and list(out_r[:12 * nr]) == list(out_o[:12 * no])
+        full += nr == 100
+    assert full > 0   # the -n cap is exercised
+    R.ref_pw_ctx_free(ctx)
+    O.orc_index_free(oidx)
+    R.ref_index_free(ridx)
+    R.ref_volume_free(rv)
+
+
 def mutate(rng, s, err):
     out = []
     for b in s:

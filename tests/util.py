@@ -259,3 +259,44 @@ def m4_lines(m4, gapped=False):
             s += "\t%d\t%d" % (m["qext"], m["sext"])
         out.append(s)
     return sorted(out)
+
+
+def repeat_reads(seed=21, unit=4000, copies=10, n_reads=260, mean=5000, err=0.05, div=0.01):
+    """Repeat-rich synthetic reads: a genome made of `copies` diverged copies of one random unit plus
+    unique flanks.  Exact 13-mers then occur 30-200 times in the volume, which exercises what uniform
+    genomes never do: long index lists, the >128 cutoff, 40-seed bucket overflow (insert_loc) far
+    from self hits, ties in DDF scoring and full candidate lists."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 4, size=unit)
+    parts = [rng.integers(0, 4, size=3000)]
+    for _ in range(copies):
+        u = base.copy()
+        m = rng.random(unit) < div
+        u[m] = rng.integers(0, 4, size=int(m.sum()))
+        parts.append(u)
+        parts.append(rng.integers(0, 4, size=int(rng.integers(200, 1500))))
+    genome = np.concatenate(parts)
+    G = len(genome)
+    reads = []
+    for _ in range(n_reads):
+        L = int(max(2500, rng.normal(mean, 800)))
+        L = min(L, G)
+        s = int(rng.integers(0, G - L + 1))
+        t = genome[s:s + L]
+        u = rng.random(L)
+        keep = u >= err * 0.3
+        sub = (u >= err * 0.3) & (u < err * 0.4)
+        t = t.copy()
+        t[sub] = (t[sub] + 1 + rng.integers(0, 3, size=int(sub.sum()))) & 3
+        t = t[keep]
+        ins = rng.random(len(t)) < err * 0.6
+        out = np.empty(len(t) + int(ins.sum()), dtype=np.int64)
+        idx = np.arange(len(t)) + np.cumsum(ins) - ins
+        out[:] = -1
+        out[idx] = t
+        gaps = out < 0
+        out[gaps] = rng.integers(0, 4, size=int(gaps.sum()))
+        if rng.random() < 0.5:
+            out = (3 - out)[::-1]
+        reads.append(bytes(b"ACGT"[int(c)] for c in out))
+    return reads
