@@ -169,7 +169,9 @@ class Context:
             if ptr.value:
                 self.L.mecat_b200_free(self.h, ptr)
             return np.zeros(0, dtype=dtype)
-        arr = np.frombuffer(C.string_at(ptr.value, n * dtype.itemsize), dtype=dtype).copy()
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype).copy()     # one copy out of the library-owned buffer
+        del buf
         self.L.mecat_b200_free(self.h, ptr)
         return arr
 

@@ -6,7 +6,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 
@@ -124,6 +126,8 @@ void mecat_b200_destroy(mecat_b200_ctx* c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->resolve_timers();
+	for (auto& b : c->blocks) b.used = false;
+	c->trim();
 	for (auto& e : c->pool) cudaEventDestroy(e);
 	cudaFree(c->d_counters);
 	cudaStreamDestroy(c->stream);
@@ -164,7 +168,7 @@ int mecat_b200_volume_release(mecat_b200_ctx* c, void* dvol)
 {
 	if (check(c)) return 1;
 	cudaSetDevice(c->device);
-	volume_release((DVolume*)dvol);
+	volume_release(c, (DVolume*)dvol);
 	return 0;
 }
 
@@ -183,7 +187,7 @@ int mecat_b200_index_release(mecat_b200_ctx* c, void* index)
 {
 	if (check(c)) return 1;
 	cudaSetDevice(c->device);
-	index_release((DIndex*)index);
+	index_release(c, (DIndex*)index);
 	return 0;
 }
 
@@ -221,9 +225,9 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
 	mecat_extend_result* d_res = nullptr;
 	int rc = 0;
 	auto body = [&]() -> int {
-		MB_CUDA(c, cudaMalloc(&d_tasks, sizeof(ExtendTask) * ntasks));
-		MB_CUDA(c, cudaMalloc(&d_halves, sizeof(ExtendHalf) * 2 * ntasks));
-		MB_CUDA(c, cudaMalloc(&d_res, sizeof(mecat_extend_result) * ntasks));
+		MB_CUDA(c, c->alloc(&d_tasks, (size_t)(ntasks)));
+		MB_CUDA(c, c->alloc(&d_halves, (size_t)(2 * ntasks)));
+		MB_CUDA(c, c->alloc(&d_res, (size_t)(ntasks)));
 		MB_CUDA(c, cudaMemcpyAsync(d_tasks, tasks, sizeof(ExtendTask) * ntasks, cudaMemcpyHostToDevice, c->stream));
 		if (extend_launch(c, Q, S, d_tasks, ntasks, d_halves)) return 1;
 		{
@@ -243,7 +247,7 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
 		return 0;
 	};
 	rc = body();
-	cudaFree(d_tasks); cudaFree(d_halves); cudaFree(d_res);
+	c->dfree(d_tasks); c->dfree(d_halves); c->dfree(d_res);
 	return rc;
 }
 
@@ -270,8 +274,8 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 	std::vector<int32_t> h_counts(N);
 	std::vector<int64_t> h_outpos(N + 1);
 	auto body = [&]() -> int {
-		MB_CUDA(c, cudaMalloc(&d_cands, sizeof(RawCand) * (size_t)N * maxc));
-		MB_CUDA(c, cudaMalloc(&d_counts, sizeof(int32_t) * (size_t)N));
+		MB_CUDA(c, c->alloc(&d_cands, (size_t)((size_t)N * maxc)));
+		MB_CUDA(c, c->alloc(&d_counts, (size_t)((size_t)N)));
 		if (seed_candidates(c, idx, ref, reads, p, d_cands, d_counts)) return 1;
 		MB_CUDA(c, cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -297,10 +301,10 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			return 0;
 		}
 		if (total == 0) return 0;
-		MB_CUDA(c, cudaMalloc(&d_outpos, sizeof(int64_t) * (size_t)(N + 1)));
+		MB_CUDA(c, c->alloc(&d_outpos, (size_t)((size_t)(N + 1))));
 		MB_CUDA(c, cudaMemcpyAsync(d_outpos, h_outpos.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->stream));
 		if (p->task == 0) {
-			MB_CUDA(c, cudaMalloc(&d_ec, sizeof(mecat_candidate) * total));
+			MB_CUDA(c, c->alloc(&d_ec, (size_t)(total)));
 			{
 				KScope ks(c, MECAT_K_MERGE);
 				k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
@@ -322,10 +326,10 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			return 0;
 		}
 		// task 1: extend every candidate, then assemble M4 records per read
-		MB_CUDA(c, cudaMalloc(&d_tasks, sizeof(ExtendTask) * total));
-		MB_CUDA(c, cudaMalloc(&d_halves, sizeof(ExtendHalf) * 2 * total));
-		MB_CUDA(c, cudaMalloc(&d_res, sizeof(mecat_extend_result) * total));
-		MB_CUDA(c, cudaMalloc(&d_scores, sizeof(int32_t) * total));
+		MB_CUDA(c, c->alloc(&d_tasks, (size_t)(total)));
+		MB_CUDA(c, c->alloc(&d_halves, (size_t)(2 * total)));
+		MB_CUDA(c, c->alloc(&d_res, (size_t)(total)));
+		MB_CUDA(c, c->alloc(&d_scores, (size_t)(total)));
 		{
 			KScope ks(c, MECAT_K_MERGE);
 			k_make_ec<<<N, 32, 0, c->stream>>>(d_cands, d_counts, d_outpos, maxc, N, reads->offsz, reads->start_read_id,
@@ -353,45 +357,67 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1);
 		}
 		WallTimer host_timer;
-		// fill_m4record + append_m4v (sort, containment filter) per read, on the host like the reference
-		mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * total);
-		if (!out) MB_FAIL(c, "pw_tile: out of host memory");
-		size_t nout = 0;
-		std::vector<mecat_m4> loc;
-		std::vector<char> valid;
-		for (int r = 0; r < N; ++r) {
-			loc.clear();
-			const int64_t qsize = reads->h_offsz[2 * r + 1];
-			const int64_t qid = r + reads->start_read_id;
-			for (int64_t k = h_outpos[r]; k < h_outpos[r + 1]; ++k) {
-				const mecat_extend_result& R = h_res[k];
-				if (!R.ok) continue;
-				const ExtendTask& t = h_tasks[k];
-				mecat_m4 m;
-				memset(&m, 0, sizeof m);
-				m.qid = t.sread + ref->start_read_id; m.sid = qid; m.ident = R.ident; m.vscore = h_score[k]; m.qdir = 0;
-				m.qoff = R.sstart; m.qend = R.send; m.qsize = ref->h_offsz[2 * t.sread + 1]; m.ssize = qsize; m.qext = t.sstart;
-				if (!t.qstrand) { m.sdir = 0; m.soff = R.qstart; m.send = R.qend; m.sext = t.qstart; }
-				else { m.sdir = 1; m.soff = qsize - R.qend; m.send = qsize - R.qstart; m.sext = qsize - 1 - t.qstart; }
-				loc.push_back(m);
-			}
-			if (loc.empty()) continue;
-			std::sort(loc.begin(), loc.end(), M4Less());
-			valid.assign(loc.size(), 1);
-			for (size_t i = 0; i < loc.size();) {
-				size_t j = i + 1;
-				while (j < loc.size() && loc[j].qid == loc[i].qid) ++j;
-				for (size_t a = i; a < j; ++a) {
-					if (!valid[a]) continue;
-					for (size_t b = a + 1; b < j; ++b) {
-						if (!valid[b] || loc[a].sdir != loc[b].sdir) continue;
-						if (loc[b].qoff + 100 >= loc[a].qoff && loc[b].qend - 100 <= loc[a].qend &&
-						    loc[b].soff + 100 >= loc[a].soff && loc[b].send - 100 <= loc[a].send) valid[b] = 0;
-					}
+		// fill_m4record + append_m4v (sort, containment filter) per read, on the host like the
+		// reference -- same std::sort, same comparator, so ties fall the same way -- spread over
+		// host threads by read ranges; chunks are concatenated in read order.
+		const int nthreads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
+		const int nchunks = std::min(N, nthreads * 4);
+		std::vector<std::vector<mecat_m4>> parts((size_t)nchunks);
+		auto work = [&](int chunk) {
+			const int r_lo = (int)((int64_t)N * chunk / nchunks), r_hi = (int)((int64_t)N * (chunk + 1) / nchunks);
+			std::vector<mecat_m4>& dst = parts[(size_t)chunk];
+			std::vector<mecat_m4> loc;
+			std::vector<char> valid;
+			for (int r = r_lo; r < r_hi; ++r) {
+				loc.clear();
+				const int64_t qsize = reads->h_offsz[2 * r + 1];
+				const int64_t qid = r + reads->start_read_id;
+				for (int64_t k = h_outpos[r]; k < h_outpos[r + 1]; ++k) {
+					const mecat_extend_result& R = h_res[k];
+					if (!R.ok) continue;
+					const ExtendTask& t = h_tasks[k];
+					mecat_m4 m;
+					memset(&m, 0, sizeof m);
+					m.qid = t.sread + ref->start_read_id; m.sid = qid; m.ident = R.ident; m.vscore = h_score[k]; m.qdir = 0;
+					m.qoff = R.sstart; m.qend = R.send; m.qsize = ref->h_offsz[2 * t.sread + 1]; m.ssize = qsize; m.qext = t.sstart;
+					if (!t.qstrand) { m.sdir = 0; m.soff = R.qstart; m.send = R.qend; m.sext = t.qstart; }
+					else { m.sdir = 1; m.soff = qsize - R.qend; m.send = qsize - R.qstart; m.sext = qsize - 1 - t.qstart; }
+					loc.push_back(m);
 				}
-				i = j;
+				if (loc.empty()) continue;
+				std::sort(loc.begin(), loc.end(), M4Less());
+				valid.assign(loc.size(), 1);
+				for (size_t i = 0; i < loc.size();) {
+					size_t j = i + 1;
+					while (j < loc.size() && loc[j].qid == loc[i].qid) ++j;
+					for (size_t a = i; a < j; ++a) {
+						if (!valid[a]) continue;
+						for (size_t b = a + 1; b < j; ++b) {
+							if (!valid[b] || loc[a].sdir != loc[b].sdir) continue;
+							if (loc[b].qoff + 100 >= loc[a].qoff && loc[b].qend - 100 <= loc[a].qend &&
+							    loc[b].soff + 100 >= loc[a].soff && loc[b].send - 100 <= loc[a].send) valid[b] = 0;
+						}
+					}
+					i = j;
+				}
+				for (size_t i = 0; i < loc.size(); ++i) if (valid[i]) dst.push_back(loc[i]);
 			}
-			for (size_t i = 0; i < loc.size(); ++i) if (valid[i]) out[nout++] = loc[i];
+		};
+		{
+			std::atomic<int> next(0);
+			std::vector<std::thread> pool;
+			auto runner = [&]() { for (int ch; (ch = next.fetch_add(1)) < nchunks;) work(ch); };
+			for (int t = 1; t < nthreads; ++t) pool.emplace_back(runner);
+			runner();
+			for (auto& th : pool) th.join();
+		}
+		size_t nout = 0;
+		for (auto& v : parts) nout += v.size();
+		mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * (nout ? nout : 1));
+		if (!out) MB_FAIL(c, "pw_tile: out of host memory");
+		{
+			size_t at = 0;
+			for (auto& v : parts) { if (!v.empty()) memcpy(out + at, v.data(), sizeof(mecat_m4) * v.size()); at += v.size(); }
 		}
 		c->stats.host_ms += host_timer.stop();
 		c->stats.num_records += (int64_t)nout;
@@ -399,8 +425,8 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		return 0;
 	};
 	int rc = body();
-	cudaFree(d_cands); cudaFree(d_counts); cudaFree(d_outpos); cudaFree(d_ec);
-	cudaFree(d_tasks); cudaFree(d_halves); cudaFree(d_res); cudaFree(d_scores);
+	c->dfree(d_cands); c->dfree(d_counts); c->dfree(d_outpos); c->dfree(d_ec);
+	c->dfree(d_tasks); c->dfree(d_halves); c->dfree(d_res); c->dfree(d_scores);
 	return rc;
 }
 

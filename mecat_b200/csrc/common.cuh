@@ -52,6 +52,48 @@ struct Ctx
 	std::string err;
 	mecat_b200_stats stats;
 	unsigned long long* d_counters = nullptr;   // 16 device counters (statistics, arena cursors)
+	// Device memory pool: the per-tile buffers have the same sizes call after call, so freed
+	// blocks are kept and handed out again (cudaMalloc / cudaFree of multi-GB blocks cost
+	// milliseconds each).  Everything is returned to the driver by trim() / destroy.
+	struct Block { void* p; size_t bytes; bool used; };
+	std::vector<Block> blocks;
+	cudaError_t dmalloc(void** out, size_t bytes)
+	{
+		if (bytes == 0) bytes = 256;
+		int best = -1;
+		for (size_t i = 0; i < blocks.size(); ++i)
+			if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= bytes + bytes / 4 + (1u << 20) &&
+			    (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = (int)i;
+		if (best >= 0) { blocks[best].used = true; *out = blocks[best].p; return cudaSuccess; }
+		void* p = nullptr;
+		cudaError_t e = cudaMalloc(&p, bytes);
+		if (e != cudaSuccess) {
+			trim();                       // give cached blocks back and retry once
+			(void)cudaGetLastError();
+			e = cudaMalloc(&p, bytes);
+			if (e != cudaSuccess) return e;
+		}
+		blocks.push_back({p, bytes, true});
+		*out = p;
+		return cudaSuccess;
+	}
+	void dfree(void* p)
+	{
+		if (!p) return;
+		for (auto& b : blocks) if (b.p == p) { b.used = false; return; }
+		cudaFree(p);
+	}
+	void trim()
+	{
+		size_t k = 0;
+		for (size_t i = 0; i < blocks.size(); ++i) {
+			if (blocks[i].used) blocks[k++] = blocks[i];
+			else cudaFree(blocks[i].p);
+		}
+		blocks.resize(k);
+	}
+	template <typename T> cudaError_t alloc(T** out, size_t count) { return dmalloc((void**)out, count * sizeof(T)); }
+
 	// per-kernel CUDA-event timing on `stream`
 	struct Pending { int slot; cudaEvent_t a, b; };
 	std::vector<Pending> pending;
@@ -110,9 +152,9 @@ struct KScope
 
 // ---- internal entry points (one per translation unit)
 int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out);
-void volume_release(DVolume* v);
+void volume_release(Ctx* c, DVolume* v);
 int index_build(Ctx* c, const DVolume* v, DIndex** out);
-void index_release(DIndex* i);
+void index_release(Ctx* c, DIndex* i);
 
 struct ExtendTask          // device-side extension request (global array)
 {

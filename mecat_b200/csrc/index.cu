@@ -194,10 +194,10 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 	uint32_t* d_total = nullptr;
 	const int ntiles = (int)(NCODES / SCAN_TILE);
 	auto body = [&]() -> int {
-		MB_CUDA(c, cudaMalloc(&d_counts, sizeof(uint32_t) * (size_t)NCODES));
-		MB_CUDA(c, cudaMalloc(&I->begin, sizeof(uint32_t) * ((size_t)NCODES + 4)));
-		MB_CUDA(c, cudaMalloc(&d_tiles, sizeof(uint32_t) * (size_t)ntiles));
-		MB_CUDA(c, cudaMalloc(&d_total, sizeof(uint32_t)));
+		MB_CUDA(c, c->alloc(&d_counts, (size_t)NCODES));
+		MB_CUDA(c, c->alloc(&I->begin, (size_t)NCODES + 4));
+		MB_CUDA(c, c->alloc(&d_tiles, (size_t)ntiles));
+		MB_CUDA(c, c->alloc(&d_total, 1));
 		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
 		const int grid_reads = v->num_reads < 1 ? 1 : (v->num_reads > 65535 * 8 ? 65535 * 8 : v->num_reads);
 		if (v->num_reads > 0) {
@@ -216,7 +216,7 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
 		MB_CUDA(c, cudaMemcpyAsync(I->begin + NCODES, &total, sizeof total, cudaMemcpyHostToDevice, c->stream));
 		I->num_kmers = total;
-		MB_CUDA(c, cudaMalloc(&I->pos, sizeof(int32_t) * ((size_t)total + 1)));
+		MB_CUDA(c, c->alloc(&I->pos, (size_t)total + 1));
 		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
 		if (total) {
 			{
@@ -236,17 +236,17 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 		return 0;
 	};
 	int rc = body();
-	cudaFree(d_counts); cudaFree(d_tiles); cudaFree(d_total);
-	if (rc) { index_release(I); return rc; }
+	c->dfree(d_counts); c->dfree(d_tiles); c->dfree(d_total);
+	if (rc) { index_release(c, I); return rc; }
 	*out = I;
 	return 0;
 }
 
-void index_release(DIndex* i)
+void index_release(Ctx* c, DIndex* i)
 {
 	if (!i) return;
-	cudaFree(i->begin);
-	cudaFree(i->pos);
+	c->dfree(i->begin);
+	c->dfree(i->pos);
 	delete i;
 }
 

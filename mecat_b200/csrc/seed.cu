@@ -841,7 +841,7 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 	auto body = [&]() -> int {
 		// per-CTA scratch
 		const size_t per = (((size_t)kcap * 4 + 255) & ~255ull) + (((size_t)kcap + 255) & ~255ull) + (size_t)hcap * 8 * 3 + (size_t)(hcap + 64) * 4;
-		MB_CUDA(c, cudaMalloc(&d_pool, per * nctas));
+		MB_CUDA(c, c->dmalloc((void**)&d_pool, per * nctas));
 		std::vector<SeedScratch> hs(nctas);
 		for (int i = 0; i < nctas; ++i) {
 			unsigned char* b = d_pool + per * i;
@@ -852,12 +852,12 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 			hs[i].okeys = (unsigned long long*)b; b += (size_t)hcap * 8;
 			hs[i].bstart = (uint32_t*)b;
 		}
-		MB_CUDA(c, cudaMalloc(&d_scratch, sizeof(SeedScratch) * nctas));
+		MB_CUDA(c, c->alloc(&d_scratch, (size_t)nctas));
 		MB_CUDA(c, cudaMemcpyAsync(d_scratch, hs.data(), sizeof(SeedScratch) * nctas, cudaMemcpyHostToDevice, c->stream));
-		MB_CUDA(c, cudaMalloc(&d_arena, arena_bytes));
-		MB_CUDA(c, cudaMalloc(&d_desc, sizeof(StrandDesc) * 2 * (size_t)batch));
-		MB_CUDA(c, cudaMalloc(&d_lists, sizeof(RawCand) * 2 * (size_t)batch * maxc));
-		MB_CUDA(c, cudaMalloc(&d_nlist, sizeof(int32_t) * 2 * (size_t)batch));
+		MB_CUDA(c, c->dmalloc((void**)&d_arena, arena_bytes));
+		MB_CUDA(c, c->alloc(&d_desc, 2 * (size_t)batch));
+		MB_CUDA(c, c->alloc(&d_lists, 2 * (size_t)batch * maxc));
+		MB_CUDA(c, c->alloc(&d_nlist, 2 * (size_t)batch));
 		unsigned long long* d_cursor = c->d_counters + 1;
 		unsigned int* d_work = (unsigned int*)(c->d_counters + 2);
 		unsigned long long* d_hits = c->d_counters + 3;
@@ -916,7 +916,7 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 		return 0;
 	};
 	int rc = body();
-	cudaFree(d_arena); cudaFree(d_desc); cudaFree(d_scratch); cudaFree(d_pool); cudaFree(d_lists); cudaFree(d_nlist);
+	c->dfree(d_arena); c->dfree(d_desc); c->dfree(d_scratch); c->dfree(d_pool); c->dfree(d_lists); c->dfree(d_nlist);
 	return rc;
 }
 

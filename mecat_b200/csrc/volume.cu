@@ -58,15 +58,15 @@ int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out)
 		char b[256];
 		snprintf(b, sizeof b, "volume_upload: %s: %s", what, cudaGetErrorString(e));
 		c->err = b;
-		cudaFree(d_pac);
-		volume_release(d);
+		c->dfree(d_pac);
+		volume_release(c, d);
 		return 1;
 	};
 	cudaError_t e;
-	if ((e = cudaMalloc(&d_pac, src_words * 4 + 4)) != cudaSuccess) return fail(e, "cudaMalloc pac");
-	if ((e = cudaMalloc(&d->fwd, d->words * 4)) != cudaSuccess) return fail(e, "cudaMalloc fwd");
-	if ((e = cudaMalloc(&d->rev, d->words * 4)) != cudaSuccess) return fail(e, "cudaMalloc rev");
-	if ((e = cudaMalloc(&d->offsz, sizeof(int2) * (size_t)(v->num_reads ? v->num_reads : 1))) != cudaSuccess) return fail(e, "cudaMalloc offsets");
+	if ((e = c->dmalloc((void**)&d_pac, src_words * 4 + 4)) != cudaSuccess) return fail(e, "cudaMalloc pac");
+	if ((e = c->dmalloc((void**)&d->fwd, d->words * 4)) != cudaSuccess) return fail(e, "cudaMalloc fwd");
+	if ((e = c->dmalloc((void**)&d->rev, d->words * 4)) != cudaSuccess) return fail(e, "cudaMalloc rev");
+	if ((e = c->dmalloc((void**)&d->offsz, sizeof(int2) * (size_t)(v->num_reads ? v->num_reads : 1))) != cudaSuccess) return fail(e, "cudaMalloc offsets");
 	if ((e = cudaMemsetAsync(d_pac, 0, src_words * 4 + 4, c->stream)) != cudaSuccess) return fail(e, "memset");
 	if (pac_bytes && (e = cudaMemcpyAsync(d_pac, v->pac, pac_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "H2D pac");
 	if (v->num_reads && (e = cudaMemcpyAsync(d->offsz, v->offset_size, sizeof(int2) * (size_t)v->num_reads, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "H2D offsets");
@@ -80,17 +80,17 @@ int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out)
 	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e, "orient kernels");
 	c->resolve_timers();
 	c->stats.h2d_bytes += (int64_t)pac_bytes + (int64_t)sizeof(int2) * v->num_reads;
-	cudaFree(d_pac);
+	c->dfree(d_pac);
 	*out = d;
 	return 0;
 }
 
-void volume_release(DVolume* v)
+void volume_release(Ctx* c, DVolume* v)
 {
 	if (!v) return;
-	cudaFree(v->offsz);
-	cudaFree(v->fwd);
-	cudaFree(v->rev);
+	c->dfree(v->offsz);
+	c->dfree(v->fwd);
+	c->dfree(v->rev);
 	delete v;
 }
 
