@@ -23,22 +23,25 @@
 //   columns up to the run end = (x + y + d) / 2,   matches = (x + y - d) / 2.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace mb {
 
 namespace {
 
 constexpr int EXT_WARPS = 4;
-constexpr int KOFF = 404;                 // > max_d for the largest block (0.3 * (599 + 718) = 395)
-constexpr int VL_N = (2 * KOFF + 8) / 2;  // entries per parity
+constexpr int EXT_CTAS_PER_SM = 8;
+constexpr int KOFF = 512;                 // even, > max_d of the largest block (0.3 * (599 + 718) = 395)
+constexpr int VL_N = 256;                 // ring of diagonals per parity: the live band spans <= 2*216+4 diagonals
 constexpr int SEQ_WORDS = 48;             // 719 bases = 45 words (+1 funnel, +2 slack)
 constexpr uint32_t NO_ANCHOR = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct WarpSmem
 {
-	uint32_t sq[SEQ_WORDS];
-	uint32_t st[SEQ_WORDS];
-	uint2 vl[2][VL_N];        // .x = furthest x on the diagonal, .y = packed anchor
+	uint2 sq[SEQ_WORDS];      // .x = packed word i, .y = word i+1: any 16-base window is one LDS.64 + funnel shift
+	uint2 st[SEQ_WORDS];
+	uint2 vl[2][VL_N];        // per parity of k: .x = furthest x on the diagonal, .y = packed anchor
 };
 
 struct Walk                   // one sequence seen as a forward walk
@@ -49,204 +52,230 @@ struct Walk                   // one sequence seen as a forward walk
 	int len;
 };
 
-__device__ __forceinline__ uint32_t pack_anchor(int x, int y, int d) { return (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)d << 20); }
-
-__device__ __forceinline__ uint32_t seq16(const uint32_t* s, int i)
+__device__ __forceinline__ uint32_t seq16(const uint2* s, int i)
 {
-	int w = i >> 4;
-	return __funnelshift_r(s[w], s[w + 1], (i & 15) << 1);
+	const uint2 w = s[i >> 4];
+	return __funnelshift_r(w.x, w.y, (i & 15) << 1);
 }
 
 __device__ __forceinline__ int dtrunc_mul(double a, int b) { return (int)__dmul_rn(a, (double)b); }
 
 }  // namespace
 
-__global__ void __launch_bounds__(EXT_WARPS * 32)
+// Persistent warps: every warp pulls (candidate, direction) items from a global counter, so a
+// long chain never pins three idle warps of its CTA.
+__global__ void __launch_bounds__(EXT_WARPS * 32, EXT_CTAS_PER_SM)
 k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, const int2* __restrict__ qoffsz, int qN,
          const uint32_t* __restrict__ sfwd, const uint32_t* __restrict__ srev, const int2* __restrict__ soffsz, int sN,
          const ExtendTask* __restrict__ tasks, size_t ntasks, ExtendHalf* __restrict__ halves,
-         unsigned long long* __restrict__ block_counter)
+         unsigned long long* __restrict__ block_counter, unsigned long long* __restrict__ work_counter)
 {
 	__shared__ WarpSmem smem[EXT_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const size_t item = (size_t)blockIdx.x * EXT_WARPS + warp;
-	if (item >= 2 * ntasks) return;
 	WarpSmem& S = smem[warp];
-	const ExtendTask t = tasks[item >> 1];
-	const int right = (int)(item & 1);
-
-	const int2 qo = qoffsz[t.qread], so = soffsz[t.sread];
-	Walk Q, T;
-	if (right) {
-		if (!t.qstrand) { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + t.qstart); Q.comp = 0; }
-		else { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - qo.y + t.qstart); Q.comp = FULL; }
-		Q.len = qo.y - t.qstart;
-		T.arr = sfwd; T.g0 = (uint32_t)(so.x + t.sstart); T.comp = 0; T.len = so.y - t.sstart;
-	} else {
-		if (!t.qstrand) { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - t.qstart); Q.comp = 0; }
-		else { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + qo.y - t.qstart); Q.comp = FULL; }
-		Q.len = t.qstart;
-		T.arr = srev; T.g0 = (uint32_t)(sN - so.x - t.sstart); T.comp = 0; T.len = t.sstart;
-	}
-
-	int qi = 0, ti = 0;
-	int cols = 0, mats = 0, qadv = 0, tadv = 0;
 	unsigned nblocks = 0;
 
 	for (;;) {
-		// ---- retrieve_next_aln_block
-		const int qleft = Q.len - qi, tleft = T.len - ti;
-		int qblk, tblk;
-		bool last;
-		if (qleft < 600 || tleft < 600) {
-			int a = (int)__dadd_rn((double)tleft, __dmul_rn((double)tleft, 0.2));
-			int b = (int)__dadd_rn((double)qleft, __dmul_rn((double)qleft, 0.2));
-			qblk = min(qleft, a);
-			tblk = min(tleft, b);
-			last = true;
-		} else { qblk = tblk = 500; last = false; }
-		const int tol = dtrunc_mul(0.3, max(qblk, tblk));
-		const int max_d = dtrunc_mul(.3, qblk + tblk);
-		++nblocks;
+		unsigned long long item = 0;
+		if (lane == 0) item = atomicAdd(work_counter, 1ull);
+		item = __shfl_sync(FULL, item, 0);
+		if (item >= 2 * ntasks) break;
+		const ExtendTask t = tasks[item >> 1];
+		const int right = (int)(item & 1);
 
-		// ---- stage operands, clear the diagonal arrays (fill(U,0), fill(V,0))
-		{
-			const int qw = (qblk + 15) / 16 + 1, tw = (tblk + 15) / 16 + 1;
-			for (int i = lane; i < qw; i += 32) S.sq[i] = ld_bases32(Q.arr, Q.g0 + (uint32_t)qi + 16u * i) ^ Q.comp;
-			for (int i = lane; i < tw; i += 32) S.st[i] = ld_bases32(T.arr, T.g0 + (uint32_t)ti + 16u * i) ^ T.comp;
-			const uint2 z = make_uint2(0u, NO_ANCHOR);
-			for (int i = lane; i < 2 * VL_N; i += 32) (&S.vl[0][0])[i] = z;
+		const int2 qo = qoffsz[t.qread], so = soffsz[t.sread];
+		Walk Q, T;
+		if (right) {
+			if (!t.qstrand) { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + t.qstart); Q.comp = 0; }
+			else { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - qo.y + t.qstart); Q.comp = FULL; }
+			Q.len = qo.y - t.qstart;
+			T.arr = sfwd; T.g0 = (uint32_t)(so.x + t.sstart); T.comp = 0; T.len = so.y - t.sstart;
+		} else {
+			if (!t.qstrand) { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - t.qstart); Q.comp = 0; }
+			else { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + qo.y - t.qstart); Q.comp = FULL; }
+			Q.len = t.qstart;
+			T.arr = srev; T.g0 = (uint32_t)(sN - so.x - t.sstart); T.comp = 0; T.len = t.sstart;
 		}
-		__syncwarp();
 
-		// ---- Align
-		int min_k = 0, max_k = 0, best_m = -1;
-		int last_min = 0, last_max = 0, rows = 0;
-		bool aligned = false;
-		int ex = 0, ey = 0, ed = 0;
-		uint32_t ea = NO_ANCHOR;
-		for (int d = 0; d < max_d; ++d) {
-			if (max_k - min_k > 2 * tol) break;
-			const int n = ((max_k - min_k) >> 1) + 1;
-			int rowmax = -1;
-			for (int base = 0; base < n; base += 32) {
-				const int j = base + lane;
-				const bool act = j < n;
-				const int k = min_k + 2 * j;
-				int x = 0, y = 0;
-				uint32_t anc = NO_ANCHOR;
-				bool hit = false;
-				if (act) {
-					const int kk = k + KOFF, p = kk & 1;
-					const uint2 lf = S.vl[p ^ 1][(kk - 1) >> 1], rt = S.vl[p ^ 1][(kk + 1) >> 1];
-					if (k == min_k || (k != max_k && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
-					else { x = (int)lf.x + 1; anc = lf.y; }
-					y = x - k;
-					const int x1 = x;
-					while (x < qblk && y < tblk) {
-						const uint32_t diff = seq16(S.sq, x) ^ seq16(S.st, y);
-						int m = diff ? ((__ffs(diff) - 1) >> 1) : 16;
-						m = min(m, min(qblk - x, tblk - y));
-						x += m; y += m;
-						if (m < 16) break;
-					}
-					if (x - x1 >= 4) anc = pack_anchor(x, y, d);
-					S.vl[p][kk >> 1] = make_uint2((uint32_t)x, anc);
-					hit = (x >= qblk) || (y >= tblk);
+		int qi = 0, ti = 0;
+		int cols = 0, mats = 0, qadv = 0, tadv = 0;
+
+		for (;;) {
+			// ---- retrieve_next_aln_block
+			const int qleft = Q.len - qi, tleft = T.len - ti;
+			int qblk, tblk;
+			bool last;
+			if (qleft < 600 || tleft < 600) {
+				int a = (int)__dadd_rn((double)tleft, __dmul_rn((double)tleft, 0.2));
+				int b = (int)__dadd_rn((double)qleft, __dmul_rn((double)qleft, 0.2));
+				qblk = min(qleft, a);
+				tblk = min(tleft, b);
+				last = true;
+			} else { qblk = tblk = 500; last = false; }
+			const int tol = dtrunc_mul(0.3, max(qblk, tblk));
+			const int max_d = dtrunc_mul(.3, qblk + tblk);
+			const int endsum = min(qblk, tblk);   // a cell can only touch an end once x + y >= this
+			++nblocks;
+
+			// ---- stage operands.  The reference zero-fills its V/U arrays per block; a row only ever
+			// reads cells the previous row wrote (band edges take the single in-band neighbour), so
+			// the one cell that must read as zero is V[1] at d = 0.
+			__syncwarp();
+			{
+				const int qw = (qblk + 15) / 16 + 1, tw = (tblk + 15) / 16 + 1;
+				for (int i = lane; i < qw; i += 32) {
+					const uint32_t b0 = Q.g0 + (uint32_t)qi + 16u * i;
+					S.sq[i] = make_uint2(ld_bases32(Q.arr, b0) ^ Q.comp, ld_bases32(Q.arr, b0 + 16u) ^ Q.comp);
 				}
-				const unsigned hm = __ballot_sync(FULL, hit);
-				rowmax = max(rowmax, __reduce_max_sync(FULL, act ? x + y : -1));
-				if (hm) {
-					const int src = __ffs(hm) - 1;
-					ex = __shfl_sync(FULL, x, src);
-					ey = __shfl_sync(FULL, y, src);
-					ea = __shfl_sync(FULL, anc, src);
-					ed = d;
-					aligned = true;
-					break;
+				for (int i = lane; i < tw; i += 32) {
+					const uint32_t b0 = T.g0 + (uint32_t)ti + 16u * i;
+					S.st[i] = make_uint2(ld_bases32(T.arr, b0) ^ T.comp, ld_bases32(T.arr, b0 + 16u) ^ T.comp);
 				}
+				if (lane == 0) S.vl[1][((KOFF + 1) >> 1) & (VL_N - 1)] = make_uint2(0u, NO_ANCHOR);
 			}
 			__syncwarp();
-			if (aligned) break;
-			best_m = max(best_m, rowmax);
-			// re-band to the diagonals within `tol` of the best, widened by one
-			int lo = 0x7fffffff, hi = -0x7fffffff;
-			for (int base = 0; base < n; base += 32) {
-				const int j = base + lane;
-				const int k = min_k + 2 * j;
-				bool keep = false;
-				if (j < n) {
-					const int kk = k + KOFF;
-					keep = 2 * (int)S.vl[kk & 1][kk >> 1].x - k >= best_m - tol;
-				}
-				const unsigned km = __ballot_sync(FULL, keep);
-				if (km) {
-					lo = min(lo, min_k + 2 * (base + __ffs(km) - 1));
-					hi = max(hi, min_k + 2 * (base + 31 - __clz(km)));
-				}
-			}
-			last_min = min_k; last_max = max_k; ++rows;
-			min_k = lo - 1; max_k = hi + 1;
-		}
-		if (!aligned && rows > 0) {
-			// best (x+y) cell: first k of the last completed row that reaches best_m
-			const int n = ((last_max - last_min) >> 1) + 1;
-			for (int base = 0; base < n; base += 32) {
-				const int j = base + lane;
-				const int k = last_min + 2 * j;
-				uint2 c = make_uint2(0u, NO_ANCHOR);
-				bool is = false;
-				if (j < n) {
-					const int kk = k + KOFF;
-					c = S.vl[kk & 1][kk >> 1];
-					is = 2 * (int)c.x - k == best_m;
-				}
-				const unsigned bm = __ballot_sync(FULL, is);
-				if (bm) {
-					const int src = __ffs(bm) - 1;
-					const int bx = __shfl_sync(FULL, (int)c.x, src);
-					const int bk = __shfl_sync(FULL, k, src);
-					const uint32_t ba = __shfl_sync(FULL, c.y, src);
-					if (bx > 0) { ex = bx; ey = bx - bk; ed = rows - 1; ea = ba; }
-					break;
-				}
-			}
-		}
-		__syncwarp();
 
-		// ---- trim_mismatch_end + chain bookkeeping (dw_in_one_direction)
-		if (ea == NO_ANCHOR) break;
-		const int ax = (int)(ea & 1023u), ay = (int)((ea >> 10) & 1023u), ad = (int)(ea >> 20);
-		const int acols = (ax + ay + ad) >> 1, amat = (ax + ay - ad) >> 1;
-		if (acols < 6) break;
-		const bool full_map = (qblk - ex <= 20) || (tblk - ey <= 20);
-		if (last || !full_map) {
-			cols += acols; mats += amat; qadv += ax; tadv += ay;
-			break;
+			// ---- Align
+			int min_k = 0, max_k = 0, best_m = -1;
+			int last_min = 0, last_max = 0, rows = 0;
+			bool aligned = false;
+			int ex = 0, ey = 0;
+			uint32_t ea = NO_ANCHOR;
+			for (int d = 0; d < max_d; ++d) {
+				if (max_k - min_k > 2 * tol) break;
+				const int n = ((max_k - min_k) >> 1) + 1;
+				const int kk0 = min_k + KOFF;
+				uint2* own = S.vl[kk0 & 1];
+				const uint2* oth = S.vl[(kk0 & 1) ^ 1];
+				const int o0 = kk0 >> 1, l0 = (kk0 - 1) >> 1;    // own[o0 + j], neighbours oth[l0 + j] (k-1) and oth[l0 + j + 1] (k+1)
+				const uint32_t dbits = (uint32_t)d << 20;
+				int rowmax = -1;
+				int u0 = -1, u1 = -1;                            // x + y of passes 0 / 1 kept for the re-banding
+				for (int base = 0; base < n; base += 32) {
+					const int j = base + lane;
+					const bool act = j < n;
+					const int k = min_k + 2 * j;
+					int x = 0, u = -1;
+					uint32_t anc = NO_ANCHOR;
+					if (act) {
+						const uint2 lf = oth[(l0 + j) & (VL_N - 1)], rt = oth[(l0 + j + 1) & (VL_N - 1)];
+						if (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
+						else { x = (int)lf.x + 1; anc = lf.y; }
+						int y = x - k;
+						const int x1 = x;
+						while (x < qblk && y < tblk) {
+							const uint32_t diff = seq16(S.sq, x) ^ seq16(S.st, y);
+							int m = diff ? ((__ffs(diff) - 1) >> 1) : 16;
+							m = min(m, min(qblk - x, tblk - y));
+							x += m; y += m;
+							if (m < 16) break;
+						}
+						if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
+						own[(o0 + j) & (VL_N - 1)] = make_uint2((uint32_t)x, anc);
+						u = x + y;
+					}
+					const int pm = __reduce_max_sync(FULL, u);
+					rowmax = max(rowmax, pm);
+					if (base == 0) u0 = u; else if (base == 32) u1 = u;
+					if (pm >= endsum) {
+						const unsigned hm = __ballot_sync(FULL, act && (x >= qblk || x - k >= tblk));
+						if (hm) {
+							const int src = __ffs(hm) - 1;
+							ex = __shfl_sync(FULL, x, src);
+							ey = ex - __shfl_sync(FULL, k, src);
+							ea = __shfl_sync(FULL, anc, src);
+							aligned = true;
+							break;
+						}
+					}
+				}
+				__syncwarp();
+				if (aligned) break;
+				best_m = max(best_m, rowmax);
+				// re-band to the diagonals within `tol` of the best, widened by one
+				const int thr = best_m - tol;
+				int lo = 0x7fffffff, hi = -0x7fffffff;
+				{
+					const unsigned km = __ballot_sync(FULL, u0 >= thr && u0 >= 0);
+					if (km) { lo = min_k + 2 * (__ffs(km) - 1); hi = min_k + 2 * (31 - __clz(km)); }
+				}
+				if (n > 32) {
+					const unsigned km = __ballot_sync(FULL, u1 >= thr && u1 >= 0);
+					if (km) { lo = min(lo, min_k + 2 * (32 + __ffs(km) - 1)); hi = max(hi, min_k + 2 * (32 + 31 - __clz(km))); }
+					for (int base = 64; base < n; base += 32) {
+						const int j = base + lane;
+						bool keep = false;
+						if (j < n) keep = 2 * (int)own[(o0 + j) & (VL_N - 1)].x - (min_k + 2 * j) >= thr;
+						const unsigned km2 = __ballot_sync(FULL, keep);
+						if (km2) { lo = min(lo, min_k + 2 * (base + __ffs(km2) - 1)); hi = max(hi, min_k + 2 * (base + 31 - __clz(km2))); }
+					}
+				}
+				last_min = min_k; last_max = max_k; ++rows;
+				min_k = lo - 1; max_k = hi + 1;
+			}
+			if (!aligned && rows > 0) {
+				// best (x+y) cell: first k of the last completed row that reaches best_m
+				const int n = ((last_max - last_min) >> 1) + 1;
+				const int kk0 = last_min + KOFF;
+				const uint2* own = S.vl[kk0 & 1];
+				const int o0 = kk0 >> 1;
+				for (int base = 0; base < n; base += 32) {
+					const int j = base + lane;
+					const int k = last_min + 2 * j;
+					uint2 c = make_uint2(0u, NO_ANCHOR);
+					bool is = false;
+					if (j < n) {
+						c = own[(o0 + j) & (VL_N - 1)];
+						is = 2 * (int)c.x - k == best_m;
+					}
+					const unsigned bm = __ballot_sync(FULL, is);
+					if (bm) {
+						const int src = __ffs(bm) - 1;
+						const int bx = __shfl_sync(FULL, (int)c.x, src);
+						const int bk = __shfl_sync(FULL, k, src);
+						const uint32_t ba = __shfl_sync(FULL, c.y, src);
+						if (bx > 0) { ex = bx; ey = bx - bk; ea = ba; }
+						break;
+					}
+				}
+			}
+
+			// ---- trim_mismatch_end + chain bookkeeping (dw_in_one_direction)
+			if (ea == NO_ANCHOR) break;
+			const int ax = (int)(ea & 1023u), ay = (int)((ea >> 10) & 1023u), ad = (int)(ea >> 20);
+			const int acols = (ax + ay + ad) >> 1, amat = (ax + ay - ad) >> 1;
+			if (acols < 6) break;
+			const bool full_map = (qblk - ex <= 20) || (tblk - ey <= 20);
+			if (last || !full_map) {
+				cols += acols; mats += amat; qadv += ax; tadv += ay;
+				break;
+			}
+			cols += acols - 4; mats += amat - 4; qadv += ax - 4; tadv += ay - 4;
+			qi += ax - 4; ti += ay - 4;
 		}
-		cols += acols - 4; mats += amat - 4; qadv += ax - 4; tadv += ay - 4;
-		qi += ax - 4; ti += ay - 4;
+		if (lane == 0) {
+			ExtendHalf h;
+			h.cols = cols; h.matches = mats; h.qadv = qadv; h.tadv = tadv;
+			halves[item] = h;
+		}
 	}
-	if (lane == 0) {
-		ExtendHalf h;
-		h.cols = cols; h.matches = mats; h.qadv = qadv; h.tadv = tadv;
-		halves[item] = h;
-		if (block_counter) atomicAdd(block_counter, (unsigned long long)nblocks);
-	}
+	if (lane == 0 && block_counter && nblocks) atomicAdd(block_counter, (unsigned long long)nblocks);
 }
 
 int extend_launch(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* d_tasks, size_t ntasks,
                   ExtendHalf* d_halves)
 {
 	if (!ntasks) return 0;
-	unsigned long long* d_counter = c->d_counters;
+	unsigned long long* d_counter = c->d_counters;          // [0] block statistics, [4] work queue head
 	MB_CUDA(c, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), c->stream));
+	MB_CUDA(c, cudaMemsetAsync(d_counter + 4, 0, sizeof(unsigned long long), c->stream));
 	const size_t items = 2 * ntasks;
-	const unsigned grid = (unsigned)((items + EXT_WARPS - 1) / EXT_WARPS);
+	const size_t want = (items + EXT_WARPS - 1) / EXT_WARPS;
+	const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)c->sm_count * EXT_CTAS_PER_SM);
 	{
 		KScope ks(c, MECAT_K_EXTEND);
 		k_extend<<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
-		                                                 s->num_bases, d_tasks, ntasks, d_halves, d_counter);
+		                                                 s->num_bases, d_tasks, ntasks, d_halves, d_counter, d_counter + 4);
 	}
 	MB_CUDA(c, cudaGetLastError());
 	unsigned long long nb = 0;
