@@ -33,6 +33,8 @@ constexpr int SEED_THREADS = 1024;
 constexpr int CNT_SLOTS = 65536;            // hashed 16-bit hit counters (128 KB)
 constexpr int BIT_WORDS = 2048;             // hashed interest bitmap (65536 bits) / anchor claim slots
 constexpr uint32_t CNT_SAT = 0x8000u;       // counters stop growing here (no wrap with <= 1024 racing adds)
+constexpr int KCACHE = 2048;               // sampled k-mers whose list info is cached in shared memory
+constexpr int SCAP = 8192;                  // collected hits that sort in shared memory
 constexpr int MAX_KM = 32766;               // seed ordinals are `short` in the reference (pw_impl.h:31)
 
 struct BucketHdr          // 16 bytes, one per collected bucket, ascending seg inside a strand
@@ -65,8 +67,6 @@ struct SeedScratch        // per-CTA global scratch
 	uint32_t* bstart;     // first entry of each bucket (+1 sentinel)
 	unsigned long long* okeys;  // walk-order sort keys
 };
-
-__device__ __forceinline__ uint32_t seg_hash(uint32_t seg) { return (seg * 0x9E3779B1u) >> 16; }
 
 // 13-mer code (first base most significant) of a query strand at sampled ordinal km
 __device__ __forceinline__ uint32_t query_code(const uint32_t* __restrict__ arr, uint32_t g0, uint32_t comp, int km)
@@ -223,14 +223,18 @@ __device__ int replay_overflow(unsigned long long* ent, int na, int* sl, int* ss
 __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 {
 	extern __shared__ uint32_t smem_u32[];
-	uint32_t* cnt = smem_u32;                         // CNT_SLOTS / 2 words
-	uint32_t* anchor_tab = cnt + CNT_SLOTS / 2;       // BIT_WORDS claim slots (bucket ids)
-	uint32_t* want_bits = anchor_tab + BIT_WORDS;     // BIT_WORDS words = 65536 hashed bits
-	int* misc = (int*)(want_bits + BIT_WORDS);        // 64 ints: scan scratch [0..33), counters
+	uint32_t* cnt = smem_u32;                         // CNT_SLOTS / 2 words: 16-bit hit counters, slot = bucket & 0xFFFF
+	uint32_t* want_bits = cnt + CNT_SLOTS / 2;        // BIT_WORDS words = 65536 interest bits, same slot map
+	uint32_t* kbs = want_bits + BIT_WORDS;            // KCACHE list begins
+	uint8_t* kcs = (uint8_t*)(kbs + KCACHE);          // KCACHE list lengths
+	int* misc = (int*)(kcs + KCACHE);                 // 64 ints: scan scratch [0..33), counters
 	int* wslots = misc + 64;                          // per warp: 3 x 41 ints for the overflow replay
+	// once the counters are dead (after pass 2) their 128 KB hold the sort buffers
+	unsigned long long* skeys = (unsigned long long*)cnt;          // SCAP collected hits
+	unsigned long long* sent = skeys + SCAP;                       // SCAP accepted hits
 	__shared__ unsigned int s_item;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-	const SeedScratch sc = P.scratch[blockIdx.x];
+	const SeedScratch gsc = P.scratch[blockIdx.x];
 
 	for (;;) {
 		__syncthreads();
@@ -249,69 +253,71 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		const uint32_t g0 = strand ? (uint32_t)(P.qN - qo.x - L) : (uint32_t)qo.x;
 		const uint32_t comp = strand ? FULL : 0u;
 		const int W = (L + SEGW - 1) / SEGW;          // reach of a candidate's neighbour vote, in buckets
+		// list begin / length per sampled k-mer: shared memory for ordinary reads, global scratch for very long ones
+		uint32_t* kb = nk <= KCACHE ? kbs : gsc.kb;
+		uint8_t* kc = nk <= KCACHE ? kcs : gsc.kc;
 
 		// ---- clear
-		for (int i = tid; i < CNT_SLOTS / 2; i += blockDim.x) cnt[i] = 0u;
-		for (int i = tid; i < BIT_WORDS; i += blockDim.x) { anchor_tab[i] = 0xFFFFFFFFu; want_bits[i] = 0u; }
+		for (int i = tid; i < CNT_SLOTS / 2 + BIT_WORDS; i += blockDim.x) cnt[i] = 0u;
 		if (tid < 64) misc[tid] = 0;
 		// ---- k-mer lookup
 		for (int km = tid; km < nk; km += blockDim.x) {
 			const uint32_t code = query_code(arr, g0, comp, km);
 			const uint32_t b = P.begin[code], e = P.begin[code + 1];
-			sc.kb[km] = b;
-			sc.kc[km] = (uint8_t)(e - b);
+			kb[km] = b;
+			kc[km] = (uint8_t)(e - b);
 		}
 		__syncthreads();
-		// ---- pass 1: hashed hit counts per bucket
-		unsigned long long myhits = 0;
+		// ---- pass 1: hit counts per bucket slot.  The slot map keeps neighbouring buckets adjacent,
+		// aliases (buckets 65536 apart) only inflate counts: every later decision is a superset.
+		unsigned myhits = 0;
 		for (int km = warp; km < nk; km += nwarps) {
-			const int n = sc.kc[km];
-			const uint32_t b = sc.kb[km];
+			const int n = kc[km];
+			const uint32_t b = kb[km];
 			for (int h = lane; h < n; h += 32) {
-				const uint32_t seg = (uint32_t)P.pos[b + h] / SEGW;
-				const uint32_t hh = seg_hash(seg);
+				const uint32_t hh = ((uint32_t)P.pos[b + h] / SEGW) & (CNT_SLOTS - 1);
 				const uint32_t cur = (cnt[hh >> 1] >> ((hh & 1u) << 4)) & 0xFFFFu;
 				if (cur < CNT_SAT) atomicAdd(&cnt[hh >> 1], 1u << ((hh & 1u) << 4));
 				++myhits;
 			}
 		}
 		__syncthreads();
-		// ---- pass 2: possible anchors mark the buckets they may need
-		for (int km = warp; km < nk; km += nwarps) {
-			const int n = sc.kc[km];
-			const uint32_t b = sc.kb[km];
-			for (int h = lane; h < n; h += 32) {
-				const uint32_t seg = (uint32_t)P.pos[b + h] / SEGW;
-				const uint32_t hh = seg_hash(seg);
-				uint32_t c = (cnt[hh >> 1] >> ((hh & 1u) << 4)) & 0xFFFFu;
-				if (seg > 0) { const uint32_t hp = seg_hash(seg - 1); c += (cnt[hp >> 1] >> ((hp & 1u) << 4)) & 0xFFFFu; }
-				if ((int)c >= P.gate) {
-					// One thread per possible anchor marks its window.  The claim table is keyed by the
-					// exact bucket id: a slot held by a different bucket only costs a redundant marking,
-					// it can never suppress one (a hashed "already done" bit could, and did).
-					uint32_t* slot = &anchor_tab[hh & (BIT_WORDS - 1)];
-					if (*(volatile uint32_t*)slot != seg && atomicCAS(slot, 0xFFFFFFFFu, seg) != seg) {
-						const int lo = max(0, (int)seg - W), hi = (int)seg + W;
-						for (int s2 = lo; s2 <= hi; ++s2) {
-							const uint32_t h2 = seg_hash((uint32_t)s2), bit = 1u << (h2 & 31u);
-							if (!(want_bits[h2 >> 5] & bit)) atomicOr(&want_bits[h2 >> 5], bit);
-						}
-					}
+		// ---- pass 2: scan the slot table.  A bucket can only pass the reference's index_score >= 2k
+		// gate if its own count plus its left neighbour's reaches the gate; such a slot marks the
+		// +-W slots a candidate anchored there can reach (previous bucket, neighbour votes).
+		for (int w = tid; w < CNT_SLOTS / 2; w += blockDim.x) {
+			const uint32_t cw = cnt[w];
+			if (cw == 0u) continue;
+			const uint32_t pw = cnt[(w + CNT_SLOTS / 2 - 1) & (CNT_SLOTS / 2 - 1)];
+			const int c0 = (int)(cw & 0xFFFFu), c1 = (int)(cw >> 16), cm = (int)(pw >> 16);
+#pragma unroll
+			for (int half = 0; half < 2; ++half) {
+				const int c = half ? c1 + c0 : c0 + cm;
+				const int own = half ? c1 : c0;
+				if (own == 0 || c < P.gate) continue;
+				const int slot = 2 * w + half;
+				int lo = slot - W, hi = slot + W;              // inclusive, modulo CNT_SLOTS
+				if (hi - lo + 1 >= CNT_SLOTS) { lo = 0; hi = CNT_SLOTS - 1; }
+				for (int wb = (lo >> 5); wb <= (hi >> 5); ++wb) {
+					const int first = max(lo, wb << 5) - (wb << 5), lastb = min(hi, (wb << 5) + 31) - (wb << 5);
+					const uint32_t mask = (lastb == 31 ? 0xFFFFFFFFu : ((1u << (lastb + 1)) - 1u)) & ~((1u << first) - 1u);
+					uint32_t* dst = &want_bits[wb & (BIT_WORDS - 1)];
+					if ((*dst & mask) != mask) atomicOr(dst, mask);
 				}
 			}
 		}
 		__syncthreads();
-		// ---- pass 3: collect the hits of wanted buckets
+		// ---- pass 3: collect the hits of wanted buckets (shared memory first, overflow to global scratch)
 		for (int km = warp; km < nk; km += nwarps) {
-			const int n = sc.kc[km];
-			const uint32_t b = sc.kb[km];
+			const int n = kc[km];
+			const uint32_t b = kb[km];
 			for (int h0 = 0; h0 < n; h0 += 32) {
 				const int h = h0 + lane;
 				bool take = false;
 				uint32_t p = 0;
 				if (h < n) {
 					p = (uint32_t)P.pos[b + h];
-					const uint32_t h2 = seg_hash(p / SEGW);
+					const uint32_t h2 = (p / SEGW) & (CNT_SLOTS - 1);
 					take = (want_bits[h2 >> 5] >> (h2 & 31u)) & 1u;
 				}
 				const unsigned m = __ballot_sync(FULL, take);
@@ -321,20 +327,32 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 					base = __shfl_sync(FULL, base, 0);
 					if (take) {
 						const int at = base + __popc(m & ((1u << lane) - 1u));
-						if (at < P.hcap)
-							sc.keys[at] = ((unsigned long long)(p / SEGW) << 27) | ((unsigned long long)km << 11) | (unsigned long long)(p % SEGW);
+						const unsigned long long key = ((unsigned long long)(p / SEGW) << 27) | ((unsigned long long)km << 11) | (unsigned long long)(p % SEGW);
+						if (at < SCAP) skeys[at] = key;          // the counters are dead: their memory takes the keys
+						else if (at < P.hcap) gsc.keys[at] = key;
 					}
 				}
 			}
 		}
 		if (P.hit_counter) {
-			myhits = __reduce_add_sync(FULL, (unsigned)myhits);
-			if (lane == 0 && myhits) atomicAdd(P.hit_counter, myhits);
+			myhits = __reduce_add_sync(FULL, myhits);
+			if (lane == 0 && myhits) atomicAdd(P.hit_counter, (unsigned long long)myhits);
 		}
 		__syncthreads();
 		const int ncol = misc[40];
 		if (ncol > P.hcap) { if (tid == 0) { D.status = 3; P.desc[item] = D; } continue; }
 		if (ncol == 0) { if (tid == 0) P.desc[item] = D; continue; }
+		// Ordinary strands sort and de-duplicate in the 128 KB the counters occupied; only strands with
+		// more than SCAP collected hits fall back to the per-CTA global scratch.
+		const bool in_smem = ncol <= SCAP;
+		SeedScratch sc = gsc;
+		if (in_smem) {
+			sc.keys = skeys; sc.ent = sent;
+			sc.bstart = (uint32_t*)skeys;                        // keys are dead once `ent` is built
+		} else {
+			for (int i = tid; i < SCAP; i += blockDim.x) gsc.keys[i] = skeys[i];
+			__syncthreads();
+		}
 		int n2 = 1;
 		while (n2 < ncol) n2 <<= 1;
 		for (int i = ncol + tid; i < n2; i += blockDim.x) sc.keys[i] = ~0ull;
@@ -366,6 +384,8 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 			nb += tot;
 		}
 		if (tid == 0) sc.bstart[nb] = (uint32_t)nent;
+		// walk-order keys: behind bstart in shared memory when few buckets, else global scratch
+		if (in_smem && nb <= SCAP / 4) sc.okeys = skeys + SCAP / 2 + 1;
 		__syncthreads();
 		// ---- arena space: headers, entries (<= 40 per bucket), order list
 		int nstore = 0;
@@ -422,9 +442,30 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 				}
 				score = na;
 			} else {
-				int* sl = wslots + warp * 123;
-				score = replay_overflow(e, na, sl, sl + 41, sl + 82, lane);
-				for (int i = lane; i < SLOTS; i += 32) out[i] = make_ushort2((unsigned short)sl[i], (unsigned short)sl[41 + i]);
+				// More than 40 accepted hits.  Self hits (the read against its own copy in the index) are
+				// exactly collinear: off = c + 10 * seed.  Then every pair is DDF consistent, every
+				// insert_loc call sees minval == 40 and just overwrites slot 39, and the score never drops:
+				// slots 0..38 = first 39 hits, slot 39 = last hit, score = number of accepted hits.
+				bool col = true;
+				const unsigned long long k00 = e[0];
+				const int c0 = (int)(k00 & 2047u) - STRIDE * ((int)((k00 >> 11) & 0xFFFFu) + 1);
+				for (int i = lane; i < na; i += 32) {
+					const unsigned long long k = e[i];
+					col = col && ((int)(k & 2047u) - STRIDE * ((int)((k >> 11) & 0xFFFFu) + 1) == c0);
+				}
+				if (__all_sync(FULL, col)) {
+					for (int i = lane; i < na; i += 32) {
+						const unsigned long long k = e[i];
+						if (i < SLOTS - 1) out[i] = make_ushort2((unsigned short)(k & 2047u), (unsigned short)(((k >> 11) & 0xFFFFu) + 1));
+						if (i == na - 1) out[SLOTS - 1] = make_ushort2((unsigned short)(k & 2047u), (unsigned short)(((k >> 11) & 0xFFFFu) + 1));
+						e[i] = (k & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)(i + 1) << 48);
+					}
+					score = na;
+				} else {
+					int* sl = wslots + warp * 123;
+					score = replay_overflow(e, na, sl, sl + 41, sl + 82, lane);
+					for (int i = lane; i < SLOTS; i += 32) out[i] = make_ushort2((unsigned short)sl[i], (unsigned short)sl[41 + i]);
+				}
 			}
 			if (lane == 0) {
 				const unsigned long long k0 = e[0];
@@ -828,7 +869,7 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 	if (batch > N) batch = N;
 	unsigned long long arena_bytes = 1ull << 30;
 
-	const size_t smem = (size_t)(CNT_SLOTS / 2 + 2 * BIT_WORDS) * 4 + 64 * 4 + (size_t)(SEED_THREADS / 32) * 123 * 4;
+	const size_t smem = (size_t)(CNT_SLOTS / 2 + BIT_WORDS + KCACHE) * 4 + KCACHE + 64 * 4 + (size_t)(SEED_THREADS / 32) * 123 * 4;
 	MB_CUDA(c, cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
 	unsigned char* d_arena = nullptr;
