@@ -29,10 +29,10 @@ namespace mb {
 
 namespace {
 
-constexpr int EXT_WARPS = 4;
-constexpr int EXT_CTAS_PER_SM = 8;
-constexpr int KOFF = 512;                 // even, > max_d of the largest block (0.3 * (599 + 718) = 395)
-constexpr int VL_N = 256;                 // ring of diagonals per parity: the live band spans <= 2*216+4 diagonals
+constexpr int EXT_WARPS = 6;
+constexpr int EXT_CTAS_PER_SM = 5;        // 5 x 6 warps x 7.3 KB of per-warp state = 219 KB of shared memory per SM
+constexpr int KOFF = 404;                 // even, > max_d of the largest block (0.3 * (599 + 718) = 395)
+constexpr int VL_N = KOFF + 4;            // diagonals per parity
 constexpr int SEQ_WORDS = 48;             // 719 bases = 45 words (+1 funnel, +2 slack)
 constexpr uint32_t NO_ANCHOR = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -41,7 +41,7 @@ struct WarpSmem
 {
 	uint2 sq[SEQ_WORDS];      // .x = packed word i, .y = word i+1: any 16-base window is one LDS.64 + funnel shift
 	uint2 st[SEQ_WORDS];
-	uint2 vl[2][VL_N];        // per parity of k: .x = furthest x on the diagonal, .y = packed anchor
+	uint2 vl[2][VL_N];        // per parity of k, index (k + KOFF) >> 1: .x = furthest x, .y = packed anchor
 };
 
 struct Walk                   // one sequence seen as a forward walk
@@ -131,7 +131,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 					const uint32_t b0 = T.g0 + (uint32_t)ti + 16u * i;
 					S.st[i] = make_uint2(ld_bases32(T.arr, b0) ^ T.comp, ld_bases32(T.arr, b0 + 16u) ^ T.comp);
 				}
-				if (lane == 0) S.vl[1][((KOFF + 1) >> 1) & (VL_N - 1)] = make_uint2(0u, NO_ANCHOR);
+				if (lane == 0) S.vl[1][(KOFF + 1) >> 1] = make_uint2(0u, NO_ANCHOR);
 			}
 			__syncwarp();
 
@@ -141,56 +141,84 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			bool aligned = false;
 			int ex = 0, ey = 0;
 			uint32_t ea = NO_ANCHOR;
+			const uint2* sq = S.sq;
+			const uint2* st = S.st;
+			// one furthest-reaching cell: lane-local, reads the other-parity array, writes its own
+			auto cell = [&](const uint2* oth, uint2* own, int j, int n, int k, uint32_t dbits, int& x, uint32_t& anc) {
+				const uint2 lf = oth[j], rt = oth[j + 1];
+				if (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
+				else { x = (int)lf.x + 1; anc = lf.y; }
+				int y = x - k;
+				const int x1 = x;
+				while (x < qblk && y < tblk) {
+					const uint32_t diff = seq16(sq, x) ^ seq16(st, y);
+					const int m = __clz(__brev(diff)) >> 1;      // matching bases in this 16-base window
+					x += m; y += m;
+					if (m < 16) break;
+				}
+				const int over = max(max(x - qblk, y - tblk), 0);    // the window may run past a block end
+				x -= over; y -= over;
+				if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
+				own[j] = make_uint2((uint32_t)x, anc);
+				return x + y;
+			};
 			for (int d = 0; d < max_d; ++d) {
 				if (max_k - min_k > 2 * tol) break;
 				const int n = ((max_k - min_k) >> 1) + 1;
 				const int kk0 = min_k + KOFF;
-				uint2* own = S.vl[kk0 & 1];
-				const uint2* oth = S.vl[(kk0 & 1) ^ 1];
-				const int o0 = kk0 >> 1, l0 = (kk0 - 1) >> 1;    // own[o0 + j], neighbours oth[l0 + j] (k-1) and oth[l0 + j + 1] (k+1)
+				uint2* own = &S.vl[kk0 & 1][kk0 >> 1];                 // own[j]       <-> diagonal min_k + 2j
+				const uint2* oth = &S.vl[(kk0 & 1) ^ 1][(kk0 - 1) >> 1]; // oth[j], [j+1] <-> diagonals k-1, k+1
 				const uint32_t dbits = (uint32_t)d << 20;
-				int rowmax = -1;
-				int u0 = -1, u1 = -1;                            // x + y of passes 0 / 1 kept for the re-banding
-				for (int base = 0; base < n; base += 32) {
-					const int j = base + lane;
-					const bool act = j < n;
-					const int k = min_k + 2 * j;
-					int x = 0, u = -1;
-					uint32_t anc = NO_ANCHOR;
-					if (act) {
-						const uint2 lf = oth[(l0 + j) & (VL_N - 1)], rt = oth[(l0 + j + 1) & (VL_N - 1)];
-						if (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
-						else { x = (int)lf.x + 1; anc = lf.y; }
-						int y = x - k;
-						const int x1 = x;
-						while (x < qblk && y < tblk) {
-							const uint32_t diff = seq16(S.sq, x) ^ seq16(S.st, y);
-							int m = diff ? ((__ffs(diff) - 1) >> 1) : 16;
-							m = min(m, min(qblk - x, tblk - y));
-							x += m; y += m;
-							if (m < 16) break;
-						}
-						if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
-						own[(o0 + j) & (VL_N - 1)] = make_uint2((uint32_t)x, anc);
-						u = x + y;
-					}
-					const int pm = __reduce_max_sync(FULL, u);
-					rowmax = max(rowmax, pm);
-					if (base == 0) u0 = u; else if (base == 32) u1 = u;
-					if (pm >= endsum) {
-						const unsigned hm = __ballot_sync(FULL, act && (x >= qblk || x - k >= tblk));
-						if (hm) {
-							const int src = __ffs(hm) - 1;
-							ex = __shfl_sync(FULL, x, src);
-							ey = ex - __shfl_sync(FULL, k, src);
-							ea = __shfl_sync(FULL, anc, src);
-							aligned = true;
-							break;
-						}
+				// pass 0: diagonals 0..31 of the band (most rows have no other pass)
+				int x0 = 0, u0 = -1;
+				uint32_t a0 = NO_ANCHOR;
+				if (lane < n) u0 = cell(oth, own, lane, n, min_k + 2 * lane, dbits, x0, a0);
+				int rowmax = __reduce_max_sync(FULL, u0);
+				int x1 = 0, u1 = -1;
+				uint32_t a1 = NO_ANCHOR;
+				if (n > 32) {
+					if (lane + 32 < n) u1 = cell(oth, own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1);
+					rowmax = max(rowmax, __reduce_max_sync(FULL, u1));
+					for (int base = 64; base < n; base += 32) {
+						const int j = base + lane;
+						int xx = 0, uu = -1;
+						uint32_t aa = NO_ANCHOR;
+						if (j < n) uu = cell(oth, own, j, n, min_k + 2 * j, dbits, xx, aa);
+						rowmax = max(rowmax, __reduce_max_sync(FULL, uu));
 					}
 				}
 				__syncwarp();
-				if (aligned) break;
+				if (rowmax >= endsum) {
+					// some cell may have reached a block end: the lowest such diagonal ends the block
+					unsigned hm = __ballot_sync(FULL, u0 >= 0 && (x0 >= qblk || u0 - x0 >= tblk));
+					if (hm) {
+						const int src = __ffs(hm) - 1;
+						ex = __shfl_sync(FULL, x0, src); ey = __shfl_sync(FULL, u0, src) - ex; ea = __shfl_sync(FULL, a0, src);
+						aligned = true;
+					} else if (n > 32) {
+						hm = __ballot_sync(FULL, u1 >= 0 && (x1 >= qblk || u1 - x1 >= tblk));
+						if (hm) {
+							const int src = __ffs(hm) - 1;
+							ex = __shfl_sync(FULL, x1, src); ey = __shfl_sync(FULL, u1, src) - ex; ea = __shfl_sync(FULL, a1, src);
+							aligned = true;
+						}
+						for (int base = 64; base < n && !aligned; base += 32) {
+							const int j = base + lane;
+							uint2 c = make_uint2(0u, NO_ANCHOR);
+							bool h = false;
+							if (j < n) { c = own[j]; const int yy = (int)c.x - (min_k + 2 * j); h = (int)c.x >= qblk || yy >= tblk; }
+							hm = __ballot_sync(FULL, h);
+							if (hm) {
+								const int src = __ffs(hm) - 1;
+								ex = __shfl_sync(FULL, (int)c.x, src);
+								ey = ex - (min_k + 2 * (base + src));
+								ea = __shfl_sync(FULL, c.y, src);
+								aligned = true;
+							}
+						}
+					}
+					if (aligned) break;
+				}
 				best_m = max(best_m, rowmax);
 				// re-band to the diagonals within `tol` of the best, widened by one
 				const int thr = best_m - tol;
@@ -205,7 +233,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 					for (int base = 64; base < n; base += 32) {
 						const int j = base + lane;
 						bool keep = false;
-						if (j < n) keep = 2 * (int)own[(o0 + j) & (VL_N - 1)].x - (min_k + 2 * j) >= thr;
+						if (j < n) keep = 2 * (int)own[j].x - (min_k + 2 * j) >= thr;
 						const unsigned km2 = __ballot_sync(FULL, keep);
 						if (km2) { lo = min(lo, min_k + 2 * (base + __ffs(km2) - 1)); hi = max(hi, min_k + 2 * (base + 31 - __clz(km2))); }
 					}
@@ -217,15 +245,14 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				// best (x+y) cell: first k of the last completed row that reaches best_m
 				const int n = ((last_max - last_min) >> 1) + 1;
 				const int kk0 = last_min + KOFF;
-				const uint2* own = S.vl[kk0 & 1];
-				const int o0 = kk0 >> 1;
+				const uint2* own = &S.vl[kk0 & 1][kk0 >> 1];
 				for (int base = 0; base < n; base += 32) {
 					const int j = base + lane;
 					const int k = last_min + 2 * j;
 					uint2 c = make_uint2(0u, NO_ANCHOR);
 					bool is = false;
 					if (j < n) {
-						c = own[(o0 + j) & (VL_N - 1)];
+						c = own[j];
 						is = 2 * (int)c.x - k == best_m;
 					}
 					const unsigned bm = __ballot_sync(FULL, is);
