@@ -126,6 +126,10 @@ void mecat_b200_volume_unload(mecat_volume* v);
  * device once and re-laid out in both walking directions. */
 int mecat_b200_volume_upload(mecat_b200_ctx* ctx, const mecat_volume* v, void** dvol);
 int mecat_b200_volume_release(mecat_b200_ctx* ctx, void* dvol);
+/* Same, but the packed bytes are already in device memory (a query volume received from a peer
+ * GPU over NCCL in the block rotation): only the small offset table comes from the host. */
+int mecat_b200_volume_from_device(mecat_b200_ctx* ctx, int32_t num_reads, int32_t num_bases, int32_t start_read_id,
+                                  const int32_t* host_offset_size, const void* device_pac, void** dvol);
 
 /* ---- A1: k-mer index of an index volume ----------------------------------------------
  * replaces create_ref_index (src/common/lookup_table.cpp:64-160). */
@@ -143,6 +147,11 @@ int mecat_b200_index_export(mecat_b200_ctx* ctx, void* index, int64_t* num_kmers
  * reference's own order.  *records = mecat_candidate[] or mecat_m4[]. */
 int mecat_b200_pw_tile(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads,
                        const mecat_pw_params* p, void** records, size_t* n);
+
+/* Same for the query reads [read_begin, read_end) only (read_end < 0 = all): lets several GPUs
+ * share one tile (mirror-paired indices). */
+int mecat_b200_pw_tile_range(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads,
+                             const mecat_pw_params* p, int read_begin, int read_end, void** records, size_t* n);
 
 /* Same, with host buffers in and out (upload + index build + tile + download): the
  * end-to-end call a host driver makes per tile when nothing is cached. */

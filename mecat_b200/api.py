@@ -55,7 +55,7 @@ EXPORTS = [
     "mecat_b200_volume_upload",
     "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
-    "mecat_b200_extend_batch", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
+    "mecat_b200_extend_batch", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
 ]
 
 _lib = None
@@ -87,6 +87,8 @@ def load_library():
     L.mecat_b200_pw_overlaps.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_raw_candidates.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_extend_batch.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.mecat_b200_pw_tile_range.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_volume_from_device.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp, C.POINTER(vp)]
     L.mecat_b200_split_dataset.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.c_char_p, C.c_int]
     L.mecat_b200_volume_load.argtypes = [C.c_char_p, VP]
     L.mecat_b200_volume_unload.argtypes = [VP]
@@ -219,6 +221,21 @@ class Context:
         self._check(self.L.mecat_b200_pw_tile(self.h, index, dref, dreads, C.byref(params), C.byref(out), C.byref(n)),
                     "pw_tile")
         return self._take(out, n.value, EC_DTYPE if params.task == 0 else M4_DTYPE)
+
+    def pw_tile_range(self, index, dref, dreads, params, read_begin, read_end):
+        out, n = C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_pw_tile_range(self.h, index, dref, dreads, C.byref(params), read_begin, read_end,
+                                                    C.byref(out), C.byref(n)), "pw_tile_range")
+        return self._take(out, n.value, EC_DTYPE if params.task == 0 else M4_DTYPE)
+
+    def volume_from_device(self, num_reads, num_bases, start_read_id, host_offset_size, device_ptr):
+        """host_offset_size: int32 numpy [num_reads, 2]; device_ptr: address of the packed bytes in device memory."""
+        d = C.c_void_p()
+        osz = np.ascontiguousarray(host_offset_size, dtype=np.int32)
+        self._check(self.L.mecat_b200_volume_from_device(self.h, num_reads, num_bases, start_read_id,
+                                                         osz.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(device_ptr),
+                                                         C.byref(d)), "volume_from_device")
+        return d
 
     def pw_raw_candidates(self, index, dref, dreads, params, num_reads):
         """Test hook: (rows[n,12], counts[num_reads]) = the candidate_save lists of every read."""

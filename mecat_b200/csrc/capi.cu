@@ -254,8 +254,10 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
 // ------------------------------------------------------------------------------------------
 // One (index volume, query volume) tile.
 static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* reads, const mecat_pw_params* p,
-                        void** records, size_t* n, int32_t** raw_rows, int32_t** raw_counts)
+                        int read_begin, int read_end, void** records, size_t* n, int32_t** raw_rows, int32_t** raw_counts)
 {
+	if (read_begin < 0) read_begin = 0;
+	if (read_end < 0 || read_end > reads->num_reads) read_end = reads->num_reads;
 	if (p->num_candidates < 1) MB_FAIL(c, "pw_tile: number of candidates must be > 0");
 	if (p->tech != 0) MB_FAIL(c, "pw_tile: only -x 0 (pacbio, diff aligner) is on this path");
 	if (p->task != 0 && p->task != 1) MB_FAIL(c, "pw_tile: task (-j) must be 0 or 1, not %d", p->task);
@@ -276,7 +278,8 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 	auto body = [&]() -> int {
 		MB_CUDA(c, c->alloc(&d_cands, (size_t)((size_t)N * maxc)));
 		MB_CUDA(c, c->alloc(&d_counts, (size_t)((size_t)N)));
-		if (seed_candidates(c, idx, ref, reads, p, d_cands, d_counts)) return 1;
+		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)N, c->stream));
+		if (seed_candidates(c, idx, ref, reads, p, read_begin, read_end, d_cands, d_counts)) return 1;
 		MB_CUDA(c, cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
 		size_t total = 0;
@@ -436,9 +439,32 @@ int mecat_b200_pw_tile(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvo
 	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !records || !n) return 1;
 	cudaSetDevice(c->device);
 	WallTimer t;
-	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, records, n, nullptr, nullptr);
+	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, 0, -1, records, n, nullptr, nullptr);
 	c->stats.total_ms += t.stop();
 	return rc;
+}
+
+int mecat_b200_pw_tile_range(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvol_reads, const mecat_pw_params* p,
+                             int read_begin, int read_end, void** records, size_t* n)
+{
+	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !records || !n) return 1;
+	cudaSetDevice(c->device);
+	WallTimer t;
+	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, read_begin, read_end, records, n, nullptr, nullptr);
+	c->stats.total_ms += t.stop();
+	return rc;
+}
+
+int mecat_b200_volume_from_device(mecat_b200_ctx* c, int32_t num_reads, int32_t num_bases, int32_t start_read_id,
+                                  const int32_t* host_offset_size, const void* device_pac, void** dvol)
+{
+	if (check(c) || !dvol || !host_offset_size || !device_pac) return 1;
+	cudaSetDevice(c->device);
+	DVolume* d = nullptr;
+	int rc = volume_from_device(c, num_reads, num_bases, start_read_id, host_offset_size, (const uint8_t*)device_pac, &d);
+	if (rc) return rc;
+	*dvol = d;
+	return 0;
 }
 
 int mecat_b200_pw_raw_candidates(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvol_reads,
@@ -446,7 +472,7 @@ int mecat_b200_pw_raw_candidates(mecat_b200_ctx* c, void* index, void* dvol_ref,
 {
 	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !rows || !counts || !n) return 1;
 	cudaSetDevice(c->device);
-	return pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, nullptr, n, rows, counts);
+	return pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, 0, -1, nullptr, n, rows, counts);
 }
 
 static int pw_host(mecat_b200_ctx* c, const mecat_volume* ref, const mecat_volume* reads, const mecat_pw_params* p, int task,

@@ -174,7 +174,9 @@ struct RawCand             // candidate_save, pw_impl.h:21-25
 // Seeding + scoring + candidate selection for every read of `reads`; fills d_cands
 // (num_reads x maxc RawCand, the per-read list in reference order) and d_counts.
 int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume* reads,
-                    const mecat_pw_params* p, RawCand* d_cands, int32_t* d_counts);
+                    const mecat_pw_params* p, int read_begin, int read_end, RawCand* d_cands, int32_t* d_counts);
+int volume_from_device(Ctx* c, int num_reads, int num_bases, int start_read_id, const int32_t* h_offsz,
+                       const uint8_t* d_pac, DVolume** out);
 
 // ---- device helpers
 __device__ __forceinline__ uint32_t ld_bases32(const uint32_t* __restrict__ a, uint32_t base)

@@ -854,10 +854,11 @@ __global__ void k_merge(const RawCand* __restrict__ lists, const int32_t* __rest
 }  // namespace
 
 int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume* reads, const mecat_pw_params* p,
-                    RawCand* d_cands, int32_t* d_counts)
+                    int read_begin, int read_end, RawCand* d_cands, int32_t* d_counts)
 {
-	const int N = reads->num_reads;
-	if (N == 0) return 0;
+	// reads outside [read_begin, read_end) get no candidates (d_counts is cleared by the caller)
+	const int N = read_end;
+	if (read_end <= read_begin) return 0;
 	const int maxc = p->num_candidates;
 	const int max_nk = reads->max_read >= KMER ? (reads->max_read - KMER) / STRIDE + 1 : 1;
 	if (max_nk > MAX_KM) MB_FAIL(c, "seeding: reads longer than %d bp are outside this path (seed ordinals are 16-bit in the reference)", MAX_KM * STRIDE);
@@ -866,7 +867,7 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 	while (hcap < 16 * max_nk && hcap < (1 << 22)) hcap <<= 1;
 	const int nctas = c->sm_count;
 	int batch = 8192;
-	if (batch > N) batch = N;
+	if (batch > read_end - read_begin) batch = read_end - read_begin;
 	unsigned long long arena_bytes = 1ull << 30;
 
 	const size_t smem = (size_t)(CNT_SLOTS / 2 + BIT_WORDS + KCACHE) * 4 + KCACHE + 64 * 4 + (size_t)(SEED_THREADS / 32) * 123 * 4;
@@ -904,7 +905,7 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 		unsigned long long* d_hits = c->d_counters + 3;
 		MB_CUDA(c, cudaMemsetAsync(d_hits, 0, 8, c->stream));
 		h_desc.resize(2 * (size_t)batch);
-		for (int r0 = 0; r0 < N;) {
+		for (int r0 = read_begin; r0 < N;) {
 			const int nb = std::min(batch, N - r0);
 			MB_CUDA(c, cudaMemsetAsync(c->d_counters + 1, 0, 16, c->stream));   // cursor + work counter
 			SeedParams S;

@@ -314,6 +314,32 @@ def test_off_diagonal_tile_matches_oracle(gpu_ctx, small_vol):
             report("offdiag_m4", util.m4_lines(got, True), util.m4_lines(want, True))
 
 
+def test_tile_range_halves_equal_whole_tile(gpu_ctx, small_vol):
+    """mecat_b200_pw_tile_range: two GPUs splitting a query volume produce, concatenated, exactly the
+    whole-tile records (the multi-GPU schedule relies on it); also the device-resident constructor."""
+    import mecat_b200
+    import torch
+    hv = host_volume(small_vol)
+    d = gpu_ctx.upload(hv)
+    idx = gpu_ctx.index_build(d)
+    pac = torch.zeros((len(small_vol.pac) + 3) // 4 * 4, dtype=torch.uint8)
+    pac.numpy()[:len(small_vol.pac)] = small_vol.pac
+    pac_d = pac.cuda()
+    torch.cuda.synchronize()
+    d2 = gpu_ctx.volume_from_device(small_vol.num_reads, small_vol.num_bases, 0, small_vol.offset_size, pac_d.data_ptr())
+    n = small_vol.num_reads
+    for task in (0, 1):
+        p = mecat_b200.pw_params(task=task)
+        whole = gpu_ctx.pw_tile(idx, d, d, p)
+        a = gpu_ctx.pw_tile_range(idx, d, d2, p, 0, n // 2)
+        b = gpu_ctx.pw_tile_range(idx, d, d2, p, n // 2, n)
+        assert len(a) and len(b)
+        assert whole.tobytes() == a.tobytes() + b.tobytes()
+    gpu_ctx.release_volume(d2)
+    gpu_ctx.release_index(idx)
+    gpu_ctx.release_volume(d)
+
+
 def test_candidate_cap_and_order(gpu_ctx, small_vol):
     """-n 3: per read the first 3 candidates of the -n 100 list, in the same order."""
     import mecat_b200

@@ -1,7 +1,10 @@
 // tools/gen_reads.cpp -- TEST/BENCH TOOLING (synthetic PacBio-CLR-like reads).
 //
 //   gen_reads <out.fasta> <num_reads> <genome_len> <seed> [mean_len=15000] [sd_len=1500]
-//             [err=0.15] [genome_out.fasta]
+//             [err=0.15] [genome_out.fasta | -] [first_read=0]
+//
+// first_read: ordinal of the first read written (reads first_read .. first_read+num_reads-1 of the
+// same infinite, seed-defined read sequence), so several processes can each write their own slice.
 //
 // genome  : iid uniform ACGT of length G, base i = splitmix64(seed, i) & 3 (counter based).
 // read r  : own xoshiro256** stream seeded by (seed, r) so the output does not depend on
@@ -57,7 +60,8 @@ int main(int argc, char** argv)
 	const double mean = argc > 5 ? atof(argv[5]) : 15000.0;
 	const double sd = argc > 6 ? atof(argv[6]) : 1500.0;
 	const double err = argc > 7 ? atof(argv[7]) : 0.15;
-	const char* genome_out = argc > 8 ? argv[8] : NULL;
+	const char* genome_out = (argc > 8 && strcmp(argv[8], "-") != 0) ? argv[8] : NULL;
+	const long first_read = argc > 9 ? atol(argv[9]) : 0;
 	const double p_del = 0.30 * err, p_sub = 0.10 * err, p_ins = 0.60 * err;
 
 	std::vector<uint8_t> genome(G);
@@ -94,7 +98,7 @@ int main(int argc, char** argv)
 		for (int t = 0; t < nt; ++t)
 			th.emplace_back([&, t]() {
 				for (long j = t; j < cnt; j += nt) {
-					long r = base + j;
+					long r = first_read + base + j;
 					Rng rng(seed, (uint64_t)r + 1);
 					double u1 = rng.uni(), u2 = rng.uni();
 					if (u1 < 1e-300) u1 = 1e-300;
