@@ -10,9 +10,11 @@ second of wall time, whole job, on synthetic PacBio-CLR reads (15 kb, 15 % error
 A "step" is one pass of the hot path over the whole workload:
   N = 1   BASELINE configs[1]: all-vs-all on 100 000 x 15 kb reads (one 1.59 Gbase volume):
           k-mer index build + seeding/scoring of every read + extension of every candidate.
-  N > 1   N such volumes (N x 100 000 reads, genome N x 100 Mb, same 15x coverage), all
-          N(N+1)/2 (index volume, query volume) tiles; packed query volumes rotate round the
-          ring of ranks over NCCL/NVLink, rank g serves indices g and N-1-g (mecat_b200/multi.py).
+  N > 1   default (--mode strong): the SAME configs[1] tile shared by N GPUs: every rank builds one
+          slice of the k-mer index, slices are exchanged over NCCL, query reads are split N ways.
+          --mode ring: N such volumes (N x 100 000 reads, genome N x 100 Mb), all N(N+1)/2 tiles;
+          packed query volumes rotate round the ring of ranks over NCCL/NVLink, rank g serves
+          indices g and N-1-g (BASELINE configs[4] style; mecat_b200/multi.py).
 `value`  = records / step time with the packed volume(s) already resident in HBM.
 `e2e`    = the same through the host-buffer C-ABI call (mecat_b200_pw_overlaps): pinned host
            volume -> H2D -> index -> tile -> D2H records, all inside the timed region.
@@ -231,8 +233,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from mecat_b200 import multi
-        return multi.run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample,
-                               roofline_for)
+        fn = multi.run_bench if args.mode == "ring" else multi.run_bench_strong
+        return fn(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for)
     torch.cuda.set_device(local)
     d = tmp_root()
     nreads = args.reads or READS_PER_VOLUME
@@ -342,11 +344,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=0, help="debug only: reduced workload (result is not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="strong", choices=["strong", "ring"],
+                    help="N > 1 only. strong: N GPUs share the configs[1] tile (default). ring: N volumes, "
+                         "N(N+1)/2 tiles, query volumes rotate over NCCL (BASELINE configs[4] style)")
     args = ap.parse_args()
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version there) go to stderr.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

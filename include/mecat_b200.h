@@ -135,6 +135,16 @@ int mecat_b200_volume_from_device(mecat_b200_ctx* ctx, int32_t num_reads, int32_
  * replaces create_ref_index (src/common/lookup_table.cpp:64-160). */
 int mecat_b200_index_build(mecat_b200_ctx* ctx, void* dvol_ref, void** index);
 int mecat_b200_index_release(mecat_b200_ctx* ctx, void* index);
+/* The same build in two stages, for several GPUs that each own a slice [code_lo, code_hi) of the
+ * 2^26 k-mer codes (multiples of 256): count_part histograms the slice; the caller all-gathers the
+ * count slices (device array from index_device_arrays); finish_part scans all codes and fills /
+ * orders the positions of its slice, which the caller then broadcasts. */
+int mecat_b200_index_count_part(mecat_b200_ctx* ctx, void* dvol_ref, uint32_t code_lo, uint32_t code_hi, void** index);
+int mecat_b200_index_finish_part(mecat_b200_ctx* ctx, void* dvol_ref, void* index, uint32_t code_lo, uint32_t code_hi);
+/* device addresses of the index arrays: counts (2^26 uint32, only between the two stages, else NULL),
+ * begin (2^26+1 uint32), positions (*num_kmers int32) */
+int mecat_b200_index_device_arrays(mecat_b200_ctx* ctx, void* index, void** d_counts, void** d_begin, void** d_positions,
+                                   int64_t* num_kmers);
 /* test hook: number of kept k-mer starts and (optionally) the CSR arrays copied to the host:
  * begin = 2^26+1 uint32, positions = *num_kmers int32; either pointer may be NULL. */
 int mecat_b200_index_export(mecat_b200_ctx* ctx, void* index, int64_t* num_kmers, uint32_t* begin,

@@ -53,7 +53,8 @@ EXPORTS = [
     "mecat_b200_abi_version", "mecat_b200_device_count", "mecat_b200_init", "mecat_b200_destroy",
     "mecat_b200_last_error", "mecat_b200_free", "mecat_b200_get_stats", "mecat_b200_reset_stats",
     "mecat_b200_volume_upload",
-    "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_release", "mecat_b200_index_export",
+    "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_count_part", "mecat_b200_index_finish_part",
+    "mecat_b200_index_device_arrays", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
     "mecat_b200_extend_batch", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
 ]
@@ -81,6 +82,9 @@ def load_library():
     L.mecat_b200_volume_release.argtypes = [vp, vp]
     L.mecat_b200_index_build.argtypes = [vp, vp, C.POINTER(vp)]
     L.mecat_b200_index_release.argtypes = [vp, vp]
+    L.mecat_b200_index_count_part.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.mecat_b200_index_finish_part.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32]
+    L.mecat_b200_index_device_arrays.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
     L.mecat_b200_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
     L.mecat_b200_pw_tile.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_candidates.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -203,6 +207,21 @@ class Context:
         i = C.c_void_p()
         self._check(self.L.mecat_b200_index_build(self.h, dvol, C.byref(i)), "index_build")
         return i
+
+    def index_count_part(self, dvol, code_lo, code_hi):
+        i = C.c_void_p()
+        self._check(self.L.mecat_b200_index_count_part(self.h, dvol, code_lo, code_hi, C.byref(i)), "index_count_part")
+        return i
+
+    def index_finish_part(self, dvol, index, code_lo, code_hi):
+        self._check(self.L.mecat_b200_index_finish_part(self.h, dvol, index, code_lo, code_hi), "index_finish_part")
+
+    def index_device_arrays(self, index):
+        """(counts_ptr, begin_ptr, positions_ptr, num_kmers): raw device addresses (for NCCL exchanges)."""
+        a, b, p, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._check(self.L.mecat_b200_index_device_arrays(self.h, index, C.byref(a), C.byref(b), C.byref(p), C.byref(n)),
+                    "index_device_arrays")
+        return a.value, b.value, p.value, n.value
 
     def release_index(self, i):
         self.L.mecat_b200_index_release(self.h, i)

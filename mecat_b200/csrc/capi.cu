@@ -183,6 +183,36 @@ int mecat_b200_index_build(mecat_b200_ctx* c, void* dvol_ref, void** index)
 	return 0;
 }
 
+int mecat_b200_index_count_part(mecat_b200_ctx* c, void* dvol_ref, uint32_t code_lo, uint32_t code_hi, void** index)
+{
+	if (check(c) || !dvol_ref || !index) return 1;
+	cudaSetDevice(c->device);
+	DIndex* idx = nullptr;
+	int rc = index_count_part(c, (DVolume*)dvol_ref, code_lo, code_hi, &idx);
+	if (rc) return rc;
+	*index = idx;
+	return 0;
+}
+
+int mecat_b200_index_finish_part(mecat_b200_ctx* c, void* dvol_ref, void* index, uint32_t code_lo, uint32_t code_hi)
+{
+	if (check(c) || !dvol_ref || !index) return 1;
+	cudaSetDevice(c->device);
+	return index_finish_part(c, (DVolume*)dvol_ref, (DIndex*)index, code_lo, code_hi);
+}
+
+int mecat_b200_index_device_arrays(mecat_b200_ctx* c, void* index, void** d_counts, void** d_begin, void** d_positions,
+                                   int64_t* num_kmers)
+{
+	if (check(c) || !index) return 1;
+	DIndex* I = (DIndex*)index;
+	if (d_counts) *d_counts = I->counts;
+	if (d_begin) *d_begin = I->begin;
+	if (d_positions) *d_positions = I->pos;
+	if (num_kmers) *num_kmers = I->num_kmers;
+	return 0;
+}
+
 int mecat_b200_index_release(mecat_b200_ctx* c, void* index)
 {
 	if (check(c)) return 1;

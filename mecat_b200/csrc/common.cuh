@@ -41,6 +41,7 @@ struct DIndex
 {
 	uint32_t* begin = nullptr;      // NCODES + 1 (CSR over kept k-mers)
 	int32_t* pos = nullptr;         // kept k-mer start positions, ascending inside a list
+	uint32_t* counts = nullptr;     // histogram / fill cursors; only alive between the two build stages
 	int64_t num_kmers = 0;
 };
 
@@ -154,6 +155,8 @@ struct KScope
 int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out);
 void volume_release(Ctx* c, DVolume* v);
 int index_build(Ctx* c, const DVolume* v, DIndex** out);
+int index_count_part(Ctx* c, const DVolume* v, uint32_t code_lo, uint32_t code_hi, DIndex** out);
+int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uint32_t code_hi);
 void index_release(Ctx* c, DIndex* i);
 
 struct ExtendTask          // device-side extension request (global array)

@@ -23,18 +23,26 @@ __device__ __forceinline__ uint32_t kmer_code_at(const uint32_t* __restrict__ fw
 	return rev_groups2(ld_bases32(fwd, p)) >> 6;
 }
 
+// [code_lo, code_hi): the slice of the code space this launch (this GPU) is responsible for
 __global__ void k_kmer_count(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
-                             uint32_t* __restrict__ counts)
+                             uint32_t* __restrict__ counts, uint32_t code_lo, uint32_t code_hi)
 {
 	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
 		const int2 o = offsz[r];
 		const int nk = o.y - (KMER - 1);
-		for (int i = threadIdx.x; i < nk; i += blockDim.x) atomicAdd(&counts[kmer_code_at(fwd, (uint32_t)(o.x + i))], 1u);
+		for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+			const uint32_t code = kmer_code_at(fwd, (uint32_t)(o.x + i));
+			if (code - code_lo < code_hi - code_lo) atomicAdd(&counts[code], 1u);
+		}
 	}
 }
 
+// cursor[code] starts at begin[code] for kept k-mers and at DROPPED for the others, so one atomic
+// both tests the >128 cutoff and yields the slot.
+constexpr uint32_t DROPPED = 0x80000000u;
+
 __global__ void k_kmer_fill(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
-                            const uint32_t* __restrict__ begin, uint32_t* __restrict__ cursor, int32_t* __restrict__ pos)
+                            uint32_t* __restrict__ cursor, int32_t* __restrict__ pos, uint32_t code_lo, uint32_t code_hi)
 {
 	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
 		const int2 o = offsz[r];
@@ -42,8 +50,9 @@ __global__ void k_kmer_fill(const uint32_t* __restrict__ fwd, const int2* __rest
 		for (int i = threadIdx.x; i < nk; i += blockDim.x) {
 			const uint32_t p = (uint32_t)(o.x + i);
 			const uint32_t code = kmer_code_at(fwd, p);
-			const uint32_t b = begin[code];
-			if (begin[code + 1] != b) pos[b + atomicAdd(&cursor[code], 1u)] = (int32_t)p;
+			if (code - code_lo >= code_hi - code_lo) continue;
+			const uint32_t slot = atomicAdd(&cursor[code], 1u);
+			if (!(slot & DROPPED)) pos[slot] = (int32_t)p;
 		}
 	}
 }
@@ -90,14 +99,15 @@ __global__ void __launch_bounds__(1024) k_scan_top(uint32_t* __restrict__ tile_s
 	if (threadIdx.x == 1023) *total = part[1023];
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_scan_down(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ tile_sum,
+// writes begin[] and turns counts[] into the fill cursors
+__global__ void __launch_bounds__(SCAN_T) k_scan_down(uint32_t* __restrict__ counts, const uint32_t* __restrict__ tile_sum,
                                                        uint32_t* __restrict__ begin)
 {
 	// thread t owns SCAN_E consecutive codes so that the running sum stays in registers
 	__shared__ uint32_t wsum[SCAN_T / 32];
 	const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_E;
 	uint32_t v[SCAN_E];
-	const uint4* src = reinterpret_cast<const uint4*>(counts + base);
+	uint4* src = reinterpret_cast<uint4*>(counts + base);
 #pragma unroll
 	for (int e = 0; e < SCAN_E / 4; ++e) {
 		uint4 q = src[e];
@@ -125,6 +135,10 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_down(const uint32_t* __restrict
 	uint4* dst = reinterpret_cast<uint4*>(begin + base);
 #pragma unroll
 	for (int e = 0; e < SCAN_E / 4; ++e) dst[e] = make_uint4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+#pragma unroll
+	for (int e = 0; e < SCAN_E; ++e) if (v[e] == 0) o[e] = DROPPED;    // empty or over the cutoff: nothing is stored
+#pragma unroll
+	for (int e = 0; e < SCAN_E / 4; ++e) src[e] = make_uint4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
 }
 
 // ---- per-list ascending sort: one warp per k-mer list, R registers per lane (list <= 32*R)
@@ -168,10 +182,11 @@ __device__ __forceinline__ void warp_sort_list(int32_t* __restrict__ p, int n, i
 
 constexpr int SORT_WARPS = 8, SORT_CODES_PER_WARP = 32;
 
-__global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_lists(const uint32_t* __restrict__ begin, int32_t* __restrict__ pos)
+__global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_lists(const uint32_t* __restrict__ begin, int32_t* __restrict__ pos,
+                                                                 uint32_t code_lo)
 {
 	const int lane = threadIdx.x & 31;
-	const uint32_t c0 = ((uint32_t)blockIdx.x * SORT_WARPS + (threadIdx.x >> 5)) * SORT_CODES_PER_WARP;
+	const uint32_t c0 = code_lo + ((uint32_t)blockIdx.x * SORT_WARPS + (threadIdx.x >> 5)) * SORT_CODES_PER_WARP;
 	const uint32_t b_lane = begin[c0 + lane];
 	const uint32_t b_next = begin[c0 + lane + 1];
 	for (int i = 0; i < SORT_CODES_PER_WARP; ++i) {
@@ -186,29 +201,49 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_lists(const uint32_t* 
 
 }  // namespace
 
-int index_build(Ctx* c, const DVolume* v, DIndex** out)
+static int grid_for_reads(const DVolume* v) { return v->num_reads < 1 ? 1 : (v->num_reads > 65535 * 8 ? 65535 * 8 : v->num_reads); }
+
+// Stage 1: histogram of the k-mers whose code lies in [code_lo, code_hi) (all codes for one GPU).
+int index_count_part(Ctx* c, const DVolume* v, uint32_t code_lo, uint32_t code_hi, DIndex** out)
 {
+	if (code_lo > code_hi || code_hi > NCODES || (code_lo % (SORT_WARPS * SORT_CODES_PER_WARP)) || (code_hi % (SORT_WARPS * SORT_CODES_PER_WARP)))
+		MB_FAIL(c, "index: code range must be aligned to %d", SORT_WARPS * SORT_CODES_PER_WARP);
 	DIndex* I = new DIndex;
-	uint32_t* d_counts = nullptr;
+	auto body = [&]() -> int {
+		MB_CUDA(c, c->alloc(&I->counts, (size_t)NCODES));
+		MB_CUDA(c, c->alloc(&I->begin, (size_t)NCODES + 4));
+		MB_CUDA(c, cudaMemsetAsync(I->counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
+		if (v->num_reads > 0 && code_hi > code_lo) {
+			KScope ks(c, MECAT_K_COUNT);
+			k_kmer_count<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->counts, code_lo, code_hi);
+		}
+		MB_CUDA(c, cudaGetLastError());
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->resolve_timers();
+		return 0;
+	};
+	int rc = body();
+	if (rc) { index_release(c, I); return rc; }
+	*out = I;
+	return 0;
+}
+
+// Stage 2 (after the counts of all code slices are in place): cutoff + scan over all codes, then
+// positions and per-list order for [code_lo, code_hi).
+int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uint32_t code_hi)
+{
 	uint32_t* d_tiles = nullptr;
 	uint32_t* d_total = nullptr;
 	const int ntiles = (int)(NCODES / SCAN_TILE);
 	auto body = [&]() -> int {
-		MB_CUDA(c, c->alloc(&d_counts, (size_t)NCODES));
-		MB_CUDA(c, c->alloc(&I->begin, (size_t)NCODES + 4));
+		if (!I->counts) MB_FAIL(c, "index: finish called twice");
 		MB_CUDA(c, c->alloc(&d_tiles, (size_t)ntiles));
 		MB_CUDA(c, c->alloc(&d_total, 1));
-		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
-		const int grid_reads = v->num_reads < 1 ? 1 : (v->num_reads > 65535 * 8 ? 65535 * 8 : v->num_reads);
-		if (v->num_reads > 0) {
-			KScope ks(c, MECAT_K_COUNT);
-			k_kmer_count<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, d_counts);
-		}
 		{
 			KScope ks(c, MECAT_K_SCAN, 3);
-			k_scan_reduce<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles);
+			k_scan_reduce<<<ntiles, SCAN_T, 0, c->stream>>>(I->counts, d_tiles);
 			k_scan_top<<<1, 1024, 0, c->stream>>>(d_tiles, ntiles, d_total);
-			k_scan_down<<<ntiles, SCAN_T, 0, c->stream>>>(d_counts, d_tiles, I->begin);
+			k_scan_down<<<ntiles, SCAN_T, 0, c->stream>>>(I->counts, d_tiles, I->begin);
 		}
 		MB_CUDA(c, cudaGetLastError());
 		uint32_t total = 0;
@@ -217,15 +252,14 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 		MB_CUDA(c, cudaMemcpyAsync(I->begin + NCODES, &total, sizeof total, cudaMemcpyHostToDevice, c->stream));
 		I->num_kmers = total;
 		MB_CUDA(c, c->alloc(&I->pos, (size_t)total + 1));
-		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
-		if (total) {
+		if (total && code_hi > code_lo) {
 			{
 				KScope ks(c, MECAT_K_FILL);
-				k_kmer_fill<<<grid_reads, 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->begin, d_counts, I->pos);
+				k_kmer_fill<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->counts, I->pos, code_lo, code_hi);
 			}
 			{
 				KScope ks(c, MECAT_K_SORT);
-				k_sort_lists<<<NCODES / (SORT_WARPS * SORT_CODES_PER_WARP), SORT_WARPS * 32, 0, c->stream>>>(I->begin, I->pos);
+				k_sort_lists<<<(code_hi - code_lo) / (SORT_WARPS * SORT_CODES_PER_WARP), SORT_WARPS * 32, 0, c->stream>>>(I->begin, I->pos, code_lo);
 			}
 			MB_CUDA(c, cudaGetLastError());
 		}
@@ -236,7 +270,16 @@ int index_build(Ctx* c, const DVolume* v, DIndex** out)
 		return 0;
 	};
 	int rc = body();
-	c->dfree(d_counts); c->dfree(d_tiles); c->dfree(d_total);
+	c->dfree(d_tiles); c->dfree(d_total);
+	c->dfree(I->counts); I->counts = nullptr;
+	return rc;
+}
+
+int index_build(Ctx* c, const DVolume* v, DIndex** out)
+{
+	DIndex* I = nullptr;
+	int rc = index_count_part(c, v, 0, NCODES, &I);
+	if (!rc) rc = index_finish_part(c, v, I, 0, NCODES);
 	if (rc) { index_release(c, I); return rc; }
 	*out = I;
 	return 0;
@@ -247,6 +290,7 @@ void index_release(Ctx* c, DIndex* i)
 	if (!i) return;
 	c->dfree(i->begin);
 	c->dfree(i->pos);
+	c->dfree(i->counts);
 	delete i;
 }
 

@@ -70,7 +70,162 @@ def run_ring(world, rank, own_block, buf_a, buf_b, exchange, compute):
                 spare = other
 
 
-# ------------------------------------------------------------------------------------------ benchmark
+def code_slices(world):
+    """Equal slices of the 2^26 k-mer codes, aligned to 256 codes (the index kernels' granularity)."""
+    n = 1 << 26
+    cuts = [((n * r // world) // 256) * 256 for r in range(world)] + [n]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def read_slices(world, num_reads):
+    return [(num_reads * r // world, num_reads * (r + 1) // world) for r in range(world)]
+
+
+class _DevMem:
+    """Raw device memory as a __cuda_array_interface__ object (zero-copy torch view of library memory)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, count, torch_dtype, itemsize):
+    import torch
+    return torch.as_tensor(_DevMem(ptr, count * itemsize), device="cuda").view(torch_dtype)
+
+
+# ------------------------------------------------------------------------------------------ benchmark (strong scaling)
+def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for):
+    """N GPUs share ONE tile (BASELINE configs[1]): every rank holds the packed volume, builds the
+    slice [code_lo, code_hi) of the k-mer index, the slices are exchanged over NCCL (all-gather of the
+    histogram, broadcast of every position slice), and rank r seeds / extends reads r*n/N..(r+1)*n/N."""
+    import torch
+    import torch.distributed as dist
+    import mecat_b200
+
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    def log(*a):
+        print("[bench r%d]" % rank, *a, file=sys.stderr, flush=True)
+
+    READS, GENOME, SEED = 100000, 100000000, 11
+    if args.reads:
+        READS = args.reads; GENOME = args.reads * 1000
+    d = tmp_root()
+    fa = os.path.join(d, "reads_%d_%d.fa" % (READS, SEED))
+    wrk = os.path.join(d, "wrk_%d" % READS)
+    if rank == 0:
+        make_reads(fa, READS, GENOME, SEED)
+        mecat_b200.split_dataset(fa, wrk)
+    dist.barrier()
+    vol = mecat_b200.HostVolume.load(os.path.join(wrk, "vol0"))
+    pac = torch.empty(len(vol.pac), dtype=torch.uint8, pin_memory=True)
+    pac.numpy()[:] = vol.pac
+    osz = torch.from_numpy(vol.offset_size.reshape(-1).copy()).pin_memory()
+    hv = mecat_b200.HostVolume(osz.numpy().reshape(-1, 2), pac.numpy(), vol.num_bases, 0)
+    hv._keep = (pac, osz)
+    params = mecat_b200.pw_params(task=1)
+    ctx = mecat_b200.Context(local)
+    lo, hi = code_slices(world)[rank]
+    rb, re = read_slices(world, vol.num_reads)[rank]
+    cuts = torch.tensor([c[0] for c in code_slices(world)] + [1 << 26], dtype=torch.int64, device=dev)
+    resident = [None]
+
+    def one_step(e2e):
+        if e2e or resident[0] is None:
+            if resident[0] is not None:
+                ctx.release_volume(resident[0])
+            resident[0] = ctx.upload(hv)
+        dvol = resident[0]
+        idx = ctx.index_count_part(dvol, lo, hi)
+        cptr, bptr, _, _ = ctx.index_device_arrays(idx)
+        counts = device_view(cptr, 1 << 26, torch.int32, 4)
+        if world > 1:
+            parts = [counts[a:b] for a, b in code_slices(world)]
+            if len({p.numel() for p in parts}) == 1:
+                dist.all_gather_into_tensor(counts, parts[rank].clone())
+            else:
+                for q in range(world):
+                    dist.broadcast(parts[q], src=q)
+            torch.cuda.synchronize()
+        ctx.index_finish_part(dvol, idx, lo, hi)
+        if world > 1:
+            _, bptr, pptr, nk = ctx.index_device_arrays(idx)
+            begin = device_view(bptr, (1 << 26) + 1, torch.int32, 4)
+            bounds = begin[cuts].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            pos = device_view(pptr, nk, torch.int32, 4)
+            reqs = [dist.broadcast(pos[int(bounds[q]):int(bounds[q + 1])], src=q, async_op=True) for q in range(world)
+                    if bounds[q + 1] > bounds[q]]
+            for r in reqs:
+                r.wait()
+            torch.cuda.synchronize()
+        rec = ctx.pw_tile_range(idx, dvol, dvol, params, rb, re)
+        ctx.release_index(idx)
+        return len(rec)
+
+    def timed(nsteps, e2e):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(nsteps):
+            n += one_step(e2e)
+        torch.cuda.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return int(c.item()), float(t.item())
+
+    for i in range(args.warmup):
+        n, dt = timed(1, False)
+        if rank == 0:
+            log("warmup %d: %d pairs in %.3f s" % (i, n, dt))
+    ctx.reset_stats()
+    sampler = ClockSampler(local) if rank == 0 else None
+    pairs, dt = timed(args.steps, False)
+    stats = ctx.stats()
+    clocks = sampler.stop() if sampler else None
+    esteps = max(1, min(args.steps, 3))
+    ctx.reset_stats()
+    epairs, edt = timed(esteps, True)
+    estats = ctx.stats()
+    io = torch.tensor([estats["h2d_bytes"], estats["d2h_bytes"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        cfg = workload_config(1)
+        cfg["parallelism"] = ("%d gpus sharing one tile: k-mer index built in %d code slices exchanged over NCCL "
+                              "(all-gather + broadcasts), query reads split %d ways" % (world, world, world))
+        if args.reads:
+            cfg = dict(cfg, reads=READS, genome=GENOME, workload="REDUCED debug workload (%d reads)" % READS)
+        line = {
+            "metric": METRIC, "value": pairs / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()) // esteps,
+                    "d2h_bytes_per_step": int(io[1].item()) // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
+            "gpu_launches": stats["gpu_launches"] * world,
+            "roofline": roofline_for(stats, peaks),
+            "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                             "sample": "measured at N=1 only (bench.py --gpus 1)"},
+            "pairs_per_step": pairs // args.steps,
+            "kernel_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
+        }
+        print(json.dumps(line))
+    if resident[0] is not None:
+        ctx.release_volume(resident[0])
+    ctx.close()
+    dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ benchmark (block rotation)
 def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for):
     import torch
     import torch.distributed as dist

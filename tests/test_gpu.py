@@ -87,6 +87,43 @@ def test_index_matches_oracle(gpu_ctx, small_vol):
     O.orc_index_free(oidx)
 
 
+def test_index_built_in_code_slices_equals_one_shot(gpu_ctx, small_vol):
+    """The two-stage, sliced build used by N GPUs sharing a tile (count_part / exchange / finish_part),
+    replayed on one GPU for 2 and 3 slices, gives the same CSR arrays as index_build."""
+    import torch
+    from mecat_b200 import multi
+    d = gpu_ctx.upload(host_volume(small_vol))
+    ref = gpu_ctx.index_build(d)
+    rbegin, rpos = gpu_ctx.index_export(ref)
+    gpu_ctx.release_index(ref)
+    NC = 1 << 26
+    for world in (2, 3):
+        sl = multi.code_slices(world)
+        parts = [gpu_ctx.index_count_part(d, lo, hi) for lo, hi in sl]
+        views = [multi.device_view(gpu_ctx.index_device_arrays(p)[0], NC, torch.int32, 4) for p in parts]
+        for q, (lo, hi) in enumerate(sl):           # "all-gather" of the histogram slices
+            for r in range(world):
+                if r != q:
+                    views[r][lo:hi].copy_(views[q][lo:hi])
+        torch.cuda.synchronize()
+        for p, (lo, hi) in zip(parts, sl):
+            gpu_ctx.index_finish_part(d, p, lo, hi)
+        arrs = [gpu_ctx.index_device_arrays(p) for p in parts]
+        begin0 = multi.device_view(arrs[0][1], NC + 1, torch.int32, 4)
+        pos = [multi.device_view(a[2], a[3], torch.int32, 4) for a in arrs]
+        for q, (lo, hi) in enumerate(sl):           # "broadcast" of every position slice
+            b0, b1 = int(begin0[lo].item()) & 0xFFFFFFFF, int(begin0[hi].item()) & 0xFFFFFFFF
+            for r in range(world):
+                if r != q:
+                    pos[r][b0:b1].copy_(pos[q][b0:b1])
+        torch.cuda.synchronize()
+        for p in parts:
+            b, ps = gpu_ctx.index_export(p)
+            assert (b == rbegin).all() and len(ps) == len(rpos) and (ps == rpos).all()
+            gpu_ctx.release_index(p)
+    gpu_ctx.release_volume(d)
+
+
 # ---------------------------------------------------------------- A8-A11
 def oracle_extend(vq, vs, tasks, min_aln):
     O = util.oracle()
@@ -338,6 +375,39 @@ def test_tile_range_halves_equal_whole_tile(gpu_ctx, small_vol):
     gpu_ctx.release_volume(d2)
     gpu_ctx.release_index(idx)
     gpu_ctx.release_volume(d)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_gpu_schedule_reproduces_every_tile(gpu_ctx, small_vol, world):
+    """The N-rank schedule (mecat_b200/multi.py) replayed rank by rank on one GPU: the union of all
+    ranks' records equals the oracle's records of every (index volume, query volume) tile."""
+    import mecat_b200
+    from mecat_b200 import multi
+    seqs = [bytes(b"ACGT"[c] for c in small_vol.codes(i)) for i in range(small_vol.num_reads)]
+    n = small_vol.num_reads
+    cuts = [n * i // world for i in range(world + 1)]
+    vols = [PackedVolume.from_seqs(seqs[cuts[i]:cuts[i + 1]], cuts[i]) for i in range(world)]
+    dv = [gpu_ctx.upload(host_volume(v)) for v in vols]
+    idx = [gpu_ctx.index_build(d) for d in dv]
+    reads = [v.num_reads for v in vols]
+    for task in (0, 1):
+        p = mecat_b200.pw_params(task=task)
+        got = {}
+        for rank in range(world):
+            for step in range(world):
+                for s, v, rb, re in multi.tile_work(world, rank, step, reads):
+                    rec = gpu_ctx.pw_tile_range(idx[s], dv[s], dv[v], p, rb, re)
+                    got.setdefault((s, v), []).append((rb, rec))
+        for s in range(world):
+            for v in range(s, world):
+                want = util.oracle_pw_tile(vols[s], vols[v], util.pw_params(task=task), threads=4)
+                parts = [r for _, r in sorted(got[(s, v)], key=lambda x: x[0])]
+                mine = np.concatenate(parts) if parts else want[:0]
+                assert mine.tobytes() == want.tobytes(), (task, s, v, len(mine), len(want))
+    for i in idx:
+        gpu_ctx.release_index(i)
+    for d in dv:
+        gpu_ctx.release_volume(d)
 
 
 def test_candidate_cap_and_order(gpu_ctx, small_vol):
