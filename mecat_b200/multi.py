@@ -77,8 +77,22 @@ def code_slices(world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def read_slices(world, num_reads):
-    return [(num_reads * r // world, num_reads * (r + 1) // world) for r in range(world)]
+def read_slices(world, num_reads, diagonal=True, seed_w=185.0, extend_w=454.0):
+    """Split points of a tile's query reads.  In a diagonal tile (query volume == index volume) read q
+    can only pair with reads <= q (pw_impl.cpp:370), so extension work grows linearly with the read
+    ordinal while seeding work is flat: cost(x) = seed_w * x + extend_w * x^2 for the first fraction x
+    of the reads (weights = measured kernel milliseconds of the two phases on configs[1]).  Off
+    diagonal tiles are uniform."""
+    if not diagonal or world == 1:
+        return [(num_reads * r // world, num_reads * (r + 1) // world) for r in range(world)]
+    a, b = seed_w, extend_w
+    cuts = []
+    for r in range(world + 1):
+        t = (a + b) * r / world
+        x = (-a + (a * a + 4.0 * b * t) ** 0.5) / (2.0 * b)
+        cuts.append(min(num_reads, int(round(x * num_reads))))
+    cuts[0], cuts[-1] = 0, num_reads
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
 class _DevMem:

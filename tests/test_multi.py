@@ -103,3 +103,15 @@ def test_ring_rotation_over_gloo(world):
                 tiles.add((s, v, rb, re))
     pairs = {(s, v) for s, v, _, _ in tiles}
     assert pairs == {(s, v) for s in range(world) for v in range(s, world)}
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_read_and_code_slices_partition(world):
+    n = 100003
+    for diag in (True, False):
+        sl = multi.read_slices(world, n, diagonal=diag)
+        assert sl[0][0] == 0 and sl[-1][1] == n and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+        assert all(b > a for a, b in sl)
+    cs = multi.code_slices(world)
+    assert cs[0][0] == 0 and cs[-1][1] == 1 << 26 and all(a[1] == b[0] for a, b in zip(cs, cs[1:]))
+    assert all(lo % 256 == 0 and hi % 256 == 0 for lo, hi in cs)
