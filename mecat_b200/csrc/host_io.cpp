@@ -42,18 +42,22 @@ struct VolumeBuilder
 	std::vector<uint8_t> pac;
 	int64_t curr = 0;
 	int num_reads = 0;
-	void clear() { offsz.clear(); pac.clear(); curr = 0; num_reads = 0; }
+	void clear() { offsz.clear(); pac.assign(pac.size(), 0); curr = 0; num_reads = 0; }
 	void add(const std::string& s)
 	{
 		offsz.push_back((int32_t)curr);
 		offsz.push_back((int32_t)s.size());
 		const size_t need = (size_t)((curr + (int64_t)s.size() + 1 + 3) / 4) + 1;
-		if (pac.size() < need) pac.resize(need, 0);
-		for (size_t i = 0; i < s.size(); ++i, ++curr) {
-			const uint8_t c = kEnc.t[(unsigned char)s[i]];
-			// same OR as PackedDB::set_char: codes > 3 spill into neighbours exactly like the reference
-			pac[curr >> 2] |= (uint8_t)(c << (((~curr) & 3) << 1));
+		if (pac.size() < need) pac.resize(need + need / 2, 0);
+		const unsigned char* p = (const unsigned char*)s.data();
+		size_t n = s.size(), i = 0;
+		// same OR as PackedDB::set_char: codes > 3 spill into neighbours exactly like the reference
+		for (; i < n && (curr & 3); ++i, ++curr) pac[curr >> 2] |= (uint8_t)(kEnc.t[p[i]] << (((~curr) & 3) << 1));
+		for (; i + 4 <= n; i += 4, curr += 4) {
+			const unsigned a = kEnc.t[p[i]], b = kEnc.t[p[i + 1]], c = kEnc.t[p[i + 2]], d = kEnc.t[p[i + 3]];
+			pac[curr >> 2] |= (uint8_t)((a << 6) | (b << 4) | (c << 2) | d);
 		}
+		for (; i < n; ++i, ++curr) pac[curr >> 2] |= (uint8_t)(kEnc.t[p[i]] << (((~curr) & 3) << 1));
 		++curr;   // pad base, split_database.cpp:251
 		++num_reads;
 	}
@@ -72,45 +76,82 @@ struct VolumeBuilder
 
 // Line reader with the reference's record rules: '>' or '@' starts a record, '+' ends it and
 // swallows one quality line, '#'/'!' lines are comments, data lines stop at ';'.
+// Block-buffered: lines are returned as (pointer, length) views into a 16 MB window.
 struct FastaStream
 {
 	FILE* f;
 	std::vector<char> buf;
-	std::string pending;
-	bool have_pending = false;
-	explicit FastaStream(const char* path) : f(fopen(path, "rb")), buf(8u << 20) { if (f) setvbuf(f, buf.data(), _IOFBF, buf.size()); }
+	size_t beg = 0, end = 0;
+	bool eof = false;
+	std::string carry;          // a line that straddles two windows
+	const char* held = NULL;    // one line of push-back
+	size_t held_n = 0;
+	explicit FastaStream(const char* path) : f(fopen(path, "rb")), buf(16u << 20) {}
 	~FastaStream() { if (f) fclose(f); }
-	bool line(std::string& out)
+	bool fill()
 	{
-		if (have_pending) { out.swap(pending); have_pending = false; return true; }
-		out.clear();
-		int c;
-		bool any = false;
-		while ((c = getc_unlocked(f)) != EOF) {
-			any = true;
-			if (c == '\n') return true;
-			if (c == '\r') { int d = getc_unlocked(f); if (d != '\n' && d != EOF) ungetc(d, f); return true; }
-			out.push_back((char)c);
-		}
-		return any;
+		if (eof) return false;
+		beg = 0;
+		end = fread(buf.data(), 1, buf.size(), f);
+		if (end == 0) { eof = true; return false; }
+		return true;
 	}
-	void unget(std::string& l) { pending.swap(l); have_pending = true; }
+	// next line without its terminator ('\n', '\r\n' or '\r'); false at end of input
+	bool line(const char*& p, size_t& n)
+	{
+		if (held) { p = held; n = held_n; held = NULL; return true; }
+		carry.clear();
+		bool any = false;
+		for (;;) {
+			if (beg == end && !fill()) {
+				if (!any) return false;
+				p = carry.data(); n = carry.size();
+				return true;
+			}
+			any = true;
+			const char* s = buf.data() + beg;
+			size_t len = end - beg, i;
+			{
+				const char* nl = (const char*)memchr(s, '\n', len);
+				i = nl ? (size_t)(nl - s) : len;
+				const char* cr = (const char*)memchr(s, '\r', i);   // a lone '\r' also ends a line
+				if (cr) i = (size_t)(cr - s);
+			}
+			if (i < len) {
+				const bool cr = s[i] == '\r';
+				if (carry.empty()) { p = s; n = i; }
+				else { carry.append(s, i); p = carry.data(); n = carry.size(); }
+				beg += i + 1;
+				if (cr) {                                  // swallow the '\n' of a '\r\n' pair
+					if (beg == end) { std::string keep(p, n); fill(); carry.swap(keep); p = carry.data(); n = carry.size(); }
+					if (beg < end && buf[beg] == '\n') ++beg;
+				}
+				return true;
+			}
+			carry.append(s, len);
+			beg = end;
+		}
+	}
+	void unget(const char* p, size_t n) { held = p; held_n = n; }
 	// returns -1 at end of input, -2 on malformed input, else the sequence length
 	int64_t next(std::string& seq, std::string& err)
 	{
 		seq.clear();
 		bool need_defline = true, got_defline = false;
-		std::string l;
-		while (line(l)) {
-			if (l.empty()) continue;
+		const char* l;
+		size_t n;
+		std::string keep;
+		while (line(l, n)) {
+			if (n == 0) continue;
 			const int c = (unsigned char)l[0];
 			if (c == '>' || c == '@') {
 				if (need_defline) { need_defline = false; got_defline = true; continue; }
-				unget(l);
+				if (l == carry.data()) { keep.assign(l, n); carry.swap(keep); l = carry.data(); }
+				unget(l, n);
 				break;
 			} else if (c == '+') {
-				std::string q;
-				if (!line(q)) { err = "quality score line is missing"; return -2; }
+				const char* q; size_t qn;
+				if (!line(q, qn)) { err = "quality score line is missing"; return -2; }
 				break;
 			} else if (c == '#' || c == '!') {
 				continue;
@@ -118,7 +159,15 @@ struct FastaStream
 				err = "input doesn't start with a defline or comment";
 				return -2;
 			}
-			for (size_t p = 0; p < l.size(); ++p) {
+			// fast path: a line made only of nucleotide letters is appended as is
+			size_t p = 0;
+			{
+				unsigned bad = 0;
+				for (size_t q = 0; q < n; ++q) bad |= kEnc.t[(unsigned char)l[q]];   // 16 only for non-nucleotides
+				p = (bad & 16u) ? 0 : n;
+			}
+			if (p == n) { seq.append(l, n); continue; }
+			for (p = 0; p < n; ++p) {
 				const int ch = (unsigned char)l[p];
 				if (ch == ';') break;
 				if (kEnc.t[ch] < 16) seq.push_back((char)ch);
