@@ -76,6 +76,25 @@ typedef struct {
 	double ident;
 } mecat_extend_result;
 
+/* Gapped extension WITH alignment strings.  Like mecat_extend_task plus an optional window on the
+ * subject (swin_len > 0: the target is bases [swin_off, swin_off+swin_len) of read sread and
+ * sstart is relative to the window -- mecat2ref cuts such a window out of the reference,
+ * src/mecat2ref/mecat2ref_aux.cpp:86-121). */
+typedef struct {
+	int32_t qread, qstrand, qstart;
+	int32_t sread, sstart;
+	int32_t swin_off, swin_len;
+} mecat_align_task;
+
+/* policy 0: DiffAligner::go accessors; policy 1: the M5Record fields GetAlignment fills
+ * (src/mecat2cns/dw.cpp:482-553: coordinates and strings trimmed to a 4-match run at both ends).
+ * str_offset: offset of this task's NUL-terminated strings in both string arenas, -1 if !ok. */
+typedef struct {
+	int32_t ok, qstart, qend, sstart, send, columns, matches, pad_;
+	double ident;
+	int64_t str_offset;
+} mecat_align_result;
+
 /* Device time per kernel (milliseconds, CUDA events on the context's own stream, summed over
  * launches since the last reset) and traffic counters.  Indices into kernel_ms / kernel_launches: */
 enum {
@@ -182,6 +201,16 @@ int mecat_b200_pw_raw_candidates(mecat_b200_ctx* ctx, void* index, void* dvol_re
 int mecat_b200_extend_batch(mecat_b200_ctx* ctx, int policy, void* dvol_query, void* dvol_subject,
                             const mecat_extend_task* tasks, size_t ntasks, int min_align_size,
                             mecat_extend_result** results);
+
+/* ---- A8-A11 / R1 / C1-C2: batched gapped extension with alignment strings ------------------
+ * policy 0 replaces GapAligner::go + query/target_mapped_string per candidate
+ *   (src/mecat2ref/mecat2ref_aux.cpp:152-163, src/common/diff_gapalign.cpp:295-349);
+ * policy 1 replaces ns_banded_sw::GetAlignment per candidate with error rate `err`
+ *   (src/mecat2cns/mecat_correction.cpp:424, src/mecat2cns/dw.cpp:482-553).
+ * Strings are ASCII over ACGT- ; *qstrings / *sstrings hold *string_bytes bytes each. */
+int mecat_b200_align_batch(mecat_b200_ctx* ctx, int policy, double err, void* dvol_query, void* dvol_subject,
+                           const mecat_align_task* tasks, size_t ntasks, int min_align_size,
+                           mecat_align_result** results, char** qstrings, char** sstrings, size_t* string_bytes);
 
 #ifdef __cplusplus
 }

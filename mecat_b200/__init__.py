@@ -6,7 +6,7 @@ Layout:
   build.py     in-tree build of libmecat_b200.so / bin/mecat2pw
 """
 from .api import (Context, HostVolume, MecatB200Error, PwParams, pw_params, split_dataset, load_library, LIB_PATH, EXPORTS,
-                  EC_DTYPE, M4_DTYPE, TASK_DTYPE, RESULT_DTYPE)
+                  EC_DTYPE, M4_DTYPE, TASK_DTYPE, RESULT_DTYPE, ALIGN_TASK_DTYPE, ALIGN_RESULT_DTYPE)
 
 __all__ = ["Context", "HostVolume", "MecatB200Error", "PwParams", "pw_params", "split_dataset", "load_library", "LIB_PATH", "EXPORTS",
-           "EC_DTYPE", "M4_DTYPE", "TASK_DTYPE", "RESULT_DTYPE"]
+           "EC_DTYPE", "M4_DTYPE", "TASK_DTYPE", "RESULT_DTYPE", "ALIGN_TASK_DTYPE", "ALIGN_RESULT_DTYPE"]

@@ -49,6 +49,10 @@ TASK_DTYPE = np.dtype([(n, "<i4") for n in ("qread", "qstrand", "qstart", "sread
 RESULT_DTYPE = np.dtype([("ok", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("sstart", "<i4"), ("send", "<i4"),
                          ("columns", "<i4"), ("matches", "<i4"), ("pad", "<i4"), ("ident", "<f8")])
 
+ALIGN_TASK_DTYPE = np.dtype([(n, "<i4") for n in ("qread", "qstrand", "qstart", "sread", "sstart", "swin_off", "swin_len")])
+ALIGN_RESULT_DTYPE = np.dtype([("ok", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("sstart", "<i4"), ("send", "<i4"),
+                               ("columns", "<i4"), ("matches", "<i4"), ("pad", "<i4"), ("ident", "<f8"), ("str_offset", "<i8")])
+
 EXPORTS = [
     "mecat_b200_abi_version", "mecat_b200_device_count", "mecat_b200_init", "mecat_b200_destroy",
     "mecat_b200_last_error", "mecat_b200_free", "mecat_b200_get_stats", "mecat_b200_reset_stats",
@@ -56,7 +60,7 @@ EXPORTS = [
     "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_count_part", "mecat_b200_index_finish_part",
     "mecat_b200_index_device_arrays", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
-    "mecat_b200_extend_batch", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
+    "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
 ]
 
 _lib = None
@@ -91,6 +95,8 @@ def load_library():
     L.mecat_b200_pw_overlaps.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_raw_candidates.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_extend_batch.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.mecat_b200_align_batch.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp),
+                                         C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_tile_range.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_volume_from_device.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp, C.POINTER(vp)]
     L.mecat_b200_split_dataset.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.c_char_p, C.c_int]
@@ -240,6 +246,22 @@ class Context:
         self._check(self.L.mecat_b200_pw_tile(self.h, index, dref, dreads, C.byref(params), C.byref(out), C.byref(n)),
                     "pw_tile")
         return self._take(out, n.value, EC_DTYPE if params.task == 0 else M4_DTYPE)
+
+    def align_batch(self, dquery, dsubject, tasks, min_align_size, policy=0, err=0.15):
+        """Returns (results, qstrings, sstrings): result['str_offset'] indexes the two NUL-separated byte blobs."""
+        tasks = np.ascontiguousarray(tasks, dtype=ALIGN_TASK_DTYPE)
+        res, qs, ss, nb = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_align_batch(self.h, policy, err, dquery, dsubject, tasks.ctypes.data_as(C.c_void_p),
+                                                  len(tasks), min_align_size, C.byref(res), C.byref(qs), C.byref(ss),
+                                                  C.byref(nb)), "align_batch")
+        r = self._take(res, len(tasks), ALIGN_RESULT_DTYPE)
+        q = C.string_at(qs.value, nb.value) if qs.value else b""
+        s = C.string_at(ss.value, nb.value) if ss.value else b""
+        if qs.value:
+            self.L.mecat_b200_free(self.h, qs)
+        if ss.value:
+            self.L.mecat_b200_free(self.h, ss)
+        return r, q, s
 
     def pw_tile_range(self, index, dref, dreads, params, read_begin, read_end):
         out, n = C.c_void_p(), C.c_size_t()

@@ -24,7 +24,7 @@ HOSTCXX = "/usr/bin/g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
               "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2,-pthread", "-Xptxas", "-v"]
 
-CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "capi.cu"]
+CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "align.cu", "capi.cu"]
 
 
 def _newer(src_list, out):

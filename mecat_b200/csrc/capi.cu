@@ -281,6 +281,42 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
 	return rc;
 }
 
+int mecat_b200_align_batch(mecat_b200_ctx* c, int policy, double err, void* dq, void* ds, const mecat_align_task* tasks,
+                           size_t ntasks, int min_align_size, mecat_align_result** results, char** qstrings,
+                           char** sstrings, size_t* string_bytes)
+{
+	if (check(c) || !dq || !ds || !results || !qstrings || !sstrings || !string_bytes) return 1;
+	if (policy != 0 && policy != 1) MB_FAIL(c, "align_batch: policy must be 0 (pw/ref) or 1 (cns), not %d", policy);
+	cudaSetDevice(c->device);
+	*results = nullptr; *qstrings = nullptr; *sstrings = nullptr; *string_bytes = 0;
+	if (!ntasks) return 0;
+	const DVolume* Q = (const DVolume*)dq;
+	const DVolume* S = (const DVolume*)ds;
+	static_assert(sizeof(AlignTask) == sizeof(mecat_align_task), "task layout");
+	for (size_t i = 0; i < ntasks; ++i) {
+		const mecat_align_task& t = tasks[i];
+		if (t.qread < 0 || t.qread >= Q->num_reads || t.sread < 0 || t.sread >= S->num_reads)
+			MB_FAIL(c, "align_batch: task %zu names a read outside its volume", i);
+		const int ql = Q->h_offsz[2 * t.qread + 1], sl_full = S->h_offsz[2 * t.sread + 1];
+		if (t.swin_len < 0 || t.swin_off < 0 || (t.swin_len > 0 && (int64_t)t.swin_off + t.swin_len > sl_full))
+			MB_FAIL(c, "align_batch: task %zu subject window outside its read", i);
+		const int sl = t.swin_len > 0 ? t.swin_len : sl_full;
+		if (t.qstart < 0 || t.qstart > ql || t.sstart < 0 || t.sstart > sl)
+			MB_FAIL(c, "align_batch: task %zu start point outside its sequence", i);
+	}
+	mecat_align_result* res = (mecat_align_result*)malloc(sizeof(mecat_align_result) * ntasks);
+	if (!res) MB_FAIL(c, "align_batch: out of host memory");
+	std::vector<char> qs, ss;
+	if (align_batch(c, policy, err, Q, S, (const AlignTask*)tasks, ntasks, min_align_size, res, qs, ss)) { free(res); return 1; }
+	char* a = (char*)malloc(qs.size() + 1);
+	char* b = (char*)malloc(ss.size() + 1);
+	if (!a || !b) { free(res); free(a); free(b); MB_FAIL(c, "align_batch: out of host memory"); }
+	if (!qs.empty()) { memcpy(a, qs.data(), qs.size()); memcpy(b, ss.data(), ss.size()); }
+	a[qs.size()] = 0; b[ss.size()] = 0;
+	*results = res; *qstrings = a; *sstrings = b; *string_bytes = qs.size();
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // One (index volume, query volume) tile.
 static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* reads, const mecat_pw_params* p,

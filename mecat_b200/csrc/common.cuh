@@ -170,6 +170,13 @@ struct ExtendHalf          // result of one direction of one task
 int extend_launch(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* d_tasks, size_t ntasks,
                   ExtendHalf* d_halves /* 2*ntasks: left then right */);
 
+struct AlignTask           // = mecat_align_task
+{
+	int32_t qread, qstrand, qstart, sread, sstart, swin_off, swin_len;
+};
+int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t ntasks,
+                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr);
+
 struct RawCand             // candidate_save, pw_impl.h:21-25
 {
 	int32_t loc1, loc2, left1, left2, right1, right2, score, num1, num2, readno, readstart, chain;

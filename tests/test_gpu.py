@@ -192,6 +192,86 @@ def test_extend_matches_oracle(gpu_ctx, small_vol):
     assert not bad, "%d of %d extension results differ; first: %r" % (len(bad), len(tasks), bad[0])
 
 
+def _oracle_strings(vq, vs, t, policy, min_aln, err=0.15):
+    """Oracle result of one align task: (ok, qs, qe, ss, se, qstr, sstr)."""
+    O = util.oracle()
+    q = np.concatenate([[0], vq.codes(int(t["qread"]), int(t["qstrand"])), [0]]).astype(np.int8)
+    full = vs.codes(int(t["sread"]), 0)
+    if int(t["swin_len"]) > 0:
+        full = full[int(t["swin_off"]):int(t["swin_off"]) + int(t["swin_len"])]
+    s = np.concatenate([[0], full, [0]]).astype(np.int8)
+    cap = len(q) + len(s) + 64
+    qa, sa = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    out = (C.c_int32 * 8)()
+    ident = C.c_double()
+    qp, sp = C.cast(q.ctypes.data + 1, C.c_char_p), C.cast(s.ctypes.data + 1, C.c_char_p)
+    if policy == 0:
+        O.orc_diff_go(qp, int(t["qstart"]), len(q) - 2, sp, int(t["sstart"]), len(s) - 2, min_aln, out, C.byref(ident), qa, sa, cap)
+        return (out[0], out[1], out[2], out[3], out[4], qa.value if out[0] else b"", sa.value if out[0] else b"")
+    ok = O.orc_cns_get_alignment(qp, int(t["qstart"]), len(q) - 2, sp, int(t["sstart"]), len(s) - 2, err, min_aln, out, qa, sa, cap)
+    return (int(ok), out[1], out[2], out[3], out[4], qa.value if ok else b"", sa.value if ok else b"")
+
+
+@pytest.mark.parametrize("policy,min_aln", [(0, 1000), (0, 1), (1, 2000), (1, 1)])
+def test_align_with_strings_matches_oracle(gpu_ctx, small_vol, policy, min_aln):
+    """R1 (pw/ref flavour with mapped strings, incl. subject windows) and C1-C2 (cns GetAlignment)."""
+    import mecat_b200
+    O = util.oracle()
+    cv = small_vol.c()
+    oidx = O.orc_index_build(C.byref(cv))
+    p = util.pw_params(task=0)
+    out = (C.c_int32 * (12 * 101))()
+    tasks = []
+    for rid in range(0, small_vol.num_reads, 2):
+        n = O.orc_pw_candidates(oidx, C.byref(cv), C.byref(cv), rid, C.byref(p), out)
+        for i in range(n):
+            c = out[12 * i:12 * i + 12]
+            qstart, sstart = c[1], c[0]
+            if qstart and sstart:
+                qstart += 6; sstart += 6
+            sidx = c[9]
+            if policy == 0 and i % 3 == 0:
+                # a window on the subject like mecat2ref's extract_sequences
+                sl = int(small_vol.offset_size[sidx][1])
+                lo = max(0, sstart - 2500); hi = min(sl, sstart + 3000)
+                tasks.append((rid, c[11], qstart, sidx, sstart - lo, lo, hi - lo))
+            else:
+                tasks.append((rid, c[11], qstart, sidx, sstart, 0, 0))
+    O.orc_index_free(oidx)
+    rng = np.random.default_rng(8)
+    nr = small_vol.num_reads
+    for it in range(120):     # unrelated pairs, end points
+        a, b = int(rng.integers(0, nr)), int(rng.integers(0, nr))
+        la, lb = int(small_vol.offset_size[a][1]), int(small_vol.offset_size[b][1])
+        qs, ss = [(0, 0), (la, lb), (la // 2, lb // 3), (int(rng.integers(0, la + 1)), int(rng.integers(0, lb + 1)))][it % 4]
+        tasks.append((a, it & 1, qs, b, ss, 0, 0))
+    tasks = np.array(tasks, dtype=mecat_b200.ALIGN_TASK_DTYPE)
+    d = gpu_ctx.upload(host_volume(small_vol))
+    res, qstr, sstr = gpu_ctx.align_batch(d, d, tasks, min_aln, policy=policy, err=0.15)
+    gpu_ctx.release_volume(d)
+    bad = []
+    nok = 0
+    for i, t in enumerate(tasks):
+        w = _oracle_strings(small_vol, small_vol, t, policy, min_aln)
+        r = res[i]
+        if int(r["ok"]):
+            o = int(r["str_offset"]); n = int(r["columns"])
+            g = (1, int(r["qstart"]), int(r["qend"]), int(r["sstart"]), int(r["send"]), qstr[o:o + n], sstr[o:o + n])
+            assert qstr[o + n] == 0 and sstr[o + n] == 0
+            nok += 1
+        else:
+            g = (0,) + tuple(w[1:5]) + (b"", b"") if not w[0] else (0, 0, 0, 0, 0, b"", b"")
+        if g != w:
+            bad.append((i, tuple(int(x) for x in t), g[:5], w[:5], len(g[5]), len(w[5])))
+    if bad:
+        os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(util.ROOT, "gpurun_out", "mismatch_align_p%d_%d.txt" % (policy, min_aln)), "w") as f:
+            for b in bad:
+                f.write(repr(b) + "\n")
+    assert nok > 100
+    assert not bad, "%d of %d differ; first %r" % (len(bad), len(tasks), bad[0])
+
+
 # ---------------------------------------------------------------- A2-A6
 def test_raw_candidates_match_oracle(gpu_ctx, small_vol):
     O = util.oracle()

@@ -294,3 +294,50 @@ def test_oracle_extension_against_reference():
         O.orc_diff_align_block(qp, len(q), tp, len(t), fwd, blk_o)
         assert list(blk_r) == list(blk_o), (it, len(q), len(t), fwd)
     R.ref_diff_free(aligner)
+
+
+@needs_ref
+def test_cns_alignment_against_reference():
+    """C1-C2 (mecat2cns/dw.cpp GetAlignment) and C4 (normalize_gaps) on random related pairs."""
+    R, O = util.ref(), util.oracle()
+    rng = np.random.default_rng(17)
+    drd = R.ref_cns_drd_new()
+    cap = 120000
+    out_r = (C.c_int32 * 8)(); out_o = (C.c_int32 * 8)()
+    qa_r, sa_r = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    qa_o, sa_o = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    nq_r, nt_r = C.create_string_buffer(2 * cap), C.create_string_buffer(2 * cap)
+    nq_o, nt_o = C.create_string_buffer(2 * cap), C.create_string_buffer(2 * cap)
+    n_ok = 0
+    for it in range(80):
+        L = int(rng.integers(300, 9000))
+        base = rng.integers(0, 4, size=L).astype(np.int8)
+        err = [0.02, 0.08, 0.15, 0.22, 0.4][it % 5]
+        q = mutate(rng, base, err)
+        t = mutate(rng, base, err)
+        if it % 9 == 0:
+            t = rng.integers(0, 4, size=L).astype(np.int8)
+        f = rng.random()
+        qstart = int(f * len(q)); tstart = min(len(t), int(f * len(t)))
+        if it % 11 == 0:
+            qstart, tstart = 0, 0
+        if it % 13 == 0:
+            qstart, tstart = len(q), len(t)
+        qb = np.concatenate([[0], q, [0]]).astype(np.int8)
+        tb = np.concatenate([[0], t, [0]]).astype(np.int8)
+        qp, tp = qb.ctypes.data + 1, tb.ctypes.data + 1
+        for min_aln, e in ((1, 0.15), (2000, 0.15), (500, 0.20)):
+            okr = R.ref_cns_get_alignment(drd, qp, qstart, len(q), tp, tstart, len(t), e, min_aln, out_r, qa_r, sa_r, cap)
+            oko = O.orc_cns_get_alignment(C.cast(qp, C.c_char_p), qstart, len(q), C.cast(tp, C.c_char_p), tstart, len(t), e,
+                                          min_aln, out_o, qa_o, sa_o, cap)
+            assert bool(okr) == bool(oko), (it, min_aln, e)
+            if okr:
+                n_ok += 1
+                assert list(out_r[:5]) == list(out_o[:5])
+                assert qa_r.value == qa_o.value and sa_r.value == sa_o.value
+                n = len(qa_r.value)
+                a = R.ref_normalize_gaps(qa_r.value, sa_r.value, n, 1, nq_r, nt_r, 2 * cap)
+                b = O.orc_normalize_gaps(qa_o.value, sa_o.value, n, 1, nq_o, nt_o, 2 * cap)
+                assert a == b and nq_r.value == nq_o.value and nt_r.value == nt_o.value
+    assert n_ok > 60
+    R.ref_cns_drd_free(drd)
