@@ -212,6 +212,39 @@ int mecat_b200_align_batch(mecat_b200_ctx* ctx, int policy, double err, void* dv
                            const mecat_align_task* tasks, size_t ntasks, int min_align_size,
                            mecat_align_result** results, char** qstrings, char** sstrings, size_t* string_bytes);
 
+/* ---- C1-C7: consensus of a set of reads (mecat2cns -i 0) -----------------------------------
+ * replaces consensus_one_partition_can / reads_correction_func_can / consensus_one_read_can_pacbio
+ * (src/mecat2cns/reads_correction_can.cpp:21-86, src/mecat2cns/mecat_correction.cpp:389-450).
+ * ec: candidates already normalised like the partition files (the read to correct is `sid`,
+ * sdir == 0; src/mecat2cns/overlaps_partition.cpp:141-165), any order; reads with fewer than
+ * min_cov candidates or shorter than 0.95 * min_size are skipped like the reference does.
+ * dvol_reads must hold every read named by ec (read id = index + start_read_id).
+ * Mirrors ConsensusOptions (src/mecat2cns/options.h:9-23): -r, -a, -c, -l. */
+typedef struct {
+	double min_mapping_ratio;   /* -r, default 0.9  */
+	int32_t min_align_size;     /* -a, default 2000 */
+	int32_t min_cov;            /* -c, default 6    */
+	int64_t min_size;           /* -l, default 5000 */
+} mecat_cns_params;
+
+/* CnsResult (src/common/alignment.h): corrected piece [beg, end) of read id; sequence at
+ * seqs[seq_offset .. seq_offset + seq_len) (ASCII, not NUL separated). */
+typedef struct {
+	int64_t id, beg, end, seq_offset, seq_len;
+} mecat_cns_piece;
+
+int mecat_b200_cns_reads(mecat_b200_ctx* ctx, void* dvol_reads, const mecat_candidate* ec, size_t nec,
+                         const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs,
+                         size_t* seq_bytes);
+
+/* test hooks (host only, no device needed): the candidate trial order and the per-read consensus that
+ * mecat_b200_cns_reads applies to its GPU alignment results; they compute no alignments. */
+void mecat_b200_cns_sort_candidates(mecat_candidate* c, int n);
+int mecat_b200_cns_consensus_host(const mecat_candidate* cand, int ncand, const mecat_align_result* res, const char* qstr,
+                                  const char* sstr, const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces,
+                                  char** seqs, size_t* seq_bytes);
+void mecat_b200_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

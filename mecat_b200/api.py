@@ -31,6 +31,14 @@ KERNEL_NAMES = ["orient", "index_count", "index_scan", "index_fill", "index_sort
                 "finalize"]
 
 
+class CnsParams(C.Structure):
+    _fields_ = [("min_mapping_ratio", C.c_double), ("min_align_size", C.c_int32), ("min_cov", C.c_int32),
+                ("min_size", C.c_int64)]
+
+
+CNS_PIECE_DTYPE = np.dtype([("id", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("seq_offset", "<i8"), ("seq_len", "<i8")])
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_float * 16), ("kernel_launches", C.c_int64 * 16),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("host_ms", C.c_float), ("total_ms", C.c_float),
@@ -60,7 +68,8 @@ EXPORTS = [
     "mecat_b200_volume_release", "mecat_b200_index_build", "mecat_b200_index_count_part", "mecat_b200_index_finish_part",
     "mecat_b200_index_device_arrays", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
-    "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
+    "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_cns_reads", "mecat_b200_cns_sort_candidates",
+    "mecat_b200_cns_consensus_host", "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
 ]
 
 _lib = None
@@ -97,6 +106,12 @@ def load_library():
     L.mecat_b200_extend_batch.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.mecat_b200_align_batch.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_cns_reads.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(CnsParams), C.POINTER(vp), C.POINTER(C.c_size_t),
+                                       C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_cns_sort_candidates.argtypes = [vp, C.c_int]
+    L.mecat_b200_cns_consensus_host.argtypes = [vp, C.c_int, vp, C.c_char_p, C.c_char_p, C.POINTER(CnsParams), C.POINTER(vp),
+                                                C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_host_free.argtypes = [vp]
     L.mecat_b200_pw_tile_range.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_volume_from_device.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp, C.POINTER(vp)]
     L.mecat_b200_split_dataset.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.c_char_p, C.c_int]
@@ -143,6 +158,35 @@ def split_dataset(reads_path, wrk_dir, max_volume_bases=0):
         names = [l.strip() for l in f if l.strip()]
     assert len(names) == n.value
     return names
+
+
+def normalise_candidates(can, min_read_size):
+    """The two partition-file records of every `.can` line (reference partition_candidates +
+    normalise_candidate, src/mecat2cns/overlaps_partition.cpp:141-165,176-224): one with each read as the
+    read to correct (`sid`), strands flipped so that sdir == 0.  `can`: EC_DTYPE array as read from a .can."""
+    can = can[(can["qsize"] >= min_read_size) & (can["ssize"] >= min_read_size)]
+    a = np.zeros(len(can), dtype=EC_DTYPE)                 # query becomes the target
+    a["qdir"], a["qid"], a["qext"], a["qsize"] = can["sdir"], can["sid"], can["sext"], can["ssize"]
+    a["sdir"], a["sid"], a["sext"], a["ssize"] = can["qdir"], can["qid"], can["qext"], can["qsize"]
+    a["score"] = can["score"]
+    b = can.copy()                                         # subject stays the target
+    out = np.empty(2 * len(can), dtype=EC_DTYPE)
+    out[0::2], out[1::2] = a, b
+    rev = out["sdir"] == 1
+    out["qdir"][rev] = 1 - out["qdir"][rev]
+    out["sdir"][rev] = 0
+    for f in ("qoff", "qend", "soff", "send"):
+        out[f] = 0
+    return out
+
+
+def read_can(path):
+    """`.can` text (qid sid qdir sdir qext sext score qsize ssize) -> EC_DTYPE array."""
+    raw = np.loadtxt(path, dtype=np.int64, ndmin=2)
+    ec = np.zeros(len(raw), dtype=EC_DTYPE)
+    for i, f in enumerate(("qid", "sid", "qdir", "sdir", "qext", "sext", "score", "qsize", "ssize")):
+        ec[f] = raw[:, i]
+    return ec
 
 
 def pw_params(task=1, num_candidates=100, min_align_size=2000, min_kmer_match=4, tech=0):
@@ -262,6 +306,20 @@ class Context:
         if ss.value:
             self.L.mecat_b200_free(self.h, ss)
         return r, q, s
+
+    def cns_reads(self, dvol, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000):
+        """mecat2cns -i 0 on normalised candidates (EC_DTYPE array).  Returns [(id, beg, end, seq bytes), ...]."""
+        ec = np.ascontiguousarray(candidates, dtype=EC_DTYPE)
+        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size)
+        pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_cns_reads(self.h, dvol, ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p), C.byref(pieces),
+                                                C.byref(n), C.byref(seqs), C.byref(nb)), "cns_reads")
+        pc = self._take(pieces, n.value, CNS_PIECE_DTYPE)
+        blob = C.string_at(seqs.value, nb.value) if seqs.value else b""
+        if seqs.value:
+            self.L.mecat_b200_free(self.h, seqs)
+        return [(int(x["id"]), int(x["beg"]), int(x["end"]), blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])])
+                for x in pc]
 
     def pw_tile_range(self, index, dref, dreads, params, read_begin, read_end):
         out, n = C.c_void_p(), C.c_size_t()

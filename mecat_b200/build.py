@@ -1,7 +1,8 @@
 """Builds the in-tree native artefacts:
 
   mecat_b200/libmecat_b200.so   CUDA kernels + C ABI (include/mecat_b200.h), sm_100a only
-  mecat_b200/bin/mecat2pw       C++ host driver with the reference's CLI (links the library)
+  mecat_b200/bin/mecat2pw       C++ host drivers with the reference's CLIs (link the library)
+  mecat_b200/bin/mecat2cns
   mecat_b200/bin/gen_reads      seeded synthetic CLR read generator (tools/gen_reads.cpp; test/bench tooling)
 
 nvcc cross-compiles without a GPU.  Nothing here touches oracle/.
@@ -37,7 +38,7 @@ def _newer(src_list, out):
 def _compile(cu):
     src = os.path.join(CSRC, cu)
     obj = os.path.join(OBJ, cu.replace(".cu", ".o"))
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "mecat_b200.h")]
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns.h"), os.path.join(ROOT, "include", "mecat_b200.h")]
     if not _newer(deps, obj):
         return obj, ""
     p = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
@@ -52,10 +53,11 @@ def build(verbose=False):
     with cf.ThreadPoolExecutor(max_workers=len(CU)) as ex:
         res = list(ex.map(_compile, CU))
     objs = [r[0] for r in res]
-    hio_src, hio_obj = os.path.join(CSRC, "host_io.cpp"), os.path.join(OBJ, "host_io.o")
-    if _newer([hio_src, os.path.join(ROOT, "include", "mecat_b200.h")], hio_obj):
-        subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-fPIC", "-c", hio_src, "-o", hio_obj])
-    objs.append(hio_obj)
+    for name in ("host_io", "cns", "cns_api"):
+        src, obj = os.path.join(CSRC, name + ".cpp"), os.path.join(OBJ, name + ".o")
+        if _newer([src, os.path.join(ROOT, "include", "mecat_b200.h"), os.path.join(CSRC, "cns.h")], obj):
+            subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj])
+        objs.append(obj)
     log = "\n".join(r[1] for r in res if r[1])
     if log:
         with open(os.path.join(ROOT, "build", "ptxas.log"), "w") as f:
@@ -66,11 +68,11 @@ def build(verbose=False):
         subprocess.check_call([NVCC, "-shared", "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a",
                                "-o", LIB] + objs)
     host = os.path.join(CSRC, "host")
-    exe = os.path.join(BIN, "mecat2pw")
-    srcs = [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith(".cpp")] if os.path.isdir(host) else []
-    if srcs and _newer(srcs + [LIB] + [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")], exe):
-        subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe]
-                              + srcs + ["-L", HERE, "-lmecat_b200", "-Wl,-rpath,$ORIGIN/.."])
+    for name in ("mecat2pw", "mecat2cns"):
+        src, exe = os.path.join(host, name + ".cpp"), os.path.join(BIN, name)
+        if os.path.exists(src) and _newer([src, LIB, os.path.join(ROOT, "include", "mecat_b200.h")], exe):
+            subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                                   "-L", HERE, "-lmecat_b200", "-Wl,-rpath,$ORIGIN/.."])
     gen_src, gen_exe = os.path.join(ROOT, "tools", "gen_reads.cpp"), os.path.join(BIN, "gen_reads")
     if _newer([gen_src], gen_exe):
         subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-o", gen_exe, gen_src])

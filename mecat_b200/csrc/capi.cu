@@ -4,6 +4,7 @@
 // assembly that the reference does on the CPU after its hot loops
 // (candidate_detect pw_impl.cpp:767-793, fill_m4record :467-506, append_m4v :576-610).
 #include "common.cuh"
+#include "cns.h"
 
 #include <algorithm>
 #include <atomic>
@@ -314,6 +315,101 @@ int mecat_b200_align_batch(mecat_b200_ctx* c, int policy, double err, void* dq, 
 	if (!qs.empty()) { memcpy(a, qs.data(), qs.size()); memcpy(b, ss.data(), ss.size()); }
 	a[qs.size()] = 0; b[ss.size()] = 0;
 	*results = res; *qstrings = a; *sstrings = b; *string_bytes = qs.size();
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// mecat2cns -i 0 for a set of reads: GPU extensions (policy 1) + host-thread consensus.
+int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candidate* ec_in, size_t nec, const mecat_cns_params* p,
+                         mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
+{
+	if (check(c) || !dvol_reads || (!ec_in && nec) || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
+	cudaSetDevice(c->device);
+	*pieces = nullptr; *npieces = 0; *seqs = nullptr; *seq_bytes = 0;
+	const DVolume* V = (const DVolume*)dvol_reads;
+	const int id0 = V->start_read_id;
+	for (size_t i = 0; i < nec; ++i) {
+		const mecat_candidate& e = ec_in[i];
+		if (e.sid < id0 || e.sid >= id0 + V->num_reads || e.qid < id0 || e.qid >= id0 + V->num_reads)
+			MB_FAIL(c, "cns_reads: candidate %zu names a read outside the volume", i);
+		if (e.sdir != 0) MB_FAIL(c, "cns_reads: candidate %zu is not normalised (sdir must be 0)", i);
+		if (e.qsize != V->h_offsz[2 * (e.qid - id0) + 1] || e.ssize != V->h_offsz[2 * (e.sid - id0) + 1])
+			MB_FAIL(c, "cns_reads: candidate %zu disagrees with the volume about read sizes", i);
+		if (e.qext < 0 || e.qext >= e.qsize || e.sext < 0 || e.sext >= e.ssize)
+			MB_FAIL(c, "cns_reads: candidate %zu extension point outside its read", i);
+	}
+	std::vector<mecat_candidate> ec(ec_in, ec_in + nec);
+	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
+	struct Group { size_t b, e; };
+	std::vector<Group> groups;
+	for (size_t i = 0; i < nec;) {
+		size_t j = i + 1;
+		while (j < nec && ec[j].sid == ec[i].sid) ++j;
+		// reads_correction_func_can, reads_correction_can.cpp:27-33
+		if ((int64_t)(j - i) >= p->min_cov && !(ec[i].ssize < p->min_size * 0.95)) {
+			mbcns::sort_candidates(ec.data() + i, (int)(j - i));
+			groups.push_back(Group{i, std::min(j, i + 200)});
+		}
+		i = j;
+	}
+	mbcns::Params P;
+	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
+	std::vector<mbcns::Piece> all;
+	const int nthreads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
+	const size_t TASKS_PER_BATCH = 40000;
+	std::vector<AlignTask> tasks;
+	std::vector<mecat_align_result> res;
+	std::vector<char> qs, ss;
+	for (size_t g0 = 0; g0 < groups.size();) {
+		size_t g1 = g0, nt = 0;
+		while (g1 < groups.size() && (nt == 0 || nt + (groups[g1].e - groups[g1].b) <= TASKS_PER_BATCH)) { nt += groups[g1].e - groups[g1].b; ++g1; }
+		tasks.clear();
+		for (size_t g = g0; g < g1; ++g)
+			for (size_t k = groups[g].b; k < groups[g].e; ++k) {
+				const mecat_candidate& e = ec[k];
+				AlignTask t;
+				t.qread = e.qid - id0; t.qstrand = e.qdir; t.qstart = e.qdir ? e.qsize - 1 - e.qext : e.qext;   // mecat_correction.cpp:421-423
+				t.sread = e.sid - id0; t.sstart = e.sext; t.swin_off = 0; t.swin_len = 0;
+				tasks.push_back(t);
+			}
+		res.resize(tasks.size());
+		if (align_batch(c, 1, 0.15, V, V, tasks.data(), tasks.size(), p->min_align_size, res.data(), qs, ss)) return 1;
+		WallTimer host_timer;
+		std::vector<std::vector<mbcns::Piece>> per((size_t)(g1 - g0));
+		std::vector<size_t> first((size_t)(g1 - g0) + 1, 0);
+		for (size_t g = g0; g < g1; ++g) first[g - g0 + 1] = first[g - g0] + (groups[g].e - groups[g].b);
+		std::atomic<size_t> next(g0);
+		auto runner = [&]() {
+			mbcns::Scratch scratch;
+			for (size_t g; (g = next.fetch_add(1)) < g1;) {
+				const mecat_candidate* cand = ec.data() + groups[g].b;
+				const int n = (int)(groups[g].e - groups[g].b);
+				mbcns::consensus_one_read(cand[0].sid, cand[0].ssize, cand, n, res.data() + first[g - g0], qs.data(), ss.data(), P,
+				                          scratch, per[g - g0]);
+			}
+		};
+		std::vector<std::thread> pool;
+		for (int t = 1; t < nthreads; ++t) pool.emplace_back(runner);
+		runner();
+		for (auto& th : pool) th.join();
+		for (auto& v : per) for (auto& pc : v) all.push_back(std::move(pc));
+		c->stats.host_ms += host_timer.stop();
+		g0 = g1;
+	}
+	size_t bytes = 0;
+	for (auto& pc : all) bytes += pc.seq.size();
+	mecat_cns_piece* out = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (all.size() ? all.size() : 1));
+	char* sq = (char*)malloc(bytes + 1);
+	if (!out || !sq) { free(out); free(sq); MB_FAIL(c, "cns_reads: out of host memory"); }
+	size_t at = 0;
+	for (size_t i = 0; i < all.size(); ++i) {
+		out[i].id = all[i].id; out[i].beg = all[i].beg; out[i].end = all[i].end; out[i].seq_offset = (int64_t)at; out[i].seq_len = (int64_t)all[i].seq.size();
+		memcpy(sq + at, all[i].seq.data(), all[i].seq.size());
+		at += all[i].seq.size();
+	}
+	sq[bytes] = 0;
+	c->stats.num_records += (int64_t)all.size();
+	*pieces = out; *npieces = all.size(); *seqs = sq; *seq_bytes = bytes;
 	return 0;
 }
 

@@ -1,0 +1,236 @@
+// mecat_b200/csrc/host/mecat2cns.cpp -- host driver with the reference's mecat2cns command line.
+//
+//   mecat2cns [options] <candidates.can> <reads.fasta> <corrected.fasta>
+//
+// Same flags (src/mecat2cns/options.cpp:201-303), same corrected-FASTA records
+// (`>{id}_{beg}_{end}_{len}`, src/mecat2cns/reads_correction_can.cpp:44-46) as the reference's
+// `-i 0` path.  The candidate file is normalised in memory exactly like partition_candidates /
+// normalise_candidate (src/mecat2cns/overlaps_partition.cpp:141-224) and processed in the same
+// batches of `-p` reads, but no `.partN` scratch files are written next to the input.  All gapped
+// extensions run on the GPU (mecat_b200_cns_reads); `-t` is accepted and ignored.
+// Not on this path (refused with a message): `-i 1` (M4 input) and `-x 1` (nanopore).
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "mecat_b200.h"
+
+namespace {
+
+struct Options
+{
+	int input_type = 1;
+	int num_threads = 1;
+	long long batch_size = 100000;
+	double min_mapping_ratio = 0.9;
+	int min_align_size = 2000;
+	int min_cov = 6;
+	long long min_size = 5000;
+	int tech = 0;
+	int num_partition_files = 10;
+	bool usage = false;
+	const char* overlaps = NULL;
+	const char* reads = NULL;
+	const char* output = NULL;
+};
+
+void print_usage(const char* prog)
+{
+	fprintf(stderr, "usage:\n%s [options] input reads output\n\noptions:\n", prog);
+	fprintf(stderr, "-x <0/1>\tsequencing platform: 0 = PACBIO, 1 = NANOPORE\n\t\tdefault: 0\n");
+	fprintf(stderr, "-i <0/1>\tinput type: 0 = candidate, 1 = m4\n");
+	fprintf(stderr, "-t <Integer>\tnumber of threads (CPU) -- accepted, unused: extensions run on the GPU\n");
+	fprintf(stderr, "-p <Integer>\tbatch size that the reads will be partitioned\n");
+	fprintf(stderr, "-r <Real>\tminimum mapping ratio\n");
+	fprintf(stderr, "-a <Integer>\tminimum overlap size\n");
+	fprintf(stderr, "-c <Integer>\tminimum coverage under consideration\n");
+	fprintf(stderr, "-l <Integer>\tminimum length of corrected sequence\n");
+	fprintf(stderr, "-k <Integer>\tnumber of partition files when partitioning overlap results\n");
+	fprintf(stderr, "-h\t\tprint usage info.\n");
+	fprintf(stderr, "\ndefault values (pacbio): -i 1 -t 1 -p 100000 -r 0.9 -a 2000 -c 6 -l 5000 -k 10\n");
+}
+
+int parse_arguments(int argc, char* argv[], Options& t)
+{
+	for (int i = 0; i + 1 < argc; ++i)
+		if (strcmp(argv[i], "-x") == 0) {
+			if (argv[i + 1][0] == '1') t.tech = 1;
+			else if (argv[i + 1][0] != '0') { fprintf(stderr, "invalid argument to option 'x': %s\n", argv[i + 1]); return 1; }
+			break;
+		}
+	if (t.tech == 1) { t.min_mapping_ratio = 0.4; t.min_align_size = 400; t.min_size = 2000; }
+	int c;
+	opterr = 0;
+	while ((c = getopt(argc, argv, "i:t:p:r:a:c:l:x:k:h")) != -1) {
+		switch (c) {
+		case 'i':
+			if (optarg[0] == '0') t.input_type = 0;
+			else if (optarg[0] == '1') t.input_type = 1;
+			else { fprintf(stderr, "invalid argument to option 'i': %s\n", optarg); return 1; }
+			break;
+		case 't': t.num_threads = atoi(optarg); break;
+		case 'p': t.batch_size = atoll(optarg); break;
+		case 'r': t.min_mapping_ratio = atof(optarg); break;
+		case 'a': t.min_align_size = atoi(optarg); break;
+		case 'c': t.min_cov = atoi(optarg); break;
+		case 'l': t.min_size = atoll(optarg); break;
+		case 'h': t.usage = true; break;
+		case 'x': break;
+		case 'k': t.num_partition_files = atoi(optarg); break;
+		case '?': fprintf(stderr, "unrecognised option '%c'\n", (char)optopt); return 1;
+		case ':': fprintf(stderr, "argument to option '%c' is missing.\n", (char)optopt); return 1;
+		}
+	}
+	bool ok = true;
+	if (t.num_threads <= 0) { fprintf(stderr, "cpu threads must be greater than 0\n"); ok = false; }
+	if (t.batch_size <= 0) { fprintf(stderr, "batch size must be greater than 0\n"); ok = false; }
+	if (t.min_mapping_ratio < 0.0) { fprintf(stderr, "mapping ratio must be >= 0.0\n"); ok = false; }
+	if (t.min_cov < 0) { fprintf(stderr, "coverage must be >= 0\n"); ok = false; }
+	if (argc < 3) return 1;
+	t.overlaps = argv[argc - 3];
+	t.reads = argv[argc - 2];
+	t.output = argv[argc - 1];
+	return ok ? 0 : 1;
+}
+
+struct StderrTimer
+{
+	std::string name;
+	timeval t0;
+	explicit StderrTimer(const std::string& n) : name(n) { fprintf(stderr, "[%s] begins.\n", name.c_str()); gettimeofday(&t0, NULL); }
+	~StderrTimer()
+	{
+		timeval t1;
+		gettimeofday(&t1, NULL);
+		fprintf(stderr, "[%s] takes %.2f secs.\n", name.c_str(), t1.tv_sec - t0.tv_sec + 1.0 * (t1.tv_usec - t0.tv_usec) / 1000000);
+	}
+};
+
+// `.can` lines: qid sid qdir sdir qext sext score qsize ssize (src/common/alignment.cpp:9-16)
+bool load_candidates(const char* path, std::vector<mecat_candidate>& out)
+{
+	FILE* f = fopen(path, "r");
+	if (!f) return false;
+	char line[512];
+	while (fgets(line, sizeof line, f)) {
+		mecat_candidate e;
+		memset(&e, 0, sizeof e);
+		if (sscanf(line, "%d %d %d %d %d %d %d %d %d", &e.qid, &e.sid, &e.qdir, &e.sdir, &e.qext, &e.sext, &e.score, &e.qsize, &e.ssize) == 9)
+			out.push_back(e);
+	}
+	fclose(f);
+	return true;
+}
+
+// normalise_candidate, overlaps_partition.cpp:141-165
+mecat_candidate normalise(const mecat_candidate& s, bool subject_is_target)
+{
+	mecat_candidate d;
+	memset(&d, 0, sizeof d);
+	if (subject_is_target) {
+		d.qdir = s.qdir; d.qid = s.qid; d.qext = s.qext; d.qsize = s.qsize;
+		d.sdir = s.sdir; d.sid = s.sid; d.sext = s.sext; d.ssize = s.ssize;
+	} else {
+		d.qdir = s.sdir; d.qid = s.sid; d.qext = s.sext; d.qsize = s.ssize;
+		d.sdir = s.qdir; d.sid = s.qid; d.sext = s.qext; d.ssize = s.qsize;
+	}
+	d.score = s.score;
+	if (d.sdir == 1) { d.qdir = 1 - d.qdir; d.sdir = 1 - d.sdir; }
+	return d;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+	Options opt;
+	const int r = parse_arguments(argc, argv, opt);
+	if (r) { print_usage(argv[0]); return 1; }
+	if (opt.usage) { print_usage(argv[0]); return 0; }
+	if (opt.tech != 0) { fprintf(stderr, "mecat2cns: -x 1 (nanopore) is not part of the GPU path; use the reference binary for it.\n"); return 1; }
+	if (opt.input_type != 0) { fprintf(stderr, "mecat2cns: only `-i 0` (candidate input) is on the GPU path so far; use the reference binary for `-i 1`.\n"); return 1; }
+	if (mecat_b200_device_count() < 1) { fprintf(stderr, "mecat2cns: no CUDA device found (this build has no CPU path)\n"); return 1; }
+
+	std::vector<mecat_candidate> raw, ec;
+	{
+		StderrTimer t("partition_candidates");
+		if (!load_candidates(opt.overlaps, raw)) { fprintf(stderr, "cannot open file '%s' for reading\n", opt.overlaps); return 1; }
+		ec.reserve(raw.size() * 2);
+		for (const mecat_candidate& e : raw) {
+			if (e.qsize < opt.min_size || e.ssize < opt.min_size) continue;     // overlaps_partition.cpp:205
+			ec.push_back(normalise(e, false));
+			ec.push_back(normalise(e, true));
+		}
+		raw.clear(); raw.shrink_to_fit();
+	}
+
+	// all reads in one packed volume (the reference keeps them in one PackedDB, packed_db.cpp:194)
+	char tmpl[] = "/tmp/mecat2cns_XXXXXX";
+	const char* wrk = mkdtemp(tmpl);
+	if (!wrk) { fprintf(stderr, "cannot create a scratch directory\n"); return 1; }
+	mecat_volume vol;
+	memset(&vol, 0, sizeof vol);
+	{
+		StderrTimer t("load_fasta_db");
+		int nvols = 0;
+		char err[512];
+		if (mecat_b200_split_dataset(opt.reads, wrk, 0, &nvols, err, sizeof err)) { fprintf(stderr, "%s\n", err); return 1; }
+		const std::string v0 = std::string(wrk) + "/vol0";
+		if (nvols != 1) {
+			fprintf(stderr, "mecat2cns: the read set needs %d volumes; consensus over more than one 2.14 Gbase volume is not built yet\n", nvols);
+			return 1;
+		}
+		if (mecat_b200_volume_load(v0.c_str(), &vol)) { fprintf(stderr, "failed to open file '%s'.\n", v0.c_str()); return 1; }
+		unlink(v0.c_str());
+		unlink((std::string(wrk) + "/fileindex.txt").c_str());
+		rmdir(wrk);
+	}
+
+	mecat_b200_ctx* ctx = NULL;
+	if (mecat_b200_init(&ctx, 0, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU 0\n"); return 1; }
+	void* dvol = NULL;
+	if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); return 1; }
+
+	std::ofstream out(opt.output);
+	if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
+	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
+	const mecat_cns_params P = {opt.min_mapping_ratio, opt.min_align_size, opt.min_cov, opt.min_size};
+	bool ok = true;
+	for (size_t i = 0; ok && i < ec.size();) {
+		const long long part = ec[i].sid / opt.batch_size;
+		size_t j = i;
+		while (j < ec.size() && ec[j].sid / opt.batch_size == part) ++j;
+		char info[128];
+		snprintf(info, sizeof info, "processing reads %lld --- %lld", part * opt.batch_size, (part + 1) * opt.batch_size - 1);
+		StderrTimer t(info);
+		mecat_cns_piece* pieces = NULL;
+		char* seqs = NULL;
+		size_t np = 0, nb = 0;
+		if (mecat_b200_cns_reads(ctx, dvol, ec.data() + i, j - i, &P, &pieces, &np, &seqs, &nb)) {
+			fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx));
+			ok = false;
+			break;
+		}
+		for (size_t k = 0; k < np; ++k) {
+			out << ">" << pieces[k].id << "_" << pieces[k].beg << "_" << pieces[k].end << "_" << pieces[k].seq_len << "\n";
+			out.write(seqs + pieces[k].seq_offset, (std::streamsize)pieces[k].seq_len);
+			out << "\n";
+		}
+		mecat_b200_free(ctx, pieces);
+		mecat_b200_free(ctx, seqs);
+		i = j;
+	}
+	mecat_b200_volume_release(ctx, dvol);
+	mecat_b200_destroy(ctx);
+	mecat_b200_volume_unload(&vol);
+	return ok ? 0 : 1;
+}

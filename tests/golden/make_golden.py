@@ -57,6 +57,22 @@ def main():
             m["num_" + ext] = len(lines)
             if job == 0:
                 m["vol0_sha256"] = sha(os.path.join(wrk, "vol0"))
+        # mecat2cns -i 0 on the .can above (written next to a copy: it drops partition files beside its input)
+        can = os.path.join(tmp, "in.can")
+        for tag, args in (("cns_default", []), ("cns_relaxed", ["-l", "2000", "-c", "4", "-a", "1000"])):
+            if name == "cfg0" and tag == "cns_relaxed":
+                continue
+            with open(can, "w") as f:
+                f.write(open(os.path.join(tmp, "out.can")).read())
+            out = os.path.join(tmp, tag + ".fa")
+            subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-i", "0", "-t", "1"] + args + [can, fa, out],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            lines = open(out).read().splitlines()
+            recs = sorted(zip(lines[0::2], lines[1::2]))
+            with gzip.open(os.path.join(HERE, "%s.%s.fa.gz" % (name, tag)), "wt") as f:
+                for h, q in recs:
+                    f.write(h + "\n" + q + "\n")
+            m["num_" + tag] = len(recs)
         if name == "small":
             with open(fa, "rb") as f, gzip.open(os.path.join(HERE, "small.fa.gz"), "wb") as g:
                 shutil.copyfileobj(f, g)

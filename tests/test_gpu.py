@@ -490,6 +490,46 @@ def test_multi_gpu_schedule_reproduces_every_tile(gpu_ctx, small_vol, world):
         gpu_ctx.release_volume(d)
 
 
+def _gold_fasta(name, tag):
+    with gzip.open(os.path.join(util.GOLDEN, "%s.%s.fa.gz" % (name, tag)), "rt") as f:
+        lines = f.read().splitlines()
+    return sorted(zip(lines[0::2], lines[1::2]))
+
+
+def _gold_can(name):
+    import io
+    import mecat_b200
+    with gzip.open(os.path.join(util.GOLDEN, "%s.can.gz" % name), "rt") as f:
+        return mecat_b200.read_can(io.StringIO(f.read()))
+
+
+def _cns(gpu_ctx, vol, can, ratio, a, c, l):
+    import mecat_b200
+    d = gpu_ctx.upload(host_volume(vol))
+    ec = mecat_b200.normalise_candidates(can, l)
+    pieces = gpu_ctx.cns_reads(d, ec, ratio, a, c, l)
+    gpu_ctx.release_volume(d)
+    return sorted((">%d_%d_%d_%d" % (i, b, e, len(s)), s.decode()) for i, b, e, s in pieces)
+
+
+def test_cns_small_matches_reference(gpu_ctx, small_vol):
+    """mecat2cns -i 0 (rows C1-C7) against the corrected FASTA of the unmodified reference binary."""
+    can = _gold_can("small")
+    assert _cns(gpu_ctx, small_vol, can, 0.9, 2000, 6, 5000) == _gold_fasta("small", "cns_default")
+    got = _cns(gpu_ctx, small_vol, can, 0.9, 1000, 4, 2000)
+    want = _gold_fasta("small", "cns_relaxed")
+    assert len(got) == len(want)
+    assert got == want
+
+
+def test_cns_cfg0_matches_reference(gpu_ctx, cfg0_vol):
+    got = _cns(gpu_ctx, cfg0_vol, _gold_can("cfg0"), 0.9, 2000, 6, 5000)
+    want = _gold_fasta("cfg0", "cns_default")
+    assert len(got) == len(want)
+    bad = [g[0] for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:5]
+
+
 def test_candidate_cap_and_order(gpu_ctx, small_vol):
     """-n 3: per read the first 3 candidates of the -n 100 list, in the same order."""
     import mecat_b200
