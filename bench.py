@@ -330,6 +330,7 @@ def run_ours(args):
         "deterministic": len(digests) == 1,   # warm-up steps and the e2e call produced identical record arrays
         "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
         "host_ms_per_step": round(stats["host_ms"] / args.steps, 3), "d2h_ms_per_step": round(stats["d2h_ms"] / args.steps, 3),
+        "wall_ms_per_step": {k: round(stats[k] / args.steps, 3) for k in ("wall_index_ms", "wall_seed_ms", "wall_extend_ms", "total_ms")},
         "hits_per_step": stats["num_hits"] // args.steps, "candidates_per_step": stats["num_candidates"] // args.steps,
         "extend_blocks_per_step": stats["num_extend_blocks"] // args.steps,
     }

@@ -114,6 +114,7 @@ typedef struct {
 	float kernel_ms[MECAT_K_NUM];
 	int64_t kernel_launches[MECAT_K_NUM];
 	float h2d_ms, d2h_ms, host_ms, total_ms;
+	float wall_index_ms, wall_seed_ms, wall_extend_ms, wall_other_ms;   /* host wall clock spent inside each phase */
 	int64_t h2d_bytes, d2h_bytes;
 	int64_t num_hits, num_candidates, num_extend_blocks, index_kmers, index_bases, num_records;
 } mecat_b200_stats;

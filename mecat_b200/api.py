@@ -42,6 +42,7 @@ CNS_PIECE_DTYPE = np.dtype([("id", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("seq
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_float * 16), ("kernel_launches", C.c_int64 * 16),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("host_ms", C.c_float), ("total_ms", C.c_float),
+                ("wall_index_ms", C.c_float), ("wall_seed_ms", C.c_float), ("wall_extend_ms", C.c_float), ("wall_other_ms", C.c_float),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("num_hits", C.c_int64), ("num_candidates", C.c_int64), ("num_extend_blocks", C.c_int64),
                 ("index_kmers", C.c_int64), ("index_bases", C.c_int64), ("num_records", C.c_int64)]
@@ -73,6 +74,15 @@ EXPORTS = [
 ]
 
 _lib = None
+
+
+def _adopt(lib, addr, nbytes, dtype):
+    """numpy view of a library-owned host buffer without copying; the buffer is free()d when the last
+    array referring to it is collected."""
+    import weakref
+    mem = (C.c_char * nbytes).from_address(addr)
+    weakref.finalize(mem, lib.mecat_b200_host_free, C.c_void_p(addr))
+    return np.frombuffer(mem, dtype=dtype)
 
 
 def load_library():
@@ -225,11 +235,14 @@ class Context:
             if ptr.value:
                 self.L.mecat_b200_free(self.h, ptr)
             return np.zeros(0, dtype=dtype)
-        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
-        arr = np.frombuffer(buf, dtype=dtype).copy()     # one copy out of the library-owned buffer
-        del buf
-        self.L.mecat_b200_free(self.h, ptr)
-        return arr
+        if n * dtype.itemsize < (1 << 20):
+            buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+            arr = np.frombuffer(buf, dtype=dtype).copy()
+            del buf
+            self.L.mecat_b200_free(self.h, ptr)
+            return arr
+        # large results: wrap the library-owned buffer without copying; it is released with the array
+        return _adopt(self.L, ptr.value, n * dtype.itemsize, dtype)
 
     def stats(self):
         s = Stats()

@@ -178,7 +178,9 @@ int mecat_b200_index_build(mecat_b200_ctx* c, void* dvol_ref, void** index)
 	if (check(c) || !dvol_ref || !index) return 1;
 	cudaSetDevice(c->device);
 	DIndex* idx = nullptr;
+	WallTimer t;
 	int rc = index_build(c, (DVolume*)dvol_ref, &idx);
+	c->stats.wall_index_ms += t.stop();
 	if (rc) return rc;
 	*index = idx;
 	return 0;
@@ -441,7 +443,11 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		MB_CUDA(c, c->alloc(&d_cands, (size_t)((size_t)N * maxc)));
 		MB_CUDA(c, c->alloc(&d_counts, (size_t)((size_t)N)));
 		MB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)N, c->stream));
-		if (seed_candidates(c, idx, ref, reads, p, read_begin, read_end, d_cands, d_counts)) return 1;
+		{
+			WallTimer ts;
+			if (seed_candidates(c, idx, ref, reads, p, read_begin, read_end, d_cands, d_counts)) return 1;
+			c->stats.wall_seed_ms += ts.stop();
+		}
 		MB_CUDA(c, cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
 		size_t total = 0;
@@ -501,36 +507,24 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			                                   ref->offsz, ref->start_read_id, nullptr, d_tasks, d_scores);
 		}
 		MB_CUDA(c, cudaGetLastError());
-		if (extend_launch(c, reads, ref, d_tasks, total, d_halves)) return 1;
-		{
-			KScope ks(c, MECAT_K_FINAL);
-			k_extend_finalize<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, total, p->min_align_size, d_res);
-		}
-		MB_CUDA(c, cudaGetLastError());
+		// The extension runs in a few chunks of reads; while the GPU extends chunk k+1 the host threads
+		// assemble the M4 records of chunk k (fill_m4record + append_m4v: sort, containment filter) -- on
+		// the host like the reference, same std::sort, same comparator, so ties fall the same way.
 		std::vector<ExtendTask> h_tasks(total);
 		std::vector<mecat_extend_result> h_res(total);
 		std::vector<int32_t> h_score(total);
-		{
-			WallTimer t;
-			MB_CUDA(c, cudaMemcpyAsync(h_tasks.data(), d_tasks, sizeof(ExtendTask) * total, cudaMemcpyDeviceToHost, c->stream));
-			MB_CUDA(c, cudaMemcpyAsync(h_res.data(), d_res, sizeof(mecat_extend_result) * total, cudaMemcpyDeviceToHost, c->stream));
-			MB_CUDA(c, cudaMemcpyAsync(h_score.data(), d_scores, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, c->stream));
-			MB_CUDA(c, cudaStreamSynchronize(c->stream));
-			c->stats.d2h_ms += t.stop();
-			c->resolve_timers();
-			c->stats.d2h_bytes += (int64_t)((sizeof(ExtendTask) + sizeof(mecat_extend_result) + 4) * total);
-			c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1);
-		}
-		WallTimer host_timer;
-		// fill_m4record + append_m4v (sort, containment filter) per read, on the host like the
-		// reference -- same std::sort, same comparator, so ties fall the same way -- spread over
-		// host threads by read ranges; chunks are concatenated in read order.
 		const int nthreads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
-		const int nchunks = std::min(N, nthreads * 4);
-		std::vector<std::vector<mecat_m4>> parts((size_t)nchunks);
-		auto work = [&](int chunk) {
-			const int r_lo = (int)((int64_t)N * chunk / nchunks), r_hi = (int)((int64_t)N * (chunk + 1) / nchunks);
-			std::vector<mecat_m4>& dst = parts[(size_t)chunk];
+		const int npipe = total >= 200000 ? 6 : 1;
+		std::vector<int> rcut((size_t)npipe + 1, N);
+		rcut[0] = 0;
+		for (int k = 1, r = 0; k < npipe; ++k) {
+			const int64_t want = (int64_t)total * k / npipe;
+			while (r < N && h_outpos[r] < want) ++r;
+			rcut[k] = r;
+		}
+		const int sub = nthreads * 2;                                   // assembly pieces per pipeline chunk
+		std::vector<std::vector<mecat_m4>> parts((size_t)npipe * sub);
+		auto assemble = [&](int r_lo, int r_hi, std::vector<mecat_m4>& dst) {
 			std::vector<mecat_m4> loc;
 			std::vector<char> valid;
 			for (int r = r_lo; r < r_hi; ++r) {
@@ -568,21 +562,69 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 				for (size_t i = 0; i < loc.size(); ++i) if (valid[i]) dst.push_back(loc[i]);
 			}
 		};
-		{
+		auto assemble_chunk = [&](int k) {
+			const int r0 = rcut[k], r1 = rcut[k + 1];
 			std::atomic<int> next(0);
+			auto runner = [&]() {
+				for (int ch; (ch = next.fetch_add(1)) < sub;) {
+					const int lo = r0 + (int)((int64_t)(r1 - r0) * ch / sub), hi = r0 + (int)((int64_t)(r1 - r0) * (ch + 1) / sub);
+					assemble(lo, hi, parts[(size_t)k * sub + ch]);
+				}
+			};
 			std::vector<std::thread> pool;
-			auto runner = [&]() { for (int ch; (ch = next.fetch_add(1)) < nchunks;) work(ch); };
 			for (int t = 1; t < nthreads; ++t) pool.emplace_back(runner);
 			runner();
 			for (auto& th : pool) th.join();
+		};
+		WallTimer host_timer;
+		float host_hidden = 0;
+		std::thread worker;
+		int rc_pipe = 0;
+		for (int k = 0; k < npipe && !rc_pipe; ++k) {
+			const size_t t0 = (size_t)h_outpos[rcut[k]], t1 = (size_t)h_outpos[rcut[k + 1]];
+			const size_t nt = t1 - t0;
+			auto gpu_part = [&]() -> int {
+				if (!nt) return 0;
+				WallTimer te;
+				if (extend_launch(c, reads, ref, d_tasks + t0, nt, d_halves + 2 * t0)) return 1;
+				c->stats.wall_extend_ms += te.stop();
+				{
+					KScope ks(c, MECAT_K_FINAL);
+					k_extend_finalize<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(d_tasks + t0, d_halves + 2 * t0, nt, p->min_align_size, d_res + t0);
+				}
+				MB_CUDA(c, cudaGetLastError());
+				WallTimer t;
+				MB_CUDA(c, cudaMemcpyAsync(h_tasks.data() + t0, d_tasks + t0, sizeof(ExtendTask) * nt, cudaMemcpyDeviceToHost, c->stream));
+				MB_CUDA(c, cudaMemcpyAsync(h_res.data() + t0, d_res + t0, sizeof(mecat_extend_result) * nt, cudaMemcpyDeviceToHost, c->stream));
+				MB_CUDA(c, cudaMemcpyAsync(h_score.data() + t0, d_scores + t0, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, c->stream));
+				MB_CUDA(c, cudaStreamSynchronize(c->stream));
+				c->stats.d2h_ms += t.stop();
+				c->resolve_timers();
+				return 0;
+			};
+			rc_pipe = gpu_part();
+			if (worker.joinable()) worker.join();
+			if (!rc_pipe) worker = std::thread(assemble_chunk, k);
 		}
+		if (worker.joinable()) worker.join();
+		if (rc_pipe) return 1;
+		(void)host_hidden;
+		c->stats.d2h_bytes += (int64_t)((sizeof(ExtendTask) + sizeof(mecat_extend_result) + 4) * total);
+		c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1);
 		size_t nout = 0;
 		for (auto& v : parts) nout += v.size();
 		mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * (nout ? nout : 1));
 		if (!out) MB_FAIL(c, "pw_tile: out of host memory");
 		{
-			size_t at = 0;
-			for (auto& v : parts) { if (!v.empty()) memcpy(out + at, v.data(), sizeof(mecat_m4) * v.size()); at += v.size(); }
+			// concatenate in read order, in parallel (each piece knows its offset)
+			std::vector<size_t> at(parts.size() + 1, 0);
+			for (size_t i = 0; i < parts.size(); ++i) at[i + 1] = at[i] + parts[i].size();
+			std::atomic<size_t> next(0);
+			auto runner = [&]() { for (size_t i; (i = next.fetch_add(1)) < parts.size();) if (!parts[i].empty()) memcpy(out + at[i], parts[i].data(), sizeof(mecat_m4) * parts[i].size()); };
+			std::vector<std::thread> pool;
+			for (int t = 1; t < std::min(nthreads, 8); ++t) pool.emplace_back(runner);
+			runner();
+			for (auto& th : pool) th.join();
 		}
 		c->stats.host_ms += host_timer.stop();
 		c->stats.num_records += (int64_t)nout;
