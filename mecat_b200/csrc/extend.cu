@@ -41,7 +41,7 @@ struct WarpSmem
 {
 	uint2 sq[SEQ_WORDS];      // .x = packed word i, .y = word i+1: any 16-base window is one LDS.64 + funnel shift
 	uint2 st[SEQ_WORDS];
-	uint2 vl[2][VL_N];        // per parity of k, index (k + KOFF) >> 1: .x = furthest x, .y = packed anchor
+	uint2 vl[2 * VL_N];       // index k + KOFF: .x = furthest x on diagonal k, .y = packed anchor (one address per row)
 };
 
 struct Walk                   // one sequence seen as a forward walk
@@ -131,7 +131,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 					const uint32_t b0 = T.g0 + (uint32_t)ti + 16u * i;
 					S.st[i] = make_uint2(ld_bases32(T.arr, b0) ^ T.comp, ld_bases32(T.arr, b0 + 16u) ^ T.comp);
 				}
-				if (lane == 0) S.vl[1][(KOFF + 1) >> 1] = make_uint2(0u, NO_ANCHOR);
+				if (lane == 0) S.vl[KOFF + 1] = make_uint2(0u, NO_ANCHOR);
 			}
 			__syncwarp();
 
@@ -144,8 +144,8 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			const uint2* sq = S.sq;
 			const uint2* st = S.st;
 			// one furthest-reaching cell: lane-local, reads the other-parity array, writes its own
-			auto cell = [&](const uint2* oth, uint2* own, int j, int n, int k, uint32_t dbits, int& x, uint32_t& anc) {
-				const uint2 lf = oth[j], rt = oth[j + 1];
+			auto cell = [&](uint2* own, int j, int n, int k, uint32_t dbits, int& x, uint32_t& anc) {
+				const uint2 lf = own[2 * j - 1], rt = own[2 * j + 1];
 				if (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
 				else { x = (int)lf.x + 1; anc = lf.y; }
 				int y = x - k;
@@ -159,31 +159,29 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				const int over = max(max(x - qblk, y - tblk), 0);    // the window may run past a block end
 				x -= over; y -= over;
 				if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
-				own[j] = make_uint2((uint32_t)x, anc);
+				own[2 * j] = make_uint2((uint32_t)x, anc);
 				return x + y;
 			};
 			for (int d = 0; d < max_d; ++d) {
 				if (max_k - min_k > 2 * tol) break;
 				const int n = ((max_k - min_k) >> 1) + 1;
-				const int kk0 = min_k + KOFF;
-				uint2* own = &S.vl[kk0 & 1][kk0 >> 1];                 // own[j]       <-> diagonal min_k + 2j
-				const uint2* oth = &S.vl[(kk0 & 1) ^ 1][(kk0 - 1) >> 1]; // oth[j], [j+1] <-> diagonals k-1, k+1
+				uint2* own = &S.vl[min_k + KOFF];                      // own[2j] <-> diagonal min_k + 2j; neighbours own[2j -+ 1]
 				const uint32_t dbits = (uint32_t)d << 20;
 				// pass 0: diagonals 0..31 of the band (most rows have no other pass)
 				int x0 = 0, u0 = -1;
 				uint32_t a0 = NO_ANCHOR;
-				if (lane < n) u0 = cell(oth, own, lane, n, min_k + 2 * lane, dbits, x0, a0);
+				if (lane < n) u0 = cell(own, lane, n, min_k + 2 * lane, dbits, x0, a0);
 				int rowmax = __reduce_max_sync(FULL, u0);
 				int x1 = 0, u1 = -1;
 				uint32_t a1 = NO_ANCHOR;
 				if (n > 32) {
-					if (lane + 32 < n) u1 = cell(oth, own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1);
+					if (lane + 32 < n) u1 = cell(own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1);
 					rowmax = max(rowmax, __reduce_max_sync(FULL, u1));
 					for (int base = 64; base < n; base += 32) {
 						const int j = base + lane;
 						int xx = 0, uu = -1;
 						uint32_t aa = NO_ANCHOR;
-						if (j < n) uu = cell(oth, own, j, n, min_k + 2 * j, dbits, xx, aa);
+						if (j < n) uu = cell(own, j, n, min_k + 2 * j, dbits, xx, aa);
 						rowmax = max(rowmax, __reduce_max_sync(FULL, uu));
 					}
 				}
@@ -206,7 +204,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 							const int j = base + lane;
 							uint2 c = make_uint2(0u, NO_ANCHOR);
 							bool h = false;
-							if (j < n) { c = own[j]; const int yy = (int)c.x - (min_k + 2 * j); h = (int)c.x >= qblk || yy >= tblk; }
+							if (j < n) { c = own[2 * j]; const int yy = (int)c.x - (min_k + 2 * j); h = (int)c.x >= qblk || yy >= tblk; }
 							hm = __ballot_sync(FULL, h);
 							if (hm) {
 								const int src = __ffs(hm) - 1;
@@ -233,7 +231,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 					for (int base = 64; base < n; base += 32) {
 						const int j = base + lane;
 						bool keep = false;
-						if (j < n) keep = 2 * (int)own[j].x - (min_k + 2 * j) >= thr;
+						if (j < n) keep = 2 * (int)own[2 * j].x - (min_k + 2 * j) >= thr;
 						const unsigned km2 = __ballot_sync(FULL, keep);
 						if (km2) { lo = min(lo, min_k + 2 * (base + __ffs(km2) - 1)); hi = max(hi, min_k + 2 * (base + 31 - __clz(km2))); }
 					}
@@ -244,15 +242,14 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			if (!aligned && rows > 0) {
 				// best (x+y) cell: first k of the last completed row that reaches best_m
 				const int n = ((last_max - last_min) >> 1) + 1;
-				const int kk0 = last_min + KOFF;
-				const uint2* own = &S.vl[kk0 & 1][kk0 >> 1];
+				const uint2* own = &S.vl[last_min + KOFF];
 				for (int base = 0; base < n; base += 32) {
 					const int j = base + lane;
 					const int k = last_min + 2 * j;
 					uint2 c = make_uint2(0u, NO_ANCHOR);
 					bool is = false;
 					if (j < n) {
-						c = own[j];
+						c = own[2 * j];
 						is = 2 * (int)c.x - k == best_m;
 					}
 					const unsigned bm = __ballot_sync(FULL, is);

@@ -270,15 +270,35 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		__syncthreads();
 		// ---- pass 1: hit counts per bucket slot.  The slot map keeps neighbouring buckets adjacent,
 		// aliases (buckets 65536 apart) only inflate counts: every later decision is a superset.
+		// Four lists per warp iteration: their position loads are issued together (the passes are bound by
+		// L2/DRAM latency of these gathers, not by bandwidth).
 		unsigned myhits = 0;
-		for (int km = warp; km < nk; km += nwarps) {
-			const int n = kc[km];
-			const uint32_t b = kb[km];
-			for (int h = lane; h < n; h += 32) {
-				const uint32_t hh = ((uint32_t)P.pos[b + h] / SEGW) & (CNT_SLOTS - 1);
+		constexpr int U = 4;
+		for (int km0 = warp; km0 < nk; km0 += U * nwarps) {
+			int n[U];
+			uint32_t b[U], p0[U], p1[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int km = km0 + u * nwarps;
+				n[u] = km < nk ? (int)kc[km] : 0;
+				b[u] = km < nk ? kb[km] : 0u;
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				p0[u] = lane < n[u] ? (uint32_t)P.pos[b[u] + lane] : 0u;
+				p1[u] = lane + 32 < n[u] ? (uint32_t)P.pos[b[u] + lane + 32] : 0u;
+			}
+			auto count_one = [&](uint32_t pp) {
+				const uint32_t hh = (pp / SEGW) & (CNT_SLOTS - 1);
 				const uint32_t cur = (cnt[hh >> 1] >> ((hh & 1u) << 4)) & 0xFFFFu;
 				if (cur < CNT_SAT) atomicAdd(&cnt[hh >> 1], 1u << ((hh & 1u) << 4));
 				++myhits;
+			};
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				if (lane < n[u]) count_one(p0[u]);
+				if (lane + 32 < n[u]) count_one(p1[u]);
+				for (int h = lane + 64; h < n[u]; h += 32) count_one((uint32_t)P.pos[b[u] + h]);
 			}
 		}
 		__syncthreads();
@@ -308,15 +328,23 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		}
 		__syncthreads();
 		// ---- pass 3: collect the hits of wanted buckets (shared memory first, overflow to global scratch)
-		for (int km = warp; km < nk; km += nwarps) {
-			const int n = kc[km];
-			const uint32_t b = kb[km];
-			for (int h0 = 0; h0 < n; h0 += 32) {
-				const int h = h0 + lane;
+		for (int km0 = warp; km0 < nk; km0 += U * nwarps) {
+			int n[U];
+			uint32_t b[U], p0[U], p1[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int km = km0 + u * nwarps;
+				n[u] = km < nk ? (int)kc[km] : 0;
+				b[u] = km < nk ? kb[km] : 0u;
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				p0[u] = lane < n[u] ? (uint32_t)P.pos[b[u] + lane] : 0u;
+				p1[u] = lane + 32 < n[u] ? (uint32_t)P.pos[b[u] + lane + 32] : 0u;
+			}
+			auto collect = [&](bool have, uint32_t p, int km) {
 				bool take = false;
-				uint32_t p = 0;
-				if (h < n) {
-					p = (uint32_t)P.pos[b + h];
+				if (have) {
 					const uint32_t h2 = (p / SEGW) & (CNT_SLOTS - 1);
 					take = (want_bits[h2 >> 5] >> (h2 & 31u)) & 1u;
 				}
@@ -331,6 +359,17 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 						if (at < SCAP) skeys[at] = key;          // the counters are dead: their memory takes the keys
 						else if (at < P.hcap) gsc.keys[at] = key;
 					}
+				}
+			};
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				if (n[u] == 0) continue;
+				const int km = km0 + u * nwarps;
+				collect(lane < n[u], p0[u], km);
+				if (n[u] > 32) collect(lane + 32 < n[u], p1[u], km);
+				for (int h0 = 64; h0 < n[u]; h0 += 32) {
+					const int h = h0 + lane;
+					collect(h < n[u], h < n[u] ? (uint32_t)P.pos[b[u] + h] : 0u, km);
 				}
 			}
 		}
