@@ -13,48 +13,77 @@
 // ascending order the atomics lost.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace mb {
 
 namespace {
 
-__device__ __forceinline__ uint32_t kmer_code_at(const uint32_t* __restrict__ fwd, uint32_t p)
-{
-	// 13 bases starting at p, first base most significant (lookup_table.cpp:79-90)
-	return rev_groups2(ld_bases32(fwd, p)) >> 6;
-}
+constexpr uint32_t CODE_MASK = (1u << (2 * KMER)) - 1;
+constexpr int RUN = 16;      // consecutive k-mer starts handled by one thread
 
-// [code_lo, code_hi): the slice of the code space this launch (this GPU) is responsible for
-__global__ void k_kmer_count(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
-                             uint32_t* __restrict__ counts, uint32_t code_lo, uint32_t code_hi)
+// Calls f(code, p) for every 13-mer start p of the read at `o` (offset, size).  A thread takes RUN
+// consecutive starts: one 3-word window, the first code by a 2-bit-group reversal (first base most
+// significant, lookup_table.cpp:79-90) and the next fifteen by rolling in one base each.
+template <class F>
+__device__ __forceinline__ void for_each_kmer(const uint32_t* __restrict__ fwd, const int2 o, F f)
 {
-	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
-		const int2 o = offsz[r];
-		const int nk = o.y - (KMER - 1);
-		for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-			const uint32_t code = kmer_code_at(fwd, (uint32_t)(o.x + i));
-			if (code - code_lo < code_hi - code_lo) atomicAdd(&counts[code], 1u);
+	const int nk = o.y - (KMER - 1);
+	for (int i0 = threadIdx.x * RUN; i0 < nk; i0 += blockDim.x * RUN) {
+		const uint32_t p = (uint32_t)(o.x + i0);
+		const uint32_t w = p >> 4, sh = (p & 15u) << 1;
+		const uint32_t a0 = __ldg(fwd + w), a1 = __ldg(fwd + w + 1), a2 = __ldg(fwd + w + 2);
+		const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh);
+		uint32_t code = rev_groups2(w0) >> 6;
+		f(code, p);
+		if (nk - i0 >= RUN) {
+#pragma unroll
+			for (int j = 1; j < RUN; ++j) {
+				const int b = KMER - 1 + j;
+				const uint32_t base = (b < 16 ? w0 >> (2 * b) : w1 >> (2 * (b - 16))) & 3u;
+				code = ((code << 2) & CODE_MASK) | base;
+				f(code, p + j);
+			}
+		} else {
+			const int n = nk - i0;
+#pragma unroll
+			for (int j = 1; j < RUN; ++j) {
+				if (j >= n) break;
+				const int b = KMER - 1 + j;
+				const uint32_t base = (b < 16 ? w0 >> (2 * b) : w1 >> (2 * (b - 16))) & 3u;
+				code = ((code << 2) & CODE_MASK) | base;
+				f(code, p + j);
+			}
 		}
 	}
+}
+
+// [code_lo, code_hi): the slice of the code space this launch is responsible for
+__global__ void __launch_bounds__(256) k_kmer_count(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
+                                                    uint32_t* __restrict__ counts, uint32_t code_lo, uint32_t code_hi)
+{
+	const uint32_t span = code_hi - code_lo;
+	for (int r = blockIdx.x; r < nreads; r += gridDim.x)
+		for_each_kmer(fwd, offsz[r], [&](uint32_t code, uint32_t) {
+			if (code - code_lo < span) atomicAdd(&counts[code], 1u);
+		});
 }
 
 // cursor[code] starts at begin[code] for kept k-mers and at DROPPED for the others, so one atomic
 // both tests the >128 cutoff and yields the slot.
 constexpr uint32_t DROPPED = 0x80000000u;
 
-__global__ void k_kmer_fill(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
-                            uint32_t* __restrict__ cursor, int32_t* __restrict__ pos, uint32_t code_lo, uint32_t code_hi)
+__global__ void __launch_bounds__(256) k_kmer_fill(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
+                                                   uint32_t* __restrict__ cursor, int32_t* __restrict__ pos, uint32_t code_lo, uint32_t code_hi)
 {
-	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
-		const int2 o = offsz[r];
-		const int nk = o.y - (KMER - 1);
-		for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-			const uint32_t p = (uint32_t)(o.x + i);
-			const uint32_t code = kmer_code_at(fwd, p);
-			if (code - code_lo >= code_hi - code_lo) continue;
-			const uint32_t slot = atomicAdd(&cursor[code], 1u);
-			if (!(slot & DROPPED)) pos[slot] = (int32_t)p;
-		}
-	}
+	const uint32_t span = code_hi - code_lo;
+	for (int r = blockIdx.x; r < nreads; r += gridDim.x)
+		for_each_kmer(fwd, offsz[r], [&](uint32_t code, uint32_t p) {
+			if (code - code_lo < span) {
+				const uint32_t slot = atomicAdd(&cursor[code], 1u);
+				if (!(slot & DROPPED)) pos[slot] = (int32_t)p;
+			}
+		});
 }
 
 // ---- exclusive scan of min(count, cutoff -> 0) over 2^26 codes: reduce / top / down-sweep
@@ -201,6 +230,16 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_sort_lists(const uint32_t* 
 
 }  // namespace
 
+// Number of code sub-ranges a histogram / scatter over [code_lo, code_hi) is split into; `full` is the
+// measured optimum for the whole 2^26 code space (profiles/README.md), scaled for a slice of it.
+static int index_passes(const char* env, int full, uint32_t code_lo, uint32_t code_hi)
+{
+	const char* e = getenv(env);      // tuning knob; the result does not depend on it
+	if (e) full = atoi(e);
+	const int n = (int)(((uint64_t)full * (code_hi - code_lo) + (1u << 25)) >> 26);
+	return n < 1 ? 1 : (n > 256 ? 256 : n);
+}
+
 static int grid_for_reads(const DVolume* v) { return v->num_reads < 1 ? 1 : (v->num_reads > 65535 * 8 ? 65535 * 8 : v->num_reads); }
 
 // Stage 1: histogram of the k-mers whose code lies in [code_lo, code_hi) (all codes for one GPU).
@@ -214,8 +253,16 @@ int index_count_part(Ctx* c, const DVolume* v, uint32_t code_lo, uint32_t code_h
 		MB_CUDA(c, c->alloc(&I->begin, (size_t)NCODES + 4));
 		MB_CUDA(c, cudaMemsetAsync(I->counts, 0, sizeof(uint32_t) * (size_t)NCODES, c->stream));
 		if (v->num_reads > 0 && code_hi > code_lo) {
-			KScope ks(c, MECAT_K_COUNT);
-			k_kmer_count<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->counts, code_lo, code_hi);
+			// The histogram is built in passes over sub-ranges of the codes: recomputing the codes costs
+			// ~1 ms per pass, but the counters of one sub-range (4 * 2^26 / passes bytes) stay in the 126 MB
+			// L2, so the random atomics stop being DRAM read-modify-writes of 32-byte sectors.
+			const int passes = index_passes("MECAT_B200_COUNT_PASSES", 4, code_lo, code_hi);
+			KScope ks(c, MECAT_K_COUNT, passes);
+			for (int r = 0; r < passes; ++r) {
+				const uint32_t lo = code_lo + (uint32_t)((uint64_t)(code_hi - code_lo) * r / passes);
+				const uint32_t hi = code_lo + (uint32_t)((uint64_t)(code_hi - code_lo) * (r + 1) / passes);
+				if (hi > lo) k_kmer_count<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->counts, lo, hi);
+			}
 		}
 		MB_CUDA(c, cudaGetLastError());
 		MB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -254,8 +301,16 @@ int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uin
 		MB_CUDA(c, c->alloc(&I->pos, (size_t)total + 1));
 		if (total && code_hi > code_lo) {
 			{
-				KScope ks(c, MECAT_K_FILL);
-				k_kmer_fill<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->counts, I->pos, code_lo, code_hi);
+				// same idea for the scatter: per pass the cursors are L2 resident.  The destination slice of
+				// pos[] (197 MB at 32 passes) is not, ncu still shows one 32-byte DRAM sector written per
+				// position (profiles/r1_ncu_fill_pass.csv); more passes cost more re-scans than they save.
+				const int passes = index_passes("MECAT_B200_FILL_PASSES", 32, code_lo, code_hi);
+				KScope ks(c, MECAT_K_FILL, passes);
+				for (int r = 0; r < passes; ++r) {
+					const uint32_t lo = code_lo + (uint32_t)((uint64_t)(code_hi - code_lo) * r / passes);
+					const uint32_t hi = code_lo + (uint32_t)((uint64_t)(code_hi - code_lo) * (r + 1) / passes);
+					if (hi > lo) k_kmer_fill<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, I->counts, I->pos, lo, hi);
+				}
 			}
 			{
 				KScope ks(c, MECAT_K_SORT);
