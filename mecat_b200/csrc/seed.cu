@@ -74,20 +74,41 @@ __device__ __forceinline__ uint32_t query_code(const uint32_t* __restrict__ arr,
 	return rev_groups2(ld_bases32(arr, g0 + (uint32_t)(km * STRIDE)) ^ comp) >> 6;
 }
 
-// block-wide bitonic sort of n64 (power of two) keys
+// block-wide bitonic sort of n (power of two) 64-bit keys.  Two strides are folded into one step
+// (a thread holds the 4 keys i, i+h, i+2h, i+3h), which halves the barriers and the shared-memory
+// round trips; all index arithmetic is shifts (strides are powers of two).
+__device__ __forceinline__ void cmpex(unsigned long long& x, unsigned long long& y, bool up)
+{
+	if ((x > y) == up) { const unsigned long long t = x; x = y; y = t; }
+}
+
 __device__ void block_sort(unsigned long long* a, int n)
 {
-	for (int size = 2; size <= n; size <<= 1)
-		for (int stride = size >> 1; stride > 0; stride >>= 1) {
+	for (int size = 2; size <= n; size <<= 1) {
+		int ls = 31 - __clz(size) - 1;                 // log2 of the first stride, size / 2
+		for (; ls >= 1; ls -= 2) {                     // strides 2^ls and 2^(ls-1) together
+			const int lh = ls - 1, h = 1 << lh;
 			__syncthreads();
-			for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-				const int i = ((t / stride) * stride * 2) + (t % stride);
-				const int j = i + stride;
-				const bool up = (i & size) == 0;
-				const unsigned long long x = a[i], y = a[j];
-				if ((x > y) == up) { a[i] = y; a[j] = x; }
+			for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
+				const int i0 = ((t >> lh) << (lh + 2)) | (t & (h - 1));
+				const bool up = (i0 & size) == 0;
+				unsigned long long k0 = a[i0], k1 = a[i0 + h], k2 = a[i0 + 2 * h], k3 = a[i0 + 3 * h];
+				cmpex(k0, k2, up); cmpex(k1, k3, up);
+				cmpex(k0, k1, up); cmpex(k2, k3, up);
+				a[i0] = k0; a[i0 + h] = k1; a[i0 + 2 * h] = k2; a[i0 + 3 * h] = k3;
 			}
 		}
+		if (ls == 0) {                                 // left-over stride 1
+			__syncthreads();
+			for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+				const int i = t << 1;
+				const bool up = (i & size) == 0;
+				unsigned long long x = a[i], y = a[i + 1];
+				cmpex(x, y, up);
+				a[i] = x; a[i + 1] = y;
+			}
+		}
+	}
 	__syncthreads();
 }
 
