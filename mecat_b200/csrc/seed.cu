@@ -192,6 +192,47 @@ __device__ int replay_overflow(unsigned long long* ent, int na, int* sl, int* ss
 	__syncwarp();
 	int score = SLOTS;
 	for (int t = SLOTS; t < na; ++t) {
+		// Fast forward.  While all 40 slots are mutually consistent (every count is 39), a newcomer
+		// either agrees with all of them and overwrites slot 39, or disagrees with at least two and
+		// is dropped; both leave slots 0..38 and all counts as they are and keep the score increment.
+		// Only slot 39 (the last accepted hit) carries over, so 32 newcomers are judged at once; the
+		// first one that would evict a slot (exactly one disagreement) goes through the general step.
+		const bool clean = __all_sync(FULL, cc[lane] == SLOTS - 1 && (lane + 32 >= SLOTS || cc[lane + 32] == SLOTS - 1));
+		if (clean) {
+			int last_l = sl[SLOTS - 1], last_s = ss[SLOTS - 1];
+			const int gap = score - t;       // score minus hits seen: every settled hit keeps its increment
+			bool stop = false;
+			while (t < na && !stop) {
+				const int me = t + lane;
+				const bool valid = me < na;
+				const unsigned long long e = valid ? ent[me] : 0ull;
+				const int nl = (int)(e & 2047u), ns = (int)((e >> 11) & 0xFFFFu) + 1;
+				int v38 = 0;
+				for (int x = 0; x < SLOTS - 1; ++x) v38 += (int)pair_ok(sl[x], ss[x], nl, ns);
+				const unsigned amask = __ballot_sync(FULL, valid && v38 == SLOTS - 1);      // would-be accepts
+				const unsigned below = amask & ((1u << lane) - 1u);
+				const int src = below ? 31 - __clz(below) : 0;
+				int pl = __shfl_sync(FULL, nl, src), ps = __shfl_sync(FULL, ns, src);
+				if (!below) { pl = last_l; ps = last_s; }
+				const bool plast = pair_ok(pl, ps, nl, ns);
+				const bool viol = valid && ((v38 == SLOTS - 1 && !plast) || (v38 == SLOTS - 2 && plast));
+				const unsigned vmask = __ballot_sync(FULL, viol);
+				const int upto = vmask ? __ffs(vmask) - 1 : min(32, na - t);                 // hits settled here
+				if (lane < upto) ent[me] = (e & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)((me + 1 + gap) & 0xFFFF) << 48);
+				const unsigned done = amask & (upto >= 32 ? FULL : ((1u << upto) - 1u));
+				if (done) {
+					const int w = 31 - __clz(done);
+					last_l = __shfl_sync(FULL, nl, w); last_s = __shfl_sync(FULL, ns, w);
+				}
+				t += upto;
+				stop = vmask != 0u;
+			}
+			__syncwarp();
+			if (lane == 0) { sl[SLOTS - 1] = last_l; ss[SLOTS - 1] = last_s; }
+			__syncwarp();
+			score = t + gap;
+			if (t >= na) break;
+		}
 		const unsigned long long e = ent[t];
 		const int nl = (int)(e & 2047u), ns = (int)((e >> 11) & 0xFFFFu) + 1;
 		++score;
