@@ -130,6 +130,7 @@ void mecat_b200_destroy(mecat_b200_ctx* c)
 	for (auto& b : c->blocks) b.used = false;
 	c->trim();
 	for (auto& e : c->pool) cudaEventDestroy(e);
+	for (auto& h : c->hstage) if (h.p) cudaFreeHost(h.p);
 	cudaFree(c->d_counters);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -510,15 +511,21 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		// The extension runs in a few chunks of reads; while the GPU extends chunk k+1 the host threads
 		// assemble the M4 records of chunk k (fill_m4record + append_m4v: sort, containment filter) -- on
 		// the host like the reference, same std::sort, same comparator, so ties fall the same way.
-		std::vector<ExtendTask> h_tasks(total);
-		std::vector<mecat_extend_result> h_res(total);
-		std::vector<int32_t> h_score(total);
+		ExtendTask* h_tasks = nullptr;
+		mecat_extend_result* h_res = nullptr;
+		int32_t* h_score = nullptr;
+		MB_CUDA(c, c->host_stage(0, sizeof(ExtendTask) * total, (void**)&h_tasks));
+		MB_CUDA(c, c->host_stage(1, sizeof(mecat_extend_result) * total, (void**)&h_res));
+		MB_CUDA(c, c->host_stage(2, sizeof(int32_t) * total, (void**)&h_score));
 		const int nthreads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
-		const int npipe = total >= 200000 ? 6 : 1;
+		// chunk ends as fractions of the candidates: the last chunks are small because the assembly of the
+		// final one is the only host work the GPU cannot hide
+		static const double cuts[] = {0.16, 0.32, 0.48, 0.64, 0.78, 0.89, 0.96, 1.0};
+		const int npipe = total >= 200000 ? (int)(sizeof cuts / sizeof cuts[0]) : 1;
 		std::vector<int> rcut((size_t)npipe + 1, N);
 		rcut[0] = 0;
 		for (int k = 1, r = 0; k < npipe; ++k) {
-			const int64_t want = (int64_t)total * k / npipe;
+			const int64_t want = (int64_t)((double)total * cuts[k - 1]);
 			while (r < N && h_outpos[r] < want) ++r;
 			rcut[k] = r;
 		}
@@ -594,9 +601,9 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 				}
 				MB_CUDA(c, cudaGetLastError());
 				WallTimer t;
-				MB_CUDA(c, cudaMemcpyAsync(h_tasks.data() + t0, d_tasks + t0, sizeof(ExtendTask) * nt, cudaMemcpyDeviceToHost, c->stream));
-				MB_CUDA(c, cudaMemcpyAsync(h_res.data() + t0, d_res + t0, sizeof(mecat_extend_result) * nt, cudaMemcpyDeviceToHost, c->stream));
-				MB_CUDA(c, cudaMemcpyAsync(h_score.data() + t0, d_scores + t0, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, c->stream));
+				MB_CUDA(c, cudaMemcpyAsync(h_tasks + t0, d_tasks + t0, sizeof(ExtendTask) * nt, cudaMemcpyDeviceToHost, c->stream));
+				MB_CUDA(c, cudaMemcpyAsync(h_res + t0, d_res + t0, sizeof(mecat_extend_result) * nt, cudaMemcpyDeviceToHost, c->stream));
+				MB_CUDA(c, cudaMemcpyAsync(h_score + t0, d_scores + t0, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, c->stream));
 				MB_CUDA(c, cudaStreamSynchronize(c->stream));
 				c->stats.d2h_ms += t.stop();
 				c->resolve_timers();

@@ -95,6 +95,26 @@ struct Ctx
 	}
 	template <typename T> cudaError_t alloc(T** out, size_t count) { return dmalloc((void**)out, count * sizeof(T)); }
 
+	// Pinned host staging buffers for the per-tile result copies: grow-only, reused tile after tile
+	// (a fresh pageable vector of ~70 MB costs its zero fill and page faults on every tile, and
+	// pageable D2H copies are staged by the driver).
+	struct HostStage { void* p = nullptr; size_t bytes = 0; };
+	HostStage hstage[4];
+	cudaError_t host_stage(int slot, size_t bytes, void** out)
+	{
+		HostStage& h = hstage[slot];
+		if (h.bytes < bytes) {
+			if (h.p) cudaFreeHost(h.p);
+			h.p = nullptr; h.bytes = 0;
+			const size_t want = bytes + bytes / 8 + 4096;
+			cudaError_t e = cudaHostAlloc(&h.p, want, cudaHostAllocDefault);
+			if (e != cudaSuccess) { h.p = nullptr; return e; }
+			h.bytes = want;
+		}
+		*out = h.p;
+		return cudaSuccess;
+	}
+
 	// per-kernel CUDA-event timing on `stream`
 	struct Pending { int slot; cudaEvent_t a, b; };
 	std::vector<Pending> pending;

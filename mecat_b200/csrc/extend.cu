@@ -36,6 +36,7 @@ constexpr int VL_N = KOFF + 4;            // diagonals per parity
 constexpr int SEQ_WORDS = 48;             // 719 bases = 45 words (+1 funnel, +2 slack)
 constexpr uint32_t NO_ANCHOR = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int IDLE = -0x7fffffff - 1;     // x + y of a lane without a cell: below every threshold, and IDLE - 0 does not wrap
 
 struct WarpSmem
 {
@@ -114,7 +115,6 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			} else { qblk = tblk = 500; last = false; }
 			const int tol = dtrunc_mul(0.3, max(qblk, tblk));
 			const int max_d = dtrunc_mul(.3, qblk + tblk);
-			const int endsum = min(qblk, tblk);   // a cell can only touch an end once x + y >= this
 			++nblocks;
 
 			// ---- stage operands.  The reference zero-fills its V/U arrays per block; a row only ever
@@ -150,11 +150,13 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				else { x = (int)lf.x + 1; anc = lf.y; }
 				int y = x - k;
 				const int x1 = x;
-				while (x < qblk && y < tblk) {
+				// x <= qblk and y <= tblk here (a cell that reached an end finished the block); the staged
+				// words cover one window past either end, and whatever matches there is clamped away below
+				for (;;) {
 					const uint32_t diff = seq16(sq, x) ^ seq16(st, y);
 					const int m = __clz(__brev(diff)) >> 1;      // matching bases in this 16-base window
 					x += m; y += m;
-					if (m < 16) break;
+					if (m < 16 || x >= qblk || y >= tblk) break;
 				}
 				const int over = max(max(x - qblk, y - tblk), 0);    // the window may run past a block end
 				x -= over; y -= over;
@@ -168,33 +170,34 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				uint2* own = &S.vl[min_k + KOFF];                      // own[2j] <-> diagonal min_k + 2j; neighbours own[2j -+ 1]
 				const uint32_t dbits = (uint32_t)d << 20;
 				// pass 0: diagonals 0..31 of the band (most rows have no other pass)
-				int x0 = 0, u0 = -1;
+				int x0 = 0, u0 = IDLE;
 				uint32_t a0 = NO_ANCHOR;
 				if (lane < n) u0 = cell(own, lane, n, min_k + 2 * lane, dbits, x0, a0);
 				int rowmax = __reduce_max_sync(FULL, u0);
-				int x1 = 0, u1 = -1;
+				int x1 = 0, u1 = IDLE;
 				uint32_t a1 = NO_ANCHOR;
 				if (n > 32) {
 					if (lane + 32 < n) u1 = cell(own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1);
 					rowmax = max(rowmax, __reduce_max_sync(FULL, u1));
 					for (int base = 64; base < n; base += 32) {
 						const int j = base + lane;
-						int xx = 0, uu = -1;
+						int xx = 0, uu = IDLE;
 						uint32_t aa = NO_ANCHOR;
 						if (j < n) uu = cell(own, j, n, min_k + 2 * j, dbits, xx, aa);
 						rowmax = max(rowmax, __reduce_max_sync(FULL, uu));
 					}
 				}
 				__syncwarp();
-				if (rowmax >= endsum) {
+				// x >= qblk needs x + y >= 2 qblk - k, y >= tblk needs x + y >= 2 tblk + k
+				if (rowmax >= min(2 * qblk - max_k, 2 * tblk + min_k)) {
 					// some cell may have reached a block end: the lowest such diagonal ends the block
-					unsigned hm = __ballot_sync(FULL, u0 >= 0 && (x0 >= qblk || u0 - x0 >= tblk));
+					unsigned hm = __ballot_sync(FULL, x0 >= qblk || u0 - x0 >= tblk);
 					if (hm) {
 						const int src = __ffs(hm) - 1;
 						ex = __shfl_sync(FULL, x0, src); ey = __shfl_sync(FULL, u0, src) - ex; ea = __shfl_sync(FULL, a0, src);
 						aligned = true;
 					} else if (n > 32) {
-						hm = __ballot_sync(FULL, u1 >= 0 && (x1 >= qblk || u1 - x1 >= tblk));
+						hm = __ballot_sync(FULL, x1 >= qblk || u1 - x1 >= tblk);
 						if (hm) {
 							const int src = __ffs(hm) - 1;
 							ex = __shfl_sync(FULL, x1, src); ey = __shfl_sync(FULL, u1, src) - ex; ea = __shfl_sync(FULL, a1, src);
@@ -222,11 +225,11 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				const int thr = best_m - tol;
 				int lo = 0x7fffffff, hi = -0x7fffffff;
 				{
-					const unsigned km = __ballot_sync(FULL, u0 >= thr && u0 >= 0);
+					const unsigned km = __ballot_sync(FULL, u0 >= thr);
 					if (km) { lo = min_k + 2 * (__ffs(km) - 1); hi = min_k + 2 * (31 - __clz(km)); }
 				}
 				if (n > 32) {
-					const unsigned km = __ballot_sync(FULL, u1 >= thr && u1 >= 0);
+					const unsigned km = __ballot_sync(FULL, u1 >= thr);
 					if (km) { lo = min(lo, min_k + 2 * (32 + __ffs(km) - 1)); hi = max(hi, min_k + 2 * (32 + 31 - __clz(km))); }
 					for (int base = 64; base < n; base += 32) {
 						const int j = base + lane;
