@@ -108,6 +108,12 @@ enum {
 	MECAT_K_MERGE = 7,   /* per-read candidate merge + record assembly               */
 	MECAT_K_EXTEND = 8,  /* O(nd) diff extension                                     */
 	MECAT_K_FINAL = 9,   /* extension result assembly                                */
+	MECAT_K_CNS_ACCEPT = 10,   /* cns: accept loop of every read (C3)                */
+	MECAT_K_CNS_NORMVOTE = 11, /* cns: normalize_gaps + pile-up votes (C4-C5)        */
+	MECAT_K_CNS_SEGMENT = 12,  /* cns: effective ranges, covered runs (C6)           */
+	MECAT_K_CNS_REGION = 13,   /* cns: position flags, anchors, ambiguous regions    */
+	MECAT_K_CNS_POA = 14,      /* cns: one partial-order graph per region (C7)       */
+	MECAT_K_CNS_ASSEMBLE = 15, /* cns: corrected bases of every segment              */
 	MECAT_K_NUM = 16
 };
 typedef struct {
@@ -238,12 +244,11 @@ int mecat_b200_cns_reads(mecat_b200_ctx* ctx, void* dvol_reads, const mecat_cand
                          const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs,
                          size_t* seq_bytes);
 
-/* test hooks (host only, no device needed): the candidate trial order and the per-read consensus that
- * mecat_b200_cns_reads applies to its GPU alignment results; they compute no alignments. */
+/* Trial order of one read's candidates (CmpExtensionCandidateByScore, src/mecat2cns/mecat_correction.cpp:362-370,409);
+ * host only.  mecat_b200_cns_reads applies it itself; exported so that callers feeding mecat_b200_align_batch can
+ * reproduce the order. */
 void mecat_b200_cns_sort_candidates(mecat_candidate* c, int n);
-int mecat_b200_cns_consensus_host(const mecat_candidate* cand, int ncand, const mecat_align_result* res, const char* qstr,
-                                  const char* sstr, const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces,
-                                  char** seqs, size_t* seq_bytes);
+/* frees host buffers handed out by this library (same as mecat_b200_free without a context) */
 void mecat_b200_host_free(void* p);
 
 #ifdef __cplusplus

@@ -28,7 +28,7 @@ class PwParams(C.Structure):
 
 
 KERNEL_NAMES = ["orient", "index_count", "index_scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
-                "finalize"]
+                "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"]
 
 
 class CnsParams(C.Structure):
@@ -70,7 +70,7 @@ EXPORTS = [
     "mecat_b200_index_device_arrays", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
     "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_cns_reads", "mecat_b200_cns_sort_candidates",
-    "mecat_b200_cns_consensus_host", "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
+    "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
 ]
 
 _lib = None
@@ -119,8 +119,6 @@ def load_library():
     L.mecat_b200_cns_reads.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(CnsParams), C.POINTER(vp), C.POINTER(C.c_size_t),
                                        C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_cns_sort_candidates.argtypes = [vp, C.c_int]
-    L.mecat_b200_cns_consensus_host.argtypes = [vp, C.c_int, vp, C.c_char_p, C.c_char_p, C.POINTER(CnsParams), C.POINTER(vp),
-                                                C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_host_free.argtypes = [vp]
     L.mecat_b200_pw_tile_range.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_volume_from_device.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp, C.POINTER(vp)]

@@ -25,7 +25,7 @@ HOSTCXX = "/usr/bin/g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
               "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2,-pthread", "-Xptxas", "-v"]
 
-CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "align.cu", "capi.cu"]
+CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "align.cu", "cns.cu", "capi.cu"]
 
 
 def _newer(src_list, out):
@@ -38,7 +38,7 @@ def _newer(src_list, out):
 def _compile(cu):
     src = os.path.join(CSRC, cu)
     obj = os.path.join(OBJ, cu.replace(".cu", ".o"))
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns.h"), os.path.join(ROOT, "include", "mecat_b200.h")]
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns_pipeline.h"), os.path.join(CSRC, "cns_core.cuh"), os.path.join(ROOT, "include", "mecat_b200.h")]
     if not _newer(deps, obj):
         return obj, ""
     p = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
@@ -53,9 +53,9 @@ def build(verbose=False):
     with cf.ThreadPoolExecutor(max_workers=len(CU)) as ex:
         res = list(ex.map(_compile, CU))
     objs = [r[0] for r in res]
-    for name in ("host_io", "cns", "cns_api"):
+    for name in ("host_io",):
         src, obj = os.path.join(CSRC, name + ".cpp"), os.path.join(OBJ, name + ".o")
-        if _newer([src, os.path.join(ROOT, "include", "mecat_b200.h"), os.path.join(CSRC, "cns.h")], obj):
+        if _newer([src, os.path.join(ROOT, "include", "mecat_b200.h"), os.path.join(CSRC, "cns_pipeline.h"), os.path.join(CSRC, "cns_core.cuh")], obj):
             subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj])
         objs.append(obj)
     log = "\n".join(r[1] for r in res if r[1])

@@ -433,11 +433,27 @@ __global__ void k_aln_pack(const AlnSlot* __restrict__ slots, size_t ntasks, con
 }
 
 // ------------------------------------------------------------------------------------------ host
-int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t ntasks,
-                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr)
+size_t align_task_columns(const DVolume* q, const DVolume* s, const AlignTask& t)
 {
-	qstr.clear(); sstr.clear();
-	if (!ntasks) return 0;
+	const int ql = q->h_offsz[2 * t.qread + 1];
+	const int sl = t.swin_len > 0 ? t.swin_len : s->h_offsz[2 * t.sread + 1];
+	return ((size_t)t.qstart + t.sstart + 8) + ((size_t)(ql - t.qstart) + (sl - t.sstart) + 8);
+}
+
+void align_dev_release(Ctx* c, AlignDev* d)
+{
+	c->dfree(d->d_info); c->dfree(d->d_packq); c->dfree(d->d_packt); c->dfree(d->d_outoff);
+	*d = AlignDev();
+}
+
+// One arena batch: the tasks' worst-case columns (align_task_columns) must sum to at most ALIGN_ARENA.  The
+// results stay in device memory (out); align_batch() below copies them to the host, the consensus stage of
+// mecat2cns (cns.cu) consumes them in place.
+int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t nb,
+                       int min_aln, AlignDev* out, std::vector<int32_t>& info)
+{
+	*out = AlignDev();
+	if (!nb) return 0;
 	if (policy == 1 && !(err > 0.0 && err <= 0.16)) MB_FAIL(c, "align_batch: error rate %.3f is outside this path (pacbio, <= 0.16)", err);
 	const int grid = c->sm_count * 5;
 	const size_t nwarps = (size_t)grid * AL_WARPS;
@@ -445,102 +461,116 @@ int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume*
 	short* d_min = nullptr;
 	AlignTask* d_tasks = nullptr;
 	AlnSlot* d_slots = nullptr;
-	char *d_colq = nullptr, *d_colt = nullptr, *d_packq = nullptr, *d_packt = nullptr;
-	int32_t* d_info = nullptr;
-	unsigned long long* d_outoff = nullptr;
-	const size_t ARENA = 3ull << 30;         // column arena per batch of tasks
+	char *d_colq = nullptr, *d_colt = nullptr;
 	auto body = [&]() -> int {
+		std::vector<AlnSlot> slots;
+		size_t used = 0;
+		for (size_t i = 0; i < nb; ++i) {
+			const AlignTask& t = h_tasks[i];
+			const int ql = q->h_offsz[2 * t.qread + 1];
+			const int sl = t.swin_len > 0 ? t.swin_len : s->h_offsz[2 * t.sread + 1];
+			const size_t capL = (size_t)t.qstart + t.sstart + 8, capR = (size_t)(ql - t.qstart) + (sl - t.sstart) + 8;
+			AlnSlot a; memset(&a, 0, sizeof a);
+			a.off = used; a.cap = (int32_t)capL; used += capL; slots.push_back(a);
+			a.off = used; a.cap = (int32_t)capR; used += capR; slots.push_back(a);
+		}
+		if (used > ALIGN_ARENA) MB_FAIL(c, "align_batch: %zu tasks need more than the %zu-byte column arena", nb, (size_t)ALIGN_ARENA);
 		MB_CUDA(c, c->alloc(&d_dir, nwarps * MAXROWS * DIRW));
 		MB_CUDA(c, c->alloc(&d_min, nwarps * MAXROWS));
-		MB_CUDA(c, c->dmalloc((void**)&d_colq, ARENA));
-		MB_CUDA(c, c->dmalloc((void**)&d_colt, ARENA));
-		std::vector<AlnSlot> slots;
-		std::vector<int32_t> info;
-		std::vector<unsigned long long> outoff;
-		size_t done = 0;
-		while (done < ntasks) {
-			// batch = as many tasks as fit the arena with worst-case slots (columns <= q + t bases of the direction)
-			slots.clear();
-			size_t used = 0, nb = 0;
-			while (done + nb < ntasks) {
-				const AlignTask& t = h_tasks[done + nb];
-				const int ql = q->h_offsz[2 * t.qread + 1];
-				const int sl = t.swin_len > 0 ? t.swin_len : s->h_offsz[2 * t.sread + 1];
-				const size_t capL = (size_t)t.qstart + t.sstart + 8, capR = (size_t)(ql - t.qstart) + (sl - t.sstart) + 8;
-				if (used + capL + capR > ARENA) break;
-				AlnSlot a; memset(&a, 0, sizeof a);
-				a.off = used; a.cap = (int32_t)capL; used += capL; slots.push_back(a);
-				a.off = used; a.cap = (int32_t)capR; used += capR; slots.push_back(a);
-				++nb;
-			}
-			if (nb == 0) MB_FAIL(c, "align_batch: one task needs more than the %zu-byte column arena", ARENA);
-			c->dfree(d_tasks); c->dfree(d_slots); c->dfree(d_info); c->dfree(d_outoff);
-			d_tasks = nullptr; d_slots = nullptr; d_info = nullptr; d_outoff = nullptr;
-			MB_CUDA(c, c->alloc(&d_tasks, nb));
-			MB_CUDA(c, c->alloc(&d_slots, 2 * nb));
-			MB_CUDA(c, c->alloc(&d_info, 8 * nb));
-			MB_CUDA(c, c->alloc(&d_outoff, nb + 1));
-			MB_CUDA(c, cudaMemcpyAsync(d_tasks, h_tasks + done, sizeof(AlignTask) * nb, cudaMemcpyHostToDevice, c->stream));
-			MB_CUDA(c, cudaMemcpyAsync(d_slots, slots.data(), sizeof(AlnSlot) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
-			MB_CUDA(c, cudaMemsetAsync(c->d_counters + 4, 0, 8, c->stream));
-			{
-				KScope ks(c, MECAT_K_EXTEND);
-				if (policy == 0)
-					k_align<0><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
-					                                                  d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
-				else
-					k_align<1><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
-					                                                  d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
-			}
-			{
-				KScope ks(c, MECAT_K_FINAL);
-				const unsigned g2 = (unsigned)((nb * 32 + 127) / 128);
-				if (policy == 0) k_aln_sizes<0><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, d_info);
-				else k_aln_sizes<1><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, d_info);
-			}
-			MB_CUDA(c, cudaGetLastError());
-			info.resize(8 * nb);
-			MB_CUDA(c, cudaMemcpyAsync(info.data(), d_info, sizeof(int32_t) * 8 * nb, cudaMemcpyDeviceToHost, c->stream));
-			MB_CUDA(c, cudaStreamSynchronize(c->stream));
-			outoff.resize(nb + 1);
-			size_t total = 0;
-			for (size_t i = 0; i < nb; ++i) { outoff[i] = total; if (info[8 * i]) total += (size_t)info[8 * i + 5] + 1; }
-			outoff[nb] = total;
-			c->dfree(d_packq); c->dfree(d_packt); d_packq = d_packt = nullptr;
-			MB_CUDA(c, c->dmalloc((void**)&d_packq, total + 16));
-			MB_CUDA(c, c->dmalloc((void**)&d_packt, total + 16));
-			MB_CUDA(c, cudaMemcpyAsync(d_outoff, outoff.data(), sizeof(unsigned long long) * (nb + 1), cudaMemcpyHostToDevice, c->stream));
-			{
-				KScope ks(c, MECAT_K_FINAL);
-				k_aln_pack<<<(unsigned)nb, 128, 0, c->stream>>>(d_slots, nb, d_info, d_outoff, d_colq, d_colt, d_packq, d_packt);
-			}
-			MB_CUDA(c, cudaGetLastError());
-			const size_t base = qstr.size();
-			qstr.resize(base + total); sstr.resize(base + total);
-			if (total) {
-				MB_CUDA(c, cudaMemcpyAsync(qstr.data() + base, d_packq, total, cudaMemcpyDeviceToHost, c->stream));
-				MB_CUDA(c, cudaMemcpyAsync(sstr.data() + base, d_packt, total, cudaMemcpyDeviceToHost, c->stream));
-			}
-			MB_CUDA(c, cudaStreamSynchronize(c->stream));
-			c->resolve_timers();
-			c->stats.h2d_bytes += (int64_t)((sizeof(AlignTask) + 2 * sizeof(AlnSlot) + 8) * nb);
-			c->stats.d2h_bytes += (int64_t)(32 * nb + 2 * total);
-			for (size_t i = 0; i < nb; ++i) {
-				mecat_align_result& r = h_results[done + i];
-				const int32_t* o = &info[8 * i];
-				r.ok = o[0]; r.qstart = o[1]; r.qend = o[2]; r.sstart = o[3]; r.send = o[4];
-				r.columns = o[5]; r.matches = o[6]; r.pad_ = 0;
-				r.str_offset = o[0] ? (int64_t)(base + outoff[i]) : -1;
-				r.ident = (o[0] && o[5]) ? 100.0 * o[6] / o[5] : 0.0;
-			}
-			done += nb;
+		MB_CUDA(c, c->dmalloc((void**)&d_colq, ALIGN_ARENA));      // fixed size: the pool hands the same block back
+		MB_CUDA(c, c->dmalloc((void**)&d_colt, ALIGN_ARENA));
+		MB_CUDA(c, c->alloc(&d_tasks, nb));
+		MB_CUDA(c, c->alloc(&d_slots, 2 * nb));
+		MB_CUDA(c, c->alloc(&out->d_info, 8 * nb));
+		MB_CUDA(c, c->alloc(&out->d_outoff, nb + 1));
+		MB_CUDA(c, cudaMemcpyAsync(d_tasks, h_tasks, sizeof(AlignTask) * nb, cudaMemcpyHostToDevice, c->stream));
+		MB_CUDA(c, cudaMemcpyAsync(d_slots, slots.data(), sizeof(AlnSlot) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
+		MB_CUDA(c, cudaMemsetAsync(c->d_counters + 4, 0, 8, c->stream));
+		{
+			KScope ks(c, MECAT_K_EXTEND);
+			if (policy == 0)
+				k_align<0><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
+				                                                  d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
+			else
+				k_align<1><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
+				                                                  d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
 		}
+		{
+			KScope ks(c, MECAT_K_FINAL);
+			const unsigned g2 = (unsigned)((nb * 32 + 127) / 128);
+			if (policy == 0) k_aln_sizes<0><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, out->d_info);
+			else k_aln_sizes<1><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, out->d_info);
+		}
+		MB_CUDA(c, cudaGetLastError());
+		info.resize(8 * nb);
+		MB_CUDA(c, cudaMemcpyAsync(info.data(), out->d_info, sizeof(int32_t) * 8 * nb, cudaMemcpyDeviceToHost, c->stream));
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		std::vector<unsigned long long> outoff(nb + 1);
+		size_t total = 0;
+		for (size_t i = 0; i < nb; ++i) { outoff[i] = total; if (info[8 * i]) total += (size_t)info[8 * i + 5] + 1; }
+		outoff[nb] = total;
+		MB_CUDA(c, c->dmalloc((void**)&out->d_packq, total + 16));
+		MB_CUDA(c, c->dmalloc((void**)&out->d_packt, total + 16));
+		MB_CUDA(c, cudaMemcpyAsync(out->d_outoff, outoff.data(), sizeof(unsigned long long) * (nb + 1), cudaMemcpyHostToDevice, c->stream));
+		{
+			KScope ks(c, MECAT_K_FINAL);
+			k_aln_pack<<<(unsigned)nb, 128, 0, c->stream>>>(d_slots, nb, out->d_info, out->d_outoff, d_colq, d_colt, out->d_packq, out->d_packt);
+		}
+		MB_CUDA(c, cudaGetLastError());
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));      // outoff (host vector) was the source of an async copy
+		out->total = total;
+		c->stats.h2d_bytes += (int64_t)((sizeof(AlignTask) + 2 * sizeof(AlnSlot) + 8) * nb);
+		c->stats.d2h_bytes += (int64_t)(32 * nb);
 		return 0;
 	};
 	int rc = body();
 	c->dfree(d_dir); c->dfree(d_min); c->dfree(d_tasks); c->dfree(d_slots); c->dfree(d_colq); c->dfree(d_colt);
-	c->dfree(d_packq); c->dfree(d_packt); c->dfree(d_info); c->dfree(d_outoff);
+	if (rc) align_dev_release(c, out);
 	return rc;
+}
+
+int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t ntasks,
+                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr)
+{
+	qstr.clear(); sstr.clear();
+	if (!ntasks) return 0;
+	std::vector<int32_t> info;
+	size_t done = 0;
+	while (done < ntasks) {
+		size_t used = 0, nb = 0;
+		while (done + nb < ntasks) {
+			const size_t need = align_task_columns(q, s, h_tasks[done + nb]);
+			if (used + need > ALIGN_ARENA) break;
+			used += need; ++nb;
+		}
+		if (nb == 0) MB_FAIL(c, "align_batch: one task needs more than the %zu-byte column arena", (size_t)ALIGN_ARENA);
+		AlignDev dev;
+		if (align_batch_device(c, policy, err, q, s, h_tasks + done, nb, min_aln, &dev, info)) return 1;
+		const size_t base = qstr.size(), total = dev.total;
+		qstr.resize(base + total); sstr.resize(base + total);
+		cudaError_t e = cudaSuccess;
+		if (total) {
+			e = cudaMemcpyAsync(qstr.data() + base, dev.d_packq, total, cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(sstr.data() + base, dev.d_packt, total, cudaMemcpyDeviceToHost, c->stream);
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		align_dev_release(c, &dev);
+		if (e != cudaSuccess) MB_FAIL(c, "align_batch: D2H: %s", cudaGetErrorString(e));
+		c->resolve_timers();
+		c->stats.d2h_bytes += (int64_t)(2 * total);
+		size_t at = 0;
+		for (size_t i = 0; i < nb; ++i) {
+			mecat_align_result& r = h_results[done + i];
+			const int32_t* o = &info[8 * i];
+			r.ok = o[0]; r.qstart = o[1]; r.qend = o[2]; r.sstart = o[3]; r.send = o[4];
+			r.columns = o[5]; r.matches = o[6]; r.pad_ = 0;
+			r.str_offset = o[0] ? (int64_t)(base + at) : -1;
+			if (o[0]) at += (size_t)o[5] + 1;
+			r.ident = (o[0] && o[5]) ? 100.0 * o[6] / o[5] : 0.0;
+		}
+		done += nb;
+	}
+	return 0;
 }
 
 }  // namespace mb

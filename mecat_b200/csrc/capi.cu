@@ -4,7 +4,7 @@
 // assembly that the reference does on the CPU after its hot loops
 // (candidate_detect pw_impl.cpp:767-793, fill_m4record :467-506, append_m4v :576-610).
 #include "common.cuh"
-#include "cns.h"
+#include "cns_pipeline.h"
 
 #include <algorithm>
 #include <atomic>
@@ -322,7 +322,20 @@ int mecat_b200_align_batch(mecat_b200_ctx* c, int policy, double err, void* dq, 
 }
 
 // ------------------------------------------------------------------------------------------
-// mecat2cns -i 0 for a set of reads: GPU extensions (policy 1) + host-thread consensus.
+// mecat2cns -i 0 for a set of reads: GPU extensions (policy 1, align.cu) feeding the GPU consensus stage (cns.cu).
+// The host groups the candidates by read, orders them for the accept loop and cuts batches; alignments, votes,
+// graphs and corrected bases stay in device memory until the finished pieces are copied back.
+void mecat_b200_cns_sort_candidates(mecat_candidate* cnd, int n)   // CmpExtensionCandidateByScore, mecat_correction.cpp:362-370
+{
+	std::sort(cnd, cnd + n, [](const mecat_candidate& a, const mecat_candidate& b) {
+		if (a.score != b.score) return a.score > b.score;
+		if (a.qid != b.qid) return a.qid < b.qid;
+		return a.qext < b.qext;
+	});
+}
+
+void mecat_b200_host_free(void* p) { free(p); }
+
 int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candidate* ec_in, size_t nec, const mecat_cns_params* p,
                          mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
 {
@@ -350,53 +363,51 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 		while (j < nec && ec[j].sid == ec[i].sid) ++j;
 		// reads_correction_func_can, reads_correction_can.cpp:27-33
 		if ((int64_t)(j - i) >= p->min_cov && !(ec[i].ssize < p->min_size * 0.95)) {
-			mbcns::sort_candidates(ec.data() + i, (int)(j - i));
-			groups.push_back(Group{i, std::min(j, i + 200)});
+			mecat_b200_cns_sort_candidates(ec.data() + i, (int)(j - i));
+			groups.push_back(Group{i, std::min(j, i + (size_t)mbcns::MAX_TRIED)});
 		}
 		i = j;
 	}
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	std::vector<mbcns::Piece> all;
-	const int nthreads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
 	const size_t TASKS_PER_BATCH = 40000;
 	std::vector<AlignTask> tasks;
-	std::vector<mecat_align_result> res;
-	std::vector<char> qs, ss;
+	std::vector<int32_t> info, first, rsize, tqid, tqsize;
+	std::vector<int64_t> rid;
 	for (size_t g0 = 0; g0 < groups.size();) {
-		size_t g1 = g0, nt = 0;
-		while (g1 < groups.size() && (nt == 0 || nt + (groups[g1].e - groups[g1].b) <= TASKS_PER_BATCH)) { nt += groups[g1].e - groups[g1].b; ++g1; }
-		tasks.clear();
-		for (size_t g = g0; g < g1; ++g)
-			for (size_t k = groups[g].b; k < groups[g].e; ++k) {
+		// a batch = whole reads, as many as fit the column arena of the extension kernels
+		tasks.clear(); first.assign(1, 0); rsize.clear(); rid.clear(); tqid.clear(); tqsize.clear();
+		size_t g1 = g0, cols = 0;
+		while (g1 < groups.size()) {
+			size_t need = 0;
+			const size_t mark = tasks.size();
+			for (size_t k = groups[g1].b; k < groups[g1].e; ++k) {
 				const mecat_candidate& e = ec[k];
 				AlignTask t;
 				t.qread = e.qid - id0; t.qstrand = e.qdir; t.qstart = e.qdir ? e.qsize - 1 - e.qext : e.qext;   // mecat_correction.cpp:421-423
 				t.sread = e.sid - id0; t.sstart = e.sext; t.swin_off = 0; t.swin_len = 0;
+				need += align_task_columns(V, V, t);
 				tasks.push_back(t);
 			}
-		res.resize(tasks.size());
-		if (align_batch(c, 1, 0.15, V, V, tasks.data(), tasks.size(), p->min_align_size, res.data(), qs, ss)) return 1;
-		WallTimer host_timer;
-		std::vector<std::vector<mbcns::Piece>> per((size_t)(g1 - g0));
-		std::vector<size_t> first((size_t)(g1 - g0) + 1, 0);
-		for (size_t g = g0; g < g1; ++g) first[g - g0 + 1] = first[g - g0] + (groups[g].e - groups[g].b);
-		std::atomic<size_t> next(g0);
-		auto runner = [&]() {
-			mbcns::Scratch scratch;
-			for (size_t g; (g = next.fetch_add(1)) < g1;) {
-				const mecat_candidate* cand = ec.data() + groups[g].b;
-				const int n = (int)(groups[g].e - groups[g].b);
-				mbcns::consensus_one_read(cand[0].sid, cand[0].ssize, cand, n, res.data() + first[g - g0], qs.data(), ss.data(), P,
-				                          scratch, per[g - g0]);
-			}
-		};
-		std::vector<std::thread> pool;
-		for (int t = 1; t < nthreads; ++t) pool.emplace_back(runner);
-		runner();
-		for (auto& th : pool) th.join();
-		for (auto& v : per) for (auto& pc : v) all.push_back(std::move(pc));
-		c->stats.host_ms += host_timer.stop();
+			if (g1 > g0 && (cols + need > ALIGN_ARENA || tasks.size() > TASKS_PER_BATCH)) { tasks.resize(mark); break; }
+			if (cols + need > ALIGN_ARENA) MB_FAIL(c, "cns_reads: the candidates of read %d alone exceed the column arena", ec[groups[g1].b].sid);
+			cols += need;
+			for (size_t k = groups[g1].b; k < groups[g1].e; ++k) { tqid.push_back(ec[k].qid); tqsize.push_back(ec[k].qsize); }
+			first.push_back((int32_t)tasks.size());
+			rsize.push_back(ec[groups[g1].b].ssize);
+			rid.push_back(ec[groups[g1].b].sid);
+			++g1;
+		}
+		AlignDev dev;
+		if (align_batch_device(c, 1, 0.15, V, V, tasks.data(), tasks.size(), p->min_align_size, &dev, info)) return 1;
+		mbcns::BatchIn in;
+		in.R = (int)(g1 - g0); in.T = (int64_t)tasks.size();
+		in.h_first = first.data(); in.h_read_size = rsize.data(); in.h_read_id = rid.data(); in.h_tqid = tqid.data(); in.h_tqsize = tqsize.data();
+		in.d_info = dev.d_info; in.d_q = dev.d_packq; in.d_s = dev.d_packt; in.d_outoff = dev.d_outoff;
+		const int rc = cns_consensus_device(c, in, P, all);
+		align_dev_release(c, &dev);
+		if (rc) return 1;
 		g0 = g1;
 	}
 	size_t bytes = 0;

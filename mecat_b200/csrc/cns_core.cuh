@@ -1,0 +1,671 @@
+// mecat_b200/csrc/cns_core.cuh -- bodies of the consensus kernels of mecat2cns (rows C3-C7).
+//
+// Every function here is the work of ONE GPU thread on one unit (a read, an accepted alignment, a
+// template segment, an ambiguous region); cns.cu launches them as kernels.  The bodies are plain
+// integer / byte code over raw arrays and carry CNS_HD (= __host__ __device__ under nvcc), so the CPU
+// test-suite can also compile this header with g++ and execute the very same statements without a GPU
+// (tests/cns_host_harness.cpp); the product library instantiates the device side only.
+//
+// Semantics follow the reference (src/mecat2cns):
+//   consensus_one_read_can_pacbio, check_ovlp_mapping_range, check_cov_stats   mecat_correction.cpp:191-200,373-450
+//   normalize_gaps                                                             reads_correction_aux.cpp:3-79
+//   meap_add_one_aln, identify_one_consensus_item, meap_consensus_one_segment  mecat_correction.cpp:15-108
+//   get_effective_ranges, consensus_worker                                     mecat_correction.cpp:119-239
+//   CnsAln::retrieve_aln_subseqs                                               reads_correction_aux.h:47-68
+//   AlnGraphBoost (mini partial-order graph of one ambiguous region)           MECAT_AlnGraphBoost.C:76-592
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CNS_HD __host__ __device__
+#else
+#define CNS_HD
+#endif
+
+namespace mbcns {
+
+constexpr int MAX_ACCEPT = 60;      // mecat_correction.cpp:407 (MAX_CNS_OVLPS)
+constexpr int MAX_TRIED = 200;      // mecat_correction.cpp:410 (MAX_EXAMINED_OVLPS)
+constexpr int COV_FULL = 20;        // check_cov_stats, mecat_correction.cpp:373-386
+constexpr int COV_NEED = 200;
+
+enum { FMAT = 1, FDEL = 2, FINS = 4, UNDS = 8 };
+
+// vote word of one template position: mat | ins << 8 | del << 16 (CnsTableItem's three uint8 counters; at most
+// 60 alignments vote, so no byte ever carries into its neighbour)
+CNS_HD inline int vote_mat(uint32_t w) { return (int)(w & 255u); }
+CNS_HD inline int vote_ins(uint32_t w) { return (int)((w >> 8) & 255u); }
+CNS_HD inline int vote_del(uint32_t w) { return (int)((w >> 16) & 255u); }
+
+CNS_HD inline void vote_add(uint32_t* p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+	atomicAdd(p, v);
+#else
+	*p += v;
+#endif
+}
+
+// identify_one_consensus_item, mecat_correction.cpp:15-24 (int compared with a double product)
+CNS_HD inline uint8_t classify(uint32_t w)
+{
+	const int mat = vote_mat(w), ins = vote_ins(w), del = vote_del(w);
+	const int cov = mat + ins;
+	uint8_t f = 0;
+	if ((double)mat >= (double)cov * 0.8) f |= FMAT;
+	if ((double)ins >= (double)cov * 0.8) f |= FINS;
+	if (!f) f |= UNDS;
+	if ((double)del >= (double)cov * 0.4) f |= FDEL;
+	return f;
+}
+
+// ------------------------------------------------------------------------------------------ C3
+CNS_HD inline int popcount64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return __popcll(x);
+#else
+	return __builtin_popcountll(x);
+#endif
+}
+
+// check_cov_stats works on one coverage byte per template position (at most 60, so SWAR on 8 bytes never carries)
+CNS_HD inline int count_full(const uint8_t* cov, int b, int e)       // positions in [b, e) covered >= COV_FULL times
+{
+	int full = 0, k = b;
+	while (k < e && ((uintptr_t)(cov + k) & 7u)) { full += cov[k] >= COV_FULL; ++k; }
+	for (; k + 8 <= e; k += 8) {
+		const uint64_t w = *(const uint64_t*)(cov + k);
+		full += popcount64((w + 0x0101010101010101ull * (uint64_t)(128 - COV_FULL)) & 0x8080808080808080ull);
+	}
+	for (; k < e; ++k) full += cov[k] >= COV_FULL;
+	return full;
+}
+CNS_HD inline void bump_cov(uint8_t* cov, int b, int e)
+{
+	int k = b;
+	while (k < e && ((uintptr_t)(cov + k) & 7u)) { ++cov[k]; ++k; }
+	for (; k + 8 <= e; k += 8) *(uint64_t*)(cov + k) += 0x0101010101010101ull;
+	for (; k < e; ++k) ++cov[k];
+}
+
+// The accept loop of one read: candidates in trial order, at most 200 looked at, at most 60 accepted, one
+// per partner read, mapping-range and coverage gates.  info = 8 ints per task {ok, qstart, qend, sstart,
+// send, columns, ...} as written by the extension kernels.  Returns the number accepted; acc[k] = task.
+CNS_HD inline int accept_read(int t0, int t1, const int32_t* info, const int32_t* t_qid, const int32_t* t_qsize, int ssize,
+                              double ratio, uint8_t* cov, int32_t* acc)
+{
+	int used[MAX_ACCEPT];
+	int added = 0, tried = 0;
+	const int qss = (int)((double)ssize * ratio);
+	for (int t = t0; t < t1 && added < MAX_ACCEPT && tried < MAX_TRIED; ++t) {
+		++tried;
+		const int qid = t_qid[t];
+		bool seen = false;
+		for (int k = 0; k < added; ++k) if (used[k] == qid) { seen = true; break; }
+		if (seen) continue;
+		const int32_t* o = info + 8 * (int64_t)t;
+		if (!o[0]) continue;
+		const int oq = o[2] - o[1], os = o[4] - o[3];
+		const int qqs = (int)((double)t_qsize[t] * ratio);
+		if (!(oq >= qqs || os >= qss)) continue;
+		// a position can only be COV_FULL deep once COV_FULL alignments have been accepted
+		const int full = added >= COV_FULL ? count_full(cov, o[3], o[4]) : 0;
+		if (!(o[4] - o[3] >= full + COV_NEED)) continue;
+		bump_cov(cov, o[3], o[4]);
+		used[added] = qid;
+		acc[added] = t;
+		++added;
+	}
+	return added;
+}
+
+// ------------------------------------------------------------------------------------------ C4
+// normalize_gaps: mismatch columns become a (gap, base)/(base, gap) pair, then every gap is pushed right
+// while the base behind its run equals the base opposite.  nq/nt need 2n + 1 bytes; the terminator the
+// reference's std::string supplies at index len is written explicitly.  Returns the normalised length.
+CNS_HD inline int normalize_gaps(const char* q, const char* t, int n, char* nq, char* nt)
+{
+	int len = 0;
+	for (int i = 0; i < n; ++i) {
+		const char a = q[i], b = t[i];
+		if (a != b && a != '-' && b != '-') { nq[len] = '-'; nt[len] = b; ++len; nq[len] = a; nt[len] = '-'; ++len; }
+		else { nq[len] = a; nt[len] = b; ++len; }
+	}
+	nq[len] = 0; nt[len] = 0;
+	for (int i = 0; i < len - 1; ++i) {
+		if (nt[i] == '-') {
+			int j = i;
+			for (;;) {
+				const char c = nt[++j];
+				if (c != '-' || j > len - 1) { if (c == nq[i]) { nt[i] = c; nt[j] = '-'; } break; }
+			}
+		}
+		if (nq[i] == '-') {
+			int j = i;
+			for (;;) {
+				const char c = nq[++j];
+				if (c != '-' || j > len - 1) { if (c == nt[i]) { nq[i] = c; nq[j] = '-'; } break; }
+			}
+		}
+	}
+	return len;
+}
+
+// ------------------------------------------------------------------------------------------ C5
+// meap_add_one_aln on a normalised alignment.  votes/base are the read's arrays (index = template position).
+CNS_HD inline void add_votes(const char* q, const char* s, int n, int soff, uint32_t* votes, char* base)
+{
+	int i = 0;
+	while (i < n) {
+		const char a = q[i], b = s[i];
+		if (a == '-' && b == '-') { ++i; continue; }
+		if (a == b) { vote_add(votes + soff, 1u); base[soff] = b; ++soff; ++i; }
+		else if (a == '-') { vote_add(votes + soff, 1u << 8); ++soff; ++i; }
+		else {
+			int j = i + 1;
+			while (j < n && s[j] == '-') ++j;
+			vote_add(votes + soff - 1, 1u << 16);
+			i = j;
+		}
+	}
+}
+
+// Column of every template position of a normalised alignment, the way CnsAln's cursor counts them
+// (reads_correction_aux.h:47-68): the cursor starts on column 0 at template position soff and a column
+// idx >= 1 advances the position iff its template character is a base.  colidx[p - soff] = first column
+// at position p.  Returns the last position reached (the entries [0, ret - soff] are written).
+CNS_HD inline int column_index(const char* s, int n, int soff, int32_t* colidx)
+{
+	int p = soff;
+	colidx[0] = 0;
+	for (int idx = 1; idx < n; ++idx)
+		if (s[idx] != '-') { ++p; colidx[p - soff] = idx; }
+	return p;
+}
+
+// ------------------------------------------------------------------------------------------ C6 (ranges)
+struct Range { int start, end; };
+
+// get_effective_ranges, mecat_correction.cpp:119-153.  m (nm <= 60 entries) is reordered; returns the count in e.
+CNS_HD inline int effective_ranges(Range* m, int nm, Range* e, int read_size, double size95)
+{
+	if (nm == 0) return 0;
+	for (int i = 0; i < nm; ++i)
+		if (m[i].start <= 500 && read_size - m[i].end <= 500) { e[0].start = 0; e[0].end = read_size; return 1; }
+	for (int i = 1; i < nm; ++i) {                       // (start up, end down); equal keys are identical entries
+		const Range x = m[i];
+		int j = i - 1;
+		while (j >= 0 && (m[j].start > x.start || (m[j].start == x.start && m[j].end < x.end))) { m[j + 1] = m[j]; --j; }
+		m[j + 1] = x;
+	}
+	int ne = 0, i = 0, left = m[0].start, right;
+	while (i < nm) {
+		int j = i + 1;
+		while (j < nm && m[j].end <= m[i].end) ++j;
+		if (j == nm) {
+			right = m[i].end;
+			if ((double)(right - left) >= size95) { e[ne].start = left; e[ne].end = right; ++ne; }
+			break;
+		}
+		if (m[i].end - m[j].start < 1000) {
+			right = m[i].end < m[j].start ? m[i].end : m[j].start;
+			if ((double)(right - left) >= size95) { e[ne].start = left; e[ne].end = right; ++ne; }
+			left = m[i].end > m[j].start ? m[i].end : m[j].start;
+		}
+		i = j;
+	}
+	return ne;
+}
+
+// consensus_worker's run search inside the effective ranges (mecat_correction.cpp:203-239): maximal runs
+// with coverage >= min_cov that are at least 0.95 * min_size long.  segs receives up to cap {beg, end}
+// pairs; the return value is the number found (callers size cap so that it always fits).
+CNS_HD inline int find_segments(const Range* e, int ne, const uint32_t* votes, int min_cov, double size95, int32_t* segs, int cap)
+{
+	int ns = 0;
+	for (int r = 0; r < ne; ++r) {
+		const int R = e[r].end;
+		int beg = e[r].start;
+		while (beg < R) {
+			while (beg < R && vote_mat(votes[beg]) + vote_ins(votes[beg]) < min_cov) ++beg;
+			int end = beg + 1;
+			while (end < R && vote_mat(votes[end]) + vote_ins(votes[end]) >= min_cov) ++end;
+			if ((double)(end - beg) >= size95) {
+				if (ns < cap) { segs[2 * ns] = beg; segs[2 * ns + 1] = end; }
+				++ns;
+			}
+			beg = end;
+		}
+	}
+	return ns;
+}
+
+// ------------------------------------------------------------------------------------------ C6 (segment walk)
+// One ambiguous region between two anchors of a segment, i.e. one mini-POA.
+struct Region
+{
+	int32_t read;         // batch-local read
+	int32_t sb, se;       // template interval [sb, se], se = next anchor (or the segment end)
+	int32_t prev_se;      // se of the read's previous region (-1: none): the state CnsAln's cursors are in
+	int32_t min_weight;   // int(0.4 * coverage of the anchor)
+};
+
+// meap_consensus_one_segment's walk over the anchors (positions whose flag has FMAT).  flags[0..n) must hold
+// classify() of the segment.  Calls on_anchor(i, j, refine) for each anchor i with next anchor j.
+template <class F>
+CNS_HD inline void walk_anchors(const uint8_t* flags, int n, F&& on_anchor)
+{
+	int i = 0;
+	while (i < n && !(flags[i] & FMAT)) ++i;
+	while (i < n) {
+		int j = i + 1;
+		while (j < n && !(flags[j] & FMAT)) ++j;
+		bool refine = false;
+		for (int k = i; k < j; ++k) if (flags[k] & (UNDS | FDEL)) { refine = true; break; }
+		on_anchor(i, j, refine);
+		i = j;
+	}
+}
+
+// ------------------------------------------------------------------------------------------ C7 (slices)
+// An accepted alignment after normalisation, as the mini-POA sees it.
+struct KeptAln
+{
+	const char* q; const char* s;     // normalised strings
+	const int32_t* colidx;            // column_index()
+	int32_t size, soff, send, tend;   // columns, template interval [soff, send), last position column_index reached
+};
+
+struct Slice { int32_t c0, c1, start; };   // columns [c0, c1] and the backbone position of the first one
+
+CNS_HD inline int kept_column(const KeptAln& a, int pos)    // column the cursor rests on once it has reached `pos`
+{
+	if (pos <= a.soff) return 0;
+	if (pos > a.tend) return a.size - 1;
+	return a.colidx[pos - a.soff];
+}
+
+// CnsAln::retrieve_aln_subseqs for the region [sb, se].  The reference keeps one forward-only cursor per
+// alignment; regions are asked for in increasing order and never overlap, so the cursor state before this
+// call is a function of the previous region's end alone (prev_se), which makes regions independent.
+CNS_HD inline bool kept_slice(const KeptAln& a, int sb, int se, int prev_se, Slice& out)
+{
+	if (se <= a.soff || sb >= a.send) return false;
+	const int before = prev_se > a.soff ? kept_column(a, prev_se) : 0;
+	if (before >= a.size - 1) return false;
+	out.c0 = kept_column(a, sb);
+	out.c1 = kept_column(a, se);
+	out.start = (a.soff > sb ? a.soff : sb) - sb + 1;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------ C7 (graph)
+// AlnGraphBoost on flat arrays.  Adjacency lists are intrusive doubly linked lists threaded through the edges,
+// which gives the iteration orders of boost::adjacency_list<vecS, vecS, bidirectionalS> (insertion order,
+// order-preserving removal) that the tie-breaks of the best-path search depend on.
+struct PoaNode
+{
+	int32_t coverage, weight, bb;              // bb: _bbMap (node -> backbone node, 0 when never set)
+	int32_t in_head, in_tail, in_cnt;
+	int32_t out_head, out_tail, out_cnt;
+	char base; uint8_t backbone; uint8_t pad[2];
+};
+struct PoaEdge
+{
+	int32_t u, v, count, visited;
+	int32_t in_next, in_prev;                  // position in v's in-list
+	int32_t out_next, out_prev;                // position in u's out-list
+};
+
+// sizes of the per-graph scratch, in elements, for a graph with N nodes and E0 edges before merging
+CNS_HD inline int64_t poa_edge_cap(int64_t nodes, int64_t e0) { return e0 + nodes + 2; }
+CNS_HD inline int64_t poa_aux_ints(int64_t nodes) { return 8 * nodes + 64; }
+
+enum { POA_OK = 0, POA_ERR_EDGES = 1, POA_ERR_QUEUE = 2, POA_ERR_STACK = 3, POA_ERR_EMPTY_LIST = 4, POA_ERR_NODES = 5 };
+
+struct Poa
+{
+	PoaNode* nd; PoaEdge* ed; int32_t* aux;
+	int nn, ncap, ecap, nedges, efree, enter, exit_, err;
+	int auxcap;
+
+	CNS_HD void fail(int code) { if (!err) err = code; }
+
+	CNS_HD int new_edge_slot()
+	{
+		if (efree >= 0) { const int e = efree; efree = ed[e].out_next; return e; }
+		if (nedges >= ecap) { fail(POA_ERR_EDGES); return -1; }
+		return nedges++;
+	}
+	CNS_HD int add_edge(int u, int v)
+	{
+		const int e = new_edge_slot();
+		if (e < 0) return -1;
+		PoaEdge& E = ed[e];
+		E.u = u; E.v = v; E.count = 0; E.visited = 0;
+		E.out_next = -1; E.out_prev = nd[u].out_tail;
+		if (nd[u].out_tail >= 0) ed[nd[u].out_tail].out_next = e; else nd[u].out_head = e;
+		nd[u].out_tail = e; ++nd[u].out_cnt;
+		E.in_next = -1; E.in_prev = nd[v].in_tail;
+		if (nd[v].in_tail >= 0) ed[nd[v].in_tail].in_next = e; else nd[v].in_head = e;
+		nd[v].in_tail = e; ++nd[v].in_cnt;
+		return e;
+	}
+	CNS_HD void unlink_out(int e)      // remove e from its source's out-list
+	{
+		PoaEdge& E = ed[e];
+		PoaNode& U = nd[E.u];
+		if (E.out_prev >= 0) ed[E.out_prev].out_next = E.out_next; else U.out_head = E.out_next;
+		if (E.out_next >= 0) ed[E.out_next].out_prev = E.out_prev; else U.out_tail = E.out_prev;
+		--U.out_cnt;
+	}
+	CNS_HD void unlink_in(int e)       // remove e from its target's in-list
+	{
+		PoaEdge& E = ed[e];
+		PoaNode& V = nd[E.v];
+		if (E.in_prev >= 0) ed[E.in_prev].in_next = E.in_next; else V.in_head = E.in_next;
+		if (E.in_next >= 0) ed[E.in_next].in_prev = E.in_prev; else V.in_tail = E.in_prev;
+		--V.in_cnt;
+	}
+	CNS_HD void release(int e) { ed[e].out_next = efree; efree = e; }
+	CNS_HD void clear_vertex(int n)    // boost::clear_vertex: drop every edge of n
+	{
+		for (int e = nd[n].out_head; e >= 0;) { const int nx = ed[e].out_next; unlink_in(e); release(e); e = nx; }
+		for (int e = nd[n].in_head; e >= 0;) { const int nx = ed[e].in_next; unlink_out(e); release(e); e = nx; }
+		nd[n].out_head = nd[n].out_tail = nd[n].in_head = nd[n].in_tail = -1;
+		nd[n].out_cnt = nd[n].in_cnt = 0;
+	}
+	CNS_HD int find_edge(int u, int v) const
+	{
+		for (int e = nd[u].out_head; e >= 0; e = ed[e].out_next) if (ed[e].v == v) return e;
+		return -1;
+	}
+	CNS_HD void link(int u, int v)     // AlnGraphBoost::addEdge: bump the edge u -> v or create it
+	{
+		bool have = false;
+		for (int e = nd[v].in_head; e >= 0; e = ed[e].in_next) if (ed[e].u == u) { ++ed[e].count; have = true; }
+		if (!have) { const int e = add_edge(u, v); if (e >= 0) ++ed[e].count; }
+	}
+	CNS_HD void init_node(int i)
+	{
+		PoaNode& n = nd[i];
+		n.coverage = 0; n.weight = 0; n.bb = 0;
+		n.in_head = n.in_tail = n.out_head = n.out_tail = -1;
+		n.in_cnt = n.out_cnt = 0;
+		n.base = 'N'; n.backbone = 0; n.pad[0] = n.pad[1] = 0;
+	}
+
+	// AlnGraphBoost(size_t blen), MECAT_AlnGraphBoost.C:76-97
+	CNS_HD void init(PoaNode* nodes, int node_cap, PoaEdge* edges, int edge_cap, int32_t* aux_, int aux_cap, int blen)
+	{
+		nd = nodes; ed = edges; aux = aux_; ncap = node_cap; ecap = edge_cap; auxcap = aux_cap;
+		nedges = 0; efree = -1; err = 0;
+		nn = blen + 2;
+		if (nn > ncap) { fail(POA_ERR_NODES); nn = 0; enter = exit_ = 0; return; }
+		for (int i = 0; i < nn; ++i) init_node(i);
+		for (int i = 0; i < blen + 1; ++i) add_edge(i, i + 1);
+		enter = 0; exit_ = blen + 1;
+		nd[enter].base = '^'; nd[enter].backbone = 1;
+		for (int i = 1; i <= blen; ++i) { nd[i].backbone = 1; nd[i].weight = 1; nd[i].base = 'N'; nd[i].bb = i; }
+		nd[exit_].base = '$'; nd[exit_].backbone = 1;
+	}
+
+	// addAln, MECAT_AlnGraphBoost.C:99-152, on columns [c0, c1] of a normalised alignment
+	CNS_HD void add_alignment(const char* q, const char* t, int c0, int c1, int start)
+	{
+		if (err) return;
+		int pos = start, prev = enter;
+		for (int i = c0; i <= c1; ++i) {
+			const char a = q[i], b = t[i];
+			if (a == '-' && b == '-') continue;
+			const int cur = pos;
+			if (a == b) {
+				PoaNode& B = nd[nd[cur].bb];
+				++B.coverage; B.base = b;
+				++nd[cur].weight;
+				link(prev, cur);
+				++pos; prev = cur;
+			} else if (a == '-') {
+				PoaNode& B = nd[nd[cur].bb];
+				++B.coverage; B.base = b;
+				++pos;
+			} else {
+				if (nn >= ncap) { fail(POA_ERR_NODES); return; }
+				const int nv = nn++;
+				init_node(nv);
+				nd[nv].base = a; ++nd[nv].weight;
+				nd[nv].bb = pos;
+				link(prev, nv);
+				prev = nv;
+			}
+		}
+		link(prev, exit_);
+	}
+
+	// smallest base above `last` among list[0..cnt); -1 when none (std::map<char, ...> iteration order)
+	CNS_HD int next_base(const int32_t* list, int cnt, int last) const
+	{
+		int best = -1;
+		for (int k = 0; k < cnt; ++k) {
+			const int b = (int)(signed char)nd[list[k]].base;
+			if (b > last && (best < 0 || b < best)) best = b;
+		}
+		return best;
+	}
+
+	// mergeInNodes, MECAT_AlnGraphBoost.C:219-287.  The recursion on the anchor node is unrolled on an explicit
+	// stack in aux[sp0 ...): a frame is the snapshot of the predecessors with a single out-edge, its length and
+	// the last base processed.
+	CNS_HD void merge_in(int n0, int sp0)
+	{
+		int sp = sp0;
+		auto push_frame = [&](int n) {
+			const int begin = sp;
+			for (int e = nd[n].in_head; e >= 0; e = ed[e].in_next) {
+				const int u = ed[e].u;
+				if (nd[u].out_cnt == 1) { if (sp + 3 > auxcap) { fail(POA_ERR_STACK); return; } aux[sp++] = u; }
+			}
+			if (sp + 2 > auxcap) { fail(POA_ERR_STACK); return; }
+			const int entries = sp - begin;
+			aux[sp++] = entries;
+			aux[sp++] = -1000;          // last base done
+		};
+		push_frame(n0);
+		while (sp > sp0 && !err) {
+			const int cnt = aux[sp - 2];
+			int32_t* list = aux + (sp - 2 - cnt);
+			const int b = next_base(list, cnt, aux[sp - 1]);
+			if (b < 0) { sp -= cnt + 2; continue; }
+			aux[sp - 1] = b;
+			int an = -1, members = 0;
+			for (int k = 0; k < cnt; ++k) if ((int)(signed char)nd[list[k]].base == b) { if (an < 0) an = list[k]; ++members; }
+			if (members <= 1) continue;
+			const int an_out = nd[an].out_head;
+			if (an_out < 0) { fail(POA_ERR_EMPTY_LIST); return; }
+			for (int k = 0; k < cnt; ++k) {
+				const int x = list[k];
+				if (x == an || (int)(signed char)nd[x].base != b) continue;
+				if (nd[x].out_head < 0) { fail(POA_ERR_EMPTY_LIST); return; }
+				ed[an_out].count += ed[nd[x].out_head].count;
+				nd[an].weight += nd[x].weight;
+			}
+			for (int k = 0; k < cnt; ++k) {
+				const int x = list[k];
+				if (x == an || (int)(signed char)nd[x].base != b) continue;
+				for (int ie = nd[x].in_head; ie >= 0; ie = ed[ie].in_next) {
+					const int n1 = ed[ie].u;
+					const int e = find_edge(n1, an);
+					if (e >= 0) ed[e].count += ed[ie].count;
+					else { const int ne = add_edge(n1, an); if (ne < 0) return; ed[ne].count = ed[ie].count; ed[ne].visited = ed[ie].visited; }
+				}
+				clear_vertex(x);
+			}
+			push_frame(an);
+		}
+	}
+
+	// mergeOutNodes, MECAT_AlnGraphBoost.C:289-357 (no recursion)
+	CNS_HD void merge_out(int n, int sp0)
+	{
+		int cnt = 0;
+		int32_t* list = aux + sp0;
+		for (int e = nd[n].out_head; e >= 0; e = ed[e].out_next) {
+			const int v = ed[e].v;
+			if (nd[v].in_cnt == 1) { if (sp0 + cnt + 1 > auxcap) { fail(POA_ERR_STACK); return; } list[cnt++] = v; }
+		}
+		int last = -1000;
+		for (;;) {
+			const int b = next_base(list, cnt, last);
+			if (b < 0 || err) break;
+			last = b;
+			int an = -1, members = 0;
+			for (int k = 0; k < cnt; ++k) if ((int)(signed char)nd[list[k]].base == b) { if (an < 0) an = list[k]; ++members; }
+			if (members <= 1) continue;
+			const int an_in = nd[an].in_head;
+			if (an_in < 0) { fail(POA_ERR_EMPTY_LIST); return; }
+			for (int k = 0; k < cnt; ++k) {
+				const int x = list[k];
+				if (x == an || (int)(signed char)nd[x].base != b) continue;
+				if (nd[x].in_head < 0) { fail(POA_ERR_EMPTY_LIST); return; }
+				ed[an_in].count += ed[nd[x].in_head].count;
+				nd[an].weight += nd[x].weight;
+			}
+			for (int k = 0; k < cnt; ++k) {
+				const int x = list[k];
+				if (x == an || (int)(signed char)nd[x].base != b) continue;
+				for (int oe = nd[x].out_head; oe >= 0; oe = ed[oe].out_next) {
+					const int n2 = ed[oe].v;
+					const int e = find_edge(an, n2);
+					if (e >= 0) ed[e].count += ed[oe].count;
+					else { const int ne = add_edge(an, n2); if (ne < 0) return; ed[ne].count = ed[oe].count; ed[ne].visited = ed[oe].visited; }
+				}
+				clear_vertex(x);
+			}
+		}
+	}
+
+	// mergeNodes, MECAT_AlnGraphBoost.C:199-217.  aux = [queue of qcap ints | merge stack]
+	CNS_HD void merge_nodes()
+	{
+		if (err) return;
+		const int qcap = 2 * ncap + 16;
+		int head = 0, tail = 0;          // monotone counters into the circular queue aux[0, qcap)
+		aux[tail++ % qcap] = enter;
+		while (head < tail && !err) {
+			const int u = aux[head++ % qcap];
+			merge_in(u, qcap);
+			merge_out(u, qcap);
+			for (int e = nd[u].out_head; e >= 0; e = ed[e].out_next) {
+				ed[e].visited = 1;
+				const int v = ed[e].v;
+				int open = 0;
+				for (int ie = nd[v].in_head; ie >= 0; ie = ed[ie].in_next) if (!ed[ie].visited) ++open;
+				if (open == 0) {
+					if (tail - head >= qcap) { fail(POA_ERR_QUEUE); return; }
+					aux[tail++ % qcap] = v;
+				}
+			}
+		}
+	}
+
+	// consensus + bestPath, MECAT_AlnGraphBoost.C:417-458,508-592.  Writes the bases of the best path into out
+	// (needs nn bytes) and returns, through off/len, the longest run of nodes with weight >= min_weight.
+	// aux = [queue | float score per node | best edge per node]
+	CNS_HD void consensus(int min_weight, char* out, int& off, int& len)
+	{
+		off = 0; len = 0;
+		if (err) return;
+		const int qcap = 2 * ncap + 16;
+		float* score = (float*)(aux + qcap);
+		int32_t* best_edge = aux + qcap + ncap;
+		for (int i = 0; i < nn; ++i) { score[i] = 0.0f; best_edge[i] = -1; }
+		for (int e = 0; e < nedges; ++e) ed[e].visited = 0;
+		int head = 0, tail = 0;
+		aux[tail++ % qcap] = exit_;
+		while (head < tail) {
+			const int n = aux[head++ % qcap];
+			bool found = false;
+			float best = -3.402823466e+38f;
+			int best_e = -1;
+			for (int e = nd[n].out_head; e >= 0; e = ed[e].out_next) {
+				const int v = ed[e].v;
+				const float s = score[v];
+				float ns;
+				if (nd[v].backbone && nd[v].weight == 1) ns = s - 10.0f;
+				else ns = (float)ed[e].count - (float)nd[nd[v].bb].coverage * 0.5f + s;
+				if (ns > best) { best = ns; best_e = e; found = true; }
+			}
+			if (found) { score[n] = best; best_edge[n] = best_e; }
+			for (int ie = nd[n].in_head; ie >= 0; ie = ed[ie].in_next) {
+				ed[ie].visited = 1;
+				const int u = ed[ie].u;
+				int open = 0;
+				for (int oe = nd[u].out_head; oe >= 0; oe = ed[oe].out_next) if (!ed[oe].visited) ++open;
+				if (open == 0) {
+					if (tail - head >= qcap) { fail(POA_ERR_QUEUE); return; }
+					aux[tail++ % qcap] = u;
+				}
+			}
+		}
+		int offs = 0, best_offs = 0, length = 0, idx = 0;
+		bool met = false;
+		for (int p = enter, guard = 0; guard <= nn; ++guard) {
+			const PoaNode& N = nd[p];
+			if (!(N.base == '^' || N.base == '$')) {
+				out[idx] = N.base;
+				if (!met && N.weight >= min_weight) { offs = idx; met = true; }
+				else if (met && N.weight < min_weight) {
+					if (idx - offs > length) { best_offs = offs; length = idx - offs; }
+					met = false;
+				}
+				++idx;
+			}
+			if (best_edge[p] < 0) break;
+			p = ed[best_edge[p]].v;
+		}
+		if (met && idx - offs > length) { best_offs = offs; length = idx - offs; }
+		off = best_offs; len = length;
+	}
+};
+
+// Node and initial-edge demand of one region: counted from the slices before the graph is built, so that
+// every graph gets an arena of exactly its own size.
+CNS_HD inline void region_demand(const KeptAln* kept, int nkept, int sb, int se, int prev_se, int& nodes, int& edges0)
+{
+	const int blen = se - sb + 1;
+	int n = blen + 2, e = blen + 1;
+	for (int k = 0; k < nkept; ++k) {
+		Slice sl;
+		if (!kept_slice(kept[k], sb, se, prev_se, sl)) continue;
+		const char* q = kept[k].q; const char* s = kept[k].s;
+		for (int i = sl.c0; i <= sl.c1; ++i) {
+			const char a = q[i], b = s[i];
+			if (a == '-') continue;
+			++e;                              // a match or an extra base links one edge
+			if (a != b) ++n;                  // an extra base also creates a node
+		}
+		++e;                                  // link to the exit node
+	}
+	nodes = n; edges0 = e;
+}
+
+// meap_cns_one_indel, mecat_correction.cpp:63-78: graph of one region -> best-path bases in out[0..), the kept run
+// in off/len.  Returns a POA_* status.
+CNS_HD inline int region_consensus(const KeptAln* kept, int nkept, int sb, int se, int prev_se, int min_weight,
+                                   PoaNode* nodes, int node_cap, PoaEdge* edges, int edge_cap, int32_t* aux, int aux_cap,
+                                   char* out, int& off, int& len)
+{
+	Poa g;
+	g.init(nodes, node_cap, edges, edge_cap, aux, aux_cap, se - sb + 1);
+	for (int k = 0; k < nkept; ++k) {
+		Slice sl;
+		if (kept_slice(kept[k], sb, se, prev_se, sl)) g.add_alignment(kept[k].q, kept[k].s, sl.c0, sl.c1, sl.start);
+	}
+	g.merge_nodes();
+	g.consensus(min_weight, out, off, len);
+	if (g.err) { off = 0; len = 0; }
+	return g.err;
+}
+
+}  // namespace mbcns

@@ -1,0 +1,417 @@
+// mecat_b200/csrc/cns_pipeline.h -- the consensus stage of mecat2cns (rows C3-C7) as a sequence of kernels.
+//
+// consensus_batch() takes the GetAlignment results of a batch of reads where the extension kernels left
+// them (device memory) and produces the corrected pieces.  Every stage is a launch of one functor over
+// n independent units (reads, accepted alignments, ambiguous regions, segments) with cns_core.cuh as the
+// per-unit body; exclusive scans between the stages size the next stage's arenas exactly, so no stage
+// needs a capacity guess or a retry.  The code is written against a small backend interface:
+//   * cns.cu provides the CUDA backend (functor -> k_cns<F><<<...>>>, device scans, device memory) and is
+//     the only backend in the product library;
+//   * tests/cns_host_harness.cpp provides a host backend so that the CPU test-suite can run the same stage
+//     sequence and bodies against the reference's golden output without a GPU.
+//
+//   stage            unit                reference
+//   AcceptFn         read                consensus_one_read_can_pacbio accept loop, mecat_correction.cpp:389-450
+//   FlattenFn        read                (layout only)
+//   NormVoteFn       accepted alignment  normalize_gaps + meap_add_one_aln + CnsAln cursor index
+//   SegmentFn        read                get_effective_ranges + consensus_worker run search
+//   RegionCountFn    read                identify_one_consensus_item + meap_consensus_one_segment (anchor walk)
+//   RegionFillFn     read                "
+//   DemandFn         region              node / edge demand of the region's graph
+//   PoaFn            region              meap_cns_one_indel: AlnGraphBoost build, merge, best path
+//   TargetCapFn      segment             (layout only)
+//   AssembleFn       segment             meap_consensus_one_segment: anchors + refined interiors -> corrected bases
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "cns_core.cuh"
+
+namespace mbcns {
+
+struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; };
+struct Piece { int64_t id, beg, end; std::string seq; };   // CnsResult, src/common/alignment.h
+
+// kernel slots for the per-stage timers of the backend
+enum { ST_ACCEPT = 0, ST_NORMVOTE = 1, ST_SEGMENT = 2, ST_REGION = 3, ST_POA = 4, ST_ASSEMBLE = 5, ST_NUM = 6 };
+
+struct BatchIn
+{
+	int R = 0;                     // reads of the batch (each with its candidate range, in trial order)
+	int64_t T = 0;                 // extension tasks of the batch
+	const int32_t* h_first = nullptr;      // [R + 1] task range of read r
+	const int32_t* h_read_size = nullptr;  // [R]
+	const int64_t* h_read_id = nullptr;    // [R]
+	const int32_t* h_tqid = nullptr;       // [T] partner read of task t
+	const int32_t* h_tqsize = nullptr;     // [T] its length
+	// device side, as left by the extension kernels (align.cu)
+	const int32_t* d_info = nullptr;                // [8 T] {ok, qstart, qend, sstart, send, columns, matches, -}
+	const char* d_q = nullptr;                      // gapped strings, task t at d_outoff[t]
+	const char* d_s = nullptr;
+	const unsigned long long* d_outoff = nullptr;   // [T + 1]
+};
+
+// ---------------------------------------------------------------------------------------------- functors
+struct AcceptFn
+{
+	const int32_t* first; const int32_t* info; const int32_t* tqid; const int32_t* tqsize; const int32_t* read_size;
+	const int64_t* pos_off; uint8_t* cov; double ratio; int32_t* acc; int32_t* nacc;
+	CNS_HD void operator()(int64_t r) const
+	{
+		nacc[r] = accept_read(first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT);
+	}
+};
+
+struct FlattenFn      // accepted alignment A = aln_first[r] + k; capacities of its normalised strings and column index
+{
+	const int32_t* info; const int32_t* acc; const int32_t* nacc; const int64_t* aln_first;
+	int32_t* aln_task; int32_t* aln_read; int32_t* cap_norm; int32_t* cap_col;
+	CNS_HD void operator()(int64_t r) const
+	{
+		for (int k = 0; k < nacc[r]; ++k) {
+			const int64_t A = aln_first[r] + k;
+			const int t = acc[r * MAX_ACCEPT + k];
+			const int32_t* o = info + 8 * (int64_t)t;
+			aln_task[A] = t; aln_read[A] = (int32_t)r;
+			cap_norm[A] = 2 * o[5] + 2;
+			cap_col[A] = o[4] - o[3] + 2;
+		}
+	}
+};
+
+struct NormVoteFn
+{
+	const int32_t* info; const char* q; const char* s; const unsigned long long* outoff;
+	const int32_t* aln_task; const int32_t* aln_read; const int64_t* norm_off; const int64_t* col_off; const int64_t* pos_off;
+	char* nq; char* nt; int32_t* colidx; uint32_t* votes; char* base; KeptAln* kept;
+	CNS_HD void operator()(int64_t A) const
+	{
+		const int t = aln_task[A];
+		const int32_t* o = info + 8 * (int64_t)t;
+		char* a = nq + norm_off[A];
+		char* b = nt + norm_off[A];
+		const int len = normalize_gaps(q + outoff[t], s + outoff[t], o[5], a, b);
+		const int64_t po = pos_off[aln_read[A]];
+		add_votes(a, b, len, o[3], votes + po, base + po);
+		KeptAln K;
+		K.q = a; K.s = b; K.colidx = colidx + col_off[A];
+		K.size = len; K.soff = o[3]; K.send = o[4];
+		K.tend = column_index(b, len, o[3], colidx + col_off[A]);
+		kept[A] = K;
+	}
+};
+
+struct SegmentFn
+{
+	const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept; const int32_t* read_size; const int64_t* pos_off;
+	const uint32_t* votes; int min_cov; double size95; const int64_t* seg_slot; int32_t* segs; int32_t* nseg;
+	CNS_HD void operator()(int64_t r) const
+	{
+		Range m[MAX_ACCEPT], e[MAX_ACCEPT];
+		const int n = nacc[r];
+		for (int k = 0; k < n; ++k) { m[k].start = kept[aln_first[r] + k].soff; m[k].end = kept[aln_first[r] + k].send; }
+		const int ne = effective_ranges(m, n, e, read_size[r], size95);
+		const int cap = (int)(seg_slot[r + 1] - seg_slot[r]);
+		const int ns = find_segments(e, ne, votes + pos_off[r], min_cov, size95, segs + 2 * seg_slot[r], cap);
+		nseg[r] = ns <= cap ? ns : -1;       // -1: capacity formula violated (reported by the host as an error)
+	}
+};
+
+// Both passes over a read's segments.  FILL = false: classify the positions (flags) and count the regions;
+// FILL = true: write the regions and each segment's first region.
+template <bool FILL>
+struct RegionFn
+{
+	const int32_t* nseg; const int64_t* seg_slot; const int32_t* segs; const int64_t* pos_off; const uint32_t* votes;
+	uint8_t* flags; int32_t* nreg; const int64_t* reg_first; const int64_t* seg_first; Region* regions; int64_t* seg_reg;
+	CNS_HD void operator()(int64_t r) const
+	{
+		const int64_t po = pos_off[r];
+		int64_t g = FILL ? reg_first[r] : 0;
+		int prev_se = -1;
+		for (int k = 0; k < nseg[r]; ++k) {
+			const int beg = segs[2 * (seg_slot[r] + k)], end = segs[2 * (seg_slot[r] + k) + 1];
+			const int n = end - beg;
+			uint8_t* f = flags + po + beg;
+			const uint32_t* v = votes + po + beg;
+			if (!FILL) for (int i = 0; i < n; ++i) f[i] = classify(v[i]);
+			if (FILL) seg_reg[seg_first[r] + k] = g;
+			walk_anchors(f, n, [&](int i, int j, bool refine) {
+				if (!refine) return;
+				if (FILL) {
+					Region G;
+					G.read = (int32_t)r; G.sb = i + beg; G.se = j + beg; G.prev_se = prev_se;
+					G.min_weight = (int)((double)(vote_mat(v[i]) + vote_ins(v[i])) * 0.4);
+					regions[g] = G;
+					prev_se = j + beg;
+				}
+				++g;
+			});
+		}
+		if (!FILL) nreg[r] = (int32_t)g;
+	}
+};
+
+struct DemandFn
+{
+	const Region* regions; const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept; int32_t* dn; int32_t* de;
+	CNS_HD void operator()(int64_t g) const
+	{
+		const Region G = regions[g];
+		int n, e;
+		region_demand(kept + aln_first[G.read], nacc[G.read], G.sb, G.se, G.prev_se, n, e);
+		dn[g] = n; de[g] = e;
+	}
+};
+
+struct PoaFn
+{
+	const Region* regions; const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept;
+	const int64_t* node_off; const int64_t* edge0_off;
+	PoaNode* nodes; PoaEdge* edges; int32_t* aux; char* gout; int32_t* goff; int32_t* glen; int32_t* gerr;
+	CNS_HD void operator()(int64_t g) const
+	{
+		const Region G = regions[g];
+		const int64_t n0 = node_off[g], e0 = edge0_off[g];
+		const int ncap = (int)(node_off[g + 1] - n0);
+		const int ecap = (int)poa_edge_cap(ncap, edge0_off[g + 1] - e0);
+		int off, len;
+		gerr[g] = region_consensus(kept + aln_first[G.read], nacc[G.read], G.sb, G.se, G.prev_se, G.min_weight,
+		                           nodes + n0, ncap, edges + (e0 + n0 + 2 * g), ecap, aux + (8 * n0 + 64 * g), (int)poa_aux_ints(ncap),
+		                           gout + n0, off, len);
+		goff[g] = off; glen[g] = len;
+	}
+};
+
+struct TargetCapFn     // upper bound of a segment's corrected length: its positions plus the nodes of its regions
+{
+	const int32_t* seg_read; const int32_t* seg_beg; const int32_t* seg_end; const int64_t* seg_reg; const int64_t* node_off;
+	const int64_t* reg_first; const int64_t* seg_first; const int32_t* nseg; int64_t NS; int32_t* cap;
+	CNS_HD int64_t reg_end(int64_t S) const      // one past the last region of segment S
+	{
+		const int r = seg_read[S];
+		return (S + 1 < seg_first[r] + nseg[r]) ? seg_reg[S + 1] : reg_first[r + 1];
+	}
+	CNS_HD void operator()(int64_t S) const
+	{
+		cap[S] = (int32_t)((seg_end[S] - seg_beg[S]) + (node_off[reg_end(S)] - node_off[seg_reg[S]]) + 1);
+	}
+};
+
+struct AssembleFn
+{
+	const int32_t* seg_read; const int32_t* seg_beg; const int32_t* seg_end; const int64_t* seg_reg; const int64_t* pos_off;
+	const uint8_t* flags; const char* base; const int64_t* node_off; const char* gout; const int32_t* goff; const int32_t* glen;
+	const int64_t* tgt_off; char* target; int32_t* tlen;
+	CNS_HD void operator()(int64_t S) const
+	{
+		const int beg = seg_beg[S], n = seg_end[S] - beg;
+		const int64_t po = pos_off[seg_read[S]] + beg;
+		char* out = target + tgt_off[S];
+		int64_t g = seg_reg[S];
+		int len = 0;
+		walk_anchors(flags + po, n, [&](int i, int, bool refine) {
+			out[len++] = base[po + i];
+			if (!refine) return;
+			const int l = glen[g];
+			if (l > 2) {
+				const char* src = gout + node_off[g] + goff[g] + 1;
+				for (int k = 0; k < l - 2; ++k) out[len++] = src[k];
+			}
+			++g;
+		});
+		tlen[S] = len;
+	}
+};
+
+struct SegFlattenFn
+{
+	const int32_t* nseg; const int64_t* seg_slot; const int32_t* segs; const int64_t* seg_first;
+	int32_t* seg_read; int32_t* seg_beg; int32_t* seg_end;
+	CNS_HD void operator()(int64_t r) const
+	{
+		for (int k = 0; k < nseg[r]; ++k) {
+			const int64_t S = seg_first[r] + k;
+			seg_read[S] = (int32_t)r; seg_beg[S] = segs[2 * (seg_slot[r] + k)]; seg_end[S] = segs[2 * (seg_slot[r] + k) + 1];
+		}
+	}
+};
+
+// output_cns_result, mecat_correction.cpp:156-188 (host: splits pieces longer than 60 000 bases)
+inline void emit_piece(std::vector<Piece>& out, int64_t id, int64_t beg, int64_t end, const char* seq, size_t size)
+{
+	const size_t MaxSeq = 60000, Ovlp = 10000, Blk = MaxSeq - Ovlp - 1000;
+	if (size <= MaxSeq) { out.push_back(Piece{id, beg, end, std::string(seq, size)}); return; }
+	const size_t cutoff = size - Ovlp - 1000;
+	size_t L = 0, R;
+	do {
+		R = L + Blk;
+		if (R >= cutoff) R = size;
+		Piece p;
+		p.id = id; p.beg = (int64_t)L + beg;
+		p.end = (R < size && (int64_t)R + beg < end) ? (int64_t)R + beg : end;
+		p.seq.assign(seq + L, R - L);
+		out.push_back(p);
+		L = R - Ovlp;
+	} while (R < size);
+}
+
+// ---------------------------------------------------------------------------------------------- pipeline
+// Backend B:
+//   template <class T> T* alloc(size_t n)            device array, freed by end_batch(); nullptr + error on failure
+//   bool upload(T* d, const T* h, size_t n), bool download(T* h, const T* d, size_t n), bool fill(void* d, int byte, size_t bytes)
+//   template <class F> bool launch(int64_t n, const F& f, int stage)
+//   bool scan(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* total)   d_out[0..n] exclusive prefix, total on the host
+//   void fail(const char* msg), void end_batch()
+template <class B>
+int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece>& out)
+{
+	struct Guard { B& b; ~Guard() { b.end_batch(); } } guard{be};
+	const int R = in.R;
+	const int64_t T = in.T;
+	if (R == 0) return 0;
+	const double ratio = P.min_mapping_ratio - 0.02;
+	const double size95 = 0.95 * (double)P.min_size;
+
+	// per-read position arenas and segment slots
+	std::vector<int64_t> h_pos((size_t)R + 1, 0), h_slot((size_t)R + 1, 0);
+	for (int r = 0; r < R; ++r) {
+		h_pos[r + 1] = h_pos[r] + in.h_read_size[r] + 1;
+		const double unit = size95 > 1.0 ? size95 : 1.0;
+		h_slot[r + 1] = h_slot[r] + (int64_t)((double)in.h_read_size[r] / unit) + MAX_ACCEPT + 1;
+	}
+	const int64_t POS = h_pos[R];
+#define CNS_TRY(x) do { if (!(x)) return 1; } while (0)
+#define CNS_ALLOC(var, type, count) type* var = be.template alloc<type>((size_t)(count)); if (!var) return 1
+	CNS_ALLOC(d_first, int32_t, R + 1);
+	CNS_ALLOC(d_rsize, int32_t, R);
+	CNS_ALLOC(d_tqid, int32_t, T);
+	CNS_ALLOC(d_tqsize, int32_t, T);
+	CNS_ALLOC(d_pos, int64_t, R + 1);
+	CNS_ALLOC(d_slot, int64_t, R + 1);
+	CNS_ALLOC(d_cov, uint8_t, POS);
+	CNS_ALLOC(d_votes, uint32_t, POS);
+	CNS_ALLOC(d_base, char, POS);
+	CNS_ALLOC(d_acc, int32_t, (int64_t)R * MAX_ACCEPT);
+	CNS_ALLOC(d_nacc, int32_t, R);
+	CNS_ALLOC(d_alnfirst, int64_t, R + 1);
+	CNS_TRY(be.upload(d_first, in.h_first, (size_t)R + 1));
+	CNS_TRY(be.upload(d_rsize, in.h_read_size, (size_t)R));
+	CNS_TRY(be.upload(d_tqid, in.h_tqid, (size_t)T));
+	CNS_TRY(be.upload(d_tqsize, in.h_tqsize, (size_t)T));
+	CNS_TRY(be.upload(d_pos, h_pos.data(), (size_t)R + 1));
+	CNS_TRY(be.upload(d_slot, h_slot.data(), (size_t)R + 1));
+	CNS_TRY(be.fill(d_cov, 0, (size_t)POS));
+	CNS_TRY(be.fill(d_votes, 0, (size_t)POS * 4));
+	CNS_TRY(be.fill(d_base, 'N', (size_t)POS));
+
+	// C3: which alignments vote
+	CNS_TRY(be.launch(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc}, ST_ACCEPT));
+	int64_t NA = 0;
+	CNS_TRY(be.scan(d_nacc, d_alnfirst, R, &NA));
+	if (NA == 0) return 0;
+	CNS_ALLOC(d_alntask, int32_t, NA);
+	CNS_ALLOC(d_alnread, int32_t, NA);
+	CNS_ALLOC(d_capnorm, int32_t, NA);
+	CNS_ALLOC(d_capcol, int32_t, NA);
+	CNS_ALLOC(d_normoff, int64_t, NA + 1);
+	CNS_ALLOC(d_coloff, int64_t, NA + 1);
+	CNS_ALLOC(d_kept, KeptAln, NA);
+	CNS_TRY(be.launch(R, FlattenFn{in.d_info, d_acc, d_nacc, d_alnfirst, d_alntask, d_alnread, d_capnorm, d_capcol}, ST_ACCEPT));
+	int64_t NORM = 0, COL = 0;
+	CNS_TRY(be.scan(d_capnorm, d_normoff, NA, &NORM));
+	CNS_TRY(be.scan(d_capcol, d_coloff, NA, &COL));
+	CNS_ALLOC(d_nq, char, NORM);
+	CNS_ALLOC(d_nt, char, NORM);
+	CNS_ALLOC(d_colidx, int32_t, COL);
+
+	// C4 + C5: normalise, vote, index the columns
+	CNS_TRY(be.launch(NA, NormVoteFn{in.d_info, in.d_q, in.d_s, in.d_outoff, d_alntask, d_alnread, d_normoff, d_coloff, d_pos,
+	                                 d_nq, d_nt, d_colidx, d_votes, d_base, d_kept}, ST_NORMVOTE));
+
+	// C6: covered runs of each read
+	CNS_ALLOC(d_segs, int32_t, 2 * h_slot[R]);
+	CNS_ALLOC(d_nseg, int32_t, R);
+	CNS_ALLOC(d_segfirst, int64_t, R + 1);
+	CNS_TRY(be.launch(R, SegmentFn{d_nacc, d_alnfirst, d_kept, d_rsize, d_pos, d_votes, P.min_cov, size95, d_slot, d_segs, d_nseg}, ST_SEGMENT));
+	std::vector<int32_t> h_nseg((size_t)R);
+	CNS_TRY(be.download(h_nseg.data(), d_nseg, (size_t)R));
+	for (int r = 0; r < R; ++r) if (h_nseg[r] < 0) { be.fail("cns: segment slots of a read overflowed"); return 1; }
+	int64_t NS = 0;
+	CNS_TRY(be.scan(d_nseg, d_segfirst, R, &NS));
+	if (NS == 0) return 0;
+
+	// C6: anchors and ambiguous regions of every segment
+	uint8_t* d_flags = d_cov;      // the accept loop is done with its coverage bytes
+	CNS_ALLOC(d_nreg, int32_t, R);
+	CNS_ALLOC(d_regfirst, int64_t, R + 1);
+	CNS_ALLOC(d_segreg, int64_t, NS + 1);
+	CNS_ALLOC(d_segread, int32_t, NS);
+	CNS_ALLOC(d_segbeg, int32_t, NS);
+	CNS_ALLOC(d_segend, int32_t, NS);
+	CNS_TRY(be.launch(R, SegFlattenFn{d_nseg, d_slot, d_segs, d_segfirst, d_segread, d_segbeg, d_segend}, ST_SEGMENT));
+	CNS_TRY(be.launch(R, RegionFn<false>{d_nseg, d_slot, d_segs, d_pos, d_votes, d_flags, d_nreg, nullptr, nullptr, nullptr, nullptr}, ST_REGION));
+	int64_t NG = 0;
+	CNS_TRY(be.scan(d_nreg, d_regfirst, R, &NG));
+	CNS_ALLOC(d_regions, Region, NG + 1);
+	CNS_TRY(be.launch(R, RegionFn<true>{d_nseg, d_slot, d_segs, d_pos, d_votes, d_flags, d_nreg, d_regfirst, d_segfirst, d_regions, d_segreg}, ST_REGION));
+
+	// C7: one graph per region, each in an arena of exactly its demand
+	CNS_ALLOC(d_dn, int32_t, NG + 1);
+	CNS_ALLOC(d_de, int32_t, NG + 1);
+	CNS_ALLOC(d_nodeoff, int64_t, NG + 1);
+	CNS_ALLOC(d_edgeoff, int64_t, NG + 1);
+	CNS_ALLOC(d_goff, int32_t, NG + 1);
+	CNS_ALLOC(d_glen, int32_t, NG + 1);
+	CNS_ALLOC(d_gerr, int32_t, NG + 1);
+	int64_t NODES = 0, EDGES0 = 0;
+	if (NG) CNS_TRY(be.launch(NG, DemandFn{d_regions, d_nacc, d_alnfirst, d_kept, d_dn, d_de}, ST_POA));
+	CNS_TRY(be.scan(d_dn, d_nodeoff, NG, &NODES));
+	CNS_TRY(be.scan(d_de, d_edgeoff, NG, &EDGES0));
+	CNS_ALLOC(d_nodes, PoaNode, NODES);
+	CNS_ALLOC(d_edges, PoaEdge, EDGES0 + NODES + 2 * NG);
+	CNS_ALLOC(d_aux, int32_t, 8 * NODES + 64 * NG);
+	CNS_ALLOC(d_gout, char, NODES);
+	if (NG) CNS_TRY(be.launch(NG, PoaFn{d_regions, d_nacc, d_alnfirst, d_kept, d_nodeoff, d_edgeoff, d_nodes, d_edges, d_aux, d_gout,
+	                                    d_goff, d_glen, d_gerr}, ST_POA));
+
+	// corrected bases of every segment
+	CNS_ALLOC(d_tcap, int32_t, NS);
+	CNS_ALLOC(d_tgtoff, int64_t, NS + 1);
+	CNS_ALLOC(d_tlen, int32_t, NS);
+	CNS_TRY(be.launch(NS, TargetCapFn{d_segread, d_segbeg, d_segend, d_segreg, d_nodeoff, d_regfirst, d_segfirst, d_nseg, NS, d_tcap}, ST_ASSEMBLE));
+	int64_t TGT = 0;
+	CNS_TRY(be.scan(d_tcap, d_tgtoff, NS, &TGT));
+	CNS_ALLOC(d_target, char, TGT);
+	CNS_TRY(be.launch(NS, AssembleFn{d_segread, d_segbeg, d_segend, d_segreg, d_pos, d_flags, d_base, d_nodeoff, d_gout, d_goff, d_glen,
+	                                 d_tgtoff, d_target, d_tlen}, ST_ASSEMBLE));
+
+	// results to the host
+	std::vector<int32_t> h_segread((size_t)NS), h_segbeg((size_t)NS), h_segend((size_t)NS), h_tlen((size_t)NS), h_gerr((size_t)NG);
+	std::vector<int64_t> h_tgtoff((size_t)NS + 1);
+	std::vector<char> h_target((size_t)TGT);
+	CNS_TRY(be.download(h_segread.data(), d_segread, (size_t)NS));
+	CNS_TRY(be.download(h_segbeg.data(), d_segbeg, (size_t)NS));
+	CNS_TRY(be.download(h_segend.data(), d_segend, (size_t)NS));
+	CNS_TRY(be.download(h_tlen.data(), d_tlen, (size_t)NS));
+	CNS_TRY(be.download(h_tgtoff.data(), d_tgtoff, (size_t)NS + 1));
+	CNS_TRY(be.download(h_target.data(), d_target, (size_t)TGT));
+	if (NG) CNS_TRY(be.download(h_gerr.data(), d_gerr, (size_t)NG));
+	for (int64_t g = 0; g < NG; ++g)
+		if (h_gerr[g]) {
+			char msg[128];
+			snprintf(msg, sizeof msg, "cns: region graph %lld ran out of scratch (code %d)", (long long)g, h_gerr[g]);
+			be.fail(msg);
+			return 1;
+		}
+	for (int64_t S = 0; S < NS; ++S)
+		if ((int64_t)h_tlen[S] >= P.min_size)
+			emit_piece(out, in.h_read_id[h_segread[S]], h_segbeg[S], h_segend[S], h_target.data() + h_tgtoff[S], (size_t)h_tlen[S]);
+#undef CNS_TRY
+#undef CNS_ALLOC
+	return 0;
+}
+
+}  // namespace mbcns

@@ -194,8 +194,28 @@ struct AlignTask           // = mecat_align_task
 {
 	int32_t qread, qstrand, qstart, sread, sstart, swin_off, swin_len;
 };
+// results of one arena batch of extensions with strings, still in device memory
+struct AlignDev
+{
+	int32_t* d_info = nullptr;                  // 8 ints per task {ok, qstart, qend, sstart, send, columns, matches, -}
+	char* d_packq = nullptr;                    // gapped strings, task t at d_outoff[t], NUL after each
+	char* d_packt = nullptr;
+	unsigned long long* d_outoff = nullptr;     // ntasks + 1
+	size_t total = 0;
+};
+constexpr size_t ALIGN_ARENA = 3ull << 30;      // column arena of one batch
+size_t align_task_columns(const DVolume* q, const DVolume* s, const AlignTask& t);
+int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t nb,
+                       int min_aln, AlignDev* out, std::vector<int32_t>& info);
+void align_dev_release(Ctx* c, AlignDev* d);
 int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t ntasks,
                 int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr);
+
+}  // namespace mb
+namespace mbcns { struct BatchIn; struct Params; struct Piece; }
+namespace mb {
+// consensus stage of mecat2cns on the extension results of one batch (cns.cu)
+int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, std::vector<mbcns::Piece>& out);
 
 struct RawCand             // candidate_save, pw_impl.h:21-25
 {

@@ -229,6 +229,17 @@ int main(int argc, char* argv[])
 		mecat_b200_free(ctx, seqs);
 		i = j;
 	}
+	if (getenv("MECAT_B200_STATS")) {       // per-kernel CUDA-event times of the whole run, one line
+		mecat_b200_stats st;
+		if (!mecat_b200_get_stats(ctx, &st)) {
+			static const char* names[MECAT_K_NUM] = {"orient", "index_count", "scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
+			                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"};
+			fprintf(stderr, "[kernel ms]");
+			for (int k = 0; k < MECAT_K_NUM; ++k)
+				if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);
+			fprintf(stderr, "\n");
+		}
+	}
 	mecat_b200_volume_release(ctx, dvol);
 	mecat_b200_destroy(ctx);
 	mecat_b200_volume_unload(&vol);

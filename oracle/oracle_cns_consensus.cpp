@@ -1,8 +1,9 @@
-// mecat_b200/csrc/cns.cpp -- per-read consensus of mecat2cns on the host (C3-C7).
+// oracle/oracle_cns_consensus.cpp -- TEST INFRASTRUCTURE ONLY (see oracle.h).
 //
-// The gapped extensions of a read's candidates (C1-C2, 82 % of the reference's CPU time) run on the
-// GPU (align.cu, policy 1).  What remains per read is sequential bookkeeping on small data and runs
-// here on host threads, with the semantics of
+// CPU restatement of the per-read consensus of mecat2cns (rows C3-C7), given the GetAlignment results of
+// the read's candidates.  Pinned against corrected FASTA written by the UNMODIFIED reference binary
+// (tests/golden/*.cns_*.fa.gz, tests/test_cns_host.py).  The product computes the same on the GPU
+// (mecat_b200/csrc/cns.cu); this file is what the GPU kernels are checked against.  Semantics of
 //   consensus_one_read_can_pacbio, check_ovlp_mapping_range, check_cov_stats   src/mecat2cns/mecat_correction.cpp:191-200,362-450
 //   normalize_gaps                                                             src/mecat2cns/reads_correction_aux.cpp:3-79
 //   meap_add_one_aln, identify_one_consensus_item, meap_consensus_one_segment  mecat_correction.cpp:15-108
@@ -12,7 +13,9 @@
 // The graph is a small adjacency structure with the iteration orders of the reference's
 // boost::adjacency_list<vecS, vecS, bidirectionalS> (edge lists in insertion order, order-preserving
 // removal), because tie-breaks in the best-path search depend on them.
-#include "cns.h"
+#include "oracle_cns_consensus.h"
+
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -21,7 +24,7 @@
 #include <queue>
 #include <set>
 
-namespace mbcns {
+namespace orccns {
 
 namespace {
 
@@ -455,4 +458,37 @@ void consensus_one_read(int64_t read_id, int read_size, const mecat_candidate* c
 	}
 }
 
-}  // namespace mbcns
+}  // namespace orccns
+
+// ------------------------------------------------------------------ C entry points (ctypes)
+extern "C" {
+
+void orc_cns_sort_candidates(mecat_candidate* c, int n) { orccns::sort_candidates(c, n); }
+
+int orc_cns_consensus(const mecat_candidate* cand, int ncand, const mecat_align_result* res, const char* qstr,
+                      const char* sstr, const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces,
+                      char** seqs, size_t* seq_bytes)
+{
+	if (!cand || ncand <= 0 || !res || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
+	orccns::Params P;
+	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
+	orccns::Scratch scratch;
+	std::vector<orccns::Piece> out;
+	orccns::consensus_one_read(cand[0].sid, cand[0].ssize, cand, ncand, res, qstr, sstr, P, scratch, out);
+	size_t bytes = 0;
+	for (auto& pc : out) bytes += pc.seq.size();
+	mecat_cns_piece* o = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (out.size() ? out.size() : 1));
+	char* sq = (char*)malloc(bytes + 1);
+	if (!o || !sq) { free(o); free(sq); return 1; }
+	size_t at = 0;
+	for (size_t i = 0; i < out.size(); ++i) {
+		o[i].id = out[i].id; o[i].beg = out[i].beg; o[i].end = out[i].end; o[i].seq_offset = (int64_t)at; o[i].seq_len = (int64_t)out[i].seq.size();
+		memcpy(sq + at, out[i].seq.data(), out[i].seq.size());
+		at += out[i].seq.size();
+	}
+	sq[bytes] = 0;
+	*pieces = o; *npieces = out.size(); *seqs = sq; *seq_bytes = bytes;
+	return 0;
+}
+
+}  // extern "C"

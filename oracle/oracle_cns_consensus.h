@@ -1,13 +1,14 @@
-// mecat_b200/csrc/cns.h -- host-side consensus of one read (see cns.cpp).
+// oracle/oracle_cns_consensus.h -- TEST INFRASTRUCTURE ONLY: CPU consensus of one read (oracle_cns_consensus.cpp).
+// Uses the record layouts of the public C header (candidates, alignment results, pieces); nothing else of the product.
 #pragma once
 #include <stdint.h>
 
 #include <string>
 #include <vector>
 
-#include "../../include/mecat_b200.h"
+#include "../include/mecat_b200.h"
 
-namespace mbcns {
+namespace orccns {
 
 struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; };
 struct Piece { int64_t id, beg, end; std::string seq; };   // CnsResult, src/common/alignment.h
@@ -30,4 +31,4 @@ void sort_candidates(mecat_candidate* c, int n);
 void consensus_one_read(int64_t read_id, int read_size, const mecat_candidate* cand, int ncand, const mecat_align_result* res,
                         const char* qstr, const char* sstr, const Params& P, Scratch& scratch, std::vector<Piece>& out);
 
-}  // namespace mbcns
+}  // namespace orccns

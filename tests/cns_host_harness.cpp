@@ -1,0 +1,100 @@
+// tests/cns_host_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Runs the product's consensus stage sequence (mecat_b200/csrc/cns_pipeline.h) and kernel bodies
+// (mecat_b200/csrc/cns_core.cuh) on the host: "device memory" is malloc, a kernel launch is a loop over the
+// units, a scan is a loop.  This lets the CPU test-suite check the statements the GPU executes against the
+// reference's golden output and the oracle without a GPU.  It is compiled by tests/util.py into
+// tests/_build/libcns_harness.so and is never part of the product library.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../include/mecat_b200.h"
+#include "../mecat_b200/csrc/cns_pipeline.h"
+
+namespace {
+
+struct HostBackend
+{
+	std::vector<void*> owned;
+	std::string err;
+	template <class T> T* alloc(size_t n)
+	{
+		void* p = calloc(n ? n : 1, sizeof(T));
+		if (!p) { err = "out of memory"; return nullptr; }
+		memset(p, 0xAB, (n ? n : 1) * sizeof(T));      // like device memory: never zero by luck
+		owned.push_back(p);
+		return (T*)p;
+	}
+	template <class T> bool upload(T* d, const T* h, size_t n) { if (n) memcpy(d, h, n * sizeof(T)); return true; }
+	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
+	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
+	template <class F> bool launch(int64_t n, const F& f, int) { for (int64_t i = 0; i < n; ++i) f(i); return true; }
+	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)
+	{
+		int64_t s = 0;
+		for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
+		out[n] = s; *total = s;
+		return true;
+	}
+	void fail(const char* m) { err = m; }
+	void end_batch() { for (void* p : owned) free(p); owned.clear(); }
+};
+
+}  // namespace
+
+extern "C" {
+
+// R reads; read r owns the candidates / results [first[r], first[r+1]) in trial order.  Strings of result t start at
+// res[t].str_offset in qstr / sstr (NUL terminated).
+int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, const mecat_align_result* res, const char* qstr,
+                      const char* sstr, const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs,
+                      size_t* seq_bytes, char* errbuf, int errcap)
+{
+	const int64_t T = first[R];
+	std::vector<int32_t> rsize((size_t)R), tqid((size_t)T), tqsize((size_t)T), info((size_t)T * 8);
+	std::vector<int64_t> rid((size_t)R);
+	std::vector<unsigned long long> outoff((size_t)T + 1, 0);
+	for (int r = 0; r < R; ++r) { rsize[r] = cand[first[r]].ssize; rid[r] = cand[first[r]].sid; }
+	for (int64_t t = 0; t < T; ++t) {
+		tqid[t] = cand[t].qid; tqsize[t] = cand[t].qsize;
+		int32_t* o = &info[8 * t];
+		o[0] = res[t].ok; o[1] = res[t].qstart; o[2] = res[t].qend; o[3] = res[t].sstart; o[4] = res[t].send;
+		o[5] = res[t].columns; o[6] = res[t].matches; o[7] = 0;
+		outoff[t] = res[t].ok ? (unsigned long long)res[t].str_offset : 0;
+	}
+	mbcns::BatchIn in;
+	in.R = R; in.T = T; in.h_first = first; in.h_read_size = rsize.data(); in.h_read_id = rid.data();
+	in.h_tqid = tqid.data(); in.h_tqsize = tqsize.data();
+	in.d_info = info.data(); in.d_q = qstr; in.d_s = sstr; in.d_outoff = outoff.data();
+	mbcns::Params P;
+	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
+	HostBackend be;
+	std::vector<mbcns::Piece> out;
+	if (mbcns::consensus_batch(be, in, P, out)) {
+		if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", be.err.c_str());
+		return 1;
+	}
+	size_t bytes = 0;
+	for (auto& pc : out) bytes += pc.seq.size();
+	mecat_cns_piece* o = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (out.size() ? out.size() : 1));
+	char* sq = (char*)malloc(bytes + 1);
+	if (!o || !sq) { free(o); free(sq); return 1; }
+	size_t at = 0;
+	for (size_t i = 0; i < out.size(); ++i) {
+		o[i].id = out[i].id; o[i].beg = out[i].beg; o[i].end = out[i].end; o[i].seq_offset = (int64_t)at; o[i].seq_len = (int64_t)out[i].seq.size();
+		memcpy(sq + at, out[i].seq.data(), out[i].seq.size());
+		at += out[i].seq.size();
+	}
+	sq[bytes] = 0;
+	*pieces = o; *npieces = out.size(); *seqs = sq; *seq_bytes = bytes;
+	return 0;
+}
+
+void harness_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -7,6 +7,10 @@ Cases (reads come from oracle/gen_reads, a seeded deterministic generator):
   small : 250 reads, mean 6 kb, genome 100 kb, seed 3   -> FASTA committed (gzip)
   cfg0  : 1000 reads, mean 15 kb, genome 1 Mb, seed 7   -> BASELINE.json configs[0]; FASTA
           regenerated on demand, its sha256 is committed
+  deep  : 300 reads, mean 6 kb, genome 15 kb, seed 5    -> ~120x coverage: every read has the full 100 candidates,
+          so mecat2cns reaches its 60-alignment cap and its 20x coverage gate (check_cov_stats); only the
+          candidates and the corrected FASTA (-l 2000 -c 4 -a 1000) are kept, FASTA regenerated on demand
+  python tests/golden/make_golden.py [case ...]   regenerates only the named cases
 For each: vol0 sha256 (split_raw_dataset), sorted `mecat2pw -j 0` lines, sorted
 `mecat2pw -j 1 -g 1` lines.
 """
@@ -27,6 +31,7 @@ from util import gen_reads, REF_DIR  # noqa: E402
 CASES = {
     "small": dict(n=250, genome=100000, seed=3, mean=6000, sd=1500),
     "cfg0": dict(n=1000, genome=1000000, seed=7, mean=15000, sd=1500),
+    "deep": dict(n=300, genome=15000, seed=5, mean=6000, sd=1000),
 }
 
 
@@ -40,13 +45,19 @@ def sha(path):
 
 def main():
     meta = {}
+    if os.path.exists(os.path.join(HERE, "golden.json")):
+        meta = json.load(open(os.path.join(HERE, "golden.json")))
     for name, c in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         tmp = tempfile.mkdtemp(prefix="golden_")
         fa = os.path.join(tmp, "reads.fa")
         gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
         m = dict(c)
         m["fasta_sha256"] = sha(fa)
         for job, ext, extra in ((0, "can", []), (1, "m4", ["-g", "1"])):
+            if name == "deep" and job == 1:
+                continue
             wrk = os.path.join(tmp, "wrk%d" % job)
             out = os.path.join(tmp, "out." + ext)
             subprocess.check_call([os.path.join(REF_DIR, "mecat2pw"), "-j", str(job), "-d", fa, "-o", out, "-w", wrk,
@@ -60,7 +71,7 @@ def main():
         # mecat2cns -i 0 on the .can above (written next to a copy: it drops partition files beside its input)
         can = os.path.join(tmp, "in.can")
         for tag, args in (("cns_default", []), ("cns_relaxed", ["-l", "2000", "-c", "4", "-a", "1000"])):
-            if name == "cfg0" and tag == "cns_relaxed":
+            if (name == "cfg0" and tag == "cns_relaxed") or (name == "deep" and tag == "cns_default"):
                 continue
             with open(can, "w") as f:
                 f.write(open(os.path.join(tmp, "out.can")).read())

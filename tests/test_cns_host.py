@@ -1,7 +1,12 @@
-"""CPU test of the host half of mecat2cns (rows C3-C7): the product's per-read consensus
-(mecat_b200/csrc/cns.cpp, reached through its test hook) is fed GetAlignment results computed by the
-oracle (pinned against the reference in test_oracle.py) and must reproduce the corrected FASTA that the
-UNMODIFIED reference binary `mecat2cns -i 0` wrote for the same candidates (tests/golden)."""
+"""CPU tests of the consensus half of mecat2cns (rows C3-C7), fed with GetAlignment results computed by the
+oracle (pinned against the reference in test_oracle.py):
+
+  * the oracle's restatement of C3-C7 (oracle/oracle_cns_consensus.cpp) must reproduce the corrected FASTA that
+    the UNMODIFIED reference binary `mecat2cns -i 0` wrote for the same candidates (tests/golden) -- this pins it;
+  * the product's consensus kernels -- stage sequence (csrc/cns_pipeline.h) and per-thread bodies
+    (csrc/cns_core.cuh), compiled for the host by tests/cns_host_harness.cpp, where a launch is a loop -- must
+    reproduce the same FASTA, all reads in ONE batch so that every arena offset and scan is exercised.
+The GPU run of the same kernels is checked in test_gpu.py (test_cns_*)."""
 import ctypes as C
 import gzip
 import io
@@ -29,16 +34,20 @@ def gold_can(name):
         return mecat_b200.read_can(io.StringIO(f.read()))
 
 
-def correct_with_oracle_alignments(vol, can, ratio, min_aln, min_cov, min_size):
-    """mecat2cns -i 0 with the alignments taken from the oracle and everything else from the product."""
+_aln_cache = {}
+
+
+def oracle_alignments(vol, can, min_aln, min_cov, min_size, keep=None):
+    """Per read to correct: candidates in trial order + the oracle's GetAlignment of each.  Returns
+    (first[R+1], candidates[T], results[T], qblob, sblob).  keep: optional predicate on the read id."""
+    key = (id(vol), min_aln, min_cov, min_size, keep)
+    if key in _aln_cache:
+        return _aln_cache[key]
     import mecat_b200
-    from mecat_b200.api import ALIGN_RESULT_DTYPE, CnsParams, CNS_PIECE_DTYPE, EC_DTYPE
-    L = mecat_b200.load_library()
+    from mecat_b200.api import ALIGN_RESULT_DTYPE
     O = util.oracle()
     ec = mecat_b200.normalise_candidates(can, min_size)
     ec = ec[np.argsort(ec["sid"], kind="stable")]
-    p = CnsParams(ratio, min_aln, min_cov, min_size)
-    out = []
     codes = {}
 
     def seq(rid, strand):
@@ -48,6 +57,8 @@ def correct_with_oracle_alignments(vol, can, ratio, min_aln, min_cov, min_size):
         return codes[k]
 
     o5 = (C.c_int32 * 8)()
+    first, cands, results = [0], [], []
+    qblob, sblob = bytearray(), bytearray()
     i = 0
     while i < len(ec):
         j = i + 1
@@ -55,12 +66,13 @@ def correct_with_oracle_alignments(vol, can, ratio, min_aln, min_cov, min_size):
             j += 1
         grp = np.ascontiguousarray(ec[i:j])
         i = j
+        if keep is not None and not keep(int(grp["sid"][0])):
+            continue
         if len(grp) < min_cov or grp["ssize"][0] < min_size * 0.95:
             continue
-        L.mecat_b200_cns_sort_candidates(grp.ctypes.data_as(C.c_void_p), len(grp))
+        O.orc_cns_sort_candidates(grp.ctypes.data_as(C.c_void_p), len(grp))
         grp = grp[:200]
         res = np.zeros(len(grp), dtype=ALIGN_RESULT_DTYPE)
-        qblob, sblob = bytearray(), bytearray()
         t = seq(int(grp["sid"][0]), 0)
         cap = 2 * len(t) + 70000
         qa, sa = C.create_string_buffer(cap), C.create_string_buffer(cap)
@@ -75,19 +87,56 @@ def correct_with_oracle_alignments(vol, can, ratio, min_aln, min_cov, min_size):
                 sblob += sa.value + b"\0"
             else:
                 res[k]["str_offset"] = -1
+        cands.append(grp)
+        results.append(res)
+        first.append(first[-1] + len(grp))
+    out = (np.array(first, dtype=np.int32), np.concatenate(cands), np.concatenate(results), bytes(qblob) + b"\0", bytes(sblob) + b"\0")
+    _aln_cache[key] = out
+    return out
+
+
+def _pieces(free, pieces, n, seqs, nb):
+    from mecat_b200.api import CNS_PIECE_DTYPE
+    pc = np.frombuffer(C.string_at(pieces.value, n.value * CNS_PIECE_DTYPE.itemsize), dtype=CNS_PIECE_DTYPE)
+    blob = C.string_at(seqs.value, nb.value)
+    out = []
+    for x in pc:
+        s = blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])].decode()
+        out.append((">%d_%d_%d_%d" % (x["id"], x["beg"], x["end"], len(s)), s))
+    free(pieces)
+    free(seqs)
+    return out
+
+
+def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None):
+    from mecat_b200.api import CnsParams
+    O = util.oracle()
+    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep)
+    p = CnsParams(ratio, min_aln, min_cov, min_size)
+    out = []
+    for r in range(len(first) - 1):
+        a, b = int(first[r]), int(first[r + 1])
+        c, x = np.ascontiguousarray(cand[a:b]), np.ascontiguousarray(res[a:b])
         pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
-        rc = L.mecat_b200_cns_consensus_host(grp.ctypes.data_as(C.c_void_p), len(grp), res.ctypes.data_as(C.c_void_p),
-                                             bytes(qblob) + b"\0", bytes(sblob) + b"\0", C.byref(p), C.byref(pieces), C.byref(n),
-                                             C.byref(seqs), C.byref(nb))
+        rc = O.orc_cns_consensus(c.ctypes.data_as(C.c_void_p), b - a, x.ctypes.data_as(C.c_void_p), qblob, sblob, C.byref(p),
+                                 C.byref(pieces), C.byref(n), C.byref(seqs), C.byref(nb))
         assert rc == 0
-        pc = np.frombuffer(C.string_at(pieces.value, n.value * CNS_PIECE_DTYPE.itemsize), dtype=CNS_PIECE_DTYPE)
-        blob = C.string_at(seqs.value, nb.value)
-        for x in pc:
-            s = blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])].decode()
-            out.append((">%d_%d_%d_%d" % (x["id"], x["beg"], x["end"], len(s)), s))
-        L.mecat_b200_host_free(pieces)
-        L.mecat_b200_host_free(seqs)
+        out += _pieces(O.orc_free, pieces, n, seqs, nb)
     return sorted(out)
+
+
+def correct_with_kernel_bodies(vol, can, ratio, min_aln, min_cov, min_size, keep=None):
+    from mecat_b200.api import CnsParams
+    H = util.cns_harness()
+    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep)
+    p = CnsParams(ratio, min_aln, min_cov, min_size)
+    pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    rc = H.harness_cns_batch(len(first) - 1, first.ctypes.data_as(C.c_void_p), cand.ctypes.data_as(C.c_void_p),
+                             res.ctypes.data_as(C.c_void_p), qblob, sblob, C.cast(C.byref(p), C.c_void_p), C.byref(pieces), C.byref(n),
+                             C.byref(seqs), C.byref(nb), err, 256)
+    assert rc == 0, err.value
+    return sorted(_pieces(H.harness_free, pieces, n, seqs, nb))
 
 
 @pytest.fixture(scope="module")
@@ -95,12 +144,6 @@ def small_vol():
     with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f:
         seqs = [l for l in f.read().split(b"\n") if l and not l.startswith(b">")]
     return PackedVolume.from_seqs(seqs)
-
-
-@pytest.fixture(scope="module", autouse=True)
-def built():
-    from mecat_b200 import build
-    build.build()
 
 
 def compare(got, want):
@@ -113,12 +156,45 @@ def compare(got, want):
                 % (len(got), len(want), only_g[:5], only_w[:5], diff[:5]))
 
 
-def test_consensus_default_parameters(small_vol):
-    got = correct_with_oracle_alignments(small_vol, gold_can("small"), 0.9, 2000, 6, 5000)
-    compare(got, gold_fasta("small", "cns_default"))
+PARAMS = {"cns_default": (0.9, 2000, 6, 5000),
+          # -l 2000 -c 4 -a 1000: many more reads qualify (148 corrected pieces, thousands of mini-POA regions)
+          "cns_relaxed": (0.9, 1000, 4, 2000)}
 
 
-def test_consensus_relaxed_parameters(small_vol):
-    # -l 2000 -c 4 -a 1000: many more reads qualify (148 corrected pieces, thousands of mini-POA regions)
-    got = correct_with_oracle_alignments(small_vol, gold_can("small"), 0.9, 1000, 4, 2000)
-    compare(got, gold_fasta("small", "cns_relaxed"))
+@pytest.mark.parametrize("tag", sorted(PARAMS))
+def test_oracle_consensus_matches_reference(small_vol, tag):
+    compare(correct_with_oracle(small_vol, gold_can("small"), *PARAMS[tag]), gold_fasta("small", tag))
+
+
+@pytest.mark.parametrize("tag", sorted(PARAMS))
+def test_kernel_bodies_match_reference(small_vol, tag):
+    compare(correct_with_kernel_bodies(small_vol, gold_can("small"), *PARAMS[tag]), gold_fasta("small", tag))
+
+
+# ---------------------------------------------------------------- deep coverage (~120x): 60-alignment cap, 20x coverage gate
+def _every_sixth(rid):
+    return rid % 6 == 0
+
+
+@pytest.fixture(scope="module")
+def deep_vol(tmp_path_factory):
+    import hashlib
+    c = GOLD["deep"]
+    fa = str(tmp_path_factory.mktemp("deep") / "deep.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == c["fasta_sha256"]
+    return PackedVolume.from_seqs(util.read_fasta(fa))
+
+
+def _deep_gold():
+    return [(h, s) for h, s in gold_fasta("deep", "cns_relaxed") if _every_sixth(int(h[1:].split("_")[0]))]
+
+
+def test_oracle_consensus_deep_coverage(deep_vol):
+    want = _deep_gold()
+    assert len(want) >= 40
+    compare(correct_with_oracle(deep_vol, gold_can("deep"), *PARAMS["cns_relaxed"], keep=_every_sixth), want)
+
+
+def test_kernel_bodies_deep_coverage(deep_vol):
+    compare(correct_with_kernel_bodies(deep_vol, gold_can("deep"), *PARAMS["cns_relaxed"], keep=_every_sixth), _deep_gold())

@@ -530,6 +530,30 @@ def test_cns_cfg0_matches_reference(gpu_ctx, cfg0_vol):
     assert not bad, bad[:5]
 
 
+def test_cns_deep_coverage_matches_reference(gpu_ctx, tmp_path):
+    """~120x coverage: every read has the full candidate list, so the accept loop reaches its 60-alignment cap and
+    the 20x coverage gate, and the region graphs carry up to 60 paths (golden: unmodified mecat2cns -l 2000 -c 4 -a 1000)."""
+    c = GOLD["deep"]
+    fa = str(tmp_path / "deep.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == c["fasta_sha256"]
+    vol = PackedVolume.from_seqs(util.read_fasta(fa))
+    got = _cns(gpu_ctx, vol, _gold_can("deep"), 0.9, 1000, 4, 2000)
+    want = _gold_fasta("deep", "cns_relaxed")
+    assert len(got) == len(want) == c["num_cns_relaxed"]
+    bad = [g[0] for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:5]
+
+
+def test_cns_consensus_runs_on_the_gpu(gpu_ctx, small_vol):
+    """The consensus stages (accept, normalise/vote, segments, regions, graphs, assembly) are kernel launches."""
+    gpu_ctx.reset_stats()
+    _cns(gpu_ctx, small_vol, _gold_can("small"), 0.9, 1000, 4, 2000)
+    st = gpu_ctx.stats()
+    for k in ("cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"):
+        assert st["kernel_launches"][k] > 0, k
+
+
 def test_candidate_cap_and_order(gpu_ctx, small_vol):
     """-n 3: per read the first 3 candidates of the -n 100 list, in the same order."""
     import mecat_b200

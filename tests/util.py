@@ -113,6 +113,31 @@ def build_oracle():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
 
 
+_harness = None
+
+
+def cns_harness():
+    """Host build of the product's consensus stage sequence and kernel bodies (tests/cns_host_harness.cpp)."""
+    global _harness
+    if _harness is not None:
+        return _harness
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcns_harness.so")
+    src = [os.path.join(ROOT, "tests", "cns_host_harness.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "cns_pipeline.h"),
+           os.path.join(ROOT, "mecat_b200", "csrc", "cns_core.cuh"), os.path.join(ROOT, "include", "mecat_b200.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
+    L = C.CDLL(so)
+    vp = C.c_void_p
+    L.harness_cns_batch.restype = C.c_int
+    L.harness_cns_batch.argtypes = [C.c_int, vp, vp, vp, C.c_char_p, C.c_char_p, vp, C.POINTER(vp), C.POINTER(C.c_size_t),
+                                    C.POINTER(vp), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
+    L.harness_free.argtypes = [vp]
+    _harness = L
+    return L
+
+
 def gen_reads(path, n, genome_len, seed, mean=15000, sd=1500, err=0.15, genome_out=None):
     exe = os.path.join(ROOT, "mecat_b200", "bin", "gen_reads")
     if not os.path.exists(exe):
@@ -158,6 +183,10 @@ def oracle():
     L.orc_pw_tile.restype = C.c_int
     L.orc_pw_tile.argtypes = [VP, VP, PP, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_free.argtypes = [C.c_void_p]
+    L.orc_cns_sort_candidates.argtypes = [C.c_void_p, C.c_int]
+    L.orc_cns_consensus.restype = C.c_int
+    L.orc_cns_consensus.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_cns_get_alignment.restype = C.c_int
     L.orc_cns_get_alignment.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double,
                                         C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_int]

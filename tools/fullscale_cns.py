@@ -43,9 +43,10 @@ def main():
     gout = os.path.join(a.tmp, "gpu.fa")
     t = time.time()
     with open(os.path.join(a.tmp, "gpu.log"), "w") as lg:
-        subprocess.check_call([os.path.join(ROOT, "mecat_b200", "bin", "mecat2cns"), "-i", "0", "-t", "1", can, fa, gout], stdout=lg, stderr=lg)
+        subprocess.check_call([os.path.join(ROOT, "mecat_b200", "bin", "mecat2cns"), "-i", "0", "-t", "1", can, fa, gout], stdout=lg, stderr=lg,
+                              env=dict(os.environ, MECAT_B200_STATS="1"))
     res["gpu_cli_seconds"] = time.time() - t
-    res["gpu_log"] = [l for l in open(os.path.join(a.tmp, "gpu.log")).read().splitlines() if "takes" in l]
+    res["gpu_log"] = [l for l in open(os.path.join(a.tmp, "gpu.log")).read().splitlines() if "takes" in l or "kernel ms" in l]
     n, bases, sha = records(gout)
     res.update(gpu_records=n, gpu_corrected_bases=bases, gpu_sha256=sha)
     if not a.skip_ref:
