@@ -446,7 +446,7 @@ void align_dev_release(Ctx* c, AlignDev* d)
 	*d = AlignDev();
 }
 
-// One arena batch: the tasks' worst-case columns (align_task_columns) must sum to at most ALIGN_ARENA.  The
+// One arena batch: the tasks' worst-case columns (align_task_columns) must sum to at most Ctx::align_arena.  The
 // results stay in device memory (out); align_batch() below copies them to the host, the consensus stage of
 // mecat2cns (cns.cu) consumes them in place.
 int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t nb,
@@ -474,11 +474,11 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 			a.off = used; a.cap = (int32_t)capL; used += capL; slots.push_back(a);
 			a.off = used; a.cap = (int32_t)capR; used += capR; slots.push_back(a);
 		}
-		if (used > ALIGN_ARENA) MB_FAIL(c, "align_batch: %zu tasks need more than the %zu-byte column arena", nb, (size_t)ALIGN_ARENA);
+		if (used > c->align_arena) MB_FAIL(c, "align_batch: %zu tasks need more than the %zu-byte column arena", nb, c->align_arena);
 		MB_CUDA(c, c->alloc(&d_dir, nwarps * MAXROWS * DIRW));
 		MB_CUDA(c, c->alloc(&d_min, nwarps * MAXROWS));
-		MB_CUDA(c, c->dmalloc((void**)&d_colq, ALIGN_ARENA));      // fixed size: the pool hands the same block back
-		MB_CUDA(c, c->dmalloc((void**)&d_colt, ALIGN_ARENA));
+		MB_CUDA(c, c->dmalloc((void**)&d_colq, c->align_arena));      // fixed size: the pool hands the same block back
+		MB_CUDA(c, c->dmalloc((void**)&d_colt, c->align_arena));
 		MB_CUDA(c, c->alloc(&d_tasks, nb));
 		MB_CUDA(c, c->alloc(&d_slots, 2 * nb));
 		MB_CUDA(c, c->alloc(&out->d_info, 8 * nb));
@@ -540,10 +540,10 @@ int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume*
 		size_t used = 0, nb = 0;
 		while (done + nb < ntasks) {
 			const size_t need = align_task_columns(q, s, h_tasks[done + nb]);
-			if (used + need > ALIGN_ARENA) break;
+			if (used + need > c->align_arena) break;
 			used += need; ++nb;
 		}
-		if (nb == 0) MB_FAIL(c, "align_batch: one task needs more than the %zu-byte column arena", (size_t)ALIGN_ARENA);
+		if (nb == 0) MB_FAIL(c, "align_batch: one task needs more than the %zu-byte column arena", c->align_arena);
 		AlignDev dev;
 		if (align_batch_device(c, policy, err, q, s, h_tasks + done, nb, min_aln, &dev, info)) return 1;
 		const size_t base = qstr.size(), total = dev.total;

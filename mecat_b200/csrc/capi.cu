@@ -114,6 +114,16 @@ int mecat_b200_init(mecat_b200_ctx** out, int device, void* /*nccl_comm_or_null*
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
 	memset(&c->stats, 0, sizeof c->stats);
+	{
+		// column arenas of the string-producing extension: 1/16 of the device memory each (11 GB on a 180 GB B200), so a
+		// batch holds a few hundred thousand extensions and the consensus stages behind it see enough units per launch
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+			size_t a = total_b / 16;
+			if (const char* e = getenv("MECAT_B200_ALIGN_ARENA_MB")) a = (size_t)atoll(e) << 20;   // test hook: force several batches
+			c->align_arena = std::max<size_t>(64ull << 20, std::min<size_t>(a, 12ull << 30));
+		}
+	}
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 4; }
 	if (cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return 5; }
 	cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
@@ -371,7 +381,7 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	std::vector<mbcns::Piece> all;
-	const size_t TASKS_PER_BATCH = 40000;
+	const size_t TASKS_PER_BATCH = 240000;
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;
 	std::vector<int64_t> rid;
@@ -390,8 +400,8 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 				need += align_task_columns(V, V, t);
 				tasks.push_back(t);
 			}
-			if (g1 > g0 && (cols + need > ALIGN_ARENA || tasks.size() > TASKS_PER_BATCH)) { tasks.resize(mark); break; }
-			if (cols + need > ALIGN_ARENA) MB_FAIL(c, "cns_reads: the candidates of read %d alone exceed the column arena", ec[groups[g1].b].sid);
+			if (g1 > g0 && (cols + need > c->align_arena || tasks.size() > TASKS_PER_BATCH)) { tasks.resize(mark); break; }
+			if (cols + need > c->align_arena) MB_FAIL(c, "cns_reads: the candidates of read %d alone exceed the column arena", ec[groups[g1].b].sid);
 			cols += need;
 			for (size_t k = groups[g1].b; k < groups[g1].e; ++k) { tqid.push_back(ec[k].qid); tqsize.push_back(ec[k].qsize); }
 			first.push_back((int32_t)tasks.size());

@@ -19,6 +19,21 @@ __global__ void __launch_bounds__(128) k_cns(const F f, const int64_t n)
 	if (i < n) f(i);
 }
 
+struct WarpLanes
+{
+	static constexpr int count = 32;
+	__device__ int lane() const { return (int)(threadIdx.x & 31u); }
+	__device__ int sum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+	__device__ void sync() const { __syncwarp(); }
+};
+
+template <class F>
+__global__ void __launch_bounds__(128) k_cns_warp(const F f, const int64_t n)
+{
+	const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (i < n) f(i, WarpLanes());
+}
+
 // exclusive prefix sum of n int32 values into n + 1 int64 values; one CTA, each thread owns a contiguous chunk
 __global__ void __launch_bounds__(1024) k_cns_scan(const int32_t* __restrict__ in, int64_t* __restrict__ out, const int64_t n)
 {
@@ -85,6 +100,13 @@ struct DevBackend
 		if (n <= 0) return true;
 		KScope ks(c, MECAT_K_CNS_ACCEPT + stage);
 		k_cns<F><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(f, n);
+		return check(cudaGetLastError(), "launch");
+	}
+	template <class F> bool launch_warp(int64_t n, const F& f, int stage)
+	{
+		if (n <= 0) return true;
+		KScope ks(c, MECAT_K_CNS_ACCEPT + stage);
+		k_cns_warp<F><<<(unsigned)((n + 3) / 4), 128, 0, c->stream>>>(f, n);
 		return check(cudaGetLastError(), "launch");
 	}
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)

@@ -69,31 +69,56 @@ CNS_HD inline int popcount64(uint64_t x)
 #endif
 }
 
-// check_cov_stats works on one coverage byte per template position (at most 60, so SWAR on 8 bytes never carries)
-CNS_HD inline int count_full(const uint8_t* cov, int b, int e)       // positions in [b, e) covered >= COV_FULL times
+// Some units are worked on by a whole warp.  The body is written once against a "lanes" object: SoloLane (one
+// lane, used by the host harness) or the device's WarpLanes (cns.cu: 32 lanes, shuffles).  Control flow that
+// depends on reduced values is uniform across the lanes.
+struct SoloLane
 {
-	int full = 0, k = b;
-	while (k < e && ((uintptr_t)(cov + k) & 7u)) { full += cov[k] >= COV_FULL; ++k; }
-	for (; k + 8 <= e; k += 8) {
-		const uint64_t w = *(const uint64_t*)(cov + k);
-		full += popcount64((w + 0x0101010101010101ull * (uint64_t)(128 - COV_FULL)) & 0x8080808080808080ull);
+	static constexpr int count = 1;
+	CNS_HD int lane() const { return 0; }
+	CNS_HD int sum(int v) const { return v; }
+	CNS_HD void sync() const {}
+};
+
+// check_cov_stats works on one coverage byte per template position (at most 60, so SWAR on 8 bytes never carries).
+// The lanes split the aligned 8-byte words of [b, e); lane 0 takes the ragged ends.
+template <class L>
+CNS_HD inline int count_full(const L& lanes, const uint8_t* cov, int b, int e)   // positions in [b, e) covered >= COV_FULL times
+{
+	int head = b + (int)((8 - ((uintptr_t)(cov + b) & 7u)) & 7u);
+	if (head > e) head = e;
+	const int words = (e - head) >> 3, tail = head + 8 * words;
+	int full = 0;
+	if (lanes.lane() == 0) {
+		for (int k = b; k < head; ++k) full += cov[k] >= COV_FULL;
+		for (int k = tail; k < e; ++k) full += cov[k] >= COV_FULL;
 	}
-	for (; k < e; ++k) full += cov[k] >= COV_FULL;
-	return full;
+	const uint64_t* w = (const uint64_t*)(cov + head);
+	for (int k = lanes.lane(); k < words; k += L::count)
+		full += popcount64((w[k] + 0x0101010101010101ull * (uint64_t)(128 - COV_FULL)) & 0x8080808080808080ull);
+	return lanes.sum(full);
 }
-CNS_HD inline void bump_cov(uint8_t* cov, int b, int e)
+template <class L>
+CNS_HD inline void bump_cov(const L& lanes, uint8_t* cov, int b, int e)
 {
-	int k = b;
-	while (k < e && ((uintptr_t)(cov + k) & 7u)) { ++cov[k]; ++k; }
-	for (; k + 8 <= e; k += 8) *(uint64_t*)(cov + k) += 0x0101010101010101ull;
-	for (; k < e; ++k) ++cov[k];
+	int head = b + (int)((8 - ((uintptr_t)(cov + b) & 7u)) & 7u);
+	if (head > e) head = e;
+	const int words = (e - head) >> 3, tail = head + 8 * words;
+	if (lanes.lane() == 0) {
+		for (int k = b; k < head; ++k) ++cov[k];
+		for (int k = tail; k < e; ++k) ++cov[k];
+	}
+	uint64_t* w = (uint64_t*)(cov + head);
+	for (int k = lanes.lane(); k < words; k += L::count) w[k] += 0x0101010101010101ull;
+	lanes.sync();
 }
 
 // The accept loop of one read: candidates in trial order, at most 200 looked at, at most 60 accepted, one
 // per partner read, mapping-range and coverage gates.  info = 8 ints per task {ok, qstart, qend, sstart,
 // send, columns, ...} as written by the extension kernels.  Returns the number accepted; acc[k] = task.
-CNS_HD inline int accept_read(int t0, int t1, const int32_t* info, const int32_t* t_qid, const int32_t* t_qsize, int ssize,
-                              double ratio, uint8_t* cov, int32_t* acc)
+template <class L>
+CNS_HD inline int accept_read(const L& lanes, int t0, int t1, const int32_t* info, const int32_t* t_qid, const int32_t* t_qsize,
+                              int ssize, double ratio, uint8_t* cov, int32_t* acc)
 {
 	int used[MAX_ACCEPT];
 	int added = 0, tried = 0;
@@ -110,11 +135,11 @@ CNS_HD inline int accept_read(int t0, int t1, const int32_t* info, const int32_t
 		const int qqs = (int)((double)t_qsize[t] * ratio);
 		if (!(oq >= qqs || os >= qss)) continue;
 		// a position can only be COV_FULL deep once COV_FULL alignments have been accepted
-		const int full = added >= COV_FULL ? count_full(cov, o[3], o[4]) : 0;
+		const int full = added >= COV_FULL ? count_full(lanes, cov, o[3], o[4]) : 0;
 		if (!(o[4] - o[3] >= full + COV_NEED)) continue;
-		bump_cov(cov, o[3], o[4]);
+		bump_cov(lanes, cov, o[3], o[4]);
 		used[added] = qid;
-		acc[added] = t;
+		if (lanes.lane() == 0) acc[added] = t;
 		++added;
 	}
 	return added;
@@ -182,6 +207,119 @@ CNS_HD inline int column_index(const char* s, int n, int soff, int32_t* colidx)
 	for (int idx = 1; idx < n; ++idx)
 		if (s[idx] != '-') { ++p; colidx[p - soff] = idx; }
 	return p;
+}
+
+// ------------------------------------------------------------------------------------------ C4 + C5 fused
+// normalize_gaps, meap_add_one_aln and column_index in ONE left-to-right pass with O(1) state, for the kernel
+// that owns an accepted alignment.  Observation: the gap push only ever moves a base LEFT into a gap column,
+// and it visits columns in ascending order, so when column i is visited every base whose expanded column is
+// below i has been emitted already.  The current content of column i is therefore "the next unplaced base of
+// that string if it sits exactly on column i, else a gap", and the look-ahead of the reference's inner loops
+// (first non-gap character behind i) is simply that next unplaced base.  Three sequential readers walk the
+// expanded columns (mismatch -> gap/base pair): M knows where the alignment ends, Q and T stand on the next
+// unplaced base of each string.  Columns are final when emitted, so votes and the cursor index are taken on
+// the fly.  Sequential byte streams are read through 16-byte register windows.
+struct ByteWindow          // forward-only reader of a byte stream through aligned 16-byte loads
+{
+	const char* base; int64_t at; unsigned long long lo, hi;
+	CNS_HD void open(const char* p) { base = p; at = -1; lo = hi = 0; }
+	CNS_HD char get(int64_t i)                 // i never decreases between calls by more than the window
+	{
+		const uintptr_t addr = (uintptr_t)(base + i);
+		const int64_t blk = (int64_t)(addr >> 4);
+		if (blk != at) {
+			const unsigned long long* w = (const unsigned long long*)(addr & ~(uintptr_t)15);
+			lo = w[0]; hi = w[1]; at = blk;
+		}
+		const int k = (int)(addr & 15u);
+		return (char)(((k < 8 ? lo : hi) >> ((k & 7) * 8)) & 255u);
+	}
+};
+
+struct ExpandedReader      // walks the expanded columns of (q, t)[0..n): mismatch (a, b) -> ('-', b), (a, '-')
+{
+	ByteWindow wq, wt;
+	int n, i, half, col;   // original column, 0/1 inside a mismatch pair, expanded column
+	char a, b;             // original characters of column i
+	CNS_HD void open(const char* q, const char* t, int n_)
+	{
+		wq.open(q); wt.open(t); n = n_; i = 0; half = 0; col = 0;
+		if (n > 0) { a = wq.get(0); b = wt.get(0); }
+	}
+	CNS_HD bool valid() const { return i < n; }
+	CNS_HD bool mismatch() const { return a != b && a != '-' && b != '-'; }
+	CNS_HD char qchar() const { return mismatch() ? (half ? a : '-') : a; }
+	CNS_HD char tchar() const { return mismatch() ? (half ? '-' : b) : b; }
+	CNS_HD void next()
+	{
+		++col;
+		if (mismatch() && !half) { half = 1; return; }
+		half = 0; ++i;
+		if (i < n) { a = wq.get(i); b = wt.get(i); }
+	}
+	CNS_HD void seek_q() { while (valid() && qchar() == '-') next(); }     // stand on the next base of q
+	CNS_HD void seek_t() { while (valid() && tchar() == '-') next(); }
+};
+
+struct ByteSink            // forward-only writer, 8 bytes per store; the destination must be 8-byte aligned
+{
+	char* base; int64_t n; unsigned long long acc;
+	CNS_HD void open(char* p) { base = p; n = 0; acc = 0; }
+	CNS_HD void put(char c)
+	{
+		acc |= (unsigned long long)(unsigned char)c << ((n & 7) * 8);
+		if ((++n & 7) == 0) { *(unsigned long long*)(base + n - 8) = acc; acc = 0; }
+	}
+	CNS_HD void close() { if (n & 7) *(unsigned long long*)(base + (n & ~(int64_t)7)) = acc; }   // pads with NULs
+};
+
+// Returns the normalised length; nq/nt (8-byte aligned, 2n + 8 bytes) receive the normalised strings followed by
+// a NUL, votes/base the read's pile-up, colidx the cursor index; *tend the last template position indexed.
+CNS_HD inline int normalize_vote_index(const char* q0, const char* t0, int n, int soff0, char* nq, char* nt, uint32_t* votes,
+                                       char* base, int32_t* colidx, int* tend)
+{
+	ExpandedReader M, Q, T;
+	M.open(q0, t0, n); Q.open(q0, t0, n); T.open(q0, t0, n);
+	Q.seek_q(); T.seek_t();
+	ByteSink oq, ot;
+	oq.open(nq); ot.open(nt);
+	int soff = soff0, cp = soff0;
+	bool in_del_run = false;
+	colidx[0] = 0;
+	int i = 0;
+	while (M.valid()) {
+		M.next();
+		const bool last = !M.valid();
+		char qc = (Q.valid() && Q.col == i) ? Q.qchar() : '-';
+		char tc = (T.valid() && T.col == i) ? T.tchar() : '-';
+		const bool q_here = qc != '-', t_here = tc != '-';
+		if (!last) {
+			if (!t_here && q_here) {
+				if (T.valid() && T.tchar() == qc) { tc = qc; T.next(); T.seek_t(); }
+			} else if (!q_here && t_here) {
+				if (Q.valid() && Q.qchar() == tc) { qc = tc; Q.next(); Q.seek_q(); }
+			}
+		}
+		if (q_here) { Q.next(); Q.seek_q(); }
+		if (t_here) { T.next(); T.seek_t(); }
+		oq.put(qc); ot.put(tc);
+		// CnsAln cursor index (column_index)
+		if (i >= 1 && tc != '-') { ++cp; colidx[cp - soff0] = i; }
+		// meap_add_one_aln
+		if (qc == '-' && tc == '-') { }
+		else if (in_del_run && tc == '-') { }
+		else {
+			in_del_run = false;
+			if (qc == tc) { vote_add(votes + soff, 1u); base[soff] = tc; ++soff; }
+			else if (qc == '-') { vote_add(votes + soff, 1u << 8); ++soff; }
+			else { vote_add(votes + soff - 1, 1u << 16); in_del_run = true; }
+		}
+		++i;
+	}
+	oq.put(0); ot.put(0);
+	oq.close(); ot.close();
+	*tend = cp;
+	return i;
 }
 
 // ------------------------------------------------------------------------------------------ C6 (ranges)

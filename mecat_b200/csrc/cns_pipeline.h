@@ -23,6 +23,8 @@
 //   AssembleFn       segment             meap_consensus_one_segment: anchors + refined interiors -> corrected bases
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -58,9 +60,11 @@ struct AcceptFn
 {
 	const int32_t* first; const int32_t* info; const int32_t* tqid; const int32_t* tqsize; const int32_t* read_size;
 	const int64_t* pos_off; uint8_t* cov; double ratio; int32_t* acc; int32_t* nacc;
-	CNS_HD void operator()(int64_t r) const
+	template <class L>
+	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
-		nacc[r] = accept_read(first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT);
+		const int n = accept_read(lanes, first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT);
+		if (lanes.lane() == 0) nacc[r] = n;
 	}
 };
 
@@ -75,7 +79,7 @@ struct FlattenFn      // accepted alignment A = aln_first[r] + k; capacities of 
 			const int t = acc[r * MAX_ACCEPT + k];
 			const int32_t* o = info + 8 * (int64_t)t;
 			aln_task[A] = t; aln_read[A] = (int32_t)r;
-			cap_norm[A] = 2 * o[5] + 2;
+			cap_norm[A] = ((2 * o[5] + 2 + 15) & ~15) + 16;     // 16-byte aligned slots, room for the writer's last 8-byte store
 			cap_col[A] = o[4] - o[3] + 2;
 		}
 	}
@@ -92,13 +96,12 @@ struct NormVoteFn
 		const int32_t* o = info + 8 * (int64_t)t;
 		char* a = nq + norm_off[A];
 		char* b = nt + norm_off[A];
-		const int len = normalize_gaps(q + outoff[t], s + outoff[t], o[5], a, b);
 		const int64_t po = pos_off[aln_read[A]];
-		add_votes(a, b, len, o[3], votes + po, base + po);
+		int tend;
+		const int len = normalize_vote_index(q + outoff[t], s + outoff[t], o[5], o[3], a, b, votes + po, base + po, colidx + col_off[A], &tend);
 		KeptAln K;
 		K.q = a; K.s = b; K.colidx = colidx + col_off[A];
-		K.size = len; K.soff = o[3]; K.send = o[4];
-		K.tend = column_index(b, len, o[3], colidx + col_off[A]);
+		K.size = len; K.soff = o[3]; K.send = o[4]; K.tend = tend;
 		kept[A] = K;
 	}
 };
@@ -262,7 +265,8 @@ inline void emit_piece(std::vector<Piece>& out, int64_t id, int64_t beg, int64_t
 // Backend B:
 //   template <class T> T* alloc(size_t n)            device array, freed by end_batch(); nullptr + error on failure
 //   bool upload(T* d, const T* h, size_t n), bool download(T* h, const T* d, size_t n), bool fill(void* d, int byte, size_t bytes)
-//   template <class F> bool launch(int64_t n, const F& f, int stage)
+//   template <class F> bool launch(int64_t n, const F& f, int stage)        f(i), one thread per unit
+//   template <class F> bool launch_warp(int64_t n, const F& f, int stage)   f(i, lanes), one warp per unit
 //   bool scan(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* total)   d_out[0..n] exclusive prefix, total on the host
 //   void fail(const char* msg), void end_batch()
 template <class B>
@@ -308,7 +312,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	CNS_TRY(be.fill(d_base, 'N', (size_t)POS));
 
 	// C3: which alignments vote
-	CNS_TRY(be.launch(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc}, ST_ACCEPT));
+	CNS_TRY(be.launch_warp(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc}, ST_ACCEPT));
 	int64_t NA = 0;
 	CNS_TRY(be.scan(d_nacc, d_alnfirst, R, &NA));
 	if (NA == 0) return 0;
@@ -370,6 +374,9 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	if (NG) CNS_TRY(be.launch(NG, DemandFn{d_regions, d_nacc, d_alnfirst, d_kept, d_dn, d_de}, ST_POA));
 	CNS_TRY(be.scan(d_dn, d_nodeoff, NG, &NODES));
 	CNS_TRY(be.scan(d_de, d_edgeoff, NG, &EDGES0));
+	if (getenv("MECAT_CNS_DEBUG"))
+		fprintf(stderr, "[cns batch] reads %d tasks %lld accepted %lld segments %lld regions %lld nodes %lld edges0 %lld norm bytes %lld\n", R,
+		        (long long)T, (long long)NA, (long long)NS, (long long)NG, (long long)NODES, (long long)EDGES0, (long long)NORM);
 	CNS_ALLOC(d_nodes, PoaNode, NODES);
 	CNS_ALLOC(d_edges, PoaEdge, EDGES0 + NODES + 2 * NG);
 	CNS_ALLOC(d_aux, int32_t, 8 * NODES + 64 * NG);

@@ -53,6 +53,7 @@ struct Ctx
 	std::string err;
 	mecat_b200_stats stats;
 	unsigned long long* d_counters = nullptr;   // 16 device counters (statistics, arena cursors)
+	size_t align_arena = 3ull << 30;            // bytes per column arena of one extension-with-strings batch (two arenas); set at init
 	// Device memory pool: the per-tile buffers have the same sizes call after call, so freed
 	// blocks are kept and handed out again (cudaMalloc / cudaFree of multi-GB blocks cost
 	// milliseconds each).  Everything is returned to the driver by trim() / destroy.
@@ -203,7 +204,6 @@ struct AlignDev
 	unsigned long long* d_outoff = nullptr;     // ntasks + 1
 	size_t total = 0;
 };
-constexpr size_t ALIGN_ARENA = 3ull << 30;      // column arena of one batch
 size_t align_task_columns(const DVolume* q, const DVolume* s, const AlignTask& t);
 int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t nb,
                        int min_aln, AlignDev* out, std::vector<int32_t>& info);

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,7 @@ struct HostBackend
 	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
 	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
 	template <class F> bool launch(int64_t n, const F& f, int) { for (int64_t i = 0; i < n; ++i) f(i); return true; }
+	template <class F> bool launch_warp(int64_t n, const F& f, int) { mbcns::SoloLane one; for (int64_t i = 0; i < n; ++i) f(i, one); return true; }
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)
 	{
 		int64_t s = 0;
@@ -67,6 +69,14 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 		o[5] = res[t].columns; o[6] = res[t].matches; o[7] = 0;
 		outoff[t] = res[t].ok ? (unsigned long long)res[t].str_offset : 0;
 	}
+	// the kernels read the gapped strings through aligned 16-byte windows: give the blobs the slack device arenas have
+	size_t blob = 0;
+	for (int64_t t = 0; t < T; ++t) if (res[t].ok) blob = std::max(blob, (size_t)res[t].str_offset + (size_t)res[t].columns + 1);
+	std::vector<char> qpad(blob + 64, 0), spad(blob + 64, 0);
+	char* qa = qpad.data() + ((16 - ((uintptr_t)qpad.data() & 15)) & 15) + 16;
+	char* sa = spad.data() + ((16 - ((uintptr_t)spad.data() & 15)) & 15) + 16;
+	if (blob) { memcpy(qa, qstr, blob); memcpy(sa, sstr, blob); }
+	qstr = qa; sstr = sa;
 	mbcns::BatchIn in;
 	in.R = R; in.T = T; in.h_first = first; in.h_read_size = rsize.data(); in.h_read_id = rid.data();
 	in.h_tqid = tqid.data(); in.h_tqsize = tqsize.data();
@@ -96,5 +106,34 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 }
 
 void harness_free(void* p) { free(p); }
+
+// Unit check of the fused single-pass kernel body (normalize_vote_index) against the three literal restatements
+// (normalize_gaps, add_votes, column_index) on one gapped alignment.  Returns 0 when every output agrees.
+int harness_normalize_compare(const char* q, const char* t, int n, int soff, int positions)
+{
+	std::vector<char> qp((size_t)n + 64, 0), tp((size_t)n + 64, 0);
+	char* qa = qp.data() + ((16 - ((uintptr_t)qp.data() & 15)) & 15) + 16 + 3;      // deliberately unaligned start
+	char* ta = tp.data() + ((16 - ((uintptr_t)tp.data() & 15)) & 15) + 16 + 5;
+	memcpy(qa, q, (size_t)n); memcpy(ta, t, (size_t)n);
+	const size_t cap = 2 * (size_t)n + 64;
+	std::vector<char> nq1(cap, 1), nt1(cap, 1);
+	std::vector<unsigned long long> nq2s(cap / 8 + 1, ~0ull), nt2s(cap / 8 + 1, ~0ull);
+	char* nq2 = (char*)nq2s.data(); char* nt2 = (char*)nt2s.data();
+	std::vector<uint32_t> v1((size_t)positions + 2, 0), v2((size_t)positions + 2, 0);
+	std::vector<char> b1((size_t)positions + 2, 'N'), b2((size_t)positions + 2, 'N');
+	std::vector<int32_t> c1((size_t)positions + 2, -7), c2((size_t)positions + 2, -7);
+	const int len1 = mbcns::normalize_gaps(qa, ta, n, nq1.data(), nt1.data());
+	mbcns::add_votes(nq1.data(), nt1.data(), len1, soff, v1.data() + 1, b1.data() + 1);
+	const int tend1 = mbcns::column_index(nt1.data(), len1, soff, c1.data());
+	int tend2 = -1;
+	const int len2 = mbcns::normalize_vote_index(qa, ta, n, soff, nq2, nt2, v2.data() + 1, b2.data() + 1, c2.data(), &tend2);
+	if (len1 != len2) return 1;
+	if (memcmp(nq1.data(), nq2, (size_t)len1 + 1) || memcmp(nt1.data(), nt2, (size_t)len1 + 1)) return 2;
+	if (v1 != v2) return 3;
+	if (b1 != b2) return 4;
+	if (tend1 != tend2) return 5;
+	if (c1 != c2) return 6;
+	return 0;
+}
 
 }  // extern "C"

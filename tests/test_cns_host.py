@@ -198,3 +198,32 @@ def test_oracle_consensus_deep_coverage(deep_vol):
 
 def test_kernel_bodies_deep_coverage(deep_vol):
     compare(correct_with_kernel_bodies(deep_vol, gold_can("deep"), *PARAMS["cns_relaxed"], keep=_every_sixth), _deep_gold())
+
+
+def test_fused_normalise_vote_kernel_body_matches_literal_restatement():
+    """normalize_vote_index (one streaming pass, what the GPU thread runs) against normalize_gaps + add_votes +
+    column_index written literally after the reference, on random gapped alignments rich in homopolymers, long gap
+    runs, mismatches and adjacent opposite gaps (the cases where pushed gaps travel and collide)."""
+    H = util.cns_harness()
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        n = int(rng.integers(1, 400))
+        alphabet = b"ACGT"[:int(rng.integers(1, 5))]          # small alphabets make pushes travel far
+        q, t = bytearray(), bytearray()
+        pgap = rng.uniform(0.05, 0.5)
+        for _ in range(n):
+            r = rng.random()
+            a = alphabet[int(rng.integers(len(alphabet)))]
+            b = alphabet[int(rng.integers(len(alphabet)))] if rng.random() < 0.3 else a
+            if r < pgap / 2:
+                q.append(ord("-")); t.append(b)
+            elif r < pgap:
+                q.append(a); t.append(ord("-"))
+            else:
+                q.append(a); t.append(b)
+        if trial % 50 == 0:                                  # the reference never produces these, the code must still agree
+            k = int(rng.integers(n))
+            q[k] = t[k] = ord("-")
+        positions = sum(1 for c in t if c != ord("-")) + 2
+        rc = H.harness_normalize_compare(bytes(q), bytes(t), n, 1, positions)
+        assert rc == 0, (trial, rc, bytes(q), bytes(t))
