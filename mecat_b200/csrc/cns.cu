@@ -34,26 +34,65 @@ __global__ void __launch_bounds__(128) k_cns_warp(const F f, const int64_t n)
 	if (i < n) f(i, WarpLanes());
 }
 
-// exclusive prefix sum of n int32 values into n + 1 int64 values; one CTA, each thread owns a contiguous chunk
-__global__ void __launch_bounds__(1024) k_cns_scan(const int32_t* __restrict__ in, int64_t* __restrict__ out, const int64_t n)
+// Exclusive prefix sum of n int32 values into n + 1 int64 values, three launches: totals of 4 096-element tiles
+// (coalesced), a one-CTA scan of the tile totals, and the tile-local scan with its tile offset added.
+constexpr int SCAN_TILE = 4096;      // 1 024 threads x 4 consecutive values
+
+__device__ __forceinline__ int64_t block_exclusive(int64_t v, int64_t* total)     // 1 024 threads
 {
-	__shared__ int64_t part[1024];
-	const int tid = threadIdx.x;
-	const int64_t chunk = (n + 1023) / 1024;
-	const int64_t b = min(n, (int64_t)tid * chunk), e = min(n, b + chunk);
-	int64_t s = 0;
-	for (int64_t i = b; i < e; ++i) s += in[i];
-	part[tid] = s;
+	__shared__ int64_t wsum[32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int64_t inc = v;
+	for (int d = 1; d < 32; d <<= 1) { const int64_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+	if (lane == 31) wsum[warp] = inc;
 	__syncthreads();
-	for (int d = 1; d < 1024; d <<= 1) {
-		const int64_t v = tid >= d ? part[tid - d] : 0;
+	if (warp == 0) {
+		int64_t w = wsum[lane], winc = w;
+		for (int d = 1; d < 32; d <<= 1) { const int64_t o = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += o; }
+		wsum[lane] = winc - w;
+		if (lane == 31) *total = winc;
+	}
+	__syncthreads();
+	return wsum[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) k_cns_scan_tiles(const int32_t* __restrict__ in, int64_t* __restrict__ tile_sum, const int64_t n)
+{
+	__shared__ int64_t total;
+	const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+	int64_t s = 0;
+	for (int k = 0; k < 4; ++k) if (i0 + k < n) s += in[i0 + k];
+	block_exclusive(s, &total);
+	__syncthreads();
+	if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_cns_scan_top(int64_t* __restrict__ tile_sum, const int64_t ntiles, int64_t* __restrict__ grand)
+{
+	__shared__ int64_t total;
+	int64_t carry = 0;
+	for (int64_t base = 0; base < ntiles; base += 1024) {
+		const int64_t i = base + threadIdx.x;
+		const int64_t v = i < ntiles ? tile_sum[i] : 0;
+		const int64_t ex = block_exclusive(v, &total);
+		if (i < ntiles) tile_sum[i] = carry + ex;
 		__syncthreads();
-		part[tid] += v;
+		carry += total;
 		__syncthreads();
 	}
-	int64_t run = part[tid] - s;
-	for (int64_t i = b; i < e; ++i) { out[i] = run; run += in[i]; }
-	if (tid == 1023) out[n] = part[1023];
+	if (threadIdx.x == 0) *grand = carry;
+}
+
+__global__ void __launch_bounds__(1024) k_cns_scan_apply(const int32_t* __restrict__ in, const int64_t* __restrict__ tile_off,
+                                                         int64_t* __restrict__ out, const int64_t n)
+{
+	__shared__ int64_t total;
+	const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+	int32_t v[4];
+	int64_t s = 0;
+	for (int k = 0; k < 4; ++k) { v[k] = i0 + k < n ? in[i0 + k] : 0; s += v[k]; }
+	int64_t run = tile_off[blockIdx.x] + block_exclusive(s, &total);
+	for (int k = 0; k < 4; ++k) if (i0 + k < n) { out[i0 + k] = run; run += v[k]; }
 }
 
 struct DevBackend
@@ -111,12 +150,30 @@ struct DevBackend
 	}
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)
 	{
+		if (n <= 0) { *total = 0; const int64_t zero = 0; return upload(out, &zero, 1); }
+		const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+		int64_t* tiles = alloc<int64_t>((size_t)ntiles);
+		if (!tiles) return false;
 		{
-			KScope ks(c, MECAT_K_SCAN);
-			k_cns_scan<<<1, 1024, 0, c->stream>>>(in, out, n);
+			KScope ks(c, MECAT_K_SCAN, 3);
+			k_cns_scan_tiles<<<(unsigned)ntiles, 1024, 0, c->stream>>>(in, tiles, n);
+			k_cns_scan_top<<<1, 1024, 0, c->stream>>>(tiles, ntiles, out + n);
+			k_cns_scan_apply<<<(unsigned)ntiles, 1024, 0, c->stream>>>(in, tiles, out, n);
 		}
 		if (!check(cudaGetLastError(), "launch")) return false;
 		return download(total, out + n, 1);
+	}
+	bool release(void* p)      // the pool only marks the block free; work queued on the stream before the next owner's is ordered
+	{
+		for (size_t i = 0; i < owned.size(); ++i)
+			if (owned[i] == p) { c->dfree(p); owned[i] = owned.back(); owned.pop_back(); return true; }
+		c->err = "cns: release of an unknown block";
+		return false;
+	}
+	int64_t poa_budget_bytes() const
+	{
+		if (const char* e = getenv("MECAT_B200_POA_BUDGET_MB")) return (int64_t)atoll(e) << 20;      // test hook: force several waves
+		return 24ll << 30;
 	}
 	void fail(const char* m) { c->err = m; }
 	void end_batch()

@@ -215,10 +215,9 @@ CNS_HD inline int column_index(const char* s, int n, int soff, int32_t* colidx)
 // and it visits columns in ascending order, so when column i is visited every base whose expanded column is
 // below i has been emitted already.  The current content of column i is therefore "the next unplaced base of
 // that string if it sits exactly on column i, else a gap", and the look-ahead of the reference's inner loops
-// (first non-gap character behind i) is simply that next unplaced base.  Three sequential readers walk the
-// expanded columns (mismatch -> gap/base pair): M knows where the alignment ends, Q and T stand on the next
-// unplaced base of each string.  Columns are final when emitted, so votes and the cursor index are taken on
-// the fly.  Sequential byte streams are read through 16-byte register windows.
+// (first non-gap character behind i) is simply that next unplaced base.  Two forward scanners stand on the next
+// unplaced base of each string, the main loop walks the columns.  Columns are final when emitted, so votes and
+// the cursor index are taken on the fly.  Sequential byte streams are read through 16-byte register windows.
 struct ByteWindow          // forward-only reader of a byte stream through aligned 16-byte loads
 {
 	const char* base; int64_t at; unsigned long long lo, hi;
@@ -236,31 +235,6 @@ struct ByteWindow          // forward-only reader of a byte stream through align
 	}
 };
 
-struct ExpandedReader      // walks the expanded columns of (q, t)[0..n): mismatch (a, b) -> ('-', b), (a, '-')
-{
-	ByteWindow wq, wt;
-	int n, i, half, col;   // original column, 0/1 inside a mismatch pair, expanded column
-	char a, b;             // original characters of column i
-	CNS_HD void open(const char* q, const char* t, int n_)
-	{
-		wq.open(q); wt.open(t); n = n_; i = 0; half = 0; col = 0;
-		if (n > 0) { a = wq.get(0); b = wt.get(0); }
-	}
-	CNS_HD bool valid() const { return i < n; }
-	CNS_HD bool mismatch() const { return a != b && a != '-' && b != '-'; }
-	CNS_HD char qchar() const { return mismatch() ? (half ? a : '-') : a; }
-	CNS_HD char tchar() const { return mismatch() ? (half ? '-' : b) : b; }
-	CNS_HD void next()
-	{
-		++col;
-		if (mismatch() && !half) { half = 1; return; }
-		half = 0; ++i;
-		if (i < n) { a = wq.get(i); b = wt.get(i); }
-	}
-	CNS_HD void seek_q() { while (valid() && qchar() == '-') next(); }     // stand on the next base of q
-	CNS_HD void seek_t() { while (valid() && tchar() == '-') next(); }
-};
-
 struct ByteSink            // forward-only writer, 8 bytes per store; the destination must be 8-byte aligned
 {
 	char* base; int64_t n; unsigned long long acc;
@@ -275,46 +249,66 @@ struct ByteSink            // forward-only writer, 8 bytes per store; the destin
 
 // Returns the normalised length; nq/nt (8-byte aligned, 2n + 8 bytes) receive the normalised strings followed by
 // a NUL, votes/base the read's pile-up, colidx the cursor index; *tend the last template position indexed.
+// The loop runs over the ORIGINAL columns; a mismatch column (a, b) stands for the two expanded columns
+// ('-', b), (a, '-'), so the base of t sits in half 0 and the base of q in half 1 of such a column.
 CNS_HD inline int normalize_vote_index(const char* q0, const char* t0, int n, int soff0, char* nq, char* nt, uint32_t* votes,
                                        char* base, int32_t* colidx, int* tend)
 {
-	ExpandedReader M, Q, T;
-	M.open(q0, t0, n); Q.open(q0, t0, n); T.open(q0, t0, n);
-	Q.seek_q(); T.seek_t();
+	ByteWindow mq, mt, wq, wqt, wt;
+	mq.open(q0); mt.open(t0); wq.open(q0); wqt.open(t0); wt.open(t0);
+	// heads: next unplaced base of q (column jq, half hq, character bq) and of t (column jt, half 0, character bt)
+	int jq = 0, jt = 0, hq = 0;
+	char bq = 0, bt = 0;
+	auto seek_q = [&](int from) {
+		for (jq = from; jq < n; ++jq) {
+			const char c = wq.get(jq);
+			if (c != '-') { const char o = wqt.get(jq); bq = c; hq = (o != '-' && o != c) ? 1 : 0; return; }
+		}
+		bq = 0;
+	};
+	auto seek_t = [&](int from) {
+		for (jt = from; jt < n; ++jt) {
+			const char c = wt.get(jt);
+			if (c != '-') { bt = c; return; }
+		}
+		bt = 0;
+	};
+	seek_q(0); seek_t(0);
 	ByteSink oq, ot;
 	oq.open(nq); ot.open(nt);
 	int soff = soff0, cp = soff0;
 	bool in_del_run = false;
 	colidx[0] = 0;
-	int i = 0;
-	while (M.valid()) {
-		M.next();
-		const bool last = !M.valid();
-		char qc = (Q.valid() && Q.col == i) ? Q.qchar() : '-';
-		char tc = (T.valid() && T.col == i) ? T.tchar() : '-';
-		const bool q_here = qc != '-', t_here = tc != '-';
-		if (!last) {
-			if (!t_here && q_here) {
-				if (T.valid() && T.tchar() == qc) { tc = qc; T.next(); T.seek_t(); }
-			} else if (!q_here && t_here) {
-				if (Q.valid() && Q.qchar() == tc) { qc = tc; Q.next(); Q.seek_q(); }
+	int i = 0;                                   // expanded column
+	for (int i0 = 0; i0 < n; ++i0) {
+		const char a = mq.get(i0), b = mt.get(i0);
+		const int halves = (a != b && a != '-' && b != '-') ? 2 : 1;
+		for (int h = 0; h < halves; ++h, ++i) {
+			const bool last = i0 == n - 1 && h == halves - 1;
+			const bool q_here = jq == i0 && hq == h, t_here = jt == i0 && h == 0;
+			char qc = q_here ? bq : '-', tc = t_here ? bt : '-';
+			if (!last) {
+				if (!t_here && q_here) {
+					if (jt < n && bt == qc) { tc = qc; seek_t(jt + 1); }
+				} else if (!q_here && t_here) {
+					if (jq < n && bq == tc) { qc = tc; seek_q(jq + 1); }
+				}
+			}
+			if (q_here) seek_q(jq + 1);
+			if (t_here) seek_t(jt + 1);
+			oq.put(qc); ot.put(tc);
+			// CnsAln cursor index (column_index)
+			if (i >= 1 && tc != '-') { ++cp; colidx[cp - soff0] = i; }
+			// meap_add_one_aln
+			if (qc == '-' && tc == '-') { }
+			else if (in_del_run && tc == '-') { }
+			else {
+				in_del_run = false;
+				if (qc == tc) { vote_add(votes + soff, 1u); base[soff] = tc; ++soff; }
+				else if (qc == '-') { vote_add(votes + soff, 1u << 8); ++soff; }
+				else { vote_add(votes + soff - 1, 1u << 16); in_del_run = true; }
 			}
 		}
-		if (q_here) { Q.next(); Q.seek_q(); }
-		if (t_here) { T.next(); T.seek_t(); }
-		oq.put(qc); ot.put(tc);
-		// CnsAln cursor index (column_index)
-		if (i >= 1 && tc != '-') { ++cp; colidx[cp - soff0] = i; }
-		// meap_add_one_aln
-		if (qc == '-' && tc == '-') { }
-		else if (in_del_run && tc == '-') { }
-		else {
-			in_del_run = false;
-			if (qc == tc) { vote_add(votes + soff, 1u); base[soff] = tc; ++soff; }
-			else if (qc == '-') { vote_add(votes + soff, 1u << 8); ++soff; }
-			else { vote_add(votes + soff - 1, 1u << 16); in_del_run = true; }
-		}
-		++i;
 	}
 	oq.put(0); ot.put(0);
 	oq.close(); ot.close();

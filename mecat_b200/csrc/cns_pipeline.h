@@ -173,16 +173,19 @@ struct PoaFn
 {
 	const Region* regions; const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept;
 	const int64_t* node_off; const int64_t* edge0_off;
+	int64_t g_base, n_base, e_base;      // first region of this wave and its offsets: the arenas hold one wave
 	PoaNode* nodes; PoaEdge* edges; int32_t* aux; char* gout; int32_t* goff; int32_t* glen; int32_t* gerr;
-	CNS_HD void operator()(int64_t g) const
+	CNS_HD void operator()(int64_t k) const
 	{
+		const int64_t g = g_base + k;
 		const Region G = regions[g];
 		const int64_t n0 = node_off[g], e0 = edge0_off[g];
 		const int ncap = (int)(node_off[g + 1] - n0);
 		const int ecap = (int)poa_edge_cap(ncap, edge0_off[g + 1] - e0);
+		const int64_t rn = n0 - n_base, re = e0 - e_base;
 		int off, len;
 		gerr[g] = region_consensus(kept + aln_first[G.read], nacc[G.read], G.sb, G.se, G.prev_se, G.min_weight,
-		                           nodes + n0, ncap, edges + (e0 + n0 + 2 * g), ecap, aux + (8 * n0 + 64 * g), (int)poa_aux_ints(ncap),
+		                           nodes + rn, ncap, edges + (re + rn + 2 * k), ecap, aux + (8 * rn + 64 * k), (int)poa_aux_ints(ncap),
 		                           gout + n0, off, len);
 		goff[g] = off; glen[g] = len;
 	}
@@ -268,6 +271,8 @@ inline void emit_piece(std::vector<Piece>& out, int64_t id, int64_t beg, int64_t
 //   template <class F> bool launch(int64_t n, const F& f, int stage)        f(i), one thread per unit
 //   template <class F> bool launch_warp(int64_t n, const F& f, int stage)   f(i, lanes), one warp per unit
 //   bool scan(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* total)   d_out[0..n] exclusive prefix, total on the host
+//   bool release(void* d)                            early free of an alloc() block (stream ordered)
+//   int64_t poa_budget_bytes()                       scratch budget of one wave of region graphs
 //   void fail(const char* msg), void end_batch()
 template <class B>
 int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece>& out)
@@ -377,12 +382,41 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	if (getenv("MECAT_CNS_DEBUG"))
 		fprintf(stderr, "[cns batch] reads %d tasks %lld accepted %lld segments %lld regions %lld nodes %lld edges0 %lld norm bytes %lld\n", R,
 		        (long long)T, (long long)NA, (long long)NS, (long long)NG, (long long)NODES, (long long)EDGES0, (long long)NORM);
-	CNS_ALLOC(d_nodes, PoaNode, NODES);
-	CNS_ALLOC(d_edges, PoaEdge, EDGES0 + NODES + 2 * NG);
-	CNS_ALLOC(d_aux, int32_t, 8 * NODES + 64 * NG);
 	CNS_ALLOC(d_gout, char, NODES);
-	if (NG) CNS_TRY(be.launch(NG, PoaFn{d_regions, d_nacc, d_alnfirst, d_kept, d_nodeoff, d_edgeoff, d_nodes, d_edges, d_aux, d_gout,
-	                                    d_goff, d_glen, d_gerr}, ST_POA));
+	{
+		// The graphs run in waves whose scratch fits the backend's budget.  Scratch bytes of regions [a, b) =
+		// cost(b) - cost(a) with cost(g) = 104 nodes_before(g) + 32 edges0_before(g) + 320 g (see PoaFn, poa_edge_cap,
+		// poa_aux_ints); wave ends are found by bisection on the device-resident prefix sums.
+		const int64_t budget = be.poa_budget_bytes();
+		auto cost_at = [&](int64_t g, int64_t& n, int64_t& e) -> bool {
+			if (g == NG) { n = NODES; e = EDGES0; return true; }
+			return be.download(&n, d_nodeoff + g, 1) && be.download(&e, d_edgeoff + g, 1);
+		};
+		int64_t a = 0, na = 0, ea = 0;
+		while (a < NG) {
+			int64_t b = NG, nb = NODES, eb = EDGES0;
+			if (104 * (nb - na) + 32 * (eb - ea) + 320 * (b - a) > budget) {
+				int64_t lo = a + 1, hi = NG;                 // largest b in [a + 1, NG] whose wave fits; a + 1 always accepted
+				while (lo < hi) {
+					const int64_t mid = lo + (hi - lo + 1) / 2;
+					int64_t nm, em;
+					CNS_TRY(cost_at(mid, nm, em));
+					if (104 * (nm - na) + 32 * (em - ea) + 320 * (mid - a) <= budget) lo = mid; else hi = mid - 1;
+				}
+				b = lo;
+				CNS_TRY(cost_at(b, nb, eb));
+			}
+			const int64_t dn = nb - na, de = eb - ea, dg = b - a;
+			PoaNode* d_nodes = be.template alloc<PoaNode>((size_t)dn);
+			PoaEdge* d_edges = be.template alloc<PoaEdge>((size_t)(de + dn + 2 * dg));
+			int32_t* d_aux = be.template alloc<int32_t>((size_t)(8 * dn + 64 * dg));
+			if (!d_nodes || !d_edges || !d_aux) return 1;
+			CNS_TRY(be.launch(dg, PoaFn{d_regions, d_nacc, d_alnfirst, d_kept, d_nodeoff, d_edgeoff, a, na, ea, d_nodes, d_edges, d_aux, d_gout,
+			                            d_goff, d_glen, d_gerr}, ST_POA));
+			CNS_TRY(be.release(d_nodes)); CNS_TRY(be.release(d_edges)); CNS_TRY(be.release(d_aux));
+			a = b; na = nb; ea = eb;
+		}
+	}
 
 	// corrected bases of every segment
 	CNS_ALLOC(d_tcap, int32_t, NS);

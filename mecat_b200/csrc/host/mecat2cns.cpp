@@ -196,9 +196,12 @@ int main(int argc, char* argv[])
 	}
 
 	mecat_b200_ctx* ctx = NULL;
-	if (mecat_b200_init(&ctx, 0, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU 0\n"); return 1; }
 	void* dvol = NULL;
-	if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); return 1; }
+	{
+		StderrTimer t("gpu init + volume upload");
+		if (mecat_b200_init(&ctx, 0, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU 0\n"); return 1; }
+		if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); return 1; }
+	}
 
 	std::ofstream out(opt.output);
 	if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }

@@ -43,6 +43,14 @@ struct HostBackend
 		out[n] = s; *total = s;
 		return true;
 	}
+	bool release(void* p)
+	{
+		for (size_t i = 0; i < owned.size(); ++i) if (owned[i] == p) { free(p); owned[i] = owned.back(); owned.pop_back(); return true; }
+		err = "release of an unknown block";
+		return false;
+	}
+	int64_t poa_budget_bytes() const { return budget; }
+	int64_t budget = 1 << 20;          // small on purpose: the golden tests run the region graphs in many waves
 	void fail(const char* m) { err = m; }
 	void end_batch() { for (void* p : owned) free(p); owned.clear(); }
 };

@@ -545,6 +545,21 @@ def test_cns_deep_coverage_matches_reference(gpu_ctx, tmp_path):
     assert not bad, bad[:5]
 
 
+def test_cns_small_batches_and_graph_waves(small_vol, monkeypatch):
+    """The same output when the extension arena only holds a few reads per batch and the region graphs have to run in
+    many scratch waves (both limits are normally sized from the device memory)."""
+    import mecat_b200
+    monkeypatch.setenv("MECAT_B200_ALIGN_ARENA_MB", "64")
+    monkeypatch.setenv("MECAT_B200_POA_BUDGET_MB", "8")
+    with mecat_b200.Context(0) as ctx:
+        ctx.reset_stats()
+        got = _cns(ctx, small_vol, _gold_can("small"), 0.9, 1000, 4, 2000)
+        st = ctx.stats()
+    assert got == _gold_fasta("small", "cns_relaxed")
+    assert st["kernel_launches"]["extend"] >= 3        # several extension batches ...
+    assert st["kernel_launches"]["cns_poa"] >= 3 * st["kernel_launches"]["cns_normvote"]   # ... and several graph waves in each
+
+
 def test_cns_consensus_runs_on_the_gpu(gpu_ctx, small_vol):
     """The consensus stages (accept, normalise/vote, segments, regions, graphs, assembly) are kernel launches."""
     gpu_ctx.reset_stats()
