@@ -119,9 +119,8 @@ int mecat_b200_init(mecat_b200_ctx** out, int device, void* /*nccl_comm_or_null*
 		// batch holds a few hundred thousand extensions and the consensus stages behind it see enough units per launch
 		size_t free_b = 0, total_b = 0;
 		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
-			size_t a = total_b / 16;
-			if (const char* e = getenv("MECAT_B200_ALIGN_ARENA_MB")) a = (size_t)atoll(e) << 20;   // test hook: force several batches
-			c->align_arena = std::max<size_t>(64ull << 20, std::min<size_t>(a, 12ull << 30));
+			c->align_arena = std::max<size_t>(64ull << 20, std::min<size_t>(total_b / 16, 12ull << 30));
+			if (const char* e = getenv("MECAT_B200_ALIGN_ARENA_MB")) c->align_arena = std::max<size_t>(1, (size_t)atoll(e)) << 20;   // test hook: force several batches
 		}
 	}
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 4; }

@@ -19,12 +19,19 @@ __global__ void __launch_bounds__(128) k_cns(const F f, const int64_t n)
 	if (i < n) f(i);
 }
 
-struct WarpLanes
+struct WarpLanes          // the lanes interface of cns_core.cuh on a real warp
 {
 	static constexpr int count = 32;
-	__device__ int lane() const { return (int)(threadIdx.x & 31u); }
-	__device__ int sum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
-	__device__ void sync() const { __syncwarp(); }
+	template <class F> __device__ void each(F&& f) const { f((int)(threadIdx.x & 31u)); __syncwarp(); }
+	template <class F> __device__ int sum(F&& f) const { return __reduce_add_sync(0xffffffffu, f((int)(threadIdx.x & 31u))); }
+	template <class F> __device__ uint32_t ballot(F&& f) const { return __ballot_sync(0xffffffffu, f((int)(threadIdx.x & 31u))); }
+	template <class F> __device__ void ballot2(F&& f, uint32_t& m0, uint32_t& m1) const
+	{
+		const int v = f((int)(threadIdx.x & 31u));
+		m0 = __ballot_sync(0xffffffffu, v & 1);
+		m1 = __ballot_sync(0xffffffffu, v & 2);
+	}
+	__device__ bool leader() const { return (threadIdx.x & 31u) == 0; }
 };
 
 template <class F>

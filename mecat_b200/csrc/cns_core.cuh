@@ -69,16 +69,67 @@ CNS_HD inline int popcount64(uint64_t x)
 #endif
 }
 
-// Some units are worked on by a whole warp.  The body is written once against a "lanes" object: SoloLane (one
-// lane, used by the host harness) or the device's WarpLanes (cns.cu: 32 lanes, shuffles).  Control flow that
-// depends on reduced values is uniform across the lanes.
-struct SoloLane
+// Some units are worked on by a whole warp.  Their bodies are written once against a "lanes" object with 32 lanes:
+//   each(f)      f(lane) on every lane; memory effects are visible to all lanes afterwards
+//   sum(f)       sum of f(lane) over the lanes, the same value on every lane
+//   ballot(f)    bit l = f(l); ballot2(f, m0, m1) for two predicates at once (f returns bit 0 | bit 1 << 1)
+//   leader()     true on exactly one lane (single writes)
+// Everything outside the callbacks is uniform (every lane computes the same scalars).  cns.cu's WarpLanes maps this
+// to warp intrinsics; EmuLanes below runs the 32 lanes in a loop and is what the host harness uses, so the mask
+// arithmetic the GPU executes is the arithmetic the CPU tests check.
+struct EmuLanes
 {
-	static constexpr int count = 1;
-	CNS_HD int lane() const { return 0; }
-	CNS_HD int sum(int v) const { return v; }
-	CNS_HD void sync() const {}
+	static constexpr int count = 32;
+	template <class F> void each(F&& f) const { for (int l = 0; l < count; ++l) f(l); }
+	template <class F> int sum(F&& f) const { int s = 0; for (int l = 0; l < count; ++l) s += f(l); return s; }
+	template <class F> uint32_t ballot(F&& f) const { uint32_t m = 0; for (int l = 0; l < count; ++l) if (f(l)) m |= 1u << l; return m; }
+	template <class F> void ballot2(F&& f, uint32_t& m0, uint32_t& m1) const
+	{
+		m0 = m1 = 0;
+		for (int l = 0; l < count; ++l) { const int v = f(l); if (v & 1) m0 |= 1u << l; if (v & 2) m1 |= 1u << l; }
+	}
+	bool leader() const { return true; }
 };
+
+CNS_HD inline int popcount32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return __popc(x);
+#else
+	return __builtin_popcount(x);
+#endif
+}
+CNS_HD inline int lowest_bit(uint32_t x)       // x != 0
+{
+#if defined(__CUDA_ARCH__)
+	return __ffs((int)x) - 1;
+#else
+	return __builtin_ctz(x);
+#endif
+}
+CNS_HD inline int highest_bit(uint32_t x)      // x != 0
+{
+#if defined(__CUDA_ARCH__)
+	return 31 - __clz((int)x);
+#else
+	return 31 - __builtin_clz(x);
+#endif
+}
+CNS_HD inline uint32_t bit_range(int lo, int hi)   // bits [lo, hi), 0 <= lo <= hi <= 32
+{
+	return (uint32_t)(((1ull << hi) - 1ull) & ~((1ull << lo) - 1ull));
+}
+
+// first position p in [from, to) with pred(p), else to; 32 positions per step
+template <class L, class Pred>
+CNS_HD inline int find_first(const L& lanes, int from, int to, Pred&& pred)
+{
+	for (int base = from; base < to; base += L::count) {
+		const uint32_t m = lanes.ballot([&](int l) { const int p = base + l; return p < to && pred(p); });
+		if (m) return base + lowest_bit(m);
+	}
+	return to;
+}
 
 // check_cov_stats works on one coverage byte per template position (at most 60, so SWAR on 8 bytes never carries).
 // The lanes split the aligned 8-byte words of [b, e); lane 0 takes the ragged ends.
@@ -88,15 +139,17 @@ CNS_HD inline int count_full(const L& lanes, const uint8_t* cov, int b, int e)  
 	int head = b + (int)((8 - ((uintptr_t)(cov + b) & 7u)) & 7u);
 	if (head > e) head = e;
 	const int words = (e - head) >> 3, tail = head + 8 * words;
-	int full = 0;
-	if (lanes.lane() == 0) {
-		for (int k = b; k < head; ++k) full += cov[k] >= COV_FULL;
-		for (int k = tail; k < e; ++k) full += cov[k] >= COV_FULL;
-	}
 	const uint64_t* w = (const uint64_t*)(cov + head);
-	for (int k = lanes.lane(); k < words; k += L::count)
-		full += popcount64((w[k] + 0x0101010101010101ull * (uint64_t)(128 - COV_FULL)) & 0x8080808080808080ull);
-	return lanes.sum(full);
+	return lanes.sum([&](int lane) {
+		int full = 0;
+		if (lane == 0) {
+			for (int k = b; k < head; ++k) full += cov[k] >= COV_FULL;
+			for (int k = tail; k < e; ++k) full += cov[k] >= COV_FULL;
+		}
+		for (int k = lane; k < words; k += L::count)
+			full += popcount64((w[k] + 0x0101010101010101ull * (uint64_t)(128 - COV_FULL)) & 0x8080808080808080ull);
+		return full;
+	});
 }
 template <class L>
 CNS_HD inline void bump_cov(const L& lanes, uint8_t* cov, int b, int e)
@@ -104,13 +157,14 @@ CNS_HD inline void bump_cov(const L& lanes, uint8_t* cov, int b, int e)
 	int head = b + (int)((8 - ((uintptr_t)(cov + b) & 7u)) & 7u);
 	if (head > e) head = e;
 	const int words = (e - head) >> 3, tail = head + 8 * words;
-	if (lanes.lane() == 0) {
-		for (int k = b; k < head; ++k) ++cov[k];
-		for (int k = tail; k < e; ++k) ++cov[k];
-	}
 	uint64_t* w = (uint64_t*)(cov + head);
-	for (int k = lanes.lane(); k < words; k += L::count) w[k] += 0x0101010101010101ull;
-	lanes.sync();
+	lanes.each([&](int lane) {
+		if (lane == 0) {
+			for (int k = b; k < head; ++k) ++cov[k];
+			for (int k = tail; k < e; ++k) ++cov[k];
+		}
+		for (int k = lane; k < words; k += L::count) w[k] += 0x0101010101010101ull;
+	});
 }
 
 // The accept loop of one read: candidates in trial order, at most 200 looked at, at most 60 accepted, one
@@ -139,7 +193,7 @@ CNS_HD inline int accept_read(const L& lanes, int t0, int t1, const int32_t* inf
 		if (!(o[4] - o[3] >= full + COV_NEED)) continue;
 		bump_cov(lanes, cov, o[3], o[4]);
 		used[added] = qid;
-		if (lanes.lane() == 0) acc[added] = t;
+		if (lanes.leader()) acc[added] = t;
 		++added;
 	}
 	return added;
@@ -381,6 +435,8 @@ struct Region
 	int32_t sb, se;       // template interval [sb, se], se = next anchor (or the segment end)
 	int32_t prev_se;      // se of the read's previous region (-1: none): the state CnsAln's cursors are in
 	int32_t min_weight;   // int(0.4 * coverage of the anchor)
+	int32_t seg;          // batch-wide segment the region belongs to
+	int32_t rank;         // ordinal of the anchor sb among the segment's anchors
 };
 
 // meap_consensus_one_segment's walk over the anchors (positions whose flag has FMAT).  flags[0..n) must hold
@@ -398,6 +454,78 @@ CNS_HD inline void walk_anchors(const uint8_t* flags, int n, F&& on_anchor)
 		on_anchor(i, j, refine);
 		i = j;
 	}
+}
+
+// ---- the same two searches, 32 positions per step (what the kernels run; the sequential forms above stay as the
+// literal restatements the unit tests compare them with)
+template <class L>
+CNS_HD inline int find_segments(const L& lanes, const Range* e, int ne, const uint32_t* votes, int min_cov, double size95, int32_t* segs, int cap)
+{
+	int ns = 0;
+	auto covered = [&](int p) { return vote_mat(votes[p]) + vote_ins(votes[p]) >= min_cov; };
+	for (int r = 0; r < ne; ++r) {
+		const int R = e[r].end;
+		int beg = e[r].start;
+		while (beg < R) {
+			beg = find_first(lanes, beg, R, covered);
+			int end = beg + 1;
+			if (end < R) end = find_first(lanes, end, R, [&](int p) { return !covered(p); });
+			if ((double)(end - beg) >= size95) {
+				if (ns < cap && lanes.leader()) { segs[2 * ns] = beg; segs[2 * ns + 1] = end; }
+				++ns;
+			}
+			beg = end;
+		}
+	}
+	return ns;
+}
+
+// Anchor walk of one segment, 32 positions per step and without a sequential loop over the anchors: for a lane
+// standing on an anchor, the previous anchor is the highest anchor bit below it (or the carry from earlier chunks),
+// its interval needs refining iff a problem bit lies in between, and ordinals are popcounts of the bits below.
+struct AnchorCarry
+{
+	int nanchors = 0;         // anchors seen so far in this segment
+	int last_anchor = -1;     // position (segment relative) of the last one
+	bool pending = false;     // a problem flag since (and including) the last anchor
+	int nregions = 0;         // refine intervals closed so far in this segment
+	int last_se_abs = -1;     // read coordinate where the read's latest region ended (-1: none yet)
+};
+
+// Positions [base, base + 32) of a segment of n positions that starts at read coordinate beg.  flag(p) returns
+// classify() of segment position p.  visit(lane, pos, rank, prevpos, closes, ordinal, prev_se_abs) runs on every
+// anchor lane: pos / prevpos = this and the previous anchor (segment relative, prevpos -1 for the first), rank =
+// ordinal of this anchor, closes = the interval [prevpos, pos) is a region, ordinal = regions of this segment
+// closed before this anchor, prev_se_abs = end of the read's latest region before that.
+template <class L, class FlagFn, class Visit>
+CNS_HD inline void anchor_chunk(const L& lanes, int base, int n, int beg, FlagFn&& flag, AnchorCarry& c, Visit&& visit)
+{
+	uint32_t A, P;
+	lanes.ballot2([&](int l) {
+		const int p = base + l;
+		if (p >= n) return 0;
+		const int f = flag(p);
+		return ((f & FMAT) ? 1 : 0) | ((f & (UNDS | FDEL)) ? 2 : 0);
+	}, A, P);
+	const AnchorCarry c0 = c;
+	const uint32_t R = lanes.ballot([&](int l) {
+		if (!((A >> l) & 1u)) return false;
+		const uint32_t below = A & bit_range(0, l);
+		if (below) return (P & bit_range(highest_bit(below), l)) != 0;
+		return c0.last_anchor >= 0 && (c0.pending || (P & bit_range(0, l)) != 0);
+	});
+	lanes.each([&](int l) {
+		if (!((A >> l) & 1u)) return;
+		const uint32_t below = A & bit_range(0, l), rbelow = R & bit_range(0, l);
+		const int prevpos = below ? base + highest_bit(below) : c0.last_anchor;
+		const int prev_se = rbelow ? beg + base + highest_bit(rbelow) : c0.last_se_abs;
+		visit(l, base + l, c0.nanchors + popcount32(below), prevpos, ((R >> l) & 1u) != 0, c0.nregions + popcount32(rbelow), prev_se);
+	});
+	if (A) { const int hi = highest_bit(A); c.last_anchor = base + hi; c.pending = (P & bit_range(hi, 32)) != 0; }
+	else if (c.last_anchor >= 0) c.pending = c.pending || P != 0;
+	c.nanchors += popcount32(A);
+	if (R) c.last_se_abs = beg + base + highest_bit(R);
+	c.nregions += popcount32(R);
 }
 
 // ------------------------------------------------------------------------------------------ C7 (slices)

@@ -11,16 +11,16 @@
 //     sequence and bodies against the reference's golden output without a GPU.
 //
 //   stage            unit                reference
-//   AcceptFn         read                consensus_one_read_can_pacbio accept loop, mecat_correction.cpp:389-450
+//   AcceptFn         read (warp)         consensus_one_read_can_pacbio accept loop, mecat_correction.cpp:389-450
 //   FlattenFn        read                (layout only)
 //   NormVoteFn       accepted alignment  normalize_gaps + meap_add_one_aln + CnsAln cursor index
-//   SegmentFn        read                get_effective_ranges + consensus_worker run search
-//   RegionCountFn    read                identify_one_consensus_item + meap_consensus_one_segment (anchor walk)
-//   RegionFillFn     read                "
+//   SegmentFn        read (warp)         get_effective_ranges + consensus_worker run search
+//   RegionFn<0/1>    read (warp)         identify_one_consensus_item + meap_consensus_one_segment's anchor walk: count, then write, the regions
 //   DemandFn         region              node / edge demand of the region's graph
 //   PoaFn            region              meap_cns_one_indel: AlnGraphBoost build, merge, best path
-//   TargetCapFn      segment             (layout only)
-//   AssembleFn       segment             meap_consensus_one_segment: anchors + refined interiors -> corrected bases
+//   InteriorLenFn, TargetLenFn               (layout only: exact corrected length of every segment)
+//   AssembleFn       segment             meap_consensus_one_segment: every anchor's base to its final place
+//   InteriorFn       region              the refined interior behind its anchor
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
@@ -64,7 +64,7 @@ struct AcceptFn
 	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
 		const int n = accept_read(lanes, first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT);
-		if (lanes.lane() == 0) nacc[r] = n;
+		if (lanes.leader()) nacc[r] = n;
 	}
 };
 
@@ -110,50 +110,68 @@ struct SegmentFn
 {
 	const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept; const int32_t* read_size; const int64_t* pos_off;
 	const uint32_t* votes; int min_cov; double size95; const int64_t* seg_slot; int32_t* segs; int32_t* nseg;
-	CNS_HD void operator()(int64_t r) const
+	template <class L>
+	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
 		Range m[MAX_ACCEPT], e[MAX_ACCEPT];
 		const int n = nacc[r];
 		for (int k = 0; k < n; ++k) { m[k].start = kept[aln_first[r] + k].soff; m[k].end = kept[aln_first[r] + k].send; }
 		const int ne = effective_ranges(m, n, e, read_size[r], size95);
 		const int cap = (int)(seg_slot[r + 1] - seg_slot[r]);
-		const int ns = find_segments(e, ne, votes + pos_off[r], min_cov, size95, segs + 2 * seg_slot[r], cap);
-		nseg[r] = ns <= cap ? ns : -1;       // -1: capacity formula violated (reported by the host as an error)
+		const int ns = find_segments(lanes, e, ne, votes + pos_off[r], min_cov, size95, segs + 2 * seg_slot[r], cap);
+		if (lanes.leader()) nseg[r] = ns <= cap ? ns : -1;       // -1: capacity formula violated (reported by the host as an error)
 	}
 };
 
-// Both passes over a read's segments.  FILL = false: classify the positions (flags) and count the regions;
-// FILL = true: write the regions and each segment's first region.
+// Both passes over a read's segments, a warp per read.  FILL = false: classify the positions (flags) and count the
+// regions; FILL = true: write the regions, each segment's first region and its number of anchors.
 template <bool FILL>
 struct RegionFn
 {
 	const int32_t* nseg; const int64_t* seg_slot; const int32_t* segs; const int64_t* pos_off; const uint32_t* votes;
 	uint8_t* flags; int32_t* nreg; const int64_t* reg_first; const int64_t* seg_first; Region* regions; int64_t* seg_reg;
-	CNS_HD void operator()(int64_t r) const
+	int32_t* seg_anchors;
+	template <class L>
+	CNS_HD void operator()(int64_t r, const L& lanes) const
 	{
 		const int64_t po = pos_off[r];
 		int64_t g = FILL ? reg_first[r] : 0;
-		int prev_se = -1;
+		int last_se_abs = -1;
 		for (int k = 0; k < nseg[r]; ++k) {
 			const int beg = segs[2 * (seg_slot[r] + k)], end = segs[2 * (seg_slot[r] + k) + 1];
 			const int n = end - beg;
 			uint8_t* f = flags + po + beg;
 			const uint32_t* v = votes + po + beg;
-			if (!FILL) for (int i = 0; i < n; ++i) f[i] = classify(v[i]);
-			if (FILL) seg_reg[seg_first[r] + k] = g;
-			walk_anchors(f, n, [&](int i, int j, bool refine) {
-				if (!refine) return;
-				if (FILL) {
+			const int64_t S = FILL ? seg_first[r] + k : 0;
+			if (!FILL) lanes.each([&](int l) { for (int i = l; i < n; i += L::count) f[i] = classify(v[i]); });
+			AnchorCarry c;
+			c.last_se_abs = last_se_abs;
+			for (int base = 0; base < n; base += L::count)
+				anchor_chunk(lanes, base, n, beg, [&](int p) { return (int)f[p]; }, c,
+				             [&](int, int pos, int rank, int prevpos, bool closes, int ordinal, int prev_se) {
+					if (!FILL || !closes) return;
 					Region G;
-					G.read = (int32_t)r; G.sb = i + beg; G.se = j + beg; G.prev_se = prev_se;
-					G.min_weight = (int)((double)(vote_mat(v[i]) + vote_ins(v[i])) * 0.4);
-					regions[g] = G;
-					prev_se = j + beg;
+					G.read = (int32_t)r; G.sb = prevpos + beg; G.se = pos + beg; G.prev_se = prev_se;
+					G.min_weight = (int)((double)(vote_mat(v[prevpos]) + vote_ins(v[prevpos])) * 0.4);
+					G.seg = (int32_t)S; G.rank = rank - 1;
+					regions[g + ordinal] = G;
+				});
+			if (c.last_anchor >= 0 && c.pending) {           // the interval from the last anchor to the segment end
+				if (FILL && lanes.leader()) {
+					Region G;
+					G.read = (int32_t)r; G.sb = c.last_anchor + beg; G.se = end; G.prev_se = c.last_se_abs;
+					G.min_weight = (int)((double)(vote_mat(v[c.last_anchor]) + vote_ins(v[c.last_anchor])) * 0.4);
+					G.seg = (int32_t)S; G.rank = c.nanchors - 1;
+					regions[g + c.nregions] = G;
 				}
-				++g;
-			});
+				c.last_se_abs = end;
+				++c.nregions;
+			}
+			if (FILL && lanes.leader()) { seg_reg[S] = g; seg_anchors[S] = c.nanchors; }
+			g += c.nregions;
+			last_se_abs = c.last_se_abs;
 		}
-		if (!FILL) nreg[r] = (int32_t)g;
+		if (!FILL && lanes.leader()) nreg[r] = (int32_t)g;
 	}
 };
 
@@ -191,44 +209,58 @@ struct PoaFn
 	}
 };
 
-struct TargetCapFn     // upper bound of a segment's corrected length: its positions plus the nodes of its regions
+struct InteriorLenFn   // bases a region contributes between its two anchors: the best path without its first and last node
 {
-	const int32_t* seg_read; const int32_t* seg_beg; const int32_t* seg_end; const int64_t* seg_reg; const int64_t* node_off;
-	const int64_t* reg_first; const int64_t* seg_first; const int32_t* nseg; int64_t NS; int32_t* cap;
+	const int32_t* glen; int32_t* ilen;
+	CNS_HD void operator()(int64_t g) const { ilen[g] = glen[g] > 2 ? glen[g] - 2 : 0; }
+};
+
+struct TargetLenFn     // exact corrected length of a segment: its anchors plus the interiors of its regions
+{
+	const int32_t* seg_read; const int64_t* seg_reg; const int64_t* reg_first; const int64_t* seg_first; const int32_t* nseg;
+	const int32_t* seg_anchors; const int64_t* isum; int32_t* tlen;
 	CNS_HD int64_t reg_end(int64_t S) const      // one past the last region of segment S
 	{
 		const int r = seg_read[S];
 		return (S + 1 < seg_first[r] + nseg[r]) ? seg_reg[S + 1] : reg_first[r + 1];
 	}
-	CNS_HD void operator()(int64_t S) const
-	{
-		cap[S] = (int32_t)((seg_end[S] - seg_beg[S]) + (node_off[reg_end(S)] - node_off[seg_reg[S]]) + 1);
-	}
+	CNS_HD void operator()(int64_t S) const { tlen[S] = (int32_t)(seg_anchors[S] + (isum[reg_end(S)] - isum[seg_reg[S]])); }
 };
 
-struct AssembleFn
+struct AssembleFn      // a warp per segment: every anchor's base goes to its final place (rank + interiors before it)
 {
 	const int32_t* seg_read; const int32_t* seg_beg; const int32_t* seg_end; const int64_t* seg_reg; const int64_t* pos_off;
-	const uint8_t* flags; const char* base; const int64_t* node_off; const char* gout; const int32_t* goff; const int32_t* glen;
-	const int64_t* tgt_off; char* target; int32_t* tlen;
-	CNS_HD void operator()(int64_t S) const
+	const uint8_t* flags; const char* base; const int64_t* isum; const int64_t* tgt_off; char* target;
+	template <class L>
+	CNS_HD void operator()(int64_t S, const L& lanes) const
 	{
 		const int beg = seg_beg[S], n = seg_end[S] - beg;
 		const int64_t po = pos_off[seg_read[S]] + beg;
+		const uint8_t* f = flags + po;
 		char* out = target + tgt_off[S];
-		int64_t g = seg_reg[S];
-		int len = 0;
-		walk_anchors(flags + po, n, [&](int i, int, bool refine) {
-			out[len++] = base[po + i];
-			if (!refine) return;
-			const int l = glen[g];
-			if (l > 2) {
-				const char* src = gout + node_off[g] + goff[g] + 1;
-				for (int k = 0; k < l - 2; ++k) out[len++] = src[k];
-			}
-			++g;
-		});
-		tlen[S] = len;
+		const int64_t g0 = seg_reg[S];
+		AnchorCarry c;
+		for (int b0 = 0; b0 < n; b0 += L::count)
+			anchor_chunk(lanes, b0, n, beg, [&](int p) { return (int)f[p]; }, c,
+			             [&](int, int pos, int rank, int, bool closes, int ordinal, int) {
+				const int64_t g = g0 + ordinal + (closes ? 1 : 0);       // regions whose interior precedes this anchor
+				out[rank + (isum[g] - isum[g0])] = base[po + pos];
+			});
+	}
+};
+
+struct InteriorFn      // a thread per region: its interior goes right behind its anchor
+{
+	const Region* regions; const int64_t* seg_reg; const int64_t* isum; const int64_t* tgt_off; const int64_t* node_off;
+	const char* gout; const int32_t* goff; const int32_t* ilen; char* target;
+	CNS_HD void operator()(int64_t g) const
+	{
+		const int l = ilen[g];
+		if (l <= 0) return;
+		const Region G = regions[g];
+		char* dst = target + tgt_off[G.seg] + G.rank + 1 + (isum[g] - isum[seg_reg[G.seg]]);
+		const char* src = gout + node_off[g] + goff[g] + 1;
+		for (int k = 0; k < l; ++k) dst[k] = src[k];
 	}
 };
 
@@ -344,7 +376,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	CNS_ALLOC(d_segs, int32_t, 2 * h_slot[R]);
 	CNS_ALLOC(d_nseg, int32_t, R);
 	CNS_ALLOC(d_segfirst, int64_t, R + 1);
-	CNS_TRY(be.launch(R, SegmentFn{d_nacc, d_alnfirst, d_kept, d_rsize, d_pos, d_votes, P.min_cov, size95, d_slot, d_segs, d_nseg}, ST_SEGMENT));
+	CNS_TRY(be.launch_warp(R, SegmentFn{d_nacc, d_alnfirst, d_kept, d_rsize, d_pos, d_votes, P.min_cov, size95, d_slot, d_segs, d_nseg}, ST_SEGMENT));
 	std::vector<int32_t> h_nseg((size_t)R);
 	CNS_TRY(be.download(h_nseg.data(), d_nseg, (size_t)R));
 	for (int r = 0; r < R; ++r) if (h_nseg[r] < 0) { be.fail("cns: segment slots of a read overflowed"); return 1; }
@@ -361,11 +393,13 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	CNS_ALLOC(d_segbeg, int32_t, NS);
 	CNS_ALLOC(d_segend, int32_t, NS);
 	CNS_TRY(be.launch(R, SegFlattenFn{d_nseg, d_slot, d_segs, d_segfirst, d_segread, d_segbeg, d_segend}, ST_SEGMENT));
-	CNS_TRY(be.launch(R, RegionFn<false>{d_nseg, d_slot, d_segs, d_pos, d_votes, d_flags, d_nreg, nullptr, nullptr, nullptr, nullptr}, ST_REGION));
+	CNS_ALLOC(d_seganchors, int32_t, NS);
+	CNS_TRY(be.launch_warp(R, RegionFn<false>{d_nseg, d_slot, d_segs, d_pos, d_votes, d_flags, d_nreg, nullptr, nullptr, nullptr, nullptr, nullptr}, ST_REGION));
 	int64_t NG = 0;
 	CNS_TRY(be.scan(d_nreg, d_regfirst, R, &NG));
 	CNS_ALLOC(d_regions, Region, NG + 1);
-	CNS_TRY(be.launch(R, RegionFn<true>{d_nseg, d_slot, d_segs, d_pos, d_votes, d_flags, d_nreg, d_regfirst, d_segfirst, d_regions, d_segreg}, ST_REGION));
+	CNS_TRY(be.launch_warp(R, RegionFn<true>{d_nseg, d_slot, d_segs, d_pos, d_votes, d_flags, d_nreg, d_regfirst, d_segfirst, d_regions, d_segreg,
+	                                         d_seganchors}, ST_REGION));
 
 	// C7: one graph per region, each in an arena of exactly its demand
 	CNS_ALLOC(d_dn, int32_t, NG + 1);
@@ -418,16 +452,19 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 		}
 	}
 
-	// corrected bases of every segment
-	CNS_ALLOC(d_tcap, int32_t, NS);
+	// corrected bases of every segment: exact lengths first, then anchors and interiors straight to their final places
+	CNS_ALLOC(d_ilen, int32_t, NG + 1);
+	CNS_ALLOC(d_isum, int64_t, NG + 1);
 	CNS_ALLOC(d_tgtoff, int64_t, NS + 1);
 	CNS_ALLOC(d_tlen, int32_t, NS);
-	CNS_TRY(be.launch(NS, TargetCapFn{d_segread, d_segbeg, d_segend, d_segreg, d_nodeoff, d_regfirst, d_segfirst, d_nseg, NS, d_tcap}, ST_ASSEMBLE));
-	int64_t TGT = 0;
-	CNS_TRY(be.scan(d_tcap, d_tgtoff, NS, &TGT));
+	int64_t ISUM = 0, TGT = 0;
+	if (NG) CNS_TRY(be.launch(NG, InteriorLenFn{d_glen, d_ilen}, ST_ASSEMBLE));
+	CNS_TRY(be.scan(d_ilen, d_isum, NG, &ISUM));
+	CNS_TRY(be.launch(NS, TargetLenFn{d_segread, d_segreg, d_regfirst, d_segfirst, d_nseg, d_seganchors, d_isum, d_tlen}, ST_ASSEMBLE));
+	CNS_TRY(be.scan(d_tlen, d_tgtoff, NS, &TGT));
 	CNS_ALLOC(d_target, char, TGT);
-	CNS_TRY(be.launch(NS, AssembleFn{d_segread, d_segbeg, d_segend, d_segreg, d_pos, d_flags, d_base, d_nodeoff, d_gout, d_goff, d_glen,
-	                                 d_tgtoff, d_target, d_tlen}, ST_ASSEMBLE));
+	CNS_TRY(be.launch_warp(NS, AssembleFn{d_segread, d_segbeg, d_segend, d_segreg, d_pos, d_flags, d_base, d_isum, d_tgtoff, d_target}, ST_ASSEMBLE));
+	if (NG) CNS_TRY(be.launch(NG, InteriorFn{d_regions, d_segreg, d_isum, d_tgtoff, d_nodeoff, d_gout, d_goff, d_ilen, d_target}, ST_ASSEMBLE));
 
 	// results to the host
 	std::vector<int32_t> h_segread((size_t)NS), h_segbeg((size_t)NS), h_segend((size_t)NS), h_tlen((size_t)NS), h_gerr((size_t)NG);

@@ -18,7 +18,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <fstream>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -195,56 +197,92 @@ int main(int argc, char* argv[])
 		rmdir(wrk);
 	}
 
-	mecat_b200_ctx* ctx = NULL;
-	void* dvol = NULL;
-	{
-		StderrTimer t("gpu init + volume upload");
-		if (mecat_b200_init(&ctx, 0, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU 0\n"); return 1; }
-		if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); return 1; }
-	}
-
-	std::ofstream out(opt.output);
-	if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
+	// One host thread per GPU (MECAT_GPUS=n, default 1): every device holds a replica of the packed reads, the reads to
+	// correct are cut into contiguous slices of the id-sorted candidate list (balanced by candidate count, cut at read
+	// boundaries), no data moves between devices.  Slices are written in id order, so the output does not depend on n.
+	int ngpus = 1;
+	if (const char* g = getenv("MECAT_GPUS")) ngpus = atoi(g);
+	const int have = mecat_b200_device_count();
+	if (ngpus < 1) ngpus = 1;
+	if (ngpus > have) ngpus = have;
 	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
 	const mecat_cns_params P = {opt.min_mapping_ratio, opt.min_align_size, opt.min_cov, opt.min_size};
-	bool ok = true;
-	for (size_t i = 0; ok && i < ec.size();) {
-		const long long part = ec[i].sid / opt.batch_size;
-		size_t j = i;
-		while (j < ec.size() && ec[j].sid / opt.batch_size == part) ++j;
-		char info[128];
-		snprintf(info, sizeof info, "processing reads %lld --- %lld", part * opt.batch_size, (part + 1) * opt.batch_size - 1);
-		StderrTimer t(info);
-		mecat_cns_piece* pieces = NULL;
-		char* seqs = NULL;
-		size_t np = 0, nb = 0;
-		if (mecat_b200_cns_reads(ctx, dvol, ec.data() + i, j - i, &P, &pieces, &np, &seqs, &nb)) {
-			fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx));
-			ok = false;
-			break;
-		}
-		for (size_t k = 0; k < np; ++k) {
-			out << ">" << pieces[k].id << "_" << pieces[k].beg << "_" << pieces[k].end << "_" << pieces[k].seq_len << "\n";
-			out.write(seqs + pieces[k].seq_offset, (std::streamsize)pieces[k].seq_len);
-			out << "\n";
-		}
-		mecat_b200_free(ctx, pieces);
-		mecat_b200_free(ctx, seqs);
-		i = j;
+	std::vector<size_t> cut((size_t)ngpus + 1, ec.size());
+	cut[0] = 0;
+	for (int g = 1; g < ngpus; ++g) {
+		size_t k = ec.size() * (size_t)g / (size_t)ngpus;
+		while (k > 0 && k < ec.size() && ec[k].sid == ec[k - 1].sid) ++k;
+		cut[g] = std::max(k, cut[g - 1]);
 	}
-	if (getenv("MECAT_B200_STATS")) {       // per-kernel CUDA-event times of the whole run, one line
-		mecat_b200_stats st;
-		if (!mecat_b200_get_stats(ctx, &st)) {
-			static const char* names[MECAT_K_NUM] = {"orient", "index_count", "scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
-			                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"};
-			fprintf(stderr, "[kernel ms]");
-			for (int k = 0; k < MECAT_K_NUM; ++k)
-				if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);
-			fprintf(stderr, "\n");
+	struct Part { long long part; std::string text; };
+	std::vector<std::vector<Part>> results((size_t)ngpus);
+	std::atomic<int> failed(0);
+	auto worker = [&](int dev) {
+		mecat_b200_ctx* ctx = NULL;
+		void* dvol = NULL;
+		{
+			StderrTimer t("gpu " + std::to_string(dev) + " init + volume upload");
+			if (mecat_b200_init(&ctx, dev, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU %d\n", dev); failed = 1; return; }
+			if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); failed = 1; return; }
 		}
+		for (size_t i = cut[dev]; !failed && i < cut[dev + 1];) {
+			const long long part = ec[i].sid / opt.batch_size;
+			size_t j = i;
+			while (j < cut[dev + 1] && ec[j].sid / opt.batch_size == part) ++j;
+			char info[128];
+			snprintf(info, sizeof info, "gpu %d processing reads %lld --- %lld", dev, part * opt.batch_size, (part + 1) * opt.batch_size - 1);
+			StderrTimer t(info);
+			mecat_cns_piece* pieces = NULL;
+			char* seqs = NULL;
+			size_t np = 0, nb = 0;
+			if (mecat_b200_cns_reads(ctx, dvol, ec.data() + i, j - i, &P, &pieces, &np, &seqs, &nb)) {
+				fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx));
+				failed = 1;
+				break;
+			}
+			Part out;
+			out.part = part;
+			out.text.reserve(nb + 48 * np);
+			char head[128];
+			for (size_t k = 0; k < np; ++k) {
+				const int hl = snprintf(head, sizeof head, ">%lld_%lld_%lld_%lld\n", (long long)pieces[k].id, (long long)pieces[k].beg,
+				                        (long long)pieces[k].end, (long long)pieces[k].seq_len);
+				out.text.append(head, (size_t)hl);
+				out.text.append(seqs + pieces[k].seq_offset, (size_t)pieces[k].seq_len);
+				out.text.push_back('\n');
+			}
+			results[(size_t)dev].push_back(std::move(out));
+			mecat_b200_free(ctx, pieces);
+			mecat_b200_free(ctx, seqs);
+			i = j;
+		}
+		if (dev == 0 && getenv("MECAT_B200_STATS")) {       // per-kernel CUDA-event times of device 0's share, one line
+			mecat_b200_stats st;
+			if (!mecat_b200_get_stats(ctx, &st)) {
+				static const char* names[MECAT_K_NUM] = {"orient", "index_count", "scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
+				                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"};
+				fprintf(stderr, "[kernel ms]");
+				for (int k = 0; k < MECAT_K_NUM; ++k)
+					if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);
+				fprintf(stderr, "\n");
+			}
+		}
+		mecat_b200_volume_release(ctx, dvol);
+		mecat_b200_destroy(ctx);
+	};
+	{
+		std::vector<std::thread> th;
+		for (int d = 1; d < ngpus; ++d) th.emplace_back(worker, d);
+		worker(0);
+		for (auto& t : th) t.join();
 	}
-	mecat_b200_volume_release(ctx, dvol);
-	mecat_b200_destroy(ctx);
+	const bool ok = !failed;
+	if (ok) {
+		StderrTimer t("write results");
+		std::ofstream out(opt.output, std::ios::binary);
+		if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
+		for (auto& per_dev : results) for (auto& pt : per_dev) out.write(pt.text.data(), (std::streamsize)pt.text.size());
+	}
 	mecat_b200_volume_unload(&vol);
 	return ok ? 0 : 1;
 }

@@ -35,7 +35,7 @@ struct HostBackend
 	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
 	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
 	template <class F> bool launch(int64_t n, const F& f, int) { for (int64_t i = 0; i < n; ++i) f(i); return true; }
-	template <class F> bool launch_warp(int64_t n, const F& f, int) { mbcns::SoloLane one; for (int64_t i = 0; i < n; ++i) f(i, one); return true; }
+	template <class F> bool launch_warp(int64_t n, const F& f, int) { mbcns::EmuLanes one; for (int64_t i = 0; i < n; ++i) f(i, one); return true; }
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)
 	{
 		int64_t s = 0;

@@ -549,8 +549,8 @@ def test_cns_small_batches_and_graph_waves(small_vol, monkeypatch):
     """The same output when the extension arena only holds a few reads per batch and the region graphs have to run in
     many scratch waves (both limits are normally sized from the device memory)."""
     import mecat_b200
-    monkeypatch.setenv("MECAT_B200_ALIGN_ARENA_MB", "64")
-    monkeypatch.setenv("MECAT_B200_POA_BUDGET_MB", "8")
+    monkeypatch.setenv("MECAT_B200_ALIGN_ARENA_MB", "8")
+    monkeypatch.setenv("MECAT_B200_POA_BUDGET_MB", "2")
     with mecat_b200.Context(0) as ctx:
         ctx.reset_stats()
         got = _cns(ctx, small_vol, _gold_can("small"), 0.9, 1000, 4, 2000)
@@ -558,6 +558,40 @@ def test_cns_small_batches_and_graph_waves(small_vol, monkeypatch):
     assert got == _gold_fasta("small", "cns_relaxed")
     assert st["kernel_launches"]["extend"] >= 3        # several extension batches ...
     assert st["kernel_launches"]["cns_poa"] >= 3 * st["kernel_launches"]["cns_normvote"]   # ... and several graph waves in each
+
+
+def _run_cli(exe, args, env=None):
+    import subprocess
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([os.path.join(util.ROOT, "mecat_b200", "bin", exe)] + args, env=e, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p
+
+
+def test_command_line_drivers_match_reference(gpu_ctx, tmp_path):
+    """mecat2pw -j 0 | mecat2cns -i 0 through the C++ drivers (reference flags and file formats): candidate lines and
+    corrected FASTA equal the unmodified reference binaries' output; with two devices the read-sharded run is identical."""
+    import mecat_b200
+    fa = str(tmp_path / "small.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f, open(fa, "wb") as g:
+        g.write(f.read())
+    can = str(tmp_path / "small.can")
+    _run_cli("mecat2pw", ["-j", "0", "-d", fa, "-o", can, "-w", str(tmp_path / "wrk"), "-t", "2"])
+    assert sorted(open(can).read().splitlines()) == gold_lines("small", "can")
+    want = _gold_fasta("small", "cns_relaxed")
+
+    def corrected(path):
+        lines = open(path).read().splitlines()
+        return sorted(zip(lines[0::2], lines[1::2]))
+
+    out1 = str(tmp_path / "cns1.fa")
+    _run_cli("mecat2cns", ["-i", "0", "-t", "2", "-l", "2000", "-c", "4", "-a", "1000", can, fa, out1])
+    assert corrected(out1) == want
+    if mecat_b200.load_library().mecat_b200_device_count() >= 2:
+        out2 = str(tmp_path / "cns2.fa")
+        _run_cli("mecat2cns", ["-i", "0", "-t", "2", "-l", "2000", "-c", "4", "-a", "1000", can, fa, out2], env={"MECAT_GPUS": "2"})
+        assert open(out2).read() == open(out1).read()
 
 
 def test_cns_consensus_runs_on_the_gpu(gpu_ctx, small_vol):
