@@ -41,6 +41,49 @@ __global__ void __launch_bounds__(128) k_cns_warp(const F f, const int64_t n)
 	if (i < n) f(i, WarpLanes());
 }
 
+// The region graphs of one wave, a thread per region.  A graph is pointer chasing over a few hundred bytes of nodes
+// and edges; in global memory every step of it is an L2 / DRAM round trip (ncu: 14 KB of DRAM traffic per region for
+// a 2 KB arena, long-scoreboard bound).  So the CTA owns a pool of shared memory: each thread asks for the bytes its
+// graph needs with 16-bit indices, a CTA-wide scan hands out slices, and the threads whose slice fits build their
+// graph there; the rest wait for the next round of the same pool.  Only graphs too large for the pool (or for 16-bit
+// indices) use their exact-size arena in global memory.
+constexpr int POA_BLOCK = 128;
+constexpr int POA_POOL = 108 * 1024;       // two CTAs per SM
+
+__global__ void __launch_bounds__(POA_BLOCK) k_cns_poa(const mbcns::PoaFn f, const int64_t n)
+{
+	extern __shared__ __align__(16) char pool[];
+	__shared__ int wsum[POA_BLOCK / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int64_t k = (int64_t)blockIdx.x * POA_BLOCK + tid;
+	bool pending = k < n;
+	int need = 0;
+	if (pending) {
+		int ncap, e0;
+		f.shape(k, ncap, e0);
+		const int64_t b = mbcns::PoaFn::small(ncap, e0) ? mbcns::poa_arena_bytes<int16_t>(ncap, e0) : (int64_t)POA_POOL + 1;
+		if (b > POA_POOL) {                  // too large for the pool: its own global arena
+			if (mbcns::PoaFn::small(ncap, e0)) f.solve<int16_t>(k, f.wide_arena(k)); else f.solve<int32_t>(k, f.wide_arena(k));
+			pending = false;
+		} else need = (int)b;
+	}
+	while (__syncthreads_or(pending)) {
+		// exclusive scan of the pending requests over the CTA
+		const int v = pending ? need : 0;
+		int inc = v;
+		for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+		if (lane == 31) wsum[warp] = inc;
+		__syncthreads();
+		int off = inc - v;
+		for (int w = 0; w < warp; ++w) off += wsum[w];
+		if (pending && off + need <= POA_POOL) {
+			f.solve<int16_t>(k, pool + off);
+			pending = false;
+		}
+		__syncthreads();                     // the pool and wsum are reused by the next round
+	}
+}
+
 // Exclusive prefix sum of n int32 values into n + 1 int64 values, three launches: totals of 4 096-element tiles
 // (coalesced), a one-CTA scan of the tile totals, and the tile-local scan with its tile offset added.
 constexpr int SCAN_TILE = 4096;      // 1 024 threads x 4 consecutive values
@@ -153,6 +196,18 @@ struct DevBackend
 		if (n <= 0) return true;
 		KScope ks(c, MECAT_K_CNS_ACCEPT + stage);
 		k_cns_warp<F><<<(unsigned)((n + 3) / 4), 128, 0, c->stream>>>(f, n);
+		return check(cudaGetLastError(), "launch");
+	}
+	bool launch_graphs(int64_t n, const mbcns::PoaFn& f, int stage)
+	{
+		if (n <= 0) return true;
+		static bool configured = false;
+		if (!configured) {
+			if (!check(cudaFuncSetAttribute(k_cns_poa, cudaFuncAttributeMaxDynamicSharedMemorySize, POA_POOL), "shared memory opt-in")) return false;
+			configured = true;
+		}
+		KScope ks(c, MECAT_K_CNS_ACCEPT + stage);
+		k_cns_poa<<<(unsigned)((n + POA_BLOCK - 1) / POA_BLOCK), POA_BLOCK, POA_POOL, c->stream>>>(f, n);
 		return check(cudaGetLastError(), "launch");
 	}
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)

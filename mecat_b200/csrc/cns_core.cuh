@@ -564,29 +564,45 @@ CNS_HD inline bool kept_slice(const KeptAln& a, int sb, int se, int prev_se, Sli
 // AlnGraphBoost on flat arrays.  Adjacency lists are intrusive doubly linked lists threaded through the edges,
 // which gives the iteration orders of boost::adjacency_list<vecS, vecS, bidirectionalS> (insertion order,
 // order-preserving removal) that the tie-breaks of the best-path search depend on.
-struct PoaNode
+// The index type I is int32_t in general and int16_t for graphs small enough (the common case), which halves the
+// scratch so that it fits the shared-memory pool of the graph kernel (cns.cu).
+template <class I> struct PoaNodeT
 {
-	int32_t coverage, weight, bb;              // bb: _bbMap (node -> backbone node, 0 when never set)
-	int32_t in_head, in_tail, in_cnt;
-	int32_t out_head, out_tail, out_cnt;
-	char base; uint8_t backbone; uint8_t pad[2];
+	I coverage, weight, bb;                    // bb: _bbMap (node -> backbone node, 0 when never set)
+	I in_head, in_tail, in_cnt;
+	I out_head, out_tail, out_cnt;
+	char base; uint8_t backbone;
 };
-struct PoaEdge
+template <class I> struct PoaEdgeT
 {
-	int32_t u, v, count, visited;
-	int32_t in_next, in_prev;                  // position in v's in-list
-	int32_t out_next, out_prev;                // position in u's out-list
+	I u, v, count, visited;
+	I in_next, in_prev;                        // position in v's in-list
+	I out_next, out_prev;                      // position in u's out-list
 };
+static_assert(sizeof(PoaNodeT<int16_t>) == 20 && sizeof(PoaNodeT<int32_t>) == 40, "node layout");
+static_assert(sizeof(PoaEdgeT<int16_t>) == 16 && sizeof(PoaEdgeT<int32_t>) == 32, "edge layout");
 
-// sizes of the per-graph scratch, in elements, for a graph with N nodes and E0 edges before merging
+// Scratch of one graph with N nodes and E0 edge creations before merging (region_demand): edge slots, queue/stack
+// slots, and the bytes of the whole arena laid out as [score float N | nodes N | edges | queue+stack | best edge N].
 CNS_HD inline int64_t poa_edge_cap(int64_t nodes, int64_t e0) { return e0 + nodes + 2; }
-CNS_HD inline int64_t poa_aux_ints(int64_t nodes) { return 8 * nodes + 64; }
+CNS_HD inline int64_t poa_aux_slots(int64_t nodes) { return 8 * nodes + 64; }
+template <class I> CNS_HD inline int64_t poa_arena_bytes(int64_t nodes, int64_t e0)
+{
+	const int64_t b = 4 * nodes + (int64_t)sizeof(PoaNodeT<I>) * nodes + (int64_t)sizeof(PoaEdgeT<I>) * poa_edge_cap(nodes, e0) +
+	                  (int64_t)sizeof(I) * (poa_aux_slots(nodes) + nodes);
+	return (b + 3) & ~(int64_t)3;
+}
+// poa_arena_bytes<int32_t> is linear: 112 nodes + 32 e0 + 320 (the prefix sums of nodes and e0 locate every arena)
+constexpr int POA_SMALL_LIMIT = 30000;     // nodes and edge slots below this -> int16_t indices are safe
 
 enum { POA_OK = 0, POA_ERR_EDGES = 1, POA_ERR_QUEUE = 2, POA_ERR_STACK = 3, POA_ERR_EMPTY_LIST = 4, POA_ERR_NODES = 5 };
 
-struct Poa
+template <class I>
+struct PoaT
 {
-	PoaNode* nd; PoaEdge* ed; int32_t* aux;
+	typedef PoaNodeT<I> PoaNode;
+	typedef PoaEdgeT<I> PoaEdge;
+	PoaNode* nd; PoaEdge* ed; I* aux; float* score; I* best_edge;
 	int nn, ncap, ecap, nedges, efree, enter, exit_, err;
 	int auxcap;
 
@@ -653,13 +669,18 @@ struct Poa
 		n.coverage = 0; n.weight = 0; n.bb = 0;
 		n.in_head = n.in_tail = n.out_head = n.out_tail = -1;
 		n.in_cnt = n.out_cnt = 0;
-		n.base = 'N'; n.backbone = 0; n.pad[0] = n.pad[1] = 0;
+		n.base = 'N'; n.backbone = 0;
 	}
 
 	// AlnGraphBoost(size_t blen), MECAT_AlnGraphBoost.C:76-97
-	CNS_HD void init(PoaNode* nodes, int node_cap, PoaEdge* edges, int edge_cap, int32_t* aux_, int aux_cap, int blen)
+	CNS_HD void init(char* arena, int node_cap, int edge_cap, int blen)
 	{
-		nd = nodes; ed = edges; aux = aux_; ncap = node_cap; ecap = edge_cap; auxcap = aux_cap;
+		ncap = node_cap; ecap = edge_cap; auxcap = (int)poa_aux_slots(node_cap);
+		score = (float*)arena;
+		nd = (PoaNode*)(arena + 4 * (int64_t)ncap);
+		ed = (PoaEdge*)(nd + ncap);
+		aux = (I*)(ed + ecap);
+		best_edge = aux + auxcap;
 		nedges = 0; efree = -1; err = 0;
 		nn = blen + 2;
 		if (nn > ncap) { fail(POA_ERR_NODES); nn = 0; enter = exit_ = 0; return; }
@@ -704,7 +725,7 @@ struct Poa
 	}
 
 	// smallest base above `last` among list[0..cnt); -1 when none (std::map<char, ...> iteration order)
-	CNS_HD int next_base(const int32_t* list, int cnt, int last) const
+	CNS_HD int next_base(const I* list, int cnt, int last) const
 	{
 		int best = -1;
 		for (int k = 0; k < cnt; ++k) {
@@ -724,20 +745,20 @@ struct Poa
 			const int begin = sp;
 			for (int e = nd[n].in_head; e >= 0; e = ed[e].in_next) {
 				const int u = ed[e].u;
-				if (nd[u].out_cnt == 1) { if (sp + 3 > auxcap) { fail(POA_ERR_STACK); return; } aux[sp++] = u; }
+				if (nd[u].out_cnt == 1) { if (sp + 3 > auxcap) { fail(POA_ERR_STACK); return; } aux[sp++] = (I)u; }
 			}
 			if (sp + 2 > auxcap) { fail(POA_ERR_STACK); return; }
 			const int entries = sp - begin;
-			aux[sp++] = entries;
-			aux[sp++] = -1000;          // last base done
+			aux[sp++] = (I)entries;
+			aux[sp++] = (I)-1000;          // last base done
 		};
 		push_frame(n0);
 		while (sp > sp0 && !err) {
 			const int cnt = aux[sp - 2];
-			int32_t* list = aux + (sp - 2 - cnt);
+			I* list = aux + (sp - 2 - cnt);
 			const int b = next_base(list, cnt, aux[sp - 1]);
 			if (b < 0) { sp -= cnt + 2; continue; }
-			aux[sp - 1] = b;
+			aux[sp - 1] = (I)b;
 			int an = -1, members = 0;
 			for (int k = 0; k < cnt; ++k) if ((int)(signed char)nd[list[k]].base == b) { if (an < 0) an = list[k]; ++members; }
 			if (members <= 1) continue;
@@ -769,10 +790,10 @@ struct Poa
 	CNS_HD void merge_out(int n, int sp0)
 	{
 		int cnt = 0;
-		int32_t* list = aux + sp0;
+		I* list = aux + sp0;
 		for (int e = nd[n].out_head; e >= 0; e = ed[e].out_next) {
 			const int v = ed[e].v;
-			if (nd[v].in_cnt == 1) { if (sp0 + cnt + 1 > auxcap) { fail(POA_ERR_STACK); return; } list[cnt++] = v; }
+			if (nd[v].in_cnt == 1) { if (sp0 + cnt + 1 > auxcap) { fail(POA_ERR_STACK); return; } list[cnt++] = (I)v; }
 		}
 		int last = -1000;
 		for (;;) {
@@ -811,7 +832,7 @@ struct Poa
 		if (err) return;
 		const int qcap = 2 * ncap + 16;
 		int head = 0, tail = 0;          // monotone counters into the circular queue aux[0, qcap)
-		aux[tail++ % qcap] = enter;
+		aux[tail++ % qcap] = (I)enter;
 		while (head < tail && !err) {
 			const int u = aux[head++ % qcap];
 			merge_in(u, qcap);
@@ -823,7 +844,7 @@ struct Poa
 				for (int ie = nd[v].in_head; ie >= 0; ie = ed[ie].in_next) if (!ed[ie].visited) ++open;
 				if (open == 0) {
 					if (tail - head >= qcap) { fail(POA_ERR_QUEUE); return; }
-					aux[tail++ % qcap] = v;
+					aux[tail++ % qcap] = (I)v;
 				}
 			}
 		}
@@ -837,12 +858,10 @@ struct Poa
 		off = 0; len = 0;
 		if (err) return;
 		const int qcap = 2 * ncap + 16;
-		float* score = (float*)(aux + qcap);
-		int32_t* best_edge = aux + qcap + ncap;
-		for (int i = 0; i < nn; ++i) { score[i] = 0.0f; best_edge[i] = -1; }
+		for (int i = 0; i < nn; ++i) { score[i] = 0.0f; best_edge[i] = (I)-1; }
 		for (int e = 0; e < nedges; ++e) ed[e].visited = 0;
 		int head = 0, tail = 0;
-		aux[tail++ % qcap] = exit_;
+		aux[tail++ % qcap] = (I)exit_;
 		while (head < tail) {
 			const int n = aux[head++ % qcap];
 			bool found = false;
@@ -856,7 +875,7 @@ struct Poa
 				else ns = (float)ed[e].count - (float)nd[nd[v].bb].coverage * 0.5f + s;
 				if (ns > best) { best = ns; best_e = e; found = true; }
 			}
-			if (found) { score[n] = best; best_edge[n] = best_e; }
+			if (found) { score[n] = best; best_edge[n] = (I)best_e; }
 			for (int ie = nd[n].in_head; ie >= 0; ie = ed[ie].in_next) {
 				ed[ie].visited = 1;
 				const int u = ed[ie].u;
@@ -864,7 +883,7 @@ struct Poa
 				for (int oe = nd[u].out_head; oe >= 0; oe = ed[oe].out_next) if (!ed[oe].visited) ++open;
 				if (open == 0) {
 					if (tail - head >= qcap) { fail(POA_ERR_QUEUE); return; }
-					aux[tail++ % qcap] = u;
+					aux[tail++ % qcap] = (I)u;
 				}
 			}
 		}
@@ -911,13 +930,13 @@ CNS_HD inline void region_demand(const KeptAln* kept, int nkept, int sb, int se,
 }
 
 // meap_cns_one_indel, mecat_correction.cpp:63-78: graph of one region -> best-path bases in out[0..), the kept run
-// in off/len.  Returns a POA_* status.
+// in off/len.  arena: poa_arena_bytes<I>(node_cap, e0) bytes, 4-byte aligned.  Returns a POA_* status.
+template <class I>
 CNS_HD inline int region_consensus(const KeptAln* kept, int nkept, int sb, int se, int prev_se, int min_weight,
-                                   PoaNode* nodes, int node_cap, PoaEdge* edges, int edge_cap, int32_t* aux, int aux_cap,
-                                   char* out, int& off, int& len)
+                                   char* arena, int node_cap, int edge_cap, char* out, int& off, int& len)
 {
-	Poa g;
-	g.init(nodes, node_cap, edges, edge_cap, aux, aux_cap, se - sb + 1);
+	PoaT<I> g;
+	g.init(arena, node_cap, edge_cap, se - sb + 1);
 	for (int k = 0; k < nkept; ++k) {
 		Slice sl;
 		if (kept_slice(kept[k], sb, se, prev_se, sl)) g.add_alignment(kept[k].q, kept[k].s, sl.c0, sl.c1, sl.start);

@@ -191,21 +191,39 @@ struct PoaFn
 {
 	const Region* regions; const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept;
 	const int64_t* node_off; const int64_t* edge0_off;
-	int64_t g_base, n_base, e_base;      // first region of this wave and its offsets: the arenas hold one wave
-	PoaNode* nodes; PoaEdge* edges; int32_t* aux; char* gout; int32_t* goff; int32_t* glen; int32_t* gerr;
-	CNS_HD void operator()(int64_t k) const
+	int64_t g_base, n_base, e_base;      // first region of this wave and its offsets: the arena holds one wave
+	char* arena; char* gout; int32_t* goff; int32_t* glen; int32_t* gerr;
+	// capacities of the wave's k-th graph and the place of its int32-layout arena
+	CNS_HD void shape(int64_t k, int& ncap, int& e0) const
+	{
+		const int64_t g = g_base + k;
+		ncap = (int)(node_off[g + 1] - node_off[g]);
+		e0 = (int)(edge0_off[g + 1] - edge0_off[g]);
+	}
+	CNS_HD char* wide_arena(int64_t k) const
+	{
+		const int64_t g = g_base + k;
+		return arena + 112 * (node_off[g] - n_base) + 32 * (edge0_off[g] - e_base) + 320 * k;
+	}
+	CNS_HD static bool small(int ncap, int e0) { return ncap < POA_SMALL_LIMIT && poa_edge_cap(ncap, e0) < POA_SMALL_LIMIT; }
+	// the graph of the wave's k-th region with index type I in the given scratch
+	template <class I>
+	CNS_HD void solve(int64_t k, char* scratch) const
 	{
 		const int64_t g = g_base + k;
 		const Region G = regions[g];
-		const int64_t n0 = node_off[g], e0 = edge0_off[g];
-		const int ncap = (int)(node_off[g + 1] - n0);
-		const int ecap = (int)poa_edge_cap(ncap, edge0_off[g + 1] - e0);
-		const int64_t rn = n0 - n_base, re = e0 - e_base;
-		int off, len;
-		gerr[g] = region_consensus(kept + aln_first[G.read], nacc[G.read], G.sb, G.se, G.prev_se, G.min_weight,
-		                           nodes + rn, ncap, edges + (re + rn + 2 * k), ecap, aux + (8 * rn + 64 * k), (int)poa_aux_ints(ncap),
-		                           gout + n0, off, len);
+		int ncap, e0, off, len;
+		shape(k, ncap, e0);
+		gerr[g] = region_consensus<I>(kept + aln_first[G.read], nacc[G.read], G.sb, G.se, G.prev_se, G.min_weight, scratch, ncap,
+		                              (int)poa_edge_cap(ncap, e0), gout + node_off[g], off, len);
 		goff[g] = off; glen[g] = len;
+	}
+	// a thread per region entirely in its global arena (the GPU kernel prefers shared memory, cns.cu: k_cns_poa)
+	CNS_HD void operator()(int64_t k) const
+	{
+		int ncap, e0;
+		shape(k, ncap, e0);
+		if (small(ncap, e0)) solve<int16_t>(k, wide_arena(k)); else solve<int32_t>(k, wide_arena(k));
 	}
 };
 
@@ -302,6 +320,7 @@ inline void emit_piece(std::vector<Piece>& out, int64_t id, int64_t beg, int64_t
 //   bool upload(T* d, const T* h, size_t n), bool download(T* h, const T* d, size_t n), bool fill(void* d, int byte, size_t bytes)
 //   template <class F> bool launch(int64_t n, const F& f, int stage)        f(i), one thread per unit
 //   template <class F> bool launch_warp(int64_t n, const F& f, int stage)   f(i, lanes), one warp per unit
+//   bool launch_graphs(int64_t n, const PoaFn& f, int stage)               the region graphs of one wave
 //   bool scan(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* total)   d_out[0..n] exclusive prefix, total on the host
 //   bool release(void* d)                            early free of an alloc() block (stream ordered)
 //   int64_t poa_budget_bytes()                       scratch budget of one wave of region graphs
@@ -418,9 +437,9 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 		        (long long)T, (long long)NA, (long long)NS, (long long)NG, (long long)NODES, (long long)EDGES0, (long long)NORM);
 	CNS_ALLOC(d_gout, char, NODES);
 	{
-		// The graphs run in waves whose scratch fits the backend's budget.  Scratch bytes of regions [a, b) =
-		// cost(b) - cost(a) with cost(g) = 104 nodes_before(g) + 32 edges0_before(g) + 320 g (see PoaFn, poa_edge_cap,
-		// poa_aux_ints); wave ends are found by bisection on the device-resident prefix sums.
+		// The graphs run in waves whose global scratch fits the backend's budget.  Scratch bytes of regions [a, b) =
+		// cost(b) - cost(a) with cost(g) = 112 nodes_before(g) + 32 edges0_before(g) + 320 g (poa_arena_bytes<int32_t>);
+		// wave ends are found by bisection on the device-resident prefix sums.
 		const int64_t budget = be.poa_budget_bytes();
 		auto cost_at = [&](int64_t g, int64_t& n, int64_t& e) -> bool {
 			if (g == NG) { n = NODES; e = EDGES0; return true; }
@@ -429,25 +448,22 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 		int64_t a = 0, na = 0, ea = 0;
 		while (a < NG) {
 			int64_t b = NG, nb = NODES, eb = EDGES0;
-			if (104 * (nb - na) + 32 * (eb - ea) + 320 * (b - a) > budget) {
+			if (112 * (nb - na) + 32 * (eb - ea) + 320 * (b - a) > budget) {
 				int64_t lo = a + 1, hi = NG;                 // largest b in [a + 1, NG] whose wave fits; a + 1 always accepted
 				while (lo < hi) {
 					const int64_t mid = lo + (hi - lo + 1) / 2;
 					int64_t nm, em;
 					CNS_TRY(cost_at(mid, nm, em));
-					if (104 * (nm - na) + 32 * (em - ea) + 320 * (mid - a) <= budget) lo = mid; else hi = mid - 1;
+					if (112 * (nm - na) + 32 * (em - ea) + 320 * (mid - a) <= budget) lo = mid; else hi = mid - 1;
 				}
 				b = lo;
 				CNS_TRY(cost_at(b, nb, eb));
 			}
-			const int64_t dn = nb - na, de = eb - ea, dg = b - a;
-			PoaNode* d_nodes = be.template alloc<PoaNode>((size_t)dn);
-			PoaEdge* d_edges = be.template alloc<PoaEdge>((size_t)(de + dn + 2 * dg));
-			int32_t* d_aux = be.template alloc<int32_t>((size_t)(8 * dn + 64 * dg));
-			if (!d_nodes || !d_edges || !d_aux) return 1;
-			CNS_TRY(be.launch(dg, PoaFn{d_regions, d_nacc, d_alnfirst, d_kept, d_nodeoff, d_edgeoff, a, na, ea, d_nodes, d_edges, d_aux, d_gout,
-			                            d_goff, d_glen, d_gerr}, ST_POA));
-			CNS_TRY(be.release(d_nodes)); CNS_TRY(be.release(d_edges)); CNS_TRY(be.release(d_aux));
+			char* d_arena = be.template alloc<char>((size_t)(112 * (nb - na) + 32 * (eb - ea) + 320 * (b - a)));
+			if (!d_arena) return 1;
+			CNS_TRY(be.launch_graphs(b - a, PoaFn{d_regions, d_nacc, d_alnfirst, d_kept, d_nodeoff, d_edgeoff, a, na, ea, d_arena, d_gout,
+			                                      d_goff, d_glen, d_gerr}, ST_POA));
+			CNS_TRY(be.release(d_arena));
 			a = b; na = nb; ea = eb;
 		}
 	}

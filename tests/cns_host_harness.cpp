@@ -36,6 +36,15 @@ struct HostBackend
 	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
 	template <class F> bool launch(int64_t n, const F& f, int) { for (int64_t i = 0; i < n; ++i) f(i); return true; }
 	template <class F> bool launch_warp(int64_t n, const F& f, int) { mbcns::EmuLanes one; for (int64_t i = 0; i < n; ++i) f(i, one); return true; }
+	// graphs: narrow (int16_t) indices where the product uses them, or wide everywhere when a test asks for it
+	bool launch_graphs(int64_t n, const mbcns::PoaFn& f, int)
+	{
+		for (int64_t k = 0; k < n; ++k) {
+			if (force_wide) f.solve<int32_t>(k, f.wide_arena(k)); else f(k);
+		}
+		return true;
+	}
+	bool force_wide = false;
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)
 	{
 		int64_t s = 0;
@@ -92,6 +101,7 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	HostBackend be;
+	be.force_wide = getenv("MECAT_HARNESS_WIDE_GRAPHS") != nullptr;
 	std::vector<mbcns::Piece> out;
 	if (mbcns::consensus_batch(be, in, P, out)) {
 		if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", be.err.c_str());

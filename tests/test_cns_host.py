@@ -156,6 +156,12 @@ def compare(got, want):
                 % (len(got), len(want), only_g[:5], only_w[:5], diff[:5]))
 
 
+def test_kernel_bodies_with_wide_graph_indices(small_vol, monkeypatch):
+    """The region graphs with 32-bit indices everywhere (the GPU uses them for graphs too large for 16-bit ones)."""
+    monkeypatch.setenv("MECAT_HARNESS_WIDE_GRAPHS", "1")
+    compare(correct_with_kernel_bodies(small_vol, gold_can("small"), 0.9, 1000, 4, 2000), gold_fasta("small", "cns_relaxed"))
+
+
 PARAMS = {"cns_default": (0.9, 2000, 6, 5000),
           # -l 2000 -c 4 -a 1000: many more reads qualify (148 corrected pieces, thousands of mini-POA regions)
           "cns_relaxed": (0.9, 1000, 4, 2000)}
