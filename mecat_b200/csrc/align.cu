@@ -455,7 +455,9 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 	*out = AlignDev();
 	if (!nb) return 0;
 	if (policy == 1 && !(err > 0.0 && err <= 0.16)) MB_FAIL(c, "align_batch: error rate %.3f is outside this path (pacbio, <= 0.16)", err);
-	const int grid = c->sm_count * 5;
+	int per_sm = 7;      // 28 warps per SM: the smem (7.3 KB per warp) and register (68) limit; measured 541 / 470 / 430 / 407 ms at 4 / 5 / 6 / 7
+	if (const char* e = getenv("MECAT_B200_ALIGN_CTAS")) per_sm = std::max(1, atoi(e));   // tuning hook
+	const int grid = c->sm_count * per_sm;
 	const size_t nwarps = (size_t)grid * AL_WARPS;
 	uint32_t* d_dir = nullptr;
 	short* d_min = nullptr;

@@ -363,6 +363,8 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 		if (e.qext < 0 || e.qext >= e.qsize || e.sext < 0 || e.sext >= e.ssize)
 			MB_FAIL(c, "cns_reads: candidate %zu extension point outside its read", i);
 	}
+	const bool debug = getenv("MECAT_CNS_DEBUG") != nullptr;
+	WallTimer t_prep;
 	std::vector<mecat_candidate> ec(ec_in, ec_in + nec);
 	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
 	struct Group { size_t b, e; };
@@ -384,7 +386,9 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;
 	std::vector<int64_t> rid;
+	if (debug) fprintf(stderr, "[cns_reads] validate + sort + group: %.1f ms\n", t_prep.stop());
 	for (size_t g0 = 0; g0 < groups.size();) {
+		WallTimer t_batch;
 		// a batch = whole reads, as many as fit the column arena of the extension kernels
 		tasks.clear(); first.assign(1, 0); rsize.clear(); rid.clear(); tqid.clear(); tqsize.clear();
 		size_t g1 = g0, cols = 0;
@@ -408,8 +412,10 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 			rid.push_back(ec[groups[g1].b].sid);
 			++g1;
 		}
+		const float ms_tasks = t_batch.stop();
 		AlignDev dev;
 		if (align_batch_device(c, 1, 0.15, V, V, tasks.data(), tasks.size(), p->min_align_size, &dev, info)) return 1;
+		const float ms_align = t_batch.stop();
 		mbcns::BatchIn in;
 		in.R = (int)(g1 - g0); in.T = (int64_t)tasks.size();
 		in.h_first = first.data(); in.h_read_size = rsize.data(); in.h_read_id = rid.data(); in.h_tqid = tqid.data(); in.h_tqsize = tqsize.data();
@@ -417,8 +423,11 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 		const int rc = cns_consensus_device(c, in, P, all);
 		align_dev_release(c, &dev);
 		if (rc) return 1;
+		if (debug) fprintf(stderr, "[cns_reads] batch of %zu reads / %zu tasks: task list %.1f ms, extensions %.1f ms, consensus %.1f ms\n", g1 - g0,
+		                   tasks.size(), ms_tasks, ms_align - ms_tasks, t_batch.stop() - ms_align);
 		g0 = g1;
 	}
+	WallTimer t_out;
 	size_t bytes = 0;
 	for (auto& pc : all) bytes += pc.seq.size();
 	mecat_cns_piece* out = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (all.size() ? all.size() : 1));
@@ -432,6 +441,7 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	}
 	sq[bytes] = 0;
 	c->stats.num_records += (int64_t)all.size();
+	if (debug) fprintf(stderr, "[cns_reads] result buffers: %.1f ms\n", t_out.stop());
 	*pieces = out; *npieces = all.size(); *seqs = sq; *seq_bytes = bytes;
 	return 0;
 }

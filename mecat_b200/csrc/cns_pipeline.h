@@ -25,6 +25,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -334,6 +335,16 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	if (R == 0) return 0;
 	const double ratio = P.min_mapping_ratio - 0.02;
 	const double size95 = 0.95 * (double)P.min_size;
+	const bool debug = getenv("MECAT_CNS_DEBUG") != nullptr;
+	struct timespec ts0;
+	clock_gettime(CLOCK_MONOTONIC, &ts0);
+	auto lap = [&](const char* what) {       // debug only: wall time since the previous lap (stages end in a scan or download, i.e. a sync)
+		if (!debug) return;
+		struct timespec t1;
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		fprintf(stderr, "[cns batch] %-28s %8.1f ms\n", what, (t1.tv_sec - ts0.tv_sec) * 1e3 + (t1.tv_nsec - ts0.tv_nsec) * 1e-6);
+		ts0 = t1;
+	};
 
 	// per-read position arenas and segment slots
 	std::vector<int64_t> h_pos((size_t)R + 1, 0), h_slot((size_t)R + 1, 0);
@@ -371,6 +382,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	CNS_TRY(be.launch_warp(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc}, ST_ACCEPT));
 	int64_t NA = 0;
 	CNS_TRY(be.scan(d_nacc, d_alnfirst, R, &NA));
+	lap("setup + accept");
 	if (NA == 0) return 0;
 	CNS_ALLOC(d_alntask, int32_t, NA);
 	CNS_ALLOC(d_alnread, int32_t, NA);
@@ -391,6 +403,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	CNS_TRY(be.launch(NA, NormVoteFn{in.d_info, in.d_q, in.d_s, in.d_outoff, d_alntask, d_alnread, d_normoff, d_coloff, d_pos,
 	                                 d_nq, d_nt, d_colidx, d_votes, d_base, d_kept}, ST_NORMVOTE));
 
+	lap("flatten + norm/vote launch");
 	// C6: covered runs of each read
 	CNS_ALLOC(d_segs, int32_t, 2 * h_slot[R]);
 	CNS_ALLOC(d_nseg, int32_t, R);
@@ -401,6 +414,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	for (int r = 0; r < R; ++r) if (h_nseg[r] < 0) { be.fail("cns: segment slots of a read overflowed"); return 1; }
 	int64_t NS = 0;
 	CNS_TRY(be.scan(d_nseg, d_segfirst, R, &NS));
+	lap("norm/vote + segments");
 	if (NS == 0) return 0;
 
 	// C6: anchors and ambiguous regions of every segment
@@ -435,6 +449,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	if (getenv("MECAT_CNS_DEBUG"))
 		fprintf(stderr, "[cns batch] reads %d tasks %lld accepted %lld segments %lld regions %lld nodes %lld edges0 %lld norm bytes %lld\n", R,
 		        (long long)T, (long long)NA, (long long)NS, (long long)NG, (long long)NODES, (long long)EDGES0, (long long)NORM);
+	lap("regions + demand");
 	CNS_ALLOC(d_gout, char, NODES);
 	{
 		// The graphs run in waves whose global scratch fits the backend's budget.  Scratch bytes of regions [a, b) =
@@ -468,6 +483,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 		}
 	}
 
+	lap("graph waves (launch)");
 	// corrected bases of every segment: exact lengths first, then anchors and interiors straight to their final places
 	CNS_ALLOC(d_ilen, int32_t, NG + 1);
 	CNS_ALLOC(d_isum, int64_t, NG + 1);
@@ -482,6 +498,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	CNS_TRY(be.launch_warp(NS, AssembleFn{d_segread, d_segbeg, d_segend, d_segreg, d_pos, d_flags, d_base, d_isum, d_tgtoff, d_target}, ST_ASSEMBLE));
 	if (NG) CNS_TRY(be.launch(NG, InteriorFn{d_regions, d_segreg, d_isum, d_tgtoff, d_nodeoff, d_gout, d_goff, d_ilen, d_target}, ST_ASSEMBLE));
 
+	lap("graphs + assemble");
 	// results to the host
 	std::vector<int32_t> h_segread((size_t)NS), h_segbeg((size_t)NS), h_segend((size_t)NS), h_tlen((size_t)NS), h_gerr((size_t)NG);
 	std::vector<int64_t> h_tgtoff((size_t)NS + 1);
@@ -500,9 +517,11 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 			be.fail(msg);
 			return 1;
 		}
+	lap("downloads");
 	for (int64_t S = 0; S < NS; ++S)
 		if ((int64_t)h_tlen[S] >= P.min_size)
 			emit_piece(out, in.h_read_id[h_segread[S]], h_segbeg[S], h_segend[S], h_target.data() + h_tgtoff[S], (size_t)h_tlen[S]);
+	lap("emit pieces");
 #undef CNS_TRY
 #undef CNS_ALLOC
 	return 0;
