@@ -31,12 +31,13 @@ constexpr int DIRW = 12;                  // ballot words per row (band <= 2*180
 constexpr int MAXROWS = 400;
 constexpr uint32_t NO_ANCHOR = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int IDLE = -0x7fffffff - 1;     // x + y of a lane without a cell (see extend.cu)
 
 struct WarpSmem
 {
 	uint2 sq[SEQ_WORDS];
 	uint2 st[SEQ_WORDS];
-	uint2 vl[2][VL_N];
+	uint2 vl[2 * VL_N];       // index k + KOFF: .x = furthest x on diagonal k, .y = packed anchor (interleaved parities, as in extend.cu)
 	uint32_t path[(MAXROWS + 31) / 32 + 1];   // recovered path: bit d = edit d came from diagonal k+1
 };
 
@@ -124,7 +125,6 @@ k_align(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 				tol = dtrunc_mul(0.3, qblk);
 				max_d = (int)__dmul_rn(__dmul_rn(2.0, err), (double)(qblk + tblk));
 			}
-			const int endsum = min(qblk, tblk);
 
 			__syncwarp();
 			{
@@ -137,7 +137,7 @@ k_align(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 					const uint32_t b0 = T.g0 + (uint32_t)ti + 16u * i;
 					S.st[i] = make_uint2(ld_bases32(T.arr, b0) ^ T.comp, ld_bases32(T.arr, b0 + 16u) ^ T.comp);
 				}
-				if (lane == 0) S.vl[1][(KOFF + 1) >> 1] = make_uint2(0u, NO_ANCHOR);
+				if (lane == 0) S.vl[KOFF + 1] = make_uint2(0u, NO_ANCHOR);
 			}
 			__syncwarp();
 
@@ -149,73 +149,107 @@ k_align(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 			uint32_t ea = NO_ANCHOR;
 			const uint2* sq = S.sq;
 			const uint2* st = S.st;
+			// one furthest-reaching cell (extend.cu's): lane-local, reads the other parity's neighbours, writes its own slot
+			auto cell = [&](uint2* own, int j, int n, int k, uint32_t dbits, int& x, uint32_t& anc, bool& from_right) {
+				const uint2 lf = own[2 * j - 1], rt = own[2 * j + 1];
+				from_right = (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x));
+				if (from_right) { x = (int)rt.x; anc = rt.y; }
+				else { x = (int)lf.x + 1; anc = lf.y; }
+				int y = x - k;
+				const int x1 = x;
+				for (;;) {
+					const uint32_t diff = seq16(sq, x) ^ seq16(st, y);
+					const int m = __clz(__brev(diff)) >> 1;
+					x += m; y += m;
+					if (m < 16 || x >= qblk || y >= tblk) break;
+				}
+				const int over = max(max(x - qblk, y - tblk), 0);
+				x -= over; y -= over;
+				if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
+				own[2 * j] = make_uint2((uint32_t)x, anc);
+				return x + y;
+			};
 			for (int d = 0; d < max_d; ++d) {
 				if (max_k - min_k > 2 * tol) break;
 				const int n = ((max_k - min_k) >> 1) + 1;
-				const int kk0 = min_k + KOFF;
-				uint2* own = &S.vl[kk0 & 1][kk0 >> 1];
-				const uint2* oth = &S.vl[(kk0 & 1) ^ 1][(kk0 - 1) >> 1];
+				uint2* own = &S.vl[min_k + KOFF];
 				const uint32_t dbits = (uint32_t)d << 20;
-				int rowmax = -1;
-				if (lane == 0) rowmin[d] = (short)min_k;
-				for (int base = 0; base < n; base += 32) {
-					const int j = base + lane;
-					int u = -1;
-					bool from_right = false;
-					if (j < n) {
-						const int k = min_k + 2 * j;
-						const uint2 lf = oth[j], rt = oth[j + 1];
-						int x;
-						uint32_t anc;
-						from_right = (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x));
-						if (from_right) { x = (int)rt.x; anc = rt.y; }
-						else { x = (int)lf.x + 1; anc = lf.y; }
-						int y = x - k;
-						const int x1 = x;
-						while (x < qblk && y < tblk) {
-							const uint32_t diff = seq16(sq, x) ^ seq16(st, y);
-							const int m = __clz(__brev(diff)) >> 1;
-							x += m; y += m;
-							if (m < 16) break;
-						}
-						const int over = max(max(x - qblk, y - tblk), 0);
-						x -= over; y -= over;
-						if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
-						own[j] = make_uint2((uint32_t)x, anc);
-						u = x + y;
+				uint32_t* dirrow = rowdir + d * DIRW;
+				// pass 0 and 1 keep their cells in registers (most rows have no further pass)
+				int x0 = 0, u0 = IDLE, x1 = 0, u1 = IDLE;
+				uint32_t a0 = NO_ANCHOR, a1 = NO_ANCHOR;
+				bool fr = false;
+				if (lane < n) u0 = cell(own, lane, n, min_k + 2 * lane, dbits, x0, a0, fr);
+				unsigned dm = __ballot_sync(FULL, fr);
+				if (lane == 0) { rowmin[d] = (short)min_k; dirrow[0] = dm; }
+				int rowmax = __reduce_max_sync(FULL, u0);
+				if (n > 32) {
+					fr = false;
+					if (lane + 32 < n) u1 = cell(own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1, fr);
+					dm = __ballot_sync(FULL, fr);
+					if (lane == 0) dirrow[1] = dm;
+					rowmax = max(rowmax, __reduce_max_sync(FULL, u1));
+					for (int base = 64; base < n; base += 32) {
+						const int j = base + lane;
+						int xx = 0, uu = IDLE;
+						uint32_t aa = NO_ANCHOR;
+						fr = false;
+						if (j < n) uu = cell(own, j, n, min_k + 2 * j, dbits, xx, aa, fr);
+						dm = __ballot_sync(FULL, fr);
+						if (lane == 0) dirrow[base >> 5] = dm;
+						rowmax = max(rowmax, __reduce_max_sync(FULL, uu));
 					}
-					const unsigned dm = __ballot_sync(FULL, from_right);
-					if (lane == 0) rowdir[d * DIRW + (base >> 5)] = dm;
-					rowmax = max(rowmax, __reduce_max_sync(FULL, u));
 				}
 				__syncwarp();
-				if (rowmax >= endsum) {
-					for (int base = 0; base < n && !aligned; base += 32) {
-						const int j = base + lane;
-						uint2 c = make_uint2(0u, NO_ANCHOR);
-						bool h = false;
-						if (j < n) { c = own[j]; const int yy = (int)c.x - (min_k + 2 * j); h = (int)c.x >= qblk || yy >= tblk; }
-						const unsigned hm = __ballot_sync(FULL, h);
+				// x >= qblk needs x + y >= 2 qblk - k, y >= tblk needs x + y >= 2 tblk + k
+				if (rowmax >= min(2 * qblk - max_k, 2 * tblk + min_k)) {
+					unsigned hm = __ballot_sync(FULL, x0 >= qblk || u0 - x0 >= tblk);
+					if (hm) {
+						const int src = __ffs(hm) - 1;
+						ex = __shfl_sync(FULL, x0, src); ey = __shfl_sync(FULL, u0, src) - ex; ea = __shfl_sync(FULL, a0, src);
+						aligned = true;
+					} else if (n > 32) {
+						hm = __ballot_sync(FULL, x1 >= qblk || u1 - x1 >= tblk);
 						if (hm) {
 							const int src = __ffs(hm) - 1;
-							ex = __shfl_sync(FULL, (int)c.x, src);
-							ey = ex - (min_k + 2 * (base + src));
-							ea = __shfl_sync(FULL, c.y, src);
-							ed = d;
+							ex = __shfl_sync(FULL, x1, src); ey = __shfl_sync(FULL, u1, src) - ex; ea = __shfl_sync(FULL, a1, src);
 							aligned = true;
 						}
+						for (int base = 64; base < n && !aligned; base += 32) {
+							const int j = base + lane;
+							uint2 c = make_uint2(0u, NO_ANCHOR);
+							bool h = false;
+							if (j < n) { c = own[2 * j]; const int yy = (int)c.x - (min_k + 2 * j); h = (int)c.x >= qblk || yy >= tblk; }
+							hm = __ballot_sync(FULL, h);
+							if (hm) {
+								const int src = __ffs(hm) - 1;
+								ex = __shfl_sync(FULL, (int)c.x, src);
+								ey = ex - (min_k + 2 * (base + src));
+								ea = __shfl_sync(FULL, c.y, src);
+								aligned = true;
+							}
+						}
 					}
-					if (aligned) break;
+					if (aligned) { ed = d; break; }
 				}
 				best_m = max(best_m, rowmax);
+				// re-band to the diagonals within `tol` of the best, widened by one
 				const int thr = best_m - tol;
 				int lo = 0x7fffffff, hi = -0x7fffffff;
-				for (int base = 0; base < n; base += 32) {
-					const int j = base + lane;
-					bool keep = false;
-					if (j < n) keep = 2 * (int)own[j].x - (min_k + 2 * j) >= thr;
-					const unsigned km = __ballot_sync(FULL, keep);
-					if (km) { lo = min(lo, min_k + 2 * (base + __ffs(km) - 1)); hi = max(hi, min_k + 2 * (base + 31 - __clz(km))); }
+				{
+					const unsigned km = __ballot_sync(FULL, u0 >= thr);
+					if (km) { lo = min_k + 2 * (__ffs(km) - 1); hi = min_k + 2 * (31 - __clz(km)); }
+				}
+				if (n > 32) {
+					const unsigned km = __ballot_sync(FULL, u1 >= thr);
+					if (km) { lo = min(lo, min_k + 2 * (32 + __ffs(km) - 1)); hi = max(hi, min_k + 2 * (32 + 31 - __clz(km))); }
+					for (int base = 64; base < n; base += 32) {
+						const int j = base + lane;
+						bool keep = false;
+						if (j < n) keep = 2 * (int)own[2 * j].x - (min_k + 2 * j) >= thr;
+						const unsigned km2 = __ballot_sync(FULL, keep);
+						if (km2) { lo = min(lo, min_k + 2 * (base + __ffs(km2) - 1)); hi = max(hi, min_k + 2 * (base + 31 - __clz(km2))); }
+					}
 				}
 				last_min = min_k; last_max = max_k; ++rows;
 				min_k = lo - 1; max_k = hi + 1;
@@ -223,14 +257,13 @@ k_align(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 			if (POLICY == 0 && !aligned && rows > 0) {
 				// pw flavour only: best (x+y) cell of the last completed row (diff_gapalign.cpp:197-216)
 				const int n = ((last_max - last_min) >> 1) + 1;
-				const int kk0 = last_min + KOFF;
-				const uint2* own = &S.vl[kk0 & 1][kk0 >> 1];
+				const uint2* own = &S.vl[last_min + KOFF];
 				for (int base = 0; base < n; base += 32) {
 					const int j = base + lane;
 					const int k = last_min + 2 * j;
 					uint2 c = make_uint2(0u, NO_ANCHOR);
 					bool is = false;
-					if (j < n) { c = own[j]; is = 2 * (int)c.x - k == best_m; }
+					if (j < n) { c = own[2 * j]; is = 2 * (int)c.x - k == best_m; }
 					const unsigned bm = __ballot_sync(FULL, is);
 					if (bm) {
 						const int src = __ffs(bm) - 1;

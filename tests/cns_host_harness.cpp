@@ -125,6 +125,56 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 
 void harness_free(void* p) { free(p); }
 
+// Unit check of the 32-positions-per-step anchor walk (anchor_chunk, what the GPU warps run) against the literal
+// sequential walk (walk_anchors, written after meap_consensus_one_segment) on one flag array.  Returns 0 when the
+// anchors, their ranks, the refine intervals, their ordinals and their chaining (prev_se) all agree.
+int harness_anchor_compare(const uint8_t* flags, int n, int beg)
+{
+	struct Ival { int i, j; bool refine; };
+	std::vector<Ival> want;
+	mbcns::walk_anchors(flags, n, [&](int i, int j, bool refine) { want.push_back(Ival{i, j, refine}); });
+	struct Seen { int pos, rank, prevpos, ordinal, prev_se; bool closes; };
+	std::vector<Seen> got;
+	mbcns::EmuLanes lanes;
+	mbcns::AnchorCarry c;
+	for (int base = 0; base < n; base += 32)
+		mbcns::anchor_chunk(lanes, base, n, beg, [&](int p) { return (int)flags[p]; }, c,
+		                    [&](int, int pos, int rank, int prevpos, bool closes, int ordinal, int prev_se) {
+			got.push_back(Seen{pos, rank, prevpos, ordinal, prev_se, closes});
+		});
+	if (got.size() != want.size()) return 1;
+	if ((int)want.size() != c.nanchors) return 2;
+	int regions = 0, last_se = -1;
+	for (size_t a = 0; a < want.size(); ++a) {
+		const Seen& g = got[a];
+		if (g.pos != want[a].i || g.rank != (int)a) return 3;
+		if (g.prevpos != (a ? want[a - 1].i : -1)) return 4;
+		const bool closes = a > 0 && want[a - 1].refine;          // the interval that ends at this anchor
+		if (g.closes != closes) return 5;
+		if (g.ordinal != regions) return 6;
+		if (g.prev_se != last_se) return 7;
+		if (closes) { ++regions; last_se = beg + g.pos; }
+	}
+	const bool tail = !want.empty() && want.back().refine;        // the interval from the last anchor to the end
+	if ((c.last_anchor >= 0 && c.pending) != tail) return 8;
+	if (c.nregions != regions || c.last_se_abs != last_se) return 9;
+	if (!want.empty() && c.last_anchor != want.back().i) return 10;
+	return 0;
+}
+
+// The 32-positions-per-step run search (find_segments with lanes) against the literal one.
+int harness_segments_compare(const uint32_t* votes, const int32_t* ranges, int nranges, int min_cov, double size95)
+{
+	std::vector<mbcns::Range> e((size_t)nranges);
+	for (int k = 0; k < nranges; ++k) { e[k].start = ranges[2 * k]; e[k].end = ranges[2 * k + 1]; }
+	const int cap = 4096;
+	std::vector<int32_t> a(2 * cap, -1), b(2 * cap, -1);
+	const int na = mbcns::find_segments(e.data(), nranges, votes, min_cov, size95, a.data(), cap);
+	const int nb = mbcns::find_segments(mbcns::EmuLanes(), e.data(), nranges, votes, min_cov, size95, b.data(), cap);
+	if (na != nb) return 1;
+	return a == b ? 0 : 2;
+}
+
 // Unit check of the fused single-pass kernel body (normalize_vote_index) against the three literal restatements
 // (normalize_gaps, add_votes, column_index) on one gapped alignment.  Returns 0 when every output agrees.
 int harness_normalize_compare(const char* q, const char* t, int n, int soff, int positions)

@@ -233,3 +233,45 @@ def test_fused_normalise_vote_kernel_body_matches_literal_restatement():
         positions = sum(1 for c in t if c != ord("-")) + 2
         rc = H.harness_normalize_compare(bytes(q), bytes(t), n, 1, positions)
         assert rc == 0, (trial, rc, bytes(q), bytes(t))
+
+
+def test_lane_parallel_anchor_walk_matches_sequential_walk():
+    """anchor_chunk (32 positions per step: previous anchor, refine interval, ordinals from bit masks and popcounts)
+    against the literal walk of meap_consensus_one_segment on random flag arrays of every density."""
+    H = util.cns_harness()
+    rng = np.random.default_rng(11)
+    FMAT, FDEL, FINS, UNDS = 1, 2, 4, 8
+    for trial in range(600):
+        n = int(rng.integers(1, 300)) if trial % 3 else int(rng.integers(1, 70))
+        p_anchor = rng.choice([0.0, 0.02, 0.3, 0.8, 0.97, 1.0])
+        p_prob = rng.choice([0.0, 0.05, 0.3, 0.9])
+        f = np.zeros(n, dtype=np.uint8)
+        for i in range(n):
+            if rng.random() < p_anchor:
+                f[i] = FMAT | (FDEL if rng.random() < p_prob else 0)
+            else:
+                f[i] = (UNDS if rng.random() < p_prob else FINS) | (FDEL if rng.random() < p_prob / 2 else 0)
+        rc = H.harness_anchor_compare(f.ctypes.data_as(C.c_void_p), n, int(rng.integers(0, 1000)))
+        assert rc == 0, (trial, rc, f.tolist())
+
+
+def test_lane_parallel_segment_search_matches_sequential_search():
+    H = util.cns_harness()
+    rng = np.random.default_rng(12)
+    for trial in range(300):
+        n = int(rng.integers(1, 600))
+        votes = np.zeros(n + 2, dtype=np.uint32)
+        level, i = 0, 0
+        while i < n:                                            # piecewise-constant coverage with short dips
+            run = int(rng.integers(1, 80))
+            level = int(rng.integers(0, 9))
+            mat = int(rng.integers(0, level + 1))
+            votes[i:i + run] = mat | ((level - mat) << 8) | (int(rng.integers(0, 5)) << 16)
+            i += run
+        cuts = sorted(set(int(x) for x in rng.integers(0, n + 1, size=int(rng.integers(2, 8)))))
+        ranges = np.array([[a, b] for a, b in zip(cuts[:-1], cuts[1:])][::2], dtype=np.int32).reshape(-1, 2)
+        if len(ranges) == 0:
+            continue
+        rc = H.harness_segments_compare(votes.ctypes.data_as(C.c_void_p), ranges.ctypes.data_as(C.c_void_p), len(ranges),
+                                        int(rng.integers(1, 8)), float(rng.choice([0.5, 1.0, 3.0, 20.0, 57.0])))
+        assert rc == 0, (trial, rc)

@@ -134,6 +134,10 @@ def cns_harness():
     L.harness_cns_batch.argtypes = [C.c_int, vp, vp, vp, C.c_char_p, C.c_char_p, vp, C.POINTER(vp), C.POINTER(C.c_size_t),
                                     C.POINTER(vp), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
     L.harness_free.argtypes = [vp]
+    L.harness_anchor_compare.restype = C.c_int
+    L.harness_anchor_compare.argtypes = [vp, C.c_int, C.c_int]
+    L.harness_segments_compare.restype = C.c_int
+    L.harness_segments_compare.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     L.harness_normalize_compare.restype = C.c_int
     L.harness_normalize_compare.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
     _harness = L
