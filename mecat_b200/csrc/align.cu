@@ -512,8 +512,11 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 		if (used > c->align_arena) MB_FAIL(c, "align_batch: %zu tasks need more than the %zu-byte column arena", nb, c->align_arena);
 		MB_CUDA(c, c->alloc(&d_dir, nwarps * MAXROWS * DIRW));
 		MB_CUDA(c, c->alloc(&d_min, nwarps * MAXROWS));
-		MB_CUDA(c, c->dmalloc((void**)&d_colq, c->align_arena));      // fixed size: the pool hands the same block back
-		MB_CUDA(c, c->dmalloc((void**)&d_colt, c->align_arena));
+		size_t arena = 256ull << 20;                       // power-of-two sizes: the pool hands the same block back batch after batch
+		while (arena < used + 16) arena <<= 1;
+		arena = std::min(arena, std::max(c->align_arena, used + 16));
+		MB_CUDA(c, c->dmalloc((void**)&d_colq, arena));
+		MB_CUDA(c, c->dmalloc((void**)&d_colt, arena));
 		MB_CUDA(c, c->alloc(&d_tasks, nb));
 		MB_CUDA(c, c->alloc(&d_slots, 2 * nb));
 		MB_CUDA(c, c->alloc(&out->d_info, 8 * nb));

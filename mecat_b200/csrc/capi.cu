@@ -366,7 +366,8 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	const bool debug = getenv("MECAT_CNS_DEBUG") != nullptr;
 	WallTimer t_prep;
 	std::vector<mecat_candidate> ec(ec_in, ec_in + nec);
-	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
+	auto by_sid = [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; };
+	if (!std::is_sorted(ec.begin(), ec.end(), by_sid)) std::stable_sort(ec.begin(), ec.end(), by_sid);
 	struct Group { size_t b, e; };
 	std::vector<Group> groups;
 	for (size_t i = 0; i < nec;) {
@@ -381,7 +382,7 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	}
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
-	std::vector<mbcns::Piece> all;
+	CnsBlob all;
 	const size_t TASKS_PER_BATCH = 240000;
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;
@@ -428,21 +429,17 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 		g0 = g1;
 	}
 	WallTimer t_out;
-	size_t bytes = 0;
-	for (auto& pc : all) bytes += pc.seq.size();
-	mecat_cns_piece* out = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (all.size() ? all.size() : 1));
-	char* sq = (char*)malloc(bytes + 1);
-	if (!out || !sq) { free(out); free(sq); MB_FAIL(c, "cns_reads: out of host memory"); }
-	size_t at = 0;
-	for (size_t i = 0; i < all.size(); ++i) {
-		out[i].id = all[i].id; out[i].beg = all[i].beg; out[i].end = all[i].end; out[i].seq_offset = (int64_t)at; out[i].seq_len = (int64_t)all[i].seq.size();
-		memcpy(sq + at, all[i].seq.data(), all[i].seq.size());
-		at += all[i].seq.size();
-	}
+	if (all.oom) MB_FAIL(c, "cns_reads: out of host memory");
+	const size_t bytes = all.len, np = all.recs.size();
+	mecat_cns_piece* out = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (np ? np : 1));
+	char* sq = all.buf ? all.buf : (char*)malloc(1);
+	if (!out || !sq) { free(out); MB_FAIL(c, "cns_reads: out of host memory"); }
+	all.buf = nullptr;                       // the blob now belongs to the caller (mecat_b200_free)
+	if (np) memcpy(out, all.recs.data(), sizeof(mecat_cns_piece) * np);
 	sq[bytes] = 0;
-	c->stats.num_records += (int64_t)all.size();
+	c->stats.num_records += (int64_t)np;
 	if (debug) fprintf(stderr, "[cns_reads] result buffers: %.1f ms\n", t_out.stop());
-	*pieces = out; *npieces = all.size(); *seqs = sq; *seq_bytes = bytes;
+	*pieces = out; *npieces = np; *seqs = sq; *seq_bytes = bytes;
 	return 0;
 }
 

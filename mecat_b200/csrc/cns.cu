@@ -183,6 +183,15 @@ struct DevBackend
 		c->stats.d2h_bytes += (int64_t)(n * sizeof(T));
 		return check(cudaStreamSynchronize(c->stream), "kernel");
 	}
+	const char* download_staged(const char* d, size_t n)      // through the context's pinned staging buffer
+	{
+		void* h = nullptr;
+		if (!check(c->host_stage(3, n + 1, &h), "pinned staging")) return nullptr;
+		if (n && !check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream), "D2H")) return nullptr;
+		c->stats.d2h_bytes += (int64_t)n;
+		if (!check(cudaStreamSynchronize(c->stream), "kernel")) return nullptr;
+		return (const char*)h;
+	}
 	bool fill(void* d, int byte, size_t bytes) { return !bytes || check(cudaMemsetAsync(d, byte, bytes, c->stream), "memset"); }
 	template <class F> bool launch(int64_t n, const F& f, int stage)
 	{
@@ -201,11 +210,8 @@ struct DevBackend
 	bool launch_graphs(int64_t n, const mbcns::PoaFn& f, int stage)
 	{
 		if (n <= 0) return true;
-		static bool configured = false;
-		if (!configured) {
-			if (!check(cudaFuncSetAttribute(k_cns_poa, cudaFuncAttributeMaxDynamicSharedMemorySize, POA_POOL), "shared memory opt-in")) return false;
-			configured = true;
-		}
+		// per device, so per call (one host thread per GPU shares this code)
+		if (!check(cudaFuncSetAttribute(k_cns_poa, cudaFuncAttributeMaxDynamicSharedMemorySize, POA_POOL), "shared memory opt-in")) return false;
 		KScope ks(c, MECAT_K_CNS_ACCEPT + stage);
 		k_cns_poa<<<(unsigned)((n + POA_BLOCK - 1) / POA_BLOCK), POA_BLOCK, POA_POOL, c->stream>>>(f, n);
 		return check(cudaGetLastError(), "launch");
@@ -249,7 +255,7 @@ struct DevBackend
 
 }  // namespace
 
-int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, std::vector<mbcns::Piece>& out)
+int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, CnsBlob& out)
 {
 	DevBackend be{c, {}};
 	return mbcns::consensus_batch(be, in, P, out);

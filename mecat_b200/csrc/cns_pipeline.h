@@ -296,24 +296,29 @@ struct SegFlattenFn
 	}
 };
 
-// output_cns_result, mecat_correction.cpp:156-188 (host: splits pieces longer than 60 000 bases)
-inline void emit_piece(std::vector<Piece>& out, int64_t id, int64_t beg, int64_t end, const char* seq, size_t size)
+// output_cns_result, mecat_correction.cpp:156-188 (host: splits pieces longer than 60 000 bases).  Sink: add(id, beg, end, seq, len).
+template <class Sink>
+inline void emit_piece(Sink& out, int64_t id, int64_t beg, int64_t end, const char* seq, size_t size)
 {
 	const size_t MaxSeq = 60000, Ovlp = 10000, Blk = MaxSeq - Ovlp - 1000;
-	if (size <= MaxSeq) { out.push_back(Piece{id, beg, end, std::string(seq, size)}); return; }
+	if (size <= MaxSeq) { out.add(id, beg, end, seq, size); return; }
 	const size_t cutoff = size - Ovlp - 1000;
 	size_t L = 0, R;
 	do {
 		R = L + Blk;
 		if (R >= cutoff) R = size;
-		Piece p;
-		p.id = id; p.beg = (int64_t)L + beg;
-		p.end = (R < size && (int64_t)R + beg < end) ? (int64_t)R + beg : end;
-		p.seq.assign(seq + L, R - L);
-		out.push_back(p);
+		const int64_t pb = (int64_t)L + beg;
+		const int64_t pe = (R < size && (int64_t)R + beg < end) ? (int64_t)R + beg : end;
+		out.add(id, pb, pe, seq + L, R - L);
 		L = R - Ovlp;
 	} while (R < size);
 }
+
+struct PieceVector      // sink that keeps every piece as its own string (tests)
+{
+	std::vector<Piece> pieces;
+	void add(int64_t id, int64_t beg, int64_t end, const char* seq, size_t len) { pieces.push_back(Piece{id, beg, end, std::string(seq, len)}); }
+};
 
 // ---------------------------------------------------------------------------------------------- pipeline
 // Backend B:
@@ -323,11 +328,12 @@ inline void emit_piece(std::vector<Piece>& out, int64_t id, int64_t beg, int64_t
 //   template <class F> bool launch_warp(int64_t n, const F& f, int stage)   f(i, lanes), one warp per unit
 //   bool launch_graphs(int64_t n, const PoaFn& f, int stage)               the region graphs of one wave
 //   bool scan(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* total)   d_out[0..n] exclusive prefix, total on the host
+//   const char* download_staged(const char* d, size_t n)   bulk result bytes in a host buffer owned by the backend
 //   bool release(void* d)                            early free of an alloc() block (stream ordered)
 //   int64_t poa_budget_bytes()                       scratch budget of one wave of region graphs
 //   void fail(const char* msg), void end_batch()
-template <class B>
-int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece>& out)
+template <class B, class Sink>
+int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 {
 	struct Guard { B& b; ~Guard() { b.end_batch(); } } guard{be};
 	const int R = in.R;
@@ -502,13 +508,13 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	// results to the host
 	std::vector<int32_t> h_segread((size_t)NS), h_segbeg((size_t)NS), h_segend((size_t)NS), h_tlen((size_t)NS), h_gerr((size_t)NG);
 	std::vector<int64_t> h_tgtoff((size_t)NS + 1);
-	std::vector<char> h_target((size_t)TGT);
 	CNS_TRY(be.download(h_segread.data(), d_segread, (size_t)NS));
 	CNS_TRY(be.download(h_segbeg.data(), d_segbeg, (size_t)NS));
 	CNS_TRY(be.download(h_segend.data(), d_segend, (size_t)NS));
 	CNS_TRY(be.download(h_tlen.data(), d_tlen, (size_t)NS));
 	CNS_TRY(be.download(h_tgtoff.data(), d_tgtoff, (size_t)NS + 1));
-	CNS_TRY(be.download(h_target.data(), d_target, (size_t)TGT));
+	const char* h_target = be.download_staged(d_target, (size_t)TGT);      // valid until the batch ends
+	if (!h_target) return 1;
 	if (NG) CNS_TRY(be.download(h_gerr.data(), d_gerr, (size_t)NG));
 	for (int64_t g = 0; g < NG; ++g)
 		if (h_gerr[g]) {
@@ -520,7 +526,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, std::vector<Piece
 	lap("downloads");
 	for (int64_t S = 0; S < NS; ++S)
 		if ((int64_t)h_tlen[S] >= P.min_size)
-			emit_piece(out, in.h_read_id[h_segread[S]], h_segbeg[S], h_segend[S], h_target.data() + h_tgtoff[S], (size_t)h_tlen[S]);
+			emit_piece(out, in.h_read_id[h_segread[S]], h_segbeg[S], h_segend[S], h_target + h_tgtoff[S], (size_t)h_tlen[S]);
 	lap("emit pieces");
 #undef CNS_TRY
 #undef CNS_ALLOC

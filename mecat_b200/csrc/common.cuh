@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -212,10 +214,35 @@ int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume*
                 int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr);
 
 }  // namespace mb
-namespace mbcns { struct BatchIn; struct Params; struct Piece; }
+namespace mbcns { struct BatchIn; struct Params; }
 namespace mb {
+// Corrected pieces as the C ABI hands them out: records + one malloc'ed blob of bases that grows by doubling, so a
+// piece is copied exactly once on its way from the pinned staging buffer to the caller.
+struct CnsBlob
+{
+	std::vector<mecat_cns_piece> recs;
+	char* buf = nullptr;
+	size_t len = 0, cap = 0;
+	bool oom = false;
+	~CnsBlob() { free(buf); }
+	void add(int64_t id, int64_t beg, int64_t end, const char* seq, size_t n)
+	{
+		if (len + n + 1 > cap) {
+			size_t want = cap ? cap * 2 : (size_t)1 << 20;
+			while (want < len + n + 1) want *= 2;
+			char* nb = (char*)realloc(buf, want);
+			if (!nb) { oom = true; return; }
+			buf = nb; cap = want;
+		}
+		memcpy(buf + len, seq, n);
+		mecat_cns_piece r;
+		r.id = id; r.beg = beg; r.end = end; r.seq_offset = (int64_t)len; r.seq_len = (int64_t)n;
+		recs.push_back(r);
+		len += n;
+	}
+};
 // consensus stage of mecat2cns on the extension results of one batch (cns.cu)
-int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, std::vector<mbcns::Piece>& out);
+int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, CnsBlob& out);
 
 struct RawCand             // candidate_save, pw_impl.h:21-25
 {

@@ -33,6 +33,7 @@ struct HostBackend
 	}
 	template <class T> bool upload(T* d, const T* h, size_t n) { if (n) memcpy(d, h, n * sizeof(T)); return true; }
 	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
+	const char* download_staged(const char* d, size_t) { return d; }
 	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
 	template <class F> bool launch(int64_t n, const F& f, int) { for (int64_t i = 0; i < n; ++i) f(i); return true; }
 	template <class F> bool launch_warp(int64_t n, const F& f, int) { mbcns::EmuLanes one; for (int64_t i = 0; i < n; ++i) f(i, one); return true; }
@@ -102,8 +103,9 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	HostBackend be;
 	be.force_wide = getenv("MECAT_HARNESS_WIDE_GRAPHS") != nullptr;
-	std::vector<mbcns::Piece> out;
-	if (mbcns::consensus_batch(be, in, P, out)) {
+	mbcns::PieceVector sink;
+	std::vector<mbcns::Piece>& out = sink.pieces;
+	if (mbcns::consensus_batch(be, in, P, sink)) {
 		if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", be.err.c_str());
 		return 1;
 	}
