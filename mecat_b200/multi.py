@@ -77,7 +77,7 @@ def code_slices(world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def read_slices(world, num_reads, diagonal=True, seed_w=185.0, extend_w=454.0):
+def read_slices(world, num_reads, diagonal=True, seed_w=131.0, extend_w=417.0):
     """Split points of a tile's query reads.  In a diagonal tile (query volume == index volume) read q
     can only pair with reads <= q (pw_impl.cpp:370), so extension work grows linearly with the read
     ordinal while seeding work is flat: cost(x) = seed_w * x + extend_w * x^2 for the first fraction x
@@ -146,14 +146,26 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
     rb, re = read_slices(world, vol.num_reads)[rank]
     cuts = torch.tensor([c[0] for c in code_slices(world)] + [1 << 26], dtype=torch.int64, device=dev)
     resident = [None]
+    # index exchange: "allgather" = one padded all-gather of the position slices (all NVLink ports busy at once) followed by
+    # a device-side compaction; "broadcast" = one broadcast per slice (the first implementation, kept for comparison)
+    exchange = os.environ.get("MECAT_STRONG_EXCHANGE", "allgather")
+    phase = {"count": 0.0, "counts_allgather": 0.0, "finish": 0.0, "positions_exchange": 0.0, "tile": 0.0}
+
+    def lap(name, t0):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        phase[name] += (t1 - t0) * 1e3
+        return t1
 
     def one_step(e2e):
+        t0 = time.perf_counter()
         if e2e or resident[0] is None:
             if resident[0] is not None:
                 ctx.release_volume(resident[0])
             resident[0] = ctx.upload(hv)
         dvol = resident[0]
         idx = ctx.index_count_part(dvol, lo, hi)
+        t0 = lap("count", t0)
         cptr, bptr, _, _ = ctx.index_device_arrays(idx)
         counts = device_view(cptr, 1 << 26, torch.int32, 4)
         if world > 1:
@@ -164,19 +176,35 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
                 for q in range(world):
                     dist.broadcast(parts[q], src=q)
             torch.cuda.synchronize()
+        t0 = lap("counts_allgather", t0)
         ctx.index_finish_part(dvol, idx, lo, hi)
+        t0 = lap("finish", t0)
         if world > 1:
             _, bptr, pptr, nk = ctx.index_device_arrays(idx)
             begin = device_view(bptr, (1 << 26) + 1, torch.int32, 4)
             bounds = begin[cuts].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
             pos = device_view(pptr, nk, torch.int32, 4)
-            reqs = [dist.broadcast(pos[int(bounds[q]):int(bounds[q + 1])], src=q, async_op=True) for q in range(world)
-                    if bounds[q + 1] > bounds[q]]
-            for r in reqs:
-                r.wait()
+            sizes = [int(bounds[q + 1] - bounds[q]) for q in range(world)]
+            if exchange == "allgather" and max(sizes) > 0:
+                m = (max(sizes) + 63) // 64 * 64
+                send = torch.empty(m, dtype=torch.int32, device=dev)
+                send[:sizes[rank]] = pos[int(bounds[rank]):int(bounds[rank + 1])]
+                recv = torch.empty(world * m, dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(recv, send)
+                for q in range(world):
+                    if q != rank and sizes[q]:
+                        pos[int(bounds[q]):int(bounds[q + 1])] = recv[q * m:q * m + sizes[q]]
+                del send, recv
+            else:
+                reqs = [dist.broadcast(pos[int(bounds[q]):int(bounds[q + 1])], src=q, async_op=True) for q in range(world)
+                        if bounds[q + 1] > bounds[q]]
+                for r in reqs:
+                    r.wait()
             torch.cuda.synchronize()
+        t0 = lap("positions_exchange", t0)
         rec = ctx.pw_tile_range(idx, dvol, dvol, params, rb, re)
         ctx.release_index(idx)
+        lap("tile", t0)
         return len(rec)
 
     def timed(nsteps, e2e):
@@ -198,9 +226,12 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
         if rank == 0:
             log("warmup %d: %d pairs in %.3f s" % (i, n, dt))
     ctx.reset_stats()
+    for k in phase:
+        phase[k] = 0.0
     sampler = ClockSampler(local) if rank == 0 else None
     pairs, dt = timed(args.steps, False)
     stats = ctx.stats()
+    phase_ms = {k: round(v / args.steps, 3) for k, v in phase.items()}
     clocks = sampler.stop() if sampler else None
     esteps = max(1, min(args.steps, 3))
     ctx.reset_stats()
@@ -230,6 +261,7 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                              "sample": "measured at N=1 only (bench.py --gpus 1)"},
             "pairs_per_step": pairs // args.steps,
+            "phase_ms_per_step_rank0": phase_ms, "index_exchange": exchange,
             "kernel_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
         }
         print(json.dumps(line))
@@ -380,9 +412,12 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
         if rank == 0:
             log("warmup %d: %d pairs in %.2f s" % (i, n, dt))
     ctx.reset_stats()
+    for k in phase:
+        phase[k] = 0.0
     sampler = ClockSampler(local) if rank == 0 else None
     pairs, dt = timed(args.steps, False)
     stats = ctx.stats()
+    phase_ms = {k: round(v / args.steps, 3) for k, v in phase.items()}
     clocks = sampler.stop() if sampler else None
     esteps = max(1, min(args.steps, 2))
     ctx.reset_stats()
