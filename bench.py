@@ -194,7 +194,7 @@ def pinned_volume(vol):
     return hv
 
 
-def roofline_for(stats, peaks):
+def roofline_for(stats, peaks, nsteps=None):
     """Roofline entry for the dominant kernel of the timed steps."""
     km = stats["kernel_ms"]
     launches = stats["kernel_launches"]
@@ -204,22 +204,40 @@ def roofline_for(stats, peaks):
     H = stats["num_hits"]
     C = stats["num_candidates"]
     ncodes = 1 << 26
-    steps = max(1, launches["index_count"])
-    alg = {
-        # bytes the algorithm must move per launch
+    steps = nsteps or max(1, launches["index_scan"] // 3 or launches["index_count"])     # index builds in the timed region
+    algs = {
+        # bytes the algorithm must move, summed over the timed steps
         "index_count": B / 4 + 4.0 * K + 4.0 * ncodes * steps,            # packed bases in, one counter update per k-mer
         "index_fill": B / 4 + 4.0 * K + 8.0 * ncodes * steps,             # packed bases in, begin[] in, one position out per kept k-mer
         "index_sort": 8.0 * K + 4.0 * ncodes * steps,                     # positions in and out, begin[] in
         "index_scan": 12.0 * ncodes * steps,
         "seed": 3 * 4.0 * H + 0.0,                                        # three streaming passes over the hit positions
         "extend": C * (2 * 15000 / 4 + 52 + 32),                          # two packed reads in, one record out per candidate
-    }.get(name, 0.0)
+    }
+    alg = algs.get(name, 0.0)
     ms = km[name]
     achieved = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (bytes per step of
+    # the whole workload, profiles/ncu_traffic.json), scaled to one launch like `achieved`
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        per_step = t.get(name, {}).get("dram_bytes_per_step")
+        if per_step and launches[name]:
+            traffic = per_step * steps / launches[name]
+    except Exception:
+        pass
+    every = {}
+    for k, a in algs.items():
+        if km.get(k, 0) > 0:
+            g = a / (km[k] * 1e-3) / 1e9
+            every[k] = {"ms_per_step": round(km[k] / steps, 3), "algorithmic_gb_per_step": round(a / steps / 1e9, 3),
+                        "gbps": round(g, 1), "frac_of_hbm_peak": round(g / peak, 4) if peak else None}
     return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "traffic": None,
+            "frac": achieved / peak if peak else None, "traffic": traffic,
             "ms_per_launch": ms / max(1, launches[name]), "launches": launches[name],
+            "algorithmic_bytes_per_launch": alg / max(1, launches[name]), "all_kernels": every,
             "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
             "kernel_ms_share": {k: round(v / max(1e-9, sum(km.values())), 4) for k, v in km.items() if v > 0}}
 
@@ -308,7 +326,7 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = roofline_for(stats, peaks)
+    roof = roofline_for(stats, peaks, args.steps)
     cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "skipped (--no-cpu)"}
     if not args.no_cpu:
         cp, cdt, cores, desc, kind = cpu_sample()

@@ -257,7 +257,7 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
             "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()) // esteps,
                     "d2h_bytes_per_step": int(io[1].item()) // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
             "gpu_launches": stats["gpu_launches"] * world,
-            "roofline": roofline_for(stats, peaks),
+            "roofline": roofline_for(stats, peaks, args.steps),
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                              "sample": "measured at N=1 only (bench.py --gpus 1)"},
             "pairs_per_step": pairs // args.steps,
