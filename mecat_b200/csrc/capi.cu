@@ -383,7 +383,7 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	CnsBlob all;
-	const size_t TASKS_PER_BATCH = 240000;
+	const size_t TASKS_PER_BATCH = 400000;       // with the column arena (12 GB at ~30 kB per task) this bounds a batch; more units per launch suit the latency-bound stages
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;
 	std::vector<int64_t> rid;

@@ -594,6 +594,21 @@ def test_command_line_drivers_match_reference(gpu_ctx, tmp_path):
         assert open(out2).read() == open(out1).read()
 
 
+def test_cns_degenerate_inputs(gpu_ctx, small_vol):
+    """No candidates, and candidates that no read can use (coverage gate above every read's candidate count / no read
+    long enough): an empty result, not an error."""
+    import mecat_b200
+    d = gpu_ctx.upload(host_volume(small_vol))
+    can = _gold_can("small")
+    empty = mecat_b200.normalise_candidates(can[:0], 2000)
+    assert gpu_ctx.cns_reads(d, empty, 0.9, 1000, 4, 2000) == []
+    ec = mecat_b200.normalise_candidates(can, 2000)
+    assert gpu_ctx.cns_reads(d, ec, 0.9, 1000, 1000, 2000) == []          # -c 1000: no read has that many candidates
+    assert gpu_ctx.cns_reads(d, ec, 0.9, 1000, 4, 10 ** 6) == []          # -l 1e6: no read is long enough
+    assert gpu_ctx.cns_reads(d, ec, 0.9, 10 ** 6, 4, 2000) == []          # -a 1e6: no alignment is accepted
+    gpu_ctx.release_volume(d)
+
+
 def test_cns_consensus_runs_on_the_gpu(gpu_ctx, small_vol):
     """The consensus stages (accept, normalise/vote, segments, regions, graphs, assembly) are kernel launches."""
     gpu_ctx.reset_stats()

@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=20000)
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--tasks", type=int, default=40000)
     a = ap.parse_args()
     import mecat_b200
     import util
@@ -40,6 +41,7 @@ def main():
         # extension point in strand orientation, like pairwise_mapping / consensus_one_read_can_pacbio
         tasks["qstart"] = np.where(ec["qdir"] == 1, ec["qsize"] - 1 - ec["qext"], ec["qext"])
         tasks["sstart"] = ec["sext"]
+        tasks = np.ascontiguousarray(tasks[:a.tasks])          # the string blobs of one call must stay below 2 GiB for ctypes
         out["tasks"] = int(len(tasks))
         for policy, name, min_aln in ((0, "policy0_pw_ref_strings", 1000), (1, "policy1_cns_strings", 2000)):
             best = None
