@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(128) k_cns_warp(const F f, const int64_t n)
 // The region graphs of one wave, a thread per region.  A graph is pointer chasing over a few hundred bytes of nodes
 // and edges; in global memory every step of it is an L2 / DRAM round trip (ncu: 14 KB of DRAM traffic per region for
 // a 2 KB arena, long-scoreboard bound).  So the CTA owns a pool of shared memory: each thread asks for the bytes its
-// graph needs with 16-bit indices, a CTA-wide scan hands out slices, and the threads whose slice fits build their
+// graph needs with the narrowest index type that holds it (8 bits for most), a CTA-wide scan hands out slices, and the threads whose slice fits build their
 // graph there; the rest wait for the next round of the same pool.  Only graphs too large for the pool (or for 16-bit
 // indices) use their exact-size arena in global memory.
-constexpr int POA_BLOCK = 128;
-constexpr int POA_POOL = 108 * 1024;       // two CTAs per SM
+constexpr int POA_BLOCK = 192;
+constexpr int POA_POOL = 108 * 1024;       // two CTAs per SM; ~0.5 KB per graph with 8-bit indices
 
 __global__ void __launch_bounds__(POA_BLOCK) k_cns_poa(const mbcns::PoaFn f, const int64_t n)
 {
@@ -57,13 +57,14 @@ __global__ void __launch_bounds__(POA_BLOCK) k_cns_poa(const mbcns::PoaFn f, con
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int64_t k = (int64_t)blockIdx.x * POA_BLOCK + tid;
 	bool pending = k < n;
-	int need = 0;
+	int need = 0, width = 4;
 	if (pending) {
 		int ncap, e0;
 		f.shape(k, ncap, e0);
-		const int64_t b = mbcns::PoaFn::small(ncap, e0) ? mbcns::poa_arena_bytes<int16_t>(ncap, e0) : (int64_t)POA_POOL + 1;
+		width = mbcns::PoaFn::width(ncap, e0);
+		const int64_t b = mbcns::PoaFn::bytes_for(width, ncap, e0);
 		if (b > POA_POOL) {                  // too large for the pool: its own global arena
-			if (mbcns::PoaFn::small(ncap, e0)) f.solve<int16_t>(k, f.wide_arena(k)); else f.solve<int32_t>(k, f.wide_arena(k));
+			f.solve_width(width, k, f.wide_arena(k));
 			pending = false;
 		} else need = (int)b;
 	}
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(POA_BLOCK) k_cns_poa(const mbcns::PoaFn f, con
 		int off = inc - v;
 		for (int w = 0; w < warp; ++w) off += wsum[w];
 		if (pending && off + need <= POA_POOL) {
-			f.solve<int16_t>(k, pool + off);
+			f.solve_width(width, k, pool + off);
 			pending = false;
 		}
 		__syncthreads();                     // the pool and wsum are reused by the next round

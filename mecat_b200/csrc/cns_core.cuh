@@ -564,8 +564,9 @@ CNS_HD inline bool kept_slice(const KeptAln& a, int sb, int se, int prev_se, Sli
 // AlnGraphBoost on flat arrays.  Adjacency lists are intrusive doubly linked lists threaded through the edges,
 // which gives the iteration orders of boost::adjacency_list<vecS, vecS, bidirectionalS> (insertion order,
 // order-preserving removal) that the tie-breaks of the best-path search depend on.
-// The index type I is int32_t in general and int16_t for graphs small enough (the common case), which halves the
-// scratch so that it fits the shared-memory pool of the graph kernel (cns.cu).
+// The index type I is int32_t in general, int16_t for graphs below 30 000 nodes / edge slots and int8_t for graphs below
+// 120 (the common case: ~8 nodes, ~34 edge slots), which shrinks the scratch of a graph to ~0.5 KB so that a few hundred
+// of them fit the shared-memory pool of the graph kernel (cns.cu).
 template <class I> struct PoaNodeT
 {
 	I coverage, weight, bb;                    // bb: _bbMap (node -> backbone node, 0 when never set)
@@ -579,8 +580,8 @@ template <class I> struct PoaEdgeT
 	I in_next, in_prev;                        // position in v's in-list
 	I out_next, out_prev;                      // position in u's out-list
 };
-static_assert(sizeof(PoaNodeT<int16_t>) == 20 && sizeof(PoaNodeT<int32_t>) == 40, "node layout");
-static_assert(sizeof(PoaEdgeT<int16_t>) == 16 && sizeof(PoaEdgeT<int32_t>) == 32, "edge layout");
+static_assert(sizeof(PoaNodeT<int8_t>) == 11 && sizeof(PoaNodeT<int16_t>) == 20 && sizeof(PoaNodeT<int32_t>) == 40, "node layout");
+static_assert(sizeof(PoaEdgeT<int8_t>) == 8 && sizeof(PoaEdgeT<int16_t>) == 16 && sizeof(PoaEdgeT<int32_t>) == 32, "edge layout");
 
 // Scratch of one graph with N nodes and E0 edge creations before merging (region_demand): edge slots, queue/stack
 // slots, and the bytes of the whole arena laid out as [score float N | nodes N | edges | queue+stack | best edge N].
@@ -594,6 +595,8 @@ template <class I> CNS_HD inline int64_t poa_arena_bytes(int64_t nodes, int64_t 
 }
 // poa_arena_bytes<int32_t> is linear: 112 nodes + 32 e0 + 320 (the prefix sums of nodes and e0 locate every arena)
 constexpr int POA_SMALL_LIMIT = 30000;     // nodes and edge slots below this -> int16_t indices are safe
+constexpr int POA_TINY_LIMIT = 120;        // ... and below this int8_t ones (every count in a graph is bounded by its edge slots)
+constexpr int POA_NO_BASE = -128;          // "no base processed yet" marker of the merge stack: below every base character, fits int8_t
 
 enum { POA_OK = 0, POA_ERR_EDGES = 1, POA_ERR_QUEUE = 2, POA_ERR_STACK = 3, POA_ERR_EMPTY_LIST = 4, POA_ERR_NODES = 5 };
 
@@ -750,7 +753,7 @@ struct PoaT
 			if (sp + 2 > auxcap) { fail(POA_ERR_STACK); return; }
 			const int entries = sp - begin;
 			aux[sp++] = (I)entries;
-			aux[sp++] = (I)-1000;          // last base done
+			aux[sp++] = (I)POA_NO_BASE;    // last base done
 		};
 		push_frame(n0);
 		while (sp > sp0 && !err) {
@@ -795,7 +798,7 @@ struct PoaT
 			const int v = ed[e].v;
 			if (nd[v].in_cnt == 1) { if (sp0 + cnt + 1 > auxcap) { fail(POA_ERR_STACK); return; } list[cnt++] = (I)v; }
 		}
-		int last = -1000;
+		int last = POA_NO_BASE;
 		for (;;) {
 			const int b = next_base(list, cnt, last);
 			if (b < 0 || err) break;

@@ -206,7 +206,20 @@ struct PoaFn
 		const int64_t g = g_base + k;
 		return arena + 112 * (node_off[g] - n_base) + 32 * (edge0_off[g] - e_base) + 320 * k;
 	}
-	CNS_HD static bool small(int ncap, int e0) { return ncap < POA_SMALL_LIMIT && poa_edge_cap(ncap, e0) < POA_SMALL_LIMIT; }
+	// index width a graph of this shape needs: 1 (int8_t), 2 (int16_t) or 4 (int32_t) bytes
+	CNS_HD static int width(int ncap, int e0)
+	{
+		const int64_t m = ncap > poa_edge_cap(ncap, e0) ? ncap : poa_edge_cap(ncap, e0);
+		return m < POA_TINY_LIMIT ? 1 : m < POA_SMALL_LIMIT ? 2 : 4;
+	}
+	CNS_HD static int64_t bytes_for(int w, int ncap, int e0)
+	{
+		return w == 1 ? poa_arena_bytes<int8_t>(ncap, e0) : w == 2 ? poa_arena_bytes<int16_t>(ncap, e0) : poa_arena_bytes<int32_t>(ncap, e0);
+	}
+	CNS_HD void solve_width(int w, int64_t k, char* scratch) const
+	{
+		if (w == 1) solve<int8_t>(k, scratch); else if (w == 2) solve<int16_t>(k, scratch); else solve<int32_t>(k, scratch);
+	}
 	// the graph of the wave's k-th region with index type I in the given scratch
 	template <class I>
 	CNS_HD void solve(int64_t k, char* scratch) const
@@ -219,12 +232,14 @@ struct PoaFn
 		                              (int)poa_edge_cap(ncap, e0), gout + node_off[g], off, len);
 		goff[g] = off; glen[g] = len;
 	}
-	// a thread per region entirely in its global arena (the GPU kernel prefers shared memory, cns.cu: k_cns_poa)
-	CNS_HD void operator()(int64_t k) const
+	// a thread per region entirely in its global arena (the GPU kernel prefers shared memory, cns.cu: k_cns_poa);
+	// min_width lets tests force wider indices than the graph needs
+	CNS_HD void operator()(int64_t k, int min_width = 1) const
 	{
 		int ncap, e0;
 		shape(k, ncap, e0);
-		if (small(ncap, e0)) solve<int16_t>(k, wide_arena(k)); else solve<int32_t>(k, wide_arena(k));
+		const int w = width(ncap, e0);
+		solve_width(w > min_width ? w : min_width, k, wide_arena(k));
 	}
 };
 

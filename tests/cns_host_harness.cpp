@@ -40,12 +40,10 @@ struct HostBackend
 	// graphs: narrow (int16_t) indices where the product uses them, or wide everywhere when a test asks for it
 	bool launch_graphs(int64_t n, const mbcns::PoaFn& f, int)
 	{
-		for (int64_t k = 0; k < n; ++k) {
-			if (force_wide) f.solve<int32_t>(k, f.wide_arena(k)); else f(k);
-		}
+		for (int64_t k = 0; k < n; ++k) f(k, min_width);
 		return true;
 	}
-	bool force_wide = false;
+	int min_width = 1;
 	bool scan(const int32_t* in, int64_t* out, int64_t n, int64_t* total)
 	{
 		int64_t s = 0;
@@ -102,7 +100,7 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	HostBackend be;
-	be.force_wide = getenv("MECAT_HARNESS_WIDE_GRAPHS") != nullptr;
+	if (const char* e = getenv("MECAT_HARNESS_GRAPH_INDEX_BYTES")) be.min_width = atoi(e);      // 2 or 4: wider indices than needed
 	mbcns::PieceVector sink;
 	std::vector<mbcns::Piece>& out = sink.pieces;
 	if (mbcns::consensus_batch(be, in, P, sink)) {

@@ -156,9 +156,11 @@ def compare(got, want):
                 % (len(got), len(want), only_g[:5], only_w[:5], diff[:5]))
 
 
-def test_kernel_bodies_with_wide_graph_indices(small_vol, monkeypatch):
-    """The region graphs with 32-bit indices everywhere (the GPU uses them for graphs too large for 16-bit ones)."""
-    monkeypatch.setenv("MECAT_HARNESS_WIDE_GRAPHS", "1")
+@pytest.mark.parametrize("index_bytes", ["2", "4"])
+def test_kernel_bodies_with_wider_graph_indices(small_vol, monkeypatch, index_bytes):
+    """The region graphs are templated on their index type: 8-bit for the common tiny graph, 16- and 32-bit for larger
+    ones.  Forcing the wider types on every graph must give the same corrected reads."""
+    monkeypatch.setenv("MECAT_HARNESS_GRAPH_INDEX_BYTES", index_bytes)
     compare(correct_with_kernel_bodies(small_vol, gold_can("small"), 0.9, 1000, 4, 2000), gold_fasta("small", "cns_relaxed"))
 
 
