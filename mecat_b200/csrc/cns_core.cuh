@@ -308,15 +308,16 @@ struct ByteSink            // forward-only writer, 8 bytes per store; the destin
 CNS_HD inline int normalize_vote_index(const char* q0, const char* t0, int n, int soff0, char* nq, char* nt, uint32_t* votes,
                                        char* base, int32_t* colidx, int* tend)
 {
-	ByteWindow mq, mt, wq, wqt, wt;
-	mq.open(q0); mt.open(t0); wq.open(q0); wqt.open(t0); wt.open(t0);
-	// heads: next unplaced base of q (column jq, half hq, character bq) and of t (column jt, half 0, character bt)
-	int jq = 0, jt = 0, hq = 0;
+	ByteWindow mq, mt, wq, wt;
+	mq.open(q0); mt.open(t0); wq.open(q0); wt.open(t0);
+	// heads: next unplaced base of q (column jq, character bq; it sits in the LAST half of its column) and of t
+	// (column jt, character bt; first half)
+	int jq = 0, jt = 0;
 	char bq = 0, bt = 0;
 	auto seek_q = [&](int from) {
 		for (jq = from; jq < n; ++jq) {
 			const char c = wq.get(jq);
-			if (c != '-') { const char o = wqt.get(jq); bq = c; hq = (o != '-' && o != c) ? 1 : 0; return; }
+			if (c != '-') { bq = c; return; }
 		}
 		bq = 0;
 	};
@@ -333,35 +334,40 @@ CNS_HD inline int normalize_vote_index(const char* q0, const char* t0, int n, in
 	int soff = soff0, cp = soff0;
 	bool in_del_run = false;
 	colidx[0] = 0;
-	int i = 0;                                   // expanded column
-	for (int i0 = 0; i0 < n; ++i0) {
-		const char a = mq.get(i0), b = mt.get(i0);
-		const int halves = (a != b && a != '-' && b != '-') ? 2 : 1;
-		for (int h = 0; h < halves; ++h, ++i) {
-			const bool last = i0 == n - 1 && h == halves - 1;
-			const bool q_here = jq == i0 && hq == h, t_here = jt == i0 && h == 0;
-			char qc = q_here ? bq : '-', tc = t_here ? bt : '-';
-			if (!last) {
-				if (!t_here && q_here) {
-					if (jt < n && bt == qc) { tc = qc; seek_t(jt + 1); }
-				} else if (!q_here && t_here) {
-					if (jq < n && bq == tc) { qc = tc; seek_q(jq + 1); }
-				}
+	// One expanded column per iteration (a mismatch column takes two), so that the 32 alignments a warp works on all do
+	// useful work in every iteration even though their columns differ.
+	int i = 0, i0 = 0, h = 0, halves = 1;        // expanded column, original column, half, halves of the original column
+	char a = 0, b = 0;
+	if (n > 0) { a = mq.get(0); b = mt.get(0); halves = (a != b && a != '-' && b != '-') ? 2 : 1; }
+	while (i0 < n) {
+		const bool last = i0 == n - 1 && h == halves - 1;
+		const bool q_here = jq == i0 && h == halves - 1, t_here = jt == i0 && h == 0;
+		char qc = q_here ? bq : '-', tc = t_here ? bt : '-';
+		if (!last) {
+			if (!t_here && q_here) {
+				if (jt < n && bt == qc) { tc = qc; seek_t(jt + 1); }
+			} else if (!q_here && t_here) {
+				if (jq < n && bq == tc) { qc = tc; seek_q(jq + 1); }
 			}
-			if (q_here) seek_q(jq + 1);
-			if (t_here) seek_t(jt + 1);
-			oq.put(qc); ot.put(tc);
-			// CnsAln cursor index (column_index)
-			if (i >= 1 && tc != '-') { ++cp; colidx[cp - soff0] = i; }
-			// meap_add_one_aln
-			if (qc == '-' && tc == '-') { }
-			else if (in_del_run && tc == '-') { }
-			else {
-				in_del_run = false;
-				if (qc == tc) { vote_add(votes + soff, 1u); base[soff] = tc; ++soff; }
-				else if (qc == '-') { vote_add(votes + soff, 1u << 8); ++soff; }
-				else { vote_add(votes + soff - 1, 1u << 16); in_del_run = true; }
-			}
+		}
+		if (q_here) seek_q(jq + 1);
+		if (t_here) seek_t(jt + 1);
+		oq.put(qc); ot.put(tc);
+		// CnsAln cursor index (column_index)
+		if (i >= 1 && tc != '-') { ++cp; colidx[cp - soff0] = i; }
+		// meap_add_one_aln
+		if (qc == '-' && tc == '-') { }
+		else if (in_del_run && tc == '-') { }
+		else {
+			in_del_run = false;
+			if (qc == tc) { vote_add(votes + soff, 1u); base[soff] = tc; ++soff; }
+			else if (qc == '-') { vote_add(votes + soff, 1u << 8); ++soff; }
+			else { vote_add(votes + soff - 1, 1u << 16); in_del_run = true; }
+		}
+		++i;
+		if (++h == halves) {
+			h = 0; ++i0;
+			if (i0 < n) { a = mq.get(i0); b = mt.get(i0); halves = (a != b && a != '-' && b != '-') ? 2 : 1; }
 		}
 	}
 	oq.put(0); ot.put(0);
