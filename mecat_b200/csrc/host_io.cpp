@@ -5,11 +5,16 @@
 //   FastaReader::read_one_seq                       src/common/fasta_reader.cpp:6-60
 //   add_one_seq + PackedDB::set_char                src/common/split_database.cpp:104-119, packed_db.h:98-101
 //   fileindex.txt                                   src/common/split_database.cpp:195-200,374-393
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -43,16 +48,36 @@ struct VolumeBuilder
 	int64_t curr = 0;
 	int num_reads = 0;
 	void clear() { offsz.clear(); pac.assign(pac.size(), 0); curr = 0; num_reads = 0; }
-	void add(const std::string& s)
+	// p[0..n): nucleotide letters; acgt: every letter is one of ACGTacgt (the common case, packed 8 letters at a time)
+	void add(const char* seq, size_t n, bool acgt)
 	{
 		offsz.push_back((int32_t)curr);
-		offsz.push_back((int32_t)s.size());
-		const size_t need = (size_t)((curr + (int64_t)s.size() + 1 + 3) / 4) + 1;
+		offsz.push_back((int32_t)n);
+		const size_t need = (size_t)((curr + (int64_t)n + 1 + 3) / 4) + 9;
 		if (pac.size() < need) pac.resize(need + need / 2, 0);
-		const unsigned char* p = (const unsigned char*)s.data();
-		size_t n = s.size(), i = 0;
+		const unsigned char* p = (const unsigned char*)seq;
+		size_t i = 0;
 		// same OR as PackedDB::set_char: codes > 3 spill into neighbours exactly like the reference
 		for (; i < n && (curr & 3); ++i, ++curr) pac[curr >> 2] |= (uint8_t)(kEnc.t[p[i]] << (((~curr) & 3) << 1));
+		if (acgt) {
+			// A 0x41, C 0x43, G 0x47, T 0x54 (either case): bits 2..1 give 0, 1, 3, 2; x ^ (x >> 1) turns that into 0, 1, 2, 3.
+			// Four codes in the bytes of a 32-bit word collapse into one output byte (first letter in the top bits) with
+			// one multiply: the wanted terms land in bits 24..31, every cross term stays below bit 24.
+			// (locals only inside the loop: a uint8_t store may alias any member, which would force `curr` through memory)
+			uint8_t* __restrict out = pac.data() + (curr >> 2);
+			const size_t groups = (n - i) / 8;
+			const unsigned char* __restrict in = p + i;
+			for (size_t g = 0; g < groups; ++g) {
+				uint64_t x;
+				memcpy(&x, in + 8 * g, 8);
+				uint64_t c = (x >> 1) & 0x0303030303030303ull;
+				c ^= (c >> 1) & 0x0101010101010101ull;
+				const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+				out[2 * g] = (uint8_t)((lo * 0x40100401u) >> 24);
+				out[2 * g + 1] = (uint8_t)((hi * 0x40100401u) >> 24);
+			}
+			i += 8 * groups; curr += (int64_t)(8 * groups);
+		}
 		for (; i + 4 <= n; i += 4, curr += 4) {
 			const unsigned a = kEnc.t[p[i]], b = kEnc.t[p[i + 1]], c = kEnc.t[p[i + 2]], d = kEnc.t[p[i + 3]];
 			pac[curr >> 2] |= (uint8_t)((a << 6) | (b << 4) | (c << 2) | d);
@@ -76,77 +101,74 @@ struct VolumeBuilder
 
 // Line reader with the reference's record rules: '>' or '@' starts a record, '+' ends it and
 // swallows one quality line, '#'/'!' lines are comments, data lines stop at ';'.
-// Block-buffered: lines are returned as (pointer, length) views into a 16 MB window.
+// One deliberate difference: the reference's BufferLineReader reports an EMPTY line as end of input once its last
+// 16 MB buffer has been loaded (buffer_line_iterator.cpp:31,44), i.e. a blank line silently truncates a small file;
+// here blank lines are skipped wherever they occur, which is what read_one_seq itself intends (fasta_reader.cpp:13).
+// The file is mapped (or, when it cannot be, read) whole, so lines are stable (pointer, length) views and a record
+// that is one clean line -- the usual long-read FASTA -- is packed straight from the mapping without a copy.
 struct FastaStream
 {
-	FILE* f;
-	std::vector<char> buf;
-	size_t beg = 0, end = 0;
-	bool eof = false;
-	std::string carry;          // a line that straddles two windows
+	const char* base = NULL;
+	size_t size = 0, pos = 0;
+	void* map = NULL;
+	std::vector<char> owned;    // fallback when the input cannot be mapped
+	bool ok = false;
 	const char* held = NULL;    // one line of push-back
 	size_t held_n = 0;
-	explicit FastaStream(const char* path) : f(fopen(path, "rb")), buf(16u << 20) {}
-	~FastaStream() { if (f) fclose(f); }
-	bool fill()
+	explicit FastaStream(const char* path)
 	{
-		if (eof) return false;
-		beg = 0;
-		end = fread(buf.data(), 1, buf.size(), f);
-		if (end == 0) { eof = true; return false; }
-		return true;
+		const int fd = open(path, O_RDONLY);
+		if (fd < 0) return;
+		struct stat st;
+		if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+			void* m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (m != MAP_FAILED) {
+				map = m; base = (const char*)m; size = (size_t)st.st_size;
+				madvise(m, size, MADV_SEQUENTIAL);
+			}
+		}
+		if (!map) {                     // pipes, empty files, exotic file systems
+			char tmp[1 << 16];
+			ssize_t r;
+			while ((r = read(fd, tmp, sizeof tmp)) > 0) owned.insert(owned.end(), tmp, tmp + r);
+			base = owned.data(); size = owned.size();
+		}
+		close(fd);
+		ok = true;
 	}
+	~FastaStream() { if (map) munmap(map, size); }
 	// next line without its terminator ('\n', '\r\n' or '\r'); false at end of input
 	bool line(const char*& p, size_t& n)
 	{
 		if (held) { p = held; n = held_n; held = NULL; return true; }
-		carry.clear();
-		bool any = false;
-		for (;;) {
-			if (beg == end && !fill()) {
-				if (!any) return false;
-				p = carry.data(); n = carry.size();
-				return true;
-			}
-			any = true;
-			const char* s = buf.data() + beg;
-			size_t len = end - beg, i;
-			{
-				const char* nl = (const char*)memchr(s, '\n', len);
-				i = nl ? (size_t)(nl - s) : len;
-				const char* cr = (const char*)memchr(s, '\r', i);   // a lone '\r' also ends a line
-				if (cr) i = (size_t)(cr - s);
-			}
-			if (i < len) {
-				const bool cr = s[i] == '\r';
-				if (carry.empty()) { p = s; n = i; }
-				else { carry.append(s, i); p = carry.data(); n = carry.size(); }
-				beg += i + 1;
-				if (cr) {                                  // swallow the '\n' of a '\r\n' pair
-					if (beg == end) { std::string keep(p, n); fill(); carry.swap(keep); p = carry.data(); n = carry.size(); }
-					if (beg < end && buf[beg] == '\n') ++beg;
-				}
-				return true;
-			}
-			carry.append(s, len);
-			beg = end;
-		}
+		if (pos >= size) return false;
+		const char* s = base + pos;
+		const size_t len = size - pos;
+		const char* nl = (const char*)memchr(s, '\n', len);
+		size_t i = nl ? (size_t)(nl - s) : len;
+		const char* cr = (const char*)memchr(s, '\r', i);   // a lone '\r' also ends a line
+		if (cr) i = (size_t)(cr - s);
+		p = s; n = i;
+		pos += i < len ? i + 1 : i;
+		if (cr && pos < size && base[pos] == '\n') ++pos;   // the '\n' of a '\r\n' pair
+		return true;
 	}
 	void unget(const char* p, size_t n) { held = p; held_n = n; }
-	// returns -1 at end of input, -2 on malformed input, else the sequence length
-	int64_t next(std::string& seq, std::string& err)
+	// Returns -1 at end of input, -2 on malformed input, else the sequence length; the sequence is [sp, sp + length)
+	// (a view into the input or into `seq`), acgt tells whether every letter is one of ACGTacgt.
+	int64_t next(std::string& seq, const char*& sp, bool& acgt, std::string& err)
 	{
 		seq.clear();
+		sp = NULL; acgt = true;
+		size_t view_n = 0;
 		bool need_defline = true, got_defline = false;
 		const char* l;
 		size_t n;
-		std::string keep;
 		while (line(l, n)) {
 			if (n == 0) continue;
 			const int c = (unsigned char)l[0];
 			if (c == '>' || c == '@') {
 				if (need_defline) { need_defline = false; got_defline = true; continue; }
-				if (l == carry.data()) { keep.assign(l, n); carry.swap(keep); l = carry.data(); }
 				unget(l, n);
 				break;
 			} else if (c == '+') {
@@ -159,23 +181,28 @@ struct FastaStream
 				err = "input doesn't start with a defline or comment";
 				return -2;
 			}
-			// fast path: a line made only of nucleotide letters is appended as is
-			size_t p = 0;
-			{
-				unsigned bad = 0;
-				for (size_t q = 0; q < n; ++q) bad |= kEnc.t[(unsigned char)l[q]];   // 16 only for non-nucleotides
-				p = (bad & 16u) ? 0 : n;
+			// fast path: a line made only of nucleotide letters is taken as is
+			unsigned bits = 0;
+			for (size_t q = 0; q < n; ++q) bits |= kEnc.t[(unsigned char)l[q]];   // 16 only for non-nucleotides, 4 | 8 for non-ACGT codes
+			if (bits & 12u) acgt = false;
+			if (!(bits & 16u)) {
+				if (!sp && seq.empty()) { sp = l; view_n = n; continue; }          // first data line: keep the view
+				if (sp) { seq.assign(sp, view_n); sp = NULL; }                      // a second line: fall back to a copy
+				seq.append(l, n);
+				continue;
 			}
-			if (p == n) { seq.append(l, n); continue; }
-			for (p = 0; p < n; ++p) {
+			if (sp) { seq.assign(sp, view_n); sp = NULL; }
+			for (size_t p = 0; p < n; ++p) {
 				const int ch = (unsigned char)l[p];
 				if (ch == ';') break;
-				if (kEnc.t[ch] < 16) seq.push_back((char)ch);
+				if (kEnc.t[ch] < 16) { seq.push_back((char)ch); if (kEnc.t[ch] > 3) acgt = false; }
 				else if (!(ch == ' ' || (ch >= 9 && ch <= 13))) { err = "invalid residue in sequence data"; return -2; }
 			}
 		}
+		if (sp) return (int64_t)view_n;
 		if (seq.empty() && got_defline) { err = "sequence data is missing"; return -2; }
 		if (!got_defline && seq.empty()) return -1;
+		sp = seq.data();
 		return (int64_t)seq.size();
 	}
 };
@@ -201,12 +228,21 @@ int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_
 	if (!reads_path || !wrk_dir || !num_volumes) return fail("split_dataset: null argument");
 	const int64_t cap = max_volume_bases > 0 ? max_volume_bases : kMaxVolumeBases;
 	FastaStream in(reads_path);
-	if (!in.f) return fail(std::string("cannot open file '") + reads_path + "' for reading");
+	if (!in.ok) return fail(std::string("cannot open file '") + reads_path + "' for reading");
 	FILE* idx = fopen(join(wrk_dir, "fileindex.txt").c_str(), "w");
 	if (!idx) return fail(std::string("cannot write into '") + wrk_dir + "'");
 	VolumeBuilder v;
+	{
+		// one allocation up front: a volume never holds more bases than the input has bytes (growing a vector of this size
+		// by reallocation cost more than the packing itself)
+		const int64_t bases = std::min<int64_t>(cap, (int64_t)in.size) + 1;
+		v.pac.assign((size_t)(bases / 4) + 64, 0);
+		v.offsz.reserve((size_t)std::min<int64_t>(bases / 1000 + 16, 1 << 24));
+	}
 	int vol = 0, rid = 0;
 	std::string seq, e;
+	const char* sp = NULL;
+	bool acgt = true;
 	auto flush = [&]() -> int {
 		const std::string name = join(wrk_dir, "vol" + std::to_string(vol++));
 		fprintf(idx, "%s\n", name.c_str());
@@ -216,12 +252,12 @@ int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_
 		return 0;
 	};
 	for (;;) {
-		const int64_t n = in.next(seq, e);
+		const int64_t n = in.next(seq, sp, acgt, e);
 		if (n == -1) break;
 		if (n == -2) { fclose(idx); return fail("FastaReader: " + e); }
 		if (v.curr + n + 1 > cap && v.curr > 0) { if (flush()) { fclose(idx); return fail("cannot write volume file"); } }
 		if (n + 1 > cap) { fclose(idx); return fail("a read is longer than the volume cap"); }
-		v.add(seq);
+		v.add(sp, (size_t)n, acgt);
 	}
 	if (v.curr > 0 && flush()) { fclose(idx); return fail("cannot write volume file"); }
 	fclose(idx);

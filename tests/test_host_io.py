@@ -1,0 +1,121 @@
+"""CPU tests of the host-side data formats (mecat_b200/csrc/host_io.cpp): the library's FASTA/FASTQ reader and 2-bit
+packer must write the volume files the reference's split_raw_dataset writes, byte for byte.
+
+  * against the committed sha256 of `volN` written by the UNMODIFIED reference for the golden read sets;
+  * against the unmodified reference binary itself on awkward inputs (multi-line records, lower case, IUPAC codes that
+    spill into neighbouring bases like PackedDB::set_char does, CRLF / lone CR line ends, FASTQ records, comments,
+    `;` tails) -- only where oracle/_ref has been built (this container)."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+
+GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))
+REF_PW = os.path.join(util.REF_DIR, "mecat2pw")
+needs_ref_binary = pytest.mark.skipif(not os.path.exists(REF_PW), reason="oracle/_ref/mecat2pw not built (needs /root/reference)")
+
+
+def sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def test_split_matches_reference_volume_of_the_golden_reads(tmp_path):
+    import mecat_b200
+    fa = str(tmp_path / "small.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f, open(fa, "wb") as g:
+        g.write(f.read())
+    vols = mecat_b200.split_dataset(fa, str(tmp_path / "wrk"))
+    assert [os.path.basename(v) for v in vols] == ["vol0"]
+    assert sha(vols[0]) == GOLD["small"]["vol0_sha256"]
+    c = GOLD["cfg0"]
+    fa = str(tmp_path / "cfg0.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    vols = mecat_b200.split_dataset(fa, str(tmp_path / "wrk0"))
+    assert sha(vols[0]) == c["vol0_sha256"]
+
+
+def awkward_inputs():
+    rng = np.random.default_rng(3)
+
+    def seq(n, alphabet="ACGT"):
+        return "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=n))
+
+    cases = {}
+    cases["multiline_lowercase"] = "".join(">r%d some description\n%s\n" % (i, "\n".join(
+        seq(int(rng.integers(1, 90)), "ACGTacgt") for _ in range(int(rng.integers(1, 6))))) for i in range(40))
+    cases["iupac_codes"] = "".join(">r%d\n%s\n" % (i, seq(int(rng.integers(1, 200)), "ACGTNRYKMSWBDHVnryk-")) for i in range(60))
+    cases["crlf"] = "".join(">r%d\r\n%s\r\n" % (i, seq(int(rng.integers(1, 150)))) for i in range(30))
+    cases["lone_cr"] = "".join(">r%d\r%s\r" % (i, seq(int(rng.integers(1, 150)))) for i in range(30))
+    cases["fastq"] = "".join("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)) for i, s in enumerate(seq(int(rng.integers(1, 120))) for _ in range(30)))
+    # (no blank lines: the reference's BufferLineReader reports an EMPTY line as end of input once its last 16 MB buffer
+    # is loaded, buffer_line_iterator.cpp:31,44 -- a quirk of its buffering that the library does not reproduce)
+    cases["comments_semicolons"] = "# a comment\n" + "".join(
+        ">r%d\n! note\n%s ;trailing words\n%s\n" % (i, seq(int(rng.integers(1, 80))), seq(int(rng.integers(1, 80)))) for i in range(25))
+    cases["spaces_inside"] = "".join(">r%d\n%s %s\t%s\n" % (i, seq(9), seq(17), seq(30)) for i in range(20))
+    cases["no_final_newline"] = ">a\nACGTACGTAC\n>b\nGGGTTTAAACCC"
+    cases["one_base_reads"] = "".join(">r%d\n%s\n" % (i, "ACGT"[i % 4]) for i in range(37))
+    cases["long_acgt"] = "".join(">r%d\n%s\n" % (i, seq(int(rng.integers(3000, 9000)))) for i in range(12))
+    return cases
+
+
+@needs_ref_binary
+@pytest.mark.parametrize("name", sorted(awkward_inputs()))
+def test_split_matches_reference_binary_on_awkward_inputs(tmp_path, name):
+    import mecat_b200
+    text = awkward_inputs()[name]
+    fa = str(tmp_path / "in.fa")
+    with open(fa, "w", newline="") as f:
+        f.write(text)
+    ref_wrk = str(tmp_path / "ref_wrk")
+    p = subprocess.run([REF_PW, "-j", "0", "-d", fa, "-o", str(tmp_path / "ref.can"), "-w", ref_wrk, "-t", "1"],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-500:]
+    vols = mecat_b200.split_dataset(fa, str(tmp_path / "wrk"))
+    ref_vols = sorted(f for f in os.listdir(ref_wrk) if f.startswith("vol"))
+    assert [os.path.basename(v) for v in vols] == ref_vols
+    for v in vols:
+        assert open(v, "rb").read() == open(os.path.join(ref_wrk, os.path.basename(v)), "rb").read(), os.path.basename(v)
+
+
+def test_split_into_several_volumes_round_trips(tmp_path):
+    """A small volume cap (the reference's own debug knob) cuts the reads into several volumes; loading them back gives
+    every read once, in order, with the right bases."""
+    import mecat_b200
+    rng = np.random.default_rng(9)
+    reads = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(50, 400)))) for _ in range(200)]
+    fa = str(tmp_path / "r.fa")
+    with open(fa, "w") as f:
+        for i, s in enumerate(reads):
+            f.write(">%d\n%s\n" % (i, s))
+    vols = mecat_b200.split_dataset(fa, str(tmp_path / "wrk"), max_volume_bases=5000)
+    assert len(vols) > 3
+    got, next_id = [], 0
+    for v in vols:
+        hv = mecat_b200.HostVolume.load(v)
+        assert hv.start_read_id == next_id
+        for off, size in hv.offset_size:
+            codes = [(hv.pac[(off + i) >> 2] >> (2 * (3 - ((off + i) & 3)))) & 3 for i in range(size)]
+            got.append("".join("ACGT"[c] for c in codes))
+        next_id += len(hv.offset_size)
+    assert got == reads
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("ACGT\n>a\nACGT\n", "defline"),
+    (">a\n>b\nACGT\n", "missing"),
+    (">a\nAC!GT\n", "invalid residue"),
+    ("@a\nACGT\n+\n", "quality"),
+])
+def test_split_reports_malformed_input_like_the_reference_reader(tmp_path, text, msg):
+    import mecat_b200
+    fa = str(tmp_path / "bad.fa")
+    open(fa, "w").write(text)
+    with pytest.raises(mecat_b200.MecatB200Error) as e:
+        mecat_b200.split_dataset(fa, str(tmp_path / "wrk"))
+    assert msg in str(e.value)
