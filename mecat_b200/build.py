@@ -70,7 +70,7 @@ def build(verbose=False):
     host = os.path.join(CSRC, "host")
     for name in ("mecat2pw", "mecat2cns"):
         src, exe = os.path.join(host, name + ".cpp"), os.path.join(BIN, name)
-        if os.path.exists(src) and _newer([src, LIB, os.path.join(ROOT, "include", "mecat_b200.h")], exe):
+        if os.path.exists(src) and _newer([src, LIB, os.path.join(ROOT, "include", "mecat_b200.h"), os.path.join(host, "format.h")], exe):
             subprocess.check_call([HOSTCXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
                                    "-L", HERE, "-lmecat_b200", "-Wl,-rpath,$ORIGIN/.."])
     gen_src, gen_exe = os.path.join(ROOT, "tools", "gen_reads.cpp"), os.path.join(BIN, "gen_reads")

@@ -267,8 +267,11 @@ int main(int argc, char* argv[])
 				fprintf(stderr, "\n");
 			}
 		}
-		mecat_b200_volume_release(ctx, dvol);
-		mecat_b200_destroy(ctx);
+		{
+			StderrTimer t("gpu " + std::to_string(dev) + " release");
+			mecat_b200_volume_release(ctx, dvol);
+			mecat_b200_destroy(ctx);
+		}
 	};
 	{
 		std::vector<std::thread> th;

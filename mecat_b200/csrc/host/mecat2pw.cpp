@@ -19,6 +19,7 @@
 #include <sys/time.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <fstream>
 #include <iostream>
@@ -28,6 +29,7 @@
 #include <vector>
 
 #include "mecat_b200.h"
+#include "format.h"
 
 namespace {
 
@@ -142,21 +144,21 @@ std::string results_name(const char* wrk, int vid, bool working)
 
 void write_candidates(std::ostream& out, const mecat_candidate* ec, size_t n)
 {
-	for (size_t i = 0; i < n; ++i) {
-		const mecat_candidate& e = ec[i];
-		out << e.qid << '\t' << e.sid << '\t' << e.qdir << '\t' << e.sdir << '\t' << e.qext << '\t' << e.sext << '\t'
-		    << e.score << '\t' << e.qsize << '\t' << e.ssize << '\n';
-	}
+	mbfmt::TextBuf b;
+	b.s.reserve(n * 48 + 64);
+	mbfmt::format_candidates(b, ec, n);
+	out.write(b.s.data(), (std::streamsize)b.s.size());
 }
 
 void write_m4(std::ostream& out, const mecat_m4* m, size_t n, bool gapped)
 {
-	for (size_t i = 0; i < n; ++i) {
-		const mecat_m4& r = m[i];
-		out << r.qid << '\t' << r.sid << '\t' << r.ident << '\t' << r.vscore << '\t' << r.qdir << '\t' << r.qoff << '\t'
-		    << r.qend << '\t' << r.qsize << '\t' << r.sdir << '\t' << r.soff << '\t' << r.send << '\t' << r.ssize;
-		if (gapped) out << '\t' << r.qext << '\t' << r.sext;
-		out << "\n";
+	const size_t chunk = 1 << 18;              // bounded text buffer
+	mbfmt::TextBuf b;
+	b.s.reserve(std::min(n, chunk) * 96 + 64);
+	for (size_t i = 0; i < n; i += chunk) {
+		b.s.clear();
+		mbfmt::format_m4(b, m + i, std::min(chunk, n - i), gapped);
+		out.write(b.s.data(), (std::streamsize)b.s.size());
 	}
 }
 

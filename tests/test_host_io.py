@@ -119,3 +119,51 @@ def test_split_reports_malformed_input_like_the_reference_reader(tmp_path, text,
     with pytest.raises(mecat_b200.MecatB200Error) as e:
         mecat_b200.split_dataset(fa, str(tmp_path / "wrk"))
     assert msg in str(e.value)
+
+
+def _format_harness():
+    import ctypes as C
+    out_dir = os.path.join(util.ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libformat_harness.so")
+    src = [os.path.join(util.ROOT, "tests", "format_harness.cpp"), os.path.join(util.ROOT, "mecat_b200", "csrc", "host", "format.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
+    L = C.CDLL(so)
+    for f in (L.harness_format_m4, L.harness_ostream_m4):
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
+    for f in (L.harness_format_can, L.harness_ostream_can):
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    return L
+
+
+def test_result_text_equals_the_reference_stream_formatting():
+    """The drivers format .can / .m4 lines without iostreams; the characters must be the ones `operator<<` of the
+    reference's records produces (integers of every sign and width, the identity as a default-formatted double)."""
+    import ctypes as C
+    L = _format_harness()
+    rng = np.random.default_rng(21)
+    n = 4000
+    m4 = np.zeros(n, dtype=util.M4_DTYPE)
+    for f in ("qid", "sid", "qoff", "qend", "qsize", "soff", "send", "ssize", "qext", "sext"):
+        m4[f] = rng.integers(-5, 1 << 40, size=n) >> rng.integers(0, 40, size=n)
+    m4["vscore"] = rng.integers(-2 ** 31, 2 ** 31 - 1, size=n)
+    m4["qdir"] = rng.integers(0, 2, size=n); m4["sdir"] = rng.integers(0, 2, size=n)
+    m4["ident"] = np.where(rng.random(n) < 0.9, rng.uniform(60, 100, size=n), rng.choice([0.0, 100.0, 7e-05, 1e+20, 99.99995, 123456.7, 85.5], size=n))
+    m4["ident"][:200] = np.round(m4["ident"][:200], 2)
+    m4[0] = tuple([-(2 ** 63)] * 2 + [75.0, -2 ** 31, 1] + [2 ** 63 - 1] * 3 + [0, 0] + [0] * 5)
+    cap = 400 * n
+    for gapped in (0, 1):
+        a, b = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        la = L.harness_format_m4(m4.ctypes.data_as(C.c_void_p), n, gapped, a, cap)
+        lb = L.harness_ostream_m4(m4.ctypes.data_as(C.c_void_p), n, gapped, b, cap)
+        assert la == lb and la <= cap and a.raw[:la] == b.raw[:lb]
+    ec = np.zeros(n, dtype=util.EC_DTYPE)
+    for f in ec.dtype.names:
+        ec[f] = rng.integers(-2 ** 31, 2 ** 31 - 1, size=n) >> rng.integers(0, 31, size=n)
+    a, b = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    la = L.harness_format_can(ec.ctypes.data_as(C.c_void_p), n, a, cap)
+    lb = L.harness_ostream_can(ec.ctypes.data_as(C.c_void_p), n, b, cap)
+    assert la == lb and a.raw[:la] == b.raw[:lb]
