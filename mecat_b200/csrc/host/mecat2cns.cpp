@@ -162,6 +162,11 @@ int main(int argc, char* argv[])
 	if (opt.input_type != 0) { fprintf(stderr, "mecat2cns: only `-i 0` (candidate input) is on the GPU path so far; use the reference binary for `-i 1`.\n"); return 1; }
 	if (mecat_b200_device_count() < 1) { fprintf(stderr, "mecat2cns: no CUDA device found (this build has no CPU path)\n"); return 1; }
 
+	// Creating the CUDA context of device 0 takes about a second; it runs next to the candidate and FASTA loading.
+	mecat_b200_ctx* ctx0 = NULL;
+	int ctx0_rc = 0;
+	std::thread warm([&]() { ctx0_rc = mecat_b200_init(&ctx0, 0, NULL); });
+	struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{warm};
 	std::vector<mecat_candidate> raw, ec;
 	{
 		StderrTimer t("partition_candidates");
@@ -214,15 +219,17 @@ int main(int argc, char* argv[])
 		while (k > 0 && k < ec.size() && ec[k].sid == ec[k - 1].sid) ++k;
 		cut[g] = std::max(k, cut[g - 1]);
 	}
+	if (warm.joinable()) warm.join();
+	if (ctx0_rc) ctx0 = NULL;
 	struct Part { long long part; std::string text; };
 	std::vector<std::vector<Part>> results((size_t)ngpus);
 	std::atomic<int> failed(0);
 	auto worker = [&](int dev) {
-		mecat_b200_ctx* ctx = NULL;
+		mecat_b200_ctx* ctx = dev == 0 ? ctx0 : NULL;
 		void* dvol = NULL;
 		{
 			StderrTimer t("gpu " + std::to_string(dev) + " init + volume upload");
-			if (mecat_b200_init(&ctx, dev, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU %d\n", dev); failed = 1; return; }
+			if (!ctx && mecat_b200_init(&ctx, dev, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU %d\n", dev); failed = 1; return; }
 			if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); failed = 1; return; }
 		}
 		for (size_t i = cut[dev]; !failed && i < cut[dev + 1];) {

@@ -49,7 +49,7 @@ def main():
         subprocess.check_call([os.path.join(ROOT, "mecat_b200", "bin", "mecat2pw"), "-j", str(a.job), "-d", fa, "-o", gout,
                                "-w", os.path.join(a.tmp, "wg"), "-t", "1"] + extra, stdout=lg, stderr=lg)
     res["gpu_cli_seconds"] = time.time() - t
-    res["gpu_log"] = open(os.path.join(a.tmp, "gpu.log")).read().splitlines()[-12:]
+    res["gpu_log"] = [l for l in open(os.path.join(a.tmp, "gpu.log")).read().splitlines() if "takes" in l]
     gsha, gn, gsorted = sorted_sha(gout)
     res["gpu_records"] = gn
     res["gpu_sorted_sha256"] = gsha
