@@ -142,6 +142,11 @@ int mecat_b200_reset_stats(mecat_b200_ctx* ctx);
  * reference's 2 140 000 000-base cap (MCS, split_database.h:6). */
 int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_t max_volume_bases,
                              int* num_volumes, char* err, int err_cap);
+/* All reads of a FASTA/FASTQ file as one packed volume in host memory; replaces PackedDB::load_fasta_db
+ * (src/common/packed_db.cpp:194) for mecat2cns.  Same bytes as vol0 of mecat_b200_split_dataset; fails when the reads
+ * need more than one volume.  Release with mecat_b200_volume_unload. */
+int mecat_b200_volume_from_fasta(const char* reads_path, mecat_volume* out, char* err, int err_cap);
+
 /* replaces load_volume / delete_volume_t (split_database.cpp:156-181,95-101). */
 int mecat_b200_volume_load(const char* path, mecat_volume* out);
 void mecat_b200_volume_unload(mecat_volume* v);

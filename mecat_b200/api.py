@@ -70,7 +70,7 @@ EXPORTS = [
     "mecat_b200_index_device_arrays", "mecat_b200_index_release", "mecat_b200_index_export",
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
     "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_cns_reads", "mecat_b200_cns_sort_candidates",
-    "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload",
+    "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload", "mecat_b200_volume_from_fasta",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def load_library():
     L.mecat_b200_volume_from_device.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp, C.POINTER(vp)]
     L.mecat_b200_split_dataset.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.c_char_p, C.c_int]
     L.mecat_b200_volume_load.argtypes = [C.c_char_p, VP]
+    L.mecat_b200_volume_from_fasta.argtypes = [C.c_char_p, VP, C.c_char_p, C.c_int]
     L.mecat_b200_volume_unload.argtypes = [VP]
     _lib = L
     return L
@@ -152,6 +153,21 @@ class HostVolume:
             os_ = np.frombuffer(f.read(8 * n), dtype="<i4").reshape(-1, 2).copy()
             pac = np.frombuffer(f.read((nb + 3) // 4), dtype=np.uint8).copy()
         return HostVolume(os_, pac, nb, sid)
+
+
+def volume_from_fasta(reads_path):
+    """All reads of a FASTA/FASTQ file as one HostVolume (the reference's PackedDB::load_fasta_db), no files written."""
+    L = load_library()
+    v = Volume()
+    err = C.create_string_buffer(512)
+    if L.mecat_b200_volume_from_fasta(reads_path.encode(), C.byref(v), err, 512) != 0:
+        raise MecatB200Error(err.value.decode())
+    try:
+        os_ = np.ctypeslib.as_array(v.offset_size, shape=(2 * v.num_reads,)).reshape(-1, 2).copy() if v.num_reads else np.zeros((0, 2), np.int32)
+        pac = np.ctypeslib.as_array(v.pac, shape=((v.num_bases + 3) // 4,)).copy()
+    finally:
+        L.mecat_b200_volume_unload(C.byref(v))
+    return HostVolume(os_, pac, v.num_bases, v.start_read_id)
 
 
 def split_dataset(reads_path, wrk_dir, max_volume_bases=0):

@@ -181,25 +181,12 @@ int main(int argc, char* argv[])
 	}
 
 	// all reads in one packed volume (the reference keeps them in one PackedDB, packed_db.cpp:194)
-	char tmpl[] = "/tmp/mecat2cns_XXXXXX";
-	const char* wrk = mkdtemp(tmpl);
-	if (!wrk) { fprintf(stderr, "cannot create a scratch directory\n"); return 1; }
 	mecat_volume vol;
 	memset(&vol, 0, sizeof vol);
 	{
 		StderrTimer t("load_fasta_db");
-		int nvols = 0;
 		char err[512];
-		if (mecat_b200_split_dataset(opt.reads, wrk, 0, &nvols, err, sizeof err)) { fprintf(stderr, "%s\n", err); return 1; }
-		const std::string v0 = std::string(wrk) + "/vol0";
-		if (nvols != 1) {
-			fprintf(stderr, "mecat2cns: the read set needs %d volumes; consensus over more than one 2.14 Gbase volume is not built yet\n", nvols);
-			return 1;
-		}
-		if (mecat_b200_volume_load(v0.c_str(), &vol)) { fprintf(stderr, "failed to open file '%s'.\n", v0.c_str()); return 1; }
-		unlink(v0.c_str());
-		unlink((std::string(wrk) + "/fileindex.txt").c_str());
-		rmdir(wrk);
+		if (mecat_b200_volume_from_fasta(opt.reads, &vol, err, sizeof err)) { fprintf(stderr, "mecat2cns: %s\n", err); return 1; }
 	}
 
 	// One host thread per GPU (MECAT_GPUS=n, default 1): every device holds a replica of the packed reads, the reads to

@@ -267,6 +267,39 @@ int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_
 
 // load_volume (split_database.cpp:156-181).  Buffers are malloc'ed; release with
 // mecat_b200_volume_unload.
+// All reads of a FASTA/FASTQ file as ONE packed volume in memory (PackedDB::load_fasta_db, src/common/packed_db.cpp:194,
+// as mecat2cns uses it): the same records and bytes split_dataset would write into vol0, without the file round trip.
+int mecat_b200_volume_from_fasta(const char* reads_path, mecat_volume* out, char* err, int err_cap)
+{
+	auto fail = [&](const std::string& m) { if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", m.c_str()); return 1; };
+	if (!reads_path || !out) return fail("volume_from_fasta: null argument");
+	FastaStream in(reads_path);
+	if (!in.ok) return fail(std::string("cannot open file '") + reads_path + "' for reading");
+	VolumeBuilder v;
+	const int64_t bases = std::min<int64_t>(kMaxVolumeBases, (int64_t)in.size) + 1;
+	v.pac.assign((size_t)(bases / 4) + 64, 0);
+	std::string seq, e;
+	const char* sp = NULL;
+	bool acgt = true;
+	for (;;) {
+		const int64_t n = in.next(seq, sp, acgt, e);
+		if (n == -1) break;
+		if (n == -2) return fail("FastaReader: " + e);
+		if (v.curr + n + 1 > kMaxVolumeBases) return fail("the read set needs more than one 2.14 Gbase volume");
+		v.add(sp, (size_t)n, acgt);
+	}
+	const size_t nr = (size_t)v.num_reads, bytes = (size_t)((v.curr + 3) / 4);
+	int32_t* os = (int32_t*)malloc(sizeof(int32_t) * 2 * (nr ? nr : 1));
+	uint8_t* pac = (uint8_t*)malloc(bytes + 16);
+	if (!os || !pac) { free(os); free(pac); return fail("out of memory"); }
+	if (nr) memcpy(os, v.offsz.data(), sizeof(int32_t) * 2 * nr);
+	memcpy(pac, v.pac.data(), bytes);
+	memset(pac + bytes, 0, 16);
+	out->num_reads = v.num_reads; out->num_bases = (int32_t)v.curr; out->start_read_id = 0;
+	out->offset_size = os; out->pac = pac;
+	return 0;
+}
+
 int mecat_b200_volume_load(const char* path, mecat_volume* out)
 {
 	if (!path || !out) return 1;

@@ -40,6 +40,20 @@ def test_split_matches_reference_volume_of_the_golden_reads(tmp_path):
     assert sha(vols[0]) == c["vol0_sha256"]
 
 
+def test_volume_from_fasta_equals_the_split_volume(tmp_path):
+    """The in-memory loader mecat2cns uses gives exactly the records and bytes of vol0."""
+    import mecat_b200
+    fa = str(tmp_path / "small.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f, open(fa, "wb") as g:
+        g.write(f.read())
+    hv = mecat_b200.volume_from_fasta(fa)
+    ref = mecat_b200.HostVolume.load(mecat_b200.split_dataset(fa, str(tmp_path / "wrk"))[0])
+    assert hv.num_bases == ref.num_bases and hv.start_read_id == 0
+    assert np.array_equal(hv.offset_size, ref.offset_size) and np.array_equal(hv.pac, ref.pac)
+    with pytest.raises(mecat_b200.MecatB200Error):
+        mecat_b200.volume_from_fasta(str(tmp_path / "missing.fa"))
+
+
 def awkward_inputs():
     rng = np.random.default_rng(3)
 
