@@ -16,6 +16,7 @@
 
 #include "../include/mecat_b200.h"
 #include "../mecat_b200/csrc/cns_pipeline.h"
+#include "cns_literal.h"
 
 namespace {
 

@@ -125,7 +125,8 @@ def cns_harness():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libcns_harness.so")
     src = [os.path.join(ROOT, "tests", "cns_host_harness.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "cns_pipeline.h"),
-           os.path.join(ROOT, "mecat_b200", "csrc", "cns_core.cuh"), os.path.join(ROOT, "include", "mecat_b200.h")]
+           os.path.join(ROOT, "mecat_b200", "csrc", "cns_core.cuh"), os.path.join(ROOT, "include", "mecat_b200.h"),
+           os.path.join(ROOT, "tests", "cns_literal.h")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
     L = C.CDLL(so)
