@@ -14,6 +14,9 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
+
+#include <vector>
 
 namespace mb {
 
@@ -84,6 +87,92 @@ __global__ void __launch_bounds__(256) k_kmer_fill(const uint32_t* __restrict__ 
 				if (!(slot & DROPPED)) pos[slot] = (int32_t)p;
 			}
 		});
+}
+
+// ---- scatter by multi-split.  The fill above recomputes every k-mer of the volume once per code-range pass (32 passes)
+// because a pass must keep its cursors and its slice of pos[] L2 resident.  The multi-split computes the k-mers ONCE:
+// k_kmer_split bins (code, position) pairs into partitions of 2^19 codes -- each CTA ranks a tile of 4 096 k-mers in
+// shared memory, reserves room in every partition with one global atomic per partition and tile, and writes its pairs
+// there -- and k_pairs_scatter then walks the pairs partition by partition (coalesced), so that the cursors (2 MB) and
+// the destination slice of pos[] (~50 MB) of the partitions in flight stay in L2.
+constexpr int PART_BITS = 19;
+constexpr uint32_t PART_CODES = 1u << PART_BITS;
+constexpr int MAX_PARTS = (int)(NCODES >> PART_BITS);     // 128
+
+__global__ void __launch_bounds__(256) k_part_totals(const uint32_t* __restrict__ counts, uint32_t code_lo, uint32_t code_hi,
+                                                     uint32_t* __restrict__ totals)
+{
+	__shared__ uint32_t red[8];
+	const uint32_t lo = code_lo + blockIdx.x * PART_CODES;
+	const uint32_t hi = min(code_hi, lo + PART_CODES);
+	uint32_t s = 0;
+	for (uint32_t c = lo + threadIdx.x; c < hi; c += 256) s += counts[c];
+	s = __reduce_add_sync(0xFFFFFFFFu, s);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += red[w]; totals[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(256) k_kmer_split(const uint32_t* __restrict__ fwd, const int2* __restrict__ offsz, int nreads,
+                                                    uint32_t code_lo, uint32_t code_hi, int nparts, uint32_t* __restrict__ pcur,
+                                                    uint2* __restrict__ pairs)
+{
+	__shared__ uint32_t hist[MAX_PARTS];
+	__shared__ uint32_t base[MAX_PARTS];
+	const uint32_t span = code_hi - code_lo;
+	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
+		const int2 o = offsz[r];
+		const int nk = o.y - (KMER - 1);
+		for (int t0 = 0; t0 < nk; t0 += 256 * RUN) {              // one tile of 4 096 k-mer starts per iteration, all threads in step
+			for (int q = threadIdx.x; q < nparts; q += 256) hist[q] = 0;
+			__syncthreads();
+			const int i0 = t0 + threadIdx.x * RUN;
+			uint32_t code[RUN], where[RUN];                           // where = partition << 16 | rank inside the CTA's tile
+			int n = 0;
+			if (i0 < nk) {
+				n = min(RUN, nk - i0);
+				const uint32_t p = (uint32_t)(o.x + i0);
+				const uint32_t w = p >> 4, sh = (p & 15u) << 1;
+				const uint32_t a0 = __ldg(fwd + w), a1 = __ldg(fwd + w + 1), a2 = __ldg(fwd + w + 2);
+				const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh);
+				uint32_t c = rev_groups2(w0) >> 6;
+#pragma unroll
+				for (int j = 0; j < RUN; ++j) {
+					if (j > 0) {
+						const int b = KMER - 1 + j;
+						const uint32_t nb = (b < 16 ? w0 >> (2 * b) : w1 >> (2 * (b - 16))) & 3u;
+						c = ((c << 2) & CODE_MASK) | nb;
+					}
+					code[j] = c;
+					where[j] = 0xFFFFFFFFu;
+					if (j < n && c - code_lo < span) {
+						const uint32_t q = (c - code_lo) >> PART_BITS;
+						where[j] = (q << 16) | atomicAdd(&hist[q], 1u);
+					}
+				}
+			}
+			__syncthreads();
+			for (int q = threadIdx.x; q < nparts; q += 256) { const uint32_t h = hist[q]; base[q] = h ? atomicAdd(&pcur[q], h) : 0u; }
+			__syncthreads();
+			if (i0 < nk) {
+				const uint32_t p = (uint32_t)(o.x + i0);
+#pragma unroll
+				for (int j = 0; j < RUN; ++j)
+					if (where[j] != 0xFFFFFFFFu) pairs[base[where[j] >> 16] + (where[j] & 0xFFFFu)] = make_uint2(code[j], p + (uint32_t)j);
+			}
+			__syncthreads();
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_pairs_scatter(const uint2* __restrict__ pairs, size_t n, uint32_t* __restrict__ cursor,
+                                                       int32_t* __restrict__ pos)
+{
+	const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const uint2 kp = pairs[i];
+	const uint32_t slot = atomicAdd(&cursor[kp.x], 1u);
+	if (!(slot & DROPPED)) pos[slot] = (int32_t)kp.y;
 }
 
 // ---- exclusive scan of min(count, cutoff -> 0) over 2^26 codes: reduce / top / down-sweep
@@ -281,11 +370,35 @@ int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uin
 {
 	uint32_t* d_tiles = nullptr;
 	uint32_t* d_total = nullptr;
+	uint32_t* d_pcur = nullptr;
+	uint2* d_pairs = nullptr;
 	const int ntiles = (int)(NCODES / SCAN_TILE);
 	auto body = [&]() -> int {
 		if (!I->counts) MB_FAIL(c, "index: finish called twice");
 		MB_CUDA(c, c->alloc(&d_tiles, (size_t)ntiles));
 		MB_CUDA(c, c->alloc(&d_total, 1));
+		// multi-split scatter (default) or the code-range passes it replaced (MECAT_B200_FILL=passes)
+		const char* fill_env = getenv("MECAT_B200_FILL");
+		const bool split = !(fill_env && !strcmp(fill_env, "passes")) && code_hi > code_lo && v->num_reads > 0;
+		const int nparts = split ? (int)((code_hi - code_lo + PART_CODES - 1) >> PART_BITS) : 0;
+		std::vector<uint32_t> h_pbase((size_t)nparts + 1, 0);
+		if (split) {
+			// k-mers per partition of 2^19 codes, from the histogram before the scan turns it into cursors
+			MB_CUDA(c, c->alloc(&d_pcur, (size_t)nparts));
+			{
+				KScope ks(c, MECAT_K_FILL);
+				k_part_totals<<<nparts, 256, 0, c->stream>>>(I->counts, code_lo, code_hi, d_pcur);
+			}
+			MB_CUDA(c, cudaGetLastError());
+			std::vector<uint32_t> tot((size_t)nparts);
+			MB_CUDA(c, cudaMemcpyAsync(tot.data(), d_pcur, sizeof(uint32_t) * nparts, cudaMemcpyDeviceToHost, c->stream));
+			MB_CUDA(c, cudaStreamSynchronize(c->stream));
+			uint64_t run = 0;
+			for (int q = 0; q < nparts; ++q) { h_pbase[q] = (uint32_t)run; run += tot[q]; }
+			if (run > 0xFFFFFFFFull) MB_FAIL(c, "index: more than 2^32 k-mers in one volume");
+			h_pbase[nparts] = (uint32_t)run;
+			MB_CUDA(c, cudaMemcpyAsync(d_pcur, h_pbase.data(), sizeof(uint32_t) * nparts, cudaMemcpyHostToDevice, c->stream));
+		}
 		{
 			KScope ks(c, MECAT_K_SCAN, 3);
 			k_scan_reduce<<<ntiles, SCAN_T, 0, c->stream>>>(I->counts, d_tiles);
@@ -299,7 +412,20 @@ int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uin
 		MB_CUDA(c, cudaMemcpyAsync(I->begin + NCODES, &total, sizeof total, cudaMemcpyHostToDevice, c->stream));
 		I->num_kmers = total;
 		MB_CUDA(c, c->alloc(&I->pos, (size_t)total + 1));
-		if (total && code_hi > code_lo) {
+		if (total && code_hi > code_lo && split) {
+			const size_t npairs = h_pbase[nparts];
+			MB_CUDA(c, c->alloc(&d_pairs, npairs + 1));
+			{
+				KScope ks(c, MECAT_K_FILL, 2);
+				k_kmer_split<<<grid_for_reads(v), 256, 0, c->stream>>>(v->fwd, v->offsz, v->num_reads, code_lo, code_hi, nparts, d_pcur, d_pairs);
+				if (npairs) k_pairs_scatter<<<(unsigned)((npairs + 255) / 256), 256, 0, c->stream>>>(d_pairs, npairs, I->counts, I->pos);
+			}
+			{
+				KScope ks(c, MECAT_K_SORT);
+				k_sort_lists<<<(code_hi - code_lo) / (SORT_WARPS * SORT_CODES_PER_WARP), SORT_WARPS * 32, 0, c->stream>>>(I->begin, I->pos, code_lo);
+			}
+			MB_CUDA(c, cudaGetLastError());
+		} else if (total && code_hi > code_lo) {
 			{
 				// same idea for the scatter: per pass the cursors are L2 resident.  The destination slice of
 				// pos[] (197 MB at 32 passes) is not, ncu still shows one 32-byte DRAM sector written per
@@ -325,7 +451,7 @@ int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uin
 		return 0;
 	};
 	int rc = body();
-	c->dfree(d_tiles); c->dfree(d_total);
+	c->dfree(d_tiles); c->dfree(d_total); c->dfree(d_pcur); c->dfree(d_pairs);
 	c->dfree(I->counts); I->counts = nullptr;
 	return rc;
 }
