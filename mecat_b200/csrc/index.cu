@@ -117,20 +117,21 @@ __global__ void __launch_bounds__(256) k_kmer_split(const uint32_t* __restrict__
                                                     uint32_t code_lo, uint32_t code_hi, int nparts, uint32_t* __restrict__ pcur,
                                                     uint2* __restrict__ pairs)
 {
-	__shared__ uint32_t hist[MAX_PARTS];
-	__shared__ uint32_t base[MAX_PARTS];
+	__shared__ uint32_t hist[MAX_PARTS];       // pairs of this tile per partition
+	__shared__ uint32_t offs[MAX_PARTS + 1];   // their exclusive prefix: the tile's pairs are staged partition by partition
+	__shared__ uint32_t base[MAX_PARTS];       // where the partition's run starts in the global pair array
+	__shared__ uint2 buf[256 * RUN];           // staged pairs: the write-out is then runs of consecutive pairs per partition
 	const uint32_t span = code_hi - code_lo;
 	for (int r = blockIdx.x; r < nreads; r += gridDim.x) {
 		const int2 o = offsz[r];
 		const int nk = o.y - (KMER - 1);
 		for (int t0 = 0; t0 < nk; t0 += 256 * RUN) {              // one tile of 4 096 k-mer starts per iteration, all threads in step
-			for (int q = threadIdx.x; q < nparts; q += 256) hist[q] = 0;
+			for (int q = threadIdx.x; q < MAX_PARTS; q += 256) hist[q] = 0;
 			__syncthreads();
 			const int i0 = t0 + threadIdx.x * RUN;
 			uint32_t code[RUN], where[RUN];                           // where = partition << 16 | rank inside the CTA's tile
-			int n = 0;
 			if (i0 < nk) {
-				n = min(RUN, nk - i0);
+				const int n = min(RUN, nk - i0);
 				const uint32_t p = (uint32_t)(o.x + i0);
 				const uint32_t w = p >> 4, sh = (p & 15u) << 1;
 				const uint32_t a0 = __ldg(fwd + w), a1 = __ldg(fwd + w + 1), a2 = __ldg(fwd + w + 2);
@@ -152,13 +153,33 @@ __global__ void __launch_bounds__(256) k_kmer_split(const uint32_t* __restrict__
 				}
 			}
 			__syncthreads();
-			for (int q = threadIdx.x; q < nparts; q += 256) { const uint32_t h = hist[q]; base[q] = h ? atomicAdd(&pcur[q], h) : 0u; }
+			if (threadIdx.x < 32) {                                   // exclusive prefix of the 128 counters, one room reservation each
+				const int l = threadIdx.x;
+				const uint32_t h0 = hist[4 * l], h1 = hist[4 * l + 1], h2 = hist[4 * l + 2], h3 = hist[4 * l + 3];
+				const uint32_t sum = h0 + h1 + h2 + h3;
+				uint32_t inc = sum;
+				for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (l >= d) inc += v; }
+				const uint32_t ex = inc - sum;
+				offs[4 * l] = ex; offs[4 * l + 1] = ex + h0; offs[4 * l + 2] = ex + h0 + h1; offs[4 * l + 3] = ex + h0 + h1 + h2;
+				if (l == 31) offs[MAX_PARTS] = inc;
+				if (h0) base[4 * l] = atomicAdd(&pcur[4 * l], h0);
+				if (h1) base[4 * l + 1] = atomicAdd(&pcur[4 * l + 1], h1);
+				if (h2) base[4 * l + 2] = atomicAdd(&pcur[4 * l + 2], h2);
+				if (h3) base[4 * l + 3] = atomicAdd(&pcur[4 * l + 3], h3);
+			}
 			__syncthreads();
 			if (i0 < nk) {
 				const uint32_t p = (uint32_t)(o.x + i0);
 #pragma unroll
 				for (int j = 0; j < RUN; ++j)
-					if (where[j] != 0xFFFFFFFFu) pairs[base[where[j] >> 16] + (where[j] & 0xFFFFu)] = make_uint2(code[j], p + (uint32_t)j);
+					if (where[j] != 0xFFFFFFFFu) buf[offs[where[j] >> 16] + (where[j] & 0xFFFFu)] = make_uint2(code[j], p + (uint32_t)j);
+			}
+			__syncthreads();
+			const uint32_t total = offs[MAX_PARTS];
+			for (uint32_t e = threadIdx.x; e < total; e += 256) {
+				const uint2 kp = buf[e];
+				const uint32_t q = (kp.x - code_lo) >> PART_BITS;
+				pairs[base[q] + (e - offs[q])] = kp;
 			}
 			__syncthreads();
 		}
