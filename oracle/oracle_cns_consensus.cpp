@@ -465,6 +465,21 @@ extern "C" {
 
 void orc_cns_sort_candidates(mecat_candidate* c, int n) { orccns::sort_candidates(c, n); }
 
+// One region graph (AlnGraphBoost restatement) on its own: backbone of blen positions, naln gapped alignments
+// (q[i], t[i] of equal length, first column at backbone position start[i]).  Returns the length of the consensus
+// written to out, or -1 when it does not fit cap.
+int orc_poa_consensus(int blen, int naln, const char* const* q, const char* const* t, const int* start, int min_weight, char* out, int cap)
+{
+	orccns::Poa g(blen);
+	for (int i = 0; i < naln; ++i) g.add_alignment(std::string(q[i]), std::string(t[i]), start[i]);
+	g.merge_nodes();
+	std::string cns;
+	g.consensus(min_weight, cns);
+	if ((int)cns.size() > cap) return -1;
+	memcpy(out, cns.data(), cns.size());
+	return (int)cns.size();
+}
+
 int orc_cns_consensus(const mecat_candidate* cand, int ncand, const mecat_align_result* res, const char* qstr,
                       const char* sstr, const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces,
                       char** seqs, size_t* seq_bytes)

@@ -11,6 +11,7 @@
 #include "mecat2pw/pw_impl.cpp"          // -I$(REF)/src ; brings in seeding(), get_candidates(), ...
 #include "mecat2cns/dw.h"
 #include "mecat2cns/reads_correction_aux.h"
+#include "mecat2cns/MECAT_AlnGraphBoost.H"
 
 #include <cstdint>
 #include <cstring>
@@ -225,6 +226,19 @@ int ref_normalize_gaps(const char* qstr, const char* tstr, int n, int push, char
 	memcpy(qout, qn.c_str(), qn.size() + 1);
 	memcpy(tout, tn.c_str(), tn.size() + 1);
 	return (int)qn.size();
+}
+
+// C7: one AlnGraphBoost region graph exactly as meap_cns_one_indel drives it (mecat_correction.cpp:63-78)
+int ref_poa_consensus(int blen, int naln, const char* const* q, const char* const* t, const int* start, int min_weight, char* out, int cap)
+{
+	ns_meap_cns::AlnGraphBoost ag(blen);
+	for (int i = 0; i < naln; ++i) ag.addAln(std::string(q[i]), std::string(t[i]), (size_t)start[i]);
+	ag.mergeNodes();
+	std::string cns;
+	ag.consensus(min_weight, cns);
+	if ((int)cns.size() > cap) return -1;
+	memcpy(out, cns.data(), cns.size());
+	return (int)cns.size();
 }
 
 } // extern "C"

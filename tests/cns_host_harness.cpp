@@ -126,6 +126,40 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 
 void harness_free(void* p) { free(p); }
 
+// One region graph with the product's flat-array implementation (PoaT<I>, I = 1 / 2 / 4 byte indices) in an arena of
+// exactly the size the pipeline would give it.  Returns the consensus length (bytes in out), or -(100 + POA_ERR_*).
+int harness_poa_consensus(int blen, int naln, const char* const* q, const char* const* t, const int* start, int min_weight,
+                          int index_bytes, char* out, int cap)
+{
+	int nodes = blen + 2, e0 = blen + 1;
+	for (int i = 0; i < naln; ++i) {
+		for (const char *a = q[i], *b = t[i]; *a; ++a, ++b) {
+			if (*a == '-') continue;
+			++e0;
+			if (*a != *b) ++nodes;
+		}
+		++e0;
+	}
+	const int ecap = (int)mbcns::poa_edge_cap(nodes, e0);
+	std::vector<char> arena((size_t)mbcns::poa_arena_bytes<int32_t>(nodes, e0) + 16, (char)0xAB);
+	std::vector<char> path((size_t)nodes + 1);
+	int off = 0, len = 0, err = 0;
+	auto run = [&](auto tag) {
+		typedef decltype(tag) I;
+		mbcns::PoaT<I> g;
+		g.init(arena.data(), nodes, ecap, blen);
+		for (int i = 0; i < naln; ++i) g.add_alignment(q[i], t[i], 0, (int)strlen(q[i]) - 1, start[i]);
+		g.merge_nodes();
+		g.consensus(min_weight, path.data(), off, len);
+		err = g.err;
+	};
+	if (index_bytes == 1) run((int8_t)0); else if (index_bytes == 2) run((int16_t)0); else run((int32_t)0);
+	if (err) return -(100 + err);
+	if (len > cap) return -1;
+	memcpy(out, path.data() + off, (size_t)len);
+	return len;
+}
+
 // Unit check of the 32-positions-per-step anchor walk (anchor_chunk, what the GPU warps run) against the literal
 // sequential walk (walk_anchors, written after meap_consensus_one_segment) on one flag array.  Returns 0 when the
 // anchors, their ranks, the refine intervals, their ordinals and their chaining (prev_se) all agree.

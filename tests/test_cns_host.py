@@ -277,3 +277,57 @@ def test_lane_parallel_segment_search_matches_sequential_search():
         rc = H.harness_segments_compare(votes.ctypes.data_as(C.c_void_p), ranges.ctypes.data_as(C.c_void_p), len(ranges),
                                         int(rng.integers(1, 8)), float(rng.choice([0.5, 1.0, 3.0, 20.0, 57.0])))
         assert rc == 0, (trial, rc)
+
+
+def test_region_graph_matches_oracle_graph_on_random_pileups():
+    """The flat-array graph of the kernels (intrusive adjacency lists, explicit merge stack, exact-size arena; 8-, 16- and
+    32-bit indices) against the oracle's restatement of AlnGraphBoost on random pile-ups: up to 60 alignments over a short
+    backbone, tiny alphabets (so that many sibling nodes merge, recursively), long insertion runs, double gaps, partial
+    coverage.  Every run must finish without touching its capacity limits and give the oracle's consensus; where
+    oracle/_ref is built, the oracle itself is compared with the UNMODIFIED reference class on the same pile-ups."""
+    H, O = util.cns_harness(), util.oracle()
+    R = util.ref() if util.have_ref() else None
+    rng = np.random.default_rng(17)
+    for trial in range(1500):
+        blen = int(rng.integers(2, 16))
+        alphabet = "ACGT"[:int(rng.integers(1, 5))]
+        backbone = "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=blen))
+        naln = int(rng.integers(1, 61)) if trial % 4 else int(rng.integers(1, 6))
+        p_ins, p_del = rng.uniform(0, 0.5), rng.uniform(0, 0.3)
+        qs, ts, starts = [], [], []
+        for _ in range(naln):
+            pos = int(rng.integers(1, blen + 1))
+            starts.append(pos)
+            q, t = [], []
+            last = int(rng.integers(pos, blen + 1))
+            while pos <= last:
+                r = rng.random()
+                if r < p_ins:
+                    q.append(alphabet[int(rng.integers(len(alphabet)))]); t.append("-")
+                elif r < p_ins + p_del:
+                    q.append("-"); t.append(backbone[pos - 1]); pos += 1
+                elif r < p_ins + p_del + 0.02:
+                    q.append("-"); t.append("-")
+                else:
+                    q.append(backbone[pos - 1]); t.append(backbone[pos - 1]); pos += 1
+            if not q:
+                q, t = [backbone[starts[-1] - 1]], [backbone[starts[-1] - 1]]
+            qs.append("".join(q).encode()); ts.append("".join(t).encode())
+        qa = (C.c_char_p * naln)(*qs); ta = (C.c_char_p * naln)(*ts); sa = (C.c_int * naln)(*starts)
+        min_weight = int(rng.integers(0, max(2, naln // 2)))
+        cap = 4096
+        want = C.create_string_buffer(cap)
+        nw = O.orc_poa_consensus(blen, naln, qa, ta, sa, min_weight, want, cap)
+        assert nw >= 0
+        if R is not None:                                       # the unmodified AlnGraphBoost (Boost.Graph) pins the oracle here
+            ref = C.create_string_buffer(cap)
+            nr = R.ref_poa_consensus(blen, naln, qa, ta, sa, min_weight, ref, cap)
+            assert nr == nw and ref.raw[:nr] == want.raw[:nw], (trial, "oracle differs from the reference", backbone, qs, ts, starts, min_weight)
+        for index_bytes in (1, 2, 4):
+            nodes = blen + 2 + sum(1 for q, t in zip(qs, ts) for a, b in zip(q, t) if a != 45 and a != b)
+            e0 = blen + 1 + sum(1 for q in qs for a in q if a != 45) + naln
+            if index_bytes == 1 and max(nodes, e0 + nodes + 2) >= 120:
+                continue                                        # the kernels use wider indices for such a graph
+            got = C.create_string_buffer(cap)
+            ng = H.harness_poa_consensus(blen, naln, qa, ta, sa, min_weight, index_bytes, got, cap)
+            assert ng == nw and got.raw[:ng] == want.raw[:nw], (trial, index_bytes, ng, nw, backbone, qs, ts, starts, min_weight)

@@ -135,6 +135,8 @@ def cns_harness():
     L.harness_cns_batch.argtypes = [C.c_int, vp, vp, vp, C.c_char_p, C.c_char_p, vp, C.POINTER(vp), C.POINTER(C.c_size_t),
                                     C.POINTER(vp), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
     L.harness_free.argtypes = [vp]
+    L.harness_poa_consensus.restype = C.c_int
+    L.harness_poa_consensus.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.harness_anchor_compare.restype = C.c_int
     L.harness_anchor_compare.argtypes = [vp, C.c_int, C.c_int]
     L.harness_segments_compare.restype = C.c_int
@@ -191,6 +193,8 @@ def oracle():
     L.orc_pw_tile.argtypes = [VP, VP, PP, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_free.argtypes = [C.c_void_p]
     L.orc_cns_sort_candidates.argtypes = [C.c_void_p, C.c_int]
+    L.orc_poa_consensus.restype = C.c_int
+    L.orc_poa_consensus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.orc_cns_consensus.restype = C.c_int
     L.orc_cns_consensus.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -263,6 +267,8 @@ def ref():
     L.ref_diff_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, i32p,
                               C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     L.ref_diff_align_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, i32p]
+    L.ref_poa_consensus.restype = C.c_int
+    L.ref_poa_consensus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.ref_cns_drd_new.restype = C.c_void_p
     L.ref_cns_drd_free.argtypes = [C.c_void_p]
     L.ref_cns_get_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
