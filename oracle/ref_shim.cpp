@@ -23,6 +23,12 @@ int Align(const char* query, const int q_len, const char* target, const int t_le
           const int band_tolerance, const int get_aln_str, Alignment* align,
           int* V, int* U, DPathData2* d_path, PathPoint* aln_path, const int right_extend);
 
+// defined in mecat_correction.cpp without a header declaration
+namespace ns_meap_cns {
+void get_effective_ranges(std::vector<MappingRange>& mranges, std::vector<MappingRange>& eranges, const int read_size, const int min_size);
+void meap_add_one_aln(const std::string& qaln, const std::string& saln, index_t start_soff, CnsTableItem* cns_table, const char* org_seq);
+}
+
 extern "C" {
 
 // ---------------------------------------------------------------- volumes
@@ -222,6 +228,32 @@ int ref_normalize_gaps(const char* qstr, const char* tstr, int n, int push, char
 {
 	std::string qn, tn;
 	normalize_gaps(qstr, tstr, n, qn, tn, push != 0);
+	if ((int)qn.size() + 1 > cap) return -1;
+	memcpy(qout, qn.c_str(), qn.size() + 1);
+	memcpy(tout, tn.c_str(), tn.size() + 1);
+	return (int)qn.size();
+}
+
+// C6: get_effective_ranges (mecat_correction.cpp:118-153; defined there without a header declaration)
+int ref_effective_ranges(const int* in, int n, int read_size, int min_size, int* out, int cap)
+{
+	std::vector<MappingRange> m, e;
+	for (int i = 0; i < n; ++i) m.push_back(MappingRange(in[2 * i], in[2 * i + 1]));
+	ns_meap_cns::get_effective_ranges(m, e, read_size, min_size);
+	if ((int)e.size() > cap) return -1;
+	for (size_t i = 0; i < e.size(); ++i) { out[2 * i] = e[i].start; out[2 * i + 1] = e[i].end; }
+	return (int)e.size();
+}
+
+// C4 + C5: normalize_gaps then meap_add_one_aln into a table of `positions` items.  out = positions x {base, mat, ins, del};
+// the normalised strings go to qout / tout.  Returns the normalised length.
+int ref_normalize_and_vote(const char* qstr, const char* tstr, int n, int soff, int positions, unsigned char* out, char* qout, char* tout, int cap)
+{
+	std::string qn, tn;
+	normalize_gaps(qstr, tstr, n, qn, tn, true);
+	std::vector<CnsTableItem> table((size_t)positions);
+	ns_meap_cns::meap_add_one_aln(qn, tn, soff, table.data(), NULL);
+	for (int i = 0; i < positions; ++i) { out[4 * i] = (unsigned char)table[i].base; out[4 * i + 1] = table[i].mat_cnt; out[4 * i + 2] = table[i].ins_cnt; out[4 * i + 3] = table[i].del_cnt; }
 	if ((int)qn.size() + 1 > cap) return -1;
 	memcpy(qout, qn.c_str(), qn.size() + 1);
 	memcpy(tout, tn.c_str(), tn.size() + 1);

@@ -126,6 +126,38 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 
 void harness_free(void* p) { free(p); }
 
+// The kernels' get_effective_ranges on n {start, end} pairs; returns the number of ranges written to out.
+int harness_effective_ranges(const int* in, int n, int read_size, long long min_size, int* out)
+{
+	mbcns::Range m[mbcns::MAX_ACCEPT], e[mbcns::MAX_ACCEPT];
+	for (int i = 0; i < n; ++i) { m[i].start = in[2 * i]; m[i].end = in[2 * i + 1]; }
+	const int ne = mbcns::effective_ranges(m, n, e, read_size, 0.95 * (double)min_size);
+	for (int i = 0; i < ne; ++i) { out[2 * i] = e[i].start; out[2 * i + 1] = e[i].end; }
+	return ne;
+}
+
+// The kernels' one-pass normalise + vote on one gapped alignment: normalised strings to nq / nt, votes as
+// positions x {base, mat, ins, del}.  Returns the normalised length.
+int harness_normalize_and_vote(const char* q, const char* t, int n, int soff, int positions, unsigned char* out, char* nq_out, char* nt_out)
+{
+	std::vector<char> qp((size_t)n + 64, 0), tp((size_t)n + 64, 0);
+	char* qa = qp.data() + ((16 - ((uintptr_t)qp.data() & 15)) & 15) + 16 + 1;
+	char* ta = tp.data() + ((16 - ((uintptr_t)tp.data() & 15)) & 15) + 16 + 7;
+	memcpy(qa, q, (size_t)n); memcpy(ta, t, (size_t)n);
+	std::vector<unsigned long long> a((size_t)(2 * n + 64) / 8 + 1, 0), b((size_t)(2 * n + 64) / 8 + 1, 0);
+	std::vector<uint32_t> votes((size_t)positions + 2, 0);
+	std::vector<char> base((size_t)positions + 2, 'N');
+	std::vector<int32_t> colidx((size_t)positions + 4, 0);
+	int tend = 0;
+	const int len = mbcns::normalize_vote_index(qa, ta, n, soff, (char*)a.data(), (char*)b.data(), votes.data(), base.data(), colidx.data(), &tend);
+	for (int i = 0; i < positions; ++i) {
+		out[4 * i] = (unsigned char)base[i]; out[4 * i + 1] = (unsigned char)mbcns::vote_mat(votes[i]);
+		out[4 * i + 2] = (unsigned char)mbcns::vote_ins(votes[i]); out[4 * i + 3] = (unsigned char)mbcns::vote_del(votes[i]);
+	}
+	memcpy(nq_out, a.data(), (size_t)len + 1); memcpy(nt_out, b.data(), (size_t)len + 1);
+	return len;
+}
+
 // One region graph with the product's flat-array implementation (PoaT<I>, I = 1 / 2 / 4 byte indices) in an arena of
 // exactly the size the pipeline would give it.  Returns the consensus length (bytes in out), or -(100 + POA_ERR_*).
 int harness_poa_consensus(int blen, int naln, const char* const* q, const char* const* t, const int* start, int min_weight,

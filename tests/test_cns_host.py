@@ -331,3 +331,60 @@ def test_region_graph_matches_oracle_graph_on_random_pileups():
             got = C.create_string_buffer(cap)
             ng = H.harness_poa_consensus(blen, naln, qa, ta, sa, min_weight, index_bytes, got, cap)
             assert ng == nw and got.raw[:ng] == want.raw[:nw], (trial, index_bytes, ng, nw, backbone, qs, ts, starts, min_weight)
+
+
+needs_ref = pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/libmecatref.so not built (needs /root/reference)")
+
+
+@needs_ref
+def test_effective_ranges_kernel_body_against_the_reference_function():
+    """get_effective_ranges (mecat_correction.cpp:118-153) of the UNMODIFIED reference against the kernels' version on random
+    mapping ranges: nested, chained, touching, duplicated, with and without a read-spanning one."""
+    H, R = util.cns_harness(), util.ref()
+    rng = np.random.default_rng(23)
+    for trial in range(3000):
+        read_size = int(rng.integers(2000, 40000))
+        n = int(rng.integers(1, 61))
+        starts = rng.integers(0, read_size - 1, size=n)
+        if trial % 3 == 0:
+            starts = (starts // 700) * 700                       # many equal starts
+        ends = np.minimum(read_size, starts + rng.integers(1, read_size, size=n))
+        if trial % 7 == 0:
+            starts[0], ends[0] = int(rng.integers(0, 520)), read_size - int(rng.integers(0, 520))
+        pairs = np.ascontiguousarray(np.stack([starts, ends], axis=1).astype(np.int32))
+        min_size = int(rng.choice([1, 500, 2000, 5000, 12000]))
+        a, b = np.zeros(2 * 64, dtype=np.int32), np.zeros(2 * 64, dtype=np.int32)
+        na = R.ref_effective_ranges(pairs.ctypes.data_as(C.c_void_p), n, read_size, min_size, a.ctypes.data_as(C.c_void_p), 64)
+        nb = H.harness_effective_ranges(pairs.ctypes.data_as(C.c_void_p), n, read_size, min_size, b.ctypes.data_as(C.c_void_p))
+        assert na == nb and a[:2 * na].tolist() == b[:2 * nb].tolist(), (trial, pairs.tolist(), read_size, min_size)
+
+
+@needs_ref
+def test_one_pass_normalise_vote_against_the_reference_functions():
+    """normalize_gaps + meap_add_one_aln of the UNMODIFIED reference against the kernels' single streaming pass: same
+    normalised strings, same vote table (base, match, insert, delete counts per template position)."""
+    H, R = util.cns_harness(), util.ref()
+    rng = np.random.default_rng(29)
+    for trial in range(600):
+        n = int(rng.integers(1, 500))
+        alphabet = b"ACGT"[:int(rng.integers(1, 5))]
+        pgap = rng.uniform(0.05, 0.5)
+        q, t = bytearray(), bytearray()
+        for k in range(n):
+            a = alphabet[int(rng.integers(len(alphabet)))]
+            b = alphabet[int(rng.integers(len(alphabet)))] if rng.random() < 0.3 else a
+            r = rng.random()
+            if k == 0 or k == n - 1 or r >= pgap:                 # GetAlignment's output starts and ends on a column with both bases
+                q.append(a); t.append(b if 0 < k < n - 1 else a)
+            elif r < pgap / 2:
+                q.append(ord("-")); t.append(b)
+            else:
+                q.append(a); t.append(ord("-"))
+        positions = sum(1 for c in t if c != ord("-")) + 3
+        cap = 2 * n + 16
+        out_r, out_h = np.zeros(4 * positions, dtype=np.uint8), np.zeros(4 * positions, dtype=np.uint8)
+        qr, tr, qh, th = (C.create_string_buffer(cap) for _ in range(4))
+        lr = R.ref_normalize_and_vote(bytes(q), bytes(t), n, 1, positions, out_r.ctypes.data_as(C.c_void_p), qr, tr, cap)
+        lh = H.harness_normalize_and_vote(bytes(q), bytes(t), n, 1, positions, out_h.ctypes.data_as(C.c_void_p), qh, th)
+        assert lr == lh and qr.value == qh.value and tr.value == th.value, (trial, bytes(q), bytes(t))
+        assert out_r.tolist() == out_h.tolist(), (trial, bytes(q), bytes(t))

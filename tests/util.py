@@ -135,6 +135,10 @@ def cns_harness():
     L.harness_cns_batch.argtypes = [C.c_int, vp, vp, vp, C.c_char_p, C.c_char_p, vp, C.POINTER(vp), C.POINTER(C.c_size_t),
                                     C.POINTER(vp), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
     L.harness_free.argtypes = [vp]
+    L.harness_effective_ranges.restype = C.c_int
+    L.harness_effective_ranges.argtypes = [vp, C.c_int, C.c_int, C.c_longlong, vp]
+    L.harness_normalize_and_vote.restype = C.c_int
+    L.harness_normalize_and_vote.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, vp, C.c_char_p, C.c_char_p]
     L.harness_poa_consensus.restype = C.c_int
     L.harness_poa_consensus.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.harness_anchor_compare.restype = C.c_int
@@ -267,6 +271,10 @@ def ref():
     L.ref_diff_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, i32p,
                               C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     L.ref_diff_align_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, i32p]
+    L.ref_effective_ranges.restype = C.c_int
+    L.ref_effective_ranges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.ref_normalize_and_vote.restype = C.c_int
+    L.ref_normalize_and_vote.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
     L.ref_poa_consensus.restype = C.c_int
     L.ref_poa_consensus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.ref_cns_drd_new.restype = C.c_void_p
