@@ -95,6 +95,28 @@ def read_slices(world, num_reads, diagonal=True, seed_w=131.0, extend_w=417.0):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def exchange_slices(dist, pos, bounds, rank, world, mode="allgather"):
+    """Strong-scaling index exchange: rank q owns pos[bounds[q]:bounds[q+1]] (its code slice of the k-mer positions);
+    afterwards every rank holds all of pos.  "allgather": ONE padded all-gather (every NVLink port busy at once) followed
+    by a local compaction of the foreign slices; "broadcast": one broadcast per slice (the first implementation).
+    Works on any backend / device the tensor lives on (NCCL on GPUs, gloo in the CPU tests)."""
+    import torch
+    sizes = [int(bounds[q + 1] - bounds[q]) for q in range(world)]
+    if mode == "allgather" and max(sizes) > 0:
+        m = (max(sizes) + 63) // 64 * 64
+        send = torch.empty(m, dtype=pos.dtype, device=pos.device)
+        send[:sizes[rank]] = pos[int(bounds[rank]):int(bounds[rank + 1])]
+        recv = torch.empty(world * m, dtype=pos.dtype, device=pos.device)
+        dist.all_gather_into_tensor(recv, send)
+        for q in range(world):
+            if q != rank and sizes[q]:
+                pos[int(bounds[q]):int(bounds[q + 1])] = recv[q * m:q * m + sizes[q]]
+    else:
+        reqs = [dist.broadcast(pos[int(bounds[q]):int(bounds[q + 1])], src=q, async_op=True) for q in range(world) if sizes[q] > 0]
+        for r in reqs:
+            r.wait()
+
+
 class _DevMem:
     """Raw device memory as a __cuda_array_interface__ object (zero-copy torch view of library memory)."""
 
@@ -184,22 +206,7 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
             begin = device_view(bptr, (1 << 26) + 1, torch.int32, 4)
             bounds = begin[cuts].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
             pos = device_view(pptr, nk, torch.int32, 4)
-            sizes = [int(bounds[q + 1] - bounds[q]) for q in range(world)]
-            if exchange == "allgather" and max(sizes) > 0:
-                m = (max(sizes) + 63) // 64 * 64
-                send = torch.empty(m, dtype=torch.int32, device=dev)
-                send[:sizes[rank]] = pos[int(bounds[rank]):int(bounds[rank + 1])]
-                recv = torch.empty(world * m, dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(recv, send)
-                for q in range(world):
-                    if q != rank and sizes[q]:
-                        pos[int(bounds[q]):int(bounds[q + 1])] = recv[q * m:q * m + sizes[q]]
-                del send, recv
-            else:
-                reqs = [dist.broadcast(pos[int(bounds[q]):int(bounds[q + 1])], src=q, async_op=True) for q in range(world)
-                        if bounds[q + 1] > bounds[q]]
-                for r in reqs:
-                    r.wait()
+            exchange_slices(dist, pos, bounds, rank, world, exchange)
             torch.cuda.synchronize()
         t0 = lap("positions_exchange", t0)
         rec = ctx.pw_tile_range(idx, dvol, dvol, params, rb, re)

@@ -115,3 +115,43 @@ def test_read_and_code_slices_partition(world):
     cs = multi.code_slices(world)
     assert cs[0][0] == 0 and cs[-1][1] == 1 << 26 and all(a[1] == b[0] for a, b in zip(cs, cs[1:]))
     assert all(lo % 256 == 0 and hi % 256 == 0 for lo, hi in cs)
+
+
+def _exchange_worker(rank, world, port, mode, out):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # uneven slices, one of them empty when there are three ranks
+    sizes = [1000, 37, 0][:world] if world == 3 else [129, 1000]
+    bounds = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    full = torch.arange(int(bounds[-1]), dtype=torch.int32) * 7 + 3           # what every rank must end up with
+    pos = torch.full_like(full, -1)
+    pos[int(bounds[rank]):int(bounds[rank + 1])] = full[int(bounds[rank]):int(bounds[rank + 1])]   # only the own slice is known
+    multi.exchange_slices(dist, pos, bounds, rank, world, mode)
+    ok = bool(torch.equal(pos, full))
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        out.put(flags)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,mode", [(2, "allgather"), (3, "allgather"), (2, "broadcast")])
+def test_index_slice_exchange_over_gloo(world, mode):
+    """Strong scaling: every rank builds one code slice of the k-mer positions; after the exchange all ranks hold all
+    slices (padded all-gather + compaction, or the per-slice broadcasts it replaced)."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    flags = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert flags == [True] * world
