@@ -10,6 +10,9 @@ Cases (reads come from oracle/gen_reads, a seeded deterministic generator):
   deep  : 300 reads, mean 6 kb, genome 15 kb, seed 5    -> ~120x coverage: every read has the full 100 candidates,
           so mecat2cns reaches its 60-alignment cap and its 20x coverage gate (check_cov_stats); only the
           candidates and the corrected FASTA (-l 2000 -c 4 -a 1000) are kept, FASTA regenerated on demand
+  refmap: 300 reads, mean 6 kb, genome 100 kb, seed 5  -> `mecat2ref -m 1` (M4) and `-m 0` (ref format with alignment
+          strings) of the reads against their own genome: fixtures for the mecat2ref driver,
+          which is not built yet; reads and genome are regenerated on demand (sha256 committed)
   python tests/golden/make_golden.py [case ...]   regenerates only the named cases
 For each: vol0 sha256 (split_raw_dataset), sorted `mecat2pw -j 0` lines, sorted
 `mecat2pw -j 1 -g 1` lines.
@@ -33,6 +36,36 @@ CASES = {
     "cfg0": dict(n=1000, genome=1000000, seed=7, mean=15000, sd=1500),
     "deep": dict(n=300, genome=15000, seed=5, mean=6000, sd=1000),
 }
+REFMAP = dict(n=300, genome=100000, seed=5, mean=6000, sd=1500)
+
+
+def make_refmap(meta):
+    c = REFMAP
+    tmp = tempfile.mkdtemp(prefix="golden_ref_")
+    fa, genome = os.path.join(tmp, "reads.fa"), os.path.join(tmp, "genome.fa")
+    gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], genome_out=genome)
+    m = dict(c)
+    m["fasta_sha256"] = sha(fa)
+    m["genome_sha256"] = sha(genome)
+    for fmt, ext in ((1, "m4"), (0, "ref")):
+        out = os.path.join(tmp, "out." + ext)
+        subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w" + ext),
+                               "-t", "4", "-m", str(fmt)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        text = open(out).read()
+        if fmt == 1:
+            lines = sorted(text.splitlines())
+            with gzip.open(os.path.join(HERE, "refmap.m4.gz"), "wt") as f:
+                f.write("\n".join(lines) + "\n")
+            m["num_m4"] = len(lines)
+        else:
+            recs = text.split("\n")
+            groups = sorted("\n".join(recs[i:i + 3]) for i in range(0, len(recs) - 1, 3))     # header, query string, subject string
+            with gzip.open(os.path.join(HERE, "refmap.ref.gz"), "wt") as f:
+                f.write("\n".join(groups) + "\n")
+            m["num_ref"] = len(groups)
+    meta["refmap"] = m
+    shutil.rmtree(tmp)
+
 
 
 def sha(path):
@@ -89,6 +122,8 @@ def main():
                 shutil.copyfileobj(f, g)
         meta[name] = m
         shutil.rmtree(tmp)
+    if len(sys.argv) == 1 or "refmap" in sys.argv[1:]:
+        make_refmap(meta)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))
