@@ -79,6 +79,11 @@ int orc_cns_get_alignment(const char* q, int qstart, int qsize, const char* t, i
 /* ---- C4 */
 int orc_normalize_gaps(const char* qstr, const char* tstr, int n, int push, char* qout, char* tout, int cap);
 
+/* ---- mecat2ref end to end (next row of the scope table; no CUDA path yet): the text `mecat2ref -m format` writes,
+ * format 0 = ref (header + two alignment strings), 1 = m4.  malloc'ed, free with orc_free. */
+int orc_ref_map(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format,
+                char** text, size_t* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from util import gen_reads, REF_DIR  # noqa: E402
+from util import gen_reads, make_refmap_hard, REF_DIR  # noqa: E402
 
 CASES = {
     "small": dict(n=250, genome=100000, seed=3, mean=6000, sd=1500),
@@ -64,6 +64,21 @@ def make_refmap(meta):
                 f.write("\n".join(groups) + "\n")
             m["num_ref"] = len(groups)
     meta["refmap"] = m
+    shutil.rmtree(tmp)
+    # second fixture: inputs that leave the main path (util.make_refmap_hard)
+    tmp = tempfile.mkdtemp(prefix="golden_ref2_")
+    fa, genome = os.path.join(tmp, "reads.fa"), os.path.join(tmp, "genome.fa")
+    make_refmap_hard(fa, genome)
+    m = {"fasta_sha256": sha(fa), "genome_sha256": sha(genome)}
+    out = os.path.join(tmp, "out.ref")
+    subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w"), "-t", "3", "-m", "0"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    recs = open(out).read().split("\n")
+    groups = sorted("\n".join(recs[i:i + 3]) for i in range(0, len(recs) - 1, 3))
+    with gzip.open(os.path.join(HERE, "refmap_hard.ref.gz"), "wt") as f:
+        f.write("\n".join(groups) + "\n")
+    m["num_ref"] = len(groups)
+    meta["refmap_hard"] = m
     shutil.rmtree(tmp)
 
 

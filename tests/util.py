@@ -197,6 +197,8 @@ def oracle():
     L.orc_pw_tile.argtypes = [VP, VP, PP, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_free.argtypes = [C.c_void_p]
     L.orc_cns_sort_candidates.argtypes = [C.c_void_p, C.c_int]
+    L.orc_ref_map.restype = C.c_int
+    L.orc_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_poa_consensus.restype = C.c_int
     L.orc_poa_consensus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.orc_cns_consensus.restype = C.c_int
@@ -350,3 +352,67 @@ def repeat_reads(seed=21, unit=4000, copies=10, n_reads=260, mean=5000, err=0.05
             out = (3 - out)[::-1]
         reads.append(bytes(b"ACGT"[int(c)] for c in out))
     return reads
+
+
+def make_refmap_hard(reads_path, genome_path, seed=19):
+    """Deterministic inputs that push mecat2ref off its main path: three contigs (one holding a 3 kb repeat of another),
+    noisy reads (15 % errors), chimeric reads glued from two places (clipped alignments -> rescue_clipped_align), reads with
+    a stretch of N, short reads, very noisy reads (second, more sensitive pass) and lower-case letters."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rand_seq(n):
+        return acgt[rng.integers(0, 4, size=n)].tobytes().decode()
+
+    contigs = [rand_seq(60000), rand_seq(35000), rand_seq(20000)]
+    contigs[1] = contigs[1][:10000] + contigs[0][20000:23000] + contigs[1][13000:]
+    contigs[2] = contigs[2][:5000] + "N" * 300 + contigs[2][5300:]
+    with open(genome_path, "w") as f:
+        for i, c in enumerate(contigs):
+            f.write(">chr%d some description\n" % (i + 1))
+            for k in range(0, len(c), 70):
+                f.write(c[k:k + 70] + "\n")
+
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+
+    def noisy(s, err):
+        out = []
+        for ch in s:
+            r = rng.random()
+            if r < err * 0.3:
+                continue
+            if r < err * 0.4:
+                out.append("ACGT"[int(rng.integers(4))])
+                continue
+            out.append(ch)
+            if rng.random() < err * 0.6:
+                out.append("ACGT"[int(rng.integers(4))])
+        return "".join(out)
+
+    def piece(length):
+        c = contigs[int(rng.integers(len(contigs)))]
+        length = min(length, len(c) - 1)
+        b = int(rng.integers(0, len(c) - length))
+        s = c[b:b + length]
+        if rng.random() < 0.5:
+            s = "".join(comp[x] for x in reversed(s))
+        return s
+
+    reads = []
+    for i in range(160):
+        kind = i % 8
+        if kind < 4:
+            reads.append(noisy(piece(int(rng.integers(3000, 12000))), 0.15))
+        elif kind == 4:
+            reads.append(noisy(piece(int(rng.integers(4000, 7000))), 0.15) + noisy(piece(int(rng.integers(4000, 7000))), 0.15))
+        elif kind == 5:
+            reads.append(noisy(piece(int(rng.integers(2500, 5000))), 0.28))
+        elif kind == 6:
+            s = noisy(piece(int(rng.integers(5000, 9000))), 0.12)
+            reads.append(s[:2000] + "N" * 50 + s[2050:])
+        else:
+            s = noisy(piece(int(rng.integers(1200, 2500))), 0.1)
+            reads.append(s[:600] + s[600:900].lower() + s[900:])
+    with open(reads_path, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">read_%d\n%s\n" % (i, r))
