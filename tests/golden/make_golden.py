@@ -65,6 +65,22 @@ def make_refmap(meta):
             m["num_ref"] = len(groups)
     meta["refmap"] = m
     shutil.rmtree(tmp)
+    # BASELINE configs[0]-sized reads (1 000 x 15 kb) against their 1 Mb genome: M4 only
+    c = dict(n=1000, genome=1000000, seed=7, mean=15000, sd=1500)
+    tmp = tempfile.mkdtemp(prefix="golden_ref1_")
+    fa, genome = os.path.join(tmp, "reads.fa"), os.path.join(tmp, "genome.fa")
+    gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], genome_out=genome)
+    m = dict(c)
+    m["fasta_sha256"] = sha(fa); m["genome_sha256"] = sha(genome)
+    out = os.path.join(tmp, "out.m4")
+    subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w"), "-t", "8", "-m", "1"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = sorted(open(out).read().splitlines())
+    with gzip.open(os.path.join(HERE, "refmap_cfg0.m4.gz"), "wt") as f:
+        f.write("\n".join(lines) + "\n")
+    m["num_m4"] = len(lines)
+    meta["refmap_cfg0"] = m
+    shutil.rmtree(tmp)
     # second fixture: inputs that leave the main path (util.make_refmap_hard)
     tmp = tempfile.mkdtemp(prefix="golden_ref2_")
     fa, genome = os.path.join(tmp, "reads.fa"), os.path.join(tmp, "genome.fa")

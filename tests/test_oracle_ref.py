@@ -72,3 +72,17 @@ def test_hard_inputs_match_reference(tmp_path):
     gh, wh = [g.split("\n")[0] for g in got], [w.split("\n")[0] for w in want]
     assert gh == wh, (len(gh), len(wh), sorted(set(gh) - set(wh))[:5], sorted(set(wh) - set(gh))[:5])
     assert got == want
+
+
+def test_cfg0_sized_reads_match_reference(tmp_path):
+    """1 000 x 15 kb reads (BASELINE configs[0]'s read set) against their 1 Mb genome, M4 output."""
+    c = GOLD["refmap_cfg0"]
+    fa, genome = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], genome_out=genome)
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == c["fasta_sha256"]
+    got = sorted(run_oracle(fa, genome, 1).splitlines())
+    with gzip.open(os.path.join(util.GOLDEN, "refmap_cfg0.m4.gz"), "rt") as f:
+        want = f.read().splitlines()
+    assert len(got) == len(want) == c["num_m4"]
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:3]
