@@ -162,7 +162,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        # the workload of our arm at this N: the configs[1] tile in the default --mode strong, N volumes in --mode ring
+        "config": dict(workload_config(args.gpus if (args.gpus > 1 and args.mode == "ring") else 1),
+                       parallelism="reference CPU binary, %d host threads (no GPU)" % cores),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

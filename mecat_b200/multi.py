@@ -254,7 +254,7 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
             pass
         cfg = workload_config(1)
         cfg["parallelism"] = ("%d gpus sharing one tile: k-mer index built in %d code slices exchanged over NCCL "
-                              "(all-gather + broadcasts), query reads split %d ways" % (world, world, world))
+                              "(all-gather), query reads split %d ways" % (world, world, world))
         if args.reads:
             cfg = dict(cfg, reads=READS, genome=GENOME, workload="REDUCED debug workload (%d reads)" % READS)
         line = {
