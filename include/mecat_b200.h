@@ -114,7 +114,10 @@ enum {
 	MECAT_K_CNS_REGION = 13,   /* cns: position flags, anchors, ambiguous regions    */
 	MECAT_K_CNS_POA = 14,      /* cns: one partial-order graph per region (C7)       */
 	MECAT_K_CNS_ASSEMBLE = 15, /* cns: corrected bases of every segment              */
-	MECAT_K_NUM = 16
+	MECAT_K_REF_COUNT = 16,    /* ref: index hits per strand (sizes the block tables) */
+	MECAT_K_REF_SEED = 17,     /* ref: seeding, DDF scoring, candidate walk           */
+	MECAT_K_REF_RESCUE = 18,   /* ref: candidates beyond clipped alignment ends       */
+	MECAT_K_NUM = 19
 };
 typedef struct {
 	float kernel_ms[MECAT_K_NUM];
@@ -253,6 +256,63 @@ int mecat_b200_cns_reads(mecat_b200_ctx* ctx, void* dvol_reads, const mecat_cand
  * host only.  mecat_b200_cns_reads applies it itself; exported so that callers feeding mecat_b200_align_batch can
  * reproduce the order. */
 void mecat_b200_cns_sort_candidates(mecat_candidate* c, int n);
+/* ---- mecat2ref: reads against a reference genome ---------------------
+ * The reference genome as creat_ref_index keeps it (src/mecat2ref/mecat2ref_impl_large.cpp:133-271): all sequences
+ * concatenated (REFSEQ), here 2-bit packed like mecat_volume.pac with every letter other than ACGT packed as A
+ * (extract_sequences aligns them as A, src/mecat2ref/mecat2ref_aux.cpp:86-121), plus the maximal runs of ACGT letters:
+ * the index holds the 13-mers inside a run only (:199-206).  Fewer than 2^31 - 2^20 bases. */
+typedef struct {
+	int64_t num_bases;
+	const uint8_t* pac;
+	int32_t num_runs;
+	const int64_t* run_start_len;   /* num_runs x {start, length}, ascending, disjoint */
+} mecat_ref_genome;
+
+/* A batch of reads for mecat2ref.  vol holds the strands 2-bit packed (letters other than ACGT, either case, as A).
+ * Read r has read_len[r] bases; its forward strand is volume read fwd_read[r]; its reverse strand is the reverse
+ * complement of volume read rev_read[r] when rev_is_rc[r], else volume read rev_read[r] as packed (the reference
+ * complements upper-case ACGT only, mecat2ref_impl_large.cpp:374-400, so a read with other letters carries its reverse
+ * strand explicitly).  bad: ascending base offsets inside vol of letters that are not upper-case ACGT; a k-mer covering
+ * one is not looked up (transnum_buchang, :64-90).  Strands taken by reverse complement must be free of them. */
+typedef struct {
+	int32_t num_reads;
+	const mecat_volume* vol;
+	const int32_t* read_len;
+	const int32_t* fwd_read;
+	const int32_t* rev_read;
+	const int32_t* rev_is_rc;
+	int64_t num_bad;
+	const int64_t* bad;
+} mecat_ref_reads;
+
+/* Mirrors meap_ref_options (src/mecat2ref/mecat2ref.cpp:22-50): -n, -b, -x; want_strings = the output format prints
+ * the alignment strings (-m 0). */
+typedef struct {
+	int32_t num_candidates;   /* -n, default 10 */
+	int32_t num_output;       /* -b, default 10 */
+	int32_t want_strings;
+	int32_t tech;             /* -x, 0 = pacbio (the only technology of this path) */
+} mecat_ref_params;
+
+/* TempResult (src/mecat2ref/mecat2ref_aux.h:16-25) of one printed alignment: read = index inside the batch, dir 0 = F
+ * 1 = R, [qb, qe) on the strand that aligned, [sb, se) on the concatenated reference; columns / matches of the
+ * alignment strings, which start at str_offset in both string blobs (NUL terminated; -1 without want_strings). */
+typedef struct {
+	int32_t read, dir, vscore, qb, qe, qs;
+	int64_t sb, se;
+	int32_t columns, matches;
+	int64_t str_offset;
+} mecat_ref_result;
+
+/* replaces creat_ref_index (mecat2ref_impl_large.cpp:133-271): upload + k-mer index of the genome */
+int mecat_b200_ref_index_build(mecat_b200_ctx* ctx, const mecat_ref_genome* g, void** refidx);
+int mecat_b200_ref_index_release(mecat_b200_ctx* ctx, void* refidx);
+/* replaces reference_mapping for a batch of reads (mecat2ref_impl_large.cpp:274-891: both seeding passes, candidate
+ * selection, extend_candidate, rescue_clipped_align, output_results).  Records of a read are adjacent and in the
+ * reference's order, at most num_output per read. */
+int mecat_b200_ref_map(mecat_b200_ctx* ctx, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
+                       mecat_ref_result** results, size_t* n, char** qstrings, char** sstrings, size_t* string_bytes);
+
 /* frees host buffers handed out by this library (same as mecat_b200_free without a context) */
 void mecat_b200_host_free(void* p);
 

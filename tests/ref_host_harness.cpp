@@ -1,0 +1,218 @@
+// tests/ref_host_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Runs the product's mecat2ref stage sequence (mecat_b200/csrc/ref_pipeline.h), kernel bodies (ref_core.cuh) and host
+// I/O (host/refio.h) on the host: "device memory" is malloc, a kernel launch is a loop over the units, the k-mer index
+// is a plain two-pass CSR build, and the gapped extension -- a separate, GPU-tested kernel of the product (align.cu) --
+// is played by the oracle's orc_diff_go.  This lets the CPU test-suite check the statements the GPU executes against
+// the golden output of the unmodified mecat2ref binary without a GPU.  Compiled by tests/util.py into
+// tests/_build/libref_harness.so; never part of the product library.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../include/mecat_b200.h"
+#include "../mecat_b200/csrc/host/refio.h"
+#include "../mecat_b200/csrc/ref_pipeline.h"
+#include "../oracle/oracle.h"
+
+namespace {
+
+std::vector<uint32_t> words_of(const uint8_t* pac, int64_t n)      // the device layout of volume.cu: base p at bits 2 (p % 16) of word p / 16
+{
+	std::vector<uint32_t> w((size_t)(n / 16 + 9), 0u);
+	for (int64_t p = 0; p < n; ++p) {
+		const uint32_t b = (pac[p >> 2] >> (((~p) & 3) << 1)) & 3u;
+		w[(size_t)(p >> 4)] |= b << ((p & 15) << 1);
+	}
+	return w;
+}
+
+struct HostBackend
+{
+	std::vector<void*> owned;
+	std::string err;
+	// what the extension hook needs: both volumes, unpacked
+	const uint32_t* rfwd = nullptr; const int32_t* roffsz = nullptr;
+	const uint32_t* gfwd = nullptr;
+	int64_t tasks_run = 0, batches = 0;
+
+	template <class T> T* alloc(size_t n)
+	{
+		void* p = malloc((n ? n : 1) * sizeof(T));
+		if (!p) { err = "out of memory"; return nullptr; }
+		memset(p, 0xAB, (n ? n : 1) * sizeof(T));      // like device memory: never zero by luck
+		owned.push_back(p);
+		return (T*)p;
+	}
+	template <class T> bool upload(T* d, const T* h, size_t n) { if (n) memcpy(d, h, n * sizeof(T)); return true; }
+	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
+	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
+	template <class F> bool launch(int64_t n, const F& f, int stage)
+	{
+		if (stage == mbref::ST_SEED) ++batches;
+		for (int64_t i = 0; i < n; ++i) f(i);
+		return true;
+	}
+	bool release(void* p)
+	{
+		for (size_t i = 0; i < owned.size(); ++i) if (owned[i] == p) { free(p); owned[i] = owned.back(); owned.pop_back(); return true; }
+		err = "release of an unknown block";
+		return false;
+	}
+	void fail(const char* m) { err = m; }
+	void end_batch() { for (void* p : owned) free(p); owned.clear(); }
+
+	static int base(const uint32_t* w, int64_t p) { return (int)((w[p >> 4] >> ((p & 15) << 1)) & 3u); }
+	bool align(const mecat_align_task* tasks, size_t n, bool want_strings, mecat_align_result* res, std::vector<char>& qs, std::vector<char>& ss)
+	{
+		qs.clear(); ss.clear();
+		std::vector<char> q, t, qa, ta;
+		for (size_t i = 0; i < n; ++i) {
+			const mecat_align_task& k = tasks[i];
+			const int64_t off = roffsz[2 * k.qread];
+			const int len = roffsz[2 * k.qread + 1];
+			q.resize((size_t)len);
+			for (int j = 0; j < len; ++j) q[(size_t)j] = (char)(k.qstrand ? 3 - base(rfwd, off + len - 1 - j) : base(rfwd, off + j));
+			t.resize((size_t)k.swin_len);
+			for (int j = 0; j < k.swin_len; ++j) t[(size_t)j] = (char)base(gfwd, (int64_t)k.swin_off + j);
+			const int cap = 2 * (len + k.swin_len) + 64;
+			qa.resize((size_t)cap); ta.resize((size_t)cap);
+			int32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+			double ident = 0;
+			const int ok = orc_diff_go(q.data(), k.qstart, len, t.data(), k.sstart, k.swin_len, 1000, o, &ident, qa.data(), ta.data(), cap);
+			mecat_align_result& r = res[i];
+			memset(&r, 0, sizeof r);
+			r.ok = ok; r.str_offset = -1;
+			if (!ok) continue;
+			r.qstart = o[1]; r.qend = o[2]; r.sstart = o[3]; r.send = o[4]; r.columns = o[5]; r.matches = o[6]; r.ident = ident;
+			if (want_strings) {
+				r.str_offset = (int64_t)qs.size();
+				qs.insert(qs.end(), qa.data(), qa.data() + o[5] + 1);
+				ss.insert(ss.end(), ta.data(), ta.data() + o[5] + 1);
+				qs.back() = 0; ss.back() = 0;
+			}
+			++tasks_run;
+		}
+		return true;
+	}
+};
+
+// CSR k-mer index in the product's layout (index.cu): codes A0 C1 G2 T3 with the first base most significant, 0-based
+// starts ascending, lists of more than 128 starts dropped
+void build_index(const uint32_t* gfwd, const std::vector<int64_t>& runs, std::vector<uint32_t>& begin, std::vector<int32_t>& pos)
+{
+	const uint32_t ncodes = 1u << 26, mask = ncodes - 1;
+	std::vector<uint32_t> cnt(ncodes, 0u);
+	for (int pass = 0; pass < 2; ++pass) {
+		for (size_t r = 0; r + 1 < runs.size(); r += 2) {
+			uint32_t code = 0;
+			for (int64_t j = 0; j < runs[r + 1]; ++j) {
+				const int64_t p = runs[r] + j;
+				code = ((code << 2) | ((gfwd[p >> 4] >> ((p & 15) << 1)) & 3u)) & mask;
+				if (j < 12) continue;
+				if (pass == 0) ++cnt[code];
+				else if (cnt[code] != 0xffffffffu) pos[begin[code] + cnt[code]++] = (int32_t)(p - 12);
+			}
+		}
+		if (pass == 0) {
+			begin.assign((size_t)ncodes + 1, 0u);
+			uint32_t total = 0;
+			for (uint32_t c = 0; c < ncodes; ++c) {
+				begin[c] = total;
+				if (cnt[c] > 128) cnt[c] = 0xffffffffu; else { total += cnt[c]; cnt[c] = 0; }
+			}
+			begin[ncodes] = total;
+			pos.assign(total, 0);
+		}
+	}
+}
+
+}  // namespace
+
+extern "C" {
+
+// mecat2ref -d reads -r reference -n num_candidates -b num_output -m format through the product's host I/O, stage
+// sequence and kernel bodies.  reads_per_call / table_budget force several ABI-sized calls and table batches.
+int harness_ref_map(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format, int reads_per_call,
+                    long table_budget, char** text, size_t* bytes, long* stats /* tasks, seed launches */, char* errbuf, int errcap)
+{
+	auto fail = [&](const std::string& m) { if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", m.c_str()); return 1; };
+	refio::Genome G;
+	refio::Reads R;
+	std::string err;
+	if (!refio::load_genome(reference_path, G, err) || !refio::load_reads(reads_path, R, err)) return fail(err);
+	const std::vector<uint32_t> gw = words_of(G.seq.pac.data(), G.seq.n);
+	std::vector<uint32_t> begin;
+	std::vector<int32_t> pos;
+	build_index(gw.data(), G.runs, begin, pos);
+	std::string out;
+	long ntasks = 0, nbatches = 0;
+	const int total = (int)R.seq.size();
+	if (reads_per_call < 1) reads_per_call = total ? total : 1;
+	for (int first = 0; first < total; first += reads_per_call) {
+		const int count = std::min(reads_per_call, total - first);
+		refio::ReadBatch B;
+		for (int i = 0; i < count; ++i) B.add_read(R.seq[(size_t)(first + i)]);
+		const mecat_ref_reads view = B.view();
+		const std::vector<uint32_t> rw = words_of(view.vol->pac, view.vol->num_bases);
+		HostBackend be;
+		be.rfwd = rw.data(); be.roffsz = view.vol->offset_size; be.gfwd = gw.data();
+		mbref::MapIn in;
+		in.R = view.num_reads; in.h_len = view.read_len; in.h_fread = view.fwd_read; in.h_rread = view.rev_read; in.h_rrc = view.rev_is_rc;
+		in.seqcount = G.seq.n;
+		in.d_fwd = rw.data(); in.d_offsz = view.vol->offset_size; in.d_bad = view.bad; in.nbad = view.num_bad;
+		in.d_ibegin = begin.data(); in.d_ipos = pos.data();
+		mbref::Params P;
+		P.num_candidates = num_candidates; P.num_output = num_output; P.want_strings = format == 0;
+		if (table_budget > 0) P.table_budget = table_budget;
+		mbref::Sink sink;
+		if (mbref::map_reads(be, in, P, sink)) return fail(be.err);
+		refio::format_results(out, G, R.name, first, sink.recs.data(), sink.recs.size(), sink.q.data(), sink.s.data(), format);
+		ntasks += be.tasks_run; nbatches += be.batches;
+	}
+	char* p = (char*)malloc(out.size() + 1);
+	if (!p) return fail("out of memory");
+	memcpy(p, out.data(), out.size());
+	p[out.size()] = 0;
+	*text = p; *bytes = out.size();
+	if (stats) { stats[0] = ntasks; stats[1] = nbatches; }
+	return 0;
+}
+
+// the float forms of the DDF test as the reference writes them, next to the integer form of the kernels
+int harness_ddf_forms(int a, int b, int bc)
+{
+	const float len = (float)bc;
+	int r = mbref::ddf_close(a, b, bc) ? 1 : 0;
+	if (b != 0) {
+		const bool f32 = fabs(a / (b * len) - 1) < 0.25;                 // find_location, mecat2ref_aux.cpp:23
+		const bool f32d = fabs(a / (b * len) - 1.0) < 0.25;              // insert_loc, mecat2ref_impl_large.cpp:107
+		const bool f64 = fabs(a / (b * bc * 1.0) - 1.0) < 0.25;          // the neighbour votes, :520,:551
+		r |= (f32 ? 2 : 0) | (f32d ? 4 : 0) | (f64 ? 8 : 0);
+	}
+	return r;
+}
+
+// number of (a, b) pairs in [-amax, amax] x [-bmax, bmax] (b != 0) and strides on which any float form disagrees with the integer form
+long harness_ddf_sweep(int amax, int bmax, int bc_lo, int bc_hi)
+{
+	long bad = 0;
+	for (int bc = bc_lo; bc <= bc_hi; ++bc)
+		for (int b = -bmax; b <= bmax; ++b) {
+			if (!b) continue;
+			for (int a = -amax; a <= amax; ++a) {
+				const int r = harness_ddf_forms(a, b, bc);
+				if (r != 0 && r != 15) ++bad;
+			}
+		}
+	return bad;
+}
+
+void harness_free(void* p) { free(p); }
+
+}  // extern "C"

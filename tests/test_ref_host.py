@@ -1,0 +1,148 @@
+"""mecat2ref: the product's stage sequence (mecat_b200/csrc/ref_pipeline.h), kernel bodies
+(ref_core.cuh) and host I/O (host/refio.h) run on the host by tests/ref_host_harness.cpp -- a launch becomes a loop, the
+gapped extension is the oracle's -- against the output of the UNMODIFIED `mecat2ref` binary (tests/golden/refmap*) and,
+for other option values, against the pinned oracle."""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+import util
+
+GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))
+
+
+def run_harness(genome, fa, n=10, b=10, fmt=1, per_call=0, budget=0):
+    L = util.ref_harness()
+    text, nb = C.c_void_p(), C.c_size_t()
+    st = (C.c_long * 2)()
+    err = C.create_string_buffer(512)
+    rc = L.harness_ref_map(genome.encode(), fa.encode(), n, b, fmt, per_call, budget, C.byref(text), C.byref(nb), st, err, 512)
+    assert rc == 0, err.value
+    s = C.string_at(text.value, nb.value).decode()
+    L.harness_free(text)
+    return s, list(st)
+
+
+def run_oracle(genome, fa, n, b, fmt):
+    O = util.oracle()
+    text, nb = C.c_void_p(), C.c_size_t()
+    assert O.orc_ref_map(genome.encode(), fa.encode(), n, b, fmt, C.byref(text), C.byref(nb)) == 0
+    s = C.string_at(text.value, nb.value).decode()
+    O.orc_free(text)
+    return s
+
+
+def groups(s):
+    lines = s.rstrip("\n").split("\n") if s else []
+    return sorted("\n".join(lines[i:i + 3]) for i in range(0, len(lines), 3))
+
+
+def golden_groups(name):
+    with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
+        return groups(f.read())
+
+
+@pytest.fixture(scope="module")
+def refmap_inputs(tmp_path_factory):
+    c = GOLD["refmap"]
+    d = tmp_path_factory.mktemp("refmap_host")
+    fa, genome = str(d / "reads.fa"), str(d / "genome.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], genome_out=genome)
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == c["fasta_sha256"]
+    return fa, genome
+
+
+@pytest.fixture(scope="module")
+def hard_inputs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("refmap_hard_host")
+    fa, genome = str(d / "reads.fa"), str(d / "genome.fa")
+    util.make_refmap_hard(fa, genome)
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == GOLD["refmap_hard"]["fasta_sha256"]
+    return fa, genome
+
+
+def test_m4_matches_reference(refmap_inputs):
+    fa, genome = refmap_inputs
+    s, st = run_harness(genome, fa, fmt=1)
+    with gzip.open(os.path.join(util.GOLDEN, "refmap.m4.gz"), "rt") as f:
+        want = f.read().splitlines()
+    got = sorted(s.splitlines())
+    assert len(got) == len(want) == GOLD["refmap"]["num_m4"]
+    assert got == want
+    assert st[0] >= len(got)        # every record is an extension that ran
+
+
+def test_ref_format_matches_reference_in_small_batches(refmap_inputs):
+    """Several ABI-sized calls of 70 reads and a table budget small enough for many table batches per call."""
+    fa, genome = refmap_inputs
+    s, st = run_harness(genome, fa, fmt=0, per_call=70, budget=200_000)
+    assert st[1] > 10
+    assert groups(s) == golden_groups("refmap.ref.gz")
+
+
+def test_hard_inputs_match_reference(hard_inputs):
+    """Three contigs with a shared repeat and a run of N, chimeric reads (clipped ends: RescueFn), very noisy reads (the
+    second pass), reads with N and lower-case stretches (explicit reverse strands, k-mers that are not looked up), short
+    reads."""
+    fa, genome = hard_inputs
+    s, st = run_harness(genome, fa, fmt=0)
+    assert st[1] == 2               # both passes ran
+    assert groups(s) == golden_groups("refmap_hard.ref.gz")
+
+
+@pytest.mark.parametrize("n,b", [(3, 2), (1, 1), (50, 4)])
+def test_candidate_and_output_caps_match_oracle(refmap_inputs, hard_inputs, n, b):
+    fa, genome = hard_inputs
+    assert groups(run_harness(genome, fa, n, b, 0)[0]) == groups(run_oracle(genome, fa, n, b, 0))
+    fa, genome = refmap_inputs
+    assert sorted(run_harness(genome, fa, n, b, 1, per_call=37)[0].splitlines()) == sorted(run_oracle(genome, fa, n, b, 1).splitlines())
+
+
+def test_cfg0_sized_reads_match_reference(tmp_path):
+    """1 000 x 15 kb reads (BASELINE configs[0]'s read set) against their 1 Mb genome, M4 output."""
+    c = GOLD["refmap_cfg0"]
+    fa, genome = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], genome_out=genome)
+    got = sorted(run_harness(genome, fa, fmt=1)[0].splitlines())
+    with gzip.open(os.path.join(util.GOLDEN, "refmap_cfg0.m4.gz"), "rt") as f:
+        want = f.read().splitlines()
+    assert len(got) == len(want) == c["num_m4"]
+    assert got == want
+
+
+def test_fastq_reads_and_empty_inputs(tmp_path, refmap_inputs):
+    """FASTQ reads are numbered from 1 (chang_fastqfile); a read file without reads maps nothing."""
+    fa, genome = refmap_inputs
+    seqs = util.read_fasta(fa)[:40]
+    fq = str(tmp_path / "reads.fq")
+    with open(fq, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    got = run_harness(genome, fq, fmt=1)[0]
+    assert got and sorted(got.splitlines()) == sorted(run_oracle(genome, fq, 10, 10, 1).splitlines())
+    assert min(int(l.split("\t")[0]) for l in got.splitlines()) >= 1
+    empty = str(tmp_path / "none.fa")
+    open(empty, "w").close()
+    assert run_harness(genome, empty, fmt=1)[0] == ""
+
+
+def test_ddf_integer_form_equals_the_float_forms():
+    """|dloc / (dseed * BC) - 1| < 0.25: float32 in insert_loc / find_location, float64 in the neighbour votes, integers in
+    the kernels (ref_core.cuh ddf_close).  Exhaustive over block-sized operands for every stride, random wide operands."""
+    L = util.ref_harness()
+    assert L.harness_ddf_sweep(4200, 420, 5, 20) == 0
+    rng = random.Random(5)
+    for _ in range(200_000):
+        bc = rng.randint(5, 20)
+        b = rng.randint(-20_000, 20_000)
+        if b == 0:
+            assert L.harness_ddf_forms(rng.randint(-10, 10), 0, bc) == 0
+            continue
+        centre = b * bc * rng.choice((0.75, 1.0, 1.25))
+        a = int(centre) + rng.randint(-3, 3)
+        assert L.harness_ddf_forms(a, b, bc) in (0, 15), (a, b, bc)

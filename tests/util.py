@@ -151,6 +151,39 @@ def cns_harness():
     return L
 
 
+_ref_harness = None
+
+
+def ref_harness():
+    """Host build of the product's mecat2ref stage sequence, kernel bodies and host I/O (tests/ref_host_harness.cpp); the
+    gapped extension inside it is the oracle's."""
+    global _ref_harness
+    if _ref_harness is not None:
+        return _ref_harness
+    build_oracle()
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libref_harness.so")
+    src = [os.path.join(ROOT, "tests", "ref_host_harness.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "ref_pipeline.h"),
+           os.path.join(ROOT, "mecat_b200", "csrc", "ref_core.cuh"), os.path.join(ROOT, "mecat_b200", "csrc", "host", "refio.h"),
+           os.path.join(ROOT, "include", "mecat_b200.h"), os.path.join(ORACLE_DIR, "liboracle.so")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so, src[0], "-L", ORACLE_DIR, "-loracle",
+                               "-Wl,-rpath," + ORACLE_DIR])
+    L = C.CDLL(so)
+    vp = C.c_void_p
+    L.harness_ref_map.restype = C.c_int
+    L.harness_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(vp), C.POINTER(C.c_size_t),
+                                  C.POINTER(C.c_long), C.c_char_p, C.c_int]
+    L.harness_ddf_forms.restype = C.c_int
+    L.harness_ddf_forms.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.harness_ddf_sweep.restype = C.c_long
+    L.harness_ddf_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.harness_free.argtypes = [vp]
+    _ref_harness = L
+    return L
+
+
 def gen_reads(path, n, genome_len, seed, mean=15000, sd=1500, err=0.15, genome_out=None):
     exe = os.path.join(ROOT, "mecat_b200", "bin", "gen_reads")
     if not os.path.exists(exe):
