@@ -28,7 +28,9 @@ class PwParams(C.Structure):
 
 
 KERNEL_NAMES = ["orient", "index_count", "index_scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
-                "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"]
+                "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble",
+                "ref_count", "ref_seed", "ref_rescue"]
+K_NUM = len(KERNEL_NAMES)      # MECAT_K_NUM
 
 
 class CnsParams(C.Structure):
@@ -40,13 +42,31 @@ CNS_PIECE_DTYPE = np.dtype([("id", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("seq
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernel_ms", C.c_float * 16), ("kernel_launches", C.c_int64 * 16),
+    _fields_ = [("kernel_ms", C.c_float * K_NUM), ("kernel_launches", C.c_int64 * K_NUM),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("host_ms", C.c_float), ("total_ms", C.c_float),
                 ("wall_index_ms", C.c_float), ("wall_seed_ms", C.c_float), ("wall_extend_ms", C.c_float), ("wall_other_ms", C.c_float),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("num_hits", C.c_int64), ("num_candidates", C.c_int64), ("num_extend_blocks", C.c_int64),
                 ("index_kmers", C.c_int64), ("index_bases", C.c_int64), ("num_records", C.c_int64)]
 
+
+class RefGenomeC(C.Structure):      # mecat_ref_genome
+    _fields_ = [("num_bases", C.c_int64), ("pac", C.POINTER(C.c_uint8)), ("num_runs", C.c_int32),
+                ("run_start_len", C.POINTER(C.c_int64))]
+
+
+class RefReadsC(C.Structure):       # mecat_ref_reads
+    _fields_ = [("num_reads", C.c_int32), ("vol", C.POINTER(Volume)), ("read_len", C.POINTER(C.c_int32)),
+                ("fwd_read", C.POINTER(C.c_int32)), ("rev_read", C.POINTER(C.c_int32)), ("rev_is_rc", C.POINTER(C.c_int32)),
+                ("num_bad", C.c_int64), ("bad", C.POINTER(C.c_int64))]
+
+
+class RefParams(C.Structure):       # mecat_ref_params
+    _fields_ = [("num_candidates", C.c_int32), ("num_output", C.c_int32), ("want_strings", C.c_int32), ("tech", C.c_int32)]
+
+
+REF_RESULT_DTYPE = np.dtype([("read", "<i4"), ("dir", "<i4"), ("vscore", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("qs", "<i4"),
+                             ("sb", "<i8"), ("se", "<i8"), ("columns", "<i4"), ("matches", "<i4"), ("str_offset", "<i8")])
 
 EC_DTYPE = np.dtype([(n, "<i4") for n in
                      ("qdir", "qid", "qext", "qsize", "qoff", "qend", "sdir", "sid", "sext", "ssize", "soff",
@@ -71,6 +91,7 @@ EXPORTS = [
     "mecat_b200_pw_tile", "mecat_b200_pw_candidates", "mecat_b200_pw_overlaps", "mecat_b200_pw_raw_candidates",
     "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_cns_reads", "mecat_b200_cns_sort_candidates",
     "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload", "mecat_b200_volume_from_fasta",
+    "mecat_b200_ref_index_build", "mecat_b200_ref_index_release", "mecat_b200_ref_map",
 ]
 
 _lib = None
@@ -126,6 +147,10 @@ def load_library():
     L.mecat_b200_volume_load.argtypes = [C.c_char_p, VP]
     L.mecat_b200_volume_from_fasta.argtypes = [C.c_char_p, VP, C.c_char_p, C.c_int]
     L.mecat_b200_volume_unload.argtypes = [VP]
+    L.mecat_b200_ref_index_build.argtypes = [vp, C.POINTER(RefGenomeC), C.POINTER(vp)]
+    L.mecat_b200_ref_index_release.argtypes = [vp, vp]
+    L.mecat_b200_ref_map.argtypes = [vp, vp, C.POINTER(RefReadsC), C.POINTER(RefParams), C.POINTER(vp), C.POINTER(C.c_size_t),
+                                     C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -153,6 +178,133 @@ class HostVolume:
             os_ = np.frombuffer(f.read(8 * n), dtype="<i4").reshape(-1, 2).copy()
             pac = np.frombuffer(f.read((nb + 3) // 4), dtype=np.uint8).copy()
         return HostVolume(os_, pac, nb, sid)
+
+
+_CODE = np.full(256, 255, dtype=np.uint8)
+for _i, _ch in enumerate(b"ACGT"):
+    _CODE[_ch] = _i
+    _CODE[_ch + 32] = _i            # lower case aligns like upper case (extract_sequences)
+_UPPER = np.zeros(256, dtype=bool)
+_UPPER[list(b"ACGT")] = True
+
+
+def pack_bases(codes):
+    """2 bits per base in the reference's volume layout: base i in byte i >> 2 at shift ((~i) & 3) << 1."""
+    n = len(codes)
+    c = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+    c[:n] = codes
+    c = c.reshape(-1, 4)
+    return (c[:, 0] << 6 | c[:, 1] << 4 | c[:, 2] << 2 | c[:, 3]).astype(np.uint8)
+
+
+class RefGenome:
+    """The genome as mecat2ref's creat_ref_index keeps it (all sequences concatenated, upper-cased), packed for
+    mecat_b200_ref_index_build.  `from_fasta` reads plain FASTA (a header is a line starting with '>')."""
+
+    def __init__(self, names, seqs):
+        self.names = list(names)
+        self.starts, self.sizes = [], []
+        at = 0
+        for s in seqs:
+            self.starts.append(at)
+            self.sizes.append(len(s))
+            at += len(s)
+        raw = np.frombuffer(b"".join(seqs).upper(), dtype=np.uint8)
+        good = _UPPER[raw]
+        self.num_bases = int(len(raw))
+        self.pac = np.ascontiguousarray(pack_bases(np.where(good, _CODE[raw], 0).astype(np.uint8)))
+        edge = np.flatnonzero(np.diff(np.concatenate(([0], good.view(np.int8), [0]))))
+        self.runs = np.ascontiguousarray(np.stack([edge[0::2], edge[1::2] - edge[0::2]], axis=1).astype(np.int64))
+
+    @staticmethod
+    def from_fasta(path):
+        names, seqs, cur = [], [], []
+        with open(path, "rb") as f:
+            for line in f:
+                if line.startswith(b">"):
+                    if names:
+                        seqs.append(b"".join(cur))
+                    names.append(line[1:].split()[0].decode() if line[1:].split() else "")
+                    cur = []
+                else:
+                    cur.append(line.rstrip(b"\r\n"))
+        if names:
+            seqs.append(b"".join(cur))
+        return RefGenome(names, seqs)
+
+    def c(self):
+        return RefGenomeC(self.num_bases, self.pac.ctypes.data_as(C.POINTER(C.c_uint8)), len(self.runs),
+                          self.runs.ctypes.data_as(C.POINTER(C.c_int64)))
+
+    def contig_of(self, offset):
+        """(index, start, size) of the sequence holding a concatenated offset (get_chr_id)."""
+        k = int(np.searchsorted(np.asarray(self.starts), offset, side="right")) - 1
+        return k, self.starts[k], self.sizes[k]
+
+
+class RefReads:
+    """A batch of reads packed for mecat_b200_ref_map: reads of upper-case ACGT are packed once; any other read also
+    carries its reverse strand, built the way the reference builds it (complement of upper-case ACGT only)."""
+
+    _COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+    def __init__(self, seqs):
+        strands, self.read_len, self.fwd_read, self.rev_read, self.rev_is_rc = [], [], [], [], []
+        for s in seqs:
+            s = bytes(s)
+            self.read_len.append(len(s))
+            self.fwd_read.append(len(strands))
+            strands.append(s)
+            if _UPPER[np.frombuffer(s, dtype=np.uint8)].all():
+                self.rev_read.append(self.fwd_read[-1])
+                self.rev_is_rc.append(1)
+            else:
+                self.rev_read.append(len(strands))
+                self.rev_is_rc.append(0)
+                strands.append(s[::-1].translate(self._COMP))
+        offsz, at = [], 0
+        for s in strands:
+            offsz.append((at, len(s)))
+            at += len(s) + 1                                   # one pad base between reads
+        raw = np.frombuffer(b"A".join(strands) + b"A", dtype=np.uint8) if strands else np.zeros(0, np.uint8)
+        good = _UPPER[raw]
+        pad = np.zeros(len(raw), dtype=bool)
+        if strands:
+            pad[np.asarray([o + n for o, n in offsz])] = True
+        self.bad = np.ascontiguousarray(np.flatnonzero(~good & ~pad).astype(np.int64))
+        code = _CODE[raw]
+        self.volume = HostVolume(np.asarray(offsz, dtype=np.int32).reshape(-1, 2), pack_bases(np.where(code > 3, 0, code).astype(np.uint8)),
+                                 len(raw))
+        self._arrays = [np.ascontiguousarray(a, dtype=np.int32) for a in (self.read_len, self.fwd_read, self.rev_read, self.rev_is_rc)]
+
+    def c(self):
+        self._vol = self.volume.c()
+        p = [a.ctypes.data_as(C.POINTER(C.c_int32)) for a in self._arrays]
+        return RefReadsC(len(self.read_len), C.pointer(self._vol), p[0], p[1], p[2], p[3], len(self.bad),
+                         self.bad.ctypes.data_as(C.POINTER(C.c_int64)))
+
+
+def format_ref_results(genome, read_names, records, qstrings=b"", sstrings=b"", fmt=1):
+    """The text mecat2ref writes for `records` of Context.ref_map (print_ref_result / print_m4_result,
+    src/mecat2ref/output.cpp:8-88): fmt 0 = ref (header + both alignment strings), 1 = m4."""
+    out = []
+    for r in records:
+        k, start, size = genome.contig_of(int(r["sb"]))
+        qb, qe, qs = int(r["qb"]), int(r["qe"]), int(r["qs"])
+        if r["dir"]:
+            qb, qe = qs - qe, qs - qb
+        name, sb, se = genome.names[k], int(r["sb"]) - start, int(r["se"]) - start
+        if fmt == 0:
+            o, n = int(r["str_offset"]), int(r["columns"])
+            out.append("%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n%s\n%s\n" % (
+                read_names[int(r["read"])], name, "R" if r["dir"] else "F", int(r["vscore"]), qb, qe, qs, sb, se, size,
+                qstrings[o:o + n].decode(), sstrings[o:o + n].decode()))
+        else:
+            ident = float(int(r["matches"])) / float(int(r["columns"]))
+            ident *= 100.0
+            out.append("%d\t%s\t%.4f\t%d\t%d\t%d\t%d\t%d\t0\t%d\t%d\t%d\n" % (
+                read_names[int(r["read"])], name, ident, int(r["vscore"]), 1 if r["dir"] else 0, qb, qe, qs, sb, se, size))
+    return "".join(out)
 
 
 def volume_from_fasta(reads_path):
@@ -372,6 +524,33 @@ class Context:
         cnt = self._take(counts, num_reads, i4)
         r = self._take(rows, max(1, n.value) * 12, i4).reshape(-1, 12)[:n.value]
         return r, cnt
+
+    # ---- mecat2ref
+    def ref_index_build(self, genome):
+        i = C.c_void_p()
+        g = genome.c()
+        self._check(self.L.mecat_b200_ref_index_build(self.h, C.byref(g), C.byref(i)), "ref_index_build")
+        return i
+
+    def release_ref_index(self, i):
+        self.L.mecat_b200_ref_index_release(self.h, i)
+
+    def ref_map(self, refidx, reads, num_candidates=10, num_output=10, want_strings=True):
+        """mecat2ref on a RefReads batch.  Returns (records, qstrings, sstrings): REF_RESULT_DTYPE records in output order
+        (a read's records adjacent); record['str_offset'] indexes the two NUL-separated byte blobs."""
+        p = RefParams(num_candidates, num_output, 1 if want_strings else 0, 0)
+        r = reads.c()
+        res, n, qs, ss, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_ref_map(self.h, refidx, C.byref(r), C.byref(p), C.byref(res), C.byref(n), C.byref(qs),
+                                              C.byref(ss), C.byref(nb)), "ref_map")
+        rec = self._take(res, n.value, REF_RESULT_DTYPE)
+        q = C.string_at(qs.value, nb.value) if qs.value else b""
+        s = C.string_at(ss.value, nb.value) if ss.value else b""
+        if qs.value:
+            self.L.mecat_b200_free(self.h, qs)
+        if ss.value:
+            self.L.mecat_b200_free(self.h, ss)
+        return rec, q, s
 
     # ---- host-buffer entry points (the end-to-end calls)
     def pw_candidates(self, ref, reads, params=None):

@@ -568,7 +568,7 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 }
 
 int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t ntasks,
-                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr)
+                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr, bool want_strings)
 {
 	qstr.clear(); sstr.clear();
 	if (!ntasks) return 0;
@@ -584,7 +584,7 @@ int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume*
 		if (nb == 0) MB_FAIL(c, "align_batch: one task needs more than the %zu-byte column arena", c->align_arena);
 		AlignDev dev;
 		if (align_batch_device(c, policy, err, q, s, h_tasks + done, nb, min_aln, &dev, info)) return 1;
-		const size_t base = qstr.size(), total = dev.total;
+		const size_t base = qstr.size(), total = want_strings ? dev.total : 0;
 		qstr.resize(base + total); sstr.resize(base + total);
 		cudaError_t e = cudaSuccess;
 		if (total) {
@@ -602,7 +602,7 @@ int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume*
 			const int32_t* o = &info[8 * i];
 			r.ok = o[0]; r.qstart = o[1]; r.qend = o[2]; r.sstart = o[3]; r.send = o[4];
 			r.columns = o[5]; r.matches = o[6]; r.pad_ = 0;
-			r.str_offset = o[0] ? (int64_t)(base + at) : -1;
+			r.str_offset = (o[0] && want_strings) ? (int64_t)(base + at) : -1;
 			if (o[0]) at += (size_t)o[5] + 1;
 			r.ident = (o[0] && o[5]) ? 100.0 * o[6] / o[5] : 0.0;
 		}

@@ -5,6 +5,7 @@
 // (candidate_detect pw_impl.cpp:767-793, fill_m4record :467-506, append_m4v :576-610).
 #include "common.cuh"
 #include "cns_pipeline.h"
+#include "ref_pipeline.h"
 
 #include <algorithm>
 #include <atomic>
@@ -344,6 +345,48 @@ void mecat_b200_cns_sort_candidates(mecat_candidate* cnd, int n)   // CmpExtensi
 }
 
 void mecat_b200_host_free(void* p) { free(p); }
+
+// ------------------------------------------------------------------------------------------
+// mecat2ref: genome upload + k-mer index, then batches of reads through refmap.cu
+int mecat_b200_ref_index_build(mecat_b200_ctx* c, const mecat_ref_genome* g, void** refidx)
+{
+	if (check(c) || !g || !refidx) return 1;
+	cudaSetDevice(c->device);
+	WallTimer wt;
+	RefIndex* R = nullptr;
+	const int rc = ref_index_build(c, g, &R);
+	c->stats.wall_index_ms += wt.stop();
+	if (rc) return rc;
+	*refidx = R;
+	return 0;
+}
+
+int mecat_b200_ref_index_release(mecat_b200_ctx* c, void* refidx)
+{
+	if (check(c)) return 1;
+	cudaSetDevice(c->device);
+	ref_index_release(c, (RefIndex*)refidx);
+	return 0;
+}
+
+int mecat_b200_ref_map(mecat_b200_ctx* c, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
+                       mecat_ref_result** results, size_t* n, char** qstrings, char** sstrings, size_t* string_bytes)
+{
+	if (check(c) || !refidx || !reads || !p || !results || !n || !qstrings || !sstrings || !string_bytes) return 1;
+	cudaSetDevice(c->device);
+	*results = nullptr; *n = 0; *qstrings = nullptr; *sstrings = nullptr; *string_bytes = 0;
+	mbref::Sink sink;
+	if (ref_map(c, (const RefIndex*)refidx, reads, p, sink)) return 1;
+	mecat_ref_result* res = (mecat_ref_result*)malloc(sizeof(mecat_ref_result) * (sink.recs.size() ? sink.recs.size() : 1));
+	char* a = (char*)malloc(sink.q.size() + 1);
+	char* b = (char*)malloc(sink.s.size() + 1);
+	if (!res || !a || !b) { free(res); free(a); free(b); MB_FAIL(c, "ref_map: out of host memory"); }
+	if (!sink.recs.empty()) memcpy(res, sink.recs.data(), sizeof(mecat_ref_result) * sink.recs.size());
+	memcpy(a, sink.q.data(), sink.q.size()); a[sink.q.size()] = 0;
+	memcpy(b, sink.s.data(), sink.s.size()); b[sink.s.size()] = 0;
+	*results = res; *n = sink.recs.size(); *qstrings = a; *sstrings = b; *string_bytes = sink.q.size();
+	return 0;
+}
 
 int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candidate* ec_in, size_t nec, const mecat_cns_params* p,
                          mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)

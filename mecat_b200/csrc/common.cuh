@@ -210,8 +210,9 @@ size_t align_task_columns(const DVolume* q, const DVolume* s, const AlignTask& t
 int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t nb,
                        int min_aln, AlignDev* out, std::vector<int32_t>& info);
 void align_dev_release(Ctx* c, AlignDev* d);
+// want_strings = false: only the results come back (coordinates, columns, matches); the strings stay on the device
 int align_batch(Ctx* c, int policy, double err, const DVolume* q, const DVolume* s, const AlignTask* h_tasks, size_t ntasks,
-                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr);
+                int min_aln, mecat_align_result* h_results, std::vector<char>& qstr, std::vector<char>& sstr, bool want_strings = true);
 
 }  // namespace mb
 namespace mbcns { struct BatchIn; struct Params; }
@@ -243,6 +244,19 @@ struct CnsBlob
 };
 // consensus stage of mecat2cns on the extension results of one batch (cns.cu)
 int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, CnsBlob& out);
+
+// mecat2ref (refmap.cu): the genome as a one-read volume plus its k-mer index
+struct RefIndex
+{
+	DVolume* genome = nullptr;
+	DIndex* index = nullptr;
+};
+}  // namespace mb
+namespace mbref { struct Sink; }
+namespace mb {
+int ref_index_build(Ctx* c, const mecat_ref_genome* g, RefIndex** out);
+void ref_index_release(Ctx* c, RefIndex* R);
+int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out);
 
 struct RawCand             // candidate_save, pw_impl.h:21-25
 {

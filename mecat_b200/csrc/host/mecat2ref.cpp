@@ -1,0 +1,198 @@
+// mecat_b200/csrc/host/mecat2ref.cpp -- host driver with the reference's mecat2ref command line.
+//
+//   mecat2ref -d reads -r reference -o output -w wrk_dir [-t threads] [-n candidates] [-b best] [-m 0|1] [-x 0]
+//
+// Same flags and defaults as src/mecat2ref/mecat2ref.cpp:53-190, same records as its ref (-m 0) and m4 (-m 1) output
+// (src/mecat2ref/output.cpp:8-88; the records of a read are together, reads in input order).  The genome is indexed once
+// on the GPU (mecat_b200_ref_index_build); the reads go through mecat_b200_ref_map in batches -- seeding, DDF scoring,
+// gapped extension and clipped-end rescue all run on the device.  `-t` is accepted and unused.  With MECAT_GPUS=n every
+// device holds a replica of the genome index and maps its share of the read batches (no collective; the output does not
+// depend on n).  Not on this path (refused with a message): -m 2 (SAM) and -x 1 (nanopore).  The reference's scratch
+// files (wrk_dir/N.fq, N.r, chrindex.txt, ./config.txt) are not written; the working directory is still created.
+#include <dirent.h>
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mecat_b200.h"
+#include "refio.h"
+
+namespace {
+
+struct Options
+{
+	const char* reads = NULL;
+	const char* reference = NULL;
+	const char* wrk_dir = NULL;
+	const char* output = NULL;
+	int num_cores = 1, num_candidates = 10, num_output = 10, output_format = 0, tech = 0;
+};
+
+void print_usage(const char* prog)
+{
+	fprintf(stderr, "\n\nusage:\n%s [-d reads] [-r reference] [-o output] [-w working dir] [-t threads]\n\noptions:\n", prog);
+	fprintf(stderr, "-d <string>\treads file name\n-r <string>\treference file name\n-o <string>\toutput file name\n");
+	fprintf(stderr, "-w <string>\tworking folder name, will be created if not exist\n");
+	fprintf(stderr, "-t <integer>\tnumber of cput threads -- accepted, unused: the mapping runs on the GPU\n\t\tdefault: 1\n");
+	fprintf(stderr, "-n <integer>\tnumber of of candidates for gap extension\n\t\tdefault: 10\n");
+	fprintf(stderr, "-b <integer>\toutput the best b alignments\n\t\tdefault: 10\n");
+	fprintf(stderr, "-m <0/1/2>\toutput format: 0 = ref, 1 = m4, 2 = sam (sam is not on this path)\n\t\tdefault: 0\n");
+	fprintf(stderr, "-x <0/1>\tsequencing technology: 0 = pacbio, 1 = nanopore (nanopore is not on this path)\n\t\tdefault: 0\n");
+}
+
+int parse(int argc, char* argv[], Options& o)
+{
+	int c;
+	opterr = 0;
+	while ((c = getopt(argc, argv, "d:r:w:o:t:n:b:m:x:")) != -1) {
+		switch (c) {
+		case 'd': o.reads = optarg; break;
+		case 'r': o.reference = optarg; break;
+		case 'w': o.wrk_dir = optarg; break;
+		case 'o': o.output = optarg; break;
+		case 't': o.num_cores = atoi(optarg); break;
+		case 'n': o.num_candidates = atoi(optarg); break;
+		case 'b': o.num_output = atoi(optarg); break;
+		case 'm': o.output_format = atoi(optarg); break;
+		case 'x':
+			if (optarg[0] == '0') o.tech = 0;
+			else if (optarg[0] == '1') o.tech = 1;
+			else { fprintf(stderr, "invalid argument to option 'x': %s\n", optarg); return -1; }
+			break;
+		default:
+			if (optopt && strchr("drwotnbmx", optopt)) fprintf(stderr, "Error: argument to option '%c' is missing!\n", optopt);
+			else fprintf(stderr, "Error: unrecogised option '%c'\n", optopt);
+			return -1;
+		}
+	}
+	const char* msg = NULL;
+	if (!o.reads) msg = "dataset must be specified";
+	else if (!o.reference) msg = "reference must be specified";
+	else if (!o.output) msg = "output must be specified";
+	else if (!o.wrk_dir) msg = "working directory must be specified";
+	else if (o.num_cores < 1) msg = "cpu cores must be > 0";
+	else if (o.num_candidates < 1) msg = "candidates must be > 0";
+	else if (o.num_output < 1) msg = "output alignments must be > 0";
+	if (msg) { fprintf(stderr, "Error: %s\n", msg); return -1; }
+	if (o.num_output > o.num_candidates) {
+		fprintf(stderr, "warning: number of output (%d) is greater than number of candidates (%d), we reset it to %d", o.num_output, o.num_candidates,
+		        o.num_candidates);
+		o.num_output = o.num_candidates;
+	}
+	DIR* d = opendir(o.wrk_dir);
+	if (d) closedir(d);
+	else if (mkdir(o.wrk_dir, S_IRWXU) == -1) { fprintf(stderr, "Fail to create folder %s!\n", o.wrk_dir); return -1; }
+	return 0;
+}
+
+double now()
+{
+	struct timeval t;
+	gettimeofday(&t, NULL);
+	return (double)t.tv_sec + 1e-6 * (double)t.tv_usec;
+}
+
+struct Batch { int first, count; std::string text; };
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+	Options o;
+	if (parse(argc, argv, o) == -1) { print_usage(argv[0]); return 1; }
+	if (o.tech != 0) { fprintf(stderr, "mecat2ref (b200): -x 1 (nanopore) is not on this path\n"); return 1; }
+	if (o.output_format != 0 && o.output_format != 1) { fprintf(stderr, "mecat2ref (b200): output format %d is not on this path (0 = ref, 1 = m4)\n", o.output_format); return 1; }
+	const double t0 = now();
+	int ndev = 1;
+	if (const char* e = getenv("MECAT_GPUS")) ndev = std::max(1, atoi(e));
+	if (ndev > mecat_b200_device_count()) { fprintf(stderr, "mecat2ref (b200): MECAT_GPUS=%d but %d CUDA device(s) visible\n", ndev, mecat_b200_device_count()); return 1; }
+
+	// the CUDA contexts come up while the host parses and packs the genome
+	std::vector<mecat_b200_ctx*> ctx((size_t)ndev, (mecat_b200_ctx*)NULL);
+	std::vector<int> init_rc((size_t)ndev, 0);
+	std::vector<std::thread> starters;
+	for (int d = 0; d < ndev; ++d) starters.emplace_back([&, d]() { init_rc[(size_t)d] = mecat_b200_init(&ctx[(size_t)d], d, NULL); });
+	refio::Genome G;
+	refio::Reads R;
+	std::string err;
+	const bool loaded = refio::load_genome(o.reference, G, err) && refio::load_reads(o.reads, R, err);
+	for (auto& t : starters) t.join();
+	for (int d = 0; d < ndev; ++d)
+		if (init_rc[(size_t)d]) { fprintf(stderr, "mecat2ref (b200): no usable CUDA device %d (there is no CPU fallback)\n", d); return 1; }
+	if (!loaded) { fprintf(stderr, "mecat2ref (b200): %s\n", err.c_str()); return 1; }
+	const double t_load = now();
+
+	// batches of reads: one ABI call each.  A volume holds < 2^31 bases; the ref format returns two strings per record.
+	const int64_t max_bases = 1900000000ll;
+	const int max_reads = o.output_format == 0 ? 20000 : 1 << 30;
+	std::vector<Batch> batches;
+	const int total = (int)R.seq.size();
+	int64_t all_bases = 0;
+	for (const std::string& s : R.seq) all_bases += 2 * (int64_t)s.size() + 2;
+	const int64_t share = std::max<int64_t>(1 << 20, (all_bases + ndev - 1) / ndev);
+	for (int first = 0; first < total;) {
+		int count = 0;
+		int64_t bases = 0;
+		while (first + count < total && count < max_reads) {
+			const int64_t need = 2 * (int64_t)R.seq[(size_t)(first + count)].size() + 2;      // worst case: both strands packed
+			if (count && (bases + need > max_bases || bases + need > share)) break;
+			bases += need; ++count;
+		}
+		Batch b; b.first = first; b.count = count;
+		batches.push_back(b);
+		first += count;
+	}
+
+	std::atomic<int> next(0), failed(0);
+	std::vector<double> t_index((size_t)ndev, 0.0);
+	auto worker = [&](int d) {
+		mecat_b200_ctx* c = ctx[(size_t)d];
+		const double a = now();
+		void* idx = NULL;
+		const mecat_ref_genome g = G.view();
+		if (mecat_b200_ref_index_build(c, &g, &idx)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; return; }
+		t_index[(size_t)d] = now() - a;
+		mecat_ref_params p;
+		p.num_candidates = o.num_candidates; p.num_output = o.num_output; p.want_strings = o.output_format == 0; p.tech = o.tech;
+		for (;;) {
+			const int k = next.fetch_add(1);
+			if (k >= (int)batches.size() || failed) break;
+			Batch& b = batches[(size_t)k];
+			refio::ReadBatch B;
+			for (int i = 0; i < b.count; ++i) B.add_read(R.seq[(size_t)(b.first + i)]);
+			const mecat_ref_reads view = B.view();
+			mecat_ref_result* res = NULL;
+			char *qs = NULL, *ss = NULL;
+			size_t n = 0, nbytes = 0;
+			if (mecat_b200_ref_map(c, idx, &view, &p, &res, &n, &qs, &ss, &nbytes)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; break; }
+			refio::format_results(b.text, G, R.name, b.first, res, n, qs, ss, o.output_format);
+			mecat_b200_free(c, res); mecat_b200_free(c, qs); mecat_b200_free(c, ss);
+		}
+		mecat_b200_ref_index_release(c, idx);
+	};
+	std::vector<std::thread> workers;
+	for (int d = 0; d < ndev; ++d) workers.emplace_back(worker, d);
+	for (auto& t : workers) t.join();
+	if (failed) return 1;
+	const double t_map = now();
+
+	fprintf(stderr, "output file name: %s\n", o.output);
+	FILE* out = fopen(o.output, "w");
+	if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
+	for (const Batch& b : batches) fwrite(b.text.data(), 1, b.text.size(), out);
+	fclose(out);
+	for (int d = 0; d < ndev; ++d) mecat_b200_destroy(ctx[(size_t)d]);
+	const double t1 = now();
+	fprintf(stderr, "mecat2ref (b200): %d reads, %lld reference bases, %d device(s): load %.2f s, index %.2f s, mapping %.2f s, write %.2f s, total %.2f s\n",
+	        total, (long long)G.seq.n, ndev, t_load - t0, t_index[0], t_map - t_load - t_index[0], t1 - t_map, t1 - t0);
+	return 0;
+}

@@ -1,0 +1,184 @@
+// mecat_b200/csrc/refmap.cu -- mecat2ref on the GPU: CUDA backend of ref_pipeline.h.
+//
+// The stage sequence lives in ref_pipeline.h, the per-unit bodies in ref_core.cuh; here every stage functor F becomes a
+// launch of k_ref<F> (one thread per strand / clipped end), memory comes from the context's pool, and the extension
+// hook is the library's own gapped aligner with strings (align.cu, row R1) on windows of the genome.  The genome is an
+// ordinary device volume with one "read"; its k-mer index is the index of index.cu built over a second offset table
+// that cuts the genome's ACGT runs into chunks, so that a chunk is one CTA's work and no k-mer spans another letter.
+#include "common.cuh"
+#include "ref_pipeline.h"
+
+namespace mb {
+
+namespace {
+
+template <class F>
+__global__ void __launch_bounds__(128) k_ref(const F f, const int64_t n)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) f(i);
+}
+
+struct RefBackend
+{
+	Ctx* c;
+	const DVolume* reads;
+	const DVolume* genome;
+	std::vector<void*> owned;
+
+	bool check(cudaError_t e, const char* what)
+	{
+		if (e == cudaSuccess) return true;
+		char b[256];
+		snprintf(b, sizeof b, "ref: %s: %s", what, cudaGetErrorString(e));
+		c->err = b;
+		return false;
+	}
+	template <class T> T* alloc(size_t n)
+	{
+		void* p = nullptr;
+		const cudaError_t e = c->dmalloc(&p, (n ? n : 1) * sizeof(T));
+		if (e != cudaSuccess) {
+			char b[256];
+			snprintf(b, sizeof b, "ref: device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+			c->err = b;
+			return nullptr;
+		}
+		owned.push_back(p);
+		return (T*)p;
+	}
+	template <class T> bool upload(T* d, const T* h, size_t n)
+	{
+		if (!n) return true;
+		c->stats.h2d_bytes += (int64_t)(n * sizeof(T));
+		// the sources are host vectors that may go out of scope: finish the copy before returning
+		return check(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream), "H2D") &&
+		       check(cudaStreamSynchronize(c->stream), "H2D");
+	}
+	template <class T> bool download(T* h, const T* d, size_t n)
+	{
+		if (n && !check(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream), "D2H")) return false;
+		c->stats.d2h_bytes += (int64_t)(n * sizeof(T));
+		return check(cudaStreamSynchronize(c->stream), "kernel");
+	}
+	bool fill(void* d, int byte, size_t bytes) { return !bytes || check(cudaMemsetAsync(d, byte, bytes, c->stream), "memset"); }
+	template <class F> bool launch(int64_t n, const F& f, int stage)
+	{
+		if (n <= 0) return true;
+		KScope ks(c, MECAT_K_REF_COUNT + stage);
+		k_ref<F><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(f, n);
+		return check(cudaGetLastError(), "launch");
+	}
+	bool release(void* p)      // the pool only marks the block free; work queued on the stream before the next owner's is ordered
+	{
+		for (size_t i = 0; i < owned.size(); ++i)
+			if (owned[i] == p) { c->dfree(p); owned[i] = owned.back(); owned.pop_back(); return true; }
+		c->err = "ref: release of an unknown block";
+		return false;
+	}
+	bool align(const mecat_align_task* tasks, size_t n, bool want_strings, mecat_align_result* res, std::vector<char>& qs, std::vector<char>& ss)
+	{
+		static_assert(sizeof(AlignTask) == sizeof(mecat_align_task), "AlignTask mirrors mecat_align_task");
+		c->stats.num_candidates += (int64_t)n;
+		return align_batch(c, 0, 0.0, reads, genome, (const AlignTask*)tasks, n, 1000 /* extend_candidate's min_aln, mecat2ref_aux.cpp:152 */,
+		                   res, qs, ss, want_strings) == 0;
+	}
+	void fail(const char* m) { c->err = m; }
+	void end_batch()
+	{
+		cudaStreamSynchronize(c->stream);
+		for (void* p : owned) c->dfree(p);
+		owned.clear();
+		c->resolve_timers();
+	}
+};
+
+constexpr int64_t INDEX_CHUNK = 32768;      // k-mer starts per chunk of a run: one CTA's work in the index kernels
+
+}  // namespace
+
+int ref_index_build(Ctx* c, const mecat_ref_genome* g, RefIndex** out)
+{
+	if (!g || g->num_bases < 0 || g->num_runs < 0 || (g->num_bases && !g->pac)) MB_FAIL(c, "ref_index_build: bad genome");
+	if (g->num_bases >= (1ll << 31) - (1ll << 20)) MB_FAIL(c, "ref_index_build: %lld bases; this path holds positions in 32 bits (< 2^31 - 2^20)", (long long)g->num_bases);
+	RefIndex* R = new RefIndex;
+	const int32_t one[2] = {0, (int32_t)g->num_bases};
+	mecat_volume v;
+	v.num_reads = 1; v.num_bases = (int32_t)g->num_bases; v.start_read_id = 0; v.offset_size = one; v.pac = g->pac;
+	if (volume_upload(c, &v, &R->genome)) { delete R; return 1; }
+	// the index's view of the same bases: chunks of the ACGT runs, overlapping by the 12 bases a k-mer needs beyond its start
+	std::vector<int32_t> chunks;
+	int64_t prev_end = 0;
+	for (int32_t r = 0; r < g->num_runs; ++r) {
+		const int64_t s = g->run_start_len[2 * r], n = g->run_start_len[2 * r + 1];
+		if (s < prev_end || n < 0 || s + n > g->num_bases) { ref_index_release(c, R); MB_FAIL(c, "ref_index_build: run %d out of order or out of range", r); }
+		prev_end = s + n;
+		for (int64_t k = 0; k + KMER <= n; k += INDEX_CHUNK) {
+			chunks.push_back((int32_t)(s + k));
+			chunks.push_back((int32_t)std::min(n - k, INDEX_CHUNK + KMER - 1));
+		}
+	}
+	DVolume view;
+	view.num_reads = (int32_t)(chunks.size() / 2); view.num_bases = R->genome->num_bases; view.fwd = R->genome->fwd; view.rev = R->genome->rev;
+	view.words = R->genome->words;
+	auto body = [&]() -> int {
+		MB_CUDA(c, c->dmalloc((void**)&view.offsz, sizeof(int2) * (chunks.size() / 2 + 1)));
+		if (!chunks.empty()) MB_CUDA(c, cudaMemcpyAsync(view.offsz, chunks.data(), sizeof(int32_t) * chunks.size(), cudaMemcpyHostToDevice, c->stream));
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		return index_build(c, &view, &R->index);
+	};
+	const int rc = body();
+	c->dfree(view.offsz);
+	if (rc) { ref_index_release(c, R); return rc; }
+	*out = R;
+	return 0;
+}
+
+void ref_index_release(Ctx* c, RefIndex* R)
+{
+	if (!R) return;
+	index_release(c, R->index);
+	volume_release(c, R->genome);
+	delete R;
+}
+
+int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out)
+{
+	if (!R || !reads || !p || !reads->vol) MB_FAIL(c, "ref_map: null argument");
+	if (p->tech != 0) MB_FAIL(c, "ref_map: only -x 0 (pacbio) is on this path");
+	const mecat_volume* v = reads->vol;
+	for (int32_t r = 0; r < reads->num_reads; ++r) {
+		const int32_t f = reads->fwd_read[r], w = reads->rev_read[r];
+		if (f < 0 || f >= v->num_reads || w < 0 || w >= v->num_reads || v->offset_size[2 * f + 1] != reads->read_len[r] ||
+		    v->offset_size[2 * w + 1] != reads->read_len[r])
+			MB_FAIL(c, "ref_map: read %d does not match its volume reads", r);
+	}
+	DVolume* dv = nullptr;
+	if (volume_upload(c, v, &dv)) return 1;
+	int64_t* d_bad = nullptr;
+	auto body = [&]() -> int {
+		MB_CUDA(c, c->dmalloc((void**)&d_bad, sizeof(int64_t) * (size_t)(reads->num_bad + 1)));
+		if (reads->num_bad) MB_CUDA(c, cudaMemcpyAsync(d_bad, reads->bad, sizeof(int64_t) * (size_t)reads->num_bad, cudaMemcpyHostToDevice, c->stream));
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * reads->num_bad;
+		mbref::MapIn in;
+		in.R = reads->num_reads; in.h_len = reads->read_len; in.h_fread = reads->fwd_read; in.h_rread = reads->rev_read; in.h_rrc = reads->rev_is_rc;
+		in.seqcount = R->genome->num_bases;
+		in.d_fwd = dv->fwd; in.d_offsz = (const int32_t*)dv->offsz; in.d_bad = d_bad; in.nbad = reads->num_bad;
+		in.d_ibegin = R->index->begin; in.d_ipos = R->index->pos;
+		mbref::Params P;
+		P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
+		if (const char* e = getenv("MECAT_B200_REF_TABLE_MB")) P.table_budget = (int64_t)atoll(e) << 20;      // test hook: force several table batches
+		RefBackend be{c, dv, R->genome, {}};
+		const int rc = mbref::map_reads(be, in, P, out);
+		if (rc) be.end_batch();
+		return rc;
+	};
+	const int rc = body();
+	c->dfree(d_bad);
+	volume_release(c, dv);
+	if (!rc) c->stats.num_records += (int64_t)out.recs.size();
+	return rc;
+}
+
+}  // namespace mb

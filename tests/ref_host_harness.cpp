@@ -132,6 +132,35 @@ void build_index(const uint32_t* gfwd, const std::vector<int64_t>& runs, std::ve
 	}
 }
 
+// one ABI-shaped call on the host: what mecat_b200_ref_index_build + mecat_b200_ref_map do on the device
+struct HostIndex { std::vector<uint32_t> gw, begin; std::vector<int32_t> pos; int64_t n = 0; };
+
+void index_genome(const mecat_ref_genome* g, HostIndex& I)
+{
+	I.n = g->num_bases;
+	I.gw = words_of(g->pac, g->num_bases);
+	std::vector<int64_t> runs(g->run_start_len, g->run_start_len + 2 * (size_t)g->num_runs);
+	build_index(I.gw.data(), runs, I.begin, I.pos);
+}
+
+int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_params* p, long table_budget, mbref::Sink& sink, long* stats, std::string& err)
+{
+	const std::vector<uint32_t> rw = words_of(view->vol->pac, view->vol->num_bases);
+	HostBackend be;
+	be.rfwd = rw.data(); be.roffsz = view->vol->offset_size; be.gfwd = I.gw.data();
+	mbref::MapIn in;
+	in.R = view->num_reads; in.h_len = view->read_len; in.h_fread = view->fwd_read; in.h_rread = view->rev_read; in.h_rrc = view->rev_is_rc;
+	in.seqcount = I.n;
+	in.d_fwd = rw.data(); in.d_offsz = view->vol->offset_size; in.d_bad = view->bad; in.nbad = view->num_bad;
+	in.d_ibegin = I.begin.data(); in.d_ipos = I.pos.data();
+	mbref::Params P;
+	P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
+	if (table_budget > 0) P.table_budget = table_budget;
+	if (mbref::map_reads(be, in, P, sink)) { err = be.err; return 1; }
+	if (stats) { stats[0] += be.tasks_run; stats[1] += be.batches; }
+	return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -146,41 +175,50 @@ int harness_ref_map(const char* reference_path, const char* reads_path, int num_
 	refio::Reads R;
 	std::string err;
 	if (!refio::load_genome(reference_path, G, err) || !refio::load_reads(reads_path, R, err)) return fail(err);
-	const std::vector<uint32_t> gw = words_of(G.seq.pac.data(), G.seq.n);
-	std::vector<uint32_t> begin;
-	std::vector<int32_t> pos;
-	build_index(gw.data(), G.runs, begin, pos);
+	HostIndex I;
+	const mecat_ref_genome gv = G.view();
+	index_genome(&gv, I);
 	std::string out;
-	long ntasks = 0, nbatches = 0;
+	if (stats) stats[0] = stats[1] = 0;
 	const int total = (int)R.seq.size();
 	if (reads_per_call < 1) reads_per_call = total ? total : 1;
+	mecat_ref_params p;
+	p.num_candidates = num_candidates; p.num_output = num_output; p.want_strings = format == 0; p.tech = 0;
 	for (int first = 0; first < total; first += reads_per_call) {
 		const int count = std::min(reads_per_call, total - first);
 		refio::ReadBatch B;
 		for (int i = 0; i < count; ++i) B.add_read(R.seq[(size_t)(first + i)]);
 		const mecat_ref_reads view = B.view();
-		const std::vector<uint32_t> rw = words_of(view.vol->pac, view.vol->num_bases);
-		HostBackend be;
-		be.rfwd = rw.data(); be.roffsz = view.vol->offset_size; be.gfwd = gw.data();
-		mbref::MapIn in;
-		in.R = view.num_reads; in.h_len = view.read_len; in.h_fread = view.fwd_read; in.h_rread = view.rev_read; in.h_rrc = view.rev_is_rc;
-		in.seqcount = G.seq.n;
-		in.d_fwd = rw.data(); in.d_offsz = view.vol->offset_size; in.d_bad = view.bad; in.nbad = view.num_bad;
-		in.d_ibegin = begin.data(); in.d_ipos = pos.data();
-		mbref::Params P;
-		P.num_candidates = num_candidates; P.num_output = num_output; P.want_strings = format == 0;
-		if (table_budget > 0) P.table_budget = table_budget;
 		mbref::Sink sink;
-		if (mbref::map_reads(be, in, P, sink)) return fail(be.err);
+		if (map_packed(I, &view, &p, table_budget, sink, stats, err)) return fail(err);
 		refio::format_results(out, G, R.name, first, sink.recs.data(), sink.recs.size(), sink.q.data(), sink.s.data(), format);
-		ntasks += be.tasks_run; nbatches += be.batches;
 	}
-	char* p = (char*)malloc(out.size() + 1);
-	if (!p) return fail("out of memory");
-	memcpy(p, out.data(), out.size());
-	p[out.size()] = 0;
-	*text = p; *bytes = out.size();
-	if (stats) { stats[0] = ntasks; stats[1] = nbatches; }
+	char* o = (char*)malloc(out.size() + 1);
+	if (!o) return fail("out of memory");
+	memcpy(o, out.data(), out.size());
+	o[out.size()] = 0;
+	*text = o; *bytes = out.size();
+	return 0;
+}
+
+// the host twin of mecat_b200_ref_index_build + mecat_b200_ref_map: same structures in, same records out (lets the CPU
+// suite check the Python packing and formatting of mecat_b200/api.py)
+int harness_ref_map_packed(const mecat_ref_genome* g, const mecat_ref_reads* reads, const mecat_ref_params* p, mecat_ref_result** results, size_t* n,
+                           char** qstrings, char** sstrings, size_t* string_bytes)
+{
+	HostIndex I;
+	index_genome(g, I);
+	mbref::Sink sink;
+	std::string err;
+	if (map_packed(I, reads, p, 0, sink, NULL, err)) return 1;
+	mecat_ref_result* res = (mecat_ref_result*)malloc(sizeof(mecat_ref_result) * (sink.recs.size() ? sink.recs.size() : 1));
+	char* a = (char*)malloc(sink.q.size() + 1);
+	char* b = (char*)malloc(sink.s.size() + 1);
+	if (!res || !a || !b) return 1;
+	if (!sink.recs.empty()) memcpy(res, sink.recs.data(), sizeof(mecat_ref_result) * sink.recs.size());
+	memcpy(a, sink.q.data(), sink.q.size()); a[sink.q.size()] = 0;
+	memcpy(b, sink.s.data(), sink.s.size()); b[sink.s.size()] = 0;
+	*results = res; *n = sink.recs.size(); *qstrings = a; *sstrings = b; *string_bytes = sink.q.size();
 	return 0;
 }
 

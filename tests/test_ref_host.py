@@ -131,6 +131,35 @@ def test_fastq_reads_and_empty_inputs(tmp_path, refmap_inputs):
     assert run_harness(genome, empty, fmt=1)[0] == ""
 
 
+def packed_via_python(genome_path, reads_path, fmt, n=10, b=10):
+    """Python packing (mecat_b200.api RefGenome / RefReads) -> the host twin of the ABI call -> Python formatting."""
+    import numpy as np
+    from mecat_b200 import api
+    L = util.ref_harness()
+    G = api.RefGenome.from_fasta(genome_path)
+    seqs = util.read_fasta(reads_path)
+    R = api.RefReads(seqs)
+    g, r, p = G.c(), R.c(), api.RefParams(n, b, 1 if fmt == 0 else 0, 0)
+    res, cnt, qs, ss, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+    assert L.harness_ref_map_packed(C.byref(g), C.byref(r), C.byref(p), C.byref(res), C.byref(cnt), C.byref(qs), C.byref(ss), C.byref(nb)) == 0
+    rec = np.frombuffer(C.string_at(res.value, cnt.value * api.REF_RESULT_DTYPE.itemsize), dtype=api.REF_RESULT_DTYPE)
+    q, s = C.string_at(qs.value, nb.value), C.string_at(ss.value, nb.value)
+    for ptr in (res, qs, ss):
+        L.harness_free(ptr)
+    return api.format_ref_results(G, list(range(len(seqs))), rec, q, s, fmt)
+
+
+def test_python_packing_and_formatting(refmap_inputs, hard_inputs):
+    """The structures mecat_b200/api.py builds for mecat_b200_ref_index_build / mecat_b200_ref_map and the text it formats
+    from the records, against the reference's golden output (the GPU tests use the same helpers)."""
+    fa, genome = hard_inputs
+    assert groups(packed_via_python(genome, fa, 0)) == golden_groups("refmap_hard.ref.gz")
+    fa, genome = refmap_inputs
+    with gzip.open(os.path.join(util.GOLDEN, "refmap.m4.gz"), "rt") as f:
+        want = f.read().splitlines()
+    assert sorted(packed_via_python(genome, fa, 1).splitlines()) == want
+
+
 def test_ddf_integer_form_equals_the_float_forms():
     """|dloc / (dseed * BC) - 1| < 0.25: float32 in insert_loc / find_location, float64 in the neighbour votes, integers in
     the kernels (ref_core.cuh ddf_close).  Exhaustive over block-sized operands for every stride, random wide operands."""

@@ -175,6 +175,8 @@ def ref_harness():
     L.harness_ref_map.restype = C.c_int
     L.harness_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(vp), C.POINTER(C.c_size_t),
                                   C.POINTER(C.c_long), C.c_char_p, C.c_int]
+    L.harness_ref_map_packed.restype = C.c_int
+    L.harness_ref_map_packed.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.harness_ddf_forms.restype = C.c_int
     L.harness_ddf_forms.argtypes = [C.c_int, C.c_int, C.c_int]
     L.harness_ddf_sweep.restype = C.c_long
