@@ -5,7 +5,7 @@
 // Same flags and defaults as src/mecat2ref/mecat2ref.cpp:53-190, same records as its ref (-m 0) and m4 (-m 1) output
 // (src/mecat2ref/output.cpp:8-88; the records of a read are together, reads in input order).  The genome is indexed once
 // on the GPU (mecat_b200_ref_index_build); the reads go through mecat_b200_ref_map in batches -- seeding, DDF scoring,
-// gapped extension and clipped-end rescue all run on the device.  `-t` is accepted and unused.  With MECAT_GPUS=n every
+// gapped extension and clipped-end rescue all run on the device.  `-t` only sizes the host threads that pack the reads.  With MECAT_GPUS=n every
 // device holds a replica of the genome index and maps its share of the read batches (no collective; the output does not
 // depend on n).  Not on this path (refused with a message): -m 2 (SAM) and -x 1 (nanopore).  The reference's scratch
 // files (wrk_dir/N.fq, N.r, chrindex.txt, ./config.txt) are not written; the working directory is still created.
@@ -42,7 +42,7 @@ void print_usage(const char* prog)
 	fprintf(stderr, "\n\nusage:\n%s [-d reads] [-r reference] [-o output] [-w working dir] [-t threads]\n\noptions:\n", prog);
 	fprintf(stderr, "-d <string>\treads file name\n-r <string>\treference file name\n-o <string>\toutput file name\n");
 	fprintf(stderr, "-w <string>\tworking folder name, will be created if not exist\n");
-	fprintf(stderr, "-t <integer>\tnumber of cput threads -- accepted, unused: the mapping runs on the GPU\n\t\tdefault: 1\n");
+	fprintf(stderr, "-t <integer>\tnumber of cput threads (host-side packing only: the mapping runs on the GPU)\n\t\tdefault: 1\n");
 	fprintf(stderr, "-n <integer>\tnumber of of candidates for gap extension\n\t\tdefault: 10\n");
 	fprintf(stderr, "-b <integer>\toutput the best b alignments\n\t\tdefault: 10\n");
 	fprintf(stderr, "-m <0/1/2>\toutput format: 0 = ref, 1 = m4, 2 = sam (sam is not on this path)\n\t\tdefault: 0\n");
@@ -132,18 +132,17 @@ int main(int argc, char* argv[])
 	const double t_load = now();
 
 	// batches of reads: one ABI call each.  A volume holds < 2^31 bases; the ref format returns two strings per record.
-	const int64_t max_bases = 1900000000ll;
+	const int64_t max_bases = 1000000000ll;      // explicit reverse strands of reads with other letters still fit
 	const int max_reads = o.output_format == 0 ? 20000 : 1 << 30;
 	std::vector<Batch> batches;
-	const int total = (int)R.seq.size();
-	int64_t all_bases = 0;
-	for (const std::string& s : R.seq) all_bases += 2 * (int64_t)s.size() + 2;
+	const int total = (int)R.size();
+	const int64_t all_bases = (int64_t)R.arena.size() + total;
 	const int64_t share = std::max<int64_t>(1 << 20, (all_bases + ndev - 1) / ndev);
 	for (int first = 0; first < total;) {
 		int count = 0;
 		int64_t bases = 0;
 		while (first + count < total && count < max_reads) {
-			const int64_t need = 2 * (int64_t)R.seq[(size_t)(first + count)].size() + 2;      // worst case: both strands packed
+			const int64_t need = R.length((size_t)(first + count)) + 1;
 			if (count && (bases + need > max_bases || bases + need > share)) break;
 			bases += need; ++count;
 		}
@@ -152,6 +151,8 @@ int main(int argc, char* argv[])
 		first += count;
 	}
 
+	const int hw = (int)std::thread::hardware_concurrency();
+	const int host_threads = std::max(1, std::min(hw > 0 ? hw : 1, std::max(o.num_cores, 8)) / ndev);
 	std::atomic<int> next(0), failed(0);
 	std::vector<double> t_index((size_t)ndev, 0.0);
 	auto worker = [&](int d) {
@@ -168,7 +169,7 @@ int main(int argc, char* argv[])
 			if (k >= (int)batches.size() || failed) break;
 			Batch& b = batches[(size_t)k];
 			refio::ReadBatch B;
-			for (int i = 0; i < b.count; ++i) B.add_read(R.seq[(size_t)(b.first + i)]);
+			B.build(R, (size_t)b.first, (size_t)b.count, host_threads);
 			const mecat_ref_reads view = B.view();
 			mecat_ref_result* res = NULL;
 			char *qs = NULL, *ss = NULL;

@@ -12,11 +12,17 @@
 //                      get_chr_id, mecat2ref.cpp:280-356
 // Used by the mecat2ref driver and by the host harness of the CPU test-suite.
 #pragma once
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/mecat_b200.h"
@@ -73,123 +79,276 @@ inline bool read_file(const char* path, std::string& all)
 	return true;
 }
 
+struct MappedFile      // the input file, mapped read-only (falls back to reading it for non-regular files)
+{
+	const char* p = NULL;
+	size_t n = 0;
+	std::string copy;
+	bool mapped = false;
+	bool open(const char* path)
+	{
+		const int fd = ::open(path, O_RDONLY);
+		if (fd < 0) return false;
+		struct stat st;
+		if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+			void* m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (m != MAP_FAILED) { p = (const char*)m; n = (size_t)st.st_size; mapped = true; madvise(m, n, MADV_SEQUENTIAL); }
+		}
+		::close(fd);
+		if (mapped) return true;
+		if (!read_file(path, copy)) return false;
+		p = copy.data(); n = copy.size();
+		return true;
+	}
+	~MappedFile() { if (mapped) munmap((void*)p, n); }
+};
+
 inline bool load_genome(const char* path, Genome& G, std::string& err)
 {
-	std::string all;
-	if (!read_file(path, all)) { err = std::string("cannot open ") + path; return false; }
-	int64_t run_start = -1;
-	size_t i = 0;
-	while (i < all.size()) {
-		const unsigned char ch = (unsigned char)all[i];
-		if (ch == '>') {
-			size_t e = all.find('\n', i);
-			if (e == std::string::npos) e = all.size();
-			size_t k = i + 1;
-			while (k < e && all[k] != ' ' && all[k] != '\t') ++k;
-			if (!G.chr.empty()) G.chr.back().size = G.seq.n - G.chr.back().start;
-			Chr c; c.start = G.seq.n; c.name = all.substr(i + 1, k - i - 1);
+	MappedFile F;
+	if (!F.open(path)) { err = std::string("cannot open ") + path; return false; }
+	// per character: bits 0-1 = code after upper-casing, bit 7 = not ACGT (packs as A, ends a run), bit 6 = line end (skipped)
+	uint8_t T[256];
+	for (int c = 0; c < 256; ++c) {
+		const unsigned char up = c > 'Z' ? (unsigned char)toupper(c) : (unsigned char)c;
+		T[c] = upper_acgt(up) ? (uint8_t)code_ci(up) : (uint8_t)0x80;
+	}
+	T[(unsigned char)'\n'] = 0x40; T[(unsigned char)'\r'] = 0x40;
+	std::vector<uint8_t>& pac = G.seq.pac;
+	pac.assign(F.n / 4 + 16, 0);          // never more bases than characters
+	int64_t n = 0, run_start = -1;
+	const char* p = F.p;
+	const char* end = F.p + F.n;
+	while (p < end) {
+		if (*p == '>') {
+			const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+			const char* e = nl ? nl : end;
+			const char* k = p + 1;
+			while (k < e && *k != ' ' && *k != '\t') ++k;
+			if (!G.chr.empty()) G.chr.back().size = n - G.chr.back().start;
+			Chr c; c.start = n; c.name.assign(p + 1, (size_t)(k - p - 1));
 			G.chr.push_back(c);
-			i = e;
+			p = e;
 			continue;
 		}
-		++i;
-		if (ch == '\n' || ch == '\r') continue;
-		const unsigned char up = ch > 'Z' ? (unsigned char)toupper(ch) : ch;
-		const bool good = upper_acgt(up);
-		if (good && run_start < 0) run_start = G.seq.n;
-		if (!good && run_start >= 0) { G.runs.push_back(run_start); G.runs.push_back(G.seq.n - run_start); run_start = -1; }
-		G.seq.push(good ? code_ci(up) : 0);
+		const char* gt = (const char*)memchr(p, '>', (size_t)(end - p));
+		const char* stop = gt ? gt : end;
+		while (p < stop) {
+			// fast path: four ACGT letters inside a run, byte aligned
+			if ((n & 3) == 0 && run_start >= 0) {
+				uint8_t* out = pac.data() + (n >> 2);
+				const char* q = p;
+				while (q + 4 <= stop) {
+					const uint8_t a = T[(unsigned char)q[0]], b = T[(unsigned char)q[1]], c = T[(unsigned char)q[2]], d = T[(unsigned char)q[3]];
+					if ((a | b | c | d) & 0xC0) break;
+					*out++ = (uint8_t)(a << 6 | b << 4 | c << 2 | d);
+					q += 4;
+				}
+				n += q - p;
+				p = q;
+				if (p >= stop) break;
+			}
+			const uint8_t v = T[(unsigned char)*p++];
+			if (v & 0x40) continue;
+			if (v & 0x80) { if (run_start >= 0) { G.runs.push_back(run_start); G.runs.push_back(n - run_start); run_start = -1; } }
+			else if (run_start < 0) run_start = n;
+			pac[(size_t)(n >> 2)] |= (uint8_t)((v & 3u) << (((~n) & 3) << 1));
+			++n;
+		}
 	}
-	if (run_start >= 0) { G.runs.push_back(run_start); G.runs.push_back(G.seq.n - run_start); }
-	if (!G.chr.empty()) G.chr.back().size = G.seq.n - G.chr.back().start;
+	pac.resize((size_t)((n + 3) / 4));
+	G.seq.n = n;
+	if (run_start >= 0) { G.runs.push_back(run_start); G.runs.push_back(n - run_start); }
+	if (!G.chr.empty()) G.chr.back().size = n - G.chr.back().start;
 	if (G.chr.empty()) { err = std::string("no sequence in ") + path; return false; }
 	return true;
 }
 
+// All reads of a file: the letters of every read, line ends removed, in one arena.
 struct Reads
 {
 	std::vector<int32_t> name;           // the number the reference prints for the read
-	std::vector<std::string> seq;
+	std::string arena;
+	std::vector<int64_t> start;          // [size() + 1] offsets into the arena
+	size_t size() const { return name.size(); }
+	const char* data(size_t i) const { return arena.data() + start[i]; }
+	int64_t length(size_t i) const { return start[i + 1] - start[i]; }
+	std::string str(size_t i) const { return std::string(data(i), (size_t)length(i)); }
 };
+
+// appends [b, e) to the arena without '\n' and '\r'
+inline void append_letters(std::string& arena, const char* b, const char* e)
+{
+	while (b < e) {
+		const char* nl = (const char*)memchr(b, '\n', (size_t)(e - b));
+		const char* stop = nl ? nl : e;
+		if (memchr(b, '\r', (size_t)(stop - b))) { for (const char* q = b; q < stop; ++q) if (*q != '\r') arena.push_back(*q); }
+		else arena.append(b, (size_t)(stop - b));
+		b = nl ? nl + 1 : e;
+	}
+}
 
 inline bool load_reads(const char* path, Reads& R, std::string& err)
 {
-	std::string all;
-	if (!read_file(path, all)) { err = std::string("cannot open ") + path; return false; }
-	if (all.empty()) return true;
-	if (all[0] == '>') {
-		size_t i = 0;
+	MappedFile F;
+	if (!F.open(path)) { err = std::string("cannot open ") + path; return false; }
+	R.start.assign(1, 0);
+	if (F.n == 0) return true;
+	const char* p = F.p;
+	const char* end = F.p + F.n;
+	R.arena.reserve(F.n);
+	if (*p == '>') {
+		// chang_fastqfile reads character by character: a '>' anywhere opens a header that runs to the end of its line,
+		// everything else up to the next '>' is sequence
 		int next = 0;
-		while (i < all.size()) {
-			if (all[i] == '>') {
-				while (i < all.size() && all[i] != '\n') ++i;
+		while (p < end) {
+			if (*p == '>') {
+				if (next) R.start.push_back((int64_t)R.arena.size());
 				R.name.push_back(next++);
-				R.seq.push_back(std::string());
+				const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+				p = nl ? nl : end;
 			} else {
-				if (all[i] != '\n' && all[i] != '\r') R.seq.back().push_back(all[i]);
-				++i;
+				const char* gt = (const char*)memchr(p, '>', (size_t)(end - p));
+				const char* stop = gt ? gt : end;
+				append_letters(R.arena, p, stop);
+				p = stop;
 			}
 		}
+		R.start.push_back((int64_t)R.arena.size());
 	} else {
-		std::vector<std::string> lines;
-		size_t i = 0;
-		while (i < all.size()) {
-			const size_t e = all.find('\n', i);
-			std::string l = all.substr(i, e == std::string::npos ? std::string::npos : e - i);
-			if (!l.empty() && l[l.size() - 1] == '\r') l.erase(l.size() - 1);
-			lines.push_back(l);
-			if (e == std::string::npos) break;
-			i = e + 1;
-		}
+		// FASTQ: records of four lines, the second one is the sequence
 		int next = 0;
-		for (size_t k = 0; k + 3 < lines.size(); k += 4) { R.name.push_back(++next); R.seq.push_back(lines[k + 1]); }
+		const char* line[4];
+		const char* line_end[4];
+		int k = 0;
+		bool more = true;
+		while (more && p < end) {
+			const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+			line[k] = p; line_end[k] = nl ? nl : end;
+			if (!nl) more = false; else p = nl + 1;
+			if (++k == 4) {
+				const char* b = line[1];
+				const char* e = line_end[1];
+				if (e > b && e[-1] == '\r') --e;
+				R.name.push_back(++next);
+				R.arena.append(b, (size_t)(e - b));
+				R.start.push_back((int64_t)R.arena.size());
+				k = 0;
+			}
+		}
 	}
 	return true;
 }
 
 // Reads [first, first + count) packed as one volume.  A read made of upper-case ACGT only is packed once (its reverse
-// strand is the reverse complement of the packed bases); any other read also gets its reverse strand packed explicitly,
-// built the way the reference builds it.
+// strand is the reverse complement of the packed bases); any other read also gets its reverse strand packed explicitly
+// behind the forward strands, built the way the reference builds it.
 struct ReadBatch
 {
-	Packer bases;
+	std::vector<uint8_t> pac;
+	int64_t nbases = 0;
 	std::vector<int32_t> offsz, len, fread, rread, rrc;
 	std::vector<int64_t> bad;
 	mecat_volume vol;
 	mecat_ref_reads view()
 	{
-		vol.num_reads = (int32_t)(offsz.size() / 2); vol.num_bases = (int32_t)bases.n; vol.start_read_id = 0;
-		vol.offset_size = offsz.data(); vol.pac = bases.pac.data();
+		vol.num_reads = (int32_t)(offsz.size() / 2); vol.num_bases = (int32_t)nbases; vol.start_read_id = 0;
+		vol.offset_size = offsz.data(); vol.pac = pac.data();
 		mecat_ref_reads r;
 		r.num_reads = (int32_t)len.size(); r.vol = &vol; r.read_len = len.data(); r.fwd_read = fread.data(); r.rev_read = rread.data();
 		r.rev_is_rc = rrc.data(); r.num_bad = (int64_t)bad.size(); r.bad = bad.data();
 		return r;
 	}
-	int32_t add_sequence(const std::string& s)
+
+	// bits 0-1: code (anything but ACGT in either case packs as A); bit 7: not upper-case ACGT
+	static const uint8_t* table()
 	{
-		const int32_t id = (int32_t)(offsz.size() / 2);
-		offsz.push_back((int32_t)bases.n); offsz.push_back((int32_t)s.size());
-		for (size_t i = 0; i < s.size(); ++i) {
-			const int c = code_ci((unsigned char)s[i]);
-			if (!upper_acgt((unsigned char)s[i])) bad.push_back(bases.n);
-			bases.push(c < 0 ? 0 : c);
+		static uint8_t t[256];
+		static bool done = false;
+		if (!done) {
+			for (int c = 0; c < 256; ++c) { const int k = code_ci((unsigned char)c); t[c] = (uint8_t)((k < 0 ? 0 : k) | (upper_acgt((unsigned char)c) ? 0 : 0x80)); }
+			done = true;
 		}
-		bases.push(0);      // one pad base between reads, like the reference's volumes
-		return id;
+		return t;
 	}
-	void add_read(const std::string& s)
+	// n letters at base offset `base`; bytes shared with a neighbouring read are OR-ed in atomically (several threads pack)
+	static bool pack_letters(uint8_t* pac, int64_t base, const char* s, int64_t n, std::vector<int64_t>& bad)
 	{
-		bool plain = true;
-		for (size_t i = 0; i < s.size() && plain; ++i) plain = upper_acgt((unsigned char)s[i]);
-		len.push_back((int32_t)s.size());
-		const int32_t f = add_sequence(s);
-		fread.push_back(f);
-		if (plain) { rread.push_back(f); rrc.push_back(1); return; }
-		std::string r(s.rbegin(), s.rend());
-		for (char& c : r) c = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c;
-		rread.push_back(add_sequence(r)); rrc.push_back(0);
+		const uint8_t* t = table();
+		const unsigned char* u = (const unsigned char*)s;
+		unsigned flags = 0;
+		int64_t i = 0;
+		auto one = [&](int64_t k) {
+			const uint8_t v = t[u[k]];
+			if (v & 0x80) { flags |= 0x80; bad.push_back(base + k); }
+			__atomic_fetch_or(&pac[(base + k) >> 2], (uint8_t)((v & 3) << (((~(base + k)) & 3) << 1)), __ATOMIC_RELAXED);
+		};
+		while (i < n && ((base + i) & 3)) one(i++);
+		uint8_t* out = pac + ((base + i) >> 2);
+		for (; i + 4 <= n; i += 4) {
+			const uint8_t a = t[u[i]], b = t[u[i + 1]], c = t[u[i + 2]], d = t[u[i + 3]];
+			if ((a | b | c | d) & 0x80) {
+				flags |= 0x80;
+				if (a & 0x80) bad.push_back(base + i);
+				if (b & 0x80) bad.push_back(base + i + 1);
+				if (c & 0x80) bad.push_back(base + i + 2);
+				if (d & 0x80) bad.push_back(base + i + 3);
+			}
+			*out++ = (uint8_t)((a & 3) << 6 | (b & 3) << 4 | (c & 3) << 2 | (d & 3));
+		}
+		while (i < n) one(i++);
+		return flags == 0;
 	}
-	int64_t packed_bases() const { return bases.n; }
+
+	void build(const Reads& R, size_t first, size_t count, int threads)
+	{
+		len.resize(count); fread.resize(count); rread.resize(count); rrc.resize(count);
+		offsz.resize(2 * count);
+		int64_t at = 0;
+		for (size_t i = 0; i < count; ++i) {
+			const int64_t n = R.length(first + i);
+			len[i] = (int32_t)n; fread[i] = (int32_t)i; rread[i] = (int32_t)i; rrc[i] = 1;
+			offsz[2 * i] = (int32_t)at; offsz[2 * i + 1] = (int32_t)n;
+			at += n + 1;                      // one pad base between reads, like the reference's volumes
+		}
+		pac.assign((size_t)((at + 3) / 4 + 8), 0);
+		if (threads < 1) threads = 1;
+		if ((size_t)threads > count) threads = count ? (int)count : 1;
+		std::vector<std::vector<int64_t>> tbad((size_t)threads);
+		std::vector<uint8_t> plain(count, 1);
+		auto first_at = [&](int64_t pos) {      // first read whose offset is >= pos
+			size_t a = 0, b = count;
+			while (a < b) { const size_t m = (a + b) / 2; if (offsz[2 * m] < pos) a = m + 1; else b = m; }
+			return a;
+		};
+		auto work = [&](int t) {                // a contiguous range of reads with about 1/threads of the bases
+			const size_t r0 = first_at(at * t / threads), r1 = first_at(at * (t + 1) / threads);
+			for (size_t r = r0; r < r1; ++r) plain[r] = pack_letters(pac.data(), offsz[2 * r], R.data(first + r), len[r], tbad[(size_t)t]) ? 1 : 0;
+		};
+		if (threads == 1) work(0);
+		else {
+			std::vector<std::thread> pool;
+			for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+			for (auto& th : pool) th.join();
+		}
+		bad.clear();
+		for (auto& v : tbad) bad.insert(bad.end(), v.begin(), v.end());
+		// explicit reverse strands of the reads that are not plain
+		for (size_t r = 0; r < count; ++r) {
+			if (plain[r]) continue;
+			std::string s(R.data(first + r), (size_t)len[r]);
+			std::reverse(s.begin(), s.end());
+			for (char& c : s) c = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c;
+			rread[r] = (int32_t)(offsz.size() / 2); rrc[r] = 0;
+			offsz.push_back((int32_t)at); offsz.push_back(len[r]);
+			pac.resize((size_t)((at + len[r] + 1 + 3) / 4 + 8), 0);
+			pack_letters(pac.data(), at, s.data(), len[r], bad);
+			at += len[r] + 1;
+		}
+		nbases = at;
+	}
+	// volume bases a range of reads needs at most (both strands packed)
+	static int64_t worst_case_bases(const Reads& R, size_t first, size_t count) { return 2 * (R.start[first + count] - R.start[first]) + 2 * (int64_t)count; }
 };
 
 inline int chr_of(const std::vector<Chr>& chr, int64_t offset)      // get_chr_id, mecat2ref.cpp:280-298

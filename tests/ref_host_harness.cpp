@@ -170,6 +170,7 @@ extern "C" {
 int harness_ref_map(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format, int reads_per_call,
                     long table_budget, char** text, size_t* bytes, long* stats /* tasks, seed launches */, char* errbuf, int errcap)
 {
+	const int pack_threads = getenv("MECAT_HARNESS_PACK_THREADS") ? atoi(getenv("MECAT_HARNESS_PACK_THREADS")) : 3;
 	auto fail = [&](const std::string& m) { if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", m.c_str()); return 1; };
 	refio::Genome G;
 	refio::Reads R;
@@ -180,14 +181,14 @@ int harness_ref_map(const char* reference_path, const char* reads_path, int num_
 	index_genome(&gv, I);
 	std::string out;
 	if (stats) stats[0] = stats[1] = 0;
-	const int total = (int)R.seq.size();
+	const int total = (int)R.size();
 	if (reads_per_call < 1) reads_per_call = total ? total : 1;
 	mecat_ref_params p;
 	p.num_candidates = num_candidates; p.num_output = num_output; p.want_strings = format == 0; p.tech = 0;
 	for (int first = 0; first < total; first += reads_per_call) {
 		const int count = std::min(reads_per_call, total - first);
 		refio::ReadBatch B;
-		for (int i = 0; i < count; ++i) B.add_read(R.seq[(size_t)(first + i)]);
+		B.build(R, (size_t)first, (size_t)count, pack_threads);
 		const mecat_ref_reads view = B.view();
 		mbref::Sink sink;
 		if (map_packed(I, &view, &p, table_budget, sink, stats, err)) return fail(err);

@@ -131,6 +131,45 @@ def test_fastq_reads_and_empty_inputs(tmp_path, refmap_inputs):
     assert run_harness(genome, empty, fmt=1)[0] == ""
 
 
+def test_awkward_files_parse_like_the_reference(tmp_path, refmap_inputs):
+    """Multi-line records with CRLF line ends, blank lines, header descriptions, a lower-case genome, a '>' inside a
+    sequence line (chang_fastqfile opens a header there), FASTQ without a final newline and with an incomplete last
+    record: the memchr-based readers of host/refio.h against the oracle's character-by-character ones."""
+    fa, genome = refmap_inputs
+    seqs = util.read_fasta(fa)[:30]
+    g = util.read_fasta(genome)[0]
+    genome2 = str(tmp_path / "genome.fa")
+    with open(genome2, "wb") as f:
+        f.write(b">chrA some description\there\r\n")
+        half = len(g) // 2
+        for i in range(0, half, 70):
+            f.write(g[i:min(i + 70, half)].lower() + b"\r\n")
+        f.write(b"\n>chrB\n" + g[half:] + b"\n\n")
+    reads2 = str(tmp_path / "reads.fa")
+    with open(reads2, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">read%d extra words\r\n" % i)
+            for k in range(0, len(s), 80):
+                f.write(s[k:k + 80] + (b"\r\n" if i % 2 else b"\n"))
+            if i == 7:
+                f.write(b"\n")
+            if i == 11:
+                f.write(s[:3000] + b">glued " + b"\n" + s[3000:9000] + b"\n")
+    for fmt in (0, 1):
+        got, want = run_harness(genome2, reads2, fmt=fmt)[0], run_oracle(genome2, reads2, 10, 10, fmt)
+        assert want and got == want           # same records in the same order: one call, all reads found in the first pass
+    fq = str(tmp_path / "reads.fq")
+    with open(fq, "wb") as f:
+        for i, s in enumerate(seqs[:12]):
+            f.write(b"@r%d\r\n" % i + s + b"\r\n+\r\n" + b"I" * len(s) + b"\r\n")
+        f.write(b"@last\n" + seqs[12] + b"\n+\n" + b"I" * len(seqs[12]))             # complete, no final newline
+    got, want = run_harness(genome2, fq, fmt=1)[0], run_oracle(genome2, fq, 10, 10, 1)
+    assert want and got == want
+    with open(fq, "ab") as f:
+        f.write(b"\n@cut\n" + seqs[13] + b"\n+\n")                                     # three lines: not a record
+    assert run_harness(genome2, fq, fmt=1)[0] == want == run_oracle(genome2, fq, 10, 10, 1)
+
+
 def packed_via_python(genome_path, reads_path, fmt, n=10, b=10):
     """Python packing (mecat_b200.api RefGenome / RefReads) -> the host twin of the ABI call -> Python formatting."""
     import numpy as np
