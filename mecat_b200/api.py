@@ -286,7 +286,7 @@ class RefReads:
 
 def format_ref_results(genome, read_names, records, qstrings=b"", sstrings=b"", fmt=1):
     """The text mecat2ref writes for `records` of Context.ref_map (print_ref_result / print_m4_result,
-    src/mecat2ref/output.cpp:8-88): fmt 0 = ref (header + both alignment strings), 1 = m4."""
+    src/mecat2ref/output.cpp:8-191): fmt 0 = ref (header + both alignment strings), 1 = m4, 2 = sam records."""
     out = []
     for r in records:
         k, start, size = genome.contig_of(int(r["sb"]))
@@ -299,6 +299,30 @@ def format_ref_results(genome, read_names, records, qstrings=b"", sstrings=b"", 
             out.append("%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n%s\n%s\n" % (
                 read_names[int(r["read"])], name, "R" if r["dir"] else "F", int(r["vscore"]), qb, qe, qs, sb, se, size,
                 qstrings[o:o + n].decode(), sstrings[o:o + n].decode()))
+        elif fmt == 2:
+            o, n = int(r["str_offset"]), int(r["columns"])
+            qm, sm = qstrings[o:o + n], sstrings[o:o + n]
+            cigar = ["%dH" % int(r["qb"])] if r["qb"] else []
+            i = 0
+            while i < n:
+                j = i + 1
+                if qm[i] == 45:
+                    while j < n and qm[j] == 45:
+                        j += 1
+                    cigar.append("%dD" % (j - i))
+                elif sm[i] == 45:
+                    while j < n and sm[j] == 45:
+                        j += 1
+                    cigar.append("%dI" % (j - i))
+                else:
+                    while j < n and qm[j] != 45 and sm[j] != 45:
+                        j += 1
+                    cigar.append("%dM" % (j - i))
+                i = j
+            if int(r["qe"]) != qs:
+                cigar.append("%dH" % (qs - int(r["qe"])))
+            out.append("%d\t%d\t%s\t%d\t255\t%s\t*\t0\t0\t%s\t*\n" % (
+                read_names[int(r["read"])], 16 if r["dir"] else 0, name, sb + 1, "".join(cigar), qm.replace(b"-", b"").decode()))
         else:
             ident = float(int(r["matches"])) / float(int(r["columns"]))
             ident *= 100.0

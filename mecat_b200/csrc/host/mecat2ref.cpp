@@ -2,12 +2,12 @@
 //
 //   mecat2ref -d reads -r reference -o output -w wrk_dir [-t threads] [-n candidates] [-b best] [-m 0|1] [-x 0]
 //
-// Same flags and defaults as src/mecat2ref/mecat2ref.cpp:53-190, same records as its ref (-m 0) and m4 (-m 1) output
-// (src/mecat2ref/output.cpp:8-88; the records of a read are together, reads in input order).  The genome is indexed once
+// Same flags and defaults as src/mecat2ref/mecat2ref.cpp:53-190, same records as its ref (-m 0), m4 (-m 1) and sam (-m 2)
+// output (src/mecat2ref/output.cpp:8-191; the records of a read are together, reads in input order).  The genome is indexed once
 // on the GPU (mecat_b200_ref_index_build); the reads go through mecat_b200_ref_map in batches -- seeding, DDF scoring,
 // gapped extension and clipped-end rescue all run on the device.  `-t` only sizes the host threads that pack the reads.  With MECAT_GPUS=n every
 // device holds a replica of the genome index and maps its share of the read batches (no collective; the output does not
-// depend on n).  Not on this path (refused with a message): -m 2 (SAM) and -x 1 (nanopore).  The reference's scratch
+// depend on n).  Not on this path (refused with a message): -x 1 (nanopore).  The reference's scratch
 // files (wrk_dir/N.fq, N.r, chrindex.txt, ./config.txt) are not written; the working directory is still created.
 #include <dirent.h>
 #include <getopt.h>
@@ -45,7 +45,7 @@ void print_usage(const char* prog)
 	fprintf(stderr, "-t <integer>\tnumber of cput threads (host-side packing only: the mapping runs on the GPU)\n\t\tdefault: 1\n");
 	fprintf(stderr, "-n <integer>\tnumber of of candidates for gap extension\n\t\tdefault: 10\n");
 	fprintf(stderr, "-b <integer>\toutput the best b alignments\n\t\tdefault: 10\n");
-	fprintf(stderr, "-m <0/1/2>\toutput format: 0 = ref, 1 = m4, 2 = sam (sam is not on this path)\n\t\tdefault: 0\n");
+	fprintf(stderr, "-m <0/1/2>\toutput format: 0 = ref, 1 = m4, 2 = sam\n\t\tdefault: 0\n");
 	fprintf(stderr, "-x <0/1>\tsequencing technology: 0 = pacbio, 1 = nanopore (nanopore is not on this path)\n\t\tdefault: 0\n");
 }
 
@@ -110,7 +110,7 @@ int main(int argc, char* argv[])
 	Options o;
 	if (parse(argc, argv, o) == -1) { print_usage(argv[0]); return 1; }
 	if (o.tech != 0) { fprintf(stderr, "mecat2ref (b200): -x 1 (nanopore) is not on this path\n"); return 1; }
-	if (o.output_format != 0 && o.output_format != 1) { fprintf(stderr, "mecat2ref (b200): output format %d is not on this path (0 = ref, 1 = m4)\n", o.output_format); return 1; }
+	if (o.output_format < 0 || o.output_format > 2) { fprintf(stderr, "mecat2ref (b200): unknown output format %d (0 = ref, 1 = m4, 2 = sam)\n", o.output_format); return 1; }
 	const double t0 = now();
 	int ndev = 1;
 	if (const char* e = getenv("MECAT_GPUS")) ndev = std::max(1, atoi(e));
@@ -133,7 +133,7 @@ int main(int argc, char* argv[])
 
 	// batches of reads: one ABI call each.  A volume holds < 2^31 bases; the ref format returns two strings per record.
 	const int64_t max_bases = 1000000000ll;      // explicit reverse strands of reads with other letters still fit
-	const int max_reads = o.output_format == 0 ? 20000 : 1 << 30;
+	const int max_reads = o.output_format != 1 ? 20000 : 1 << 30;
 	std::vector<Batch> batches;
 	const int total = (int)R.size();
 	const int64_t all_bases = (int64_t)R.arena.size() + total;
@@ -163,7 +163,7 @@ int main(int argc, char* argv[])
 		if (mecat_b200_ref_index_build(c, &g, &idx)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; return; }
 		t_index[(size_t)d] = now() - a;
 		mecat_ref_params p;
-		p.num_candidates = o.num_candidates; p.num_output = o.num_output; p.want_strings = o.output_format == 0; p.tech = o.tech;
+		p.num_candidates = o.num_candidates; p.num_output = o.num_output; p.want_strings = o.output_format != 1; p.tech = o.tech;
 		for (;;) {
 			const int k = next.fetch_add(1);
 			if (k >= (int)batches.size() || failed) break;
@@ -189,6 +189,11 @@ int main(int argc, char* argv[])
 	fprintf(stderr, "output file name: %s\n", o.output);
 	FILE* out = fopen(o.output, "w");
 	if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
+	if (o.output_format == 2) {
+		std::string head;
+		refio::sam_header(head, G, argc, argv);
+		fwrite(head.data(), 1, head.size(), out);
+	}
 	for (const Batch& b : batches) fwrite(b.text.data(), 1, b.text.size(), out);
 	fclose(out);
 	for (int d = 0; d < ndev; ++d) mecat_b200_destroy(ctx[(size_t)d]);

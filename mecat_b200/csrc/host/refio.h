@@ -366,7 +366,36 @@ inline int chr_of(const std::vector<Chr>& chr, int64_t offset)      // get_chr_i
 	return mid;
 }
 
-// format 0 = ref (header line + the two alignment strings), 1 = m4.  `names`: the printed number of read r.
+// The header of a SAM file (print_sam_header / print_sam_references / print_sam_program, src/mecat2ref/output.cpp:92-116)
+inline void sam_header(std::string& out, const Genome& G, int argc, char* const argv[])
+{
+	char line[1400];
+	out += "@HD\tVN:1.4\tSO:unknown\tGO:query\n";
+	for (const Chr& c : G.chr) { snprintf(line, sizeof line, "@SQ\tSN:%s\tLN:%ld\n", c.name.c_str(), (long)c.size); out += line; }
+	out += "@PG\tID:0\tVN:0.0.1\tCL:";
+	for (int i = 0; i < argc; ++i) { out += argv[i]; out += ' '; }
+	out += "\tPN:mecat2ref\n";
+}
+
+// output_cigar, output.cpp:118-155: hard clips for the unaligned read ends, runs of D (gap in the read), I (gap in the
+// reference) and M
+inline void sam_cigar(std::string& out, int qstart, int qend, int qsize, const char* qmap, const char* smap, int n)
+{
+	char tmp[32];
+	auto op = [&](int len, char c) { snprintf(tmp, sizeof tmp, "%d%c", len, c); out += tmp; };
+	if (qstart) op(qstart, 'H');
+	int i = 0;
+	while (i < n) {
+		int j = i + 1;
+		if (qmap[i] == '-') { while (j < n && qmap[j] == '-') ++j; op(j - i, 'D'); }
+		else if (smap[i] == '-') { while (j < n && smap[j] == '-') ++j; op(j - i, 'I'); }
+		else { while (j < n && qmap[j] != '-' && smap[j] != '-') ++j; op(j - i, 'M'); }
+		i = j;
+	}
+	if (qend != qsize) op(qsize - qend, 'H');
+}
+
+// format 0 = ref (header line + the two alignment strings), 1 = m4, 2 = sam records.  `names`: the printed number of read r.
 inline void format_results(std::string& out, const Genome& G, const std::vector<int32_t>& names, int32_t first_read, const mecat_ref_result* recs, size_t n,
                            const char* qstr, const char* sstr, int format)
 {
@@ -383,13 +412,22 @@ inline void format_results(std::string& out, const Genome& G, const std::vector<
 			out += line;
 			out.append(qstr + r.str_offset, (size_t)r.columns); out += '\n';
 			out.append(sstr + r.str_offset, (size_t)r.columns); out += '\n';
-		} else {
+		} else if (format == 1) {
 			double ident = (double)r.matches;        // print_m4_result counts the equal columns of the two strings
 			ident = ident / (double)r.columns;
 			ident *= 100.0;
 			snprintf(line, sizeof line, "%d\t%s\t%.4f\t%d\t%d\t%d\t%d\t%d\t0\t%ld\t%ld\t%ld\n", id, c.name.c_str(), ident, r.vscore, r.dir ? 1 : 0, qb, qe,
 			         r.qs, (long)(r.sb - c.start), (long)(r.se - c.start), (long)c.size);
 			out += line;
+		} else {
+			// output_sam, output.cpp:157-191: coordinates of the strand that aligned, SEQ = the aligned read bases
+			const char* qm = qstr + r.str_offset;
+			snprintf(line, sizeof line, "%d\t%d\t%s\t%ld\t255\t", id, r.dir ? 0x10 : 0, c.name.c_str(), (long)(r.sb - c.start) + 1);
+			out += line;
+			sam_cigar(out, r.qb, r.qe, r.qs, qm, sstr + r.str_offset, r.columns);
+			out += "\t*\t0\t0\t";
+			for (int k = 0; k < r.columns; ++k) if (qm[k] != '-') out += qm[k];
+			out += "\t*\n";
 		}
 	}
 }

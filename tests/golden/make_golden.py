@@ -50,7 +50,7 @@ def make_refmap(meta):
     for fmt, ext in ((1, "m4"), (0, "ref")):
         out = os.path.join(tmp, "out." + ext)
         subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w" + ext),
-                               "-t", "4", "-m", str(fmt)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                               "-t", "4", "-m", str(fmt)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
         text = open(out).read()
         if fmt == 1:
             lines = sorted(text.splitlines())
@@ -74,7 +74,7 @@ def make_refmap(meta):
     m["fasta_sha256"] = sha(fa); m["genome_sha256"] = sha(genome)
     out = os.path.join(tmp, "out.m4")
     subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w"), "-t", "8", "-m", "1"],
-                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
     lines = sorted(open(out).read().splitlines())
     with gzip.open(os.path.join(HERE, "refmap_cfg0.m4.gz"), "wt") as f:
         f.write("\n".join(lines) + "\n")
@@ -88,12 +88,22 @@ def make_refmap(meta):
     m = {"fasta_sha256": sha(fa), "genome_sha256": sha(genome)}
     out = os.path.join(tmp, "out.ref")
     subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w"), "-t", "3", "-m", "0"],
-                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)      # the binary leaves ./config.txt behind
     recs = open(out).read().split("\n")
     groups = sorted("\n".join(recs[i:i + 3]) for i in range(0, len(recs) - 1, 3))
     with gzip.open(os.path.join(HERE, "refmap_hard.ref.gz"), "wt") as f:
         f.write("\n".join(groups) + "\n")
     m["num_ref"] = len(groups)
+    # the same inputs as SAM (-m 2): header lines except @PG (it holds the command line), then the records, sorted
+    out = os.path.join(tmp, "out.sam")
+    subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "ws"), "-t", "3", "-m", "2"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
+    lines = open(out).read().splitlines()
+    head = [l for l in lines if l.startswith("@") and not l.startswith("@PG")]
+    recs = sorted(l for l in lines if not l.startswith("@"))
+    with gzip.open(os.path.join(HERE, "refmap_hard.sam.gz"), "wt") as f:
+        f.write("\n".join(head + recs) + "\n")
+    m["num_sam"] = len(recs)
     meta["refmap_hard"] = m
     shutil.rmtree(tmp)
 

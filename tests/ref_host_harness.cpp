@@ -184,7 +184,7 @@ int harness_ref_map(const char* reference_path, const char* reads_path, int num_
 	const int total = (int)R.size();
 	if (reads_per_call < 1) reads_per_call = total ? total : 1;
 	mecat_ref_params p;
-	p.num_candidates = num_candidates; p.num_output = num_output; p.want_strings = format == 0; p.tech = 0;
+	p.num_candidates = num_candidates; p.num_output = num_output; p.want_strings = format != 1; p.tech = 0;
 	for (int first = 0; first < total; first += reads_per_call) {
 		const int count = std::min(reads_per_call, total - first);
 		refio::ReadBatch B;

@@ -58,7 +58,7 @@ def map_through_abi(ctx, genome_path, reads_path, fmt, n=10, b=10):
     seqs = util.read_fasta(reads_path)
     idx = ctx.ref_index_build(G)
     try:
-        rec, q, s = ctx.ref_map(idx, api.RefReads(seqs), n, b, want_strings=fmt == 0)
+        rec, q, s = ctx.ref_map(idx, api.RefReads(seqs), n, b, want_strings=fmt != 1)
     finally:
         ctx.release_ref_index(idx)
     return api.format_ref_results(G, list(range(len(seqs))), rec, q, s, fmt), rec
@@ -140,12 +140,20 @@ def test_small_table_batches_give_the_same_records(refmap_inputs):
 
 
 def test_command_line_driver_matches_reference(gpu_ctx, refmap_inputs, hard_inputs, tmp_path):
-    """bin/mecat2ref with the reference's flags: ref and m4 files equal the unmodified binary's, also with two devices."""
+    """bin/mecat2ref with the reference's flags: ref, sam and m4 files equal the unmodified binary's, also with two devices."""
     import mecat_b200
     fa, genome = hard_inputs
     out = str(tmp_path / "hard.ref")
     run_cli(["-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w1"), "-t", "2", "-m", "0"])
     assert groups(open(out).read()) == groups(golden("refmap_hard.ref.gz"))
+    out = str(tmp_path / "hard.sam")
+    run_cli(["-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w1"), "-m", "2"])
+    lines = open(out).read().splitlines()
+    with gzip.open(os.path.join(util.GOLDEN, "refmap_hard.sam.gz"), "rt") as f:
+        want = f.read().splitlines()
+    assert [l for l in lines if l.startswith("@") and not l.startswith("@PG")] == [l for l in want if l.startswith("@")]
+    assert sum(l.startswith("@PG\tID:0\tVN:0.0.1\tCL:") and l.endswith("\tPN:mecat2ref") for l in lines) == 1
+    assert sorted(l for l in lines if not l.startswith("@")) == [l for l in want if not l.startswith("@")]
     fa, genome = refmap_inputs
     out = str(tmp_path / "refmap.m4")
     run_cli(["-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w2"), "-t", "2", "-m", "1"])

@@ -95,6 +95,22 @@ def test_hard_inputs_match_reference(hard_inputs):
     assert groups(s) == golden_groups("refmap_hard.ref.gz")
 
 
+def golden_sam():
+    with gzip.open(os.path.join(util.GOLDEN, "refmap_hard.sam.gz"), "rt") as f:
+        lines = f.read().splitlines()
+    return [l for l in lines if l.startswith("@")], [l for l in lines if not l.startswith("@")]
+
+
+def test_sam_records_match_reference(hard_inputs):
+    """-m 2: flag, 1-based position, CIGAR with hard clips and SEQ of every record of the unmodified binary's SAM file."""
+    fa, genome = hard_inputs
+    _, want = golden_sam()
+    got = sorted(run_harness(genome, fa, fmt=2)[0].splitlines())
+    assert len(got) == len(want) == GOLD["refmap_hard"]["num_sam"]
+    assert got == want
+    assert sorted(packed_via_python(genome, fa, 2).splitlines()) == want
+
+
 @pytest.mark.parametrize("n,b", [(3, 2), (1, 1), (50, 4)])
 def test_candidate_and_output_caps_match_oracle(refmap_inputs, hard_inputs, n, b):
     fa, genome = hard_inputs
@@ -178,7 +194,7 @@ def packed_via_python(genome_path, reads_path, fmt, n=10, b=10):
     G = api.RefGenome.from_fasta(genome_path)
     seqs = util.read_fasta(reads_path)
     R = api.RefReads(seqs)
-    g, r, p = G.c(), R.c(), api.RefParams(n, b, 1 if fmt == 0 else 0, 0)
+    g, r, p = G.c(), R.c(), api.RefParams(n, b, 1 if fmt != 1 else 0, 0)
     res, cnt, qs, ss, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_void_p(), C.c_size_t()
     assert L.harness_ref_map_packed(C.byref(g), C.byref(r), C.byref(p), C.byref(res), C.byref(cnt), C.byref(qs), C.byref(ss), C.byref(nb)) == 0
     rec = np.frombuffer(C.string_at(res.value, cnt.value * api.REF_RESULT_DTYPE.itemsize), dtype=api.REF_RESULT_DTYPE)
