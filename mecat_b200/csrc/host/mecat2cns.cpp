@@ -254,7 +254,8 @@ int main(int argc, char* argv[])
 			mecat_b200_stats st;
 			if (!mecat_b200_get_stats(ctx, &st)) {
 				static const char* names[MECAT_K_NUM] = {"orient", "index_count", "scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
-				                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble"};
+				                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble",
+				                                         "ref_count", "ref_seed", "ref_rescue"};
 				fprintf(stderr, "[kernel ms]");
 				for (int k = 0; k < MECAT_K_NUM; ++k)
 					if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);

@@ -178,6 +178,18 @@ int main(int argc, char* argv[])
 			refio::format_results(b.text, G, R.name, b.first, res, n, qs, ss, o.output_format);
 			mecat_b200_free(c, res); mecat_b200_free(c, qs); mecat_b200_free(c, ss);
 		}
+		if (d == 0 && getenv("MECAT_B200_STATS")) {       // per-kernel CUDA-event times of device 0's share, one line
+			mecat_b200_stats st;
+			if (!mecat_b200_get_stats(c, &st)) {
+				static const char* names[MECAT_K_NUM] = {"orient", "index_count", "scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
+				                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble",
+				                                         "ref_count", "ref_seed", "ref_rescue"};
+				fprintf(stderr, "[kernel ms]");
+				for (int k = 0; k < MECAT_K_NUM; ++k)
+					if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);
+				fprintf(stderr, " h2d=%.1fMB d2h=%.1fMB\n", st.h2d_bytes / 1e6, st.d2h_bytes / 1e6);
+			}
+		}
 		mecat_b200_ref_index_release(c, idx);
 	};
 	std::vector<std::thread> workers;

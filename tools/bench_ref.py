@@ -39,9 +39,9 @@ def main():
     gout = os.path.join(a.tmp, "gpu.out")
     t = time.time()
     p = subprocess.run([os.path.join(ROOT, "mecat_b200", "bin", "mecat2ref"), "-d", fa, "-r", genome_fa, "-o", gout, "-w", os.path.join(a.tmp, "wg"),
-                        "-m", str(a.format)], capture_output=True, text=True, env=dict(os.environ, MECAT_GPUS=str(a.gpus)))
+                        "-m", str(a.format)], capture_output=True, text=True, env=dict(os.environ, MECAT_GPUS=str(a.gpus), MECAT_B200_STATS="1"))
     res["gpu_cli_seconds"] = time.time() - t
-    res["gpu_log"] = p.stderr.splitlines()[-3:]
+    res["gpu_log"] = p.stderr.splitlines()[-4:]
     assert p.returncode == 0, p.stderr[-2000:]
     res["gpu_reads_per_second_cli"] = a.reads / res["gpu_cli_seconds"]
     if a.format == 1:
