@@ -124,6 +124,21 @@ def test_candidate_and_output_caps_match_oracle(gpu_ctx, hard_inputs, n, b):
     assert groups(text) == groups(run_oracle(genome, fa, n, b, 0))
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(util.REF_DIR, "mecat2ref")), reason="needs the unmodified binary (oracle/_ref travels with the snapshot)")
+@pytest.mark.parametrize("n,b", [(10, 10), (40, 5)])
+def test_repeat_rich_inputs_match_the_unmodified_binary(gpu_ctx, tmp_path, n, b):
+    """Differential run against oracle/_ref/mecat2ref on a repeat-rich genome (util.make_refmap_repeats): full candidate
+    lists, block-consuming votes, insert_loc evictions, rescue between repeat copies, both passes."""
+    fa, genome, out = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa"), str(tmp_path / "ref.out")
+    util.make_refmap_repeats(fa, genome, seed=3, num_reads=200)
+    subprocess.check_call([os.path.join(util.REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-t", "4", "-m", "0",
+                           "-n", str(n), "-b", str(b)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path))
+    text, _ = map_through_abi(gpu_ctx, genome, fa, 0, n, b)
+    want = groups(open(out).read())
+    assert len(want) > 3 * 200
+    assert groups(text) == want
+
+
 def test_small_table_batches_give_the_same_records(refmap_inputs):
     """A 1 MB budget for the block tables cuts the 300 reads into many batches (own context: the budget is read per call)."""
     import mecat_b200

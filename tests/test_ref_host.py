@@ -95,6 +95,22 @@ def test_hard_inputs_match_reference(hard_inputs):
     assert groups(s) == golden_groups("refmap_hard.ref.gz")
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(util.REF_DIR, "mecat2ref")), reason="needs the unmodified binary (oracle/_ref, built where /root/reference exists)")
+@pytest.mark.parametrize("n,b", [(10, 10), (40, 5)])
+def test_repeat_rich_inputs_match_the_unmodified_binary(tmp_path, n, b):
+    """Differential run against oracle/_ref/mecat2ref itself on a repeat-rich genome (util.make_refmap_repeats): full
+    candidate lists, block-consuming votes, rescue between repeat copies, both passes; small calls and table batches."""
+    import subprocess
+    fa, genome, out = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa"), str(tmp_path / "ref.out")
+    util.make_refmap_repeats(fa, genome, seed=2, num_reads=120)
+    subprocess.check_call([os.path.join(util.REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-t", "4", "-m", "0",
+                           "-n", str(n), "-b", str(b)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path))
+    got, st = run_harness(genome, fa, n, b, 0, per_call=50, budget=3_000_000)
+    want = groups(open(out).read())
+    assert len(want) > 3 * 120 and st[1] > 6
+    assert groups(got) == want
+
+
 def golden_sam():
     with gzip.open(os.path.join(util.GOLDEN, "refmap_hard.sam.gz"), "rt") as f:
         lines = f.read().splitlines()

@@ -389,6 +389,55 @@ def repeat_reads(seed=21, unit=4000, copies=10, n_reads=260, mean=5000, err=0.05
     return reads
 
 
+def make_refmap_repeats(reads_path, genome_path, seed, num_reads, copies=40):
+    """Repeat-rich inputs for mecat2ref: a 6 kb segment copied `copies` times (3 % diverged) between short unique stretches,
+    a 150-copy tandem 40-mer, a 3-mer run, a second contig with a run of N; reads of 3-45 kb with 10-30 % errors, half of
+    them reverse strand, 15 % chimeric.  Candidate lists overflow -n, neighbour votes consume blocks, rescue hops between
+    copies.  (Reads near the reference's 100 000-base buffers make the unmodified binary corrupt its heap, so none here.)"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rnd(n):
+        return acgt[rng.integers(0, 4, n)]
+
+    parts, seg = [], rnd(6000)
+    for _ in range(copies):
+        parts.append(rnd(int(rng.integers(2000, 9000))))
+        s = seg.copy()
+        m = rng.random(len(s)) < 0.03
+        s[m] = rnd(int(m.sum()))
+        parts.append(s)
+    parts += [np.tile(rnd(40), 150), rnd(30000), np.tile(rnd(3), 400), rnd(50000)]
+    g1, g2 = np.concatenate(parts), rnd(80000)
+    with open(genome_path, "wb") as f:
+        f.write(b">c1\n" + g1.tobytes() + b"\n>c2 x\n" + g2.tobytes()[:40000] + b"NNNNNNNNNN" + g2.tobytes()[40000:] + b"\n")
+    G = np.concatenate([g1, g2])
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+
+    def mutate(s, err):
+        out, r = [], rng.random(len(s))
+        for b, x in zip(s, r):
+            if x < 0.3 * err:
+                continue
+            out.append(acgt[rng.integers(0, 4)] if x < 0.4 * err else b)
+            while rng.random() < 0.6 * err:
+                out.append(acgt[rng.integers(0, 4)])
+        return np.array(out, dtype=np.uint8)
+
+    with open(reads_path, "wb") as f:
+        for i in range(num_reads):
+            n = min(int(rng.choice([3000, 8000, 15000, 30000, 45000], p=[.2, .3, .3, .15, .05])), len(G) - 1)
+            st = int(rng.integers(0, len(G) - n))
+            s = mutate(G[st:st + n], float(rng.choice([0.1, 0.15, 0.22, 0.3])))
+            if rng.random() < 0.5:
+                s = comp[s[::-1]]
+            if rng.random() < 0.15:
+                st2 = int(rng.integers(0, len(G) - 5000))
+                s = np.concatenate([s, mutate(G[st2:st2 + 5000], 0.12)])
+            f.write(b">%d\n" % i + s[:99000].tobytes() + b"\n")
+
+
 def make_refmap_hard(reads_path, genome_path, seed=19):
     """Deterministic inputs that push mecat2ref off its main path: three contigs (one holding a 3 kb repeat of another),
     noisy reads (15 % errors), chimeric reads glued from two places (clipped alignments -> rescue_clipped_align), reads with
