@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <future>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -132,12 +134,13 @@ int main(int argc, char* argv[])
 	const double t_load = now();
 
 	// batches of reads: one ABI call each.  A volume holds < 2^31 bases; the ref format returns two strings per record.
-	const int64_t max_bases = 1000000000ll;      // explicit reverse strands of reads with other letters still fit
+	int64_t max_bases = 1000000000ll;            // explicit reverse strands of reads with other letters still fit
+	if (const char* e = getenv("MECAT_B200_REF_BATCH_BASES")) max_bases = std::max(1ll, atoll(e));      // test hook: many small batches
 	const int max_reads = o.output_format != 1 ? 20000 : 1 << 30;
 	std::vector<Batch> batches;
 	const int total = (int)R.size();
 	const int64_t all_bases = (int64_t)R.arena.size() + total;
-	const int64_t share = std::max<int64_t>(1 << 20, (all_bases + ndev - 1) / ndev);
+	const int64_t share = std::max<int64_t>(std::min<int64_t>(1 << 20, max_bases), (all_bases + ndev - 1) / ndev);
 	for (int first = 0; first < total;) {
 		int count = 0;
 		int64_t bases = 0;
@@ -153,31 +156,45 @@ int main(int argc, char* argv[])
 
 	const int hw = (int)std::thread::hardware_concurrency();
 	const int host_threads = std::max(1, std::min(hw > 0 ? hw : 1, std::max(o.num_cores, 8)) / ndev);
-	std::atomic<int> next(0), failed(0);
+	std::atomic<int> failed(0);
 	std::vector<double> t_index((size_t)ndev, 0.0);
+	auto pack = [&](int k) {
+		std::unique_ptr<refio::ReadBatch> B(new refio::ReadBatch);
+		B->build(R, (size_t)batches[(size_t)k].first, (size_t)batches[(size_t)k].count, host_threads);
+		return B;
+	};
+	// Device d takes batches d, d + ndev, ...  While one batch is on the device the host packs the next one and writes
+	// the text of the previous one.
 	auto worker = [&](int d) {
 		mecat_b200_ctx* c = ctx[(size_t)d];
+		std::future<std::unique_ptr<refio::ReadBatch>> packed;
+		std::future<void> text;
+		if (d < (int)batches.size()) packed = std::async(std::launch::async, pack, d);
 		const double a = now();
 		void* idx = NULL;
 		const mecat_ref_genome g = G.view();
-		if (mecat_b200_ref_index_build(c, &g, &idx)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; return; }
+		if (mecat_b200_ref_index_build(c, &g, &idx)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; }
 		t_index[(size_t)d] = now() - a;
 		mecat_ref_params p;
 		p.num_candidates = o.num_candidates; p.num_output = o.num_output; p.want_strings = o.output_format != 1; p.tech = o.tech;
-		for (;;) {
-			const int k = next.fetch_add(1);
-			if (k >= (int)batches.size() || failed) break;
-			Batch& b = batches[(size_t)k];
-			refio::ReadBatch B;
-			B.build(R, (size_t)b.first, (size_t)b.count, host_threads);
-			const mecat_ref_reads view = B.view();
+		for (int k = d; k < (int)batches.size(); k += ndev) {
+			std::unique_ptr<refio::ReadBatch> B = packed.get();
+			if (k + ndev < (int)batches.size()) packed = std::async(std::launch::async, pack, k + ndev);
+			if (failed) continue;                   // keep draining the packer
+			const mecat_ref_reads view = B->view();
 			mecat_ref_result* res = NULL;
 			char *qs = NULL, *ss = NULL;
 			size_t n = 0, nbytes = 0;
-			if (mecat_b200_ref_map(c, idx, &view, &p, &res, &n, &qs, &ss, &nbytes)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; break; }
-			refio::format_results(b.text, G, R.name, b.first, res, n, qs, ss, o.output_format);
-			mecat_b200_free(c, res); mecat_b200_free(c, qs); mecat_b200_free(c, ss);
+			if (mecat_b200_ref_map(c, idx, &view, &p, &res, &n, &qs, &ss, &nbytes)) { fprintf(stderr, "mecat2ref (b200): %s\n", mecat_b200_last_error(c)); failed = 1; continue; }
+			if (text.valid()) text.get();
+			Batch* b = &batches[(size_t)k];
+			text = std::async(std::launch::async, [&, b, res, n, qs, ss]() {
+				refio::format_results(b->text, G, R.name, b->first, res, n, qs, ss, o.output_format);
+				mecat_b200_host_free(res); mecat_b200_host_free(qs); mecat_b200_host_free(ss);
+			});
 		}
+		if (text.valid()) text.get();
+		if (!idx) return;
 		if (d == 0 && getenv("MECAT_B200_STATS")) {       // per-kernel CUDA-event times of device 0's share, one line
 			mecat_b200_stats st;
 			if (!mecat_b200_get_stats(c, &st)) {

@@ -202,16 +202,24 @@ int harness_ref_map(const char* reference_path, const char* reads_path, int num_
 	return 0;
 }
 
-// the host twin of mecat_b200_ref_index_build + mecat_b200_ref_map: same structures in, same records out (lets the CPU
-// suite check the Python packing and formatting of mecat_b200/api.py)
-int harness_ref_map_packed(const mecat_ref_genome* g, const mecat_ref_reads* reads, const mecat_ref_params* p, mecat_ref_result** results, size_t* n,
-                           char** qstrings, char** sstrings, size_t* string_bytes)
+// the host twins of mecat_b200_ref_index_build / mecat_b200_ref_map / mecat_b200_ref_index_release: same structures in,
+// same records out (lets the CPU suite check the Python packing and formatting of mecat_b200/api.py, and -- through
+// tests/ref_abi_shim.cpp -- the command-line driver)
+void* harness_ref_index_build(const mecat_ref_genome* g)
 {
-	HostIndex I;
-	index_genome(g, I);
+	HostIndex* I = new HostIndex;
+	index_genome(g, *I);
+	return I;
+}
+
+void harness_ref_index_release(void* idx) { delete (HostIndex*)idx; }
+
+int harness_ref_map_indexed(void* idx, const mecat_ref_reads* reads, const mecat_ref_params* p, mecat_ref_result** results, size_t* n,
+                            char** qstrings, char** sstrings, size_t* string_bytes, char* errbuf, int errcap)
+{
 	mbref::Sink sink;
 	std::string err;
-	if (map_packed(I, reads, p, 0, sink, NULL, err)) return 1;
+	if (map_packed(*(const HostIndex*)idx, reads, p, 0, sink, NULL, err)) { if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", err.c_str()); return 1; }
 	mecat_ref_result* res = (mecat_ref_result*)malloc(sizeof(mecat_ref_result) * (sink.recs.size() ? sink.recs.size() : 1));
 	char* a = (char*)malloc(sink.q.size() + 1);
 	char* b = (char*)malloc(sink.s.size() + 1);
@@ -221,6 +229,15 @@ int harness_ref_map_packed(const mecat_ref_genome* g, const mecat_ref_reads* rea
 	memcpy(b, sink.s.data(), sink.s.size()); b[sink.s.size()] = 0;
 	*results = res; *n = sink.recs.size(); *qstrings = a; *sstrings = b; *string_bytes = sink.q.size();
 	return 0;
+}
+
+int harness_ref_map_packed(const mecat_ref_genome* g, const mecat_ref_reads* reads, const mecat_ref_params* p, mecat_ref_result** results, size_t* n,
+                           char** qstrings, char** sstrings, size_t* string_bytes)
+{
+	void* idx = harness_ref_index_build(g);
+	const int rc = harness_ref_map_indexed(idx, reads, p, results, n, qstrings, sstrings, string_bytes, NULL, 0);
+	harness_ref_index_release(idx);
+	return rc;
 }
 
 // the float forms of the DDF test as the reference writes them, next to the integer form of the kernels

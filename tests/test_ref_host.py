@@ -246,3 +246,55 @@ def test_ddf_integer_form_equals_the_float_forms():
         centre = b * bc * rng.choice((0.75, 1.0, 1.25))
         a = int(centre) + rng.randint(-3, 3)
         assert L.harness_ddf_forms(a, b, bc) in (0, 15), (a, b, bc)
+
+
+# ---- the command-line driver itself (mecat_b200/csrc/host/mecat2ref.cpp), linked against tests/ref_abi_shim.cpp
+def run_driver(args, env=None, ok=True):
+    import subprocess
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([util.ref_driver_on_host()] + args, env=e, capture_output=True, text=True)
+    assert (p.returncode == 0) == ok, p.stderr[-2000:]
+    return p
+
+
+def test_driver_files_match_reference(tmp_path, refmap_inputs, hard_inputs):
+    """ref, sam (with its header) and m4 files of the driver; many small batches through the packing / device / text
+    pipeline and two (shim) devices give byte-identical files."""
+    fa, genome = hard_inputs
+    out = str(tmp_path / "hard.ref")
+    run_driver(["-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-t", "3"])           # -m 0 is the default
+    assert groups(open(out).read()) == golden_groups("refmap_hard.ref.gz")
+    assert os.path.isdir(str(tmp_path / "w"))
+    out = str(tmp_path / "hard.sam")
+    run_driver(["-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-m", "2"])
+    lines = open(out).read().splitlines()
+    head, want = golden_sam()
+    assert [l for l in lines if l.startswith("@") and not l.startswith("@PG")] == head
+    assert lines[len(head)].startswith("@PG\tID:0\tVN:0.0.1\tCL:") and lines[len(head)].endswith(" -m 2 \tPN:mecat2ref")
+    assert sorted(lines[len(head) + 1:]) == want
+    fa, genome = refmap_inputs
+    one = str(tmp_path / "one.m4")
+    run_driver(["-d", fa, "-r", genome, "-o", one, "-w", str(tmp_path / "w"), "-m", "1"])
+    with gzip.open(os.path.join(util.GOLDEN, "refmap.m4.gz"), "rt") as f:
+        assert sorted(open(one).read().splitlines()) == f.read().splitlines()
+    many = str(tmp_path / "many.m4")
+    p = run_driver(["-d", fa, "-r", genome, "-o", many, "-w", str(tmp_path / "w"), "-m", "1"], env={"MECAT_B200_REF_BATCH_BASES": "100000"})
+    two = str(tmp_path / "two.m4")
+    run_driver(["-d", fa, "-r", genome, "-o", two, "-w", str(tmp_path / "w"), "-m", "1"],
+               env={"MECAT_B200_REF_BATCH_BASES": "150000", "MECAT_GPUS": "2", "MECAT_SHIM_DEVICES": "2"})
+    assert open(many).read() == open(one).read() == open(two).read()      # reads in input order whatever the batches
+
+
+def test_driver_option_handling(tmp_path, refmap_inputs):
+    """Missing arguments, -b above -n (reset with the reference's warning), refused technology, more devices than visible."""
+    fa, genome = refmap_inputs
+    out, w = str(tmp_path / "o"), str(tmp_path / "w")
+    assert "reference must be specified" in run_driver(["-d", fa, "-o", out, "-w", w], ok=False).stderr
+    assert "candidates must be > 0" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-n", "0"], ok=False).stderr
+    assert "nanopore" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-x", "1"], ok=False).stderr
+    assert "CUDA device" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w], env={"MECAT_GPUS": "3"}, ok=False).stderr
+    assert "cannot open" in run_driver(["-d", str(tmp_path / "missing.fa"), "-r", genome, "-o", out, "-w", w], ok=False).stderr
+    p = run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-m", "1", "-n", "2", "-b", "7"])
+    assert "we reset it to 2" in p.stderr
+    assert sorted(open(out).read().splitlines()) == sorted(run_oracle(genome, fa, 2, 2, 1).splitlines())

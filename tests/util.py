@@ -175,6 +175,7 @@ def ref_harness():
     L.harness_ref_map.restype = C.c_int
     L.harness_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(vp), C.POINTER(C.c_size_t),
                                   C.POINTER(C.c_long), C.c_char_p, C.c_int]
+    L.harness_ref_index_build.restype = vp
     L.harness_ref_map_packed.restype = C.c_int
     L.harness_ref_map_packed.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.harness_ddf_forms.restype = C.c_int
@@ -387,6 +388,21 @@ def repeat_reads(seed=21, unit=4000, copies=10, n_reads=260, mean=5000, err=0.05
             out = (3 - out)[::-1]
         reads.append(bytes(b"ACGT"[int(c)] for c in out))
     return reads
+
+
+def ref_driver_on_host():
+    """mecat_b200/csrc/host/mecat2ref.cpp linked against tests/ref_abi_shim.cpp + the host harness instead of the product
+    library: the command-line driver as the CPU suite can run it.  Returns the path of the executable."""
+    ref_harness()
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    exe = os.path.join(out_dir, "mecat2ref_host")
+    src = [os.path.join(ROOT, "mecat_b200", "csrc", "host", "mecat2ref.cpp"), os.path.join(ROOT, "tests", "ref_abi_shim.cpp"),
+           os.path.join(ROOT, "mecat_b200", "csrc", "host", "refio.h"), os.path.join(ROOT, "include", "mecat_b200.h"),
+           os.path.join(out_dir, "libref_harness.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe, src[0], src[1],
+                               "-L", out_dir, "-lref_harness", "-Wl,-rpath," + out_dir, "-Wl,-rpath," + ORACLE_DIR])
+    return exe
 
 
 def make_refmap_repeats(reads_path, genome_path, seed, num_reads, copies=40):
