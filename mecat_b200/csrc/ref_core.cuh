@@ -98,20 +98,26 @@ REF_HD bool ddf_close(int64_t a, int64_t b, int bc)
 	return false;
 }
 
-// Base i of the strand (A0 C1 G2 T3) out of the volume's forward words (base p at bits 2 (p mod 16) of word p / 16).
-REF_HD int strand_base(const uint32_t* fwd, uint32_t off, const Unit& u, int i)
+// The volume's forward words hold base p at bits 2 (p mod 16) of word p / 16 (volume.cu), A0 C1 G2 T3.
+// the sixteen 2-bit groups of x in reverse order
+REF_HD uint32_t reverse_groups(uint32_t x)
 {
-	const uint32_t p = u.rc ? off + (uint32_t)(u.len - 1 - i) : off + (uint32_t)i;
-	const int b = (int)((fwd[p >> 4] >> ((p & 15u) << 1)) & 3u);
-	return u.rc ? 3 - b : b;
+	x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+	x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+	x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+	return (x >> 16) | (x << 16);
 }
 
-// 13-mer starting at base i, first base most significant -- the code the index is addressed by
+// 13-mer starting at base i of the strand, first base most significant -- the code the index is addressed by.  Two word
+// loads: the 13 bases are 26 consecutive bits of the volume (first base in the low bits); the forward strand reverses
+// their order, the reverse strand reads the same bits downwards, so they only need complementing.
 REF_HD uint32_t strand_kmer(const uint32_t* fwd, uint32_t off, const Unit& u, int i)
 {
-	uint32_t code = 0;
-	for (int j = 0; j < SEED; ++j) code = (code << 2) | (uint32_t)strand_base(fwd, off, u, i + j);
-	return code;
+	const uint32_t p = u.rc ? off + (uint32_t)(u.len - SEED - i) : off + (uint32_t)i;
+	const uint32_t w = p >> 4, sh = (p & 15u) << 1;
+	const uint32_t x = (uint32_t)((((uint64_t)fwd[w + 1] << 32) | fwd[w]) >> sh);
+	const uint32_t mask = (1u << (2 * SEED)) - 1;
+	return u.rc ? ~x & mask : reverse_groups(x) >> (32 - 2 * SEED);
 }
 
 // does [lo, hi) hold a letter that is not upper-case ACGT?  (`bad`: ascending volume offsets of such letters;
