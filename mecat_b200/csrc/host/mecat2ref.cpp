@@ -139,7 +139,7 @@ int main(int argc, char* argv[])
 	const int max_reads = o.output_format != 1 ? 20000 : 1 << 30;
 	std::vector<Batch> batches;
 	const int total = (int)R.size();
-	const int64_t all_bases = (int64_t)R.arena.size() + total;
+	const int64_t all_bases = R.total + total;
 	const int64_t share = std::max<int64_t>(std::min<int64_t>(1 << 20, max_bases), (all_bases + ndev - 1) / ndev);
 	for (int first = 0; first < total;) {
 		int count = 0;

@@ -21,6 +21,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <deque>
 #include <string>
 #include <thread>
 #include <vector>
@@ -164,16 +165,20 @@ inline bool load_genome(const char* path, Genome& G, std::string& err)
 	return true;
 }
 
-// All reads of a file: the letters of every read, line ends removed, in one arena.
+// All reads of a file.  A read whose sequence is one line of the (mapped) file is used where it lies; the letters of a
+// read spread over several lines are gathered, line ends removed, in a side arena.
 struct Reads
 {
 	std::vector<int32_t> name;           // the number the reference prints for the read
-	std::string arena;
-	std::vector<int64_t> start;          // [size() + 1] offsets into the arena
+	std::vector<const char*> ptr;
+	std::vector<int64_t> len;
+	int64_t total = 0;                   // letters of all reads
+	MappedFile file;
+	std::deque<std::string> side;        // stable addresses
 	size_t size() const { return name.size(); }
-	const char* data(size_t i) const { return arena.data() + start[i]; }
-	int64_t length(size_t i) const { return start[i + 1] - start[i]; }
-	std::string str(size_t i) const { return std::string(data(i), (size_t)length(i)); }
+	const char* data(size_t i) const { return ptr[i]; }
+	int64_t length(size_t i) const { return len[i]; }
+	void add(int32_t nm, const char* p, int64_t n) { name.push_back(nm); ptr.push_back(p); len.push_back(n); total += n; }
 };
 
 // appends [b, e) to the arena without '\n' and '\r'
@@ -190,31 +195,34 @@ inline void append_letters(std::string& arena, const char* b, const char* e)
 
 inline bool load_reads(const char* path, Reads& R, std::string& err)
 {
-	MappedFile F;
+	MappedFile& F = R.file;
 	if (!F.open(path)) { err = std::string("cannot open ") + path; return false; }
-	R.start.assign(1, 0);
 	if (F.n == 0) return true;
 	const char* p = F.p;
 	const char* end = F.p + F.n;
-	R.arena.reserve(F.n);
 	if (*p == '>') {
 		// chang_fastqfile reads character by character: a '>' anywhere opens a header that runs to the end of its line,
 		// everything else up to the next '>' is sequence
 		int next = 0;
 		while (p < end) {
-			if (*p == '>') {
-				if (next) R.start.push_back((int64_t)R.arena.size());
-				R.name.push_back(next++);
-				const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-				p = nl ? nl : end;
-			} else {
-				const char* gt = (const char*)memchr(p, '>', (size_t)(end - p));
-				const char* stop = gt ? gt : end;
-				append_letters(R.arena, p, stop);
-				p = stop;
+			const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));      // p is at a '>'
+			const char* seq = nl ? nl + 1 : end;
+			// the common case: the sequence is the next line and the line after it is a header (or the end)
+			const char* l1 = seq < end ? (const char*)memchr(seq, '\n', (size_t)(end - seq)) : NULL;
+			const char* line_end = l1 ? l1 : end;
+			const char* after = l1 ? l1 + 1 : end;
+			if ((after == end || *after == '>') && !memchr(seq, '>', (size_t)(line_end - seq)) && !memchr(seq, '\r', (size_t)(line_end - seq))) {
+				R.add(next++, seq, line_end - seq);
+				p = after;
+				continue;
 			}
+			const char* gt = seq < end ? (const char*)memchr(seq, '>', (size_t)(end - seq)) : NULL;
+			const char* stop = gt ? gt : end;
+			R.side.emplace_back();
+			append_letters(R.side.back(), seq, stop);
+			R.add(next++, R.side.back().data(), (int64_t)R.side.back().size());
+			p = stop;
 		}
-		R.start.push_back((int64_t)R.arena.size());
 	} else {
 		// FASTQ: records of four lines, the second one is the sequence
 		int next = 0;
@@ -230,9 +238,7 @@ inline bool load_reads(const char* path, Reads& R, std::string& err)
 				const char* b = line[1];
 				const char* e = line_end[1];
 				if (e > b && e[-1] == '\r') --e;
-				R.name.push_back(++next);
-				R.arena.append(b, (size_t)(e - b));
-				R.start.push_back((int64_t)R.arena.size());
+				R.add(++next, b, e - b);
 				k = 0;
 			}
 		}
@@ -347,8 +353,6 @@ struct ReadBatch
 		}
 		nbases = at;
 	}
-	// volume bases a range of reads needs at most (both strands packed)
-	static int64_t worst_case_bases(const Reads& R, size_t first, size_t count) { return 2 * (R.start[first + count] - R.start[first]) + 2 * (int64_t)count; }
 };
 
 inline int chr_of(const std::vector<Chr>& chr, int64_t offset)      // get_chr_id, mecat2ref.cpp:280-298
