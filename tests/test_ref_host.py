@@ -19,7 +19,7 @@ GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))
 def run_harness(genome, fa, n=10, b=10, fmt=1, per_call=0, budget=0):
     L = util.ref_harness()
     text, nb = C.c_void_p(), C.c_size_t()
-    st = (C.c_long * 2)()
+    st = (C.c_long * 3)()
     err = C.create_string_buffer(512)
     rc = L.harness_ref_map(genome.encode(), fa.encode(), n, b, fmt, per_call, budget, C.byref(text), C.byref(nb), st, err, 512)
     assert rc == 0, err.value
@@ -92,6 +92,7 @@ def test_hard_inputs_match_reference(hard_inputs):
     fa, genome = hard_inputs
     s, st = run_harness(genome, fa, fmt=0)
     assert st[1] == 2               # both passes ran
+    assert st[2] > 20               # clipped ends went through RescueFn
     assert groups(s) == golden_groups("refmap_hard.ref.gz")
 
 
