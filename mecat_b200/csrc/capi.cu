@@ -378,13 +378,10 @@ int mecat_b200_ref_map(mecat_b200_ctx* c, void* refidx, const mecat_ref_reads* r
 	mbref::Sink sink;
 	if (ref_map(c, (const RefIndex*)refidx, reads, p, sink)) return 1;
 	mecat_ref_result* res = (mecat_ref_result*)malloc(sizeof(mecat_ref_result) * (sink.recs.size() ? sink.recs.size() : 1));
-	char* a = (char*)malloc(sink.q.size() + 1);
-	char* b = (char*)malloc(sink.s.size() + 1);
-	if (!res || !a || !b) { free(res); free(a); free(b); MB_FAIL(c, "ref_map: out of host memory"); }
+	if (!res) MB_FAIL(c, "ref_map: out of host memory");
 	if (!sink.recs.empty()) memcpy(res, sink.recs.data(), sizeof(mecat_ref_result) * sink.recs.size());
-	memcpy(a, sink.q.data(), sink.q.size()); a[sink.q.size()] = 0;
-	memcpy(b, sink.s.data(), sink.s.size()); b[sink.s.size()] = 0;
-	*results = res; *n = sink.recs.size(); *qstrings = a; *sstrings = b; *string_bytes = sink.q.size();
+	*results = res; *n = sink.recs.size(); *string_bytes = sink.q.size();
+	*qstrings = sink.q.release(); *sstrings = sink.s.release();      // the blobs as they were filled: no copy
 	return 0;
 }
 

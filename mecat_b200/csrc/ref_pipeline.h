@@ -22,6 +22,7 @@
 // library), tests/ref_host_harness.cpp a host backend for the CPU test-suite.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -60,10 +61,44 @@ struct MapIn
 	const int32_t* d_ipos = nullptr;         // 0-based k-mer starts, ascending inside a list
 };
 
+// A malloc'ed byte blob that grows by doubling and can be handed to the caller of the C ABI as it is (the alignment
+// strings of a batch are gigabytes: every copy saved counts).
+struct Blob
+{
+	char* p = nullptr;
+	size_t len = 0, cap = 0;
+	bool oom = false;
+	Blob() {}
+	Blob(const Blob&) = delete;
+	Blob& operator=(const Blob&) = delete;
+	~Blob() { free(p); }
+	void append(const char* src, size_t n)
+	{
+		if (len + n + 1 > cap) {
+			size_t want = cap ? cap * 2 : (size_t)1 << 16;
+			while (want < len + n + 1) want *= 2;
+			char* np = (char*)realloc(p, want);
+			if (!np) { oom = true; return; }
+			p = np; cap = want;
+		}
+		memcpy(p + len, src, n);
+		len += n;
+		p[len] = 0;
+	}
+	const char* data() const { return p ? p : ""; }
+	size_t size() const { return len; }
+	char* release()          // the caller owns the (NUL-terminated) bytes; never NULL
+	{
+		char* r = p ? p : (char*)calloc(1, 1);
+		p = nullptr; len = cap = 0;
+		return r;
+	}
+};
+
 struct Sink
 {
 	std::vector<mecat_ref_result> recs;
-	std::string q, s;                        // NUL-terminated alignment strings of the records (want_strings)
+	Blob q, s;                               // NUL-terminated alignment strings of the records (want_strings)
 };
 
 // ---------------------------------------------------------------------------------------------- functors
@@ -454,6 +489,7 @@ int map_reads(Backend& be, const MapIn& in, const Params& P, Sink& out)
 	int rc = map_pass(be, in, P, 0, all, second, out);
 	if (!rc) rc = map_pass(be, in, P, 1, second, none, out);
 	be.end_batch();
+	if (!rc && (out.q.oom || out.s.oom)) { be.fail("mecat2ref: out of host memory for the alignment strings"); rc = 1; }
 	return rc;
 }
 

@@ -222,13 +222,10 @@ int harness_ref_map_indexed(void* idx, const mecat_ref_reads* reads, const mecat
 	std::string err;
 	if (map_packed(*(const HostIndex*)idx, reads, p, 0, sink, NULL, err)) { if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", err.c_str()); return 1; }
 	mecat_ref_result* res = (mecat_ref_result*)malloc(sizeof(mecat_ref_result) * (sink.recs.size() ? sink.recs.size() : 1));
-	char* a = (char*)malloc(sink.q.size() + 1);
-	char* b = (char*)malloc(sink.s.size() + 1);
-	if (!res || !a || !b) return 1;
+	if (!res) return 1;
 	if (!sink.recs.empty()) memcpy(res, sink.recs.data(), sizeof(mecat_ref_result) * sink.recs.size());
-	memcpy(a, sink.q.data(), sink.q.size()); a[sink.q.size()] = 0;
-	memcpy(b, sink.s.data(), sink.s.size()); b[sink.s.size()] = 0;
-	*results = res; *n = sink.recs.size(); *qstrings = a; *sstrings = b; *string_bytes = sink.q.size();
+	*results = res; *n = sink.recs.size(); *string_bytes = sink.q.size();
+	*qstrings = sink.q.release(); *sstrings = sink.s.release();
 	return 0;
 }
 
