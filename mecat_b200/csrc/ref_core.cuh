@@ -220,9 +220,9 @@ REF_HD void seed_strand(const uint32_t* fwd, uint32_t off, const Unit& u, int zv
 		const uint32_t code = strand_kmer(fwd, off, u, i);
 		const uint32_t e = ibegin[code + 1];
 		for (uint32_t h = ibegin[code]; h < e; ++h) {
-			const int64_t pos = (int64_t)ipos[h] + 1;            // the reference's positions are 1-based (:265)
-			const int32_t blk = (int32_t)(pos / zv);
-			const int offs = (int)(pos % zv);
+			const uint32_t pos = (uint32_t)ipos[h] + 1u;         // the reference's positions are 1-based (:265); below 2^31 here
+			const int32_t blk = (int32_t)(pos / (uint32_t)zv);
+			const int offs = (int)(pos - (uint32_t)blk * (uint32_t)zv);
 			bool fresh;
 			Bucket* b = table_touch(T, blk, &fresh);
 			if (b->score == 0 || b->seednum < k + 1) {
