@@ -101,6 +101,26 @@ struct Sink
 	Blob q, s;                               // NUL-terminated alignment strings of the records (want_strings)
 };
 
+// The index's view of the genome: every maximal ACGT run cut into chunks of INDEX_CHUNK k-mer starts, each chunk
+// carrying the 12 bases a k-mer needs beyond its start.  A chunk is one "read" of the index build (index.cu: one CTA's
+// work); no k-mer spans a letter that is not ACGT, every k-mer start of a run lies in exactly one chunk.
+constexpr int64_t INDEX_CHUNK = 32768;
+inline bool index_chunks(const int64_t* run_start_len, int32_t num_runs, int64_t num_bases, std::vector<int32_t>& chunks /* {offset, size} pairs */)
+{
+	chunks.clear();
+	int64_t prev_end = 0;
+	for (int32_t r = 0; r < num_runs; ++r) {
+		const int64_t s = run_start_len[2 * r], n = run_start_len[2 * r + 1];
+		if (s < prev_end || n < 0 || s + n > num_bases) return false;
+		prev_end = s + n;
+		for (int64_t k = 0; k + SEED <= n; k += INDEX_CHUNK) {
+			chunks.push_back((int32_t)(s + k));
+			chunks.push_back((int32_t)std::min<int64_t>(n - k, INDEX_CHUNK + SEED - 1));
+		}
+	}
+	return true;
+}
+
 // ---------------------------------------------------------------------------------------------- functors
 struct CountFn
 {

@@ -93,8 +93,6 @@ struct RefBackend
 	}
 };
 
-constexpr int64_t INDEX_CHUNK = 32768;      // k-mer starts per chunk of a run: one CTA's work in the index kernels
-
 }  // namespace
 
 int ref_index_build(Ctx* c, const mecat_ref_genome* g, RefIndex** out)
@@ -108,16 +106,7 @@ int ref_index_build(Ctx* c, const mecat_ref_genome* g, RefIndex** out)
 	if (volume_upload(c, &v, &R->genome)) { delete R; return 1; }
 	// the index's view of the same bases: chunks of the ACGT runs, overlapping by the 12 bases a k-mer needs beyond its start
 	std::vector<int32_t> chunks;
-	int64_t prev_end = 0;
-	for (int32_t r = 0; r < g->num_runs; ++r) {
-		const int64_t s = g->run_start_len[2 * r], n = g->run_start_len[2 * r + 1];
-		if (s < prev_end || n < 0 || s + n > g->num_bases) { ref_index_release(c, R); MB_FAIL(c, "ref_index_build: run %d out of order or out of range", r); }
-		prev_end = s + n;
-		for (int64_t k = 0; k + KMER <= n; k += INDEX_CHUNK) {
-			chunks.push_back((int32_t)(s + k));
-			chunks.push_back((int32_t)std::min(n - k, INDEX_CHUNK + KMER - 1));
-		}
-	}
+	if (!mbref::index_chunks(g->run_start_len, g->num_runs, g->num_bases, chunks)) { ref_index_release(c, R); MB_FAIL(c, "ref_index_build: runs out of order or out of range"); }
 	DVolume view;
 	view.num_reads = (int32_t)(chunks.size() / 2); view.num_bases = R->genome->num_bases; view.fwd = R->genome->fwd; view.rev = R->genome->rev;
 	view.words = R->genome->words;

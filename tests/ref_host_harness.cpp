@@ -104,8 +104,9 @@ struct HostBackend
 };
 
 // CSR k-mer index in the product's layout (index.cu): codes A0 C1 G2 T3 with the first base most significant, 0-based
-// starts ascending, lists of more than 128 starts dropped
-void build_index(const uint32_t* gfwd, const std::vector<int64_t>& runs, std::vector<uint32_t>& begin, std::vector<int32_t>& pos)
+// starts ascending, lists of more than 128 starts dropped.  `runs`: the {offset, size} "reads" the index is built over --
+// the chunks the product cuts the genome's ACGT runs into (mbref::index_chunks), in ascending order.
+void build_index(const uint32_t* gfwd, const std::vector<int32_t>& runs, std::vector<uint32_t>& begin, std::vector<int32_t>& pos)
 {
 	const uint32_t ncodes = 1u << 26, mask = ncodes - 1;
 	std::vector<uint32_t> cnt(ncodes, 0u);
@@ -113,7 +114,7 @@ void build_index(const uint32_t* gfwd, const std::vector<int64_t>& runs, std::ve
 		for (size_t r = 0; r + 1 < runs.size(); r += 2) {
 			uint32_t code = 0;
 			for (int64_t j = 0; j < runs[r + 1]; ++j) {
-				const int64_t p = runs[r] + j;
+				const int64_t p = (int64_t)runs[r] + j;
 				code = ((code << 2) | ((gfwd[p >> 4] >> ((p & 15) << 1)) & 3u)) & mask;
 				if (j < 12) continue;
 				if (pass == 0) ++cnt[code];
@@ -140,8 +141,9 @@ void index_genome(const mecat_ref_genome* g, HostIndex& I)
 {
 	I.n = g->num_bases;
 	I.gw = words_of(g->pac, g->num_bases);
-	std::vector<int64_t> runs(g->run_start_len, g->run_start_len + 2 * (size_t)g->num_runs);
-	build_index(I.gw.data(), runs, I.begin, I.pos);
+	std::vector<int32_t> chunks;
+	if (!mbref::index_chunks(g->run_start_len, g->num_runs, g->num_bases, chunks)) chunks.clear();
+	build_index(I.gw.data(), chunks, I.begin, I.pos);
 }
 
 int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_params* p, long table_budget, mbref::Sink& sink, long* stats, std::string& err)
