@@ -313,6 +313,14 @@ int mecat_b200_ref_index_release(mecat_b200_ctx* ctx, void* refidx);
 int mecat_b200_ref_map(mecat_b200_ctx* ctx, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
                        mecat_ref_result** results, size_t* n, char** qstrings, char** sstrings, size_t* string_bytes);
 
+/* test hooks: the genome's k-mer index like mecat_b200_index_export (0-based k-mer starts; the reference's databaseindex
+ * holds them + 1), and the candidate lists the first seeding pass leaves per strand (counts = 2 per read: forward,
+ * reverse; rows = 4 ints per candidate: loc1 loc2 score chain, the fields of `candidate_save` extend_candidate reads;
+ * mecat2ref_impl_large.cpp:463-614). */
+int mecat_b200_ref_index_export(mecat_b200_ctx* ctx, void* refidx, int64_t* num_kmers, uint32_t* begin, int32_t* positions);
+int mecat_b200_ref_raw_candidates(mecat_b200_ctx* ctx, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
+                                  int32_t** rows, int32_t** counts, size_t* n);
+
 /* frees host buffers handed out by this library (same as mecat_b200_free without a context) */
 void mecat_b200_host_free(void* p);
 

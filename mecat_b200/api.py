@@ -92,6 +92,7 @@ EXPORTS = [
     "mecat_b200_extend_batch", "mecat_b200_align_batch", "mecat_b200_cns_reads", "mecat_b200_cns_sort_candidates",
     "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload", "mecat_b200_volume_from_fasta",
     "mecat_b200_ref_index_build", "mecat_b200_ref_index_release", "mecat_b200_ref_map",
+    "mecat_b200_ref_index_export", "mecat_b200_ref_raw_candidates",
 ]
 
 _lib = None
@@ -151,6 +152,9 @@ def load_library():
     L.mecat_b200_ref_index_release.argtypes = [vp, vp]
     L.mecat_b200_ref_map.argtypes = [vp, vp, C.POINTER(RefReadsC), C.POINTER(RefParams), C.POINTER(vp), C.POINTER(C.c_size_t),
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_ref_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
+    L.mecat_b200_ref_raw_candidates.argtypes = [vp, vp, C.POINTER(RefReadsC), C.POINTER(RefParams), C.POINTER(vp), C.POINTER(vp),
+                                                C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -575,6 +579,28 @@ class Context:
         if ss.value:
             self.L.mecat_b200_free(self.h, ss)
         return rec, q, s
+
+    def ref_index_export(self, refidx):
+        """Test hook: (begin[2^26 + 1], positions) of the genome's k-mer index (0-based k-mer starts)."""
+        n = C.c_int64()
+        self._check(self.L.mecat_b200_ref_index_export(self.h, refidx, C.byref(n), None, None), "ref_index_export")
+        begin = np.zeros((1 << 26) + 1, dtype=np.uint32)
+        pos = np.zeros(max(1, n.value), dtype=np.int32)
+        self._check(self.L.mecat_b200_ref_index_export(self.h, refidx, C.byref(n), begin.ctypes.data_as(C.c_void_p),
+                                                       pos.ctypes.data_as(C.c_void_p)), "ref_index_export")
+        return begin, pos[:n.value]
+
+    def ref_raw_candidates(self, refidx, reads, num_candidates=10):
+        """Test hook: (rows[n, 4] = loc1 loc2 score chain, counts[2 * reads]) of the first seeding pass, strand by strand."""
+        p = RefParams(num_candidates, num_candidates, 0, 0)
+        r = reads.c()
+        rows, counts, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_ref_raw_candidates(self.h, refidx, C.byref(r), C.byref(p), C.byref(rows), C.byref(counts),
+                                                         C.byref(n)), "ref_raw_candidates")
+        i4 = np.dtype("<i4")
+        cnt = self._take(counts, 2 * len(reads.read_len), i4)
+        row = self._take(rows, max(1, n.value) * 4, i4).reshape(-1, 4)[:n.value]
+        return row, cnt
 
     # ---- host-buffer entry points (the end-to-end calls)
     def pw_candidates(self, ref, reads, params=None):

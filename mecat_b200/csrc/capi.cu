@@ -369,6 +369,29 @@ int mecat_b200_ref_index_release(mecat_b200_ctx* c, void* refidx)
 	return 0;
 }
 
+int mecat_b200_ref_index_export(mecat_b200_ctx* c, void* refidx, int64_t* num_kmers, uint32_t* begin, int32_t* positions)
+{
+	if (check(c) || !refidx) return 1;
+	return mecat_b200_index_export(c, ((RefIndex*)refidx)->index, num_kmers, begin, positions);
+}
+
+int mecat_b200_ref_raw_candidates(mecat_b200_ctx* c, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
+                                  int32_t** rows, int32_t** counts, size_t* n)
+{
+	if (check(c) || !refidx || !reads || !p || !rows || !counts || !n) return 1;
+	cudaSetDevice(c->device);
+	mbref::Sink sink;
+	std::vector<int32_t> cnt, row;
+	if (ref_map(c, (const RefIndex*)refidx, reads, p, sink, &cnt, &row)) return 1;
+	int32_t* r = (int32_t*)malloc(sizeof(int32_t) * (row.size() ? row.size() : 1));
+	int32_t* k = (int32_t*)malloc(sizeof(int32_t) * (cnt.size() ? cnt.size() : 1));
+	if (!r || !k) { free(r); free(k); MB_FAIL(c, "ref_raw_candidates: out of host memory"); }
+	if (!row.empty()) memcpy(r, row.data(), sizeof(int32_t) * row.size());
+	if (!cnt.empty()) memcpy(k, cnt.data(), sizeof(int32_t) * cnt.size());
+	*rows = r; *counts = k; *n = row.size() / 4;
+	return 0;
+}
+
 int mecat_b200_ref_map(mecat_b200_ctx* c, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
                        mecat_ref_result** results, size_t* n, char** qstrings, char** sstrings, size_t* string_bytes)
 {

@@ -256,7 +256,8 @@ namespace mbref { struct Sink; }
 namespace mb {
 int ref_index_build(Ctx* c, const mecat_ref_genome* g, RefIndex** out);
 void ref_index_release(Ctx* c, RefIndex* R);
-int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out);
+int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out,
+            std::vector<int32_t>* dump_counts = nullptr, std::vector<int32_t>* dump_rows = nullptr);
 
 struct RawCand             // candidate_save, pw_impl.h:21-25
 {

@@ -42,6 +42,10 @@ struct Params
 	int num_output = 10;            // -b
 	bool want_strings = true;       // the ref format prints both alignment strings; the m4 format only needs their statistics
 	int64_t table_budget = 8ll << 30;
+	// test hook: the candidate list of every strand of the first pass (2 counts per read, 4 ints per candidate:
+	// loc1 loc2 score chain), as SeedFn left them
+	std::vector<int32_t>* dump_counts = nullptr;
+	std::vector<int32_t>* dump_rows = nullptr;
 };
 
 struct MapIn
@@ -361,6 +365,15 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 		std::vector<int32_t> ncand((size_t)nu);
 		std::vector<RefCand> cands((size_t)(nu * maxc));
 		if (!be.download(ncand.data(), d_ncand, (size_t)nu) || !be.download(cands.data(), d_cands, (size_t)(nu * maxc))) return 1;
+
+		if (pass == 0 && P.dump_counts && P.dump_rows)
+			for (int64_t u = 0; u < nu; ++u) {
+				P.dump_counts->push_back(ncand[(size_t)u]);
+				for (int k = 0; k < ncand[(size_t)u]; ++k) {
+					const RefCand& c = cands[(size_t)(u * maxc + k)];
+					P.dump_rows->push_back(c.loc1); P.dump_rows->push_back(c.loc2); P.dump_rows->push_back(c.score); P.dump_rows->push_back(c.chain);
+				}
+			}
 
 		// ---- the read's list: forward-strand candidates were inserted first, so they stay ahead of equal scores
 		const size_t nr = r1 - r0;

@@ -131,7 +131,8 @@ void ref_index_release(Ctx* c, RefIndex* R)
 	delete R;
 }
 
-int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out)
+int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out,
+            std::vector<int32_t>* dump_counts, std::vector<int32_t>* dump_rows)
 {
 	if (!R || !reads || !p || !reads->vol) MB_FAIL(c, "ref_map: null argument");
 	if (p->tech != 0) MB_FAIL(c, "ref_map: only -x 0 (pacbio) is on this path");
@@ -157,6 +158,7 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
 		in.d_ibegin = R->index->begin; in.d_ipos = R->index->pos;
 		mbref::Params P;
 		P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
+		P.dump_counts = dump_counts; P.dump_rows = dump_rows;
 		if (const char* e = getenv("MECAT_B200_REF_TABLE_MB")) P.table_budget = (int64_t)atoll(e) << 20;      // test hook: force several table batches
 		RefBackend be{c, dv, R->genome, {}};
 		const int rc = mbref::map_reads(be, in, P, out);

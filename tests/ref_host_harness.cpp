@@ -146,7 +146,8 @@ void index_genome(const mecat_ref_genome* g, HostIndex& I)
 	build_index(I.gw.data(), chunks, I.begin, I.pos);
 }
 
-int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_params* p, long table_budget, mbref::Sink& sink, long* stats, std::string& err)
+int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_params* p, long table_budget, mbref::Sink& sink, long* stats, std::string& err,
+               std::vector<int32_t>* dump_counts = nullptr, std::vector<int32_t>* dump_rows = nullptr)
 {
 	const std::vector<uint32_t> rw = words_of(view->vol->pac, view->vol->num_bases);
 	HostBackend be;
@@ -159,6 +160,7 @@ int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_
 	mbref::Params P;
 	P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
 	if (table_budget > 0) P.table_budget = table_budget;
+	P.dump_counts = dump_counts; P.dump_rows = dump_rows;
 	if (mbref::map_reads(be, in, P, sink)) { err = be.err; return 1; }
 	if (stats) { stats[0] += be.tasks_run; stats[1] += be.batches; stats[2] += be.rescue_units; }
 	return 0;
@@ -228,6 +230,30 @@ int harness_ref_map_indexed(void* idx, const mecat_ref_reads* reads, const mecat
 	if (!sink.recs.empty()) memcpy(res, sink.recs.data(), sizeof(mecat_ref_result) * sink.recs.size());
 	*results = res; *n = sink.recs.size(); *string_bytes = sink.q.size();
 	*qstrings = sink.q.release(); *sstrings = sink.s.release();
+	return 0;
+}
+
+// twins of the test hooks mecat_b200_ref_index_export / mecat_b200_ref_raw_candidates
+int64_t harness_ref_index_export(void* idx, uint32_t* begin, int32_t* positions)
+{
+	const HostIndex* I = (const HostIndex*)idx;
+	if (begin) memcpy(begin, I->begin.data(), sizeof(uint32_t) * I->begin.size());
+	if (positions && !I->pos.empty()) memcpy(positions, I->pos.data(), sizeof(int32_t) * I->pos.size());
+	return (int64_t)I->pos.size();
+}
+
+int harness_ref_raw_candidates(void* idx, const mecat_ref_reads* reads, const mecat_ref_params* p, int32_t** rows, int32_t** counts, size_t* n)
+{
+	mbref::Sink sink;
+	std::string err;
+	std::vector<int32_t> cnt, row;
+	if (map_packed(*(const HostIndex*)idx, reads, p, 0, sink, NULL, err, &cnt, &row)) return 1;
+	int32_t* r = (int32_t*)malloc(sizeof(int32_t) * (row.size() ? row.size() : 1));
+	int32_t* k = (int32_t*)malloc(sizeof(int32_t) * (cnt.size() ? cnt.size() : 1));
+	if (!r || !k) return 1;
+	if (!row.empty()) memcpy(r, row.data(), sizeof(int32_t) * row.size());
+	if (!cnt.empty()) memcpy(k, cnt.data(), sizeof(int32_t) * cnt.size());
+	*rows = r; *counts = k; *n = row.size() / 4;
 	return 0;
 }
 

@@ -81,6 +81,43 @@ def run_oracle(genome, fa, n, b, fmt):
     return s
 
 
+def test_index_and_first_pass_candidates_match_the_host_twin(gpu_ctx, refmap_inputs, hard_inputs, tmp_path):
+    """Function-level parity below the end-to-end records: the genome's k-mer index (both CSR arrays) and the candidate
+    list SeedFn leaves for every strand, against the same structures computed on the host by tests/ref_host_harness.cpp
+    (whose end-to-end output is pinned to the unmodified binary by tests/test_ref_host.py)."""
+    from mecat_b200 import api
+    L = util.ref_harness()
+    rep_fa, rep_genome = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa")
+    util.make_refmap_repeats(rep_fa, rep_genome, seed=5, num_reads=150)
+    for fa, genome, ncand in ((refmap_inputs[0], refmap_inputs[1], 10), (hard_inputs[0], hard_inputs[1], 10), (rep_fa, rep_genome, 40)):
+        G = api.RefGenome.from_fasta(genome)
+        R = api.RefReads(util.read_fasta(fa))
+        gc = G.c()
+        hidx = L.harness_ref_index_build(C.byref(gc))
+        hbegin = np.zeros((1 << 26) + 1, dtype=np.uint32)
+        hn = L.harness_ref_index_export(hidx, hbegin.ctypes.data_as(C.c_void_p), None)
+        hpos = np.zeros(max(1, hn), dtype=np.int32)
+        L.harness_ref_index_export(hidx, None, hpos.ctypes.data_as(C.c_void_p))
+        idx = gpu_ctx.ref_index_build(G)
+        try:
+            begin, pos = gpu_ctx.ref_index_export(idx)
+            assert len(pos) == hn and (begin == hbegin).all() and (pos == hpos[:hn]).all()
+            rows, counts = gpu_ctx.ref_raw_candidates(idx, R, ncand)
+        finally:
+            gpu_ctx.release_ref_index(idx)
+        rc, p = R.c(), api.RefParams(ncand, ncand, 0, 0)
+        hrows, hcounts, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        assert L.harness_ref_raw_candidates(hidx, C.byref(rc), C.byref(p), C.byref(hrows), C.byref(hcounts), C.byref(n)) == 0
+        want_counts = np.frombuffer(C.string_at(hcounts.value, 8 * len(R.read_len)), dtype="<i4")
+        want_rows = np.frombuffer(C.string_at(hrows.value, 16 * n.value), dtype="<i4").reshape(-1, 4)
+        for ptr in (hrows, hcounts):
+            L.harness_free(ptr)
+        L.harness_ref_index_release(hidx)
+        assert n.value > len(R.read_len) // 2
+        assert (counts == want_counts).all()
+        assert rows.shape == want_rows.shape and (rows == want_rows).all()
+
+
 def test_m4_records_match_reference(gpu_ctx, refmap_inputs):
     """300 CLR reads against their 100 kb genome, m4 records (coordinates, identity, score) of the unmodified binary."""
     fa, genome = refmap_inputs

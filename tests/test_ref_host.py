@@ -203,6 +203,60 @@ def test_awkward_files_parse_like_the_reference(tmp_path, refmap_inputs):
     assert run_harness(genome2, fq, fmt=1)[0] == want == run_oracle(genome2, fq, 10, 10, 1)
 
 
+def numpy_index(G):
+    """(codes, positions) of the kept 13-mers of an api.RefGenome, ordered by (code, position): an independent statement of
+    creat_ref_index (every 13-mer inside a run of ACGT, lists of more than 128 dropped) in the product's conventions
+    (A0 C1 G2 T3, first base most significant, 0-based starts)."""
+    import numpy as np
+    n = G.num_bases
+    pac = G.pac
+    codes = ((pac[np.arange(n) >> 2] >> (((~np.arange(n)) & 3) << 1)) & 3).astype(np.int64)
+    good = np.zeros(n, dtype=bool)
+    for s0, ln in G.runs:
+        good[s0:s0 + ln] = True
+    m = n - 12
+    kmer = np.zeros(m, dtype=np.int64)
+    for j in range(13):
+        kmer = (kmer << 2) | codes[j:j + m]
+    csum = np.concatenate(([0], np.cumsum(~good)))
+    ok = (csum[13:13 + m] - csum[:m]) == 0
+    pos = np.flatnonzero(ok)
+    kmer = kmer[ok]
+    order = np.lexsort((pos, kmer))
+    kmer, pos = kmer[order], pos[order]
+    uniq, inv, cnt = np.unique(kmer, return_inverse=True, return_counts=True)
+    keep = cnt[inv] <= 128
+    return kmer[keep], pos[keep]
+
+
+def test_index_of_the_genome_against_numpy(hard_inputs, tmp_path):
+    """The harness's index (the layout the device index has to have: GPU tests compare the two arrays) against numpy_index,
+    on the three-contig genome with its N run plus a 200-copy tandem repeat (lists above the cutoff) and runs shorter
+    than a k-mer."""
+    import numpy as np
+    from mecat_b200 import api
+    L = util.ref_harness()
+    fa, genome = hard_inputs
+    G0 = api.RefGenome.from_fasta(genome)
+    seqs = [open(genome, "rb").read().split(b"\n")[1], b"ACGTTGCAAGGCT" * 200 + b"NNACGTACGTACGNNNACGTACGTACGTTN" + b"GATTACA" * 30]
+    G = api.RefGenome(["a", "b"], seqs)
+    for g in (G0, G):
+        gc = g.c()
+        idx = L.harness_ref_index_build(C.byref(gc))
+        begin = np.zeros((1 << 26) + 1, dtype=np.uint32)
+        n = L.harness_ref_index_export(idx, begin.ctypes.data_as(C.c_void_p), None)
+        pos = np.zeros(max(1, n), dtype=np.int32)
+        L.harness_ref_index_export(idx, None, pos.ctypes.data_as(C.c_void_p))
+        L.harness_ref_index_release(idx)
+        kmer, want = numpy_index(g)
+        assert n == len(want) == int(begin[-1])
+        assert (pos[:n] == want).all()
+        uniq, first = np.unique(kmer, return_index=True)
+        assert (begin[uniq] == first).all() and (begin[uniq + 1] == np.append(first[1:], n)).all()
+        assert np.count_nonzero(np.diff(begin.astype(np.int64))) == len(uniq)
+    assert len(numpy_index(G)[0]) < G.num_bases - 12 - 13 * 150          # the tandem repeat's lists were dropped
+
+
 def packed_via_python(genome_path, reads_path, fmt, n=10, b=10):
     """Python packing (mecat_b200.api RefGenome / RefReads) -> the host twin of the ABI call -> Python formatting."""
     import numpy as np

@@ -176,6 +176,12 @@ def ref_harness():
     L.harness_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(vp), C.POINTER(C.c_size_t),
                                   C.POINTER(C.c_long), C.c_char_p, C.c_int]
     L.harness_ref_index_build.restype = vp
+    L.harness_ref_index_build.argtypes = [vp]
+    L.harness_ref_index_release.argtypes = [vp]
+    L.harness_ref_index_export.restype = C.c_int64
+    L.harness_ref_index_export.argtypes = [vp, vp, vp]
+    L.harness_ref_raw_candidates.restype = C.c_int
+    L.harness_ref_raw_candidates.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.harness_ref_map_packed.restype = C.c_int
     L.harness_ref_map_packed.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.harness_ddf_forms.restype = C.c_int
