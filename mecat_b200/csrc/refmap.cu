@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "ref_pipeline.h"
 
+#include <algorithm>
+
 namespace mb {
 
 namespace {
@@ -142,6 +144,16 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
 		if (f < 0 || f >= v->num_reads || w < 0 || w >= v->num_reads || v->offset_size[2 * f + 1] != reads->read_len[r] ||
 		    v->offset_size[2 * w + 1] != reads->read_len[r])
 			MB_FAIL(c, "ref_map: read %d does not match its volume reads", r);
+	}
+	if (reads->num_bad < 0 || (reads->num_bad && !reads->bad)) MB_FAIL(c, "ref_map: bad list of other letters");
+	for (int64_t k = 1; k < reads->num_bad; ++k)
+		if (reads->bad[k - 1] >= reads->bad[k]) MB_FAIL(c, "ref_map: the offsets of other letters must ascend");
+	for (int32_t r = 0; r < reads->num_reads && reads->num_bad; ++r) {
+		if (!reads->rev_is_rc[r]) continue;
+		// a strand taken by reverse complement cannot carry letters the reference treats differently on the two strands
+		const int64_t lo = v->offset_size[2 * reads->rev_read[r]], hi = lo + reads->read_len[r];
+		const int64_t* it = std::lower_bound(reads->bad, reads->bad + reads->num_bad, lo);
+		if (it != reads->bad + reads->num_bad && *it < hi) MB_FAIL(c, "ref_map: read %d has other letters and needs an explicit reverse strand", r);
 	}
 	DVolume* dv = nullptr;
 	if (volume_upload(c, v, &dv)) return 1;
