@@ -7,9 +7,10 @@
 //   operator<<(ExtensionCandidate) src/common/alignment.cpp:18-32
 //   output_m4record                src/mecat2pw/pw_impl.cpp:509-531
 // but every hot loop runs on the GPU through the C ABI (include/mecat_b200.h).  `-t` is
-// accepted and ignored (there are no CPU worker threads).  GPUs: MECAT_GPUS=n (default 1)
-// round-robins index volumes over the first n devices, one host thread per device; each
-// device writes the same wrk/r_N files the reference does, so resume works unchanged.
+// accepted and ignored (there are no CPU worker threads).  GPUs: MECAT_GPUS=n (default 1): one
+// host thread per device, the tiles (index volume s, query volume v >= s) are handed out one by
+// one, so the devices stay balanced although row s has num_volumes - s tiles; the text of a row
+// becomes the same wrk/r_N file the reference writes, so resume works unchanged.
 #include <dirent.h>
 #include <getopt.h>
 #include <stdio.h>
@@ -26,6 +27,7 @@
 #include <sstream>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "mecat_b200.h"
@@ -142,65 +144,79 @@ std::string results_name(const char* wrk, int vid, bool working)
 	return n + os.str();
 }
 
-void write_candidates(std::ostream& out, const mecat_candidate* ec, size_t n)
+void format_records(std::string& text, const Options& opt, const void* rec, size_t n)
 {
 	mbfmt::TextBuf b;
-	b.s.reserve(n * 48 + 64);
-	mbfmt::format_candidates(b, ec, n);
-	out.write(b.s.data(), (std::streamsize)b.s.size());
+	b.s.reserve(n * (opt.task == 0 ? 48 : 96) + 64);
+	if (opt.task == 0) mbfmt::format_candidates(b, (const mecat_candidate*)rec, n);
+	else mbfmt::format_m4(b, (const mecat_m4*)rec, n, opt.output_gapped_start_point != 0);
+	text.swap(b.s);
 }
 
-void write_m4(std::ostream& out, const mecat_m4* m, size_t n, bool gapped)
+// What one device keeps between tiles: the index volume it worked on last (create_ref_index of process_one_volume,
+// pw_impl.cpp:855) -- consecutive tiles of the same row reuse it.
+struct DeviceState
 {
-	const size_t chunk = 1 << 18;              // bounded text buffer
-	mbfmt::TextBuf b;
-	b.s.reserve(std::min(n, chunk) * 96 + 64);
-	for (size_t i = 0; i < n; i += chunk) {
-		b.s.clear();
-		mbfmt::format_m4(b, m + i, std::min(chunk, n - i), gapped);
-		out.write(b.s.data(), (std::streamsize)b.s.size());
-	}
-}
-
-bool process_one_volume(mecat_b200_ctx* ctx, const Options& opt, int svid, const std::vector<std::string>& vols, std::ostream& out)
-{
-	mecat_pw_params p = {opt.task, opt.num_candidates, opt.min_align_size, opt.min_kmer_match, opt.tech};
+	mecat_b200_ctx* ctx = NULL;
+	int svid = -1;
 	mecat_volume ref;
-	if (mecat_b200_volume_load(vols[svid].c_str(), &ref)) { fprintf(stderr, "failed to open file '%s'.\n", vols[svid].c_str()); return false; }
-	void *dref = NULL, *index = NULL;
-	bool ok = true;
+	void* dref = NULL;
+	void* index = NULL;
+	void drop()
 	{
+		if (index) mecat_b200_index_release(ctx, index);
+		if (dref) mecat_b200_volume_release(ctx, dref);
+		if (svid >= 0) mecat_b200_volume_unload(&ref);
+		index = NULL; dref = NULL; svid = -1;
+	}
+	bool use(int s, const std::vector<std::string>& vols)
+	{
+		if (svid == s) return true;
+		drop();
+		if (mecat_b200_volume_load(vols[(size_t)s].c_str(), &ref)) { fprintf(stderr, "failed to open file '%s'.\n", vols[(size_t)s].c_str()); return false; }
+		svid = s;
 		StderrTimer t("create_ref_index");
-		ok = mecat_b200_volume_upload(ctx, &ref, &dref) == 0 && mecat_b200_index_build(ctx, dref, &index) == 0;
+		if (mecat_b200_volume_upload(ctx, &ref, &dref) == 0 && mecat_b200_index_build(ctx, dref, &index) == 0) return true;
+		fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(ctx));
+		return false;
 	}
-	for (int vid = svid; ok && vid < (int)vols.size(); ++vid) {
-		char info[64];
-		snprintf(info, sizeof info, "process volume %d", vid);
-		StderrTimer t(info);
-		fprintf(stderr, "processing %s\n", vols[vid].c_str());
-		void* dreads = dref;
-		mecat_volume reads;
-		memset(&reads, 0, sizeof reads);
-		if (vid != svid) {
-			if (mecat_b200_volume_load(vols[vid].c_str(), &reads)) { fprintf(stderr, "failed to open file '%s'.\n", vols[vid].c_str()); ok = false; break; }
-			ok = mecat_b200_volume_upload(ctx, &reads, &dreads) == 0;
-		}
-		void* rec = NULL;
-		size_t n = 0;
-		if (ok) ok = mecat_b200_pw_tile(ctx, index, dref, dreads, &p, &rec, &n) == 0;
-		if (ok) {
-			if (opt.task == 0) write_candidates(out, (const mecat_candidate*)rec, n);
-			else write_m4(out, (const mecat_m4*)rec, n, opt.output_gapped_start_point != 0);
-		}
-		mecat_b200_free(ctx, rec);
-		if (vid != svid) { if (dreads) mecat_b200_volume_release(ctx, dreads); mecat_b200_volume_unload(&reads); }
+};
+
+// One tile of process_one_volume's loop (pw_impl.cpp:859-879): query volume vid against the index of volume svid.
+bool process_tile(DeviceState& D, const Options& opt, int svid, int vid, const std::vector<std::string>& vols, std::string& text)
+{
+	if (!D.use(svid, vols)) return false;
+	mecat_pw_params p = {opt.task, opt.num_candidates, opt.min_align_size, opt.min_kmer_match, opt.tech};
+	char info[64];
+	snprintf(info, sizeof info, "process volume %d", vid);
+	StderrTimer t(info);
+	fprintf(stderr, "processing %s\n", vols[(size_t)vid].c_str());
+	void* dreads = D.dref;
+	mecat_volume reads;
+	memset(&reads, 0, sizeof reads);
+	bool ok = true;
+	if (vid != svid) {
+		if (mecat_b200_volume_load(vols[(size_t)vid].c_str(), &reads)) { fprintf(stderr, "failed to open file '%s'.\n", vols[(size_t)vid].c_str()); return false; }
+		dreads = NULL;
+		ok = mecat_b200_volume_upload(D.ctx, &reads, &dreads) == 0;
 	}
-	if (!ok) fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(ctx));
-	if (index) mecat_b200_index_release(ctx, index);
-	if (dref) mecat_b200_volume_release(ctx, dref);
-	mecat_b200_volume_unload(&ref);
+	void* rec = NULL;
+	size_t n = 0;
+	if (ok) ok = mecat_b200_pw_tile(D.ctx, D.index, D.dref, dreads, &p, &rec, &n) == 0;
+	if (ok) format_records(text, opt, rec, n);
+	else fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(D.ctx));
+	mecat_b200_free(D.ctx, rec);
+	if (vid != svid) { if (dreads) mecat_b200_volume_release(D.ctx, dreads); mecat_b200_volume_unload(&reads); }
 	return ok;
 }
+
+// The tiles (s, v >= s) of one index volume and their text; r_s is written when the last one is in.
+struct Row
+{
+	int svid = 0;
+	std::vector<std::string> text;
+	std::atomic<int> left{0};
+};
 
 }  // namespace
 
@@ -241,31 +257,48 @@ int main(int argc, char* argv[])
 	if (have < 1) { fprintf(stderr, "mecat2pw: no CUDA device found (this build has no CPU path)\n"); return 1; }
 	if (ngpus < 1) ngpus = 1;
 	if (ngpus > have) ngpus = have;
-	if (ngpus > num_vols) ngpus = num_vols > 0 ? num_vols : 1;
+	// Work items are tiles, row by row; rows whose r_N exists are finished (the reference's resume protocol, pw.cpp:65-81).
+	// Any device takes the next tile: building the index of a volume costs a fraction of a tile, so several devices
+	// share a row instead of each owning rows of very different sizes (row s has num_vols - s tiles).
+	std::vector<Row> rows((size_t)num_vols);
+	std::vector<std::pair<int, int>> tiles;
+	for (int i = 0; i < num_vols; ++i) {
+		rows[(size_t)i].svid = i;
+		if (access(results_name(opt.wrk_dir, i, false).c_str(), F_OK) == 0) { fprintf(stderr, "volume %d has been finished\n", i); continue; }
+		rows[(size_t)i].text.resize((size_t)(num_vols - i));
+		rows[(size_t)i].left = num_vols - i;
+		for (int v = i; v < num_vols; ++v) tiles.push_back(std::make_pair(i, v));
+	}
+	if (ngpus > (int)tiles.size()) ngpus = tiles.empty() ? 1 : (int)tiles.size();
 
 	if (warm.joinable()) warm.join();
 	if (ctx0_rc) ctx0 = NULL;
 	std::atomic<int> next(0), failed(0);
 	auto worker = [&](int dev) {
-		mecat_b200_ctx* ctx = dev == 0 ? ctx0 : NULL;
-		if (!ctx) {
+		DeviceState D;
+		D.ctx = dev == 0 ? ctx0 : NULL;
+		if (!D.ctx) {
 			StderrTimer t("gpu " + std::to_string(dev) + " init");
-			if (mecat_b200_init(&ctx, dev, NULL)) { fprintf(stderr, "mecat2pw: cannot initialise GPU %d\n", dev); failed = 1; return; }
+			if (mecat_b200_init(&D.ctx, dev, NULL)) { fprintf(stderr, "mecat2pw: cannot initialise GPU %d\n", dev); failed = 1; return; }
 		}
 		for (;;) {
 			const int i = next.fetch_add(1);
-			if (i >= num_vols || failed) break;
-			const std::string done = results_name(opt.wrk_dir, i, false);
-			if (access(done.c_str(), F_OK) == 0) { fprintf(stderr, "volume %d has been finished\n", i); continue; }
-			const std::string working = results_name(opt.wrk_dir, i, true);
-			std::ofstream out(working.c_str());
-			if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", working.c_str()); failed = 1; break; }
-			if (!process_one_volume(ctx, opt, i, vols, out)) { failed = 1; break; }
-			out.close();
-			if (rename(working.c_str(), done.c_str()) != 0) { failed = 1; break; }
+			if (i >= (int)tiles.size() || failed) break;
+			const int s = tiles[(size_t)i].first, v = tiles[(size_t)i].second;
+			Row& row = rows[(size_t)s];
+			if (!process_tile(D, opt, s, v, vols, row.text[(size_t)(v - s)])) { failed = 1; break; }
+			if (row.left.fetch_sub(1) == 1) {          // the row is complete: r_s.working, then r_s
+				const std::string working = results_name(opt.wrk_dir, s, true), done = results_name(opt.wrk_dir, s, false);
+				std::ofstream out(working.c_str(), std::ios::binary);
+				if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", working.c_str()); failed = 1; break; }
+				for (std::string& t : row.text) { out.write(t.data(), (std::streamsize)t.size()); std::string().swap(t); }
+				out.close();
+				if (!out || rename(working.c_str(), done.c_str()) != 0) { failed = 1; break; }
+			}
 		}
+		D.drop();
 		StderrTimer t("gpu " + std::to_string(dev) + " release");
-		mecat_b200_destroy(ctx);
+		mecat_b200_destroy(D.ctx);
 	};
 	std::vector<std::thread> th;
 	for (int d = 1; d < ngpus; ++d) th.emplace_back(worker, d);

@@ -411,6 +411,22 @@ def ref_driver_on_host():
     return exe
 
 
+def pw_driver_on_host():
+    """mecat_b200/csrc/host/mecat2pw.cpp + the product's host I/O linked against tests/pw_abi_shim.cpp (the oracle plays the
+    device): the command-line driver as the CPU suite can run it.  Returns the path of the executable."""
+    build_oracle()
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "mecat2pw_host")
+    src = [os.path.join(ROOT, "mecat_b200", "csrc", "host", "mecat2pw.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "host_io.cpp"),
+           os.path.join(ROOT, "tests", "pw_abi_shim.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "host", "format.h"),
+           os.path.join(ROOT, "include", "mecat_b200.h"), os.path.join(ORACLE_DIR, "liboracle.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe] + src[:3] +
+                              ["-L", ORACLE_DIR, "-loracle", "-Wl,-rpath," + ORACLE_DIR])
+    return exe
+
+
 def make_refmap_repeats(reads_path, genome_path, seed, num_reads, copies=40):
     """Repeat-rich inputs for mecat2ref: a 6 kb segment copied `copies` times (3 % diverged) between short unique stretches,
     a 150-copy tandem 40-mer, a 3-mer run, a second contig with a run of N; reads of 3-45 kb with 10-30 % errors, half of
