@@ -112,6 +112,26 @@ def test_repeat_rich_inputs_match_the_unmodified_binary(tmp_path, n, b):
     assert groups(got) == want
 
 
+def test_kernel_bodies_under_sanitizers(tmp_path, hard_inputs):
+    """ASan + UBSan over the stage sequence and kernel bodies (small calls, tiny table budget, -n above the list sizes) on
+    the hard fixture and on a repeat-rich one."""
+    import subprocess
+    exe = os.path.join(util.ROOT, "tests", "_build", "ref_sanitize")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    util.build_oracle()
+    cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+           "-pthread", "-o", exe, os.path.join(util.ROOT, "tests", "ref_sanitize_main.cpp"), os.path.join(util.ROOT, "tests", "ref_host_harness.cpp"),
+           "-L", util.ORACLE_DIR, "-loracle", "-Wl,-rpath," + util.ORACLE_DIR]
+    if subprocess.run(cmd, capture_output=True).returncode != 0:
+        pytest.skip("this toolchain has no sanitizer runtime")
+    fa, genome = hard_inputs
+    rfa, rgenome = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa")
+    util.make_refmap_repeats(rfa, rgenome, seed=7, num_reads=60)
+    for args in ([genome, fa, "10", "10", "0", "50", "200000"], [genome, fa, "3", "2", "2", "0", "0"], [rgenome, rfa, "40", "5", "1", "25", "3000000"]):
+        p = subprocess.run([exe] + args, capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+        assert p.returncode == 0 and "rc=0" in p.stdout and "runtime error" not in p.stderr and "AddressSanitizer" not in p.stderr, p.stderr[-3000:]
+
+
 def golden_sam():
     with gzip.open(os.path.join(util.GOLDEN, "refmap_hard.sam.gz"), "rt") as f:
         lines = f.read().splitlines()
