@@ -267,15 +267,15 @@ struct ReadBatch
 	}
 
 	// bits 0-1: code (anything but ACGT in either case packs as A); bit 7: not upper-case ACGT
+	struct PackTable
+	{
+		uint8_t t[256];
+		PackTable() { for (int c = 0; c < 256; ++c) { const int k = code_ci((unsigned char)c); t[c] = (uint8_t)((k < 0 ? 0 : k) | (upper_acgt((unsigned char)c) ? 0 : 0x80)); } }
+	};
 	static const uint8_t* table()
 	{
-		static uint8_t t[256];
-		static bool done = false;
-		if (!done) {
-			for (int c = 0; c < 256; ++c) { const int k = code_ci((unsigned char)c); t[c] = (uint8_t)((k < 0 ? 0 : k) | (upper_acgt((unsigned char)c) ? 0 : 0x80)); }
-			done = true;
-		}
-		return t;
+		static const PackTable T;       // initialised once, thread-safely: several threads pack
+		return T.t;
 	}
 	// n letters at base offset `base`; bytes shared with a neighbouring read are OR-ed in atomically (several threads pack)
 	static bool pack_letters(uint8_t* pac, int64_t base, const char* s, int64_t n, std::vector<int64_t>& bad)
