@@ -373,3 +373,22 @@ def test_driver_option_handling(tmp_path, refmap_inputs):
     p = run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-m", "1", "-n", "2", "-b", "7"])
     assert "we reset it to 2" in p.stderr
     assert sorted(open(out).read().splitlines()) == sorted(run_oracle(genome, fa, 2, 2, 1).splitlines())
+
+
+def test_driver_threads_under_thread_sanitizer(tmp_path, hard_inputs):
+    """The driver's host threads -- one per device, packing threads, the packer / text tasks running beside the device
+    call -- under ThreadSanitizer, two shim devices and many small batches; the file is still the reference's."""
+    import subprocess
+    exe = os.path.join(util.ROOT, "tests", "_build", "mecat2ref_tsan")
+    util.build_oracle()
+    cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I", os.path.join(util.ROOT, "include"), "-o", exe,
+           os.path.join(util.ROOT, "mecat_b200", "csrc", "host", "mecat2ref.cpp"), os.path.join(util.ROOT, "tests", "ref_abi_shim.cpp"),
+           os.path.join(util.ROOT, "tests", "ref_host_harness.cpp"), "-L", util.ORACLE_DIR, "-loracle", "-Wl,-rpath," + util.ORACLE_DIR]
+    if subprocess.run(cmd, capture_output=True).returncode != 0:
+        pytest.skip("this toolchain has no ThreadSanitizer runtime")
+    fa, genome = hard_inputs
+    out = str(tmp_path / "hard.ref")
+    p = subprocess.run([exe, "-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-t", "4"], capture_output=True, text=True,
+                       env=dict(os.environ, MECAT_B200_REF_BATCH_BASES="150000", MECAT_GPUS="2", MECAT_SHIM_DEVICES="2"))
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
+    assert groups(open(out).read()) == golden_groups("refmap_hard.ref.gz")
