@@ -176,19 +176,23 @@ def test_repeat_rich_inputs_match_the_unmodified_binary(gpu_ctx, tmp_path, n, b)
     assert groups(text) == want
 
 
-def test_small_table_batches_give_the_same_records(refmap_inputs):
-    """A 1 MB budget for the block tables cuts the 300 reads into many batches (own context: the budget is read per call)."""
+def test_small_table_and_arena_batches_give_the_same_records(refmap_inputs):
+    """A 1 MB budget for the block tables cuts the 300 reads into many table batches, a 2 MB column arena cuts every
+    extension call into several launches (own context: both sizes are read when the context / the call starts)."""
     import mecat_b200
     fa, genome = refmap_inputs
     os.environ["MECAT_B200_REF_TABLE_MB"] = "1"
+    os.environ["MECAT_B200_ALIGN_ARENA_MB"] = "2"
     try:
         with mecat_b200.Context(0) as ctx:
-            text, _ = map_through_abi(ctx, genome, fa, 1)
+            text, _ = map_through_abi(ctx, genome, fa, 0)
             st = ctx.stats()
     finally:
         del os.environ["MECAT_B200_REF_TABLE_MB"]
-    assert sorted(text.splitlines()) == golden("refmap.m4.gz").splitlines()
+        del os.environ["MECAT_B200_ALIGN_ARENA_MB"]
+    assert groups(text) == groups(golden("refmap.ref.gz"))
     assert st["kernel_launches"]["ref_seed"] >= 4
+    assert st["kernel_launches"]["extend"] > st["kernel_launches"]["ref_seed"]
 
 
 def test_command_line_driver_matches_reference(gpu_ctx, refmap_inputs, hard_inputs, tmp_path):
