@@ -204,7 +204,8 @@ int main(int argc, char* argv[])
 				fprintf(stderr, "[kernel ms]");
 				for (int k = 0; k < MECAT_K_NUM; ++k)
 					if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);
-				fprintf(stderr, " h2d=%.1fMB d2h=%.1fMB\n", st.h2d_bytes / 1e6, st.d2h_bytes / 1e6);
+				fprintf(stderr, " hits=%lld extensions=%lld records=%lld h2d=%.1fMB d2h=%.1fMB\n", (long long)st.num_hits, (long long)st.num_candidates,
+				        (long long)st.num_records, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6);
 			}
 		}
 		mecat_b200_ref_index_release(c, idx);

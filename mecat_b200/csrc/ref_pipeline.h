@@ -329,6 +329,11 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 	}
 	std::vector<int32_t> hits((size_t)NU);
 	if (!be.download(hits.data(), d_hits, (size_t)NU)) return 1;
+	{
+		int64_t all = 0;
+		for (int32_t h : hits) all += h;
+		be.note_hits(all);          // statistics: the unit of SeedFn's algorithmic bytes
+	}
 
 	auto cap_of = [](int64_t h) { int64_t c = 4; while (c < 2 * h + 2) c <<= 1; return c; };
 	size_t r0 = 0;

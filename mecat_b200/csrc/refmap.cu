@@ -85,6 +85,7 @@ struct RefBackend
 		return align_batch(c, 0, 0.0, reads, genome, (const AlignTask*)tasks, n, 1000 /* extend_candidate's min_aln, mecat2ref_aux.cpp:152 */,
 		                   res, qs, ss, want_strings) == 0;
 	}
+	void note_hits(int64_t n) { c->stats.num_hits += n; }
 	void fail(const char* m) { c->err = m; }
 	void end_batch()
 	{

@@ -65,6 +65,7 @@ struct HostBackend
 		err = "release of an unknown block";
 		return false;
 	}
+	void note_hits(int64_t) {}
 	void fail(const char* m) { err = m; }
 	void end_batch() { for (void* p : owned) free(p); owned.clear(); }
 
