@@ -82,8 +82,49 @@ struct RefBackend
 	{
 		static_assert(sizeof(AlignTask) == sizeof(mecat_align_task), "AlignTask mirrors mecat_align_task");
 		c->stats.num_candidates += (int64_t)n;
-		return align_batch(c, 0, 0.0, reads, genome, (const AlignTask*)tasks, n, 1000 /* extend_candidate's min_aln, mecat2ref_aux.cpp:152 */,
-		                   res, qs, ss, want_strings) == 0;
+		const int min_aln = 1000;       // extend_candidate's min_aln, mecat2ref_aux.cpp:152
+		// Without strings only coordinates, columns and matches are wanted: the forward pass of the extension gives them
+		// (k_extend: no traceback, no column arenas).  Opt-in until it has run on hardware next to the default.
+		const char* mode = getenv("MECAT_B200_REF_EXTEND");
+		if (!want_strings && mode && !strcmp(mode, "forward")) { qs.clear(); ss.clear(); return align_forward(tasks, n, min_aln, res); }
+		return align_batch(c, 0, 0.0, reads, genome, (const AlignTask*)tasks, n, min_aln, res, qs, ss, want_strings) == 0;
+	}
+	// k_extend addresses its subject by read; the window of task t becomes "read" t of a second offset table over the
+	// genome's bases (the same bases, no copy), so the kernel runs as it is.
+	bool align_forward(const mecat_align_task* tasks, size_t n, int min_aln, mecat_align_result* res)
+	{
+		if (!n) return true;
+		std::vector<int32_t> win(2 * n);
+		std::vector<ExtendTask> et(n);
+		for (size_t t = 0; t < n; ++t) {
+			win[2 * t] = tasks[t].swin_off; win[2 * t + 1] = tasks[t].swin_len;
+			ExtendTask e;
+			e.qread = tasks[t].qread; e.qstrand = tasks[t].qstrand; e.qstart = tasks[t].qstart; e.sread = (int32_t)t; e.sstart = tasks[t].sstart;
+			et[t] = e;
+		}
+		DVolume view;
+		view.num_reads = (int32_t)n; view.num_bases = genome->num_bases; view.fwd = genome->fwd; view.rev = genome->rev; view.words = genome->words;
+		int32_t* d_win = alloc<int32_t>(2 * n);
+		ExtendTask* d_tasks = alloc<ExtendTask>(n);
+		ExtendHalf* d_halves = alloc<ExtendHalf>(2 * n);
+		if (!d_win || !d_tasks || !d_halves || !upload(d_win, win.data(), 2 * n) || !upload(d_tasks, et.data(), n)) return false;
+		view.offsz = (int2*)d_win;
+		if (extend_launch(c, reads, &view, d_tasks, n, d_halves)) return false;
+		std::vector<ExtendHalf> halves(2 * n);
+		if (!download(halves.data(), d_halves, 2 * n)) return false;
+		for (size_t t = 0; t < n; ++t) {       // DiffAligner::go's accessors (diff_gapalign.cpp:295-349) from the two directions
+			const ExtendHalf& L = halves[2 * t];
+			const ExtendHalf& R = halves[2 * t + 1];
+			mecat_align_result& r = res[t];
+			memset(&r, 0, sizeof r);
+			r.columns = L.cols + R.cols; r.matches = L.matches + R.matches;
+			r.qstart = tasks[t].qstart - L.qadv; r.qend = tasks[t].qstart + R.qadv;
+			r.sstart = tasks[t].sstart - L.tadv; r.send = tasks[t].sstart + R.tadv;
+			r.ok = r.columns >= min_aln;
+			r.ident = r.columns ? 100.0 * r.matches / r.columns : 0.0;
+			r.str_offset = -1;
+		}
+		return release(d_win) && release(d_tasks) && release(d_halves);
 	}
 	void note_hits(int64_t n) { c->stats.num_hits += n; }
 	void fail(const char* m) { c->err = m; }

@@ -195,6 +195,24 @@ def test_small_table_and_arena_batches_give_the_same_records(refmap_inputs):
     assert st["kernel_launches"]["extend"] > st["kernel_launches"]["ref_seed"]
 
 
+def test_forward_only_extension_gives_the_same_m4_records(gpu_ctx, refmap_inputs, hard_inputs):
+    """MECAT_B200_REF_EXTEND=forward: the m4 format's extensions run through k_extend (forward pass only, the genome
+    windows as a second offset table) instead of the kernel that also writes alignment strings; same records."""
+    os.environ["MECAT_B200_REF_EXTEND"] = "forward"
+    try:
+        fa, genome = refmap_inputs
+        gpu_ctx.reset_stats()
+        text, _ = map_through_abi(gpu_ctx, genome, fa, 1)
+        st = gpu_ctx.stats()
+        assert sorted(text.splitlines()) == golden("refmap.m4.gz").splitlines()
+        assert st["kernel_launches"]["extend"] > 0 and st["kernel_launches"]["finalize"] == 0      # no string assembly ran
+        fa, genome = hard_inputs
+        text, _ = map_through_abi(gpu_ctx, genome, fa, 1)
+        assert sorted(text.splitlines()) == sorted(run_oracle(genome, fa, 10, 10, 1).splitlines())
+    finally:
+        del os.environ["MECAT_B200_REF_EXTEND"]
+
+
 def test_command_line_driver_matches_reference(gpu_ctx, refmap_inputs, hard_inputs, tmp_path):
     """bin/mecat2ref with the reference's flags: ref, sam and m4 files equal the unmodified binary's, also with two devices."""
     import mecat_b200
