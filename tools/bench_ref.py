@@ -30,17 +30,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--tmp", default="/tmp/mecat_bench_ref")
     ap.add_argument("--skip-ref", action="store_true")
+    ap.add_argument("--forward", action="store_true", help="m4 format: forward-only extensions (MECAT_B200_REF_EXTEND=forward)")
     ap.add_argument("--driver", default=os.path.join(ROOT, "mecat_b200", "bin", "mecat2ref"), help="mecat2ref executable under test")
     a = ap.parse_args()
     os.makedirs(a.tmp, exist_ok=True)
     fa, genome_fa = os.path.join(a.tmp, "reads.fa"), os.path.join(a.tmp, "genome.fa")
     genome = a.reads * 15000 // a.coverage
     subprocess.check_call([os.path.join(ROOT, "mecat_b200", "bin", "gen_reads"), fa, str(a.reads), str(genome), "11", "15000", "1500", "0.15", genome_fa])
-    res = {"reads": a.reads, "genome": genome, "coverage": a.coverage, "cores": os.cpu_count(), "format": a.format, "gpus": a.gpus}
+    res = {"reads": a.reads, "genome": genome, "coverage": a.coverage, "cores": os.cpu_count(), "format": a.format, "gpus": a.gpus, "forward_only": a.forward}
     gout = os.path.join(a.tmp, "gpu.out")
     t = time.time()
     p = subprocess.run([a.driver, "-d", fa, "-r", genome_fa, "-o", gout, "-w", os.path.join(a.tmp, "wg"),
-                        "-m", str(a.format)], capture_output=True, text=True, env=dict(os.environ, MECAT_GPUS=str(a.gpus), MECAT_B200_STATS="1"))
+                        "-m", str(a.format)], capture_output=True, text=True, env=dict(os.environ, MECAT_GPUS=str(a.gpus), MECAT_B200_STATS="1", **({"MECAT_B200_REF_EXTEND": "forward"} if a.forward else {})))
     res["gpu_cli_seconds"] = time.time() - t
     res["gpu_log"] = p.stderr.splitlines()[-4:]
     assert p.returncode == 0, p.stderr[-2000:]

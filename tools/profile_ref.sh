@@ -13,6 +13,9 @@ cd $ROOT
 mkdir -p gpurun_out
 (time timeout 900 python -m pytest tests/test_ref_gpu.py -m gpu -q) > gpurun_out/ref_pytest_gpu.log 2>&1; tail -5 gpurun_out/ref_pytest_gpu.log
 timeout 1200 python tools/bench_ref.py --reads $READS --sample $SAMPLE > gpurun_out/bench_ref.log 2>&1; tail -30 gpurun_out/bench_ref.log
+cp gpurun_out/bench_ref_$READS.json gpurun_out/bench_ref_${READS}_strings_kernel.json
+timeout 600 python tools/bench_ref.py --reads $READS --sample $SAMPLE --forward --skip-ref > gpurun_out/bench_ref_forward.log 2>&1; tail -12 gpurun_out/bench_ref_forward.log
+cp gpurun_out/bench_ref_$READS.json gpurun_out/bench_ref_${READS}_forward.json
 cd /tmp/mecat_bench_ref
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $ROOT/gpurun_out/ref_launches.csv \
     $ROOT/mecat_b200/bin/mecat2ref -d reads.fa -r genome.fa -o ncu1.m4 -w wn1 -m 1 > /dev/null 2>&1
