@@ -66,6 +66,14 @@ def hard_inputs(tmp_path_factory):
     return fa, genome
 
 
+@pytest.fixture(scope="module")
+def repeat_inputs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("refmap_repeats_host")
+    fa, genome = str(d / "reads.fa"), str(d / "genome.fa")
+    util.make_refmap_repeats(fa, genome, seed=2, num_reads=120)
+    return fa, genome
+
+
 def test_m4_matches_reference(refmap_inputs):
     fa, genome = refmap_inputs
     s, st = run_harness(genome, fa, fmt=1)
@@ -98,12 +106,11 @@ def test_hard_inputs_match_reference(hard_inputs):
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(util.REF_DIR, "mecat2ref")), reason="needs the unmodified binary (oracle/_ref, built where /root/reference exists)")
 @pytest.mark.parametrize("n,b", [(10, 10), (40, 5)])
-def test_repeat_rich_inputs_match_the_unmodified_binary(tmp_path, n, b):
+def test_repeat_rich_inputs_match_the_unmodified_binary(tmp_path, repeat_inputs, n, b):
     """Differential run against oracle/_ref/mecat2ref itself on a repeat-rich genome (util.make_refmap_repeats): full
     candidate lists, block-consuming votes, rescue between repeat copies, both passes; small calls and table batches."""
     import subprocess
-    fa, genome, out = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa"), str(tmp_path / "ref.out")
-    util.make_refmap_repeats(fa, genome, seed=2, num_reads=120)
+    (fa, genome), out = repeat_inputs, str(tmp_path / "ref.out")
     subprocess.check_call([os.path.join(util.REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-t", "4", "-m", "0",
                            "-n", str(n), "-b", str(b)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=str(tmp_path))
     got, st = run_harness(genome, fa, n, b, 0, per_call=50, budget=3_000_000)
@@ -112,7 +119,7 @@ def test_repeat_rich_inputs_match_the_unmodified_binary(tmp_path, n, b):
     assert groups(got) == want
 
 
-def test_kernel_bodies_under_sanitizers(tmp_path, hard_inputs):
+def test_kernel_bodies_under_sanitizers(hard_inputs, repeat_inputs):
     """ASan + UBSan over the stage sequence and kernel bodies (small calls, tiny table budget, -n above the list sizes) on
     the hard fixture and on a repeat-rich one."""
     import subprocess
@@ -122,11 +129,10 @@ def test_kernel_bodies_under_sanitizers(tmp_path, hard_inputs):
     cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
            "-pthread", "-o", exe, os.path.join(util.ROOT, "tests", "ref_sanitize_main.cpp"), os.path.join(util.ROOT, "tests", "ref_host_harness.cpp"),
            "-L", util.ORACLE_DIR, "-loracle", "-Wl,-rpath," + util.ORACLE_DIR]
-    if subprocess.run(cmd, capture_output=True).returncode != 0:
+    if util.stale(exe, util.REF_HOST_SOURCES) and subprocess.run(cmd, capture_output=True).returncode != 0:
         pytest.skip("this toolchain has no sanitizer runtime")
     fa, genome = hard_inputs
-    rfa, rgenome = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa")
-    util.make_refmap_repeats(rfa, rgenome, seed=7, num_reads=60)
+    rfa, rgenome = repeat_inputs
     for args in ([genome, fa, "10", "10", "0", "50", "200000"], [genome, fa, "3", "2", "2", "0", "0"], [rgenome, rfa, "40", "5", "1", "25", "3000000"]):
         p = subprocess.run([exe] + args, capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
         assert p.returncode == 0 and "rc=0" in p.stdout and "runtime error" not in p.stderr and "AddressSanitizer" not in p.stderr, p.stderr[-3000:]
@@ -384,7 +390,7 @@ def test_driver_threads_under_thread_sanitizer(tmp_path, hard_inputs):
     cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I", os.path.join(util.ROOT, "include"), "-o", exe,
            os.path.join(util.ROOT, "mecat_b200", "csrc", "host", "mecat2ref.cpp"), os.path.join(util.ROOT, "tests", "ref_abi_shim.cpp"),
            os.path.join(util.ROOT, "tests", "ref_host_harness.cpp"), "-L", util.ORACLE_DIR, "-loracle", "-Wl,-rpath," + util.ORACLE_DIR]
-    if subprocess.run(cmd, capture_output=True).returncode != 0:
+    if util.stale(exe, util.REF_HOST_SOURCES) and subprocess.run(cmd, capture_output=True).returncode != 0:
         pytest.skip("this toolchain has no ThreadSanitizer runtime")
     fa, genome = hard_inputs
     out = str(tmp_path / "hard.ref")

@@ -396,6 +396,17 @@ def repeat_reads(seed=21, unit=4000, copies=10, n_reads=260, mean=5000, err=0.05
     return reads
 
 
+def stale(target, sources):
+    return not os.path.exists(target) or any(os.path.getmtime(f) > os.path.getmtime(target) for f in sources)
+
+
+REF_HOST_SOURCES = [os.path.join(ROOT, "tests", "ref_host_harness.cpp"), os.path.join(ROOT, "tests", "ref_abi_shim.cpp"),
+                    os.path.join(ROOT, "tests", "ref_sanitize_main.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "ref_pipeline.h"),
+                    os.path.join(ROOT, "mecat_b200", "csrc", "ref_core.cuh"), os.path.join(ROOT, "mecat_b200", "csrc", "host", "refio.h"),
+                    os.path.join(ROOT, "mecat_b200", "csrc", "host", "mecat2ref.cpp"), os.path.join(ROOT, "include", "mecat_b200.h"),
+                    os.path.join(ORACLE_DIR, "liboracle.so")]
+
+
 def ref_driver_on_host():
     """mecat_b200/csrc/host/mecat2ref.cpp linked against tests/ref_abi_shim.cpp + the host harness instead of the product
     library: the command-line driver as the CPU suite can run it.  Returns the path of the executable."""
