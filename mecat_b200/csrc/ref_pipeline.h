@@ -42,6 +42,9 @@ struct Params
 	int num_output = 10;            // -b
 	bool want_strings = true;       // the ref format prints both alignment strings; the m4 format only needs their statistics
 	int64_t table_budget = 8ll << 30;
+	// With strings wanted: extend every candidate for its coordinates only and compute alignment strings just for the
+	// records that are printed (most of a read's <= -n extensions are dropped as contained in repeat-rich genomes).
+	bool strings_for_printed_only = false;
 	// test hook: the candidate list of every strand of the first pass (2 counts per read, 4 ints per candidate:
 	// loc1 loc2 score chain), as SeedFn left them
 	std::vector<int32_t>* dump_counts = nullptr;
@@ -192,6 +195,8 @@ struct Hit             // TempResult without its strings
 	int64_t sb, se;
 	int64_t str_at;    // offset of the strings in the extension call's string buffers
 	int call;          // 0 = primary extensions, 1 = rescue extensions
+	mecat_align_task task;     // what was extended (strings_for_printed_only asks for it again, with strings)
+	int64_t win;
 };
 
 struct ReadState
@@ -407,7 +412,8 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 		}
 		std::vector<mecat_align_result> res(tasks.size());
 		std::vector<char> q0, s0, q1, s1;
-		if (!be.align(tasks.data(), tasks.size(), P.want_strings, res.data(), q0, s0)) return 1;
+		const bool strings_now = P.want_strings && !P.strings_for_printed_only;
+		if (!be.align(tasks.data(), tasks.size(), strings_now, res.data(), q0, s0)) return 1;
 		for (size_t t = 0; t < tasks.size(); ++t) {
 			if (!res[t].ok) continue;
 			ReadState& S = st[(size_t)tref[t].read];
@@ -415,6 +421,7 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 			h.dir = tref[t].unit & 1; h.vscore = tref[t].vscore; h.qb = res[t].qstart; h.qe = res[t].qend;
 			h.sb = tref[t].win + res[t].sstart; h.se = tref[t].win + res[t].send;
 			h.columns = res[t].columns; h.matches = res[t].matches; h.str_at = res[t].str_offset; h.call = 0;
+			h.task = tasks[t]; h.win = tref[t].win;
 			S.hits.push_back(h);
 			S.alns.push_back(make_aln(h, (int)S.hits.size() - 1));
 		}
@@ -459,11 +466,13 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 			rtasks.push_back(t); rquery.push_back((int)k); rwin.push_back(win);
 		}
 		std::vector<mecat_align_result> rres(rtasks.size());
-		if (!be.align(rtasks.data(), rtasks.size(), P.want_strings, rres.data(), q1, s1)) return 1;
+		if (!be.align(rtasks.data(), rtasks.size(), strings_now, rres.data(), q1, s1)) return 1;
 		std::vector<int> query_task(queries.size(), -1);
 		for (size_t t = 0; t < rtasks.size(); ++t) query_task[(size_t)rquery[t]] = (int)t;
 
 		// ---- per read: chain the rescued alignments, emit (output_results, mecat2ref_aux.cpp:454-473)
+		const size_t first_rec = out.recs.size();
+		std::vector<mecat_align_task> ptasks;        // strings_for_printed_only: the printed records' extensions
 		for (size_t i = 0; i < nr; ++i) {
 			ReadState& S = st[i];
 			const int r = reads[r0 + i];
@@ -477,6 +486,7 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 				h.dir = q.unit & 1; h.vscore = qcand[(size_t)S.first_query + p].score; h.qb = rres[(size_t)t].qstart; h.qe = rres[(size_t)t].qend;
 				h.sb = rwin[(size_t)t] + rres[(size_t)t].sstart; h.se = rwin[(size_t)t] + rres[(size_t)t].send;
 				h.columns = rres[(size_t)t].columns; h.matches = rres[(size_t)t].matches; h.str_at = rres[(size_t)t].str_offset; h.call = 1;
+				h.task = rtasks[(size_t)t]; h.win = rwin[(size_t)t];
 				S.hits.push_back(h);
 				pick_hit[p] = (int)S.hits.size() - 1;
 			}
@@ -489,7 +499,8 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 				memset(&o, 0, sizeof o);
 				o.read = r; o.dir = h.dir; o.vscore = h.vscore; o.qb = h.qb; o.qe = h.qe; o.qs = in.h_len[r];
 				o.sb = h.sb; o.se = h.se; o.columns = h.columns; o.matches = h.matches; o.str_offset = -1;
-				if (P.want_strings) {
+				if (P.want_strings && !strings_now) ptasks.push_back(h.task);
+				if (strings_now) {
 					const std::vector<char>& qs = h.call ? q1 : q0;
 					const std::vector<char>& ss = h.call ? s1 : s0;
 					o.str_offset = (int64_t)out.q.size();
@@ -506,6 +517,23 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 				if (ai.prev_id != -1) emit(ai.prev_id);
 				if (ai.next_id != -1) emit(ai.next_id);
 				++groups;
+			}
+		}
+		if (!ptasks.empty()) {
+			// the same extensions again, now with strings; both routes must agree on every coordinate
+			std::vector<mecat_align_result> pres(ptasks.size());
+			std::vector<char> q2, s2;
+			if (!be.align(ptasks.data(), ptasks.size(), true, pres.data(), q2, s2)) return 1;
+			for (size_t k = 0; k < ptasks.size(); ++k) {
+				mecat_ref_result& o = out.recs[first_rec + k];
+				const mecat_align_result& a = pres[k];
+				if (!a.ok || a.columns != o.columns || a.matches != o.matches || a.qstart != o.qb || a.qend != o.qe) {
+					be.fail("mecat2ref: the extension with strings disagrees with the forward-only extension of the same candidate");
+					return 1;
+				}
+				o.str_offset = (int64_t)out.q.size();
+				out.q.append(q2.data() + a.str_offset, (size_t)a.columns + 1);
+				out.s.append(s2.data() + a.str_offset, (size_t)a.columns + 1);
 			}
 		}
 		r0 = r1;

@@ -85,9 +85,13 @@ struct RefBackend
 		const int min_aln = 1000;       // extend_candidate's min_aln, mecat2ref_aux.cpp:152
 		// Without strings only coordinates, columns and matches are wanted: the forward pass of the extension gives them
 		// (k_extend: no traceback, no column arenas).  Opt-in until it has run on hardware next to the default.
-		const char* mode = getenv("MECAT_B200_REF_EXTEND");
-		if (!want_strings && mode && !strcmp(mode, "forward")) { qs.clear(); ss.clear(); return align_forward(tasks, n, min_aln, res); }
+		if (!want_strings && forward_only()) { qs.clear(); ss.clear(); return align_forward(tasks, n, min_aln, res); }
 		return align_batch(c, 0, 0.0, reads, genome, (const AlignTask*)tasks, n, min_aln, res, qs, ss, want_strings) == 0;
+	}
+	static bool forward_only()
+	{
+		const char* mode = getenv("MECAT_B200_REF_EXTEND");
+		return mode && !strcmp(mode, "forward");
 	}
 	// k_extend addresses its subject by read; the window of task t becomes "read" t of a second offset table over the
 	// genome's bases (the same bases, no copy), so the kernel runs as it is.
@@ -213,6 +217,7 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
 		mbref::Params P;
 		P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
 		P.dump_counts = dump_counts; P.dump_rows = dump_rows;
+		P.strings_for_printed_only = RefBackend::forward_only();
 		if (const char* e = getenv("MECAT_B200_REF_TABLE_MB")) P.table_budget = (int64_t)atoll(e) << 20;      // test hook: force several table batches
 		RefBackend be{c, dv, R->genome, {}};
 		const int rc = mbref::map_reads(be, in, P, out);

@@ -39,7 +39,7 @@ struct HostBackend
 	// what the extension hook needs: both volumes, unpacked
 	const uint32_t* rfwd = nullptr; const int32_t* roffsz = nullptr;
 	const uint32_t* gfwd = nullptr;
-	int64_t tasks_run = 0, batches = 0, rescue_units = 0;
+	int64_t tasks_run = 0, batches = 0, rescue_units = 0, string_tasks = 0;
 
 	template <class T> T* alloc(size_t n)
 	{
@@ -86,6 +86,7 @@ struct HostBackend
 			qa.resize((size_t)cap); ta.resize((size_t)cap);
 			int32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 			double ident = 0;
+			if (want_strings) ++string_tasks;
 			const int ok = orc_diff_go(q.data(), k.qstart, len, t.data(), k.sstart, k.swin_len, 1000, o, &ident, qa.data(), ta.data(), cap);
 			mecat_align_result& r = res[i];
 			memset(&r, 0, sizeof r);
@@ -162,8 +163,9 @@ int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_
 	P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
 	if (table_budget > 0) P.table_budget = table_budget;
 	P.dump_counts = dump_counts; P.dump_rows = dump_rows;
+	P.strings_for_printed_only = getenv("MECAT_HARNESS_STRINGS_FOR_PRINTED_ONLY") != NULL;
 	if (mbref::map_reads(be, in, P, sink)) { err = be.err; return 1; }
-	if (stats) { stats[0] += be.tasks_run; stats[1] += be.batches; stats[2] += be.rescue_units; }
+	if (stats) { stats[0] += be.tasks_run; stats[1] += be.batches; stats[2] += be.rescue_units; stats[3] += be.string_tasks; }
 	return 0;
 }
 
@@ -174,7 +176,7 @@ extern "C" {
 // mecat2ref -d reads -r reference -n num_candidates -b num_output -m format through the product's host I/O, stage
 // sequence and kernel bodies.  reads_per_call / table_budget force several ABI-sized calls and table batches.
 int harness_ref_map(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format, int reads_per_call,
-                    long table_budget, char** text, size_t* bytes, long* stats /* extensions that aligned, seed launches, clipped ends asked about */, char* errbuf, int errcap)
+                    long table_budget, char** text, size_t* bytes, long* stats /* extensions that aligned, seed launches, clipped ends asked about, extensions run with strings */, char* errbuf, int errcap)
 {
 	const int pack_threads = getenv("MECAT_HARNESS_PACK_THREADS") ? atoi(getenv("MECAT_HARNESS_PACK_THREADS")) : 3;
 	auto fail = [&](const std::string& m) { if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", m.c_str()); return 1; };
@@ -186,7 +188,7 @@ int harness_ref_map(const char* reference_path, const char* reads_path, int num_
 	const mecat_ref_genome gv = G.view();
 	index_genome(&gv, I);
 	std::string out;
-	if (stats) stats[0] = stats[1] = stats[2] = 0;
+	if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
 	const int total = (int)R.size();
 	if (reads_per_call < 1) reads_per_call = total ? total : 1;
 	mecat_ref_params p;

@@ -196,8 +196,8 @@ def test_small_table_and_arena_batches_give_the_same_records(refmap_inputs):
 
 
 def test_forward_only_extension_gives_the_same_m4_records(gpu_ctx, refmap_inputs, hard_inputs):
-    """MECAT_B200_REF_EXTEND=forward: the m4 format's extensions run through k_extend (forward pass only, the genome
-    windows as a second offset table) instead of the kernel that also writes alignment strings; same records."""
+    """MECAT_B200_REF_EXTEND=forward: extensions whose strings are not wanted run through k_extend (forward pass only, the
+    genome windows as a second offset table) instead of the kernel that also writes alignment strings; same records."""
     os.environ["MECAT_B200_REF_EXTEND"] = "forward"
     try:
         fa, genome = refmap_inputs
@@ -209,6 +209,13 @@ def test_forward_only_extension_gives_the_same_m4_records(gpu_ctx, refmap_inputs
         fa, genome = hard_inputs
         text, _ = map_through_abi(gpu_ctx, genome, fa, 1)
         assert sorted(text.splitlines()) == sorted(run_oracle(genome, fa, 10, 10, 1).splitlines())
+        # with strings wanted the same switch extends forward-only first and asks for the strings of the printed records
+        # only; the library itself checks that both kernels agree on every coordinate
+        gpu_ctx.reset_stats()
+        text, rec = map_through_abi(gpu_ctx, genome, fa, 0)
+        st = gpu_ctx.stats()
+        assert groups(text) == groups(golden("refmap_hard.ref.gz"))
+        assert st["kernel_launches"]["finalize"] > 0 and (rec["str_offset"] >= 0).all()
     finally:
         del os.environ["MECAT_B200_REF_EXTEND"]
 

@@ -19,7 +19,7 @@ GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))
 def run_harness(genome, fa, n=10, b=10, fmt=1, per_call=0, budget=0):
     L = util.ref_harness()
     text, nb = C.c_void_p(), C.c_size_t()
-    st = (C.c_long * 3)()
+    st = (C.c_long * 4)()
     err = C.create_string_buffer(512)
     rc = L.harness_ref_map(genome.encode(), fa.encode(), n, b, fmt, per_call, budget, C.byref(text), C.byref(nb), st, err, 512)
     assert rc == 0, err.value
@@ -136,6 +136,21 @@ def test_kernel_bodies_under_sanitizers(hard_inputs, repeat_inputs):
     for args in ([genome, fa, "10", "10", "0", "50", "200000"], [genome, fa, "3", "2", "2", "0", "0"], [rgenome, rfa, "40", "5", "1", "25", "3000000"]):
         p = subprocess.run([exe] + args, capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
         assert p.returncode == 0 and "rc=0" in p.stdout and "runtime error" not in p.stderr and "AddressSanitizer" not in p.stderr, p.stderr[-3000:]
+
+
+def test_strings_for_printed_records_only(hard_inputs, repeat_inputs, monkeypatch):
+    """The opt-in route that extends every candidate for its coordinates and computes alignment strings only for the
+    records that are printed: same text, far fewer extensions with strings on the repeat-rich genome."""
+    fa, genome = repeat_inputs
+    base, st0 = run_harness(genome, fa, 40, 5, 0, per_call=50)
+    monkeypatch.setenv("MECAT_HARNESS_STRINGS_FOR_PRINTED_ONLY", "1")
+    got, st1 = run_harness(genome, fa, 40, 5, 0, per_call=50)
+    assert got == base
+    assert st1[3] == len(groups(got)) and st1[3] * 3 < st0[3]
+    fa, genome = hard_inputs
+    assert groups(run_harness(genome, fa, fmt=0)[0]) == golden_groups("refmap_hard.ref.gz")
+    _, want = golden_sam()
+    assert sorted(run_harness(genome, fa, fmt=2, per_call=40)[0].splitlines()) == want
 
 
 def golden_sam():
