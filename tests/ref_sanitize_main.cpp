@@ -7,9 +7,9 @@
 extern "C" int harness_ref_map(const char*, const char*, int, int, int, int, long, char**, size_t*, long*, char*, int);
 int main(int argc, char** argv)
 {
-	char* text; size_t n; long st[3]; char err[512];
+	char* text; size_t n; long st[4]; char err[512];
 	int rc = harness_ref_map(argv[1], argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atol(argv[7]), &text, &n, st, err, 512);
-	printf("rc=%d bytes=%zu tasks=%ld batches=%ld rescue=%ld %s\n", rc, n, st[0], st[1], st[2], rc ? err : "");
+	printf("rc=%d bytes=%zu tasks=%ld batches=%ld rescue=%ld with_strings=%ld %s\n", rc, n, st[0], st[1], st[2], st[3], rc ? err : "");
 	free(text);
 	return rc;
 }
