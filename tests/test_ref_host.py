@@ -74,6 +74,16 @@ def repeat_inputs(tmp_path_factory):
     return fa, genome
 
 
+@pytest.fixture(scope="module")
+def repeat_small(repeat_inputs, tmp_path_factory):
+    """The first 40 reads of the repeat-rich fixture (for the slower instrumented runs)."""
+    fa, genome = repeat_inputs
+    small = str(tmp_path_factory.mktemp("refmap_repeats_small") / "reads.fa")
+    with open(fa, "rb") as f, open(small, "wb") as g:
+        g.write(b"".join(f.readlines()[:80]))
+    return small, genome
+
+
 def test_m4_matches_reference(refmap_inputs):
     fa, genome = refmap_inputs
     s, st = run_harness(genome, fa, fmt=1)
@@ -119,7 +129,7 @@ def test_repeat_rich_inputs_match_the_unmodified_binary(tmp_path, repeat_inputs,
     assert groups(got) == want
 
 
-def test_kernel_bodies_under_sanitizers(hard_inputs, repeat_inputs):
+def test_kernel_bodies_under_sanitizers(hard_inputs, repeat_small):
     """ASan + UBSan over the stage sequence and kernel bodies (small calls, tiny table budget, -n above the list sizes) on
     the hard fixture and on a repeat-rich one."""
     import subprocess
@@ -132,19 +142,19 @@ def test_kernel_bodies_under_sanitizers(hard_inputs, repeat_inputs):
     if util.stale(exe, util.REF_HOST_SOURCES) and subprocess.run(cmd, capture_output=True).returncode != 0:
         pytest.skip("this toolchain has no sanitizer runtime")
     fa, genome = hard_inputs
-    rfa, rgenome = repeat_inputs
+    rfa, rgenome = repeat_small
     for args in ([genome, fa, "10", "10", "0", "50", "200000"], [genome, fa, "3", "2", "2", "0", "0"], [rgenome, rfa, "40", "5", "1", "25", "3000000"]):
         p = subprocess.run([exe] + args, capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
         assert p.returncode == 0 and "rc=0" in p.stdout and "runtime error" not in p.stderr and "AddressSanitizer" not in p.stderr, p.stderr[-3000:]
 
 
-def test_strings_for_printed_records_only(hard_inputs, repeat_inputs, monkeypatch):
+def test_strings_for_printed_records_only(hard_inputs, repeat_small, monkeypatch):
     """The opt-in route that extends every candidate for its coordinates and computes alignment strings only for the
     records that are printed: same text, far fewer extensions with strings on the repeat-rich genome."""
-    fa, genome = repeat_inputs
-    base, st0 = run_harness(genome, fa, 40, 5, 0, per_call=50)
+    fa, genome = repeat_small
+    base, st0 = run_harness(genome, fa, 40, 5, 0, per_call=25)
     monkeypatch.setenv("MECAT_HARNESS_STRINGS_FOR_PRINTED_ONLY", "1")
-    got, st1 = run_harness(genome, fa, 40, 5, 0, per_call=50)
+    got, st1 = run_harness(genome, fa, 40, 5, 0, per_call=25)
     assert got == base
     assert st1[3] == len(groups(got)) and st1[3] * 3 < st0[3]
     fa, genome = hard_inputs
