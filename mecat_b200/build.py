@@ -39,7 +39,7 @@ def _newer(src_list, out):
 def _compile(cu):
     src = os.path.join(CSRC, cu)
     obj = os.path.join(OBJ, cu.replace(".cu", ".o"))
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns_pipeline.h"), os.path.join(CSRC, "cns_core.cuh"), os.path.join(CSRC, "ref_pipeline.h"), os.path.join(CSRC, "ref_core.cuh"),
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns_pipeline.h"), os.path.join(CSRC, "cns_core.cuh"), os.path.join(CSRC, "ref_pipeline.h"), os.path.join(CSRC, "ref_core.cuh"), os.path.join(CSRC, "dev_backend.cuh"),
             os.path.join(ROOT, "include", "mecat_b200.h")]
     if not _newer(deps, obj):
         return obj, ""

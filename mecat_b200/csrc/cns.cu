@@ -6,6 +6,7 @@
 // pool.  Inputs are the extension results exactly where align.cu left them in device memory; only the corrected
 // bases and a few counters per segment cross to the host.
 #include "common.cuh"
+#include "dev_backend.cuh"
 #include "cns_pipeline.h"
 
 namespace mb {
@@ -146,44 +147,10 @@ __global__ void __launch_bounds__(1024) k_cns_scan_apply(const int32_t* __restri
 	for (int k = 0; k < 4; ++k) if (i0 + k < n) { out[i0 + k] = run; run += v[k]; }
 }
 
-struct DevBackend
+struct DevBackend : PoolBackend
 {
-	Ctx* c;
-	std::vector<void*> owned;
+	explicit DevBackend(Ctx* ctx) : PoolBackend(ctx, "cns", false) {}
 
-	template <class T> T* alloc(size_t n)
-	{
-		void* p = nullptr;
-		const cudaError_t e = c->dmalloc(&p, (n ? n : 1) * sizeof(T));
-		if (e != cudaSuccess) {
-			char b[256];
-			snprintf(b, sizeof b, "cns: device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
-			c->err = b;
-			return nullptr;
-		}
-		owned.push_back(p);
-		return (T*)p;
-	}
-	bool check(cudaError_t e, const char* what)
-	{
-		if (e == cudaSuccess) return true;
-		char b[256];
-		snprintf(b, sizeof b, "cns: %s: %s", what, cudaGetErrorString(e));
-		c->err = b;
-		return false;
-	}
-	template <class T> bool upload(T* d, const T* h, size_t n)
-	{
-		if (!n) return true;
-		c->stats.h2d_bytes += (int64_t)(n * sizeof(T));
-		return check(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream), "H2D");
-	}
-	template <class T> bool download(T* h, const T* d, size_t n)
-	{
-		if (n && !check(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream), "D2H")) return false;
-		c->stats.d2h_bytes += (int64_t)(n * sizeof(T));
-		return check(cudaStreamSynchronize(c->stream), "kernel");
-	}
 	const char* download_staged(const char* d, size_t n)      // through the context's pinned staging buffer
 	{
 		void* h = nullptr;
@@ -193,7 +160,6 @@ struct DevBackend
 		if (!check(cudaStreamSynchronize(c->stream), "kernel")) return nullptr;
 		return (const char*)h;
 	}
-	bool fill(void* d, int byte, size_t bytes) { return !bytes || check(cudaMemsetAsync(d, byte, bytes, c->stream), "memset"); }
 	template <class F> bool launch(int64_t n, const F& f, int stage)
 	{
 		if (n <= 0) return true;
@@ -232,25 +198,10 @@ struct DevBackend
 		if (!check(cudaGetLastError(), "launch")) return false;
 		return download(total, out + n, 1);
 	}
-	bool release(void* p)      // the pool only marks the block free; work queued on the stream before the next owner's is ordered
-	{
-		for (size_t i = 0; i < owned.size(); ++i)
-			if (owned[i] == p) { c->dfree(p); owned[i] = owned.back(); owned.pop_back(); return true; }
-		c->err = "cns: release of an unknown block";
-		return false;
-	}
 	int64_t poa_budget_bytes() const
 	{
 		if (const char* e = getenv("MECAT_B200_POA_BUDGET_MB")) return (int64_t)atoll(e) << 20;      // test hook: force several waves
 		return 24ll << 30;
-	}
-	void fail(const char* m) { c->err = m; }
-	void end_batch()
-	{
-		cudaStreamSynchronize(c->stream);
-		for (void* p : owned) c->dfree(p);
-		owned.clear();
-		c->resolve_timers();
 	}
 };
 
@@ -258,7 +209,7 @@ struct DevBackend
 
 int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, CnsBlob& out)
 {
-	DevBackend be{c, {}};
+	DevBackend be(c);
 	return mbcns::consensus_batch(be, in, P, out);
 }
 

@@ -6,6 +6,7 @@
 // ordinary device volume with one "read"; its k-mer index is the index of index.cu built over a second offset table
 // that cuts the genome's ACGT runs into chunks, so that a chunk is one CTA's work and no k-mer spans another letter.
 #include "common.cuh"
+#include "dev_backend.cuh"
 #include "ref_pipeline.h"
 
 #include <algorithm>
@@ -21,62 +22,18 @@ __global__ void __launch_bounds__(128) k_ref(const F f, const int64_t n)
 	if (i < n) f(i);
 }
 
-struct RefBackend
+struct RefBackend : PoolBackend
 {
-	Ctx* c;
 	const DVolume* reads;
 	const DVolume* genome;
-	std::vector<void*> owned;
+	RefBackend(Ctx* ctx, const DVolume* r, const DVolume* g) : PoolBackend(ctx, "ref", true), reads(r), genome(g) {}
 
-	bool check(cudaError_t e, const char* what)
-	{
-		if (e == cudaSuccess) return true;
-		char b[256];
-		snprintf(b, sizeof b, "ref: %s: %s", what, cudaGetErrorString(e));
-		c->err = b;
-		return false;
-	}
-	template <class T> T* alloc(size_t n)
-	{
-		void* p = nullptr;
-		const cudaError_t e = c->dmalloc(&p, (n ? n : 1) * sizeof(T));
-		if (e != cudaSuccess) {
-			char b[256];
-			snprintf(b, sizeof b, "ref: device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
-			c->err = b;
-			return nullptr;
-		}
-		owned.push_back(p);
-		return (T*)p;
-	}
-	template <class T> bool upload(T* d, const T* h, size_t n)
-	{
-		if (!n) return true;
-		c->stats.h2d_bytes += (int64_t)(n * sizeof(T));
-		// the sources are host vectors that may go out of scope: finish the copy before returning
-		return check(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream), "H2D") &&
-		       check(cudaStreamSynchronize(c->stream), "H2D");
-	}
-	template <class T> bool download(T* h, const T* d, size_t n)
-	{
-		if (n && !check(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream), "D2H")) return false;
-		c->stats.d2h_bytes += (int64_t)(n * sizeof(T));
-		return check(cudaStreamSynchronize(c->stream), "kernel");
-	}
-	bool fill(void* d, int byte, size_t bytes) { return !bytes || check(cudaMemsetAsync(d, byte, bytes, c->stream), "memset"); }
 	template <class F> bool launch(int64_t n, const F& f, int stage)
 	{
 		if (n <= 0) return true;
 		KScope ks(c, MECAT_K_REF_COUNT + stage);
 		k_ref<F><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(f, n);
 		return check(cudaGetLastError(), "launch");
-	}
-	bool release(void* p)      // the pool only marks the block free; work queued on the stream before the next owner's is ordered
-	{
-		for (size_t i = 0; i < owned.size(); ++i)
-			if (owned[i] == p) { c->dfree(p); owned[i] = owned.back(); owned.pop_back(); return true; }
-		c->err = "ref: release of an unknown block";
-		return false;
 	}
 	bool align(const mecat_align_task* tasks, size_t n, bool want_strings, mecat_align_result* res, std::vector<char>& qs, std::vector<char>& ss)
 	{
@@ -131,14 +88,6 @@ struct RefBackend
 		return release(d_win) && release(d_tasks) && release(d_halves);
 	}
 	void note_hits(int64_t n) { c->stats.num_hits += n; }
-	void fail(const char* m) { c->err = m; }
-	void end_batch()
-	{
-		cudaStreamSynchronize(c->stream);
-		for (void* p : owned) c->dfree(p);
-		owned.clear();
-		c->resolve_timers();
-	}
 };
 
 }  // namespace
@@ -219,7 +168,7 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
 		P.dump_counts = dump_counts; P.dump_rows = dump_rows;
 		P.strings_for_printed_only = RefBackend::forward_only();
 		if (const char* e = getenv("MECAT_B200_REF_TABLE_MB")) P.table_budget = (int64_t)atoll(e) << 20;      // test hook: force several table batches
-		RefBackend be{c, dv, R->genome, {}};
+		RefBackend be(c, dv, R->genome);
 		const int rc = mbref::map_reads(be, in, P, out);
 		if (rc) be.end_batch();
 		return rc;
