@@ -114,6 +114,8 @@ int main(int argc, char* argv[])
 	if (o.tech != 0) { fprintf(stderr, "mecat2ref (b200): -x 1 (nanopore) is not on this path\n"); return 1; }
 	if (o.output_format < 0 || o.output_format > 2) { fprintf(stderr, "mecat2ref (b200): unknown output format %d (0 = ref, 1 = m4, 2 = sam)\n", o.output_format); return 1; }
 	const double t0 = now();
+	FILE* out = fopen(o.output, "w");          // before any work: an unwritable output should not cost a mapping run
+	if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
 	int ndev = 1;
 	if (const char* e = getenv("MECAT_GPUS")) ndev = std::max(1, atoi(e));
 	if (ndev > mecat_b200_device_count()) { fprintf(stderr, "mecat2ref (b200): MECAT_GPUS=%d but %d CUDA device(s) visible\n", ndev, mecat_b200_device_count()); return 1; }
@@ -217,8 +219,6 @@ int main(int argc, char* argv[])
 	const double t_map = now();
 
 	fprintf(stderr, "output file name: %s\n", o.output);
-	FILE* out = fopen(o.output, "w");
-	if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
 	if (o.output_format == 2) {
 		std::string head;
 		refio::sam_header(head, G, argc, argv);

@@ -401,6 +401,7 @@ def test_driver_option_handling(tmp_path, refmap_inputs):
     assert "nanopore" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-x", "1"], ok=False).stderr
     assert "CUDA device" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w], env={"MECAT_GPUS": "3"}, ok=False).stderr
     assert "cannot open" in run_driver(["-d", str(tmp_path / "missing.fa"), "-r", genome, "-o", out, "-w", w], ok=False).stderr
+    assert "for writing" in run_driver(["-d", fa, "-r", genome, "-o", str(tmp_path / "no" / "such" / "dir" / "o"), "-w", w], ok=False).stderr
     p = run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-m", "1", "-n", "2", "-b", "7"])
     assert "we reset it to 2" in p.stderr
     assert sorted(open(out).read().splitlines()) == sorted(run_oracle(genome, fa, 2, 2, 1).splitlines())
