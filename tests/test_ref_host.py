@@ -145,6 +145,8 @@ def test_kernel_bodies_under_sanitizers(hard_inputs, repeat_small):
     rfa, rgenome = repeat_small
     for args in ([genome, fa, "10", "10", "0", "50", "200000"], [genome, fa, "3", "2", "2", "0", "0"], [rgenome, rfa, "40", "5", "1", "25", "3000000"]):
         p = subprocess.run([exe] + args, capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+        if "Shadow memory range interleaves" in p.stderr or "ReserveShadowMemoryRange failed" in p.stderr:
+            pytest.skip("AddressSanitizer cannot start in this environment")
         assert p.returncode == 0 and "rc=0" in p.stdout and "runtime error" not in p.stderr and "AddressSanitizer" not in p.stderr, p.stderr[-3000:]
 
 
@@ -422,5 +424,7 @@ def test_driver_threads_under_thread_sanitizer(tmp_path, hard_inputs):
     out = str(tmp_path / "hard.ref")
     p = subprocess.run([exe, "-d", fa, "-r", genome, "-o", out, "-w", str(tmp_path / "w"), "-t", "4"], capture_output=True, text=True,
                        env=dict(os.environ, MECAT_B200_REF_BATCH_BASES="150000", MECAT_GPUS="2", MECAT_SHIM_DEVICES="2"))
+    if "FATAL: ThreadSanitizer" in p.stderr:
+        pytest.skip("ThreadSanitizer cannot start in this environment")
     assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
     assert groups(open(out).read()) == golden_groups("refmap_hard.ref.gz")
