@@ -42,16 +42,10 @@ inline int code_ci(unsigned char c)       // A0 C1 G2 T3 in either case, -1 for 
 }
 inline bool upper_acgt(unsigned char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
-struct Packer          // the reference's volume layout: base i in byte i >> 2 at shift ((~i) & 3) << 1
+struct Packed          // 2 bits per base in the reference's volume layout: base i in byte i >> 2 at shift ((~i) & 3) << 1
 {
 	std::vector<uint8_t> pac;
 	int64_t n = 0;
-	void push(int code)
-	{
-		if ((n & 3) == 0) pac.push_back(0);
-		pac.back() |= (uint8_t)(code << (((~n) & 3) << 1));
-		++n;
-	}
 };
 
 struct Chr { int64_t start = 0, size = 0; std::string name; };
@@ -59,7 +53,7 @@ struct Chr { int64_t start = 0, size = 0; std::string name; };
 struct Genome
 {
 	std::vector<Chr> chr;
-	Packer seq;                          // all sequences concatenated, letters other than ACGT packed as A
+	Packed seq;                          // all sequences concatenated, letters other than ACGT packed as A
 	std::vector<int64_t> runs;           // {start, length} of every maximal run of ACGT: no k-mer of the index spans another letter
 	mecat_ref_genome view() const
 	{
