@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <atomic>
 #include <fstream>
+#include <functional>
+#include <future>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -182,9 +184,30 @@ struct DeviceState
 	}
 };
 
-// One tile of process_one_volume's loop (pw_impl.cpp:859-879): query volume vid against the index of volume svid.
-bool process_tile(DeviceState& D, const Options& opt, int svid, int vid, const std::vector<std::string>& vols, std::string& text)
+// A query volume read from disk ahead of its tile (while the device is busy with the tile before it).
+struct Loaded
 {
+	int vid = -1;
+	bool ok = false;
+	mecat_volume vol;
+};
+
+Loaded load_query_volume(int vid, const std::vector<std::string>& vols)
+{
+	Loaded l;
+	l.vid = vid;
+	memset(&l.vol, 0, sizeof l.vol);
+	l.ok = mecat_b200_volume_load(vols[(size_t)vid].c_str(), &l.vol) == 0;
+	return l;
+}
+
+// One tile of process_one_volume's loop (pw_impl.cpp:859-879): query volume vid against the index of volume svid.
+// `pre`: the query volume if it was read ahead (consumed here), else it is read now.
+bool process_tile(DeviceState& D, const Options& opt, int svid, int vid, const std::vector<std::string>& vols, Loaded* pre, std::string& text)
+{
+	Loaded q;
+	if (pre && pre->vid == vid) { q = *pre; pre->vid = -1; pre->ok = false; }
+	struct Unloader { Loaded& l; ~Unloader() { if (l.ok) mecat_b200_volume_unload(&l.vol); } } unloader{q};
 	if (!D.use(svid, vols)) return false;
 	mecat_pw_params p = {opt.task, opt.num_candidates, opt.min_align_size, opt.min_kmer_match, opt.tech};
 	char info[64];
@@ -192,13 +215,12 @@ bool process_tile(DeviceState& D, const Options& opt, int svid, int vid, const s
 	StderrTimer t(info);
 	fprintf(stderr, "processing %s\n", vols[(size_t)vid].c_str());
 	void* dreads = D.dref;
-	mecat_volume reads;
-	memset(&reads, 0, sizeof reads);
 	bool ok = true;
 	if (vid != svid) {
-		if (mecat_b200_volume_load(vols[(size_t)vid].c_str(), &reads)) { fprintf(stderr, "failed to open file '%s'.\n", vols[(size_t)vid].c_str()); return false; }
+		if (q.vid != vid) q = load_query_volume(vid, vols);
+		if (!q.ok) { fprintf(stderr, "failed to open file '%s'.\n", vols[(size_t)vid].c_str()); return false; }
 		dreads = NULL;
-		ok = mecat_b200_volume_upload(D.ctx, &reads, &dreads) == 0;
+		ok = mecat_b200_volume_upload(D.ctx, &q.vol, &dreads) == 0;
 	}
 	void* rec = NULL;
 	size_t n = 0;
@@ -206,7 +228,7 @@ bool process_tile(DeviceState& D, const Options& opt, int svid, int vid, const s
 	if (ok) format_records(text, opt, rec, n);
 	else fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(D.ctx));
 	mecat_b200_free(D.ctx, rec);
-	if (vid != svid) { if (dreads) mecat_b200_volume_release(D.ctx, dreads); mecat_b200_volume_unload(&reads); }
+	if (vid != svid && dreads) mecat_b200_volume_release(D.ctx, dreads);
 	return ok;
 }
 
@@ -276,17 +298,25 @@ int main(int argc, char* argv[])
 	std::atomic<int> next(0), failed(0);
 	auto worker = [&](int dev) {
 		DeviceState D;
+		Loaded held;                                   // the volume read ahead for the tile this device takes next
 		D.ctx = dev == 0 ? ctx0 : NULL;
 		if (!D.ctx) {
 			StderrTimer t("gpu " + std::to_string(dev) + " init");
 			if (mecat_b200_init(&D.ctx, dev, NULL)) { fprintf(stderr, "mecat2pw: cannot initialise GPU %d\n", dev); failed = 1; return; }
 		}
-		for (;;) {
-			const int i = next.fetch_add(1);
-			if (i >= (int)tiles.size() || failed) break;
+		// A device holds one tile ahead of the one it works on, so that the query volume of the next tile is read from
+		// disk while the device is busy.
+		std::future<Loaded> ahead;
+		int i = next.fetch_add(1);
+		while (i < (int)tiles.size() && !failed) {
+			const int j = next.fetch_add(1);
+			if (j < (int)tiles.size() && tiles[(size_t)j].first != tiles[(size_t)j].second)
+				ahead = std::async(std::launch::async, load_query_volume, tiles[(size_t)j].second, std::cref(vols));
 			const int s = tiles[(size_t)i].first, v = tiles[(size_t)i].second;
 			Row& row = rows[(size_t)s];
-			if (!process_tile(D, opt, s, v, vols, row.text[(size_t)(v - s)])) { failed = 1; break; }
+			Loaded pre = held;
+			held = Loaded();
+			if (!process_tile(D, opt, s, v, vols, &pre, row.text[(size_t)(v - s)])) { failed = 1; break; }
 			if (row.left.fetch_sub(1) == 1) {          // the row is complete: r_s.working, then r_s
 				const std::string working = results_name(opt.wrk_dir, s, true), done = results_name(opt.wrk_dir, s, false);
 				std::ofstream out(working.c_str(), std::ios::binary);
@@ -295,7 +325,11 @@ int main(int argc, char* argv[])
 				out.close();
 				if (!out || rename(working.c_str(), done.c_str()) != 0) { failed = 1; break; }
 			}
+			if (ahead.valid()) held = ahead.get();
+			i = j;
 		}
+		if (ahead.valid()) held = ahead.get();
+		if (held.ok) mecat_b200_volume_unload(&held.vol);
 		D.drop();
 		StderrTimer t("gpu " + std::to_string(dev) + " release");
 		mecat_b200_destroy(D.ctx);
