@@ -1,7 +1,8 @@
 #!/bin/bash
 # One GPU-box pass that refreshes the evidence under gpurun_out/ (copied into profiles/ afterwards):
 # GPU tests, headline bench (both arms), ncu launch list + full capture of the dominant kernel of the bench,
-# ncu launch list + full capture of the mecat2cns kernels, command-line timings at 100 000 reads.
+# ncu launch list + full capture of the mecat2cns kernels, command-line timings at 100 000 reads, the mecat2ref pass
+# (tools/profile_ref.sh).
 set -x
 ROOT=${GRAFT_REPO_ROOT:-$(cd "$(dirname "$0")/.." && pwd)}
 cd $ROOT
@@ -13,4 +14,5 @@ ncu --set full --clock-control none --import-source on -k regex:'k_extend$' -c 8
 bash tools/profile_cns.sh 4000
 python tools/fullscale_cns.py --reads 100000 --skip-ref > gpurun_out/final_cns100k.log 2>&1; grep -E "kernel ms|takes|seconds|sha|records" gpurun_out/final_cns100k.log
 python tools/fullscale_parity.py --skip-ref > gpurun_out/final_pw100k.log 2>&1; grep -E "takes|seconds|sha|records" gpurun_out/final_pw100k.log
+bash tools/profile_ref.sh 20000 2000
 ls -la gpurun_out | tail -20
