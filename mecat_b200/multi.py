@@ -419,12 +419,9 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
         if rank == 0:
             log("warmup %d: %d pairs in %.2f s" % (i, n, dt))
     ctx.reset_stats()
-    for k in phase:
-        phase[k] = 0.0
     sampler = ClockSampler(local) if rank == 0 else None
     pairs, dt = timed(args.steps, False)
     stats = ctx.stats()
-    phase_ms = {k: round(v / args.steps, 3) for k, v in phase.items()}
     clocks = sampler.stop() if sampler else None
     esteps = max(1, min(args.steps, 2))
     ctx.reset_stats()

@@ -3,9 +3,7 @@ candidate walk, gapped extension on genome windows, clipped-end rescue -- throug
 mecat_b200_ref_map) and through the `mecat2ref` command-line driver, against the output of the UNMODIFIED reference binary
 (tests/golden/refmap*) and the pinned oracle.
 
-First hardware run pending: this file was written after the round's GPU minutes were spent.  The same stage sequence and
-kernel bodies pass these fixtures on the host (tests/test_ref_host.py); the file sorts after test_gpu.py so that the
-measured suites run first."""
+The same stage sequence and kernel bodies pass these fixtures on the host (tests/test_ref_host.py)."""
 import ctypes as C
 import gzip
 import hashlib
@@ -176,23 +174,40 @@ def test_repeat_rich_inputs_match_the_unmodified_binary(gpu_ctx, tmp_path, n, b)
     assert groups(text) == want
 
 
-def test_small_table_and_arena_batches_give_the_same_records(refmap_inputs):
-    """A 1 MB budget for the block tables cuts the 300 reads into many table batches, a 2 MB column arena cuts every
-    extension call into several launches (own context: both sizes are read when the context / the call starts)."""
+def _map_with_env(refmap_inputs, env):
+    """Own context: both budgets are read when the context / the call starts."""
     import mecat_b200
     fa, genome = refmap_inputs
-    os.environ["MECAT_B200_REF_TABLE_MB"] = "1"
-    os.environ["MECAT_B200_ALIGN_ARENA_MB"] = "2"
+    os.environ.update(env)
     try:
         with mecat_b200.Context(0) as ctx:
             text, _ = map_through_abi(ctx, genome, fa, 0)
             st = ctx.stats()
     finally:
-        del os.environ["MECAT_B200_REF_TABLE_MB"]
-        del os.environ["MECAT_B200_ALIGN_ARENA_MB"]
+        for k in env:
+            del os.environ[k]
+    return text, st["kernel_launches"]
+
+
+def test_small_table_batches_give_the_same_records(refmap_inputs):
+    """A 1 MB budget for the block tables cuts the 300 reads into several table batches."""
+    text, launches = _map_with_env(refmap_inputs, {"MECAT_B200_REF_TABLE_MB": "1"})
     assert groups(text) == groups(golden("refmap.ref.gz"))
-    assert st["kernel_launches"]["ref_seed"] >= 4
-    assert st["kernel_launches"]["extend"] > st["kernel_launches"]["ref_seed"]
+    assert launches["ref_seed"] >= 4
+
+
+def test_small_arena_batches_give_the_same_records(refmap_inputs):
+    """A 1 MB column arena cuts the extension call of the (single) table batch into several launches: 300 extensions of
+    6 kb reads on 2.2x windows need ~6 MB of columns."""
+    text, launches = _map_with_env(refmap_inputs, {"MECAT_B200_ALIGN_ARENA_MB": "1"})
+    assert groups(text) == groups(golden("refmap.ref.gz"))
+    assert launches["extend"] >= 3
+
+
+def test_small_table_and_arena_batches_together(refmap_inputs):
+    text, launches = _map_with_env(refmap_inputs, {"MECAT_B200_REF_TABLE_MB": "1", "MECAT_B200_ALIGN_ARENA_MB": "1"})
+    assert groups(text) == groups(golden("refmap.ref.gz"))
+    assert launches["ref_seed"] >= 4 and launches["extend"] >= launches["ref_seed"]
 
 
 def test_forward_only_extension_gives_the_same_m4_records(gpu_ctx, refmap_inputs, hard_inputs):
