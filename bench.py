@@ -19,7 +19,8 @@ A "step" is one pass of the hot path over the whole workload:
 `e2e`    = the same through the host-buffer C-ABI call (mecat_b200_pw_overlaps): pinned host
            volume -> H2D -> index -> tile -> D2H records, all inside the timed region.
 `--impl reference` times the UNMODIFIED reference binary (oracle/_ref/mecat2pw -j 1, all host
-threads) on a bounded sample of the same read model (see cpu_sample()).
+threads) on a bounded sample of the same read model (see sample_size(), cpu_sample()); its `config` names that sample
+and `cpu_baseline.full_size` carries the committed full-size run of the same binary.
 Inputs (>= 400 MB packed + 6 GB index) are far larger than the 126 MB L2: no flush needed.
 """
 import argparse
@@ -41,8 +42,27 @@ GENOME_PER_VOLUME = 100000000
 SEED = 11
 METRIC = "overlapped read-pairs/sec (mecat2pw)"
 UNIT = "pairs/s"
-SAMPLE_READS = 6000           # bounded CPU sample: 6 000 reads from a 6 Mb genome (same 15x coverage)
-SAMPLE_GENOME = 6000000
+REFERENCE_BUDGET_S = 240.0    # wall-clock budget of the reference arm's repetitions (the sample is never shrunk to fit it)
+
+
+def sample_size(cores):
+    """Bounded CPU sample: same read model and 15x coverage as the workload.  The reference hands reads to its threads in
+    chunks of 500 (CHUNK_SIZE, src/mecat2pw/pw_impl.h:15), so a sample needs >= 4 chunks per host thread or the threads
+    starve: 2 000 reads per thread, at least 20 000, at most 40 000 reads (a 16-thread run of 32 000 reads takes ~1 min)."""
+    reads = min(40000, max(20000, 2000 * cores))
+    return reads, reads * 1000
+
+
+def full_size_record():
+    """The committed full-size run of the unmodified binary on the workload itself (tools/fullscale_parity.py)."""
+    try:
+        r = json.load(open(os.path.join(ROOT, "profiles", "r1_fullscale_parity_100k_j1.json")))
+        return {"pairs": r["ref_records"], "seconds": round(r["ref_cli_seconds"], 2), "cores": r["cores"],
+                "value": round(r["ref_records"] / r["ref_cli_seconds"], 1), "unit": UNIT,
+                "what": "oracle/_ref/mecat2pw -j 1 -t %d on all %d reads, command-line wall clock, recorded once on a GPU box "
+                        "(profiles/r1_fullscale_parity_100k_j1.json); not re-measured by this run" % (r["cores"], r["reads"])}
+    except Exception:
+        return None
 
 
 def log(*a):
@@ -120,10 +140,10 @@ def cpu_sample(threads=None, keep=None):
     bounded sample and returns (pairs, seconds, cores, description)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "mecat2pw")
     cores = threads or os.cpu_count() or 1
-    desc = ("mecat2pw -j 1 -t %d on %d synthetic CLR reads (15 kb, 15%% err, genome %d, seed %d): same read model "
-            "and coverage as the workload, ~1/17 of its reads, so the index volume is 17x smaller and the CPU sees "
-            "~17x fewer random 13-mer hits per read than at full size (optimistic for the CPU)"
-            % (cores, SAMPLE_READS, SAMPLE_GENOME, SEED))
+    SAMPLE_READS, SAMPLE_GENOME = sample_size(cores)
+    desc = ("SAMPLE, not the full workload: unmodified mecat2pw -j 1 -t %d, command-line wall clock, on %d synthetic CLR reads "
+            "(15 kb, 15%% err, genome %d, seed %d): same read model and 15x coverage as the workload, %d chunks of 500 reads per "
+            "host thread" % (cores, SAMPLE_READS, SAMPLE_GENOME, SEED, SAMPLE_READS // 500 // cores))
     if not os.path.exists(exe):
         return None, None, cores, "oracle/_ref/mecat2pw not built", "unavailable"
     d = tmp_root()
@@ -144,28 +164,45 @@ def cpu_sample(threads=None, keep=None):
 
 
 def run_reference(args):
+    """Reference arm: the unmodified binary on the bounded sample.  The SAMPLE is sized for the host (sample_size) and the
+    number of REPETITIONS is what gets capped: runs are timed until --steps is reached or REFERENCE_BUDGET_S is spent
+    (one run of the sample takes about a minute; a warm-up run only when a run is short).  `config` names the sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     times, pairs = [], 0
-    for i in range(args.warmup + args.steps):
+    cores = os.cpu_count() or 1
+    t_all = time.perf_counter()
+    pairs, dt, cores, desc, kind = cpu_sample()
+    if pairs is None:
+        print(json.dumps({"impl": "reference", "unavailable": desc}))
+        return
+    log("[bench] reference run 0: %d pairs in %.2f s" % (pairs, dt))
+    warm = 0
+    if args.warmup > 0 and dt < 20.0:
+        warm = 1                      # a short run: treat the first one as warm-up (page cache, read generation)
+    else:
+        times.append(dt)
+    while len(times) < args.steps and (time.perf_counter() - t_all) + (times[-1] if times else dt) < REFERENCE_BUDGET_S:
         pairs, dt, cores, desc, kind = cpu_sample()
-        if pairs is None:
-            print(json.dumps({"impl": "reference", "unavailable": desc}))
-            return
-        if i >= args.warmup:
-            times.append(dt)
-        log("[bench] reference step %d: %d pairs in %.2f s" % (i, pairs, dt))
+        times.append(dt)
+        log("[bench] reference run %d: %d pairs in %.2f s" % (len(times) + warm - 1, pairs, dt))
     total = sum(times)
     value = pairs * len(times) / total
+    sreads, sgenome = sample_size(cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        # the workload of our arm at this N: the configs[1] tile in the default --mode strong, N volumes in --mode ring
-        "config": dict(workload_config(args.gpus if (args.gpus > 1 and args.mode == "ring") else 1),
-                       parallelism="reference CPU binary, %d host threads (no GPU)" % cores),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "repetitions": {"timed": len(times), "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
+                        "why": "each run is a whole mecat2pw job on the sample (~1 min); repetitions are capped at %d s of wall "
+                               "clock, the sample is not shrunk" % int(REFERENCE_BUDGET_S)},
+        "config": {"workload": "SAMPLE of the GPU arm's workload: mecat2pw -j 1 all-vs-all on %d synthetic PacBio-CLR reads (15 kb mean, "
+                               "15%% error, 15x) -- the GPU arm runs all %d reads; the CPU's full-size rate is in cpu_baseline.full_size"
+                               % (sreads, READS_PER_VOLUME),
+                   "reads": sreads, "genome": sgenome, "seed": SEED, "params": "-n 100 -a 2000 -k 4 -x 0",
+                   "parallelism": "reference CPU binary, %d host threads (no GPU)" % cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "full_size": full_size_record()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -196,8 +233,24 @@ def pinned_volume(vol):
     return hv
 
 
-def roofline_for(stats, peaks, nsteps=None):
-    """Roofline entry for the dominant kernel of the timed steps."""
+def ncu_counters():
+    """Per-unit counters taken from the committed ncu captures of this command (profiles/ncu_counters.json): DRAM bytes per
+    step and warp-instructions per extension block / per index hit.  They cannot be measured outside a profiler, so the
+    bench multiplies them with the unit counts and event times it measures live."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))
+    except Exception:
+        return {}
+
+
+def roofline_for(stats, peaks, nsteps=None, world=1, clocks=None):
+    """Roofline entries for the timed steps.  `world` > 1: the caller's statistics are one rank's
+    (strong mode); the index kernels then work on 1/world of the k-mer codes and every algorithmic figure is per rank.
+
+    * the entry itself: the dominant kernel against the HBM roof (the contract's form);
+    * "issue": the same kernel against the instruction-issue roof it actually runs into (4 warp schedulers per SM, one
+      warp-instruction per cycle each), plus furthest-point cells per second;
+    * "hbm_kernel": the largest kernel that IS bound by memory traffic (the hit-streaming `seed` kernel)."""
     km = stats["kernel_ms"]
     launches = stats["kernel_launches"]
     name = max(km, key=lambda k: km[k])
@@ -207,41 +260,66 @@ def roofline_for(stats, peaks, nsteps=None):
     C = stats["num_candidates"]
     ncodes = 1 << 26
     steps = nsteps or max(1, launches["index_scan"] // 3 or launches["index_count"])     # index builds in the timed region
+    w = float(max(1, world))
     algs = {
-        # bytes the algorithm must move, summed over the timed steps
-        "index_count": B / 4 + 4.0 * K + 4.0 * ncodes * steps,            # packed bases in, one counter update per k-mer
-        "index_fill": B / 4 + 4.0 * K + 8.0 * ncodes * steps,             # packed bases in, begin[] in, one position out per kept k-mer
-        "index_sort": 8.0 * K + 4.0 * ncodes * steps,                     # positions in and out, begin[] in
-        "index_scan": 12.0 * ncodes * steps,
+        # bytes the algorithm must move, summed over the timed steps; a rank of a strong-scaling run
+        # reads every packed base but histograms / fills / sorts only its slice of the codes
+        "index_count": B / 4 + (4.0 * K + 4.0 * ncodes * steps) / w,      # packed bases in, one counter update per k-mer
+        "index_fill": B / 4 + (4.0 * K + 8.0 * ncodes * steps) / w,       # packed bases in, begin[] in, one position out per kept k-mer
+        "index_sort": (8.0 * K + 4.0 * ncodes * steps) / w,               # positions in and out, begin[] in
+        "index_scan": 12.0 * ncodes * steps / w,
         "seed": 3 * 4.0 * H + 0.0,                                        # three streaming passes over the hit positions
         "extend": C * (2 * 15000 / 4 + 52 + 32),                          # two packed reads in, one record out per candidate
     }
-    alg = algs.get(name, 0.0)
-    ms = km[name]
-    achieved = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-    peak = peaks.get("hbm_gbs", 6650.0)
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (bytes per step of
-    # the whole workload, profiles/ncu_traffic.json), scaled to one launch like `achieved`
-    traffic = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        per_step = t.get(name, {}).get("dram_bytes_per_step")
-        if per_step and launches[name]:
-            traffic = per_step * steps / launches[name]
-    except Exception:
-        pass
+    cnt = ncu_counters()
+
+    def entry(kname):
+        alg = algs.get(kname, 0.0)
+        ms = km[kname]
+        achieved = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        peak = peaks.get("hbm_gbs", 6650.0)
+        # DRAM traffic from the committed `ncu --set full` capture of this command at N = 1 (bytes per step of the whole
+        # workload), scaled to one launch like `achieved`; a rank of an N-GPU run moves 1/N of it
+        traffic = None
+        per_step = cnt.get(kname, {}).get("dram_bytes_per_step")
+        if per_step and launches[kname]:
+            traffic = per_step * steps / w / launches[kname]
+        return {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "ms_per_launch": ms / max(1, launches[kname]), "launches": launches[kname],
+                "algorithmic_bytes_per_launch": alg / max(1, launches[kname]),
+                "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}
+
+    roof = entry(name)
+    peak = roof["peak"]
     every = {}
     for k, a in algs.items():
         if km.get(k, 0) > 0:
             g = a / (km[k] * 1e-3) / 1e9
             every[k] = {"ms_per_step": round(km[k] / steps, 3), "algorithmic_gb_per_step": round(a / steps / 1e9, 3),
                         "gbps": round(g, 1), "frac_of_hbm_peak": round(g / peak, 4) if peak else None}
-    return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "traffic": traffic,
-            "ms_per_launch": ms / max(1, launches[name]), "launches": launches[name],
-            "algorithmic_bytes_per_launch": alg / max(1, launches[name]), "all_kernels": every,
-            "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
-            "kernel_ms_share": {k: round(v / max(1e-9, sum(km.values())), 4) for k, v in km.items() if v > 0}}
+    roof["all_kernels"] = every
+    roof["kernel_ms_share"] = {k: round(v / max(1e-9, sum(km.values())), 4) for k, v in km.items() if v > 0}
+    # the issue roof of the extension kernel
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    sms = 148
+    blocks = stats.get("num_extend_blocks", 0)
+    cells = stats.get("num_extend_cells", 0)
+    wipb = cnt.get("extend", {}).get("warp_inst_per_block")
+    if km.get("extend", 0) > 0 and blocks:
+        sec = km["extend"] * 1e-3
+        issue_peak = 4.0 * sms * sm_mhz * 1e6
+        iss = {"kernel": "extend", "bound": "issue", "unit": "warp-instructions/s", "peak": issue_peak,
+               "peak_source": "4 schedulers x %d SMs x %.0f MHz (SM clock sampled during the timed region)" % (sms, sm_mhz),
+               "blocks_per_s": blocks / sec, "cells_per_s": cells / sec if cells else None,
+               "warp_inst_per_block": wipb, "warp_inst_source": cnt.get("extend", {}).get("source")}
+        if wipb:
+            iss["achieved"] = wipb * blocks / sec
+            iss["frac"] = iss["achieved"] / issue_peak
+        roof["issue"] = iss
+    if name != "seed" and km.get("seed", 0) > 0:
+        roof["hbm_kernel"] = entry("seed")
+    return roof
 
 
 def run_ours(args):
@@ -328,12 +406,13 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = roofline_for(stats, peaks, args.steps)
+    roof = roofline_for(stats, peaks, args.steps, clocks=clocks)
     cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "skipped (--no-cpu)"}
     if not args.no_cpu:
         cp, cdt, cores, desc, kind = cpu_sample()
         if cp is not None:
-            cb = {"value": cp / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "seconds": cdt, "pairs": cp}
+            cb = {"value": cp / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "seconds": cdt, "pairs": cp,
+                  "full_size": full_size_record()}
         else:
             cb = {"value": None, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     line = {

@@ -85,7 +85,7 @@ int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out)
 	const size_t pac_bytes = ((size_t)v->num_bases + 3) / 4;
 	const size_t src_words = (pac_bytes + 3) / 4;
 	uint32_t* d_pac = nullptr;
-	MB_CUDA(c, c->dmalloc((void**)&d_pac, src_words * 4 + 4));
+	MB_CUDA(c, c->dmalloc((void**)&d_pac, src_words * 4 + 8));      // an empty volume still gets its 8 zero bytes
 	cudaError_t e = cudaMemsetAsync(d_pac + (src_words ? src_words - 1 : 0), 0, 8, c->stream);
 	if (e == cudaSuccess && pac_bytes) e = cudaMemcpyAsync(d_pac, v->pac, pac_bytes, cudaMemcpyHostToDevice, c->stream);
 	if (e != cudaSuccess) { c->dfree(d_pac); MB_FAIL(c, "volume_upload: H2D: %s", cudaGetErrorString(e)); }

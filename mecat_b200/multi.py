@@ -264,7 +264,7 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
             "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()) // esteps,
                     "d2h_bytes_per_step": int(io[1].item()) // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
             "gpu_launches": stats["gpu_launches"] * world,
-            "roofline": roofline_for(stats, peaks, args.steps),
+            "roofline": roofline_for(stats, peaks, args.steps, world=world, clocks=clocks),
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                              "sample": "measured at N=1 only (bench.py --gpus 1)"},
             "pairs_per_step": pairs // args.steps,
@@ -446,7 +446,7 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
             "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(h2d[0].item()) // esteps,
                     "d2h_bytes_per_step": int(h2d[1].item()) // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
             "gpu_launches": stats["gpu_launches"] * world,
-            "roofline": roofline_for(stats, peaks),
+            "roofline": roofline_for(stats, peaks, clocks=clocks),
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                              "sample": "measured at N=1 only (bench.py --gpus 1)"},
             "pairs_per_step": pairs // args.steps,
