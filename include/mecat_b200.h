@@ -126,6 +126,8 @@ typedef struct {
 	float wall_index_ms, wall_seed_ms, wall_extend_ms, wall_other_ms;   /* host wall clock spent inside each phase */
 	int64_t h2d_bytes, d2h_bytes;
 	int64_t num_hits, num_candidates, num_extend_blocks, index_kmers, index_bases, num_records;
+	int64_t num_extend_cells;    /* furthest-point cell updates of the O(nd) extension (k_extend_lanes) */
+	int64_t num_extend_spills;   /* extension chains finished by the wide-band kernel                  */
 } mecat_b200_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */

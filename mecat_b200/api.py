@@ -47,7 +47,8 @@ class Stats(C.Structure):
                 ("wall_index_ms", C.c_float), ("wall_seed_ms", C.c_float), ("wall_extend_ms", C.c_float), ("wall_other_ms", C.c_float),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("num_hits", C.c_int64), ("num_candidates", C.c_int64), ("num_extend_blocks", C.c_int64),
-                ("index_kmers", C.c_int64), ("index_bases", C.c_int64), ("num_records", C.c_int64)]
+                ("index_kmers", C.c_int64), ("index_bases", C.c_int64), ("num_records", C.c_int64),
+                ("num_extend_cells", C.c_int64), ("num_extend_spills", C.c_int64)]
 
 
 class RefGenomeC(C.Structure):      # mecat_ref_genome

@@ -610,8 +610,12 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		const int nthreads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
 		// chunk ends as fractions of the candidates: the last chunks are small because the assembly of the
 		// final one is the only host work the GPU cannot hide
-		static const double cuts[] = {0.16, 0.32, 0.48, 0.64, 0.78, 0.89, 0.96, 1.0};
-		const int npipe = total >= 200000 ? (int)(sizeof cuts / sizeof cuts[0]) : 1;
+		static const double cuts8[] = {0.16, 0.32, 0.48, 0.64, 0.78, 0.89, 0.96, 1.0};
+		static const double cuts3[] = {0.45, 0.85, 1.0};
+		static const double cuts1[] = {1.0};
+		int npipe = total >= 200000 ? 8 : 1;
+		if (const char* e = getenv("MECAT_B200_PIPE")) npipe = atoi(e) >= 8 ? 8 : atoi(e) >= 3 ? 3 : 1;      // tuning hook
+		const double* cuts = npipe == 8 ? cuts8 : npipe == 3 ? cuts3 : cuts1;
 		std::vector<int> rcut((size_t)npipe + 1, N);
 		rcut[0] = 0;
 		for (int k = 1, r = 0; k < npipe; ++k) {
