@@ -329,8 +329,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 or args.mode == "ring":
         from mecat_b200 import multi
+        if world == 1:      # a single process still goes through torch.distributed (one-rank NCCL group)
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1"); os.environ.setdefault("LOCAL_RANK", "0")
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29581")
         fn = multi.run_bench if args.mode == "ring" else multi.run_bench_strong
         return fn(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for)
     torch.cuda.set_device(local)
@@ -445,8 +448,11 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="debug only: reduced workload (result is not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="strong", choices=["strong", "ring"],
-                    help="N > 1 only. strong: N GPUs share the configs[1] tile (default). ring: N volumes, "
-                         "N(N+1)/2 tiles, query volumes rotate over NCCL (BASELINE configs[4] style)")
+                    help="strong (default): N GPUs share the configs[1] tile. ring: the BASELINE configs[4] job -- --volumes "
+                         "volumes (default 8 x 125 000 reads = 1 M reads, 36 tiles) at any N that divides it, volume sets "
+                         "rotate over NCCL; also runs at N = 1 (the baseline of its 1 -> 8 scaling)")
+    ap.add_argument("--volumes", type=int, default=0, help="--mode ring: number of volumes (default 8)")
+    ap.add_argument("--ring-reads", type=int, default=0, help="--mode ring: reads per volume (default 125 000)")
     args = ap.parse_args()
     # Only the JSON line may reach stdout: libraries (NCCL prints its version there) go to stderr.
     real_stdout = os.dup(1)

@@ -77,6 +77,7 @@ struct ExtendSpill
 // Persistent warps: every warp pulls (candidate, direction) items from a global counter, so a
 // long chain never pins three idle warps of its CTA.  spills == nullptr: items 0 .. 2 ntasks - 1 from their start;
 // otherwise the nspills chains of the list, each resumed at its recorded block.
+template <bool RESUME>
 __global__ void __launch_bounds__(EXT_WARPS * 32, EXT_CTAS_PER_SM)
 k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, const int2* __restrict__ qoffsz, int qN,
          const uint32_t* __restrict__ sfwd, const uint32_t* __restrict__ srev, const int2* __restrict__ soffsz, int sN,
@@ -88,7 +89,8 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	WarpSmem& S = smem[warp];
 	unsigned nblocks = 0;
-	const unsigned long long nwork = spills ? nspills : 2ull * ntasks;
+	unsigned ncells = 0;                                    // < 2^32 per warp and launch
+	const unsigned long long nwork = RESUME ? nspills : 2ull * ntasks;
 
 	for (;;) {
 		unsigned long long item = 0;
@@ -97,7 +99,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 		if (item >= nwork) break;
 		ExtendSpill sp;
 		sp.item = (uint32_t)item; sp.qi = sp.ti = sp.cols = sp.mats = sp.qadv = sp.tadv = 0;
-		if (spills) { sp = spills[item]; item = sp.item; }
+		if (RESUME) { sp = spills[item]; item = sp.item; }
 		const ExtendTask t = tasks[item >> 1];
 		const int right = (int)(item & 1);
 
@@ -184,6 +186,7 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			for (int d = 0; d < max_d; ++d) {
 				if (max_k - min_k > 2 * tol) break;
 				const int n = ((max_k - min_k) >> 1) + 1;
+				ncells += (unsigned)n;
 				uint2* own = &S.vl[min_k + KOFF];                      // own[2j] <-> diagonal min_k + 2j; neighbours own[2j -+ 1]
 				const uint32_t dbits = (uint32_t)d << 20;
 				// pass 0: diagonals 0..31 of the band (most rows have no other pass)
@@ -303,7 +306,10 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			halves[item] = h;
 		}
 	}
-	if (lane == 0 && block_counter && nblocks) atomicAdd(block_counter, (unsigned long long)nblocks);
+	if (lane == 0 && block_counter && nblocks) {
+		atomicAdd(block_counter, (unsigned long long)nblocks);
+		atomicAdd(block_counter + 5, (unsigned long long)ncells);               // furthest-point cells (whole rows; the reference stops a row at the first end cell)
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -667,14 +673,22 @@ int extend_launch(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* 
 		const size_t want = (work + EXT_WARPS - 1) / EXT_WARPS;
 		const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)c->sm_count * EXT_CTAS_PER_SM);
 		KScope ks(c, MECAT_K_EXTEND);
-		k_extend<<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
-		                                                 s->num_bases, d_tasks, ntasks, d_halves, d_counter, d_counter + 4,
-		                                                 spills, nspills);
+		if (spills)
+			k_extend<true><<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
+			                                                       s->num_bases, d_tasks, ntasks, d_halves, d_counter, d_counter + 4,
+			                                                       spills, nspills);
+		else
+			k_extend<false><<<grid, EXT_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz,
+			                                                        s->num_bases, d_tasks, ntasks, d_halves, d_counter, d_counter + 4,
+			                                                        nullptr, 0);
 	};
 	auto body = [&]() -> int {
 		if (mode == 0) {
 			wide(nullptr, 0);
 			MB_CUDA(c, cudaGetLastError());
+			MB_CUDA(c, cudaMemcpyAsync(h, d_counter, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+			MB_CUDA(c, cudaStreamSynchronize(c->stream));
+			c->stats.num_extend_cells += (int64_t)h[5];
 		} else {
 			MB_CUDA(c, c->alloc(&d_spills, items));
 			const size_t smem = (size_t)PR_WARPS * PR_WARP_WORDS * sizeof(uint32_t);

@@ -70,9 +70,8 @@ def run_ring(world, rank, own_block, buf_a, buf_b, exchange, compute):
                 spare = other
 
 
-def code_slices(world):
+def code_slices(world, n=1 << 26):
     """Equal slices of the 2^26 k-mer codes, aligned to 256 codes (the index kernels' granularity)."""
-    n = 1 << 26
     cuts = [((n * r // world) // 256) * 256 for r in range(world)] + [n]
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
@@ -129,140 +128,212 @@ def device_view(ptr, count, torch_dtype, itemsize):
     return torch.as_tensor(_DevMem(ptr, count * itemsize), device="cuda").view(torch_dtype)
 
 
-# ------------------------------------------------------------------------------------------ benchmark (strong scaling)
-def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for):
-    """N GPUs share ONE tile (BASELINE configs[1]): every rank holds the packed volume, builds the
-    slice [code_lo, code_hi) of the k-mer index, the slices are exchanged over NCCL (all-gather of the
-    histogram, broadcast of every position slice), and rank r seeds / extends reads r*n/N..(r+1)*n/N."""
+# ------------------------------------------------------------------------------------------ bench plumbing
+class Env:
+    """What the two bench drivers below need from the machine: the process group, the device, a context of the library.
+    On a GPU box that is NCCL + cuda:<local rank> + mecat_b200.Context; the CPU suite injects gloo + "cpu" + a stub
+    context (tests/test_multi.py), so the drivers' control flow runs in the `-m "not gpu"` tests as well."""
+
+    def __init__(self, dist, torch, rank, world, device, ctx, ncodes=1 << 26, pin=True):
+        self.dist, self.torch, self.rank, self.world, self.device, self.ctx = dist, torch, rank, world, device, ctx
+        self.ncodes, self.pin = ncodes, pin
+        self.cuda = str(device).startswith("cuda")
+
+    def sync(self):
+        if self.cuda:
+            self.torch.cuda.synchronize()
+
+    def view(self, ptr, count, dtype, itemsize):
+        """Library device memory as a tensor (zero copy); the stub context hands out tensors directly."""
+        if not self.cuda:
+            return ptr[:count]
+        return device_view(ptr, count, dtype, itemsize)
+
+    def pinned(self, t):
+        return t.pin_memory() if (self.cuda and self.pin) else t
+
+    def log(self, *a):
+        print("[bench r%d]" % self.rank, *a, file=sys.stderr, flush=True)
+
+    def timed(self, nsteps, one_step, *args):
+        """Barrier + device sync on both sides, MAX over ranks of the wall time, SUM over ranks of the records."""
+        torch, dist = self.torch, self.dist
+        dist.barrier(); self.sync()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(nsteps):
+            n += one_step(*args)
+        self.sync(); dist.barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([n], dtype=torch.int64, device=self.device)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return int(c.item()), float(t.item())
+
+
+def gpu_env():
     import torch
     import torch.distributed as dist
     import mecat_b200
-
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    env = Env(dist, torch, rank, world, dev, mecat_b200.Context(local))
+    env.local = local
+    return env
 
-    def log(*a):
-        print("[bench r%d]" % rank, *a, file=sys.stderr, flush=True)
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def byte_slices(nbytes, world):
+    """Equal 16-byte aligned slices of the packed volume: every rank uploads one, NVLink carries the rest."""
+    chunk = ((nbytes + world - 1) // world + 15) // 16 * 16
+    return chunk, [(min(nbytes, r * chunk), min(nbytes, (r + 1) * chunk)) for r in range(world)]
+
+
+# ------------------------------------------------------------------------------------------ benchmark (strong scaling)
+def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for,
+                     env=None, volume=None):
+    """N GPUs share ONE tile (BASELINE configs[1]): every rank builds the slice [code_lo, code_hi) of the k-mer index,
+    the slices are exchanged over NCCL (all-gather of the histogram, padded all-gather of the position slices), and rank r
+    seeds / extends its slice of the query reads.  End to end every rank uploads 1/N of the packed volume over PCIe and
+    the ranks all-gather it over NVLink (one 0.4 GB input, not N uploads of it).
+    `env` / `volume`: injected by the CPU tests (gloo, stub context, small volume)."""
+    import mecat_b200
+    env = env or gpu_env()
+    torch, dist, ctx, rank, world, dev = env.torch, env.dist, env.ctx, env.rank, env.world, env.device
+    log = env.log
 
     READS, GENOME, SEED = 100000, 100000000, 11
     if args.reads:
         READS = args.reads; GENOME = args.reads * 1000
-    d = tmp_root()
-    fa = os.path.join(d, "reads_%d_%d.fa" % (READS, SEED))
-    wrk = os.path.join(d, "wrk_%d" % READS)
-    if rank == 0:
-        make_reads(fa, READS, GENOME, SEED)
-        mecat_b200.split_dataset(fa, wrk)
-    dist.barrier()
-    vol = mecat_b200.HostVolume.load(os.path.join(wrk, "vol0"))
-    pac = torch.empty(len(vol.pac), dtype=torch.uint8, pin_memory=True)
-    pac.numpy()[:] = vol.pac
-    osz = torch.from_numpy(vol.offset_size.reshape(-1).copy()).pin_memory()
-    hv = mecat_b200.HostVolume(osz.numpy().reshape(-1, 2), pac.numpy(), vol.num_bases, 0)
-    hv._keep = (pac, osz)
+    if volume is None:
+        d = tmp_root()
+        fa = os.path.join(d, "reads_%d_%d.fa" % (READS, SEED))
+        wrk = os.path.join(d, "wrk_%d" % READS)
+        if rank == 0:
+            make_reads(fa, READS, GENOME, SEED)
+            mecat_b200.split_dataset(fa, wrk)
+        dist.barrier()
+        volume = mecat_b200.HostVolume.load(os.path.join(wrk, "vol0"))
+    vol = volume
+    nbytes = len(vol.pac)
+    chunk, bsl = byte_slices(nbytes, world)
+    pac = env.pinned(torch.zeros(chunk * world, dtype=torch.uint8))
+    pac.numpy()[:nbytes] = vol.pac
+    osz = env.pinned(torch.from_numpy(vol.offset_size.reshape(-1).copy()))
+    osz_np = vol.offset_size.reshape(-1, 2)
     params = mecat_b200.pw_params(task=1)
-    ctx = mecat_b200.Context(local)
-    lo, hi = code_slices(world)[rank]
+    lo, hi = code_slices(world, env.ncodes)[rank]
     rb, re = read_slices(world, vol.num_reads)[rank]
-    cuts = torch.tensor([c[0] for c in code_slices(world)] + [1 << 26], dtype=torch.int64, device=dev)
+    cuts = torch.tensor([c[0] for c in code_slices(world, env.ncodes)] + [env.ncodes], dtype=torch.int64, device=dev)
     resident = [None]
+    pac_d = torch.empty(chunk * world, dtype=torch.uint8, device=dev)
     # index exchange: "allgather" = one padded all-gather of the position slices (all NVLink ports busy at once) followed by
     # a device-side compaction; "broadcast" = one broadcast per slice (the first implementation, kept for comparison)
     exchange = os.environ.get("MECAT_STRONG_EXCHANGE", "allgather")
-    phase = {"count": 0.0, "counts_allgather": 0.0, "finish": 0.0, "positions_exchange": 0.0, "tile": 0.0}
+    phase = {"upload": 0.0, "count": 0.0, "counts_allgather": 0.0, "finish": 0.0, "positions_exchange": 0.0, "tile": 0.0}
+    io = {"h2d": 0, "nvlink": 0}
 
     def lap(name, t0):
-        torch.cuda.synchronize()
+        env.sync()
         t1 = time.perf_counter()
         phase[name] += (t1 - t0) * 1e3
         return t1
+
+    def upload():
+        # own byte slice over PCIe, the other N - 1 over NVLink
+        a, b = bsl[rank]
+        mine = pac_d[rank * chunk:(rank + 1) * chunk]
+        mine[:b - a].copy_(pac[a:b], non_blocking=True)
+        io["h2d"] += (b - a) + osz.numel() * 4
+        if world > 1:
+            dist.all_gather_into_tensor(pac_d, mine.clone())
+            io["nvlink"] += (world - 1) * chunk
+        env.sync()
+        return ctx.volume_from_device(vol.num_reads, vol.num_bases, 0, osz_np, pac_d.data_ptr() if env.cuda else pac_d)
 
     def one_step(e2e):
         t0 = time.perf_counter()
         if e2e or resident[0] is None:
             if resident[0] is not None:
                 ctx.release_volume(resident[0])
-            resident[0] = ctx.upload(hv)
+            resident[0] = upload()
         dvol = resident[0]
+        t0 = lap("upload", t0)
         idx = ctx.index_count_part(dvol, lo, hi)
         t0 = lap("count", t0)
         cptr, bptr, _, _ = ctx.index_device_arrays(idx)
-        counts = device_view(cptr, 1 << 26, torch.int32, 4)
+        counts = env.view(cptr, env.ncodes, torch.int32, 4)
         if world > 1:
-            parts = [counts[a:b] for a, b in code_slices(world)]
+            parts = [counts[a:b] for a, b in code_slices(world, env.ncodes)]
             if len({p.numel() for p in parts}) == 1:
                 dist.all_gather_into_tensor(counts, parts[rank].clone())
             else:
                 for q in range(world):
                     dist.broadcast(parts[q], src=q)
-            torch.cuda.synchronize()
+            env.sync()
         t0 = lap("counts_allgather", t0)
         ctx.index_finish_part(dvol, idx, lo, hi)
         t0 = lap("finish", t0)
         if world > 1:
             _, bptr, pptr, nk = ctx.index_device_arrays(idx)
-            begin = device_view(bptr, (1 << 26) + 1, torch.int32, 4)
+            begin = env.view(bptr, env.ncodes + 1, torch.int32, 4)
             bounds = begin[cuts].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-            pos = device_view(pptr, nk, torch.int32, 4)
+            pos = env.view(pptr, nk, torch.int32, 4)
             exchange_slices(dist, pos, bounds, rank, world, exchange)
-            torch.cuda.synchronize()
+            env.sync()
         t0 = lap("positions_exchange", t0)
         rec = ctx.pw_tile_range(idx, dvol, dvol, params, rb, re)
         ctx.release_index(idx)
         lap("tile", t0)
         return len(rec)
 
-    def timed(nsteps, e2e):
-        dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n = 0
-        for _ in range(nsteps):
-            n += one_step(e2e)
-        torch.cuda.synchronize(); dist.barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([n], dtype=torch.int64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        return int(c.item()), float(t.item())
-
     for i in range(args.warmup):
-        n, dt = timed(1, False)
+        n, dt = env.timed(1, one_step, False)
         if rank == 0:
             log("warmup %d: %d pairs in %.3f s" % (i, n, dt))
     ctx.reset_stats()
     for k in phase:
         phase[k] = 0.0
-    sampler = ClockSampler(local) if rank == 0 else None
-    pairs, dt = timed(args.steps, False)
+    sampler = ClockSampler(getattr(env, "local", 0)) if rank == 0 else None
+    pairs, dt = env.timed(args.steps, one_step, False)
     stats = ctx.stats()
     phase_ms = {k: round(v / args.steps, 3) for k, v in phase.items()}
     clocks = sampler.stop() if sampler else None
     esteps = max(1, min(args.steps, 3))
     ctx.reset_stats()
-    epairs, edt = timed(esteps, True)
+    io["h2d"] = io["nvlink"] = 0
+    for k in phase:
+        phase[k] = 0.0
+    epairs, edt = env.timed(esteps, one_step, True)
     estats = ctx.stats()
-    io = torch.tensor([estats["h2d_bytes"], estats["d2h_bytes"]], dtype=torch.int64, device=dev)
-    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    ephase_ms = {k: round(v / esteps, 3) for k, v in phase.items()}
+    iot = torch.tensor([estats["h2d_bytes"] + io["h2d"], estats["d2h_bytes"], io["nvlink"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(iot, op=dist.ReduceOp.SUM)
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = measured_peaks()
         cfg = workload_config(1)
         cfg["parallelism"] = ("%d gpus sharing one tile: k-mer index built in %d code slices exchanged over NCCL "
-                              "(all-gather), query reads split %d ways" % (world, world, world))
+                              "(all-gather), query reads split %d ways; end to end each rank uploads 1/%d of the packed "
+                              "volume and the ranks all-gather it over NVLink" % (world, world, world, world))
         if args.reads:
             cfg = dict(cfg, reads=READS, genome=GENOME, workload="REDUCED debug workload (%d reads)" % READS)
         line = {
             "metric": METRIC, "value": pairs / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()) // esteps,
-                    "d2h_bytes_per_step": int(io[1].item()) // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
+            "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(iot[0].item()) // esteps,
+                    "d2h_bytes_per_step": int(iot[1].item()) // esteps, "nvlink_bytes_per_step": int(iot[2].item()) // esteps,
+                    "ms_per_step": 1000.0 * edt / esteps, "steps": esteps, "phase_ms_per_step_rank0": ephase_ms},
             "gpu_launches": stats["gpu_launches"] * world,
             "roofline": roofline_for(stats, peaks, args.steps, world=world, clocks=clocks),
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
@@ -276,63 +347,111 @@ def run_bench_strong(args, METRIC, UNIT, workload_config, make_reads, tmp_root, 
         ctx.release_volume(resident[0])
     ctx.close()
     dist.destroy_process_group()
+    return line
 
 
 # ------------------------------------------------------------------------------------------ benchmark (block rotation)
-def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for):
-    import torch
-    import torch.distributed as dist
+def volume_sets(world, volumes):
+    """Volumes owned by each rank (consecutive, volumes % world == 0)."""
+    p = volumes // world
+    return [list(range(r * p, (r + 1) * p)) for r in range(world)]
+
+
+def ring_work(world, rank, step, volumes, reads_in_volume):
+    """Work items (index volume s, query volume v, read_begin, read_end) of one ring step of the V-volume job: the set of
+    volumes resident on `rank` at `step` is the one `rank - step` owns; the rank serves the index volumes of its own set
+    and of its mirror rank's set, and the two ranks of a pair split every visiting volume's reads (a diagonal tile at
+    the point that balances its triangular extension work, read_slices)."""
+    sets = volume_sets(world, volumes)
+    mirror = world - 1 - rank
+    served = sorted(set(sets[rank]) | set(sets[mirror]))
+    items = []
+    for v in sets[block_at(world, rank, step)]:
+        for s in served:
+            if s > v:
+                continue
+            n = reads_in_volume[v]
+            if mirror == rank:
+                rb, re = 0, n
+            else:
+                cut = read_slices(2, n, diagonal=(s == v))[0][1]
+                rb, re = (0, cut) if rank < mirror else (cut, n)
+            if re > rb:
+                items.append((s, v, rb, re))
+    return items
+
+
+def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for,
+              env=None, host_volumes=None):
+    """BASELINE configs[4] as a strong-scaling job: V volumes (default 8 x 125 000 reads = 1 M reads over a 1 Gb genome,
+    36 tiles), the same at every N that divides V.  Rank g owns V/N volumes, keeps the k-mer indices of its own and of
+    rank N-1-g's volumes, and the packed volume sets rotate round the ring of ranks over NCCL send/recv (double buffered
+    behind the compute).  N = 1 runs all tiles on one device -- the baseline of the 1 -> 8 scaling figure.
+    `env` / `host_volumes`: injected by the CPU tests (gloo, stub context, small volumes)."""
     import mecat_b200
+    env = env or gpu_env()
+    torch, dist, ctx, rank, world, dev = env.torch, env.dist, env.ctx, env.rank, env.world, env.device
+    log = env.log
 
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-
-    def log(*a):
-        print("[bench r%d]" % rank, *a, file=sys.stderr, flush=True)
-
-    READS, GENOME, SEED = 100000, 100000000, 11
+    V = args.volumes or 8
+    if V % world:
+        raise SystemExit("--mode ring needs a number of volumes (%d) that the number of GPUs (%d) divides" % (V, world))
+    READS, SEED = args.ring_reads or 125000, 11
     if args.reads:
-        READS = args.reads; GENOME = args.reads * 1000
-    d = tmp_root()
-    fa = os.path.join(d, "reads_w%d_r%d_%d_%d.fa" % (world, rank, READS, SEED))
-    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "gen_reads")
-    if not (os.path.exists(fa) and os.path.getsize(fa) > READS * 2000):
+        READS = args.reads
+    GENOME = READS * 1000                                    # 15x of 15 kb reads, per volume
+    sets = volume_sets(world, V)
+    own_vols = sets[rank]
+    p = len(own_vols)
+    if host_volumes is None:
+        d = tmp_root()
+        exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "gen_reads")
+        host_volumes = {}
         import subprocess
-        # reads [rank*READS, (rank+1)*READS) of the N*READS-read data set over the N*GENOME genome
-        subprocess.check_call([exe, fa + ".tmp", str(READS), str(GENOME * world), str(SEED), "15000", "1500", "0.15", "-",
-                               str(rank * READS)])
-        os.replace(fa + ".tmp", fa)
-    wrk = os.path.join(d, "wrk_w%d_r%d_%d" % (world, rank, READS))
-    names = mecat_b200.split_dataset(fa, wrk)
-    assert len(names) == 1
-    vol = mecat_b200.HostVolume.load(names[0])
-    vol.start_read_id = rank * READS
-    os.remove(fa)
+        for v in own_vols:
+            fa = os.path.join(d, "reads_V%d_v%d_%d_%d.fa" % (V, v, READS, SEED))
+            wrk = os.path.join(d, "wrk_V%d_v%d_%d" % (V, v, READS))
+            if not os.path.exists(os.path.join(wrk, "vol0")):
+                # reads [v*READS, (v+1)*READS) of the V*READS-read data set over the V*GENOME genome: the same data at every N
+                subprocess.check_call([exe, fa + ".tmp", str(READS), str(GENOME * V), str(SEED), "15000", "1500", "0.15", "-",
+                                       str(v * READS)])
+                os.replace(fa + ".tmp", fa)
+                names = mecat_b200.split_dataset(fa, wrk)
+                assert len(names) == 1, "a ring volume must fit one volume file"
+                os.remove(fa)
+            hv = mecat_b200.HostVolume.load(os.path.join(wrk, "vol0"))
+            hv.start_read_id = v * READS
+            host_volumes[v] = hv
     # pinned host copies (source of the H2D inside the e2e region)
-    pac_h = torch.empty((len(vol.pac) + 3) // 4 * 4, dtype=torch.uint8, pin_memory=True)
-    pac_h.zero_(); pac_h.numpy()[:len(vol.pac)] = vol.pac
-    osz_h = torch.from_numpy(vol.offset_size.reshape(-1).copy()).pin_memory()
+    pac_h, osz_h = {}, {}
+    for v in own_vols:
+        hv = host_volumes[v]
+        t = env.pinned(torch.zeros((len(hv.pac) + 3) // 4 * 4, dtype=torch.uint8))
+        t.numpy()[:len(hv.pac)] = hv.pac
+        pac_h[v] = t
+        osz_h[v] = env.pinned(torch.from_numpy(hv.offset_size.reshape(-1).copy()))
 
-    # every rank learns every block's shape
-    meta = torch.tensor([vol.num_reads, vol.num_bases, vol.start_read_id, pac_h.numel()], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta)
-    metas = [tuple(int(x) for x in m.tolist()) for m in metas]
+    # every rank learns every volume's shape
+    meta = torch.zeros((V, 4), dtype=torch.int64, device=dev)
+    for v in own_vols:
+        hv = host_volumes[v]
+        meta[v] = torch.tensor([hv.num_reads, hv.num_bases, hv.start_read_id, pac_h[v].numel()], dtype=torch.int64)
+    dist.all_reduce(meta, op=dist.ReduceOp.SUM)
+    metas = [tuple(int(x) for x in m.tolist()) for m in meta.cpu()]
     max_pac = max(m[3] for m in metas); max_reads = max(m[0] for m in metas)
-    reads_in_block = [m[0] for m in metas]
+    reads_in_volume = [m[0] for m in metas]
     nxt, prv = ring_neighbours(world, rank)
+    mirror = world - 1 - rank
     params = mecat_b200.pw_params(task=1)
-    ctx = mecat_b200.Context(local)
 
-    class Block:
+    class Block:                                              # one rank's set of packed volumes in device memory
         def __init__(self):
-            self.pac = torch.empty(max_pac, dtype=torch.uint8, device=dev)
-            self.osz = torch.empty(max_reads * 2, dtype=torch.int32, device=dev)
-            self.v = -1
+            self.pac = [torch.empty(max_pac, dtype=torch.uint8, device=dev) for _ in range(p)]
+            self.osz = [torch.empty(max_reads * 2, dtype=torch.int32, device=dev) for _ in range(p)]
+            self.v = -1                                       # owner rank of the set it holds
 
-    bufs = [Block(), Block(), Block(), Block()]     # own block, two ring buffers, the mirror's block
+    nbuf = 1 if world == 1 else (3 if mirror == rank else 4)  # own set, two ring buffers, the mirror's set
+    bufs = [Block() for _ in range(nbuf)]
 
     class Handle:
         def __init__(self, reqs, blk, v):
@@ -344,115 +463,126 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
             self.blk.v = self.v
 
     def exchange_with(dst, src, send_blk, recv_blk, recv_v):
-        ops = [dist.P2POp(dist.isend, send_blk.pac, dst), dist.P2POp(dist.isend, send_blk.osz, dst),
-               dist.P2POp(dist.irecv, recv_blk.pac, src), dist.P2POp(dist.irecv, recv_blk.osz, src)]
+        ops = []
+        for i in range(p):
+            ops += [dist.P2POp(dist.isend, send_blk.pac[i], dst), dist.P2POp(dist.isend, send_blk.osz[i], dst)]
+        for i in range(p):
+            ops += [dist.P2POp(dist.irecv, recv_blk.pac[i], src), dist.P2POp(dist.irecv, recv_blk.osz[i], src)]
         return Handle(dist.batch_isend_irecv(ops), recv_blk, recv_v)
 
-    def dvolume_of(blk):
-        nr, nb, sid, _ = metas[blk.v]
-        torch.cuda.synchronize()
-        osz = blk.osz[:2 * nr].cpu().numpy().reshape(-1, 2)
-        return ctx.volume_from_device(nr, nb, sid, osz, blk.pac.data_ptr())
+    def dvolumes_of(blk):
+        env.sync()
+        out = {}
+        for i, v in enumerate(sets[blk.v]):
+            nr, nb, sid, _ = metas[v]
+            osz = blk.osz[i][:2 * nr].cpu().numpy().reshape(-1, 2)
+            out[v] = ctx.volume_from_device(nr, nb, sid, osz, blk.pac[i].data_ptr() if env.cuda else blk.pac[i])
+        return out
+
+    io = {"h2d": 0, "nvlink": 0}
 
     def one_step(e2e):
         """Whole job once.  Returns the number of records this rank produced."""
-        own, ring_a, ring_b, mir = bufs
-        # own block to the device (inside the timed region only for e2e; resident otherwise)
+        own = bufs[0]
+        # own volumes to the device (inside the timed region only for e2e; resident otherwise)
         if e2e or own.v != rank:
-            own.pac[:pac_h.numel()].copy_(pac_h, non_blocking=True)
-            own.osz[:osz_h.numel()].copy_(osz_h, non_blocking=True)
+            for i, v in enumerate(own_vols):
+                own.pac[i][:pac_h[v].numel()].copy_(pac_h[v], non_blocking=True)
+                own.osz[i][:osz_h[v].numel()].copy_(osz_h[v], non_blocking=True)
+                io["h2d"] += pac_h[v].numel() + osz_h[v].numel() * 4
             own.v = rank
-        mirror = world - 1 - rank
         dvols, idxs = {}, {}
         h = None
         if mirror != rank:
-            h = exchange_with(mirror, mirror, own, mir, mirror)
-        dvols[rank] = dvolume_of(own)
-        idxs[rank] = ctx.index_build(dvols[rank])
+            h = exchange_with(mirror, mirror, own, bufs[3], mirror)
+            io["nvlink"] += p * (max_pac + max_reads * 8)
+        dvols.update(dvolumes_of(own))
+        for v in own_vols:
+            idxs[v] = ctx.index_build(dvols[v])
         if h is not None:
             h.wait()
-            dvols[mirror] = dvolume_of(mir)
-            idxs[mirror] = ctx.index_build(dvols[mirror])
+            dvols.update(dvolumes_of(bufs[3]))
+            for v in sets[mirror]:
+                idxs[v] = ctx.index_build(dvols[v])
         produced = [0]
 
         def exchange(cur, sp):
-            step_v = (cur.v - 1) % world
-            return exchange_with(nxt, prv, cur, sp, step_v)
+            io["nvlink"] += p * (max_pac + max_reads * 8)
+            return exchange_with(nxt, prv, cur, sp, (cur.v - 1) % world)
 
         def compute(step, blk):
-            v = blk.v
-            assert v == block_at(world, rank, step)
-            items = tile_work(world, rank, step, reads_in_block)
+            assert blk.v == block_at(world, rank, step)
+            items = ring_work(world, rank, step, V, reads_in_volume)
             if not items:
                 return
-            dq = dvols[v] if v in dvols else dvolume_of(blk)
-            for s, vv, rb, re in items:
-                rec = ctx.pw_tile_range(idxs[s], dvols[s], dq, params, rb, re)
+            dq = {v: dvols[v] for v in sets[blk.v] if v in dvols}
+            fresh = None
+            if len(dq) < len(sets[blk.v]):
+                fresh = dvolumes_of(blk)
+                dq = fresh
+            for s, v, rb, re in items:
+                rec = ctx.pw_tile_range(idxs[s], dvols[s], dq[v], params, rb, re)
                 produced[0] += len(rec)
-            if v not in dvols:
-                ctx.release_volume(dq)
+            if fresh:
+                for dv in fresh.values():
+                    ctx.release_volume(dv)
 
-        run_ring(world, rank, own, ring_a, ring_b, exchange, compute)
+        if world == 1:
+            compute(0, own)
+        else:
+            run_ring(world, rank, own, bufs[1], bufs[2], exchange, compute)
         for i in idxs.values():
             ctx.release_index(i)
         for dv in dvols.values():
             ctx.release_volume(dv)
         return produced[0]
 
-    def timed(nsteps, e2e):
-        dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n = 0
-        for _ in range(nsteps):
-            n += one_step(e2e)
-        torch.cuda.synchronize(); dist.barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([n], dtype=torch.int64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        return int(c.item()), float(t.item())
-
     bufs[0].v = -1
     for i in range(args.warmup):
-        n, dt = timed(1, False)
+        n, dt = env.timed(1, one_step, False)
         if rank == 0:
             log("warmup %d: %d pairs in %.2f s" % (i, n, dt))
     ctx.reset_stats()
-    sampler = ClockSampler(local) if rank == 0 else None
-    pairs, dt = timed(args.steps, False)
+    sampler = ClockSampler(getattr(env, "local", 0)) if rank == 0 else None
+    pairs, dt = env.timed(args.steps, one_step, False)
     stats = ctx.stats()
     clocks = sampler.stop() if sampler else None
     esteps = max(1, min(args.steps, 2))
     ctx.reset_stats()
-    epairs, edt = timed(esteps, True)
+    io["h2d"] = io["nvlink"] = 0
+    epairs, edt = env.timed(esteps, one_step, True)
     estats = ctx.stats()
-    h2d = torch.tensor([estats["h2d_bytes"] + pac_h.numel() * esteps + osz_h.numel() * 4 * esteps, estats["d2h_bytes"]],
-                       dtype=torch.int64, device=dev)
-    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    iot = torch.tensor([estats["h2d_bytes"] + io["h2d"], estats["d2h_bytes"], io["nvlink"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(iot, op=dist.ReduceOp.SUM)
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        cfg = workload_config(world)
+        peaks = measured_peaks()
+        tiles = V * (V + 1) // 2
+        cfg = {"workload": "mecat2pw -j 1 all-vs-all, %d volumes x %d synthetic PacBio-CLR reads (15 kb mean, 15%% error, 15x "
+                           "over a %d Mb genome) = %d reads, %d tiles (BASELINE configs[4] shape; equal volumes instead of the "
+                           "splitter's 7 full volumes + a sliver)" % (V, READS, V * GENOME // 1000000, V * READS, tiles),
+               "reads": V * READS, "genome": V * GENOME, "seed": SEED, "volumes": V, "tiles": tiles,
+               "params": "-n 100 -a 2000 -k 4 -x 0", "l2": "inputs larger than L2 (no flush)",
+               "parallelism": "1 gpu, all tiles" if world == 1 else
+               "%d gpus: %d volume(s) per rank, volume sets rotate round the ring over NCCL send/recv, rank g serves the "
+               "indices of ranks g and %d-g (mirror pairing)" % (world, p, world - 1)}
         if args.reads:
-            cfg = dict(cfg, reads=world * READS, genome=world * GENOME, workload="REDUCED debug workload (%d reads per rank)" % READS)
+            cfg["workload"] = "REDUCED debug workload: " + cfg["workload"]
         line = {
             "metric": METRIC, "value": pairs / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(h2d[0].item()) // esteps,
-                    "d2h_bytes_per_step": int(h2d[1].item()) // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
+            "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": int(iot[0].item()) // esteps,
+                    "d2h_bytes_per_step": int(iot[1].item()) // esteps, "nvlink_bytes_per_step": int(iot[2].item()) // esteps,
+                    "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
             "gpu_launches": stats["gpu_launches"] * world,
             "roofline": roofline_for(stats, peaks, clocks=clocks),
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                              "sample": "measured at N=1 only (bench.py --gpus 1)"},
             "pairs_per_step": pairs // args.steps,
             "kernel_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
-            "nvlink_bytes_per_step_per_rank": int((world - 1 + (1 if world - 1 - rank != rank else 0)) * (max_pac + max_reads * 8)),
         }
         print(json.dumps(line))
     ctx.close()
     dist.destroy_process_group()
+    return line
