@@ -246,11 +246,16 @@ int main(int argc, char* argv[])
 {
 	Options opt;
 	if (parse_arguments(argc, argv, &opt)) { print_usage(argv[0]); return 1; }
-	// Creating the CUDA context of device 0 takes about a second; it runs next to the FASTA split.
-	mecat_b200_ctx* ctx0 = NULL;
-	int ctx0_rc = 0;
-	std::thread warm([&]() { if (mecat_b200_device_count() > 0) ctx0_rc = mecat_b200_init(&ctx0, 0, NULL); });
-	struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{warm};
+	// Creating a CUDA context takes one to two seconds; all devices' contexts come up next to the FASTA split.
+	int want_gpus = 1;
+	if (const char* g = getenv("MECAT_GPUS")) want_gpus = std::max(1, atoi(g));
+	const int have = mecat_b200_device_count();
+	if (have < 1) { fprintf(stderr, "mecat2pw: no CUDA device found (this build has no CPU path)\n"); return 1; }
+	want_gpus = std::min(want_gpus, have);
+	std::vector<mecat_b200_ctx*> warm_ctx((size_t)want_gpus, (mecat_b200_ctx*)NULL);
+	std::vector<std::thread> warm;
+	for (int d = 0; d < want_gpus; ++d) warm.emplace_back([&, d]() { if (mecat_b200_init(&warm_ctx[(size_t)d], d, NULL)) warm_ctx[(size_t)d] = NULL; });
+	struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } warm_joiner{warm};
 	int num_vols = 0;
 	{
 		StderrTimer t("split_raw_dataset");
@@ -273,12 +278,7 @@ int main(int argc, char* argv[])
 	}
 	if ((int)vols.size() != num_vols) { fprintf(stderr, "volume index is inconsistent\n"); return 1; }
 
-	int ngpus = 1;
-	if (const char* g = getenv("MECAT_GPUS")) ngpus = atoi(g);
-	const int have = mecat_b200_device_count();
-	if (have < 1) { fprintf(stderr, "mecat2pw: no CUDA device found (this build has no CPU path)\n"); return 1; }
-	if (ngpus < 1) ngpus = 1;
-	if (ngpus > have) ngpus = have;
+	int ngpus = want_gpus;
 	// Work items are tiles, row by row; rows whose r_N exists are finished (the reference's resume protocol, pw.cpp:65-81).
 	// Any device takes the next tile: building the index of a volume costs a fraction of a tile, so several devices
 	// share a row instead of each owning rows of very different sizes (row s has num_vols - s tiles).
@@ -293,17 +293,14 @@ int main(int argc, char* argv[])
 	}
 	if (ngpus > (int)tiles.size()) ngpus = tiles.empty() ? 1 : (int)tiles.size();
 
-	if (warm.joinable()) warm.join();
-	if (ctx0_rc) ctx0 = NULL;
+	for (auto& x : warm) if (x.joinable()) x.join();
+	for (int d = ngpus; d < want_gpus; ++d) if (warm_ctx[(size_t)d]) { mecat_b200_destroy(warm_ctx[(size_t)d]); warm_ctx[(size_t)d] = NULL; }
 	std::atomic<int> next(0), failed(0);
 	auto worker = [&](int dev) {
 		DeviceState D;
 		Loaded held;                                   // the volume read ahead for the tile this device takes next
-		D.ctx = dev == 0 ? ctx0 : NULL;
-		if (!D.ctx) {
-			StderrTimer t("gpu " + std::to_string(dev) + " init");
-			if (mecat_b200_init(&D.ctx, dev, NULL)) { fprintf(stderr, "mecat2pw: cannot initialise GPU %d\n", dev); failed = 1; return; }
-		}
+		D.ctx = warm_ctx[(size_t)dev];
+		if (!D.ctx) { fprintf(stderr, "mecat2pw: cannot initialise GPU %d\n", dev); failed = 1; return; }
 		// A device holds one tile ahead of the one it works on, so that the query volume of the next tile is read from
 		// disk while the device is busy.
 		std::future<Loaded> ahead;
@@ -331,13 +328,16 @@ int main(int argc, char* argv[])
 		if (ahead.valid()) held = ahead.get();
 		if (held.ok) mecat_b200_volume_unload(&held.vol);
 		D.drop();
-		StderrTimer t("gpu " + std::to_string(dev) + " release");
-		mecat_b200_destroy(D.ctx);
 	};
 	std::vector<std::thread> th;
 	for (int d = 1; d < ngpus; ++d) th.emplace_back(worker, d);
 	worker(0);
 	for (auto& t : th) t.join();
+	{
+		// contexts go when every device is done (device 0 last)
+		StderrTimer t("gpu release");
+		for (int d = ngpus - 1; d >= 0; --d) if (warm_ctx[(size_t)d]) mecat_b200_destroy(warm_ctx[(size_t)d]);
+	}
 	if (failed) return 1;
 
 	// merge_results: r_0 .. r_{n-1} concatenated in volume order (pw.cpp:34-46)

@@ -12,10 +12,16 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <deque>
+#include <future>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mecat_b200.h"
@@ -115,6 +121,9 @@ struct FastaStream
 	bool ok = false;
 	const char* held = NULL;    // one line of push-back
 	size_t held_n = 0;
+	bool saw_fastq = false;     // a '@' or '+' line was seen: record boundaries are not those of plain FASTA
+	// a view of [lo, hi) of another stream's bytes (split_parallel: one per thread)
+	FastaStream(const FastaStream& whole, size_t lo, size_t hi) : base(whole.base), size(hi), pos(lo), ok(true) {}
 	explicit FastaStream(const char* path)
 	{
 		const int fd = open(path, O_RDONLY);
@@ -167,6 +176,7 @@ struct FastaStream
 		while (line(l, n)) {
 			if (n == 0) continue;
 			const int c = (unsigned char)l[0];
+			if (c == '@' || c == '+') saw_fastq = true;
 			if (c == '>' || c == '@') {
 				if (need_defline) { need_defline = false; got_defline = true; continue; }
 				unget(l, n);
@@ -214,6 +224,186 @@ std::string join(const char* dir, const std::string& name)
 	return p + name;
 }
 
+// ---- the split on several host threads (plain FASTA only; anything else takes the sequential path above)
+//
+// The sequential split parses and packs ~1.1 GB of FASTA per second -- 13 s for the 15 GB of BASELINE configs[4], more than
+// the 36 tiles take on 8 GPUs.  In plain FASTA a '>' at the start of a line always begins a record, so the file can be cut
+// at such lines and parsed by one thread per piece (same record rules: FastaStream::next); the volume a read lands in
+// depends on all reads before it, which is a cheap sequential pass over (length) records; packing is then parallel again,
+// volume by volume, with the first and last partial byte of a read OR-ed in atomically (neighbouring reads share bytes),
+// and a finished volume is written while the next one is packed.  A '@' or '+' line anywhere (FASTQ), a malformed record
+// or an input that cannot be mapped makes the whole call fall back to the sequential path, which also owns the error texts.
+struct ParsedRead { const char* sp; uint32_t n; bool acgt; };
+
+inline void or_byte(uint8_t* p, uint8_t v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+
+// VolumeBuilder::add into a shared, zeroed buffer at base offset `curr`
+void pack_read_at(uint8_t* pac, int64_t curr, const char* seq, size_t n, bool acgt)
+{
+	const unsigned char* p = (const unsigned char*)seq;
+	size_t i = 0;
+	for (; i < n && (curr & 3); ++i, ++curr) or_byte(pac + (curr >> 2), (uint8_t)(kEnc.t[p[i]] << (((~curr) & 3) << 1)));
+	if (acgt) {
+		uint8_t* __restrict out = pac + (curr >> 2);
+		const size_t groups = (n - i) / 8;
+		const unsigned char* __restrict in = p + i;
+		for (size_t g = 0; g < groups; ++g) {
+			uint64_t x;
+			memcpy(&x, in + 8 * g, 8);
+			uint64_t c = (x >> 1) & 0x0303030303030303ull;
+			c ^= (c >> 1) & 0x0101010101010101ull;
+			const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+			out[2 * g] = (uint8_t)((lo * 0x40100401u) >> 24);
+			out[2 * g + 1] = (uint8_t)((hi * 0x40100401u) >> 24);
+		}
+		i += 8 * groups; curr += (int64_t)(8 * groups);
+	}
+	// whole bytes belong to this read alone; a code > 3 may spill into the byte's other bases exactly like PackedDB::set_char
+	for (; i + 4 <= n; i += 4, curr += 4) {
+		const unsigned a = kEnc.t[p[i]], b = kEnc.t[p[i + 1]], c = kEnc.t[p[i + 2]], d = kEnc.t[p[i + 3]];
+		pac[curr >> 2] = (uint8_t)((a << 6) | (b << 4) | (c << 2) | d);
+	}
+	for (; i < n; ++i, ++curr) or_byte(pac + (curr >> 2), (uint8_t)(kEnc.t[p[i]] << (((~curr) & 3) << 1)));
+}
+
+int split_threads(size_t input_bytes)
+{
+	if (const char* e = getenv("MECAT_B200_SPLIT_THREADS")) return std::max(1, atoi(e));     // 1 = sequential path; test hook for small files
+	if (input_bytes < (64u << 20)) return 1;
+	const int hw = (int)std::thread::hardware_concurrency();
+	return std::max(1, std::min(hw > 0 ? hw : 1, 32));
+}
+
+// returns 0 = done, 1 = failed while writing (err set), 2 = not applicable: use the sequential path
+int split_parallel(const FastaStream& in, const char* wrk_dir, int64_t cap, int threads, int* num_volumes, std::string& err)
+{
+	if (!in.map || threads < 2 || in.size == 0) return 2;
+	{
+		// plain FASTA starts (after blank and comment lines) with '>'
+		size_t q = 0;
+		while (q < in.size) {
+			const char c = in.base[q];
+			if (c == '\n' || c == '\r') { ++q; continue; }
+			if (c == '#' || c == '!') { while (q < in.size && in.base[q] != '\n' && in.base[q] != '\r') ++q; continue; }
+			break;
+		}
+		if (q >= in.size || in.base[q] != '>') return 2;
+	}
+	// cut points: the first line start holding '>' at or after every nominal boundary
+	std::vector<size_t> cut((size_t)threads + 1, in.size);
+	cut[0] = 0;
+	for (int t = 1; t < threads; ++t) {
+		size_t q = in.size / (size_t)threads * (size_t)t;
+		if (q < cut[(size_t)t - 1]) q = cut[(size_t)t - 1];
+		for (;;) {
+			while (q < in.size && in.base[q] != '\n' && in.base[q] != '\r') ++q;
+			while (q < in.size && (in.base[q] == '\n' || in.base[q] == '\r')) ++q;
+			if (q >= in.size || in.base[q] == '>') break;
+		}
+		cut[(size_t)t] = std::min(q, in.size);
+	}
+	const bool timing = getenv("MECAT_B200_SPLIT_TIMING") != NULL;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+	const double t_start = now();
+	struct Piece { std::vector<ParsedRead> reads; std::deque<std::string> owned; bool bad = false; };
+	std::vector<Piece> pieces((size_t)threads);
+	{
+		std::vector<std::thread> pool;
+		for (int t = 0; t < threads; ++t)
+			pool.emplace_back([&, t]() {
+				Piece& P = pieces[(size_t)t];
+				if (cut[(size_t)t] >= cut[(size_t)t + 1]) return;
+				FastaStream part(in, cut[(size_t)t], cut[(size_t)t + 1]);
+				std::string seq, e;
+				const char* sp = NULL;
+				bool acgt = true;
+				for (;;) {
+					const int64_t n = part.next(seq, sp, acgt, e);
+					if (n == -1) break;
+					if (n == -2 || part.saw_fastq || n > 0x7fffffffLL) { P.bad = true; return; }
+					ParsedRead r;
+					if (sp == seq.data()) { P.owned.push_back(seq); sp = P.owned.back().data(); }    // a copy was needed: keep it
+					r.sp = sp; r.n = (uint32_t)n; r.acgt = acgt;
+					P.reads.push_back(r);
+				}
+				if (part.saw_fastq) P.bad = true;
+			});
+		for (auto& th : pool) th.join();
+	}
+	for (const Piece& P : pieces) if (P.bad) return 2;
+	const double t_parsed = now();
+	// volumes: the reference's rule, read by read (split_database.cpp:240-259)
+	struct Vol { size_t first_piece, first_read; int64_t curr = 0; int num_reads = 0; std::vector<int32_t> offsz; };
+	std::vector<Vol> vols;
+	std::vector<std::vector<std::pair<int, int64_t>>> where((size_t)threads);     // per read: volume, base offset
+	{
+		Vol v; v.first_piece = 0; v.first_read = 0;
+		for (int t = 0; t < threads; ++t) {
+			where[(size_t)t].resize(pieces[(size_t)t].reads.size());
+			for (size_t i = 0; i < pieces[(size_t)t].reads.size(); ++i) {
+				const int64_t n = pieces[(size_t)t].reads[i].n;
+				if (v.curr + n + 1 > cap && v.curr > 0) { vols.push_back(std::move(v)); v = Vol(); }
+				if (n + 1 > cap) return 2;                       // the sequential path reports it
+				where[(size_t)t][i] = std::make_pair((int)vols.size(), v.curr);
+				v.offsz.push_back((int32_t)v.curr); v.offsz.push_back((int32_t)n);
+				v.curr += n + 1; ++v.num_reads;
+			}
+		}
+		if (v.curr > 0) vols.push_back(std::move(v));
+	}
+	FILE* idx = fopen(join(wrk_dir, "fileindex.txt").c_str(), "w");
+	if (!idx) { err = std::string("cannot write into '") + wrk_dir + "'"; return 1; }
+	std::future<int> writer;
+	int rid = 0, rc = 0;
+	for (size_t vi = 0; vi < vols.size() && !rc; ++vi) {
+		const Vol& V = vols[vi];
+		const size_t bytes = (size_t)((V.curr + 3) / 4);
+		std::shared_ptr<std::vector<uint8_t>> pac(new std::vector<uint8_t>(bytes + 16, 0));
+		{
+			std::atomic<size_t> next(0);
+			const size_t grain = 256;
+			// flat list of (piece, read) of this volume, handed out in grains
+			std::vector<std::pair<int, size_t>> items;
+			items.reserve((size_t)V.num_reads);
+			for (int t = 0; t < threads; ++t)
+				for (size_t i = 0; i < where[(size_t)t].size(); ++i)
+					if (where[(size_t)t][i].first == (int)vi) items.push_back(std::make_pair(t, i));
+			std::vector<std::thread> pool;
+			for (int t = 0; t < threads; ++t)
+				pool.emplace_back([&]() {
+					for (size_t a; (a = next.fetch_add(grain)) < items.size();)
+						for (size_t k = a; k < std::min(items.size(), a + grain); ++k) {
+							const ParsedRead& r = pieces[(size_t)items[k].first].reads[items[k].second];
+							pack_read_at(pac->data(), where[(size_t)items[k].first][items[k].second].second, r.sp, r.n, r.acgt);
+						}
+				});
+			for (auto& th : pool) th.join();
+		}
+		if (writer.valid() && writer.get()) { rc = 1; break; }
+		const std::string name = join(wrk_dir, "vol" + std::to_string(vi));
+		fprintf(idx, "%s\n", name.c_str());
+		const int32_t hdr[3] = {V.num_reads, (int32_t)V.curr, rid};
+		rid += V.num_reads;
+		const std::vector<int32_t>* offsz = &V.offsz;
+		writer = std::async(std::launch::async, [name, hdr, offsz, pac, bytes]() -> int {
+			FILE* f = fopen(name.c_str(), "wb");
+			if (!f) return 1;
+			bool ok = fwrite(hdr, 4, 3, f) == 3 && fwrite(offsz->data(), 4, offsz->size(), f) == offsz->size() &&
+			          fwrite(pac->data(), 1, bytes, f) == bytes;
+			ok = (fclose(f) == 0) && ok;
+			return ok ? 0 : 1;
+		});
+	}
+	const double t_packed = now();
+	if (writer.valid() && writer.get()) rc = 1;
+	fclose(idx);
+	if (rc) { err = "cannot write volume file"; return 1; }
+	*num_volumes = (int)vols.size();
+	if (timing) fprintf(stderr, "[split] %d threads: parse %.2f s, assign + pack (+ writes behind it) %.2f s, last write %.2f s\n", threads,
+	                    t_parsed - t_start, t_packed - t_parsed, now() - t_packed);
+	return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -229,6 +419,12 @@ int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_
 	const int64_t cap = max_volume_bases > 0 ? max_volume_bases : kMaxVolumeBases;
 	FastaStream in(reads_path);
 	if (!in.ok) return fail(std::string("cannot open file '") + reads_path + "' for reading");
+	{
+		std::string perr;
+		const int prc = split_parallel(in, wrk_dir, cap, split_threads(in.size), num_volumes, perr);
+		if (prc == 0) return 0;
+		if (prc == 1) return fail(perr);
+	}
 	FILE* idx = fopen(join(wrk_dir, "fileindex.txt").c_str(), "w");
 	if (!idx) return fail(std::string("cannot write into '") + wrk_dir + "'");
 	VolumeBuilder v;

@@ -964,8 +964,11 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 	const int max_nk = reads->max_read >= KMER ? (reads->max_read - KMER) / STRIDE + 1 : 1;
 	if (max_nk > MAX_KM) MB_FAIL(c, "seeding: reads longer than %d bp are outside this path (seed ordinals are 16-bit in the reference)", MAX_KM * STRIDE);
 	const int kcap = max_nk + 32;
+	// per-strand capacity for the collected hits of wanted buckets: the true upper bound, every sampled k-mer with a full
+	// list (MAX_OCC positions) -- a strand of a repeat-rich volume gets close to it (15 kb read: 1 500 x 128 = 192 000
+	// hits, 7 MB of scratch per CTA), and the reference maps such reads like any other
 	int hcap = 1 << 16;
-	while (hcap < 16 * max_nk && hcap < (1 << 22)) hcap <<= 1;
+	while ((long long)hcap < (long long)MAX_OCC * max_nk && hcap < (1 << 23)) hcap <<= 1;
 	const int nctas = c->sm_count;
 	int batch = 8192;
 	if (batch > read_end - read_begin) batch = read_end - read_begin;

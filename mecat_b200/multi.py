@@ -440,112 +440,105 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
     metas = [tuple(int(x) for x in m.tolist()) for m in meta.cpu()]
     max_pac = max(m[3] for m in metas); max_reads = max(m[0] for m in metas)
     reads_in_volume = [m[0] for m in metas]
-    nxt, prv = ring_neighbours(world, rank)
     mirror = world - 1 - rank
     params = mecat_b200.pw_params(task=1)
 
-    class Block:                                              # one rank's set of packed volumes in device memory
-        def __init__(self):
-            self.pac = [torch.empty(max_pac, dtype=torch.uint8, device=dev) for _ in range(p)]
-            self.osz = [torch.empty(max_reads * 2, dtype=torch.int32, device=dev) for _ in range(p)]
-            self.v = -1                                       # owner rank of the set it holds
+    # Packed volumes in device memory: slot v of `pac_all` / `osz_all` holds volume v.  A rank fills the slots of its own
+    # volumes from pinned host memory; the others arrive over NVLink in ONE NCCL all-gather per step (NCCL's ring algorithm
+    # rotates the blocks from rank to rank), posted before the own indices are built and waited for after.  The first
+    # version rotated the sets with a send/recv pair per ring step, double buffered behind the step's tiles: a rank could
+    # not start step t+1 before its left neighbour had started step t, and the tiles per step are uneven (rank 3 of 8 has
+    # none in steps 1-3 and two in steps 4-7), so every step cost the slowest rank's time: 4.5x on 8 GPUs
+    # (profiles/r2_bench_ring_n8_stepwise.json).  Transport and compute are independent now.
+    pac_all = torch.zeros((V, max_pac), dtype=torch.uint8, device=dev)
+    osz_all = torch.zeros((V, max_reads * 2), dtype=torch.int32, device=dev)
+    own_lo, own_hi = own_vols[0], own_vols[-1] + 1
 
-    nbuf = 1 if world == 1 else (3 if mirror == rank else 4)  # own set, two ring buffers, the mirror's set
-    bufs = [Block() for _ in range(nbuf)]
+    def dvolume(v):
+        nr, nb, sid, _ = metas[v]
+        osz = osz_all[v][:2 * nr].cpu().numpy().reshape(-1, 2)
+        return ctx.volume_from_device(nr, nb, sid, osz, pac_all[v].data_ptr() if env.cuda else pac_all[v])
 
-    class Handle:
-        def __init__(self, reqs, blk, v):
-            self.reqs, self.blk, self.v = reqs, blk, v
-
-        def wait(self):
-            for r in self.reqs:
-                r.wait()
-            self.blk.v = self.v
-
-    def exchange_with(dst, src, send_blk, recv_blk, recv_v):
-        ops = []
-        for i in range(p):
-            ops += [dist.P2POp(dist.isend, send_blk.pac[i], dst), dist.P2POp(dist.isend, send_blk.osz[i], dst)]
-        for i in range(p):
-            ops += [dist.P2POp(dist.irecv, recv_blk.pac[i], src), dist.P2POp(dist.irecv, recv_blk.osz[i], src)]
-        return Handle(dist.batch_isend_irecv(ops), recv_blk, recv_v)
-
-    def dvolumes_of(blk):
-        env.sync()
-        out = {}
-        for i, v in enumerate(sets[blk.v]):
-            nr, nb, sid, _ = metas[v]
-            osz = blk.osz[i][:2 * nr].cpu().numpy().reshape(-1, 2)
-            out[v] = ctx.volume_from_device(nr, nb, sid, osz, blk.pac[i].data_ptr() if env.cuda else blk.pac[i])
-        return out
-
+    served = sorted(set(sets[rank]) | set(sets[mirror]))
+    items = [it for step in range(world) for it in ring_work(world, rank, step, V, reads_in_volume)]
+    needed = sorted({s for s, _, _, _ in items} | {v for _, v, _, _ in items})
     io = {"h2d": 0, "nvlink": 0}
+    phase = {"upload": 0.0, "index": 0.0, "gather_wait": 0.0, "volumes": 0.0, "tiles": 0.0}
+    uploaded = [False]
+
+    def clock(name, t0):
+        t1 = time.perf_counter()
+        phase[name] += (t1 - t0) * 1e3
+        return t1
 
     def one_step(e2e):
         """Whole job once.  Returns the number of records this rank produced."""
-        own = bufs[0]
+        t0 = time.perf_counter()
         # own volumes to the device (inside the timed region only for e2e; resident otherwise)
-        if e2e or own.v != rank:
-            for i, v in enumerate(own_vols):
-                own.pac[i][:pac_h[v].numel()].copy_(pac_h[v], non_blocking=True)
-                own.osz[i][:osz_h[v].numel()].copy_(osz_h[v], non_blocking=True)
+        if e2e or not uploaded[0]:
+            for v in own_vols:
+                pac_all[v][:pac_h[v].numel()].copy_(pac_h[v], non_blocking=True)
+                osz_all[v][:osz_h[v].numel()].copy_(osz_h[v], non_blocking=True)
                 io["h2d"] += pac_h[v].numel() + osz_h[v].numel() * 4
-            own.v = rank
+            uploaded[0] = True
+        handles = []
+        if world > 1:
+            env.sync()
+            handles.append(dist.all_gather_into_tensor(pac_all.view(-1), pac_all[own_lo:own_hi].reshape(-1).clone(), async_op=True))
+            handles.append(dist.all_gather_into_tensor(osz_all.view(-1), osz_all[own_lo:own_hi].reshape(-1).clone(), async_op=True))
+            io["nvlink"] += (world - 1) * p * (max_pac + max_reads * 8)
+        env.sync() if world == 1 else None
         dvols, idxs = {}, {}
-        h = None
-        if mirror != rank:
-            h = exchange_with(mirror, mirror, own, bufs[3], mirror)
-            io["nvlink"] += p * (max_pac + max_reads * 8)
-        dvols.update(dvolumes_of(own))
-        for v in own_vols:
-            idxs[v] = ctx.index_build(dvols[v])
-        if h is not None:
-            h.wait()
-            dvols.update(dvolumes_of(bufs[3]))
-            for v in sets[mirror]:
-                idxs[v] = ctx.index_build(dvols[v])
-        produced = [0]
-
-        def exchange(cur, sp):
-            io["nvlink"] += p * (max_pac + max_reads * 8)
-            return exchange_with(nxt, prv, cur, sp, (cur.v - 1) % world)
-
-        def compute(step, blk):
-            assert blk.v == block_at(world, rank, step)
-            items = ring_work(world, rank, step, V, reads_in_volume)
-            if not items:
-                return
-            dq = {v: dvols[v] for v in sets[blk.v] if v in dvols}
-            fresh = None
-            if len(dq) < len(sets[blk.v]):
-                fresh = dvolumes_of(blk)
-                dq = fresh
-            for s, v, rb, re in items:
-                rec = ctx.pw_tile_range(idxs[s], dvols[s], dq[v], params, rb, re)
-                produced[0] += len(rec)
-            if fresh:
-                for dv in fresh.values():
-                    ctx.release_volume(dv)
-
+        t0 = clock("upload", t0)
         if world == 1:
-            compute(0, own)
+            for v in own_vols:
+                dvols[v] = dvolume(v)
         else:
-            run_ring(world, rank, own, bufs[1], bufs[2], exchange, compute)
+            # the own slots are not written by the gather (NCCL copies the send buffer into them, same bytes): safe to read
+            for v in own_vols:
+                dvols[v] = dvolume(v)
+        t0 = clock("volumes", t0)
+        for v in own_vols:
+            if v in served:
+                idxs[v] = ctx.index_build(dvols[v])
+        t0 = clock("index", t0)
+        for h in handles:
+            h.wait()
+        env.sync()
+        t0 = clock("gather_wait", t0)
+        for v in needed:
+            if v not in dvols:
+                dvols[v] = dvolume(v)
+        t0 = clock("volumes", t0)
+        for v in served:
+            if v not in idxs:
+                idxs[v] = ctx.index_build(dvols[v])
+        t0 = clock("index", t0)
+        produced = 0
+        for s, v, rb, re in items:
+            rec = ctx.pw_tile_range(idxs[s], dvols[s], dvols[v], params, rb, re)
+            produced += len(rec)
+        t0 = clock("tiles", t0)
         for i in idxs.values():
             ctx.release_index(i)
         for dv in dvols.values():
             ctx.release_volume(dv)
-        return produced[0]
+        return produced
 
-    bufs[0].v = -1
     for i in range(args.warmup):
         n, dt = env.timed(1, one_step, False)
         if rank == 0:
             log("warmup %d: %d pairs in %.2f s" % (i, n, dt))
     ctx.reset_stats()
+    for k in phase:
+        phase[k] = 0.0
     sampler = ClockSampler(getattr(env, "local", 0)) if rank == 0 else None
     pairs, dt = env.timed(args.steps, one_step, False)
     stats = ctx.stats()
+    phase_ms = {k: round(v / args.steps, 3) for k, v in phase.items()}
+    busy = torch.tensor([sum(phase.values()) / args.steps], dtype=torch.float64, device=dev)
+    busy_all = [torch.zeros_like(busy) for _ in range(world)]
+    dist.all_gather(busy_all, busy)
     clocks = sampler.stop() if sampler else None
     esteps = max(1, min(args.steps, 2))
     ctx.reset_stats()
@@ -564,8 +557,8 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
                "reads": V * READS, "genome": V * GENOME, "seed": SEED, "volumes": V, "tiles": tiles,
                "params": "-n 100 -a 2000 -k 4 -x 0", "l2": "inputs larger than L2 (no flush)",
                "parallelism": "1 gpu, all tiles" if world == 1 else
-               "%d gpus: %d volume(s) per rank, volume sets rotate round the ring over NCCL send/recv, rank g serves the "
-               "indices of ranks g and %d-g (mirror pairing)" % (world, p, world - 1)}
+               "%d gpus: %d volume(s) per rank, packed volumes travel rank to rank in one NCCL all-gather (ring) per step, "
+               "rank g serves the indices of ranks g and %d-g (mirror pairing), no other exchange" % (world, p, world - 1)}
         if args.reads:
             cfg["workload"] = "REDUCED debug workload: " + cfg["workload"]
         line = {
@@ -580,6 +573,7 @@ def run_bench(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSa
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                              "sample": "measured at N=1 only (bench.py --gpus 1)"},
             "pairs_per_step": pairs // args.steps,
+            "phase_ms_per_step_rank0": phase_ms, "busy_ms_per_step_by_rank": [round(float(b.item()), 1) for b in busy_all],
             "kernel_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in stats["kernel_ms"].items()},
         }
         print(json.dumps(line))

@@ -383,6 +383,23 @@ def test_repeat_tiles(gpu_ctx, repeat_vol):
     report("repeat_m4", util.m4_lines(got, True), util.m4_lines(want, True))
 
 
+def test_repeat_heavy_long_reads(gpu_ctx):
+    """15 kb reads over a genome of 12 near-identical copies at ~11x: a sampled k-mer has ~80 index hits, a strand
+    collects > 100 000 hits of buckets that pass the gate -- more than the 65 536 a strand's scratch used to hold (the
+    tile failed with `more candidate seeds than the per-strand capacity`; the reference maps such reads like any other)."""
+    import mecat_b200
+    vol = PackedVolume.from_seqs(util.repeat_reads(seed=33, unit=4000, copies=12, n_reads=48, mean=15000, err=0.02, div=0.005))
+    hv = host_volume(vol)
+    want = util.oracle_pw_tile(vol, vol, util.pw_params(task=0), threads=8)
+    gpu_ctx.reset_stats()
+    got = gpu_ctx.pw_overlaps(hv, hv, mecat_b200.pw_params(task=0))
+    assert gpu_ctx.stats()["num_hits"] > 2 * 48 * 65536 // 2          # the strands really are that heavy
+    report("repeat_heavy_can", util.ec_lines(got), util.ec_lines(want))
+    want = util.oracle_pw_tile(vol, vol, util.pw_params(task=1), threads=8)
+    got = gpu_ctx.pw_overlaps(hv, hv, mecat_b200.pw_params(task=1))
+    report("repeat_heavy_m4", util.m4_lines(got, True), util.m4_lines(want, True))
+
+
 def test_deterministic_across_runs(gpu_ctx, cfg0_vol):
     hv = host_volume(cfg0_vol)
     a = gpu_ctx.pw_overlaps(hv, hv)

@@ -181,3 +181,26 @@ def test_result_text_equals_the_reference_stream_formatting():
     la = L.harness_format_can(ec.ctypes.data_as(C.c_void_p), n, a, cap)
     lb = L.harness_ostream_can(ec.ctypes.data_as(C.c_void_p), n, b, cap)
     assert la == lb and a.raw[:la] == b.raw[:lb]
+
+
+@pytest.mark.parametrize("threads", [2, 5, 16])
+def test_threaded_split_equals_the_sequential_split(tmp_path, threads, monkeypatch):
+    """mecat_b200_split_dataset cuts plain FASTA at '>' lines and parses / packs it on several threads; every awkward input
+    (and a multi-volume cap) must give the very bytes of the one-thread path -- FASTQ and malformed pieces fall back to it."""
+    import mecat_b200
+    cases = dict(awkward_inputs())
+    rng = np.random.default_rng(17)
+    cases["many_reads_small_cap"] = "".join(">%d\n%s\n" % (i, "".join("ACGT"[c] for c in rng.integers(0, 4, size=int(rng.integers(1, 700)))))
+                                            for i in range(600))
+    for name, text in sorted(cases.items()):
+        fa = str(tmp_path / (name + ".fa"))
+        with open(fa, "w", newline="") as f:
+            f.write(text)
+        cap = 9000 if name == "many_reads_small_cap" else 0
+        monkeypatch.setenv("MECAT_B200_SPLIT_THREADS", "1")
+        seq = mecat_b200.split_dataset(fa, str(tmp_path / (name + "_w1")), max_volume_bases=cap)
+        monkeypatch.setenv("MECAT_B200_SPLIT_THREADS", str(threads))
+        par = mecat_b200.split_dataset(fa, str(tmp_path / (name + "_wn")), max_volume_bases=cap)
+        assert [os.path.basename(v) for v in par] == [os.path.basename(v) for v in seq], name
+        for a, b in zip(seq, par):
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, os.path.basename(a))
