@@ -398,7 +398,7 @@ __global__ void k_aln_sizes(const AlignTask* __restrict__ tasks, const AlnSlot* 
 			else { a = colq[R.off + (c - L.cols)]; b = colt[R.off + (c - L.cols)]; }
 		};
 		// first run of 4 matching columns from the left (dw.cpp:499-512)
-		int run = 0, start = -1, qrb = 0, trb = 0;
+		int run = 0, start = -1, qrb = 0, trb = 0, mcut = 0;      // mcut: matching columns that the trimming drops
 		for (int base = 0; base < n && start < 0; base += 32) {
 			const int c = base + lane;
 			char a = 0, b = 1;
@@ -408,14 +408,14 @@ __global__ void k_aln_sizes(const AlignTask* __restrict__ tasks, const AlnSlot* 
 			const unsigned tm = __ballot_sync(0xFFFFFFFFu, c < n && b != '-');
 			for (int s = 0; s < 32 && base + s < n; ++s) {
 				run = ((m >> s) & 1u) ? run + 1 : 0;
-				qrb += (qm >> s) & 1u; trb += (tm >> s) & 1u;
+				qrb += (qm >> s) & 1u; trb += (tm >> s) & 1u; mcut += (m >> s) & 1u;
 				if (run == 4) { start = base + s - 3; break; }
 			}
 		}
 		if (start < 0) ok = 0;
 		int qre = 0, tre = 0, endc = -1;
 		if (ok) {
-			qrb -= 4; trb -= 4;
+			qrb -= 4; trb -= 4; mcut -= 4;
 			run = 0;
 			for (int base = n - 1; base >= 0 && endc < 0; base -= 32) {
 				const int c = base - lane;
@@ -426,15 +426,16 @@ __global__ void k_aln_sizes(const AlignTask* __restrict__ tasks, const AlnSlot* 
 				const unsigned tm = __ballot_sync(0xFFFFFFFFu, c >= 0 && b != '-');
 				for (int s = 0; s < 32 && base - s >= 0; ++s) {
 					run = ((m >> s) & 1u) ? run + 1 : 0;
-					qre += (qm >> s) & 1u; tre += (tm >> s) & 1u;
+					qre += (qm >> s) & 1u; tre += (tm >> s) & 1u; mcut += (m >> s) & 1u;
 					if (run == 4) { endc = base - s + 3; break; }
 				}
 			}
 			if (endc < 0) ok = 0;
 		}
 		if (ok) {
-			qre -= 4; tre -= 4;
+			qre -= 4; tre -= 4; mcut -= 4;
 			first = start; size = endc + 1 - start;
+			mats -= mcut;                 // matches, columns and strings all describe the trimmed alignment
 			qs += qrb; qe -= qre; ss += trb; se -= tre;
 		}
 	}

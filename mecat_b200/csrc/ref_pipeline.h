@@ -542,8 +542,9 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 	return 0;
 }
 
-// mecat2ref on R reads: records of a read are together and in the reference's order; the reads of the second pass
-// follow those of the first.
+// mecat2ref on R reads: records of a read are together and in the reference's order, reads in input order -- also the
+// reads that needed the second seeding pass, whose records are produced after everyone's first pass (the reference runs
+// a read's second pass right after its first; with -t 1 its output is in input order).
 template <class Backend>
 int map_reads(Backend& be, const MapIn& in, const Params& P, Sink& out)
 {
@@ -555,6 +556,8 @@ int map_reads(Backend& be, const MapIn& in, const Params& P, Sink& out)
 	int rc = map_pass(be, in, P, 0, all, second, out);
 	if (!rc) rc = map_pass(be, in, P, 1, second, none, out);
 	be.end_batch();
+	if (!rc && !second.empty())       // records keep their string offsets; a read's records stay adjacent and in order
+		std::stable_sort(out.recs.begin(), out.recs.end(), [](const mecat_ref_result& a, const mecat_ref_result& b) { return a.read < b.read; });
 	if (!rc && (out.q.oom || out.s.oom)) { be.fail("mecat2ref: out of host memory for the alignment strings"); rc = 1; }
 	return rc;
 }

@@ -258,6 +258,9 @@ def test_align_with_strings_matches_oracle(gpu_ctx, small_vol, policy, min_aln):
             o = int(r["str_offset"]); n = int(r["columns"])
             g = (1, int(r["qstart"]), int(r["qend"]), int(r["sstart"]), int(r["send"]), qstr[o:o + n], sstr[o:o + n])
             assert qstr[o + n] == 0 and sstr[o + n] == 0
+            # matches / ident describe the returned strings (for the cns flavour: after its trimming to 4-match runs)
+            same = sum(1 for x, y in zip(qstr[o:o + n], sstr[o:o + n]) if x == y)
+            assert int(r["matches"]) == same and abs(float(r["ident"]) - 100.0 * same / n) < 1e-9 and float(r["ident"]) <= 100.0
             nok += 1
         else:
             g = (0,) + tuple(w[1:5]) + (b"", b"") if not w[0] else (0, 0, 0, 0, 0, b"", b"")

@@ -35,4 +35,4 @@ res = {"reads": $READS, "gpus": $N, "rc": $RC, "volumes": vols, "tiles": len(til
 json.dump(res, open("gpurun_out/r2_cfg4_cli_n$N.json", "w"), indent=1)
 print(json.dumps(res))
 PY
-tail -3 /tmp/cfg4/cli_n$N.err
+cp /tmp/cfg4/cli_n$N.err gpurun_out/r2_cfg4_cli_n$N.err; tail -3 /tmp/cfg4/cli_n$N.err
