@@ -153,6 +153,11 @@ int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_
 int mecat_b200_volume_from_fasta(const char* reads_path, mecat_volume* out, char* err, int err_cap);
 
 /* replaces load_volume / delete_volume_t (split_database.cpp:156-181,95-101). */
+/* The whole read set as volumes in host memory, cut like mecat_b200_split_dataset cuts its files (max_volume_bases <= 0: the
+ * reference's 2.14 Gbase); for read sets beyond one volume (mecat_b200_cns_reads_multi).  *vols: malloc'ed array. */
+int mecat_b200_volumes_from_fasta(const char* reads_path, int64_t max_volume_bases, mecat_volume** vols, int* num_volumes,
+                                  char* err, int err_cap);
+void mecat_b200_volumes_unload(mecat_volume* vols, int num_volumes);
 int mecat_b200_volume_load(const char* path, mecat_volume* out);
 void mecat_b200_volume_unload(mecat_volume* v);
 
@@ -253,6 +258,14 @@ typedef struct {
 int mecat_b200_cns_reads(mecat_b200_ctx* ctx, void* dvol_reads, const mecat_candidate* ec, size_t nec,
                          const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs,
                          size_t* seq_bytes);
+
+/* The same for reads that span several resident volumes (the read ids of volume v+1 continue those of volume v): any read
+ * set the splitter can cut, e.g. the 8 volumes of BASELINE configs[4].  The reference keeps the whole data set in one
+ * PackedDB (src/common/packed_db.cpp:194); here the reads a run of templates needs are gathered into a working volume on
+ * the device.  Results are independent of how the reads are cut into volumes. */
+int mecat_b200_cns_reads_multi(mecat_b200_ctx* ctx, void* const* dvols_reads, int num_volumes, const mecat_candidate* ec, size_t nec,
+                               const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs,
+                               size_t* seq_bytes);
 
 /* Trial order of one read's candidates (CmpExtensionCandidateByScore, src/mecat2cns/mecat_correction.cpp:362-370,409);
  * host only.  mecat_b200_cns_reads applies it itself; exported so that callers feeding mecat_b200_align_batch can

@@ -94,6 +94,7 @@ EXPORTS = [
     "mecat_b200_host_free", "mecat_b200_pw_tile_range", "mecat_b200_volume_from_device", "mecat_b200_split_dataset", "mecat_b200_volume_load", "mecat_b200_volume_unload", "mecat_b200_volume_from_fasta",
     "mecat_b200_ref_index_build", "mecat_b200_ref_index_release", "mecat_b200_ref_map",
     "mecat_b200_ref_index_export", "mecat_b200_ref_raw_candidates",
+    "mecat_b200_cns_reads_multi", "mecat_b200_volumes_from_fasta", "mecat_b200_volumes_unload",
 ]
 
 _lib = None
@@ -141,6 +142,10 @@ def load_library():
                                          C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_cns_reads.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(CnsParams), C.POINTER(vp), C.POINTER(C.c_size_t),
                                        C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_cns_reads_multi.argtypes = [vp, C.POINTER(vp), C.c_int, vp, C.c_size_t, C.POINTER(CnsParams), C.POINTER(vp),
+                                             C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_volumes_from_fasta.argtypes = [C.c_char_p, C.c_int64, C.POINTER(VP), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.mecat_b200_volumes_unload.argtypes = [VP, C.c_int]
     L.mecat_b200_cns_sort_candidates.argtypes = [vp, C.c_int]
     L.mecat_b200_host_free.argtypes = [vp]
     L.mecat_b200_pw_tile_range.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -351,6 +356,26 @@ def volume_from_fasta(reads_path):
     return HostVolume(os_, pac, v.num_bases, v.start_read_id)
 
 
+def volumes_from_fasta(reads_path, max_volume_bases=0):
+    """All reads of a FASTA/FASTQ file as a list of HostVolumes cut like split_dataset cuts its files, no files written."""
+    L = load_library()
+    arr = C.POINTER(Volume)()
+    n = C.c_int()
+    err = C.create_string_buffer(512)
+    if L.mecat_b200_volumes_from_fasta(reads_path.encode(), max_volume_bases, C.byref(arr), C.byref(n), err, 512) != 0:
+        raise MecatB200Error(err.value.decode())
+    out = []
+    try:
+        for i in range(n.value):
+            v = arr[i]
+            os_ = np.ctypeslib.as_array(v.offset_size, shape=(2 * v.num_reads,)).reshape(-1, 2).copy() if v.num_reads else np.zeros((0, 2), np.int32)
+            pac = np.ctypeslib.as_array(v.pac, shape=((v.num_bases + 3) // 4,)).copy()
+            out.append(HostVolume(os_, pac, v.num_bases, v.start_read_id))
+    finally:
+        L.mecat_b200_volumes_unload(arr, n.value)
+    return out
+
+
 def split_dataset(reads_path, wrk_dir, max_volume_bases=0):
     """FASTA/FASTQ -> wrk_dir/volN + fileindex.txt (the reference's split_raw_dataset). Returns the volume paths."""
     L = load_library()
@@ -522,6 +547,21 @@ class Context:
         pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         self._check(self.L.mecat_b200_cns_reads(self.h, dvol, ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p), C.byref(pieces),
                                                 C.byref(n), C.byref(seqs), C.byref(nb)), "cns_reads")
+        pc = self._take(pieces, n.value, CNS_PIECE_DTYPE)
+        blob = C.string_at(seqs.value, nb.value) if seqs.value else b""
+        if seqs.value:
+            self.L.mecat_b200_free(self.h, seqs)
+        return [(int(x["id"]), int(x["beg"]), int(x["end"]), blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])])
+                for x in pc]
+
+    def cns_reads_multi(self, dvols, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000):
+        """cns_reads for a read set that spans several resident volumes (consecutive read ids)."""
+        ec = np.ascontiguousarray(candidates, dtype=EC_DTYPE)
+        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size)
+        arr = (C.c_void_p * len(dvols))(*[d.value if hasattr(d, "value") else d for d in dvols])
+        pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_cns_reads_multi(self.h, arr, len(dvols), ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p),
+                                                      C.byref(pieces), C.byref(n), C.byref(seqs), C.byref(nb)), "cns_reads_multi")
         pc = self._take(pieces, n.value, CNS_PIECE_DTYPE)
         blob = C.string_at(seqs.value, nb.value) if seqs.value else b""
         if seqs.value:

@@ -408,55 +408,44 @@ int mecat_b200_ref_map(mecat_b200_ctx* c, void* refidx, const mecat_ref_reads* r
 	return 0;
 }
 
-int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candidate* ec_in, size_t nec, const mecat_cns_params* p,
-                         mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
+// The reads to correct of one call: candidates sorted by template read (sid), one group per template that has enough of
+// them (reads_correction_func_can, reads_correction_can.cpp:27-33), candidates in trial order, at most MAX_TRIED.
+struct CnsGroup { size_t b, e; };
+
+static void cns_groups(std::vector<mecat_candidate>& ec, const mecat_cns_params* p, std::vector<CnsGroup>& groups)
 {
-	if (check(c) || !dvol_reads || (!ec_in && nec) || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
-	cudaSetDevice(c->device);
-	*pieces = nullptr; *npieces = 0; *seqs = nullptr; *seq_bytes = 0;
-	const DVolume* V = (const DVolume*)dvol_reads;
-	const int id0 = V->start_read_id;
-	for (size_t i = 0; i < nec; ++i) {
-		const mecat_candidate& e = ec_in[i];
-		if (e.sid < id0 || e.sid >= id0 + V->num_reads || e.qid < id0 || e.qid >= id0 + V->num_reads)
-			MB_FAIL(c, "cns_reads: candidate %zu names a read outside the volume", i);
-		if (e.sdir != 0) MB_FAIL(c, "cns_reads: candidate %zu is not normalised (sdir must be 0)", i);
-		if (e.qsize != V->h_offsz[2 * (e.qid - id0) + 1] || e.ssize != V->h_offsz[2 * (e.sid - id0) + 1])
-			MB_FAIL(c, "cns_reads: candidate %zu disagrees with the volume about read sizes", i);
-		if (e.qext < 0 || e.qext >= e.qsize || e.sext < 0 || e.sext >= e.ssize)
-			MB_FAIL(c, "cns_reads: candidate %zu extension point outside its read", i);
-	}
-	const bool debug = getenv("MECAT_CNS_DEBUG") != nullptr;
-	WallTimer t_prep;
-	std::vector<mecat_candidate> ec(ec_in, ec_in + nec);
 	auto by_sid = [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; };
 	if (!std::is_sorted(ec.begin(), ec.end(), by_sid)) std::stable_sort(ec.begin(), ec.end(), by_sid);
-	struct Group { size_t b, e; };
-	std::vector<Group> groups;
+	const size_t nec = ec.size();
 	for (size_t i = 0; i < nec;) {
 		size_t j = i + 1;
 		while (j < nec && ec[j].sid == ec[i].sid) ++j;
-		// reads_correction_func_can, reads_correction_can.cpp:27-33
 		if ((int64_t)(j - i) >= p->min_cov && !(ec[i].ssize < p->min_size * 0.95)) {
 			mecat_b200_cns_sort_candidates(ec.data() + i, (int)(j - i));
-			groups.push_back(Group{i, std::min(j, i + (size_t)mbcns::MAX_TRIED)});
+			groups.push_back(CnsGroup{i, std::min(j, i + (size_t)mbcns::MAX_TRIED)});
 		}
 		i = j;
 	}
+}
+
+// Extensions + consensus of groups [g0, gend) whose reads all live in V (candidate ids are V's).  Pieces are appended to
+// `all` under the candidates' template ids.
+static int cns_core(mecat_b200_ctx* c, const DVolume* V, const std::vector<mecat_candidate>& ec, const std::vector<CnsGroup>& groups,
+                    size_t g0, size_t gend, const mecat_cns_params* p, CnsBlob& all, bool debug)
+{
+	const int id0 = V->start_read_id;
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
-	CnsBlob all;
 	const size_t TASKS_PER_BATCH = 400000;       // with the column arena (12 GB at ~30 kB per task) this bounds a batch; more units per launch suit the latency-bound stages
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;
 	std::vector<int64_t> rid;
-	if (debug) fprintf(stderr, "[cns_reads] validate + sort + group: %.1f ms\n", t_prep.stop());
-	for (size_t g0 = 0; g0 < groups.size();) {
+	while (g0 < gend) {
 		WallTimer t_batch;
 		// a batch = whole reads, as many as fit the column arena of the extension kernels
 		tasks.clear(); first.assign(1, 0); rsize.clear(); rid.clear(); tqid.clear(); tqsize.clear();
 		size_t g1 = g0, cols = 0;
-		while (g1 < groups.size()) {
+		while (g1 < gend) {
 			size_t need = 0;
 			const size_t mark = tasks.size();
 			for (size_t k = groups[g1].b; k < groups[g1].e; ++k) {
@@ -491,7 +480,11 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 		                   tasks.size(), ms_tasks, ms_align - ms_tasks, t_batch.stop() - ms_align);
 		g0 = g1;
 	}
-	WallTimer t_out;
+	return 0;
+}
+
+static int cns_hand_out(mecat_b200_ctx* c, CnsBlob& all, mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
+{
 	if (all.oom) MB_FAIL(c, "cns_reads: out of host memory");
 	const size_t bytes = all.len, np = all.recs.size();
 	mecat_cns_piece* out = (mecat_cns_piece*)malloc(sizeof(mecat_cns_piece) * (np ? np : 1));
@@ -501,9 +494,136 @@ int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candid
 	if (np) memcpy(out, all.recs.data(), sizeof(mecat_cns_piece) * np);
 	sq[bytes] = 0;
 	c->stats.num_records += (int64_t)np;
-	if (debug) fprintf(stderr, "[cns_reads] result buffers: %.1f ms\n", t_out.stop());
 	*pieces = out; *npieces = np; *seqs = sq; *seq_bytes = bytes;
 	return 0;
+}
+
+int mecat_b200_cns_reads(mecat_b200_ctx* c, void* dvol_reads, const mecat_candidate* ec_in, size_t nec, const mecat_cns_params* p,
+                         mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
+{
+	if (check(c) || !dvol_reads || (!ec_in && nec) || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
+	cudaSetDevice(c->device);
+	*pieces = nullptr; *npieces = 0; *seqs = nullptr; *seq_bytes = 0;
+	const DVolume* V = (const DVolume*)dvol_reads;
+	const int id0 = V->start_read_id;
+	for (size_t i = 0; i < nec; ++i) {
+		const mecat_candidate& e = ec_in[i];
+		if (e.sid < id0 || e.sid >= id0 + V->num_reads || e.qid < id0 || e.qid >= id0 + V->num_reads)
+			MB_FAIL(c, "cns_reads: candidate %zu names a read outside the volume", i);
+		if (e.sdir != 0) MB_FAIL(c, "cns_reads: candidate %zu is not normalised (sdir must be 0)", i);
+		if (e.qsize != V->h_offsz[2 * (e.qid - id0) + 1] || e.ssize != V->h_offsz[2 * (e.sid - id0) + 1])
+			MB_FAIL(c, "cns_reads: candidate %zu disagrees with the volume about read sizes", i);
+		if (e.qext < 0 || e.qext >= e.qsize || e.sext < 0 || e.sext >= e.ssize)
+			MB_FAIL(c, "cns_reads: candidate %zu extension point outside its read", i);
+	}
+	const bool debug = getenv("MECAT_CNS_DEBUG") != nullptr;
+	WallTimer t_prep;
+	std::vector<mecat_candidate> ec(ec_in, ec_in + nec);
+	std::vector<CnsGroup> groups;
+	cns_groups(ec, p, groups);
+	CnsBlob all;
+	if (debug) fprintf(stderr, "[cns_reads] validate + sort + group: %.1f ms\n", t_prep.stop());
+	if (cns_core(c, V, ec, groups, 0, groups.size(), p, all, debug)) return 1;
+	return cns_hand_out(c, all, pieces, npieces, seqs, seq_bytes);
+}
+
+// The same for a read set that spans several resident volumes (PackedDB::load_fasta_db keeps the whole data set in one
+// store with 64-bit offsets, src/common/packed_db.cpp:194; a device volume addresses 2^31 bases).  The templates are
+// taken in runs whose reads -- templates plus the reads of their (at most MAX_TRIED) candidates -- fit one working
+// volume; that volume is gathered ON THE DEVICE from the resident ones (volume_gather, no host copy of bases) and the
+// run goes through the single-volume path with working-volume ids, which are mapped back on the pieces.
+int mecat_b200_cns_reads_multi(mecat_b200_ctx* c, void* const* dvols, int nvols, const mecat_candidate* ec_in, size_t nec,
+                               const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
+{
+	if (check(c) || !dvols || nvols < 1 || (!ec_in && nec) || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
+	cudaSetDevice(c->device);
+	*pieces = nullptr; *npieces = 0; *seqs = nullptr; *seq_bytes = 0;
+	std::vector<const DVolume*> V((size_t)nvols);
+	for (int v = 0; v < nvols; ++v) {
+		V[(size_t)v] = (const DVolume*)dvols[v];
+		if (!V[(size_t)v]) MB_FAIL(c, "cns_reads_multi: null volume %d", v);
+		if (v > 0 && V[(size_t)v]->start_read_id != V[(size_t)v - 1]->start_read_id + V[(size_t)v - 1]->num_reads)
+			MB_FAIL(c, "cns_reads_multi: volume %d does not continue the read ids of volume %d", v, v - 1);
+	}
+	const int64_t id0 = V[0]->start_read_id, idn = (int64_t)V.back()->start_read_id + V.back()->num_reads;
+	auto locate = [&](int64_t id, int& vol, int& rd) {           // volumes are few: binary search over their first ids
+		int lo = 0, hi = nvols - 1;
+		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (V[(size_t)mid]->start_read_id <= id) lo = mid; else hi = mid - 1; }
+		vol = lo; rd = (int)(id - V[(size_t)lo]->start_read_id);
+	};
+	for (size_t i = 0; i < nec; ++i) {
+		const mecat_candidate& e = ec_in[i];
+		if (e.sid < id0 || e.sid >= idn || e.qid < id0 || e.qid >= idn) MB_FAIL(c, "cns_reads_multi: candidate %zu names a read outside the volumes", i);
+		if (e.sdir != 0) MB_FAIL(c, "cns_reads_multi: candidate %zu is not normalised (sdir must be 0)", i);
+		int qv, qr, sv, sr;
+		locate(e.qid, qv, qr); locate(e.sid, sv, sr);
+		if (e.qsize != V[(size_t)qv]->h_offsz[2 * (size_t)qr + 1] || e.ssize != V[(size_t)sv]->h_offsz[2 * (size_t)sr + 1])
+			MB_FAIL(c, "cns_reads_multi: candidate %zu disagrees with the volumes about read sizes", i);
+		if (e.qext < 0 || e.qext >= e.qsize || e.sext < 0 || e.sext >= e.ssize)
+			MB_FAIL(c, "cns_reads_multi: candidate %zu extension point outside its read", i);
+	}
+	const bool debug = getenv("MECAT_CNS_DEBUG") != nullptr;
+	std::vector<mecat_candidate> ec(ec_in, ec_in + nec);
+	std::vector<CnsGroup> groups;
+	cns_groups(ec, p, groups);
+	// bases one working volume may hold (test hook: MECAT_B200_CNS_WORK_BASES forces many small working volumes)
+	int64_t work_cap = 1500000000LL;
+	if (const char* e = getenv("MECAT_B200_CNS_WORK_BASES")) work_cap = std::max<int64_t>(1, atoll(e));
+	CnsBlob all;
+	std::vector<int32_t> local((size_t)(idn - id0), -1);        // global read -> read of the working volume
+	std::vector<int32_t> src_vol, src_read;
+	std::vector<int64_t> global_of;
+	std::vector<mecat_candidate> run;
+	std::vector<CnsGroup> run_groups;
+	for (size_t g0 = 0; g0 < groups.size();) {
+		src_vol.clear(); src_read.clear(); global_of.clear(); run.clear(); run_groups.clear();
+		int64_t bases = 0;
+		size_t g1 = g0;
+		auto want = [&](int64_t id, int64_t size, std::vector<int64_t>& fresh) {
+			if (local[(size_t)(id - id0)] >= 0) return;
+			local[(size_t)(id - id0)] = -2;                         // claimed by the group under inspection
+			fresh.push_back(id);
+			bases += size + 1;
+		};
+		while (g1 < groups.size()) {
+			std::vector<int64_t> fresh;
+			const int64_t before = bases;
+			want(ec[groups[g1].b].sid, ec[groups[g1].b].ssize, fresh);
+			for (size_t k = groups[g1].b; k < groups[g1].e; ++k) want(ec[k].qid, ec[k].qsize, fresh);
+			if (g1 > g0 && bases > work_cap) {                      // does not fit any more: the run ends before this group
+				for (int64_t id : fresh) local[(size_t)(id - id0)] = -1;
+				bases = before;
+				break;
+			}
+			if (bases > 0x7ff00000LL) MB_FAIL(c, "cns_reads_multi: the reads of template %d alone exceed one working volume", ec[groups[g1].b].sid);
+			for (int64_t id : fresh) {
+				int v, r;
+				locate(id, v, r);
+				local[(size_t)(id - id0)] = (int32_t)global_of.size();
+				src_vol.push_back(v); src_read.push_back(r); global_of.push_back(id);
+			}
+			CnsGroup lg; lg.b = run.size();
+			for (size_t k = groups[g1].b; k < groups[g1].e; ++k) {
+				mecat_candidate e = ec[k];
+				e.qid = local[(size_t)(e.qid - id0)]; e.sid = local[(size_t)(e.sid - id0)];
+				run.push_back(e);
+			}
+			lg.e = run.size();
+			run_groups.push_back(lg);
+			++g1;
+		}
+		DVolume* W = nullptr;
+		if (volume_gather(c, V.data(), src_vol.data(), src_read.data(), (int)global_of.size(), &W)) return 1;
+		if (debug) fprintf(stderr, "[cns_reads_multi] templates %zu..%zu: working volume of %zu reads, %lld bases\n", g0, g1, global_of.size(), (long long)bases);
+		const size_t first_rec = all.recs.size();
+		const int rc = cns_core(c, W, run, run_groups, 0, run_groups.size(), p, all, debug);
+		volume_release(c, W);
+		if (rc) return 1;
+		for (size_t k = first_rec; k < all.recs.size(); ++k) all.recs[k].id = global_of[(size_t)all.recs[k].id];
+		for (int64_t id : global_of) local[(size_t)(id - id0)] = -1;
+		g0 = g1;
+	}
+	return cns_hand_out(c, all, pieces, npieces, seqs, seq_bytes);
 }
 
 // ------------------------------------------------------------------------------------------

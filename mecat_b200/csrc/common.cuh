@@ -177,6 +177,8 @@ struct KScope
 // ---- internal entry points (one per translation unit)
 int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out);
 void volume_release(Ctx* c, DVolume* v);
+// working volume made of n reads taken from resident volumes: read i = read h_src_read[i] of src[h_src_vol[i]]
+int volume_gather(Ctx* c, const DVolume* const* src, const int32_t* h_src_vol, const int32_t* h_src_read, int n, DVolume** out);
 int index_build(Ctx* c, const DVolume* v, DIndex** out);
 int index_count_part(Ctx* c, const DVolume* v, uint32_t code_lo, uint32_t code_hi, DIndex** out);
 int index_finish_part(Ctx* c, const DVolume* v, DIndex* I, uint32_t code_lo, uint32_t code_hi);

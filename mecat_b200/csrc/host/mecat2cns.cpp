@@ -7,7 +7,9 @@
 // `-i 0` path.  The candidate file is normalised in memory exactly like partition_candidates /
 // normalise_candidate (src/mecat2cns/overlaps_partition.cpp:141-224) and processed in the same
 // batches of `-p` reads, but no `.partN` scratch files are written next to the input.  All gapped
-// extensions run on the GPU (mecat_b200_cns_reads); `-t` is accepted and ignored.
+// extensions run on the GPU (mecat_b200_cns_reads_multi); `-t` is accepted and ignored.  The read set may be of any size:
+// it is kept as volumes of at most 2.14 Gbase (the splitter's cut, MECAT_VOLUME_BASES as in mecat2pw), all resident on
+// every device.
 // Not on this path (refused with a message): `-i 1` (M4 input) and `-x 1` (nanopore).
 #include <getopt.h>
 #include <stdio.h>
@@ -180,13 +182,14 @@ int main(int argc, char* argv[])
 		raw.clear(); raw.shrink_to_fit();
 	}
 
-	// all reads in one packed volume (the reference keeps them in one PackedDB, packed_db.cpp:194)
-	mecat_volume vol;
-	memset(&vol, 0, sizeof vol);
+	// all reads, packed, as one or more volumes (the reference keeps them in one PackedDB with 64-bit offsets, packed_db.cpp:194)
+	mecat_volume* vols = NULL;
+	int nvols = 0;
 	{
 		StderrTimer t("load_fasta_db");
 		char err[512];
-		if (mecat_b200_volume_from_fasta(opt.reads, &vol, err, sizeof err)) { fprintf(stderr, "mecat2cns: %s\n", err); return 1; }
+		const char* cap = getenv("MECAT_VOLUME_BASES");   // test hook: smaller volumes, as in mecat2pw
+		if (mecat_b200_volumes_from_fasta(opt.reads, cap ? atoll(cap) : 0, &vols, &nvols, err, sizeof err)) { fprintf(stderr, "mecat2cns: %s\n", err); return 1; }
 	}
 
 	// One host thread per GPU (MECAT_GPUS=n, default 1): every device holds a replica of the packed reads, the reads to
@@ -213,11 +216,12 @@ int main(int argc, char* argv[])
 	std::atomic<int> failed(0);
 	auto worker = [&](int dev) {
 		mecat_b200_ctx* ctx = dev == 0 ? ctx0 : NULL;
-		void* dvol = NULL;
+		std::vector<void*> dvols((size_t)nvols, (void*)NULL);
 		{
 			StderrTimer t("gpu " + std::to_string(dev) + " init + volume upload");
 			if (!ctx && mecat_b200_init(&ctx, dev, NULL)) { fprintf(stderr, "mecat2cns: cannot initialise GPU %d\n", dev); failed = 1; return; }
-			if (mecat_b200_volume_upload(ctx, &vol, &dvol)) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); failed = 1; return; }
+			for (int v = 0; v < nvols; ++v)
+				if (mecat_b200_volume_upload(ctx, &vols[v], &dvols[(size_t)v])) { fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx)); failed = 1; return; }
 		}
 		for (size_t i = cut[dev]; !failed && i < cut[dev + 1];) {
 			const long long part = ec[i].sid / opt.batch_size;
@@ -229,7 +233,8 @@ int main(int argc, char* argv[])
 			mecat_cns_piece* pieces = NULL;
 			char* seqs = NULL;
 			size_t np = 0, nb = 0;
-			if (mecat_b200_cns_reads(ctx, dvol, ec.data() + i, j - i, &P, &pieces, &np, &seqs, &nb)) {
+			if (nvols == 0) { i = j; continue; }
+			if (mecat_b200_cns_reads_multi(ctx, dvols.data(), nvols, ec.data() + i, j - i, &P, &pieces, &np, &seqs, &nb)) {
 				fprintf(stderr, "mecat2cns: %s\n", mecat_b200_last_error(ctx));
 				failed = 1;
 				break;
@@ -264,7 +269,7 @@ int main(int argc, char* argv[])
 		}
 		{
 			StderrTimer t("gpu " + std::to_string(dev) + " release");
-			mecat_b200_volume_release(ctx, dvol);
+			for (void* d : dvols) if (d) mecat_b200_volume_release(ctx, d);
 			mecat_b200_destroy(ctx);
 		}
 	};
@@ -281,6 +286,6 @@ int main(int argc, char* argv[])
 		if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
 		for (auto& per_dev : results) for (auto& pt : per_dev) out.write(pt.text.data(), (std::streamsize)pt.text.size());
 	}
-	mecat_b200_volume_unload(&vol);
+	mecat_b200_volumes_unload(vols, nvols);
 	return ok ? 0 : 1;
 }

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <atomic>
 #include <deque>
+#include <functional>
 #include <future>
 #include <memory>
 #include <string>
@@ -274,8 +275,13 @@ int split_threads(size_t input_bytes)
 	return std::max(1, std::min(hw > 0 ? hw : 1, 32));
 }
 
-// returns 0 = done, 1 = failed while writing (err set), 2 = not applicable: use the sequential path
-int split_parallel(const FastaStream& in, const char* wrk_dir, int64_t cap, int threads, int* num_volumes, std::string& err)
+// What becomes of a finished volume: a file of the work directory (mecat2pw) or a volume in host memory (mecat2cns).
+// Called in volume order from one thread at a time; the buffers stay valid until the call returns.
+typedef std::function<int(int vi, int num_reads, int64_t num_bases, int start_read_id, const std::vector<int32_t>& offsz,
+                          const uint8_t* pac, size_t bytes)> VolumeSink;
+
+// returns 0 = done, 1 = the sink failed (err set), 2 = not applicable: use the sequential path
+int split_parallel(const FastaStream& in, int64_t cap, int threads, int* num_volumes, std::string& err, const VolumeSink& sink)
 {
 	if (!in.map || threads < 2 || in.size == 0) return 2;
 	{
@@ -351,8 +357,6 @@ int split_parallel(const FastaStream& in, const char* wrk_dir, int64_t cap, int 
 		}
 		if (v.curr > 0) vols.push_back(std::move(v));
 	}
-	FILE* idx = fopen(join(wrk_dir, "fileindex.txt").c_str(), "w");
-	if (!idx) { err = std::string("cannot write into '") + wrk_dir + "'"; return 1; }
 	std::future<int> writer;
 	int rid = 0, rc = 0;
 	for (size_t vi = 0; vi < vols.size() && !rc; ++vi) {
@@ -380,24 +384,18 @@ int split_parallel(const FastaStream& in, const char* wrk_dir, int64_t cap, int 
 			for (auto& th : pool) th.join();
 		}
 		if (writer.valid() && writer.get()) { rc = 1; break; }
-		const std::string name = join(wrk_dir, "vol" + std::to_string(vi));
-		fprintf(idx, "%s\n", name.c_str());
-		const int32_t hdr[3] = {V.num_reads, (int32_t)V.curr, rid};
+		const int first_id = rid;
 		rid += V.num_reads;
-		const std::vector<int32_t>* offsz = &V.offsz;
-		writer = std::async(std::launch::async, [name, hdr, offsz, pac, bytes]() -> int {
-			FILE* f = fopen(name.c_str(), "wb");
-			if (!f) return 1;
-			bool ok = fwrite(hdr, 4, 3, f) == 3 && fwrite(offsz->data(), 4, offsz->size(), f) == offsz->size() &&
-			          fwrite(pac->data(), 1, bytes, f) == bytes;
-			ok = (fclose(f) == 0) && ok;
-			return ok ? 0 : 1;
+		const Vol* vp = &V;
+		const int vnum = (int)vi;
+		// the sink of volume vi runs behind the packing of volume vi + 1
+		writer = std::async(std::launch::async, [&sink, vp, vnum, first_id, pac, bytes]() -> int {
+			return sink(vnum, vp->num_reads, vp->curr, first_id, vp->offsz, pac->data(), bytes);
 		});
 	}
 	const double t_packed = now();
 	if (writer.valid() && writer.get()) rc = 1;
-	fclose(idx);
-	if (rc) { err = "cannot write volume file"; return 1; }
+	if (rc) { err = "cannot store a volume"; return 1; }
 	*num_volumes = (int)vols.size();
 	if (timing) fprintf(stderr, "[split] %d threads: parse %.2f s, assign + pack (+ writes behind it) %.2f s, last write %.2f s\n", threads,
 	                    t_parsed - t_start, t_packed - t_parsed, now() - t_packed);
@@ -420,10 +418,29 @@ int mecat_b200_split_dataset(const char* reads_path, const char* wrk_dir, int64_
 	FastaStream in(reads_path);
 	if (!in.ok) return fail(std::string("cannot open file '") + reads_path + "' for reading");
 	{
+		// volume files + fileindex.txt, written as the volumes come
 		std::string perr;
-		const int prc = split_parallel(in, wrk_dir, cap, split_threads(in.size), num_volumes, perr);
-		if (prc == 0) return 0;
-		if (prc == 1) return fail(perr);
+		std::vector<std::string> names;
+		const VolumeSink to_file = [&](int vi, int num_reads, int64_t num_bases, int start_read_id, const std::vector<int32_t>& offsz,
+		                               const uint8_t* pac, size_t bytes) -> int {
+			const std::string name = join(wrk_dir, "vol" + std::to_string(vi));
+			names.push_back(name);
+			FILE* f = fopen(name.c_str(), "wb");
+			if (!f) return 1;
+			const int32_t hdr[3] = {num_reads, (int32_t)num_bases, start_read_id};
+			bool ok = fwrite(hdr, 4, 3, f) == 3 && fwrite(offsz.data(), 4, offsz.size(), f) == offsz.size() && fwrite(pac, 1, bytes, f) == bytes;
+			ok = (fclose(f) == 0) && ok;
+			return ok ? 0 : 1;
+		};
+		const int prc = split_parallel(in, cap, split_threads(in.size), num_volumes, perr, to_file);
+		if (prc == 0) {
+			FILE* idx = fopen(join(wrk_dir, "fileindex.txt").c_str(), "w");
+			if (!idx) return fail(std::string("cannot write into '") + wrk_dir + "'");
+			for (const std::string& n : names) fprintf(idx, "%s\n", n.c_str());
+			fclose(idx);
+			return 0;
+		}
+		if (prc == 1) return fail("cannot write volume file");
 	}
 	FILE* idx = fopen(join(wrk_dir, "fileindex.txt").c_str(), "w");
 	if (!idx) return fail(std::string("cannot write into '") + wrk_dir + "'");
@@ -494,6 +511,79 @@ int mecat_b200_volume_from_fasta(const char* reads_path, mecat_volume* out, char
 	out->num_reads = v.num_reads; out->num_bases = (int32_t)v.curr; out->start_read_id = 0;
 	out->offset_size = os; out->pac = pac;
 	return 0;
+}
+
+// The whole read set as volumes in host memory (several when it exceeds the cap): what mecat2cns needs for read sets
+// larger than 2.14 Gbase.  Same bytes as the files mecat_b200_split_dataset writes.  Release with mecat_b200_volumes_unload.
+int mecat_b200_volumes_from_fasta(const char* reads_path, int64_t max_volume_bases, mecat_volume** vols_out, int* num_volumes,
+                                  char* err, int err_cap)
+{
+	auto fail = [&](const std::string& m) { if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", m.c_str()); return 1; };
+	if (!reads_path || !vols_out || !num_volumes) return fail("volumes_from_fasta: null argument");
+	const int64_t cap = max_volume_bases > 0 ? max_volume_bases : kMaxVolumeBases;
+	FastaStream in(reads_path);
+	if (!in.ok) return fail(std::string("cannot open file '") + reads_path + "' for reading");
+	std::vector<mecat_volume> got;
+	bool oom = false;
+	auto keep = [&](int num_reads, int64_t num_bases, int start_read_id, const int32_t* offsz, const uint8_t* pac, size_t bytes) -> int {
+		const size_t nr = (size_t)num_reads;
+		int32_t* os = (int32_t*)malloc(sizeof(int32_t) * 2 * (nr ? nr : 1));
+		uint8_t* pc = (uint8_t*)malloc(bytes + 16);
+		if (!os || !pc) { free(os); free(pc); oom = true; return 1; }
+		if (nr) memcpy(os, offsz, sizeof(int32_t) * 2 * nr);
+		memcpy(pc, pac, bytes);
+		memset(pc + bytes, 0, 16);
+		mecat_volume v;
+		v.num_reads = num_reads; v.num_bases = (int32_t)num_bases; v.start_read_id = start_read_id; v.offset_size = os; v.pac = pc;
+		got.push_back(v);
+		return 0;
+	};
+	auto drop_all = [&]() { for (mecat_volume& v : got) mecat_b200_volume_unload(&v); got.clear(); };
+	{
+		std::string perr;
+		int nv = 0;
+		const VolumeSink to_memory = [&](int, int num_reads, int64_t num_bases, int start_read_id, const std::vector<int32_t>& offsz,
+		                                 const uint8_t* pac, size_t bytes) -> int { return keep(num_reads, num_bases, start_read_id, offsz.data(), pac, bytes); };
+		const int prc = split_parallel(in, cap, split_threads(in.size), &nv, perr, to_memory);
+		if (prc == 1) { drop_all(); return fail(oom ? "out of memory" : perr); }
+		if (prc == 2) {
+			drop_all();
+			VolumeBuilder v;
+			const int64_t bases = std::min<int64_t>(cap, (int64_t)in.size) + 1;
+			v.pac.assign((size_t)(bases / 4) + 64, 0);
+			std::string seq, e;
+			const char* sp = NULL;
+			bool acgt = true;
+			int rid = 0;
+			auto flush = [&]() -> int {
+				if (keep(v.num_reads, v.curr, rid, v.offsz.data(), v.pac.data(), (size_t)((v.curr + 3) / 4))) return 1;
+				rid += v.num_reads;
+				v.clear();
+				return 0;
+			};
+			for (;;) {
+				const int64_t n = in.next(seq, sp, acgt, e);
+				if (n == -1) break;
+				if (n == -2) { drop_all(); return fail("FastaReader: " + e); }
+				if (v.curr + n + 1 > cap && v.curr > 0) { if (flush()) { drop_all(); return fail("out of memory"); } }
+				if (n + 1 > cap) { drop_all(); return fail("a read is longer than the volume cap"); }
+				v.add(sp, (size_t)n, acgt);
+			}
+			if (v.curr > 0 && flush()) { drop_all(); return fail("out of memory"); }
+		}
+	}
+	mecat_volume* arr = (mecat_volume*)malloc(sizeof(mecat_volume) * (got.size() ? got.size() : 1));
+	if (!arr) { drop_all(); return fail("out of memory"); }
+	for (size_t i = 0; i < got.size(); ++i) arr[i] = got[i];
+	*vols_out = arr; *num_volumes = (int)got.size();
+	return 0;
+}
+
+void mecat_b200_volumes_unload(mecat_volume* vols, int num_volumes)
+{
+	if (!vols) return;
+	for (int i = 0; i < num_volumes; ++i) mecat_b200_volume_unload(&vols[i]);
+	free(vols);
 }
 
 int mecat_b200_volume_load(const char* path, mecat_volume* out)

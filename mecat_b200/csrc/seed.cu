@@ -29,12 +29,22 @@ namespace mb {
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int SEED_THREADS = 1024;
-constexpr int CNT_SLOTS = 65536;            // hashed 16-bit hit counters (128 KB)
+constexpr int CNT_SLOTS = 65536;            // hashed hit counters, slot = bucket & 0xFFFF
 constexpr int BIT_WORDS = 2048;             // hashed interest bitmap (65536 bits) / anchor claim slots
-constexpr uint32_t CNT_SAT = 0x8000u;       // counters stop growing here (no wrap with <= 1024 racing adds)
+constexpr uint32_t CNT_SAT = 0x8000u;       // 16-bit counters stop growing here (no wrap with <= 1024 racing adds)
+constexpr uint32_t CNT_SAT8 = 128u;         // 8-bit counters: an add that finds 128 or more takes itself back
+// Two shapes of k_seed (template parameter CTAS = CTAs per SM):
+//   1: one CTA of 1 024 threads per SM, 16-bit counters (128 KB), 8 192 collected hits sort in shared memory;
+//   2: two CTAs of 512 threads per SM, 8-bit counters (64 KB), 4 096 hits sort in shared memory.  The kernel is a chain of
+//      block-wide phases separated by barriers (ncu at one CTA per SM: 3 of 11 stall cycles per issue are barrier waits,
+//      issue slots 55 % busy); with two strands in flight per SM one CTA's barrier hides behind the other's gathers.
+template <int CTAS> struct SeedShape
+{
+	static constexpr int THREADS = 1024 / CTAS;
+	static constexpr int CNT_WORDS = CTAS == 1 ? CNT_SLOTS / 2 : CNT_SLOTS / 4;
+	static constexpr int SCAP = 8192 / CTAS;   // collected hits that sort in shared memory (the counters' memory)
+};
 constexpr int KCACHE = 2048;               // sampled k-mers whose list info is cached in shared memory
-constexpr int SCAP = 8192;                  // collected hits that sort in shared memory
 constexpr int MAX_KM = 32766;               // seed ordinals are `short` in the reference (pw_impl.h:31)
 
 struct BucketHdr          // 16 bytes, one per collected bucket, ascending seg inside a strand
@@ -282,11 +292,14 @@ __device__ int replay_overflow(unsigned long long* ent, int na, int* sl, int* ss
 	return score;
 }
 
-__global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
+template <int CTAS>
+__global__ void __launch_bounds__(SeedShape<CTAS>::THREADS, CTAS) k_seed(SeedParams P)
 {
+	constexpr int SCAP = SeedShape<CTAS>::SCAP;
+	constexpr int CNT_WORDS = SeedShape<CTAS>::CNT_WORDS;
 	extern __shared__ uint32_t smem_u32[];
-	uint32_t* cnt = smem_u32;                         // CNT_SLOTS / 2 words: 16-bit hit counters, slot = bucket & 0xFFFF
-	uint32_t* want_bits = cnt + CNT_SLOTS / 2;        // BIT_WORDS words = 65536 interest bits, same slot map
+	uint32_t* cnt = smem_u32;                         // CNT_WORDS words of 16-bit (CTAS = 1) or 8-bit hit counters
+	uint32_t* want_bits = cnt + CNT_WORDS;            // BIT_WORDS words = 65536 interest bits, same slot map
 	uint32_t* kbs = want_bits + BIT_WORDS;            // KCACHE list begins
 	uint8_t* kcs = (uint8_t*)(kbs + KCACHE);          // KCACHE list lengths
 	int* misc = (int*)(kcs + KCACHE);                 // 64 ints: scan scratch [0..33), counters
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		uint8_t* kc = nk <= KCACHE ? kcs : gsc.kc;
 
 		// ---- clear
-		for (int i = tid; i < CNT_SLOTS / 2 + BIT_WORDS; i += blockDim.x) cnt[i] = 0u;
+		for (int i = tid; i < CNT_WORDS + BIT_WORDS; i += blockDim.x) cnt[i] = 0u;
 		if (tid < 64) misc[tid] = 0;
 		// ---- k-mer lookup
 		for (int km = tid; km < nk; km += blockDim.x) {
@@ -338,46 +351,68 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		constexpr int U = 4;
 		for (int km0 = warp; km0 < nk; km0 += U * nwarps) {
 			int n[U];
-			uint32_t b[U], p0[U], p1[U];
+			uint32_t b[U], p0[U], p1[U] = {0u, 0u, 0u, 0u};
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
 				const int km = km0 + u * nwarps;
 				n[u] = km < nk ? (int)kc[km] : 0;
 				b[u] = km < nk ? kb[km] : 0u;
 			}
+			// most lists hold <= 32 positions (mean ~26 at 1.5 Gbase): the second gather and everything behind it is skipped
+			// for the whole warp unless one of the four lists is longer
+			const bool long_list = max(max(n[0], n[1]), max(n[2], n[3])) > 32;
 #pragma unroll
-			for (int u = 0; u < U; ++u) {
-				p0[u] = lane < n[u] ? (uint32_t)P.pos[b[u] + lane] : 0u;
-				p1[u] = lane + 32 < n[u] ? (uint32_t)P.pos[b[u] + lane + 32] : 0u;
+			for (int u = 0; u < U; ++u) p0[u] = lane < n[u] ? (uint32_t)P.pos[b[u] + lane] : 0u;
+			if (long_list) {
+#pragma unroll
+				for (int u = 0; u < U; ++u) p1[u] = lane + 32 < n[u] ? (uint32_t)P.pos[b[u] + lane + 32] : 0u;
 			}
 			auto count_one = [&](uint32_t pp) {
 				const uint32_t hh = (pp / SEGW) & (CNT_SLOTS - 1);
-				const uint32_t cur = (cnt[hh >> 1] >> ((hh & 1u) << 4)) & 0xFFFFu;
-				if (cur < CNT_SAT) atomicAdd(&cnt[hh >> 1], 1u << ((hh & 1u) << 4));
+				if (CTAS == 1) {
+					const uint32_t cur = (cnt[hh >> 1] >> ((hh & 1u) << 4)) & 0xFFFFu;
+					if (cur < CNT_SAT) atomicAdd(&cnt[hh >> 1], 1u << ((hh & 1u) << 4));
+				} else {
+					// 8-bit counter: add, and take the add back when the counter had reached the cap.  Adds and their
+					// take-backs are one integer addition on the word, so a transient carry into the neighbour byte
+					// cancels exactly; the atomics of one counter return successive values, so it ends at <= 128.
+					const uint32_t sh = (hh & 3u) << 3;
+					if (((cnt[hh >> 2] >> sh) & 0xFFu) < CNT_SAT8) {
+						const uint32_t old = atomicAdd(&cnt[hh >> 2], 1u << sh);
+						if (((old >> sh) & 0xFFu) >= CNT_SAT8) atomicSub(&cnt[hh >> 2], 1u << sh);
+					}
+				}
 				++myhits;
 			};
 #pragma unroll
-			for (int u = 0; u < U; ++u) {
-				if (lane < n[u]) count_one(p0[u]);
-				if (lane + 32 < n[u]) count_one(p1[u]);
-				for (int h = lane + 64; h < n[u]; h += 32) count_one((uint32_t)P.pos[b[u] + h]);
+			for (int u = 0; u < U; ++u) if (lane < n[u]) count_one(p0[u]);
+			if (long_list) {
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					if (lane + 32 < n[u]) count_one(p1[u]);
+					for (int h = lane + 64; h < n[u]; h += 32) count_one((uint32_t)P.pos[b[u] + h]);
+				}
 			}
 		}
 		__syncthreads();
 		// ---- pass 2: scan the slot table.  A bucket can only pass the reference's index_score >= 2k
 		// gate if its own count plus its left neighbour's reaches the gate; such a slot marks the
 		// +-W slots a candidate anchored there can reach (previous bucket, neighbour votes).
-		for (int w = tid; w < CNT_SLOTS / 2; w += blockDim.x) {
+		for (int w = tid; w < CNT_WORDS; w += blockDim.x) {
 			const uint32_t cw = cnt[w];
 			if (cw == 0u) continue;
-			const uint32_t pw = cnt[(w + CNT_SLOTS / 2 - 1) & (CNT_SLOTS / 2 - 1)];
-			const int c0 = (int)(cw & 0xFFFFu), c1 = (int)(cw >> 16), cm = (int)(pw >> 16);
+			const uint32_t pw = cnt[(w + CNT_WORDS - 1) & (CNT_WORDS - 1)];
+			constexpr int PER = CTAS == 1 ? 2 : 4;            // counters per word
+			constexpr int BITS = 32 / PER;
+			constexpr uint32_t CMASK = (1u << BITS) - 1u;
+			int left = (int)(pw >> (32 - BITS));              // the last counter of the word before
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				const int c = half ? c1 + c0 : c0 + cm;
-				const int own = half ? c1 : c0;
+			for (int q = 0; q < PER; ++q) {
+				const int own = (int)((cw >> (q * BITS)) & CMASK);
+				const int c = own + left;
+				left = own;
 				if (own == 0 || c < P.gate) continue;
-				const int slot = 2 * w + half;
+				const int slot = PER * w + q;
 				int lo = slot - W, hi = slot + W;              // inclusive, modulo CNT_SLOTS
 				if (hi - lo + 1 >= CNT_SLOTS) { lo = 0; hi = CNT_SLOTS - 1; }
 				for (int wb = (lo >> 5); wb <= (hi >> 5); ++wb) {
@@ -392,17 +427,19 @@ __global__ void __launch_bounds__(SEED_THREADS, 1) k_seed(SeedParams P)
 		// ---- pass 3: collect the hits of wanted buckets (shared memory first, overflow to global scratch)
 		for (int km0 = warp; km0 < nk; km0 += U * nwarps) {
 			int n[U];
-			uint32_t b[U], p0[U], p1[U];
+			uint32_t b[U], p0[U], p1[U] = {0u, 0u, 0u, 0u};
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
 				const int km = km0 + u * nwarps;
 				n[u] = km < nk ? (int)kc[km] : 0;
 				b[u] = km < nk ? kb[km] : 0u;
 			}
+			const bool long_list = max(max(n[0], n[1]), max(n[2], n[3])) > 32;
 #pragma unroll
-			for (int u = 0; u < U; ++u) {
-				p0[u] = lane < n[u] ? (uint32_t)P.pos[b[u] + lane] : 0u;
-				p1[u] = lane + 32 < n[u] ? (uint32_t)P.pos[b[u] + lane + 32] : 0u;
+			for (int u = 0; u < U; ++u) p0[u] = lane < n[u] ? (uint32_t)P.pos[b[u] + lane] : 0u;
+			if (long_list) {
+#pragma unroll
+				for (int u = 0; u < U; ++u) p1[u] = lane + 32 < n[u] ? (uint32_t)P.pos[b[u] + lane + 32] : 0u;
 			}
 			auto collect = [&](bool have, uint32_t p, int km) {
 				bool take = false;
@@ -969,13 +1006,19 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 	// hits, 7 MB of scratch per CTA), and the reference maps such reads like any other
 	int hcap = 1 << 16;
 	while ((long long)hcap < (long long)MAX_OCC * max_nk && hcap < (1 << 23)) hcap <<= 1;
-	const int nctas = c->sm_count;
+	// MECAT_B200_SEED_CTAS = 1 | 2: shape of k_seed (see SeedShape)
+	int seed_ctas = 2;
+	if (const char* e = getenv("MECAT_B200_SEED_CTAS")) seed_ctas = atoi(e) == 1 ? 1 : 2;
+	const int nctas = c->sm_count * seed_ctas;
+	const int seed_threads = 1024 / seed_ctas;
+	const int cnt_words = seed_ctas == 1 ? CNT_SLOTS / 2 : CNT_SLOTS / 4;
 	int batch = 8192;
 	if (batch > read_end - read_begin) batch = read_end - read_begin;
 	unsigned long long arena_bytes = 1ull << 30;
 
-	const size_t smem = (size_t)(CNT_SLOTS / 2 + BIT_WORDS + KCACHE) * 4 + KCACHE + 64 * 4 + (size_t)(SEED_THREADS / 32) * 123 * 4;
-	MB_CUDA(c, cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const size_t smem = (size_t)(cnt_words + BIT_WORDS + KCACHE) * 4 + KCACHE + 64 * 4 + (size_t)(seed_threads / 32) * 123 * 4;
+	MB_CUDA(c, cudaFuncSetAttribute(k_seed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	MB_CUDA(c, cudaFuncSetAttribute(k_seed<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
 	unsigned char* d_arena = nullptr;
 	StrandDesc* d_desc = nullptr;
@@ -1020,7 +1063,8 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 			S.desc = d_desc; S.scratch = d_scratch; S.kcap = kcap; S.hcap = hcap; S.hit_counter = d_hits;
 			{
 				KScope ks(c, MECAT_K_SEED);
-				k_seed<<<nctas, SEED_THREADS, smem, c->stream>>>(S);
+				if (seed_ctas == 1) k_seed<1><<<nctas, seed_threads, smem, c->stream>>>(S);
+				else k_seed<2><<<nctas, seed_threads, smem, c->stream>>>(S);
 			}
 			MB_CUDA(c, cudaGetLastError());
 			// status check (arena overflow -> retry the batch with fewer reads)

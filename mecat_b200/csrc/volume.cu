@@ -115,6 +115,88 @@ int volume_from_device(Ctx* c, int num_reads, int num_bases, int start_read_id, 
 	return rc;
 }
 
+// ---- a working volume gathered from reads of several resident volumes (mecat2cns on read sets larger than one volume)
+struct GatherRead
+{
+	const uint32_t* src;      // forward words of the source volume
+	uint32_t src_off;         // first base of the read there
+	uint32_t dst_off;         // first base of the read in the working volume
+	int32_t len;
+};
+
+// One warp per read: destination word j of the read's span takes 16 bases from the source at the matching offset.  The
+// first and the last word of a span are shared with the neighbouring reads (and the pad base between them, which stays
+// 0 like in PackedDB), so they are OR-ed into a zeroed array; the words in between are plain stores.
+__global__ void __launch_bounds__(256) k_gather_reads(const GatherRead* __restrict__ reads, int n, uint32_t* __restrict__ fwd)
+{
+	const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (warp >= n) return;
+	const GatherRead r = reads[warp];
+	if (r.len <= 0) return;
+	const uint32_t w0 = r.dst_off >> 4, w1 = (r.dst_off + (uint32_t)r.len - 1u) >> 4;
+	for (uint32_t w = w0 + (uint32_t)lane; w <= w1; w += 32u) {
+		// bases [16 w, 16 w + 16) of the working volume, clipped to the read
+		const int64_t first = (int64_t)w * 16 - (int64_t)r.dst_off;          // read coordinate of the word's first base (may be < 0)
+		const int lo = first < 0 ? (int)-first : 0;                          // bases of the word before the read
+		const int64_t left = (int64_t)r.len - first;
+		const int hi = left < 16 ? (int)left : 16;                          // bases of the word inside the read end at `hi`
+		uint32_t x = ld_bases32(r.src, (uint32_t)((int64_t)r.src_off + first + lo)) << (2 * lo);
+		if (hi < 16) x &= (1u << (2 * hi)) - 1u;
+		if (lo > 0) x &= ~((1u << (2 * lo)) - 1u);
+		if (w == w0 || w == w1) atomicOr(fwd + w, x);
+		else fwd[w] = x;
+	}
+}
+
+int volume_gather(Ctx* c, const DVolume* const* src, const int32_t* h_src_vol, const int32_t* h_src_read, int n, DVolume** out)
+{
+	DVolume* d = new DVolume;
+	std::vector<GatherRead> g((size_t)n);
+	d->h_offsz.resize(2 * (size_t)n);
+	int64_t curr = 0;
+	for (int i = 0; i < n; ++i) {
+		const DVolume* S = src[h_src_vol[i]];
+		const int32_t off = S->h_offsz[2 * (size_t)h_src_read[i]], len = S->h_offsz[2 * (size_t)h_src_read[i] + 1];
+		if (curr + len + 1 > 0x7fffffffLL) { delete d; MB_FAIL(c, "volume_gather: the working set of reads exceeds one volume"); }
+		g[(size_t)i].src = S->fwd; g[(size_t)i].src_off = (uint32_t)off; g[(size_t)i].dst_off = (uint32_t)curr; g[(size_t)i].len = len;
+		d->h_offsz[2 * (size_t)i] = (int32_t)curr; d->h_offsz[2 * (size_t)i + 1] = len;
+		if (len > d->max_read) d->max_read = len;
+		curr += len + 1;                   // pad base, split_database.cpp:251
+	}
+	d->num_reads = n; d->num_bases = (int32_t)curr; d->start_read_id = 0;
+	d->words = ((size_t)curr + 15) / 16 + 8;
+	GatherRead* d_g = nullptr;
+	auto fail = [&](cudaError_t e, const char* what) {
+		char b[256];
+		snprintf(b, sizeof b, "volume_gather: %s: %s", what, cudaGetErrorString(e));
+		c->err = b;
+		c->dfree(d_g);
+		volume_release(c, d);
+		return 1;
+	};
+	cudaError_t e;
+	if ((e = c->dmalloc((void**)&d->fwd, d->words * 4)) != cudaSuccess) return fail(e, "cudaMalloc fwd");
+	if ((e = c->dmalloc((void**)&d->rev, d->words * 4)) != cudaSuccess) return fail(e, "cudaMalloc rev");
+	if ((e = c->dmalloc((void**)&d->offsz, sizeof(int2) * (size_t)(n ? n : 1))) != cudaSuccess) return fail(e, "cudaMalloc offsets");
+	if ((e = c->dmalloc((void**)&d_g, sizeof(GatherRead) * (size_t)(n ? n : 1))) != cudaSuccess) return fail(e, "cudaMalloc gather list");
+	if ((e = cudaMemsetAsync(d->fwd, 0, d->words * 4, c->stream)) != cudaSuccess) return fail(e, "memset");
+	if (n) {
+		if ((e = cudaMemcpyAsync(d->offsz, d->h_offsz.data(), sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "H2D offsets");
+		if ((e = cudaMemcpyAsync(d_g, g.data(), sizeof(GatherRead) * (size_t)n, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "H2D gather list");
+	}
+	{
+		KScope ks(c, MECAT_K_ORIENT, 2);
+		if (n) k_gather_reads<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, c->stream>>>(d_g, n, d->fwd);
+		k_orient_rev<<<(unsigned)((d->words + 255) / 256), 256, 0, c->stream>>>(d->fwd, d->rev, curr, d->words);
+	}
+	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e, "gather kernels");
+	c->resolve_timers();
+	c->dfree(d_g);
+	c->stats.h2d_bytes += (int64_t)(sizeof(int2) + sizeof(GatherRead)) * n;
+	*out = d;
+	return 0;
+}
+
 void volume_release(Ctx* c, DVolume* v)
 {
 	if (!v) return;

@@ -395,11 +395,11 @@ def test_repeat_heavy_long_reads(gpu_ctx):
     hv = host_volume(vol)
     want = util.oracle_pw_tile(vol, vol, util.pw_params(task=0), threads=8)
     gpu_ctx.reset_stats()
-    got = gpu_ctx.pw_overlaps(hv, hv, mecat_b200.pw_params(task=0))
+    got = gpu_ctx.pw_candidates(hv, hv)
     assert gpu_ctx.stats()["num_hits"] > 2 * 48 * 65536 // 2          # the strands really are that heavy
     report("repeat_heavy_can", util.ec_lines(got), util.ec_lines(want))
     want = util.oracle_pw_tile(vol, vol, util.pw_params(task=1), threads=8)
-    got = gpu_ctx.pw_overlaps(hv, hv, mecat_b200.pw_params(task=1))
+    got = gpu_ctx.pw_overlaps(hv, hv)
     report("repeat_heavy_m4", util.m4_lines(got, True), util.m4_lines(want, True))
 
 
@@ -611,6 +611,47 @@ def test_command_line_drivers_match_reference(gpu_ctx, tmp_path):
     if mecat_b200.load_library().mecat_b200_device_count() >= 2:
         out2 = str(tmp_path / "cns2.fa")
         _run_cli("mecat2cns", ["-i", "0", "-t", "2", "-l", "2000", "-c", "4", "-a", "1000", can, fa, out2], env={"MECAT_GPUS": "2"})
+        assert open(out2).read() == open(out1).read()
+
+
+def test_cns_on_several_volumes_matches_reference(gpu_ctx, tmp_path, monkeypatch):
+    """The read set cut into 5+ volumes (as a read set beyond 2.14 Gbase is): mecat_b200_cns_reads_multi gathers the reads
+    a run of templates needs into a working volume on the device; the corrected FASTA is the unmodified reference's, also
+    when a small working-volume cap forces many runs, and through the command-line driver (one and two devices)."""
+    import mecat_b200
+    fa = str(tmp_path / "small.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f, open(fa, "wb") as g:
+        g.write(f.read())
+    vols = mecat_b200.volumes_from_fasta(fa, max_volume_bases=320000)
+    assert len(vols) >= 5 and sum(v.num_reads for v in vols) == 250
+    dv = [gpu_ctx.upload(v) for v in vols]
+    want = _gold_fasta("small", "cns_relaxed")
+    ec = mecat_b200.normalise_candidates(_gold_can("small"), 2000)
+
+    def run():
+        pieces = gpu_ctx.cns_reads_multi(dv, ec, 0.9, 1000, 4, 2000)
+        return sorted((">%d_%d_%d_%d" % (i, b, e, len(s)), s.decode()) for i, b, e, s in pieces)
+
+    assert run() == want
+    monkeypatch.setenv("MECAT_B200_CNS_WORK_BASES", "150000")          # ~25 reads per working volume: dozens of runs
+    assert run() == want
+    monkeypatch.delenv("MECAT_B200_CNS_WORK_BASES")
+    for d in dv:
+        gpu_ctx.release_volume(d)
+    can = str(tmp_path / "small.can")
+    with gzip.open(os.path.join(util.GOLDEN, "small.can.gz"), "rb") as f, open(can, "wb") as g:
+        g.write(f.read())
+
+    def corrected(path):
+        lines = open(path).read().splitlines()
+        return sorted(zip(lines[0::2], lines[1::2]))
+
+    out1 = str(tmp_path / "cns1.fa")
+    _run_cli("mecat2cns", ["-i", "0", "-l", "2000", "-c", "4", "-a", "1000", can, fa, out1], env={"MECAT_VOLUME_BASES": "320000"})
+    assert corrected(out1) == want
+    if mecat_b200.load_library().mecat_b200_device_count() >= 2:
+        out2 = str(tmp_path / "cns2.fa")
+        _run_cli("mecat2cns", ["-i", "0", "-l", "2000", "-c", "4", "-a", "1000", can, fa, out2], env={"MECAT_VOLUME_BASES": "320000", "MECAT_GPUS": "2"})
         assert open(out2).read() == open(out1).read()
 
 

@@ -204,3 +204,24 @@ def test_threaded_split_equals_the_sequential_split(tmp_path, threads, monkeypat
         assert [os.path.basename(v) for v in par] == [os.path.basename(v) for v in seq], name
         for a, b in zip(seq, par):
             assert open(a, "rb").read() == open(b, "rb").read(), (name, os.path.basename(a))
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_volumes_from_fasta_equal_the_split_files(tmp_path, threads, monkeypatch):
+    """The in-memory loader of mecat2cns for read sets beyond one volume gives the very volumes the splitter writes."""
+    import mecat_b200
+    rng = np.random.default_rng(23)
+    fa = str(tmp_path / "r.fa")
+    with open(fa, "w") as f:
+        for i in range(300):
+            f.write(">%d\n%s\n" % (i, "".join("ACGTN"[c] for c in rng.integers(0, 5 if i % 7 == 0 else 4, size=int(rng.integers(1, 900))))))
+    monkeypatch.setenv("MECAT_B200_SPLIT_THREADS", str(threads))
+    files = mecat_b200.split_dataset(fa, str(tmp_path / "wrk"), max_volume_bases=20000)
+    vols = mecat_b200.volumes_from_fasta(fa, max_volume_bases=20000)
+    assert len(vols) == len(files) > 4
+    for path, v in zip(files, vols):
+        w = mecat_b200.HostVolume.load(path)
+        assert (v.num_reads, v.num_bases, v.start_read_id) == (w.num_reads, w.num_bases, w.start_read_id)
+        assert np.array_equal(v.offset_size, w.offset_size) and v.pac.tobytes() == w.pac.tobytes()
+    one = mecat_b200.volumes_from_fasta(fa)
+    assert len(one) == 1 and one[0].pac.tobytes() == mecat_b200.volume_from_fasta(fa).pac.tobytes()
