@@ -439,6 +439,137 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ the other two programs
+def _cli(exe, argv, env=None, cwd=None):
+    """Run a command-line driver; returns (wall seconds, stderr text)."""
+    t = time.perf_counter()
+    p = subprocess.run([exe] + argv, capture_output=True, text=True, env=dict(os.environ, **(env or {})), cwd=cwd)
+    dt = time.perf_counter() - t
+    if p.returncode != 0:
+        raise SystemExit("%s failed: %s" % (exe, p.stderr[-1500:]))
+    return dt, p.stderr
+
+
+def run_program(args):
+    """--workload ref | cns: BASELINE configs[2] / configs[3] through the command-line drivers (the product path of those
+    programs).  `value` = reads per second of the device phase the driver itself times (mapping / consensus of all reads,
+    inputs already packed), `e2e` = reads per second of the whole command line (process start to exit: FASTA in, text out).
+    --impl reference: the unmodified binary, all host threads, on a bounded sample that its `config` names."""
+    import re
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = tmp_root()
+    cores = os.cpu_count() or 1
+    nreads, genome = READS_PER_VOLUME, GENOME_PER_VOLUME
+    fa, gfa = os.path.join(d, "reads_%d_%d.fa" % (nreads, SEED)), os.path.join(d, "genome_%d_%d.fa" % (genome, SEED))
+    if not (os.path.exists(gfa) and os.path.exists(fa) and os.path.getsize(fa) > nreads * 2000):
+        subprocess.check_call([gen_exe(), fa + ".tmp", str(nreads), str(genome), str(SEED), "15000", "1500", "0.15", gfa])
+        os.replace(fa + ".tmp", fa)
+    bindir = os.path.join(ROOT, "mecat_b200", "bin")
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    ref = args.impl == "reference"
+    if args.workload == "ref":
+        metric, unit = "reads mapped/sec (mecat2ref -m 1)", "reads/s"
+        sample = min(nreads, max(8000, 500 * cores))
+        if ref:
+            sfa = os.path.join(d, "ref_sample_%d.fa" % sample)
+            if not os.path.exists(sfa):
+                with open(fa) as f, open(sfa, "w") as g:
+                    k = 0
+                    for line in f:
+                        if line.startswith(">"):
+                            k += 1
+                            if k > sample:
+                                break
+                        g.write(line)
+            exe, argv, units = os.path.join(refdir, "mecat2ref"), ["-d", sfa, "-r", gfa, "-o", os.path.join(d, "ref_ref.m4"), "-w", os.path.join(d, "wr"), "-t", str(cores), "-m", "1"], sample
+        else:
+            exe, argv, units = os.path.join(bindir, "mecat2ref"), ["-d", fa, "-r", gfa, "-o", os.path.join(d, "ref_gpu.m4"), "-w", os.path.join(d, "wg"), "-t", str(cores), "-m", "1"], nreads
+        workload = "mecat2ref -m 1: %d x 15 kb synthetic CLR reads vs their %d Mb genome (BASELINE configs[2])" % (nreads, genome // 1000000)
+    else:
+        metric, unit = "reads corrected/sec (mecat2cns -i 0)", "reads/s"
+        can = os.path.join(d, "cand_%d_%d.can" % (nreads, SEED))
+        if not os.path.exists(can):       # candidates of the same reads: mecat2pw -j 0 on the GPU (set-up, not timed)
+            subprocess.check_call([os.path.join(bindir, "mecat2pw"), "-j", "0", "-d", fa, "-o", can + ".tmp", "-w", os.path.join(d, "wcan")],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            os.replace(can + ".tmp", can)
+        sample = min(nreads, max(4000, 400 * cores))
+        if ref:
+            scan = os.path.join(d, "cand_sample_%d.can" % sample)
+            if not os.path.exists(scan):  # both orientations of a pair become templates: keep pairs with a template below `sample`
+                with open(can) as f, open(scan, "w") as g:
+                    for line in f:
+                        a = line.split("\t", 2)
+                        if int(a[0]) < sample or int(a[1]) < sample:
+                            g.write(line)
+            exe, argv, units = os.path.join(refdir, "mecat2cns"), ["-i", "0", "-t", str(cores), "-p", str(sample), scan, fa, os.path.join(d, "cns_ref.fa")], sample
+        else:
+            exe, argv, units = os.path.join(bindir, "mecat2cns"), ["-i", "0", "-t", str(cores), can, fa, os.path.join(d, "cns_gpu.fa")], nreads
+        workload = "mecat2cns -i 0 on the candidates of mecat2pw -j 0 for %d x 15 kb synthetic CLR reads (BASELINE configs[3])" % nreads
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": args.impl, "unavailable": "%s is not built" % exe}))
+        return
+    walls, phases, log = [], [], ""
+    reps = args.warmup + args.steps
+    t_all = time.perf_counter()
+    for i in range(reps):
+        if ref and walls and (time.perf_counter() - t_all) + walls[-1] > REFERENCE_BUDGET_S:
+            break
+        dt, log = _cli(exe, argv, env={"MECAT_B200_STATS": "1"}, cwd=d)
+        ph = None
+        if not ref:
+            if args.workload == "ref":
+                m = re.search(r"mapping ([0-9.]+) s", log)
+                ph = float(m.group(1)) if m else None
+            else:
+                ph = sum(float(x) for x in re.findall(r"processing reads .* takes ([0-9.]+) secs", log)) or None
+        if i >= args.warmup or ref:
+            walls.append(dt); phases.append(ph)
+        print("[bench] %s run %d: %.2f s wall%s" % (args.workload, i, dt, "" if ph is None else ", device phase %.2f s" % ph), file=sys.stderr, flush=True)
+    n = len(walls)
+    wall = sum(walls) / n
+    e2e_value = units / wall
+    phase = (sum(phases) / n) if phases and all(x is not None for x in phases) else None
+    value = units / phase if phase else e2e_value
+    kernel = None
+    m = re.search(r"\[kernel ms\](.*)", log)
+    if m:
+        kernel = {k: float(v) for k, v in re.findall(r"(\w+)=([0-9.]+)\(", m.group(1))}
+    in_bytes = os.path.getsize(fa) + (os.path.getsize(gfa) if args.workload == "ref" else os.path.getsize(os.path.join(d, "cand_%d_%d.can" % (nreads, SEED))))
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * (phase if phase else wall), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": ("SAMPLE (%d reads) of: " % units if ref else "") + workload, "reads": units, "genome": genome, "seed": SEED,
+                   "parallelism": ("reference CPU binary, %d host threads (no GPU)" % cores) if ref else "1 gpu, command-line driver"},
+        "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": 1000.0 * wall, "steps": n,
+                "h2d_bytes_per_step": 0 if ref else None, "d2h_bytes_per_step": 0 if ref else None,
+                "what": "whole command line, process start to exit (%d bytes of input files read, text output written)" % in_bytes},
+        "gpu_launches": 0 if ref else None, "kernel_ms_last_run": kernel,
+        "cpu_baseline": {"value": e2e_value if ref else None, "unit": unit, "cores": cores, "kind": "reference",
+                         "sample": ("unmodified binary on the first %d reads / templates" % units) if ref else "run bench.py --workload %s --impl reference" % args.workload},
+    }
+    if ref:
+        line["impl"] = "reference"
+        line["repetitions"] = {"timed": n, "requested_steps": args.steps}
+        if args.workload == "ref":
+            # the reference's own timers (config.txt in its working directory): the genome index is a fixed cost that a
+            # sample of the reads does not shrink, so the full-size rate is estimated from them
+            try:
+                txt = open(os.path.join(d, "config.txt")).read()
+                t_idx = float(re.search(r"Building Reference Index Time: ([0-9.]+)", txt).group(1))
+                t_map = float(re.search(r"Mapping Time: ([0-9.]+)", txt).group(1))
+                t_tot = float(re.search(r"total Time : ([0-9.]+)", txt).group(1))
+                full = t_idx + (t_tot - t_idx) * nreads / units
+                line["cpu_baseline"]["reference_timers_s"] = {"index": t_idx, "mapping": t_map, "total": t_tot}
+                line["cpu_baseline"]["full_size_estimate"] = {"value": nreads / full, "unit": unit,
+                                                              "how": "index time + (total - index) x %d / %d reads" % (nreads, units)}
+            except Exception:
+                pass
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,6 +578,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=0, help="debug only: reduced workload (result is not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="pw", choices=["pw", "ref", "cns"],
+                    help="pw (default): the headline, mecat2pw -j 1 (BASELINE configs[1]).  ref / cns: mecat2ref (configs[2]) / "
+                         "mecat2cns (configs[3]) through their command-line drivers")
     ap.add_argument("--mode", default="strong", choices=["strong", "ring"],
                     help="strong (default): N GPUs share the configs[1] tile. ring: the BASELINE configs[4] job -- --volumes "
                          "volumes (default 8 x 125 000 reads = 1 M reads, 36 tiles) at any N that divides it, volume sets "
@@ -458,7 +592,9 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w")
-    if args.impl == "reference":
+    if args.workload != "pw":
+        run_program(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -536,6 +536,8 @@ int mecat_b200_cns_reads_multi(mecat_b200_ctx* c, void* const* dvols, int nvols,
                                const mecat_cns_params* p, mecat_cns_piece** pieces, size_t* npieces, char** seqs, size_t* seq_bytes)
 {
 	if (check(c) || !dvols || nvols < 1 || (!ec_in && nec) || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
+	if (nvols == 1 && !getenv("MECAT_B200_CNS_WORK_BASES"))          // one volume is its own working volume
+		return mecat_b200_cns_reads(c, dvols[0], ec_in, nec, p, pieces, npieces, seqs, seq_bytes);
 	cudaSetDevice(c->device);
 	*pieces = nullptr; *npieces = 0; *seqs = nullptr; *seq_bytes = 0;
 	std::vector<const DVolume*> V((size_t)nvols);

@@ -57,10 +57,11 @@ struct Walk                   // one sequence seen as a forward walk
 	int len;
 };
 
+// 16 bases starting at base i of a staged operand, first base in the top two bits (the first mismatch is one CLZ)
 __device__ __forceinline__ uint32_t seq16(const uint2* s, int i)
 {
 	const uint2 w = s[i >> 4];
-	return __funnelshift_r(w.x, w.y, (i & 15) << 1);
+	return __funnelshift_l(w.y, w.x, i << 1);
 }
 
 __device__ __forceinline__ int dtrunc_mul(double a, int b) { return (int)__dmul_rn(a, (double)b); }
@@ -144,11 +145,11 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				const int qw = (qblk + 15) / 16 + 1, tw = (tblk + 15) / 16 + 1;
 				for (int i = lane; i < qw; i += 32) {
 					const uint32_t b0 = Q.g0 + (uint32_t)qi + 16u * i;
-					S.sq[i] = make_uint2(ld_bases32(Q.arr, b0) ^ Q.comp, ld_bases32(Q.arr, b0 + 16u) ^ Q.comp);
+					S.sq[i] = make_uint2(__brev(ld_bases32(Q.arr, b0) ^ Q.comp), __brev(ld_bases32(Q.arr, b0 + 16u) ^ Q.comp));
 				}
 				for (int i = lane; i < tw; i += 32) {
 					const uint32_t b0 = T.g0 + (uint32_t)ti + 16u * i;
-					S.st[i] = make_uint2(ld_bases32(T.arr, b0) ^ T.comp, ld_bases32(T.arr, b0 + 16u) ^ T.comp);
+					S.st[i] = make_uint2(__brev(ld_bases32(T.arr, b0) ^ T.comp), __brev(ld_bases32(T.arr, b0 + 16u) ^ T.comp));
 				}
 				if (lane == 0) S.vl[KOFF + 1] = make_uint2(0u, NO_ANCHOR);
 			}
@@ -163,22 +164,23 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 			const uint2* sq = S.sq;
 			const uint2* st = S.st;
 			// one furthest-reaching cell: lane-local, reads the other-parity array, writes its own
-			auto cell = [&](uint2* own, int j, int n, int k, uint32_t dbits, int& x, uint32_t& anc) {
+			auto cell = [&](uint2* own, int j, int n, int k, uint32_t dbits, int& x, uint32_t& anc, bool& hit) {
 				const uint2 lf = own[2 * j - 1], rt = own[2 * j + 1];
 				if (j == 0 || (j != n - 1 && (int)lf.x < (int)rt.x)) { x = (int)rt.x; anc = rt.y; }
 				else { x = (int)lf.x + 1; anc = lf.y; }
 				int y = x - k;
 				const int x1 = x;
-				// x <= qblk and y <= tblk here (a cell that reached an end finished the block); the staged
-				// words cover one window past either end, and whatever matches there is clamped away below
+				// x <= qblk and y <= tblk here (a cell that reached an end finished the block); the staged words cover one
+				// window past either end.  `room` = matches left on this diagonal before a block end: a window's count is
+				// capped by it, and the cell reached an end iff no room is left.
+				int room = min(qblk - x, tblk - y);
 				for (;;) {
 					const uint32_t diff = seq16(sq, x) ^ seq16(st, y);
-					const int m = __clz(__brev(diff)) >> 1;      // matching bases in this 16-base window
-					x += m; y += m;
-					if (m < 16 || x >= qblk || y >= tblk) break;
+					const int m = min(__clz((int)diff) >> 1, room);      // matching bases in this 16-base window
+					x += m; y += m; room -= m;
+					if (m < 16) break;
 				}
-				const int over = max(max(x - qblk, y - tblk), 0);    // the window may run past a block end
-				x -= over; y -= over;
+				hit = room == 0;
 				if (x - x1 >= 4) anc = (uint32_t)x | ((uint32_t)y << 10) | dbits;
 				own[2 * j] = make_uint2((uint32_t)x, anc);
 				return x + y;
@@ -192,32 +194,34 @@ k_extend(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, c
 				// pass 0: diagonals 0..31 of the band (most rows have no other pass)
 				int x0 = 0, u0 = IDLE;
 				uint32_t a0 = NO_ANCHOR;
-				if (lane < n) u0 = cell(own, lane, n, min_k + 2 * lane, dbits, x0, a0);
+				bool h0 = false, h1 = false, hx = false;
+				if (lane < n) u0 = cell(own, lane, n, min_k + 2 * lane, dbits, x0, a0, h0);
 				int rowmax = __reduce_max_sync(FULL, u0);
 				int x1 = 0, u1 = IDLE;
 				uint32_t a1 = NO_ANCHOR;
 				if (n > 32) {
-					if (lane + 32 < n) u1 = cell(own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1);
+					if (lane + 32 < n) u1 = cell(own, lane + 32, n, min_k + 2 * (lane + 32), dbits, x1, a1, h1);
 					rowmax = max(rowmax, __reduce_max_sync(FULL, u1));
 					for (int base = 64; base < n; base += 32) {
 						const int j = base + lane;
 						int xx = 0, uu = IDLE;
 						uint32_t aa = NO_ANCHOR;
-						if (j < n) uu = cell(own, j, n, min_k + 2 * j, dbits, xx, aa);
+						bool hh = false;
+						if (j < n) uu = cell(own, j, n, min_k + 2 * j, dbits, xx, aa, hh);
+						hx = hx || hh;
 						rowmax = max(rowmax, __reduce_max_sync(FULL, uu));
 					}
 				}
 				__syncwarp();
-				// x >= qblk needs x + y >= 2 qblk - k, y >= tblk needs x + y >= 2 tblk + k
-				if (rowmax >= min(2 * qblk - max_k, 2 * tblk + min_k)) {
-					// some cell may have reached a block end: the lowest such diagonal ends the block
-					unsigned hm = __ballot_sync(FULL, x0 >= qblk || u0 - x0 >= tblk);
+				if (__any_sync(FULL, h0 || h1 || hx)) {
+					// some cell reached a block end: the lowest such diagonal ends the block
+					unsigned hm = __ballot_sync(FULL, h0);
 					if (hm) {
 						const int src = __ffs(hm) - 1;
 						ex = __shfl_sync(FULL, x0, src); ey = __shfl_sync(FULL, u0, src) - ex; ea = __shfl_sync(FULL, a0, src);
 						aligned = true;
 					} else if (n > 32) {
-						hm = __ballot_sync(FULL, x1 >= qblk || u1 - x1 >= tblk);
+						hm = __ballot_sync(FULL, h1);
 						if (hm) {
 							const int src = __ffs(hm) - 1;
 							ex = __shfl_sync(FULL, x1, src); ey = __shfl_sync(FULL, u1, src) - ex; ea = __shfl_sync(FULL, a1, src);

@@ -62,5 +62,5 @@ def test_roofline_object_contract():
 def test_command_line_defaults():
     p = subprocess.run([sys.executable, os.path.join(util.ROOT, "bench.py"), "--help"], capture_output=True, text=True)
     assert p.returncode == 0
-    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--mode", "--workload", "--volumes"):
         assert flag in p.stdout
