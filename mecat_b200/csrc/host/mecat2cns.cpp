@@ -211,6 +211,10 @@ int main(int argc, char* argv[])
 	}
 	if (warm.joinable()) warm.join();
 	if (ctx0_rc) ctx0 = NULL;
+	// MECAT_B200_FAST_EXIT (default 1): skip the block-by-block release of the devices' memory pools at the end; the
+	// process exits as soon as the corrected reads are written and closed (0: explicit release, as a library user would)
+	const char* fe = getenv("MECAT_B200_FAST_EXIT");
+	const bool fast_exit = !fe || atoi(fe) != 0;
 	struct Part { long long part; std::string text; };
 	std::vector<std::vector<Part>> results((size_t)ngpus);
 	std::atomic<int> failed(0);
@@ -267,6 +271,7 @@ int main(int argc, char* argv[])
 				fprintf(stderr, "\n");
 			}
 		}
+		if (fast_exit) return;                 // the process ends right after the output is written: nothing to hand back
 		{
 			StderrTimer t("gpu " + std::to_string(dev) + " release");
 			for (void* d : dvols) if (d) mecat_b200_volume_release(ctx, d);
@@ -285,7 +290,10 @@ int main(int argc, char* argv[])
 		std::ofstream out(opt.output, std::ios::binary);
 		if (!out) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
 		for (auto& per_dev : results) for (auto& pt : per_dev) out.write(pt.text.data(), (std::streamsize)pt.text.size());
+		out.close();
+		if (!out) { fprintf(stderr, "cannot write '%s'\n", opt.output); return 1; }
 	}
+	if (ok && fast_exit) { fflush(stdout); fflush(stderr); _exit(0); }
 	mecat_b200_volumes_unload(vols, nvols);
 	return ok ? 0 : 1;
 }

@@ -26,6 +26,7 @@
 #include <functional>
 #include <future>
 #include <iostream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -146,13 +147,30 @@ std::string results_name(const char* wrk, int vid, bool working)
 	return n + os.str();
 }
 
+int g_format_threads = 1;      // host threads a device thread may use to write its tile's text (set in main)
+
 void format_records(std::string& text, const Options& opt, const void* rec, size_t n)
 {
-	mbfmt::TextBuf b;
-	b.s.reserve(n * (opt.task == 0 ? 48 : 96) + 64);
-	if (opt.task == 0) mbfmt::format_candidates(b, (const mecat_candidate*)rec, n);
-	else mbfmt::format_m4(b, (const mecat_m4*)rec, n, opt.output_gapped_start_point != 0);
-	text.swap(b.s);
+	auto piece = [&](size_t lo, size_t hi, std::string& out) {
+		mbfmt::TextBuf b;
+		b.s.reserve((hi - lo) * (opt.task == 0 ? 48 : 96) + 64);
+		if (opt.task == 0) mbfmt::format_candidates(b, (const mecat_candidate*)rec + lo, hi - lo);
+		else mbfmt::format_m4(b, (const mecat_m4*)rec + lo, hi - lo, opt.output_gapped_start_point != 0);
+		out.swap(b.s);
+	};
+	const int T = n < 200000 ? 1 : g_format_threads;
+	if (T <= 1) { piece(0, n, text); return; }
+	// lines are independent: T slices formatted side by side, then joined in order
+	std::vector<std::string> parts((size_t)T);
+	std::vector<std::thread> pool;
+	for (int t = 1; t < T; ++t) pool.emplace_back(piece, n * (size_t)t / (size_t)T, n * (size_t)(t + 1) / (size_t)T, std::ref(parts[(size_t)t]));
+	piece(0, n / (size_t)T, parts[0]);
+	for (auto& th : pool) th.join();
+	size_t total = 0;
+	for (const std::string& p : parts) total += p.size();
+	text.clear();
+	text.reserve(total);
+	for (const std::string& p : parts) text.append(p);
 }
 
 // What one device keeps between tiles: the index volume it worked on last (create_ref_index of process_one_volume,
@@ -279,6 +297,10 @@ int main(int argc, char* argv[])
 	if ((int)vols.size() != num_vols) { fprintf(stderr, "volume index is inconsistent\n"); return 1; }
 
 	int ngpus = want_gpus;
+	{
+		const int hw = (int)std::thread::hardware_concurrency();
+		g_format_threads = std::max(1, std::min(8, (hw > 0 ? hw : 1) / std::max(1, ngpus)));
+	}
 	// Work items are tiles, row by row; rows whose r_N exists are finished (the reference's resume protocol, pw.cpp:65-81).
 	// Any device takes the next tile: building the index of a volume costs a fraction of a tile, so several devices
 	// share a row instead of each owning rows of very different sizes (row s has num_vols - s tiles).
@@ -333,20 +355,30 @@ int main(int argc, char* argv[])
 	for (int d = 1; d < ngpus; ++d) th.emplace_back(worker, d);
 	worker(0);
 	for (auto& t : th) t.join();
-	{
-		// contexts go when every device is done (device 0 last)
-		StderrTimer t("gpu release");
-		for (int d = ngpus - 1; d >= 0; --d) if (warm_ctx[(size_t)d]) mecat_b200_destroy(warm_ctx[(size_t)d]);
-	}
 	if (failed) return 1;
 
 	// merge_results: r_0 .. r_{n-1} concatenated in volume order (pw.cpp:34-46)
-	StderrTimer merge_timer("merge_results");
+	std::unique_ptr<StderrTimer> merge_timer(new StderrTimer("merge_results"));
 	std::ofstream merged(opt.output, std::ios::binary);
 	if (!merged) { fprintf(stderr, "cannot open '%s' for writing\n", opt.output); return 1; }
 	for (int i = 0; i < num_vols; ++i) {
 		std::ifstream in(results_name(opt.wrk_dir, i, false).c_str(), std::ios::binary);
 		if (in.peek() != std::ifstream::traits_type::eof()) merged << in.rdbuf();
+	}
+	merged.close();
+	merge_timer.reset();
+	if (!merged) { fprintf(stderr, "cannot write '%s'\n", opt.output); return 1; }
+	// The contexts go last, device 0 last of all.  Returning tens of GB of pooled device memory block by block takes
+	// ~1.5 s per device; everything this process owns is written and closed by now, so with MECAT_B200_FAST_EXIT unset or
+	// 1 the process ends here and the driver reclaims the devices at once (MECAT_B200_FAST_EXIT=0: explicit release).
+	const char* fe = getenv("MECAT_B200_FAST_EXIT");
+	if (!fe || atoi(fe) != 0) {
+		fflush(stdout); fflush(stderr);
+		_exit(0);
+	}
+	{
+		StderrTimer t("gpu release");
+		for (int d = ngpus - 1; d >= 0; --d) if (warm_ctx[(size_t)d]) mecat_b200_destroy(warm_ctx[(size_t)d]);
 	}
 	return 0;
 }

@@ -114,8 +114,13 @@ int main(int argc, char* argv[])
 	if (o.tech != 0) { fprintf(stderr, "mecat2ref (b200): -x 1 (nanopore) is not on this path\n"); return 1; }
 	if (o.output_format < 0 || o.output_format > 2) { fprintf(stderr, "mecat2ref (b200): unknown output format %d (0 = ref, 1 = m4, 2 = sam)\n", o.output_format); return 1; }
 	const double t0 = now();
-	FILE* out = fopen(o.output, "w");          // before any work: an unwritable output should not cost a mapping run
-	if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
+	{
+		// before any work: an unwritable output should not cost a mapping run -- but an existing result is only replaced once
+		// the new one is complete (append mode creates, never truncates)
+		FILE* probe = fopen(o.output, "a");
+		if (!probe) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
+		fclose(probe);
+	}
 	int ndev = 1;
 	if (const char* e = getenv("MECAT_GPUS")) ndev = std::max(1, atoi(e));
 	if (ndev > mecat_b200_device_count()) { fprintf(stderr, "mecat2ref (b200): MECAT_GPUS=%d but %d CUDA device(s) visible\n", ndev, mecat_b200_device_count()); return 1; }
@@ -219,16 +224,25 @@ int main(int argc, char* argv[])
 	const double t_map = now();
 
 	fprintf(stderr, "output file name: %s\n", o.output);
+	FILE* out = fopen(o.output, "w");
+	if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); return 1; }
 	if (o.output_format == 2) {
 		std::string head;
 		refio::sam_header(head, G, argc, argv);
 		fwrite(head.data(), 1, head.size(), out);
 	}
-	for (const Batch& b : batches) fwrite(b.text.data(), 1, b.text.size(), out);
-	fclose(out);
-	for (int d = 0; d < ndev; ++d) mecat_b200_destroy(ctx[(size_t)d]);
+	bool wrote = true;
+	for (const Batch& b : batches) wrote = fwrite(b.text.data(), 1, b.text.size(), out) == b.text.size() && wrote;
+	wrote = (fclose(out) == 0) && wrote;
+	if (!wrote) { fprintf(stderr, "mecat2ref (b200): cannot write %s\n", o.output); return 1; }
+	// MECAT_B200_FAST_EXIT (default 1): the output is on disk; releasing the devices' memory pools block by block would only
+	// delay the exit (0: explicit release)
+	const char* fe = getenv("MECAT_B200_FAST_EXIT");
+	const bool fast_exit = !fe || atoi(fe) != 0;
+	if (!fast_exit) for (int d = 0; d < ndev; ++d) mecat_b200_destroy(ctx[(size_t)d]);
 	const double t1 = now();
 	fprintf(stderr, "mecat2ref (b200): %d reads, %lld reference bases, %d device(s): load %.2f s, index %.2f s, mapping %.2f s, write %.2f s, total %.2f s\n",
 	        total, (long long)G.seq.n, ndev, t_load - t0, t_index[0], t_map - t_load - t_index[0], t1 - t_map, t1 - t0);
+	if (fast_exit) { fflush(stdout); fflush(stderr); _exit(0); }
 	return 0;
 }

@@ -49,7 +49,7 @@ def test_tiles_are_shared_between_devices_and_rows_resume(small_fa, tmp_path):
     second per tile on its 2^26-entry index, whatever the tile holds).  One device and three devices write byte-identical
     files (rows in volume order, tiles in order inside a row); the records are the oracle's, tile by tile; a finished row
     (r_N present) is not recomputed."""
-    env = {"MECAT_VOLUME_BASES": "250000", "MECAT_SHIM_REPORT": "1"}
+    env = {"MECAT_VOLUME_BASES": "250000", "MECAT_SHIM_REPORT": "1", "MECAT_B200_FAST_EXIT": "0"}   # the shim reports when device 0 is released
     part = str(tmp_path / "part.fa")
     with open(small_fa, "rb") as f, open(part, "wb") as g:
         g.write(b"".join(f.readlines()[:260]))
