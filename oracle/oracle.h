@@ -61,6 +61,10 @@ int orc_pw_candidates(const void* idx, const orc_volume* ref, const orc_volume* 
  * qstr/tstr (optional, cap bytes each) receive the ASCII alignment. */
 int orc_diff_go(const char* q, int qstart, int qsize, const char* t, int tstart, int tsize, int min_aln,
                 int32_t* out, double* ident, char* qstr, char* tstr, int cap);
+/* ---- nanopore extension (XdropAligner::go, common/xdrop_gapalign.cpp:10-439); same conventions as orc_diff_go,
+ * ok = qend - qoff >= min_aln, out[5] = aligned columns, out[6] = columns with equal letters */
+int orc_xdrop_go(const char* q, int qstart, int qsize, const char* t, int tstart, int tsize, int min_aln,
+                 int32_t* out, double* ident, char* qstr, char* tstr, int cap);
 /* one block: aln_q_e aln_t_e dist aln_str_size trim_ok qcnt tcnt acnt */
 void orc_diff_align_block(const char* q, int qlen, const char* t, int tlen, int right_extend, int32_t* out);
 

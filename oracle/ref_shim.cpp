@@ -188,6 +188,22 @@ int ref_diff_go(void* ap, const char* q, int qstart, int qsize, const char* t, i
 	return ok;
 }
 
+// ---------------------------------------------------------------- nanopore extension (XdropAligner)
+void* ref_xdrop_new() { return new XdropAligner(0); }
+void ref_xdrop_free(void* a) { delete (XdropAligner*)a; }
+int ref_xdrop_go(void* ap, const char* q, int qstart, int qsize, const char* t, int tstart, int tsize,
+                 int min_aln, int* out, double* ident, const char** qstr, const char** tstr)
+{
+	XdropAligner* a = (XdropAligner*)ap;
+	bool ok = a->go(q, qstart, qsize, t, tstart, tsize, min_aln);
+	out[0] = ok; out[1] = a->query_start(); out[2] = a->query_end();
+	out[3] = a->target_start(); out[4] = a->target_end(); out[5] = a->aln_size;
+	*ident = a->calc_ident();
+	if (qstr) *qstr = a->query_mapped_string();
+	if (tstr) *tstr = a->target_mapped_string();
+	return ok;
+}
+
 // One block: Align() + trim (diff_gapalign.cpp:107, gapalign.cpp:48), for fine-grained checks.
 // out = aln_q_e, aln_t_e, dist, aln_str_size, trim_ok, qcnt, tcnt, acnt
 void ref_diff_align_block(void* ap, const char* q, int qlen, const char* t, int tlen, int right_extend, int* out)

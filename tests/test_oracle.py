@@ -296,6 +296,93 @@ def test_oracle_extension_against_reference():
     R.ref_diff_free(aligner)
 
 
+def xdrop_cases(rng, n=70):
+    """Pairs for the nanopore extension: related sequences at several divergences (substitutions included, which
+    the diff aligner never emits), unrelated ones, tiny ones, start points at either end and at the ends."""
+    cases = []
+    for it in range(n):
+        L = int(rng.integers(30, 5000))
+        base = rng.integers(0, 4, size=L).astype(np.int8)
+        err = [0.0, 0.05, 0.12, 0.2, 0.35, 0.6][it % 6]
+        q = mutate(rng, base, err)
+        t = mutate(rng, base, err)
+        if it % 7 == 0:
+            t = rng.integers(0, 4, size=L).astype(np.int8)
+        if it % 9 == 0:      # low complexity: wide bands
+            q = np.tile(np.array([0, 1], dtype=np.int8), L // 2)
+            t = mutate(rng, q, 0.1)
+        if len(q) < 10 or len(t) < 10:
+            continue
+        f = rng.random()
+        qstart = int(f * len(q)); tstart = min(len(t), int(f * len(t)))
+        if it % 11 == 0:
+            qstart, tstart = 0, 0
+        if it % 13 == 0:
+            qstart, tstart = len(q), len(t)
+        cases.append((q, qstart, t, tstart))
+    return cases
+
+
+@needs_ref
+def test_oracle_xdrop_extension_against_reference():
+    """XdropAligner::go (the -x 1 aligner, xdrop_gapalign.cpp) on random pairs: coordinates, identity and both
+    alignment strings of the restatement equal the unmodified class."""
+    R, O = util.ref(), util.oracle()
+    rng = np.random.default_rng(23)
+    aligner = R.ref_xdrop_new()
+    out_r = (C.c_int32 * 8)(); out_o = (C.c_int32 * 8)()
+    id_r, id_o = C.c_double(), C.c_double()
+    qs_r, ts_r = C.c_char_p(), C.c_char_p()
+    cap = 60000
+    qs_o, ts_o = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    nonempty = 0
+    for q, qstart, t, tstart in xdrop_cases(rng):
+        qb = np.concatenate([[0], q, [0]]).astype(np.int8)
+        tb = np.concatenate([[0], t, [0]]).astype(np.int8)
+        qp = qb.ctypes.data + 1
+        tp = tb.ctypes.data + 1
+        for min_aln in (1, 500):
+            R.ref_xdrop_go(aligner, qp, qstart, len(q), tp, tstart, len(t), min_aln, out_r, C.byref(id_r), C.byref(qs_r), C.byref(ts_r))
+            O.orc_xdrop_go(C.cast(qp, C.c_char_p), qstart, len(q), C.cast(tp, C.c_char_p), tstart, len(t), min_aln, out_o,
+                           C.byref(id_o), qs_o, ts_o, cap)
+            assert list(out_r[:6]) == list(out_o[:6]), (len(q), len(t), qstart, tstart)
+            assert id_r.value == id_o.value
+            n = out_r[5]
+            nonempty += n > 100
+            assert qs_r.value[:n] == qs_o.value[:n] and ts_r.value[:n] == ts_o.value[:n]
+    assert nonempty > 40
+    R.ref_xdrop_free(aligner)
+
+
+def test_xdrop_kernel_body_matches_oracle():
+    """The statements the GPU executes for the -x 1 extension (csrc/xdrop_core.cuh, run on the host through
+    tests/xdrop_host_harness.cpp over packed 2-bit words) against the oracle: coordinates, columns, matches, strings;
+    with and without columns."""
+    O, H = util.oracle(), util.xdrop_harness()
+    rng = np.random.default_rng(29)
+    out_o = (C.c_int32 * 8)(); out_h = (C.c_int32 * 8)(); out_n = (C.c_int32 * 8)()
+    id_o = C.c_double()
+    cap = 60000
+    qs_o, ts_o = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    qs_h, ts_h = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    checked = 0
+    for q, qstart, t, tstart in xdrop_cases(rng, 120):
+        qb = np.concatenate([[0], q, [0]]).astype(np.int8)
+        tb = np.concatenate([[0], t, [0]]).astype(np.int8)
+        qp = qb.ctypes.data + 1
+        tp = tb.ctypes.data + 1
+        for min_aln in (1, 500):
+            O.orc_xdrop_go(C.cast(qp, C.c_char_p), qstart, len(q), C.cast(tp, C.c_char_p), tstart, len(t), min_aln, out_o,
+                           C.byref(id_o), qs_o, ts_o, cap)
+            H.xh_go(qp, qstart, len(q), tp, tstart, len(t), min_aln, out_h, qs_h, ts_h, cap, 1)
+            H.xh_go(qp, qstart, len(q), tp, tstart, len(t), min_aln, out_n, None, None, 0, 0)
+            assert list(out_o[:7]) == list(out_h[:7]) == list(out_n[:7]), (len(q), len(t), qstart, tstart)
+            n = out_o[5]
+            assert qs_o.value[:n] == qs_h.value[:n] and ts_o.value[:n] == ts_h.value[:n]
+            checked += n > 100
+    assert checked > 80
+
+
 @needs_ref
 def test_cns_alignment_against_reference():
     """C1-C2 (mecat2cns/dw.cpp GetAlignment) and C4 (normalize_gaps) on random related pairs."""

@@ -151,6 +151,28 @@ def cns_harness():
     return L
 
 
+_xdrop_harness = None
+
+
+def xdrop_harness():
+    """Host build of the product's nanopore extension body (tests/xdrop_host_harness.cpp over csrc/xdrop_core.cuh)."""
+    global _xdrop_harness
+    if _xdrop_harness is not None:
+        return _xdrop_harness
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libxdrop_harness.so")
+    src = [os.path.join(ROOT, "tests", "xdrop_host_harness.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "xdrop_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so, src[0]])
+    L = C.CDLL(so)
+    L.xh_go.restype = C.c_int
+    L.xh_go.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                        C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    _xdrop_harness = L
+    return L
+
+
 _ref_harness = None
 
 
@@ -234,6 +256,9 @@ def oracle():
     L.orc_diff_go.restype = C.c_int
     L.orc_diff_go.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, i32p,
                               C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_int]
+    L.orc_xdrop_go.restype = C.c_int
+    L.orc_xdrop_go.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, i32p,
+                              C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_int]
     L.orc_diff_align_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, i32p]
     L.orc_pw_tile.restype = C.c_int
     L.orc_pw_tile.argtypes = [VP, VP, PP, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -315,6 +340,9 @@ def ref():
     L.ref_diff_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, i32p,
                               C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
     L.ref_diff_align_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, i32p]
+    L.ref_xdrop_new.restype = C.c_void_p
+    L.ref_xdrop_free.argtypes = [C.c_void_p]
+    L.ref_xdrop_go.argtypes = L.ref_diff_go.argtypes
     L.ref_effective_ranges.restype = C.c_int
     L.ref_effective_ranges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.ref_normalize_and_vote.restype = C.c_int
