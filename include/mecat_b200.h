@@ -40,7 +40,7 @@ typedef struct {
 	int32_t num_candidates;  /* -n, default 100                                      */
 	int32_t min_align_size;  /* -a, default 2000 (pacbio)                            */
 	int32_t min_kmer_match;  /* -k, default 4 (pacbio)                               */
-	int32_t tech;            /* -x, 0 = pacbio (the only technology of this path)    */
+	int32_t tech;            /* -x, 0 = pacbio, 1 = nanopore (XdropAligner, min_kmer_dist 400; pw_impl.cpp:638-642,843-849) */
 } mecat_pw_params;
 
 /* ExtensionCandidate, src/common/alignment.h:8-13 (13 x int32 = 52 bytes). */
@@ -219,7 +219,8 @@ int mecat_b200_pw_raw_candidates(mecat_b200_ctx* ctx, void* index, void* dvol_re
 
 /* ---- A8-A11: batched gapped extension --------------------------------------------------
  * replaces GapAligner::go per candidate (pw_impl.cpp:688, mecat2ref_aux.cpp:152).
- * policy 0 = pw/ref flavour (common/diff_gapalign.cpp). */
+ * policy 0 = pw/ref flavour (common/diff_gapalign.cpp); policy 2 = the nanopore flavour, XdropAligner::go
+ * (common/xdrop_gapalign.cpp:10-439: ok = query span >= min_align_size, matches = columns with equal letters). */
 int mecat_b200_extend_batch(mecat_b200_ctx* ctx, int policy, void* dvol_query, void* dvol_subject,
                             const mecat_extend_task* tasks, size_t ntasks, int min_align_size,
                             mecat_extend_result** results);
@@ -229,6 +230,7 @@ int mecat_b200_extend_batch(mecat_b200_ctx* ctx, int policy, void* dvol_query, v
  *   (src/mecat2ref/mecat2ref_aux.cpp:152-163, src/common/diff_gapalign.cpp:295-349);
  * policy 1 replaces ns_banded_sw::GetAlignment per candidate with error rate `err`
  *   (src/mecat2cns/mecat_correction.cpp:424, src/mecat2cns/dw.cpp:482-553).
+ * policy 2 replaces XdropAligner::go + mapped strings (src/common/xdrop_gapalign.cpp:351-439), the aligner of `-x 1`;
  * Strings are ASCII over ACGT- ; *qstrings / *sstrings hold *string_bytes bytes each. */
 int mecat_b200_align_batch(mecat_b200_ctx* ctx, int policy, double err, void* dvol_query, void* dvol_subject,
                            const mecat_align_task* tasks, size_t ntasks, int min_align_size,
@@ -306,7 +308,7 @@ typedef struct {
 	int32_t num_candidates;   /* -n, default 10 */
 	int32_t num_output;       /* -b, default 10 */
 	int32_t want_strings;
-	int32_t tech;             /* -x, 0 = pacbio (the only technology of this path) */
+	int32_t tech;             /* -x, 0 = pacbio (DiffAligner), 1 = nanopore (XdropAligner; mecat2ref_impl_large.cpp:329-332) */
 } mecat_ref_params;
 
 /* TempResult (src/mecat2ref/mecat2ref_aux.h:16-25) of one printed alignment: read = index inside the batch, dir 0 = F

@@ -16,6 +16,7 @@
 // parallel.  Columns go to a per-(task, direction) slot in walking order; k_aln_assemble reverses
 // the left part, appends the right part, applies the flavour's trimming and packs the strings.
 #include "common.cuh"
+#include "xdrop_core.cuh"
 
 #include <algorithm>
 
@@ -24,17 +25,23 @@ namespace mb {
 namespace {
 
 constexpr int AL_WARPS = 4;
-constexpr int KOFF = 404;                 // even, > max_d of any accepted block
-constexpr int VL_N = KOFF + 4;
+// Row budget of a block: max_d is 0.3 (q + t) <= 395 for the pw / ref flavour and 2 err (q + t) for the cns flavour -- 360 at
+// err 0.15 (pacbio), 480 at err 0.20 (nanopore consensus, mecat_correction.cpp:487), which gets the WIDE instance.
+template <bool WIDE> struct AlDims
+{
+	static constexpr int KOFF = WIDE ? 484 : 404;      // even, > max_d of any accepted block
+	static constexpr int VL_N = KOFF + 4;
+	static constexpr int MAXROWS = WIDE ? 480 : 400;
+};
 constexpr int SEQ_WORDS = 48;
 constexpr int DIRW = 12;                  // ballot words per row (band <= 2*180+1 diagonals)
-constexpr int MAXROWS = 400;
 constexpr uint32_t NO_ANCHOR = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int IDLE = -0x7fffffff - 1;     // x + y of a lane without a cell (see extend.cu)
 
-struct WarpSmem
+template <bool WIDE> struct WarpSmem
 {
+	static constexpr int VL_N = AlDims<WIDE>::VL_N, MAXROWS = AlDims<WIDE>::MAXROWS;
 	uint2 sq[SEQ_WORDS];
 	uint2 st[SEQ_WORDS];
 	uint2 vl[2 * VL_N];       // index k + KOFF: .x = furthest x on diagonal k, .y = packed anchor (interleaved parities, as in extend.cu)
@@ -53,15 +60,7 @@ __device__ __forceinline__ int dtrunc_mul(double a, int b) { return (int)__dmul_
 
 }  // namespace
 
-struct AlnSlot                 // where one (task, direction) writes its columns, and what it produced
-{
-	unsigned long long off;    // byte offset of the slot in both column arenas
-	int32_t cap;               // capacity in columns
-	int32_t cols, matches, qadv, tadv;
-	int32_t overflow;
-};
-
-template <int POLICY>
+template <int POLICY, bool WIDE>
 __global__ void __launch_bounds__(AL_WARPS * 32)
 k_align(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, const int2* __restrict__ qoffsz, int qN,
         const uint32_t* __restrict__ sfwd, const uint32_t* __restrict__ srev, const int2* __restrict__ soffsz, int sN,
@@ -69,9 +68,10 @@ k_align(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
         char* __restrict__ colt, uint32_t* __restrict__ dir_scratch, short* __restrict__ min_scratch, double err,
         unsigned long long* __restrict__ work_counter)
 {
-	__shared__ WarpSmem smem[AL_WARPS];
+	constexpr int KOFF = AlDims<WIDE>::KOFF, MAXROWS = AlDims<WIDE>::MAXROWS;
+	__shared__ WarpSmem<WIDE> smem[AL_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	WarpSmem& S = smem[warp];
+	WarpSmem<WIDE>& S = smem[warp];
 	const size_t gw = (size_t)blockIdx.x * AL_WARPS + warp;
 	uint32_t* rowdir = dir_scratch + gw * (size_t)(MAXROWS * DIRW);
 	short* rowmin = min_scratch + gw * (size_t)MAXROWS;
@@ -387,6 +387,15 @@ __global__ void k_aln_sizes(const AlignTask* __restrict__ tasks, const AlnSlot* 
 	if (i >= ntasks) return;
 	const AlignTask t = tasks[i];
 	const AlnSlot L = slots[2 * i], R = slots[2 * i + 1];
+	if (POLICY == 2) {
+		// XdropAligner::go (xdrop_gapalign.cpp:351-439): the left part without its last column, ok by the query span
+		if (lane == 0) {
+			const mbx::Half hl = {L.cols, L.matches, L.qadv, L.tadv, L.overflow >> 1, L.overflow & 1};
+			const mbx::Half hr = {R.cols, R.matches, R.qadv, R.tadv, R.overflow >> 1, R.overflow & 1};
+			mbx::finish(t.qstart, t.sstart, hl, hr, min_aln, out + 8 * i);
+		}
+		return;
+	}
 	const int n = L.cols + R.cols;
 	int ok = (n >= min_aln) && !L.overflow && !R.overflow;
 	int qs = t.qstart - L.qadv, qe = t.qstart + R.qadv, ss = t.sstart - L.tadv, se = t.sstart + R.tadv;
@@ -488,8 +497,10 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 {
 	*out = AlignDev();
 	if (!nb) return 0;
-	if (policy == 1 && !(err > 0.0 && err <= 0.16)) MB_FAIL(c, "align_batch: error rate %.3f is outside this path (pacbio, <= 0.16)", err);
-	int per_sm = 7;      // 28 warps per SM: the smem (7.3 KB per warp) and register (68) limit; measured 541 / 470 / 430 / 407 ms at 4 / 5 / 6 / 7
+	if (policy == 1 && !(err > 0.0 && err <= 0.2)) MB_FAIL(c, "align_batch: error rate %.3f is outside this path (<= 0.20)", err);
+	const bool wide = policy == 1 && err > 0.16;
+	const int MAXROWS = wide ? AlDims<true>::MAXROWS : AlDims<false>::MAXROWS;
+	int per_sm = wide ? 6 : 7;      // 28 warps per SM: the smem (7.3 KB per warp) and register (68) limit; measured 541 / 470 / 430 / 407 ms at 4 / 5 / 6 / 7
 	if (const char* e = getenv("MECAT_B200_ALIGN_CTAS")) per_sm = std::max(1, atoi(e));   // tuning hook
 	const int grid = c->sm_count * per_sm;
 	const size_t nwarps = (size_t)grid * AL_WARPS;
@@ -511,8 +522,10 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 			a.off = used; a.cap = (int32_t)capR; used += capR; slots.push_back(a);
 		}
 		if (used > c->align_arena) MB_FAIL(c, "align_batch: %zu tasks need more than the %zu-byte column arena", nb, c->align_arena);
-		MB_CUDA(c, c->alloc(&d_dir, nwarps * MAXROWS * DIRW));
-		MB_CUDA(c, c->alloc(&d_min, nwarps * MAXROWS));
+		if (policy != 2) {
+			MB_CUDA(c, c->alloc(&d_dir, nwarps * MAXROWS * DIRW));
+			MB_CUDA(c, c->alloc(&d_min, nwarps * MAXROWS));
+		}
 		size_t arena = 256ull << 20;                       // power-of-two sizes: the pool hands the same block back batch after batch
 		while (arena < used + 16) arena <<= 1;
 		arena = std::min(arena, std::max(c->align_arena, used + 16));
@@ -525,19 +538,25 @@ int align_batch_device(Ctx* c, int policy, double err, const DVolume* q, const D
 		MB_CUDA(c, cudaMemcpyAsync(d_tasks, h_tasks, sizeof(AlignTask) * nb, cudaMemcpyHostToDevice, c->stream));
 		MB_CUDA(c, cudaMemcpyAsync(d_slots, slots.data(), sizeof(AlnSlot) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
 		MB_CUDA(c, cudaMemsetAsync(c->d_counters + 4, 0, 8, c->stream));
-		{
+		if (policy == 2) {
+			if (xdrop_fill_slots(c, q, s, d_tasks, nb, d_slots, d_colq, d_colt)) return 1;
+		} else {
 			KScope ks(c, MECAT_K_EXTEND);
 			if (policy == 0)
-				k_align<0><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
+				k_align<0, false><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
 				                                                  d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
+			else if (wide)
+				k_align<1, true><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
+				                                                        d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
 			else
-				k_align<1><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
-				                                                  d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
+				k_align<1, false><<<grid, AL_WARPS * 32, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
+				                                                         d_tasks, nb, d_slots, d_colq, d_colt, d_dir, d_min, err, c->d_counters + 4);
 		}
 		{
 			KScope ks(c, MECAT_K_FINAL);
 			const unsigned g2 = (unsigned)((nb * 32 + 127) / 128);
 			if (policy == 0) k_aln_sizes<0><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, out->d_info);
+			else if (policy == 2) k_aln_sizes<2><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, out->d_info);
 			else k_aln_sizes<1><<<g2, 128, 0, c->stream>>>(d_tasks, d_slots, nb, min_aln, d_colq, d_colt, out->d_info);
 		}
 		MB_CUDA(c, cudaGetLastError());

@@ -250,7 +250,7 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
                             size_t ntasks, int min_align_size, mecat_extend_result** results)
 {
 	if (check(c) || !dq || !ds || !results) return 1;
-	if (policy != 0) MB_FAIL(c, "extend_batch: policy %d not available (0 = pw/ref flavour)", policy);
+	if (policy != 0 && policy != 2) MB_FAIL(c, "extend_batch: policy %d not available (0 = pw/ref flavour, 2 = nanopore pw/ref flavour)", policy);
 	cudaSetDevice(c->device);
 	*results = nullptr;
 	if (!ntasks) return 0;
@@ -273,8 +273,10 @@ int mecat_b200_extend_batch(mecat_b200_ctx* c, int policy, void* dq, void* ds, c
 		MB_CUDA(c, c->alloc(&d_halves, (size_t)(2 * ntasks)));
 		MB_CUDA(c, c->alloc(&d_res, (size_t)(ntasks)));
 		MB_CUDA(c, cudaMemcpyAsync(d_tasks, tasks, sizeof(ExtendTask) * ntasks, cudaMemcpyHostToDevice, c->stream));
-		if (extend_launch(c, Q, S, d_tasks, ntasks, d_halves)) return 1;
-		{
+		if (policy == 2) {
+			if (xdrop_extend(c, Q, S, d_tasks, ntasks, min_align_size, d_res)) return 1;
+		} else {
+			if (extend_launch(c, Q, S, d_tasks, ntasks, d_halves)) return 1;
 			KScope ks(c, MECAT_K_FINAL);
 			k_extend_finalize<<<(unsigned)((ntasks + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, ntasks, min_align_size, d_res);
 		}
@@ -300,7 +302,7 @@ int mecat_b200_align_batch(mecat_b200_ctx* c, int policy, double err, void* dq, 
                            char** sstrings, size_t* string_bytes)
 {
 	if (check(c) || !dq || !ds || !results || !qstrings || !sstrings || !string_bytes) return 1;
-	if (policy != 0 && policy != 1) MB_FAIL(c, "align_batch: policy must be 0 (pw/ref) or 1 (cns), not %d", policy);
+	if (policy < 0 || policy > 2) MB_FAIL(c, "align_batch: policy must be 0 (pw/ref), 1 (cns) or 2 (nanopore pw/ref), not %d", policy);
 	cudaSetDevice(c->device);
 	*results = nullptr; *qstrings = nullptr; *sstrings = nullptr; *string_bytes = 0;
 	if (!ntasks) return 0;
@@ -636,7 +638,7 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 	if (read_begin < 0) read_begin = 0;
 	if (read_end < 0 || read_end > reads->num_reads) read_end = reads->num_reads;
 	if (p->num_candidates < 1) MB_FAIL(c, "pw_tile: number of candidates must be > 0");
-	if (p->tech != 0) MB_FAIL(c, "pw_tile: only -x 0 (pacbio, diff aligner) is on this path");
+	if (p->tech != 0 && p->tech != 1) MB_FAIL(c, "pw_tile: technology (-x) must be 0 (pacbio) or 1 (nanopore), not %d", p->tech);
 	if (p->task != 0 && p->task != 1) MB_FAIL(c, "pw_tile: task (-j) must be 0 or 1, not %d", p->task);
 	const int N = reads->num_reads, maxc = p->num_candidates;
 	*n = 0;
@@ -811,9 +813,13 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			auto gpu_part = [&]() -> int {
 				if (!nt) return 0;
 				WallTimer te;
-				if (extend_launch(c, reads, ref, d_tasks + t0, nt, d_halves + 2 * t0)) return 1;
-				c->stats.wall_extend_ms += te.stop();
-				{
+				if (p->tech == 1) {
+					// nanopore: XdropAligner instead of DiffAligner (pw_impl.cpp:638-642)
+					if (xdrop_extend(c, reads, ref, d_tasks + t0, nt, p->min_align_size, d_res + t0)) return 1;
+					c->stats.wall_extend_ms += te.stop();
+				} else {
+					if (extend_launch(c, reads, ref, d_tasks + t0, nt, d_halves + 2 * t0)) return 1;
+					c->stats.wall_extend_ms += te.stop();
 					KScope ks(c, MECAT_K_FINAL);
 					k_extend_finalize<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(d_tasks + t0, d_halves + 2 * t0, nt, p->min_align_size, d_res + t0);
 				}

@@ -199,6 +199,20 @@ struct AlignTask           // = mecat_align_task
 {
 	int32_t qread, qstrand, qstart, sread, sstart, swin_off, swin_len;
 };
+struct AlnSlot                 // where one (task, direction) writes its columns, and what it produced
+{
+	unsigned long long off;    // byte offset of the slot in both column arenas
+	int32_t cap;               // capacity in columns
+	int32_t cols, matches, qadv, tadv;
+	int32_t overflow;          // bit 0: the slot was too small; bits 1-3 (nanopore extension): flags of the last column, xdrop_core.cuh
+};
+// nanopore (-x 1) extension, xdrop.cu: fills the slots (and, with column arenas, the columns) of 2 * nb chains ...
+int xdrop_fill_slots(Ctx* c, const DVolume* q, const DVolume* s, const AlignTask* d_tasks, size_t nb, AlnSlot* d_slots,
+                     char* d_colq, char* d_colt);
+// ... and the string-free form for mecat2pw -j 1: XdropAligner::go's accessors per task
+int xdrop_extend(Ctx* c, const DVolume* q, const DVolume* s, const ExtendTask* d_tasks, size_t ntasks, int min_aln,
+                 mecat_extend_result* d_res);
+
 // results of one arena batch of extensions with strings, still in device memory
 struct AlignDev
 {

@@ -620,7 +620,12 @@ int orc_pw_tile(const orc_volume* ref, const orc_volume* reads, const orc_pw_par
 						} else {
 							unpack_read(ref, sidx, 0, subj);
 							const char* q = cd.chain ? rev.data() : fwd.data();
-							diff_go(q, qstart, qsize, subj.data(), sstart, ssize, P->min_align_size, W, R, false);
+							if (P->tech == 1) {       // XdropAligner for nanopore reads, pw_impl.cpp:638-642
+								int32_t o[8]; double id = 0;
+								R.ok = orc_xdrop_go(q, qstart, qsize, subj.data(), sstart, ssize, P->min_align_size, o, &id, NULL, NULL, 0) != 0;
+								R.qs = o[1]; R.qe = o[2]; R.ts = o[3]; R.te = o[4]; R.size = o[5]; R.matches = o[6]; R.ident = id;
+							} else
+								diff_go(q, qstart, qsize, subj.data(), sstart, ssize, P->min_align_size, W, R, false);
 							if (!R.ok) continue;
 							M4 m; memset(&m, 0, sizeof m);   // fill_m4record, pw_impl.cpp:467-506
 							m.qid = cd.readno; m.sid = qid; m.ident = R.ident; m.vscore = cd.score; m.qdir = 0;

@@ -13,6 +13,8 @@ Cases (reads come from oracle/gen_reads, a seeded deterministic generator):
   refmap: 300 reads, mean 6 kb, genome 100 kb, seed 5  -> `mecat2ref -m 1` (M4) and `-m 0` (ref format with alignment
           strings) of the reads against their own genome: fixtures for the mecat2ref driver,
           which is not built yet; reads and genome are regenerated on demand (sha256 committed)
+  x1    : the small / cfg0 / deep / refmap inputs with `-x 1` (nanopore: XdropAligner, min_kmer_dist 400, the nanopore
+          consensus variant) -- SURVEY.md section 8(f) item 2
   python tests/golden/make_golden.py [case ...]   regenerates only the named cases
 For each: vol0 sha256 (split_raw_dataset), sorted `mecat2pw -j 0` lines, sorted
 `mecat2pw -j 1 -g 1` lines.
@@ -108,6 +110,77 @@ def make_refmap(meta):
     shutil.rmtree(tmp)
 
 
+def make_nanopore(meta):
+    """`-x 1` (nanopore) goldens: the same reads through the reference's other aligner and parameter set --
+    mecat2pw -x 1 (-j 0: min_kmer_dist 400, -k 2; -j 1: XdropAligner, -a 500), mecat2cns -x 1 -i 0 (error rate 0.20, up to
+    100 alignments per read, the whole read as the only effective range), mecat2ref -x 1 (XdropAligner)."""
+    m = {}
+    for name in ("small", "cfg0"):
+        c = CASES[name]
+        tmp = tempfile.mkdtemp(prefix="golden_x1_")
+        fa = os.path.join(tmp, "reads.fa")
+        gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+        for job, ext, extra in ((0, "can", []), (1, "m4", ["-g", "1"])):
+            if name == "cfg0" and job == 0:
+                continue
+            out = os.path.join(tmp, "out." + ext)
+            subprocess.check_call([os.path.join(REF_DIR, "mecat2pw"), "-j", str(job), "-x", "1", "-d", fa, "-o", out, "-w", os.path.join(tmp, "wrk%d" % job),
+                                   "-t", "8"] + extra, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            lines = sorted(open(out).read().splitlines())
+            with gzip.open(os.path.join(HERE, "%s.x1.%s.gz" % (name, ext)), "wt") as f:
+                f.write("\n".join(lines) + "\n")
+            m["%s_num_%s" % (name, ext)] = len(lines)
+        if name == "small":
+            can = os.path.join(tmp, "in.can")
+            shutil.copy(os.path.join(tmp, "out.can"), can)
+            m["small_num_cns"] = run_cns_x1(can, fa, os.path.join(HERE, "small.x1.cns.fa.gz"), tmp)
+        shutil.rmtree(tmp)
+    # the deep fixture's own (pacbio) candidates through the nanopore consensus: 100 candidates per read at ~120x
+    c = CASES["deep"]
+    tmp = tempfile.mkdtemp(prefix="golden_x1d_")
+    fa = os.path.join(tmp, "reads.fa")
+    gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    can = os.path.join(tmp, "in.can")
+    with gzip.open(os.path.join(HERE, "deep.can.gz"), "rt") as f, open(can, "w") as g:
+        g.write(f.read())
+    m["deep_num_cns"] = run_cns_x1(can, fa, os.path.join(HERE, "deep.x1.cns.fa.gz"), tmp)
+    shutil.rmtree(tmp)
+    # mecat2ref -x 1 on the refmap fixture
+    c = REFMAP
+    tmp = tempfile.mkdtemp(prefix="golden_x1r_")
+    fa, genome = os.path.join(tmp, "reads.fa"), os.path.join(tmp, "genome.fa")
+    gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], genome_out=genome)
+    for fmt, ext in ((1, "m4"), (0, "ref")):
+        out = os.path.join(tmp, "out." + ext)
+        subprocess.check_call([os.path.join(REF_DIR, "mecat2ref"), "-d", fa, "-r", genome, "-o", out, "-w", os.path.join(tmp, "w" + ext),
+                               "-t", "4", "-m", str(fmt), "-x", "1"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
+        text = open(out).read()
+        if fmt == 1:
+            lines = sorted(text.splitlines())
+            with gzip.open(os.path.join(HERE, "refmap.x1.m4.gz"), "wt") as f:
+                f.write("\n".join(lines) + "\n")
+            m["refmap_num_m4"] = len(lines)
+        else:
+            recs = text.split("\n")
+            groups = sorted("\n".join(recs[i:i + 3]) for i in range(0, len(recs) - 1, 3))
+            with gzip.open(os.path.join(HERE, "refmap.x1.ref.gz"), "wt") as f:
+                f.write("\n".join(groups) + "\n")
+            m["refmap_num_ref"] = len(groups)
+    shutil.rmtree(tmp)
+    meta["x1"] = m
+
+
+def run_cns_x1(can, fa, dest, tmp):
+    out = os.path.join(tmp, "cns_x1.fa")
+    subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-x", "1", "-i", "0", "-t", "1", can, fa, out],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = open(out).read().splitlines()
+    recs = sorted(zip(lines[0::2], lines[1::2]))
+    with gzip.open(dest, "wt") as f:
+        for h, q in recs:
+            f.write(h + "\n" + q + "\n")
+    return len(recs)
+
 
 def sha(path):
     h = hashlib.sha256()
@@ -123,6 +196,8 @@ def main():
         meta = json.load(open(os.path.join(HERE, "golden.json")))
     for name, c in CASES.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
+        if name == "x1":
             continue
         tmp = tempfile.mkdtemp(prefix="golden_")
         fa = os.path.join(tmp, "reads.fa")
@@ -165,6 +240,8 @@ def main():
         shutil.rmtree(tmp)
     if len(sys.argv) == 1 or "refmap" in sys.argv[1:]:
         make_refmap(meta)
+    if len(sys.argv) == 1 or "x1" in sys.argv[1:]:
+        make_nanopore(meta)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))

@@ -49,6 +49,15 @@ def test_oracle_m4_matches_reference_binary(small_vol):
     assert util.m4_lines(m4, gapped=True) == gold_lines("small", "m4")
 
 
+def test_oracle_nanopore_matches_reference_binary(small_vol):
+    """-x 1: min_kmer_dist 400 and -k 2 for the candidates, XdropAligner and -a 500 for the overlaps
+    (pw_impl.cpp:638-642,843-849, pw_options.cpp:43-49); goldens of the unmodified binary."""
+    ec = util.oracle_pw_tile(small_vol, small_vol, pw_params(task=0, a=500, k=2, x=1), threads=4)
+    assert util.ec_lines(ec) == gold_lines("small.x1", "can")
+    m4 = util.oracle_pw_tile(small_vol, small_vol, pw_params(task=1, a=500, k=2, x=1), threads=4)
+    assert util.m4_lines(m4, gapped=True) == gold_lines("small.x1", "m4")
+
+
 def test_oracle_num_candidates_cap(small_vol):
     # -n 3 keeps the first 3 lines per read of the -n 100 output (SURVEY.md section 7 item 8)
     full = util.oracle_pw_tile(small_vol, small_vol, pw_params(task=0), threads=4)
