@@ -243,12 +243,16 @@ int mecat_b200_align_batch(mecat_b200_ctx* ctx, int policy, double err, void* dv
  * sdir == 0; src/mecat2cns/overlaps_partition.cpp:141-165), any order; reads with fewer than
  * min_cov candidates or shorter than 0.95 * min_size are skipped like the reference does.
  * dvol_reads must hold every read named by ec (read id = index + start_read_id).
- * Mirrors ConsensusOptions (src/mecat2cns/options.h:9-23): -r, -a, -c, -l. */
+ * Mirrors ConsensusOptions (src/mecat2cns/options.h:9-23): -r, -a, -c, -l, -x. */
 typedef struct {
 	double min_mapping_ratio;   /* -r, default 0.9  */
 	int32_t min_align_size;     /* -a, default 2000 */
 	int32_t min_cov;            /* -c, default 6    */
 	int64_t min_size;           /* -l, default 5000 */
+	int32_t tech;               /* -x, 0 = pacbio; 1 = nanopore: consensus_one_read_can_nanopore (mecat_correction.cpp:453-512:
+	                               error rate 0.20, up to 100 alignments per read, the whole read as the one effective range);
+	                               its defaults are -r 0.4 -a 400 -c 6 -l 2000 (options.cpp:21-29) */
+	int32_t pad_;
 } mecat_cns_params;
 
 /* CnsResult (src/common/alignment.h): corrected piece [beg, end) of read id; sequence at

@@ -35,7 +35,7 @@ K_NUM = len(KERNEL_NAMES)      # MECAT_K_NUM
 
 class CnsParams(C.Structure):
     _fields_ = [("min_mapping_ratio", C.c_double), ("min_align_size", C.c_int32), ("min_cov", C.c_int32),
-                ("min_size", C.c_int64)]
+                ("min_size", C.c_int64), ("tech", C.c_int32), ("pad_", C.c_int32)]
 
 
 CNS_PIECE_DTYPE = np.dtype([("id", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("seq_offset", "<i8"), ("seq_len", "<i8")])
@@ -540,10 +540,10 @@ class Context:
             self.L.mecat_b200_free(self.h, ss)
         return r, q, s
 
-    def cns_reads(self, dvol, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000):
+    def cns_reads(self, dvol, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0):
         """mecat2cns -i 0 on normalised candidates (EC_DTYPE array).  Returns [(id, beg, end, seq bytes), ...]."""
         ec = np.ascontiguousarray(candidates, dtype=EC_DTYPE)
-        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size)
+        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size, tech, 0)
         pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         self._check(self.L.mecat_b200_cns_reads(self.h, dvol, ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p), C.byref(pieces),
                                                 C.byref(n), C.byref(seqs), C.byref(nb)), "cns_reads")
@@ -554,10 +554,10 @@ class Context:
         return [(int(x["id"]), int(x["beg"]), int(x["end"]), blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])])
                 for x in pc]
 
-    def cns_reads_multi(self, dvols, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000):
+    def cns_reads_multi(self, dvols, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0):
         """cns_reads for a read set that spans several resident volumes (consecutive read ids)."""
         ec = np.ascontiguousarray(candidates, dtype=EC_DTYPE)
-        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size)
+        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size, tech, 0)
         arr = (C.c_void_p * len(dvols))(*[d.value if hasattr(d, "value") else d for d in dvols])
         pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         self._check(self.L.mecat_b200_cns_reads_multi(self.h, arr, len(dvols), ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p),
@@ -604,10 +604,10 @@ class Context:
     def release_ref_index(self, i):
         self.L.mecat_b200_ref_index_release(self.h, i)
 
-    def ref_map(self, refidx, reads, num_candidates=10, num_output=10, want_strings=True):
+    def ref_map(self, refidx, reads, num_candidates=10, num_output=10, want_strings=True, tech=0):
         """mecat2ref on a RefReads batch.  Returns (records, qstrings, sstrings): REF_RESULT_DTYPE records in output order
         (a read's records adjacent); record['str_offset'] indexes the two NUL-separated byte blobs."""
-        p = RefParams(num_candidates, num_output, 1 if want_strings else 0, 0)
+        p = RefParams(num_candidates, num_output, 1 if want_strings else 0, tech)
         r = reads.c()
         res, n, qs, ss, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_void_p(), C.c_size_t()
         self._check(self.L.mecat_b200_ref_map(self.h, refidx, C.byref(r), C.byref(p), C.byref(res), C.byref(n), C.byref(qs),

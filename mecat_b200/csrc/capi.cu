@@ -438,6 +438,8 @@ static int cns_core(mecat_b200_ctx* c, const DVolume* V, const std::vector<mecat
 	const int id0 = V->start_read_id;
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
+	P.tech = p->tech;
+	const double err = p->tech == 1 ? 0.20 : 0.15;     // GetAlignment's error rate, mecat_correction.cpp:424,487
 	const size_t TASKS_PER_BATCH = 400000;       // with the column arena (12 GB at ~30 kB per task) this bounds a batch; more units per launch suit the latency-bound stages
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;
@@ -469,7 +471,7 @@ static int cns_core(mecat_b200_ctx* c, const DVolume* V, const std::vector<mecat
 		}
 		const float ms_tasks = t_batch.stop();
 		AlignDev dev;
-		if (align_batch_device(c, 1, 0.15, V, V, tasks.data(), tasks.size(), p->min_align_size, &dev, info)) return 1;
+		if (align_batch_device(c, 1, err, V, V, tasks.data(), tasks.size(), p->min_align_size, &dev, info)) return 1;
 		const float ms_align = t_batch.stop();
 		mbcns::BatchIn in;
 		in.R = (int)(g1 - g0); in.T = (int64_t)tasks.size();

@@ -24,7 +24,8 @@
 
 namespace mbcns {
 
-constexpr int MAX_ACCEPT = 60;      // mecat_correction.cpp:407 (MAX_CNS_OVLPS)
+constexpr int MAX_ACCEPT = 100;     // capacity: MAX_CNS_OVLPS, reads_correction_aux.h:32 (the nanopore cap, mecat_correction.cpp:482)
+constexpr int MAX_ACCEPT_PACBIO = 60;   // max_added of consensus_one_read_can_pacbio, mecat_correction.cpp:407
 constexpr int MAX_TRIED = 200;      // mecat_correction.cpp:410 (MAX_EXAMINED_OVLPS)
 constexpr int COV_FULL = 20;        // check_cov_stats, mecat_correction.cpp:373-386
 constexpr int COV_NEED = 200;
@@ -131,7 +132,7 @@ CNS_HD inline int find_first(const L& lanes, int from, int to, Pred&& pred)
 	return to;
 }
 
-// check_cov_stats works on one coverage byte per template position (at most 60, so SWAR on 8 bytes never carries).
+// check_cov_stats works on one coverage byte per template position (at most 100, so SWAR on 8 bytes never carries).
 // The lanes split the aligned 8-byte words of [b, e); lane 0 takes the ragged ends.
 template <class L>
 CNS_HD inline int count_full(const L& lanes, const uint8_t* cov, int b, int e)   // positions in [b, e) covered >= COV_FULL times
@@ -172,12 +173,12 @@ CNS_HD inline void bump_cov(const L& lanes, uint8_t* cov, int b, int e)
 // send, columns, ...} as written by the extension kernels.  Returns the number accepted; acc[k] = task.
 template <class L>
 CNS_HD inline int accept_read(const L& lanes, int t0, int t1, const int32_t* info, const int32_t* t_qid, const int32_t* t_qsize,
-                              int ssize, double ratio, uint8_t* cov, int32_t* acc)
+                              int ssize, double ratio, uint8_t* cov, int32_t* acc, int max_accept)
 {
 	int used[MAX_ACCEPT];
 	int added = 0, tried = 0;
 	const int qss = (int)((double)ssize * ratio);
-	for (int t = t0; t < t1 && added < MAX_ACCEPT && tried < MAX_TRIED; ++t) {
+	for (int t = t0; t < t1 && added < max_accept && tried < MAX_TRIED; ++t) {
 		++tried;
 		const int qid = t_qid[t];
 		bool seen = false;
@@ -315,7 +316,7 @@ CNS_HD inline int normalize_vote_index(const char* q0, const char* t0, int n, in
 // ------------------------------------------------------------------------------------------ C6 (ranges)
 struct Range { int start, end; };
 
-// get_effective_ranges, mecat_correction.cpp:119-153.  m (nm <= 60 entries) is reordered; returns the count in e.
+// get_effective_ranges, mecat_correction.cpp:119-153.  m (nm <= MAX_ACCEPT entries) is reordered; returns the count in e.
 CNS_HD inline int effective_ranges(Range* m, int nm, Range* e, int read_size, double size95)
 {
 	if (nm == 0) return 0;

@@ -34,7 +34,7 @@
 
 namespace mbcns {
 
-struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; };
+struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; int tech = 0; };
 struct Piece { int64_t id, beg, end; std::string seq; };   // CnsResult, src/common/alignment.h
 
 // kernel slots for the per-stage timers of the backend
@@ -60,11 +60,11 @@ struct BatchIn
 struct AcceptFn
 {
 	const int32_t* first; const int32_t* info; const int32_t* tqid; const int32_t* tqsize; const int32_t* read_size;
-	const int64_t* pos_off; uint8_t* cov; double ratio; int32_t* acc; int32_t* nacc;
+	const int64_t* pos_off; uint8_t* cov; double ratio; int32_t* acc; int32_t* nacc; int max_accept;
 	template <class L>
 	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
-		const int n = accept_read(lanes, first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT);
+		const int n = accept_read(lanes, first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT, max_accept);
 		if (lanes.leader()) nacc[r] = n;
 	}
 };
@@ -110,14 +110,16 @@ struct NormVoteFn
 struct SegmentFn
 {
 	const int32_t* nacc; const int64_t* aln_first; const KeptAln* kept; const int32_t* read_size; const int64_t* pos_off;
-	const uint32_t* votes; int min_cov; double size95; const int64_t* seg_slot; int32_t* segs; int32_t* nseg;
+	const uint32_t* votes; int min_cov; double size95; const int64_t* seg_slot; int32_t* segs; int32_t* nseg; int whole_read;
 	template <class L>
 	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
 		Range m[MAX_ACCEPT], e[MAX_ACCEPT];
 		const int n = nacc[r];
 		for (int k = 0; k < n; ++k) { m[k].start = kept[aln_first[r] + k].soff; m[k].end = kept[aln_first[r] + k].send; }
-		const int ne = effective_ranges(m, n, e, read_size[r], size95);
+		int ne;
+		if (whole_read) { e[0].start = 0; e[0].end = read_size[r]; ne = 1; }      // nanopore: mecat_correction.cpp:508-509
+		else ne = effective_ranges(m, n, e, read_size[r], size95);
 		const int cap = (int)(seg_slot[r + 1] - seg_slot[r]);
 		const int ns = find_segments(lanes, e, ne, votes + pos_off[r], min_cov, size95, segs + 2 * seg_slot[r], cap);
 		if (lanes.leader()) nseg[r] = ns <= cap ? ns : -1;       // -1: capacity formula violated (reported by the host as an error)
@@ -400,7 +402,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 	CNS_TRY(be.fill(d_base, 'N', (size_t)POS));
 
 	// C3: which alignments vote
-	CNS_TRY(be.launch_warp(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc}, ST_ACCEPT));
+	CNS_TRY(be.launch_warp(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc, P.tech == 1 ? MAX_ACCEPT : MAX_ACCEPT_PACBIO}, ST_ACCEPT));
 	int64_t NA = 0;
 	CNS_TRY(be.scan(d_nacc, d_alnfirst, R, &NA));
 	lap("setup + accept");
@@ -429,7 +431,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 	CNS_ALLOC(d_segs, int32_t, 2 * h_slot[R]);
 	CNS_ALLOC(d_nseg, int32_t, R);
 	CNS_ALLOC(d_segfirst, int64_t, R + 1);
-	CNS_TRY(be.launch_warp(R, SegmentFn{d_nacc, d_alnfirst, d_kept, d_rsize, d_pos, d_votes, P.min_cov, size95, d_slot, d_segs, d_nseg}, ST_SEGMENT));
+	CNS_TRY(be.launch_warp(R, SegmentFn{d_nacc, d_alnfirst, d_kept, d_rsize, d_pos, d_votes, P.min_cov, size95, d_slot, d_segs, d_nseg, P.tech == 1 ? 1 : 0}, ST_SEGMENT));
 	std::vector<int32_t> h_nseg((size_t)R);
 	CNS_TRY(be.download(h_nseg.data(), d_nseg, (size_t)R));
 	for (int r = 0; r < R; ++r) if (h_nseg[r] < 0) { be.fail("cns: segment slots of a read overflowed"); return 1; }

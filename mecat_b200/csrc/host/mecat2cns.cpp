@@ -61,6 +61,7 @@ void print_usage(const char* prog)
 	fprintf(stderr, "-k <Integer>\tnumber of partition files when partitioning overlap results\n");
 	fprintf(stderr, "-h\t\tprint usage info.\n");
 	fprintf(stderr, "\ndefault values (pacbio): -i 1 -t 1 -p 100000 -r 0.9 -a 2000 -c 6 -l 5000 -k 10\n");
+	fprintf(stderr, "default values (nanopore, -x 1): -i 1 -t 1 -p 100000 -r 0.4 -a 400 -c 6 -l 2000 -k 10\n");
 }
 
 int parse_arguments(int argc, char* argv[], Options& t)
@@ -160,7 +161,6 @@ int main(int argc, char* argv[])
 	const int r = parse_arguments(argc, argv, opt);
 	if (r) { print_usage(argv[0]); return 1; }
 	if (opt.usage) { print_usage(argv[0]); return 0; }
-	if (opt.tech != 0) { fprintf(stderr, "mecat2cns: -x 1 (nanopore) is not part of the GPU path; use the reference binary for it.\n"); return 1; }
 	if (opt.input_type != 0) { fprintf(stderr, "mecat2cns: only `-i 0` (candidate input) is on the GPU path so far; use the reference binary for `-i 1`.\n"); return 1; }
 	if (mecat_b200_device_count() < 1) { fprintf(stderr, "mecat2cns: no CUDA device found (this build has no CPU path)\n"); return 1; }
 
@@ -201,7 +201,7 @@ int main(int argc, char* argv[])
 	if (ngpus < 1) ngpus = 1;
 	if (ngpus > have) ngpus = have;
 	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
-	const mecat_cns_params P = {opt.min_mapping_ratio, opt.min_align_size, opt.min_cov, opt.min_size};
+	const mecat_cns_params P = {opt.min_mapping_ratio, opt.min_align_size, opt.min_cov, opt.min_size, opt.tech, 0};
 	std::vector<size_t> cut((size_t)ngpus + 1, ec.size());
 	cut[0] = 0;
 	for (int g = 1; g < ngpus; ++g) {

@@ -113,10 +113,6 @@ int parse_arguments(int argc, char* argv[], Options* o)
 	else if (o->num_threads < 1) { fprintf(stderr, "number of cpu threads must be > 0.\n"); ret = 1; }
 	else if (o->num_candidates < 1) { fprintf(stderr, "number of candidates must be > 0.\n"); ret = 1; }
 	if (ret) return ret;
-	if (o->tech != 0) {
-		fprintf(stderr, "-x 1 (nanopore, X-drop aligner) is not part of the GPU path; use the reference binary for it.\n");
-		return 1;
-	}
 	DIR* dir = opendir(o->wrk_dir);
 	if (!dir) {
 		if (mkdir(o->wrk_dir, S_IRWXU) == -1) { fprintf(stderr, "fail to create folder '%s'!\n", o->wrk_dir); exit(1); }

@@ -48,7 +48,7 @@ void print_usage(const char* prog)
 	fprintf(stderr, "-n <integer>\tnumber of of candidates for gap extension\n\t\tdefault: 10\n");
 	fprintf(stderr, "-b <integer>\toutput the best b alignments\n\t\tdefault: 10\n");
 	fprintf(stderr, "-m <0/1/2>\toutput format: 0 = ref, 1 = m4, 2 = sam\n\t\tdefault: 0\n");
-	fprintf(stderr, "-x <0/1>\tsequencing technology: 0 = pacbio, 1 = nanopore (nanopore is not on this path)\n\t\tdefault: 0\n");
+	fprintf(stderr, "-x <0/1>\tsequencing technology: 0 = pacbio, 1 = nanopore\n\t\tdefault: 0\n");
 }
 
 int parse(int argc, char* argv[], Options& o)
@@ -111,7 +111,7 @@ int main(int argc, char* argv[])
 {
 	Options o;
 	if (parse(argc, argv, o) == -1) { print_usage(argv[0]); return 1; }
-	if (o.tech != 0) { fprintf(stderr, "mecat2ref (b200): -x 1 (nanopore) is not on this path\n"); return 1; }
+
 	if (o.output_format < 0 || o.output_format > 2) { fprintf(stderr, "mecat2ref (b200): unknown output format %d (0 = ref, 1 = m4, 2 = sam)\n", o.output_format); return 1; }
 	const double t0 = now();
 	{

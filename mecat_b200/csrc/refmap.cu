@@ -26,7 +26,8 @@ struct RefBackend : PoolBackend
 {
 	const DVolume* reads;
 	const DVolume* genome;
-	RefBackend(Ctx* ctx, const DVolume* r, const DVolume* g) : PoolBackend(ctx, "ref", true), reads(r), genome(g) {}
+	int tech;                      // -x: 0 = DiffAligner, 1 = XdropAligner (mecat2ref_impl_large.cpp:329-332)
+	RefBackend(Ctx* ctx, const DVolume* r, const DVolume* g, int tech_) : PoolBackend(ctx, "ref", true), reads(r), genome(g), tech(tech_) {}
 
 	template <class F> bool launch(int64_t n, const F& f, int stage)
 	{
@@ -42,6 +43,7 @@ struct RefBackend : PoolBackend
 		const int min_aln = 1000;       // extend_candidate's min_aln, mecat2ref_aux.cpp:152
 		// Without strings only coordinates, columns and matches are wanted: the forward pass of the extension gives them
 		// (k_extend: no traceback, no column arenas).  Opt-in until it has run on hardware next to the default.
+		if (tech == 1) return align_batch(c, 2, 0.0, reads, genome, (const AlignTask*)tasks, n, min_aln, res, qs, ss, want_strings) == 0;
 		if (!want_strings && forward_only()) { qs.clear(); ss.clear(); return align_forward(tasks, n, min_aln, res); }
 		return align_batch(c, 0, 0.0, reads, genome, (const AlignTask*)tasks, n, min_aln, res, qs, ss, want_strings) == 0;
 	}
@@ -132,7 +134,7 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
             std::vector<int32_t>* dump_counts, std::vector<int32_t>* dump_rows)
 {
 	if (!R || !reads || !p || !reads->vol) MB_FAIL(c, "ref_map: null argument");
-	if (p->tech != 0) MB_FAIL(c, "ref_map: only -x 0 (pacbio) is on this path");
+	if (p->tech != 0 && p->tech != 1) MB_FAIL(c, "ref_map: technology (-x) must be 0 (pacbio) or 1 (nanopore), not %d", p->tech);
 	const mecat_volume* v = reads->vol;
 	for (int32_t r = 0; r < reads->num_reads; ++r) {
 		const int32_t f = reads->fwd_read[r], w = reads->rev_read[r];
@@ -166,9 +168,9 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
 		mbref::Params P;
 		P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
 		P.dump_counts = dump_counts; P.dump_rows = dump_rows;
-		P.strings_for_printed_only = RefBackend::forward_only();
+		P.strings_for_printed_only = p->tech == 0 && RefBackend::forward_only();
 		if (const char* e = getenv("MECAT_B200_REF_TABLE_MB")) P.table_budget = (int64_t)atoll(e) << 20;      // test hook: force several table batches
-		RefBackend be(c, dv, R->genome);
+		RefBackend be(c, dv, R->genome, p->tech);
 		const int rc = mbref::map_reads(be, in, P, out);
 		if (rc) be.end_batch();
 		return rc;

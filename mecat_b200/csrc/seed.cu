@@ -1085,7 +1085,7 @@ int seed_candidates(Ctx* c, const DIndex* idx, const DVolume* ref, const DVolume
 			Wp.arena = d_arena; Wp.desc = d_desc; Wp.read0 = r0; Wp.nreads = nb;
 			Wp.qoffsz = reads->offsz; Wp.q_start_id = reads->start_read_id;
 			Wp.roffsz = ref->offsz; Wp.r_nreads = ref->num_reads; Wp.r_start_id = ref->start_read_id;
-			Wp.gate = 2 * p->min_kmer_match; Wp.min_span = p->tech == 1 ? 400 : 1800;   // min_kmer_dist, pw_impl.cpp:843-849 Wp.maxc = maxc;
+			Wp.gate = 2 * p->min_kmer_match; Wp.min_span = p->tech == 1 ? 400 : 1800 /* min_kmer_dist, pw_impl.cpp:843-849 */; Wp.maxc = maxc;
 			Wp.lists = d_lists; Wp.nlist = d_nlist;
 			{
 				KScope ks(c, MECAT_K_WALK);

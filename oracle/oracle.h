@@ -88,6 +88,9 @@ int orc_normalize_gaps(const char* qstr, const char* tstr, int n, int push, char
 int orc_ref_map(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format,
                 char** text, size_t* bytes);
 
+int orc_ref_map_x(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format, int tech,
+                  char** text, size_t* bytes);
+
 #ifdef __cplusplus
 }
 #endif

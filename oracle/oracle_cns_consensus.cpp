@@ -387,7 +387,8 @@ void consensus_one_read(int64_t read_id, int read_size, const mecat_candidate* c
 	const double ratio = P.min_mapping_ratio - 0.02;
 	std::set<int> used;
 	int added = 0, tried = 0;
-	for (int i = 0; i < ncand && added < 60 && tried < 200; ++i) {
+	const int max_added = P.tech == 1 ? 100 : 60;      // mecat_correction.cpp:407 / MAX_CNS_OVLPS at :482
+	for (int i = 0; i < ncand && added < max_added && tried < 200; ++i) {
 		++tried;
 		const mecat_candidate& ec = cand[i];
 		if (used.count(ec.qid)) continue;
@@ -411,7 +412,8 @@ void consensus_one_read(int64_t read_id, int read_size, const mecat_candidate* c
 	}
 	std::vector<Range> mr, er;
 	for (const Kept& k : S.kept) mr.push_back(Range{k.soff, k.send});
-	effective_ranges(mr, er, read_size, P.min_size);
+	if (P.tech == 1) er.push_back(Range{0, read_size});        // consensus_one_read_can_nanopore, mecat_correction.cpp:508-509
+	else effective_ranges(mr, er, read_size, P.min_size);
 
 	// consensus_worker
 	Vote* table = S.table.data();
@@ -487,6 +489,7 @@ int orc_cns_consensus(const mecat_candidate* cand, int ncand, const mecat_align_
 	if (!cand || ncand <= 0 || !res || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
 	orccns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
+	P.tech = p->tech;
 	orccns::Scratch scratch;
 	std::vector<orccns::Piece> out;
 	orccns::consensus_one_read(cand[0].sid, cand[0].ssize, cand, ncand, res, qstr, sstr, P, scratch, out);

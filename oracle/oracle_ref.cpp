@@ -20,6 +20,8 @@
 #include <string>
 #include <vector>
 
+static int g_ref_tech = 0;      // -x of the run in progress (orc_ref_map_x)
+
 namespace {
 
 // mecat2ref_defs.h:16-28
@@ -257,7 +259,8 @@ struct Mapper
 		double ident;
 		const int cap = 2 * (int)(q.size() + t.size()) + 64;
 		std::vector<char> qs((size_t)cap), ts((size_t)cap);
-		if (!orc_diff_go(q.data(), read_start, read_len, t.data(), (int)left_ref, (int)t.size(), 1000, o, &ident, qs.data(), ts.data(), cap)) return false;
+		// the aligner follows the technology: DiffAligner, or XdropAligner for -x 1 (mecat2ref_impl_large.cpp:329-332)
+		if (!(g_ref_tech == 1 ? orc_xdrop_go : orc_diff_go)(q.data(), read_start, read_len, t.data(), (int)left_ref, (int)t.size(), 1000, o, &ident, qs.data(), ts.data(), cap)) return false;
 		TempResult r;
 		r.read_id = read_name; r.read_dir = can.chain; r.vscore = can.score;
 		r.qb = o[1]; r.qe = o[2]; r.qs = read_len;
@@ -632,6 +635,16 @@ int orc_ref_map(const char* reference_path, const char* reads_path, int num_cand
 	p[out.size()] = 0;
 	*text = p; *bytes = out.size();
 	return 0;
+}
+
+// the same with -x: 0 = pacbio (DiffAligner), 1 = nanopore (XdropAligner); nothing else of mecat2ref depends on it
+int orc_ref_map_x(const char* reference_path, const char* reads_path, int num_candidates, int num_output, int format, int tech,
+                  char** text, size_t* bytes)
+{
+	g_ref_tech = tech;
+	const int rc = orc_ref_map(reference_path, reads_path, num_candidates, num_output, format, text, bytes);
+	g_ref_tech = 0;
+	return rc;
 }
 
 }  // extern "C"

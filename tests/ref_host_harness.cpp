@@ -22,6 +22,8 @@
 
 namespace {
 
+int g_tech = 0;      // -x of the run: which oracle aligner plays the extension kernel (harness_set_tech)
+
 std::vector<uint32_t> words_of(const uint8_t* pac, int64_t n)      // the device layout of volume.cu: base p at bits 2 (p % 16) of word p / 16
 {
 	std::vector<uint32_t> w((size_t)(n / 16 + 9), 0u);
@@ -87,7 +89,7 @@ struct HostBackend
 			int32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 			double ident = 0;
 			if (want_strings) ++string_tasks;
-			const int ok = orc_diff_go(q.data(), k.qstart, len, t.data(), k.sstart, k.swin_len, 1000, o, &ident, qa.data(), ta.data(), cap);
+			const int ok = (g_tech == 1 ? orc_xdrop_go : orc_diff_go)(q.data(), k.qstart, len, t.data(), k.sstart, k.swin_len, 1000, o, &ident, qa.data(), ta.data(), cap);
 			mecat_align_result& r = res[i];
 			memset(&r, 0, sizeof r);
 			r.ok = ok; r.str_offset = -1;
@@ -172,6 +174,8 @@ int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_
 }  // namespace
 
 extern "C" {
+
+void harness_set_tech(int tech) { g_tech = tech; }
 
 // mecat2ref -d reads -r reference -n num_candidates -b num_output -m format through the product's host I/O, stage
 // sequence and kernel bodies.  reads_per_call / table_budget force several ABI-sized calls and table batches.

@@ -37,10 +37,10 @@ def gold_can(name):
 _aln_cache = {}
 
 
-def oracle_alignments(vol, can, min_aln, min_cov, min_size, keep=None):
+def oracle_alignments(vol, can, min_aln, min_cov, min_size, keep=None, err=0.15):
     """Per read to correct: candidates in trial order + the oracle's GetAlignment of each.  Returns
     (first[R+1], candidates[T], results[T], qblob, sblob).  keep: optional predicate on the read id."""
-    key = (id(vol), min_aln, min_cov, min_size, keep)
+    key = (id(vol), min_aln, min_cov, min_size, keep, err)
     if key in _aln_cache:
         return _aln_cache[key]
     import mecat_b200
@@ -80,7 +80,7 @@ def oracle_alignments(vol, can, min_aln, min_cov, min_size, keep=None):
             q = seq(int(e["qid"]), int(e["qdir"]))
             qext = int(e["qsize"]) - 1 - int(e["qext"]) if e["qdir"] else int(e["qext"])
             ok = O.orc_cns_get_alignment(C.cast(q.ctypes.data + 1, C.c_char_p), qext, len(q) - 2,
-                                         C.cast(t.ctypes.data + 1, C.c_char_p), int(e["sext"]), len(t) - 2, 0.15, min_aln, o5, qa, sa, cap)
+                                         C.cast(t.ctypes.data + 1, C.c_char_p), int(e["sext"]), len(t) - 2, err, min_aln, o5, qa, sa, cap)
             if ok:
                 res[k] = (1, o5[1], o5[2], o5[3], o5[4], len(qa.value), 0, 0, 0.0, len(qblob))
                 qblob += qa.value + b"\0"
@@ -108,11 +108,11 @@ def _pieces(free, pieces, n, seqs, nb):
     return out
 
 
-def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None):
+def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None, tech=0):
     from mecat_b200.api import CnsParams
     O = util.oracle()
-    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep)
-    p = CnsParams(ratio, min_aln, min_cov, min_size)
+    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep, 0.20 if tech else 0.15)
+    p = CnsParams(ratio, min_aln, min_cov, min_size, tech, 0)
     out = []
     for r in range(len(first) - 1):
         a, b = int(first[r]), int(first[r + 1])
@@ -125,11 +125,11 @@ def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None):
     return sorted(out)
 
 
-def correct_with_kernel_bodies(vol, can, ratio, min_aln, min_cov, min_size, keep=None):
+def correct_with_kernel_bodies(vol, can, ratio, min_aln, min_cov, min_size, keep=None, tech=0):
     from mecat_b200.api import CnsParams
     H = util.cns_harness()
-    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep)
-    p = CnsParams(ratio, min_aln, min_cov, min_size)
+    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep, 0.20 if tech else 0.15)
+    p = CnsParams(ratio, min_aln, min_cov, min_size, tech, 0)
     pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
     err = C.create_string_buffer(256)
     rc = H.harness_cns_batch(len(first) - 1, first.ctypes.data_as(C.c_void_p), cand.ctypes.data_as(C.c_void_p),
@@ -206,6 +206,33 @@ def test_oracle_consensus_deep_coverage(deep_vol):
 
 def test_kernel_bodies_deep_coverage(deep_vol):
     compare(correct_with_kernel_bodies(deep_vol, gold_can("deep"), *PARAMS["cns_relaxed"], keep=_every_sixth), _deep_gold())
+
+
+# ---------------------------------------------------------------- nanopore consensus (-x 1)
+NANOPORE = (0.4, 400, 6, 2000)      # the -x 1 defaults: -r 0.4 -a 400 -c 6 -l 2000 (options.cpp:21-29)
+
+
+def gold_can_x1():
+    import mecat_b200
+    with gzip.open(os.path.join(util.GOLDEN, "small.x1.can.gz"), "rt") as f:
+        return mecat_b200.read_can(io.StringIO(f.read()))
+
+
+def test_nanopore_consensus_matches_reference(small_vol):
+    """consensus_one_read_can_nanopore (mecat_correction.cpp:453-512): error rate 0.20, up to 100 alignments, the whole
+    read as the one effective range -- oracle and kernel bodies against `mecat2cns -x 1 -i 0` of the unmodified binary."""
+    want = gold_fasta("small.x1", "cns")
+    assert len(want) == GOLD["x1"]["small_num_cns"]
+    compare(correct_with_oracle(small_vol, gold_can_x1(), *NANOPORE, tech=1), want)
+    compare(correct_with_kernel_bodies(small_vol, gold_can_x1(), *NANOPORE, tech=1), want)
+
+
+def test_nanopore_consensus_deep_coverage(deep_vol):
+    """~120x: more than 60 alignments are accepted per read (the nanopore cap is 100) before the 20x gate closes."""
+    want = [(h, s) for h, s in gold_fasta("deep.x1", "cns") if _every_sixth(int(h[1:].split("_")[0]))]
+    assert len(want) >= 40
+    compare(correct_with_oracle(deep_vol, gold_can("deep"), *NANOPORE, keep=_every_sixth, tech=1), want)
+    compare(correct_with_kernel_bodies(deep_vol, gold_can("deep"), *NANOPORE, keep=_every_sixth, tech=1), want)
 
 
 def test_fused_normalise_vote_kernel_body_matches_literal_restatement():

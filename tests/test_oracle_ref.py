@@ -25,10 +25,10 @@ def refmap_inputs(tmp_path_factory):
     return fa, genome
 
 
-def run_oracle(fa, genome, fmt):
+def run_oracle(fa, genome, fmt, tech=0):
     O = util.oracle()
     text, n = C.c_void_p(), C.c_size_t()
-    assert O.orc_ref_map(genome.encode(), fa.encode(), 10, 10, fmt, C.byref(text), C.byref(n)) == 0
+    assert O.orc_ref_map_x(genome.encode(), fa.encode(), 10, 10, fmt, tech, C.byref(text), C.byref(n)) == 0
     s = C.string_at(text.value, n.value).decode()
     O.orc_free(text)
     return s
@@ -86,3 +86,22 @@ def test_cfg0_sized_reads_match_reference(tmp_path):
     assert len(got) == len(want) == c["num_m4"]
     bad = [(g, w) for g, w in zip(got, want) if g != w]
     assert not bad, bad[:3]
+
+
+def test_nanopore_outputs_match_reference(refmap_inputs):
+    """mecat2ref -x 1: the same program with XdropAligner as its aligner (mecat2ref_impl_large.cpp:329-332); M4 and ref
+    format of the unmodified binary."""
+    fa, genome = refmap_inputs
+    got = sorted(run_oracle(fa, genome, 1, tech=1).splitlines())
+    with gzip.open(os.path.join(util.GOLDEN, "refmap.x1.m4.gz"), "rt") as f:
+        want = f.read().splitlines()
+    assert len(got) == len(want) == GOLD["x1"]["refmap_num_m4"]
+    assert got == want
+    lines = run_oracle(fa, genome, 0, tech=1).split("\n")
+    got = sorted("\n".join(lines[i:i + 3]) for i in range(0, len(lines) - 1, 3))
+    with gzip.open(os.path.join(util.GOLDEN, "refmap.x1.ref.gz"), "rt") as f:
+        want = f.read().rstrip("\n").split("\n")
+    want = ["\n".join(want[i:i + 3]) for i in range(0, len(want), 3)]
+    assert len(got) == len(want) == GOLD["x1"]["refmap_num_ref"]
+    bad = [g.split("\n")[0] for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:5]

@@ -91,4 +91,14 @@ def test_option_handling(small_fa, tmp_path):
     w = str(tmp_path / "w")
     assert "output must be specified" in run_driver(["-d", small_fa, "-w", w], ok=False).stderr
     assert "task (-j) must be 0 or 1" in run_driver(["-j", "3", "-d", small_fa, "-o", str(tmp_path / "o"), "-w", w], ok=False).stderr
-    assert "nanopore" in run_driver(["-x", "1", "-d", small_fa, "-o", str(tmp_path / "o"), "-w", w], ok=False).stderr
+    assert "invalid argument" in run_driver(["-x", "2", "-d", small_fa, "-o", str(tmp_path / "o"), "-w", w], ok=False).stderr
+
+
+def test_nanopore_option_sets_the_other_defaults(small_fa, tmp_path):
+    """-x 1: -a 500 -k 2 unless given, min_kmer_dist 400 and the X-drop aligner behind the tile call; the unmodified
+    binary's candidate and overlap lines for `-x 1`."""
+    can, m4 = str(tmp_path / "o.can"), str(tmp_path / "o.m4")
+    run_driver(["-j", "0", "-x", "1", "-d", small_fa, "-o", can, "-w", str(tmp_path / "w0"), "-t", "2"])
+    assert sorted(open(can).read().splitlines()) == gold("small.x1.can.gz")
+    run_driver(["-j", "1", "-g", "1", "-x", "1", "-d", small_fa, "-o", m4, "-w", str(tmp_path / "w1")])
+    assert sorted(open(m4).read().splitlines()) == gold("small.x1.m4.gz")

@@ -428,3 +428,28 @@ def test_driver_threads_under_thread_sanitizer(tmp_path, hard_inputs):
         pytest.skip("ThreadSanitizer cannot start in this environment")
     assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
     assert groups(open(out).read()) == golden_groups("refmap_hard.ref.gz")
+
+
+def test_nanopore_stage_sequence_matches_reference(refmap_inputs, hard_inputs):
+    """-x 1: the same stages with the other aligner behind the extension hook (mecat2ref_impl_large.cpp:329-332); golden
+    of the unmodified binary on the refmap fixture, the pinned oracle on the hard one (rescue between chimeric parts)."""
+    L = util.ref_harness()
+    L.harness_set_tech(1)
+    try:
+        fa, genome = refmap_inputs
+        assert sorted(run_harness(genome, fa, fmt=1)[0].splitlines()) == sorted(golden_lines("refmap.x1.m4.gz"))
+        assert groups(run_harness(genome, fa, fmt=0)[0]) == golden_groups("refmap.x1.ref.gz")
+        fa, genome = hard_inputs
+        O = util.oracle()
+        text, nb = C.c_void_p(), C.c_size_t()
+        assert O.orc_ref_map_x(genome.encode(), fa.encode(), 10, 10, 0, 1, C.byref(text), C.byref(nb)) == 0
+        want = C.string_at(text.value, nb.value).decode()
+        O.orc_free(text)
+        assert groups(run_harness(genome, fa, fmt=0, per_call=7)[0]) == groups(want)
+    finally:
+        L.harness_set_tech(0)
+
+
+def golden_lines(name):
+    with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
+        return f.read().splitlines()

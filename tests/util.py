@@ -197,6 +197,7 @@ def ref_harness():
     L.harness_ref_map.restype = C.c_int
     L.harness_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(vp), C.POINTER(C.c_size_t),
                                   C.POINTER(C.c_long), C.c_char_p, C.c_int]
+    L.harness_set_tech.argtypes = [C.c_int]
     L.harness_ref_index_build.restype = vp
     L.harness_ref_index_build.argtypes = [vp]
     L.harness_ref_index_release.argtypes = [vp]
@@ -266,6 +267,8 @@ def oracle():
     L.orc_cns_sort_candidates.argtypes = [C.c_void_p, C.c_int]
     L.orc_ref_map.restype = C.c_int
     L.orc_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.orc_ref_map_x.restype = C.c_int
+    L.orc_ref_map_x.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_poa_consensus.restype = C.c_int
     L.orc_poa_consensus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.orc_cns_consensus.restype = C.c_int
