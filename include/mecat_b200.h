@@ -204,6 +204,15 @@ int mecat_b200_pw_tile(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* d
 int mecat_b200_pw_tile_range(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads,
                              const mecat_pw_params* p, int read_begin, int read_end, void** records, size_t* n);
 
+/* Same tile, but the result comes back as the LINES of the reference's output file -- operator<<(ExtensionCandidate)
+ * for task 0, output_m4record for task 1 (src/common/alignment.cpp:18-32,58-78, src/mecat2pw/pw_impl.cpp:509-531;
+ * gapped = `-g 1`: with the two extension points) -- written on the device, so the records never visit the host.
+ * *text: malloc'ed, NUL terminated, *bytes long; release with mecat_b200_free. */
+int mecat_b200_pw_tile_text(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads, const mecat_pw_params* p,
+                            int gapped, char** text, size_t* bytes, size_t* num_records);
+/* The same text for records the caller holds: kind 0 = mecat_candidate[], kind 1 = mecat_m4[]. */
+int mecat_b200_records_text(mecat_b200_ctx* ctx, int kind, int gapped, const void* records, size_t n, char** text, size_t* bytes);
+
 /* Same, with host buffers in and out (upload + index build + tile + download): the
  * end-to-end call a host driver makes per tile when nothing is cached. */
 int mecat_b200_pw_candidates(mecat_b200_ctx* ctx, const mecat_volume* ref, const mecat_volume* reads,

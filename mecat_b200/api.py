@@ -95,6 +95,7 @@ EXPORTS = [
     "mecat_b200_ref_index_build", "mecat_b200_ref_index_release", "mecat_b200_ref_map",
     "mecat_b200_ref_index_export", "mecat_b200_ref_raw_candidates",
     "mecat_b200_cns_reads_multi", "mecat_b200_volumes_from_fasta", "mecat_b200_volumes_unload",
+    "mecat_b200_pw_tile_text", "mecat_b200_records_text",
 ]
 
 _lib = None
@@ -134,6 +135,8 @@ def load_library():
     L.mecat_b200_index_device_arrays.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
     L.mecat_b200_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
     L.mecat_b200_pw_tile.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_pw_tile_text.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.mecat_b200_records_text.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_candidates.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_overlaps.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_raw_candidates.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -523,6 +526,28 @@ class Context:
         self._check(self.L.mecat_b200_pw_tile(self.h, index, dref, dreads, C.byref(params), C.byref(out), C.byref(n)),
                     "pw_tile")
         return self._take(out, n.value, EC_DTYPE if params.task == 0 else M4_DTYPE)
+
+    def pw_tile_text(self, index, dref, dreads, params, gapped=False):
+        """One tile as the text of the reference's output file (written on the device).  Returns (bytes, number of records)."""
+        text, nb, n = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(self.L.mecat_b200_pw_tile_text(self.h, index, dref, dreads, C.byref(params), 1 if gapped else 0, C.byref(text),
+                                                   C.byref(nb), C.byref(n)), "pw_tile_text")
+        out = C.string_at(text.value, nb.value) if text.value else b""
+        if text.value:
+            self.L.mecat_b200_free(self.h, text)
+        return out, n.value
+
+    def records_text(self, records, gapped=False):
+        """`.can` / `.m4` lines of EC_DTYPE / M4_DTYPE records, formatted on the device."""
+        kind = 0 if records.dtype == EC_DTYPE else 1
+        rec = np.ascontiguousarray(records)
+        text, nb = C.c_void_p(), C.c_size_t()
+        self._check(self.L.mecat_b200_records_text(self.h, kind, 1 if gapped else 0, rec.ctypes.data_as(C.c_void_p), len(rec), C.byref(text),
+                                                   C.byref(nb)), "records_text")
+        out = C.string_at(text.value, nb.value) if text.value else b""
+        if text.value:
+            self.L.mecat_b200_free(self.h, text)
+        return out
 
     def align_batch(self, dquery, dsubject, tasks, min_align_size, policy=0, err=0.15):
         """Returns (results, qstrings, sstrings): result['str_offset'] indexes the two NUL-separated byte blobs."""

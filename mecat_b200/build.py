@@ -26,7 +26,7 @@ HOSTCXX = "/usr/bin/g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
               "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2,-pthread", "-Xptxas", "-v"]
 
-CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "align.cu", "xdrop.cu", "cns.cu", "refmap.cu", "capi.cu"]
+CU = ["volume.cu", "index.cu", "seed.cu", "extend.cu", "align.cu", "xdrop.cu", "records.cu", "cns.cu", "refmap.cu", "capi.cu"]
 
 
 def _newer(src_list, out):
@@ -39,7 +39,7 @@ def _newer(src_list, out):
 def _compile(cu):
     src = os.path.join(CSRC, cu)
     obj = os.path.join(OBJ, cu.replace(".cu", ".o"))
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns_pipeline.h"), os.path.join(CSRC, "cns_core.cuh"), os.path.join(CSRC, "ref_pipeline.h"), os.path.join(CSRC, "ref_core.cuh"), os.path.join(CSRC, "dev_backend.cuh"), os.path.join(CSRC, "xdrop_core.cuh"),
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cns_pipeline.h"), os.path.join(CSRC, "cns_core.cuh"), os.path.join(CSRC, "ref_pipeline.h"), os.path.join(CSRC, "ref_core.cuh"), os.path.join(CSRC, "dev_backend.cuh"), os.path.join(CSRC, "xdrop_core.cuh"), os.path.join(CSRC, "m4_core.cuh"),
             os.path.join(ROOT, "include", "mecat_b200.h")]
     if not _newer(deps, obj):
         return obj, ""

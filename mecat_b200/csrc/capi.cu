@@ -634,9 +634,12 @@ int mecat_b200_cns_reads_multi(mecat_b200_ctx* c, void* const* dvols, int nvols,
 
 // ------------------------------------------------------------------------------------------
 // One (index volume, query volume) tile.
+// text != NULL: the tile's result as the lines of the reference's output file instead of records (gapped: `-g 1`).
 static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* reads, const mecat_pw_params* p,
-                        int read_begin, int read_end, void** records, size_t* n, int32_t** raw_rows, int32_t** raw_counts)
+                        int read_begin, int read_end, void** records, size_t* n, int32_t** raw_rows, int32_t** raw_counts,
+                        char** text = nullptr, size_t* text_bytes = nullptr, int gapped = 0)
 {
+	if (text) { *text = nullptr; *text_bytes = 0; }
 	if (read_begin < 0) read_begin = 0;
 	if (read_end < 0 || read_end > reads->num_reads) read_end = reads->num_reads;
 	if (p->num_candidates < 1) MB_FAIL(c, "pw_tile: number of candidates must be > 0");
@@ -691,6 +694,26 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 		if (total == 0) return 0;
 		MB_CUDA(c, c->alloc(&d_outpos, (size_t)((size_t)(N + 1))));
 		MB_CUDA(c, cudaMemcpyAsync(d_outpos, h_outpos.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->stream));
+		// device text -> malloc'ed host text
+		auto text_out = [&](int kind, const void* d_recs, size_t nrec) -> int {
+			char* d_text = nullptr;
+			size_t bytes = 0;
+			if (records_text_device(c, kind, gapped, d_recs, nrec, &d_text, &bytes)) return 1;
+			char* h = (char*)malloc(bytes + 1);
+			if (!h) { c->dfree(d_text); MB_FAIL(c, "pw_tile: out of host memory"); }
+			WallTimer t;
+			cudaError_t e = bytes ? cudaMemcpyAsync(h, d_text, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+			c->stats.d2h_ms += t.stop();
+			c->dfree(d_text);
+			if (e != cudaSuccess) { free(h); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
+			h[bytes] = 0;
+			c->resolve_timers();
+			c->stats.d2h_bytes += (int64_t)bytes;
+			c->stats.num_records += (int64_t)nrec;
+			*text = h; *text_bytes = bytes; *n = nrec;
+			return 0;
+		};
 		if (p->task == 0) {
 			MB_CUDA(c, c->alloc(&d_ec, (size_t)(total)));
 			{
@@ -699,6 +722,7 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 				                                   ref->offsz, ref->start_read_id, d_ec, nullptr, nullptr);
 			}
 			MB_CUDA(c, cudaGetLastError());
+			if (text) { c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1); return text_out(0, d_ec, total); }
 			mecat_candidate* h = (mecat_candidate*)malloc(sizeof(mecat_candidate) * total);
 			if (!h) MB_FAIL(c, "pw_tile: out of host memory");
 			WallTimer t;
@@ -724,6 +748,43 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			                                   ref->offsz, ref->start_read_id, nullptr, d_tasks, d_scores);
 		}
 		MB_CUDA(c, cudaGetLastError());
+		// A12 on the device (default): one extension launch over all candidates, then fill_m4record / std::sort /
+		// containment filter per read in kernels (records.cu); only the kept records -- or their text -- go to the host.
+		// MECAT_B200_M4=host selects the earlier form (host threads behind extension chunks).
+		const char* m4_mode = getenv("MECAT_B200_M4");
+		if (!(m4_mode && !strcmp(m4_mode, "host"))) {
+			WallTimer te;
+			if (p->tech == 1) {
+				if (xdrop_extend(c, reads, ref, d_tasks, total, p->min_align_size, d_res)) return 1;
+			} else {
+				if (extend_launch(c, reads, ref, d_tasks, total, d_halves)) return 1;
+				KScope ks(c, MECAT_K_FINAL);
+				k_extend_finalize<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_tasks, d_halves, total, p->min_align_size, d_res);
+			}
+			MB_CUDA(c, cudaGetLastError());
+			mecat_m4* d_m4 = nullptr;
+			size_t nout = 0;
+			if (m4_assemble(c, reads, ref, d_tasks, d_res, d_scores, d_outpos, N, total, &d_m4, &nout)) return 1;
+			c->stats.wall_extend_ms += te.stop();
+			c->stats.h2d_bytes += (int64_t)sizeof(int64_t) * (N + 1);
+			int rc2 = 0;
+			if (text) rc2 = nout ? text_out(1, d_m4, nout) : 0;
+			else {
+				mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * (nout ? nout : 1));
+				if (!out) { c->dfree(d_m4); MB_FAIL(c, "pw_tile: out of host memory"); }
+				WallTimer t;
+				cudaError_t e = nout ? cudaMemcpyAsync(out, d_m4, sizeof(mecat_m4) * nout, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+				if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+				c->stats.d2h_ms += t.stop();
+				if (e != cudaSuccess) { free(out); c->dfree(d_m4); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
+				c->resolve_timers();
+				c->stats.d2h_bytes += (int64_t)(sizeof(mecat_m4) * nout);
+				c->stats.num_records += (int64_t)nout;
+				*records = out; *n = nout;
+			}
+			c->dfree(d_m4);
+			return rc2;
+		}
 		// The extension runs in a few chunks of reads; while the GPU extends chunk k+1 the host threads
 		// assemble the M4 records of chunk k (fill_m4record + append_m4v: sort, containment filter) -- on
 		// the host like the reference, same std::sort, same comparator, so ties fall the same way.
@@ -860,6 +921,19 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			for (auto& th : pool) th.join();
 		}
 		c->stats.host_ms += host_timer.stop();
+		if (text) {      // host-assembled records, device text
+			mecat_m4* d_m4 = nullptr;
+			int rc2 = 0;
+			if (nout) {
+				MB_CUDA(c, c->alloc(&d_m4, nout));
+				MB_CUDA(c, cudaMemcpyAsync(d_m4, out, sizeof(mecat_m4) * nout, cudaMemcpyHostToDevice, c->stream));
+				c->stats.h2d_bytes += (int64_t)(sizeof(mecat_m4) * nout);
+				rc2 = text_out(1, d_m4, nout);
+				c->dfree(d_m4);
+			}
+			free(out);
+			return rc2;
+		}
 		c->stats.num_records += (int64_t)nout;
 		*records = out; *n = nout;
 		return 0;
@@ -890,6 +964,52 @@ int mecat_b200_pw_tile_range(mecat_b200_ctx* c, void* index, void* dvol_ref, voi
 	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, read_begin, read_end, records, n, nullptr, nullptr);
 	c->stats.total_ms += t.stop();
 	return rc;
+}
+
+int mecat_b200_pw_tile_text(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvol_reads, const mecat_pw_params* p, int gapped,
+                            char** text, size_t* bytes, size_t* num_records)
+{
+	if (check(c) || !index || !dvol_ref || !dvol_reads || !p || !text || !bytes || !num_records) return 1;
+	cudaSetDevice(c->device);
+	WallTimer t;
+	void* unused = nullptr;
+	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, 0, -1, &unused, num_records, nullptr, nullptr, text, bytes, gapped);
+	c->stats.total_ms += t.stop();
+	return rc;
+}
+
+int mecat_b200_records_text(mecat_b200_ctx* c, int kind, int gapped, const void* records, size_t n, char** text, size_t* bytes)
+{
+	if (check(c) || (n && !records) || !text || !bytes) return 1;
+	if (kind != 0 && kind != 1) MB_FAIL(c, "records_text: kind must be 0 (candidates) or 1 (m4 records), not %d", kind);
+	cudaSetDevice(c->device);
+	*text = nullptr; *bytes = 0;
+	const size_t rec = kind == 0 ? sizeof(mecat_candidate) : sizeof(mecat_m4);
+	void* d_rec = nullptr;
+	char* d_text = nullptr;
+	char* h = nullptr;
+	auto body = [&]() -> int {
+		size_t nb = 0;
+		if (n) {
+			MB_CUDA(c, c->dmalloc(&d_rec, rec * n));
+			MB_CUDA(c, cudaMemcpyAsync(d_rec, records, rec * n, cudaMemcpyHostToDevice, c->stream));
+			if (records_text_device(c, kind, gapped, d_rec, n, &d_text, &nb)) return 1;
+		}
+		h = (char*)malloc(nb + 1);
+		if (!h) MB_FAIL(c, "records_text: out of host memory");
+		if (nb) MB_CUDA(c, cudaMemcpyAsync(h, d_text, nb, cudaMemcpyDeviceToHost, c->stream));
+		MB_CUDA(c, cudaStreamSynchronize(c->stream));
+		h[nb] = 0;
+		c->resolve_timers();
+		c->stats.h2d_bytes += (int64_t)(rec * n); c->stats.d2h_bytes += (int64_t)nb;
+		*bytes = nb;
+		return 0;
+	};
+	const int rc = body();
+	c->dfree(d_rec); c->dfree(d_text);
+	if (rc) { free(h); return rc; }
+	*text = h;
+	return 0;
 }
 
 int mecat_b200_volume_from_device(mecat_b200_ctx* c, int32_t num_reads, int32_t num_bases, int32_t start_read_id,

@@ -207,6 +207,15 @@ struct DevBackend : PoolBackend
 
 }  // namespace
 
+// exclusive prefix sum of n int32 counts into n + 1 int64 offsets (all on the device), the total also on the host
+int device_exclusive_scan(Ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* h_total)
+{
+	DevBackend be(c);
+	const bool ok = be.scan(d_in, d_out, n, h_total);
+	be.end_batch();
+	return ok ? 0 : 1;
+}
+
 int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, CnsBlob& out)
 {
 	DevBackend be(c);

@@ -261,6 +261,17 @@ struct CnsBlob
 // consensus stage of mecat2cns on the extension results of one batch (cns.cu)
 int cns_consensus_device(Ctx* c, const mbcns::BatchIn& in, const mbcns::Params& P, CnsBlob& out);
 
+int device_exclusive_scan(Ctx* c, const int32_t* d_in, int64_t* d_out /* n + 1 */, int64_t n, int64_t* h_total);
+
+// records.cu: A12 on the device (fill_m4record + append_m4v per read) and the text of the result files.
+// m4_assemble: per query read r the candidates [h_outpos[r], h_outpos[r+1]) with their extension results; leaves the kept
+// records in *d_m4 (pool memory, release with dfree), read by read in the reference's order.
+int m4_assemble(Ctx* c, const DVolume* reads, const DVolume* ref, const ExtendTask* d_tasks, const mecat_extend_result* d_res,
+                const int32_t* d_scores, const int64_t* d_outpos, int nreads, size_t total, mecat_m4** d_m4, size_t* nout);
+// kind 0: mecat_candidate -> `.can` lines, kind 1: mecat_m4 -> `.m4` lines (gapped: with the two extension points).
+// *d_text is pool memory (release with dfree).
+int records_text_device(Ctx* c, int kind, int gapped, const void* d_records, size_t n, char** d_text, size_t* bytes);
+
 // mecat2ref (refmap.cu): the genome as a one-read volume plus its k-mer index
 struct RefIndex
 {

@@ -238,9 +238,19 @@ bool process_tile(DeviceState& D, const Options& opt, int svid, int vid, const s
 	}
 	void* rec = NULL;
 	size_t n = 0;
-	if (ok) ok = mecat_b200_pw_tile(D.ctx, D.index, D.dref, dreads, &p, &rec, &n) == 0;
-	if (ok) format_records(text, opt, rec, n);
-	else fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(D.ctx));
+	// the lines of the tile are written on the device (MECAT_B200_TEXT=host: records to the host, printed by host threads)
+	static const bool host_text = getenv("MECAT_B200_TEXT") && !strcmp(getenv("MECAT_B200_TEXT"), "host");
+	if (ok && !host_text) {
+		char* lines = NULL;
+		size_t bytes = 0;
+		ok = mecat_b200_pw_tile_text(D.ctx, D.index, D.dref, dreads, &p, opt.output_gapped_start_point != 0, &lines, &bytes, &n) == 0;
+		if (ok) text.assign(lines ? lines : "", bytes);
+		mecat_b200_free(D.ctx, lines);
+	} else if (ok) {
+		ok = mecat_b200_pw_tile(D.ctx, D.index, D.dref, dreads, &p, &rec, &n) == 0;
+		if (ok) format_records(text, opt, rec, n);
+	}
+	if (!ok) fprintf(stderr, "mecat2pw: %s\n", mecat_b200_last_error(D.ctx));
 	mecat_b200_free(D.ctx, rec);
 	if (vid != svid && dreads) mecat_b200_volume_release(D.ctx, dreads);
 	return ok;

@@ -13,6 +13,7 @@
 #include <string>
 
 #include "../include/mecat_b200.h"
+#include "../mecat_b200/csrc/host/format.h"
 #include "../oracle/oracle.h"
 
 struct mecat_b200_ctx { std::string err; int device; };
@@ -47,6 +48,25 @@ int mecat_b200_pw_tile(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* d
 	if (index != dvol_ref) { ctx->err = "tile run against the index of another volume"; return 1; }
 	++g_tiles;
 	return orc_pw_tile((const orc_volume*)dvol_ref, (const orc_volume*)dvol_reads, (const orc_pw_params*)p, 2, records, n);
+}
+
+// the tile as text: the oracle's records through the drivers' host formatter (the device formatter of the product is
+// compared with it line by line in tests/test_records_host.py and on the GPU)
+int mecat_b200_pw_tile_text(mecat_b200_ctx* ctx, void* index, void* dvol_ref, void* dvol_reads, const mecat_pw_params* p, int gapped,
+                            char** text, size_t* bytes, size_t* num_records)
+{
+	void* rec = NULL;
+	size_t n = 0;
+	if (mecat_b200_pw_tile(ctx, index, dvol_ref, dvol_reads, p, &rec, &n)) return 1;
+	mbfmt::TextBuf b;
+	if (p->task == 0) mbfmt::format_candidates(b, (const mecat_candidate*)rec, n);
+	else mbfmt::format_m4(b, (const mecat_m4*)rec, n, gapped != 0);
+	free(rec);
+	char* out = (char*)malloc(b.s.size() + 1);
+	memcpy(out, b.s.data(), b.s.size());
+	out[b.s.size()] = 0;
+	*text = out; *bytes = b.s.size(); *num_records = n;
+	return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,116 @@
+"""GPU parity tests (-m gpu) of the record assembly (row A12) and result text on the device:
+fill_m4record / std::sort / containment filter in kernels (records.cu) against the golden `.m4` of the unmodified binary
+and against the earlier host-thread form, the lines written on the device against the golden files byte for byte."""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+from util import PackedVolume
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))
+
+
+def gold_lines(name, ext):
+    with gzip.open(os.path.join(util.GOLDEN, "%s.%s.gz" % (name, ext)), "rt") as f:
+        return f.read().splitlines()
+
+
+def host_volume(v):
+    import mecat_b200
+    return mecat_b200.HostVolume(v.offset_size, v.pac, v.num_bases, v.start_read_id)
+
+
+@pytest.fixture(scope="module")
+def small_vol():
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f:
+        seqs = [l for l in f.read().split(b"\n") if l and not l.startswith(b">")]
+    return PackedVolume.from_seqs(seqs)
+
+
+@pytest.fixture(scope="module")
+def cfg0_vol(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cfg0")
+    fa = str(d / "cfg0.fa")
+    c = GOLD["cfg0"]
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    assert hashlib.sha256(open(fa, "rb").read()).hexdigest() == c["fasta_sha256"]
+    return PackedVolume.from_seqs(util.read_fasta(fa))
+
+
+@pytest.fixture(scope="module")
+def deep_vol(tmp_path_factory):
+    c = GOLD["deep"]
+    fa = str(tmp_path_factory.mktemp("deep") / "deep.fa")
+    util.gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    return PackedVolume.from_seqs(util.read_fasta(fa))
+
+
+def test_device_assembly_equals_host_assembly_record_for_record(gpu_ctx, cfg0_vol, deep_vol, monkeypatch):
+    """Same records in the same order from the kernels and from the host threads (std::sort, containment filter); the
+    ~120x fixture gives every read 100 candidates, many of them of the same pair (ties, partitions beyond 16 records)."""
+    for vol in (cfg0_vol, deep_vol):
+        hv = host_volume(vol)
+        monkeypatch.setenv("MECAT_B200_M4", "host")
+        a = gpu_ctx.pw_overlaps(hv, hv)
+        monkeypatch.setenv("MECAT_B200_M4", "device")
+        b = gpu_ctx.pw_overlaps(hv, hv)
+        assert len(a) == len(b) > 1000
+        assert a.tobytes() == b.tobytes()
+
+
+def test_tile_text_is_the_reference_file(gpu_ctx, small_vol, cfg0_vol):
+    """mecat_b200_pw_tile_text: the lines of `.can` and `.m4 -g 1` written on the device, against the unmodified binary's
+    files (sorted: the reference's threads interleave reads), and against the host formatter line for line in order."""
+    import mecat_b200
+    from mecat_b200 import api
+    for name, vol in (("small", small_vol), ("cfg0", cfg0_vol)):
+        hv = host_volume(vol)
+        d = gpu_ctx.upload(hv)
+        idx = gpu_ctx.index_build(d)
+        try:
+            for task, ext, gapped in ((0, "can", False), (1, "m4", True), (1, None, False)):
+                p = mecat_b200.pw_params(task=task)
+                text, n = gpu_ctx.pw_tile_text(idx, d, d, p, gapped=gapped)
+                rec = gpu_ctx.pw_tile(idx, d, d, p)
+                assert n == len(rec)
+                lines = text.decode().splitlines()
+                want = util.ec_lines(rec) if task == 0 else util.m4_lines(rec, gapped=gapped)
+                assert sorted(lines) == want                     # util's formatter (printf %g) on the records
+                if ext:
+                    assert sorted(lines) == gold_lines(name, ext)
+                assert text.endswith(b"\n") and text.count(b"\n") == n
+                # record order is kept: line i is record i
+                first = lines[0].split("\t")
+                assert int(first[0]) == int(rec[0]["qid"]) and int(first[1]) == int(rec[0]["sid"])
+                assert gpu_ctx.records_text(rec, gapped=gapped) == text
+        finally:
+            gpu_ctx.release_index(idx)
+            gpu_ctx.release_volume(d)
+
+
+def test_records_text_of_extreme_values(gpu_ctx):
+    """Device formatter on field values the fixtures do not reach (negative scores, 40-bit ids, identities across the
+    whole printable range) against printf."""
+    import mecat_b200
+    rng = np.random.default_rng(5)
+    m4 = np.zeros(20000, dtype=mecat_b200.M4_DTYPE)
+    for name in m4.dtype.names:
+        if name == "ident":
+            m4[name] = 100.0 * rng.integers(0, 30000, len(m4)) / rng.integers(30000, 60000, len(m4))
+        elif name not in ("pad", "pad_"):
+            hi = 2 ** 31 - 1 if m4.dtype[name].itemsize == 4 else 2 ** 40
+            m4[name] = rng.integers(0, hi, len(m4))
+    m4["vscore"][:10] = -5
+    m4["ident"][:8] = [0.0, 100.0, 99.99995, 9.999995, 1e-4, 3.0517578125e-05, 12.5, 99.999949999]
+    got = gpu_ctx.records_text(m4, gapped=True).decode().splitlines()
+    assert sorted(got) == util.m4_lines(m4, gapped=True)
+    assert got[0].split("\t")[0] == str(int(m4[0]["qid"])) and got[-1].split("\t")[1] == str(int(m4[-1]["sid"]))
+    assert gpu_ctx.records_text(m4[:0]) == b""

@@ -151,6 +151,36 @@ def cns_harness():
     return L
 
 
+_m4_harness = None
+
+
+def m4_harness():
+    """Host build of the product's record assembly / text bodies (tests/m4_host_harness.cpp over csrc/m4_core.cuh)."""
+    global _m4_harness
+    if _m4_harness is not None:
+        return _m4_harness
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libm4_harness.so")
+    src = [os.path.join(ROOT, "tests", "m4_host_harness.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "m4_core.cuh"),
+           os.path.join(ROOT, "mecat_b200", "csrc", "host", "format.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so, src[0]])
+    L = C.CDLL(so)
+    L.mh_sort_random.restype = C.c_long
+    L.mh_sort_random.argtypes = [C.c_int, C.c_int, C.c_uint]
+    L.mh_sort_adversary.restype = C.c_long
+    L.mh_sort_adversary.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    L.mh_fmt_ratios.restype = C.c_long
+    L.mh_fmt_ratios.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
+    L.mh_fmt_values.restype = C.c_long
+    L.mh_fmt_values.argtypes = [C.c_void_p, C.c_long, C.c_char_p, C.c_int]
+    L.mh_lines.restype = C.c_long
+    L.mh_lines.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+    _m4_harness = L
+    return L
+
+
 _xdrop_harness = None
 
 
