@@ -172,6 +172,17 @@ int mecat_b200_volume_release(mecat_b200_ctx* ctx, void* dvol);
 int mecat_b200_volume_from_device(mecat_b200_ctx* ctx, int32_t num_reads, int32_t num_bases, int32_t start_read_id,
                                   const int32_t* host_offset_size, const void* device_pac, void** dvol);
 
+/* 2-bit packing on the device: replaces add_one_seq / PackedDB::set_char for a whole volume (src/common/split_database.cpp:
+ * 103-119, src/common/packed_db.h:98-101; same bytes, including how codes above 3 -- N, other IUPAC letters -- spill inside
+ * their byte).  text: letters of the reads (host memory, e.g. the mapped FASTA file); read i has offset_size[2i+1] letters
+ * starting at text[src_offset[i]] (contiguous: a read spread over several lines is copied together by the caller) and lands
+ * at base offset_size[2i] of the volume -- the offsets the reference's splitting rule gives (one pad base after every read,
+ * split_database.cpp:240-259).  The volume stays resident (*dvol); pac_out, when not NULL, receives the (num_bases+3)/4
+ * packed bytes for the volume file. */
+int mecat_b200_volume_from_text(mecat_b200_ctx* ctx, const char* text, size_t text_bytes, const int64_t* src_offset,
+                                const int32_t* offset_size, int32_t num_reads, int32_t num_bases, int32_t start_read_id,
+                                uint8_t* pac_out, void** dvol);
+
 /* ---- A1: k-mer index of an index volume ----------------------------------------------
  * replaces create_ref_index (src/common/lookup_table.cpp:64-160). */
 int mecat_b200_index_build(mecat_b200_ctx* ctx, void* dvol_ref, void** index);

@@ -95,7 +95,7 @@ EXPORTS = [
     "mecat_b200_ref_index_build", "mecat_b200_ref_index_release", "mecat_b200_ref_map",
     "mecat_b200_ref_index_export", "mecat_b200_ref_raw_candidates",
     "mecat_b200_cns_reads_multi", "mecat_b200_volumes_from_fasta", "mecat_b200_volumes_unload",
-    "mecat_b200_pw_tile_text", "mecat_b200_records_text",
+    "mecat_b200_pw_tile_text", "mecat_b200_records_text", "mecat_b200_volume_from_text",
 ]
 
 _lib = None
@@ -135,6 +135,7 @@ def load_library():
     L.mecat_b200_index_device_arrays.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
     L.mecat_b200_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
     L.mecat_b200_pw_tile.argtypes = [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_volume_from_text.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.POINTER(vp)]
     L.mecat_b200_pw_tile_text.argtypes = [vp, vp, vp, vp, PP, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.mecat_b200_records_text.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mecat_b200_pw_candidates.argtypes = [vp, VP, VP, PP, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -526,6 +527,19 @@ class Context:
         self._check(self.L.mecat_b200_pw_tile(self.h, index, dref, dreads, C.byref(params), C.byref(out), C.byref(n)),
                     "pw_tile")
         return self._take(out, n.value, EC_DTYPE if params.task == 0 else M4_DTYPE)
+
+    def volume_from_text(self, text, src_offset, offset_size, num_bases, start_read_id=0, want_pac=True):
+        """Pack a volume on the device from the letters of its reads.  Returns (device volume, packed bytes or None)."""
+        src = np.ascontiguousarray(src_offset, dtype=np.int64)
+        osz = np.ascontiguousarray(offset_size, dtype=np.int32).reshape(-1)
+        n = len(src)
+        pac = np.zeros((num_bases + 3) // 4, dtype=np.uint8) if want_pac else None
+        d = C.c_void_p()
+        buf = (C.c_char * len(text)).from_buffer_copy(text) if len(text) else None
+        self._check(self.L.mecat_b200_volume_from_text(self.h, C.cast(buf, C.c_void_p) if buf is not None else None, len(text),
+                                                       src.ctypes.data_as(C.c_void_p), osz.ctypes.data_as(C.c_void_p), n, num_bases, start_read_id,
+                                                       pac.ctypes.data_as(C.c_void_p) if want_pac else None, C.byref(d)), "volume_from_text")
+        return d, pac
 
     def pw_tile_text(self, index, dref, dreads, params, gapped=False):
         """One tile as the text of the reference's output file (written on the device).  Returns (bytes, number of records)."""

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <chrono>
 #include <thread>
 #include <cstdlib>
@@ -90,7 +92,55 @@ struct M4Less   // CmpM4RecordByQidAndOvlpSize, pw_impl.cpp:539-548
 
 int check(mecat_b200_ctx* c) { return c ? 0 : 1; }
 
+// registry of the pinned result blocks of all contexts: block -> owning context (nullptr: the context is gone, the block
+// is still in the caller's hands and is unpinned when it comes back)
+std::mutex g_out_mu;
+std::unordered_map<void*, mb::Ctx*> g_out;
+
+void host_out_destroy(mb::Ctx* c)
+{
+	std::lock_guard<std::mutex> g(g_out_mu);
+	for (auto& h : c->host_out) {
+		if (h.used) g_out[h.p] = nullptr;
+		else { g_out.erase(h.p); cudaFreeHost(h.p); }
+	}
+	c->host_out.clear();
+}
+
 }  // namespace
+
+namespace mb {
+
+void* host_out_alloc(Ctx* c, size_t bytes)
+{
+	if (bytes == 0) bytes = 64;
+	std::lock_guard<std::mutex> g(g_out_mu);
+	int best = -1;
+	for (size_t i = 0; i < c->host_out.size(); ++i)
+		if (!c->host_out[i].used && c->host_out[i].bytes >= bytes && (best < 0 || c->host_out[i].bytes < c->host_out[(size_t)best].bytes)) best = (int)i;
+	if (best >= 0) { c->host_out[(size_t)best].used = true; return c->host_out[(size_t)best].p; }
+	for (size_t i = 0; i < c->host_out.size();)          // free blocks too small to serve this size again: let them go
+		if (!c->host_out[i].used) { g_out.erase(c->host_out[i].p); cudaFreeHost(c->host_out[i].p); c->host_out[i] = c->host_out.back(); c->host_out.pop_back(); }
+		else ++i;
+	void* p = nullptr;
+	const size_t want = bytes + bytes / 8 + 4096;
+	if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+	c->host_out.push_back({p, want, true});
+	g_out[p] = c;
+	return p;
+}
+
+bool host_out_release(void* p)
+{
+	std::lock_guard<std::mutex> g(g_out_mu);
+	auto it = g_out.find(p);
+	if (it == g_out.end()) return false;
+	if (!it->second) { cudaFreeHost(p); g_out.erase(it); return true; }
+	for (auto& h : it->second->host_out) if (h.p == p) h.used = false;
+	return true;
+}
+
+}  // namespace mb
 
 extern "C" {
 
@@ -141,13 +191,19 @@ void mecat_b200_destroy(mecat_b200_ctx* c)
 	c->trim();
 	for (auto& e : c->pool) cudaEventDestroy(e);
 	for (auto& h : c->hstage) if (h.p) cudaFreeHost(h.p);
+	host_out_destroy(c);
 	cudaFree(c->d_counters);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
 
 const char* mecat_b200_last_error(mecat_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
-void mecat_b200_free(mecat_b200_ctx*, void* p) { free(p); }
+void mecat_b200_free(mecat_b200_ctx*, void* p)
+{
+	if (!p) return;
+	if (host_out_release(p)) return;       // a pinned result block: back to its context's pool
+	free(p);
+}
 
 int mecat_b200_get_stats(mecat_b200_ctx* c, mecat_b200_stats* out)
 {
@@ -346,7 +402,7 @@ void mecat_b200_cns_sort_candidates(mecat_candidate* cnd, int n)   // CmpExtensi
 	});
 }
 
-void mecat_b200_host_free(void* p) { free(p); }
+void mecat_b200_host_free(void* p) { mecat_b200_free(nullptr, p); }
 
 // ------------------------------------------------------------------------------------------
 // mecat2ref: genome upload + k-mer index, then batches of reads through refmap.cu
@@ -699,14 +755,14 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			char* d_text = nullptr;
 			size_t bytes = 0;
 			if (records_text_device(c, kind, gapped, d_recs, nrec, &d_text, &bytes)) return 1;
-			char* h = (char*)malloc(bytes + 1);
+			char* h = (char*)host_out_alloc(c, bytes + 1);
 			if (!h) { c->dfree(d_text); MB_FAIL(c, "pw_tile: out of host memory"); }
 			WallTimer t;
 			cudaError_t e = bytes ? cudaMemcpyAsync(h, d_text, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
 			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 			c->stats.d2h_ms += t.stop();
 			c->dfree(d_text);
-			if (e != cudaSuccess) { free(h); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
+			if (e != cudaSuccess) { host_out_release(h); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
 			h[bytes] = 0;
 			c->resolve_timers();
 			c->stats.d2h_bytes += (int64_t)bytes;
@@ -770,13 +826,13 @@ static int pw_tile_impl(mecat_b200_ctx* c, DIndex* idx, DVolume* ref, DVolume* r
 			int rc2 = 0;
 			if (text) rc2 = nout ? text_out(1, d_m4, nout) : 0;
 			else {
-				mecat_m4* out = (mecat_m4*)malloc(sizeof(mecat_m4) * (nout ? nout : 1));
+				mecat_m4* out = (mecat_m4*)host_out_alloc(c, sizeof(mecat_m4) * (nout ? nout : 1));
 				if (!out) { c->dfree(d_m4); MB_FAIL(c, "pw_tile: out of host memory"); }
 				WallTimer t;
 				cudaError_t e = nout ? cudaMemcpyAsync(out, d_m4, sizeof(mecat_m4) * nout, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
 				if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 				c->stats.d2h_ms += t.stop();
-				if (e != cudaSuccess) { free(out); c->dfree(d_m4); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
+				if (e != cudaSuccess) { host_out_release(out); c->dfree(d_m4); MB_FAIL(c, "pw_tile: D2H: %s", cudaGetErrorString(e)); }
 				c->resolve_timers();
 				c->stats.d2h_bytes += (int64_t)(sizeof(mecat_m4) * nout);
 				c->stats.num_records += (int64_t)nout;
@@ -964,6 +1020,18 @@ int mecat_b200_pw_tile_range(mecat_b200_ctx* c, void* index, void* dvol_ref, voi
 	int rc = pw_tile_impl(c, (DIndex*)index, (DVolume*)dvol_ref, (DVolume*)dvol_reads, p, read_begin, read_end, records, n, nullptr, nullptr);
 	c->stats.total_ms += t.stop();
 	return rc;
+}
+
+int mecat_b200_volume_from_text(mecat_b200_ctx* c, const char* text, size_t text_bytes, const int64_t* src_offset, const int32_t* offset_size,
+                                int32_t num_reads, int32_t num_bases, int32_t start_read_id, uint8_t* pac_out, void** dvol)
+{
+	if (check(c) || !dvol) return 1;
+	cudaSetDevice(c->device);
+	DVolume* d = nullptr;
+	const int rc = volume_from_text(c, text, text_bytes, src_offset, offset_size, num_reads, num_bases, start_read_id, pac_out, &d);
+	if (rc) return rc;
+	*dvol = d;
+	return 0;
 }
 
 int mecat_b200_pw_tile_text(mecat_b200_ctx* c, void* index, void* dvol_ref, void* dvol_reads, const mecat_pw_params* p, int gapped,

@@ -118,6 +118,13 @@ struct Ctx
 		return cudaSuccess;
 	}
 
+	// Pinned host blocks handed OUT to the caller as results (records, text) and taken back by mecat_b200_free /
+	// mecat_b200_host_free: a D2H copy into fresh pageable memory costs its page faults and a staged copy (100 MB of M4
+	// records: ~30 ms against ~2 ms), and pinning a fresh block per tile costs as much, so freed blocks are kept
+	// (capi.cu: host_out_alloc / host_out_release; a process-wide registry, because the binding frees without a context).
+	struct HostOut { void* p; size_t bytes; bool used; };
+	std::vector<HostOut> host_out;
+
 	// per-kernel CUDA-event timing on `stream`
 	struct Pending { int slot; cudaEvent_t a, b; };
 	std::vector<Pending> pending;
@@ -175,8 +182,14 @@ struct KScope
 	} while (0)
 
 // ---- internal entry points (one per translation unit)
+void* host_out_alloc(Ctx* c, size_t bytes);      // nullptr when out of memory
+bool host_out_release(void* p);                   // false: not one of these blocks (a malloc'ed result)
 int volume_upload(Ctx* c, const mecat_volume* v, DVolume** out);
 void volume_release(Ctx* c, DVolume* v);
+// a volume packed on the device from the letters of its reads (volume.cu: k_pack_text); pac_out (optional, host): the
+// reference's packed bytes, for the volume file
+int volume_from_text(Ctx* c, const char* text, size_t text_bytes, const int64_t* src_off, const int32_t* h_offsz, int num_reads,
+                     int num_bases, int start_read_id, uint8_t* pac_out, DVolume** out);
 // working volume made of n reads taken from resident volumes: read i = read h_src_read[i] of src[h_src_vol[i]]
 int volume_gather(Ctx* c, const DVolume* const* src, const int32_t* h_src_vol, const int32_t* h_src_read, int n, DVolume** out);
 int index_build(Ctx* c, const DVolume* v, DIndex** out);

@@ -115,6 +115,92 @@ int volume_from_device(Ctx* c, int num_reads, int num_bases, int start_read_id, 
 	return rc;
 }
 
+// ---- 2-bit packing on the device: add_one_seq / PackedDB::set_char for every read of a volume
+// (src/common/split_database.cpp:103-119, src/common/packed_db.h:98-101).  The host has found the records (where each
+// read's letters start in the text, and the volume offsets the reference's splitting rule gives them); one warp packs one
+// read, a lane 16 letters at a time into one 32-bit word of `pac`: letter -> code through get_dna_encode_table
+// (src/common/defs.cpp:3-36), code << shift OR-ed into its byte and cut to the byte, so that a code above 3 (N = 14, any
+// other character 16) spills into the bases packed before it in the same byte exactly like set_char does.  The first and
+// last word of a read are shared with its neighbours and are OR-ed in atomically.
+struct PackRead { int64_t src; int32_t dst, len; };
+
+__global__ void __launch_bounds__(256) k_pack_text(const unsigned char* __restrict__ text, const PackRead* __restrict__ reads, int n,
+                                                   uint32_t* __restrict__ pac32)
+{
+	__shared__ uint8_t enc[256];
+	{
+		// get_dna_encode_table: IUPAC letters in either case, '-' = 15, everything else 16
+		const int t = threadIdx.x;
+		uint8_t v = 16;
+		const int u = t >= 'a' && t <= 'z' ? t - 32 : t;
+		switch (u) {
+		case 'A': v = 0; break; case 'C': v = 1; break; case 'G': v = 2; break; case 'T': v = 3; break;
+		case 'R': v = 4; break; case 'Y': v = 5; break; case 'M': v = 6; break; case 'K': v = 7; break;
+		case 'W': v = 8; break; case 'S': v = 9; break; case 'B': v = 10; break; case 'D': v = 11; break;
+		case 'H': v = 12; break; case 'V': v = 13; break; case 'N': v = 14; break; case '-': v = 15; break;
+		}
+		enc[t] = v;
+	}
+	__syncthreads();
+	const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (warp >= n) return;
+	const PackRead r = reads[warp];
+	if (r.len <= 0) return;
+	const unsigned char* src = text + r.src;
+	const uint32_t w0 = (uint32_t)r.dst >> 4, w1 = ((uint32_t)r.dst + (uint32_t)r.len - 1u) >> 4;
+	for (uint32_t w = w0 + (uint32_t)lane; w <= w1; w += 32u) {
+		const int64_t first = (int64_t)w * 16 - (int64_t)r.dst;            // read coordinate of the word's first base
+		uint32_t x = 0;
+		#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			const int64_t i = first + k;
+			if (i < 0 || i >= r.len) continue;
+			const uint32_t code = enc[src[i]];
+			// base 16 w + k lives in byte k / 4 of the word at shift ((~k) & 3) * 2; the OR is cut to that byte
+			x |= ((code << (((~k) & 3) << 1)) & 0xFFu) << ((k >> 2) << 3);
+		}
+		if (w == w0 || w == w1) atomicOr(pac32 + w, x);
+		else pac32[w] = x;
+	}
+}
+
+int volume_from_text(Ctx* c, const char* text, size_t text_bytes, const int64_t* src_off, const int32_t* h_offsz, int num_reads,
+                     int num_bases, int start_read_id, uint8_t* pac_out, DVolume** out)
+{
+	if (num_reads < 0 || num_bases < 0 || (num_reads && (!text || !src_off || !h_offsz))) MB_FAIL(c, "volume_from_text: bad arguments");
+	std::vector<PackRead> pr((size_t)num_reads);
+	for (int i = 0; i < num_reads; ++i) {
+		const int32_t off = h_offsz[2 * i], len = h_offsz[2 * i + 1];
+		if (off < 0 || len < 0 || (int64_t)off + len > num_bases || src_off[i] < 0 || (uint64_t)src_off[i] + (uint64_t)len > text_bytes)
+			MB_FAIL(c, "volume_from_text: read %d out of range", i);
+		pr[(size_t)i].src = src_off[i]; pr[(size_t)i].dst = off; pr[(size_t)i].len = len;
+	}
+	const size_t pac_bytes = ((size_t)num_bases + 3) / 4, words = (pac_bytes + 3) / 4 + 2;
+	unsigned char* d_text = nullptr;
+	PackRead* d_pr = nullptr;
+	uint32_t* d_pac = nullptr;
+	auto body = [&]() -> int {
+		MB_CUDA(c, c->dmalloc((void**)&d_text, text_bytes + 16));
+		MB_CUDA(c, c->alloc(&d_pr, (size_t)(num_reads ? num_reads : 1)));
+		MB_CUDA(c, c->alloc(&d_pac, words));
+		MB_CUDA(c, cudaMemsetAsync(d_pac, 0, words * 4, c->stream));
+		if (text_bytes) MB_CUDA(c, cudaMemcpyAsync(d_text, text, text_bytes, cudaMemcpyHostToDevice, c->stream));
+		if (num_reads) MB_CUDA(c, cudaMemcpyAsync(d_pr, pr.data(), sizeof(PackRead) * (size_t)num_reads, cudaMemcpyHostToDevice, c->stream));
+		if (num_reads) {
+			KScope ks(c, MECAT_K_ORIENT);
+			k_pack_text<<<(unsigned)(((size_t)num_reads * 32 + 255) / 256), 256, 0, c->stream>>>(d_text, d_pr, num_reads, d_pac);
+		}
+		MB_CUDA(c, cudaGetLastError());
+		if (pac_out && pac_bytes) MB_CUDA(c, cudaMemcpyAsync(pac_out, d_pac, pac_bytes, cudaMemcpyDeviceToHost, c->stream));
+		c->stats.h2d_bytes += (int64_t)(text_bytes + sizeof(PackRead) * (size_t)num_reads);
+		if (pac_out) c->stats.d2h_bytes += (int64_t)pac_bytes;
+		return volume_build(c, num_reads, num_bases, start_read_id, h_offsz, d_pac, words - 1, out);     // synchronises the stream
+	};
+	const int rc = body();
+	c->dfree(d_text); c->dfree(d_pr); c->dfree(d_pac);
+	return rc;
+}
+
 // ---- a working volume gathered from reads of several resident volumes (mecat2cns on read sets larger than one volume)
 struct GatherRead
 {

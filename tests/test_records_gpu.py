@@ -114,3 +114,51 @@ def test_records_text_of_extreme_values(gpu_ctx):
     assert sorted(got) == util.m4_lines(m4, gapped=True)
     assert got[0].split("\t")[0] == str(int(m4[0]["qid"])) and got[-1].split("\t")[1] == str(int(m4[-1]["sid"]))
     assert gpu_ctx.records_text(m4[:0]) == b""
+
+
+def test_device_packing_equals_host_packing(gpu_ctx, small_vol, tmp_path):
+    """mecat_b200_volume_from_text (2-bit packing on the device) against the product's host packer, which is pinned to the
+    unmodified split_raw_dataset on the same kind of input (tests/test_host_io.py): reads with N runs, lower case, IUPAC
+    letters, '-' and characters outside the table (codes above 3 spill inside their byte like PackedDB::set_char)."""
+    import mecat_b200
+    rng = np.random.default_rng(12)
+    seqs = []
+    for i in range(small_vol.num_reads):
+        s = bytearray(b"ACGT"[c] for c in small_vol.codes(i))
+        if i % 5 == 1:
+            for _ in range(6):
+                p = int(rng.integers(0, max(1, len(s) - 40))); L = min(int(rng.integers(1, 30)), len(s) - p); s[p:p + L] = b"N" * L
+            for _ in range(20):
+                p = int(rng.integers(0, len(s))); s[p] = b"NnRYKMSWBDHVacgt-"[int(rng.integers(0, 17))]
+        if i % 7 == 2:
+            s = bytearray(bytes(s).lower())
+        if i % 11 == 3:
+            s = s[:int(rng.integers(1, 9))]             # tiny reads: several reads inside one packed word
+        seqs.append(bytes(s))
+    fa = str(tmp_path / "awkward.fa")
+    with open(fa, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">%d\n%s\n" % (i, s))
+    hv = mecat_b200.volume_from_fasta(fa)
+    text = open(fa, "rb").read()
+    src, osz, at, curr = [], [], 0, 0
+    for i, s in enumerate(seqs):
+        at = text.index(b"\n", at) + 1          # past the header line
+        src.append(at); osz += [curr, len(s)]
+        at += len(s) + 1; curr += len(s) + 1
+    assert curr == hv.num_bases and np.array_equal(np.array(osz, dtype=np.int32).reshape(-1, 2), np.asarray(hv.offset_size).reshape(-1, 2))
+    d, pac = gpu_ctx.volume_from_text(text, src, osz, curr)
+    try:
+        want = np.frombuffer(bytes(hv.pac[:(curr + 3) // 4]), dtype=np.uint8)
+        bad = np.nonzero(pac != want)[0]
+        assert len(bad) == 0, (len(bad), bad[:5], pac[bad[:5]], want[bad[:5]])
+        # the resident volume is the one an upload of the host volume gives: same index, same candidates
+        d2 = gpu_ctx.upload(hv)
+        i1, i2 = gpu_ctx.index_build(d), gpu_ctx.index_build(d2)
+        b1, p1 = gpu_ctx.index_export(i1); b2, p2 = gpu_ctx.index_export(i2)
+        assert (b1 == b2).all() and (p1 == p2).all()
+        p = mecat_b200.pw_params(task=0)
+        assert gpu_ctx.pw_tile(i1, d, d, p).tobytes() == gpu_ctx.pw_tile(i2, d2, d2, p).tobytes()
+        gpu_ctx.release_index(i1); gpu_ctx.release_index(i2); gpu_ctx.release_volume(d2)
+    finally:
+        gpu_ctx.release_volume(d)
