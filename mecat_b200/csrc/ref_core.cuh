@@ -317,6 +317,293 @@ REF_HD int walk_strand(const Unit& u, int zv, int gate, int64_t seqcount, int ch
 	return ncand;
 }
 
+// ------------------------------------------------------------------------------------------ a warp per strand
+// The same seeding loop and candidate walk with the 32 lanes of a warp on one strand (SeedWarpFn).  What is sequential
+// in the reference stays sequential -- hits in (k-mer, position) order, blocks in first-touch order -- and is done by
+// the leading lane; the lanes share the parts that are wide:
+//   * the k-mers of the next 32 ordinals, their index lists and the table slots / records their first hits will touch
+//     are fetched by 32 lanes at once, so the leader's dependent chain (slot -> record -> left neighbour) finds them in
+//     cache;
+//   * insert_loc's 21 x 20 / 2 pair tests (every second hit of a true locus: a block of 1 000 bases receives ~50 seeds,
+//     20 are kept) and find_location's k (k - 1) / 2: a lane per entry;
+//   * the neighbour votes of the walk: a lane per stored seed.
+// `lanes` is the interface of cns_core.cuh plus lead / min_val / max_val; per-warp scratch (WarpScratch) carries what
+// the lanes hand each other.  Results are identical to seed_strand + walk_strand (checked strand by strand in the CPU
+// suite, tests/test_ref_host.py, and on the device against the thread-per-strand form).
+struct WarpScratch
+{
+	uint32_t lb[32], le[32];                 // index list bounds of the 32 k-mers being fetched
+	int t_loc[2 * SM], t_seed[2 * SM], t_score[2 * SM];
+	int sink;                                // keeps the prefetching loads alive
+};
+
+struct EmuLanes        // the host stand-in of a warp: the lanes run one after the other
+{
+	static constexpr int count = 32;
+	template <class F> void each(F&& f) const { for (int l = 0; l < count; ++l) f(l); }
+	template <class F> int sum(F&& f) const { int s = 0; for (int l = 0; l < count; ++l) s += f(l); return s; }
+	template <class F> uint32_t ballot(F&& f) const { uint32_t m = 0; for (int l = 0; l < count; ++l) if (f(l)) m |= 1u << l; return m; }
+	template <class F> int min_val(F&& f) const { int m = f(0); for (int l = 1; l < count; ++l) { const int v = f(l); if (v < m) m = v; } return m; }
+	template <class F> int lead(F&& f) const { return f(); }
+	bool leader() const { return true; }
+	void sync() const {}
+};
+
+REF_HD int low_bit(uint32_t x)       // x != 0
+{
+#if defined(__CUDA_ARCH__)
+	return __ffs((int)x) - 1;
+#else
+	return __builtin_ctz(x);
+#endif
+}
+
+// do entries i < j of a block agree?  (the test of insert_loc and find_location without its distance cap)
+REF_HD bool pair_agrees(int loc_i, int seed_i, int loc_j, int seed_j, int bc)
+{
+	return seed_j - seed_i > 0 && loc_j - loc_i > 0 && ddf_close(loc_j - loc_i, seed_j - seed_i, bc);
+}
+
+// insert_loc with a lane per entry.  Entry i < SM is the block's i-th seed, entry SM the new one.
+template <class L>
+REF_HD void insert_loc_w(const L& lanes, Bucket* b, int loc, int seedn, int bc)
+{
+	auto eloc = [&](int i) { return i < SM ? (int)b->loczhi[i] : loc; };
+	auto eseed = [&](int i) { return i < SM ? (int)b->seedno[i] : seedn; };
+	auto score_of = [&](int l) {
+		if (l > SM) return 10000;
+		int s = 0;
+		const int li = eloc(l), si = eseed(l);
+		for (int j = 0; j < l; ++j) s += pair_agrees(eloc(j), eseed(j), li, si, bc) ? 1 : 0;
+		for (int j = l + 1; j <= SM; ++j) s += pair_agrees(li, si, eloc(j), eseed(j), bc) ? 1 : 0;
+		return s;
+	};
+	const int minval = lanes.min_val(score_of);
+	const int mini = low_bit(lanes.ballot([&](int l) { return score_of(l) == minval; }));     // the first entry with the lowest score
+	lanes.sync();
+	if (lanes.leader()) {
+		if (minval == SM) { b->loczhi[SM - 1] = (int16_t)loc; b->seedno[SM - 1] = (int16_t)seedn; }
+		else if (minval < SM && mini < SM) {
+			for (int i = mini; i < SM - 1; ++i) { b->loczhi[i] = b->loczhi[i + 1]; b->seedno[i] = b->seedno[i + 1]; }
+			b->loczhi[SM - 1] = (int16_t)loc; b->seedno[SM - 1] = (int16_t)seedn;
+			--b->score;
+		}
+	}
+	lanes.sync();
+}
+
+template <class L>
+REF_HD void seed_strand_w(const L& lanes, const uint32_t* fwd, uint32_t off, const Unit& u, int zv, const uint32_t* ibegin, const int32_t* ipos,
+                          const int64_t* bad, int64_t nbad, Table& T, WarpScratch& W)
+{
+	const int n = sampled_kmers(u.len, u.bc);
+	for (int k0 = 0; k0 < n; k0 += 32) {
+		// the next 32 k-mers: list bounds, and a first look at what their hits will touch (pulls it into cache)
+		lanes.each([&](int l) {
+			const int k = k0 + l;
+			uint32_t b = 0, e = 0;
+			if (k < n) {
+				const int i = k * u.bc;
+				if (!(nbad && !u.rc && covers_bad(bad, nbad, (int64_t)off + i, (int64_t)off + i + SEED))) {
+					const uint32_t code = strand_kmer(fwd, off, u, i);
+					b = ibegin[code]; e = ibegin[code + 1];
+				}
+			}
+			W.lb[l] = b; W.le[l] = e;
+			int acc = 0;
+			for (uint32_t h = b; h < e && h < b + 4; ++h) {
+				const uint32_t pos = (uint32_t)ipos[h] + 1u;
+				const int32_t blk = (int32_t)(pos / (uint32_t)zv);
+				const uint32_t hs = ((uint32_t)(blk + 1) * 2654435761u) >> T.shift;
+				const Slot sl = T.slots[hs];
+				acc += sl.key;
+				if (sl.key == blk + 1) acc += T.recs[sl.rec].score;
+			}
+			if (acc == 0x7fffffff) W.sink = acc;
+		});
+		lanes.sync();
+		for (int j = 0; j < 32 && k0 + j < n; ++j) {
+			const int k = k0 + j;
+			const uint32_t e = W.le[j];
+			for (uint32_t h = W.lb[j]; h < e; ++h) {
+				const uint32_t pos = (uint32_t)ipos[h] + 1u;
+				const int32_t blk = (int32_t)(pos / (uint32_t)zv);
+				const int offs = (int)(pos - (uint32_t)blk * (uint32_t)zv);
+				// the leader touches the block and takes the hit if the block has room; 2 * record + 1 asks for an eviction
+				const int r = lanes.lead([&]() {
+					bool fresh;
+					Bucket* b = table_touch(T, blk, &fresh);
+					const int rec = (int)(b - T.recs);
+					if (!(b->score == 0 || b->seednum < k + 1)) { b->seednum = (int16_t)(k + 1); return 2 * rec; }
+					const int loc = ++b->score;
+					if (loc > SM) return 2 * rec + 1;
+					b->loczhi[loc - 1] = (int16_t)offs; b->seedno[loc - 1] = (int16_t)(k + 1);
+					int s_k = b->score;
+					if (blk > 0) { const Bucket* p = table_find(T, blk - 1); if (p) s_k += p->score; }
+					b->index_score = (int16_t)s_k; b->score2 = b->score; b->seednum = (int16_t)(k + 1);
+					return 2 * rec;
+				});
+				if ((r >> 1) >= T.nrec) T.nrec = (r >> 1) + 1;
+				if (r & 1) {
+					Bucket* b = T.recs + (r >> 1);
+					insert_loc_w(lanes, b, offs, k + 1, u.bc);
+					if (lanes.leader()) {
+						int s_k = b->score;
+						if (blk > 0) { const Bucket* p = table_find(T, blk - 1); if (p) s_k += p->score; }
+						b->index_score = (int16_t)s_k; b->score2 = b->score; b->seednum = (int16_t)(k + 1);
+					}
+					lanes.sync();
+				}
+			}
+		}
+		lanes.sync();
+	}
+}
+
+// find_location over the entries in W.t_loc / W.t_seed: the pair counts with a lane per entry, the rest as it is
+template <class L>
+REF_HD int find_location_w(const L& lanes, WarpScratch& W, int* loc, int k, int* rep_loc, int bc, int read_len)
+{
+	lanes.each([&](int l) {
+		for (int i = l; i < k; i += L::count) {
+			int s = 0;
+			const int li = W.t_loc[i], si = W.t_seed[i];
+			for (int j = 0; j < k; ++j) {
+				if (j == i) continue;
+				const int dl = j > i ? W.t_loc[j] - li : li - W.t_loc[j], ds = j > i ? W.t_seed[j] - si : si - W.t_seed[j];
+				if (ds > 0 && dl > 0 && dl < read_len && ddf_close(dl, ds, bc)) ++s;
+			}
+			W.t_score[i] = s;
+		}
+	});
+	lanes.sync();
+	// selection of the anchor: find_location's own lines on the finished counts (every lane, same result)
+	int maxval = 0, maxi = 0, rep = 0, lasti = 0;
+	const int* t_loc = W.t_loc; const int* t_seedn = W.t_seed; const int* t_score = W.t_score;
+	for (int i = 0; i < k; ++i) {
+		if (maxval < t_score[i]) { maxval = t_score[i]; maxi = i; rep = 0; }
+		else if (maxval == t_score[i]) { ++rep; lasti = i; }
+	}
+	loc[0] = loc[1] = loc[2] = loc[3] = 0;
+	if (maxval < 5) return 0;
+	if (rep == maxval) {
+		loc[0] = t_loc[maxi]; loc[1] = t_seedn[maxi];
+		*rep_loc = maxi;
+		loc[2] = t_loc[lasti]; loc[3] = t_seedn[lasti];
+		return 1;
+	}
+	for (int j = 0; j <= maxi; ++j) {
+		bool take = j == maxi;
+		if (!take) {
+			const int dl = t_loc[maxi] - t_loc[j], ds = t_seedn[maxi] - t_seedn[j];
+			take = ds > 0 && dl > 0 && dl < read_len && ddf_close(dl, ds, bc);
+		}
+		if (take) {
+			if (loc[0] == 0) { loc[0] = t_loc[j]; loc[1] = t_seedn[j]; *rep_loc = j; }
+			else { loc[2] = t_loc[j]; loc[3] = t_seedn[j]; }
+		}
+	}
+	for (int j = maxi + 1; j < k; ++j) {
+		const int dl = t_loc[j] - t_loc[maxi], ds = t_seedn[j] - t_seedn[maxi];
+		if (ds > 0 && dl > 0 && dl <= read_len && ddf_close(dl, ds, bc)) {
+			if (loc[0] == 0) { loc[0] = t_loc[j]; loc[1] = t_seedn[j]; *rep_loc = j; }
+			else { loc[2] = t_loc[j]; loc[3] = t_seedn[j]; }
+		}
+	}
+	return 1;
+}
+
+template <class L>
+REF_HD int walk_strand_w(const L& lanes, const Unit& u, int zv, int gate, int64_t seqcount, int chain, Table& T, RefCand* cand, int maxc,
+                         WarpScratch& W)
+{
+	int ncand = 0;
+	const int nrec = T.nrec;
+	for (int base = 0; base < nrec; base += 32) {
+		// 32 records at a time: which of them pass the gate NOW (a vote of an earlier one may have emptied a later one:
+		// the score is read again when its turn comes)
+		uint32_t pass = lanes.ballot([&](int l) { const int i = base + l; return i < nrec && T.recs[i].index_score > gate; });
+		while (pass) {
+			const int i = base + low_bit(pass);
+			pass &= pass - 1;
+			Bucket* spr = T.recs + i;
+			if (spr->score == 0) continue;
+			const int blk = spr->blk;
+			const int s_k = spr->score;
+			const Bucket* prev = blk > 0 ? table_find(T, blk - 1) : nullptr;
+			const int pscore = prev ? prev->score : 0;
+			int64_t start_loc = (int64_t)blk * zv;
+			const int np = pscore > 0 ? (pscore < SM ? pscore : SM) : 0, ns = s_k < SM ? s_k : SM;
+			if (pscore > 0) start_loc = (int64_t)(blk - 1) * zv;
+			const int n = np + ns;
+			lanes.each([&](int l) {
+				for (int q = l; q < n; q += L::count) {
+					if (q < np) { W.t_loc[q] = prev->loczhi[q]; W.t_seed[q] = prev->seedno[q]; }
+					else { W.t_loc[q] = spr->loczhi[q - np] + (np ? zv : 0); W.t_seed[q] = spr->seedno[q - np]; }
+				}
+			});
+			lanes.sync();
+			int loc[4], rep = 0;
+			if (!find_location_w(lanes, W, loc, n, &rep, u.bc, u.len)) { lanes.sync(); continue; }
+			const int rep_score = W.t_score[rep], loc_seed = W.t_seed[rep];
+			lanes.sync();
+			if (rep_score < 6) continue;
+			int score = rep_score;
+			const int64_t loc_list = start_loc + loc[0];
+			const int qoff = (loc[1] - 1) * u.bc;
+			const int64_t left1 = loc_list + SEED - 1, right1 = seqcount - loc_list;
+			const int64_t left2 = qoff + SEED - 1, right2 = u.len - qoff;
+			const int num1 = (int)(left1 >= left2 ? left2 : left1), num2 = (int)(right1 >= right2 ? right2 : right1);
+			// neighbour votes: a lane per stored seed of the neighbour
+			{
+				int64_t bk = (int64_t)blk - 2;
+				for (int k = num1 / zv; bk >= 0 && k >= 0; --k, --bk) {
+					Bucket* p = table_find(T, (int32_t)bk);
+					if (!p || !(p->score > 0)) continue;
+					const int64_t sl = bk * zv;
+					const int scnt = p->score < SM ? p->score : SM;
+					const int s = lanes.sum([&](int l) { return l < scnt && ddf_close(loc_list - sl - p->loczhi[l], loc_seed - p->seedno[l], u.bc) ? 1 : 0; });
+					score += s;
+					lanes.sync();
+					if (5 * s > 2 * scnt && lanes.leader()) p->score = 0;
+					lanes.sync();
+				}
+			}
+			{
+				int64_t bk = (int64_t)blk + 1;
+				for (int k = num2 / zv; k > 0; --k, ++bk) {
+					Bucket* p = table_find(T, (int32_t)bk);
+					if (!p || !(p->score > 0)) continue;
+					const int64_t sl = bk * zv;
+					const int scnt = p->score < SM ? p->score : SM;
+					const int s = lanes.sum([&](int l) { return l < scnt && ddf_close(sl + p->loczhi[l] - loc_list, p->seedno[l] - loc_seed, u.bc) ? 1 : 0; });
+					score += s;
+					lanes.sync();
+					if (5 * s > 2 * scnt && lanes.leader()) p->score = 0;
+					lanes.sync();
+				}
+			}
+			int low = 0, high = ncand - 1;
+			while (low <= high) {
+				const int mid = (low + high) / 2;
+				if (cand[mid].score < score) high = mid - 1; else low = mid + 1;
+			}
+			const int at = high + 1;
+			if (ncand < maxc || at < maxc) {
+				const int last = ncand < maxc ? ncand : maxc - 1;
+				if (lanes.leader()) {
+					for (int q = last; q > at; --q) cand[q] = cand[q - 1];
+					RefCand c; c.loc1 = (int32_t)loc_list; c.loc2 = qoff; c.score = score; c.chain = chain;
+					cand[at] = c;
+				}
+				if (ncand < maxc) ++ncand;
+				lanes.sync();
+			}
+		}
+	}
+	return ncand;
+}
+
 // One end of one alignment that stops inside the read (get_left / get_right_clipped_candidate + fill_clipped_candidate,
 // mecat2ref_aux.cpp:186-303): the best-filled block beyond the clipped end proposes one more candidate.
 struct RescueQuery { int32_t unit, side, qoff, qend, read_len, pad_; int64_t soff, send; };

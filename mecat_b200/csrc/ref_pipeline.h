@@ -42,6 +42,7 @@ struct Params
 	int num_output = 10;            // -b
 	bool want_strings = true;       // the ref format prints both alignment strings; the m4 format only needs their statistics
 	int64_t table_budget = 8ll << 30;
+	bool seed_per_thread = false;   // SeedFn (a thread per strand) instead of SeedWarpFn (a warp per strand): the earlier form, kept for cross-checks
 	// With strings wanted: extend every candidate for its coordinates only and compute alignment strings just for the
 	// records that are printed (most of a read's <= -n extensions are dropped as contained in repeat-rich genomes).
 	bool strings_for_printed_only = false;
@@ -164,6 +165,22 @@ struct SeedFn
 		seed_strand(fwd, (uint32_t)offsz[2 * U.vread], U, zv, ibegin, ipos, bad, nbad, T);
 		tab.nrec[u] = T.nrec;
 		ncand[u] = walk_strand(U, zv, gate, seqcount, (int)(u & 1), T, cands + u * maxc, maxc);
+	}
+};
+
+struct SeedWarpFn       // the same unit of work on the 32 lanes of a warp (ref_core.cuh: seed_strand_w, walk_strand_w)
+{
+	const Unit* units; const int32_t* offsz; const uint32_t* fwd; const uint32_t* ibegin; const int32_t* ipos; const int64_t* bad; int64_t nbad;
+	TableRefs tab; int zv, gate, maxc; int64_t seqcount; RefCand* cands; int32_t* ncand;
+	template <class L>
+	REF_HD void operator()(int64_t u, const L& lanes, WarpScratch& W) const
+	{
+		const Unit U = units[u];
+		Table T = tab.open(u, true);
+		seed_strand_w(lanes, fwd, (uint32_t)offsz[2 * U.vread], U, zv, ibegin, ipos, bad, nbad, T, W);
+		if (lanes.leader()) tab.nrec[u] = T.nrec;
+		const int n = walk_strand_w(lanes, U, zv, gate, seqcount, (int)(u & 1), T, cands + u * maxc, maxc, W);
+		if (lanes.leader()) ncand[u] = n;
 	}
 };
 
@@ -368,9 +385,12 @@ int map_pass(Backend& be, const MapIn& in, const Params& P, int pass, const std:
 		if (!be.upload(d_rec_off, rec_off.data(), (size_t)nu + 1) || !be.upload(d_slot_off, slot_off.data(), (size_t)nu + 1)) return 1;
 		if (!be.fill(d_slots, 0, (size_t)nslots * sizeof(Slot))) return 1;
 		const TableRefs tab{d_rec_off, d_slot_off, d_slots, d_recs, d_nrec};
-		{
+		if (P.seed_per_thread) {
 			SeedFn f{d_units + u0, in.d_offsz, in.d_fwd, in.d_ibegin, in.d_ipos, in.d_bad, in.nbad, tab, zv, gate, maxc, in.seqcount, d_cands, d_ncand};
 			if (!be.launch(nu, f, ST_SEED)) return 1;
+		} else {
+			SeedWarpFn f{d_units + u0, in.d_offsz, in.d_fwd, in.d_ibegin, in.d_ipos, in.d_bad, in.nbad, tab, zv, gate, maxc, in.seqcount, d_cands, d_ncand};
+			if (!be.launch_seed_warp(nu, f, ST_SEED)) return 1;
 		}
 		std::vector<int32_t> ncand((size_t)nu);
 		std::vector<RefCand> cands((size_t)(nu * maxc));

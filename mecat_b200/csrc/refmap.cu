@@ -22,6 +22,34 @@ __global__ void __launch_bounds__(128) k_ref(const F f, const int64_t n)
 	if (i < n) f(i);
 }
 
+struct RefWarpLanes         // the lanes interface of ref_core.cuh on a real warp
+{
+	static constexpr int count = 32;
+	__device__ static int lane() { return (int)(threadIdx.x & 31u); }
+	template <class F> __device__ void each(F&& f) const { f(lane()); }
+	template <class F> __device__ int sum(F&& f) const { return __reduce_add_sync(0xffffffffu, f(lane())); }
+	template <class F> __device__ uint32_t ballot(F&& f) const { return __ballot_sync(0xffffffffu, f(lane())); }
+	template <class F> __device__ int min_val(F&& f) const { return __reduce_min_sync(0xffffffffu, f(lane())); }
+	template <class F> __device__ int lead(F&& f) const
+	{
+		int v = 0;
+		if (lane() == 0) v = f();
+		__syncwarp();                               // the leader's stores are visible to the other lanes behind this
+		return __shfl_sync(0xffffffffu, v, 0);
+	}
+	__device__ bool leader() const { return lane() == 0; }
+	__device__ void sync() const { __syncwarp(); }
+};
+
+constexpr int SEED_WARPS = 4;
+
+__global__ void __launch_bounds__(SEED_WARPS * 32) k_ref_seed_warp(const mbref::SeedWarpFn f, const int64_t n)
+{
+	__shared__ mbref::WarpScratch scratch[SEED_WARPS];
+	const int64_t u = (int64_t)blockIdx.x * SEED_WARPS + (threadIdx.x >> 5);
+	if (u < n) f(u, RefWarpLanes(), scratch[threadIdx.x >> 5]);
+}
+
 struct RefBackend : PoolBackend
 {
 	const DVolume* reads;
@@ -34,6 +62,13 @@ struct RefBackend : PoolBackend
 		if (n <= 0) return true;
 		KScope ks(c, MECAT_K_REF_COUNT + stage);
 		k_ref<F><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(f, n);
+		return check(cudaGetLastError(), "launch");
+	}
+	bool launch_seed_warp(int64_t n, const mbref::SeedWarpFn& f, int stage)
+	{
+		if (n <= 0) return true;
+		KScope ks(c, MECAT_K_REF_COUNT + stage);
+		k_ref_seed_warp<<<(unsigned)((n + SEED_WARPS - 1) / SEED_WARPS), SEED_WARPS * 32, 0, c->stream>>>(f, n);
 		return check(cudaGetLastError(), "launch");
 	}
 	bool align(const mecat_align_task* tasks, size_t n, bool want_strings, mecat_align_result* res, std::vector<char>& qs, std::vector<char>& ss)
@@ -169,6 +204,7 @@ int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat
 		P.num_candidates = p->num_candidates; P.num_output = p->num_output; P.want_strings = p->want_strings != 0;
 		P.dump_counts = dump_counts; P.dump_rows = dump_rows;
 		P.strings_for_printed_only = p->tech == 0 && RefBackend::forward_only();
+		if (const char* e = getenv("MECAT_B200_REF_SEED")) P.seed_per_thread = !strcmp(e, "thread");      // the earlier kernel shape, for cross-checks
 		if (const char* e = getenv("MECAT_B200_REF_TABLE_MB")) P.table_budget = (int64_t)atoll(e) << 20;      // test hook: force several table batches
 		RefBackend be(c, dv, R->genome, p->tech);
 		const int rc = mbref::map_reads(be, in, P, out);

@@ -19,6 +19,8 @@ int harness_ref_map_indexed(void* idx, const mecat_ref_reads* reads, const mecat
                             char** qstrings, char** sstrings, size_t* string_bytes, char* errbuf, int errcap);
 }
 
+extern "C" void harness_set_tech(int tech);
+
 struct mecat_b200_ctx { std::string err; int device; };
 
 extern "C" {
@@ -38,6 +40,7 @@ int mecat_b200_ref_map(mecat_b200_ctx* ctx, void* refidx, const mecat_ref_reads*
 {
 	char err[512];
 	err[0] = 0;
+	harness_set_tech(p->tech);       // which oracle aligner plays the extension kernel (one run uses one technology)
 	const int rc = harness_ref_map_indexed(refidx, reads, p, results, n, qstrings, sstrings, string_bytes, err, (int)sizeof err);
 	if (rc) ctx->err = err;
 	return rc;

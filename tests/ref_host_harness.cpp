@@ -54,6 +54,14 @@ struct HostBackend
 	template <class T> bool upload(T* d, const T* h, size_t n) { if (n) memcpy(d, h, n * sizeof(T)); return true; }
 	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
 	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
+	bool launch_seed_warp(int64_t n, const mbref::SeedWarpFn& f, int stage)
+	{
+		if (stage == mbref::ST_SEED) ++batches;
+		mbref::WarpScratch W;
+		memset(&W, 0xAB, sizeof W);
+		for (int64_t i = 0; i < n; ++i) f(i, mbref::EmuLanes(), W);
+		return true;
+	}
 	template <class F> bool launch(int64_t n, const F& f, int stage)
 	{
 		if (stage == mbref::ST_SEED) ++batches;
@@ -166,6 +174,7 @@ int map_packed(const HostIndex& I, const mecat_ref_reads* view, const mecat_ref_
 	if (table_budget > 0) P.table_budget = table_budget;
 	P.dump_counts = dump_counts; P.dump_rows = dump_rows;
 	P.strings_for_printed_only = getenv("MECAT_HARNESS_STRINGS_FOR_PRINTED_ONLY") != NULL;
+	P.seed_per_thread = getenv("MECAT_HARNESS_SEED_PER_THREAD") != NULL;      // the scalar bodies instead of the warp-shaped ones
 	if (mbref::map_reads(be, in, P, sink)) { err = be.err; return 1; }
 	if (stats) { stats[0] += be.tasks_run; stats[1] += be.batches; stats[2] += be.rescue_units; stats[3] += be.string_tasks; }
 	return 0;

@@ -293,3 +293,27 @@ def test_degenerate_inputs(gpu_ctx, refmap_inputs):
         assert len(rec) == 0
     finally:
         gpu_ctx.release_ref_index(tiny)
+
+
+def test_warp_per_strand_seeding_equals_thread_per_strand(gpu_ctx, hard_inputs, tmp_path, monkeypatch):
+    """k_ref_seed_warp (SeedWarpFn: lanes share the prefetch, insert_loc, find_location and the neighbour votes; the
+    default) against k_ref<SeedFn> (a thread per strand) on the device: same candidate lists per strand, same records, on the
+    hard fixture and on a repeat-rich one (full candidate lists, evictions in most blocks, consumed neighbours)."""
+    from mecat_b200 import api
+    rep_fa, rep_genome = str(tmp_path / "reads.fa"), str(tmp_path / "genome.fa")
+    util.make_refmap_repeats(rep_fa, rep_genome, seed=9, num_reads=200)
+    for fa, genome, ncand in ((hard_inputs[0], hard_inputs[1], 10), (rep_fa, rep_genome, 40)):
+        G = api.RefGenome.from_fasta(genome)
+        R = api.RefReads(util.read_fasta(fa))
+        idx = gpu_ctx.ref_index_build(G)
+        try:
+            out = {}
+            for mode in ("warp", "thread"):
+                monkeypatch.setenv("MECAT_B200_REF_SEED", mode)
+                rows, counts = gpu_ctx.ref_raw_candidates(idx, R, ncand)
+                rec, q, s = gpu_ctx.ref_map(idx, R, ncand, ncand, want_strings=False)
+                out[mode] = (rows.tobytes(), counts.tobytes(), rec.tobytes())
+            assert out["warp"] == out["thread"]
+            assert len(out["warp"][2]) > 1000
+        finally:
+            gpu_ctx.release_ref_index(idx)

@@ -395,12 +395,13 @@ def test_driver_files_match_reference(tmp_path, refmap_inputs, hard_inputs):
 
 
 def test_driver_option_handling(tmp_path, refmap_inputs):
-    """Missing arguments, -b above -n (reset with the reference's warning), refused technology, more devices than visible."""
+    """Missing arguments, -b above -n (reset with the reference's warning), -x 1, more devices than visible."""
     fa, genome = refmap_inputs
     out, w = str(tmp_path / "o"), str(tmp_path / "w")
     assert "reference must be specified" in run_driver(["-d", fa, "-o", out, "-w", w], ok=False).stderr
     assert "candidates must be > 0" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-n", "0"], ok=False).stderr
-    assert "nanopore" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-x", "1"], ok=False).stderr
+    run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w, "-m", "1", "-x", "1"])           # nanopore: the other aligner
+    assert sorted(open(out).read().splitlines()) == sorted(golden_lines("refmap.x1.m4.gz"))
     assert "CUDA device" in run_driver(["-d", fa, "-r", genome, "-o", out, "-w", w], env={"MECAT_GPUS": "3"}, ok=False).stderr
     assert "cannot open" in run_driver(["-d", str(tmp_path / "missing.fa"), "-r", genome, "-o", out, "-w", w], ok=False).stderr
     assert "for writing" in run_driver(["-d", fa, "-r", genome, "-o", str(tmp_path / "no" / "such" / "dir" / "o"), "-w", w], ok=False).stderr
@@ -453,3 +454,15 @@ def test_nanopore_stage_sequence_matches_reference(refmap_inputs, hard_inputs):
 def golden_lines(name):
     with gzip.open(os.path.join(util.GOLDEN, name), "rt") as f:
         return f.read().splitlines()
+
+
+def test_warp_shaped_seeding_equals_the_scalar_form(refmap_inputs, hard_inputs, repeat_inputs, monkeypatch):
+    """SeedWarpFn (a warp per strand: lane-parallel insert_loc / find_location / neighbour votes, the default) and SeedFn
+    (a thread per strand) must leave the same output; the repeat-rich fixture fills candidate lists, consumes blocks by
+    votes and evicts seeds in most blocks."""
+    for (fa, genome), n, fmt in ((refmap_inputs, 10, 1), (hard_inputs, 10, 0), (repeat_inputs, 40, 1)):
+        monkeypatch.delenv("MECAT_HARNESS_SEED_PER_THREAD", raising=False)
+        a, sa = run_harness(genome, fa, n=n, fmt=fmt)
+        monkeypatch.setenv("MECAT_HARNESS_SEED_PER_THREAD", "1")
+        b, sb = run_harness(genome, fa, n=n, fmt=fmt)
+        assert a == b and sa[0] == sb[0] and len(a) > 1000
