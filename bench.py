@@ -135,12 +135,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU reference
-def cpu_sample(threads=None, keep=None):
+def cpu_sample(threads=None, keep=None, tech=0):
     """Runs the unmodified reference binary (oracle/_ref/mecat2pw -j 1 -t <all cores>) on the
     bounded sample and returns (pairs, seconds, cores, description)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "mecat2pw")
     cores = threads or os.cpu_count() or 1
     SAMPLE_READS, SAMPLE_GENOME = sample_size(cores)
+    if tech == 1:
+        # the X-drop aligner costs the CPU ~6x more per candidate: 8 000 reads (one chunk of 500 per thread) keep the arm within minutes
+        SAMPLE_READS, SAMPLE_GENOME = 8000, 8000000
     desc = ("SAMPLE, not the full workload: unmodified mecat2pw -j 1 -t %d, command-line wall clock, on %d synthetic CLR reads "
             "(15 kb, 15%% err, genome %d, seed %d): same read model and 15x coverage as the workload, %d chunks of 500 reads per "
             "host thread" % (cores, SAMPLE_READS, SAMPLE_GENOME, SEED, SAMPLE_READS // 500 // cores))
@@ -152,7 +155,7 @@ def cpu_sample(threads=None, keep=None):
     wrk = tempfile.mkdtemp(prefix="refwrk_", dir=d)
     out = os.path.join(wrk, "out.m4")
     t = time.perf_counter()
-    subprocess.check_call([exe, "-j", "1", "-d", fa, "-o", out, "-w", os.path.join(wrk, "w"), "-t", str(cores)],
+    subprocess.check_call([exe, "-j", "1", "-d", fa, "-o", out, "-w", os.path.join(wrk, "w"), "-t", str(cores)] + (["-x", "1"] if tech == 1 else []),
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     dt = time.perf_counter() - t
     with open(out, "rb") as f:
@@ -173,7 +176,7 @@ def run_reference(args):
     times, pairs = [], 0
     cores = os.cpu_count() or 1
     t_all = time.perf_counter()
-    pairs, dt, cores, desc, kind = cpu_sample()
+    pairs, dt, cores, desc, kind = cpu_sample(tech=args.tech)
     if pairs is None:
         print(json.dumps({"impl": "reference", "unavailable": desc}))
         return
@@ -184,12 +187,14 @@ def run_reference(args):
     else:
         times.append(dt)
     while len(times) < args.steps and (time.perf_counter() - t_all) + (times[-1] if times else dt) < REFERENCE_BUDGET_S:
-        pairs, dt, cores, desc, kind = cpu_sample()
+        pairs, dt, cores, desc, kind = cpu_sample(tech=args.tech)
         times.append(dt)
         log("[bench] reference run %d: %d pairs in %.2f s" % (len(times) + warm - 1, pairs, dt))
     total = sum(times)
     value = pairs * len(times) / total
     sreads, sgenome = sample_size(cores)
+    if args.tech == 1:
+        sreads, sgenome = 8000, 8000000
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -200,7 +205,7 @@ def run_reference(args):
         "config": {"workload": "SAMPLE of the GPU arm's workload: mecat2pw -j 1 all-vs-all on %d synthetic PacBio-CLR reads (15 kb mean, "
                                "15%% error, 15x) -- the GPU arm runs all %d reads; the CPU's full-size rate is in cpu_baseline.full_size"
                                % (sreads, READS_PER_VOLUME),
-                   "reads": sreads, "genome": sgenome, "seed": SEED, "params": "-n 100 -a 2000 -k 4 -x 0",
+                   "reads": sreads, "genome": sgenome, "seed": SEED, "params": "-n 100 -a 2000 -k 4 -x 0" if args.tech == 0 else "-n 100 -a 500 -k 2 -x 1",
                    "parallelism": "reference CPU binary, %d host threads (no GPU)" % cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "full_size": full_size_record()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -338,7 +343,7 @@ def run_ours(args):
         return fn(args, METRIC, UNIT, workload_config, make_reads, tmp_root, ClockSampler, cpu_sample, roofline_for)
     torch.cuda.set_device(local)
     d = tmp_root()
-    nreads = args.reads or READS_PER_VOLUME
+    nreads = args.reads or (20000 if args.tech == 1 else READS_PER_VOLUME)
     genome = int(GENOME_PER_VOLUME * (nreads / READS_PER_VOLUME))
     fa = os.path.join(d, "reads_%d_%d.fa" % (nreads, SEED))
     make_reads(fa, nreads, genome, SEED)
@@ -349,7 +354,7 @@ def run_ours(args):
     vol = mecat_b200.HostVolume.load(names[0])
     hv = pinned_volume(vol)
     log("[bench] split + load: %.1f s; %d reads, %d bases" % (time.time() - t, vol.num_reads, vol.num_bases))
-    params = mecat_b200.pw_params(task=1)
+    params = mecat_b200.pw_params(task=1) if args.tech == 0 else mecat_b200.pw_params(task=1, min_align_size=500, min_kmer_match=2, tech=1)
     ctx = mecat_b200.Context(local)
     dvol = ctx.upload(hv)
 
@@ -412,7 +417,7 @@ def run_ours(args):
     roof = roofline_for(stats, peaks, args.steps, clocks=clocks)
     cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "skipped (--no-cpu)"}
     if not args.no_cpu:
-        cp, cdt, cores, desc, kind = cpu_sample()
+        cp, cdt, cores, desc, kind = cpu_sample(tech=args.tech)
         if cp is not None:
             cb = {"value": cp / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "seconds": cdt, "pairs": cp,
                   "full_size": full_size_record()}
@@ -421,8 +426,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": pairs / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic", "config": workload_config(1) if not args.reads else
-        dict(workload_config(1), reads=nreads, genome=genome, workload="REDUCED debug workload (%d reads)" % nreads),
+        "dtype": "int32", "data": "synthetic", "config": workload_config(1) if not args.reads and args.tech == 0 else
+        dict(workload_config(1), reads=nreads, genome=genome, workload=("REDUCED debug workload (%d reads)" % nreads) if args.tech == 0 else
+             "mecat2pw -j 1 -x 1 (nanopore parameter set: X-drop aligner, -a 500 -k 2, min_kmer_dist 400) all-vs-all on %d synthetic reads "
+             "(15 kb mean, 15%% error, 15x); not the headline configuration" % nreads, params="-n 100 -a 500 -k 2 -x 1"),
         "clocks": clocks,
         "e2e": {"value": epairs / edt, "unit": UNIT, "h2d_bytes_per_step": estats["h2d_bytes"] // esteps,
                 "d2h_bytes_per_step": estats["d2h_bytes"] // esteps, "ms_per_step": 1000.0 * edt / esteps, "steps": esteps},
@@ -578,6 +585,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=0, help="debug only: reduced workload (result is not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tech", type=int, default=0, choices=[0, 1], help="-x of mecat2pw: 1 = the nanopore parameter set (workload pw only; 20 000 reads by default)")
     ap.add_argument("--workload", default="pw", choices=["pw", "ref", "cns"],
                     help="pw (default): the headline, mecat2pw -j 1 (BASELINE configs[1]).  ref / cns: mecat2ref (configs[2]) / "
                          "mecat2cns (configs[3]) through their command-line drivers")

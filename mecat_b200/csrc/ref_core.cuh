@@ -418,6 +418,10 @@ REF_HD void seed_strand_w(const L& lanes, const uint32_t* fwd, uint32_t off, con
 				const Slot sl = T.slots[hs];
 				acc += sl.key;
 				if (sl.key == blk + 1) acc += T.recs[sl.rec].score;
+				// the left neighbour, whose score goes into the block's index_score
+				const uint32_t hn = ((uint32_t)blk * 2654435761u) >> T.shift;
+				const Slot sn = T.slots[hn];
+				if (blk > 0 && sn.key == blk) acc += T.recs[sn.rec].score;
 			}
 			if (acc == 0x7fffffff) W.sink = acc;
 		});

@@ -43,7 +43,9 @@ struct RefWarpLanes         // the lanes interface of ref_core.cuh on a real war
 
 constexpr int SEED_WARPS = 4;
 
-__global__ void __launch_bounds__(SEED_WARPS * 32) k_ref_seed_warp(const mbref::SeedWarpFn f, const int64_t n)
+// 16 CTAs of 4 warps per SM (32 registers per thread): the kernel waits on memory (ncu: 12 long-scoreboard stall cycles per
+// issue at 36 warps per SM), so resident warps count for more than registers
+__global__ void __launch_bounds__(SEED_WARPS * 32, 16) k_ref_seed_warp(const mbref::SeedWarpFn f, const int64_t n)
 {
 	__shared__ mbref::WarpScratch scratch[SEED_WARPS];
 	const int64_t u = (int64_t)blockIdx.x * SEED_WARPS + (threadIdx.x >> 5);

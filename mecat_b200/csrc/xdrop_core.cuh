@@ -103,7 +103,7 @@ XD_HD void block_dp(const Seq& Q, int q0, int M, const Seq& T, int t0, int N, co
 	if (M <= 0 || N <= 0) return;
 	const int oe = GAP_OPEN + GAP_EXTEND;
 	const int xd = X_DROPOFF < oe ? oe : X_DROPOFF;
-	Cell* sc = S.sc;
+	Cell* __restrict__ sc = S.sc;
 	RowWriter W; W.bad = 0;
 	int next_word = 0;
 	int score = -oe, i;
@@ -125,32 +125,49 @@ XD_HD void block_dp(const Seq& Q, int q0, int M, const Seq& T, int t0, int N, co
 		W.begin(S.tb, next_word);
 		score = NEG;
 		int gap_row = NEG, last_b = first_b, b;
-		for (b = first_b; b < b_size; ++b) {
-			const int bc = base_at(T, t0 + b);
-			const Cell c = sc[b];
-			int gap_col = c.gap;
-			const int next = c.best + (ac == bc ? REWARD : PENALTY);
-			uint32_t script = OP_SUB;
-			if (score < gap_col) { script = OP_GAP_B; score = gap_col; }
-			if (score < gap_row) { script = OP_GAP_A; score = gap_row; }
-			if (best_score - score > xd) {
-				if (first_b == b) ++first_b;
-				else sc[b].best = NEG;
-			} else {
-				last_b = b;
-				if (score > best_score) { best_score = score; ae = a; be = b; }
-				Cell o;
-				gap_col -= GAP_EXTEND;
-				if (gap_col < score - oe) o.gap = score - oe;
-				else { o.gap = gap_col; script |= F_EXT_A; }
-				gap_row -= GAP_EXTEND;
-				if (gap_row < score - oe) gap_row = score - oe;
-				else script |= F_EXT_B;
-				o.best = score;
-				sc[b] = o;
+		// four cells per round: their score-row entries and subject bases are loaded together (independent loads in
+		// flight instead of one dependent load per cell), then the cells are finished one after the other as before
+		for (b = first_b; b < b_size;) {
+			const int nb = b_size - b < 4 ? b_size - b : 4;
+			Cell pre[4];
+			int pbc[4];
+#if defined(__CUDA_ARCH__)
+			#pragma unroll
+#endif
+			for (int j = 0; j < 4; ++j)
+				if (j < nb) { pre[j] = sc[b + j]; pbc[j] = base_at(T, t0 + b + j); }
+#if defined(__CUDA_ARCH__)
+			#pragma unroll
+#endif
+			for (int j = 0; j < 4; ++j) {
+				if (j >= nb) break;
+				const int bc = pbc[j];
+				const Cell c = pre[j];
+				int gap_col = c.gap;
+				const int next = c.best + (ac == bc ? REWARD : PENALTY);
+				uint32_t script = OP_SUB;
+				if (score < gap_col) { script = OP_GAP_B; score = gap_col; }
+				if (score < gap_row) { script = OP_GAP_A; score = gap_row; }
+				if (best_score - score > xd) {
+					if (first_b == b) ++first_b;
+					else sc[b].best = NEG;
+				} else {
+					last_b = b;
+					if (score > best_score) { best_score = score; ae = a; be = b; }
+					Cell o;
+					gap_col -= GAP_EXTEND;
+					if (gap_col < score - oe) o.gap = score - oe;
+					else { o.gap = gap_col; script |= F_EXT_A; }
+					gap_row -= GAP_EXTEND;
+					if (gap_row < score - oe) gap_row = score - oe;
+					else script |= F_EXT_B;
+					o.best = score;
+					sc[b] = o;
+				}
+				score = next;
+				W.put(script);
+				++b;
 			}
-			score = next;
-			W.put(script);
 		}
 		if (first_b == b_size) { next_word += W.end(); break; }
 		if (last_b < b_size - 1) b_size = last_b + 1;
