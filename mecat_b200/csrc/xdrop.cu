@@ -16,6 +16,7 @@ namespace mb {
 namespace {
 
 constexpr int XD_THREADS = 128;
+constexpr size_t XD_RING_BYTES = sizeof(mbx::RingCell) * mbx::RING * XD_THREADS;      // 64 KB per CTA: three CTAs per SM
 
 struct TaskView { int32_t qread, qstrand, qstart, sread, sstart, swin_off, swin_len; };
 __device__ __forceinline__ TaskView view_of(const AlignTask& t) { return {t.qread, t.qstrand, t.qstart, t.sread, t.sstart, t.swin_off, t.swin_len}; }
@@ -36,6 +37,8 @@ k_xdrop(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 	S.tb = (uint32_t*)p; p += 4 * (size_t)TB_WORDS;
 	S.row_first = (int32_t*)p; p += 4 * (size_t)ROWS;
 	S.row_word = (int32_t*)p;
+	extern __shared__ RingCell ring_smem[];           // RING x blockDim entries: entry i of thread t at [i * blockDim + t]
+	S.ring = ring_smem + threadIdx.x; S.ring_stride = (int)blockDim.x;
 	for (;;) {
 		const unsigned long long item = atomicAdd(work_counter, 1ull);
 		if (item >= 2 * ntasks) break;
@@ -86,7 +89,7 @@ __global__ void k_xdrop_finalize(const ExtendTask* __restrict__ tasks, const Aln
 // persistent threads: as many as the chains can use and the device memory left allows (232 KB of scratch each)
 int xdrop_threads(Ctx* c, size_t nchains, int* grid)
 {
-	int per_sm = 512;
+	int per_sm = 384;          // three CTAs of 128 threads: the shared-memory rings (64 KB per CTA) set the limit
 	if (const char* e = getenv("MECAT_B200_XDROP_THREADS")) per_sm = std::max(XD_THREADS, atoi(e) / XD_THREADS * XD_THREADS);   // tuning hook
 	size_t want = (size_t)c->sm_count * per_sm;
 	want = std::min(want, (nchains + XD_THREADS - 1) / XD_THREADS * XD_THREADS);
@@ -111,9 +114,10 @@ int xdrop_run(Ctx* c, const DVolume* q, const DVolume* s, const TaskT* d_tasks, 
 	auto body = [&]() -> int {
 		MB_CUDA(c, c->dmalloc((void**)&d_scratch, (size_t)grid * XD_THREADS * mbx::SCRATCH_BYTES));
 		MB_CUDA(c, cudaMemsetAsync(c->d_counters + 4, 0, 8, c->stream));
+		MB_CUDA(c, cudaFuncSetAttribute(k_xdrop<COLS, TaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XD_RING_BYTES));
 		{
 			KScope ks(c, MECAT_K_EXTEND);
-			k_xdrop<COLS, TaskT><<<grid, XD_THREADS, 0, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
+			k_xdrop<COLS, TaskT><<<grid, XD_THREADS, XD_RING_BYTES, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
 			                                                       d_tasks, nb, d_slots, d_colq, d_colt, d_scratch, c->d_counters + 4);
 		}
 		MB_CUDA(c, cudaGetLastError());

@@ -62,12 +62,40 @@ struct Half           // what one chain produced
 	int32_t overflow;  // the column slot was too small (cannot happen with slots sized by align_task_columns)
 };
 
+struct RingCell { int16_t best, gap; };      // a score-row entry in shared memory; -32768 stands for NEG
+
 struct Scratch        // private to one thread
 {
-	Cell* sc;          // SC_CELLS
+	Cell* sc;          // SC_CELLS (global memory: the score row of blocks whose band outgrows the ring)
 	uint32_t* tb;      // TB_WORDS
 	int32_t* row_first;// ROWS
 	int32_t* row_word; // ROWS
+	RingCell* ring;    // RING entries, `ring_stride` apart (shared memory, interleaved between the threads of a CTA so that
+	int ring_stride;   // every lane stays in its own bank); nullptr: no ring
+};
+
+// The score row of the X-drop programme only lives between the first cell still inside the drop-off and the sentinel
+// behind the last one: ~60 cells on related sequences, a few hundred on unrelated ones (band statistics in DESIGN.md).
+// RingRow keeps that window in shared memory (cell b at entry b mod RING, 16-bit scores: a stored value is a real score
+// within [-40, 720] or exactly NEG); a block whose window would not fit is redone with the row in global memory.
+constexpr int RING = 128;
+struct GlobalRow
+{
+	Cell* p;
+	XD_HD Cell get(int b) const { return p[b]; }
+	XD_HD void put(int b, Cell c) const { p[b] = c; }
+	XD_HD void put_best(int b, int v) const { p[b].best = v; }
+	XD_HD bool room(int, int) const { return true; }
+};
+struct RingRow
+{
+	RingCell* p; int stride;
+	XD_HD static int16_t enc(int v) { return v == NEG ? (int16_t)-32768 : (int16_t)v; }
+	XD_HD static int dec(int16_t v) { return v == (int16_t)-32768 ? NEG : (int)v; }
+	XD_HD Cell get(int b) const { const RingCell r = p[(b & (RING - 1)) * stride]; Cell c; c.best = dec(r.best); c.gap = dec(r.gap); return c; }
+	XD_HD void put(int b, Cell c) const { RingCell r; r.best = enc(c.best); r.gap = enc(c.gap); p[(b & (RING - 1)) * stride] = r; }
+	XD_HD void put_best(int b, int v) const { p[(b & (RING - 1)) * stride].best = enc(v); }
+	XD_HD bool room(int first_b, int b) const { return b - first_b < RING; }      // may cell b be written while first_b is live?
 };
 constexpr size_t SCRATCH_BYTES = sizeof(Cell) * SC_CELLS + 4 * (size_t)TB_WORDS + 8 * (size_t)ROWS;
 
@@ -97,23 +125,24 @@ struct RowWriter
 
 // xdrop_align without its trace-back walk (xdrop_gapalign.cpp:10-158): fills the trace-back of the block, returns the
 // end cell of the best path.  A = query block (M bases from q0), B = subject block (N bases from t0).
-XD_HD void block_dp(const Seq& Q, int q0, int M, const Seq& T, int t0, int N, const Scratch& S, int& ae, int& be, int& bad)
+// Returns false when the row does not fit `sc` (RingRow only): nothing of the block is valid then.
+template <class Row>
+XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, int t0, int N, const Scratch& S, int& ae, int& be, int& bad)
 {
 	ae = be = 0;
-	if (M <= 0 || N <= 0) return;
+	if (M <= 0 || N <= 0) return true;
 	const int oe = GAP_OPEN + GAP_EXTEND;
 	const int xd = X_DROPOFF < oe ? oe : X_DROPOFF;
-	Cell* __restrict__ sc = S.sc;
 	RowWriter W; W.bad = 0;
 	int next_word = 0;
 	int score = -oe, i;
-	sc[0].best = 0; sc[0].gap = -oe;
+	{ Cell c0; c0.best = 0; c0.gap = -oe; sc.put(0, c0); }
 	S.row_first[0] = 0; S.row_word[0] = 0;
 	W.begin(S.tb, 0);
 	W.put(OP_SUB);                                   // cell (0, 0): never read
 	for (i = 1; i <= N; ++i) {
 		if (score < -xd) break;
-		sc[i].best = score; sc[i].gap = score - oe;
+		{ Cell ci; ci.best = score; ci.gap = score - oe; sc.put(i, ci); }
 		score -= GAP_EXTEND;
 		W.put(OP_GAP_A);
 	}
@@ -135,7 +164,7 @@ XD_HD void block_dp(const Seq& Q, int q0, int M, const Seq& T, int t0, int N, co
 			#pragma unroll
 #endif
 			for (int j = 0; j < 4; ++j)
-				if (j < nb) { pre[j] = sc[b + j]; pbc[j] = base_at(T, t0 + b + j); }
+				if (j < nb) { pre[j] = sc.get(b + j); pbc[j] = base_at(T, t0 + b + j); }
 #if defined(__CUDA_ARCH__)
 			#pragma unroll
 #endif
@@ -150,7 +179,7 @@ XD_HD void block_dp(const Seq& Q, int q0, int M, const Seq& T, int t0, int N, co
 				if (score < gap_row) { script = OP_GAP_A; score = gap_row; }
 				if (best_score - score > xd) {
 					if (first_b == b) ++first_b;
-					else sc[b].best = NEG;
+					else sc.put_best(b, NEG);
 				} else {
 					last_b = b;
 					if (score > best_score) { best_score = score; ae = a; be = b; }
@@ -162,27 +191,41 @@ XD_HD void block_dp(const Seq& Q, int q0, int M, const Seq& T, int t0, int N, co
 					if (gap_row < score - oe) gap_row = score - oe;
 					else script |= F_EXT_B;
 					o.best = score;
-					sc[b] = o;
+					sc.put(b, o);
 				}
 				score = next;
 				W.put(script);
 				++b;
 			}
 		}
+#if defined(XD_STATS)
+		{ const int w = b_size - S.row_first[a]; ++g_rows; g_cells += w; if (w > g_maxw) g_maxw = w; if (w > g_blockmax) g_blockmax = w; }
+#endif
 		if (first_b == b_size) { next_word += W.end(); break; }
 		if (last_b < b_size - 1) b_size = last_b + 1;
 		else {
 			while (gap_row >= best_score - xd && b_size < N) {
-				sc[b_size].best = gap_row; sc[b_size].gap = gap_row - oe;
+				if (!sc.room(first_b, b_size)) return false;
+				Cell ce; ce.best = gap_row; ce.gap = gap_row - oe;
+				sc.put(b_size, ce);
 				gap_row -= GAP_EXTEND;
 				W.put(OP_GAP_A);
 				++b_size;
 			}
 		}
 		next_word += W.end();
-		if (b_size < N) { sc[b_size].best = NEG; sc[b_size].gap = NEG; ++b_size; }
+		if (b_size < N) {
+			if (!sc.room(first_b, b_size)) return false;
+			Cell cs; cs.best = NEG; cs.gap = NEG;
+			sc.put(b_size, cs);
+			++b_size;
+		}
 	}
 	bad |= W.bad;
+#if defined(XD_STATS)
+	++g_blocks; ++g_hist[g_blockmax / 32 > 15 ? 15 : g_blockmax / 32]; g_blockmax = 0;
+#endif
+	return true;
 }
 
 XD_HD uint32_t tb_get(const Scratch& S, int a, int b)
@@ -221,7 +264,9 @@ XD_HD void chain(const Seq& Q, const Seq& T, const Scratch& S, char* oq, char* o
 			qblk = qleft < a ? qleft : a; tblk = tleft < b ? tleft : b; lastblk = true;
 		} else { qblk = tblk = BLOCK; lastblk = false; }
 		int ae, be, bad = 0;
-		block_dp(Q, qi, qblk, T, ti, tblk, S, ae, be, bad);
+		bool done = false;
+		if (S.ring) { RingRow rr; rr.p = S.ring; rr.stride = S.ring_stride; done = block_dp(rr, Q, qi, qblk, T, ti, tblk, S, ae, be, bad); }
+		if (!done) { bad = 0; GlobalRow gr; gr.p = S.sc; block_dp(gr, Q, qi, qblk, T, ti, tblk, S, ae, be, bad); }
 		if (bad) { overflow = 1; break; }
 		const bool full = (qblk - ae <= 20 || tblk - be <= 20);
 		const bool whole = !full || lastblk;                     // this block's alignment is appended as it is and ends the chain

@@ -366,7 +366,8 @@ def test_oracle_xdrop_extension_against_reference():
 def test_xdrop_kernel_body_matches_oracle():
     """The statements the GPU executes for the -x 1 extension (csrc/xdrop_core.cuh, run on the host through
     tests/xdrop_host_harness.cpp over packed 2-bit words) against the oracle: coordinates, columns, matches, strings;
-    with and without columns."""
+    with and without columns; with the score row in the 128-entry ring (unrelated and low-complexity pairs outgrow it and
+    are redone with the global row) and with the global row only."""
     O, H = util.oracle(), util.xdrop_harness()
     rng = np.random.default_rng(29)
     out_o = (C.c_int32 * 8)(); out_h = (C.c_int32 * 8)(); out_n = (C.c_int32 * 8)()
@@ -386,6 +387,8 @@ def test_xdrop_kernel_body_matches_oracle():
             H.xh_go(qp, qstart, len(q), tp, tstart, len(t), min_aln, out_h, qs_h, ts_h, cap, 1)
             H.xh_go(qp, qstart, len(q), tp, tstart, len(t), min_aln, out_n, None, None, 0, 0)
             assert list(out_o[:7]) == list(out_h[:7]) == list(out_n[:7]), (len(q), len(t), qstart, tstart)
+            H.xh_go(qp, qstart, len(q), tp, tstart, len(t), min_aln, out_n, None, None, 0, 2)      # score row in global memory only
+            assert list(out_o[:7]) == list(out_n[:7])
             n = out_o[5]
             assert qs_o.value[:n] == qs_h.value[:n] and ts_o.value[:n] == ts_h.value[:n]
             checked += n > 100

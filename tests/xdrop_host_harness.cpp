@@ -40,6 +40,9 @@ extern "C" int xh_go(const char* q, int qstart, int qsize, const char* t, int ts
 	S.tb = (uint32_t*)p; p += 4 * (size_t)TB_WORDS;
 	S.row_first = (int32_t*)p; p += 4 * (size_t)ROWS;
 	S.row_word = (int32_t*)p;
+	std::vector<RingCell> ring((size_t)RING * 3);          // stride 3: like the interleaved shared-memory layout of the kernel
+	S.ring = (want_cols & 2) ? nullptr : ring.data(); S.ring_stride = 3;      // bit 1 of want_cols: the global row only
+	want_cols &= 1;
 	Half H[2];
 	std::vector<char> cq[2], ct[2];
 	for (int right = 0; right < 2; ++right) {
