@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(XD_THREADS)
 k_xdrop(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, const int2* __restrict__ qoffsz, int qN,
         const uint32_t* __restrict__ sfwd, const uint32_t* __restrict__ srev, const int2* __restrict__ soffsz, int sN,
         const TaskT* __restrict__ tasks, size_t ntasks, AlnSlot* __restrict__ slots, char* __restrict__ colq,
-        char* __restrict__ colt, unsigned char* __restrict__ scratch, unsigned long long* __restrict__ work_counter)
+        char* __restrict__ colt, unsigned char* __restrict__ scratch, unsigned long long* __restrict__ work_counter,
+        const uint32_t* __restrict__ order)
 {
 	using namespace mbx;
 	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,9 +40,17 @@ k_xdrop(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 	S.row_word = (int32_t*)p;
 	extern __shared__ RingCell ring_smem[];           // RING x blockDim entries: entry i of thread t at [i * blockDim + t]
 	S.ring = ring_smem + threadIdx.x; S.ring_stride = (int)blockDim.x;
+	// A warp takes 32 chains at a time from a list ordered by expected length (k_xd_class / k_xd_place), so that its lanes
+	// start together, walk blocks of the same shape in step and finish at about the same time: a lane that asked for its
+	// next chain on its own would never meet the others again (each lane a divergent path of its own, 1/32 of the warp).
+	const int lane = (int)(threadIdx.x & 31u);
 	for (;;) {
-		const unsigned long long item = atomicAdd(work_counter, 1ull);
-		if (item >= 2 * ntasks) break;
+		unsigned long long base = 0;
+		if (lane == 0) base = atomicAdd(work_counter, 32ull);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= 2 * ntasks) break;
+		if (base + lane < 2 * ntasks) {                    // (the lanes past the end idle through this last round)
+		const unsigned long long item = order[base + lane];
 		const TaskView t = view_of(tasks[item >> 1]);
 		const int right = (int)(item & 1);
 		const int2 qo = qoffsz[t.qread];
@@ -65,7 +74,41 @@ k_xdrop(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 		slot.cols = H.cols; slot.matches = H.matches; slot.qadv = H.qadv; slot.tadv = H.tadv;
 		slot.overflow = H.overflow | (H.last << 1);
 		slots[item] = slot;
+		}
+		__syncwarp();
 	}
+}
+
+// Expected length class of a chain: the shorter of what is left of the two sequences in its direction, in steps of 256
+// bases (64 classes, the last one open ended).
+constexpr int XD_CLASSES = 64;
+template <class TaskT>
+__device__ __forceinline__ int chain_class(const TaskT& task, int right, const int2* __restrict__ qoffsz, const int2* __restrict__ soffsz)
+{
+	const TaskView t = view_of(task);
+	const int ql = qoffsz[t.qread].y, sl = t.swin_len > 0 ? t.swin_len : soffsz[t.sread].y;
+	const int len = right ? min(ql - t.qstart, sl - t.sstart) : min(t.qstart, t.sstart);
+	return min(XD_CLASSES - 1, max(len, 0) >> 8);
+}
+template <class TaskT>
+__global__ void k_xd_class(const TaskT* __restrict__ tasks, size_t nitems, const int2* __restrict__ qoffsz, const int2* __restrict__ soffsz,
+                           unsigned int* __restrict__ hist)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < nitems) atomicAdd(hist + chain_class(tasks[i >> 1], (int)(i & 1), qoffsz, soffsz), 1u);
+}
+// hist -> first place of every class, longest class first (one thread: 64 entries)
+__global__ void k_xd_scan(unsigned int* __restrict__ hist)
+{
+	unsigned int at = 0;
+	for (int c = XD_CLASSES - 1; c >= 0; --c) { const unsigned int n = hist[c]; hist[c] = at; at += n; }
+}
+template <class TaskT>
+__global__ void k_xd_place(const TaskT* __restrict__ tasks, size_t nitems, const int2* __restrict__ qoffsz, const int2* __restrict__ soffsz,
+                           unsigned int* __restrict__ cursor, uint32_t* __restrict__ order)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < nitems) order[atomicAdd(cursor + chain_class(tasks[i >> 1], (int)(i & 1), qoffsz, soffsz), 1u)] = (uint32_t)i;
 }
 
 __global__ void k_xdrop_finalize(const ExtendTask* __restrict__ tasks, const AlnSlot* __restrict__ slots, size_t n, int min_aln,
@@ -111,20 +154,33 @@ int xdrop_run(Ctx* c, const DVolume* q, const DVolume* s, const TaskT* d_tasks, 
 	int grid = 0;
 	xdrop_threads(c, 2 * nb, &grid);
 	unsigned char* d_scratch = nullptr;
+	uint32_t* d_order = nullptr;
+	unsigned int* d_hist = nullptr;
+	if (2 * nb >= 0xFFFFFFFFull) MB_FAIL(c, "xdrop: %zu tasks in one batch", nb);
 	auto body = [&]() -> int {
 		MB_CUDA(c, c->dmalloc((void**)&d_scratch, (size_t)grid * XD_THREADS * mbx::SCRATCH_BYTES));
+		MB_CUDA(c, c->alloc(&d_order, 2 * nb));
+		MB_CUDA(c, c->alloc(&d_hist, (size_t)XD_CLASSES));
+		MB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * XD_CLASSES, c->stream));
+		{
+			KScope ks(c, MECAT_K_MERGE, 3);
+			const unsigned g = (unsigned)((2 * nb + 255) / 256);
+			k_xd_class<TaskT><<<g, 256, 0, c->stream>>>(d_tasks, 2 * nb, q->offsz, s->offsz, d_hist);
+			k_xd_scan<<<1, 1, 0, c->stream>>>(d_hist);
+			k_xd_place<TaskT><<<g, 256, 0, c->stream>>>(d_tasks, 2 * nb, q->offsz, s->offsz, d_hist, d_order);
+		}
 		MB_CUDA(c, cudaMemsetAsync(c->d_counters + 4, 0, 8, c->stream));
 		MB_CUDA(c, cudaFuncSetAttribute(k_xdrop<COLS, TaskT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XD_RING_BYTES));
 		{
 			KScope ks(c, MECAT_K_EXTEND);
 			k_xdrop<COLS, TaskT><<<grid, XD_THREADS, XD_RING_BYTES, c->stream>>>(q->fwd, q->rev, q->offsz, q->num_bases, s->fwd, s->rev, s->offsz, s->num_bases,
-			                                                       d_tasks, nb, d_slots, d_colq, d_colt, d_scratch, c->d_counters + 4);
+			                                                       d_tasks, nb, d_slots, d_colq, d_colt, d_scratch, c->d_counters + 4, d_order);
 		}
 		MB_CUDA(c, cudaGetLastError());
 		return 0;
 	};
 	const int rc = body();
-	c->dfree(d_scratch);      // the pool only marks the block free; later work on the stream is ordered behind the kernel
+	c->dfree(d_scratch); c->dfree(d_order); c->dfree(d_hist);      // the pool only marks the blocks free; later work on the stream is ordered behind the kernel
 	return rc;
 }
 
