@@ -43,10 +43,6 @@ struct Bucket          // Back_List of one touched block (mecat2ref_aux.h:9-14)
 	int32_t blk;
 	int16_t score, score2, seednum, index_score;
 	int16_t loczhi[SM], seedno[SM];
-	// kept by the warp-shaped seeding only (insert_loc_w): pc[i] = how many of the other SM - 1 stored seeds agree with
-	// seed i, valid once pcv is set -- the eviction of the 21st, 22nd, ... seed then costs two pair tests per lane
-	uint8_t pc[SM];
-	uint8_t pcv, pad_[3];
 };
 
 struct Slot { int32_t key, rec; };   // key = block + 1, 0 = empty
@@ -85,7 +81,7 @@ REF_HD Bucket* table_touch(Table& T, int32_t blk, bool* fresh)
 	Slot s; s.key = blk + 1; s.rec = T.nrec;
 	T.slots[h] = s;
 	Bucket* b = T.recs + T.nrec++;
-	b->blk = blk; b->score = 0; b->score2 = 0; b->seednum = 0; b->index_score = 0; b->pcv = 0;
+	b->blk = blk; b->score = 0; b->score2 = 0; b->seednum = 0; b->index_score = 0;
 	*fresh = true;
 	return b;
 }
@@ -368,53 +364,28 @@ REF_HD bool pair_agrees(int loc_i, int seed_i, int loc_j, int seed_j, int bc)
 	return seed_j - seed_i > 0 && loc_j - loc_i > 0 && ddf_close(loc_j - loc_i, seed_j - seed_i, bc);
 }
 
-// insert_loc with a lane per entry and the pair counts among the SM stored seeds kept from call to call: the new seed
-// costs one test per lane, an eviction one more (the counts lose the evicted seed's agreements).  Entry i < SM is the
-// block's i-th seed, entry SM the new one; the stored seeds stay in arrival order, so index order is seed order.
+// insert_loc with a lane per entry.  Entry i < SM is the block's i-th seed, entry SM the new one.
 template <class L>
-REF_HD void insert_loc_w(const L& lanes, Bucket* b, int loc, int seedn, int bc, WarpScratch& W)
+REF_HD void insert_loc_w(const L& lanes, Bucket* b, int loc, int seedn, int bc)
 {
-	if (!b->pcv) {
-		// the block's first eviction: all pair counts among its SM seeds
-		lanes.each([&](int l) {
-			if (l >= SM) return;
-			int s = 0;
-			const int li = b->loczhi[l], si = b->seedno[l];
-			for (int j = 0; j < l; ++j) s += pair_agrees(b->loczhi[j], b->seedno[j], li, si, bc) ? 1 : 0;
-			for (int j = l + 1; j < SM; ++j) s += pair_agrees(li, si, b->loczhi[j], b->seedno[j], bc) ? 1 : 0;
-			b->pc[l] = (uint8_t)s;
-		});
-		lanes.sync();
-		if (lanes.leader()) b->pcv = 1;
-		lanes.sync();
-	}
-	// W.t_loc[l] = does seed l agree with the new one, W.t_score[l] = seed l's score among all SM + 1
-	lanes.each([&](int l) {
-		if (l >= SM) return;
-		const int a = pair_agrees(b->loczhi[l], b->seedno[l], loc, seedn, bc) ? 1 : 0;
-		W.t_loc[l] = a; W.t_score[l] = (int)b->pc[l] + a;
-	});
-	lanes.sync();
-	const int total_new = lanes.sum([&](int l) { return l < SM ? W.t_loc[l] : 0; });
-	auto score_of = [&](int l) { return l < SM ? W.t_score[l] : l == SM ? total_new : 10000; };
+	auto eloc = [&](int i) { return i < SM ? (int)b->loczhi[i] : loc; };
+	auto eseed = [&](int i) { return i < SM ? (int)b->seedno[i] : seedn; };
+	auto score_of = [&](int l) {
+		if (l > SM) return 10000;
+		int s = 0;
+		const int li = eloc(l), si = eseed(l);
+		for (int j = 0; j < l; ++j) s += pair_agrees(eloc(j), eseed(j), li, si, bc) ? 1 : 0;
+		for (int j = l + 1; j <= SM; ++j) s += pair_agrees(li, si, eloc(j), eseed(j), bc) ? 1 : 0;
+		return s;
+	};
 	const int minval = lanes.min_val(score_of);
 	const int mini = low_bit(lanes.ballot([&](int l) { return score_of(l) == minval; }));     // the first entry with the lowest score
 	lanes.sync();
-	if (minval == SM) {
-		// every pair agrees (no score can exceed SM): the new seed takes the last place and the counts stay SM - 1
-		if (lanes.leader()) { b->loczhi[SM - 1] = (int16_t)loc; b->seedno[SM - 1] = (int16_t)seedn; }
-	} else if (minval < SM && mini < SM) {
-		const int ml = b->loczhi[mini], ms = b->seedno[mini];
-		lanes.each([&](int l) {
-			if (l >= SM || l == mini) return;
-			const int g = l < mini ? (pair_agrees(b->loczhi[l], b->seedno[l], ml, ms, bc) ? 1 : 0) : (pair_agrees(ml, ms, b->loczhi[l], b->seedno[l], bc) ? 1 : 0);
-			W.t_score[l] = (int)b->pc[l] - g + W.t_loc[l];          // seed l's count among the SM seeds that stay
-		});
-		lanes.sync();
-		if (lanes.leader()) {
-			for (int i = 0; i < mini; ++i) b->pc[i] = (uint8_t)W.t_score[i];
-			for (int i = mini; i < SM - 1; ++i) { b->loczhi[i] = b->loczhi[i + 1]; b->seedno[i] = b->seedno[i + 1]; b->pc[i] = (uint8_t)W.t_score[i + 1]; }
-			b->loczhi[SM - 1] = (int16_t)loc; b->seedno[SM - 1] = (int16_t)seedn; b->pc[SM - 1] = (uint8_t)(total_new - W.t_loc[mini]);
+	if (lanes.leader()) {
+		if (minval == SM) { b->loczhi[SM - 1] = (int16_t)loc; b->seedno[SM - 1] = (int16_t)seedn; }
+		else if (minval < SM && mini < SM) {
+			for (int i = mini; i < SM - 1; ++i) { b->loczhi[i] = b->loczhi[i + 1]; b->seedno[i] = b->seedno[i + 1]; }
+			b->loczhi[SM - 1] = (int16_t)loc; b->seedno[SM - 1] = (int16_t)seedn;
 			--b->score;
 		}
 	}
@@ -479,7 +450,7 @@ REF_HD void seed_strand_w(const L& lanes, const uint32_t* fwd, uint32_t off, con
 				if ((r >> 1) >= T.nrec) T.nrec = (r >> 1) + 1;
 				if (r & 1) {
 					Bucket* b = T.recs + (r >> 1);
-					insert_loc_w(lanes, b, offs, k + 1, u.bc, W);
+					insert_loc_w(lanes, b, offs, k + 1, u.bc);
 					if (lanes.leader()) {
 						int s_k = b->score;
 						if (blk > 0) { const Bucket* p = table_find(T, blk - 1); if (p) s_k += p->score; }
