@@ -13,6 +13,6 @@ for v in "device" "TEXT=host" "M4=host TEXT=host"; do
   elif [ "$v" = "TEXT=host" ]; then MECAT_B200_TEXT=host $B/mecat2pw -j 1 -d $T/reads.fa -o $T/out.m4 -w $T/w -t 16 2> $T/log.txt
   else MECAT_B200_M4=host MECAT_B200_TEXT=host $B/mecat2pw -j 1 -d $T/reads.fa -o $T/out.m4 -w $T/w -t 16 2> $T/log.txt; fi
   e=$(date +%s.%N)
-  echo "variant [$v] rep $rep: $(echo "$e - $s" | bc) s; $(grep takes $T/log.txt | tr '\n' ' ')" | tee -a gpurun_out/r2_cli_timing.txt
+  echo "variant [$v] rep $rep: $(python -c "print(round($e - $s, 2))") s; $(grep takes $T/log.txt | tr '\n' ' ')" | tee -a gpurun_out/r2_cli_timing.txt
 done
 done
