@@ -272,7 +272,13 @@ typedef struct {
 	int32_t tech;               /* -x, 0 = pacbio; 1 = nanopore: consensus_one_read_can_nanopore (mecat_correction.cpp:453-512:
 	                               error rate 0.20, up to 100 alignments per read, the whole read as the one effective range);
 	                               its defaults are -r 0.4 -a 400 -c 6 -l 2000 (options.cpp:21-29) */
-	int32_t pad_;
+	int32_t input_type;         /* -i.  0 = candidates (`.can` of mecat2pw -j 0): consensus_one_read_can_* -- trial order by score, one
+	                               alignment per partner, mapping-ratio and coverage gates.  1 = overlaps (`.m4` of mecat2pw -j 1 -g 1):
+	                               consensus_one_read_m4_* (mecat_correction.cpp:242-360) -- `ec` is ONE partition of
+	                               partition_m4records in the order it was written (m4_to_candidate of both normalised
+	                               directions, record by record); the library orders it like the reference does (std::sort by sid,
+	                               the 60 / 100 largest overlaps of a read by std::sort) and uses every alignment that succeeds
+	                               (nanopore: that also passes the mapping-ratio test) */
 } mecat_cns_params;
 
 /* CnsResult (src/common/alignment.h): corrected piece [beg, end) of read id; sequence at

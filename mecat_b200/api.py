@@ -35,7 +35,7 @@ K_NUM = len(KERNEL_NAMES)      # MECAT_K_NUM
 
 class CnsParams(C.Structure):
     _fields_ = [("min_mapping_ratio", C.c_double), ("min_align_size", C.c_int32), ("min_cov", C.c_int32),
-                ("min_size", C.c_int64), ("tech", C.c_int32), ("pad_", C.c_int32)]
+                ("min_size", C.c_int64), ("tech", C.c_int32), ("input_type", C.c_int32)]
 
 
 CNS_PIECE_DTYPE = np.dtype([("id", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("seq_offset", "<i8"), ("seq_len", "<i8")])
@@ -414,6 +414,40 @@ def normalise_candidates(can, min_read_size):
     return out
 
 
+def m4_partitions(m4_file, min_mapping_ratio=0.9, min_read_size=5000, batch_size=100000):
+    """The records partition_m4records writes for `mecat2cns -i 1` (src/mecat2cns/overlaps_partition.cpp:345-410): per
+    partition of batch_size reads an EC_DTYPE array, records in file order -- size and mapping-range filters, then for
+    either read as the one to correct m4_to_candidate(normalize_m4record(...)) (src/common/alignment.h:71-103,170-186).
+    m4_file: path or file object of `mecat2pw -j 1 -g 1` lines.  Feed each array to cns_reads(..., input_type=1)."""
+    f = open(m4_file) if isinstance(m4_file, str) else m4_file
+    ratio = min_mapping_ratio - 0.02
+    parts = {}
+    for line in f:
+        t = line.split()
+        if len(t) < 12:
+            continue
+        if len(t) < 14:
+            raise MecatB200Error("no gapped start position is provided (mecat2pw -g 1)")
+        qid, sid = int(t[0]), int(t[1])
+        vscore, qdir, qoff, qend, qsize, sdir, soff, send, ssize, qext, sext = (int(x) for x in t[3:14])
+        if qsize < min_read_size or ssize < min_read_size:
+            continue
+        if not (qend - qoff >= int(qsize * ratio) or send - soff >= int(ssize * ratio)):
+            continue
+        for subject_is_target in (False, True):
+            if subject_is_target:
+                e = [qdir, qid, qext, qsize, qoff, qend, sdir, sid, sext, ssize, soff, send, vscore]
+            else:
+                e = [sdir, sid, sext, ssize, soff, send, qdir, qid, qext, qsize, qoff, qend, vscore]
+            if e[6] == 1:
+                e[6] = 0
+                e[0] = 1 - e[0]
+            parts.setdefault(e[7] // batch_size, []).append(tuple(e))
+    if isinstance(m4_file, str):
+        f.close()
+    return {k: np.array(v, dtype=EC_DTYPE) for k, v in sorted(parts.items())}
+
+
 def read_can(path):
     """`.can` text (qid sid qdir sdir qext sext score qsize ssize) -> EC_DTYPE array."""
     raw = np.loadtxt(path, dtype=np.int64, ndmin=2)
@@ -579,10 +613,10 @@ class Context:
             self.L.mecat_b200_free(self.h, ss)
         return r, q, s
 
-    def cns_reads(self, dvol, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0):
+    def cns_reads(self, dvol, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0, input_type=0):
         """mecat2cns -i 0 on normalised candidates (EC_DTYPE array).  Returns [(id, beg, end, seq bytes), ...]."""
         ec = np.ascontiguousarray(candidates, dtype=EC_DTYPE)
-        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size, tech, 0)
+        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size, tech, input_type)
         pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         self._check(self.L.mecat_b200_cns_reads(self.h, dvol, ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p), C.byref(pieces),
                                                 C.byref(n), C.byref(seqs), C.byref(nb)), "cns_reads")
@@ -593,10 +627,10 @@ class Context:
         return [(int(x["id"]), int(x["beg"]), int(x["end"]), blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])])
                 for x in pc]
 
-    def cns_reads_multi(self, dvols, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0):
+    def cns_reads_multi(self, dvols, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0, input_type=0):
         """cns_reads for a read set that spans several resident volumes (consecutive read ids)."""
         ec = np.ascontiguousarray(candidates, dtype=EC_DTYPE)
-        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size, tech, 0)
+        p = CnsParams(min_mapping_ratio, min_align_size, min_cov, min_size, tech, input_type)
         arr = (C.c_void_p * len(dvols))(*[d.value if hasattr(d, "value") else d for d in dvols])
         pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         self._check(self.L.mecat_b200_cns_reads_multi(self.h, arr, len(dvols), ec.ctypes.data_as(C.c_void_p), len(ec), C.byref(p),

@@ -473,6 +473,28 @@ struct CnsGroup { size_t b, e; };
 static void cns_groups(std::vector<mecat_candidate>& ec, const mecat_cns_params* p, std::vector<CnsGroup>& groups)
 {
 	auto by_sid = [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; };
+	if (p->input_type == 1) {
+		// M4 input: the order IS the reference's std::sort -- of the partition by sid (build_cns_thrd_data_can,
+		// reads_correction_aux.cpp:102; equal keys stay where the algorithm leaves them), then of a read with more overlaps
+		// than fit by overlap size (CompareOverlapByOverlapSize, mecat_correction.cpp:26-34,261-272).  This library is built
+		// without the parallel mode, so std::sort here is the sequential introsort the reference runs with one OpenMP thread.
+		std::sort(ec.begin(), ec.end(), by_sid);
+		const size_t cap = p->tech == 1 ? (size_t)mbcns::MAX_ACCEPT : (size_t)mbcns::MAX_ACCEPT_PACBIO;
+		const size_t nec = ec.size();
+		for (size_t i = 0; i < nec;) {
+			size_t j = i + 1;
+			while (j < nec && ec[j].sid == ec[i].sid) ++j;
+			if ((int64_t)(j - i) >= p->min_cov && !(ec[i].ssize < p->min_size * 0.95)) {
+				if (j - i > cap)
+					std::sort(ec.begin() + (ptrdiff_t)i, ec.begin() + (ptrdiff_t)j, [](const mecat_candidate& a, const mecat_candidate& b) {
+						return std::max(a.qend - a.qoff, a.send - a.soff) > std::max(b.qend - b.qoff, b.send - b.soff);
+					});
+				groups.push_back(CnsGroup{i, std::min(j, i + cap)});
+			}
+			i = j;
+		}
+		return;
+	}
 	if (!std::is_sorted(ec.begin(), ec.end(), by_sid)) std::stable_sort(ec.begin(), ec.end(), by_sid);
 	const size_t nec = ec.size();
 	for (size_t i = 0; i < nec;) {
@@ -494,7 +516,7 @@ static int cns_core(mecat_b200_ctx* c, const DVolume* V, const std::vector<mecat
 	const int id0 = V->start_read_id;
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
-	P.tech = p->tech;
+	P.tech = p->tech; P.input_type = p->input_type;
 	const double err = p->tech == 1 ? 0.20 : 0.15;     // GetAlignment's error rate, mecat_correction.cpp:424,487
 	const size_t TASKS_PER_BATCH = 400000;       // with the column arena (12 GB at ~30 kB per task) this bounds a batch; more units per launch suit the latency-bound stages
 	std::vector<AlignTask> tasks;

@@ -173,8 +173,26 @@ CNS_HD inline void bump_cov(const L& lanes, uint8_t* cov, int b, int e)
 // send, columns, ...} as written by the extension kernels.  Returns the number accepted; acc[k] = task.
 template <class L>
 CNS_HD inline int accept_read(const L& lanes, int t0, int t1, const int32_t* info, const int32_t* t_qid, const int32_t* t_qsize,
-                              int ssize, double ratio, uint8_t* cov, int32_t* acc, int max_accept)
+                              int ssize, double ratio, uint8_t* cov, int32_t* acc, int max_accept, int mode = 0)
 {
+	if (mode != 0) {
+		// M4 input (consensus_one_read_m4_pacbio / _nanopore, mecat_correction.cpp:242-360): the caller has chosen the
+		// read's overlaps; every alignment that succeeded is used -- mode 2 (nanopore): if it also spans enough of a read
+		int added = 0;
+		const int qss = (int)((double)ssize * ratio);
+		for (int t = t0; t < t1 && added < max_accept; ++t) {
+			const int32_t* o = info + 8 * (int64_t)t;
+			if (!o[0]) continue;
+			if (mode == 2) {
+				const int oq = o[2] - o[1], os = o[4] - o[3];
+				const int qqs = (int)((double)t_qsize[t] * ratio);
+				if (!(oq >= qqs || os >= qss)) continue;
+			}
+			if (lanes.leader()) acc[added] = t;
+			++added;
+		}
+		return added;
+	}
 	int used[MAX_ACCEPT];
 	int added = 0, tried = 0;
 	const int qss = (int)((double)ssize * ratio);

@@ -34,7 +34,7 @@
 
 namespace mbcns {
 
-struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; int tech = 0; };
+struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; int tech = 0; int input_type = 0; };
 struct Piece { int64_t id, beg, end; std::string seq; };   // CnsResult, src/common/alignment.h
 
 // kernel slots for the per-stage timers of the backend
@@ -60,11 +60,11 @@ struct BatchIn
 struct AcceptFn
 {
 	const int32_t* first; const int32_t* info; const int32_t* tqid; const int32_t* tqsize; const int32_t* read_size;
-	const int64_t* pos_off; uint8_t* cov; double ratio; int32_t* acc; int32_t* nacc; int max_accept;
+	const int64_t* pos_off; uint8_t* cov; double ratio; int32_t* acc; int32_t* nacc; int max_accept; int mode;
 	template <class L>
 	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
-		const int n = accept_read(lanes, first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT, max_accept);
+		const int n = accept_read(lanes, first[r], first[r + 1], info, tqid, tqsize, read_size[r], ratio, cov + pos_off[r], acc + r * MAX_ACCEPT, max_accept, mode);
 		if (lanes.leader()) nacc[r] = n;
 	}
 };
@@ -402,7 +402,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 	CNS_TRY(be.fill(d_base, 'N', (size_t)POS));
 
 	// C3: which alignments vote
-	CNS_TRY(be.launch_warp(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc, P.tech == 1 ? MAX_ACCEPT : MAX_ACCEPT_PACBIO}, ST_ACCEPT));
+	CNS_TRY(be.launch_warp(R, AcceptFn{d_first, in.d_info, d_tqid, d_tqsize, d_rsize, d_pos, d_cov, ratio, d_acc, d_nacc, P.tech == 1 ? MAX_ACCEPT : MAX_ACCEPT_PACBIO, P.input_type == 1 ? (P.tech == 1 ? 2 : 1) : 0}, ST_ACCEPT));
 	int64_t NA = 0;
 	CNS_TRY(be.scan(d_nacc, d_alnfirst, R, &NA));
 	lap("setup + accept");

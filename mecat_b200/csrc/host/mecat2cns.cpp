@@ -24,6 +24,7 @@
 #include <fstream>
 #include <thread>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "mecat_b200.h"
@@ -136,6 +137,46 @@ bool load_candidates(const char* path, std::vector<mecat_candidate>& out)
 	return true;
 }
 
+// `.m4` lines of mecat2pw -j 1 -g 1 (operator>>(M4Record), src/common/alignment.cpp:34-56) -> the records partition_m4records
+// writes (src/mecat2cns/overlaps_partition.cpp:345-410): size and mapping-range filters, then m4_to_candidate of
+// normalize_m4record for either read as the one to correct (src/common/alignment.h:71-103,170-186), in file order, into
+// the partition of that read (batch_size reads each).  0 = ok, 1 = cannot open, 2 = no extension points in the file.
+int load_m4_partitions(const char* path, double min_cov_ratio, long long batch_size, long long min_read_size,
+                       std::map<long long, std::vector<mecat_candidate>>& parts)
+{
+	FILE* f = fopen(path, "r");
+	if (!f) return 1;
+	char line[1024];
+	while (fgets(line, sizeof line, f)) {
+		long long qid, sid, qoff, qend, qsize, soff, send, ssize, qext = -1, sext = -1;
+		double ident;
+		int vscore, qdir, sdir;
+		const int n = sscanf(line, "%lld %lld %lf %d %d %lld %lld %lld %d %lld %lld %lld %lld %lld", &qid, &sid, &ident, &vscore, &qdir, &qoff, &qend,
+		                     &qsize, &sdir, &soff, &send, &ssize, &qext, &sext);
+		if (n < 12) continue;
+		if (n < 14) { fclose(f); return 2; }
+		if (qsize < min_read_size || ssize < min_read_size) continue;
+		const long long qm = qend - qoff, qs = (long long)((double)qsize * min_cov_ratio), sm = send - soff, ss = (long long)((double)ssize * min_cov_ratio);
+		if (!(qm >= qs || sm >= ss)) continue;            // check_m4record_mapping_range
+		for (int subject_is_target = 0; subject_is_target < 2; ++subject_is_target) {
+			mecat_candidate e;
+			memset(&e, 0, sizeof e);
+			if (subject_is_target) {
+				e.qdir = qdir; e.qid = (int32_t)qid; e.qext = (int32_t)qext; e.qsize = (int32_t)qsize; e.qoff = (int32_t)qoff; e.qend = (int32_t)qend;
+				e.sdir = sdir; e.sid = (int32_t)sid; e.sext = (int32_t)sext; e.ssize = (int32_t)ssize; e.soff = (int32_t)soff; e.send = (int32_t)send;
+			} else {                                      // reverse_m4record
+				e.qdir = sdir; e.qid = (int32_t)sid; e.qext = (int32_t)sext; e.qsize = (int32_t)ssize; e.qoff = (int32_t)soff; e.qend = (int32_t)send;
+				e.sdir = qdir; e.sid = (int32_t)qid; e.sext = (int32_t)qext; e.ssize = (int32_t)qsize; e.soff = (int32_t)qoff; e.send = (int32_t)qend;
+			}
+			e.score = vscore;
+			if (e.sdir == 1) { e.sdir = 0; e.qdir = 1 - e.qdir; }
+			parts[e.sid / batch_size].push_back(e);
+		}
+	}
+	fclose(f);
+	return 0;
+}
+
 // normalise_candidate, overlaps_partition.cpp:141-165
 mecat_candidate normalise(const mecat_candidate& s, bool subject_is_target)
 {
@@ -161,7 +202,6 @@ int main(int argc, char* argv[])
 	const int r = parse_arguments(argc, argv, opt);
 	if (r) { print_usage(argv[0]); return 1; }
 	if (opt.usage) { print_usage(argv[0]); return 0; }
-	if (opt.input_type != 0) { fprintf(stderr, "mecat2cns: only `-i 0` (candidate input) is on the GPU path so far; use the reference binary for `-i 1`.\n"); return 1; }
 	if (mecat_b200_device_count() < 1) { fprintf(stderr, "mecat2cns: no CUDA device found (this build has no CPU path)\n"); return 1; }
 
 	// Creating the CUDA context of device 0 takes about a second; it runs next to the candidate and FASTA loading.
@@ -170,7 +210,15 @@ int main(int argc, char* argv[])
 	std::thread warm([&]() { ctx0_rc = mecat_b200_init(&ctx0, 0, NULL); });
 	struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{warm};
 	std::vector<mecat_candidate> raw, ec;
-	{
+	std::map<long long, std::vector<mecat_candidate>> m4_parts;      // -i 1: the partitions, records in file order
+	if (opt.input_type == 1) {
+		StderrTimer t("partition_m4records");
+		const int rc = load_m4_partitions(opt.overlaps, opt.min_mapping_ratio - 0.02, opt.batch_size, opt.min_size, m4_parts);
+		if (rc == 1) { fprintf(stderr, "cannot open file '%s' for reading\n", opt.overlaps); return 1; }
+		if (rc == 2) { fprintf(stderr, "no gapped start position is provided, please make sure that you have run 'meap_pairwise' with option '-g 1'\n"); return 1; }
+		// one call per partition (the reference orders a partition as a whole); the partitions one after the other in `ec`
+		for (auto& kv : m4_parts) ec.insert(ec.end(), kv.second.begin(), kv.second.end());
+	} else {
 		StderrTimer t("partition_candidates");
 		if (!load_candidates(opt.overlaps, raw)) { fprintf(stderr, "cannot open file '%s' for reading\n", opt.overlaps); return 1; }
 		ec.reserve(raw.size() * 2);
@@ -200,13 +248,15 @@ int main(int argc, char* argv[])
 	const int have = mecat_b200_device_count();
 	if (ngpus < 1) ngpus = 1;
 	if (ngpus > have) ngpus = have;
-	std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
-	const mecat_cns_params P = {opt.min_mapping_ratio, opt.min_align_size, opt.min_cov, opt.min_size, opt.tech, 0};
+	if (opt.input_type == 0) std::stable_sort(ec.begin(), ec.end(), [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
+	const mecat_cns_params P = {opt.min_mapping_ratio, opt.min_align_size, opt.min_cov, opt.min_size, opt.tech, opt.input_type};
 	std::vector<size_t> cut((size_t)ngpus + 1, ec.size());
 	cut[0] = 0;
 	for (int g = 1; g < ngpus; ++g) {
 		size_t k = ec.size() * (size_t)g / (size_t)ngpus;
-		while (k > 0 && k < ec.size() && ec[k].sid == ec[k - 1].sid) ++k;
+		// -i 0: cut at a read boundary; -i 1: at a partition boundary (a partition is ordered as a whole)
+		if (opt.input_type == 0) while (k > 0 && k < ec.size() && ec[k].sid == ec[k - 1].sid) ++k;
+		else while (k > 0 && k < ec.size() && ec[k].sid / opt.batch_size == ec[k - 1].sid / opt.batch_size) ++k;
 		cut[g] = std::max(k, cut[g - 1]);
 	}
 	if (warm.joinable()) warm.join();

@@ -388,20 +388,23 @@ void consensus_one_read(int64_t read_id, int read_size, const mecat_candidate* c
 	std::set<int> used;
 	int added = 0, tried = 0;
 	const int max_added = P.tech == 1 ? 100 : 60;      // mecat_correction.cpp:407 / MAX_CNS_OVLPS at :482
-	for (int i = 0; i < ncand && added < max_added && tried < 200; ++i) {
+	const bool m4 = P.input_type == 1;      // consensus_one_read_m4_*: every overlap handed in, no trial limit, no coverage gate
+	for (int i = 0; i < ncand && added < max_added && (m4 || tried < 200); ++i) {
 		++tried;
 		const mecat_candidate& ec = cand[i];
-		if (used.count(ec.qid)) continue;
+		if (!m4 && used.count(ec.qid)) continue;
 		const mecat_align_result& r = res[i];
 		if (!r.ok) continue;
-		// check_ovlp_mapping_range
+		// check_ovlp_mapping_range (can input; for m4 input only the nanopore variant applies it, mecat_correction.cpp:347)
 		const int oq = r.qend - r.qstart, qqs = (int)(ec.qsize * ratio), os = r.send - r.sstart, qss = (int)(ec.ssize * ratio);
-		if (!(oq >= qqs || os >= qss)) continue;
-		// check_cov_stats: at least 200 positions not yet covered 20 times
-		int full = 0;
-		for (int k = r.sstart; k < r.send; ++k) if (cov[k] >= 20) ++full;
-		if (!(r.send - r.sstart >= full + 200)) continue;
-		for (int k = r.sstart; k < r.send; ++k) ++cov[k];
+		if ((!m4 || P.tech == 1) && !(oq >= qqs || os >= qss)) continue;
+		if (!m4) {
+			// check_cov_stats: at least 200 positions not yet covered 20 times
+			int full = 0;
+			for (int k = r.sstart; k < r.send; ++k) if (cov[k] >= 20) ++full;
+			if (!(r.send - r.sstart >= full + 200)) continue;
+			for (int k = r.sstart; k < r.send; ++k) ++cov[k];
+		}
 		++added;
 		used.insert(ec.qid);
 		normalize_gaps(qstr + r.str_offset, sstr + r.str_offset, r.columns, S.nq, S.nt);
@@ -467,6 +470,25 @@ extern "C" {
 
 void orc_cns_sort_candidates(mecat_candidate* c, int n) { orccns::sort_candidates(c, n); }
 
+// M4 input (-i 1): one partition's records in the order partition_m4records wrote them -> the order the reference works in:
+// std::sort by sid (build_cns_thrd_data_can, reads_correction_aux.cpp:102), then, for a read with more than `cap` overlaps,
+// std::sort by overlap size (CompareOverlapByOverlapSize, mecat_correction.cpp:26-34,261-272; the first `cap` are used).
+// This file is compiled without the parallel mode: std::sort is the sequential introsort the reference's parallel-mode
+// sort falls back to with one OpenMP thread (the fixtures of tests/golden/*.i1.* were made that way).
+void orc_cns_m4_order(mecat_candidate* c, int n, int cap)
+{
+	std::sort(c, c + n, [](const mecat_candidate& a, const mecat_candidate& b) { return a.sid < b.sid; });
+	for (int i = 0; i < n;) {
+		int j = i + 1;
+		while (j < n && c[j].sid == c[i].sid) ++j;
+		if (j - i > cap)
+			std::sort(c + i, c + j, [](const mecat_candidate& a, const mecat_candidate& b) {
+				return std::max(a.qend - a.qoff, a.send - a.soff) > std::max(b.qend - b.qoff, b.send - b.soff);
+			});
+		i = j;
+	}
+}
+
 // One region graph (AlnGraphBoost restatement) on its own: backbone of blen positions, naln gapped alignments
 // (q[i], t[i] of equal length, first column at backbone position start[i]).  Returns the length of the consensus
 // written to out, or -1 when it does not fit cap.
@@ -489,7 +511,7 @@ int orc_cns_consensus(const mecat_candidate* cand, int ncand, const mecat_align_
 	if (!cand || ncand <= 0 || !res || !p || !pieces || !npieces || !seqs || !seq_bytes) return 1;
 	orccns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
-	P.tech = p->tech;
+	P.tech = p->tech; P.input_type = p->input_type;
 	orccns::Scratch scratch;
 	std::vector<orccns::Piece> out;
 	orccns::consensus_one_read(cand[0].sid, cand[0].ssize, cand, ncand, res, qstr, sstr, P, scratch, out);

@@ -10,7 +10,7 @@
 
 namespace orccns {
 
-struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; int tech = 0; };
+struct Params { double min_mapping_ratio; int min_align_size; int min_cov; int64_t min_size; int tech = 0; int input_type = 0; };
 struct Piece { int64_t id, beg, end; std::string seq; };   // CnsResult, src/common/alignment.h
 
 struct Scratch

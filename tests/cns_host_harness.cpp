@@ -100,7 +100,7 @@ int harness_cns_batch(int R, const int32_t* first, const mecat_candidate* cand, 
 	in.d_info = info.data(); in.d_q = qstr; in.d_s = sstr; in.d_outoff = outoff.data();
 	mbcns::Params P;
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
-	P.tech = p->tech;
+	P.tech = p->tech; P.input_type = p->input_type;
 	HostBackend be;
 	if (const char* e = getenv("MECAT_HARNESS_GRAPH_INDEX_BYTES")) be.min_width = atoi(e);      // 2 or 4: wider indices than needed
 	mbcns::PieceVector sink;

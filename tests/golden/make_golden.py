@@ -15,6 +15,7 @@ Cases (reads come from oracle/gen_reads, a seeded deterministic generator):
           which is not built yet; reads and genome are regenerated on demand (sha256 committed)
   x1    : the small / cfg0 / deep / refmap inputs with `-x 1` (nanopore: XdropAligner, min_kmer_dist 400, the nanopore
           consensus variant) -- SURVEY.md section 8(f) item 2
+  i1    : `mecat2cns -i 1` (M4 input) on the sorted small / deep overlap files, one OpenMP thread
   python tests/golden/make_golden.py [case ...]   regenerates only the named cases
 For each: vol0 sha256 (split_raw_dataset), sorted `mecat2pw -j 0` lines, sorted
 `mecat2pw -j 1 -g 1` lines.
@@ -170,6 +171,46 @@ def make_nanopore(meta):
     meta["x1"] = m
 
 
+def make_m4_input(meta):
+    """`mecat2cns -i 1` (M4 input, the reference's default input type): the overlaps of `mecat2pw -j 1 -g 1` as SORTED lines
+    (the order of the lines in the file decides how equal keys fall in the reference's std::sort, so the file is part of the
+    fixture), corrected by the unmodified binary with ONE OpenMP thread -- the parallel-mode sort of the partition
+    (reads_correction_aux.cpp:102) is then the sequential introsort, which is the order this repository reproduces.
+    small: the committed small.m4.gz, relaxed options; deep (~120x): more than 60 overlaps per read, so the 60 largest are chosen."""
+    m = {}
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for name, args in (("small", ["-l", "2000", "-c", "4", "-a", "1000"]), ("deep", ["-l", "2000", "-c", "4", "-a", "1000"])):
+        c = CASES[name]
+        tmp = tempfile.mkdtemp(prefix="golden_i1_")
+        fa = os.path.join(tmp, "reads.fa")
+        gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+        m4 = os.path.join(tmp, "in.m4")
+        if name == "small":
+            with gzip.open(os.path.join(HERE, "small.m4.gz"), "rt") as f, open(m4, "w") as g:
+                g.write(f.read())
+        else:
+            raw = os.path.join(tmp, "raw.m4")
+            subprocess.check_call([os.path.join(REF_DIR, "mecat2pw"), "-j", "1", "-g", "1", "-d", fa, "-o", raw, "-w", os.path.join(tmp, "wrk"), "-t", "8"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            lines = sorted(open(raw).read().splitlines())
+            with open(m4, "w") as g:
+                g.write("\n".join(lines) + "\n")
+            with gzip.open(os.path.join(HERE, "deep.m4.gz"), "wt") as g:
+                g.write("\n".join(lines) + "\n")
+            m["deep_num_m4"] = len(lines)
+        out = os.path.join(tmp, "cns.fa")
+        subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-i", "1", "-t", "1"] + args + [m4, fa, out], env=env,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        lines = open(out).read().splitlines()
+        recs = sorted(zip(lines[0::2], lines[1::2]))
+        with gzip.open(os.path.join(HERE, "%s.i1.cns.fa.gz" % name), "wt") as f:
+            for h, q in recs:
+                f.write(h + "\n" + q + "\n")
+        m["%s_num_cns" % name] = len(recs)
+        shutil.rmtree(tmp)
+    meta["i1"] = m
+
+
 def run_cns_x1(can, fa, dest, tmp):
     out = os.path.join(tmp, "cns_x1.fa")
     subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-x", "1", "-i", "0", "-t", "1", can, fa, out],
@@ -197,7 +238,7 @@ def main():
     for name, c in CASES.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
-        if name == "x1":
+        if name in ("x1", "i1"):
             continue
         tmp = tempfile.mkdtemp(prefix="golden_")
         fa = os.path.join(tmp, "reads.fa")
@@ -242,6 +283,8 @@ def main():
         make_refmap(meta)
     if len(sys.argv) == 1 or "x1" in sys.argv[1:]:
         make_nanopore(meta)
+    if len(sys.argv) == 1 or "i1" in sys.argv[1:]:
+        make_m4_input(meta)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))

@@ -37,12 +37,72 @@ def gold_can(name):
 _aln_cache = {}
 
 
-def oracle_alignments(vol, can, min_aln, min_cov, min_size, keep=None, err=0.15):
+def _align_groups(vol, groups, min_aln, err):
+    """The oracle's GetAlignment of every candidate of every group (candidates already in their final order)."""
+    from mecat_b200.api import ALIGN_RESULT_DTYPE
+    O = util.oracle()
+    codes = {}
+
+    def seq(rid, strand):
+        k = (rid, strand)
+        if k not in codes:
+            codes[k] = np.concatenate([[0], vol.codes(rid, strand), [0]]).astype(np.int8)
+        return codes[k]
+
+    o5 = (C.c_int32 * 8)()
+    first, results = [0], []
+    qblob, sblob = bytearray(), bytearray()
+    for grp in groups:
+        res = np.zeros(len(grp), dtype=ALIGN_RESULT_DTYPE)
+        t = seq(int(grp["sid"][0]), 0)
+        cap = 2 * len(t) + 70000
+        qa, sa = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        for k, e in enumerate(grp):
+            q = seq(int(e["qid"]), int(e["qdir"]))
+            qext = int(e["qsize"]) - 1 - int(e["qext"]) if e["qdir"] else int(e["qext"])
+            ok = O.orc_cns_get_alignment(C.cast(q.ctypes.data + 1, C.c_char_p), qext, len(q) - 2,
+                                         C.cast(t.ctypes.data + 1, C.c_char_p), int(e["sext"]), len(t) - 2, err, min_aln, o5, qa, sa, cap)
+            if ok:
+                res[k] = (1, o5[1], o5[2], o5[3], o5[4], len(qa.value), 0, 0, 0.0, len(qblob))
+                qblob += qa.value + b"\0"
+                sblob += sa.value + b"\0"
+            else:
+                res[k]["str_offset"] = -1
+        results.append(res)
+        first.append(first[-1] + len(grp))
+    return (np.array(first, dtype=np.int32), np.concatenate(groups), np.concatenate(results), bytes(qblob) + b"\0", bytes(sblob) + b"\0")
+
+
+def m4_groups(name, min_cov, min_size, ratio, cap, keep=None):
+    """-i 1: the overlap file of the fixture -> per read the overlaps the reference works on, in its order (partition
+    records in file order, std::sort by sid, the `cap` largest of a read by std::sort: oracle/orc_cns_m4_order)."""
+    import mecat_b200
+    O = util.oracle()
+    with gzip.open(os.path.join(util.GOLDEN, "%s.m4.gz" % name), "rt") as f:
+        parts = mecat_b200.m4_partitions(f, ratio, min_size)
+    assert list(parts) == [0]
+    ec = np.ascontiguousarray(parts[0])
+    O.orc_cns_m4_order(ec.ctypes.data_as(C.c_void_p), len(ec), cap)
+    groups = []
+    i = 0
+    while i < len(ec):
+        j = i + 1
+        while j < len(ec) and ec["sid"][j] == ec["sid"][i]:
+            j += 1
+        if j - i >= min_cov and not ec["ssize"][i] < min_size * 0.95 and (keep is None or keep(int(ec["sid"][i]))):
+            groups.append(np.ascontiguousarray(ec[i:min(j, i + cap)]))
+        i = j
+    return groups
+
+
+def oracle_alignments(vol, can, min_aln, min_cov, min_size, keep=None, err=0.15, groups=None):
     """Per read to correct: candidates in trial order + the oracle's GetAlignment of each.  Returns
     (first[R+1], candidates[T], results[T], qblob, sblob).  keep: optional predicate on the read id."""
-    key = (id(vol), min_aln, min_cov, min_size, keep, err)
+    key = (id(vol), min_aln, min_cov, min_size, keep, err, None if groups is None else id(groups))
     if key in _aln_cache:
         return _aln_cache[key]
+    if groups is not None:
+        return _aln_cache.setdefault(key, _align_groups(vol, groups, min_aln, err))
     import mecat_b200
     from mecat_b200.api import ALIGN_RESULT_DTYPE
     O = util.oracle()
@@ -108,11 +168,11 @@ def _pieces(free, pieces, n, seqs, nb):
     return out
 
 
-def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None, tech=0):
+def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None, tech=0, groups=None):
     from mecat_b200.api import CnsParams
     O = util.oracle()
-    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep, 0.20 if tech else 0.15)
-    p = CnsParams(ratio, min_aln, min_cov, min_size, tech, 0)
+    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep, 0.20 if tech else 0.15, groups)
+    p = CnsParams(ratio, min_aln, min_cov, min_size, tech, 0 if groups is None else 1)
     out = []
     for r in range(len(first) - 1):
         a, b = int(first[r]), int(first[r + 1])
@@ -125,11 +185,11 @@ def correct_with_oracle(vol, can, ratio, min_aln, min_cov, min_size, keep=None, 
     return sorted(out)
 
 
-def correct_with_kernel_bodies(vol, can, ratio, min_aln, min_cov, min_size, keep=None, tech=0):
+def correct_with_kernel_bodies(vol, can, ratio, min_aln, min_cov, min_size, keep=None, tech=0, groups=None):
     from mecat_b200.api import CnsParams
     H = util.cns_harness()
-    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep, 0.20 if tech else 0.15)
-    p = CnsParams(ratio, min_aln, min_cov, min_size, tech, 0)
+    first, cand, res, qblob, sblob = oracle_alignments(vol, can, min_aln, min_cov, min_size, keep, 0.20 if tech else 0.15, groups)
+    p = CnsParams(ratio, min_aln, min_cov, min_size, tech, 0 if groups is None else 1)
     pieces, n, seqs, nb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
     err = C.create_string_buffer(256)
     rc = H.harness_cns_batch(len(first) - 1, first.ctypes.data_as(C.c_void_p), cand.ctypes.data_as(C.c_void_p),
@@ -233,6 +293,26 @@ def test_nanopore_consensus_deep_coverage(deep_vol):
     assert len(want) >= 40
     compare(correct_with_oracle(deep_vol, gold_can("deep"), *NANOPORE, keep=_every_sixth, tech=1), want)
     compare(correct_with_kernel_bodies(deep_vol, gold_can("deep"), *NANOPORE, keep=_every_sixth, tech=1), want)
+
+
+# ---------------------------------------------------------------- M4 input (-i 1)
+def test_m4_input_consensus_matches_reference(small_vol, deep_vol):
+    """consensus_one_read_m4_pacbio (mecat_correction.cpp:242-300): the overlaps of `mecat2pw -j 1 -g 1` as input; a
+    partition is ordered by std::sort on sid, a read with more than 60 overlaps keeps the 60 largest (std::sort again), every
+    alignment that succeeds is used.  Goldens: the unmodified `mecat2cns -i 1` with one OpenMP thread (its parallel-mode sort
+    is then the sequential introsort; tests/golden/make_golden.py i1)."""
+    ratio, min_aln, min_cov, min_size = PARAMS["cns_relaxed"]
+    g = m4_groups("small", min_cov, min_size, ratio, 60)
+    want = gold_fasta("small.i1", "cns")
+    assert len(want) == GOLD["i1"]["small_num_cns"]
+    compare(correct_with_oracle(small_vol, None, ratio, min_aln, min_cov, min_size, groups=g), want)
+    compare(correct_with_kernel_bodies(small_vol, None, ratio, min_aln, min_cov, min_size, groups=g), want)
+    g = m4_groups("deep", min_cov, min_size, ratio, 60, keep=_every_sixth)
+    assert max(len(x) for x in g) == 60
+    want = [(h, s) for h, s in gold_fasta("deep.i1", "cns") if _every_sixth(int(h[1:].split("_")[0]))]
+    assert len(want) >= 40
+    compare(correct_with_oracle(deep_vol, None, ratio, min_aln, min_cov, min_size, keep=_every_sixth, groups=g), want)
+    compare(correct_with_kernel_bodies(deep_vol, None, ratio, min_aln, min_cov, min_size, keep=_every_sixth, groups=g), want)
 
 
 def test_fused_normalise_vote_kernel_body_matches_literal_restatement():

@@ -162,3 +162,41 @@ def test_device_packing_equals_host_packing(gpu_ctx, small_vol, tmp_path):
         gpu_ctx.release_index(i1); gpu_ctx.release_index(i2); gpu_ctx.release_volume(d2)
     finally:
         gpu_ctx.release_volume(d)
+
+
+# ---------------------------------------------------------------- mecat2cns -i 1 (M4 input)
+def _gold_fasta(name, tag):
+    with gzip.open(os.path.join(util.GOLDEN, "%s.%s.fa.gz" % (name, tag)), "rt") as f:
+        lines = f.read().splitlines()
+    return sorted(zip(lines[0::2], lines[1::2]))
+
+
+def test_m4_input_consensus_matches_reference(gpu_ctx, small_vol, deep_vol, tmp_path):
+    """mecat2cns -i 1: the library orders a partition like the reference (std::sort by sid, the 60 largest overlaps of a
+    read by std::sort) and uses every alignment that succeeds (consensus_one_read_m4_pacbio, mecat_correction.cpp:242-300);
+    goldens of the unmodified binary (one OpenMP thread) on the sorted overlap files of the small and the ~120x fixture,
+    through the C ABI and through the command line."""
+    import subprocess
+    import mecat_b200
+    for name, vol in (("small", small_vol), ("deep", deep_vol)):
+        with gzip.open(os.path.join(util.GOLDEN, "%s.m4.gz" % name), "rt") as f:
+            parts = mecat_b200.m4_partitions(f, 0.9, 2000)
+        assert list(parts) == [0]
+        d = gpu_ctx.upload(host_volume(vol))
+        pieces = gpu_ctx.cns_reads(d, parts[0], 0.9, 1000, 4, 2000, input_type=1)
+        gpu_ctx.release_volume(d)
+        got = sorted((">%d_%d_%d_%d" % (i, b, e, len(s)), s.decode()) for i, b, e, s in pieces)
+        want = _gold_fasta(name + ".i1", "cns")
+        assert len(got) == len(want) == GOLD["i1"][name + "_num_cns"]
+        bad = [g[0] for g, w in zip(got, want) if g != w]
+        assert not bad, bad[:5]
+    reads, m4, out = str(tmp_path / "small.fa"), str(tmp_path / "small.m4"), str(tmp_path / "cns.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f, open(reads, "wb") as g:
+        g.write(f.read())
+    with gzip.open(os.path.join(util.GOLDEN, "small.m4.gz"), "rb") as f, open(m4, "wb") as g:
+        g.write(f.read())
+    p = subprocess.run([os.path.join(util.ROOT, "mecat_b200", "bin", "mecat2cns"), "-i", "1", "-t", "4", "-l", "2000", "-c", "4", "-a", "1000", m4, reads, out],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = open(out).read().splitlines()
+    assert sorted(zip(lines[0::2], lines[1::2])) == _gold_fasta("small.i1", "cns")

@@ -295,6 +295,7 @@ def oracle():
     L.orc_pw_tile.argtypes = [VP, VP, PP, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_free.argtypes = [C.c_void_p]
     L.orc_cns_sort_candidates.argtypes = [C.c_void_p, C.c_int]
+    L.orc_cns_m4_order.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_ref_map.restype = C.c_int
     L.orc_ref_map.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_ref_map_x.restype = C.c_int
