@@ -569,8 +569,8 @@ class Context:
         n = len(src)
         pac = np.zeros((num_bases + 3) // 4, dtype=np.uint8) if want_pac else None
         d = C.c_void_p()
-        buf = (C.c_char * len(text)).from_buffer_copy(text) if len(text) else None
-        self._check(self.L.mecat_b200_volume_from_text(self.h, C.cast(buf, C.c_void_p) if buf is not None else None, len(text),
+        # (a bytes object is handed over as a pointer to its buffer: no copy of the letters on the Python side)
+        self._check(self.L.mecat_b200_volume_from_text(self.h, text if len(text) else None, len(text),
                                                        src.ctypes.data_as(C.c_void_p), osz.ctypes.data_as(C.c_void_p), n, num_bases, start_read_id,
                                                        pac.ctypes.data_as(C.c_void_p) if want_pac else None, C.byref(d)), "volume_from_text")
         return d, pac
