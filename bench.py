@@ -553,6 +553,9 @@ def run_program(args):
         "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": 1000.0 * wall, "steps": n,
                 "h2d_bytes_per_step": 0 if ref else None, "d2h_bytes_per_step": 0 if ref else None,
                 "what": "whole command line, process start to exit (%d bytes of input files read, text output written)" % in_bytes},
+        "runs": {"wall_s": [round(x, 3) for x in walls], "device_phase_s": [None if x is None else round(x, 3) for x in phases],
+                 "median_wall_s": round(statistics.median(walls), 3),
+                 "note": "value / e2e are means over the timed runs; process start-up (CUDA context) makes single command-line runs on a shared box vary by seconds"},
         "gpu_launches": 0 if ref else None, "kernel_ms_last_run": kernel,
         "cpu_baseline": {"value": e2e_value if ref else None, "unit": unit, "cores": cores, "kind": "reference",
                          "sample": ("unmodified binary on the first %d reads / templates" % units) if ref else "run bench.py --workload %s --impl reference" % args.workload},
