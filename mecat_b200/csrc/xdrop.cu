@@ -39,7 +39,7 @@ k_xdrop(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 	S.row_first = (int32_t*)p; p += 4 * (size_t)ROWS;
 	S.row_word = (int32_t*)p;
 	extern __shared__ RingCell ring_smem[];           // RING x blockDim entries: entry i of thread t at [i * blockDim + t]
-	S.ring = ring_smem + threadIdx.x; S.ring_stride = (int)blockDim.x;
+	S.ring = ring_smem + threadIdx.x; S.ring_stride = XD_THREADS;      // (= blockDim.x; a constant folds into the addressing)
 	// A warp takes 32 chains at a time from a list ordered by expected length (k_xd_class / k_xd_place), so that its lanes
 	// start together, walk blocks of the same shape in step and finish at about the same time: a lane that asked for its
 	// next chain on its own would never meet the others again (each lane a divergent path of its own, 1/32 of the warp).

@@ -62,7 +62,7 @@ struct Half           // what one chain produced
 	int32_t overflow;  // the column slot was too small (cannot happen with slots sized by align_task_columns)
 };
 
-struct RingCell { int16_t best, gap; };      // a score-row entry in shared memory; -32768 stands for NEG
+struct RingCell { int16_t best, gap; };      // a score-row entry in shared memory
 
 struct Scratch        // private to one thread
 {
@@ -76,8 +76,12 @@ struct Scratch        // private to one thread
 
 // The score row of the X-drop programme only lives between the first cell still inside the drop-off and the sentinel
 // behind the last one: ~60 cells on related sequences, a few hundred on unrelated ones (band statistics in DESIGN.md).
-// RingRow keeps that window in shared memory (cell b at entry b mod RING, 16-bit scores: a stored value is a real score
-// within [-40, 720] or exactly NEG); a block whose window would not fit is redone with the row in global memory.
+// RingRow keeps that window in shared memory (cell b at entry b mod RING, 16-bit scores); a block whose window would not
+// fit is redone with the row in global memory.  "Minus infinity" is a property of the row type: the reference's -10^8 for
+// the 32-bit row, -16 384 for the 16-bit one.  A value derived from it is the constant plus or minus a few (it is never
+// stored: what a cell stores is a real score -- within [-40, 720] -- or the constant itself), real scores never come near
+// either constant, and every comparison of the programme is between two real values, a real value and such a derived one,
+// or two derived ones at the same small offsets -- so both constants give the same decisions.
 constexpr int RING = 128;
 struct GlobalRow
 {
@@ -86,42 +90,50 @@ struct GlobalRow
 	XD_HD void put(int b, Cell c) const { p[b] = c; }
 	XD_HD void put_best(int b, int v) const { p[b].best = v; }
 	XD_HD bool room(int, int) const { return true; }
+	XD_HD static int neg() { return NEG; }
 };
 struct RingRow
 {
 	RingCell* p; int stride;
-	XD_HD static int16_t enc(int v) { return v == NEG ? (int16_t)-32768 : (int16_t)v; }
-	XD_HD static int dec(int16_t v) { return v == (int16_t)-32768 ? NEG : (int)v; }
-	XD_HD Cell get(int b) const { const RingCell r = p[(b & (RING - 1)) * stride]; Cell c; c.best = dec(r.best); c.gap = dec(r.gap); return c; }
-	XD_HD void put(int b, Cell c) const { RingCell r; r.best = enc(c.best); r.gap = enc(c.gap); p[(b & (RING - 1)) * stride] = r; }
-	XD_HD void put_best(int b, int v) const { p[(b & (RING - 1)) * stride].best = enc(v); }
+	XD_HD Cell get(int b) const { const RingCell r = p[(b & (RING - 1)) * stride]; Cell c; c.best = r.best; c.gap = r.gap; return c; }
+	XD_HD void put(int b, Cell c) const { RingCell r; r.best = (int16_t)c.best; r.gap = (int16_t)c.gap; p[(b & (RING - 1)) * stride] = r; }
+	XD_HD void put_best(int b, int v) const { p[(b & (RING - 1)) * stride].best = (int16_t)v; }
+	XD_HD static int neg() { return -16384; }
 	XD_HD bool room(int first_b, int b) const { return b - first_b < RING; }      // may cell b be written while first_b is live?
 };
 constexpr size_t SCRATCH_BYTES = sizeof(Cell) * SC_CELLS + 4 * (size_t)TB_WORDS + 8 * (size_t)ROWS;
 
-struct RowWriter
+struct RowWriter      // 4 bits per cell into the trace-back words of a row; `flush` once per round of up to 4 cells
 {
-	uint32_t* tb; int w0, n; uint32_t acc; int bad;
-	XD_HD void begin(uint32_t* tb_, int w0_) { tb = tb_; w0 = w0_; n = 0; acc = 0; }
-	XD_HD void put(uint32_t nib)
+	uint32_t* tb; int w0, n, held; unsigned long long acc; int bad;
+	XD_HD void begin(uint32_t* tb_, int w0_) { tb = tb_; w0 = w0_; n = 0; held = 0; acc = 0; }
+	XD_HD void put(uint32_t nib) { acc |= (unsigned long long)nib << (held << 2); ++held; }      // at most 11 held between flushes
+	XD_HD void flush()
 	{
-		acc |= nib << ((n & 7) << 2);
-		++n;
-		if ((n & 7) == 0) {
-			const int w = w0 + (n >> 3) - 1;
-			if (w < TB_WORDS) tb[w] = acc; else bad = 1;
-			acc = 0;
+		if (held >= 8) {
+			const int w = w0 + (n >> 3);
+			if (w < TB_WORDS) tb[w] = (uint32_t)acc; else bad = 1;
+			acc >>= 32; held -= 8; n += 8;
 		}
 	}
 	XD_HD int end()      // words used by the row
 	{
-		if (n & 7) {
+		flush();
+		if (held) {
 			const int w = w0 + (n >> 3);
-			if (w < TB_WORDS) tb[w] = acc; else bad = 1;
+			if (w < TB_WORDS) tb[w] = (uint32_t)acc; else bad = 1;
 		}
-		return (n + 7) >> 3;
+		return (n + held + 7) >> 3;
 	}
 };
+
+// 16 bases starting at base i of the walk, base i in the low bits
+XD_HD uint32_t bases16(const Seq& s, int i)
+{
+	const uint32_t p = s.g0 + (uint32_t)i, w = p >> 4, sh = (p & 15u) << 1;
+	const unsigned long long x = ((unsigned long long)(s.arr[w + 1] ^ s.comp) << 32) | (s.arr[w] ^ s.comp);
+	return (uint32_t)(x >> sh);
+}
 
 // xdrop_align without its trace-back walk (xdrop_gapalign.cpp:10-158): fills the trace-back of the block, returns the
 // end cell of the best path.  A = query block (M bases from q0), B = subject block (N bases from t0).
@@ -133,6 +145,7 @@ XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, in
 	if (M <= 0 || N <= 0) return true;
 	const int oe = GAP_OPEN + GAP_EXTEND;
 	const int xd = X_DROPOFF < oe ? oe : X_DROPOFF;
+	const int neg = Row::neg();
 	RowWriter W; W.bad = 0;
 	int next_word = 0;
 	int score = -oe, i;
@@ -145,6 +158,7 @@ XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, in
 		{ Cell ci; ci.best = score; ci.gap = score - oe; sc.put(i, ci); }
 		score -= GAP_EXTEND;
 		W.put(OP_GAP_A);
+		W.flush();
 	}
 	next_word += W.end();
 	int b_size = i, best_score = 0, first_b = 0;
@@ -152,25 +166,25 @@ XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, in
 		const int ac = base_at(Q, q0 + a - 1);
 		S.row_first[a] = first_b; S.row_word[a] = next_word;
 		W.begin(S.tb, next_word);
-		score = NEG;
-		int gap_row = NEG, last_b = first_b, b;
+		score = neg;
+		int gap_row = neg, last_b = first_b, b;
 		// four cells per round: their score-row entries and subject bases are loaded together (independent loads in
 		// flight instead of one dependent load per cell), then the cells are finished one after the other as before
 		for (b = first_b; b < b_size;) {
 			const int nb = b_size - b < 4 ? b_size - b : 4;
 			Cell pre[4];
-			int pbc[4];
+			const uint32_t tb4 = bases16(T, t0 + b);          // the subject bases of the round (and 12 more) in one double-word fetch
 #if defined(__CUDA_ARCH__)
 			#pragma unroll
 #endif
 			for (int j = 0; j < 4; ++j)
-				if (j < nb) { pre[j] = sc.get(b + j); pbc[j] = base_at(T, t0 + b + j); }
+				if (j < nb) pre[j] = sc.get(b + j);
 #if defined(__CUDA_ARCH__)
 			#pragma unroll
 #endif
 			for (int j = 0; j < 4; ++j) {
 				if (j >= nb) break;
-				const int bc = pbc[j];
+				const int bc = (int)((tb4 >> (2 * j)) & 3u);
 				const Cell c = pre[j];
 				int gap_col = c.gap;
 				const int next = c.best + (ac == bc ? REWARD : PENALTY);
@@ -179,7 +193,7 @@ XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, in
 				if (score < gap_row) { script = OP_GAP_A; score = gap_row; }
 				if (best_score - score > xd) {
 					if (first_b == b) ++first_b;
-					else sc.put_best(b, NEG);
+					else sc.put_best(b, neg);
 				} else {
 					last_b = b;
 					if (score > best_score) { best_score = score; ae = a; be = b; }
@@ -197,6 +211,7 @@ XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, in
 				W.put(script);
 				++b;
 			}
+			W.flush();
 		}
 #if defined(XD_STATS)
 		{ const int w = b_size - S.row_first[a]; ++g_rows; g_cells += w; if (w > g_maxw) g_maxw = w; if (w > g_blockmax) g_blockmax = w; }
@@ -210,13 +225,14 @@ XD_HD bool block_dp(const Row& sc, const Seq& Q, int q0, int M, const Seq& T, in
 				sc.put(b_size, ce);
 				gap_row -= GAP_EXTEND;
 				W.put(OP_GAP_A);
+				W.flush();
 				++b_size;
 			}
 		}
 		next_word += W.end();
 		if (b_size < N) {
 			if (!sc.room(first_b, b_size)) return false;
-			Cell cs; cs.best = NEG; cs.gap = NEG;
+			Cell cs; cs.best = neg; cs.gap = neg;
 			sc.put(b_size, cs);
 			++b_size;
 		}
