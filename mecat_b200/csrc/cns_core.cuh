@@ -47,6 +47,17 @@ CNS_HD inline void vote_add(uint32_t* p, uint32_t v)
 #endif
 }
 
+CNS_HD inline uint32_t fetch_add(uint32_t* p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(p, v);
+#else
+	const uint32_t old = *p;
+	*p += v;
+	return old;
+#endif
+}
+
 // identify_one_consensus_item, mecat_correction.cpp:15-24 (int compared with a double product)
 CNS_HD inline uint8_t classify(uint32_t w)
 {

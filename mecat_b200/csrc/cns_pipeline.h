@@ -86,13 +86,32 @@ struct FlattenFn      // accepted alignment A = aln_first[r] + k; capacities of 
 	}
 };
 
+// Launch order of the one-thread-per-alignment stage: alignments of about the same length next to each other (classes of
+// 512 columns, longest first), so that the 32 threads of a warp finish together -- in read order a warp waits for the
+// longest of 32 alignments between 2 and 15 kb.  OrderCountFn histograms the classes, the host turns the 64 counts into
+// first places, OrderPlaceFn hands every alignment its place.  (Any order gives the same result: the units are independent.)
+constexpr int ORDER_CLASSES = 64;
+CNS_HD inline int order_class(int cap_norm) { const int c = cap_norm >> 10; return c < ORDER_CLASSES ? c : ORDER_CLASSES - 1; }
+struct OrderCountFn
+{
+	const int32_t* cap_norm; uint32_t* hist;
+	CNS_HD void operator()(int64_t A) const { fetch_add(hist + order_class(cap_norm[A]), 1u); }
+};
+struct OrderPlaceFn
+{
+	const int32_t* cap_norm; uint32_t* cursor; int32_t* order;
+	CNS_HD void operator()(int64_t A) const { order[fetch_add(cursor + order_class(cap_norm[A]), 1u)] = (int32_t)A; }
+};
+
 struct NormVoteFn
 {
+	const int32_t* order;
 	const int32_t* info; const char* q; const char* s; const unsigned long long* outoff;
 	const int32_t* aln_task; const int32_t* aln_read; const int64_t* norm_off; const int64_t* col_off; const int64_t* pos_off;
 	char* nq; char* nt; int32_t* colidx; uint32_t* votes; char* base; KeptAln* kept;
-	CNS_HD void operator()(int64_t A) const
+	CNS_HD void operator()(int64_t i) const
 	{
+		const int64_t A = order[i];
 		const int t = aln_task[A];
 		const int32_t* o = info + 8 * (int64_t)t;
 		char* a = nq + norm_off[A];
@@ -422,8 +441,20 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 	CNS_ALLOC(d_nt, char, NORM);
 	CNS_ALLOC(d_colidx, int32_t, COL);
 
-	// C4 + C5: normalise, vote, index the columns
-	CNS_TRY(be.launch(NA, NormVoteFn{in.d_info, in.d_q, in.d_s, in.d_outoff, d_alntask, d_alnread, d_normoff, d_coloff, d_pos,
+	// C4 + C5: normalise, vote, index the columns -- launched in order of length
+	CNS_ALLOC(d_order, int32_t, NA);
+	CNS_ALLOC(d_ohist, uint32_t, ORDER_CLASSES);
+	CNS_TRY(be.fill(d_ohist, 0, sizeof(uint32_t) * ORDER_CLASSES));
+	CNS_TRY(be.launch(NA, OrderCountFn{d_capnorm, d_ohist}, ST_NORMVOTE));
+	std::vector<uint32_t> h_ohist((size_t)ORDER_CLASSES);          // lives to the end of the batch: the upload may be asynchronous
+	CNS_TRY(be.download(h_ohist.data(), d_ohist, (size_t)ORDER_CLASSES));
+	{
+		uint32_t at = 0;
+		for (int c = ORDER_CLASSES - 1; c >= 0; --c) { const uint32_t n = h_ohist[(size_t)c]; h_ohist[(size_t)c] = at; at += n; }
+	}
+	CNS_TRY(be.upload(d_ohist, h_ohist.data(), (size_t)ORDER_CLASSES));
+	CNS_TRY(be.launch(NA, OrderPlaceFn{d_capnorm, d_ohist, d_order}, ST_NORMVOTE));
+	CNS_TRY(be.launch(NA, NormVoteFn{d_order, in.d_info, in.d_q, in.d_s, in.d_outoff, d_alntask, d_alnread, d_normoff, d_coloff, d_pos,
 	                                 d_nq, d_nt, d_colidx, d_votes, d_base, d_kept}, ST_NORMVOTE));
 
 	lap("flatten + norm/vote launch");
