@@ -33,13 +33,19 @@ struct WarpLanes          // the lanes interface of cns_core.cuh on a real warp
 		m1 = __ballot_sync(0xffffffffu, v & 2);
 	}
 	__device__ bool leader() const { return (threadIdx.x & 31u) == 0; }
+	__device__ void sync() const { __syncwarp(); }
+	__device__ void* scratch() const { return buf; }         // mbcns::LANES_SCRATCH bytes of shared memory private to the warp
+	void* buf;
 };
 
 template <class F>
 __global__ void __launch_bounds__(128) k_cns_warp(const F f, const int64_t n)
 {
+	__shared__ uint64_t scratch[4][mbcns::LANES_SCRATCH / 8];      // 4 warps per CTA (launch_warp)
 	const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (i < n) f(i, WarpLanes());
+	WarpLanes lanes;
+	lanes.buf = scratch[threadIdx.x >> 5];
+	if (i < n) f(i, lanes);
 }
 
 // The region graphs of one wave, a thread per region.  A graph is pointer chasing over a few hundred bytes of nodes

@@ -101,7 +101,11 @@ struct EmuLanes
 		for (int l = 0; l < count; ++l) { const int v = f(l); if (v & 1) m0 |= 1u << l; if (v & 2) m1 |= 1u << l; }
 	}
 	bool leader() const { return true; }
+	void sync() const {}
+	void* scratch() const { return (void*)buf; }      // LANES_SCRATCH bytes private to the "warp"
+	mutable uint64_t buf[256];
 };
+constexpr int LANES_SCRATCH = 2048;
 
 CNS_HD inline int popcount32(uint32_t x)
 {

@@ -86,32 +86,13 @@ struct FlattenFn      // accepted alignment A = aln_first[r] + k; capacities of 
 	}
 };
 
-// Launch order of the one-thread-per-alignment stage: alignments of about the same length next to each other (classes of
-// 512 columns, longest first), so that the 32 threads of a warp finish together -- in read order a warp waits for the
-// longest of 32 alignments between 2 and 15 kb.  OrderCountFn histograms the classes, the host turns the 64 counts into
-// first places, OrderPlaceFn hands every alignment its place.  (Any order gives the same result: the units are independent.)
-constexpr int ORDER_CLASSES = 64;
-CNS_HD inline int order_class(int cap_norm) { const int c = cap_norm >> 10; return c < ORDER_CLASSES ? c : ORDER_CLASSES - 1; }
-struct OrderCountFn
-{
-	const int32_t* cap_norm; uint32_t* hist;
-	CNS_HD void operator()(int64_t A) const { fetch_add(hist + order_class(cap_norm[A]), 1u); }
-};
-struct OrderPlaceFn
-{
-	const int32_t* cap_norm; uint32_t* cursor; int32_t* order;
-	CNS_HD void operator()(int64_t A) const { order[fetch_add(cursor + order_class(cap_norm[A]), 1u)] = (int32_t)A; }
-};
-
 struct NormVoteFn
 {
-	const int32_t* order;
 	const int32_t* info; const char* q; const char* s; const unsigned long long* outoff;
 	const int32_t* aln_task; const int32_t* aln_read; const int64_t* norm_off; const int64_t* col_off; const int64_t* pos_off;
 	char* nq; char* nt; int32_t* colidx; uint32_t* votes; char* base; KeptAln* kept;
-	CNS_HD void operator()(int64_t i) const
+	CNS_HD void operator()(int64_t A) const
 	{
-		const int64_t A = order[i];
 		const int t = aln_task[A];
 		const int32_t* o = info + 8 * (int64_t)t;
 		char* a = nq + norm_off[A];
@@ -133,12 +114,19 @@ struct SegmentFn
 	template <class L>
 	CNS_HD void operator()(int64_t r, const L& lanes) const      // a warp per read
 	{
-		Range m[MAX_ACCEPT], e[MAX_ACCEPT];
+		// the ranges live in the warp's scratch (shared memory on the device), not in 32 private copies: 1.6 KB of stack per
+		// thread made the driver re-size its local-memory pool at the first launch of this kernel (0.5-0.7 s, now and then)
+		Range* m = (Range*)lanes.scratch();
+		Range* e = m + MAX_ACCEPT;
+		int* pne = (int*)(e + MAX_ACCEPT);
 		const int n = nacc[r];
-		for (int k = 0; k < n; ++k) { m[k].start = kept[aln_first[r] + k].soff; m[k].end = kept[aln_first[r] + k].send; }
-		int ne;
-		if (whole_read) { e[0].start = 0; e[0].end = read_size[r]; ne = 1; }      // nanopore: mecat_correction.cpp:508-509
-		else ne = effective_ranges(m, n, e, read_size[r], size95);
+		if (lanes.leader()) {
+			for (int k = 0; k < n; ++k) { m[k].start = kept[aln_first[r] + k].soff; m[k].end = kept[aln_first[r] + k].send; }
+			if (whole_read) { e[0].start = 0; e[0].end = read_size[r]; *pne = 1; }      // nanopore: mecat_correction.cpp:508-509
+			else *pne = effective_ranges(m, n, e, read_size[r], size95);
+		}
+		lanes.sync();
+		const int ne = *pne;
 		const int cap = (int)(seg_slot[r + 1] - seg_slot[r]);
 		const int ns = find_segments(lanes, e, ne, votes + pos_off[r], min_cov, size95, segs + 2 * seg_slot[r], cap);
 		if (lanes.leader()) nseg[r] = ns <= cap ? ns : -1;       // -1: capacity formula violated (reported by the host as an error)
@@ -441,20 +429,10 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 	CNS_ALLOC(d_nt, char, NORM);
 	CNS_ALLOC(d_colidx, int32_t, COL);
 
-	// C4 + C5: normalise, vote, index the columns -- launched in order of length
-	CNS_ALLOC(d_order, int32_t, NA);
-	CNS_ALLOC(d_ohist, uint32_t, ORDER_CLASSES);
-	CNS_TRY(be.fill(d_ohist, 0, sizeof(uint32_t) * ORDER_CLASSES));
-	CNS_TRY(be.launch(NA, OrderCountFn{d_capnorm, d_ohist}, ST_NORMVOTE));
-	std::vector<uint32_t> h_ohist((size_t)ORDER_CLASSES);          // lives to the end of the batch: the upload may be asynchronous
-	CNS_TRY(be.download(h_ohist.data(), d_ohist, (size_t)ORDER_CLASSES));
-	{
-		uint32_t at = 0;
-		for (int c = ORDER_CLASSES - 1; c >= 0; --c) { const uint32_t n = h_ohist[(size_t)c]; h_ohist[(size_t)c] = at; at += n; }
-	}
-	CNS_TRY(be.upload(d_ohist, h_ohist.data(), (size_t)ORDER_CLASSES));
-	CNS_TRY(be.launch(NA, OrderPlaceFn{d_capnorm, d_ohist, d_order}, ST_NORMVOTE));
-	CNS_TRY(be.launch(NA, NormVoteFn{d_order, in.d_info, in.d_q, in.d_s, in.d_outoff, d_alntask, d_alnread, d_normoff, d_coloff, d_pos,
+	// C4 + C5: normalise, vote, index the columns.  (In read order: the 32 alignments of a warp then belong to one or two
+	// templates and share their vote / base lines.  Launching them in order of length instead -- so that a warp's threads
+	// finish together -- was measured at 593 ms against 221 ms.)
+	CNS_TRY(be.launch(NA, NormVoteFn{in.d_info, in.d_q, in.d_s, in.d_outoff, d_alntask, d_alnread, d_normoff, d_coloff, d_pos,
 	                                 d_nq, d_nt, d_colidx, d_votes, d_base, d_kept}, ST_NORMVOTE));
 
 	lap("flatten + norm/vote launch");
