@@ -124,16 +124,41 @@ struct StderrTimer
 // `.can` lines: qid sid qdir sdir qext sext score qsize ssize (src/common/alignment.cpp:9-16)
 bool load_candidates(const char* path, std::vector<mecat_candidate>& out)
 {
-	FILE* f = fopen(path, "r");
+	FILE* f = fopen(path, "rb");
 	if (!f) return false;
-	char line[512];
-	while (fgets(line, sizeof line, f)) {
-		mecat_candidate e;
-		memset(&e, 0, sizeof e);
-		if (sscanf(line, "%d %d %d %d %d %d %d %d %d", &e.qid, &e.sid, &e.qdir, &e.sdir, &e.qext, &e.sext, &e.score, &e.qsize, &e.ssize) == 9)
-			out.push_back(e);
+	// the whole file at once, then nine decimal integers per line (a million lines through sscanf took 0.4 s)
+	std::string buf;
+	{
+		char chunk[1 << 16];
+		size_t n;
+		while ((n = fread(chunk, 1, sizeof chunk, f)) > 0) buf.append(chunk, n);
 	}
 	fclose(f);
+	const char* p = buf.data();
+	const char* end = p + buf.size();
+	while (p < end) {
+		const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+		if (!eol) eol = end;
+		int v[9], k = 0;
+		const char* q = p;
+		while (k < 9) {
+			while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+			if (q >= eol) break;
+			bool neg = false;
+			if (*q == '-' || *q == '+') { neg = *q == '-'; ++q; }
+			if (q >= eol || *q < '0' || *q > '9') break;
+			long long x = 0;
+			while (q < eol && *q >= '0' && *q <= '9') { x = x * 10 + (*q - '0'); ++q; }
+			v[k++] = (int)(neg ? -x : x);
+		}
+		if (k == 9) {
+			mecat_candidate e;
+			memset(&e, 0, sizeof e);
+			e.qid = v[0]; e.sid = v[1]; e.qdir = v[2]; e.sdir = v[3]; e.qext = v[4]; e.sext = v[5]; e.score = v[6]; e.qsize = v[7]; e.ssize = v[8];
+			out.push_back(e);
+		}
+		p = eol + 1;
+	}
 	return true;
 }
 
