@@ -307,6 +307,8 @@ struct InteriorFn      // a thread per region: its interior goes right behind it
 	}
 };
 
+struct ErrCountFn { const int32_t* err; uint32_t* n; CNS_HD void operator()(int64_t g) const { if (err[g]) fetch_add(n, 1u); } };
+
 struct SegFlattenFn
 {
 	const int32_t* nseg; const int64_t* seg_slot; const int32_t* segs; const int64_t* seg_first;
@@ -532,7 +534,7 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 
 	lap("graphs + assemble");
 	// results to the host
-	std::vector<int32_t> h_segread((size_t)NS), h_segbeg((size_t)NS), h_segend((size_t)NS), h_tlen((size_t)NS), h_gerr((size_t)NG);
+	std::vector<int32_t> h_segread((size_t)NS), h_segbeg((size_t)NS), h_segend((size_t)NS), h_tlen((size_t)NS);
 	std::vector<int64_t> h_tgtoff((size_t)NS + 1);
 	CNS_TRY(be.download(h_segread.data(), d_segread, (size_t)NS));
 	CNS_TRY(be.download(h_segbeg.data(), d_segbeg, (size_t)NS));
@@ -541,14 +543,26 @@ int consensus_batch(B& be, const BatchIn& in, const Params& P, Sink& out)
 	CNS_TRY(be.download(h_tgtoff.data(), d_tgtoff, (size_t)NS + 1));
 	const char* h_target = be.download_staged(d_target, (size_t)TGT);      // valid until the batch ends
 	if (!h_target) return 1;
-	if (NG) CNS_TRY(be.download(h_gerr.data(), d_gerr, (size_t)NG));
-	for (int64_t g = 0; g < NG; ++g)
-		if (h_gerr[g]) {
-			char msg[128];
-			snprintf(msg, sizeof msg, "cns: region graph %lld ran out of scratch (code %d)", (long long)g, h_gerr[g]);
-			be.fail(msg);
-			return 1;
-		}
+	// error codes of the region graphs: counted on the device (the codes of 11 M regions were a 45 MB copy per batch); the
+	// array itself only comes to the host when something failed
+	uint32_t nerr = 0;
+	if (NG) {
+		CNS_ALLOC(d_nerr, uint32_t, 1);
+		CNS_TRY(be.fill(d_nerr, 0, sizeof(uint32_t)));
+		CNS_TRY(be.launch(NG, ErrCountFn{d_gerr, d_nerr}, ST_ASSEMBLE));
+		CNS_TRY(be.download(&nerr, d_nerr, 1));
+	}
+	if (nerr) {
+		std::vector<int32_t> h_gerr((size_t)NG);
+		CNS_TRY(be.download(h_gerr.data(), d_gerr, (size_t)NG));
+		for (int64_t g = 0; g < NG; ++g)
+			if (h_gerr[g]) {
+				char msg[128];
+				snprintf(msg, sizeof msg, "cns: region graph %lld ran out of scratch (code %d)", (long long)g, h_gerr[g]);
+				be.fail(msg);
+				return 1;
+			}
+	}
 	lap("downloads");
 	for (int64_t S = 0; S < NS; ++S)
 		if ((int64_t)h_tlen[S] >= P.min_size)
