@@ -2,8 +2,8 @@
 //
 // CUDA backend of xdrop_core.cuh: XdropAligner::go (src/common/xdrop_gapalign.cpp:10-439) for a batch of candidates.
 // A chain -- one (candidate, direction) -- is one thread's work: the X-drop row is a sequential scan (xdrop_core.cuh), so
-// the parallelism is across the chains of a batch (2 x candidates of them), pulled from a device counter by persistent
-// threads.  Every thread owns a worst-case-sized scratch block in global memory (score row + 4-bit trace-back of one
+// the parallelism is across the chains of a batch (2 x candidates of them); persistent warps take them 32 at a time from
+// a list ordered by expected length, so that the lanes of a warp stay in step.  Every thread owns a worst-case-sized scratch block in global memory (score row + 4-bit trace-back of one
 // block, 232 KB), so no chain can fail for want of memory.  Consumers: mecat2pw -j 1 -x 1 (string-free), mecat2ref -x 1
 // and mecat_b200_align_batch policy 2 (columns into the slots of align.cu, merged and packed by its kernels).
 #include "common.cuh"
@@ -21,6 +21,39 @@ constexpr size_t XD_RING_BYTES = sizeof(mbx::RingCell) * mbx::RING * XD_THREADS;
 struct TaskView { int32_t qread, qstrand, qstart, sread, sstart, swin_off, swin_len; };
 __device__ __forceinline__ TaskView view_of(const AlignTask& t) { return {t.qread, t.qstrand, t.qstart, t.sread, t.sstart, t.swin_off, t.swin_len}; }
 __device__ __forceinline__ TaskView view_of(const ExtendTask& t) { return {t.qread, t.qstrand, t.qstart, t.sread, t.sstart, 0, 0}; }
+
+// one chain: the walks of align.cu for (task, direction), the block chain of xdrop_core.cuh, the slot's counters
+template <bool COLS, class TaskT>
+__device__ __forceinline__ void run_chain(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, const int2* __restrict__ qoffsz, int qN,
+                                          const uint32_t* __restrict__ sfwd, const uint32_t* __restrict__ srev, const int2* __restrict__ soffsz, int sN,
+                                          const TaskT* __restrict__ tasks, unsigned long long item, AlnSlot* __restrict__ slots,
+                                          char* __restrict__ colq, char* __restrict__ colt, const mbx::Scratch& S)
+{
+	using namespace mbx;
+	const TaskView t = view_of(tasks[item >> 1]);
+	const int right = (int)(item & 1);
+	const int2 qo = qoffsz[t.qread];
+	int2 so = soffsz[t.sread];
+	if (t.swin_len > 0) { so.x += t.swin_off; so.y = t.swin_len; }    // subject window (mecat2ref)
+	Seq Q, T;
+	if (right) {
+		if (!t.qstrand) { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + t.qstart); Q.comp = 0; }
+		else { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - qo.y + t.qstart); Q.comp = 0xFFFFFFFFu; }
+		Q.len = qo.y - t.qstart;
+		T.arr = sfwd; T.g0 = (uint32_t)(so.x + t.sstart); T.comp = 0; T.len = so.y - t.sstart;
+	} else {
+		if (!t.qstrand) { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - t.qstart); Q.comp = 0; }
+		else { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + qo.y - t.qstart); Q.comp = 0xFFFFFFFFu; }
+		Q.len = t.qstart;
+		T.arr = srev; T.g0 = (uint32_t)(sN - so.x - t.sstart); T.comp = 0; T.len = t.sstart;
+	}
+	AlnSlot slot = slots[item];
+	Half H;
+	chain<COLS>(Q, T, S, COLS ? colq + slot.off : nullptr, COLS ? colt + slot.off : nullptr, slot.cap, H);
+	slot.cols = H.cols; slot.matches = H.matches; slot.qadv = H.qadv; slot.tadv = H.tadv;
+	slot.overflow = H.overflow | (H.last << 1);
+	slots[item] = slot;
+}
 
 template <bool COLS, class TaskT>
 __global__ void __launch_bounds__(XD_THREADS)
@@ -49,32 +82,8 @@ k_xdrop(const uint32_t* __restrict__ qfwd, const uint32_t* __restrict__ qrev, co
 		if (lane == 0) base = atomicAdd(work_counter, 32ull);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= 2 * ntasks) break;
-		if (base + lane < 2 * ntasks) {                    // (the lanes past the end idle through this last round)
-		const unsigned long long item = order[base + lane];
-		const TaskView t = view_of(tasks[item >> 1]);
-		const int right = (int)(item & 1);
-		const int2 qo = qoffsz[t.qread];
-		int2 so = soffsz[t.sread];
-		if (t.swin_len > 0) { so.x += t.swin_off; so.y = t.swin_len; }    // subject window (mecat2ref)
-		Seq Q, T;                                                             // the walks of align.cu
-		if (right) {
-			if (!t.qstrand) { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + t.qstart); Q.comp = 0; }
-			else { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - qo.y + t.qstart); Q.comp = 0xFFFFFFFFu; }
-			Q.len = qo.y - t.qstart;
-			T.arr = sfwd; T.g0 = (uint32_t)(so.x + t.sstart); T.comp = 0; T.len = so.y - t.sstart;
-		} else {
-			if (!t.qstrand) { Q.arr = qrev; Q.g0 = (uint32_t)(qN - qo.x - t.qstart); Q.comp = 0; }
-			else { Q.arr = qfwd; Q.g0 = (uint32_t)(qo.x + qo.y - t.qstart); Q.comp = 0xFFFFFFFFu; }
-			Q.len = t.qstart;
-			T.arr = srev; T.g0 = (uint32_t)(sN - so.x - t.sstart); T.comp = 0; T.len = t.sstart;
-		}
-		AlnSlot slot = slots[item];
-		Half H;
-		chain<COLS>(Q, T, S, COLS ? colq + slot.off : nullptr, COLS ? colt + slot.off : nullptr, slot.cap, H);
-		slot.cols = H.cols; slot.matches = H.matches; slot.qadv = H.qadv; slot.tadv = H.tadv;
-		slot.overflow = H.overflow | (H.last << 1);
-		slots[item] = slot;
-		}
+		if (base + lane < 2 * ntasks)                      // (the lanes past the end idle through this last round)
+			run_chain<COLS, TaskT>(qfwd, qrev, qoffsz, qN, sfwd, srev, soffsz, sN, tasks, order[base + lane], slots, colq, colt, S);
 		__syncwarp();
 	}
 }
