@@ -518,6 +518,12 @@ static int cns_core(mecat_b200_ctx* c, const DVolume* V, const std::vector<mecat
 	P.min_mapping_ratio = p->min_mapping_ratio; P.min_align_size = p->min_align_size; P.min_cov = p->min_cov; P.min_size = p->min_size;
 	P.tech = p->tech; P.input_type = p->input_type;
 	const double err = p->tech == 1 ? 0.20 : 0.15;     // GetAlignment's error rate, mecat_correction.cpp:424,487
+	{
+		// the corrected reads are about as long as their templates
+		size_t bases = 0;
+		for (size_t g = g0; g < gend; ++g) bases += (size_t)ec[groups[g].b].ssize;
+		all.reserve(bases + bases / 16);
+	}
 	const size_t TASKS_PER_BATCH = 400000;       // with the column arena (12 GB at ~30 kB per task) this bounds a batch; more units per launch suit the latency-bound stages
 	std::vector<AlignTask> tasks;
 	std::vector<int32_t> info, first, rsize, tqid, tqsize;

@@ -255,6 +255,12 @@ struct CnsBlob
 	size_t len = 0, cap = 0;
 	bool oom = false;
 	~CnsBlob() { free(buf); }
+	void reserve(size_t want)      // room for `want` more bytes in one step (a blob that doubles its way to 400 MB copies as much again)
+	{
+		if (len + want + 1 <= cap) return;
+		char* nb = (char*)realloc(buf, len + want + 1);
+		if (nb) { buf = nb; cap = len + want + 1; }
+	}
 	void add(int64_t id, int64_t beg, int64_t end, const char* seq, size_t n)
 	{
 		if (len + n + 1 > cap) {
