@@ -198,15 +198,17 @@ def make_m4_input(meta):
             with gzip.open(os.path.join(HERE, "deep.m4.gz"), "wt") as g:
                 g.write("\n".join(lines) + "\n")
             m["deep_num_m4"] = len(lines)
-        out = os.path.join(tmp, "cns.fa")
-        subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-i", "1", "-t", "1"] + args + [m4, fa, out], env=env,
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        lines = open(out).read().splitlines()
-        recs = sorted(zip(lines[0::2], lines[1::2]))
-        with gzip.open(os.path.join(HERE, "%s.i1.cns.fa.gz" % name), "wt") as f:
-            for h, q in recs:
-                f.write(h + "\n" + q + "\n")
-        m["%s_num_cns" % name] = len(recs)
+        # small also with partitions of 100 reads (-p 100: three partition files, each ordered on its own)
+        for tag, extra in (("i1", []), ("i1p100", ["-p", "100"])) if name == "small" else (("i1", []),):
+            out = os.path.join(tmp, "cns_%s.fa" % tag)
+            subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-i", "1", "-t", "1"] + extra + args + [m4, fa, out], env=env,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            lines = open(out).read().splitlines()
+            recs = sorted(zip(lines[0::2], lines[1::2]))
+            with gzip.open(os.path.join(HERE, "%s.%s.cns.fa.gz" % (name, tag)), "wt") as f:
+                for h, q in recs:
+                    f.write(h + "\n" + q + "\n")
+            m["%s_num_cns%s" % (name, "" if tag == "i1" else "_p100")] = len(recs)
         shutil.rmtree(tmp)
     meta["i1"] = m
 

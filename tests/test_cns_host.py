@@ -73,25 +73,26 @@ def _align_groups(vol, groups, min_aln, err):
     return (np.array(first, dtype=np.int32), np.concatenate(groups), np.concatenate(results), bytes(qblob) + b"\0", bytes(sblob) + b"\0")
 
 
-def m4_groups(name, min_cov, min_size, ratio, cap, keep=None):
+def m4_groups(name, min_cov, min_size, ratio, cap, keep=None, batch_size=100000):
     """-i 1: the overlap file of the fixture -> per read the overlaps the reference works on, in its order (partition
     records in file order, std::sort by sid, the `cap` largest of a read by std::sort: oracle/orc_cns_m4_order)."""
     import mecat_b200
     O = util.oracle()
     with gzip.open(os.path.join(util.GOLDEN, "%s.m4.gz" % name), "rt") as f:
-        parts = mecat_b200.m4_partitions(f, ratio, min_size)
-    assert list(parts) == [0]
-    ec = np.ascontiguousarray(parts[0])
-    O.orc_cns_m4_order(ec.ctypes.data_as(C.c_void_p), len(ec), cap)
+        parts = mecat_b200.m4_partitions(f, ratio, min_size, batch_size)
+    assert batch_size < 100000 or list(parts) == [0]
     groups = []
-    i = 0
-    while i < len(ec):
-        j = i + 1
-        while j < len(ec) and ec["sid"][j] == ec["sid"][i]:
-            j += 1
-        if j - i >= min_cov and not ec["ssize"][i] < min_size * 0.95 and (keep is None or keep(int(ec["sid"][i]))):
-            groups.append(np.ascontiguousarray(ec[i:min(j, i + cap)]))
-        i = j
+    for _, ec in sorted(parts.items()):
+        ec = np.ascontiguousarray(ec)
+        O.orc_cns_m4_order(ec.ctypes.data_as(C.c_void_p), len(ec), cap)
+        i = 0
+        while i < len(ec):
+            j = i + 1
+            while j < len(ec) and ec["sid"][j] == ec["sid"][i]:
+                j += 1
+            if j - i >= min_cov and not ec["ssize"][i] < min_size * 0.95 and (keep is None or keep(int(ec["sid"][i]))):
+                groups.append(np.ascontiguousarray(ec[i:min(j, i + cap)]))
+            i = j
     return groups
 
 
@@ -307,6 +308,11 @@ def test_m4_input_consensus_matches_reference(small_vol, deep_vol):
     assert len(want) == GOLD["i1"]["small_num_cns"]
     compare(correct_with_oracle(small_vol, None, ratio, min_aln, min_cov, min_size, groups=g), want)
     compare(correct_with_kernel_bodies(small_vol, None, ratio, min_aln, min_cov, min_size, groups=g), want)
+    # partitions of 100 reads (-p 100): each partition is ordered on its own, equal keys fall differently than above
+    g = m4_groups("small", min_cov, min_size, ratio, 60, batch_size=100)
+    want_p = gold_fasta("small.i1p100", "cns")
+    assert want_p != want
+    compare(correct_with_kernel_bodies(small_vol, None, ratio, min_aln, min_cov, min_size, groups=g), want_p)
     g = m4_groups("deep", min_cov, min_size, ratio, 60, keep=_every_sixth)
     assert max(len(x) for x in g) == 60
     want = [(h, s) for h, s in gold_fasta("deep.i1", "cns") if _every_sixth(int(h[1:].split("_")[0]))]

@@ -200,3 +200,9 @@ def test_m4_input_consensus_matches_reference(gpu_ctx, small_vol, deep_vol, tmp_
     assert p.returncode == 0, p.stderr[-2000:]
     lines = open(out).read().splitlines()
     assert sorted(zip(lines[0::2], lines[1::2])) == _gold_fasta("small.i1", "cns")
+    # partitions of 100 reads: three library calls, each partition ordered on its own like the reference's partition files
+    p = subprocess.run([os.path.join(util.ROOT, "mecat_b200", "bin", "mecat2cns"), "-i", "1", "-t", "4", "-p", "100", "-l", "2000", "-c", "4", "-a", "1000", m4, reads, out],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = open(out).read().splitlines()
+    assert sorted(zip(lines[0::2], lines[1::2])) == _gold_fasta("small.i1p100", "cns")
