@@ -1,6 +1,6 @@
 // mecat_b200/csrc/host/mecat2cns.cpp -- host driver with the reference's mecat2cns command line.
 //
-//   mecat2cns [options] <candidates.can> <reads.fasta> <corrected.fasta>
+//   mecat2cns [options] <candidates.can | overlaps.m4> <reads.fasta> <corrected.fasta>
 //
 // Same flags (src/mecat2cns/options.cpp:201-303), same corrected-FASTA records
 // (`>{id}_{beg}_{end}_{len}`, src/mecat2cns/reads_correction_can.cpp:44-46) as the reference's
@@ -10,7 +10,9 @@
 // extensions run on the GPU (mecat_b200_cns_reads_multi); `-t` is accepted and ignored.  The read set may be of any size:
 // it is kept as volumes of at most 2.14 Gbase (the splitter's cut, MECAT_VOLUME_BASES as in mecat2pw), all resident on
 // every device.
-// Not on this path (refused with a message): `-i 1` (M4 input) and `-x 1` (nanopore).
+// `-i 1` (M4 input, the default; reads_correction_m4.cpp, overlaps_partition.cpp:345-410) builds the partition records in file
+// order; the library orders them like the reference run with one OpenMP thread.  `-x 1` (nanopore) switches the defaults
+// and the consensus variant (mecat_correction.cpp:303-360, 453-512).
 #include <getopt.h>
 #include <stdio.h>
 #include <stdlib.h>

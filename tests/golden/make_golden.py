@@ -210,6 +210,24 @@ def make_m4_input(meta):
                     f.write(h + "\n" + q + "\n")
             m["%s_num_cns%s" % (name, "" if tag == "i1" else "_p100")] = len(recs)
         shutil.rmtree(tmp)
+    # nanopore defaults: -x 1 alone means -i 1 (consensus_one_read_m4_nanopore: every alignment that also passes the
+    # mapping-ratio test, up to 100 per read), on the -x 1 overlaps of the small fixture
+    c = CASES["small"]
+    tmp = tempfile.mkdtemp(prefix="golden_x1i1_")
+    fa = os.path.join(tmp, "reads.fa")
+    gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"])
+    m4 = os.path.join(tmp, "in.m4")
+    with gzip.open(os.path.join(HERE, "small.x1.m4.gz"), "rt") as f, open(m4, "w") as g:
+        g.write(f.read())
+    out = os.path.join(tmp, "cns.fa")
+    subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-x", "1", "-t", "1", m4, fa, out], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = open(out).read().splitlines()
+    recs = sorted(zip(lines[0::2], lines[1::2]))
+    with gzip.open(os.path.join(HERE, "small.x1i1.cns.fa.gz"), "wt") as f:
+        for h, q in recs:
+            f.write(h + "\n" + q + "\n")
+    m["small_x1_num_cns"] = len(recs)
+    shutil.rmtree(tmp)
     meta["i1"] = m
 
 

@@ -321,6 +321,18 @@ def test_m4_input_consensus_matches_reference(small_vol, deep_vol):
     compare(correct_with_kernel_bodies(deep_vol, None, ratio, min_aln, min_cov, min_size, keep=_every_sixth, groups=g), want)
 
 
+def test_nanopore_m4_input_consensus_matches_reference(small_vol):
+    """consensus_one_read_m4_nanopore (mecat_correction.cpp:303-360): `mecat2cns -x 1` alone means `-i 1`; the -x 1 overlaps
+    of the small fixture as input, up to 100 overlaps per read, every alignment that also passes the mapping-ratio test.
+    Golden: the unmodified `mecat2cns -x 1` with one OpenMP thread (tests/golden/make_golden.py i1)."""
+    ratio, min_aln, min_cov, min_size = NANOPORE
+    g = m4_groups("small.x1", min_cov, min_size, ratio, 100)
+    want = gold_fasta("small.x1i1", "cns")
+    assert len(want) == GOLD["i1"]["small_x1_num_cns"]
+    compare(correct_with_oracle(small_vol, None, ratio, min_aln, min_cov, min_size, tech=1, groups=g), want)
+    compare(correct_with_kernel_bodies(small_vol, None, ratio, min_aln, min_cov, min_size, tech=1, groups=g), want)
+
+
 def test_fused_normalise_vote_kernel_body_matches_literal_restatement():
     """normalize_vote_index (one streaming pass, what the GPU thread runs) against normalize_gaps + add_votes +
     column_index written literally after the reference, on random gapped alignments rich in homopolymers, long gap

@@ -250,3 +250,32 @@ def test_nanopore_consensus_matches_reference(gpu_ctx, small_vol, tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     lines = open(out).read().splitlines()
     assert sorted(zip(lines[0::2], lines[1::2])) == _gold_fasta("small.x1", "cns")
+
+
+def test_nanopore_m4_input_consensus_matches_reference(gpu_ctx, small_vol, tmp_path):
+    """mecat2cns -x 1 (which means -i 1: consensus_one_read_m4_nanopore, mecat_correction.cpp:303-360 -- a partition ordered
+    by std::sort on sid, the 100 largest overlaps of a read, every alignment that succeeds and passes the mapping-ratio
+    test) on the -x 1 overlaps of the small fixture: golden of the unmodified binary with one OpenMP thread, through the
+    C ABI and through the command line."""
+    import subprocess
+    import mecat_b200
+    with gzip.open(os.path.join(util.GOLDEN, "small.x1.m4.gz"), "rt") as f:
+        parts = mecat_b200.m4_partitions(f, 0.4, 2000)
+    assert list(parts) == [0]
+    d = gpu_ctx.upload(host_volume(small_vol))
+    pieces = gpu_ctx.cns_reads(d, parts[0], 0.4, 400, 6, 2000, tech=1, input_type=1)
+    gpu_ctx.release_volume(d)
+    got = sorted((">%d_%d_%d_%d" % (i, b, e, len(s)), s.decode()) for i, b, e, s in pieces)
+    want = _gold_fasta("small.x1i1", "cns")
+    assert len(got) == len(want) == GOLD["i1"]["small_x1_num_cns"]
+    bad = [g[0] for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:5]
+    reads, m4, out = str(tmp_path / "small.fa"), str(tmp_path / "small.x1.m4"), str(tmp_path / "x1i1.cns.fa")
+    with gzip.open(os.path.join(util.GOLDEN, "small.fa.gz"), "rb") as f, open(reads, "wb") as g:
+        g.write(f.read())
+    with gzip.open(os.path.join(util.GOLDEN, "small.x1.m4.gz"), "rb") as f, open(m4, "wb") as g:
+        g.write(f.read())
+    p = subprocess.run([os.path.join(util.ROOT, "mecat_b200", "bin", "mecat2cns"), "-x", "1", "-t", "4", m4, reads, out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = open(out).read().splitlines()
+    assert sorted(zip(lines[0::2], lines[1::2])) == want
