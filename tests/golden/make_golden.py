@@ -16,6 +16,8 @@ Cases (reads come from oracle/gen_reads, a seeded deterministic generator):
   x1    : the small / cfg0 / deep / refmap inputs with `-x 1` (nanopore: XdropAligner, min_kmer_dist 400, the nanopore
           consensus variant) -- SURVEY.md section 8(f) item 2
   i1    : `mecat2cns -i 1` (M4 input) on the sorted small / deep overlap files, one OpenMP thread
+  asm   : mecat2asmpw / mecat2trimpw (and the *50 programs) of mecat2canu on corrected-read like fixtures (tests/util.py
+          ASM_CASES): `asm` two files (-S1 -E2 and -S2 -E2), `asmdeep` one deep file through mecat2asmpw50 with one thread
   python tests/golden/make_golden.py [case ...]   regenerates only the named cases
 For each: vol0 sha256 (split_raw_dataset), sorted `mecat2pw -j 0` lines, sorted
 `mecat2pw -j 1 -g 1` lines.
@@ -32,7 +34,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from util import gen_reads, make_refmap_hard, REF_DIR  # noqa: E402
+from util import gen_reads, make_refmap_hard, REF_DIR, ASM_CASES, asm_workdir  # noqa: E402
 
 CASES = {
     "small": dict(n=250, genome=100000, seed=3, mean=6000, sd=1500),
@@ -231,6 +233,38 @@ def make_m4_input(meta):
     meta["i1"] = m
 
 
+def make_asm(meta):
+    """The overlappers mecat2canu runs on corrected reads, unmodified, compiled without
+    CFLAGS like the reference's build.  The programs write one file per thread; the goldens are the sorted lines."""
+    m = {k: dict(v) for k, v in ASM_CASES.items()}
+    def run(prog, wrk, s, e, threads):
+        for f in os.listdir(wrk):
+            if f.endswith(".r"):
+                os.remove(os.path.join(wrk, f))
+        subprocess.check_call([os.path.join(REF_DIR, prog), "-P" + wrk, "-T%d" % threads, "-S%d" % s, "-E%d" % e])
+        lines = []
+        for f in sorted(os.listdir(wrk)):
+            if f.endswith(".r"):
+                lines += open(os.path.join(wrk, f)).read().splitlines()
+        return sorted(lines)
+    def keep(name, lines):
+        with gzip.open(os.path.join(HERE, name + ".r.gz"), "wt") as f:
+            f.write("\n".join(lines) + "\n")
+        m["num_" + name.replace(".", "_")] = len(lines)
+    tmp = tempfile.mkdtemp(prefix="golden_asm_")
+    wrk = os.path.join(tmp, "asm")
+    asm_workdir("asm", wrk)
+    keep("asm.asmpw", run("mecat2asmpw", wrk, 1, 2, 4))
+    keep("asm.asmpw.s2", run("mecat2asmpw", wrk, 2, 2, 4))
+    keep("asm.trimpw", run("mecat2trimpw", wrk, 1, 2, 4))
+    wrk = os.path.join(tmp, "asmdeep")
+    asm_workdir("asmdeep", wrk)
+    keep("asmdeep.asmpw50", run("mecat2asmpw50", wrk, 1, 1, 1))
+    keep("asmdeep.trimpw50", run("mecat2trimpw50", wrk, 1, 1, 1))
+    meta["asm"] = m
+    shutil.rmtree(tmp)
+
+
 def run_cns_x1(can, fa, dest, tmp):
     out = os.path.join(tmp, "cns_x1.fa")
     subprocess.check_call([os.path.join(REF_DIR, "mecat2cns"), "-x", "1", "-i", "0", "-t", "1", can, fa, out],
@@ -305,6 +339,8 @@ def main():
         make_nanopore(meta)
     if len(sys.argv) == 1 or "i1" in sys.argv[1:]:
         make_m4_input(meta)
+    if len(sys.argv) == 1 or "asm" in sys.argv[1:]:
+        make_asm(meta)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))

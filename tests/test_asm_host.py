@@ -1,0 +1,95 @@
+"""CPU tests of mecat2asmpw / mecat2trimpw (mecat2canu/src/mecat2asmpw/*.c): the oracle
+restatement (oracle/oracle_asmpw.cpp) against goldens of the unmodified binaries, and the product's stage sequence and
+kernel bodies (mecat_b200/csrc/asm_pipeline.h, asm_core.cuh) run on the host against both."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+GOLD = json.load(open(os.path.join(util.GOLDEN, "golden.json")))["asm"]
+
+
+def gold(name):
+    with gzip.open(os.path.join(util.GOLDEN, name + ".r.gz"), "rt") as f:
+        return f.read().splitlines()
+
+
+@pytest.fixture(scope="module")
+def asm_files(tmp_path_factory):
+    return util.asm_workdir("asm", str(tmp_path_factory.mktemp("asm")))
+
+
+@pytest.fixture(scope="module")
+def deep_files(tmp_path_factory):
+    return util.asm_workdir("asmdeep", str(tmp_path_factory.mktemp("asmdeep")))
+
+
+def all_pairs(fn, files, first_file=0, **kw):
+    """-S<first_file+1> -E<n>: the index of file first_file, the reads of that file and of the following ones (main :1112-1150)."""
+    sfirst, sub = files[first_file]
+    lines = []
+    for qfirst, qry in files[first_file:]:
+        lines += util.asm_lines(fn(sub, sfirst, qry, qfirst, **kw))
+    return sorted(lines)
+
+
+def test_oracle_matches_the_unmodified_binaries(asm_files, deep_files):
+    """Two files, -S1 -E2 and -S2 -E2, both programs; on this fixture the binary's output does not depend on what earlier
+    reads left in the block array, so both conventions of the oracle reproduce it."""
+    for history in (0, 1):
+        assert all_pairs(util.asm_oracle_overlaps, asm_files, history=history) == gold("asm.asmpw")
+    assert len(gold("asm.asmpw")) == GOLD["num_asm_asmpw"]
+    assert all_pairs(util.asm_oracle_overlaps, asm_files, first_file=1) == gold("asm.asmpw.s2")
+    assert all_pairs(util.asm_oracle_overlaps, asm_files, variant=1) == gold("asm.trimpw")
+    # the deep file (MAXC = 50 cuts the candidate lists, block scores pass SM): with one thread's memory carried from read to
+    # read the restatement is the binary; with zeroed blocks a handful of candidates score differently at the cut
+    for variant, name in ((0, "asmdeep.asmpw50"), (1, "asmdeep.trimpw50")):
+        want = gold(name)
+        assert all_pairs(util.asm_oracle_overlaps, deep_files, variant=variant, maxc=50, history=1) == want
+        got = all_pairs(util.asm_oracle_overlaps, deep_files, variant=variant, maxc=50, history=0)
+        assert got != want
+        assert len(set(got) ^ set(want)) <= 16 and abs(len(got) - len(want)) <= 4
+
+
+def test_kernel_bodies_match_the_unmodified_binaries(asm_files):
+    got = all_pairs(lambda *a, **k: util.asm_harness_overlaps(*a, **k)[0], asm_files)
+    assert got == gold("asm.asmpw")
+    got = all_pairs(lambda *a, **k: util.asm_harness_overlaps(*a, **k)[0], asm_files, first_file=1, variant=1, maxc=50)
+    assert got == all_pairs(util.asm_oracle_overlaps, asm_files, first_file=1, variant=1, maxc=50)
+
+
+def test_kernel_bodies_match_the_oracle_on_the_deep_file(deep_files):
+    """More candidates than MAXC, block scores beyond SM (the neighbour votes read past a block's 60 entries: seedno[],
+    seednum, index, the next block), N letters, lower-case reads, a 300-letter and a 12-letter read."""
+    sfirst, sub = deep_files[0]
+    for variant, maxc in ((0, 50), (1, 100)):
+        want = util.asm_oracle_overlaps(sub, sfirst, sub, sfirst, variant=variant, maxc=maxc)
+        got, stats = util.asm_harness_overlaps(sub, sfirst, sub, sfirst, variant=variant, maxc=maxc)
+        assert stats[0] == 1 and stats[3] == 1
+        assert util.asm_lines(got) == util.asm_lines(want)          # same records in the same order
+    # tables cut into many batches, a record pool that runs out and splits its batch: same records
+    got, stats = util.asm_harness_overlaps(sub, sfirst, sub, sfirst, variant=1, maxc=100, budget=200000, divisor=64)
+    assert stats[0] > 400
+    assert util.asm_lines(got) == util.asm_lines(want)
+
+
+def test_integer_consistency_test_equals_the_float_forms():
+    """ddf_close / ddf_close_d (asm_core.cuh) against |a / (b * 10.0f) - 1| < 0.10 with a float quotient (find_location,
+    mecat2asmpw.c:340) and |a / (b * 10 * 1.0) - 1.0| < 0.10 with a double one (the neighbour votes, :702)."""
+    H = util.asm_harness()
+    a = np.arange(-2500, 25000, dtype=np.int64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for b in list(range(-40, 41)) + [97, 250, 999, 1500, 2000]:
+            qf = a.astype(np.float32) / (np.float32(b) * np.float32(10.0))
+            want_f = np.abs((qf - np.float32(1)).astype(np.float64)) < 0.10
+            qd = a.astype(np.float64) / (b * 10 * 1.0)
+            want_d = np.abs(qd - 1.0) < 0.10
+            got_f = np.array([H.ah_ddf_close(int(x), b, 0) for x in a], dtype=bool)
+            got_d = np.array([H.ah_ddf_close(int(x), b, 1) for x in a], dtype=bool)
+            assert (got_f == want_f).all(), b
+            assert (got_d == want_d).all(), b
+    assert H.ah_ddf_close(90, 10, 1) == 1 and H.ah_ddf_close(90, 10, 0) == 0       # the quotient 0.9 is close in double only

@@ -611,3 +611,145 @@ def make_refmap_hard(reads_path, genome_path, seed=19):
     with open(reads_path, "w") as f:
         for i, r in enumerate(reads):
             f.write(">read_%d\n%s\n" % (i, r))
+
+
+# ---------------------------------------------------------------- mecat2asmpw / mecat2trimpw fixtures
+ASM_CASES = {
+    # corrected-read like: ~16x of a 150 kb genome at 1.5 % error, two files of 300 reads
+    "asm": dict(n=600, genome=150000, seed=77, mean=4000, sd=800, err=0.015, files=2),
+    # ~56x of a 25 kb genome: more candidates per read than the *50 programs keep, blocks whose score passes SM = 60
+    # (the neighbour votes then read beyond a block's 60 entries), a few N letters, lower-case reads, two stubs
+    "asmdeep": dict(n=400, genome=25000, seed=91, mean=3500, sd=900, err=0.01, files=1),
+}
+
+
+def asm_reads(name, tmp_dir):
+    """The reads of an ASM_CASES fixture, in file order, as written to the FASTA files (case kept, N letters in)."""
+    c = ASM_CASES[name]
+    fa = os.path.join(tmp_dir, name + ".all.fa")
+    gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], err=c["err"])
+    seqs = [s for _, s in read_fasta_raw(fa)]
+    if name == "asmdeep":
+        for r in range(len(seqs)):
+            s = seqs[r]
+            if r % 37 == 5:
+                s = list(s)
+                for t in range(3):
+                    s[(r * 7919 + t * 104729) % len(s)] = "N"
+                s = "".join(s)
+            if r % 41 == 7:
+                s = s.lower()
+            if r == 100:
+                s = s[:300]
+            if r == 200:
+                s = s[:12]
+            seqs[r] = s
+    return seqs
+
+
+def read_fasta_raw(path):
+    out, name = [], None
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            name = line[1:]
+        elif line:
+            out.append((name, line))
+    return out
+
+
+def asm_workdir(name, wrk):
+    """The working directory mecat2canu hands the overlapper: NNNNNN.fasta files and `ovlprep` with the read ranges
+    (mecat2asmpw.c:1083-1090 parses `-allreads -allbases -b <first> -e <last>`).  Returns [(first_id, [reads])] per file."""
+    c = ASM_CASES[name]
+    os.makedirs(wrk, exist_ok=True)
+    seqs = asm_reads(name, wrk)
+    per = len(seqs) // c["files"]
+    files = []
+    with open(os.path.join(wrk, "ovlprep"), "w") as prep:
+        for i in range(c["files"]):
+            part = seqs[i * per:(i + 1) * per]
+            with open(os.path.join(wrk, "%06d.fasta" % (i + 1)), "w") as f:
+                for j, s in enumerate(part):
+                    f.write(">%d\n%s\n" % (i * per + j, s))
+            prep.write("-allreads -allbases -b %d -e %d\n" % (i * per + 1, (i + 1) * per))
+            files.append((i * per + 1, part))
+    return files
+
+
+def asm_text(reads):
+    """(text, starts, lengths) of a file's reads the way load_read keeps them: upper-cased, a NUL behind each."""
+    up = [s.upper() for s in reads]
+    starts, o = [], 0
+    for s in up:
+        starts.append(o)
+        o += len(s) + 1
+    return ("\0".join(up) + "\0").encode(), np.array(starts, dtype=np.int32), np.array([len(s) for s in up], dtype=np.int32)
+
+
+ASM_OVERLAP_DTYPE = np.dtype([("sread", "<i4"), ("qread", "<i4"), ("score", "<f4"), ("sbeg", "<i4"), ("send", "<i4"), ("slen", "<i4"),
+                              ("strand", "<i4"), ("qbeg", "<i4"), ("qend", "<i4"), ("qlen", "<i4")])
+
+
+def asm_lines(recs):
+    """The line the reference prints per overlap (mecat2asmpw.c:944-945)."""
+    return ["%d %d %.3f 100 0 %d %d %d %d %d %d %d" % (r["sread"], r["qread"], float(r["score"]), r["sbeg"], r["send"], r["slen"], r["strand"],
+                                                      r["qbeg"], r["qend"], r["qlen"]) for r in recs]
+
+
+def asm_oracle_overlaps(sub, sub_first, qry, qry_first, variant=0, maxc=100, history=0):
+    """oracle/oracle_asmpw.cpp: the reads of one query file against the index of one subject file."""
+    L = oracle()
+    L.orc_asm_overlaps.restype = C.c_int
+    L.orc_asm_overlaps.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    t, st, ln = asm_text(sub)
+    qt, qs, ql = asm_text(qry)
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = L.orc_asm_overlaps(t, len(t), st.ctypes.data, ln.ctypes.data, len(sub), sub_first, qt, qs.ctypes.data, ql.ctypes.data, len(qry),
+                            qry_first, variant, maxc, history, C.byref(out), C.byref(n))
+    assert rc == 0
+    arr = np.frombuffer(C.string_at(out.value, n.value * ASM_OVERLAP_DTYPE.itemsize), dtype=ASM_OVERLAP_DTYPE).copy()
+    L.orc_free(out)
+    return arr
+
+
+_asm_harness = None
+
+
+def asm_harness():
+    """Host build of the product's mecat2asmpw stage sequence and kernel bodies (tests/asm_host_harness.cpp)."""
+    global _asm_harness
+    if _asm_harness is not None:
+        return _asm_harness
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libasm_harness.so")
+    src = [os.path.join(ROOT, "tests", "asm_host_harness.cpp"), os.path.join(ROOT, "mecat_b200", "csrc", "asm_pipeline.h"),
+           os.path.join(ROOT, "mecat_b200", "csrc", "asm_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", so, src[0]])
+    L = C.CDLL(so)
+    L.ah_overlaps.restype = C.c_int
+    L.ah_overlaps.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p,
+                              C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                              C.c_void_p, C.c_char_p, C.c_int]
+    L.ah_free.argtypes = [C.c_void_p]
+    L.ah_ddf_close.restype = C.c_int
+    L.ah_ddf_close.argtypes = [C.c_int, C.c_int, C.c_int]
+    _asm_harness = L
+    return L
+
+
+def asm_harness_overlaps(sub, sub_first, qry, qry_first, variant=0, maxc=100, budget=0, divisor=0):
+    """The product's stage sequence on the host.  Returns (records, [seed batches, candidates, hits, extension passes])."""
+    H = asm_harness()
+    t, st, ln = asm_text(sub)
+    qt, qs, ql = asm_text(qry)
+    out, n, err, stats = C.c_void_p(), C.c_size_t(), C.create_string_buffer(256), (C.c_int64 * 4)()
+    rc = H.ah_overlaps(t, len(t), st.ctypes.data, ln.ctypes.data, len(sub), sub_first, qt, len(qt), qs.ctypes.data, ql.ctypes.data, len(qry),
+                       qry_first, variant, maxc, budget, divisor, C.byref(out), C.byref(n), stats, err, 256)
+    assert rc == 0, err.value
+    arr = np.frombuffer(C.string_at(out.value, n.value * ASM_OVERLAP_DTYPE.itemsize), dtype=ASM_OVERLAP_DTYPE).copy()
+    H.ah_free(out)
+    return arr, list(stats)
