@@ -117,7 +117,10 @@ enum {
 	MECAT_K_REF_COUNT = 16,    /* ref: index hits per strand (sizes the block tables) */
 	MECAT_K_REF_SEED = 17,     /* ref: seeding, DDF scoring, candidate walk           */
 	MECAT_K_REF_RESCUE = 18,   /* ref: candidates beyond clipped alignment ends       */
-	MECAT_K_NUM = 19
+	MECAT_K_ASM_INDEX = 19,    /* asmpw: k-mer index of the subject file's text       */
+	MECAT_K_ASM_SEED = 20,     /* asmpw: hit counts, block tables, candidate walk, merge */
+	MECAT_K_ASM_EXTEND = 21,   /* asmpw: chunked O(nd) alignment, gap shifting, records */
+	MECAT_K_NUM = 22
 };
 typedef struct {
 	float kernel_ms[MECAT_K_NUM];
@@ -367,6 +370,43 @@ int mecat_b200_ref_map(mecat_b200_ctx* ctx, void* refidx, const mecat_ref_reads*
 int mecat_b200_ref_index_export(mecat_b200_ctx* ctx, void* refidx, int64_t* num_kmers, uint32_t* begin, int32_t* positions);
 int mecat_b200_ref_raw_candidates(mecat_b200_ctx* ctx, void* refidx, const mecat_ref_reads* reads, const mecat_ref_params* p,
                                   int32_t** rows, int32_t** counts, size_t* n);
+
+/* ---- mecat2asmpw / mecat2trimpw: the overlappers mecat2canu runs on corrected reads ------------
+ * These programs (mecat2canu/src/mecat2asmpw/mecat2asmpw.c, mecat2trimpw.c and their *50 twins) work on letters: a file
+ * of reads is one text with a NUL behind every read (load_read :345-372, load_fastq :1000-1029), read r at read_start[r],
+ * numbered first_read_id + r (the `-b` value of the file's line in `ovlprep`).  Letters are upper-cased by the library
+ * like the loaders do; everything other than ACGT ends a k-mer and is compared as it is.  A read must be shorter than
+ * 100 000 letters (RM, :17: the reference's fixed buffers) and the text shorter than 2^31 - 4 000. */
+typedef struct {
+	const char* text;
+	int64_t num_letters;          /* including the NUL behind every read */
+	int32_t num_reads, first_read_id;
+	const int32_t* read_start;
+	const int32_t* read_len;
+} mecat_asm_reads;
+
+typedef struct {
+	int32_t variant;              /* 0 = mecat2asmpw, 1 = mecat2trimpw (gate :640, printed score :942-943) */
+	int32_t max_candidates;       /* MAXC :23: 100, the *50 programs 50 */
+} mecat_asm_params;
+
+/* One printed line (:944-945): "sread qread score 100 0 sbeg send slen strand qbeg qend qlen", score with %.3f. */
+typedef struct {
+	int32_t sread, qread;
+	float score;
+	int32_t sbeg, send, slen, strand, qbeg, qend, qlen;
+} mecat_asm_overlap;
+
+/* replaces load_read + creat_ref_index (:345-372, :397-497): the subject file on the device and its 13-mer lists */
+int mecat_b200_asm_index_build(mecat_b200_ctx* ctx, const mecat_asm_reads* subject, void** asmidx);
+int mecat_b200_asm_index_release(mecat_b200_ctx* ctx, void* asmidx);
+/* replaces pairwise_mapping (:515-984) for the reads of one query file: overlaps with subject reads numbered below the
+ * query read, in read order and per read in the order the reference aligns its candidates.  Where the reference reads
+ * block memory no seed of the strand wrote, zero is read (oracle/oracle_asmpw.cpp). */
+int mecat_b200_asm_overlaps(mecat_b200_ctx* ctx, void* asmidx, const mecat_asm_reads* query, const mecat_asm_params* p,
+                            mecat_asm_overlap** overlaps, size_t* n);
+/* test hook: the k-mer lists (begin: 4^13 + 1 entries; positions: 1-based k-mer starts as databaseindex holds them) */
+int mecat_b200_asm_index_export(mecat_b200_ctx* ctx, void* asmidx, int64_t* num_positions, uint32_t* begin, int32_t* positions);
 
 /* frees host buffers handed out by this library (same as mecat_b200_free without a context) */
 void mecat_b200_host_free(void* p);

@@ -29,7 +29,7 @@ class PwParams(C.Structure):
 
 KERNEL_NAMES = ["orient", "index_count", "index_scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
                 "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble",
-                "ref_count", "ref_seed", "ref_rescue"]
+                "ref_count", "ref_seed", "ref_rescue", "asm_index", "asm_seed", "asm_extend"]
 K_NUM = len(KERNEL_NAMES)      # MECAT_K_NUM
 
 
@@ -39,6 +39,42 @@ class CnsParams(C.Structure):
 
 
 CNS_PIECE_DTYPE = np.dtype([("id", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("seq_offset", "<i8"), ("seq_len", "<i8")])
+
+
+class AsmReadsC(C.Structure):      # mecat_asm_reads
+    _fields_ = [("text", C.c_char_p), ("num_letters", C.c_int64), ("num_reads", C.c_int32), ("first_read_id", C.c_int32),
+                ("read_start", C.POINTER(C.c_int32)), ("read_len", C.POINTER(C.c_int32))]
+
+
+class AsmParams(C.Structure):      # mecat_asm_params
+    _fields_ = [("variant", C.c_int32), ("max_candidates", C.c_int32)]
+
+
+ASM_OVERLAP_DTYPE = np.dtype([("sread", "<i4"), ("qread", "<i4"), ("score", "<f4"), ("sbeg", "<i4"), ("send", "<i4"), ("slen", "<i4"),
+                              ("strand", "<i4"), ("qbeg", "<i4"), ("qend", "<i4"), ("qlen", "<i4")])
+
+
+class AsmReads:
+    """A file of reads the way mecat2asmpw keeps it (load_read, mecat2asmpw.c:345-372): one text with a NUL behind every
+    read; read r is numbered first_read_id + r."""
+
+    def __init__(self, seqs, first_read_id):
+        self.first_read_id = int(first_read_id)
+        self.start = np.zeros(len(seqs), dtype=np.int32)
+        self.len = np.array([len(s) for s in seqs], dtype=np.int32)
+        if len(seqs):
+            self.start[1:] = np.cumsum(self.len[:-1] + 1)
+        self.text = ("\0".join(seqs) + "\0").encode() if len(seqs) else b""
+
+    def c(self):
+        return AsmReadsC(self.text, len(self.text), len(self.len), self.first_read_id, self.start.ctypes.data_as(C.POINTER(C.c_int32)),
+                         self.len.ctypes.data_as(C.POINTER(C.c_int32)))
+
+
+def asm_lines(recs):
+    """The line mecat2asmpw / mecat2trimpw print per overlap (mecat2asmpw.c:944-945)."""
+    return ["%d %d %.3f 100 0 %d %d %d %d %d %d %d" % (r["sread"], r["qread"], float(r["score"]), r["sbeg"], r["send"], r["slen"], r["strand"],
+                                                      r["qbeg"], r["qend"], r["qlen"]) for r in recs]
 
 
 class Stats(C.Structure):
@@ -96,6 +132,7 @@ EXPORTS = [
     "mecat_b200_ref_index_export", "mecat_b200_ref_raw_candidates",
     "mecat_b200_cns_reads_multi", "mecat_b200_volumes_from_fasta", "mecat_b200_volumes_unload",
     "mecat_b200_pw_tile_text", "mecat_b200_records_text", "mecat_b200_volume_from_text",
+    "mecat_b200_asm_index_build", "mecat_b200_asm_index_release", "mecat_b200_asm_overlaps", "mecat_b200_asm_index_export",
 ]
 
 _lib = None
@@ -165,6 +202,10 @@ def load_library():
     L.mecat_b200_ref_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
     L.mecat_b200_ref_raw_candidates.argtypes = [vp, vp, C.POINTER(RefReadsC), C.POINTER(RefParams), C.POINTER(vp), C.POINTER(vp),
                                                 C.POINTER(C.c_size_t)]
+    L.mecat_b200_asm_index_build.argtypes = [vp, C.POINTER(AsmReadsC), C.POINTER(vp)]
+    L.mecat_b200_asm_index_release.argtypes = [vp, vp]
+    L.mecat_b200_asm_overlaps.argtypes = [vp, vp, C.POINTER(AsmReadsC), C.POINTER(AsmParams), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mecat_b200_asm_index_export.argtypes = [vp, vp, C.POINTER(C.c_int64), vp, vp]
     _lib = L
     return L
 
@@ -626,6 +667,30 @@ class Context:
             self.L.mecat_b200_free(self.h, seqs)
         return [(int(x["id"]), int(x["beg"]), int(x["end"]), blob[int(x["seq_offset"]):int(x["seq_offset"]) + int(x["seq_len"])])
                 for x in pc]
+
+    # ---- mecat2asmpw / mecat2trimpw
+    def asm_index_build(self, reads):
+        """Index of a subject file (AsmReads): replaces load_read + creat_ref_index."""
+        d, cr = C.c_void_p(), reads.c()
+        self._check(self.L.mecat_b200_asm_index_build(self.h, C.byref(cr), C.byref(d)), "asm_index_build")
+        return d
+
+    def asm_index_release(self, idx):
+        self._check(self.L.mecat_b200_asm_index_release(self.h, idx), "asm_index_release")
+
+    def asm_index_export(self, idx):
+        n = C.c_int64()
+        self._check(self.L.mecat_b200_asm_index_export(self.h, idx, C.byref(n), None, None), "asm_index_export")
+        begin, pos = np.zeros((1 << 26) + 1, dtype=np.uint32), np.zeros(max(1, n.value), dtype=np.int32)
+        self._check(self.L.mecat_b200_asm_index_export(self.h, idx, C.byref(n), begin.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p)),
+                    "asm_index_export")
+        return begin, pos[:n.value]
+
+    def asm_overlaps(self, idx, reads, variant=0, max_candidates=100):
+        """pairwise_mapping for the reads of one query file (AsmReads) against a subject index.  Returns ASM_OVERLAP_DTYPE records."""
+        out, n, cr, p = C.c_void_p(), C.c_size_t(), reads.c(), AsmParams(variant, max_candidates)
+        self._check(self.L.mecat_b200_asm_overlaps(self.h, idx, C.byref(cr), C.byref(p), C.byref(out), C.byref(n)), "asm_overlaps")
+        return self._take(out, n.value, ASM_OVERLAP_DTYPE)
 
     def cns_reads_multi(self, dvols, candidates, min_mapping_ratio=0.9, min_align_size=2000, min_cov=6, min_size=5000, tech=0, input_type=0):
         """cns_reads for a read set that spans several resident volumes (consecutive read ids)."""

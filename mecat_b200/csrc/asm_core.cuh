@@ -93,17 +93,6 @@ struct TileSumFn
 	}
 };
 
-struct TopScanFn           // one unit: exclusive scan of the tile sums
-{
-	uint32_t* tile_sum; int64_t ntiles; uint32_t* total;
-	ASM_HD void operator()(int64_t) const
-	{
-		uint32_t run = 0;
-		for (int64_t t = 0; t < ntiles; ++t) { const uint32_t v = tile_sum[t]; tile_sum[t] = run; run += v; }
-		*total = run;
-	}
-};
-
 struct TileScanFn          // begin[c] = first slot of code c's list; count[] is cleared for the fill's cursors
 {
 	uint32_t* count; const uint32_t* tile_sum; uint32_t* begin; const uint32_t* total;

@@ -48,11 +48,17 @@ bool index_build(B& be, const char* h_text, int64_t n, const int32_t* h_start, c
 	if (!be.launch(n, fc, ST_INDEX)) return false;
 	TileSumFn fs; fs.count = count; fs.tile_sum = tile_sum;
 	if (!be.launch(ntiles, fs, ST_INDEX)) return false;
-	TopScanFn ft; ft.tile_sum = tile_sum; ft.ntiles = ntiles; ft.total = tile_sum + ntiles;
-	if (!be.launch(1, ft, ST_INDEX)) return false;
+	{   // exclusive scan of the 65 536 tile sums on the host (256 KB each way)
+		std::vector<uint32_t> h((size_t)ntiles + 1);
+		if (!be.download(h.data(), tile_sum, (size_t)ntiles)) return false;
+		uint32_t run = 0;
+		for (int64_t t = 0; t < ntiles; ++t) { const uint32_t v = h[(size_t)t]; h[(size_t)t] = run; run += v; }
+		h[(size_t)ntiles] = run;
+		I.total = run;
+		if (!be.upload(tile_sum, h.data(), (size_t)ntiles + 1)) return false;
+	}
 	TileScanFn fd; fd.count = count; fd.tile_sum = tile_sum; fd.begin = I.begin; fd.total = tile_sum + ntiles;
 	if (!be.launch(ntiles, fd, ST_INDEX)) return false;
-	if (!be.download(&I.total, tile_sum + ntiles, 1)) return false;
 	I.pos = be.template alloc<int32_t>((size_t)I.total + 1);
 	if (!I.pos) return false;
 	KmerFillFn ff; ff.text = I.text; ff.n = n; ff.begin = I.begin; ff.cursor = count; ff.pos = I.pos;

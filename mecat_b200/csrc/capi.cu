@@ -405,6 +405,47 @@ void mecat_b200_cns_sort_candidates(mecat_candidate* cnd, int n)   // CmpExtensi
 void mecat_b200_host_free(void* p) { mecat_b200_free(nullptr, p); }
 
 // ------------------------------------------------------------------------------------------
+// mecat2asmpw / mecat2trimpw (asmpw.cu)
+int mecat_b200_asm_index_build(mecat_b200_ctx* c, const mecat_asm_reads* subject, void** asmidx)
+{
+	if (check(c) || !subject || !asmidx) return 1;
+	cudaSetDevice(c->device);
+	WallTimer wt;
+	AsmIndexDev* I = nullptr;
+	const int rc = asm_index_build(c, subject, &I);
+	c->stats.wall_index_ms += wt.stop();
+	if (rc) return rc;
+	*asmidx = I;
+	return 0;
+}
+
+int mecat_b200_asm_index_release(mecat_b200_ctx* c, void* asmidx)
+{
+	if (check(c)) return 1;
+	cudaSetDevice(c->device);
+	asm_index_release(c, (AsmIndexDev*)asmidx);
+	return 0;
+}
+
+int mecat_b200_asm_index_export(mecat_b200_ctx* c, void* asmidx, int64_t* num_positions, uint32_t* begin, int32_t* positions)
+{
+	if (check(c) || !asmidx || !num_positions) return 1;
+	cudaSetDevice(c->device);
+	return asm_index_export(c, (const AsmIndexDev*)asmidx, num_positions, begin, positions);
+}
+
+int mecat_b200_asm_overlaps(mecat_b200_ctx* c, void* asmidx, const mecat_asm_reads* query, const mecat_asm_params* p,
+                            mecat_asm_overlap** overlaps, size_t* n)
+{
+	if (check(c) || !asmidx || !query || !p || !overlaps || !n) return 1;
+	cudaSetDevice(c->device);
+	WallTimer wt;
+	const int rc = asm_overlaps(c, (const AsmIndexDev*)asmidx, query, p, overlaps, n);
+	c->stats.total_ms += wt.stop();
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------
 // mecat2ref: genome upload + k-mer index, then batches of reads through refmap.cu
 int mecat_b200_ref_index_build(mecat_b200_ctx* c, const mecat_ref_genome* g, void** refidx)
 {

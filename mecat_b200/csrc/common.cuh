@@ -305,6 +305,12 @@ void ref_index_release(Ctx* c, RefIndex* R);
 int ref_map(Ctx* c, const RefIndex* R, const mecat_ref_reads* reads, const mecat_ref_params* p, mbref::Sink& out,
             std::vector<int32_t>* dump_counts = nullptr, std::vector<int32_t>* dump_rows = nullptr);
 
+struct AsmIndexDev;
+int asm_index_build(Ctx* c, const mecat_asm_reads* subject, AsmIndexDev** out);
+void asm_index_release(Ctx* c, AsmIndexDev* I);
+int asm_index_export(Ctx* c, const AsmIndexDev* I, int64_t* num_positions, uint32_t* begin, int32_t* positions);
+int asm_overlaps(Ctx* c, const AsmIndexDev* I, const mecat_asm_reads* query, const mecat_asm_params* p, mecat_asm_overlap** out, size_t* n);
+
 struct RawCand             // candidate_save, pw_impl.h:21-25
 {
 	int32_t loc1, loc2, left1, left2, right1, right2, score, num1, num2, readno, readstart, chain;

@@ -1,0 +1,156 @@
+// mecat_b200/csrc/host/mecat2asmpw.cpp -- host driver with the command line of mecat2canu's corrected-read overlappers:
+//
+//   mecat2asmpw -P<blocks dir> -T<threads> -S<first file> -E<last file>
+//
+// (mecat2canu/src/mecat2asmpw/mecat2asmpw.c:1032-1166; the pipeline's call is Overlapmecat2asmpw.pm:483-496).  One source,
+// four programs: the name decides the variant -- `mecat2trimpw*` uses the trimming gate and score (mecat2trimpw.c:640,
+// :942-943), a name ending in `50` keeps 50 candidates per read instead of 100 (MAXC, mecat2asmpw50.c:23).
+// `<dir>/ovlprep` names the read range of every block file (`-allreads -allbases -b <first> -e <last>` per line, :1083-1090),
+// `<dir>/NNNNNN.fasta` hold the reads (header line, one sequence line).  The index is built over file S; the reads of the
+// files S .. E are mapped against it (:1112-1150) on the GPU (mecat_b200_asm_index_build / mecat_b200_asm_overlaps); `-T`
+// is accepted and only decides how many `<S>_<t>.r` result files exist: the reference writes one per thread and the
+// pipeline concatenates `<S>_*.r`; here all lines go to `<S>_0.r` and the others stay empty.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include <string>
+#include <vector>
+
+#include "mecat_b200.h"
+
+namespace {
+
+struct File { std::string text; std::vector<int32_t> start, len; };
+
+// load_read / load_fastq (:345-372, :1000-1029): a header line, then the sequence as one token
+bool load_fasta(const std::string& path, File& f)
+{
+	FILE* in = fopen(path.c_str(), "rb");
+	if (!in) return false;
+	std::string buf;
+	char tmp[1 << 16];
+	size_t n;
+	while ((n = fread(tmp, 1, sizeof tmp, in)) > 0) buf.append(tmp, n);
+	fclose(in);
+	f.text.clear(); f.start.clear(); f.len.clear();
+	f.text.reserve(buf.size());
+	size_t p = 0;
+	while (p < buf.size()) {
+		size_t e = buf.find('\n', p);
+		if (e == std::string::npos) e = buf.size();
+		if (buf[p] == '>') {
+			size_t q = e + 1;
+			while (q < buf.size() && (buf[q] == '\n' || buf[q] == '\r' || buf[q] == ' ' || buf[q] == '\t')) ++q;
+			size_t r = q;
+			while (r < buf.size() && buf[r] != '\n' && buf[r] != '\r' && buf[r] != ' ' && buf[r] != '\t') ++r;
+			if (r > q && buf[q] != '>') {
+				f.start.push_back((int32_t)f.text.size());
+				f.len.push_back((int32_t)(r - q));
+				f.text.append(buf, q, r - q);
+				f.text.push_back('\0');
+				e = r;
+			}
+		}
+		p = e + 1;
+	}
+	return true;
+}
+
+double now()
+{
+	timeval t;
+	gettimeofday(&t, NULL);
+	return t.tv_sec + 1e-6 * t.tv_usec;
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+	const char* base = strrchr(argv[0], '/');
+	base = base ? base + 1 : argv[0];
+	mecat_asm_params P;
+	P.variant = strstr(base, "trimpw") ? 1 : 0;
+	const size_t bl = strlen(base);
+	P.max_candidates = bl >= 2 && !strcmp(base + bl - 2, "50") ? 50 : 100;
+	std::string dir;
+	int threads = -1, first = -1, last = -1;
+	for (int i = 1; i < argc; ++i) {           // param_read :1032-1061: the value follows the letter without a space
+		if (argv[i][0] != '-') { fprintf(stderr, "%s: unexpected argument '%s'\n", base, argv[i]); return 1; }
+		const char* v = argv[i] + 2;
+		switch (argv[i][1]) {
+		case 'P': dir = v; break;
+		case 'T': threads = atoi(v); break;
+		case 'S': first = atoi(v); break;
+		case 'E': last = atoi(v); break;
+		}
+	}
+	if (dir.empty() || threads < 1 || first < 1 || last < first) {
+		fprintf(stderr, "usage: %s -P<blocks dir> -T<threads> -S<first file> -E<last file>\n", base);
+		return 1;
+	}
+	std::vector<int> file_first, file_last;
+	{
+		FILE* fp = fopen((dir + "/ovlprep").c_str(), "r");
+		if (!fp) { fprintf(stderr, "%s: cannot open %s/ovlprep\n", base, dir.c_str()); return 1; }
+		char a[300], b[300], c[300], d[300];
+		int lo, hi;
+		while ((int)file_first.size() < last && fscanf(fp, " %299s %299s %299s %d %299s %d", a, b, c, &lo, d, &hi) == 6) { file_first.push_back(lo); file_last.push_back(hi); }
+		fclose(fp);
+	}
+	if ((int)file_first.size() < last) { fprintf(stderr, "%s: ovlprep names %zu files, -E asks for %d\n", base, file_first.size(), last); return 1; }
+	auto block_path = [&](int i) { char n[32]; snprintf(n, sizeof n, "/%06d.fasta", i); return dir + n; };
+
+	const double t0 = now();
+	File sub;
+	if (!load_fasta(block_path(first), sub) || sub.len.empty()) { fprintf(stderr, "%s: no reads in %s\n", base, block_path(first).c_str()); return 1; }
+	if ((int)sub.len.size() != file_last[first - 1] - file_first[first - 1] + 1) {
+		fprintf(stderr, "%s: %s holds %zu reads, ovlprep says %d\n", base, block_path(first).c_str(), sub.len.size(), file_last[first - 1] - file_first[first - 1] + 1);
+		return 1;
+	}
+	mecat_b200_ctx* ctx = NULL;
+	const char* dev = getenv("MECAT_DEVICE");
+	if (mecat_b200_init(&ctx, dev ? atoi(dev) : 0, NULL)) { fprintf(stderr, "%s: no CUDA device (this program has no CPU path)\n", base); return 1; }
+	mecat_asm_reads S;
+	S.text = sub.text.data(); S.num_letters = (int64_t)sub.text.size(); S.num_reads = (int32_t)sub.len.size(); S.first_read_id = file_first[first - 1];
+	S.read_start = sub.start.data(); S.read_len = sub.len.data();
+	void* idx = NULL;
+	if (mecat_b200_asm_index_build(ctx, &S, &idx)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); return 1; }
+	const double t1 = now();
+
+	std::vector<FILE*> out((size_t)threads, (FILE*)NULL);
+	for (int t = 0; t < threads; ++t) {
+		char n[64];
+		snprintf(n, sizeof n, "/%d_%d.r", first, t);
+		out[(size_t)t] = fopen((dir + n).c_str(), "w");
+		if (!out[(size_t)t]) { fprintf(stderr, "%s: cannot write %s%s\n", base, dir.c_str(), n); return 1; }
+	}
+	size_t total = 0;
+	int rc = 0;
+	for (int i = first; i <= last && !rc; ++i) {
+		File qf;
+		File* q = &sub;
+		if (i != first) { if (!load_fasta(block_path(i), qf)) { fprintf(stderr, "%s: cannot read %s\n", base, block_path(i).c_str()); rc = 1; break; } q = &qf; }
+		if (q->len.empty()) continue;
+		mecat_asm_reads Q;
+		Q.text = q->text.data(); Q.num_letters = (int64_t)q->text.size(); Q.num_reads = (int32_t)q->len.size(); Q.first_read_id = file_first[i - 1];
+		Q.read_start = q->start.data(); Q.read_len = q->len.data();
+		mecat_asm_overlap* ov = NULL;
+		size_t n = 0;
+		if (mecat_b200_asm_overlaps(ctx, idx, &Q, &P, &ov, &n)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rc = 1; break; }
+		for (size_t k = 0; k < n && !rc; ++k) {
+			const mecat_asm_overlap& o = ov[k];
+			if (fprintf(out[0], "%d %d %.3f 100 0 %d %d %d %d %d %d %d\n", o.sread, o.qread, o.score, o.sbeg, o.send, o.slen, o.strand, o.qbeg, o.qend, o.qlen) < 0) rc = 1;
+		}
+		total += n;
+		mecat_b200_free(ctx, ov);
+	}
+	for (FILE* f : out) if (fclose(f) != 0) rc = 1;
+	if (rc == 1 && total) fprintf(stderr, "%s: writing the result failed\n", base);
+	mecat_b200_asm_index_release(ctx, idx);
+	mecat_b200_destroy(ctx);
+	if (!rc) fprintf(stderr, "[%s] index %.2f s, mapping %.2f s, %zu overlaps\n", base, t1 - t0, now() - t1, total);
+	return rc;
+}

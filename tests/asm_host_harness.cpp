@@ -81,6 +81,21 @@ extern "C" int ah_overlaps(const char* text, int64_t n, const int32_t* starts, c
 	return 0;
 }
 
+// the k-mer lists of a text: begin (4^13 + 1 entries) and positions (caller's buffers; returns the number of positions)
+extern "C" int64_t ah_index(const char* text, int64_t n, const int32_t* starts, const int32_t* lens, int32_t nreads, uint32_t* begin, int32_t* pos, int64_t cap)
+{
+	using namespace mbasm;
+	HostBackend be;
+	AsmIndex I;
+	if (!index_build(be, text, n, starts, lens, nreads, 1, I)) return -1;
+	const int64_t total = I.total;
+	memcpy(begin, I.begin, sizeof(uint32_t) * (size_t)(KMERS + 1));
+	if (total <= cap) memcpy(pos, I.pos, sizeof(int32_t) * (size_t)total);
+	free(I.text); free(I.start); free(I.len); free(I.begin); free(I.pos);
+	for (void* p : be.owned) free(p);
+	return total;
+}
+
 extern "C" void ah_free(void* p) { free(p); }
 
 // the integer consistency test against the reference's float and double forms (tests/test_asm_host.py)

@@ -93,3 +93,56 @@ def test_integer_consistency_test_equals_the_float_forms():
             assert (got_f == want_f).all(), b
             assert (got_d == want_d).all(), b
     assert H.ah_ddf_close(90, 10, 1) == 1 and H.ah_ddf_close(90, 10, 0) == 0       # the quotient 0.9 is close in double only
+
+
+def _run_driver(bindir, prog, wrk, first, last, threads=3):
+    import subprocess
+    for f in os.listdir(wrk):
+        if f.endswith(".r"):
+            os.remove(os.path.join(wrk, f))
+    p = subprocess.run([os.path.join(bindir, prog), "-P" + wrk, "-T%d" % threads, "-S%d" % first, "-E%d" % last], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    names = sorted(f for f in os.listdir(wrk) if f.endswith(".r"))
+    assert names == ["%d_%d.r" % (first, t) for t in range(threads)]          # what the pipeline's `cat <S>_*.r` expects
+    lines = []
+    for f in names:
+        lines += open(os.path.join(wrk, f)).read().splitlines()
+    return sorted(lines)
+
+
+def test_command_line_driver_on_the_host(tmp_path):
+    """mecat_b200/csrc/host/mecat2asmpw.cpp (linked against the host harness instead of the library): the four program
+    names, -P -T -S -E, ovlprep and the block files in, <S>_<t>.r out -- the files of the unmodified binaries."""
+    import subprocess
+    bindir = util.asm_driver_on_host()
+    wrk = str(tmp_path / "blocks")
+    util.asm_workdir("asm", wrk)
+    assert _run_driver(bindir, "mecat2asmpw", wrk, 1, 2) == gold("asm.asmpw")
+    assert _run_driver(bindir, "mecat2asmpw", wrk, 2, 2, threads=1) == gold("asm.asmpw.s2")
+    assert _run_driver(bindir, "mecat2trimpw", wrk, 1, 2) == gold("asm.trimpw")
+    p = subprocess.run([os.path.join(bindir, "mecat2asmpw"), "-P" + wrk, "-T2", "-S1", "-E3"], capture_output=True, text=True)
+    assert p.returncode != 0 and "ovlprep" in p.stderr
+    p = subprocess.run([os.path.join(bindir, "mecat2asmpw"), "-P" + wrk, "-T2"], capture_output=True, text=True)
+    assert p.returncode != 0 and "usage" in p.stderr
+    # the *50 names keep 50 candidates per read: on the deep file that cuts the lists (the oracle with the same convention)
+    wrk = str(tmp_path / "deep")
+    files = util.asm_workdir("asmdeep", wrk)
+    want = all_pairs(util.asm_oracle_overlaps, files, variant=1, maxc=50)
+    assert _run_driver(bindir, "mecat2trimpw50", wrk, 1, 1) == want
+    assert len(want) != len(all_pairs(util.asm_oracle_overlaps, files, variant=1, maxc=100))
+
+
+def test_index_kernel_bodies_match_a_numpy_restatement(deep_files):
+    """creat_ref_index (mecat2asmpw.c:397-497) through the product's count / scan / fill / sort bodies, on the deep file
+    (N letters) with a poly-A read appended so that one list passes 256 entries and is dropped."""
+    import ctypes as C
+    sfirst, sub = deep_files[0]
+    text, starts, lens = util.asm_text(list(sub) + ["A" * 400])
+    kept, cnt, want_pos, dropped = util.asm_index_numpy(text)
+    assert dropped
+    H = util.asm_harness()
+    begin, pos = np.zeros((1 << 26) + 1, dtype=np.uint32), np.zeros(len(want_pos) + 16, dtype=np.int32)
+    n = H.ah_index(text, len(text), starts.ctypes.data, lens.ctypes.data, len(lens), begin.ctypes.data, pos.ctypes.data, len(pos))
+    assert n == len(want_pos)
+    assert (pos[:n] == want_pos).all()
+    assert (np.diff(begin.astype(np.int64))[kept] == cnt).all() and int(begin[-1]) == n

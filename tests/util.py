@@ -3,6 +3,7 @@ unmodified reference (oracle/_ref/libmecatref.so, only when it has been built) a
 numpy utilities for packed volumes.  Test infrastructure only."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 import sys
 
@@ -735,6 +736,8 @@ def asm_harness():
                               C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                               C.c_void_p, C.c_char_p, C.c_int]
     L.ah_free.argtypes = [C.c_void_p]
+    L.ah_index.restype = C.c_int64
+    L.ah_index.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     L.ah_ddf_close.restype = C.c_int
     L.ah_ddf_close.argtypes = [C.c_int, C.c_int, C.c_int]
     _asm_harness = L
@@ -753,3 +756,45 @@ def asm_harness_overlaps(sub, sub_first, qry, qry_first, variant=0, maxc=100, bu
     arr = np.frombuffer(C.string_at(out.value, n.value * ASM_OVERLAP_DTYPE.itemsize), dtype=ASM_OVERLAP_DTYPE).copy()
     H.ah_free(out)
     return arr, list(stats)
+
+
+def asm_driver_on_host():
+    """mecat_b200/csrc/host/mecat2asmpw.cpp linked against tests/asm_abi_shim.cpp + the host harness instead of the product
+    library.  Returns the directory holding the four program names."""
+    out_dir = os.path.join(ROOT, "tests", "_build", "asm_driver")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "mecat2asmpw")
+    src = [os.path.join(ROOT, "mecat_b200", "csrc", "host", "mecat2asmpw.cpp"), os.path.join(ROOT, "tests", "asm_abi_shim.cpp"),
+           os.path.join(ROOT, "tests", "asm_host_harness.cpp")]
+    deps = src + [os.path.join(ROOT, "mecat_b200", "csrc", "asm_pipeline.h"), os.path.join(ROOT, "mecat_b200", "csrc", "asm_core.cuh"),
+                  os.path.join(ROOT, "include", "mecat_b200.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe] + src)
+    for twin in ("mecat2asmpw50", "mecat2trimpw", "mecat2trimpw50"):
+        dst = os.path.join(out_dir, twin)
+        if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(exe):
+            shutil.copy2(exe, dst)
+    return out_dir
+
+
+def asm_index_numpy(text):
+    """creat_ref_index (mecat2asmpw.c:397-497) in numpy: (codes kept, their list lengths, all positions in list order).
+    13-mers in A0 T1 C2 G3; a letter other than ACGT ends a k-mer; lists of more than 256 dropped; 1-based starts."""
+    t = np.frombuffer(text, dtype=np.uint8)
+    code = np.full(256, 4, dtype=np.int64)
+    for i, c in enumerate(b"ATCG"):
+        code[c] = i
+    v = code[t]
+    n = len(v) - 12
+    kmer = np.zeros(n, dtype=np.int64)
+    ok = np.ones(n, dtype=bool)
+    for j in range(13):
+        kmer = kmer * 4 + (v[j:j + n] & 3)
+        ok &= v[j:j + n] < 4
+    starts = np.nonzero(ok)[0]
+    codes = kmer[starts]
+    order = np.lexsort((starts, codes))
+    codes, starts = codes[order], starts[order]
+    uniq, cnt = np.unique(codes, return_counts=True)
+    keep = np.repeat(cnt <= 256, cnt)
+    return uniq[cnt <= 256], cnt[cnt <= 256], (starts[keep] + 1).astype(np.int32), bool((cnt > 256).any())
