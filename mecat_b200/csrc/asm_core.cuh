@@ -40,7 +40,7 @@ constexpr int MAX_OCC = 256;        // sumvalue_x :307-314
 constexpr int MAX_READ = 100000;    // RM: the reference's fixed read buffers, :17
 constexpr int MAXC_MAX = 100;       // MAXC :23 (50 in the *50 programs)
 constexpr int64_t KMERS = (int64_t)1 << (2 * SEED);
-constexpr int TILE = 1024;          // k-mer codes per scan tile
+constexpr int TILE = 64;            // k-mer codes per scan tile: two 128-byte lines of counters per unit
 
 ASM_HD uint32_t atomic_inc(uint32_t* p)
 {
@@ -192,7 +192,7 @@ struct Table
 {
 	Slot* slots; uint32_t mask; int shift;
 	Bucket* pool; uint32_t* pool_used; uint32_t pool_cap;
-	int32_t* list; int32_t nrec;      // records of this strand in first-touch order
+	int32_t* list; int32_t nrec, cap; // records of this strand in first-touch order; cap: room in list (slots hold twice as many)
 	bool full;
 };
 
@@ -219,6 +219,7 @@ ASM_HD Bucket* table_touch(Table& T, int32_t blk)
 		if (s.key == 0) break;
 		h = (h + 1) & T.mask;
 	}
+	if (T.nrec >= T.cap) { T.full = true; return nullptr; }
 	const uint32_t id = atomic_inc(T.pool_used);
 	if (id >= T.pool_cap) { T.full = true; return nullptr; }
 	Slot s; s.key = blk + 1; s.rec = (int32_t)id;
@@ -434,7 +435,7 @@ struct TableRefs           // where the table of strand u lives
 		const uint32_t cap = (uint32_t)(slot_off[u + 1] - slot_off[u]);
 		T.slots = slots + slot_off[u]; T.mask = cap - 1; T.shift = table_shift(cap);
 		T.pool = pool; T.pool_used = pool_used; T.pool_cap = pool_cap;
-		T.list = lists + list_off[u]; T.nrec = 0; T.full = false;
+		T.list = lists + list_off[u]; T.nrec = 0; T.cap = (int32_t)(list_off[u + 1] - list_off[u]); T.full = false;
 		return T;
 	}
 };
@@ -455,6 +456,278 @@ struct SeedFn              // one strand: block table, candidate walk
 		if (T.full) { status[i] = 1; return; }
 		status[i] = 0;
 		ncand[u] = walk_strand(s, q.first_id + r, s.rc, sub, T, gate, cands + u * maxc, maxc);
+	}
+};
+
+// ---------------------------------------------------------------------------------------------- a warp per strand
+// The same strand on the 32 lanes of a warp.  `lanes` is the warp (asmpw.cu) or its host stand-in (EmuLanes): each(f)
+// runs f(lane) on every lane, ballot / sum combine a value over the lanes, lead(f) has one lane compute a value for all,
+// sync() orders the lanes' memory accesses.  Code outside these calls is the same for every lane (on the device all lanes
+// execute it with the same values; stores there are the leader's).
+struct WarpScratch
+{
+	int32_t blk[32], off[32], rec[32];
+	int t_loc[2 * SM], t_seedn[2 * SM], t_score[2 * SM];
+};
+
+struct EmuLanes            // the host stand-in of a warp: the lanes run one after the other
+{
+	template <class F> void each(F&& f) const { for (int l = 0; l < 32; ++l) f(l); }
+	template <class F> int sum(F&& f) const { int s = 0; for (int l = 0; l < 32; ++l) s += f(l); return s; }
+	template <class F> uint32_t ballot(F&& f) const { uint32_t m = 0; for (int l = 0; l < 32; ++l) if (f(l)) m |= 1u << l; return m; }
+	template <class F> int lead(F&& f) const { return f(); }
+	bool leader() const { return true; }
+	void sync() const {}
+};
+
+ASM_HD int popcount32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return __popc(x);
+#else
+	return __builtin_popcount(x);
+#endif
+}
+
+ASM_HD uint32_t atomic_add(uint32_t* p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(p, v);
+#else
+	const uint32_t o = *p; *p += v; return o;
+#endif
+}
+
+ASM_HD void add_int(int* p, int v)
+{
+#if defined(__CUDA_ARCH__)
+	atomicAdd(p, v);
+#else
+	*p += v;
+#endif
+}
+
+ASM_HD bool slot_claim(Slot* s, int32_t key)      // does the empty slot become this key's?
+{
+#if defined(__CUDA_ARCH__)
+	return atomicCAS(&s->key, 0, key) == 0;
+#else
+	if (s->key) return false;
+	s->key = key;
+	return true;
+#endif
+}
+
+// seed_strand with a lane per hit of the sampled k-mer's list (ascending positions).  Only the first hit of a k-mer in a
+// block changes the block (:599), so the acting lanes of a round hold distinct blocks: new records are numbered in lane
+// order -- first-touch order -- and the running score of a block and its left neighbour (:608) is read after every
+// lane's increment, which is what the sequential walk sees because the neighbour's hit, if any, lies at a lower position.
+template <class L>
+ASM_HD void seed_strand_w(const L& lanes, const Strand& s, const uint32_t* begin, const int32_t* pos, Table& T, WarpScratch& W)
+{
+	const int nk = sampled_kmers(s.len);
+	for (int k = 0; k < nk; ++k) {
+		const int32_t c = s.kmer(k * BC);
+		if (c < 0) continue;
+		const uint32_t e = begin[c + 1];
+		int32_t carry = -1;
+		for (uint32_t base = begin[c]; base < e; base += 32) {
+			lanes.each([&](int l) {
+				const uint32_t i = base + (uint32_t)l;
+				if (i < e) { const int32_t p = pos[i]; W.blk[l] = p / ZV; W.off[l] = p % ZV; }
+				else W.blk[l] = -1;
+			});
+			lanes.sync();
+			const uint32_t act = lanes.ballot([&](int l) { return W.blk[l] >= 0 && W.blk[l] != (l ? W.blk[l - 1] : carry); });
+			lanes.each([&](int l) {
+				if (!(act >> l & 1u)) return;
+				const Bucket* b = table_find(T, W.blk[l]);
+				W.rec[l] = b ? (int32_t)(b - T.pool) : -1;
+			});
+			lanes.sync();
+			const uint32_t fresh = lanes.ballot([&](int l) { return (act >> l & 1u) && W.rec[l] < 0; });
+			if (fresh) {
+				const int n = popcount32(fresh);
+				if (T.nrec + n > T.cap) { T.full = true; return; }
+				const uint32_t first = (uint32_t)lanes.lead([&]() { return (int)atomic_add(T.pool_used, (uint32_t)n); });
+				if (first + (uint32_t)n > T.pool_cap) { T.full = true; return; }
+				lanes.each([&](int l) {
+					if (!(fresh >> l & 1u)) return;
+					const int rank = popcount32(fresh & ((1u << l) - 1u));
+					const int32_t id = (int32_t)first + rank, blk = W.blk[l];
+					Bucket* b = T.pool + id;
+					b->blk = blk; b->index = T.nrec + rank; b->score = 0; b->seednum = 0; b->index_score = 0; b->pad_ = 0;
+					for (int i = 0; i < SM; ++i) { b->loczhi[i] = 0; b->seedno[i] = 0; }
+					T.list[T.nrec + rank] = id;
+					uint32_t h = ((uint32_t)(blk + 1) * 2654435761u) >> T.shift;
+					while (!slot_claim(T.slots + h, blk + 1)) h = (h + 1) & T.mask;
+					T.slots[h].rec = id;
+					W.rec[l] = id;
+				});
+				T.nrec += n;
+				lanes.sync();
+			}
+			lanes.each([&](int l) {
+				if (!(act >> l & 1u)) return;
+				Bucket* b = T.pool + W.rec[l];
+				const int loc = ++b->score;
+				if (loc <= SM) { b->loczhi[loc - 1] = (int16_t)W.off[l]; b->seedno[loc - 1] = (int16_t)(k + 1); }
+				b->seednum = (int16_t)(k + 1);
+			});
+			lanes.sync();
+			lanes.each([&](int l) {
+				if (!(act >> l & 1u)) return;
+				Bucket* b = T.pool + W.rec[l];
+				b->index_score = (int16_t)(b->score + (W.blk[l] > 0 ? score_of(T, W.blk[l] - 1) : 0));
+			});
+			carry = W.blk[31];
+			lanes.sync();
+		}
+	}
+}
+
+// walk_strand on a warp: the pair tests of find_location with a lane per first entry, the neighbour votes with a lane
+// per entry; the order of the blocks, the retiring of neighbours and the candidate list stay one lane's.
+template <class L>
+ASM_HD int walk_strand_w(const L& lanes, const Strand& s, int read_name, int chain, const Reads& sub, Table& T, int gate, Cand* out, int maxc, WarpScratch& W)
+{
+	int ncand = 0;
+	for (int e = 0; e < T.nrec; ++e) {
+		Bucket* b = T.pool + T.list[e];
+		if (!(b->index_score > gate) || b->score == 0) continue;
+		const int blk = b->blk, s_k = b->score;
+		const Bucket* a = blk > 0 ? table_find(T, blk - 1) : nullptr;
+		const int loc = a ? a->score : 0;
+		const int na = loc > 0 ? (loc < SM ? loc : SM) : 0, nb = s_k < SM ? s_k : SM, u_k = na + nb;
+		const int start_loc = loc > 0 ? (blk - 1) * ZV : blk * ZV;
+		lanes.sync();
+		lanes.each([&](int l) {
+			for (int i = l; i < u_k; i += 32) {
+				if (i < na) { W.t_loc[i] = a->loczhi[i]; W.t_seedn[i] = a->seedno[i]; }
+				else { W.t_loc[i] = b->loczhi[i - na] + (na ? ZV : 0); W.t_seedn[i] = b->seedno[i - na]; }
+				W.t_score[i] = 0;
+			}
+		});
+		lanes.sync();
+		lanes.each([&](int l) {
+			for (int i = l; i < u_k - 1; i += 32) {
+				int last = W.t_seedn[i], mine = 0;
+				const int li = W.t_loc[i], si = W.t_seedn[i];
+				for (int j = i + 1; j < u_k; ++j) {
+					const int sj = W.t_seedn[j], ds = sj - si, dl = W.t_loc[j] - li;
+					if (last != sj && ds > 0 && dl > 0 && dl < s.len && ddf_close(dl, ds)) { mine++; add_int(W.t_score + j, 1); last = sj; }
+				}
+				if (mine) add_int(W.t_score + i, mine);
+			}
+		});
+		lanes.sync();
+		// the choice of find_location :343-365 over the scores
+		int location[4] = {0, 0, 0, 0}, rep_loc = 0;
+		{
+			int maxval = 0, maxi = 0, rep = 0, lasti = 0;
+			for (int i = 0; i < u_k; ++i) {
+				const int v = W.t_score[i];
+				if (maxval < v) { maxval = v; maxi = i; rep = 0; }
+				else if (maxval == v) { rep++; lasti = i; }
+			}
+			if (maxval < 5) continue;
+			if (rep == maxval) {
+				location[0] = W.t_loc[maxi]; location[1] = W.t_seedn[maxi]; rep_loc = maxi; location[2] = W.t_loc[lasti]; location[3] = W.t_seedn[lasti];
+			} else {
+				const int lm = W.t_loc[maxi], sm = W.t_seedn[maxi];
+				for (int j = 0; j < u_k; ++j) {
+					bool take;
+					if (j == maxi) take = true;
+					else if (j < maxi) { const int ds = sm - W.t_seedn[j], dl = lm - W.t_loc[j]; take = ds > 0 && dl > 0 && dl < s.len && ddf_close(dl, ds); }
+					else { const int ds = W.t_seedn[j] - sm, dl = W.t_loc[j] - lm; take = ds > 0 && dl > 0 && dl <= s.len && ddf_close(dl, ds); }
+					if (!take) continue;
+					if (location[0] == 0) { location[0] = W.t_loc[j]; location[1] = W.t_seedn[j]; rep_loc = j; }
+					else { location[2] = W.t_loc[j]; location[3] = W.t_seedn[j]; }
+				}
+			}
+		}
+		if (W.t_score[rep_loc] < 6) continue;
+		Cand c;
+		c.score = W.t_score[rep_loc];
+		const int loc_seed = W.t_seedn[rep_loc];
+		location[0] += start_loc;
+		const int loc_list = location[0];
+		const int readno = read_of(sub.start, sub.n, loc_list);
+		const int readstart = sub.start[readno], readend = readno + 1 < sub.n ? sub.start[readno + 1] : 0;
+		if (sub.first_id + readno > read_name) continue;
+		if (sub.first_id + readno == read_name) {
+			if (lanes.leader()) {
+				int u = readstart / ZV, sk = readstart % ZV, k = 0;
+				Bucket* t = table_find(T, u);
+				if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (t->loczhi[j] < sk) t->loczhi[k++] = t->loczhi[j]; t->score = (int16_t)k; }
+				const int kend = readend / ZV;
+				for (++u; u < kend; ++u) { t = table_find(T, u); if (t) t->score = 0; }
+				t = table_find(T, u);
+				k = 0; sk = readend % ZV;
+				if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (t->loczhi[j] > sk) t->loczhi[k++] = t->loczhi[j]; t->score = (int16_t)k; }
+			}
+			lanes.sync();
+			continue;
+		}
+		c.readno = readno; c.readstart = readstart;
+		location[1] = (location[1] - 1) * BC;
+		c.left1 = location[0] - readstart + SEED - 1; c.right1 = readend - location[0];
+		c.left2 = location[1] + SEED - 1; c.right2 = s.len - location[1];
+		c.num1 = c.left1 >= c.left2 ? c.left2 : c.left1;
+		c.num2 = c.right1 >= c.right2 ? c.right2 : c.right1;
+		if (c.num1 + c.num2 < 400) continue;
+		c.loc1 = location[0]; c.loc2 = location[1];
+		int seedcount = 0;
+		for (int side = 0; side < 2; ++side) {
+			int u = side ? blk + 1 : blk - 2;
+			for (int k = (side ? c.num2 : c.num1) / ZV; side ? k > 0 : (u >= 0 && k >= 0); u += side ? 1 : -1, --k) {
+				Bucket* t = table_find(T, u);
+				const int sc = t ? t->score : 0;
+				if (sc <= 0) continue;
+				const int st = u * ZV;
+				const int hit = lanes.sum([&](int l) {
+					int h = 0;
+					for (int j = l; j < sc; j += 32) {
+						const int lo = loczhi_at(T, t, j), se = seedno_at(T, t, j);
+						if (side ? ddf_close_d(st + lo - loc_list, se - loc_seed) : ddf_close_d(loc_list - st - lo, loc_seed - se)) h++;
+					}
+					return h;
+				});
+				seedcount += hit;
+				if (5 * hit > 2 * sc) { if (lanes.leader()) t->score = 0; lanes.sync(); }
+			}
+		}
+		c.score += seedcount;
+		c.chain = chain;
+		ncand = lanes.lead([&]() {
+			int at = ncand;
+			while (at > 0 && out[at - 1].score < c.score) --at;
+			if (at >= maxc) return ncand;
+			const int last = ncand < maxc ? ncand : maxc - 1;
+			for (int i = last; i > at; --i) out[i] = out[i - 1];
+			out[at] = c;
+			return ncand < maxc ? ncand + 1 : ncand;
+		});
+	}
+	return ncand;
+}
+
+struct SeedWarpFn          // SeedFn on a warp
+{
+	Reads q, sub; const int32_t* units; const uint32_t* begin; const int32_t* pos; TableRefs tab; int gate, maxc;
+	Cand* cands; int32_t* ncand; int32_t* status;
+	template <class L>
+	ASM_HD void operator()(int64_t i, const L& lanes, WarpScratch& W) const
+	{
+		const int64_t u = units[i];
+		const int r = (int)(u >> 1);
+		Strand s; s.fwd = q.text + q.start[r]; s.len = q.len[r]; s.rc = (int)(u & 1);
+		if (s.len >= MAX_READ) { if (lanes.leader()) { ncand[u] = 0; status[i] = 2; } return; }
+		Table T = tab.open(i);
+		seed_strand_w(lanes, s, begin, pos, T, W);
+		if (T.full) { if (lanes.leader()) { ncand[u] = 0; status[i] = 1; } return; }
+		const int n = walk_strand_w(lanes, s, q.first_id + r, s.rc, sub, T, gate, cands + u * maxc, maxc, W);
+		if (lanes.leader()) { ncand[u] = n; status[i] = 0; }
 	}
 };
 

@@ -3,7 +3,7 @@
 // runs the same functors in a loop on the host.  Reference: mecat2canu/src/mecat2asmpw/mecat2asmpw.c (main :1063-1166
 // builds the index of one file and maps the reads of that file and of the following ones against it).
 //
-// Backend: alloc<T>(n) / release(p) / keep(p) / upload / download / fill / launch(n, f, stage) /
+// Backend: alloc<T>(n) / release(p) / keep(p) / upload / download / fill / launch(n, f, stage) / launch_seed(n, f, stage) (a warp per unit) /
 // launch_slots(n, f, slots, stage) (f(i, slot) with `slots` units in flight) / table_budget() / extend_slots() / fail(msg).
 #pragma once
 #include <stdint.h>
@@ -48,7 +48,7 @@ bool index_build(B& be, const char* h_text, int64_t n, const int32_t* h_start, c
 	if (!be.launch(n, fc, ST_INDEX)) return false;
 	TileSumFn fs; fs.count = count; fs.tile_sum = tile_sum;
 	if (!be.launch(ntiles, fs, ST_INDEX)) return false;
-	{   // exclusive scan of the 65 536 tile sums on the host (256 KB each way)
+	{   // exclusive scan of the 2^20 tile sums on the host (4 MB each way)
 		std::vector<uint32_t> h((size_t)ntiles + 1);
 		if (!be.download(h.data(), tile_sum, (size_t)ntiles)) return false;
 		uint32_t run = 0;
@@ -80,25 +80,28 @@ struct SeedState           // arrays over all strands of the call
 	Cand* cands; int32_t* ncand; std::vector<int32_t> cap;      // cap: records a strand's table can need at most
 };
 
-// strands units[lo, hi): block tables in one allocation, records from a shared pool; a pool that runs out splits the range
+// room for a strand's table: its hits bound the blocks it can touch, but a true overlap puts ~60 seeds into one block, so
+// a fraction of the bound is tried first
+inline int64_t table_room(int64_t bound, int div) { return std::min<int64_t>(bound, bound / div + 64); }
+inline uint32_t slots_for(int64_t room) { uint32_t sl = 2; while ((int64_t)sl < 2 * room) sl <<= 1; return sl; }
+
+// strands units[lo, hi): block tables in one allocation, records from a shared pool.  A table or a pool that runs out
+// splits the range and halves the divisor; a strand on its own gets its bound.
 template <class B>
 bool seed_range(B& be, const AsmIndex& I, const QuerySet& Q, SeedState& S, const std::vector<int32_t>& units, size_t lo, size_t hi, int gate, int maxc,
-                int64_t* batches)
+                int div, int64_t* batches)
 {
 	const size_t n = hi - lo;
 	if (!n) return true;
+	if (n == 1) div = 1;
 	std::vector<int64_t> slot_off(n + 1, 0), list_off(n + 1, 0);
-	int64_t bound = 0;
+	int64_t pool_cap = 0;
 	for (size_t i = 0; i < n; ++i) {
-		const int64_t c = S.cap[(size_t)units[lo + i]];
-		uint32_t sl = 2;
-		while ((int64_t)sl < 2 * c) sl <<= 1;
-		slot_off[i + 1] = slot_off[i] + sl; list_off[i + 1] = list_off[i] + c;
-		bound += c;
+		const int64_t c = table_room(S.cap[(size_t)units[lo + i]], div);
+		slot_off[i + 1] = slot_off[i] + slots_for(c); list_off[i + 1] = list_off[i] + c;
+		pool_cap += c;
 	}
-	// a strand rarely needs a record per hit (a true overlap puts ~60 seeds into one block): a quarter of the bound
-	// to begin with, the bound itself for a strand on its own
-	int64_t pool_cap = n == 1 ? bound : std::min<int64_t>(bound, bound / be.pool_divisor() + 16 * (int64_t)n);
+	if (div > 1) pool_cap = pool_cap / 2 + 64;          // few strands fill their room
 	if (pool_cap < 1) pool_cap = 1;
 	if (pool_cap > 0x7fffffff) pool_cap = 0x7fffffff;
 	Slot* slots = be.template alloc<Slot>((size_t)slot_off[n]);
@@ -112,12 +115,12 @@ bool seed_range(B& be, const AsmIndex& I, const QuerySet& Q, SeedState& S, const
 	if (!slots || !lists || !pool || !d_slot_off || !d_list_off || !d_units || !d_status || !d_used) return false;
 	if (!be.fill(slots, 0, sizeof(Slot) * (size_t)slot_off[n]) || !be.fill(d_used, 0, sizeof(uint32_t)) ||
 	    !be.upload(d_slot_off, slot_off.data(), n + 1) || !be.upload(d_list_off, list_off.data(), n + 1) || !be.upload(d_units, units.data() + lo, n)) return false;
-	SeedFn f;
+	SeedWarpFn f;
 	f.q = Q.q; f.sub = I.reads(); f.units = d_units; f.begin = I.begin; f.pos = I.pos; f.gate = gate; f.maxc = maxc;
 	f.tab.slot_off = d_slot_off; f.tab.list_off = d_list_off; f.tab.slots = slots; f.tab.lists = lists; f.tab.pool = pool; f.tab.pool_used = d_used;
 	f.tab.pool_cap = (uint32_t)pool_cap;
 	f.cands = S.cands; f.ncand = S.ncand; f.status = d_status;
-	if (!be.launch((int64_t)n, f, ST_SEED)) return false;
+	if (!be.launch_seed((int64_t)n, f, ST_SEED)) return false;
 	std::vector<int32_t> status(n);
 	if (!be.download(status.data(), d_status, n)) return false;
 	++*batches;
@@ -131,7 +134,8 @@ bool seed_range(B& be, const AsmIndex& I, const QuerySet& Q, SeedState& S, const
 	if (!full) return true;
 	if (n == 1) { be.fail("asm: block table of a single strand outgrew its bound"); return false; }
 	const size_t mid = lo + n / 2;
-	return seed_range(be, I, Q, S, units, lo, mid, gate, maxc, batches) && seed_range(be, I, Q, S, units, mid, hi, gate, maxc, batches);
+	const int half = div > 1 ? div / 2 : 1;
+	return seed_range(be, I, Q, S, units, lo, mid, gate, maxc, half, batches) && seed_range(be, I, Q, S, units, mid, hi, gate, maxc, half, batches);
 }
 
 struct Counters { int64_t seed_batches = 0, candidates = 0, hits = 0, extend_passes = 0; };
@@ -177,14 +181,12 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 		size_t hi = lo;
 		int64_t bytes = 0;
 		while (hi < units.size()) {
-			const int64_t c = S.cap[(size_t)units[hi]];
-			uint32_t sl = 2;
-			while ((int64_t)sl < 2 * c) sl <<= 1;
-			const int64_t need = (int64_t)sl * (int64_t)sizeof(Slot) + c * 4 + (c / be.pool_divisor() + 16) * (int64_t)sizeof(Bucket) + 64;
+			const int64_t c = table_room(S.cap[(size_t)units[hi]], be.pool_divisor());
+			const int64_t need = (int64_t)slots_for(c) * (int64_t)sizeof(Slot) + c * 4 + (c / 2 + 1) * (int64_t)sizeof(Bucket) + 64;
 			if (hi > lo && bytes + need > budget) break;
 			bytes += need; ++hi;
 		}
-		if (!seed_range(be, I, Q, S, units, lo, hi, gate, maxc, &batches)) return false;
+		if (!seed_range(be, I, Q, S, units, lo, hi, gate, maxc, be.pool_divisor(), &batches)) return false;
 		lo = hi;
 	}
 	if (cnt) cnt->seed_batches += batches;

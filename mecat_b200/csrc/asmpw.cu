@@ -24,6 +24,34 @@ __global__ void __launch_bounds__(128) k_asm(const F f, const int64_t n)
 	if (i < n) f(i);
 }
 
+struct AsmWarpLanes        // the lanes interface of asm_core.cuh on a real warp
+{
+	__device__ static int lane() { return (int)(threadIdx.x & 31u); }
+	template <class F> __device__ void each(F&& f) const { f(lane()); }
+	template <class F> __device__ int sum(F&& f) const { return __reduce_add_sync(0xffffffffu, f(lane())); }
+	template <class F> __device__ uint32_t ballot(F&& f) const { return __ballot_sync(0xffffffffu, f(lane())); }
+	template <class F> __device__ int lead(F&& f) const
+	{
+		int v = 0;
+		if (lane() == 0) v = f();
+		__syncwarp();                               // the leader's stores are visible to the other lanes behind this
+		return __shfl_sync(0xffffffffu, v, 0);
+	}
+	__device__ bool leader() const { return lane() == 0; }
+	__device__ void sync() const { __syncwarp(); }
+};
+
+constexpr int SEED_WARPS = 4;
+
+// a warp per strand: the lanes take the hits of a sampled k-mer's list, the pair tests of a block's entries and the
+// entries of a voting neighbour; 1.9 KB of shared memory per warp for the entries being scored
+__global__ void __launch_bounds__(SEED_WARPS * 32) k_asm_seed_warp(const mbasm::SeedWarpFn f, const int64_t n)
+{
+	__shared__ mbasm::WarpScratch scratch[SEED_WARPS];
+	const int64_t u = (int64_t)blockIdx.x * SEED_WARPS + (threadIdx.x >> 5);
+	if (u < n) f(u, AsmWarpLanes(), scratch[threadIdx.x >> 5]);
+}
+
 constexpr int SLOT_THREADS = 64;
 
 template <class F>
@@ -37,7 +65,7 @@ __global__ void __launch_bounds__(SLOT_THREADS) k_asm_slots(const F f, const int
 struct AsmBackend : PoolBackend
 {
 	int64_t budget; int divisor;
-	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(4)
+	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(8)
 	{
 		// block tables, record pool and alignment scratch of the strands in flight: 40 % of the free device memory (72 GB of
 		// a B200's 180) unless told otherwise
@@ -52,6 +80,13 @@ struct AsmBackend : PoolBackend
 		if (n <= 0) return true;
 		KScope ks(c, MECAT_K_ASM_INDEX + stage);
 		k_asm<F><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(f, n);
+		return check(cudaGetLastError(), "launch");
+	}
+	bool launch_seed(int64_t n, const mbasm::SeedWarpFn& f, int stage)
+	{
+		if (n <= 0) return true;
+		KScope ks(c, MECAT_K_ASM_INDEX + stage);
+		k_asm_seed_warp<<<(unsigned)((n + SEED_WARPS - 1) / SEED_WARPS), SEED_WARPS * 32, 0, c->stream>>>(f, n);
 		return check(cudaGetLastError(), "launch");
 	}
 	template <class F> bool launch_slots(int64_t n, const F& f, int64_t nslots, int stage)

@@ -20,7 +20,7 @@ struct HostBackend
 	std::vector<void*> owned;
 	std::string err;
 	int64_t budget = (int64_t)1 << 30;
-	int divisor = 4;
+	int divisor = 8;
 	int64_t slots = 3;
 
 	template <class T> T* alloc(size_t n)
@@ -35,6 +35,22 @@ struct HostBackend
 	template <class T> bool download(T* h, const T* d, size_t n) { if (n) memcpy(h, d, n * sizeof(T)); return true; }
 	bool fill(void* d, int byte, size_t bytes) { memset(d, byte, bytes); return true; }
 	template <class F> bool launch(int64_t n, const F& f, int) { for (int64_t i = 0; i < n; ++i) f(i); return true; }
+	// the warp form of the seeding functor with the host lanes; MECAT_B200_ASM_SEED=thread: the one-thread form of the same work
+	bool launch_seed(int64_t n, const mbasm::SeedWarpFn& f, int)
+	{
+		const char* e = getenv("MECAT_B200_ASM_SEED");
+		if (e && !strcmp(e, "thread")) {
+			mbasm::SeedFn g;
+			g.q = f.q; g.sub = f.sub; g.units = f.units; g.begin = f.begin; g.pos = f.pos; g.tab = f.tab; g.gate = f.gate; g.maxc = f.maxc;
+			g.cands = f.cands; g.ncand = f.ncand; g.status = f.status;
+			for (int64_t i = 0; i < n; ++i) g(i);
+			return true;
+		}
+		mbasm::WarpScratch W;
+		memset(&W, 0xAB, sizeof W);
+		for (int64_t i = 0; i < n; ++i) f(i, mbasm::EmuLanes(), W);
+		return true;
+	}
 	template <class F> bool launch_slots(int64_t n, const F& f, int64_t nslots, int)
 	{
 		for (int64_t i = 0; i < n; ++i) f(i, (int)(i % nslots));

@@ -69,7 +69,7 @@ def test_kernel_bodies_match_the_oracle_on_the_deep_file(deep_files):
     for variant, maxc in ((0, 50), (1, 100)):
         want = util.asm_oracle_overlaps(sub, sfirst, sub, sfirst, variant=variant, maxc=maxc)
         got, stats = util.asm_harness_overlaps(sub, sfirst, sub, sfirst, variant=variant, maxc=maxc)
-        assert stats[0] == 1 and stats[3] == 1
+        assert stats[0] >= 1 and stats[3] == 1          # a genome this small fills every block: the first table estimate runs out and the range is split
         assert util.asm_lines(got) == util.asm_lines(want)          # same records in the same order
     # tables cut into many batches, a record pool that runs out and splits its batch: same records
     got, stats = util.asm_harness_overlaps(sub, sfirst, sub, sfirst, variant=1, maxc=100, budget=200000, divisor=64)
