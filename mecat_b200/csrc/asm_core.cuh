@@ -761,7 +761,7 @@ constexpr int DP_ROW = MAX_D + 4;                     // diagonals of a row: the
 constexpr int DP_CELLS = MAX_D * (DP_ROW / 2 + 1);
 constexpr int CHUNK_COLS = 2 * MAX_CHUNK + 8;
 
-struct ExtScratch          // per resident thread
+struct ExtScratch          // per resident warp
 {
 	int32_t* V; int32_t* U;            // VU_INTS each
 	uint32_t* dp;                      // DP_CELLS: x1 | x2 << 10 | (came from k + 1) << 20
@@ -778,18 +778,34 @@ struct Side                // letters of both sequences walking away from the se
 	ASM_HD char r(int i) const { return q.at(p2 + step * i); }
 };
 
-// align :108-197 on n letters of both sequences.  Returns 1 when an end was reached; *cols columns written to S.cq / S.ct
+ASM_HD int trailing_ones(uint32_t m)      // how many low bits of m are set
+{
+	const uint32_t z = ~m;
+	if (!z) return 32;
+#if defined(__CUDA_ARCH__)
+	return __ffs((int)z) - 1;
+#else
+	return __builtin_ctz(z);
+#endif
+}
+
+// align :108-197 on n letters of both sequences, a warp per alignment: the diagonals of a row are walked one after the
+// other by every lane alike (the leader stores), the slide along a diagonal compares 32 letters per step, the columns of a
+// run of agreeing letters are written by a lane each.  Returns 1 when an end was reached; *cols columns in S.cq / S.ct
 // (subject row, query row), *qe / *te letters of each consumed.
-ASM_HDN int align_chunk(const Side& W, int n, ExtScratch& S, int* cols, int* qe, int* te)
+template <class L>
+ASM_HD int align_chunk(const L& lanes, const Side& W, int n, ExtScratch& S, int* cols, int* qe, int* te)
 {
 	const int max_d = (int)(0.10 * (n + n));
 	const int band_tol = (int)(0.10 * n), band = 2 * band_tol, off = max_d;
 	*cols = 0; *qe = 0; *te = 0;
-	for (int i = 0; i < 2 * max_d + 3; ++i) { S.V[i] = 0; S.U[i] = 0; }
+	lanes.sync();
+	lanes.each([&](int l) { for (int i = l; i < 2 * max_d + 3; i += 32) { S.V[i] = 0; S.U[i] = 0; } });
+	lanes.sync();
 	int best_m = -1, min_k = 0, max_k = 0, ncell = 0;
 	for (int d = 0; d < max_d; ++d) {
 		if (max_k - min_k > band) break;
-		S.row_start[d] = ncell; S.row_min[d] = min_k;
+		if (lanes.leader()) { S.row_start[d] = ncell; S.row_min[d] = min_k; }
 		int x = 0, y = 0, k;
 		bool aligned = false;
 		for (k = min_k; k <= max_k; k += 2) {
@@ -798,12 +814,21 @@ ASM_HDN int align_chunk(const Side& W, int n, ExtScratch& S, int* cols, int* qe,
 			else { down = 0; x = S.V[k - 1 + off] + 1; }
 			y = x - k;
 			const int x1 = x;
-			while (x < n && y < n && W.s(x) == W.r(y)) { ++x; ++y; }
-			S.dp[ncell++] = (uint32_t)x1 | ((uint32_t)x << 10) | (down << 20);
-			S.V[k + off] = x; S.U[k + off] = x + y;
+			for (;;) {
+				const uint32_t m = lanes.ballot([&](int l) { return x + l < n && y + l < n && W.s(x + l) == W.r(y + l); });
+				const int run = trailing_ones(m);
+				x += run; y += run;
+				if (run < 32) break;
+			}
+			if (lanes.leader()) {
+				S.dp[ncell] = (uint32_t)x1 | ((uint32_t)x << 10) | (down << 20);
+				S.V[k + off] = x; S.U[k + off] = x + y;      // this row writes one parity of diagonals and reads the other
+			}
+			++ncell;
 			if (x + y > best_m) best_m = x + y;
 			if (x >= n || y >= n) { aligned = true; break; }
 		}
+		lanes.sync();
 		if (aligned) {
 			*qe = x; *te = y;
 			int pos = (x + y + d) / 2;
@@ -812,12 +837,15 @@ ASM_HDN int align_chunk(const Side& W, int n, ExtScratch& S, int* cols, int* qe,
 			for (int cd = d; cd >= 0; --cd) {
 				const uint32_t e = S.dp[S.row_start[cd] + (ck - S.row_min[cd]) / 2];
 				const int x1 = (int)(e & 1023u), x2 = (int)((e >> 10) & 1023u);
-				for (int xx = x2 - 1; xx >= x1; --xx) { --pos; S.cq[pos] = W.s(xx); S.ct[pos] = W.r(xx - ck); }
+				const int len = x2 - x1, first = pos - len;
+				lanes.each([&](int l) { for (int i = l; i < len; i += 32) { S.cq[first + i] = W.s(x1 + i); S.ct[first + i] = W.r(x1 + i - ck); } });
+				pos = first;
 				if (cd == 0) break;
 				--pos;
-				if ((e >> 20) & 1u) { S.cq[pos] = '-'; S.ct[pos] = W.r(x1 - ck - 1); ck += 1; }
-				else { S.cq[pos] = W.s(x1 - 1); S.ct[pos] = '-'; ck -= 1; }
+				if ((e >> 20) & 1u) { if (lanes.leader()) { S.cq[pos] = '-'; S.ct[pos] = W.r(x1 - ck - 1); } ck += 1; }
+				else { if (lanes.leader()) { S.cq[pos] = W.s(x1 - 1); S.ct[pos] = '-'; } ck -= 1; }
 			}
+			lanes.sync();
 			return 1;
 		}
 		int new_min = max_k, new_max = min_k;
@@ -832,7 +860,8 @@ struct SideResult { int done1, done2, cols, gaps, gaps_head; bool overflow; };
 
 // one side of the seed, :733-789 / :791-846.  keep: the columns are appended to S.l1 / S.l2 (left half); otherwise only
 // counted (gap columns, and those among the first SEED columns of the side).
-ASM_HDN SideResult extend_side(Side W, int num, int len1, int len2, ExtScratch& S, bool keep)
+template <class L>
+ASM_HD SideResult extend_side(const L& lanes, Side W, int num, int len1, int len2, ExtScratch& S, bool keep)
 {
 	SideResult R; R.done1 = R.done2 = R.cols = R.gaps = R.gaps_head = 0; R.overflow = false;
 	bool more = true;
@@ -840,15 +869,16 @@ ASM_HDN SideResult extend_side(Side W, int num, int len1, int len2, ExtScratch& 
 		int n;
 		if (num > MAX_CHUNK) n = DN; else { more = false; n = num < 0 ? 0 : num; }
 		int cols, qe, te;
-		int ok = align_chunk(W, n, S, &cols, &qe, &te);
+		const int ok = align_chunk(lanes, W, n, S, &cols, &qe, &te);
 		if (!ok) break;
 		int take = cols, adv1, adv2;
 		if (more) {
 			int k, loc = 0, sci = 0, run = 0;          // back to the last run of four agreeing columns, :748-753
 			for (k = cols - 1; k > -1 && run < 4; --k) {
-				if (S.cq[k] != '-') loc++;
-				if (S.ct[k] != '-') sci++;
-				if (S.cq[k] == S.ct[k]) run++; else run = 0;
+				const char a = S.cq[k], b = S.ct[k];
+				if (a != '-') loc++;
+				if (b != '-') sci++;
+				if (a == b) run++; else run = 0;
 			}
 			loc = DN - qe + loc; sci = DN - te + sci;
 			if (loc == DN) break;
@@ -858,11 +888,17 @@ ASM_HDN SideResult extend_side(Side W, int num, int len1, int len2, ExtScratch& 
 			adv1 = qe; adv2 = te;
 		}
 		if (keep && R.cols + take > S.lcap) { R.overflow = true; break; }
-		for (int i = 0; i < take; ++i) {
-			const bool gap = S.cq[i] != S.ct[i];
-			if (gap) { R.gaps++; if (R.cols + i < SEED) R.gaps_head++; }
-			if (keep) { S.l1[R.cols + i] = S.cq[i]; S.l2[R.cols + i] = S.ct[i]; }
-		}
+		const int at = R.cols;
+		const int packed = lanes.sum([&](int l) {
+			int g = 0, gh = 0;
+			for (int i = l; i < take; i += 32) {
+				const char a = S.cq[i], b = S.ct[i];
+				if (a != b) { g++; if (at + i < SEED) gh++; }
+				if (keep) { S.l1[at + i] = a; S.l2[at + i] = b; }
+			}
+			return g | (gh << 16);
+		});
+		R.gaps += packed & 0xffff; R.gaps_head += packed >> 16;
 		R.cols += take; R.done1 += adv1; R.done2 += adv2;
 		W.p1 += (int64_t)W.step * adv1; W.p2 += W.step * adv2;
 		num = len1 - R.done1 >= len2 - R.done2 ? len2 - R.done2 : len1 - R.done1;
@@ -890,45 +926,66 @@ struct GapShifter
 		for (s = 0, j = col; s < k && j >= 0; --j, ++s) { str1[j] = W.s(a - s); str2[j] = W.r(b - s); }
 		return true;
 	}
+	// one column of the walk; only a column with a gap can change anything but the two counters
+	ASM_HD void column(int col, int len1, int len2, int& loc1, int& loc2) const
+	{
+		if (str1[col] != '-') loc1++;
+		else if (pull(col, len1 - loc1, len2 - loc2)) { if (str1[col] != '-') loc1++; }
+		if (str2[col] != '-') loc2++;
+		else if (str1[col] != '-') { if (pull(col, len1 - loc1 + 1, len2 - loc2) && str2[col] != '-') loc2++; }
+		else if (pull(col, len1 - loc1, len2 - loc2) && str2[col] != '-') loc2++;
+	}
 };
 
-ASM_HDN void shift_gaps(const Side& W, int len1, int len2, char* str1, char* str2, int n)
+// The lanes look at 32 columns at a time; columns without a gap only advance the counters, the first column with one is
+// walked by the leader (it may rewrite columns to its left, so the next look starts right behind it).
+template <class L>
+ASM_HD void shift_gaps(const L& lanes, const Side& W, int len1, int len2, char* str1, char* str2, int n)
 {
 	GapShifter G; G.W = W; G.str1 = str1; G.str2 = str2;
-	int loc1 = 0, loc2 = 0;
-	for (int col = n - 1; col > -1; --col) {
-		if (str1[col] != '-') loc1++;
-		else if (G.pull(col, len1 - loc1, len2 - loc2)) { if (str1[col] != '-') loc1++; }
-		if (str2[col] != '-') loc2++;
-		else if (str1[col] != '-') { if (G.pull(col, len1 - loc1 + 1, len2 - loc2) && str2[col] != '-') loc2++; }
-		else if (G.pull(col, len1 - loc1, len2 - loc2) && str2[col] != '-') loc2++;
+	int loc1 = 0, loc2 = 0, col = n - 1;
+	lanes.sync();
+	while (col > -1) {
+		const uint32_t plain = lanes.ballot([&](int l) { return col - l > -1 && str1[col - l] != '-' && str2[col - l] != '-'; });
+		const int run = trailing_ones(plain);
+		loc1 += run; loc2 += run; col -= run;
+		if (run == 32 || col < 0) continue;
+		const int packed = lanes.lead([&]() {
+			int a = loc1, b = loc2;
+			G.column(col, len1, len2, a, b);
+			return (a - loc1) | ((b - loc2) << 8);
+		});
+		loc1 += packed & 0xff; loc2 += packed >> 8;
+		--col;
 	}
 }
 
-struct ExtendFn            // one candidate: both sides, the left half's gap shifting, the record (:728-953)
+struct ExtendFn            // one candidate on a warp: both sides, the left half's gap shifting, the record (:728-953)
 {
 	Reads q, sub; const Cand* cands; const int32_t* ncand; int maxc, variant;
 	ExtScratch* scratch; Overlap* out; int32_t* valid; int32_t* overflow;
-	ASM_HD void operator()(int64_t i, int slot) const
+	template <class L>
+	ASM_HD void operator()(int64_t i, int slot, const L& lanes) const
 	{
 		const int r = (int)(i / maxc), ci = (int)(i % maxc);
-		valid[i] = 0;
-		if (ci >= ncand[r]) return;
+		if (ci >= ncand[r]) { if (lanes.leader()) valid[i] = 0; return; }
 		const Cand c = cands[i];
 		ExtScratch S = scratch[slot];
 		Strand st; st.fwd = q.text + q.start[r]; st.len = q.len[r]; st.rc = c.chain;
-		Side L; L.text = sub.text; L.p1 = (int64_t)c.loc1 + SEED - 2; L.q = st; L.p2 = c.loc2 + SEED - 1; L.step = -1;
-		const SideResult A = extend_side(L, c.num1, c.left1, c.left2, S, true);
-		if (A.overflow) { *overflow = 1; return; }
+		Side Lf; Lf.text = sub.text; Lf.p1 = (int64_t)c.loc1 + SEED - 2; Lf.q = st; Lf.p2 = c.loc2 + SEED - 1; Lf.step = -1;
+		const SideResult A = extend_side(lanes, Lf, c.num1, c.left1, c.left2, S, true);
+		if (A.overflow) { if (lanes.leader()) { *overflow = 1; valid[i] = 0; } return; }
 		Side Rt; Rt.text = sub.text; Rt.p1 = (int64_t)c.loc1 - 1; Rt.q = st; Rt.p2 = c.loc2; Rt.step = 1;
-		const SideResult B = extend_side(Rt, c.num2, c.right1, c.right2, S, false);
-		shift_gaps(L, A.done1 - 1, A.done2 - 1, S.l1, S.l2, A.cols);
-		int loc = 0, eit = 0, mism_left = 0;
-		for (int j = 0; j < A.cols; ++j) {
-			if (S.l1[j] != '-') loc++;
-			if (S.l2[j] != '-') eit++;
-			if (!(S.l1[j] == S.l2[j] && S.l2[j] != '-')) mism_left++;
-		}
+		const SideResult B = extend_side(lanes, Rt, c.num2, c.right1, c.right2, S, false);
+		shift_gaps(lanes, Lf, A.done1 - 1, A.done2 - 1, S.l1, S.l2, A.cols);
+		lanes.sync();
+		const int loc = lanes.sum([&](int l) { int n = 0; for (int j = l; j < A.cols; j += 32) if (S.l1[j] != '-') n++; return n; });
+		const int eit = lanes.sum([&](int l) { int n = 0; for (int j = l; j < A.cols; j += 32) if (S.l2[j] != '-') n++; return n; });
+		const int mism_left = lanes.sum([&](int l) {
+			int n = 0;
+			for (int j = l; j < A.cols; j += 32) { const char a = S.l1[j], b = S.l2[j]; if (!(a == b && b != '-')) n++; }
+			return n;
+		});
 		const int u_k = A.cols, s_k = B.cols;
 		int left_loc1, left_loc, right_loc1, right_loc;
 		if (u_k == SEED - 1) { left_loc1 = c.loc1 + SEED - loc - 1; left_loc = c.loc2 + SEED - eit; }
@@ -941,6 +998,8 @@ struct ExtendFn            // one candidate: both sides, the left half's gap shi
 		else if (u_k < SEED) { n = s_k; mism = B.gaps; }
 		else { n = u_k; mism = mism_left; }
 		left_loc1 -= c.readstart; right_loc1 -= c.readstart;
+		if (!lanes.leader()) return;
+		valid[i] = 0;
 		if (!(right_loc1 - left_loc1 > 450)) return;
 		float js;
 		if (variant == 0) { js = (float)(2 * n - mism); js = js * 30 * 4 / n; }       // :942-943

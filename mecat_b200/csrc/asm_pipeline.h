@@ -77,31 +77,38 @@ struct QuerySet            // device-side query reads of one call
 
 struct SeedState           // arrays over all strands of the call
 {
-	Cand* cands; int32_t* ncand; std::vector<int32_t> cap;      // cap: records a strand's table can need at most
+	Cand* cands; int32_t* ncand; std::vector<int32_t> cap, hits;      // cap: records a strand's table can need at most
 };
 
-// room for a strand's table: its hits bound the blocks it can touch, but a true overlap puts ~60 seeds into one block, so
-// a fraction of the bound is tried first
-inline int64_t table_room(int64_t bound, int div) { return std::min<int64_t>(bound, bound / div + 64); }
+// room for a strand's table.  Its hits bound the blocks it can touch, but far fewer are touched: a chance hit makes a
+// block of its own (expect text / 4^13 of them per sampled k-mer), a true overlap puts ~60 seeds into each of its blocks.
+// `mult` doubles every time a range ran out and was split.
+inline int64_t table_room(int64_t bound, int64_t hits, int len, int64_t text, int mult)
+{
+	const int64_t nk = sampled_kmers(len);
+	const int64_t guess = (3 * nk * text / KMERS) / 2 + hits / 16 + 64;
+	return std::min<int64_t>(bound, guess * mult);
+}
 inline uint32_t slots_for(int64_t room) { uint32_t sl = 2; while ((int64_t)sl < 2 * room) sl <<= 1; return sl; }
 
 // strands units[lo, hi): block tables in one allocation, records from a shared pool.  A table or a pool that runs out
-// splits the range and halves the divisor; a strand on its own gets its bound.
+// splits the range and doubles the room; a strand on its own gets its bound.
 template <class B>
 bool seed_range(B& be, const AsmIndex& I, const QuerySet& Q, SeedState& S, const std::vector<int32_t>& units, size_t lo, size_t hi, int gate, int maxc,
-                int div, int64_t* batches)
+                int mult, int64_t* batches)
 {
 	const size_t n = hi - lo;
 	if (!n) return true;
-	if (n == 1) div = 1;
+	if (n == 1) mult = 1 << 20;
 	std::vector<int64_t> slot_off(n + 1, 0), list_off(n + 1, 0);
 	int64_t pool_cap = 0;
 	for (size_t i = 0; i < n; ++i) {
-		const int64_t c = table_room(S.cap[(size_t)units[lo + i]], div);
+		const int32_t u = units[lo + i];
+		const int64_t c = table_room(S.cap[(size_t)u], S.hits[(size_t)u], Q.h_len[u >> 1], I.n, mult);
 		slot_off[i + 1] = slot_off[i] + slots_for(c); list_off[i + 1] = list_off[i] + c;
 		pool_cap += c;
 	}
-	if (div > 1) pool_cap = pool_cap / 2 + 64;          // few strands fill their room
+	if (n > 1) pool_cap = pool_cap / be.pool_divisor() + 64;      // few strands fill their room
 	if (pool_cap < 1) pool_cap = 1;
 	if (pool_cap > 0x7fffffff) pool_cap = 0x7fffffff;
 	Slot* slots = be.template alloc<Slot>((size_t)slot_off[n]);
@@ -134,8 +141,7 @@ bool seed_range(B& be, const AsmIndex& I, const QuerySet& Q, SeedState& S, const
 	if (!full) return true;
 	if (n == 1) { be.fail("asm: block table of a single strand outgrew its bound"); return false; }
 	const size_t mid = lo + n / 2;
-	const int half = div > 1 ? div / 2 : 1;
-	return seed_range(be, I, Q, S, units, lo, mid, gate, maxc, half, batches) && seed_range(be, I, Q, S, units, mid, hi, gate, maxc, half, batches);
+	return seed_range(be, I, Q, S, units, lo, mid, gate, maxc, 2 * mult, batches) && seed_range(be, I, Q, S, units, mid, hi, gate, maxc, 2 * mult, batches);
 }
 
 struct Counters { int64_t seed_batches = 0, candidates = 0, hits = 0, extend_passes = 0; };
@@ -170,6 +176,7 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 	if (!S.cands || !S.ncand) return false;
 	const int64_t nblocks = I.n / ZV + 2;
 	S.cap.resize((size_t)nstrand);
+	S.hits = hits;
 	for (int64_t u = 0; u < nstrand; ++u) { S.cap[(size_t)u] = (int32_t)std::min<int64_t>(hits[(size_t)u], nblocks); if (cnt) cnt->hits += hits[(size_t)u]; }
 	// batches of strands whose tables fit the budget
 	std::vector<int32_t> units((size_t)nstrand);
@@ -181,12 +188,13 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 		size_t hi = lo;
 		int64_t bytes = 0;
 		while (hi < units.size()) {
-			const int64_t c = table_room(S.cap[(size_t)units[hi]], be.pool_divisor());
-			const int64_t need = (int64_t)slots_for(c) * (int64_t)sizeof(Slot) + c * 4 + (c / 2 + 1) * (int64_t)sizeof(Bucket) + 64;
+			const int32_t u = units[hi];
+			const int64_t c = table_room(S.cap[(size_t)u], S.hits[(size_t)u], Q.h_len[u >> 1], I.n, 1);
+			const int64_t need = (int64_t)slots_for(c) * (int64_t)sizeof(Slot) + c * 4 + (c / be.pool_divisor() + 1) * (int64_t)sizeof(Bucket) + 64;
 			if (hi > lo && bytes + need > budget) break;
 			bytes += need; ++hi;
 		}
-		if (!seed_range(be, I, Q, S, units, lo, hi, gate, maxc, be.pool_divisor(), &batches)) return false;
+		if (!seed_range(be, I, Q, S, units, lo, hi, gate, maxc, 1, &batches)) return false;
 		lo = hi;
 	}
 	if (cnt) cnt->seed_batches += batches;

@@ -1,8 +1,8 @@
 // mecat_b200/csrc/asmpw.cu -- mecat2asmpw / mecat2trimpw on the GPU: CUDA backend of
 // asm_pipeline.h.  The stage sequence lives in asm_pipeline.h, the per-unit bodies in asm_core.cuh; here every stage
 // functor F becomes a launch of k_asm<F> (one thread per text position / k-mer code / strand / read), the alignment of the
-// candidates a persistent launch of k_asm_slots<F> (as many threads as scratch slots, each taking candidates in a
-// grid-stride loop), and memory comes from the context's pool.
+// strands and of the candidates launches with a warp per unit (k_asm_seed_warp; k_asm_slots: as many warps as scratch
+// slots, each taking candidates in a grid-stride loop), and memory comes from the context's pool.
 // Reference: mecat2canu/src/mecat2asmpw/mecat2asmpw.c (creat_ref_index :397-497, pairwise_mapping :515-984).
 #include "common.cuh"
 #include "dev_backend.cuh"
@@ -52,20 +52,22 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_asm_seed_warp(const mbasm::
 	if (u < n) f(u, AsmWarpLanes(), scratch[threadIdx.x >> 5]);
 }
 
-constexpr int SLOT_THREADS = 64;
+constexpr int SLOT_WARPS = 4;
 
+// a warp per scratch slot, candidates in a grid-stride loop: the lanes compare 32 letters of a diagonal per step and
+// write a run of columns together
 template <class F>
-__global__ void __launch_bounds__(SLOT_THREADS) k_asm_slots(const F f, const int64_t n, const int64_t nslots)
+__global__ void __launch_bounds__(SLOT_WARPS * 32) k_asm_slots(const F f, const int64_t n, const int64_t nslots)
 {
-	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t slot = (int64_t)blockIdx.x * SLOT_WARPS + (threadIdx.x >> 5);
 	if (slot >= nslots) return;
-	for (int64_t i = slot; i < n; i += nslots) f(i, (int)slot);
+	for (int64_t i = slot; i < n; i += nslots) f(i, (int)slot, AsmWarpLanes());
 }
 
 struct AsmBackend : PoolBackend
 {
-	int64_t budget; int divisor;
-	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(8)
+	int64_t budget; int divisor, slots_per_sm;
+	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(2), slots_per_sm(32)
 	{
 		// block tables, record pool and alignment scratch of the strands in flight: 40 % of the free device memory (72 GB of
 		// a B200's 180) unless told otherwise
@@ -74,6 +76,7 @@ struct AsmBackend : PoolBackend
 		if (budget < ((int64_t)64 << 20)) budget = (int64_t)64 << 20;
 		if (const char* e = getenv("MECAT_B200_ASM_TABLE_MB")) budget = std::max<int64_t>(1, atoll(e)) << 20;      // test hook: force several batches
 		if (const char* e = getenv("MECAT_B200_ASM_POOL_DIV")) divisor = std::max(1, atoi(e));                    // test hook: a pool that runs out
+		if (const char* e = getenv("MECAT_B200_ASM_EXTEND_WARPS")) slots_per_sm = std::max(1, atoi(e));           // alignment warps per SM
 	}
 	template <class F> bool launch(int64_t n, const F& f, int stage)
 	{
@@ -93,7 +96,7 @@ struct AsmBackend : PoolBackend
 	{
 		if (n <= 0 || nslots <= 0) return true;
 		KScope ks(c, MECAT_K_ASM_INDEX + stage);
-		k_asm_slots<F><<<(unsigned)((nslots + SLOT_THREADS - 1) / SLOT_THREADS), SLOT_THREADS, 0, c->stream>>>(f, n, nslots);
+		k_asm_slots<F><<<(unsigned)((nslots + SLOT_WARPS - 1) / SLOT_WARPS), SLOT_WARPS * 32, 0, c->stream>>>(f, n, nslots);
 		return check(cudaGetLastError(), "launch");
 	}
 	void keep(void* p)
@@ -102,7 +105,7 @@ struct AsmBackend : PoolBackend
 	}
 	int64_t table_budget() const { return budget; }
 	int pool_divisor() const { return divisor; }
-	int64_t extend_slots() const { return (int64_t)c->sm_count * 4 * SLOT_THREADS; }      // 4 CTAs of 64 threads per SM
+	int64_t extend_slots() const { return (int64_t)c->sm_count * slots_per_sm; }      // alignment warps in flight, each with its own scratch
 };
 
 // the loaders' view of a file: letters from 'a' up are upper-cased (load_read :355, load_fastq :1012)

@@ -20,7 +20,7 @@ struct HostBackend
 	std::vector<void*> owned;
 	std::string err;
 	int64_t budget = (int64_t)1 << 30;
-	int divisor = 8;
+	int divisor = 2;
 	int64_t slots = 3;
 
 	template <class T> T* alloc(size_t n)
@@ -53,7 +53,7 @@ struct HostBackend
 	}
 	template <class F> bool launch_slots(int64_t n, const F& f, int64_t nslots, int)
 	{
-		for (int64_t i = 0; i < n; ++i) f(i, (int)(i % nslots));
+		for (int64_t i = 0; i < n; ++i) f(i, (int)(i % nslots), mbasm::EmuLanes());
 		return true;
 	}
 	bool release(void* p)
