@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(SLOT_WARPS * 32) k_asm_slots(const F f, const 
 struct AsmBackend : PoolBackend
 {
 	int64_t budget; int divisor, slots_per_sm;
-	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(2), slots_per_sm(32)
+	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(1), slots_per_sm(32)
 	{
 		// block tables, record pool and alignment scratch of the strands in flight: 40 % of the free device memory (72 GB of
 		// a B200's 180) unless told otherwise

@@ -110,9 +110,11 @@ int main(int argc, char** argv)
 		fprintf(stderr, "%s: %s holds %zu reads, ovlprep says %d\n", base, block_path(first).c_str(), sub.len.size(), file_last[first - 1] - file_first[first - 1] + 1);
 		return 1;
 	}
+	const double t_load = now();
 	mecat_b200_ctx* ctx = NULL;
 	const char* dev = getenv("MECAT_DEVICE");
 	if (mecat_b200_init(&ctx, dev ? atoi(dev) : 0, NULL)) { fprintf(stderr, "%s: no CUDA device (this program has no CPU path)\n", base); return 1; }
+	const double t_init = now();
 	mecat_asm_reads S;
 	S.text = sub.text.data(); S.num_letters = (int64_t)sub.text.size(); S.num_reads = (int32_t)sub.len.size(); S.first_read_id = file_first[first - 1];
 	S.read_start = sub.start.data(); S.read_len = sub.len.data();
@@ -129,6 +131,7 @@ int main(int argc, char** argv)
 	}
 	size_t total = 0;
 	int rc = 0;
+	double t_map = 0, t_write = 0;
 	for (int i = first; i <= last && !rc; ++i) {
 		File qf;
 		File* q = &sub;
@@ -139,18 +142,23 @@ int main(int argc, char** argv)
 		Q.read_start = q->start.data(); Q.read_len = q->len.data();
 		mecat_asm_overlap* ov = NULL;
 		size_t n = 0;
+		const double m0 = now();
 		if (mecat_b200_asm_overlaps(ctx, idx, &Q, &P, &ov, &n)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rc = 1; break; }
+		const double m1 = now();
+		t_map += m1 - m0;
 		for (size_t k = 0; k < n && !rc; ++k) {
 			const mecat_asm_overlap& o = ov[k];
 			if (fprintf(out[0], "%d %d %.3f 100 0 %d %d %d %d %d %d %d\n", o.sread, o.qread, o.score, o.sbeg, o.send, o.slen, o.strand, o.qbeg, o.qend, o.qlen) < 0) rc = 1;
 		}
 		total += n;
 		mecat_b200_free(ctx, ov);
+		t_write += now() - m1;
 	}
 	for (FILE* f : out) if (fclose(f) != 0) rc = 1;
 	if (rc == 1 && total) fprintf(stderr, "%s: writing the result failed\n", base);
 	mecat_b200_asm_index_release(ctx, idx);
 	mecat_b200_destroy(ctx);
-	if (!rc) fprintf(stderr, "[%s] index %.2f s, mapping %.2f s, %zu overlaps\n", base, t1 - t0, now() - t1, total);
+	if (!rc) fprintf(stderr, "[%s] load %.2f s, device %.2f s, index %.2f s, mapping %.2f s, result files %.2f s, total %.2f s, %zu overlaps\n", base, t_load - t0,
+	                 t_init - t_load, t1 - t_init, t_map, t_write, now() - t0, total);
 	return rc;
 }

@@ -20,7 +20,7 @@ struct HostBackend
 	std::vector<void*> owned;
 	std::string err;
 	int64_t budget = (int64_t)1 << 30;
-	int divisor = 2;
+	int divisor = 1;
 	int64_t slots = 3;
 
 	template <class T> T* alloc(size_t n)

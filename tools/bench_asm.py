@@ -53,7 +53,7 @@ def main():
         recs = ctx.asm_overlaps(idx, reads, 0, 100)
         t2 = time.time()
         ctx.asm_index_release(idx)
-        if step:
+        if step or a.steps == 0:
             times.append((t1 - t0, t2 - t1))
         st = ctx.stats()
     ours = sorted(mecat_b200.asm_lines(recs))
@@ -64,8 +64,9 @@ def main():
                    "hits": st["num_hits"], "candidates": st["num_candidates"], "steps": a.steps, "all_steps_s": times}
     ctx.close()
     t0 = time.time()
-    subprocess.check_call([os.path.join(ROOT, "mecat_b200", "bin", "mecat2asmpw"), "-P" + wrk, "-T1", "-S1", "-E1"], stderr=subprocess.DEVNULL)
+    p = subprocess.run([os.path.join(ROOT, "mecat_b200", "bin", "mecat2asmpw"), "-P" + wrk, "-T1", "-S1", "-E1"], capture_output=True, text=True, check=True)
     out["ours"]["command_line_s"] = time.time() - t0
+    out["ours"]["command_line_phases"] = p.stderr.strip().splitlines()[-1]
     cli = sorted(open(os.path.join(wrk, "1_0.r")).read().splitlines())
     out["ours"]["command_line_equals_abi"] = cli == ours
     os.remove(os.path.join(wrk, "1_0.r"))
