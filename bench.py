@@ -476,7 +476,26 @@ def run_program(args):
     bindir = os.path.join(ROOT, "mecat_b200", "bin")
     refdir = os.path.join(ROOT, "oracle", "_ref")
     ref = args.impl == "reference"
-    if args.workload == "ref":
+    if args.workload == "asm":
+        # the corrected-read overlapper of mecat2canu: one block file of corrected-read like reads
+        # against itself; the reference arm runs the same workload, not a sample (it takes ~20 s on 16 cores)
+        metric, unit = "reads overlapped/sec (mecat2asmpw, one block file against itself)", "reads/s"
+        nreads, genome = 20000, 2500000
+        blocks = os.path.join(d, "asm_blocks_%d_%d" % (nreads, SEED))
+        fa = os.path.join(blocks, "000001.fasta")
+        if not (os.path.exists(fa) and os.path.exists(os.path.join(blocks, "ovlprep"))):
+            os.makedirs(blocks, exist_ok=True)
+            subprocess.check_call([gen_exe(), fa + ".tmp", str(nreads), str(genome), str(SEED), "4000", "800", "0.015", "-"])
+            os.replace(fa + ".tmp", fa)
+            with open(os.path.join(blocks, "ovlprep"), "w") as f:
+                f.write("-allreads -allbases -b 1 -e %d\n" % nreads)
+        for f in os.listdir(blocks):
+            if f.endswith(".r"):
+                os.remove(os.path.join(blocks, f))
+        exe = os.path.join(refdir if ref else bindir, "mecat2asmpw")
+        argv, units = ["-P" + blocks, "-T%d" % cores, "-S1", "-E1"], nreads
+        workload = "mecat2asmpw -S1 -E1: %d x 4 kb synthetic corrected reads (1.5 %% error, 32x of a %.1f Mb genome), every read against the index of the file" % (nreads, genome / 1e6)
+    elif args.workload == "ref":
         metric, unit = "reads mapped/sec (mecat2ref -m 1)", "reads/s"
         sample = min(nreads, max(8000, 500 * cores))
         if ref:
@@ -526,7 +545,10 @@ def run_program(args):
         dt, log = _cli(exe, argv, env={"MECAT_B200_STATS": "1"}, cwd=d)
         ph = None
         if not ref:
-            if args.workload == "ref":
+            if args.workload == "asm":
+                m = re.search(r"index ([0-9.]+) s, mapping ([0-9.]+) s", log)
+                ph = float(m.group(1)) + float(m.group(2)) if m else None
+            elif args.workload == "ref":
                 m = re.search(r"mapping ([0-9.]+) s", log)
                 ph = float(m.group(1)) if m else None
             else:
@@ -543,12 +565,12 @@ def run_program(args):
     m = re.search(r"\[kernel ms\](.*)", log)
     if m:
         kernel = {k: float(v) for k, v in re.findall(r"(\w+)=([0-9.]+)\(", m.group(1))}
-    in_bytes = os.path.getsize(fa) + (os.path.getsize(gfa) if args.workload == "ref" else os.path.getsize(os.path.join(d, "cand_%d_%d.can" % (nreads, SEED))))
+    in_bytes = os.path.getsize(fa) + (0 if args.workload == "asm" else os.path.getsize(gfa) if args.workload == "ref" else os.path.getsize(os.path.join(d, "cand_%d_%d.can" % (nreads, SEED))))
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * (phase if phase else wall), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": ("SAMPLE (%d reads) of: " % units if ref else "") + workload, "reads": units, "genome": genome, "seed": SEED,
+        "config": {"workload": ("SAMPLE (%d reads) of: " % units if ref and args.workload != "asm" else "") + workload, "reads": units, "genome": genome, "seed": SEED,
                    "parallelism": ("reference CPU binary, %d host threads (no GPU)" % cores) if ref else "1 gpu, command-line driver"},
         "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": 1000.0 * wall, "steps": n,
                 "h2d_bytes_per_step": 0 if ref else None, "d2h_bytes_per_step": 0 if ref else None,
@@ -558,7 +580,7 @@ def run_program(args):
                  "note": "value / e2e are means over the timed runs; process start-up (CUDA context) makes single command-line runs on a shared box vary by seconds"},
         "gpu_launches": 0 if ref else None, "kernel_ms_last_run": kernel,
         "cpu_baseline": {"value": e2e_value if ref else None, "unit": unit, "cores": cores, "kind": "reference",
-                         "sample": ("unmodified binary on the first %d reads / templates" % units) if ref else "run bench.py --workload %s --impl reference" % args.workload},
+                         "sample": (("unmodified binary as the reference builds it (no CFLAGS), the whole workload" if args.workload == "asm" else "unmodified binary on the first %d reads / templates" % units)) if ref else "run bench.py --workload %s --impl reference" % args.workload},
     }
     if ref:
         line["impl"] = "reference"
@@ -589,7 +611,7 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="debug only: reduced workload (result is not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--tech", type=int, default=0, choices=[0, 1], help="-x of mecat2pw: 1 = the nanopore parameter set (workload pw only; 20 000 reads by default)")
-    ap.add_argument("--workload", default="pw", choices=["pw", "ref", "cns"],
+    ap.add_argument("--workload", default="pw", choices=["pw", "ref", "cns", "asm"],
                     help="pw (default): the headline, mecat2pw -j 1 (BASELINE configs[1]).  ref / cns: mecat2ref (configs[2]) / "
                          "mecat2cns (configs[3]) through their command-line drivers")
     ap.add_argument("--mode", default="strong", choices=["strong", "ring"],

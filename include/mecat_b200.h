@@ -402,7 +402,7 @@ int mecat_b200_asm_index_build(mecat_b200_ctx* ctx, const mecat_asm_reads* subje
 int mecat_b200_asm_index_release(mecat_b200_ctx* ctx, void* asmidx);
 /* replaces pairwise_mapping (:515-984) for the reads of one query file: overlaps with subject reads numbered below the
  * query read, in read order and per read in the order the reference aligns its candidates.  Where the reference reads
- * block memory no seed of the strand wrote, zero is read (oracle/oracle_asmpw.cpp). */
+ * block memory no seed of the strand wrote, zero is read. */
 int mecat_b200_asm_overlaps(mecat_b200_ctx* ctx, void* asmidx, const mecat_asm_reads* query, const mecat_asm_params* p,
                             mecat_asm_overlap** overlaps, size_t* n);
 /* test hook: the k-mer lists (begin: 4^13 + 1 entries; positions: 1-based k-mer starts as databaseindex holds them) */

@@ -15,8 +15,8 @@
 // The reference keeps a dense array of blocks per thread; here a strand owns an open-addressing table keyed by block
 // number over records taken from a shared pool in first-touch order -- the order the reference's index_list walks.
 // Where the reference reads block memory that no seed of the strand wrote (the neighbour votes run to a block's score,
-// which keeps counting past SM because insert_loc is commented out, :605, :699-712), this code reads zero, like the
-// oracle (oracle/oracle_asmpw.cpp says why).  All bodies are shared by the CUDA backend (asmpw.cu) and the host harness
+// which keeps counting past SM because insert_loc is commented out, :605, :699-712), this code reads zero (DESIGN.md
+// section 4.11 says why).  All bodies are shared by the CUDA backend (asmpw.cu) and the host harness
 // of the CPU test-suite (tests/asm_host_harness.cpp).
 #pragma once
 #include <stdint.h>
@@ -68,6 +68,18 @@ ASM_HD int32_t text_kmer(const char* text, int64_t i, int64_t n)
 	}
 	return code;
 }
+
+// the loaders' view of a file: letters from 'a' up go through toupper (load_read :355, load_fastq :1012), which in the C
+// locale changes a .. z only
+struct UpperFn
+{
+	char* text; int64_t n;
+	ASM_HD void operator()(int64_t i) const
+	{
+		const int64_t b = i * 16, e = b + 16 < n ? b + 16 : n;
+		for (int64_t j = b; j < e; ++j) { const char c = text[j]; if (c >= 'a' && c <= 'z') text[j] = (char)(c - 32); }
+	}
+};
 
 // ---------------------------------------------------------------------------------------------- index of the subject text
 struct KmerCountFn

@@ -44,6 +44,8 @@ bool index_build(B& be, const char* h_text, int64_t n, const int32_t* h_start, c
 	if (!I.text || !I.start || !I.len || !I.begin || !count || !tile_sum) return false;
 	if (!be.fill(I.text, 0, (size_t)n + 16) || !be.upload(I.text, h_text, (size_t)n) || !be.upload(I.start, h_start, (size_t)nreads) ||
 	    !be.upload(I.len, h_len, (size_t)nreads) || !be.fill(count, 0, sizeof(uint32_t) * (size_t)KMERS)) return false;
+	UpperFn fu; fu.text = I.text; fu.n = n;
+	if (!be.launch((n + 15) / 16, fu, ST_INDEX)) return false;
 	KmerCountFn fc; fc.text = I.text; fc.n = n; fc.count = count;
 	if (!be.launch(n, fc, ST_INDEX)) return false;
 	TileSumFn fs; fs.count = count; fs.tile_sum = tile_sum;
@@ -162,6 +164,8 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 	if (!d_text || !d_start || !d_len || !d_hits) return false;
 	if (!be.fill(d_text, 0, (size_t)qn + 16) || !be.upload(d_text, h_qtext, (size_t)qn) || !be.upload(d_start, h_qstart, (size_t)nq) || !be.upload(d_len, h_qlen, (size_t)nq))
 		return false;
+	UpperFn fu; fu.text = d_text; fu.n = qn;
+	if (!be.launch((qn + 15) / 16, fu, ST_SEED)) return false;
 	QuerySet Q;
 	Q.q.text = d_text; Q.q.start = d_start; Q.q.len = d_len; Q.q.n = nq; Q.q.first_id = qfirst; Q.h_len = h_qlen; Q.max_len = 0;
 	for (int32_t r = 0; r < nq; ++r) Q.max_len = std::max(Q.max_len, h_qlen[r]);

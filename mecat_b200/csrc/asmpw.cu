@@ -69,10 +69,11 @@ struct AsmBackend : PoolBackend
 	int64_t budget; int divisor, slots_per_sm;
 	AsmBackend(Ctx* ctx) : PoolBackend(ctx, "asm", true), budget(0), divisor(1), slots_per_sm(32)
 	{
-		// block tables, record pool and alignment scratch of the strands in flight: 40 % of the free device memory (72 GB of
-		// a B200's 180) unless told otherwise
+		// block tables and record pool of the strands in flight: 4 GB hold ~10 000 strands of 4 kb reads at 32x, several
+		// resident warps per scheduler, and are allocated once (a first cudaMalloc of 12 GB cost the command line 0.5 s)
 		size_t free_b = 0, total_b = 0;
-		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = (int64_t)(free_b / 5 * 2);
+		budget = (int64_t)4 << 30;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<int64_t>(budget, (int64_t)(free_b / 5 * 2));
 		if (budget < ((int64_t)64 << 20)) budget = (int64_t)64 << 20;
 		if (const char* e = getenv("MECAT_B200_ASM_TABLE_MB")) budget = std::max<int64_t>(1, atoll(e)) << 20;      // test hook: force several batches
 		if (const char* e = getenv("MECAT_B200_ASM_POOL_DIV")) divisor = std::max(1, atoi(e));                    // test hook: a pool that runs out
@@ -108,8 +109,8 @@ struct AsmBackend : PoolBackend
 	int64_t extend_slots() const { return (int64_t)c->sm_count * slots_per_sm; }      // alignment warps in flight, each with its own scratch
 };
 
-// the loaders' view of a file: letters from 'a' up are upper-cased (load_read :355, load_fastq :1012)
-bool staged_text(Ctx* c, const mecat_asm_reads* r, const char* what, std::string& text)
+// a file of reads as the ABI describes it: every read inside the text with a NUL behind it, in order, shorter than RM
+bool check_reads(Ctx* c, const mecat_asm_reads* r, const char* what)
 {
 	char b[256];
 	if (!r->text || r->num_letters <= 0 || r->num_reads <= 0 || !r->read_start || !r->read_len) {
@@ -125,8 +126,6 @@ bool staged_text(Ctx* c, const mecat_asm_reads* r, const char* what, std::string
 			c->err = b; return false;
 		}
 	}
-	text.assign(r->text, (size_t)r->num_letters);
-	for (char& ch : text) if (ch >= 'a') ch = (char)toupper((unsigned char)ch);
 	return true;
 }
 
@@ -134,11 +133,10 @@ bool staged_text(Ctx* c, const mecat_asm_reads* r, const char* what, std::string
 
 int asm_index_build(Ctx* c, const mecat_asm_reads* subject, AsmIndexDev** out)
 {
-	std::string text;
-	if (!staged_text(c, subject, "asm_index_build", text)) return 1;
+	if (!check_reads(c, subject, "asm_index_build")) return 1;
 	AsmIndexDev* D = new AsmIndexDev;
 	AsmBackend be(c);
-	const bool ok = mbasm::index_build(be, text.data(), subject->num_letters, subject->read_start, subject->read_len, subject->num_reads,
+	const bool ok = mbasm::index_build(be, subject->text, subject->num_letters, subject->read_start, subject->read_len, subject->num_reads,
 	                                   subject->first_read_id, D->I);
 	be.end_batch();          // after a failed build this frees the index arrays too: they are kept only at its end
 	if (!ok) { delete D; return 1; }
@@ -167,12 +165,11 @@ int asm_index_export(Ctx* c, const AsmIndexDev* D, int64_t* num_positions, uint3
 int asm_overlaps(Ctx* c, const AsmIndexDev* D, const mecat_asm_reads* query, const mecat_asm_params* p, mecat_asm_overlap** out, size_t* n)
 {
 	static_assert(sizeof(mbasm::Overlap) == sizeof(mecat_asm_overlap), "Overlap mirrors mecat_asm_overlap");
-	std::string text;
-	if (!staged_text(c, query, "asm_overlaps", text)) return 1;
+	if (!check_reads(c, query, "asm_overlaps")) return 1;
 	AsmBackend be(c);
 	std::vector<mbasm::Overlap> recs;
 	mbasm::Counters cnt;
-	const bool ok = mbasm::overlaps(be, D->I, text.data(), query->num_letters, query->read_start, query->read_len, query->num_reads, query->first_read_id,
+	const bool ok = mbasm::overlaps(be, D->I, query->text, query->num_letters, query->read_start, query->read_len, query->num_reads, query->first_read_id,
 	                                p->variant, p->max_candidates, recs, &cnt);
 	be.end_batch();
 	if (!ok) return 1;

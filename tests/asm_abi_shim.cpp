@@ -21,12 +21,7 @@ struct mecat_b200_ctx { std::string err; };
 
 namespace {
 struct Subject { std::string text; std::vector<int32_t> start, len; int32_t first; };
-std::string upper(const char* t, int64_t n)      // what the library does to the letters (load_read :355)
-{
-	std::string s(t, (size_t)n);
-	for (char& c : s) if (c >= 'a') c = (char)toupper((unsigned char)c);
-	return s;
-}
+std::string upper(const char* t, int64_t n) { return std::string(t, (size_t)n); }      // the pipeline upper-cases the letters itself
 }  // namespace
 
 extern "C" {
