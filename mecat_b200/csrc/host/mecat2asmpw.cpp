@@ -9,13 +9,17 @@
 // `<dir>/NNNNNN.fasta` hold the reads (header line, one sequence line).  The index is built over file S; the reads of the
 // files S .. E are mapped against it (:1112-1150) on the GPU (mecat_b200_asm_index_build / mecat_b200_asm_overlaps); `-T`
 // is accepted and only decides how many `<S>_<t>.r` result files exist: the reference writes one per thread and the
-// pipeline concatenates `<S>_*.r`; here all lines go to `<S>_0.r` and the others stay empty.
+// pipeline concatenates `<S>_*.r`; here device k writes `<S>_<k mod T>.r` and the others stay empty.
+// Several devices (MECAT_GPUS=n, default 1; MECAT_DEVICE names the first): every device holds its own index of file S and
+// maps its share of every query file's reads (contiguous slices) -- replicas sharded by read, no exchange.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
 
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mecat_b200.h"
@@ -110,55 +114,87 @@ int main(int argc, char** argv)
 		fprintf(stderr, "%s: %s holds %zu reads, ovlprep says %d\n", base, block_path(first).c_str(), sub.len.size(), file_last[first - 1] - file_first[first - 1] + 1);
 		return 1;
 	}
-	const double t_load = now();
-	mecat_b200_ctx* ctx = NULL;
 	const char* dev = getenv("MECAT_DEVICE");
-	if (mecat_b200_init(&ctx, dev ? atoi(dev) : 0, NULL)) { fprintf(stderr, "%s: no CUDA device (this program has no CPU path)\n", base); return 1; }
-	const double t_init = now();
-	mecat_asm_reads S;
-	S.text = sub.text.data(); S.num_letters = (int64_t)sub.text.size(); S.num_reads = (int32_t)sub.len.size(); S.first_read_id = file_first[first - 1];
-	S.read_start = sub.start.data(); S.read_len = sub.len.data();
-	void* idx = NULL;
-	if (mecat_b200_asm_index_build(ctx, &S, &idx)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); return 1; }
-	const double t1 = now();
-
+	const int dev0 = dev ? atoi(dev) : 0;
+	int ngpu = getenv("MECAT_GPUS") ? atoi(getenv("MECAT_GPUS")) : 1;
+	if (ngpu < 1) ngpu = 1;
+	if (dev0 + ngpu > mecat_b200_device_count()) {
+		fprintf(stderr, "%s: devices %d .. %d asked for, %d present (this program has no CPU path)\n", base, dev0, dev0 + ngpu - 1, mecat_b200_device_count());
+		return 1;
+	}
 	std::vector<FILE*> out((size_t)threads, (FILE*)NULL);
+	std::vector<std::mutex> out_mu((size_t)threads);
 	for (int t = 0; t < threads; ++t) {
 		char n[64];
 		snprintf(n, sizeof n, "/%d_%d.r", first, t);
 		out[(size_t)t] = fopen((dir + n).c_str(), "w");
 		if (!out[(size_t)t]) { fprintf(stderr, "%s: cannot write %s%s\n", base, dir.c_str(), n); return 1; }
 	}
-	size_t total = 0;
-	int rc = 0;
-	double t_map = 0, t_write = 0;
-	for (int i = first; i <= last && !rc; ++i) {
-		File qf;
-		File* q = &sub;
-		if (i != first) { if (!load_fasta(block_path(i), qf)) { fprintf(stderr, "%s: cannot read %s\n", base, block_path(i).c_str()); rc = 1; break; } q = &qf; }
-		if (q->len.empty()) continue;
-		mecat_asm_reads Q;
-		Q.text = q->text.data(); Q.num_letters = (int64_t)q->text.size(); Q.num_reads = (int32_t)q->len.size(); Q.first_read_id = file_first[i - 1];
-		Q.read_start = q->start.data(); Q.read_len = q->len.data();
-		mecat_asm_overlap* ov = NULL;
-		size_t n = 0;
-		const double m0 = now();
-		if (mecat_b200_asm_overlaps(ctx, idx, &Q, &P, &ov, &n)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rc = 1; break; }
-		const double m1 = now();
-		t_map += m1 - m0;
-		for (size_t k = 0; k < n && !rc; ++k) {
-			const mecat_asm_overlap& o = ov[k];
-			if (fprintf(out[0], "%d %d %.3f 100 0 %d %d %d %d %d %d %d\n", o.sread, o.qread, o.score, o.sbeg, o.send, o.slen, o.strand, o.qbeg, o.qend, o.qlen) < 0) rc = 1;
+	// the query files, loaded once and shared by the devices
+	std::vector<File> qfiles((size_t)(last - first + 1));
+	for (int i = first + 1; i <= last; ++i)
+		if (!load_fasta(block_path(i), qfiles[(size_t)(i - first)])) { fprintf(stderr, "%s: cannot read %s\n", base, block_path(i).c_str()); return 1; }
+	const double t_init = now();
+	std::vector<double> t_index((size_t)ngpu, 0.0), t_map((size_t)ngpu, 0.0), t_write((size_t)ngpu, 0.0);
+	std::vector<size_t> totals((size_t)ngpu, 0);
+	std::vector<int> rcs((size_t)ngpu, 0);
+	auto work = [&](int k) {
+		mecat_b200_ctx* ctx = NULL;
+		if (mecat_b200_init(&ctx, dev0 + k, NULL)) { fprintf(stderr, "%s: no CUDA device %d (this program has no CPU path)\n", base, dev0 + k); rcs[(size_t)k] = 1; return; }
+		const double i0 = now();
+		mecat_asm_reads S;
+		S.text = sub.text.data(); S.num_letters = (int64_t)sub.text.size(); S.num_reads = (int32_t)sub.len.size(); S.first_read_id = file_first[first - 1];
+		S.read_start = sub.start.data(); S.read_len = sub.len.data();
+		void* idx = NULL;
+		if (mecat_b200_asm_index_build(ctx, &S, &idx)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rcs[(size_t)k] = 1; mecat_b200_destroy(ctx); return; }
+		t_index[(size_t)k] = now() - i0;
+		const int slot = k % threads;
+		for (int i = first; i <= last && !rcs[(size_t)k]; ++i) {
+			const File& q = i == first ? sub : qfiles[(size_t)(i - first)];
+			const int64_t nq = (int64_t)q.len.size(), lo = nq * k / ngpu, hi = nq * (k + 1) / ngpu;      // this device's reads of the file
+			if (hi <= lo) continue;
+			mecat_asm_reads Q;
+			Q.text = q.text.data(); Q.num_letters = (int64_t)q.text.size(); Q.num_reads = (int32_t)(hi - lo); Q.first_read_id = file_first[i - 1] + (int32_t)lo;
+			Q.read_start = q.start.data() + lo; Q.read_len = q.len.data() + lo;
+			mecat_asm_overlap* ov = NULL;
+			size_t n = 0;
+			const double m0 = now();
+			if (mecat_b200_asm_overlaps(ctx, idx, &Q, &P, &ov, &n)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rcs[(size_t)k] = 1; break; }
+			const double m1 = now();
+			t_map[(size_t)k] += m1 - m0;
+			{
+				std::lock_guard<std::mutex> g(out_mu[(size_t)slot]);
+				for (size_t j = 0; j < n; ++j) {
+					const mecat_asm_overlap& o = ov[j];
+					if (fprintf(out[(size_t)slot], "%d %d %.3f 100 0 %d %d %d %d %d %d %d\n", o.sread, o.qread, o.score, o.sbeg, o.send, o.slen, o.strand, o.qbeg, o.qend, o.qlen) < 0) { rcs[(size_t)k] = 2; break; }
+				}
+			}
+			totals[(size_t)k] += n;
+			mecat_b200_free(ctx, ov);
+			t_write[(size_t)k] += now() - m1;
 		}
-		total += n;
-		mecat_b200_free(ctx, ov);
-		t_write += now() - m1;
+		mecat_b200_asm_index_release(ctx, idx);
+		mecat_b200_destroy(ctx);
+	};
+	if (ngpu == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int k = 0; k < ngpu; ++k) th.emplace_back(work, k);
+		for (auto& t : th) t.join();
 	}
-	for (FILE* f : out) if (fclose(f) != 0) rc = 1;
-	if (rc == 1 && total) fprintf(stderr, "%s: writing the result failed\n", base);
-	mecat_b200_asm_index_release(ctx, idx);
-	mecat_b200_destroy(ctx);
-	if (!rc) fprintf(stderr, "[%s] load %.2f s, device %.2f s, index %.2f s, mapping %.2f s, result files %.2f s, total %.2f s, %zu overlaps\n", base, t_load - t0,
-	                 t_init - t_load, t1 - t_init, t_map, t_write, now() - t0, total);
+	int rc = 0;
+	size_t total = 0;
+	double ti = 0, tm = 0, tw = 0;
+	for (int k = 0; k < ngpu; ++k) {
+		if (rcs[(size_t)k]) rc = 1;
+		if (rcs[(size_t)k] == 2) fprintf(stderr, "%s: writing the result failed\n", base);
+		total += totals[(size_t)k];
+		if (t_index[(size_t)k] > ti) ti = t_index[(size_t)k];
+		if (t_map[(size_t)k] > tm) tm = t_map[(size_t)k];
+		if (t_write[(size_t)k] > tw) tw = t_write[(size_t)k];
+	}
+	for (FILE* f : out) if (fclose(f) != 0) { if (!rc) fprintf(stderr, "%s: writing the result failed\n", base); rc = 1; }
+	if (!rc) fprintf(stderr, "[%s] load %.2f s, index %.2f s, mapping %.2f s, result files %.2f s (slowest of %d device%s), total %.2f s, %zu overlaps\n", base, t_init - t0,
+	                 ti, tm, tw, ngpu, ngpu == 1 ? "" : "s", now() - t0, total);
 	return rc;
 }

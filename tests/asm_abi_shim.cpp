@@ -26,6 +26,7 @@ std::string upper(const char* t, int64_t n) { return std::string(t, (size_t)n); 
 
 extern "C" {
 
+int mecat_b200_device_count(void) { return getenv("MECAT_SHIM_DEVICES") ? atoi(getenv("MECAT_SHIM_DEVICES")) : 1; }
 int mecat_b200_init(mecat_b200_ctx** ctx, int, void*) { *ctx = new mecat_b200_ctx; return 0; }
 void mecat_b200_destroy(mecat_b200_ctx* ctx) { delete ctx; }
 const char* mecat_b200_last_error(mecat_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }

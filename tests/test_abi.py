@@ -39,6 +39,10 @@ def test_struct_sizes_match_reference_records():
     # ExtensionCandidate = 13 x int32 (alignment.h:8-13); M4Record = 104 bytes (alignment.h:21-37, idx_t = int64)
     assert mecat_b200.EC_DTYPE.itemsize == 52
     assert mecat_b200.M4_DTYPE.itemsize == 104
+    # one printed line of mecat2asmpw: two ids, the float score, seven ints (mecat2asmpw.c:944-945)
+    assert mecat_b200.ASM_OVERLAP_DTYPE.itemsize == 40
+    import ctypes
+    assert ctypes.sizeof(mecat_b200.api.AsmReadsC) == 40 and ctypes.sizeof(mecat_b200.AsmParams) == 8
 
 
 def test_no_cpu_fallback(lib):

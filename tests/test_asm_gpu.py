@@ -109,11 +109,12 @@ def test_command_line_drivers_match_the_unmodified_binaries(tmp_path):
     wrk = str(tmp_path / "blocks")
     util.asm_workdir("asm", wrk)
 
-    def run(prog, first, last, threads):
+    def run(prog, first, last, threads, devices=1):
         for f in os.listdir(wrk):
             if f.endswith(".r"):
                 os.remove(os.path.join(wrk, f))
-        p = subprocess.run([os.path.join(bindir, prog), "-P" + wrk, "-T%d" % threads, "-S%d" % first, "-E%d" % last], capture_output=True, text=True)
+        p = subprocess.run([os.path.join(bindir, prog), "-P" + wrk, "-T%d" % threads, "-S%d" % first, "-E%d" % last], capture_output=True, text=True,
+                           env=dict(os.environ, MECAT_GPUS=str(devices)))
         assert p.returncode == 0, p.stderr[-2000:]
         names = sorted(f for f in os.listdir(wrk) if f.endswith(".r"))
         assert names == ["%d_%d.r" % (first, t) for t in range(threads)]
@@ -125,3 +126,6 @@ def test_command_line_drivers_match_the_unmodified_binaries(tmp_path):
     assert run("mecat2asmpw", 1, 2, 4) == gold("asm.asmpw")
     assert run("mecat2asmpw50", 2, 2, 1) == gold("asm.asmpw.s2")       # fewer than 50 candidates per read here
     assert run("mecat2trimpw", 1, 2, 2) == gold("asm.trimpw")
+    import mecat_b200
+    if mecat_b200.load_library().mecat_b200_device_count() >= 2:      # an index replica per device, the reads of every file split between them
+        assert run("mecat2asmpw", 1, 2, 4, devices=2) == gold("asm.asmpw")
