@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <string>
 
@@ -36,6 +37,45 @@ struct TextBuf
 		s.append(tmp, (size_t)n);
 	}
 };
+
+// printf("%.3f") of a float (promoted to double, as the reference's fprintf sees it, mecat2asmpw.c:944): the value is
+// m x 2^e with a 24-bit m, so m x 1000 is an exact integer and the rounding (half to even on the exact value, what glibc
+// does) needs no floating point.  Finite values below 2^39 only; anything else goes through snprintf.
+inline void fixed3(TextBuf& b, float v)
+{
+	uint32_t bits;
+	memcpy(&bits, &v, 4);
+	const uint32_t ex = (bits >> 23) & 0xffu;
+	uint64_t m = bits & 0x7fffffu;
+	int e;                                     // v = m x 2^e
+	if (ex == 0) e = -149; else { m |= 0x800000u; e = (int)ex - 150; }
+	if (ex == 0xffu || e > 15) { char tmp[64]; const int n = snprintf(tmp, sizeof tmp, "%.3f", (double)v); b.s.append(tmp, (size_t)n); return; }
+	uint64_t q = m * 1000u;                    // < 2^34
+	if (e >= 0) q <<= e;
+	else if (-e >= 64) q = 0;
+	else {
+		const int sft = -e;
+		const uint64_t rem = q & ((sft == 64 ? 0 : ((uint64_t)1 << sft)) - 1), half = (uint64_t)1 << (sft - 1);
+		q >>= sft;
+		if (rem > half || (rem == half && (q & 1u))) ++q;
+	}
+	if (bits >> 31) b.chr('-');                // "-0.000" like printf
+	b.i64((int64_t)(q / 1000));
+	b.chr('.');
+	const unsigned f = (unsigned)(q % 1000);
+	b.chr((char)('0' + f / 100)); b.chr((char)('0' + f / 10 % 10)); b.chr((char)('0' + f % 10));
+}
+
+// one line of mecat2asmpw / mecat2trimpw (mecat2asmpw.c:944-945)
+inline void format_asm(TextBuf& b, const mecat_asm_overlap* o, size_t n)
+{
+	for (size_t i = 0; i < n; ++i) {
+		const mecat_asm_overlap& r = o[i];
+		b.i64(r.sread); b.chr(' '); b.i64(r.qread); b.chr(' '); fixed3(b, r.score); b.s.append(" 100 0 ", 7);
+		b.i64(r.sbeg); b.chr(' '); b.i64(r.send); b.chr(' '); b.i64(r.slen); b.chr(' '); b.i64(r.strand); b.chr(' ');
+		b.i64(r.qbeg); b.chr(' '); b.i64(r.qend); b.chr(' '); b.i64(r.qlen); b.chr('\n');
+	}
+}
 
 inline void format_candidates(TextBuf& b, const mecat_candidate* ec, size_t n)
 {

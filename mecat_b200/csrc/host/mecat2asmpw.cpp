@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "mecat_b200.h"
+#include "format.h"
 
 namespace {
 
@@ -163,11 +164,11 @@ int main(int argc, char** argv)
 			const double m1 = now();
 			t_map[(size_t)k] += m1 - m0;
 			{
+				mbfmt::TextBuf tb;
+				tb.s.reserve(n * 64);
+				mbfmt::format_asm(tb, ov, n);
 				std::lock_guard<std::mutex> g(out_mu[(size_t)slot]);
-				for (size_t j = 0; j < n; ++j) {
-					const mecat_asm_overlap& o = ov[j];
-					if (fprintf(out[(size_t)slot], "%d %d %.3f 100 0 %d %d %d %d %d %d %d\n", o.sread, o.qread, o.score, o.sbeg, o.send, o.slen, o.strand, o.qbeg, o.qend, o.qlen) < 0) { rcs[(size_t)k] = 2; break; }
-				}
+				if (fwrite(tb.s.data(), 1, tb.s.size(), out[(size_t)slot]) != tb.s.size()) rcs[(size_t)k] = 2;
 			}
 			totals[(size_t)k] += n;
 			mecat_b200_free(ctx, ov);

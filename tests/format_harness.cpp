@@ -53,3 +53,14 @@ size_t harness_ostream_can(const mecat_candidate* ec, size_t n, char* out, size_
 }
 
 }  // extern "C"
+
+// printf("%.3f") of a float by integer arithmetic (format.h fixed3): returns the length written
+extern "C" int fh_fixed3(float v, char* out, int cap)
+{
+	mbfmt::TextBuf b;
+	mbfmt::fixed3(b, v);
+	const int n = (int)b.s.size() < cap - 1 ? (int)b.s.size() : cap - 1;
+	memcpy(out, b.s.data(), (size_t)n);
+	out[n] = 0;
+	return n;
+}

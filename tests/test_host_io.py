@@ -225,3 +225,33 @@ def test_volumes_from_fasta_equal_the_split_files(tmp_path, threads, monkeypatch
         assert np.array_equal(v.offset_size, w.offset_size) and v.pac.tobytes() == w.pac.tobytes()
     one = mecat_b200.volumes_from_fasta(fa)
     assert len(one) == 1 and one[0].pac.tobytes() == mecat_b200.volume_from_fasta(fa).pac.tobytes()
+
+
+def test_fixed3_equals_printf():
+    """mecat2asmpw prints its score with fprintf("%.3f") of a float (mecat2asmpw.c:944); the driver's integer-arithmetic
+    form (format.h fixed3) must give the same characters: random values, the scores both programs can print, exact
+    ties at the fourth decimal (rounded half to even on the exact value), denormals, large values, zeros of both signs."""
+    import ctypes as C
+    L = _format_harness()
+    L.fh_fixed3.restype = C.c_int
+    L.fh_fixed3.argtypes = [C.c_float, C.c_char_p, C.c_int]
+    rng = np.random.default_rng(9)
+    vals = [rng.random(20000, dtype=np.float32) * np.float32(300.0), rng.random(5000, dtype=np.float32) * np.float32(0.3),
+            (np.arange(0, 4000, dtype=np.float32) + np.float32(0.5)) / np.float32(1000.0),          # near ties
+            np.arange(1, 2049, dtype=np.float32) / np.float32(16.0) / np.float32(1000.0) * np.float32(8.0),
+            np.array([0.0, -0.0, 0.0005, 0.0015, 0.0025, 0.0625, 0.1875, 0.3125, 1e-45, 1e-38, 1e-10, 65535.9995, 32768.0, 1e7, 3e38, -2.5, -0.0004],
+                     dtype=np.float32)]
+    n = np.arange(500, 3000, 7, dtype=np.int64)
+    for m in (0, 1, 13, 57, 211):
+        js = (2 * n - m).astype(np.float32)
+        vals.append(js * np.float32(30) * np.float32(4) / n.astype(np.float32))                     # mecat2asmpw.c:942-943
+        vals.append(np.full(len(n), m, dtype=np.float32) / (4 * n).astype(np.float32))             # mecat2trimpw.c:942-943
+    buf = C.create_string_buffer(80)
+    bad = []
+    for arr in vals:
+        for v in arr:
+            L.fh_fixed3(float(v), buf, 80)
+            want = "%.3f" % float(v)
+            if buf.value.decode() != want:
+                bad.append((float(v), buf.value.decode(), want))
+    assert not bad, bad[:5]
