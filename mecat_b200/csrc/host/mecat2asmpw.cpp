@@ -27,7 +27,7 @@
 
 namespace {
 
-struct File { std::string text; std::vector<int32_t> start, len; };
+struct File { std::string text; std::vector<int64_t> start; std::vector<int32_t> len; };
 
 // load_read / load_fastq (:345-372, :1000-1029): a header line, then the sequence as one token
 bool load_fasta(const std::string& path, File& f)
@@ -51,7 +51,7 @@ bool load_fasta(const std::string& path, File& f)
 			size_t r = q;
 			while (r < buf.size() && buf[r] != '\n' && buf[r] != '\r' && buf[r] != ' ' && buf[r] != '\t') ++r;
 			if (r > q && buf[q] != '>') {
-				f.start.push_back((int32_t)f.text.size());
+				f.start.push_back((int64_t)f.text.size());
 				f.len.push_back((int32_t)(r - q));
 				f.text.append(buf, q, r - q);
 				f.text.push_back('\0');
@@ -115,6 +115,9 @@ int main(int argc, char** argv)
 		fprintf(stderr, "%s: %s holds %zu reads, ovlprep says %d\n", base, block_path(first).c_str(), sub.len.size(), file_last[first - 1] - file_first[first - 1] + 1);
 		return 1;
 	}
+	if (sub.text.size() >= 0x7fffffffu - 4000u) { fprintf(stderr, "%s: %s holds %zu letters; the program keeps positions in 32 bits\n", base, block_path(first).c_str(), sub.text.size()); return 1; }
+	std::vector<int32_t> sub_start(sub.start.begin(), sub.start.end());
+	const int64_t part_reads = getenv("MECAT_B200_ASM_PART_READS") ? atoll(getenv("MECAT_B200_ASM_PART_READS")) : 200000;      // test hook: small parts
 	const char* dev = getenv("MECAT_DEVICE");
 	const int dev0 = dev ? atoi(dev) : 0;
 	int ngpu = getenv("MECAT_GPUS") ? atoi(getenv("MECAT_GPUS")) : 1;
@@ -145,34 +148,46 @@ int main(int argc, char** argv)
 		const double i0 = now();
 		mecat_asm_reads S;
 		S.text = sub.text.data(); S.num_letters = (int64_t)sub.text.size(); S.num_reads = (int32_t)sub.len.size(); S.first_read_id = file_first[first - 1];
-		S.read_start = sub.start.data(); S.read_len = sub.len.data();
+		S.read_start = sub_start.data(); S.read_len = sub.len.data();
 		void* idx = NULL;
 		if (mecat_b200_asm_index_build(ctx, &S, &idx)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rcs[(size_t)k] = 1; mecat_b200_destroy(ctx); return; }
 		t_index[(size_t)k] = now() - i0;
 		const int slot = k % threads;
 		for (int i = first; i <= last && !rcs[(size_t)k]; ++i) {
 			const File& q = i == first ? sub : qfiles[(size_t)(i - first)];
-			const int64_t nq = (int64_t)q.len.size(), lo = nq * k / ngpu, hi = nq * (k + 1) / ngpu;      // this device's reads of the file
-			if (hi <= lo) continue;
-			mecat_asm_reads Q;
-			Q.text = q.text.data(); Q.num_letters = (int64_t)q.text.size(); Q.num_reads = (int32_t)(hi - lo); Q.first_read_id = file_first[i - 1] + (int32_t)lo;
-			Q.read_start = q.start.data() + lo; Q.read_len = q.len.data() + lo;
-			mecat_asm_overlap* ov = NULL;
-			size_t n = 0;
-			const double m0 = now();
-			if (mecat_b200_asm_overlaps(ctx, idx, &Q, &P, &ov, &n)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rcs[(size_t)k] = 1; break; }
-			const double m1 = now();
-			t_map[(size_t)k] += m1 - m0;
-			{
-				mbfmt::TextBuf tb;
-				tb.s.reserve(n * 64);
-				mbfmt::format_asm(tb, ov, n);
-				std::lock_guard<std::mutex> g(out_mu[(size_t)slot]);
-				if (fwrite(tb.s.data(), 1, tb.s.size(), out[(size_t)slot]) != tb.s.size()) rcs[(size_t)k] = 2;
+			// a query file is taken in parts like load_fastq does (:1000-1029: at most SVM = 200 000 reads and MAXSTR = 10^9
+			// letters at a time), every part split between the devices by reads
+			const int64_t nq = (int64_t)q.len.size();
+			for (int64_t a = 0; a < nq && !rcs[(size_t)k];) {
+				int64_t b = a;
+				while (b < nq && b - a < part_reads && q.start[(size_t)b] + q.len[(size_t)b] + 1 - q.start[(size_t)a] < 1000000000) ++b;
+				if (b == a) b = a + 1;
+				const int64_t lo = a + (b - a) * k / ngpu, hi = a + (b - a) * (k + 1) / ngpu;      // this device's reads of the part
+				a = b;
+				if (hi <= lo) continue;
+				std::vector<int32_t> qstart((size_t)(hi - lo));
+				for (int64_t r = lo; r < hi; ++r) qstart[(size_t)(r - lo)] = (int32_t)(q.start[(size_t)r] - q.start[(size_t)lo]);
+				mecat_asm_reads Q;
+				Q.text = q.text.data() + q.start[(size_t)lo]; Q.num_letters = q.start[(size_t)(hi - 1)] + q.len[(size_t)(hi - 1)] + 1 - q.start[(size_t)lo];
+				Q.num_reads = (int32_t)(hi - lo); Q.first_read_id = file_first[i - 1] + (int32_t)lo;
+				Q.read_start = qstart.data(); Q.read_len = q.len.data() + lo;
+				mecat_asm_overlap* ov = NULL;
+				size_t n = 0;
+				const double m0 = now();
+				if (mecat_b200_asm_overlaps(ctx, idx, &Q, &P, &ov, &n)) { fprintf(stderr, "%s: %s\n", base, mecat_b200_last_error(ctx)); rcs[(size_t)k] = 1; break; }
+				const double m1 = now();
+				t_map[(size_t)k] += m1 - m0;
+				{
+					mbfmt::TextBuf tb;
+					tb.s.reserve(n * 64);
+					mbfmt::format_asm(tb, ov, n);
+					std::lock_guard<std::mutex> g(out_mu[(size_t)slot]);
+					if (fwrite(tb.s.data(), 1, tb.s.size(), out[(size_t)slot]) != tb.s.size()) rcs[(size_t)k] = 2;
 			}
 			totals[(size_t)k] += n;
 			mecat_b200_free(ctx, ov);
 			t_write[(size_t)k] += now() - m1;
+			}
 		}
 		mecat_b200_asm_index_release(ctx, idx);
 		mecat_b200_destroy(ctx);

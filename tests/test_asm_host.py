@@ -95,12 +95,14 @@ def test_integer_consistency_test_equals_the_float_forms():
     assert H.ah_ddf_close(90, 10, 1) == 1 and H.ah_ddf_close(90, 10, 0) == 0       # the quotient 0.9 is close in double only
 
 
-def _run_driver(bindir, prog, wrk, first, last, threads=3, devices=1):
+def _run_driver(bindir, prog, wrk, first, last, threads=3, devices=1, part_reads=None):
     import subprocess
     for f in os.listdir(wrk):
         if f.endswith(".r"):
             os.remove(os.path.join(wrk, f))
     env = dict(os.environ, MECAT_GPUS=str(devices), MECAT_SHIM_DEVICES=str(devices))
+    if part_reads:
+        env["MECAT_B200_ASM_PART_READS"] = str(part_reads)
     p = subprocess.run([os.path.join(bindir, prog), "-P" + wrk, "-T%d" % threads, "-S%d" % first, "-E%d" % last], capture_output=True, text=True, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     names = sorted(f for f in os.listdir(wrk) if f.endswith(".r"))
@@ -123,6 +125,8 @@ def test_command_line_driver_on_the_host(tmp_path):
     assert _run_driver(bindir, "mecat2trimpw", wrk, 1, 2) == gold("asm.trimpw")
     # three devices (MECAT_GPUS): each maps a third of every query file's reads against its own index; more devices than -T files
     assert _run_driver(bindir, "mecat2asmpw", wrk, 1, 2, threads=2, devices=3) == gold("asm.asmpw")
+    # query files taken in parts (load_fastq's SVM / MAXSTR batches; here 70 reads at a time), each part split between two devices
+    assert _run_driver(bindir, "mecat2asmpw", wrk, 1, 2, threads=1, devices=2, part_reads=70) == gold("asm.asmpw")
     p = subprocess.run([os.path.join(bindir, "mecat2asmpw"), "-P" + wrk, "-T2", "-S1", "-E1"], capture_output=True, text=True, env=dict(os.environ, MECAT_GPUS="2"))
     assert p.returncode != 0 and "devices" in p.stderr
     p = subprocess.run([os.path.join(bindir, "mecat2asmpw"), "-P" + wrk, "-T2", "-S1", "-E3"], capture_output=True, text=True)
