@@ -14,7 +14,9 @@ echo "-allreads -allbases -b 1 -e 40000" > $W/ovlprep
 {
 for g in 1 2 1 2 1 2; do
   rm -f $W/*.r
-  /usr/bin/time -f "MECAT_GPUS=$g wall %e s" env MECAT_GPUS=$g mecat_b200/bin/mecat2asmpw -P$W -T2 -S1 -E1
+  t0=$(date +%s%N)
+  MECAT_GPUS=$g mecat_b200/bin/mecat2asmpw -P$W -T2 -S1 -E1
+  echo "MECAT_GPUS=$g wall $(( ($(date +%s%N) - t0) / 1000000 )) ms"
   echo "MECAT_GPUS=$g sorted md5 $(cat $W/*.r | sort | md5sum | cut -c1-32) lines $(cat $W/*.r | wc -l)"
 done
 } > gpurun_out/asm_2gpu_cli.log 2>&1
