@@ -210,7 +210,7 @@ int main(int argc, char** argv)
 		if (t_write[(size_t)k] > tw) tw = t_write[(size_t)k];
 	}
 	for (FILE* f : out) if (fclose(f) != 0) { if (!rc) fprintf(stderr, "%s: writing the result failed\n", base); rc = 1; }
-	if (!rc) fprintf(stderr, "[%s] load %.2f s, index %.2f s, mapping %.2f s, result files %.2f s (slowest of %d device%s), total %.2f s, %zu overlaps\n", base, t_init - t0,
+	if (!rc) fprintf(stderr, "[%s] load and device start-up %.2f s, index %.2f s, mapping %.2f s, result files %.2f s (slowest of %d device%s), total %.2f s, %zu overlaps\n", base, t_init - t0,
 	                 ti, tm, tw, ngpu, ngpu == 1 ? "" : "s", now() - t0, total);
 	return rc;
 }
