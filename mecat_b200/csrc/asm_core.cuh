@@ -1025,4 +1025,26 @@ struct ExtendFn            // one candidate on a warp: both sides, the left half
 	}
 };
 
+// the printed overlaps of a read, counted and then gathered into the read's place of the result (read order, candidate order)
+struct KeptCountFn
+{
+	const int32_t* valid; const int32_t* ncand; int maxc; int32_t* kept;
+	ASM_HD void operator()(int64_t r) const
+	{
+		int n = 0;
+		for (int i = 0; i < ncand[r]; ++i) n += valid[r * maxc + i] ? 1 : 0;
+		kept[r] = n;
+	}
+};
+
+struct GatherFn
+{
+	const Overlap* all; const int32_t* valid; const int32_t* ncand; int maxc; const int64_t* first; Overlap* out;
+	ASM_HD void operator()(int64_t r) const
+	{
+		int64_t at = first[r];
+		for (int i = 0; i < ncand[r]; ++i) if (valid[r * maxc + i]) out[at++] = all[r * maxc + i];
+	}
+};
+
 }  // namespace mbasm

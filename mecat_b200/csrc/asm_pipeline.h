@@ -216,7 +216,6 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 	int32_t* d_valid = be.template alloc<int32_t>((size_t)total);
 	int32_t* d_over = be.template alloc<int32_t>(1);
 	if (!d_out || !d_valid || !d_over) return false;
-	std::vector<int32_t> valid((size_t)total);
 	for (int pass = 0; pass < 2; ++pass) {
 		// columns of the left half: both sequences advance together, so 2.5 x the query's length covers any sane
 		// alignment; a side that outgrows it raises the flag and the pass is repeated with the hard bound
@@ -254,14 +253,24 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 		if (!over) break;
 		if (pass == 1) { be.fail("asm: left half of an alignment outgrew both sequences"); return false; }
 	}
-	std::vector<int32_t> nm((size_t)nq);
-	std::vector<Overlap> all((size_t)total);
-	if (!be.download(valid.data(), d_valid, (size_t)total) || !be.download(all.data(), d_out, (size_t)total) || !be.download(nm.data(), nmerged, (size_t)nq)) return false;
-	for (int32_t r = 0; r < nq; ++r) {
-		if (cnt) cnt->candidates += nm[(size_t)r];
-		for (int i = 0; i < nm[(size_t)r]; ++i)
-			if (valid[(size_t)r * maxc + i]) out.push_back(all[(size_t)r * maxc + i]);
-	}
+	// only the printed overlaps come back: counted per read on the device, placed by a host scan of the counts
+	int32_t* d_kept = be.template alloc<int32_t>((size_t)nq);
+	int64_t* d_first = be.template alloc<int64_t>((size_t)nq);
+	if (!d_kept || !d_first) return false;
+	KeptCountFn fk; fk.valid = d_valid; fk.ncand = nmerged; fk.maxc = maxc; fk.kept = d_kept;
+	if (!be.launch(nq, fk, ST_EXTEND)) return false;
+	std::vector<int32_t> nm((size_t)nq), kept((size_t)nq);
+	if (!be.download(kept.data(), d_kept, (size_t)nq) || !be.download(nm.data(), nmerged, (size_t)nq)) return false;
+	std::vector<int64_t> first((size_t)nq);
+	int64_t nout = 0;
+	for (int32_t r = 0; r < nq; ++r) { first[(size_t)r] = nout; nout += kept[(size_t)r]; if (cnt) cnt->candidates += nm[(size_t)r]; }
+	Overlap* d_res = be.template alloc<Overlap>((size_t)nout);
+	if (!d_res || !be.upload(d_first, first.data(), (size_t)nq)) return false;
+	GatherFn fg; fg.all = d_out; fg.valid = d_valid; fg.ncand = nmerged; fg.maxc = maxc; fg.first = d_first; fg.out = d_res;
+	if (!be.launch(nq, fg, ST_EXTEND)) return false;
+	out.resize((size_t)nout);
+	if (!be.download(out.data(), d_res, (size_t)nout)) return false;
+	if (!be.release(d_kept) || !be.release(d_first) || !be.release(d_res)) return false;
 	return be.release(merged) && be.release(nmerged) && be.release(d_out) && be.release(d_valid) && be.release(d_over) && be.release(d_text) &&
 	       be.release(d_start) && be.release(d_len);
 }
