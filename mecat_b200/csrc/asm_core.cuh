@@ -191,11 +191,14 @@ struct HitCountFn          // index hits of a strand: bounds its table
 	}
 };
 
-struct Bucket              // Back_List :67-70 of one touched block
+struct Entries { int16_t loczhi[SM], seedno[SM]; };      // the 60 (offset, ordinal) pairs of a Back_List :67-70
+
+// One touched block.  Most blocks a strand touches hold a single chance hit, so the record carries its first pair itself
+// (24 bytes) and gets the 240 bytes of a full entry array only when a second k-mer arrives.
+struct Bucket
 {
-	int32_t blk, index;
-	int16_t score, seednum, index_score, pad_;
-	int16_t loczhi[SM], seedno[SM];
+	int32_t blk, index, ext;          // ext: its Entries in the second pool, -1 while one pair is enough
+	int16_t score, seednum, index_score, loc0, seed0, pad_;
 };
 
 struct Slot { int32_t key, rec; };    // key = block + 1, 0 = empty
@@ -204,6 +207,7 @@ struct Table
 {
 	Slot* slots; uint32_t mask; int shift;
 	Bucket* pool; uint32_t* pool_used; uint32_t pool_cap;
+	Entries* big; uint32_t* big_used; uint32_t big_cap;
 	int32_t* list; int32_t nrec, cap; // records of this strand in first-touch order; cap: room in list (slots hold twice as many)
 	bool full;
 };
@@ -237,13 +241,37 @@ ASM_HD Bucket* table_touch(Table& T, int32_t blk)
 	Slot s; s.key = blk + 1; s.rec = (int32_t)id;
 	T.slots[h] = s;
 	Bucket* b = T.pool + id;
-	b->blk = blk; b->index = T.nrec; b->score = 0; b->seednum = 0; b->index_score = 0; b->pad_ = 0;
-	for (int i = 0; i < SM; ++i) { b->loczhi[i] = 0; b->seedno[i] = 0; }
+	b->blk = blk; b->index = T.nrec; b->ext = -1; b->score = 0; b->seednum = 0; b->index_score = 0; b->loc0 = 0; b->seed0 = 0; b->pad_ = 0;
 	T.list[T.nrec++] = (int32_t)id;
 	return b;
 }
 
 ASM_HD int score_of(const Table& T, int32_t blk) { const Bucket* b = table_find(T, blk); return b ? b->score : 0; }
+
+// pair j of a block (j < SM); what was never stored reads zero
+ASM_HD int ent_loc(const Table& T, const Bucket* b, int j) { return b->ext >= 0 ? T.big[b->ext].loczhi[j] : j == 0 ? b->loc0 : 0; }
+ASM_HD int ent_seed(const Table& T, const Bucket* b, int j) { return b->ext >= 0 ? T.big[b->ext].seedno[j] : j == 0 ? b->seed0 : 0; }
+ASM_HD void ent_set_loc(const Table& T, Bucket* b, int j, int v)
+{
+	if (b->ext >= 0) T.big[b->ext].loczhi[j] = (int16_t)v;
+	else if (j == 0) b->loc0 = (int16_t)v;
+}
+// the pair a k-mer adds as the block's `loc`-th (1-based; only the first SM are kept); false when the second pool ran out
+ASM_HD bool ent_store(const Table& T, Bucket* b, int loc, int u, int seedn)
+{
+	if (loc > SM) return true;
+	if (loc == 1 && b->ext < 0) { b->loc0 = (int16_t)u; b->seed0 = (int16_t)seedn; return true; }
+	if (b->ext < 0) {
+		const uint32_t id = atomic_inc(T.big_used);
+		if (id >= T.big_cap) return false;
+		Entries* e = T.big + id;
+		for (int i = 0; i < SM; ++i) { e->loczhi[i] = 0; e->seedno[i] = 0; }
+		e->loczhi[0] = b->loc0; e->seedno[0] = b->seed0;
+		b->ext = (int32_t)id;
+	}
+	T.big[b->ext].loczhi[loc - 1] = (int16_t)u; T.big[b->ext].seedno[loc - 1] = (int16_t)seedn;
+	return true;
+}
 
 // The 124 shorts of a Back_List as the reference's overflowing loops see them: score, loczhi[60], seedno[60], seednum,
 // the two halves of index; `field` may run into the following blocks.  A block without a record is all zero, index -1.
@@ -253,13 +281,13 @@ ASM_HD int raw_short(const Table& T, int32_t blk, int field)
 	const Bucket* b = table_find(T, blk);
 	if (!b) return field >= 122 ? -1 : 0;
 	if (field == 0) return b->score;
-	if (field <= SM) return b->loczhi[field - 1];
-	if (field <= 2 * SM) return b->seedno[field - 1 - SM];
+	if (field <= SM) return ent_loc(T, b, field - 1);
+	if (field <= 2 * SM) return ent_seed(T, b, field - 1 - SM);
 	if (field == 121) return b->seednum;
 	return field == 122 ? (int16_t)(b->index & 0xffff) : (int16_t)(b->index >> 16);
 }
-ASM_HD int loczhi_at(const Table& T, const Bucket* b, int j) { return j < SM ? b->loczhi[j] : raw_short(T, b->blk, 1 + j); }
-ASM_HD int seedno_at(const Table& T, const Bucket* b, int j) { return j < SM ? b->seedno[j] : raw_short(T, b->blk, 1 + SM + j); }
+ASM_HD int loczhi_at(const Table& T, const Bucket* b, int j) { return j < SM ? ent_loc(T, b, j) : raw_short(T, b->blk, 1 + j); }
+ASM_HD int seedno_at(const Table& T, const Bucket* b, int j) { return j < SM ? ent_seed(T, b, j) : raw_short(T, b->blk, 1 + SM + j); }
 
 // |a / (10 b) - 1| < 0.10 in exact integers.  find_location evaluates it with a float quotient, the neighbour votes with
 // a double one; |10 b| < 2^18, so a quotient other than exactly 0.9 or 1.1 is many ulps from them and rounding is
@@ -293,7 +321,7 @@ ASM_HD void seed_strand(const Strand& s, const uint32_t* begin, const int32_t* p
 			if (!b) return;
 			if (b->score == 0 || b->seednum < k + 1) {
 				const int loc = ++b->score;
-				if (loc <= SM) { b->loczhi[loc - 1] = (int16_t)u; b->seedno[loc - 1] = (int16_t)(k + 1); }
+				if (!ent_store(T, b, loc, u, k + 1)) { T.full = true; return; }
 				b->index_score = (int16_t)(loc + (blk > 0 ? score_of(T, blk - 1) : 0));
 			}
 			b->seednum = (int16_t)(k + 1);
@@ -367,10 +395,10 @@ ASM_HDN int walk_strand(const Strand& s, int read_name, int chain, const Reads& 
 		const int loc = a ? a->score : 0;
 		if (loc > 0) {
 			start_loc = (blk - 1) * ZV;
-			for (int j = 0; j < loc && j < SM; ++j) { t_list[u_k] = a->loczhi[j]; t_seedn[u_k] = a->seedno[j]; u_k++; }
-			for (int j = 0; j < s_k && j < SM; ++j) { t_list[u_k] = b->loczhi[j] + ZV; t_seedn[u_k] = b->seedno[j]; u_k++; }
+			for (int j = 0; j < loc && j < SM; ++j) { t_list[u_k] = ent_loc(T, a, j); t_seedn[u_k] = ent_seed(T, a, j); u_k++; }
+			for (int j = 0; j < s_k && j < SM; ++j) { t_list[u_k] = ent_loc(T, b, j) + ZV; t_seedn[u_k] = ent_seed(T, b, j); u_k++; }
 		} else
-			for (int j = 0; j < s_k && j < SM; ++j) { t_list[u_k] = b->loczhi[j]; t_seedn[u_k] = b->seedno[j]; u_k++; }
+			for (int j = 0; j < s_k && j < SM; ++j) { t_list[u_k] = ent_loc(T, b, j); t_seedn[u_k] = ent_seed(T, b, j); u_k++; }
 		int location[4], rep_loc = 0;
 		if (!find_location(t_list, t_seedn, t_score, location, u_k, &rep_loc, s.len)) continue;
 		if (t_score[rep_loc] < 6) continue;
@@ -385,12 +413,12 @@ ASM_HDN int walk_strand(const Strand& s, int read_name, int chain, const Reads& 
 		if (sub.first_id + readno == read_name) {              // :666-673: the read's own letters leave the table
 			int u = readstart / ZV, sk = readstart % ZV, k = 0;
 			Bucket* t = table_find(T, u);
-			if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (t->loczhi[j] < sk) t->loczhi[k++] = t->loczhi[j]; t->score = (int16_t)k; }
+			if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (ent_loc(T, t, j) < sk) ent_set_loc(T, t, k++, ent_loc(T, t, j)); t->score = (int16_t)k; }
 			const int kend = readend / ZV;
 			for (++u; u < kend; ++u) { t = table_find(T, u); if (t) t->score = 0; }
 			t = table_find(T, u);
 			k = 0; sk = readend % ZV;
-			if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (t->loczhi[j] > sk) t->loczhi[k++] = t->loczhi[j]; t->score = (int16_t)k; }
+			if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (ent_loc(T, t, j) > sk) ent_set_loc(T, t, k++, ent_loc(T, t, j)); t->score = (int16_t)k; }
 			continue;
 		}
 		c.readno = readno; c.readstart = readstart;
@@ -441,12 +469,14 @@ ASM_HDN int walk_strand(const Strand& s, int read_name, int chain, const Reads& 
 struct TableRefs           // where the table of strand u lives
 {
 	const int64_t* slot_off; const int64_t* list_off; Slot* slots; int32_t* lists; Bucket* pool; uint32_t* pool_used; uint32_t pool_cap;
+	Entries* big; uint32_t* big_used; uint32_t big_cap;
 	ASM_HD Table open(int64_t u) const
 	{
 		Table T;
 		const uint32_t cap = (uint32_t)(slot_off[u + 1] - slot_off[u]);
 		T.slots = slots + slot_off[u]; T.mask = cap - 1; T.shift = table_shift(cap);
 		T.pool = pool; T.pool_used = pool_used; T.pool_cap = pool_cap;
+		T.big = big; T.big_used = big_used; T.big_cap = big_cap;
 		T.list = lists + list_off[u]; T.nrec = 0; T.cap = (int32_t)(list_off[u + 1] - list_off[u]); T.full = false;
 		return T;
 	}
@@ -568,8 +598,7 @@ ASM_HD void seed_strand_w(const L& lanes, const Strand& s, const uint32_t* begin
 					const int rank = popcount32(fresh & ((1u << l) - 1u));
 					const int32_t id = (int32_t)first + rank, blk = W.blk[l];
 					Bucket* b = T.pool + id;
-					b->blk = blk; b->index = T.nrec + rank; b->score = 0; b->seednum = 0; b->index_score = 0; b->pad_ = 0;
-					for (int i = 0; i < SM; ++i) { b->loczhi[i] = 0; b->seedno[i] = 0; }
+					b->blk = blk; b->index = T.nrec + rank; b->ext = -1; b->score = 0; b->seednum = 0; b->index_score = 0; b->loc0 = 0; b->seed0 = 0; b->pad_ = 0;
 					T.list[T.nrec + rank] = id;
 					uint32_t h = ((uint32_t)(blk + 1) * 2654435761u) >> T.shift;
 					while (!slot_claim(T.slots + h, blk + 1)) h = (h + 1) & T.mask;
@@ -583,10 +612,11 @@ ASM_HD void seed_strand_w(const L& lanes, const Strand& s, const uint32_t* begin
 				if (!(act >> l & 1u)) return;
 				Bucket* b = T.pool + W.rec[l];
 				const int loc = ++b->score;
-				if (loc <= SM) { b->loczhi[loc - 1] = (int16_t)W.off[l]; b->seedno[loc - 1] = (int16_t)(k + 1); }
+				if (!ent_store(T, b, loc, W.off[l], k + 1)) W.rec[l] = -2;
 				b->seednum = (int16_t)(k + 1);
 			});
 			lanes.sync();
+			if (lanes.ballot([&](int l) { return (act >> l & 1u) && W.rec[l] == -2; })) { T.full = true; return; }
 			lanes.each([&](int l) {
 				if (!(act >> l & 1u)) return;
 				Bucket* b = T.pool + W.rec[l];
@@ -615,8 +645,8 @@ ASM_HD int walk_strand_w(const L& lanes, const Strand& s, int read_name, int cha
 		lanes.sync();
 		lanes.each([&](int l) {
 			for (int i = l; i < u_k; i += 32) {
-				if (i < na) { W.t_loc[i] = a->loczhi[i]; W.t_seedn[i] = a->seedno[i]; }
-				else { W.t_loc[i] = b->loczhi[i - na] + (na ? ZV : 0); W.t_seedn[i] = b->seedno[i - na]; }
+				if (i < na) { W.t_loc[i] = ent_loc(T, a, i); W.t_seedn[i] = ent_seed(T, a, i); }
+				else { W.t_loc[i] = ent_loc(T, b, i - na) + (na ? ZV : 0); W.t_seedn[i] = ent_seed(T, b, i - na); }
 				W.t_score[i] = 0;
 			}
 		});
@@ -671,12 +701,12 @@ ASM_HD int walk_strand_w(const L& lanes, const Strand& s, int read_name, int cha
 			if (lanes.leader()) {
 				int u = readstart / ZV, sk = readstart % ZV, k = 0;
 				Bucket* t = table_find(T, u);
-				if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (t->loczhi[j] < sk) t->loczhi[k++] = t->loczhi[j]; t->score = (int16_t)k; }
+				if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (ent_loc(T, t, j) < sk) ent_set_loc(T, t, k++, ent_loc(T, t, j)); t->score = (int16_t)k; }
 				const int kend = readend / ZV;
 				for (++u; u < kend; ++u) { t = table_find(T, u); if (t) t->score = 0; }
 				t = table_find(T, u);
 				k = 0; sk = readend % ZV;
-				if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (t->loczhi[j] > sk) t->loczhi[k++] = t->loczhi[j]; t->score = (int16_t)k; }
+				if (t) { for (int j = 0; j < t->score && j < SM; ++j) if (ent_loc(T, t, j) > sk) ent_set_loc(T, t, k++, ent_loc(T, t, j)); t->score = (int16_t)k; }
 			}
 			lanes.sync();
 			continue;

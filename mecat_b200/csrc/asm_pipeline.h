@@ -91,6 +91,8 @@ inline int64_t table_room(int64_t bound, int64_t hits, int len, int64_t text, in
 	const int64_t guess = (3 * nk * text / KMERS) / 2 + hits / 16 + 64;
 	return std::min<int64_t>(bound, guess * mult);
 }
+// room in the second pool (full entry arrays): blocks that collect more than one k-mer -- those of true overlaps
+inline int64_t entries_room(int64_t bound, int64_t hits, int mult) { return std::min<int64_t>(bound, (hits / 16 + 64) * mult); }
 inline uint32_t slots_for(int64_t room) { uint32_t sl = 2; while ((int64_t)sl < 2 * room) sl <<= 1; return sl; }
 
 // strands units[lo, hi): block tables in one allocation, records from a shared pool.  A table or a pool that runs out
@@ -103,37 +105,42 @@ bool seed_range(B& be, const AsmIndex& I, const QuerySet& Q, SeedState& S, const
 	if (!n) return true;
 	if (n == 1) mult = 1 << 20;
 	std::vector<int64_t> slot_off(n + 1, 0), list_off(n + 1, 0);
-	int64_t pool_cap = 0;
+	int64_t pool_cap = 0, big_cap = 0;
 	for (size_t i = 0; i < n; ++i) {
 		const int32_t u = units[lo + i];
 		const int64_t c = table_room(S.cap[(size_t)u], S.hits[(size_t)u], Q.h_len[u >> 1], I.n, mult);
 		slot_off[i + 1] = slot_off[i] + slots_for(c); list_off[i + 1] = list_off[i] + c;
 		pool_cap += c;
+		big_cap += entries_room(S.cap[(size_t)u], S.hits[(size_t)u], mult);
 	}
+	if (big_cap < 1) big_cap = 1;
+	if (big_cap > 0x7fffffff) big_cap = 0x7fffffff;
 	if (n > 1) pool_cap = pool_cap / be.pool_divisor() + 64;      // few strands fill their room
 	if (pool_cap < 1) pool_cap = 1;
 	if (pool_cap > 0x7fffffff) pool_cap = 0x7fffffff;
 	Slot* slots = be.template alloc<Slot>((size_t)slot_off[n]);
 	int32_t* lists = be.template alloc<int32_t>((size_t)list_off[n]);
 	Bucket* pool = be.template alloc<Bucket>((size_t)pool_cap);
+	Entries* big = be.template alloc<Entries>((size_t)big_cap);
 	int64_t* d_slot_off = be.template alloc<int64_t>(n + 1);
 	int64_t* d_list_off = be.template alloc<int64_t>(n + 1);
 	int32_t* d_units = be.template alloc<int32_t>(n);
 	int32_t* d_status = be.template alloc<int32_t>(n);
-	uint32_t* d_used = be.template alloc<uint32_t>(1);
-	if (!slots || !lists || !pool || !d_slot_off || !d_list_off || !d_units || !d_status || !d_used) return false;
-	if (!be.fill(slots, 0, sizeof(Slot) * (size_t)slot_off[n]) || !be.fill(d_used, 0, sizeof(uint32_t)) ||
+	uint32_t* d_used = be.template alloc<uint32_t>(2);
+	if (!slots || !lists || !pool || !big || !d_slot_off || !d_list_off || !d_units || !d_status || !d_used) return false;
+	if (!be.fill(slots, 0, sizeof(Slot) * (size_t)slot_off[n]) || !be.fill(d_used, 0, 2 * sizeof(uint32_t)) ||
 	    !be.upload(d_slot_off, slot_off.data(), n + 1) || !be.upload(d_list_off, list_off.data(), n + 1) || !be.upload(d_units, units.data() + lo, n)) return false;
 	SeedWarpFn f;
 	f.q = Q.q; f.sub = I.reads(); f.units = d_units; f.begin = I.begin; f.pos = I.pos; f.gate = gate; f.maxc = maxc;
 	f.tab.slot_off = d_slot_off; f.tab.list_off = d_list_off; f.tab.slots = slots; f.tab.lists = lists; f.tab.pool = pool; f.tab.pool_used = d_used;
 	f.tab.pool_cap = (uint32_t)pool_cap;
+	f.tab.big = big; f.tab.big_used = d_used + 1; f.tab.big_cap = (uint32_t)big_cap;
 	f.cands = S.cands; f.ncand = S.ncand; f.status = d_status;
 	if (!be.launch_seed((int64_t)n, f, ST_SEED)) return false;
 	std::vector<int32_t> status(n);
 	if (!be.download(status.data(), d_status, n)) return false;
 	++*batches;
-	if (!be.release(slots) || !be.release(lists) || !be.release(pool) || !be.release(d_slot_off) || !be.release(d_list_off) || !be.release(d_units) ||
+	if (!be.release(slots) || !be.release(lists) || !be.release(pool) || !be.release(big) || !be.release(d_slot_off) || !be.release(d_list_off) || !be.release(d_units) ||
 	    !be.release(d_status) || !be.release(d_used)) return false;
 	bool full = false;
 	for (size_t i = 0; i < n; ++i) {
@@ -194,7 +201,8 @@ bool overlaps(B& be, const AsmIndex& I, const char* h_qtext, int64_t qn, const i
 		while (hi < units.size()) {
 			const int32_t u = units[hi];
 			const int64_t c = table_room(S.cap[(size_t)u], S.hits[(size_t)u], Q.h_len[u >> 1], I.n, 1);
-			const int64_t need = (int64_t)slots_for(c) * (int64_t)sizeof(Slot) + c * 4 + (c / be.pool_divisor() + 1) * (int64_t)sizeof(Bucket) + 64;
+			const int64_t need = (int64_t)slots_for(c) * (int64_t)sizeof(Slot) + c * 4 + (c / be.pool_divisor() + 1) * (int64_t)sizeof(Bucket) +
+			                     entries_room(S.cap[(size_t)u], S.hits[(size_t)u], 1) * (int64_t)sizeof(Entries) + 64;
 			if (hi > lo && bytes + need > budget) break;
 			bytes += need; ++hi;
 		}
