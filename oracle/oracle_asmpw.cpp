@@ -457,7 +457,9 @@ struct Mapper
 // Query reads likewise.  variant 0 = mecat2asmpw, 1 = mecat2trimpw; maxc = MAXC (100, the *50 programs 50).
 // history 0: every strand starts from zeroed blocks (the header's convention, what the product implements); 1: blocks
 // keep what earlier reads of this call wrote, like one reference thread that maps all reads of the file in order (-T1,
-// or any -T for files of at most PLL = 500 reads) -- this mode must reproduce the unmodified binary byte for byte.
+// or any -T for files of at most PLL = 500 reads); 2: the same, but the memory is fresh at every chunk of PLL = 500 reads
+// (:26, :556-567), what the binary does when every chunk is taken by a thread of its own (-T at least the number of
+// chunks).  Modes 1 and 2 must reproduce the unmodified binary byte for byte.
 // Records in read order, within a read in candidate order; *out is malloc'ed (10 x 4 bytes per record).
 extern "C" int orc_asm_overlaps(const char* text, int seqcount, const int32_t* starts, const int32_t* lens, int n, int first_id,
                                 const char* qtext, const int32_t* qstarts, const int32_t* qlens, int nq, int qfirst_id, int variant, int maxc,
@@ -471,7 +473,11 @@ extern "C" int orc_asm_overlaps(const char* text, int seqcount, const int32_t* s
 	m->idx.build(text, seqcount);
 	m->db.assign(seqcount / ZV + 5 + 256, Block());
 	for (Block& b : m->db) { memset(&b, 0, sizeof b); b.index = -1; }
-	for (int r = 0; r < nq; ++r) m->map_read(qtext + qstarts[r], qlens[r], qfirst_id + r);
+	for (int r = 0; r < nq; ++r) {
+		if (history == 2 && r % 500 == 0)
+			for (Block& b : m->db) { memset(&b, 0, sizeof b); b.index = -1; }
+		m->map_read(qtext + qstarts[r], qlens[r], qfirst_id + r);
+	}
 	*nout = m->out.size();
 	*out = malloc(m->out.size() * sizeof(Rec) + 1);
 	memcpy(*out, m->out.data(), m->out.size() * sizeof(Rec));

@@ -261,6 +261,14 @@ def make_asm(meta):
     asm_workdir("asmdeep", wrk)
     keep("asmdeep.asmpw50", run("mecat2asmpw50", wrk, 1, 1, 1))
     keep("asmdeep.trimpw50", run("mecat2trimpw50", wrk, 1, 1, 1))
+    # the schedule fixture: only digests of the sorted lines, one thread and one thread per chunk
+    wrk = os.path.join(tmp, "asmsched")
+    asm_workdir("asmsched", wrk)
+    t1, t4 = run("mecat2asmpw50", wrk, 1, 1, 1), run("mecat2asmpw50", wrk, 1, 1, 4)
+    m["asmsched_lines"] = len(t1)
+    m["asmsched_T1_sha256"] = hashlib.sha256("\n".join(t1).encode()).hexdigest()
+    m["asmsched_T4_sha256"] = hashlib.sha256("\n".join(t4).encode()).hexdigest()
+    m["asmsched_T1_vs_T4_lines"] = len(set(t1) ^ set(t4))
     meta["asm"] = m
     shutil.rmtree(tmp)
 

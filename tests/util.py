@@ -621,6 +621,8 @@ ASM_CASES = {
     # ~56x of a 25 kb genome: more candidates per read than the *50 programs keep, blocks whose score passes SM = 60
     # (the neighbour votes then read beyond a block's 60 entries), a few N letters, lower-case reads, two stubs
     "asmdeep": dict(n=400, genome=25000, seed=91, mean=3500, sd=900, err=0.01, files=1),
+    # three chunks of PLL = 500 reads at ~130x: the binary's output depends on its thread count here (only digests are kept)
+    "asmsched": dict(n=1500, genome=40000, seed=123, mean=3500, sd=900, err=0.01, files=1),
 }
 
 
