@@ -75,8 +75,7 @@ struct Index
 	}
 };
 
-// |a / (b * len) - 1| in the two forms the reference uses
-bool close_f(int a, int b, float len, double lim) { return fabs(a / (b * len) - 1.0) < lim; }            // insert_loc form, float quotient
+// |a / (b * len) - 1| < 0.10 in the two forms the reference uses (insert_loc, a third form, is never called: :605)
 bool close_f1(int a, int b, float len) { return fabs(a / (b * len) - 1) < 0.10; }                         // find_location form
 bool close_d(int a, int b) { return fabs(a / (b * BC * 1.0) - 1.0) < 0.10; }                              // neighbour votes, double quotient
 
