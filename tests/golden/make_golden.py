@@ -261,6 +261,10 @@ def make_asm(meta):
     asm_workdir("asmdeep", wrk)
     keep("asmdeep.asmpw50", run("mecat2asmpw50", wrk, 1, 1, 1))
     keep("asmdeep.trimpw50", run("mecat2trimpw50", wrk, 1, 1, 1))
+    wrk = os.path.join(tmp, "asmodd")
+    asm_workdir("asmodd", wrk)
+    keep("asmodd.asmpw", run("mecat2asmpw", wrk, 1, 1, 4))
+    keep("asmodd.trimpw50", run("mecat2trimpw50", wrk, 1, 1, 1))
     # the schedule fixture: only digests of the sorted lines, one thread and one thread per chunk
     wrk = os.path.join(tmp, "asmsched")
     asm_workdir("asmsched", wrk)

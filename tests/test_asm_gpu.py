@@ -88,6 +88,14 @@ def test_deep_file_matches_the_oracle(gpu_ctx, deep_files, monkeypatch):
     assert gpu_ctx.stats()["kernel_launches"]["asm_seed"] - before > 20
 
 
+def test_awkward_reads_match_the_unmodified_binaries(gpu_ctx, tmp_path):
+    """The `asmodd` fixture (tests/util.py: a duplicate, tandem repeats, poly-A, N runs, other letters, mixed case, reads of
+    1 / 13 / 14 letters, a contained read) through the C ABI against the goldens of both programs."""
+    files = util.asm_workdir("asmodd", str(tmp_path / "odd"))
+    assert sorted(gpu_pairs(gpu_ctx, files)) == gold("asmodd.asmpw")
+    assert sorted(gpu_pairs(gpu_ctx, files, variant=1, maxc=50)) == gold("asmodd.trimpw50")
+
+
 def test_bad_inputs_fail_loudly(gpu_ctx):
     import mecat_b200
     idx = gpu_ctx.asm_index_build(mecat_b200.AsmReads(["ACGT" * 100, "TTGCA" * 90], 1))

@@ -174,3 +174,17 @@ def test_oracle_reproduces_both_schedules_of_the_binary(tmp_path):
     assert digest[1] == GOLD["asmsched_T1_sha256"]
     assert digest[2] == GOLD["asmsched_T4_sha256"]
     assert digest[0] not in (digest[1], digest[2])
+
+
+def test_awkward_reads_match_the_unmodified_binaries(tmp_path):
+    """A duplicated read, tandem repeats (every k-mer of the unit ~180 times), poly-A (its list is dropped), ACGT x 600, N every
+    50 letters, a read of N only, other IUPAC letters, mixed case, reads of 1 / 13 / 14 letters, a contained read: the oracle in
+    both conventions and the product's bodies print what the binaries print."""
+    first, reads = util.asm_workdir("asmodd", str(tmp_path / "odd"))[0]
+    for variant, maxc, name in ((0, 100, "asmodd.asmpw"), (1, 50, "asmodd.trimpw50")):
+        want = gold(name)
+        assert len(want) == GOLD["num_" + name.replace(".", "_")]
+        for history in (0, 1):
+            assert sorted(util.asm_lines(util.asm_oracle_overlaps(reads, first, reads, first, variant=variant, maxc=maxc, history=history))) == want
+        got, _ = util.asm_harness_overlaps(reads, first, reads, first, variant=variant, maxc=maxc)
+        assert sorted(util.asm_lines(got)) == want

@@ -623,6 +623,8 @@ ASM_CASES = {
     "asmdeep": dict(n=400, genome=25000, seed=91, mean=3500, sd=900, err=0.01, files=1),
     # three chunks of PLL = 500 reads at ~130x: the binary's output depends on its thread count here (only digests are kept)
     "asmsched": dict(n=1500, genome=40000, seed=123, mean=3500, sd=900, err=0.01, files=1),
+    # awkward reads among ordinary ones: a duplicate, tandem repeats, poly-A, N runs, other letters, reads of 1 / 13 / 14 letters
+    "asmodd": dict(n=200, genome=30000, seed=17, mean=3000, sd=600, err=0.02, files=1),
 }
 
 
@@ -632,6 +634,19 @@ def asm_reads(name, tmp_dir):
     fa = os.path.join(tmp_dir, name + ".all.fa")
     gen_reads(fa, c["n"], c["genome"], c["seed"], c["mean"], c["sd"], err=c["err"])
     seqs = [s for _, s in read_fasta_raw(fa)]
+    if name == "asmodd":
+        unit = seqs[3][100:137]
+        seqs[11] = seqs[10]                                   # the same read twice
+        seqs[20] = unit * 100                                 # tandem repeat: every k-mer of the unit ~180 times in the file
+        seqs[21] = unit * 80
+        seqs[30] = "A" * 2000                                 # one k-mer 1 988 times: its list is dropped (> 256)
+        seqs[31] = "ACGT" * 600
+        seqs[40] = "".join("N" if i % 50 == 49 else c for i, c in enumerate(seqs[40]))
+        seqs[41] = "N" * 2000
+        seqs[50], seqs[51], seqs[52] = seqs[50][:13], seqs[51][:14], seqs[52][:1]
+        seqs[60] = "".join(c.lower() if i % 3 else c for i, c in enumerate(seqs[60]))
+        seqs[61] = "".join("RYKM"[i % 4] if i % 97 == 5 else c for i, c in enumerate(seqs[61]))
+        seqs[70] = seqs[10][500:2500]                         # contained in reads 10 and 11
     if name == "asmdeep":
         for r in range(len(seqs)):
             s = seqs[r]
