@@ -196,6 +196,14 @@ int main(int argc, char** argv)
 			t_write[(size_t)k] += now() - m1;
 			}
 		}
+		if (k == 0 && getenv("MECAT_B200_STATS")) {       // per-kernel CUDA-event times of device 0's share, one line
+			mecat_b200_stats st;
+			if (!mecat_b200_get_stats(ctx, &st))
+				fprintf(stderr, "[kernel ms] asm_index=%.1f(%lld) asm_seed=%.1f(%lld) asm_extend=%.1f(%lld) hits=%lld candidates=%lld records=%lld h2d=%.1fMB d2h=%.1fMB\n",
+				        st.kernel_ms[MECAT_K_ASM_INDEX], (long long)st.kernel_launches[MECAT_K_ASM_INDEX], st.kernel_ms[MECAT_K_ASM_SEED],
+				        (long long)st.kernel_launches[MECAT_K_ASM_SEED], st.kernel_ms[MECAT_K_ASM_EXTEND], (long long)st.kernel_launches[MECAT_K_ASM_EXTEND],
+				        (long long)st.num_hits, (long long)st.num_candidates, (long long)st.num_records, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6);
+		}
 		if (!fast_exit) { mecat_b200_asm_index_release(ctx, idx); mecat_b200_destroy(ctx); }
 	};
 	if (ngpu == 1) work(0);

@@ -207,7 +207,7 @@ int main(int argc, char* argv[])
 			if (!mecat_b200_get_stats(c, &st)) {
 				static const char* names[MECAT_K_NUM] = {"orient", "index_count", "scan", "index_fill", "index_sort", "seed", "walk", "merge", "extend",
 				                                         "finalize", "cns_accept", "cns_normvote", "cns_segment", "cns_region", "cns_poa", "cns_assemble",
-				                                         "ref_count", "ref_seed", "ref_rescue"};
+				                                         "ref_count", "ref_seed", "ref_rescue", "asm_index", "asm_seed", "asm_extend"};
 				fprintf(stderr, "[kernel ms]");
 				for (int k = 0; k < MECAT_K_NUM; ++k)
 					if (st.kernel_launches[k]) fprintf(stderr, " %s=%.1f(%lld)", names[k], st.kernel_ms[k], (long long)st.kernel_launches[k]);

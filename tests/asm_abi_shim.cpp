@@ -31,6 +31,7 @@ int mecat_b200_init(mecat_b200_ctx** ctx, int, void*) { *ctx = new mecat_b200_ct
 void mecat_b200_destroy(mecat_b200_ctx* ctx) { delete ctx; }
 const char* mecat_b200_last_error(mecat_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void mecat_b200_free(mecat_b200_ctx*, void* p) { free(p); }
+int mecat_b200_get_stats(mecat_b200_ctx*, mecat_b200_stats* out) { memset(out, 0, sizeof *out); return 0; }
 
 int mecat_b200_asm_index_build(mecat_b200_ctx*, const mecat_asm_reads* s, void** asmidx)
 {
